@@ -1,0 +1,85 @@
+"""distributed_tensorflow_b200 -- a B200-native parameter-server training framework.
+
+Same capabilities and ``tf.train``-style surface as the gctian/distributed-tensorflow
+examples (ClusterSpec ps/worker roles, between-graph and in-graph replication,
+``replica_device_setter``, async and ``SyncReplicasOptimizer`` training,
+``MonitoredTrainingSession`` + hooks, name-keyed checkpoints, chrome-trace
+timelines), rebuilt for Blackwell: PyTorch tensors, hand-written sm_100a
+kernels (tcgen05/TMEM/TMA GEMMs, fused softmax-xent, fused reduce+apply), and
+NVLink-5 peer memory for the ps<->worker data plane.
+
+Typical use mirrors the reference scripts::
+
+    import distributed_tensorflow_b200 as dtf
+    cluster = dtf.train.ClusterSpec({"ps": [...], "worker": [...]})
+    server = dtf.train.Server(cluster, job_name=..., task_index=...)
+    with dtf.device(dtf.train.replica_device_setter(cluster=cluster, worker_device=...)):
+        ...
+    with dtf.train.MonitoredTrainingSession(master=server.target, is_chief=..., hooks=[...]) as sess:
+        while not sess.should_stop():
+            sess.run(train_op, feed_dict={...})
+"""
+from __future__ import annotations
+
+import types as _types
+
+import torch as _torch
+
+from .framework import errors
+from .framework.device import DeviceSpec, device
+from .framework.graph import (Graph, GraphKeys, Tensor, add_to_collection, control_dependencies, convert_to_tensor,
+                              get_collection, get_default_graph, name_scope, reset_default_graph)
+from .framework.ops import *  # noqa: F401,F403  (op builders: matmul, relu, placeholder, ...)
+from .framework.ops import (abs, arg_max, argmax, cast, float16, float32, float64, bfloat16, int32, int64, uint8,
+                            int8, pow, tuple_ as tuple, gradients, bool_ as bool)  # noqa: F401,A004
+from .framework.variables import (AUTO_REUSE, Variable, all_variables, assign, assign_add, assign_sub,
+                                  constant_initializer, get_variable, get_variable_scope, global_variables,
+                                  global_variables_initializer, glorot_uniform_initializer,
+                                  initialize_all_variables, is_variable_initialized, local_variables,
+                                  local_variables_initializer, ones_initializer, random_normal_initializer,
+                                  random_uniform_initializer, report_uninitialized_variables,
+                                  trainable_variables, truncated_normal_initializer, variable_scope,
+                                  variables_initializer, variance_scaling_initializer, zeros_initializer)
+from .client.session import (ConfigProto, GPUOptions, InteractiveSession, RunMetadata, RunOptions, Session,
+                             get_default_session)
+from .utils import flags as _flags_mod
+from .utils import summary
+from .utils.timeline import Timeline
+
+__version__ = "0.1.0"
+
+
+def set_random_seed(seed: int) -> None:
+    """Graph-level seed: makes initialisers reproducible across tasks (same seed => same draws)."""
+    get_default_graph().seed = int(seed)
+
+
+# -- tf.app ------------------------------------------------------------------------------------------
+def _app_run(main=None, argv=None):
+    import sys
+    _flags_mod.FLAGS(sys.argv if argv is None else argv)
+    main = main or sys.modules["__main__"].main
+    sys.exit(main(sys.argv[:1] + _flags_mod.FLAGS.unparsed))
+
+
+app = _types.SimpleNamespace(flags=_flags_mod.flags, run=_app_run)
+flags = _flags_mod.flags
+
+# -- tf.nn --------------------------------------------------------------------------------------------
+from .framework import ops as _ops  # noqa: E402
+
+nn = _types.SimpleNamespace(
+    relu=_ops.relu, softmax=_ops.softmax, log_softmax=_ops.log_softmax, xw_plus_b=_ops.xw_plus_b,
+    bias_add=_ops.bias_add, sigmoid=_ops.sigmoid, tanh=_ops.tanh, conv2d=_ops.conv2d, max_pool=_ops.max_pool,
+    avg_pool=_ops.avg_pool, dropout=_ops.dropout, l2_loss=_ops.l2_loss, moments=_ops.moments,
+    batch_normalization=_ops.batch_normalization, fused_batch_norm_train=_ops.fused_batch_norm_train,
+    softmax_cross_entropy_with_logits=_ops.softmax_cross_entropy_with_logits,
+    sparse_softmax_cross_entropy_with_logits=_ops.sparse_softmax_cross_entropy_with_logits,
+    clipped_softmax_xent_sum=_ops.clipped_softmax_xent_sum,
+)
+
+# -- tf.train -----------------------------------------------------------------------------------------
+from . import train  # noqa: E402
+from .python_compat import input_data, timeline  # noqa: E402,F401
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,209 @@
+"""Dispatch layer between graph kernels and the sm_100a CUDA library.
+
+CPU tensors run plain PyTorch (so the full API is testable without a GPU).
+CUDA tensors run the hand-written kernels from ``csrc/`` through
+``ops/cuda_lib.py`` wrapped in ``torch.autograd.Function`` so the graph
+executor's reverse pass works unchanged:
+
+* ``matmul`` / ``linear``  -> tcgen05 GEMM (bf16 operands from TMA, fp32 accumulate in TMEM,
+  bias/ReLU epilogue) for forward *and* both backward GEMMs (K1, K4, K11);
+* ``clipped_softmax_xent_sum`` / ``softmax_xent`` -> fused softmax + cross-entropy
+  forward + dlogits (K2, K3);
+* ``conv2d_nhwc`` -> im2col gather + tcgen05 GEMM (K14).
+
+If a tensor is on a CUDA device and the library failed to load, these raise
+(no silent eager fallback on a GPU box).  ``DTF_FORCE_EAGER=1`` switches the
+CUDA path to cuBLAS/eager PyTorch for A/B debugging only.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+_FORCE_EAGER = os.environ.get("DTF_FORCE_EAGER", "0") == "1"
+
+
+def _use_native(t: torch.Tensor) -> bool:
+    return t.is_cuda and not _FORCE_EAGER
+
+
+def _lib():
+    from . import cuda_lib
+    return cuda_lib
+
+
+# ---------------------------------------------------------------------------
+# GEMM family
+# ---------------------------------------------------------------------------
+class _MatMulFn(torch.autograd.Function):
+    """C = op(A) @ op(B) on the tcgen05 GEMM; backward = two more tcgen05 GEMMs."""
+
+    @staticmethod
+    def forward(ctx, a, b, ta: bool, tb: bool):
+        lib = _lib()
+        ctx.save_for_backward(a, b)
+        ctx.ta, ctx.tb = ta, tb
+        return lib.gemm(a, b, ta, tb)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib()
+        a, b = ctx.saved_tensors
+        ta, tb = ctx.ta, ctx.tb
+        g = g.contiguous()
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            # A' = op(A): dA' = g @ op(B)^T ; undo op on A
+            ga = lib.gemm(b, g, tb, True) if ta else lib.gemm(g, b, False, not tb)
+        if ctx.needs_input_grad[1]:
+            gb = lib.gemm(g, a, True, ta) if tb else lib.gemm(a, g, not ta, False)
+        return ga, gb, None, None
+
+
+def matmul(a: torch.Tensor, b: torch.Tensor, ta: bool = False, tb: bool = False) -> torch.Tensor:
+    if _use_native(a) and a.dim() == 2 and b.dim() == 2 and a.is_floating_point():
+        return _MatMulFn.apply(a, b, ta, tb)
+    x = a.t() if ta else a
+    y = b.t() if tb else b
+    return torch.matmul(x, y)
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = act(x @ W + b), bias+ReLU applied in the GEMM epilogue straight out of TMEM."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu: bool):
+        lib = _lib()
+        y = lib.gemm(x, w, False, False, bias=b, relu=relu)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.relu = relu
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib()
+        x, w, y = ctx.saved_tensors
+        g = g.contiguous()
+        if ctx.relu:
+            g = lib.relu_grad(g, y)
+        gx = lib.gemm(g, w, False, True) if ctx.needs_input_grad[0] else None
+        gw = lib.gemm(x, g, True, False) if ctx.needs_input_grad[1] else None
+        gb = lib.colsum(g) if ctx.needs_input_grad[2] else None
+        return gx, gw, gb, None
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool = False) -> torch.Tensor:
+    if _use_native(x) and x.dim() == 2 and b is not None:
+        return _LinearFn.apply(x, w, b, relu)
+    y = torch.matmul(x, w)
+    if b is not None:
+        y = y + b
+    return torch.relu(y) if relu else y
+
+
+# ---------------------------------------------------------------------------
+# softmax / cross-entropy
+# ---------------------------------------------------------------------------
+class _ClippedXentSumFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, clip_min: float):
+        lib = _lib()
+        loss, dlogits = lib.softmax_xent_fwd_bwd(logits, labels, clip_min, reduce_sum=True)
+        ctx.save_for_backward(dlogits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * g, None, None
+
+
+def clipped_softmax_xent_sum(logits: torch.Tensor, labels: torch.Tensor, clip_min: float = 1e-10) -> torch.Tensor:
+    """``-sum(labels * log(clip(softmax(logits), clip_min, 1)))`` (reference distributed_mnist.py:112-113)."""
+    if _use_native(logits) and logits.dim() == 2:
+        return _ClippedXentSumFn.apply(logits, labels, float(clip_min))
+    y = torch.softmax(logits.float(), dim=-1)
+    return -(labels.float() * torch.log(torch.clamp(y, clip_min, 1.0))).sum()
+
+
+class _SoftmaxXentFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        lib = _lib()
+        loss, dlogits = lib.softmax_xent_fwd_bwd(logits, labels, 0.0, reduce_sum=False)
+        ctx.save_for_backward(dlogits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * g.unsqueeze(-1), None
+
+
+def softmax_xent(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """Per-row ``-sum(labels * log_softmax(logits))``."""
+    if _use_native(logits) and logits.dim() == 2:
+        return _SoftmaxXentFn.apply(logits, labels)
+    return -(labels.float() * torch.log_softmax(logits.float(), dim=-1)).sum(dim=-1)
+
+
+# ---------------------------------------------------------------------------
+# convolution (NHWC data, HWIO filter)
+# ---------------------------------------------------------------------------
+def _same_pad(size: int, k: int, s: int):
+    out = -(-size // s)
+    total = max((out - 1) * s + k - size, 0)
+    return total // 2, total - total // 2
+
+
+class _ConvFn(torch.autograd.Function):
+    """Implicit-GEMM convolution: NHWC patches gathered to a [N*Ho*Wo, kh*kw*Cin] bf16 matrix by a
+    hand-written gather kernel, then the tcgen05 GEMM against the [kh*kw*Cin, Cout] filter."""
+
+    @staticmethod
+    def forward(ctx, x, w, strides, pads):
+        lib = _lib()
+        kh, kw, cin, cout = w.shape
+        cols, (n, ho, wo) = lib.im2col_nhwc(x, kh, kw, strides, pads)
+        w2 = w.reshape(kh * kw * cin, cout)
+        y = lib.gemm(cols, w2, False, False)
+        ctx.save_for_backward(cols, w2)
+        ctx.meta = (x.shape, w.shape, strides, pads, (n, ho, wo))
+        return y.reshape(n, ho, wo, cout)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib()
+        cols, w2 = ctx.saved_tensors
+        xshape, wshape, strides, pads, (n, ho, wo) = ctx.meta
+        g2 = g.reshape(n * ho * wo, wshape[3]).contiguous()
+        gx = gw = None
+        if ctx.needs_input_grad[1]:
+            gw = lib.gemm(cols, g2, True, False).reshape(wshape)
+        if ctx.needs_input_grad[0]:
+            gcols = lib.gemm(g2, w2, False, True)
+            gx = lib.col2im_nhwc(gcols, xshape, wshape[0], wshape[1], strides, pads)
+        return gx, gw, None, None
+
+
+def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, strides: Sequence[int], padding: str,
+                data_format: str = "NHWC") -> torch.Tensor:
+    if data_format != "NHWC":
+        raise ValueError("only NHWC is supported (channels-last is the tensor-core layout)")
+    sh, sw = int(strides[1]), int(strides[2])
+    kh, kw = int(w.shape[0]), int(w.shape[1])
+    if padding.upper() == "SAME":
+        pt, pb = _same_pad(x.shape[1], kh, sh)
+        pl, pr = _same_pad(x.shape[2], kw, sw)
+    else:
+        pt = pb = pl = pr = 0
+    if _use_native(x):
+        return _ConvFn.apply(x, w, (sh, sw), (pt, pb, pl, pr))
+    xn = x.permute(0, 3, 1, 2)
+    if pt or pb or pl or pr:
+        xn = F.pad(xn, (pl, pr, pt, pb))
+    y = F.conv2d(xn, w.permute(3, 2, 0, 1), stride=(sh, sw))
+    return y.permute(0, 2, 3, 1)

@@ -1,0 +1,189 @@
+"""Control-plane RPC between tasks (the role gRPC plays under TF).
+
+One TCP listener per task (``multiprocessing.connection``: length-prefixed
+pickles), one handler thread per connection so blocking calls (token dequeue,
+``take_grad``) never stall other clients.  Tensors cross as CPU tensors.
+
+This path carries *control* and small tensors.  On B200 the bulk traffic
+(parameter pull, gradient push) does not use it: it goes through NVLink peer
+memory from inside the kernels (``parallel/fabric.py`` + ``ops/``).
+"""
+from __future__ import annotations
+
+import pickle
+import socket
+import threading
+import time
+import traceback
+from multiprocessing.connection import Client, Connection, Listener
+from typing import Any, Callable, Dict, Optional, Tuple
+
+import torch
+
+from ..framework import errors
+
+__all__ = ["RpcServer", "RpcClient", "parse_address", "to_wire"]
+
+_AUTHKEY = b"dtf-b200-control-plane"
+
+_ERRORS = {c.__name__: c for c in (
+    errors.OpError, errors.FailedPreconditionError, errors.AbortedError, errors.UnavailableError,
+    errors.OutOfRangeError, errors.CancelledError, errors.DeadlineExceededError, errors.NotFoundError,
+    errors.InvalidArgumentError, ValueError, KeyError, TypeError, RuntimeError, NotImplementedError)}
+
+
+def parse_address(addr: str) -> Tuple[str, int]:
+    addr = addr.strip()
+    for prefix in ("grpc://", "dtf://", "tcp://"):
+        if addr.startswith(prefix):
+            addr = addr[len(prefix):]
+    host, _, port = addr.rpartition(":")
+    if not host or host in ("localhost", "0.0.0.0"):
+        host = "127.0.0.1"
+    return host, int(port)
+
+
+def to_wire(value: Any) -> Any:
+    """Detach + move tensors to host memory, recursively."""
+    if isinstance(value, torch.Tensor):
+        t = value.detach()
+        return t.cpu() if t.device.type != "cpu" else t
+    if isinstance(value, dict):
+        return {k: to_wire(v) for k, v in value.items()}
+    if isinstance(value, (list, tuple)):
+        return type(value)(to_wire(v) for v in value)
+    return value
+
+
+class RpcServer:
+    def __init__(self, address: str, service: Any):
+        self.host, self.port = parse_address(address)
+        self._service = service
+        self._listener = Listener((self.host, self.port), authkey=_AUTHKEY, backlog=64)
+        self._closed = threading.Event()
+        self._conns = []
+        self._thread = threading.Thread(target=self._accept_loop, name="dtf-rpc-accept-%d" % self.port, daemon=True)
+        self._thread.start()
+
+    def _accept_loop(self) -> None:
+        while not self._closed.is_set():
+            try:
+                conn = self._listener.accept()
+            except (OSError, EOFError, Exception):
+                if self._closed.is_set():
+                    return
+                continue
+            self._conns.append(conn)
+            threading.Thread(target=self._serve, args=(conn,), name="dtf-rpc-conn", daemon=True).start()
+
+    def _serve(self, conn: Connection) -> None:
+        try:
+            while not self._closed.is_set():
+                try:
+                    method, args, kwargs = pickle.loads(conn.recv_bytes())
+                except (EOFError, OSError, ConnectionError):
+                    return
+                try:
+                    fn = getattr(self._service, "rpc_" + method)
+                    result = ("ok", to_wire(fn(*args, **kwargs)))
+                except BaseException as e:  # noqa: BLE001 - errors travel to the caller
+                    result = ("err", type(e).__name__, str(e), traceback.format_exc())
+                try:
+                    conn.send_bytes(pickle.dumps(result, protocol=pickle.HIGHEST_PROTOCOL))
+                except (OSError, ConnectionError, BrokenPipeError):
+                    return
+        finally:
+            try:
+                conn.close()
+            except OSError:
+                pass
+
+    def close(self) -> None:
+        self._closed.set()
+        try:
+            self._listener.close()
+        except OSError:
+            pass
+        for c in self._conns:
+            try:
+                c.close()
+            except OSError:
+                pass
+        # unblock accept()
+        try:
+            s = socket.create_connection((self.host, self.port), timeout=0.2)
+            s.close()
+        except OSError:
+            pass
+
+
+class RpcClient:
+    """Client stub; one connection per calling thread (blocking calls do not serialise threads)."""
+
+    def __init__(self, address: str, connect_timeout: float = 30.0):
+        self.address = address
+        self.host, self.port = parse_address(address)
+        self._tls = threading.local()
+        self._timeout = connect_timeout
+        self._all = []
+        self._lock = threading.Lock()
+
+    def _conn(self) -> Connection:
+        c = getattr(self._tls, "conn", None)
+        if c is None:
+            deadline = time.time() + self._timeout
+            delay = 0.02
+            while True:
+                try:
+                    c = Client((self.host, self.port), authkey=_AUTHKEY)
+                    break
+                except (ConnectionRefusedError, FileNotFoundError, OSError) as e:
+                    if time.time() > deadline:
+                        raise errors.UnavailableError("cannot reach task at %s:%d: %s" % (self.host, self.port, e))
+                    time.sleep(delay)
+                    delay = min(delay * 1.5, 0.5)
+            self._tls.conn = c
+            with self._lock:
+                self._all.append(c)
+        return c
+
+    def call(self, method: str, *args, **kwargs) -> Any:
+        try:
+            c = self._conn()
+            c.send_bytes(pickle.dumps((method, to_wire(args), to_wire(kwargs)), protocol=pickle.HIGHEST_PROTOCOL))
+            reply = pickle.loads(c.recv_bytes())
+        except (EOFError, ConnectionError, BrokenPipeError, OSError) as e:
+            self._drop()
+            raise errors.UnavailableError("task at %s:%d went away during %s: %s" % (self.host, self.port, method, e))
+        if reply[0] == "ok":
+            return reply[1]
+        _, ename, msg, tb = reply
+        exc = _ERRORS.get(ename, RuntimeError)
+        raise exc("%s\n--- remote traceback (%s:%d) ---\n%s" % (msg, self.host, self.port, tb))
+
+    def try_connect(self, timeout: float = 0.5) -> bool:
+        try:
+            s = socket.create_connection((self.host, self.port), timeout=timeout)
+            s.close()
+            return True
+        except OSError:
+            return False
+
+    def _drop(self) -> None:
+        c = getattr(self._tls, "conn", None)
+        if c is not None:
+            try:
+                c.close()
+            except OSError:
+                pass
+            self._tls.conn = None
+
+    def close(self) -> None:
+        with self._lock:
+            for c in self._all:
+                try:
+                    c.close()
+                except OSError:
+                    pass
+            self._all.clear()
+        self._tls = threading.local()

@@ -1,0 +1,281 @@
+"""In-process task server (``dtf.train.Server``).
+
+Capability parity: ``Server(cluster, job_name, task_index)`` starts
+this task's service bound to its ClusterSpec address, ``.target`` is the
+string a ``Session`` connects to and ``.join()`` blocks forever (the ps role) --
+reference ``distributed_mnist.py:75-79``, ``example_between_graph.py:33-40``,
+``example_in_graph.py:30,46``.  Every variable placed on the task lives in the
+server's :class:`ResourceStore` and outlives client sessions.
+
+The server executes graph *segments* that a session's master hands it
+(:meth:`run_segment`); a segment is a topologically ordered list of nodes whose
+device names this task.  Per-run state (values, autograd tape) stays on the
+task between segments of the same run, so forward and backward of one
+``Session.run`` can be separated by a ps round trip.
+"""
+from __future__ import annotations
+
+import os
+import threading
+import time
+import weakref
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from ..framework import errors
+from ..framework.executor import ExecContext, ResourceStore, execute
+from .cluster import ClusterSpec
+from .rpc import RpcClient, RpcServer, parse_address, to_wire
+
+__all__ = ["Server", "NodeView", "serialize_nodes", "local_server_for"]
+
+_LOCAL_SERVERS: Dict[Tuple[str, int], "weakref.ReferenceType[Server]"] = {}
+_LOCAL_LOCK = threading.Lock()
+
+
+def local_server_for(address: str) -> Optional["Server"]:
+    try:
+        key = parse_address(address)
+    except ValueError:
+        return None
+    with _LOCAL_LOCK:
+        ref = _LOCAL_SERVERS.get(key)
+    srv = ref() if ref is not None else None
+    return srv if srv is not None and srv.is_running else None
+
+
+class _GraphStub:
+    __slots__ = ("seed",)
+
+    def __init__(self, seed=None):
+        self.seed = seed
+
+
+class NodeView:
+    """Deserialised node: the attribute subset kernels read."""
+    __slots__ = ("id", "name", "op_type", "inputs", "control_inputs", "attrs", "device", "dtype", "shape", "graph")
+
+    def __init__(self, d: Dict[str, Any], graph: _GraphStub):
+        self.id, self.name, self.op_type = d["id"], d["name"], d["op_type"]
+        self.attrs, self.device, self.dtype, self.shape = d["attrs"], d["device"], d["dtype"], d["shape"]
+        self.inputs: List[Any] = d["inputs"]           # ids until linked
+        self.control_inputs: List[Any] = d["control_inputs"]
+        self.graph = graph
+
+
+def serialize_nodes(nodes: Sequence[Any]) -> List[Dict[str, Any]]:
+    out = []
+    for n in nodes:
+        out.append({"id": n.id, "name": n.name, "op_type": n.op_type, "inputs": [i.id for i in n.inputs],
+                    "control_inputs": [c.id for c in n.control_inputs], "attrs": to_wire(n.attrs),
+                    "device": n.device, "dtype": n.dtype, "shape": n.shape})
+    return out
+
+
+class _RunState:
+    __slots__ = ("ctx", "want_grad", "created")
+
+    def __init__(self, ctx: ExecContext, want_grad: bool):
+        self.ctx, self.want_grad, self.created = ctx, want_grad, time.time()
+
+
+class Server:
+    def __init__(self, server_or_cluster_def, job_name: Optional[str] = None, task_index: Optional[int] = None,
+                 protocol: Optional[str] = None, config=None, start: bool = True, gpu_index: Optional[int] = None):
+        self.cluster = server_or_cluster_def if isinstance(server_or_cluster_def, ClusterSpec) \
+            else ClusterSpec(server_or_cluster_def)
+        if job_name is None:
+            if len(self.cluster.jobs) != 1:
+                raise ValueError("job_name is required when the cluster has several jobs")
+            job_name = self.cluster.jobs[0]
+        self.job_name = job_name
+        self.task_index = int(task_index or 0)
+        self.address = self.cluster.task_address(self.job_name, self.task_index)
+        self.store = ResourceStore("/job:%s/task:%d" % (self.job_name, self.task_index))
+        self.config = config
+        # One process per GPU: DTF_GPU_INDEX (or LOCAL_RANK under torchrun) binds the task to a B200.
+        if gpu_index is None:
+            env = os.environ.get("DTF_GPU_INDEX")
+            if env is not None and env != "":
+                gpu_index = int(env)
+        self.gpu_index = gpu_index if (gpu_index is not None and gpu_index >= 0 and torch.cuda.is_available()) else None
+        self._graphs: Dict[str, Dict[int, NodeView]] = {}
+        self._runs: Dict[str, _RunState] = {}
+        self._cancel: Dict[str, threading.Event] = {}
+        self._lock = threading.RLock()
+        self._rpc: Optional[RpcServer] = None
+        self._stopped = threading.Event()
+        self._peers: Dict[Tuple[str, int], RpcClient] = {}
+        if start:
+            self.start()
+
+    # -- lifecycle ----------------------------------------------------------------------
+    def start(self) -> None:
+        if self._rpc is not None:
+            return
+        self._rpc = RpcServer(self.address, self)
+        with _LOCAL_LOCK:
+            _LOCAL_SERVERS[parse_address(self.address)] = weakref.ref(self)
+
+    @property
+    def is_running(self) -> bool:
+        return self._rpc is not None and not self._stopped.is_set()
+
+    @property
+    def target(self) -> str:
+        return "grpc://%s" % self.address
+
+    @property
+    def task(self) -> Tuple[str, int]:
+        return (self.job_name, self.task_index)
+
+    def join(self, timeout: Optional[float] = None) -> None:
+        """Block until :meth:`stop` (never, for a ps task started from the command line)."""
+        self._stopped.wait(timeout)
+
+    def stop(self) -> None:
+        self._stopped.set()
+        for ev in list(self._cancel.values()):
+            ev.set()
+        self.store.clear()
+        if self._rpc is not None:
+            self._rpc.close()
+            self._rpc = None
+        with _LOCAL_LOCK:
+            _LOCAL_SERVERS.pop(parse_address(self.address), None)
+        for c in self._peers.values():
+            c.close()
+        self._peers.clear()
+
+    def __del__(self):
+        try:
+            if self._rpc is not None:
+                self._rpc.close()
+        except Exception:
+            pass
+
+    # -- segment execution (called in-process or through rpc_run_segment) ----------------------
+    def cancel_event(self, session_id: str) -> threading.Event:
+        with self._lock:
+            ev = self._cancel.get(session_id)
+            if ev is None:
+                ev = self._cancel[session_id] = threading.Event()
+            return ev
+
+    def _run_state(self, run_id: str, opts: Dict[str, Any]) -> _RunState:
+        with self._lock:
+            st = self._runs.get(run_id)
+            if st is None:
+                tracer = None
+                if opts.get("trace"):
+                    from ..utils.timeline import StepTracer
+                    tracer = StepTracer("/job:%s/task:%d" % self.task)
+                ctx = ExecContext(self.store, self.task, self.gpu_index, tracer, opts.get("seed"))
+                ctx.leaves = set(opts.get("leaves", ()))
+                ctx.cancel_event = self.cancel_event(opts.get("session_id", ""))
+                ctx.server = self
+                st = self._runs[run_id] = _RunState(ctx, bool(opts.get("want_grad")))
+            return st
+
+    def run_segment_local(self, run_id: str, nodes: Sequence[Any], inputs: Dict[int, Any], want_ids: Sequence[int],
+                          opts: Dict[str, Any]) -> Dict[int, Any]:
+        if self._stopped.is_set():
+            raise errors.AbortedError("server %s was stopped" % self.address)
+        st = self._run_state(run_id, opts)
+        ctx = st.ctx
+        dev_default = None
+        for nid, v in inputs.items():
+            if isinstance(v, torch.Tensor):
+                if nid in ctx.leaves and v.is_floating_point():
+                    v = v.detach().requires_grad_(True)
+            ctx.values[nid] = v
+        execute(nodes, ctx, st.want_grad)
+        out = {}
+        for nid in want_ids:
+            v = ctx.values.get(nid)
+            out[nid] = v.detach() if isinstance(v, torch.Tensor) else v
+        return out
+
+    def end_run_local(self, run_id: str):
+        with self._lock:
+            st = self._runs.pop(run_id, None)
+        if st is None or st.ctx.tracer is None:
+            return None
+        return st.ctx.tracer.events()
+
+    # -- rpc surface -----------------------------------------------------------------------
+    def rpc_ping(self):
+        return {"task": self.task, "incarnation": self.store.incarnation, "pid": os.getpid()}
+
+    def rpc_get_cluster(self):
+        return {"cluster": self.cluster.as_dict(), "task": self.task}
+
+    def rpc_run_segment(self, run_id, graph_key, new_nodedefs, node_ids, inputs, want_ids, opts):
+        with self._lock:
+            g = self._graphs.setdefault(graph_key, {})
+            stub = _GraphStub(opts.get("graph_seed"))
+            fresh = []
+            for d in new_nodedefs:
+                if d["id"] not in g:
+                    nv = NodeView(d, stub)
+                    g[nv.id] = nv
+                    fresh.append(nv)
+            for nv in fresh:
+                nv.inputs = [g[i] for i in nv.inputs]
+                nv.control_inputs = [g[i] for i in nv.control_inputs if i in g]
+            nodes = [g[i] for i in node_ids]
+        return self.run_segment_local(run_id, nodes, inputs, want_ids, opts)
+
+    def rpc_end_run(self, run_id):
+        return self.end_run_local(run_id)
+
+    def rpc_cancel(self, session_id):
+        self.cancel_event(session_id).set()
+        return True
+
+    def rpc_release_session(self, session_id, graph_key=None):
+        with self._lock:
+            self._cancel.pop(session_id, None)
+            if graph_key is not None:
+                self._graphs.pop(graph_key, None)
+        return True
+
+    def rpc_snapshot(self, names=None):
+        return self.store.snapshot(names)
+
+    def rpc_variable_names(self):
+        return self.store.variable_names()
+
+    def rpc_restore(self, values: Dict[str, torch.Tensor]):
+        for k, v in values.items():
+            dev = None
+            if self.gpu_index is not None:
+                dev = torch.device("cuda", self.gpu_index)
+            self.store.assign(k, v if dev is None else v.to(dev), device=dev)
+        return sorted(values)
+
+    def rpc_reset(self):
+        self.store.clear()
+        return True
+
+    def rpc_shutdown(self):
+        threading.Thread(target=self.stop, daemon=True).start()
+        return True
+
+    # -- peers --------------------------------------------------------------------------------
+    def peer(self, job: str, task: int) -> RpcClient:
+        key = (job, int(task))
+        c = self._peers.get(key)
+        if c is None:
+            c = self._peers[key] = RpcClient(self.cluster.task_address(job, task))
+        return c
+
+    @staticmethod
+    def create_local_server(config=None, start=True) -> "Server":
+        import socket
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        return Server({"local": ["127.0.0.1:%d" % port]}, job_name="local", task_index=0, config=config, start=start)

@@ -1,0 +1,277 @@
+"""Optimizers: GradientDescent, Momentum, Adam.
+
+API parity: ``minimize`` = ``compute_gradients`` + ``apply_gradients`` (+
+``global_step += 1``); the split form is what tower averaging uses (reference
+``standalone.py:112,123,126``).  Apply ops execute **on the variable's task**:
+the gradient is pushed to the ps, the update runs ps-side
+(reference ``distributed_mnist.py:115,126``, ``example_between_graph.py:61,73``).
+
+Adam follows the TF formulation the reference trains with, not torch.optim's:
+``lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v EMA; var -= lr_t*m/(sqrt(v)+eps)``
+(epsilon outside the bias correction), with ``beta1_power``/``beta2_power``
+kept as variables colocated with the first parameter.
+
+On a CUDA ps the apply kernels are the fused sm_100a ``optimizer_apply``
+kernel (``csrc/optimizer_apply.cu``); the fabric engine additionally fuses
+the N-worker mean into the same pass (``parallel/ps_engine.py``).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from ..framework import device as _device
+from ..framework import ops as _ops
+from ..framework.graph import GraphKeys, Tensor, convert_to_tensor, get_default_graph
+from ..framework.ops import register_kernel
+from ..framework.variables import Variable, assign, assign_add, trainable_variables
+
+__all__ = ["Optimizer", "GradientDescentOptimizer", "MomentumOptimizer", "AdamOptimizer", "adam_reference_step"]
+
+
+class Optimizer:
+    GATE_NONE, GATE_OP, GATE_GRAPH = 0, 1, 2
+
+    def __init__(self, use_locking: bool = False, name: str = "Optimizer"):
+        self._use_locking = use_locking
+        self._name = name
+        self._slots: Dict[str, Dict[str, Variable]] = {}
+
+    def get_name(self) -> str:
+        return self._name
+
+    # -- gradients -----------------------------------------------------------------------------
+    def compute_gradients(self, loss, var_list: Optional[Sequence[Variable]] = None, gate_gradients=None,
+                          aggregation_method=None, colocate_gradients_with_ops=False, grad_loss=None
+                          ) -> List[Tuple[Optional[Tensor], Variable]]:
+        if var_list is None:
+            var_list = trainable_variables()
+        var_list = list(var_list)
+        if not var_list:
+            raise ValueError("No variables to optimize.")
+        loss_t = convert_to_tensor(loss)
+        # place the backward pass with the loss (the worker), not under the caller's variable scope device fn
+        with _device.device(None), _device.device(loss_t.device or None):
+            grads = _ops.gradients(loss_t, [v._node for v in var_list], name="gradients")
+        return list(zip(grads, var_list))
+
+    # -- apply ------------------------------------------------------------------------------------
+    def apply_gradients(self, grads_and_vars, global_step: Optional[Variable] = None, name: Optional[str] = None) -> Tensor:
+        gv = [(g, v) for g, v in grads_and_vars if g is not None]
+        if not gv:
+            raise ValueError("No gradients provided for any variable.")
+        g = get_default_graph()
+        var_list = [v for _, v in gv]
+        with g.name_scope(name or self._name):
+            self._create_slots(var_list)
+            prep = self._prepare()
+            updates = []
+            for grad, var in gv:
+                with _device.device(None), _device.device(var.device or None):
+                    updates.append(self._apply_dense(convert_to_tensor(grad), var, prep))
+            finish = self._finish(updates)
+            if global_step is None:
+                return _ops.group(*finish, name="update")
+            with g.control_dependencies(finish), _device.device(None), _device.device(global_step.device or None):
+                inc = assign_add(global_step, _ops.constant(1, dtype=global_step.dtype), name="update_global_step")
+            return inc
+
+    def minimize(self, loss, global_step: Optional[Variable] = None, var_list=None, gate_gradients=None,
+                 aggregation_method=None, colocate_gradients_with_ops=False, name=None, grad_loss=None) -> Tensor:
+        gv = self.compute_gradients(loss, var_list)
+        if all(g is None for g, _ in gv):
+            raise ValueError("No gradients provided for any variable, check your graph.")
+        return self.apply_gradients(gv, global_step=global_step, name=name)
+
+    # -- slots --------------------------------------------------------------------------------------
+    def _zeros_slot(self, var: Variable, slot_name: str, op_name: str) -> Variable:
+        named = self._slots.setdefault(slot_name, {})
+        s = named.get(var.var_name)
+        if s is None:
+            g = get_default_graph()
+            name = "%s/%s" % (var.var_name, op_name)
+            if name in g.variables:
+                s = g.variables[name]
+            else:
+                shape, dt = var.shape, var.dtype
+                with _device.device(None), _device.device(var.device or None), g.name_scope(None):
+                    s = Variable(lambda: _ops.zeros(shape, dt), trainable=False, name=name, _exact_name=True)
+            named[var.var_name] = s
+        return s
+
+    def _scalar_slot(self, colocate: Variable, value: float, name: str) -> Variable:
+        g = get_default_graph()
+        if name in g.variables:
+            return g.variables[name]
+        with _device.device(None), _device.device(colocate.device or None), g.name_scope(None):
+            return Variable(lambda: _ops.constant(value, dtype=torch.float32), trainable=False, name=name,
+                            _exact_name=True)
+
+    def get_slot(self, var: Variable, name: str) -> Optional[Variable]:
+        return self._slots.get(name, {}).get(var.var_name)
+
+    def get_slot_names(self) -> List[str]:
+        return sorted(self._slots)
+
+    def variables(self) -> List[Variable]:
+        out = []
+        for d in self._slots.values():
+            out.extend(d.values())
+        return out
+
+    # -- subclass hooks ---------------------------------------------------------------------------------
+    def _create_slots(self, var_list: Sequence[Variable]) -> None:
+        pass
+
+    def _prepare(self) -> Any:
+        return None
+
+    def _apply_dense(self, grad: Tensor, var: Variable, prep: Any) -> Tensor:
+        raise NotImplementedError
+
+    def _finish(self, update_ops: List[Tensor]) -> List[Tensor]:
+        return update_ops
+
+    # -- description used by the fabric engine (fused reduce+apply kernel) ---------------------------------
+    def fused_spec(self) -> Dict[str, Any]:
+        raise NotImplementedError
+
+
+def _lr_value(lr) -> float:
+    return float(lr)
+
+
+class GradientDescentOptimizer(Optimizer):
+    def __init__(self, learning_rate, use_locking: bool = False, name: str = "GradientDescent"):
+        super().__init__(use_locking, name)
+        self._lr = learning_rate
+
+    def _apply_dense(self, grad, var, prep):
+        return get_default_graph().create_node(
+            "ApplyGradientDescent", [grad], {"var_name": var.var_name, "lr": _lr_value(self._lr)},
+            "update_%s/ApplyGradientDescent" % var.var_name.replace("/", "_"), device=var.device)
+
+    def fused_spec(self):
+        return {"kind": "sgd", "lr": _lr_value(self._lr)}
+
+
+@register_kernel("ApplyGradientDescent", stateful=True)
+def _k_apply_sgd(ctx, node, grad):
+    var = ctx.store.read(node.attrs["var_name"])
+    g = grad.to(device=var.device)
+    if var.is_cuda:
+        from ..ops import cuda_lib
+        cuda_lib.apply_sgd_(var, g, node.attrs["lr"])
+    else:
+        var.sub_(g.to(var.dtype), alpha=node.attrs["lr"])
+    return None
+
+
+class MomentumOptimizer(Optimizer):
+    def __init__(self, learning_rate, momentum, use_locking: bool = False, name: str = "Momentum",
+                 use_nesterov: bool = False):
+        super().__init__(use_locking, name)
+        self._lr, self._momentum, self._nesterov = learning_rate, momentum, use_nesterov
+
+    def _create_slots(self, var_list):
+        for v in var_list:
+            self._zeros_slot(v, "momentum", self._name)
+
+    def _apply_dense(self, grad, var, prep):
+        slot = self.get_slot(var, "momentum")
+        return get_default_graph().create_node(
+            "ApplyMomentum", [grad], {"var_name": var.var_name, "accum_name": slot.var_name,
+                                      "lr": _lr_value(self._lr), "momentum": float(self._momentum),
+                                      "nesterov": bool(self._nesterov)},
+            "update_%s/ApplyMomentum" % var.var_name.replace("/", "_"), device=var.device)
+
+    def fused_spec(self):
+        return {"kind": "momentum", "lr": _lr_value(self._lr), "momentum": float(self._momentum),
+                "nesterov": bool(self._nesterov)}
+
+
+@register_kernel("ApplyMomentum", stateful=True)
+def _k_apply_momentum(ctx, node, grad):
+    a = node.attrs
+    var, acc = ctx.store.read(a["var_name"]), ctx.store.read(a["accum_name"])
+    g = grad.to(device=var.device)
+    if var.is_cuda:
+        from ..ops import cuda_lib
+        cuda_lib.apply_momentum_(var, acc, g, a["lr"], a["momentum"], a["nesterov"])
+    else:
+        g = g.to(var.dtype)
+        acc.mul_(a["momentum"]).add_(g)                       # accum = momentum*accum + grad (TF)
+        if a["nesterov"]:
+            var.sub_(g * a["lr"] + acc * (a["momentum"] * a["lr"]))
+        else:
+            var.sub_(acc, alpha=a["lr"])
+    return None
+
+
+class AdamOptimizer(Optimizer):
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8, use_locking: bool = False,
+                 name: str = "Adam"):
+        super().__init__(use_locking, name)
+        self._lr, self._beta1, self._beta2, self._eps = learning_rate, beta1, beta2, epsilon
+        self._beta1_power: Optional[Variable] = None
+        self._beta2_power: Optional[Variable] = None
+
+    def _create_slots(self, var_list):
+        first = min(var_list, key=lambda v: v.var_name)
+        if self._beta1_power is None:
+            self._beta1_power = self._scalar_slot(first, self._beta1, "beta1_power")
+            self._beta2_power = self._scalar_slot(first, self._beta2, "beta2_power")
+        for v in var_list:
+            self._zeros_slot(v, "m", self._name)
+            self._zeros_slot(v, "v", self._name + "_1")
+
+    def _get_beta_accumulators(self):
+        return self._beta1_power, self._beta2_power
+
+    def _apply_dense(self, grad, var, prep):
+        m, v = self.get_slot(var, "m"), self.get_slot(var, "v")
+        return get_default_graph().create_node(
+            "ApplyAdam", [grad, self._beta1_power._node, self._beta2_power._node],
+            {"var_name": var.var_name, "m_name": m.var_name, "v_name": v.var_name, "lr": _lr_value(self._lr),
+             "beta1": float(self._beta1), "beta2": float(self._beta2), "eps": float(self._eps)},
+            "update_%s/ApplyAdam" % var.var_name.replace("/", "_"), device=var.device)
+
+    def _finish(self, update_ops):
+        g = get_default_graph()
+        with g.control_dependencies(update_ops), _device.device(None), \
+                _device.device(self._beta1_power.device or None):
+            u1 = assign(self._beta1_power, self._beta1_power._node * self._beta1, name="update_beta1_power")
+            u2 = assign(self._beta2_power, self._beta2_power._node * self._beta2, name="update_beta2_power")
+        return list(update_ops) + [u1, u2]
+
+    def fused_spec(self):
+        return {"kind": "adam", "lr": _lr_value(self._lr), "beta1": float(self._beta1),
+                "beta2": float(self._beta2), "eps": float(self._eps)}
+
+
+@register_kernel("ApplyAdam", stateful=True)
+def _k_apply_adam(ctx, node, grad, b1p, b2p):
+    a = node.attrs
+    var, m, v = ctx.store.read(a["var_name"]), ctx.store.read(a["m_name"]), ctx.store.read(a["v_name"])
+    g = grad.to(device=var.device)
+    b1p, b2p = float(b1p), float(b2p)
+    lr_t = a["lr"] * (1.0 - b2p) ** 0.5 / (1.0 - b1p)
+    if var.is_cuda:
+        from ..ops import cuda_lib
+        cuda_lib.apply_adam_(var, m, v, g, lr_t, a["beta1"], a["beta2"], a["eps"])
+    else:
+        g = g.to(var.dtype)
+        m.mul_(a["beta1"]).add_(g, alpha=1.0 - a["beta1"])
+        v.mul_(a["beta2"]).addcmul_(g, g, value=1.0 - a["beta2"])
+        var.sub_(lr_t * m / (v.sqrt() + a["eps"]))
+    return None
+
+
+def adam_reference_step(var, m, v, g, t: int, lr=0.001, beta1=0.9, beta2=0.999, eps=1e-8):
+    """Closed-form TF-Adam step ``t`` (1-based) on plain tensors; used by tests as the oracle."""
+    lr_t = lr * (1.0 - beta2 ** t) ** 0.5 / (1.0 - beta1 ** t)
+    m = beta1 * m + (1 - beta1) * g
+    v = beta2 * v + (1 - beta2) * g * g
+    var = var - lr_t * m / (v.sqrt() + eps)
+    return var, m, v
