@@ -1,0 +1,392 @@
+"""Hooks, MonitoredTrainingSession, Saver, sync-replica state machine, distributed sessions."""
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import pytest
+import torch
+
+import distributed_tensorflow_b200 as dtf
+from distributed_tensorflow_b200.parallel.ps_state import ConditionalAccumulator, FIFOQueue
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------- accumulators / queues (A12 oracle)
+@pytest.mark.parametrize("native", [False, True])
+def test_accumulator_mean_stale_drop_and_backup_workers(native):
+    if native:
+        from distributed_tensorflow_b200.utils import native_runtime
+        if not native_runtime.available():
+            pytest.skip("native runtime not built")
+        acc = native_runtime.make_accumulator("acc")
+    else:
+        acc = ConditionalAccumulator(name="acc")
+    assert acc.apply_grad(torch.tensor([2.0, 4.0]), 0)
+    assert acc.apply_grad(torch.tensor([4.0, 8.0]), 0)
+    assert acc.num_accumulated() == 2
+    mean = acc.take_grad(2)
+    np.testing.assert_allclose(mean.numpy(), [3.0, 6.0])            # MEAN, not sum
+    acc.set_global_step(1)
+    assert not acc.apply_grad(torch.tensor([100.0, 100.0]), 0)      # stamped 0 < global step 1 -> stale, dropped
+    assert acc.num_accumulated() == 0
+    # backup workers: 3 replicas push, aggregate needs only 2 -> averages what has arrived
+    for v in (1.0, 2.0, 6.0):
+        assert acc.apply_grad(torch.tensor([v, v]), 1)
+    np.testing.assert_allclose(acc.take_grad(2).numpy(), [3.0, 3.0])
+    # take_grad blocks until enough gradients arrive
+    got = []
+    t = threading.Thread(target=lambda: got.append(acc.take_grad(1)))
+    t.start()
+    time.sleep(0.15)
+    assert not got
+    acc.set_global_step(2)
+    acc.apply_grad(torch.tensor([5.0, 5.0]), 2)
+    t.join(2)
+    np.testing.assert_allclose(got[0].numpy(), [5.0, 5.0])
+    # cancellation
+    ev = threading.Event()
+    ev.set()
+    with pytest.raises(dtf.errors.CancelledError):
+        acc.take_grad(1, cancel=ev)
+
+
+@pytest.mark.parametrize("native", [False, True])
+def test_token_queue_fifo_and_blocking(native):
+    if native:
+        from distributed_tensorflow_b200.utils import native_runtime
+        if not native_runtime.available():
+            pytest.skip("native runtime not built")
+        q = native_runtime.make_queue("q")
+    else:
+        q = FIFOQueue(name="q")
+    q.enqueue_many([1, 1, 2])
+    assert q.size() == 3 and [q.dequeue(), q.dequeue(), q.dequeue()] == [1, 1, 2]
+    got = []
+    t = threading.Thread(target=lambda: got.append(q.dequeue()))
+    t.start()
+    time.sleep(0.1)
+    assert not got
+    q.enqueue(7)
+    t.join(2)
+    assert got == [7]
+    with pytest.raises(dtf.errors.DeadlineExceededError):
+        q.dequeue(timeout=0.1)
+    q.close()
+    with pytest.raises(dtf.errors.OutOfRangeError):
+        q.dequeue()
+
+
+# ---------------------------------------------------------------- hooks
+class Recorder(dtf.train.SessionRunHook):
+    def __init__(self, log, tag):
+        self.log, self.tag = log, tag
+
+    def begin(self): self.log.append((self.tag, "begin"))
+    def after_create_session(self, s, c): self.log.append((self.tag, "after_create_session"))
+    def before_run(self, ctx): self.log.append((self.tag, "before_run"))
+    def after_run(self, ctx, vals): self.log.append((self.tag, "after_run"))
+    def end(self, s): self.log.append((self.tag, "end"))
+
+
+def _tiny_train():
+    gs = dtf.train.get_or_create_global_step()
+    w = dtf.Variable(dtf.constant([5.0]), name="w")
+    loss = dtf.reduce_sum(dtf.square(w))
+    return gs, w, loss, dtf.train.GradientDescentOptimizer(0.1).minimize(loss, global_step=gs)
+
+
+def test_hook_ordering_and_stop_at_last_step():
+    gs, w, loss, train = _tiny_train()
+    log = []
+    hooks = [Recorder(log, "a"), dtf.train.StopAtStepHook(last_step=3), Recorder(log, "b")]
+    n = 0
+    with dtf.train.MonitoredTrainingSession(hooks=hooks) as sess:
+        while not sess.should_stop():
+            sess.run(train)
+            n += 1
+    assert n == 3
+    assert log[:4] == [("a", "begin"), ("b", "begin"), ("a", "after_create_session"), ("b", "after_create_session")]
+    assert log[4:8] == [("a", "before_run"), ("b", "before_run"), ("a", "after_run"), ("b", "after_run")]
+    assert log[-2:] == [("a", "end"), ("b", "end")]
+
+
+def test_stop_at_step_num_steps_is_relative_and_args_validated(tmp_path):
+    gs, w, loss, train = _tiny_train()
+    d = str(tmp_path / "ck")
+    with dtf.train.MonitoredTrainingSession(checkpoint_dir=d, hooks=[dtf.train.StopAtStepHook(num_steps=4)],
+                                            save_checkpoint_secs=None, log_step_count_steps=None) as sess:
+        while not sess.should_stop():
+            sess.run(train)
+        assert sess.run(gs) == 4
+        dtf.train.Saver().save(sess, os.path.join(d, "model.ckpt"), global_step=gs)
+    # resume: num_steps counts from the RESTORED step (SURVEY §5 checkpoint/resume)
+    steps = []
+    with dtf.train.MonitoredTrainingSession(checkpoint_dir=d, hooks=[dtf.train.StopAtStepHook(num_steps=2)],
+                                            save_checkpoint_secs=None, log_step_count_steps=None) as sess:
+        while not sess.should_stop():
+            steps.append(int(sess.run([train, gs])[1]))
+    assert steps == [5, 6]
+    with pytest.raises(ValueError):
+        dtf.train.StopAtStepHook()
+    with pytest.raises(ValueError):
+        dtf.train.StopAtStepHook(num_steps=1, last_step=2)
+
+
+def test_subclassed_stop_hook_like_reference_runs():
+    class MyStop(dtf.train.StopAtStepHook):
+        def after_run(self, run_context, run_values):
+            if run_values.results >= self._last_step:
+                run_context.request_stop()
+    gs, w, loss, train = _tiny_train()
+    with dtf.train.MonitoredTrainingSession(hooks=[MyStop(last_step=2)]) as sess:
+        n = 0
+        while not sess.should_stop():
+            sess.run([train, gs, loss])
+            n += 1
+    assert n == 2
+
+
+# ---------------------------------------------------------------- saver
+def test_checkpoint_roundtrip_partial_restore_and_max_to_keep(tmp_path):
+    d = str(tmp_path / "ckpt")
+    gs = dtf.train.get_or_create_global_step()
+    a = dtf.Variable(dtf.constant([[1.0, 2.0], [3.0, 4.0]]), name="hid_w")
+    b = dtf.Variable(dtf.constant([9.0]), name="extra/Adam")
+    h = dtf.Variable(dtf.cast(dtf.constant([1.5, -2.5]), dtf.bfloat16), name="half")
+    saver = dtf.train.Saver(max_to_keep=2)
+    with dtf.Session() as sess:
+        sess.run(dtf.global_variables_initializer())
+        paths = []
+        for step in (1, 2, 3):
+            sess.run(dtf.assign(gs, dtf.constant(step, dtype=dtf.int64)))
+            paths.append(saver.save(sess, os.path.join(d, "model.ckpt"), global_step=gs))
+    st = dtf.train.get_checkpoint_state(d)
+    assert st.model_checkpoint_path.endswith("model.ckpt-3")
+    assert [os.path.basename(p) for p in st.all_model_checkpoint_paths] == ["model.ckpt-2", "model.ckpt-3"]
+    assert not os.path.exists(paths[0] + ".index") and os.path.exists(paths[2] + ".index")
+    assert dict(dtf.train.list_variables(d))["hid_w"] == [2, 2]
+    assert os.path.exists(paths[2] + ".meta") and os.path.exists(paths[2] + ".data-00000-of-00001")
+    # a different program restores ONLY hid_w by name (predict-style partial restore)
+    dtf.reset_default_graph()
+    a2 = dtf.Variable(dtf.zeros([2, 2]), name="hid_w")
+    with dtf.Session() as sess:
+        dtf.train.Saver().restore(sess, dtf.train.latest_checkpoint(d))
+        np.testing.assert_allclose(sess.run(a2), [[1, 2], [3, 4]])
+    # a name the checkpoint lacks -> NotFoundError; wrong shape -> InvalidArgumentError
+    dtf.reset_default_graph()
+    dtf.Variable(dtf.zeros([1]), name="missing")
+    with dtf.Session() as sess, pytest.raises(dtf.errors.NotFoundError):
+        dtf.train.Saver().restore(sess, dtf.train.latest_checkpoint(d))
+    dtf.reset_default_graph()
+    dtf.Variable(dtf.zeros([3, 3]), name="hid_w")
+    with dtf.Session() as sess, pytest.raises(dtf.errors.InvalidArgumentError):
+        dtf.train.Saver().restore(sess, dtf.train.latest_checkpoint(d))
+    # bf16 survives the round trip bit-exactly
+    r = dtf.train.NewCheckpointReader(dtf.train.latest_checkpoint(d))
+    assert r.get_tensor("half").dtype == torch.bfloat16 and r.get_tensor("half").tolist() == [1.5, -2.5]
+    assert dtf.train.get_checkpoint_state(str(tmp_path / "nope")) is None
+
+
+def test_hdfs_url_maps_to_local_root(tmp_path, monkeypatch):
+    monkeypatch.setenv("DTF_HDFS_ROOT", str(tmp_path))
+    from distributed_tensorflow_b200.train.saver import resolve_path
+    assert resolve_path("hdfs://phoenix-001.phoenix.com:8020/test/ckpt") == os.path.join(str(tmp_path), "test/ckpt")
+    v = dtf.Variable(dtf.constant([1.0]), name="v")
+    with dtf.Session() as sess:
+        sess.run(v.initializer)
+        dtf.train.Saver().save(sess, "hdfs://h:1/test/ckpt/model.ckpt", global_step=5)
+    assert dtf.train.latest_checkpoint("hdfs://h:1/test/ckpt").endswith("model.ckpt-5")
+
+
+def test_checkpoint_saver_hook_saves_on_create_steps_and_end(tmp_path):
+    gs, w, loss, train = _tiny_train()
+    d = str(tmp_path / "c")
+    with dtf.train.MonitoredTrainingSession(checkpoint_dir=d, save_checkpoint_secs=None, save_checkpoint_steps=2,
+                                            hooks=[dtf.train.StopAtStepHook(last_step=5)]) as sess:
+        while not sess.should_stop():
+            sess.run(train)
+    names = sorted(f for f in os.listdir(d) if f.endswith(".index"))
+    assert names == ["model.ckpt-0.index", "model.ckpt-2.index", "model.ckpt-4.index", "model.ckpt-5.index"]
+
+
+# ---------------------------------------------------------------- timeline / summary
+def test_timeline_and_graph_dump(tmp_path):
+    a = dtf.constant([[1.0, 2.0]])
+    with dtf.device("/cpu:0"):
+        b = dtf.matmul(a, dtf.constant([[3.0], [4.0]]), name="mm")
+    md = dtf.RunMetadata()
+    with dtf.Session() as sess:
+        sess.run(b, options=dtf.RunOptions(trace_level=dtf.RunOptions.FULL_TRACE), run_metadata=md)
+        w = dtf.summary.FileWriter(str(tmp_path / "logs"), sess.graph)
+        w.close()
+    assert any(e["name"] == "mm" and e["op"] == "MatMul" for e in md.step_stats)
+    tr = json.loads(dtf.Timeline(md.step_stats).generate_chrome_trace_format())
+    assert any(e.get("ph") == "X" and e["name"] == "mm" for e in tr["traceEvents"])
+    assert any(e.get("ph") == "M" for e in tr["traceEvents"])
+    ev = dtf.summary.read_events(w.path)
+    assert any("graph_def" in e and any(n["name"] == "mm" for n in e["graph_def"]["node"]) for e in ev)
+
+
+# ---------------------------------------------------------------- distributed sessions, in-process tasks
+def test_in_graph_replication_golden_result(cluster3, tmp_path):
+    """example_in_graph.py -> [[9],[21],[33],[45]]; one pid per device in the trace."""
+    cluster, servers = cluster3
+    with dtf.device('/job:ps/task:0/cpu:0'):
+        input_data = dtf.Variable([[1., 2., 3.], [4., 5., 6.], [7., 8., 9.], [10., 11., 12.]], name="input_data")
+        b = dtf.Variable([[1.], [1.], [2.]], name="w")
+    inputs = dtf.split(input_data, 2)
+    outputs = []
+    md = dtf.RunMetadata()
+    with dtf.Session(servers[1].target) as sess:
+        sess.run(dtf.global_variables_initializer())
+        for i in range(2):
+            with dtf.device("/job:worker/task:%d/gpu:0" % i):
+                np.testing.assert_allclose(sess.run(inputs[i]), np.arange(1 + 6 * i, 7 + 6 * i).reshape(2, 3))
+                outputs.append(dtf.matmul(inputs[i], b))            # graph grows between runs
+        with dtf.device('/job:ps/task:0/cpu:0'):
+            output = dtf.concat(outputs, axis=0)
+        res = sess.run(output, options=dtf.RunOptions(trace_level=dtf.RunOptions.FULL_TRACE), run_metadata=md)
+    np.testing.assert_allclose(res, [[9], [21], [33], [45]])
+    tasks = {e["task"] for e in md.step_stats}
+    assert tasks == {"/job:ps/task:0", "/job:worker/task:0", "/job:worker/task:1"}
+    # variables live on the ps server and persist across client sessions
+    assert servers[0].store.variable_names() == ["input_data", "w"]
+    assert servers[1].store.variable_names() == []
+    with dtf.Session(servers[2].target) as sess2:
+        np.testing.assert_allclose(sess2.run(b), [[1.], [1.], [2.]])
+
+
+def _between_graph_worker(cluster, task, is_sync, steps, results, num_workers=2, lr=0.05, backup=0):
+    """One between-graph client in its own graph (thread = stand-in for a worker process)."""
+    g = dtf.Graph()
+    with g.as_default():
+        server_target = "grpc://" + cluster.task_address("worker", task)
+        with dtf.device(dtf.train.replica_device_setter(cluster=cluster,
+                                                        worker_device="/job:worker/task:%d" % task)):
+            gs = dtf.train.get_or_create_global_step()
+            w = dtf.get_variable("weight", [1], initializer=dtf.constant_initializer(0.0))
+            b = dtf.get_variable("biase", [1], initializer=dtf.constant_initializer(0.0))
+            X, Y = dtf.placeholder(dtf.float32), dtf.placeholder(dtf.float32)
+            loss = dtf.reduce_mean(dtf.square(Y - (X * w + b)))
+            opt = dtf.train.GradientDescentOptimizer(lr)
+            hooks = [dtf.train.StopAtStepHook(last_step=steps)]
+            if is_sync:
+                opt = dtf.train.SyncReplicasOptimizer(opt, replicas_to_aggregate=num_workers - backup,
+                                                      total_num_replicas=num_workers)
+                hooks.append(opt.make_session_run_hook(task == 0))
+            train = opt.minimize(loss, global_step=gs)
+        rng = np.random.RandomState(task)
+        n = 0
+        with dtf.train.MonitoredTrainingSession(master=server_target, is_chief=(task == 0), hooks=hooks) as sess:
+            while not sess.should_stop():
+                tx = rng.rand(32).astype(np.float32)
+                _, step = sess.run([train, gs], {X: tx, Y: 2 * tx + 10})
+                n += 1
+            raw = sess.raw_session()
+        results[task] = n
+
+
+@pytest.mark.parametrize("is_sync", [False, True])
+def test_between_graph_two_workers_share_ps_variables(cluster3, is_sync):
+    cluster, servers = cluster3
+    results = {}
+    threads = [threading.Thread(target=_between_graph_worker, args=(cluster, t, is_sync, 60, results)) for t in (0, 1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not any(t.is_alive() for t in threads)
+    ps = servers[0].store
+    assert int(ps.read("global_step")) >= 60
+    assert set(ps.variable_names()) >= {"global_step", "weight", "biase"}
+    assert "weight" not in servers[1].store.variable_names()         # parameters are on the ps only
+    # both workers contributed; in sync mode each aggregate consumed one gradient from each
+    assert results[0] > 0 and results[1] > 0
+    if is_sync:
+        assert abs(results[0] - results[1]) <= 3
+        assert servers[1].store.variable_names() == ["sync_rep_local_step"]      # worker-local step counter
+
+
+def test_sync_mean_equals_single_worker_on_concatenated_batch(cluster3):
+    """Golden: mean of N per-worker gradients == gradient of the mean loss over the union batch."""
+    cluster, servers = cluster3
+    xs = [np.array([1.0, 2.0], np.float32), np.array([3.0, 5.0], np.float32)]
+    g = dtf.Graph()
+    with g.as_default():
+        with dtf.device("/job:ps/task:0"):
+            gs = dtf.train.get_or_create_global_step()
+            w = dtf.Variable(dtf.constant([0.0]), name="w")
+        grad_ph = [dtf.placeholder(dtf.float32, [1]) for _ in range(2)]
+        opt = dtf.train.SyncReplicasOptimizer(dtf.train.GradientDescentOptimizer(1.0), 2, 2)
+        # two "workers" share one client here: push both gradients, then run the chief aggregate once
+        with dtf.device("/job:worker/task:0"):
+            train0 = opt.apply_gradients([(grad_ph[0], w)], global_step=gs)
+        with dtf.Session(servers[1].target) as sess:
+            sess.run(dtf.global_variables_initializer())
+            sess.run(opt.local_step_init_op)
+            sess.run(opt.chief_init_op)
+            sess.run(opt.get_init_tokens_op())
+            push = [n for n in g.nodes if n.op_type == "AccumulatorApplyGrad"][0]
+            sess.run(push, {grad_ph[0]: [2.0]})
+            sess.run(push, {grad_ph[0]: [4.0]})
+            sess.run(opt.sync_op)                 # take_grad(2) -> mean 3 -> w -= 1.0*3 ; step 1 ; 2 tokens
+            assert sess.run(w)[0] == pytest.approx(-3.0)
+            assert sess.run(gs) == 1
+
+
+def test_recoverable_session_survives_ps_restart(ports, tmp_path):
+    """A15: kill the ps mid-training; the chief restores from the last checkpoint and continues."""
+    p = ports(2)
+    spec = {"ps": ["127.0.0.1:%d" % p[0]], "worker": ["127.0.0.1:%d" % p[1]]}
+    cluster = dtf.train.ClusterSpec(spec)
+    ps = dtf.train.Server(cluster, "ps", 0)
+    wk = dtf.train.Server(cluster, "worker", 0)
+    d = str(tmp_path / "ck")
+    try:
+        with dtf.device(dtf.train.replica_device_setter(cluster=cluster, worker_device="/job:worker/task:0")):
+            gs, w, loss, train = _tiny_train()
+        seen = []
+        with dtf.train.MonitoredTrainingSession(master=wk.target, is_chief=True, checkpoint_dir=d,
+                                                save_checkpoint_secs=None, save_checkpoint_steps=1,
+                                                log_step_count_steps=None,
+                                                hooks=[dtf.train.StopAtStepHook(last_step=8)]) as sess:
+            while not sess.should_stop():
+                _, step = sess.run([train, gs])
+                seen.append(int(step))
+                if step == 4 and len(seen) == 4:
+                    ps.stop()                                   # fault injection: the ps dies ...
+                    ps = dtf.train.Server(cluster, "ps", 0)     # ... and comes back empty
+            assert sess.num_recoveries >= 1
+        assert seen[-1] == 8 and seen[:4] == [1, 2, 3, 4]
+        assert seen[4] in (4, 5)              # resumed from the step-4 checkpoint, not from zero
+    finally:
+        ps.stop()
+        wk.stop()
+
+
+# ---------------------------------------------------------------- multi-process (real processes, gloo-free control plane)
+@pytest.mark.parametrize("mode", ["async", "sync"])
+def test_multiprocess_distributed_mnist_then_predict(tmp_path, mode):
+    d = str(tmp_path / "ck")
+    cmd = [sys.executable, os.path.join(ROOT, "examples/launch_local.py"), os.path.join(ROOT, "examples/distributed_mnist.py"),
+           "--num_ps", "1", "--num_workers", "2", "--gpus", "0", "--timeout", "150", "--",
+           "--train_steps=40", "--num_train=1500", "--log_every=20", "--train_dir=" + d, "--hidden_units=32"]
+    if mode == "sync":
+        cmd.append("--issync=True")
+    else:
+        cmd.append("--measure_staleness=True")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=200)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "global_step is" in r.stdout and "Training elapsed time" in r.stdout
+    if mode == "async":
+        assert "staleness mean" in r.stdout
+    r2 = subprocess.run([sys.executable, os.path.join(ROOT, "examples/distributed_mnist_predict.py"),
+                         "--checkpoint_dir=" + d, "--hidden_units=32"], capture_output=True, text=True, timeout=120)
+    assert r2.returncode == 0, r2.stdout + r2.stderr
+    acc = float(r2.stdout.strip().splitlines()[-1].split()[-1])
+    assert acc > 0.5
