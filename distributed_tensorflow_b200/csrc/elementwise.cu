@@ -1,0 +1,379 @@
+// Non-GEMM sm_100a kernels: conversion/staging, fused softmax-cross-entropy fwd+bwd, ReLU backward,
+// column sums, optimizer applies (SGD / Momentum / TF-Adam), im2col / col2im for NHWC convolution,
+// and a plain CUDA-core reference GEMM used by tests and for shapes TMA cannot address.
+//
+// These are bandwidth- or latency-bound; they use 128-bit vector accesses where alignment allows and
+// warp-shuffle reductions.  SURVEY kernel sites: K2/K3 (xent), K5/K6 (apply), K8 (argmax),
+// K9 (element-wise), K12 (tower mean), K14 (conv lowering).
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace dtf {
+
+DTF_DEVICE float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+DTF_DEVICE float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 [rows, cols] (ld_in) -> bf16 [rows, cols] (ld_out), optionally zero-filling pad columns
+// ---------------------------------------------------------------------------------------------
+__global__ void convert_f32_bf16_kernel(const float* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out,
+                                        long long ld_out, long long rows, long long cols, long long cols_pad) {
+  const long long total = rows * cols_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols_pad, c = i - r * cols_pad;
+    out[r * ld_out + c] = __float2bfloat16(c < cols ? in[r * ld_in + c] : 0.0f);
+  }
+}
+
+__global__ void convert_f32_bf16_vec_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = in[i];
+    out[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+__global__ void convert_u8_bf16_kernel(const uint8_t* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n,
+                                       float scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16((float)in[i] * scale);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused softmax + cross-entropy, forward and backward in one pass (one warp per row)
+//   y = softmax(logits);  t_j = labels_j * [y_j >= clip_min]
+//   loss_row = -sum_j labels_j * log(clamp(y_j, clip_min, 1))          (clip_min = 0: -sum labels*log_softmax)
+//   dlogits_i = -t_i + y_i * sum_j t_j                                 (== y - labels when nothing clips)
+// loss is either accumulated into one scalar (batch SUM, reference distributed_mnist.py:113) or per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void softmax_xent_kernel(const float* __restrict__ logits, long long ld_logits,
+                                    const float* __restrict__ labels, long long ld_labels, int rows, int cols,
+                                    float clip_min, float* __restrict__ loss_sum, float* __restrict__ loss_rows,
+                                    float* __restrict__ dlogits, long long ld_d, __nv_bfloat16* __restrict__ dlogits_bf16,
+                                    long long ld_db, int cols_pad_bf16, float* __restrict__ probs, long long ld_p,
+                                    float grad_scale) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * warps_per_block + warp;
+  if (row >= rows) return;
+  const float* z = logits + (long long)row * ld_logits;
+  const float* lab = labels + (long long)row * ld_labels;
+  float mx = -INFINITY;
+  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, z[c]);
+  mx = warp_max(mx);
+  float se = 0.f;
+  for (int c = lane; c < cols; c += 32) se += __expf(z[c] - mx);
+  se = warp_sum(se);
+  const float inv = 1.0f / se;
+  const float lse = mx + __logf(se);
+  float loss = 0.f, tsum = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    const float y = __expf(z[c] - mx) * inv;
+    const float l = lab[c];
+    if (clip_min > 0.f) {
+      loss -= l * __logf(fminf(fmaxf(y, clip_min), 1.0f));
+      tsum += (y >= clip_min) ? l : 0.f;
+    } else {
+      loss -= l * (z[c] - lse);
+      tsum += l;
+    }
+  }
+  loss = warp_sum(loss);
+  tsum = warp_sum(tsum);
+  for (int c = lane; c < cols; c += 32) {
+    const float y = __expf(z[c] - mx) * inv;
+    const float l = lab[c];
+    const float t = (clip_min > 0.f && y < clip_min) ? 0.f : l;
+    const float g = (y * tsum - t) * grad_scale;
+    if (dlogits) dlogits[(long long)row * ld_d + c] = g;
+    if (dlogits_bf16) dlogits_bf16[(long long)row * ld_db + c] = __float2bfloat16(g);
+    if (probs) probs[(long long)row * ld_p + c] = y;
+  }
+  if (dlogits_bf16)
+    for (int c = cols + lane; c < cols_pad_bf16; c += 32) dlogits_bf16[(long long)row * ld_db + c] = __float2bfloat16(0.f);
+  if (lane == 0) {
+    if (loss_rows) loss_rows[row] = loss;
+    if (loss_sum) atomicAdd(loss_sum, loss);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// relu backward, column sums, argmax, tower mean
+// ---------------------------------------------------------------------------------------------
+__global__ void relu_grad_kernel(const float* __restrict__ g, const float* __restrict__ y, float* __restrict__ out,
+                                 long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = y[i] > 0.f ? g[i] : 0.f;
+}
+
+// out[c] = sum_r in[r, c]; one block per 32 columns, 8 warps stride the rows
+__global__ void colsum_kernel(const float* __restrict__ in, long long ld, int rows, int cols, float* __restrict__ out) {
+  __shared__ float part[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int w = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < cols)
+    for (int r = w; r < rows; r += 8) s += in[(long long)r * ld + c];
+  part[w][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (w == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+    out[c] = t;
+  }
+}
+
+__global__ void argmax_rows_kernel(const float* __restrict__ in, long long ld, int rows, int cols, long long* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = lane; c < cols; c += 32) {
+    const float v = in[(long long)row * ld + c];
+    if (v > best) { best = v; bi = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) out[row] = bi;
+}
+
+// out = mean over `n_in` same-shaped inputs (tower gradient averaging)
+__global__ void mean_of_n_kernel(const float* const* __restrict__ ins, int n_in, float* __restrict__ out, long long n) {
+  const float inv = 1.0f / (float)n_in;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < n_in; ++k) s += ins[k][i];
+    out[i] = s * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// optimizer applies on flat fp32 buffers (TF formulations), optional bf16 shadow copy of the params
+// ---------------------------------------------------------------------------------------------
+struct ApplyArgs {
+  float* var;
+  float* m;        // momentum accum / Adam m
+  float* v;        // Adam v
+  const float* g;
+  __nv_bfloat16* shadow;   // optional bf16 copy of var
+  long long n;
+  int kind;        // 0 sgd, 1 momentum, 2 adam
+  float lr;        // sgd/momentum: lr ; adam: lr_t (bias-corrected)
+  float momentum;
+  int nesterov;
+  float beta1, beta2, eps;
+  float grad_scale;
+};
+
+DTF_DEVICE float apply_one(const ApplyArgs& a, long long i, float g) {
+  float w = a.var[i];
+  if (a.kind == 0) {
+    w -= a.lr * g;
+  } else if (a.kind == 1) {
+    const float acc = a.momentum * a.m[i] + g;
+    a.m[i] = acc;
+    w -= a.nesterov ? (a.lr * g + a.lr * a.momentum * acc) : (a.lr * acc);
+  } else {
+    const float m = a.beta1 * a.m[i] + (1.0f - a.beta1) * g;
+    const float v = a.beta2 * a.v[i] + (1.0f - a.beta2) * g * g;
+    a.m[i] = m;
+    a.v[i] = v;
+    w -= a.lr * m / (sqrtf(v) + a.eps);          // epsilon OUTSIDE the bias correction (TF Adam)
+  }
+  a.var[i] = w;
+  return w;
+}
+
+__global__ void optimizer_apply_kernel(const ApplyArgs a) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+    const float w = apply_one(a, i, a.g[i] * a.grad_scale);
+    if (a.shadow) a.shadow[i] = __float2bfloat16(w);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NHWC im2col (bf16 out, K padded to a multiple of 8) and col2im (fp32 accumulate) for conv lowering
+// ---------------------------------------------------------------------------------------------
+__global__ void im2col_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ cols, int n, int h, int w,
+                                   int c, int kh, int kw, int sh, int sw, int pt, int pl, int ho, int wo, long long ldc) {
+  const long long kdim = (long long)kh * kw * c;
+  const long long total = (long long)n * ho * wo * ldc;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / ldc;
+    const long long kk = i - row * ldc;
+    float v = 0.f;
+    if (kk < kdim) {
+      const int ci = (int)(kk % c);
+      const int kx = (int)((kk / c) % kw);
+      const int ky = (int)(kk / ((long long)c * kw));
+      const int ox = (int)(row % wo);
+      const int oy = (int)((row / wo) % ho);
+      const int b = (int)(row / ((long long)wo * ho));
+      const int iy = oy * sh - pt + ky, ix = ox * sw - pl + kx;
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = x[(((long long)b * h + iy) * w + ix) * c + ci];
+    }
+    cols[i] = __float2bfloat16(v);
+  }
+}
+
+__global__ void col2im_nhwc_kernel(const float* __restrict__ gcols, long long ldg, float* __restrict__ gx, int n, int h,
+                                   int w, int c, int kh, int kw, int sh, int sw, int pt, int pl, int ho, int wo) {
+  // gather form: one thread per input element sums the contributions of every patch covering it
+  const long long total = (long long)n * h * w * c;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % c);
+    const int ix = (int)((i / c) % w);
+    const int iy = (int)((i / ((long long)c * w)) % h);
+    const int b = (int)(i / ((long long)c * w * h));
+    float s = 0.f;
+    for (int ky = 0; ky < kh; ++ky) {
+      const int ty = iy + pt - ky;
+      if (ty < 0 || ty % sh) continue;
+      const int oy = ty / sh;
+      if (oy >= ho) continue;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int tx = ix + pl - kx;
+        if (tx < 0 || tx % sw) continue;
+        const int ox = tx / sw;
+        if (ox >= wo) continue;
+        const long long row = ((long long)b * ho + oy) * wo + ox;
+        s += gcols[row * ldg + ((long long)ky * kw + kx) * c + ci];
+      }
+    }
+    gx[i] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reference GEMM on CUDA cores (fp32 accumulate over bf16-rounded inputs); tests + odd shapes
+// ---------------------------------------------------------------------------------------------
+__global__ void gemm_ref_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                float* __restrict__ c, int M, int N, int K, long long lda, long long ldb, long long ldc,
+                                int a_mn, int b_mn, const float* __restrict__ bias, int relu, float alpha) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= M || n >= N) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float av = __bfloat162float(a_mn ? a[(long long)k * lda + m] : a[(long long)m * lda + k]);
+    const float bv = __bfloat162float(b_mn ? b[(long long)k * ldb + n] : b[(long long)n * ldb + k]);
+    acc += av * bv;
+  }
+  acc *= alpha;
+  if (bias) acc += bias[n];
+  if (relu) acc = fmaxf(acc, 0.f);
+  c[(long long)m * ldc + n] = acc;
+}
+
+static inline int grid_for(long long n, int block = 256) {
+  long long g = (n + block - 1) / block;
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace dtf
+
+extern "C" {
+using namespace dtf;
+
+int dtf_convert_f32_bf16(const float* in, long long ld_in, void* out, long long ld_out, long long rows, long long cols,
+                         long long cols_pad, cudaStream_t s) {
+  if (ld_in == cols && ld_out == cols && cols_pad == cols && (rows * cols) % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
+    const long long n4 = rows * cols / 4;
+    convert_f32_bf16_vec_kernel<<<grid_for(n4), 256, 0, s>>>(reinterpret_cast<const float4*>(in),
+                                                             reinterpret_cast<uint2*>(out), n4);
+  } else {
+    convert_f32_bf16_kernel<<<grid_for(rows * cols_pad), 256, 0, s>>>(in, ld_in, reinterpret_cast<__nv_bfloat16*>(out),
+                                                                      ld_out, rows, cols, cols_pad);
+  }
+  return (int)cudaGetLastError();
+}
+
+int dtf_convert_u8_bf16(const void* in, void* out, long long n, float scale, cudaStream_t s) {
+  convert_u8_bf16_kernel<<<grid_for(n), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(in),
+                                                     reinterpret_cast<__nv_bfloat16*>(out), n, scale);
+  return (int)cudaGetLastError();
+}
+
+int dtf_softmax_xent(const float* logits, long long ld_logits, const float* labels, long long ld_labels, int rows, int cols,
+                     float clip_min, float* loss_sum, float* loss_rows, float* dlogits, long long ld_d,
+                     void* dlogits_bf16, long long ld_db, int cols_pad_bf16, float* probs, long long ld_p, float grad_scale,
+                     cudaStream_t s) {
+  const int wpb = 4;
+  softmax_xent_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, s>>>(
+      logits, ld_logits, labels, ld_labels, rows, cols, clip_min, loss_sum, loss_rows, dlogits, ld_d,
+      reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ld_db, cols_pad_bf16, probs, ld_p, grad_scale);
+  return (int)cudaGetLastError();
+}
+
+int dtf_relu_grad(const float* g, const float* y, float* out, long long n, cudaStream_t s) {
+  relu_grad_kernel<<<grid_for(n), 256, 0, s>>>(g, y, out, n);
+  return (int)cudaGetLastError();
+}
+
+int dtf_colsum(const float* in, long long ld, int rows, int cols, float* out, cudaStream_t s) {
+  colsum_kernel<<<(cols + 31) / 32, 256, 0, s>>>(in, ld, rows, cols, out);
+  return (int)cudaGetLastError();
+}
+
+int dtf_argmax_rows(const float* in, long long ld, int rows, int cols, long long* out, cudaStream_t s) {
+  argmax_rows_kernel<<<(rows + 3) / 4, 128, 0, s>>>(in, ld, rows, cols, out);
+  return (int)cudaGetLastError();
+}
+
+int dtf_mean_of_n(const float* const* ins_dev, int n_in, float* out, long long n, cudaStream_t s) {
+  mean_of_n_kernel<<<grid_for(n), 256, 0, s>>>(ins_dev, n_in, out, n);
+  return (int)cudaGetLastError();
+}
+
+int dtf_optimizer_apply(float* var, float* m, float* v, const float* g, void* shadow_bf16, long long n, int kind, float lr,
+                        float momentum, int nesterov, float beta1, float beta2, float eps, float grad_scale,
+                        cudaStream_t s) {
+  ApplyArgs a;
+  a.var = var; a.m = m; a.v = v; a.g = g; a.shadow = reinterpret_cast<__nv_bfloat16*>(shadow_bf16); a.n = n;
+  a.kind = kind; a.lr = lr; a.momentum = momentum; a.nesterov = nesterov; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+  a.grad_scale = grad_scale;
+  optimizer_apply_kernel<<<grid_for(n), 256, 0, s>>>(a);
+  return (int)cudaGetLastError();
+}
+
+int dtf_im2col_nhwc(const float* x, void* cols, int n, int h, int w, int c, int kh, int kw, int sh, int sw, int pt, int pl,
+                    int ho, int wo, long long ldc, cudaStream_t s) {
+  im2col_nhwc_kernel<<<grid_for((long long)n * ho * wo * ldc), 256, 0, s>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(cols), n, h, w, c, kh, kw, sh, sw, pt, pl, ho, wo, ldc);
+  return (int)cudaGetLastError();
+}
+
+int dtf_col2im_nhwc(const float* gcols, long long ldg, float* gx, int n, int h, int w, int c, int kh, int kw, int sh, int sw,
+                    int pt, int pl, int ho, int wo, cudaStream_t s) {
+  col2im_nhwc_kernel<<<grid_for((long long)n * h * w * c), 256, 0, s>>>(gcols, ldg, gx, n, h, w, c, kh, kw, sh, sw, pt,
+                                                                       pl, ho, wo);
+  return (int)cudaGetLastError();
+}
+
+int dtf_gemm_ref(const void* a, const void* b, float* c, int M, int N, int K, long long lda, long long ldb, long long ldc,
+                 int a_mn, int b_mn, const float* bias, int relu, float alpha, cudaStream_t s) {
+  dim3 block(32, 8), grid((N + 31) / 32, (M + 7) / 8);
+  gemm_ref_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b),
+                                         c, M, N, K, lda, ldb, ldc, a_mn, b_mn, bias, relu, alpha);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,417 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a with fused epilogues and fused NVLink push/pull.
+//
+//   C[M,N] = alpha * op(A)[M,K] . op(B)[K,N]  (+ bias[N]) (ReLU) (* relu-mask) ; bf16 operands, fp32 accumulate.
+//
+// * Operands are loaded by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into a multi-stage
+//   shared-memory ring; one elected thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) with the
+//   accumulator in tensor memory; four epilogue warps read it back with tcgen05.ld.
+// * Both operands may be K-major or MN-major (UMMA descriptor + instruction-descriptor major bits), so the
+//   three GEMMs of a dense layer -- y = x.W, dW = x^T.dy, dx = dy.W^T with TF-layout W[in,out] --
+//   run without any transpose pass.
+// * Fused pull (SURVEY C1+K1): the B tensor map may point at a parameter-server GPU's published
+//   parameter buffer (peer memory over NVLink); the TMA producer first acquires the ps's version flag.
+// * Fused push (SURVEY K4+C2): C may be a gradient slot in the ps GPU's memory; the epilogue stores
+//   tiles straight from TMEM to the peer and then release-increments the ps's arrival counter.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
+// warps 2..5 = epilogue (warp w owns TMEM lanes [32*(w%4), +32)).
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+
+namespace dtf {
+
+static constexpr int kBlockM = 128;
+static constexpr int kBlockK = 64;            // bf16 elements per stage along K = one 128-byte swizzle row
+static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
+static constexpr int kThreads = 192;
+
+struct GemmParams {
+  int M, N, K;
+  int block_n;           // multiple of 16 (multiple of 64 when B is MN-major), <= 256
+  int a_mn, b_mn;        // 1 = operand stored MN-major ([K, M] / [K, N] row-major)
+  int num_kb;            // ceil(K / 64)
+  int kb_per_split;      // K blocks handled by one blockIdx.z
+  int stages;
+  void* c;
+  long long ldc;
+  int c_bf16;
+  const float* bias;
+  int relu;
+  const __nv_bfloat16* mask;   // optional [M, ldmask]: output *= (mask > 0)   (ReLU backward)
+  long long ldmask;
+  float alpha;
+  int atomic;            // split-K / accumulate: red.add into fp32 C
+  float* colsum;         // optional [N]: += column sums of the (post-mask, post-alpha) tile (bias gradient)
+  const unsigned long long* wait_flag;   // optional: acquire until *wait_flag >= wait_target before loading
+  unsigned long long wait_target;
+  unsigned long long* signal;            // optional: release-increment by 1 per CTA after the tile is stored
+  unsigned int* err;                     // optional: set to 1 when the wait timed out
+  unsigned long long timeout_ns;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ __align__(8) uint64_t empty_bar[8];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_holder;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBlockM;
+  const int n0 = blockIdx.y * p.block_n;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+  const int b_bytes = p.block_n * kBlockK * 2;
+  const int stage_bytes = kABytes + b_bytes;
+  // 128B-swizzled tiles must start on 1024-byte boundaries
+  uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)p.block_n) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_holder, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      if (p.wait_flag != nullptr) {
+        // fused pull: the parameters behind map_b (or map_a) are published by another GPU
+        if (!wait_flag_ge_u64(reinterpret_cast<const uint64_t*>(p.wait_flag), p.wait_target, p.timeout_ns)) {
+          if (p.err) atomicExch(p.err, 1u);
+        }
+        fence_proxy_async();
+      }
+      int it = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        uint8_t* a_dst = tiles + s * stage_bytes;
+        uint8_t* b_dst = a_dst + kABytes;
+        const int k0 = kb * kBlockK;
+        if (!p.a_mn) {
+          tma_load_2d(a_dst, &map_a, &full_bar[s], k0, m0);                 // box {64 k, 128 m}
+        } else {
+          tma_load_2d(a_dst, &map_a, &full_bar[s], m0, k0);                 // box {64 m, 64 k} x2
+          tma_load_2d(a_dst + 8192, &map_a, &full_bar[s], m0 + 64, k0);
+        }
+        if (!p.b_mn) {
+          tma_load_2d(b_dst, &map_b, &full_bar[s], k0, n0);                 // box {64 k, block_n}
+        } else {
+          for (int j = 0; j < p.block_n / 64; ++j)
+            tma_load_2d(b_dst + j * 8192, &map_b, &full_bar[s], n0 + 64 * j, k0);   // box {64 n, 64 k}
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, p.a_mn, p.b_mn);
+      int it = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(tiles + s * stage_bytes);
+        const uint32_t b_addr = a_addr + kABytes;
+        const uint64_t a_desc = p.a_mn ? make_smem_desc_sw128(a_addr, 8192, 1024) : make_smem_desc_sw128(a_addr, 16, 1024);
+        const uint64_t b_desc = p.b_mn ? make_smem_desc_sw128(b_addr, 8192, 1024) : make_smem_desc_sw128(b_addr, 16, 1024);
+        const uint32_t a_step = p.a_mn ? (2048u >> 4) : (32u >> 4);   // advance 16 K-elements
+        const uint32_t b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          umma_bf16(tmem_base, a_desc + (uint64_t)(a_step * k), b_desc + (uint64_t)(b_step * k), idesc,
+                    (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);      // frees the smem slot once these MMAs have consumed it
+      }
+      umma_commit(&tmem_full_bar);       // accumulator complete
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const long long grow = (long long)m0 + row;
+    const bool row_ok = grow < p.M;
+    const bool have_k = kb_end > kb_begin;
+    if (have_k) {
+      mbar_wait(&tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    float* cf = reinterpret_cast<float*>(p.c);
+    __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(p.c);
+    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      uint32_t r[16];
+      if (have_k) {
+        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = 0;
+      }
+      const int gc0 = n0 + c0;
+      if (gc0 >= p.N) break;                      // warp-uniform
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x = __uint_as_float(r[j]) * p.alpha;
+        const int gc = gc0 + j;
+        if (p.bias != nullptr && gc < p.N && (p.atomic == 0 || blockIdx.z == 0)) x += __ldg(p.bias + gc);
+        if (p.relu) x = fmaxf(x, 0.0f);
+        v[j] = x;
+      }
+      if (p.mask != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int gc = gc0 + j;
+          float mk = 0.0f;
+          if (row_ok && gc < p.N) mk = __bfloat162float(p.mask[grow * p.ldmask + gc]);
+          v[j] = mk > 0.0f ? v[j] : 0.0f;
+        }
+      }
+      if (p.colsum != nullptr) {
+        float mine = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float s = row_ok ? v[j] : 0.0f;
+          s += __shfl_xor_sync(0xffffffffu, s, 16);
+          s += __shfl_xor_sync(0xffffffffu, s, 8);
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          if (lane == j) mine = s;
+        }
+        if (lane < 16 && gc0 + lane < p.N) atomicAdd(p.colsum + gc0 + lane, mine);
+      }
+      if (row_ok) {
+        const bool full = gc0 + 16 <= p.N;
+        if (p.atomic) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (gc0 + j < p.N) atomicAdd(cf + grow * p.ldc + gc0 + j, v[j]);
+        } else if (p.c_bf16) {
+          __nv_bfloat16* dst = cb + grow * p.ldc + gc0;
+          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            uint4 w0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                  pack_bf16x2(v[6], v[7]));
+            uint4 w1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                  pack_bf16x2(v[14], v[15]));
+            reinterpret_cast<uint4*>(dst)[0] = w0;
+            reinterpret_cast<uint4*>(dst)[1] = w1;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (gc0 + j < p.N) dst[j] = __float2bfloat16(v[j]);
+          }
+        } else {
+          float* dst = cf + grow * p.ldc + gc0;
+          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (gc0 + j < p.N) dst[j] = v[j];
+          }
+        }
+      }
+    }
+    if (p.signal != nullptr) {
+      // fused push: make this CTA's tile visible system-wide, then bump the consumer's arrival counter
+      fence_acq_rel_sys();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2 && lane == 0) red_release_sys_add_u64(reinterpret_cast<uint64_t*>(p.signal), 1ull);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements),
+// box = {box_cols (<= 64 -> 128 bytes), box_rows}, 128-byte swizzle, zero fill out of bounds.
+static int make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_cols,
+                    int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+struct MapKey {
+  const void* ptr;
+  long long rows, cols, ld;
+  int bc, br;
+  bool operator<(const MapKey& o) const {
+    return std::tie(ptr, rows, cols, ld, bc, br) < std::tie(o.ptr, o.rows, o.cols, o.ld, o.bc, o.br);
+  }
+};
+static std::map<MapKey, CUtensorMap> g_maps;
+static std::mutex g_maps_mu;
+
+static int cached_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int bc, int br) {
+  MapKey k{ptr, rows, cols, ld, bc, br};
+  std::lock_guard<std::mutex> g(g_maps_mu);
+  auto it = g_maps.find(k);
+  if (it != g_maps.end()) {
+    *out = it->second;
+    return 0;
+  }
+  int rc = make_map(out, ptr, rows, cols, ld, bc, br);
+  if (rc == 0) {
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps[k] = *out;
+  }
+  return rc;
+}
+
+}  // namespace dtf
+
+extern "C" {
+
+struct DtfGemmArgs {
+  const void* a;         // bf16
+  const void* b;         // bf16
+  void* c;               // fp32 or bf16
+  long long M, N, K;
+  long long lda, ldb, ldc;
+  int a_mn, b_mn;        // storage: a_mn=0 -> A[M,K] row-major, 1 -> A^T stored as [K,M]; same for B ([N,K] / [K,N])
+  int c_bf16;
+  const float* bias;
+  int relu;
+  const void* mask;      // bf16 [M, ldmask]
+  long long ldmask;
+  float alpha;
+  int splits;            // >1: split-K with atomic accumulation into fp32 C (C must be zeroed, no relu)
+  int accumulate;        // 1: atomically add into existing fp32 C
+  float* colsum;
+  const unsigned long long* wait_flag;
+  unsigned long long wait_target;
+  unsigned long long* signal;
+  unsigned int* err;
+  unsigned long long timeout_ns;
+  int block_n_override;
+};
+
+// Returns 0 on success, <0 for argument errors, >0 for CUDA errors.
+int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
+  using namespace dtf;
+  if (g->M <= 0 || g->N <= 0 || g->K <= 0) return -2;
+  if ((g->lda % 8) || (g->ldb % 8)) return -3;                                  // TMA: 16-byte row pitch
+  if ((reinterpret_cast<uintptr_t>(g->a) & 15) || (reinterpret_cast<uintptr_t>(g->b) & 15)) return -4;
+  if (g->splits > 1 && (g->relu || g->c_bf16)) return -5;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)g->M; p.N = (int)g->N; p.K = (int)g->K;
+  p.a_mn = g->a_mn; p.b_mn = g->b_mn;
+  int bn;
+  if (g->block_n_override > 0) bn = g->block_n_override;
+  else if (g->b_mn) bn = g->N <= 64 ? 64 : (g->N <= 128 ? 128 : (g->N <= 192 ? 192 : 256));
+  else { bn = (int)((g->N + 15) / 16 * 16); if (bn > 256) bn = (g->N % 256 == 0 || g->N > 1024) ? 256 : 128; }
+  if (g->b_mn && (bn % 64)) return -6;
+  if (bn % 16 || bn > 256 || bn < 16) return -6;
+  p.block_n = bn;
+  p.num_kb = (int)((g->K + kBlockK - 1) / kBlockK);
+  int splits = g->splits > 1 ? g->splits : 1;
+  if (splits > p.num_kb) splits = p.num_kb;
+  p.kb_per_split = (p.num_kb + splits - 1) / splits;
+  splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  const int stage_bytes = kABytes + bn * kBlockK * 2;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages > p.kb_per_split) stages = p.kb_per_split < 2 ? 2 : p.kb_per_split;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  p.c = g->c; p.ldc = g->ldc; p.c_bf16 = g->c_bf16;
+  p.bias = g->bias; p.relu = g->relu;
+  p.mask = reinterpret_cast<const __nv_bfloat16*>(g->mask); p.ldmask = g->ldmask;
+  p.alpha = g->alpha;
+  p.atomic = (splits > 1 || g->accumulate) ? 1 : 0;
+  p.colsum = g->colsum;
+  p.wait_flag = g->wait_flag; p.wait_target = g->wait_target;
+  p.signal = g->signal; p.err = g->err;
+  p.timeout_ns = g->timeout_ns ? g->timeout_ns : 2000000000ull;
+
+  CUtensorMap ma, mb;
+  int rc;
+  if (!g->a_mn) rc = cached_map(&ma, g->a, g->M, g->K, g->lda, 64, kBlockM);      // [M rows, K cols]
+  else          rc = cached_map(&ma, g->a, g->K, g->M, g->lda, 64, 64);           // [K rows, M cols]
+  if (rc) return rc < 0 ? -7 : 1000 + rc;
+  if (!g->b_mn) rc = cached_map(&mb, g->b, g->N, g->K, g->ldb, 64, bn);           // [N rows, K cols]
+  else          rc = cached_map(&mb, g->b, g->K, g->N, g->ldb, 64, 64);           // [K rows, N cols]
+  if (rc) return rc < 0 ? -7 : 1000 + rc;
+
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(226 * 1024));   // 227 KB minus the static barriers
+    if (e != cudaSuccess) return 2000 + (int)e;
+    configured = 226 * 1024;
+  }
+  dim3 grid((unsigned)((g->M + kBlockM - 1) / kBlockM), (unsigned)((g->N + bn - 1) / bn), (unsigned)splits);
+  gemm_bf16_tcgen05_kernel<<<grid, kThreads, smem, stream>>>(ma, mb, p);
+  return (int)cudaGetLastError();
+}
+
+void dtf_gemm_clear_map_cache() {
+  std::lock_guard<std::mutex> g(dtf::g_maps_mu);
+  dtf::g_maps.clear();
+}
+
+}  // extern "C"

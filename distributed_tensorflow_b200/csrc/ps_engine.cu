@@ -1,0 +1,641 @@
+// Device-resident parameter-server protocol for one NVSwitch box.
+//
+//   * PsControl lives in the ps GPU's memory and is mapped (CUDA IPC / peer access) by every worker.
+//     Workers push gradient tiles into their slot in ps HBM from GEMM epilogues (gemm_tcgen05.cu) and
+//     from the fused MLP head below, then release-increment `w[rank].arrivals` over NVLink.
+//   * ps_apply_kernel is the ps "service loop" body, one launch per aggregate: block 0 waits for the
+//     required arrivals (sync: >= replicas_to_aggregate FRESH pushes, stale stamps dropped; async: any
+//     one push), broadcasts the decision, then all blocks run ONE fused pass:
+//     N-way reduce -> mean -> SGD/Momentum/TF-Adam apply -> write fp32 master + bf16 shadow (and,
+//     in publish mode, store the new bf16 parameters straight into every worker's replica over
+//     NVLink); the last block bumps global_step / beta powers and releases the tokens (one mailbox
+//     store per worker, system scope).
+//   * Tokens: the worker-side wait is fused into the first GEMM of the next step (its TMA producer
+//     acquires the mailbox before loading the parameters).
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "ps_control.h"
+
+namespace dtf {
+
+struct PsApplyParams {
+  PsControl* ctl;
+  float* master;                 // [n] fp32 parameters (padded layout)
+  float* slot_m;                 // optimizer slots (may be null)
+  float* slot_v;
+  const float* grad[DTF_MAX_WORKERS];      // per-worker gradient slots in ps memory
+  float* grad_rw[DTF_MAX_WORKERS];         // same pointers, writable (zero-after-read ranges)
+  __nv_bfloat16* shadow;                   // ps-local bf16 copy (peer-pull mode reads this)
+  __nv_bfloat16* replica[DTF_MAX_WORKERS]; // optional per-worker bf16 replicas (publish mode), peer pointers
+  WorkerMailbox* mailbox[DTF_MAX_WORKERS]; // peer pointers
+  long long n;
+  int num_workers;               // total_num_replicas
+  int replicas_to_aggregate;
+  unsigned int ctas_per_push;    // arrivals one complete push adds
+  int mode;                      // 0 sync, 1 async
+  int kind;                      // 0 sgd, 1 momentum, 2 adam
+  float lr, momentum, beta1, beta2, eps;
+  int nesterov;
+  int publish_replicas;          // 1: also store the shadow into every worker replica
+  long long zero_begin[4], zero_end[4];    // ranges of the slots to clear after reading (atomically accumulated grads)
+  int num_zero;
+  unsigned long long timeout_ns;
+  unsigned long long* trace;     // optional ring: {kind, t0, t1, step} per launch
+  int trace_cap;
+};
+
+DTF_DEVICE unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+DTF_DEVICE unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+DTF_DEVICE void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
+  __shared__ unsigned int s_mask, s_count, s_ok;
+  __shared__ unsigned long long s_seq;
+  __shared__ float s_lr;
+  PsControl* ctl = p.ctl;
+  const unsigned long long t_start = (blockIdx.x == 0 && threadIdx.x == 0) ? globaltimer_ns() : 0ull;
+
+  if (threadIdx.x == 0) {
+    const unsigned long long seq = ld_acquire_gpu_u64(&ctl->param_version) + 1ull;
+    s_seq = seq;
+    unsigned int ok = 1;
+    if (blockIdx.x == 0) {
+      // ---------------- decision: which pushes does this aggregate consume? ----------------
+      const unsigned long long gs = ctl->global_step;
+      const unsigned long long t0 = globaltimer_ns();
+      unsigned int mask = 0, count = 0;
+      unsigned int spins = 0;
+      while (true) {
+        mask = 0;
+        count = 0;
+        if (p.mode == 0) {
+          for (int w = 0; w < p.num_workers; ++w) {
+            const unsigned long long arr = ld_acquire_sys_u64(reinterpret_cast<const uint64_t*>(&ctl->w[w].arrivals));
+            if (arr >= ctl->consumed[w] + p.ctas_per_push) {
+              const unsigned long long stamp = ld_relaxed_sys_u64(reinterpret_cast<const uint64_t*>(&ctl->w[w].stamp));
+              if (stamp >= gs) {
+                mask |= 1u << w;
+                ++count;
+              } else {
+                // stale gradient (stamped before the current global step): drop it, SURVEY A12
+                ctl->consumed[w] += p.ctas_per_push;
+                ctl->dropped_stale += 1;
+              }
+            }
+          }
+          if ((int)count >= p.replicas_to_aggregate) break;
+        } else {
+          const int start = (int)((ctl->last_async_worker + 1) % (unsigned)p.num_workers);
+          for (int i = 0; i < p.num_workers; ++i) {
+            const int w = (start + i) % p.num_workers;
+            const unsigned long long arr = ld_acquire_sys_u64(reinterpret_cast<const uint64_t*>(&ctl->w[w].arrivals));
+            if (arr >= ctl->consumed[w] + p.ctas_per_push) {
+              mask = 1u << w;
+              count = 1;
+              ctl->last_async_worker = (unsigned)w;
+              // staleness = updates applied between this worker's pull and its apply
+              const unsigned long long stamp = ld_relaxed_sys_u64(reinterpret_cast<const uint64_t*>(&ctl->w[w].stamp));
+              unsigned long long st = gs > stamp ? gs - stamp : 0ull;
+              ctl->staleness_sum += st;
+              if (st > 15) st = 15;
+              ctl->staleness_hist[st] += 1;
+              break;
+            }
+          }
+          if (count) break;
+        }
+        if ((++spins & 0xFF) == 0 && (globaltimer_ns() - t0) > p.timeout_ns) {
+          ok = 0;
+          atomicExch(&ctl->err, 2u);
+          break;
+        }
+        __nanosleep(32);
+      }
+      ctl->decision_mask = mask;
+      ctl->decision_count = count ? count : 1u;
+      ctl->decision_ok = ok;
+      __threadfence();
+      st_release_gpu_u64(&ctl->decision_seq, seq);
+    } else {
+      const unsigned long long t0 = globaltimer_ns();
+      unsigned int spins = 0;
+      while (ld_acquire_gpu_u64(&ctl->decision_seq) < seq) {
+        if ((++spins & 0xFF) == 0 && (globaltimer_ns() - t0) > 2 * p.timeout_ns) break;
+        __nanosleep(32);
+      }
+    }
+    s_mask = ctl->decision_mask;
+    s_count = ctl->decision_count;
+    s_ok = ctl->decision_ok;
+    float lr = p.lr;
+    if (p.kind == 2) lr = p.lr * sqrtf(1.0f - ctl->beta2_power) / (1.0f - ctl->beta1_power);
+    s_lr = lr;
+  }
+  __syncthreads();
+  const unsigned int mask = s_mask;
+  const float inv = 1.0f / (float)s_count;
+  const float lr = s_lr;
+  const bool ok = s_ok != 0;
+
+  if (ok) {
+    // ---------------- fused reduce + mean + apply + publish ----------------
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < p.n; i0 += stride) {
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      const bool vec = (i0 + 4 <= p.n);
+      for (int w = 0; w < p.num_workers; ++w) {
+        if (!(mask & (1u << w))) continue;
+        if (vec) {
+          const float4 t = *reinterpret_cast<const float4*>(p.grad[w] + i0);
+          g[0] += t.x; g[1] += t.y; g[2] += t.z; g[3] += t.w;
+        } else {
+          for (int j = 0; j < 4 && i0 + j < p.n; ++j) g[j] += p.grad[w][i0 + j];
+        }
+      }
+      float wv[4];
+      for (int j = 0; j < 4 && i0 + j < p.n; ++j) {
+        const long long i = i0 + j;
+        const float gj = g[j] * inv;
+        float x = p.master[i];
+        if (p.kind == 0) {
+          x -= lr * gj;
+        } else if (p.kind == 1) {
+          const float acc = p.momentum * p.slot_m[i] + gj;
+          p.slot_m[i] = acc;
+          x -= p.nesterov ? (lr * gj + lr * p.momentum * acc) : (lr * acc);
+        } else {
+          const float m = p.beta1 * p.slot_m[i] + (1.0f - p.beta1) * gj;
+          const float v = p.beta2 * p.slot_v[i] + (1.0f - p.beta2) * gj * gj;
+          p.slot_m[i] = m;
+          p.slot_v[i] = v;
+          x -= lr * m / (sqrtf(v) + p.eps);
+        }
+        p.master[i] = x;
+        wv[j] = x;
+      }
+      if (vec) {
+        const uint2 packed = make_uint2(pack_bf16x2(wv[0], wv[1]), pack_bf16x2(wv[2], wv[3]));
+        if (p.shadow) *reinterpret_cast<uint2*>(p.shadow + i0) = packed;
+        if (p.publish_replicas)
+          for (int w = 0; w < p.num_workers; ++w)
+            if (p.replica[w]) *reinterpret_cast<uint2*>(p.replica[w] + i0) = packed;     // NVLink store
+      } else {
+        for (int j = 0; j < 4 && i0 + j < p.n; ++j) {
+          const __nv_bfloat16 b = __float2bfloat16(wv[j]);
+          if (p.shadow) p.shadow[i0 + j] = b;
+          if (p.publish_replicas)
+            for (int w = 0; w < p.num_workers; ++w)
+              if (p.replica[w]) p.replica[w][i0 + j] = b;
+        }
+      }
+      for (int z = 0; z < p.num_zero; ++z) {
+        if (i0 + 4 > p.zero_begin[z] && i0 < p.zero_end[z]) {
+          for (int w = 0; w < p.num_workers; ++w) {
+            if (!(mask & (1u << w))) continue;
+            for (int j = 0; j < 4; ++j) {
+              const long long i = i0 + j;
+              if (i >= p.zero_begin[z] && i < p.zero_end[z] && i < p.n) p.grad_rw[w][i] = 0.f;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---------------- completion: last block publishes the new step and releases the tokens ----------------
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(&ctl->done_ctas, 1u);
+    if (prev == gridDim.x - 1) {
+      __threadfence();
+      ctl->done_ctas = 0;
+      if (ok) {
+        for (int w = 0; w < p.num_workers; ++w)
+          if (mask & (1u << w)) ctl->consumed[w] += p.ctas_per_push;
+        const unsigned long long ngs = ctl->global_step + 1ull;
+        ctl->global_step = ngs;
+        ctl->applied_total += s_count;
+        if (p.kind == 2) {
+          ctl->beta1_power *= p.beta1;
+          ctl->beta2_power *= p.beta2;
+        }
+        __threadfence_system();
+        // tokens: every replica gets one carrying the NEW global step (sync); the pusher only (async)
+        for (int w = 0; w < p.num_workers; ++w) {
+          if (p.mailbox[w] == nullptr) continue;
+          if (p.mode == 1 && !(mask & (1u << w))) continue;
+          if (p.mode == 1) {
+            // async ack: count of this worker's applied pushes + the step it may stamp next
+            st_release_sys_u64(reinterpret_cast<uint64_t*>(&p.mailbox[w]->version), ngs);
+            red_release_sys_add_u64(reinterpret_cast<uint64_t*>(&p.mailbox[w]->token), 1ull);
+          } else {
+            st_release_sys_u64(reinterpret_cast<uint64_t*>(&p.mailbox[w]->version), ngs);
+            st_release_sys_u64(reinterpret_cast<uint64_t*>(&p.mailbox[w]->token), ngs);
+          }
+        }
+      }
+      if (p.trace && p.trace_cap > 0) {
+        const unsigned long long slot = (s_seq - 1ull) % (unsigned long long)p.trace_cap;
+        p.trace[slot * 4 + 0] = 1ull;
+        p.trace[slot * 4 + 1] = t_start ? t_start : globaltimer_ns();
+        p.trace[slot * 4 + 2] = globaltimer_ns();
+        p.trace[slot * 4 + 3] = ctl->global_step;
+      }
+      __threadfence();
+      st_release_gpu_u64(&ctl->param_version, s_seq);      // next launch's sequence number
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ps init: build the bf16 shadow (and worker replicas) from the master, publish version/tokens
+// ---------------------------------------------------------------------------------------------
+__global__ void ps_publish_kernel(const float* __restrict__ master, __nv_bfloat16* __restrict__ shadow, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    shadow[i] = __float2bfloat16(master[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused MLP head (SURVEY K2+K3+K4 small parts), ONE CTA:
+//   logits = h.W2 + b2 ; softmax ; clipped cross-entropy (batch SUM) ; dlogits ;
+//   dW2 = h^T.dlogits and db2 -> pushed to the ps slot ; dh = dlogits.W2^T * (h>0) (bf16, local) ;
+//   db1 = colsum(dh) -> pushed ; stamp + arrival signal.
+// B <= 128 rows, H <= 256 hidden units, C <= 16 classes.  W2 / b2 are read from the ps (peer
+// pointers: bf16 shadow for W2, fp32 master for b2) -- the pull of the small parameters is fused here.
+// ---------------------------------------------------------------------------------------------
+struct MlpHeadParams {
+  const __nv_bfloat16* h;       // [B, ldh] post-ReLU activations (bf16)
+  long long ldh;
+  const __nv_bfloat16* w2;      // [H, ldw2] bf16 (ps shadow; may be a peer pointer)
+  long long ldw2;
+  const float* b2;              // [C] fp32 (ps master; may be a peer pointer)
+  const float* labels;          // [B, ldl]
+  long long ldl;
+  int B, H, C;
+  float clip_min;
+  float* loss_out;              // [1] local: batch-sum loss of this step
+  float* loss_hist;             // optional [hist_cap] ring of losses
+  unsigned long long* step_counter;   // local device step counter (incremented here)
+  int hist_cap;
+  __nv_bfloat16* dh;            // [B, lddh] local bf16 (feeds the dW1 GEMM)
+  long long lddh;
+  float* gw2;                   // ps slot: [H, ldgw2]
+  long long ldgw2;
+  float* gb2;                   // ps slot: [C]
+  float* gb1;                   // ps slot: [H]
+  float* logits_out;            // optional local [B, C]
+  const WorkerMailbox* mailbox; // local mailbox (token already acquired by the first GEMM of the step)
+  PsControl* ctl;               // ps control block (peer)
+  int rank;                     // worker index
+  int stamp_from_version;       // async: stamp = mailbox->version, sync: stamp = mailbox->token
+};
+
+__global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p) {
+  extern __shared__ float sm[];
+  const int B = p.B, H = p.H, C = p.C;
+  const int CP = 16;
+  float* s_h = sm;                          // [B][H+1]
+  float* s_w2 = s_h + (size_t)B * (H + 1);  // [H][CP]
+  float* s_dl = s_w2 + (size_t)H * CP;      // [B][CP]  logits -> dlogits
+  float* s_b2 = s_dl + (size_t)B * CP;      // [CP]
+  float* s_red = s_b2 + CP;                 // [32]
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  for (int i = tid; i < B * H; i += nt) {
+    const int b = i / H, k = i - b * H;
+    s_h[b * (H + 1) + k] = __bfloat162float(p.h[(long long)b * p.ldh + k]);
+  }
+  for (int i = tid; i < H * CP; i += nt) {
+    const int k = i / CP, c = i - k * CP;
+    s_w2[i] = c < C ? __bfloat162float(p.w2[(long long)k * p.ldw2 + c]) : 0.f;
+  }
+  if (tid < CP) s_b2[tid] = tid < C ? p.b2[tid] : 0.f;
+  __syncthreads();
+
+  // logits
+  for (int i = tid; i < B * CP; i += nt) {
+    const int b = i / CP, c = i - b * CP;
+    float acc = 0.f;
+    if (c < C) {
+      const float* hr = s_h + b * (H + 1);
+      for (int k = 0; k < H; ++k) acc = fmaf(hr[k], s_w2[k * CP + c], acc);
+      acc += s_b2[c];
+    }
+    s_dl[i] = acc;
+  }
+  __syncthreads();
+  if (p.logits_out)
+    for (int i = tid; i < B * C; i += nt) p.logits_out[i] = s_dl[(i / C) * CP + (i % C)];
+
+  // softmax + clipped xent + dlogits, one thread per row
+  float my_loss = 0.f;
+  if (tid < B) {
+    float* z = s_dl + tid * CP;
+    const float* lab = p.labels + (long long)tid * p.ldl;
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, z[c]);
+    float se = 0.f;
+    float y[16];
+    for (int c = 0; c < C; ++c) { y[c] = __expf(z[c] - mx); se += y[c]; }
+    const float inv = 1.f / se;
+    float tsum = 0.f;
+    for (int c = 0; c < C; ++c) {
+      y[c] *= inv;
+      const float l = lab[c];
+      if (p.clip_min > 0.f) {
+        my_loss -= l * __logf(fminf(fmaxf(y[c], p.clip_min), 1.f));
+        tsum += (y[c] >= p.clip_min) ? l : 0.f;
+      } else {
+        my_loss -= l * (z[c] - mx - __logf(se));
+        tsum += l;
+      }
+    }
+    for (int c = 0; c < C; ++c) {
+      const float t = (p.clip_min > 0.f && y[c] < p.clip_min) ? 0.f : lab[c];
+      z[c] = y[c] * tsum - t;
+    }
+    for (int c = C; c < CP; ++c) z[c] = 0.f;
+  }
+  // block-reduce the loss
+  for (int o = 16; o > 0; o >>= 1) my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
+  if ((tid & 31) == 0) s_red[tid >> 5] = my_loss;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (nt >> 5); ++i) t += s_red[i];
+    *p.loss_out = t;
+    unsigned long long step = 0;
+    if (p.step_counter) { step = *p.step_counter; *p.step_counter = step + 1; }
+    if (p.loss_hist && p.hist_cap > 0) p.loss_hist[step % (unsigned long long)p.hist_cap] = t;
+  }
+
+  // dW2[k][c] = sum_b h[b][k] * dl[b][c]  -> ps slot (NVLink stores)
+  for (int i = tid; i < H * C; i += nt) {
+    const int k = i / C, c = i - k * C;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(s_h[b * (H + 1) + k], s_dl[b * CP + c], acc);
+    p.gw2[(long long)k * p.ldgw2 + c] = acc;
+  }
+  if (tid < C) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += s_dl[b * CP + tid];
+    p.gb2[tid] = acc;
+  }
+  // dh[b][k] = (h>0) * sum_c dl[b][c] * W2[k][c]   (bf16, local) ; keep fp32 copy in s_h for db1
+  for (int i = tid; i < B * H; i += nt) {
+    const int b = i / H, k = i - b * H;
+    float acc = 0.f;
+    if (s_h[b * (H + 1) + k] > 0.f) {
+      const float* dl = s_dl + b * CP;
+      const float* wr = s_w2 + k * CP;
+#pragma unroll
+      for (int c = 0; c < CP; ++c) acc = fmaf(dl[c], wr[c], acc);
+    }
+    p.dh[(long long)b * p.lddh + k] = __float2bfloat16(acc);
+    s_h[b * (H + 1) + k] = acc;          // each (b,k) is read and written by the same thread only
+  }
+  __syncthreads();
+  for (int k = tid; k < H; k += nt) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += s_h[b * (H + 1) + k];
+    p.gb1[k] = acc;
+  }
+  // stamp + arrival: everything this CTA pushed must be visible at the ps before the counter moves
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0 && p.ctl != nullptr) {
+    const unsigned long long stamp = p.stamp_from_version ? p.mailbox->version : p.mailbox->token;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&p.ctl->w[p.rank].stamp), "l"(stamp) : "memory");
+    red_release_sys_add_u64(reinterpret_cast<uint64_t*>(&p.ctl->w[p.rank].arrivals), 1ull);
+  }
+}
+
+// wait (on the worker) until the mailbox token reaches `target`: used when the step's first kernel
+// is not a GEMM with a fused wait (generic models), and by tests.
+__global__ void wait_token_kernel(const WorkerMailbox* mb, unsigned long long target, unsigned long long timeout_ns,
+                                  unsigned int* err) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (!wait_flag_ge_u64(reinterpret_cast<const uint64_t*>(&mb->token), target, timeout_ns) && err) atomicExch(err, 3u);
+  }
+}
+
+// push an already-computed local gradient buffer into the ps slot (generic models / graph mode):
+// vectorised NVLink stores + stamp + arrival.  One "push" = gridDim.x arrivals.
+__global__ void push_grad_kernel(const float* __restrict__ src, float* __restrict__ dst_peer, long long n, PsControl* ctl,
+                                 const WorkerMailbox* mb, int rank, int stamp_from_version, int write_stamp) {
+  const long long n4 = n / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    reinterpret_cast<float4*>(dst_peer)[i] = reinterpret_cast<const float4*>(src)[i];
+  if (blockIdx.x == 0)
+    for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) dst_peer[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (write_stamp && blockIdx.x == 0) {
+      const unsigned long long stamp = stamp_from_version ? mb->version : mb->token;
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&ctl->w[rank].stamp), "l"(stamp) : "memory");
+      __threadfence_system();
+    }
+    red_release_sys_add_u64(reinterpret_cast<uint64_t*>(&ctl->w[rank].arrivals), 1ull);
+  }
+}
+
+// pull the bf16 shadow from the ps into a local replica (generic models): peer loads, 128-bit
+__global__ void pull_shadow_kernel(const uint4* __restrict__ src_peer, uint4* __restrict__ dst, long long n16) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src_peer[i];
+}
+
+}  // namespace dtf
+
+extern "C" {
+using namespace dtf;
+
+int dtf_sizeof_ps_control() { return (int)sizeof(PsControl); }
+int dtf_sizeof_mailbox() { return (int)sizeof(WorkerMailbox); }
+int dtf_offsetof_ctl(int which) {
+  switch (which) {
+    case 0: return (int)offsetof(PsControl, global_step);
+    case 1: return (int)offsetof(PsControl, param_version);
+    case 2: return (int)offsetof(PsControl, beta1_power);
+    case 3: return (int)offsetof(PsControl, beta2_power);
+    case 4: return (int)offsetof(PsControl, dropped_stale);
+    case 5: return (int)offsetof(PsControl, applied_total);
+    case 6: return (int)offsetof(PsControl, staleness_hist);
+    case 7: return (int)offsetof(PsControl, staleness_sum);
+    case 8: return (int)offsetof(PsControl, err);
+    case 9: return (int)offsetof(PsControl, w);
+    case 10: return (int)sizeof(WorkerSlotState);
+    case 11: return (int)offsetof(PsControl, consumed);
+  }
+  return -1;
+}
+
+struct DtfPsApplyArgs {
+  void* ctl;
+  float* master;
+  float* slot_m;
+  float* slot_v;
+  float* grad[DTF_MAX_WORKERS];
+  void* shadow;
+  void* replica[DTF_MAX_WORKERS];
+  void* mailbox[DTF_MAX_WORKERS];
+  long long n;
+  int num_workers, replicas_to_aggregate;
+  unsigned int ctas_per_push;
+  int mode, kind;
+  float lr, momentum, beta1, beta2, eps;
+  int nesterov, publish_replicas;
+  long long zero_begin[4], zero_end[4];
+  int num_zero;
+  unsigned long long timeout_ns;
+  unsigned long long* trace;
+  int trace_cap;
+  int grid;
+};
+
+int dtf_ps_apply(const DtfPsApplyArgs* a, cudaStream_t s) {
+  PsApplyParams p;
+  memset(&p, 0, sizeof(p));
+  p.ctl = reinterpret_cast<PsControl*>(a->ctl);
+  p.master = a->master; p.slot_m = a->slot_m; p.slot_v = a->slot_v;
+  for (int w = 0; w < DTF_MAX_WORKERS; ++w) {
+    p.grad[w] = a->grad[w]; p.grad_rw[w] = a->grad[w];
+    p.replica[w] = reinterpret_cast<__nv_bfloat16*>(a->replica[w]);
+    p.mailbox[w] = reinterpret_cast<WorkerMailbox*>(a->mailbox[w]);
+  }
+  p.shadow = reinterpret_cast<__nv_bfloat16*>(a->shadow);
+  p.n = a->n; p.num_workers = a->num_workers; p.replicas_to_aggregate = a->replicas_to_aggregate;
+  p.ctas_per_push = a->ctas_per_push; p.mode = a->mode; p.kind = a->kind;
+  p.lr = a->lr; p.momentum = a->momentum; p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps;
+  p.nesterov = a->nesterov; p.publish_replicas = a->publish_replicas;
+  for (int z = 0; z < 4; ++z) { p.zero_begin[z] = a->zero_begin[z]; p.zero_end[z] = a->zero_end[z]; }
+  p.num_zero = a->num_zero;
+  p.timeout_ns = a->timeout_ns ? a->timeout_ns : 2000000000ull;
+  p.trace = a->trace; p.trace_cap = a->trace_cap;
+  int grid = a->grid;
+  if (grid <= 0) {
+    long long want = (a->n / 4 + 255) / 256;
+    grid = (int)(want < 1 ? 1 : (want > 148 ? 148 : want));      // all CTAs must be co-resident
+  }
+  ps_apply_kernel<<<grid, 256, 0, s>>>(p);
+  return (int)cudaGetLastError();
+}
+
+int dtf_ps_publish(const float* master, void* shadow, long long n, cudaStream_t s) {
+  long long g = (n + 255) / 256;
+  if (g > 1184) g = 1184;
+  ps_publish_kernel<<<(int)g, 256, 0, s>>>(master, reinterpret_cast<__nv_bfloat16*>(shadow), n);
+  return (int)cudaGetLastError();
+}
+
+struct DtfMlpHeadArgs {
+  const void* h; long long ldh;
+  const void* w2; long long ldw2;
+  const float* b2;
+  const float* labels; long long ldl;
+  int B, H, C;
+  float clip_min;
+  float* loss_out; float* loss_hist; unsigned long long* step_counter; int hist_cap;
+  void* dh; long long lddh;
+  float* gw2; long long ldgw2;
+  float* gb2; float* gb1;
+  float* logits_out;
+  const void* mailbox; void* ctl;
+  int rank; int stamp_from_version;
+};
+
+int dtf_mlp_head(const DtfMlpHeadArgs* a, cudaStream_t s) {
+  if (a->B > 128 || a->H > 256 || a->C > 16) return -2;
+  MlpHeadParams p;
+  p.h = reinterpret_cast<const __nv_bfloat16*>(a->h); p.ldh = a->ldh;
+  p.w2 = reinterpret_cast<const __nv_bfloat16*>(a->w2); p.ldw2 = a->ldw2;
+  p.b2 = a->b2; p.labels = a->labels; p.ldl = a->ldl; p.B = a->B; p.H = a->H; p.C = a->C; p.clip_min = a->clip_min;
+  p.loss_out = a->loss_out; p.loss_hist = a->loss_hist; p.step_counter = a->step_counter; p.hist_cap = a->hist_cap;
+  p.dh = reinterpret_cast<__nv_bfloat16*>(a->dh); p.lddh = a->lddh;
+  p.gw2 = a->gw2; p.ldgw2 = a->ldgw2; p.gb2 = a->gb2; p.gb1 = a->gb1; p.logits_out = a->logits_out;
+  p.mailbox = reinterpret_cast<const WorkerMailbox*>(a->mailbox); p.ctl = reinterpret_cast<PsControl*>(a->ctl);
+  p.rank = a->rank; p.stamp_from_version = a->stamp_from_version;
+  const size_t smem = sizeof(float) * ((size_t)a->B * (a->H + 1) + (size_t)a->H * 16 + (size_t)a->B * 16 + 16 + 32);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    configured = 200 * 1024;
+  }
+  mlp_head_kernel<<<1, 512, smem, s>>>(p);
+  return (int)cudaGetLastError();
+}
+
+int dtf_wait_token(const void* mailbox, unsigned long long target, unsigned long long timeout_ns, unsigned int* err,
+                   cudaStream_t s) {
+  wait_token_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const WorkerMailbox*>(mailbox), target,
+                                     timeout_ns ? timeout_ns : 2000000000ull, err);
+  return (int)cudaGetLastError();
+}
+
+int dtf_push_grad(const float* src, float* dst_peer, long long n, void* ctl, const void* mailbox, int rank,
+                  int stamp_from_version, int write_stamp, int grid, cudaStream_t s) {
+  push_grad_kernel<<<grid, 256, 0, s>>>(src, dst_peer, n, reinterpret_cast<PsControl*>(ctl),
+                                        reinterpret_cast<const WorkerMailbox*>(mailbox), rank, stamp_from_version,
+                                        write_stamp);
+  return (int)cudaGetLastError();
+}
+
+int dtf_pull_shadow(const void* src_peer, void* dst, long long nbytes, int grid, cudaStream_t s) {
+  pull_shadow_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(src_peer), reinterpret_cast<uint4*>(dst),
+                                          nbytes / 16);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// fabric: IPC-exportable device allocations + peer access
+// ---------------------------------------------------------------------------------------------
+int dtf_fabric_alloc(void** out, long long bytes) {
+  cudaError_t e = cudaMalloc(out, (size_t)bytes);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaMemset(*out, 0, (size_t)bytes);
+}
+int dtf_fabric_free(void* p) { return (int)cudaFree(p); }
+int dtf_fabric_export(void* p, void* handle64) {
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) return (int)e;
+  memcpy(handle64, &h, sizeof(h));
+  return 0;
+}
+int dtf_fabric_import(const void* handle64, void** out) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  return (int)cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+}
+int dtf_fabric_close(void* p) { return (int)cudaIpcCloseMemHandle(p); }
+int dtf_enable_peer(int peer) {
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+  return (int)e;
+}
+int dtf_can_access_peer(int dev, int peer) {
+  int ok = 0;
+  cudaDeviceCanAccessPeer(&ok, dev, peer);
+  return ok;
+}
+int dtf_ipc_handle_size() { return (int)sizeof(cudaIpcMemHandle_t); }
+int dtf_memcpy_d2h(void* dst, const void* src, long long n) { return (int)cudaMemcpy(dst, src, (size_t)n, cudaMemcpyDeviceToHost); }
+int dtf_memcpy_h2d(void* dst, const void* src, long long n) { return (int)cudaMemcpy(dst, src, (size_t)n, cudaMemcpyHostToDevice); }
+int dtf_memset(void* p, int v, long long n, cudaStream_t s) { return (int)cudaMemsetAsync(p, v, (size_t)n, s); }
+
+}  // extern "C"

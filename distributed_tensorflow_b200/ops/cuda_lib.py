@@ -1,0 +1,366 @@
+"""ctypes bindings to ``_lib/libdtf_kernels.so`` (hand-written sm_100a kernels, plain C ABI).
+
+The library is built in-tree by ``python __graft_entry__.py build`` (explicit
+``nvcc -gencode arch=compute_100a,code=sm_100a``).  On a machine with a CUDA
+device the library MUST load: every entry point here raises if it is missing,
+there is no silent eager fallback (DESIGN.md "no compatibility layers").
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import (POINTER, Structure, byref, c_float, c_int, c_longlong, c_uint, c_ulonglong, c_void_p)
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+MAX_WORKERS = 16
+_LIB: Optional[ctypes.CDLL] = None
+_LOCK = threading.Lock()
+
+
+def lib_path() -> str:
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return os.path.join(here, "_lib", "libdtf_kernels.so")
+
+
+class GemmArgs(Structure):
+    _fields_ = [("a", c_void_p), ("b", c_void_p), ("c", c_void_p),
+                ("M", c_longlong), ("N", c_longlong), ("K", c_longlong),
+                ("lda", c_longlong), ("ldb", c_longlong), ("ldc", c_longlong),
+                ("a_mn", c_int), ("b_mn", c_int), ("c_bf16", c_int),
+                ("bias", c_void_p), ("relu", c_int),
+                ("mask", c_void_p), ("ldmask", c_longlong),
+                ("alpha", c_float), ("splits", c_int), ("accumulate", c_int),
+                ("colsum", c_void_p),
+                ("wait_flag", c_void_p), ("wait_target", c_ulonglong),
+                ("signal", c_void_p), ("err", c_void_p), ("timeout_ns", c_ulonglong),
+                ("block_n_override", c_int)]
+
+
+class PsApplyArgs(Structure):
+    _fields_ = [("ctl", c_void_p), ("master", c_void_p), ("slot_m", c_void_p), ("slot_v", c_void_p),
+                ("grad", c_void_p * MAX_WORKERS), ("shadow", c_void_p),
+                ("replica", c_void_p * MAX_WORKERS), ("mailbox", c_void_p * MAX_WORKERS),
+                ("n", c_longlong), ("num_workers", c_int), ("replicas_to_aggregate", c_int),
+                ("ctas_per_push", c_uint), ("mode", c_int), ("kind", c_int),
+                ("lr", c_float), ("momentum", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
+                ("nesterov", c_int), ("publish_replicas", c_int),
+                ("zero_begin", c_longlong * 4), ("zero_end", c_longlong * 4), ("num_zero", c_int),
+                ("timeout_ns", c_ulonglong), ("trace", c_void_p), ("trace_cap", c_int), ("grid", c_int)]
+
+
+class MlpHeadArgs(Structure):
+    _fields_ = [("h", c_void_p), ("ldh", c_longlong), ("w2", c_void_p), ("ldw2", c_longlong),
+                ("b2", c_void_p), ("labels", c_void_p), ("ldl", c_longlong),
+                ("B", c_int), ("H", c_int), ("C", c_int), ("clip_min", c_float),
+                ("loss_out", c_void_p), ("loss_hist", c_void_p), ("step_counter", c_void_p), ("hist_cap", c_int),
+                ("dh", c_void_p), ("lddh", c_longlong), ("gw2", c_void_p), ("ldgw2", c_longlong),
+                ("gb2", c_void_p), ("gb1", c_void_p), ("logits_out", c_void_p),
+                ("mailbox", c_void_p), ("ctl", c_void_p), ("rank", c_int), ("stamp_from_version", c_int)]
+
+
+def available() -> bool:
+    return os.path.exists(lib_path())
+
+
+def load() -> ctypes.CDLL:
+    global _LIB
+    with _LOCK:
+        if _LIB is not None:
+            return _LIB
+        p = lib_path()
+        if not os.path.exists(p):
+            raise RuntimeError("sm_100a kernel library %s is missing: run `python __graft_entry__.py build`" % p)
+        lib = ctypes.CDLL(p)
+        lib.dtf_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
+        lib.dtf_gemm_bf16.restype = c_int
+        lib.dtf_ps_apply.argtypes = [POINTER(PsApplyArgs), c_void_p]
+        lib.dtf_ps_apply.restype = c_int
+        lib.dtf_mlp_head.argtypes = [POINTER(MlpHeadArgs), c_void_p]
+        lib.dtf_mlp_head.restype = c_int
+        lib.dtf_convert_f32_bf16.argtypes = [c_void_p, c_longlong, c_void_p, c_longlong, c_longlong, c_longlong,
+                                             c_longlong, c_void_p]
+        lib.dtf_convert_u8_bf16.argtypes = [c_void_p, c_void_p, c_longlong, c_float, c_void_p]
+        lib.dtf_softmax_xent.argtypes = [c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_float, c_void_p,
+                                         c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p,
+                                         c_longlong, c_float, c_void_p]
+        lib.dtf_relu_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
+        lib.dtf_colsum.argtypes = [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]
+        lib.dtf_argmax_rows.argtypes = [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]
+        lib.dtf_mean_of_n.argtypes = [c_void_p, c_int, c_void_p, c_longlong, c_void_p]
+        lib.dtf_optimizer_apply.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float,
+                                            c_float, c_int, c_float, c_float, c_float, c_float, c_void_p]
+        lib.dtf_im2col_nhwc.argtypes = [c_void_p, c_void_p] + [c_int] * 12 + [c_longlong, c_void_p]
+        lib.dtf_col2im_nhwc.argtypes = [c_void_p, c_longlong, c_void_p] + [c_int] * 12 + [c_void_p]
+        lib.dtf_gemm_ref.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_longlong,
+                                     c_longlong, c_int, c_int, c_void_p, c_int, c_float, c_void_p]
+        lib.dtf_ps_publish.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p]
+        lib.dtf_wait_token.argtypes = [c_void_p, c_ulonglong, c_ulonglong, c_void_p, c_void_p]
+        lib.dtf_push_grad.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                      c_void_p]
+        lib.dtf_pull_shadow.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_void_p]
+        lib.dtf_fabric_alloc.argtypes = [POINTER(c_void_p), c_longlong]
+        lib.dtf_fabric_free.argtypes = [c_void_p]
+        lib.dtf_fabric_export.argtypes = [c_void_p, c_void_p]
+        lib.dtf_fabric_import.argtypes = [c_void_p, POINTER(c_void_p)]
+        lib.dtf_fabric_close.argtypes = [c_void_p]
+        lib.dtf_enable_peer.argtypes = [c_int]
+        lib.dtf_can_access_peer.argtypes = [c_int, c_int]
+        lib.dtf_memcpy_d2h.argtypes = [c_void_p, c_void_p, c_longlong]
+        lib.dtf_memcpy_h2d.argtypes = [c_void_p, c_void_p, c_longlong]
+        lib.dtf_memset.argtypes = [c_void_p, c_int, c_longlong, c_void_p]
+        for name in ("dtf_convert_f32_bf16", "dtf_convert_u8_bf16", "dtf_softmax_xent", "dtf_relu_grad", "dtf_colsum",
+                     "dtf_argmax_rows", "dtf_mean_of_n", "dtf_optimizer_apply", "dtf_im2col_nhwc", "dtf_col2im_nhwc",
+                     "dtf_gemm_ref", "dtf_ps_publish", "dtf_wait_token", "dtf_push_grad", "dtf_pull_shadow",
+                     "dtf_fabric_alloc", "dtf_fabric_free", "dtf_fabric_export", "dtf_fabric_import",
+                     "dtf_fabric_close", "dtf_enable_peer", "dtf_can_access_peer", "dtf_memcpy_d2h", "dtf_memcpy_h2d",
+                     "dtf_memset", "dtf_sizeof_ps_control", "dtf_sizeof_mailbox", "dtf_offsetof_ctl",
+                     "dtf_ipc_handle_size"):
+            getattr(lib, name).restype = c_int
+        lib.dtf_offsetof_ctl.argtypes = [c_int]
+        _LIB = lib
+        return lib
+
+
+# launch counter: bench.py reports how many of OUR kernels ran in the timed region
+_launches = 0
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _bump(n: int = 1) -> None:
+    global _launches
+    _launches += n
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError("%s failed with code %d%s" % (what, rc, _cuda_err(rc)))
+
+
+def _cuda_err(rc: int) -> str:
+    if rc <= 0:
+        return {-2: " (bad shape)", -3: " (leading dimension not a multiple of 8)", -4: " (pointer not 16-byte aligned)",
+                -5: " (split-K with relu/bf16 output)", -6: " (bad BLOCK_N)", -7: " (cuTensorMapEncodeTiled unavailable)"
+                }.get(rc, "")
+    if rc >= 1000:
+        return " (cuTensorMapEncodeTiled CUresult %d)" % (rc - 1000)
+    return " (cudaError %d)" % rc
+
+
+def _stream(t: Optional[torch.Tensor] = None) -> int:
+    dev = t.device if t is not None else None
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# ---------------------------------------------------------------------------------------------------
+# conversions
+# ---------------------------------------------------------------------------------------------------
+def to_bf16_padded(x: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """Row-major 2-D tensor -> (bf16 tensor whose row pitch is a multiple of 8 elements, pitch)."""
+    assert x.dim() == 2 and x.is_cuda
+    rows, cols = x.shape
+    if x.dtype == torch.bfloat16 and x.stride(1) == 1 and x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0:
+        return x, x.stride(0)
+    ld = round_up(cols, 8)
+    if x.dtype != torch.float32 or x.stride(1) != 1:
+        x = x.float().contiguous()
+    out = torch.empty((rows, ld), dtype=torch.bfloat16, device=x.device)
+    lib = load()
+    with torch.cuda.device(x.device):
+        _check(lib.dtf_convert_f32_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), ld, rows, cols, ld, _stream(x)),
+               "convert_f32_bf16")
+    _bump()
+    return out, ld
+
+
+# ---------------------------------------------------------------------------------------------------
+# GEMM
+# ---------------------------------------------------------------------------------------------------
+def gemm_raw(a: torch.Tensor, lda: int, b: torch.Tensor, ldb: int, c: torch.Tensor, ldc: int, M: int, N: int, K: int,
+             a_mn: bool, b_mn: bool, bias: Optional[torch.Tensor] = None, relu: bool = False,
+             mask: Optional[torch.Tensor] = None, ldmask: int = 0, alpha: float = 1.0, splits: int = 1,
+             accumulate: bool = False, colsum: Optional[torch.Tensor] = None, wait_flag: int = 0, wait_target: int = 0,
+             signal: int = 0, err: int = 0, timeout_ns: int = 0, block_n: int = 0, stream: Optional[int] = None,
+             a_ptr: Optional[int] = None, b_ptr: Optional[int] = None, c_ptr: Optional[int] = None,
+             bias_ptr: Optional[int] = None, c_bf16: Optional[bool] = None) -> None:
+    """Launch the tcgen05 GEMM on raw buffers (pointers may be peer memory)."""
+    g = GemmArgs()
+    g.a = a_ptr if a_ptr is not None else a.data_ptr()
+    g.b = b_ptr if b_ptr is not None else b.data_ptr()
+    g.c = c_ptr if c_ptr is not None else c.data_ptr()
+    g.M, g.N, g.K, g.lda, g.ldb, g.ldc = M, N, K, lda, ldb, ldc
+    g.a_mn, g.b_mn = int(a_mn), int(b_mn)
+    g.c_bf16 = int(c_bf16 if c_bf16 is not None else (c is not None and c.dtype == torch.bfloat16))
+    g.bias = bias_ptr if bias_ptr is not None else _ptr(bias)
+    g.relu = int(relu)
+    g.mask, g.ldmask = _ptr(mask), ldmask
+    g.alpha, g.splits, g.accumulate = alpha, splits, int(accumulate)
+    g.colsum = _ptr(colsum)
+    g.wait_flag, g.wait_target = wait_flag or None, wait_target
+    g.signal, g.err, g.timeout_ns = signal or None, err or None, timeout_ns
+    g.block_n_override = block_n
+    lib = load()
+    st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+    _check(lib.dtf_gemm_bf16(byref(g), st), "gemm_bf16_tcgen05")
+    _bump()
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, ta: bool = False, tb: bool = False, bias: Optional[torch.Tensor] = None,
+         relu: bool = False, out_dtype: torch.dtype = torch.float32, splits: int = 1) -> torch.Tensor:
+    """``op(a) @ op(b)`` (+bias, ReLU) on the tensor cores; inputs fp32 or bf16, bf16 compute, fp32 accumulate."""
+    assert a.is_cuda and b.is_cuda and a.dim() == 2 and b.dim() == 2
+    M, K = (a.shape[1], a.shape[0]) if ta else (a.shape[0], a.shape[1])
+    Kb, N = (b.shape[1], b.shape[0]) if tb else (b.shape[0], b.shape[1])
+    if K != Kb:
+        raise ValueError("gemm: inner dimensions differ (%d vs %d)" % (K, Kb))
+    with torch.cuda.device(a.device):
+        a16, lda = to_bf16_padded(a)
+        b16, ldb = to_bf16_padded(b)
+        ldc = N if out_dtype == torch.float32 else round_up(N, 8)
+        c = (torch.zeros if splits > 1 else torch.empty)((M, ldc), dtype=out_dtype, device=a.device)
+        if bias is not None:
+            bias = bias.float().contiguous()
+        gemm_raw(a16, lda, b16, ldb, c, ldc, M, N, K, a_mn=ta, b_mn=not tb, bias=bias, relu=relu, splits=splits)
+    return c if ldc == N else c[:, :N]
+
+
+def gemm_ref(a: torch.Tensor, b: torch.Tensor, ta: bool = False, tb: bool = False, bias=None, relu=False) -> torch.Tensor:
+    """CUDA-core reference over the same bf16-rounded operands (tests)."""
+    M, K = (a.shape[1], a.shape[0]) if ta else (a.shape[0], a.shape[1])
+    N = b.shape[0] if tb else b.shape[1]
+    with torch.cuda.device(a.device):
+        a16, lda = to_bf16_padded(a)
+        b16, ldb = to_bf16_padded(b)
+        c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+        lib = load()
+        _check(lib.dtf_gemm_ref(a16.data_ptr(), b16.data_ptr(), c.data_ptr(), M, N, K, lda, ldb, N, int(ta), int(not tb),
+                                _ptr(bias), int(relu), 1.0, _stream(a)), "gemm_ref")
+    _bump()
+    return c
+
+
+# ---------------------------------------------------------------------------------------------------
+# softmax / xent, relu grad, column sums
+# ---------------------------------------------------------------------------------------------------
+def softmax_xent_fwd_bwd(logits: torch.Tensor, labels: torch.Tensor, clip_min: float, reduce_sum: bool
+                         ) -> Tuple[torch.Tensor, torch.Tensor]:
+    logits = logits.float().contiguous()
+    labels = labels.float().contiguous()
+    rows, cols = logits.shape
+    dl = torch.empty_like(logits)
+    with torch.cuda.device(logits.device):
+        if reduce_sum:
+            loss = torch.zeros((), dtype=torch.float32, device=logits.device)
+            lsum, lrows = loss.data_ptr(), None
+        else:
+            loss = torch.empty((rows,), dtype=torch.float32, device=logits.device)
+            lsum, lrows = None, loss.data_ptr()
+        lib = load()
+        _check(lib.dtf_softmax_xent(logits.data_ptr(), cols, labels.data_ptr(), cols, rows, cols, clip_min, lsum, lrows,
+                                    dl.data_ptr(), cols, None, 0, 0, None, 0, 1.0, _stream(logits)), "softmax_xent")
+    _bump()
+    return loss, dl
+
+
+def relu_grad(g: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    g = g.float().contiguous()
+    y = y.float().contiguous()
+    out = torch.empty_like(g)
+    with torch.cuda.device(g.device):
+        _check(load().dtf_relu_grad(g.data_ptr(), y.data_ptr(), out.data_ptr(), g.numel(), _stream(g)), "relu_grad")
+    _bump()
+    return out
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    x = x.float().contiguous()
+    rows, cols = x.shape
+    out = torch.empty((cols,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(load().dtf_colsum(x.data_ptr(), cols, rows, cols, out.data_ptr(), _stream(x)), "colsum")
+    _bump()
+    return out
+
+
+def argmax_rows(x: torch.Tensor) -> torch.Tensor:
+    x = x.float().contiguous()
+    rows, cols = x.shape
+    out = torch.empty((rows,), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(load().dtf_argmax_rows(x.data_ptr(), cols, rows, cols, out.data_ptr(), _stream(x)), "argmax_rows")
+    _bump()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# optimizer applies (in place)
+# ---------------------------------------------------------------------------------------------------
+def _apply(var, m, v, g, kind, lr, momentum=0.0, nesterov=False, beta1=0.0, beta2=0.0, eps=0.0, shadow=None,
+           grad_scale=1.0):
+    assert var.is_contiguous() and var.dtype == torch.float32
+    g = g.to(dtype=torch.float32).contiguous()
+    with torch.cuda.device(var.device):
+        _check(load().dtf_optimizer_apply(var.data_ptr(), _ptr(m), _ptr(v), g.data_ptr(), _ptr(shadow), var.numel(), kind,
+                                          lr, momentum, int(nesterov), beta1, beta2, eps, grad_scale, _stream(var)),
+               "optimizer_apply")
+    _bump()
+
+
+def apply_sgd_(var, g, lr, shadow=None):
+    _apply(var, None, None, g, 0, lr, shadow=shadow)
+
+
+def apply_momentum_(var, acc, g, lr, momentum, nesterov=False, shadow=None):
+    _apply(var, acc, None, g, 1, lr, momentum=momentum, nesterov=nesterov, shadow=shadow)
+
+
+def apply_adam_(var, m, v, g, lr_t, beta1, beta2, eps, shadow=None):
+    _apply(var, m, v, g, 2, lr_t, beta1=beta1, beta2=beta2, eps=eps, shadow=shadow)
+
+
+# ---------------------------------------------------------------------------------------------------
+# convolution lowering
+# ---------------------------------------------------------------------------------------------------
+def im2col_nhwc(x: torch.Tensor, kh: int, kw: int, strides: Sequence[int], pads: Sequence[int]):
+    x = x.float().contiguous()
+    n, h, w, c = x.shape
+    sh, sw = strides
+    pt, pb, pl, pr = pads
+    ho = (h + pt + pb - kh) // sh + 1
+    wo = (w + pl + pr - kw) // sw + 1
+    kdim = kh * kw * c
+    ld = round_up(kdim, 8)
+    cols = torch.empty((n * ho * wo, ld), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(load().dtf_im2col_nhwc(x.data_ptr(), cols.data_ptr(), n, h, w, c, kh, kw, sh, sw, pt, pl, ho, wo, ld,
+                                      _stream(x)), "im2col_nhwc")
+    _bump()
+    return (cols if ld == kdim else cols[:, :kdim]), (n, ho, wo)
+
+
+def col2im_nhwc(gcols: torch.Tensor, xshape, kh: int, kw: int, strides, pads) -> torch.Tensor:
+    gcols = gcols.float().contiguous()
+    n, h, w, c = xshape
+    sh, sw = strides
+    pt, pb, pl, pr = pads
+    ho = (h + pt + pb - kh) // sh + 1
+    wo = (w + pl + pr - kw) // sw + 1
+    gx = torch.empty(tuple(xshape), dtype=torch.float32, device=gcols.device)
+    with torch.cuda.device(gcols.device):
+        _check(load().dtf_col2im_nhwc(gcols.data_ptr(), gcols.shape[1], gx.data_ptr(), n, h, w, c, kh, kw, sh, sw, pt, pl,
+                                      ho, wo, _stream(gcols)), "col2im_nhwc")
+    _bump()
+    return gx

@@ -1,0 +1,537 @@
+"""Fabric parameter-server engine: the B200 fast path for ps/worker training.
+
+Same semantics as the control-plane path (``train/sync_replicas.py`` + ``parallel/server.py``) --
+variables placed on ps shards round-robin, workers pull parameters / push gradients, the ps applies
+SGD/Momentum/TF-Adam, sync mode aggregates the MEAN of fresh gradients and hands out tokens, async
+mode applies every push immediately and measures staleness -- but all of it runs on the GPUs:
+
+* parameters, optimizer slots, per-worker gradient slots and the control block live in the ps GPU's
+  HBM (padded flat layout); workers address them over NVLink peer memory (``parallel/fabric.py``);
+* a worker step is three kernels of ours: ``gemm_bf16_tcgen05`` (x.W1 + b1, ReLU; its TMA producer
+  first acquires the token and then loads W1 tiles straight from the ps -- *pull fused into the
+  first GEMM*), ``mlp_head`` (logits, softmax, clipped xent, dlogits, dW2/db2/db1 pushed to the ps,
+  dh), ``gemm_bf16_tcgen05`` (dW1 = x^T.dh whose epilogue stores the tiles into the ps gradient
+  slot and release-increments the arrival counter -- *push fused into the backward GEMM*);
+* the ps step is one kernel: ``ps_apply`` (wait for arrivals -> N-way reduce -> mean -> apply ->
+  publish bf16 shadow -> release tokens).
+
+No NCCL, cuBLAS or host round trip is on the step path.  ``torch.distributed`` is used once, to
+exchange IPC handles, and by the benchmark for barriers.
+
+Topologies: ``between-graph`` = one process per GPU (``Fabric.from_torch_distributed``); ``in-graph``
+= one process drives every GPU (all ranks local).  Ranks ``0..num_ps-1`` are ps shards, the rest are
+workers; with a single GPU the ps and the worker share it (and its stream).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from ..ops import cuda_lib
+from ..ops.cuda_lib import MAX_WORKERS, GemmArgs, MlpHeadArgs, PsApplyArgs, round_up
+from .fabric import Fabric, FabricBuffer, view_tensor
+
+__all__ = ["MLPSpec", "EngineConfig", "PSTrainEngine", "smoke_step", "VarLayout"]
+
+
+@dataclass
+class MLPSpec:
+    in_dim: int = 784
+    hidden: int = 100
+    classes: int = 10
+    batch: int = 100
+
+
+@dataclass
+class EngineConfig:
+    num_ps: int = 1
+    num_workers: int = 1
+    sync: bool = True
+    replicas_to_aggregate: Optional[int] = None
+    optimizer: Dict[str, Any] = field(default_factory=lambda: {"kind": "sgd", "lr": 0.01})
+    clip_min: float = 1e-10
+    publish_replicas: bool = False        # True: ps stores new params into every worker's replica (push-publish)
+    colocated: bool = False               # single GPU: ps shard 0 and worker 0 share device + stream
+    timeout_ns: int = 5_000_000_000
+    loss_hist: int = 4096
+    trace_cap: int = 4096
+    seed: int = 0
+
+
+@dataclass
+class VarLayout:
+    name: str
+    shape: Tuple[int, ...]
+    shard: int
+    offset: int          # element offset inside the shard's flat buffers
+    rows: int
+    cols: int
+    pitch: int           # row pitch in elements (multiple of 8 -> 16-byte bf16 rows for TMA)
+
+    @property
+    def numel_padded(self) -> int:
+        return self.rows * self.pitch
+
+
+_KIND = {"sgd": 0, "momentum": 1, "adam": 2}
+
+
+def _layout(spec: MLPSpec, num_ps: int) -> Tuple[Dict[str, VarLayout], List[int]]:
+    """Round-robin placement in creation order (global_step, hid_w, hid_b, sm_w, sm_b), SURVEY A5."""
+    order = [("global_step", ()), ("hid_w", (spec.in_dim, spec.hidden)), ("hid_b", (spec.hidden,)),
+             ("sm_w", (spec.hidden, spec.classes)), ("sm_b", (spec.classes,))]
+    sizes = [0] * num_ps
+    out: Dict[str, VarLayout] = {}
+    for i, (name, shape) in enumerate(order):
+        shard = i % num_ps
+        if name == "global_step":
+            continue                      # lives in the shard-0 control block (K7)
+        rows, cols = (shape[0], shape[1]) if len(shape) == 2 else (1, shape[0])
+        pitch = round_up(cols, 8)
+        off = round_up(sizes[shard], 64)
+        out[name] = VarLayout(name, tuple(shape), shard, off, rows, cols, pitch)
+        sizes[shard] = off + rows * pitch
+    return out, [round_up(max(s, 64), 64) for s in sizes]
+
+
+class _Rank:
+    """Per-rank device state (buffers, stream, cached launch descriptors)."""
+
+    def __init__(self, rank: int, device: int):
+        self.rank, self.device = rank, torch.device("cuda", device)
+        self.stream: Optional[torch.cuda.Stream] = None
+        self.step = 0                    # steps enqueued so far (worker) / applies enqueued (ps)
+        self.bufs: Dict[str, FabricBuffer] = {}
+
+
+class PSTrainEngine:
+    def __init__(self, spec: MLPSpec, cfg: EngineConfig, fabric: Fabric):
+        self.spec, self.cfg, self.fabric = spec, cfg, fabric
+        self.lib = cuda_lib.load()
+        if cfg.num_workers > MAX_WORKERS:
+            raise ValueError("at most %d workers" % MAX_WORKERS)
+        if spec.batch > 128 or spec.hidden > 256 or spec.classes > 16:
+            raise ValueError("the fused MLP head handles batch<=128, hidden<=256, classes<=16")
+        self.world = fabric.world_size
+        if cfg.colocated:
+            assert self.world == 1 and cfg.num_ps == 1 and cfg.num_workers == 1
+            self.ps_ranks, self.worker_ranks = [0], [0]
+        else:
+            assert self.world == cfg.num_ps + cfg.num_workers, "world = num_ps + num_workers"
+            self.ps_ranks = list(range(cfg.num_ps))
+            self.worker_ranks = list(range(cfg.num_ps, self.world))
+        self.layout, self.shard_elems = _layout(spec, cfg.num_ps)
+        self.R = cfg.replicas_to_aggregate or cfg.num_workers
+        self.opt = dict(cfg.optimizer)
+        self.kind = _KIND[self.opt["kind"]]
+        self.ctl_bytes = self.lib.dtf_sizeof_ps_control()
+        self.mb_bytes = self.lib.dtf_sizeof_mailbox()
+        self.off = {k: self.lib.dtf_offsetof_ctl(i) for i, k in enumerate(
+            ["global_step", "param_version", "beta1_power", "beta2_power", "dropped_stale", "applied_total",
+             "staleness_hist", "staleness_sum", "err", "w", "w_stride", "consumed"])}
+        self.ranks: Dict[int, _Rank] = {r: _Rank(r, d) for r, d in fabric.local_ranks.items()}
+        for rk in self.ranks.values():
+            with torch.cuda.device(rk.device):
+                rk.stream = torch.cuda.Stream(rk.device)
+        # arrivals a complete push adds on each shard: 1 for the head (if it pushes there) + dW1 tiles
+        lw = self.layout
+        self.m_tiles_w1 = (spec.in_dim + 127) // 128
+        self.ctas_per_push = [0] * cfg.num_ps
+        head_shards = {lw["sm_w"].shard, lw["sm_b"].shard, lw["hid_b"].shard}
+        for s in head_shards:
+            self.ctas_per_push[s] += 1
+        bn = 64 if spec.hidden <= 64 else (128 if spec.hidden <= 128 else (192 if spec.hidden <= 192 else 256))
+        self.block_n_w1 = bn
+        self.ctas_per_push[lw["hid_w"].shard] += self.m_tiles_w1 * ((spec.hidden + bn - 1) // bn)
+        self._allocate()
+        self._exchange()
+        self._build_launches()
+
+    # ------------------------------------------------------------------------------------------------
+    # memory
+    # ------------------------------------------------------------------------------------------------
+    def _allocate(self) -> None:
+        f, cfg, spec = self.fabric, self.cfg, self.spec
+        W = cfg.num_workers
+        for r, rk in self.ranks.items():
+            if r in self.ps_ranks:
+                s = self.ps_ranks.index(r)
+                n = self.shard_elems[s]
+                for name, nbytes in (("ctl%d" % s, self.ctl_bytes), ("master%d" % s, n * 4), ("shadow%d" % s, n * 2),
+                                     ("grads%d" % s, n * 4 * W), ("slot_m%d" % s, n * 4), ("slot_v%d" % s, n * 4),
+                                     ("trace%d" % s, cfg.trace_cap * 32)):
+                    rk.bufs[name] = f.alloc(r, name, nbytes)
+                for name in ("ctl%d" % s, "master%d" % s, "shadow%d" % s, "grads%d" % s):
+                    f.publish(r, name)
+            if r in self.worker_ranks:
+                w = self.worker_ranks.index(r)
+                ldh = round_up(spec.hidden, 8)
+                names = [("mailbox_w%d" % w, self.mb_bytes * cfg.num_ps),
+                         ("x16_w%d" % w, 128 * spec.in_dim * 2), ("labels_w%d" % w, 128 * 16 * 4),
+                         ("xf32_w%d" % w, 128 * spec.in_dim * 4),
+                         ("h_w%d" % w, 128 * ldh * 2), ("dh_w%d" % w, 128 * ldh * 2),
+                         ("misc_w%d" % w, 4096 + cfg.loss_hist * 4)]
+                for s in range(cfg.num_ps):
+                    names.append(("replica%d_w%d" % (s, w), self.shard_elems[s] * 2))
+                for name, nbytes in names:
+                    rk.bufs[name] = f.alloc(r, name, nbytes)
+                f.publish(r, "mailbox_w%d" % w)
+                if cfg.publish_replicas:
+                    for s in range(cfg.num_ps):
+                        f.publish(r, "replica%d_w%d" % (s, w))
+
+    def _exchange(self) -> None:
+        f, cfg = self.fabric, self.cfg
+        self.peer: Dict[Tuple[int, str], FabricBuffer] = {}
+        for r in self.ranks:
+            if r in self.worker_ranks:
+                for s, pr in enumerate(self.ps_ranks):
+                    for base in ("ctl", "master", "shadow", "grads"):
+                        self.peer[(r, "%s%d" % (base, s))] = f.peer(r, pr, "%s%d" % (base, s))
+            if r in self.ps_ranks:
+                for w, wr in enumerate(self.worker_ranks):
+                    self.peer[(r, "mailbox_w%d" % w)] = f.peer(r, wr, "mailbox_w%d" % w)
+                    if cfg.publish_replicas:
+                        s = self.ps_ranks.index(r)
+                        self.peer[(r, "replica%d_w%d" % (s, w))] = f.peer(r, wr, "replica%d_w%d" % (s, w))
+
+    # ------------------------------------------------------------------------------------------------
+    # parameter init / access (ps side)
+    # ------------------------------------------------------------------------------------------------
+    def _var_view(self, rk: _Rank, base: str, lay: VarLayout, dtype=torch.float32) -> torch.Tensor:
+        buf = rk.bufs["%s%d" % (base, lay.shard)]
+        es = 4 if dtype == torch.float32 else 2
+        t = buf.tensor(dtype, lay.offset * es, lay.numel_padded)
+        return t.view(lay.rows, lay.pitch)[:, :lay.cols]
+
+    def init_params(self, values: Optional[Dict[str, torch.Tensor]] = None) -> None:
+        """Chief-style initialisation on the ps shards (truncated normal / zeros like the reference model),
+        then publish the bf16 shadow (+replicas) and the initial tokens."""
+        spec, cfg = self.spec, self.cfg
+        g = torch.Generator(device="cpu")
+        g.manual_seed(cfg.seed)
+        init = {}
+        t = torch.empty(spec.in_dim, spec.hidden)
+        torch.nn.init.trunc_normal_(t, 0.0, 1.0 / math.sqrt(spec.in_dim), -2.0 / math.sqrt(spec.in_dim),
+                                    2.0 / math.sqrt(spec.in_dim), generator=g)
+        init["hid_w"] = t
+        init["hid_b"] = torch.zeros(spec.hidden)
+        t2 = torch.empty(spec.hidden, spec.classes)
+        sd = 1.0 / math.sqrt(spec.hidden)
+        torch.nn.init.trunc_normal_(t2, 0.0, sd, -2 * sd, 2 * sd, generator=g)
+        init["sm_w"] = t2
+        init["sm_b"] = torch.zeros(spec.classes)
+        if values:
+            for k, v in values.items():
+                init[k] = torch.as_tensor(v).float().reshape(self.layout[k].shape)
+        for r, rk in self.ranks.items():
+            if r not in self.ps_ranks:
+                continue
+            s = self.ps_ranks.index(r)
+            with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
+                for base in ("master", "slot_m", "slot_v", "grads", "shadow", "ctl"):
+                    rk.bufs["%s%d" % (base, s)].tensor(torch.uint8).zero_()
+                for name, lay in self.layout.items():
+                    if lay.shard != s:
+                        continue
+                    v = init[name].reshape(lay.rows, lay.cols).to(rk.device)
+                    self._var_view(rk, "master", lay).copy_(v)
+                ctl = rk.bufs["ctl%d" % s]
+                b = ctl.tensor(torch.float32, self.off["beta1_power"], 2)
+                b[0] = float(self.opt.get("beta1", 0.9))
+                b[1] = float(self.opt.get("beta2", 0.999))
+                n = self.shard_elems[s]
+                rc = self.lib.dtf_ps_publish(rk.bufs["master%d" % s].ptr, rk.bufs["shadow%d" % s].ptr, n,
+                                             rk.stream.cuda_stream)
+                assert rc == 0, rc
+                if cfg.publish_replicas:
+                    sh = rk.bufs["shadow%d" % s].tensor(torch.bfloat16)
+                    for w in range(cfg.num_workers):
+                        self.peer[(r, "replica%d_w%d" % (s, w))].tensor(torch.bfloat16).copy_(sh)
+            rk.stream.synchronize()
+        for r, rk in self.ranks.items():
+            if r in self.worker_ranks:
+                w = self.worker_ranks.index(r)
+                with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
+                    for name in ("mailbox_w%d" % w, "misc_w%d" % w, "x16_w%d" % w, "h_w%d" % w, "dh_w%d" % w,
+                                 "labels_w%d" % w):
+                        rk.bufs[name].tensor(torch.uint8).zero_()
+                rk.stream.synchronize()
+            rk.step = 0
+        self.fabric.barrier()
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """True-shape fp32 parameters + global_step gathered from the LOCAL ps shards (checkpointing)."""
+        out: Dict[str, torch.Tensor] = {}
+        for r, rk in self.ranks.items():
+            if r not in self.ps_ranks:
+                continue
+            s = self.ps_ranks.index(r)
+            rk.stream.synchronize()
+            for name, lay in self.layout.items():
+                if lay.shard == s:
+                    out[name] = self._var_view(rk, "master", lay).reshape(lay.shape).detach().cpu().clone()
+                    if self.kind >= 1:
+                        out[name + "/" + ("Momentum" if self.kind == 1 else "Adam")] = \
+                            self._var_view(rk, "slot_m", lay).reshape(lay.shape).detach().cpu().clone()
+                    if self.kind == 2:
+                        out[name + "/Adam_1"] = self._var_view(rk, "slot_v", lay).reshape(lay.shape).detach().cpu().clone()
+            if s == 0:
+                out["global_step"] = torch.tensor(self.read_ctl(0, "global_step"), dtype=torch.int64)
+                if self.kind == 2:
+                    b = rk.bufs["ctl0"].tensor(torch.float32, self.off["beta1_power"], 2).cpu()
+                    out["beta1_power"], out["beta2_power"] = b[0].clone(), b[1].clone()
+        return out
+
+    def read_ctl(self, shard: int, fld: str, count: int = 1):
+        r = self.ps_ranks[shard]
+        rk = self.ranks[r]
+        t = rk.bufs["ctl%d" % shard].tensor(torch.int64, self.off[fld], count).cpu()
+        return int(t[0]) if count == 1 else t.tolist()
+
+    def staleness(self, shard: int = 0) -> Dict[str, Any]:
+        hist = self.read_ctl(shard, "staleness_hist", 16)
+        tot = sum(hist)
+        return {"hist": hist, "mean": (self.read_ctl(shard, "staleness_sum") / tot) if tot else 0.0, "count": tot}
+
+    # ------------------------------------------------------------------------------------------------
+    # launch descriptors (built once; per step only wait targets / data pointers change)
+    # ------------------------------------------------------------------------------------------------
+    def _build_launches(self) -> None:
+        spec, cfg, lay = self.spec, self.cfg, self.layout
+        B, D, H, C = spec.batch, spec.in_dim, spec.hidden, spec.classes
+        self._w: Dict[int, Dict[str, Any]] = {}
+        for r, rk in self.ranks.items():
+            if r not in self.worker_ranks:
+                continue
+            w = self.worker_ranks.index(r)
+            ldh = round_up(H, 8)
+            misc = rk.bufs["misc_w%d" % w]
+            # misc layout: [0] loss f32 | [8] step counter u64 | [16] err u32 | [64..] unused | [4096..] loss ring
+            d: Dict[str, Any] = {"ldh": ldh, "loss_ptr": misc.ptr, "stepctr_ptr": misc.ptr + 8, "err_ptr": misc.ptr + 16,
+                                 "hist_ptr": misc.ptr + 4096}
+            mb = rk.bufs["mailbox_w%d" % w]
+
+            def src(base: str, l: VarLayout, es: int) -> int:
+                if cfg.publish_replicas and base == "shadow":
+                    return rk.bufs["replica%d_w%d" % (l.shard, w)].ptr + l.offset * es
+                return self.peer[(r, "%s%d" % (base, l.shard))].ptr + l.offset * es
+
+            def slot(l: VarLayout) -> int:
+                return self.peer[(r, "grads%d" % l.shard)].ptr + (w * self.shard_elems[l.shard] + l.offset) * 4
+
+            def ctl_arrivals(shard: int) -> int:
+                return self.peer[(r, "ctl%d" % shard)].ptr + self.off["w"] + w * self.off["w_stride"]
+
+            x16 = rk.bufs["x16_w%d" % w]
+            # ---- F1: h = relu(x . W1 + b1), W1 pulled from the ps inside the GEMM --------------------
+            g1 = GemmArgs()
+            g1.a, g1.lda = x16.ptr, D
+            g1.b, g1.ldb = src("shadow", lay["hid_w"], 2), lay["hid_w"].pitch
+            g1.c, g1.ldc, g1.c_bf16 = rk.bufs["h_w%d" % w].ptr, ldh, 1
+            g1.M, g1.N, g1.K = B, H, D
+            g1.a_mn, g1.b_mn = 0, 1
+            g1.bias, g1.relu = src("master", lay["hid_b"], 4), 1
+            g1.alpha, g1.splits = 1.0, 1
+            g1.wait_flag = mb.ptr + lay["hid_w"].shard * self.mb_bytes      # token of the shard that owns W1
+            g1.err, g1.timeout_ns = d["err_ptr"], cfg.timeout_ns
+            g1.block_n_override = self.block_n_w1
+            d["g1"] = g1
+            # ---- head ---------------------------------------------------------------------------------
+            hd = MlpHeadArgs()
+            hd.h, hd.ldh = rk.bufs["h_w%d" % w].ptr, ldh
+            hd.w2, hd.ldw2 = src("shadow", lay["sm_w"], 2), lay["sm_w"].pitch
+            hd.b2 = src("master", lay["sm_b"], 4)
+            hd.labels, hd.ldl = rk.bufs["labels_w%d" % w].ptr, C
+            hd.B, hd.H, hd.C, hd.clip_min = B, H, C, cfg.clip_min
+            hd.loss_out, hd.loss_hist, hd.step_counter, hd.hist_cap = d["loss_ptr"], d["hist_ptr"], d["stepctr_ptr"], cfg.loss_hist
+            hd.dh, hd.lddh = rk.bufs["dh_w%d" % w].ptr, ldh
+            hd.gw2, hd.ldgw2 = slot(lay["sm_w"]), lay["sm_w"].pitch
+            hd.gb2, hd.gb1 = slot(lay["sm_b"]), slot(lay["hid_b"])
+            hd.mailbox = mb.ptr
+            hd.rank, hd.stamp_from_version = w, 0 if cfg.sync else 1
+            d["head"] = hd
+            head_shards = sorted({lay["sm_w"].shard, lay["sm_b"].shard, lay["hid_b"].shard})
+            d["head_ctls"] = [self.peer[(r, "ctl%d" % s)].ptr for s in head_shards]
+            d["head_mailboxes"] = [mb.ptr + s * self.mb_bytes for s in head_shards]
+            # ---- B3: dW1 = x^T . dh pushed into the ps slot ------------------------------------------
+            g3 = GemmArgs()
+            g3.a, g3.lda = x16.ptr, D
+            g3.b, g3.ldb = rk.bufs["dh_w%d" % w].ptr, ldh
+            g3.c, g3.ldc, g3.c_bf16 = slot(lay["hid_w"]), lay["hid_w"].pitch, 0
+            g3.M, g3.N, g3.K = D, H, B
+            g3.a_mn, g3.b_mn = 1, 1
+            g3.alpha, g3.splits = 1.0, 1
+            g3.signal = ctl_arrivals(lay["hid_w"].shard)
+            g3.block_n_override = self.block_n_w1
+            d["g3"] = g3
+            d["extra_wait_shards"] = [s for s in range(cfg.num_ps) if s != lay["hid_w"].shard]
+            self._w[r] = d
+        self._p: Dict[int, PsApplyArgs] = {}
+        for r, rk in self.ranks.items():
+            if r not in self.ps_ranks:
+                continue
+            s = self.ps_ranks.index(r)
+            n = self.shard_elems[s]
+            a = PsApplyArgs()
+            a.ctl, a.master = rk.bufs["ctl%d" % s].ptr, rk.bufs["master%d" % s].ptr
+            a.slot_m, a.slot_v = rk.bufs["slot_m%d" % s].ptr, rk.bufs["slot_v%d" % s].ptr
+            a.shadow = rk.bufs["shadow%d" % s].ptr
+            for w in range(cfg.num_workers):
+                a.grad[w] = rk.bufs["grads%d" % s].ptr + w * n * 4
+                a.mailbox[w] = self.peer[(r, "mailbox_w%d" % w)].ptr + s * self.mb_bytes
+                if cfg.publish_replicas:
+                    a.replica[w] = self.peer[(r, "replica%d_w%d" % (s, w))].ptr
+            a.n, a.num_workers, a.replicas_to_aggregate = n, cfg.num_workers, self.R
+            a.ctas_per_push = self.ctas_per_push[s]
+            a.mode, a.kind = (0 if cfg.sync else 1), self.kind
+            a.lr = float(self.opt["lr"])
+            a.momentum = float(self.opt.get("momentum", 0.0))
+            a.beta1, a.beta2, a.eps = float(self.opt.get("beta1", 0.9)), float(self.opt.get("beta2", 0.999)), \
+                float(self.opt.get("eps", self.opt.get("epsilon", 1e-8)))
+            a.nesterov = int(bool(self.opt.get("nesterov", False)))
+            a.publish_replicas = int(cfg.publish_replicas)
+            a.num_zero = 0
+            a.timeout_ns = cfg.timeout_ns
+            a.trace, a.trace_cap = rk.bufs["trace%d" % s].ptr, cfg.trace_cap
+            a.grid = 0
+            self._p[r] = a
+
+    # ------------------------------------------------------------------------------------------------
+    # stepping
+    # ------------------------------------------------------------------------------------------------
+    def launches_per_worker_step(self) -> int:
+        any_w = next(iter(self._w.values()), None)
+        extra = len(any_w["extra_wait_shards"]) if any_w else 0
+        nhead = len(any_w["head_ctls"]) if any_w else 1
+        return 3 + extra + (nhead - 1)
+
+    def enqueue_worker_step(self, rank: int, x16_ptr: Optional[int] = None, labels_ptr: Optional[int] = None) -> None:
+        """Enqueue one worker step on the rank's stream; ``x16_ptr`` [B, in_dim] bf16 and ``labels_ptr``
+        [B, classes] fp32 default to the rank's staging buffers."""
+        rk, d = self.ranks[rank], self._w[rank]
+        st = rk.stream.cuda_stream
+        t = rk.step
+        lib = self.lib
+        with torch.cuda.device(rk.device):
+            for s in d["extra_wait_shards"]:
+                rc = lib.dtf_wait_token(rk.bufs["mailbox_w%d" % self.worker_ranks.index(rank)].ptr + s * self.mb_bytes,
+                                        t, self.cfg.timeout_ns, d["err_ptr"], st)
+                assert rc == 0, rc
+            g1, hd, g3 = d["g1"], d["head"], d["g3"]
+            if x16_ptr is not None:
+                g1.a = x16_ptr
+                g3.a = x16_ptr
+            if labels_ptr is not None:
+                hd.labels = labels_ptr
+            g1.wait_target = t
+            rc = lib.dtf_gemm_bf16(ctypes.byref(g1), st)
+            assert rc == 0, "F1 gemm rc=%d" % rc
+            # the head signals every shard it pushed to: one launch per distinct shard keeps the kernel simple
+            hd.ctl, hd.mailbox = d["head_ctls"][0], d["head_mailboxes"][0]
+            rc = lib.dtf_mlp_head(ctypes.byref(hd), st)
+            assert rc == 0, "mlp_head rc=%d" % rc
+            for ctl_ptr, mbp in zip(d["head_ctls"][1:], d["head_mailboxes"][1:]):
+                rc = lib.dtf_push_grad(0, 0, 0, ctl_ptr, mbp, self.worker_ranks.index(rank), hd.stamp_from_version, 1, 1, st)
+                assert rc == 0, rc
+            rc = lib.dtf_gemm_bf16(ctypes.byref(g3), st)
+            assert rc == 0, "B3 gemm rc=%d" % rc
+        cuda_lib._bump(self.launches_per_worker_step())
+        rk.step += 1
+
+    def enqueue_ps_apply(self, rank: int) -> None:
+        rk = self.ranks[rank]
+        with torch.cuda.device(rk.device):
+            rc = self.lib.dtf_ps_apply(ctypes.byref(self._p[rank]), rk.stream.cuda_stream)
+        assert rc == 0, "ps_apply rc=%d" % rc
+        cuda_lib._bump()
+
+    def stage_batch(self, rank: int, x: torch.Tensor, y: torch.Tensor) -> None:
+        """Host (pinned) or device fp32 batch -> the rank's bf16/f32 staging buffers, on the rank's stream."""
+        rk = self.ranks[rank]
+        w = self.worker_ranks.index(rank)
+        B, D, C = self.spec.batch, self.spec.in_dim, self.spec.classes
+        with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
+            xf = rk.bufs["xf32_w%d" % w].tensor(torch.float32, 0, B * D).view(B, D)
+            xf.copy_(x, non_blocking=True)
+            rk.bufs["labels_w%d" % w].tensor(torch.float32, 0, B * C).view(B, C).copy_(y, non_blocking=True)
+            rc = self.lib.dtf_convert_f32_bf16(xf.data_ptr(), D, rk.bufs["x16_w%d" % w].ptr, D, B, D, D,
+                                               rk.stream.cuda_stream)
+            assert rc == 0, rc
+        cuda_lib._bump()
+
+    def step(self, x=None, y=None, sync_loss: bool = True) -> Optional[float]:
+        """One training step for every LOCAL rank.  Workers: (optional staging of the host batch) +
+        3 kernels; ps shards: one ps_apply per aggregate (sync) or per worker push (async).
+        Returns the local worker's loss when ``sync_loss`` (a device->host read)."""
+        cfg = self.cfg
+        for r in self.worker_ranks:
+            if r in self.ranks:
+                if x is not None:
+                    self.stage_batch(r, x, y)
+                self.enqueue_worker_step(r)
+        for r in self.ps_ranks:
+            if r in self.ranks:
+                for _ in range(1 if cfg.sync else cfg.num_workers):
+                    self.enqueue_ps_apply(r)
+        if sync_loss:
+            return self.read_loss()
+        return None
+
+    def read_loss(self, rank: Optional[int] = None) -> Optional[float]:
+        for r in ([rank] if rank is not None else self.worker_ranks):
+            if r in self.ranks:
+                rk = self.ranks[r]
+                w = self.worker_ranks.index(r)
+                rk.stream.synchronize()
+                return float(rk.bufs["misc_w%d" % w].tensor(torch.float32, 0, 1).cpu()[0])
+        return None
+
+    def check_errors(self) -> None:
+        for r, rk in self.ranks.items():
+            rk.stream.synchronize()
+            if r in self.worker_ranks:
+                w = self.worker_ranks.index(r)
+                e = int(rk.bufs["misc_w%d" % w].tensor(torch.int32, 16, 1).cpu()[0])
+                if e:
+                    raise RuntimeError("worker %d: device-side wait timed out (code %d)" % (w, e))
+            if r in self.ps_ranks:
+                s = self.ps_ranks.index(r)
+                e = int(rk.bufs["ctl%d" % s].tensor(torch.int32, self.off["err"], 1).cpu()[0])
+                if e:
+                    raise RuntimeError("ps shard %d: device-side wait timed out (code %d)" % (s, e))
+
+    def synchronize(self) -> None:
+        for rk in self.ranks.values():
+            rk.stream.synchronize()
+
+    def close(self) -> None:
+        self.synchronize()
+        self.fabric.close()
+
+
+def smoke_step() -> Dict[str, Any]:
+    """One tiny forward+backward+apply of the flagship model on cuda:0 (ps and worker colocated)."""
+    torch.cuda.set_device(0)
+    fabric = Fabric(1, {0: 0})
+    eng = PSTrainEngine(MLPSpec(), EngineConfig(colocated=True, optimizer={"kind": "adam", "lr": 0.01}), fabric)
+    eng.init_params()
+    from ..utils.mnist_data import synthetic_mnist
+    xs, ys = synthetic_mnist(400, seed=7)
+    losses = []
+    for i in range(4):
+        x = torch.from_numpy(xs[i * 100:(i + 1) * 100]).pin_memory()
+        y = torch.from_numpy(ys[i * 100:(i + 1) * 100]).pin_memory()
+        losses.append(eng.step(x, y))
+    eng.check_errors()
+    gs = eng.read_ctl(0, "global_step")
+    eng.close()
+    assert gs == 4, gs
+    assert all(np.isfinite(losses)), losses
+    return {"losses": [round(l, 3) for l in losses], "global_step": gs, "launches": cuda_lib.launch_count()}
