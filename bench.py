@@ -1,0 +1,299 @@
+"""Headline benchmark: MNIST MLP samples/sec, sync-replica parameter server, device-timed, max over ranks.
+
+Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` (N>1: launched with
+``python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...``).  Rank 0 prints ONE
+JSON line.  Config named by BASELINE.json: between-graph parameter server, 784-100-10 MLP, batch 100
+per worker, clipped batch-sum cross-entropy, sync replicas (``replicas_to_aggregate = num_workers``).
+Topology: N GPUs = 1 ps + (N-1) workers (8 GPUs -> 1 ps + 7 workers); 1 GPU = ps and worker share it.
+
+* ``value``: whole-job samples/sec from the device-timed region (CUDA events on every rank's stream,
+  barrier + synchronize on both sides, MAX over ranks).  The step loop is captured in CUDA graphs.
+* inputs: a 55 000 x 784 fp32 synthetic MNIST-shaped training set resident in each worker's HBM
+  (172 MB > the 126 MB L2), batches walked in order; fp32 -> bf16 staging is part of every step.
+* ``e2e``: the same metric through ``PSTrainEngine.step(x, y)`` with, every step, the host->device copy
+  of that step's batch from pinned host memory and a device->host read of the loss.
+* ``--impl reference``: the reference is TensorFlow-1.x example scripts; TF is not installable in this
+  image (no wheel for Python 3.12, no network), so this arm reports ``unavailable``.
+* ``--impl nccl``: the in-repo torch + NCCL + cuBLAS emulation of the same workflow (``baseline/``),
+  for an apples-to-apples number on the same box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"])
+    ap.add_argument("--mode", default="sync", choices=["sync", "async"])
+    ap.add_argument("--optimizer", default="sgd", choices=["sgd", "momentum", "adam"])
+    ap.add_argument("--lr", type=float, default=0.01)
+    ap.add_argument("--hidden", type=int, default=100)
+    ap.add_argument("--batch", type=int, default=100)
+    ap.add_argument("--unroll", type=int, default=0, help="steps per CUDA graph (0: auto)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=-1, help="-1: min(steps, 1000); 0: skip")
+    ap.add_argument("--publish", action="store_true", help="ps stores params into worker replicas (push-publish)")
+    ap.add_argument("--num-train", type=int, default=55000)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int, period_ms: int = 50):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.period = period_ms
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", str(self.period)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(self.period / 1000.0 * 1.5)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        mine = []
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 8 and f[0] == str(self.gpu):
+                mine.append((ts, f))
+        inside = [f for ts, f in mine if t0 <= ts <= t1 + self.period / 1000.0] or [f for _, f in mine[-3:]]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(f[1]) for f in inside]
+        reasons = []
+        for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
+            if any(f[col].lower().startswith("active") for f in inside):
+                reasons.append(name)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(inside[0][2]), "reasons": reasons,
+                "samples": len(inside), "power_w_max": max(float(f[3]) for f in inside if f[3].replace(".", "").isdigit())
+                if any(f[3].replace(".", "").isdigit() for f in inside) else None}
+
+
+def reference_arm(args):
+    why = ("reference is 7 TensorFlow-1.x scripts with no setup.py; tensorflow 1.x has no wheel for "
+           "Python 3.12 and /opt/wheelhouse has none (pip install --no-index fails), so it cannot run here")
+    print(json.dumps({"impl": "reference", "unavailable": why, "metric": "MNIST MLP samples/sec", "n_gpus": args.gpus}))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return 0
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if args.impl == "nccl":
+        from baseline.nccl_ps import run_nccl_baseline
+        out = run_nccl_baseline(args, rank, world, local_rank)
+        if rank == 0:
+            print(json.dumps(out))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    from distributed_tensorflow_b200.ops import cuda_lib
+    from distributed_tensorflow_b200.parallel.fabric import Fabric
+    from distributed_tensorflow_b200.parallel.ps_engine import EngineConfig, MLPSpec, PSTrainEngine
+    from distributed_tensorflow_b200.utils.mnist_data import synthetic_mnist
+
+    N = args.gpus
+    spec = MLPSpec(hidden=args.hidden, batch=args.batch)
+    opt = {"kind": args.optimizer, "lr": args.lr, "momentum": 0.9}
+    if N == 1:
+        cfg = EngineConfig(num_ps=1, num_workers=1, colocated=True, sync=args.mode == "sync", optimizer=opt,
+                           publish_replicas=args.publish)
+        fabric = Fabric(1, {0: local_rank})
+    else:
+        cfg = EngineConfig(num_ps=1, num_workers=N - 1, sync=args.mode == "sync", optimizer=opt,
+                           publish_replicas=args.publish)
+        fabric = Fabric.from_torch_distributed()
+    eng = PSTrainEngine(spec, cfg, fabric)
+    eng.init_params()
+    is_worker = any(r in eng.worker_ranks for r in eng.ranks)
+    num_workers = cfg.num_workers
+
+    # ---- data: synthetic MNIST-shaped train split (fp32, 172 MB) in every worker's HBM -----------------------
+    images = labels = None
+    if is_worker:
+        images, labels = synthetic_mnist(args.num_train, seed=1)
+        for r in eng.ranks:
+            if r in eng.worker_ranks:
+                eng.attach_dataset(r, images, labels)
+
+    def barrier():
+        eng.synchronize()
+        if world > 1:
+            dist.barrier()
+        eng.synchronize()
+
+    K, W = args.steps, max(args.warmup, 3)
+    use_graph = not args.no_graph
+    unroll = args.unroll or next(u for u in (50, 40, 32, 25, 20, 16, 10, 8, 5, 4, 2, 1) if K % u == 0)
+    # ---- warm-up (eager: first-launch setup) + graph capture + graph warm-up ---------------------------------
+    eng.enqueue_local_steps(W, "dataset")
+    barrier()
+    eng.check_errors()
+    if use_graph:
+        eng.capture_graphs(unroll, "dataset")
+        eng.replay_graphs(1)
+        barrier()
+        eng.check_errors()
+
+    # ---- timed region ---------------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    evs = {}
+    launches0 = cuda_lib.launch_count()
+    t0 = time.time()
+    for r, rk in eng.ranks.items():
+        with torch.cuda.device(rk.device):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(rk.stream)
+            evs[r] = (e0, e1)
+    if use_graph:
+        eng.replay_graphs(K // unroll)
+        if K % unroll:
+            eng.enqueue_local_steps(K % unroll, "dataset")
+    else:
+        eng.enqueue_local_steps(K, "dataset")
+    for r, rk in eng.ranks.items():
+        evs[r][1].record(rk.stream)
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    launches = cuda_lib.launch_count() - launches0
+    ms_local = max(e0.elapsed_time(e1) for e0, e1 in evs.values())
+    eng.check_errors()
+    stats = torch.tensor([ms_local, float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, launches_total = float(mx[0]), int(sm[1])
+    else:
+        ms, launches_total = ms_local, launches
+    value = num_workers * spec.batch * K / (ms / 1e3)
+    loss = eng.read_loss() if is_worker else None
+    gstep = eng.read_ctl(0, "global_step") if 0 in eng.ranks else None
+
+    # ---- end-to-end: public API step(x, y) with H2D of the batch and D2H of the loss every step -----------------
+    e2e = None
+    Ke = min(K, 1000) if args.e2e_steps < 0 else args.e2e_steps
+    if Ke > 0:
+        hx = hy = None
+        if is_worker:
+            n_use = min(args.num_train, 20000)
+            hx = torch.from_numpy(images[:n_use]).pin_memory()
+            hy = torch.from_numpy(labels[:n_use]).pin_memory()
+            nb = n_use // spec.batch
+        wl = [r for r in eng.ranks if r in eng.worker_ranks]
+        woff = eng.worker_ranks.index(wl[0]) if wl else 0
+
+        def e2e_loop(n, start):
+            last = None
+            for i in range(n):
+                if is_worker:
+                    b = ((start + i) * num_workers + woff) % nb
+                    last = eng.step(hx[b * spec.batch:(b + 1) * spec.batch], hy[b * spec.batch:(b + 1) * spec.batch],
+                                    sync_loss=True)
+                else:
+                    eng.step(sync_loss=False)
+            return last
+        e2e_loop(5, 0)
+        barrier()
+        te0 = time.time()
+        ee = {}
+        for r, rk in eng.ranks.items():
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(rk.stream)
+            ee[r] = (a, b_)
+        last_loss = e2e_loop(Ke, 5)
+        for r, rk in eng.ranks.items():
+            ee[r][1].record(rk.stream)
+        barrier()
+        ems_local = max(a.elapsed_time(b_) for a, b_ in ee.values())
+        wall_ms = (time.time() - te0) * 1e3
+        t = torch.tensor([max(ems_local, 0.0), wall_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        eng.check_errors()
+        ems = float(t[0])
+        e2e = {"value": num_workers * spec.batch * Ke / (ems / 1e3), "unit": "samples/sec", "steps": Ke,
+               "ms_per_step": ems / Ke, "wall_ms_per_step": float(t[1]) / Ke,
+               "h2d_bytes_per_step": spec.batch * (spec.in_dim + spec.classes) * 4, "d2h_bytes_per_step": 4,
+               "api": "PSTrainEngine.step(x_pinned, y_pinned) -> loss", "last_loss": last_loss}
+
+    if rank == 0:
+        out = {
+            "metric": "MNIST MLP samples/sec (whole box, device-timed, max over ranks), sync-replica PS",
+            "value": value, "unit": "samples/sec", "n_gpus": N, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic MNIST-shaped 28x28 (55000x784 fp32 in HBM), random-init weights",
+            "impl": "ours",
+            "config": {"model": "MNIST MLP 784-%d-10, clipped batch-sum xent" % spec.hidden,
+                       "global_batch": num_workers * spec.batch, "per_worker_batch": spec.batch,
+                       "parallelism": ("ps1+worker1 colocated on one GPU" if N == 1 else "ps1+worker%d between-graph" % (N - 1)),
+                       "mode": args.mode, "optimizer": args.optimizer, "lr": args.lr,
+                       "l2": "inputs larger than L2: 172 MB fp32 train split cycled in HBM",
+                       "cuda_graph_unroll": unroll if use_graph else 0,
+                       "pull": "publish-replicas" if args.publish else "peer-pull fused in GEMM"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total,
+            "final_loss": loss, "global_step": gstep,
+        }
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

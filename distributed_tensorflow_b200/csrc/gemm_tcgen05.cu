@@ -49,6 +49,7 @@ struct GemmParams {
   float* colsum;         // optional [N]: += column sums of the (post-mask, post-alpha) tile (bias gradient)
   const unsigned long long* wait_flag;   // optional: acquire until *wait_flag >= wait_target before loading
   unsigned long long wait_target;
+  const unsigned long long* wait_target_ptr;   // optional: target = wait_target + *wait_target_ptr (device step counter)
   unsigned long long* signal;            // optional: release-increment by 1 per CTA after the tile is stored
   unsigned int* err;                     // optional: set to 1 when the wait timed out
   unsigned long long timeout_ns;
@@ -102,7 +103,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     if (elect_one()) {
       if (p.wait_flag != nullptr) {
         // fused pull: the parameters behind map_b (or map_a) are published by another GPU
-        if (!wait_flag_ge_u64(reinterpret_cast<const uint64_t*>(p.wait_flag), p.wait_target, p.timeout_ns)) {
+        const unsigned long long target = p.wait_target + (p.wait_target_ptr ? *p.wait_target_ptr : 0ull);
+        if (!wait_flag_ge_u64(reinterpret_cast<const uint64_t*>(p.wait_flag), target, p.timeout_ns)) {
           if (p.err) atomicExch(p.err, 1u);
         }
         fence_proxy_async();
@@ -346,6 +348,7 @@ struct DtfGemmArgs {
   unsigned int* err;
   unsigned long long timeout_ns;
   int block_n_override;
+  const unsigned long long* wait_target_ptr;
 };
 
 // Returns 0 on success, <0 for argument errors, >0 for CUDA errors.
@@ -383,7 +386,7 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
   p.alpha = g->alpha;
   p.atomic = (splits > 1 || g->accumulate) ? 1 : 0;
   p.colsum = g->colsum;
-  p.wait_flag = g->wait_flag; p.wait_target = g->wait_target;
+  p.wait_flag = g->wait_flag; p.wait_target = g->wait_target; p.wait_target_ptr = g->wait_target_ptr;
   p.signal = g->signal; p.err = g->err;
   p.timeout_ns = g->timeout_ns ? g->timeout_ns : 2000000000ull;
 

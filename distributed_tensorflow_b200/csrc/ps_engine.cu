@@ -423,12 +423,37 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
   }
 }
 
+// Input-pipeline stage for the device-resident dataset: batch index = (step * stride + offset) % nbatches,
+// where step is the worker's DEVICE step counter (so the launch is CUDA-graph replayable).  Converts the
+// fp32 images of that batch to the bf16 staging tile consumed by both GEMMs and copies the labels.
+__global__ void stage_from_dataset_kernel(const float* __restrict__ images, const float* __restrict__ labels,
+                                          long long nbatches, int B, int D, int C, long long stride, long long offset,
+                                          const unsigned long long* __restrict__ step_counter,
+                                          __nv_bfloat16* __restrict__ x16, float* __restrict__ lab_out) {
+  const unsigned long long step = step_counter ? *step_counter : 0ull;
+  const long long bi = (long long)((step * (unsigned long long)stride + (unsigned long long)offset) %
+                                   (unsigned long long)nbatches);
+  const float4* src = reinterpret_cast<const float4*>(images + bi * (long long)B * D);
+  uint2* dst = reinterpret_cast<uint2*>(x16);
+  const long long n4 = (long long)B * D / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    dst[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+  const float* ls = labels + bi * (long long)B * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)B * C;
+       i += (long long)gridDim.x * blockDim.x)
+    lab_out[i] = ls[i];
+}
+
 // wait (on the worker) until the mailbox token reaches `target`: used when the step's first kernel
 // is not a GEMM with a fused wait (generic models), and by tests.
-__global__ void wait_token_kernel(const WorkerMailbox* mb, unsigned long long target, unsigned long long timeout_ns,
+__global__ void wait_token_kernel(const WorkerMailbox* mb, unsigned long long target,
+                                  const unsigned long long* target_ptr, unsigned long long timeout_ns,
                                   unsigned int* err) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    if (!wait_flag_ge_u64(reinterpret_cast<const uint64_t*>(&mb->token), target, timeout_ns) && err) atomicExch(err, 3u);
+    const unsigned long long t = target + (target_ptr ? *target_ptr : 0ull);
+    if (!wait_flag_ge_u64(reinterpret_cast<const uint64_t*>(&mb->token), t, timeout_ns) && err) atomicExch(err, 3u);
   }
 }
 
@@ -580,9 +605,18 @@ int dtf_mlp_head(const DtfMlpHeadArgs* a, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
-int dtf_wait_token(const void* mailbox, unsigned long long target, unsigned long long timeout_ns, unsigned int* err,
-                   cudaStream_t s) {
-  wait_token_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const WorkerMailbox*>(mailbox), target,
+int dtf_stage_from_dataset(const float* images, const float* labels, long long nbatches, int B, int D, int C,
+                           long long stride, long long offset, const unsigned long long* step_counter, void* x16,
+                           float* lab_out, cudaStream_t s) {
+  if (((long long)B * D) % 4) return -2;
+  stage_from_dataset_kernel<<<40, 256, 0, s>>>(images, labels, nbatches, B, D, C, stride, offset, step_counter,
+                                               reinterpret_cast<__nv_bfloat16*>(x16), lab_out);
+  return (int)cudaGetLastError();
+}
+
+int dtf_wait_token(const void* mailbox, unsigned long long target, const unsigned long long* target_ptr,
+                   unsigned long long timeout_ns, unsigned int* err, cudaStream_t s) {
+  wait_token_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const WorkerMailbox*>(mailbox), target, target_ptr,
                                      timeout_ns ? timeout_ns : 2000000000ull, err);
   return (int)cudaGetLastError();
 }

@@ -36,7 +36,7 @@ class GemmArgs(Structure):
                 ("colsum", c_void_p),
                 ("wait_flag", c_void_p), ("wait_target", c_ulonglong),
                 ("signal", c_void_p), ("err", c_void_p), ("timeout_ns", c_ulonglong),
-                ("block_n_override", c_int)]
+                ("block_n_override", c_int), ("wait_target_ptr", c_void_p)]
 
 
 class PsApplyArgs(Structure):
@@ -97,7 +97,10 @@ def load() -> ctypes.CDLL:
         lib.dtf_gemm_ref.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_longlong,
                                      c_longlong, c_int, c_int, c_void_p, c_int, c_float, c_void_p]
         lib.dtf_ps_publish.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p]
-        lib.dtf_wait_token.argtypes = [c_void_p, c_ulonglong, c_ulonglong, c_void_p, c_void_p]
+        lib.dtf_wait_token.argtypes = [c_void_p, c_ulonglong, c_void_p, c_ulonglong, c_void_p, c_void_p]
+        lib.dtf_stage_from_dataset.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_longlong, c_longlong,
+                                               c_void_p, c_void_p, c_void_p, c_void_p]
+        lib.dtf_stage_from_dataset.restype = c_int
         lib.dtf_push_grad.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                       c_void_p]
         lib.dtf_pull_shadow.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_void_p]

@@ -406,44 +406,65 @@ class PSTrainEngine:
     # ------------------------------------------------------------------------------------------------
     # stepping
     # ------------------------------------------------------------------------------------------------
-    def launches_per_worker_step(self) -> int:
+    def launches_per_worker_step(self, source: str = "staged") -> int:
         any_w = next(iter(self._w.values()), None)
         extra = len(any_w["extra_wait_shards"]) if any_w else 0
         nhead = len(any_w["head_ctls"]) if any_w else 1
-        return 3 + extra + (nhead - 1)
+        return 3 + extra + (nhead - 1) + (1 if source == "dataset" else 0)
 
-    def enqueue_worker_step(self, rank: int, x16_ptr: Optional[int] = None, labels_ptr: Optional[int] = None) -> None:
-        """Enqueue one worker step on the rank's stream; ``x16_ptr`` [B, in_dim] bf16 and ``labels_ptr``
-        [B, classes] fp32 default to the rank's staging buffers."""
+    def attach_dataset(self, rank: int, images, labels) -> None:
+        """Stage a whole split in this worker's HBM (fp32 images [N, in_dim], one-hot labels [N, classes]).
+        Worker ``w`` of ``W`` then walks batches ``w, w+W, w+2W, ...`` (mod the number of batches): the batch
+        index is computed ON THE DEVICE from the step counter, so steps are CUDA-graph replayable."""
+        rk, d = self.ranks[rank], self._w[rank]
+        B = self.spec.batch
+        with torch.cuda.device(rk.device):
+            img = torch.as_tensor(images, dtype=torch.float32).contiguous().to(rk.device)
+            lab = torch.as_tensor(labels, dtype=torch.float32).contiguous().to(rk.device)
+        d["ds_images"], d["ds_labels"], d["ds_nbatches"] = img, lab, img.shape[0] // B
+        assert d["ds_nbatches"] >= 1
+
+    def enqueue_worker_step(self, rank: int, source: str = "staged") -> None:
+        """Enqueue one worker step on the rank's stream.  ``source='staged'``: the batch is already in the
+        rank's staging buffers (see :meth:`stage_batch`); ``'dataset'``: take the next batch of the attached
+        device-resident dataset (one extra staging kernel).  Wait targets come from the device step counter."""
         rk, d = self.ranks[rank], self._w[rank]
         st = rk.stream.cuda_stream
-        t = rk.step
         lib = self.lib
+        w = self.worker_ranks.index(rank)
+        n = 0
         with torch.cuda.device(rk.device):
+            if source == "dataset":
+                rc = lib.dtf_stage_from_dataset(d["ds_images"].data_ptr(), d["ds_labels"].data_ptr(), d["ds_nbatches"],
+                                                self.spec.batch, self.spec.in_dim, self.spec.classes,
+                                                self.cfg.num_workers, w, d["stepctr_ptr"],
+                                                rk.bufs["x16_w%d" % w].ptr, rk.bufs["labels_w%d" % w].ptr, st)
+                assert rc == 0, "stage_from_dataset rc=%d" % rc
+                n += 1
             for s in d["extra_wait_shards"]:
-                rc = lib.dtf_wait_token(rk.bufs["mailbox_w%d" % self.worker_ranks.index(rank)].ptr + s * self.mb_bytes,
-                                        t, self.cfg.timeout_ns, d["err_ptr"], st)
+                rc = lib.dtf_wait_token(rk.bufs["mailbox_w%d" % w].ptr + s * self.mb_bytes, 0, d["stepctr_ptr"],
+                                        self.cfg.timeout_ns, d["err_ptr"], st)
                 assert rc == 0, rc
+                n += 1
             g1, hd, g3 = d["g1"], d["head"], d["g3"]
-            if x16_ptr is not None:
-                g1.a = x16_ptr
-                g3.a = x16_ptr
-            if labels_ptr is not None:
-                hd.labels = labels_ptr
-            g1.wait_target = t
+            g1.wait_target, g1.wait_target_ptr = 0, d["stepctr_ptr"]
             rc = lib.dtf_gemm_bf16(ctypes.byref(g1), st)
             assert rc == 0, "F1 gemm rc=%d" % rc
-            # the head signals every shard it pushed to: one launch per distinct shard keeps the kernel simple
+            # the head signals the first shard it pushed to; further shards get a signal-only launch
             hd.ctl, hd.mailbox = d["head_ctls"][0], d["head_mailboxes"][0]
             rc = lib.dtf_mlp_head(ctypes.byref(hd), st)
             assert rc == 0, "mlp_head rc=%d" % rc
+            n += 2
             for ctl_ptr, mbp in zip(d["head_ctls"][1:], d["head_mailboxes"][1:]):
-                rc = lib.dtf_push_grad(0, 0, 0, ctl_ptr, mbp, self.worker_ranks.index(rank), hd.stamp_from_version, 1, 1, st)
+                rc = lib.dtf_push_grad(0, 0, 0, ctl_ptr, mbp, w, hd.stamp_from_version, 1, 1, st)
                 assert rc == 0, rc
+                n += 1
             rc = lib.dtf_gemm_bf16(ctypes.byref(g3), st)
             assert rc == 0, "B3 gemm rc=%d" % rc
-        cuda_lib._bump(self.launches_per_worker_step())
+            n += 1
+        cuda_lib._bump(n)
         rk.step += 1
+        self._last_step_launches = n
 
     def enqueue_ps_apply(self, rank: int) -> None:
         rk = self.ranks[rank]
@@ -466,7 +487,7 @@ class PSTrainEngine:
             assert rc == 0, rc
         cuda_lib._bump()
 
-    def step(self, x=None, y=None, sync_loss: bool = True) -> Optional[float]:
+    def step(self, x=None, y=None, sync_loss: bool = True, source: str = "dataset") -> Optional[float]:
         """One training step for every LOCAL rank.  Workers: (optional staging of the host batch) +
         3 kernels; ps shards: one ps_apply per aggregate (sync) or per worker push (async).
         Returns the local worker's loss when ``sync_loss`` (a device->host read)."""
@@ -475,7 +496,7 @@ class PSTrainEngine:
             if r in self.ranks:
                 if x is not None:
                     self.stage_batch(r, x, y)
-                self.enqueue_worker_step(r)
+                self.enqueue_worker_step(r, "staged" if x is not None else source)
         for r in self.ps_ranks:
             if r in self.ranks:
                 for _ in range(1 if cfg.sync else cfg.num_workers):
@@ -483,6 +504,48 @@ class PSTrainEngine:
         if sync_loss:
             return self.read_loss()
         return None
+
+    def enqueue_local_steps(self, n: int = 1, source: str = "dataset") -> int:
+        """Enqueue ``n`` steps for every local rank (no host sync).  Returns the kernels launched."""
+        before = cuda_lib.launch_count()
+        for _ in range(n):
+            self.step(sync_loss=False, source=source)
+        return cuda_lib.launch_count() - before
+
+    def capture_graphs(self, unroll: int = 16, source: str = "dataset") -> Dict[int, Any]:
+        """Capture ``unroll`` steps of every local rank's stream into a CUDA graph (launch-bound inner loop).
+        Everything step-dependent (wait targets, batch index) is read from device counters, so a graph can be
+        replayed any number of times.  Call after at least one eager step (first-launch attribute setup)."""
+        graphs: Dict[int, Any] = {}
+        self.synchronize()
+        for r, rk in self.ranks.items():
+            with torch.cuda.device(rk.device):
+                g = torch.cuda.CUDAGraph()
+                before = cuda_lib.launch_count()
+                with torch.cuda.graph(g, stream=rk.stream, capture_error_mode="thread_local"):
+                    for _ in range(unroll):
+                        if r in self.worker_ranks:
+                            self.enqueue_worker_step(r, source)
+                        if r in self.ps_ranks:
+                            for _k in range(1 if self.cfg.sync else self.cfg.num_workers):
+                                self.enqueue_ps_apply(r)
+                graphs[r] = (g, cuda_lib.launch_count() - before)
+                cuda_lib._bump(-(cuda_lib.launch_count() - before))      # capture launched nothing
+        self._graphs = graphs
+        self._graph_unroll = unroll
+        return graphs
+
+    def replay_graphs(self, times: int = 1) -> int:
+        """Replay the captured graphs ``times`` times on every local rank; returns kernels launched."""
+        n = 0
+        for _ in range(times):
+            for r, (g, k) in self._graphs.items():
+                rk = self.ranks[r]
+                with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
+                    g.replay()
+                n += k
+        cuda_lib._bump(n)
+        return n
 
     def read_loss(self, rank: Optional[int] = None) -> Optional[float]:
         for r in ([rank] if rank is not None else self.worker_ranks):

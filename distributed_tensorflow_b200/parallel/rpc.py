@@ -100,6 +100,13 @@ class RpcServer:
 
     def close(self) -> None:
         self._closed.set()
+        # wake the accept() call first: the port is only released once no thread is blocked on the socket
+        try:
+            s = socket.create_connection((self.host, self.port), timeout=0.5)
+            s.close()
+        except OSError:
+            pass
+        self._thread.join(2.0)
         try:
             self._listener.close()
         except OSError:
@@ -109,12 +116,6 @@ class RpcServer:
                 c.close()
             except OSError:
                 pass
-        # unblock accept()
-        try:
-            s = socket.create_connection((self.host, self.port), timeout=0.2)
-            s.close()
-        except OSError:
-            pass
 
 
 class RpcClient:
