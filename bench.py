@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"])
     ap.add_argument("--mode", default="sync", choices=["sync", "async"])
     ap.add_argument("--optimizer", default="sgd", choices=["sgd", "momentum", "adam"])
-    ap.add_argument("--lr", type=float, default=0.01)
+    ap.add_argument("--lr", type=float, default=None, help="default: 0.001 for sgd/momentum (batch-SUM loss), 0.01 for adam")
     ap.add_argument("--hidden", type=int, default=100)
     ap.add_argument("--batch", type=int, default=100)
     ap.add_argument("--unroll", type=int, default=0, help="steps per CUDA graph (0: auto)")
@@ -142,6 +142,8 @@ def main():
 
     N = args.gpus
     spec = MLPSpec(hidden=args.hidden, batch=args.batch)
+    if args.lr is None:
+        args.lr = 0.01 if args.optimizer == "adam" else 0.001
     opt = {"kind": args.optimizer, "lr": args.lr, "momentum": 0.9}
     if N == 1:
         cfg = EngineConfig(num_ps=1, num_workers=1, colocated=True, sync=args.mode == "sync", optimizer=opt,

@@ -53,7 +53,100 @@ struct GemmParams {
   unsigned long long* signal;            // optional: release-increment by 1 per CTA after the tile is stored
   unsigned int* err;                     // optional: set to 1 when the wait timed out
   unsigned long long timeout_ns;
+  long long* phase_trace;                // optional [gridsize][16] clock64 stamps (profiling builds of the step)
+  int signal_gpu_scope;                  // 1: consumer is on the same GPU (gpu-scope fence suffices)
+  const unsigned long long* stamp_src;   // optional: *stamp_dst = *stamp_src before the arrival (block 0,0,0 only)
+  unsigned long long* stamp_dst;
 };
+
+
+// One 16-column slice of the epilogue: alpha, bias, ReLU, ReLU-backward mask, bias-gradient column sums, store
+// (fp32 / bf16 / atomic accumulate).  `r` holds the fp32 accumulators of this thread's row.
+DTF_DEVICE void epilogue_chunk16(const GemmParams& p, const uint32_t* r, int c0, int n0, long long grow, bool row_ok,
+                                 bool add_bias, const float* s_bias, int lane) {
+  float* cf = reinterpret_cast<float*>(p.c);
+  __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(p.c);
+  const int gc0 = n0 + c0;
+  if (gc0 >= p.N) return;                     // warp-uniform
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float x = __uint_as_float(r[j]) * p.alpha;
+    if (add_bias) x += s_bias[c0 + j];
+    if (p.relu) x = fmaxf(x, 0.0f);
+    v[j] = x;
+  }
+  if (p.mask != nullptr) {
+    const __nv_bfloat16* mrow = p.mask + grow * p.ldmask + gc0;
+    if (row_ok && gc0 + 16 <= p.N && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0)) {
+      const uint4 m0 = reinterpret_cast<const uint4*>(mrow)[0];
+      const uint4 m1 = reinterpret_cast<const uint4*>(mrow)[1];
+      const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+        const uint32_t lo = mw[j] & 0xFFFFu, hi = mw[j] >> 16;
+        v[2 * j] = (lo != 0u && lo < 0x8000u) ? v[2 * j] : 0.0f;
+        v[2 * j + 1] = (hi != 0u && hi < 0x8000u) ? v[2 * j + 1] : 0.0f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int gc = gc0 + j;
+        float mk = 0.0f;
+        if (row_ok && gc < p.N) mk = __bfloat162float(p.mask[grow * p.ldmask + gc]);
+        v[j] = mk > 0.0f ? v[j] : 0.0f;
+      }
+    }
+  }
+  if (p.colsum != nullptr) {
+    float mine = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float s = row_ok ? v[j] : 0.0f;
+      s += __shfl_xor_sync(0xffffffffu, s, 16);
+      s += __shfl_xor_sync(0xffffffffu, s, 8);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      if (lane == j) mine = s;
+    }
+    if (lane < 16 && gc0 + lane < p.N) atomicAdd(p.colsum + gc0 + lane, mine);
+  }
+  if (row_ok) {
+    const bool full = gc0 + 16 <= p.N;
+    if (p.atomic) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (gc0 + j < p.N) atomicAdd(cf + grow * p.ldc + gc0 + j, v[j]);
+    } else if (p.c_bf16) {
+      __nv_bfloat16* dst = cb + grow * p.ldc + gc0;
+      if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        uint4 w0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                              pack_bf16x2(v[6], v[7]));
+        uint4 w1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                              pack_bf16x2(v[14], v[15]));
+        reinterpret_cast<uint4*>(dst)[0] = w0;
+        reinterpret_cast<uint4*>(dst)[1] = w1;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (gc0 + j < p.N) dst[j] = __float2bfloat16(v[j]);
+      }
+    } else {
+      float* dst = cf + grow * p.ldc + gc0;
+      if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (gc0 + j < p.N) dst[j] = v[j];
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -63,9 +156,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   __shared__ __align__(8) uint64_t empty_bar[8];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_holder;
+  __shared__ float s_bias[256];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  long long* tr = p.phase_trace ? p.phase_trace + 16 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+#define DTF_STAMP(slot) do { if (tr) tr[slot] = clock64(); } while (0)
+  if (threadIdx.x == 0) DTF_STAMP(0);
   const int m0 = blockIdx.x * kBlockM;
   const int n0 = blockIdx.y * p.block_n;
   const int kb_begin = blockIdx.z * p.kb_per_split;
@@ -97,6 +194,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
+  if (threadIdx.x == 0) DTF_STAMP(1);          // setup done (barriers, TMEM alloc)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -109,6 +207,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         }
         fence_proxy_async();
       }
+      DTF_STAMP(2);                              // token acquired
       int it = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
         const int s = it % p.stages;
@@ -131,6 +230,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             tma_load_2d(b_dst + j * 8192, &map_b, &full_bar[s], n0 + 64 * j, k0);   // box {64 n, 64 k}
         }
       }
+      DTF_STAMP(3);                              // last TMA issued
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -141,6 +241,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
         mbar_wait(&full_bar[s], ph);
+        if (it == 0) DTF_STAMP(4);               // first stage landed
         tc_fence_after();
         const uint32_t a_addr = smem_u32(tiles + s * stage_bytes);
         const uint32_t b_addr = a_addr + kABytes;
@@ -156,6 +257,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         umma_commit(&empty_bar[s]);      // frees the smem slot once these MMAs have consumed it
       }
       umma_commit(&tmem_full_bar);       // accumulator complete
+      DTF_STAMP(5);                              // last MMA issued
     }
   } else {
     // ===================== epilogue warps =====================
@@ -164,99 +266,74 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     const long long grow = (long long)m0 + row;
     const bool row_ok = grow < p.M;
     const bool have_k = kb_end > kb_begin;
+    const bool add_bias = p.bias != nullptr && (p.atomic == 0 || blockIdx.z == 0);
+    if (add_bias) {
+      // stage the bias slice in shared memory while the mainloop runs (no global-load latency in the epilogue)
+      for (int i = threadIdx.x - 64; i < p.block_n; i += 128) s_bias[i] = (n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+    }
     if (have_k) {
       mbar_wait(&tmem_full_bar, 0);
       tc_fence_after();
     }
-    float* cf = reinterpret_cast<float*>(p.c);
-    __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(p.c);
-    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-      uint32_t r[16];
-      if (have_k) {
-        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-        tmem_ld_wait();
-      } else {
+    if (threadIdx.x == 64) DTF_STAMP(6);         // accumulator ready
+    if ((p.block_n & 31) == 0) {
+      // 32 columns per TMEM load, software-pipelined: the load of slice i+1 is in flight while slice i is
+      // converted and stored (the first version waited ~575 cycles per 16-column slice)
+      uint32_t ra[32], rb[32];
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+      if (have_k) tmem_ld_32x32b_x32(tbase, ra);
+      for (int c0 = 0; c0 < p.block_n; c0 += 64) {
+        if (have_k) tmem_ld_wait();
+        else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = 0;
-      }
-      const int gc0 = n0 + c0;
-      if (gc0 >= p.N) break;                      // warp-uniform
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x = __uint_as_float(r[j]) * p.alpha;
-        const int gc = gc0 + j;
-        if (p.bias != nullptr && gc < p.N && (p.atomic == 0 || blockIdx.z == 0)) x += __ldg(p.bias + gc);
-        if (p.relu) x = fmaxf(x, 0.0f);
-        v[j] = x;
-      }
-      if (p.mask != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int gc = gc0 + j;
-          float mk = 0.0f;
-          if (row_ok && gc < p.N) mk = __bfloat162float(p.mask[grow * p.ldmask + gc]);
-          v[j] = mk > 0.0f ? v[j] : 0.0f;
+          for (int j = 0; j < 32; ++j) ra[j] = 0;
         }
-      }
-      if (p.colsum != nullptr) {
-        float mine = 0.0f;
+        if (have_k && c0 + 32 < p.block_n) tmem_ld_32x32b_x32(tbase + (uint32_t)(c0 + 32), rb);
+        epilogue_chunk16(p, ra, c0, n0, grow, row_ok, add_bias, s_bias, lane);
+        epilogue_chunk16(p, ra + 16, c0 + 16, n0, grow, row_ok, add_bias, s_bias, lane);
+        if (c0 + 32 >= p.block_n) break;
+        if (have_k) tmem_ld_wait();
+        else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float s = row_ok ? v[j] : 0.0f;
-          s += __shfl_xor_sync(0xffffffffu, s, 16);
-          s += __shfl_xor_sync(0xffffffffu, s, 8);
-          s += __shfl_xor_sync(0xffffffffu, s, 4);
-          s += __shfl_xor_sync(0xffffffffu, s, 2);
-          s += __shfl_xor_sync(0xffffffffu, s, 1);
-          if (lane == j) mine = s;
+          for (int j = 0; j < 32; ++j) rb[j] = 0;
         }
-        if (lane < 16 && gc0 + lane < p.N) atomicAdd(p.colsum + gc0 + lane, mine);
+        if (have_k && c0 + 64 < p.block_n) tmem_ld_32x32b_x32(tbase + (uint32_t)(c0 + 64), ra);
+        epilogue_chunk16(p, rb, c0 + 32, n0, grow, row_ok, add_bias, s_bias, lane);
+        epilogue_chunk16(p, rb + 16, c0 + 48, n0, grow, row_ok, add_bias, s_bias, lane);
       }
-      if (row_ok) {
-        const bool full = gc0 + 16 <= p.N;
-        if (p.atomic) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (gc0 + j < p.N) atomicAdd(cf + grow * p.ldc + gc0 + j, v[j]);
-        } else if (p.c_bf16) {
-          __nv_bfloat16* dst = cb + grow * p.ldc + gc0;
-          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-            uint4 w0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                  pack_bf16x2(v[6], v[7]));
-            uint4 w1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                                  pack_bf16x2(v[14], v[15]));
-            reinterpret_cast<uint4*>(dst)[0] = w0;
-            reinterpret_cast<uint4*>(dst)[1] = w1;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (gc0 + j < p.N) dst[j] = __float2bfloat16(v[j]);
-          }
+    } else {
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t r[16];
+        if (have_k) {
+          tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+          tmem_ld_wait();
         } else {
-          float* dst = cf + grow * p.ldc + gc0;
-          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (gc0 + j < p.N) dst[j] = v[j];
-          }
+          for (int j = 0; j < 16; ++j) r[j] = 0;
         }
+        epilogue_chunk16(p, r, c0, n0, grow, row_ok, add_bias, s_bias, lane);
       }
     }
+    if (threadIdx.x == 64) DTF_STAMP(7);         // tile stored
     if (p.signal != nullptr) {
       // fused push: make this CTA's tile visible system-wide, then bump the consumer's arrival counter
-      fence_acq_rel_sys();
+      // (one fence by one thread after the CTA-level barrier: release is cumulative, and a system-scope
+      //  membar per thread serialises for tens of microseconds)
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (warp == 2 && lane == 0) red_release_sys_add_u64(reinterpret_cast<uint64_t*>(p.signal), 1ull);
+      if (warp == 2 && lane == 0) {
+        if (p.stamp_dst != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+          asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.stamp_dst), "l"(*p.stamp_src) : "memory");
+        if (p.signal_gpu_scope) __threadfence(); else fence_acq_rel_sys();
+        red_release_sys_add_u64(reinterpret_cast<uint64_t*>(p.signal), 1ull);
+        DTF_STAMP(8);                            // fence + arrival signalled
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  if (threadIdx.x == 32) DTF_STAMP(9);           // end
 }
 
 // =================================================================================================
@@ -349,6 +426,10 @@ struct DtfGemmArgs {
   unsigned long long timeout_ns;
   int block_n_override;
   const unsigned long long* wait_target_ptr;
+  long long* phase_trace;
+  int signal_gpu_scope;
+  const unsigned long long* stamp_src;
+  unsigned long long* stamp_dst;
 };
 
 // Returns 0 on success, <0 for argument errors, >0 for CUDA errors.
@@ -389,6 +470,8 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
   p.wait_flag = g->wait_flag; p.wait_target = g->wait_target; p.wait_target_ptr = g->wait_target_ptr;
   p.signal = g->signal; p.err = g->err;
   p.timeout_ns = g->timeout_ns ? g->timeout_ns : 2000000000ull;
+  p.phase_trace = g->phase_trace;
+  p.signal_gpu_scope = g->signal_gpu_scope; p.stamp_src = g->stamp_src; p.stamp_dst = g->stamp_dst;
 
   CUtensorMap ma, mb;
   int rc;
@@ -403,9 +486,9 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(226 * 1024));   // 227 KB minus the static barriers
+                                         (int)(224 * 1024));   // 227 KB minus static barriers + bias stage
     if (e != cudaSuccess) return 2000 + (int)e;
-    configured = 226 * 1024;
+    configured = 224 * 1024;
   }
   dim3 grid((unsigned)((g->M + kBlockM - 1) / kBlockM), (unsigned)((g->N + bn - 1) / bn), (unsigned)splits);
   gemm_bf16_tcgen05_kernel<<<grid, kThreads, smem, stream>>>(ma, mb, p);

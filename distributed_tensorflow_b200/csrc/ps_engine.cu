@@ -39,11 +39,13 @@ struct PsApplyParams {
   float lr, momentum, beta1, beta2, eps;
   int nesterov;
   int publish_replicas;          // 1: also store the shadow into every worker replica
+  int system_scope;              // 0: ps and workers share one GPU (gpu-scope fences suffice)
   long long zero_begin[4], zero_end[4];    // ranges of the slots to clear after reading (atomically accumulated grads)
   int num_zero;
   unsigned long long timeout_ns;
   unsigned long long* trace;     // optional ring: {kind, t0, t1, step} per launch
   int trace_cap;
+  long long* phase_trace;        // optional [16] clock64 stamps of block 0 / the last block
 };
 
 DTF_DEVICE unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
@@ -65,6 +67,9 @@ __global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
   __shared__ unsigned long long s_seq;
   __shared__ float s_lr;
   PsControl* ctl = p.ctl;
+  long long* tr = p.phase_trace;
+#define PSTAMP(slot) do { if (tr && threadIdx.x == 0 && blockIdx.x == 0) tr[slot] = clock64(); } while (0)
+  PSTAMP(0);
   const unsigned long long t_start = (blockIdx.x == 0 && threadIdx.x == 0) ? globaltimer_ns() : 0ull;
 
   if (threadIdx.x == 0) {
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
           atomicExch(&ctl->err, 2u);
           break;
         }
-        __nanosleep(32);
+        if (spins > 4096) __nanosleep(64);
       }
       ctl->decision_mask = mask;
       ctl->decision_count = count ? count : 1u;
@@ -133,7 +138,7 @@ __global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
       unsigned int spins = 0;
       while (ld_acquire_gpu_u64(&ctl->decision_seq) < seq) {
         if ((++spins & 0xFF) == 0 && (globaltimer_ns() - t0) > 2 * p.timeout_ns) break;
-        __nanosleep(32);
+        if (spins > 4096) __nanosleep(64);
       }
     }
     s_mask = ctl->decision_mask;
@@ -144,6 +149,7 @@ __global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
     s_lr = lr;
   }
   __syncthreads();
+  PSTAMP(1);          // decision known
   const unsigned int mask = s_mask;
   const float inv = 1.0f / (float)s_count;
   const float lr = s_lr;
@@ -215,9 +221,10 @@ __global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
   }
 
   // ---------------- completion: last block publishes the new step and releases the tokens ----------------
-  __threadfence_system();
   __syncthreads();
+  PSTAMP(2);          // block 0 finished its slice
   if (threadIdx.x == 0) {
+    if (p.system_scope) __threadfence_system(); else __threadfence();      // one fence per CTA, after the barrier
     const unsigned int prev = atomicAdd(&ctl->done_ctas, 1u);
     if (prev == gridDim.x - 1) {
       __threadfence();
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
           ctl->beta1_power *= p.beta1;
           ctl->beta2_power *= p.beta2;
         }
-        __threadfence_system();
+        if (p.system_scope) __threadfence_system(); else __threadfence();
         // tokens: every replica gets one carrying the NEW global step (sync); the pusher only (async)
         for (int w = 0; w < p.num_workers; ++w) {
           if (p.mailbox[w] == nullptr) continue;
@@ -256,7 +263,9 @@ __global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
       }
       __threadfence();
       st_release_gpu_u64(&ctl->param_version, s_seq);      // next launch's sequence number
+      if (tr) { tr[3] = clock64(); tr[4] = blockIdx.x; }    // last block done (its own SM clock)
     }
+    PSTAMP(5);
   }
 }
 
@@ -301,77 +310,222 @@ struct MlpHeadParams {
   PsControl* ctl;               // ps control block (peer)
   int rank;                     // worker index
   int stamp_from_version;       // async: stamp = mailbox->version, sync: stamp = mailbox->token
+  long long* phase_trace;       // optional [16] clock64 stamps
+  float* h_acc;                 // optional [B, ld_acc] fp32 split-K partial sums of x.W1 (then h/ldh are unused)
+  long long ld_acc;
+  const float* b1;              // hidden bias (used with h_acc)
+  int sys_scope;                // 1: ps is another GPU (system-scope fence before the arrival)
 };
 
 __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p) {
   extern __shared__ float sm[];
   const int B = p.B, H = p.H, C = p.C;
-  const int CP = 16;
-  float* s_h = sm;                          // [B][H+1]
-  float* s_w2 = s_h + (size_t)B * (H + 1);  // [H][CP]
-  float* s_dl = s_w2 + (size_t)H * CP;      // [B][CP]  logits -> dlogits
-  float* s_b2 = s_dl + (size_t)B * CP;      // [CP]
+  constexpr int CP = 16;                    // classes padded to 16 (4 x float4)
+  constexpr int DS = 20;                    // row stride of the [B][16] tiles: 80 B keeps float4 rows conflict-free
+  const int HP = H + 1;                     // padded activation row (bank-conflict-free column walks)
+  float* s_h = sm;                          // [B][H+1]   activations h (fp32)
+  float* s_w2 = s_h + (size_t)B * HP;       // [H][CP]
+  float* s_dl = s_w2 + (size_t)H * CP;      // [B][DS]    logits -> dlogits
+  float* s_lab = s_dl + (size_t)B * DS;     // [B][DS]    labels
+  float* s_b2 = s_lab + (size_t)B * DS;     // [CP]
   float* s_red = s_b2 + CP;                 // [32]
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31;
+  long long* tr = p.phase_trace;
+#define HSTAMP(slot) do { if (tr && tid == 0) tr[slot] = clock64(); } while (0)
+  HSTAMP(0);
 
-  for (int i = tid; i < B * H; i += nt) {
-    const int b = i / H, k = i - b * H;
-    s_h[b * (H + 1) + k] = __bfloat162float(p.h[(long long)b * p.ldh + k]);
-  }
-  for (int i = tid; i < H * CP; i += nt) {
-    const int k = i / CP, c = i - k * CP;
-    s_w2[i] = c < C ? __bfloat162float(p.w2[(long long)k * p.ldw2 + c]) : 0.f;
-  }
-  if (tid < CP) s_b2[tid] = tid < C ? p.b2[tid] : 0.f;
-  __syncthreads();
-
-  // logits
-  for (int i = tid; i < B * CP; i += nt) {
-    const int b = i / CP, c = i - b * CP;
-    float acc = 0.f;
-    if (c < C) {
-      const float* hr = s_h + b * (H + 1);
-      for (int k = 0; k < H; ++k) acc = fmaf(hr[k], s_w2[k * CP + c], acc);
-      acc += s_b2[c];
+  // ---- phase A: issue every global load up front (128-bit where possible), then fill shared memory ----------
+  {
+    const int wv = (int)(p.ldw2 / 8);                      // uint4 per row of w2 (ldw2 == 16 -> 2)
+    const int nwvec = H * wv;
+    uint4 wreg[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = tid + u * nt;
+      wreg[u] = (i < nwvec) ? reinterpret_cast<const uint4*>(p.w2)[i] : make_uint4(0, 0, 0, 0);
     }
-    s_dl[i] = acc;
-  }
-  __syncthreads();
-  if (p.logits_out)
-    for (int i = tid; i < B * C; i += nt) p.logits_out[i] = s_dl[(i / C) * CP + (i % C)];
-
-  // softmax + clipped xent + dlogits, one thread per row
-  float my_loss = 0.f;
-  if (tid < B) {
-    float* z = s_dl + tid * CP;
-    const float* lab = p.labels + (long long)tid * p.ldl;
-    float mx = -INFINITY;
-    for (int c = 0; c < C; ++c) mx = fmaxf(mx, z[c]);
-    float se = 0.f;
-    float y[16];
-    for (int c = 0; c < C; ++c) { y[c] = __expf(z[c] - mx); se += y[c]; }
-    const float inv = 1.f / se;
-    float tsum = 0.f;
-    for (int c = 0; c < C; ++c) {
-      y[c] *= inv;
-      const float l = lab[c];
-      if (p.clip_min > 0.f) {
-        my_loss -= l * __logf(fminf(fmaxf(y[c], p.clip_min), 1.f));
-        tsum += (y[c] >= p.clip_min) ? l : 0.f;
-      } else {
-        my_loss -= l * (z[c] - mx - __logf(se));
-        tsum += l;
+    float lreg[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = tid + u * nt;
+      lreg[u] = (i < B * C) ? p.labels[(long long)(i / C) * p.ldl + (i % C)] : 0.f;
+    }
+    const float b2v = (tid < C) ? p.b2[tid] : 0.f;
+    if (p.h_acc == nullptr) {
+      // h arrives as bf16 (bias + ReLU already applied by the GEMM epilogue)
+      const int hv = (int)(p.ldh / 8);
+      const int nvec = B * hv;
+      uint4 hreg[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = tid + u * nt;
+        hreg[u] = (i < nvec) ? reinterpret_cast<const uint4*>(p.h)[i] : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = tid + u * nt;
+        if (i < nvec) {
+          const int b = i / hv, k0 = (i - b * hv) * 8;
+          const uint32_t w[4] = {hreg[u].x, hreg[u].y, hreg[u].z, hreg[u].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = k0 + 2 * j;
+            if (k < H) s_h[b * HP + k] = __uint_as_float(w[j] << 16);
+            if (k + 1 < H) s_h[b * HP + k + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+          }
+        }
+      }
+    } else {
+      // h arrives as split-K fp32 partial sums (x.W1 without bias): finish it here -- h = relu(acc + b1) --
+      // and clear the accumulator for the next step (zero-after-read)
+      const int hv4 = (int)(p.ld_acc / 4);
+      const int nvec = B * hv4;
+      float4 areg[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = tid + u * nt;
+        areg[u] = (i < nvec) ? reinterpret_cast<const float4*>(p.h_acc)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float* s_b1 = s_h + (size_t)B * HP - 0;       // staged below through s_w2 region? no: use registers
+      (void)s_b1;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = tid + u * nt;
+        if (i < nvec) {
+          reinterpret_cast<float4*>(p.h_acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int b = i / hv4, k0 = (i - b * hv4) * 4;
+          const float v[4] = {areg[u].x, areg[u].y, areg[u].z, areg[u].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j;
+            if (k < H) s_h[b * HP + k] = fmaxf(v[j] + __ldg(p.b1 + k), 0.f);
+          }
+        }
       }
     }
-    for (int c = 0; c < C; ++c) {
-      const float t = (p.clip_min > 0.f && y[c] < p.clip_min) ? 0.f : lab[c];
-      z[c] = y[c] * tsum - t;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = tid + u * nt;
+      if (i < nwvec) {
+        const int k = i / wv, c0 = (i - k * wv) * 8;
+        const uint32_t w[4] = {wreg[u].x, wreg[u].y, wreg[u].z, wreg[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c0 + 2 * j;
+          if (c < CP) s_w2[k * CP + c] = (c < C) ? __uint_as_float(w[j] << 16) : 0.f;
+          if (c + 1 < CP) s_w2[k * CP + c + 1] = (c + 1 < C) ? __uint_as_float(w[j] & 0xFFFF0000u) : 0.f;
+        }
+      }
     }
-    for (int c = C; c < CP; ++c) z[c] = 0.f;
+    for (int i = tid; i < B * DS; i += nt) s_lab[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = tid + u * nt;
+      if (i < B * C) s_lab[(i / C) * DS + (i % C)] = lreg[u];
+    }
+    if (tid < CP) s_b2[tid] = b2v;
   }
-  // block-reduce the loss
+  __syncthreads();
+  HSTAMP(1);          // inputs in shared memory
+
+  // Register-blocked over the (<=16) classes; FOUR lanes cooperate on one row / one hidden unit (each takes every
+  // 4th element of the reduction) and combine with two warp shuffles: no shared-memory atomics, every operand is
+  // loaded once per 16 FMAs.  (v1 of this kernel was shared-memory-issue bound: mio_throttle 7.1, 16-way conflicts.)
+  // ---- logits[b][:] = h[b][:] . W2 + b2 ---------------------------------------------------------------------------
+  {
+    const int b = tid >> 2, q = tid & 3;
+    float acc[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) acc[c] = 0.f;
+    if (b < B) {
+      const float* hr = s_h + b * HP;
+      for (int k = q; k < H; k += 4) {
+        const float hv = hr[k];
+        const float4* wr = reinterpret_cast<const float4*>(s_w2 + k * CP);
+#pragma unroll
+        for (int j = 0; j < CP / 4; ++j) {
+          const float4 w = wr[j];
+          acc[4 * j] = fmaf(hv, w.x, acc[4 * j]);
+          acc[4 * j + 1] = fmaf(hv, w.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(hv, w.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(hv, w.w, acc[4 * j + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+    }
+    if (b < B && q == 0) {
+      float4* dst = reinterpret_cast<float4*>(s_dl + b * DS);
+#pragma unroll
+      for (int j = 0; j < CP / 4; ++j)
+        dst[j] = make_float4(acc[4 * j] + s_b2[4 * j], acc[4 * j + 1] + s_b2[4 * j + 1], acc[4 * j + 2] + s_b2[4 * j + 2],
+                             acc[4 * j + 3] + s_b2[4 * j + 3]);
+    }
+  }
+  __syncthreads();
+  HSTAMP(2);          // logits done
+  if (p.logits_out)
+    for (int i = tid; i < B * C; i += nt) p.logits_out[i] = s_dl[(i / C) * DS + (i % C)];
+
+  // ---- softmax + clipped xent + dlogits, one thread per row (rows read/written as float4) ---------------------------
+  float my_loss = 0.f;
+  if (tid < B) {
+    float z[CP], lab[CP];
+    float4* zr = reinterpret_cast<float4*>(s_dl + tid * DS);
+    const float4* lr = reinterpret_cast<const float4*>(s_lab + tid * DS);
+#pragma unroll
+    for (int j = 0; j < CP / 4; ++j) {
+      const float4 a = zr[j], l4 = lr[j];
+      z[4 * j] = a.x; z[4 * j + 1] = a.y; z[4 * j + 2] = a.z; z[4 * j + 3] = a.w;
+      lab[4 * j] = l4.x; lab[4 * j + 1] = l4.y; lab[4 * j + 2] = l4.z; lab[4 * j + 3] = l4.w;
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) if (c < C) mx = fmaxf(mx, z[c]);
+    float se = 0.f;
+    float y[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+      y[c] = (c < C) ? __expf(z[c] - mx) : 0.f;
+      se += y[c];
+    }
+    const float inv = 1.f / se;
+    const float lse = mx + __logf(se);
+    float tsum = 0.f;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+      if (c < C) {
+        y[c] *= inv;
+        const float l = lab[c];
+        if (p.clip_min > 0.f) {
+          // log(clamp(y, clip, 1)) == max(log y, log clip) for y <= 1: one exact log-softmax, no extra MUFU per class
+          my_loss -= l * fmaxf(z[c] - lse, __logf(p.clip_min));
+          tsum += (y[c] >= p.clip_min) ? l : 0.f;
+        } else {
+          my_loss -= l * (z[c] - lse);
+          tsum += l;
+        }
+      }
+    }
+    float g[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+      g[c] = 0.f;
+      if (c < C) {
+        const float t = (p.clip_min > 0.f && y[c] < p.clip_min) ? 0.f : lab[c];
+        g[c] = y[c] * tsum - t;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CP / 4; ++j) zr[j] = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+  }
   for (int o = 16; o > 0; o >>= 1) my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
-  if ((tid & 31) == 0) s_red[tid >> 5] = my_loss;
+  if (lane == 0) s_red[tid >> 5] = my_loss;
   __syncthreads();
   if (tid == 0) {
     float t = 0.f;
@@ -381,46 +535,83 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
     if (p.step_counter) { step = *p.step_counter; *p.step_counter = step + 1; }
     if (p.loss_hist && p.hist_cap > 0) p.loss_hist[step % (unsigned long long)p.hist_cap] = t;
   }
+  HSTAMP(3);          // softmax/xent/dlogits done
 
-  // dW2[k][c] = sum_b h[b][k] * dl[b][c]  -> ps slot (NVLink stores)
-  for (int i = tid; i < H * C; i += nt) {
-    const int k = i / C, c = i - k * C;
-    float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc = fmaf(s_h[b * (H + 1) + k], s_dl[b * CP + c], acc);
-    p.gw2[(long long)k * p.ldgw2 + c] = acc;
-  }
-  if (tid < C) {
-    float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc += s_dl[b * CP + tid];
-    p.gb2[tid] = acc;
-  }
-  // dh[b][k] = (h>0) * sum_c dl[b][c] * W2[k][c]   (bf16, local) ; keep fp32 copy in s_h for db1
-  for (int i = tid; i < B * H; i += nt) {
-    const int b = i / H, k = i - b * H;
-    float acc = 0.f;
-    if (s_h[b * (H + 1) + k] > 0.f) {
-      const float* dl = s_dl + b * CP;
-      const float* wr = s_w2 + k * CP;
+  // ---- hidden-unit-owned phases: L lanes per hidden unit k, lane q takes rows b = q, q+L, ... ----------------------
+  //   dW2[k][:] = sum_b h[b][k] * dl[b][:] ;  dh[b][k] = (h[b][k] > 0) * dl[b][:] . W2[k][:] ;  db1[k] = sum_b dh[b][k]
+  {
+    const int L = (H <= 128) ? 4 : 2;
+    const int k = tid / L, q = tid % L;
+    float w2r[CP], acc[CP];
 #pragma unroll
-      for (int c = 0; c < CP; ++c) acc = fmaf(dl[c], wr[c], acc);
+    for (int c = 0; c < CP; ++c) { acc[c] = 0.f; w2r[c] = 0.f; }
+    float db1 = 0.f;
+    if (k < H) {
+      const float4* wr = reinterpret_cast<const float4*>(s_w2 + k * CP);
+#pragma unroll
+      for (int j = 0; j < CP / 4; ++j) {
+        const float4 w = wr[j];
+        w2r[4 * j] = w.x; w2r[4 * j + 1] = w.y; w2r[4 * j + 2] = w.z; w2r[4 * j + 3] = w.w;
+      }
+      for (int b = q; b < B; b += L) {
+        const float hv = s_h[b * HP + k];
+        const float4* dr = reinterpret_cast<const float4*>(s_dl + b * DS);
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < CP / 4; ++j) {
+          const float4 dl = dr[j];
+          acc[4 * j] = fmaf(hv, dl.x, acc[4 * j]);
+          acc[4 * j + 1] = fmaf(hv, dl.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(hv, dl.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(hv, dl.w, acc[4 * j + 3]);
+          d0 = fmaf(dl.x, w2r[4 * j], d0);
+          d1 = fmaf(dl.y, w2r[4 * j + 1], d1);
+          d0 = fmaf(dl.z, w2r[4 * j + 2], d0);
+          d1 = fmaf(dl.w, w2r[4 * j + 3], d1);
+        }
+        const float d = hv > 0.f ? (d0 + d1) : 0.f;
+        p.dh[(long long)b * p.lddh + k] = __float2bfloat16(d);
+        db1 += d;
+      }
     }
-    p.dh[(long long)b * p.lddh + k] = __float2bfloat16(acc);
-    s_h[b * (H + 1) + k] = acc;          // each (b,k) is read and written by the same thread only
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+      if (L == 4) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+    }
+    db1 += __shfl_xor_sync(0xffffffffu, db1, 1);
+    if (L == 4) db1 += __shfl_xor_sync(0xffffffffu, db1, 2);
+    if (k < H && q == 0) {
+      // NVLink stores straight into the ps gradient slot
+      float* gw = p.gw2 + (long long)k * p.ldgw2;
+#pragma unroll
+      for (int c = 0; c < CP; ++c)
+        if (c < C) gw[c] = acc[c];
+      p.gb1[k] = db1;
+    }
   }
-  __syncthreads();
-  for (int k = tid; k < H; k += nt) {
-    float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc += s_h[b * (H + 1) + k];
-    p.gb1[k] = acc;
+  if (tid >= nt - 32 && tid - (nt - 32) < C) {
+    const int c = tid - (nt - 32);
+    float a0 = 0.f, a1 = 0.f;
+    int b = 0;
+    for (; b + 2 <= B; b += 2) { a0 += s_dl[b * DS + c]; a1 += s_dl[(b + 1) * DS + c]; }
+    if (b < B) a0 += s_dl[b * DS + c];
+    p.gb2[c] = a0 + a1;
   }
-  // stamp + arrival: everything this CTA pushed must be visible at the ps before the counter moves
-  __threadfence_system();
-  __syncthreads();
-  if (tid == 0 && p.ctl != nullptr) {
-    const unsigned long long stamp = p.stamp_from_version ? p.mailbox->version : p.mailbox->token;
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&p.ctl->w[p.rank].stamp), "l"(stamp) : "memory");
-    red_release_sys_add_u64(reinterpret_cast<uint64_t*>(&p.ctl->w[p.rank].arrivals), 1ull);
+  HSTAMP(4);          // dW2/dh/db1 done and stored
+  // ---- stamp + arrival (optional: a later kernel of the same step may signal for the whole push instead) --------
+  if (p.ctl != nullptr) {
+    __syncthreads();
+    if (tid == 0) {
+      // ONE fence by one thread after the CTA barrier: release is cumulative, and a system-scope membar per
+      // thread serialises for tens of microseconds
+      if (p.sys_scope) __threadfence_system(); else __threadfence();
+      const unsigned long long stamp = p.stamp_from_version ? p.mailbox->version : p.mailbox->token;
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&p.ctl->w[p.rank].stamp), "l"(stamp) : "memory");
+      red_release_sys_add_u64(reinterpret_cast<uint64_t*>(&p.ctl->w[p.rank].arrivals), 1ull);
+    }
   }
+  HSTAMP(6);          // fenced + signalled
 }
 
 // Input-pipeline stage for the device-resident dataset: batch index = (step * stride + offset) % nbatches,
@@ -466,9 +657,9 @@ __global__ void push_grad_kernel(const float* __restrict__ src, float* __restric
     reinterpret_cast<float4*>(dst_peer)[i] = reinterpret_cast<const float4*>(src)[i];
   if (blockIdx.x == 0)
     for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) dst_peer[i] = src[i];
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     if (write_stamp && blockIdx.x == 0) {
       const unsigned long long stamp = stamp_from_version ? mb->version : mb->token;
       asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&ctl->w[rank].stamp), "l"(stamp) : "memory");
@@ -530,6 +721,8 @@ struct DtfPsApplyArgs {
   unsigned long long* trace;
   int trace_cap;
   int grid;
+  int system_scope;
+  long long* phase_trace;
 };
 
 int dtf_ps_apply(const DtfPsApplyArgs* a, cudaStream_t s) {
@@ -546,14 +739,14 @@ int dtf_ps_apply(const DtfPsApplyArgs* a, cudaStream_t s) {
   p.n = a->n; p.num_workers = a->num_workers; p.replicas_to_aggregate = a->replicas_to_aggregate;
   p.ctas_per_push = a->ctas_per_push; p.mode = a->mode; p.kind = a->kind;
   p.lr = a->lr; p.momentum = a->momentum; p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps;
-  p.nesterov = a->nesterov; p.publish_replicas = a->publish_replicas;
+  p.nesterov = a->nesterov; p.publish_replicas = a->publish_replicas; p.system_scope = a->system_scope;
   for (int z = 0; z < 4; ++z) { p.zero_begin[z] = a->zero_begin[z]; p.zero_end[z] = a->zero_end[z]; }
   p.num_zero = a->num_zero;
   p.timeout_ns = a->timeout_ns ? a->timeout_ns : 2000000000ull;
-  p.trace = a->trace; p.trace_cap = a->trace_cap;
+  p.trace = a->trace; p.trace_cap = a->trace_cap; p.phase_trace = a->phase_trace;
   int grid = a->grid;
   if (grid <= 0) {
-    long long want = (a->n / 4 + 255) / 256;
+    long long want = (a->n / 4 + 255) / 256;                       // one float4 per thread: a single load round trip
     grid = (int)(want < 1 ? 1 : (want > 148 ? 148 : want));      // all CTAs must be co-resident
   }
   ps_apply_kernel<<<grid, 256, 0, s>>>(p);
@@ -581,6 +774,8 @@ struct DtfMlpHeadArgs {
   float* logits_out;
   const void* mailbox; void* ctl;
   int rank; int stamp_from_version;
+  long long* phase_trace;
+  float* h_acc; long long ld_acc; const float* b1; int sys_scope;
 };
 
 int dtf_mlp_head(const DtfMlpHeadArgs* a, cudaStream_t s) {
@@ -593,8 +788,11 @@ int dtf_mlp_head(const DtfMlpHeadArgs* a, cudaStream_t s) {
   p.dh = reinterpret_cast<__nv_bfloat16*>(a->dh); p.lddh = a->lddh;
   p.gw2 = a->gw2; p.ldgw2 = a->ldgw2; p.gb2 = a->gb2; p.gb1 = a->gb1; p.logits_out = a->logits_out;
   p.mailbox = reinterpret_cast<const WorkerMailbox*>(a->mailbox); p.ctl = reinterpret_cast<PsControl*>(a->ctl);
-  p.rank = a->rank; p.stamp_from_version = a->stamp_from_version;
-  const size_t smem = sizeof(float) * ((size_t)a->B * (a->H + 1) + (size_t)a->H * 16 + (size_t)a->B * 16 + 16 + 32);
+  p.rank = a->rank; p.stamp_from_version = a->stamp_from_version; p.phase_trace = a->phase_trace;
+  p.h_acc = a->h_acc; p.ld_acc = a->ld_acc; p.b1 = a->b1; p.sys_scope = a->sys_scope;
+  const size_t smem = sizeof(float) * ((size_t)a->B * (a->H + 1) + (size_t)a->H * 16 + (size_t)a->B * 40 + 16 + 32);
+  if (a->B > 512 || a->H > 512) return -2;
+  if ((a->ldh % 8) || (a->ldw2 % 8) || a->ldh > 8 * 8 * 512 / a->B) return -3;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(mlp_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -1,0 +1,122 @@
+// Tensor-bundle data file writer/reader: positional I/O of many tensors into one
+// `<prefix>.data-00000-of-00001` file, 64-byte aligned, parallelised over a small thread pool, plus CRC32.
+// The JSON index is written by Python (train/saver.py); this is the bulk-bytes path (TF: SaveV2/RestoreV2).
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <cerrno>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+namespace {
+
+uint32_t crc_table[256];
+std::atomic<bool> crc_ready{false};
+
+void crc_init() {
+  if (crc_ready.load()) return;
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c & 1) ? (0xEDB88320u ^ (c >> 1)) : (c >> 1);
+    crc_table[i] = c;
+  }
+  crc_ready.store(true);
+}
+
+int pwrite_all(int fd, const uint8_t* p, int64_t n, int64_t off) {
+  while (n > 0) {
+    ssize_t w = pwrite(fd, p, (size_t)n, (off_t)off);
+    if (w < 0) {
+      if (errno == EINTR) continue;
+      return -errno;
+    }
+    p += w; n -= w; off += w;
+  }
+  return 0;
+}
+
+int pread_all(int fd, uint8_t* p, int64_t n, int64_t off) {
+  while (n > 0) {
+    ssize_t r = pread(fd, p, (size_t)n, (off_t)off);
+    if (r < 0) {
+      if (errno == EINTR) continue;
+      return -errno;
+    }
+    if (r == 0) return -EIO;      // truncated file
+    p += r; n -= r; off += r;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t dtf_crc32(const void* data, int64_t n) {
+  crc_init();
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = 0xFFFFFFFFu;
+  for (int64_t i = 0; i < n; ++i) c = crc_table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
+
+// Write `count` blobs at the given offsets; file is truncated to total_bytes and fsync'ed.  0 on success.
+int dtf_bundle_write(const char* path, int count, const void* const* ptrs, const int64_t* sizes, const int64_t* offsets,
+                     int64_t total_bytes, int threads) {
+  int fd = open(path, O_CREAT | O_TRUNC | O_WRONLY, 0644);
+  if (fd < 0) return -errno;
+  if (ftruncate(fd, (off_t)total_bytes) != 0) {
+    int e = -errno;
+    close(fd);
+    return e;
+  }
+  std::atomic<int> next{0}, err{0};
+  auto work = [&] {
+    for (;;) {
+      int i = next.fetch_add(1);
+      if (i >= count) return;
+      int rc = pwrite_all(fd, static_cast<const uint8_t*>(ptrs[i]), sizes[i], offsets[i]);
+      if (rc) err.store(rc);
+    }
+  };
+  if (threads < 1) threads = 1;
+  if (threads > count) threads = count > 0 ? count : 1;
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+  int rc = err.load();
+  if (!rc && fsync(fd) != 0) rc = -errno;
+  close(fd);
+  return rc;
+}
+
+// Read `count` regions into caller-provided buffers.  0 on success, -EIO on truncation.
+int dtf_bundle_read(const char* path, int count, void* const* ptrs, const int64_t* sizes, const int64_t* offsets,
+                    int threads) {
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) return -errno;
+  std::atomic<int> next{0}, err{0};
+  auto work = [&] {
+    for (;;) {
+      int i = next.fetch_add(1);
+      if (i >= count) return;
+      int rc = pread_all(fd, static_cast<uint8_t*>(ptrs[i]), sizes[i], offsets[i]);
+      if (rc) err.store(rc);
+    }
+  };
+  if (threads < 1) threads = 1;
+  if (threads > count) threads = count > 0 ? count : 1;
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+  close(fd);
+  return err.load();
+}
+
+}  // extern "C"

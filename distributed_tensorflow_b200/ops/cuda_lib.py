@@ -36,7 +36,8 @@ class GemmArgs(Structure):
                 ("colsum", c_void_p),
                 ("wait_flag", c_void_p), ("wait_target", c_ulonglong),
                 ("signal", c_void_p), ("err", c_void_p), ("timeout_ns", c_ulonglong),
-                ("block_n_override", c_int), ("wait_target_ptr", c_void_p)]
+                ("block_n_override", c_int), ("wait_target_ptr", c_void_p), ("phase_trace", c_void_p),
+                ("signal_gpu_scope", c_int), ("stamp_src", c_void_p), ("stamp_dst", c_void_p)]
 
 
 class PsApplyArgs(Structure):
@@ -48,7 +49,8 @@ class PsApplyArgs(Structure):
                 ("lr", c_float), ("momentum", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
                 ("nesterov", c_int), ("publish_replicas", c_int),
                 ("zero_begin", c_longlong * 4), ("zero_end", c_longlong * 4), ("num_zero", c_int),
-                ("timeout_ns", c_ulonglong), ("trace", c_void_p), ("trace_cap", c_int), ("grid", c_int)]
+                ("timeout_ns", c_ulonglong), ("trace", c_void_p), ("trace_cap", c_int), ("grid", c_int),
+                ("system_scope", c_int), ("phase_trace", c_void_p)]
 
 
 class MlpHeadArgs(Structure):
@@ -58,7 +60,9 @@ class MlpHeadArgs(Structure):
                 ("loss_out", c_void_p), ("loss_hist", c_void_p), ("step_counter", c_void_p), ("hist_cap", c_int),
                 ("dh", c_void_p), ("lddh", c_longlong), ("gw2", c_void_p), ("ldgw2", c_longlong),
                 ("gb2", c_void_p), ("gb1", c_void_p), ("logits_out", c_void_p),
-                ("mailbox", c_void_p), ("ctl", c_void_p), ("rank", c_int), ("stamp_from_version", c_int)]
+                ("mailbox", c_void_p), ("ctl", c_void_p), ("rank", c_int), ("stamp_from_version", c_int),
+                ("phase_trace", c_void_p), ("h_acc", c_void_p), ("ld_acc", c_longlong), ("b1", c_void_p),
+                ("sys_scope", c_int)]
 
 
 def available() -> bool:

@@ -143,7 +143,7 @@ class PSTrainEngine:
         lw = self.layout
         self.m_tiles_w1 = (spec.in_dim + 127) // 128
         self.ctas_per_push = [0] * cfg.num_ps
-        head_shards = {lw["sm_w"].shard, lw["sm_b"].shard, lw["hid_b"].shard}
+        head_shards = {lw["sm_w"].shard, lw["sm_b"].shard, lw["hid_b"].shard} - {lw["hid_w"].shard}
         for s in head_shards:
             self.ctas_per_push[s] += 1
         bn = 64 if spec.hidden <= 64 else (128 if spec.hidden <= 128 else (192 if spec.hidden <= 192 else 256))
@@ -317,6 +317,7 @@ class PSTrainEngine:
             d: Dict[str, Any] = {"ldh": ldh, "loss_ptr": misc.ptr, "stepctr_ptr": misc.ptr + 8, "err_ptr": misc.ptr + 16,
                                  "hist_ptr": misc.ptr + 4096}
             mb = rk.bufs["mailbox_w%d" % w]
+            d["mb0"] = mb.ptr
 
             def src(base: str, l: VarLayout, es: int) -> int:
                 if cfg.publish_replicas and base == "shadow":
@@ -356,8 +357,11 @@ class PSTrainEngine:
             hd.gb2, hd.gb1 = slot(lay["sm_b"]), slot(lay["hid_b"])
             hd.mailbox = mb.ptr
             hd.rank, hd.stamp_from_version = w, 0 if cfg.sync else 1
+            hd.sys_scope = 0 if cfg.colocated else 1
             d["head"] = hd
-            head_shards = sorted({lay["sm_w"].shard, lay["sm_b"].shard, lay["hid_b"].shard})
+            # Shards the head pushes to.  The dW1 GEMM (same stream, later) signals the shard that owns hid_w
+            # on behalf of the whole push: kernel-boundary ordering makes the head's stores visible first.
+            head_shards = sorted({lay["sm_w"].shard, lay["sm_b"].shard, lay["hid_b"].shard} - {lay["hid_w"].shard})
             d["head_ctls"] = [self.peer[(r, "ctl%d" % s)].ptr for s in head_shards]
             d["head_mailboxes"] = [mb.ptr + s * self.mb_bytes for s in head_shards]
             # ---- B3: dW1 = x^T . dh pushed into the ps slot ------------------------------------------
@@ -369,6 +373,10 @@ class PSTrainEngine:
             g3.a_mn, g3.b_mn = 1, 1
             g3.alpha, g3.splits = 1.0, 1
             g3.signal = ctl_arrivals(lay["hid_w"].shard)
+            g3.signal_gpu_scope = 1 if cfg.colocated else 0
+            # the GEMM's first CTA also publishes the stamp (local_step / pulled version) for this push
+            g3.stamp_src = mb.ptr + lay["hid_w"].shard * self.mb_bytes + (0 if cfg.sync else 8)
+            g3.stamp_dst = ctl_arrivals(lay["hid_w"].shard) + 8
             g3.block_n_override = self.block_n_w1
             d["g3"] = g3
             d["extra_wait_shards"] = [s for s in range(cfg.num_ps) if s != lay["hid_w"].shard]
@@ -401,6 +409,7 @@ class PSTrainEngine:
             a.timeout_ns = cfg.timeout_ns
             a.trace, a.trace_cap = rk.bufs["trace%d" % s].ptr, cfg.trace_cap
             a.grid = 0
+            a.system_scope = 0 if cfg.colocated else 1
             self._p[r] = a
 
     # ------------------------------------------------------------------------------------------------
@@ -409,8 +418,8 @@ class PSTrainEngine:
     def launches_per_worker_step(self, source: str = "staged") -> int:
         any_w = next(iter(self._w.values()), None)
         extra = len(any_w["extra_wait_shards"]) if any_w else 0
-        nhead = len(any_w["head_ctls"]) if any_w else 1
-        return 3 + extra + (nhead - 1) + (1 if source == "dataset" else 0)
+        nhead = len(any_w["head_ctls"]) if any_w else 0
+        return 3 + extra + max(nhead - 1, 0) + (1 if source == "dataset" else 0)
 
     def attach_dataset(self, rank: int, images, labels) -> None:
         """Stage a whole split in this worker's HBM (fp32 images [N, in_dim], one-hot labels [N, classes]).
@@ -434,12 +443,15 @@ class PSTrainEngine:
         w = self.worker_ranks.index(rank)
         n = 0
         with torch.cuda.device(rk.device):
-            if source == "dataset":
-                rc = lib.dtf_stage_from_dataset(d["ds_images"].data_ptr(), d["ds_labels"].data_ptr(), d["ds_nbatches"],
-                                                self.spec.batch, self.spec.in_dim, self.spec.classes,
-                                                self.cfg.num_workers, w, d["stepctr_ptr"],
-                                                rk.bufs["x16_w%d" % w].ptr, rk.bufs["labels_w%d" % w].ptr, st)
-                assert rc == 0, "stage_from_dataset rc=%d" % rc
+            def stage_next():
+                rc_ = lib.dtf_stage_from_dataset(d["ds_images"].data_ptr(), d["ds_labels"].data_ptr(), d["ds_nbatches"],
+                                                 self.spec.batch, self.spec.in_dim, self.spec.classes,
+                                                 self.cfg.num_workers, w, d["stepctr_ptr"],
+                                                 rk.bufs["x16_w%d" % w].ptr, rk.bufs["labels_w%d" % w].ptr, st)
+                assert rc_ == 0, "stage_from_dataset rc=%d" % rc_
+            if source == "dataset" and not d.get("primed"):
+                stage_next()             # first batch; afterwards each step stages its successor's batch at its END,
+                d["primed"] = True       # i.e. while the ps is aggregating (the worker would otherwise just wait)
                 n += 1
             for s in d["extra_wait_shards"]:
                 rc = lib.dtf_wait_token(rk.bufs["mailbox_w%d" % w].ptr + s * self.mb_bytes, 0, d["stepctr_ptr"],
@@ -450,8 +462,12 @@ class PSTrainEngine:
             g1.wait_target, g1.wait_target_ptr = 0, d["stepctr_ptr"]
             rc = lib.dtf_gemm_bf16(ctypes.byref(g1), st)
             assert rc == 0, "F1 gemm rc=%d" % rc
-            # the head signals the first shard it pushed to; further shards get a signal-only launch
-            hd.ctl, hd.mailbox = d["head_ctls"][0], d["head_mailboxes"][0]
+            # the head signals the first shard it ALONE pushed to (if any); further such shards get a
+            # signal-only launch; the shard owning hid_w is signalled by the dW1 GEMM for the whole push
+            if d["head_ctls"]:
+                hd.ctl, hd.mailbox = d["head_ctls"][0], d["head_mailboxes"][0]
+            else:
+                hd.ctl, hd.mailbox = None, d["mb0"]
             rc = lib.dtf_mlp_head(ctypes.byref(hd), st)
             assert rc == 0, "mlp_head rc=%d" % rc
             n += 2
@@ -462,6 +478,9 @@ class PSTrainEngine:
             rc = lib.dtf_gemm_bf16(ctypes.byref(g3), st)
             assert rc == 0, "B3 gemm rc=%d" % rc
             n += 1
+            if source == "dataset":
+                stage_next()             # reads the step counter the head just advanced -> batch of step t+1
+                n += 1
         cuda_lib._bump(n)
         rk.step += 1
         self._last_step_launches = n

@@ -1,0 +1,202 @@
+"""ctypes bindings for ``libdtf_runtime.so`` (native accumulator / token queue / bundle I/O / tracer)."""
+from __future__ import annotations
+
+import ctypes
+import threading
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint32, c_void_p
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from ..framework import errors
+
+_OK, _CANCELLED, _DEADLINE, _CLOSED, _BAD = 0, 1, 2, 3, 4
+
+
+def declare(lib: ctypes.CDLL) -> None:
+    lib.dtf_acc_create.restype = c_void_p
+    lib.dtf_acc_destroy.argtypes = [c_void_p]
+    lib.dtf_acc_apply_grad.argtypes = [c_void_p, c_void_p, c_int64, c_int64]
+    lib.dtf_acc_apply_grad.restype = c_int
+    lib.dtf_acc_take_grad.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_double]
+    lib.dtf_acc_take_grad.restype = c_int
+    lib.dtf_acc_wait_count.argtypes = [c_void_p, c_int64, c_void_p, c_double]
+    lib.dtf_acc_wait_count.restype = c_int
+    for n in ("dtf_acc_size", "dtf_acc_num_accumulated", "dtf_acc_global_step", "dtf_acc_dropped"):
+        getattr(lib, n).argtypes = [c_void_p]
+        getattr(lib, n).restype = c_int64
+    lib.dtf_acc_set_global_step.argtypes = [c_void_p, c_int64]
+    lib.dtf_acc_close.argtypes = [c_void_p]
+    lib.dtf_queue_create.restype = c_void_p
+    lib.dtf_queue_destroy.argtypes = [c_void_p]
+    lib.dtf_queue_enqueue_many.argtypes = [c_void_p, c_int64, c_int64]
+    lib.dtf_queue_enqueue_many.restype = c_int
+    lib.dtf_queue_enqueue_values.argtypes = [c_void_p, c_void_p, c_int64]
+    lib.dtf_queue_enqueue_values.restype = c_int
+    lib.dtf_queue_dequeue.argtypes = [c_void_p, POINTER(c_int64), c_void_p, c_double]
+    lib.dtf_queue_dequeue.restype = c_int
+    lib.dtf_queue_size.argtypes = [c_void_p]
+    lib.dtf_queue_size.restype = c_int64
+    lib.dtf_queue_close.argtypes = [c_void_p]
+    lib.dtf_crc32.argtypes = [c_void_p, c_int64]
+    lib.dtf_crc32.restype = c_uint32
+    lib.dtf_bundle_write.argtypes = [c_char_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int]
+    lib.dtf_bundle_write.restype = c_int
+    lib.dtf_bundle_read.argtypes = [c_char_p, c_int, c_void_p, c_void_p, c_void_p, c_int]
+    lib.dtf_bundle_read.restype = c_int
+    lib.dtf_tracer_create.argtypes = [c_int64]
+    lib.dtf_tracer_create.restype = c_void_p
+    lib.dtf_tracer_destroy.argtypes = [c_void_p]
+    lib.dtf_tracer_now_ns.restype = c_int64
+    lib.dtf_tracer_record.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32]
+    lib.dtf_tracer_drain.argtypes = [c_void_p, c_void_p, c_int64]
+    lib.dtf_tracer_drain.restype = c_int64
+
+
+class _CancelFlag:
+    """Bridges a ``threading.Event`` to the int32 the native wait loops poll."""
+
+    def __init__(self, event: Optional[threading.Event]):
+        self.event = event
+        self.flag = c_int32(0)
+        self._stop = False
+        if event is not None:
+            if event.is_set():
+                self.flag.value = 1
+            else:
+                self._t = threading.Thread(target=self._watch, daemon=True)
+                self._t.start()
+
+    def _watch(self):
+        while not self._stop:
+            if self.event.wait(0.05):
+                self.flag.value = 1
+                return
+
+    def ptr(self):
+        return ctypes.byref(self.flag) if self.event is not None else None
+
+    def done(self):
+        self._stop = True
+
+
+def _raise(rc: int, what: str):
+    if rc == _CANCELLED:
+        raise errors.CancelledError("%s cancelled" % what)
+    if rc == _DEADLINE:
+        raise errors.DeadlineExceededError("%s timed out" % what)
+    if rc == _CLOSED:
+        raise errors.CancelledError("%s: resource closed" % what)
+    raise errors.OpError("%s failed (code %d)" % (what, rc))
+
+
+class NativeAccumulator:
+    def __init__(self, lib: ctypes.CDLL, name: str = "accumulator"):
+        self._lib, self.name = lib, name
+        self._h = lib.dtf_acc_create()
+        self._shape, self._dtype, self._device = None, torch.float32, torch.device("cpu")
+
+    def apply_grad(self, grad: torch.Tensor, local_step: int) -> bool:
+        self._shape, self._device = tuple(grad.shape), grad.device
+        g = grad.detach().to(device="cpu", dtype=torch.float32).contiguous()
+        rc = self._lib.dtf_acc_apply_grad(self._h, g.data_ptr(), g.numel(), int(local_step))
+        if rc < 0:
+            raise errors.InvalidArgumentError("accumulator %s: gradient shape changed" % self.name)
+        return rc == 1
+
+    def take_grad(self, num_required: int, cancel: Optional[threading.Event] = None,
+                  timeout: Optional[float] = None) -> torch.Tensor:
+        cf = _CancelFlag(cancel)
+        try:
+            rc = self._lib.dtf_acc_wait_count(self._h, int(num_required), cf.ptr(), -1.0 if timeout is None else timeout)
+            if rc != _OK:
+                _raise(rc, "take_grad on %s" % self.name)
+            n = self._lib.dtf_acc_size(self._h)
+            out = torch.empty(n, dtype=torch.float32)
+            rc = self._lib.dtf_acc_take_grad(self._h, int(num_required), out.data_ptr(), n, cf.ptr(), 0.0)
+            if rc != _OK:
+                _raise(rc, "take_grad on %s" % self.name)
+        finally:
+            cf.done()
+        if self._shape is not None:
+            out = out.reshape(self._shape)
+        return out.to(self._device) if self._device.type != "cpu" else out
+
+    def set_global_step(self, s: int) -> None:
+        self._lib.dtf_acc_set_global_step(self._h, int(s))
+
+    def num_accumulated(self) -> int:
+        return int(self._lib.dtf_acc_num_accumulated(self._h))
+
+    @property
+    def global_step(self) -> int:
+        return int(self._lib.dtf_acc_global_step(self._h))
+
+    @property
+    def num_dropped(self) -> int:
+        return int(self._lib.dtf_acc_dropped(self._h))
+
+    def close(self) -> None:
+        self._lib.dtf_acc_close(self._h)
+
+    def __del__(self):
+        try:
+            self._lib.dtf_acc_destroy(self._h)
+        except Exception:
+            pass
+
+
+class NativeQueue:
+    def __init__(self, lib: ctypes.CDLL, name: str = "fifo_queue"):
+        self._lib, self.name = lib, name
+        self._h = lib.dtf_queue_create()
+
+    def enqueue(self, value: int) -> None:
+        self.enqueue_many([value])
+
+    def enqueue_many(self, values: Sequence[int]) -> None:
+        arr = np.asarray([int(v) for v in values], dtype=np.int64)
+        rc = self._lib.dtf_queue_enqueue_values(self._h, arr.ctypes.data, arr.size)
+        if rc != _OK:
+            raise errors.CancelledError("queue %s is closed" % self.name)
+
+    def dequeue(self, cancel: Optional[threading.Event] = None, timeout: Optional[float] = None) -> int:
+        out = c_int64(0)
+        cf = _CancelFlag(cancel)
+        try:
+            rc = self._lib.dtf_queue_dequeue(self._h, ctypes.byref(out), cf.ptr(), -1.0 if timeout is None else timeout)
+        finally:
+            cf.done()
+        if rc == _CLOSED:
+            raise errors.OutOfRangeError("queue %s is closed and empty" % self.name)
+        if rc != _OK:
+            _raise(rc, "dequeue on %s" % self.name)
+        return int(out.value)
+
+    def size(self) -> int:
+        return int(self._lib.dtf_queue_size(self._h))
+
+    def close(self, cancel_pending_enqueues: bool = False) -> None:
+        self._lib.dtf_queue_close(self._h)
+
+    def __del__(self):
+        try:
+            self._lib.dtf_queue_destroy(self._h)
+        except Exception:
+            pass
+
+
+def bundle_write(lib: ctypes.CDLL, path: str, blobs: List[Tuple[int, bytes]], total_bytes: int, threads: int = 4) -> None:
+    n = len(blobs)
+    bufs = [ctypes.create_string_buffer(b, len(b)) if len(b) else ctypes.create_string_buffer(1) for _, b in blobs]
+    ptrs = (c_void_p * max(n, 1))(*[ctypes.addressof(b) for b in bufs])
+    sizes = (c_int64 * max(n, 1))(*[len(b) for _, b in blobs])
+    offs = (c_int64 * max(n, 1))(*[o for o, _ in blobs])
+    rc = lib.dtf_bundle_write(path.encode(), n, ptrs, sizes, offs, total_bytes, threads)
+    if rc:
+        raise OSError(-rc, "bundle write failed for %s" % path)
+
+
+def crc32(lib: ctypes.CDLL, data: bytes) -> int:
+    return int(lib.dtf_crc32(data, len(data)))

@@ -79,11 +79,12 @@ def test_gemm_wait_flag_already_satisfied_and_timeout_sets_err(lib):
     c = torch.empty(64, 64, device="cuda")
     flag = torch.tensor([5], dtype=torch.int64, device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
-    lib.gemm_raw(a16, lda, b16, ldb, c, 64, 64, 64, 64, False, True, wait_flag=flag.data_ptr(), wait_target=5,
+    # b is [N, K] row-major == K-major B operand (b_mn=False)
+    lib.gemm_raw(a16, lda, b16, ldb, c, 64, 64, 64, 64, False, False, wait_flag=flag.data_ptr(), wait_target=5,
                  err=err.data_ptr())
     torch.testing.assert_close(c, _ref_mm(a, b, False, True), rtol=2e-4, atol=2e-3)
     assert int(err.item()) == 0
-    lib.gemm_raw(a16, lda, b16, ldb, c, 64, 64, 64, 64, False, True, wait_flag=flag.data_ptr(), wait_target=6,
+    lib.gemm_raw(a16, lda, b16, ldb, c, 64, 64, 64, 64, False, False, wait_flag=flag.data_ptr(), wait_target=6,
                  err=err.data_ptr(), timeout_ns=20_000_000)
     torch.cuda.synchronize()
     assert int(err.item()) == 1                      # bounded wait, no hang

@@ -1,0 +1,105 @@
+"""Multi-GPU correctness check of the fabric PS engine (run under torchrun, one rank per GPU):
+sync (mean of N worker gradients per step, tokens) and async (every push applied, staleness counted)
+against a CPU oracle that replays the same batches.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/mp_check.py
+"""
+import json
+import math
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from distributed_tensorflow_b200.parallel.fabric import Fabric  # noqa: E402
+from distributed_tensorflow_b200.parallel.ps_engine import EngineConfig, MLPSpec, PSTrainEngine  # noqa: E402
+from distributed_tensorflow_b200.utils.mnist_data import synthetic_mnist  # noqa: E402
+
+
+def grads(p, x, y):
+    r = lambda v: v.bfloat16().float()
+    h = torch.relu(r(x) @ r(p["hid_w"]) + p["hid_b"])
+    h16 = r(h)
+    logits = h16 @ r(p["sm_w"]) + p["sm_b"]
+    prob = torch.softmax(logits, -1)
+    loss = -(y * torch.log(torch.clamp(prob, 1e-10, 1.0))).sum()
+    dl = prob - y
+    dhf = (dl @ r(p["sm_w"]).t()) * (h16 > 0)
+    return {"sm_w": h16.t() @ dl, "sm_b": dl.sum(0), "hid_b": dhf.sum(0), "hid_w": r(x).t() @ r(dhf)}, float(loss)
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    num_ps = int(os.environ.get("DTF_NUM_PS", "1"))
+    W = world - num_ps
+    xs, ys = synthetic_mnist(100 * W * 8, seed=11)
+    report = {}
+    for mode in ("sync", "async"):
+        cfg = EngineConfig(num_ps=num_ps, num_workers=W, sync=(mode == "sync"), optimizer={"kind": "sgd", "lr": 0.001},
+                           seed=2)
+        eng = PSTrainEngine(MLPSpec(), cfg, Fabric.from_torch_distributed())
+        eng.init_params()
+        p0 = None
+        if rank < num_ps:
+            p0 = eng.state_dict()
+        for r in eng.ranks:
+            if r in eng.worker_ranks:
+                eng.attach_dataset(r, xs, ys)
+        steps = 6
+        eng.enqueue_local_steps(steps, "dataset")
+        eng.synchronize()
+        dist.barrier()
+        eng.check_errors()
+        sd = eng.state_dict() if rank < num_ps else {}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {k: v for k, v in sd.items()})
+        p0s = [None] * world
+        dist.all_gather_object(p0s, p0)
+        loss = eng.read_loss() if rank >= num_ps else None
+        if rank == 0:
+            final = {}
+            for g in gathered[:num_ps]:
+                final.update(g)
+            init = {}
+            for g in p0s[:num_ps]:
+                init.update({k: v for k, v in g.items() if k in ("hid_w", "hid_b", "sm_w", "sm_b")})
+            nb = xs.shape[0] // 100
+            if mode == "sync":
+                p = {k: v.clone() for k, v in init.items()}
+                for t in range(steps):
+                    acc = None
+                    for w in range(W):
+                        b = (t * W + w) % nb
+                        g, _ = grads(p, torch.from_numpy(xs[b * 100:(b + 1) * 100]), torch.from_numpy(ys[b * 100:(b + 1) * 100]))
+                        acc = g if acc is None else {k: acc[k] + g[k] for k in g}
+                    for k in p:
+                        p[k] = p[k] - 0.001 * acc[k] / W
+                err = max(float((final[k] - p[k]).abs().max() / (p[k].abs().max() + 1e-6)) for k in p)
+                report[mode] = {"global_step": int(final["global_step"]), "max_rel_err_vs_oracle": err,
+                                "ok": int(final["global_step"]) == steps and err < 3e-2}
+            else:
+                st = eng.staleness()
+                moved = max(float((final[k] - init[k]).abs().max()) for k in init)
+                report[mode] = {"global_step": int(final["global_step"]), "staleness": st, "moved": moved,
+                                "ok": int(final["global_step"]) == steps * W and st["count"] == steps * W and moved > 0}
+        dist.barrier()
+        eng.close()
+        dist.barrier()
+    if rank == 0:
+        report["world"] = world
+        report["num_ps"] = num_ps
+        print("MP_CHECK " + json.dumps(report))
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "mp_check_%d.json" % world), "w") as f:
+            json.dump(report, f, indent=1)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
