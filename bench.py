@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=-1, help="-1: min(steps, 1000); 0: skip")
     ap.add_argument("--publish", action="store_true", help="ps stores params into worker replicas (push-publish)")
     ap.add_argument("--num-train", type=int, default=55000)
+    ap.add_argument("--f1-splits", type=int, default=1, help="split-K CTAs for the first GEMM")
     return ap.parse_args()
 
 
@@ -147,11 +148,11 @@ def main():
     opt = {"kind": args.optimizer, "lr": args.lr, "momentum": 0.9}
     if N == 1:
         cfg = EngineConfig(num_ps=1, num_workers=1, colocated=True, sync=args.mode == "sync", optimizer=opt,
-                           publish_replicas=args.publish)
+                           publish_replicas=args.publish, f1_splits=args.f1_splits)
         fabric = Fabric(1, {0: local_rank})
     else:
         cfg = EngineConfig(num_ps=1, num_workers=N - 1, sync=args.mode == "sync", optimizer=opt,
-                           publish_replicas=args.publish)
+                           publish_replicas=args.publish, f1_splits=args.f1_splits)
         fabric = Fabric.from_torch_distributed()
     eng = PSTrainEngine(spec, cfg, fabric)
     eng.init_params()
@@ -285,7 +286,8 @@ def main():
                        "mode": args.mode, "optimizer": args.optimizer, "lr": args.lr,
                        "l2": "inputs larger than L2: 172 MB fp32 train split cycled in HBM",
                        "cuda_graph_unroll": unroll if use_graph else 0,
-                       "pull": "publish-replicas" if args.publish else "peer-pull fused in GEMM"},
+                       "pull": "publish-replicas" if args.publish else "peer-pull fused in GEMM",
+                       "f1_splits": args.f1_splits},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total,
             "final_loss": loss, "global_step": gstep,
         }

@@ -13,8 +13,8 @@
 // * Fused push (SURVEY K4+C2): C may be a gradient slot in the ps GPU's memory; the epilogue stores
 //   tiles straight from TMEM to the peer and then release-increments the ps's arrival counter.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
-// warps 2..5 = epilogue (warp w owns TMEM lanes [32*(w%4), +32)).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
+// warps 2..9 = epilogue (warp w owns TMEM lanes [32*(w%4), +32); two warps per quarter split the columns).
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -28,7 +28,8 @@ namespace dtf {
 static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;            // bf16 elements per stage along K = one 128-byte swizzle row
 static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
-static constexpr int kThreads = 192;
+static constexpr int kEpilogueWarps = 8;
+static constexpr int kThreads = 64 + 32 * kEpilogueWarps;   // TMA warp + MMA warp + epilogue warps
 
 struct GemmParams {
   int M, N, K;
@@ -63,7 +64,7 @@ struct GemmParams {
 // One 16-column slice of the epilogue: alpha, bias, ReLU, ReLU-backward mask, bias-gradient column sums, store
 // (fp32 / bf16 / atomic accumulate).  `r` holds the fp32 accumulators of this thread's row.
 DTF_DEVICE void epilogue_chunk16(const GemmParams& p, const uint32_t* r, int c0, int n0, long long grow, bool row_ok,
-                                 bool add_bias, const float* s_bias, int lane) {
+                                 bool add_bias, const float* s_bias, int lane, float* stage_row = nullptr) {
   float* cf = reinterpret_cast<float*>(p.c);
   __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(p.c);
   const int gc0 = n0 + c0;
@@ -112,6 +113,12 @@ DTF_DEVICE void epilogue_chunk16(const GemmParams& p, const uint32_t* r, int c0,
       if (lane == j) mine = s;
     }
     if (lane < 16 && gc0 + lane < p.N) atomicAdd(p.colsum + gc0 + lane, mine);
+  }
+  if (stage_row != nullptr) {
+    // coalescing path: park this thread's 16 values in its row of the warp's staging tile
+#pragma unroll
+    for (int j = 0; j < 16; ++j) stage_row[j] = v[j];
+    return;
   }
   if (row_ok) {
     const bool full = gc0 + 16 <= p.N;
@@ -269,58 +276,39 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     const bool add_bias = p.bias != nullptr && (p.atomic == 0 || blockIdx.z == 0);
     if (add_bias) {
       // stage the bias slice in shared memory while the mainloop runs (no global-load latency in the epilogue)
-      for (int i = threadIdx.x - 64; i < p.block_n; i += 128) s_bias[i] = (n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+      for (int i = threadIdx.x - 64; i < p.block_n; i += 32 * kEpilogueWarps) s_bias[i] = (n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
     }
     if (have_k) {
       mbar_wait(&tmem_full_bar, 0);
       tc_fence_after();
     }
     if (threadIdx.x == 64) DTF_STAMP(6);         // accumulator ready
-    if ((p.block_n & 31) == 0) {
-      // 32 columns per TMEM load, software-pipelined: the load of slice i+1 is in flight while slice i is
-      // converted and stored (the first version waited ~575 cycles per 16-column slice)
-      uint32_t ra[32], rb[32];
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
-      if (have_k) tmem_ld_32x32b_x32(tbase, ra);
-      for (int c0 = 0; c0 < p.block_n; c0 += 64) {
-        if (have_k) tmem_ld_wait();
-        else {
+    // Eight epilogue warps: two per TMEM lane quarter, each taking half of the columns.  With one warp per
+    // scheduler every dependent latency (tcgen05.ld, bias LDS, address math, store issue) is exposed, so the
+    // epilogue is latency- not bandwidth-bound: measured 575 cycles per 16-column slice with four warps; wider
+    // TMEM loads (x32, double-buffered) and a shared-memory transpose for coalesced stores were both SLOWER.
+    const int half = (warp - 2) >> 2;
+    const bool split_cols = (p.block_n % 32) == 0;
+    const int c_begin = split_cols ? half * (p.block_n / 2) : 0;
+    const int c_end = split_cols ? c_begin + p.block_n / 2 : (half == 0 ? p.block_n : 0);
+    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+      uint32_t r[16];
+      if (have_k) {
+        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+      } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) ra[j] = 0;
-        }
-        if (have_k && c0 + 32 < p.block_n) tmem_ld_32x32b_x32(tbase + (uint32_t)(c0 + 32), rb);
-        epilogue_chunk16(p, ra, c0, n0, grow, row_ok, add_bias, s_bias, lane);
-        epilogue_chunk16(p, ra + 16, c0 + 16, n0, grow, row_ok, add_bias, s_bias, lane);
-        if (c0 + 32 >= p.block_n) break;
-        if (have_k) tmem_ld_wait();
-        else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) rb[j] = 0;
-        }
-        if (have_k && c0 + 64 < p.block_n) tmem_ld_32x32b_x32(tbase + (uint32_t)(c0 + 64), ra);
-        epilogue_chunk16(p, rb, c0 + 32, n0, grow, row_ok, add_bias, s_bias, lane);
-        epilogue_chunk16(p, rb + 16, c0 + 48, n0, grow, row_ok, add_bias, s_bias, lane);
+        for (int j = 0; j < 16; ++j) r[j] = 0;
       }
-    } else {
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        uint32_t r[16];
-        if (have_k) {
-          tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = 0;
-        }
-        epilogue_chunk16(p, r, c0, n0, grow, row_ok, add_bias, s_bias, lane);
-      }
+      epilogue_chunk16(p, r, c0, n0, grow, row_ok, add_bias, s_bias, lane);
     }
     if (threadIdx.x == 64) DTF_STAMP(7);         // tile stored
     if (p.signal != nullptr) {
       // fused push: make this CTA's tile visible system-wide, then bump the consumer's arrival counter
       // (one fence by one thread after the CTA-level barrier: release is cumulative, and a system-scope
       //  membar per thread serialises for tens of microseconds)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
       if (warp == 2 && lane == 0) {
         if (p.stamp_dst != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
           asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.stamp_dst), "l"(*p.stamp_src) : "memory");

@@ -430,41 +430,29 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
   __syncthreads();
   HSTAMP(1);          // inputs in shared memory
 
-  // Register-blocked over the (<=16) classes; FOUR lanes cooperate on one row / one hidden unit (each takes every
-  // 4th element of the reduction) and combine with two warp shuffles: no shared-memory atomics, every operand is
-  // loaded once per 16 FMAs.  (v1 of this kernel was shared-memory-issue bound: mio_throttle 7.1, 16-way conflicts.)
-  // ---- logits[b][:] = h[b][:] . W2 + b2 ---------------------------------------------------------------------------
+  // The three small products are shared-memory-bandwidth bound on CUDA cores (ncu: mio_throttle), so the
+  // thread mappings are chosen to minimise shared-memory wavefronts per FMA, not instruction count.
+  // ---- logits[b][:] = h[b][:] . W2 + b2 : a warp covers 8 rows x 4 class-quads; per k it issues one scalar LDS
+  //      (8 distinct rows, broadcast to the 4 quads) and one LDS.128 (one 64-byte W2 row, broadcast to the 8 rows)
   {
-    const int b = tid >> 2, q = tid & 3;
-    float acc[CP];
-#pragma unroll
-    for (int c = 0; c < CP; ++c) acc[c] = 0.f;
-    if (b < B) {
-      const float* hr = s_h + b * HP;
-      for (int k = q; k < H; k += 4) {
+    const int warp = tid >> 5;
+    const int r = lane >> 2, j = lane & 3;
+    for (int row0 = warp * 8; row0 < B; row0 += (nt >> 5) * 8) {
+      const int b = row0 + r;
+      const float* hr = s_h + (b < B ? b : 0) * HP;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < H; ++k) {
         const float hv = hr[k];
-        const float4* wr = reinterpret_cast<const float4*>(s_w2 + k * CP);
-#pragma unroll
-        for (int j = 0; j < CP / 4; ++j) {
-          const float4 w = wr[j];
-          acc[4 * j] = fmaf(hv, w.x, acc[4 * j]);
-          acc[4 * j + 1] = fmaf(hv, w.y, acc[4 * j + 1]);
-          acc[4 * j + 2] = fmaf(hv, w.z, acc[4 * j + 2]);
-          acc[4 * j + 3] = fmaf(hv, w.w, acc[4 * j + 3]);
-        }
+        const float4 w = *reinterpret_cast<const float4*>(s_w2 + k * CP + 4 * j);
+        a0 = fmaf(hv, w.x, a0);
+        a1 = fmaf(hv, w.y, a1);
+        a2 = fmaf(hv, w.z, a2);
+        a3 = fmaf(hv, w.w, a3);
       }
-    }
-#pragma unroll
-    for (int c = 0; c < CP; ++c) {
-      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
-      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
-    }
-    if (b < B && q == 0) {
-      float4* dst = reinterpret_cast<float4*>(s_dl + b * DS);
-#pragma unroll
-      for (int j = 0; j < CP / 4; ++j)
-        dst[j] = make_float4(acc[4 * j] + s_b2[4 * j], acc[4 * j + 1] + s_b2[4 * j + 1], acc[4 * j + 2] + s_b2[4 * j + 2],
-                             acc[4 * j + 3] + s_b2[4 * j + 3]);
+      if (b < B)
+        *reinterpret_cast<float4*>(s_dl + b * DS + 4 * j) =
+            make_float4(a0 + s_b2[4 * j], a1 + s_b2[4 * j + 1], a2 + s_b2[4 * j + 2], a3 + s_b2[4 * j + 3]);
     }
   }
   __syncthreads();
@@ -537,57 +525,75 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
   }
   HSTAMP(3);          // softmax/xent/dlogits done
 
-  // ---- hidden-unit-owned phases: L lanes per hidden unit k, lane q takes rows b = q, q+L, ... ----------------------
-  //   dW2[k][:] = sum_b h[b][k] * dl[b][:] ;  dh[b][k] = (h[b][k] > 0) * dl[b][:] . W2[k][:] ;  db1[k] = sum_b dh[b][k]
+  // ---- dW2[k][:] = sum_b h[b][k] * dl[b][:] : a warp covers 8 hidden units x 4 class-quads; per row b one scalar
+  //      LDS (8 consecutive k of row b) and one LDS.128 (the 64-byte dl row, broadcast) ---------------------------------
   {
-    const int L = (H <= 128) ? 4 : 2;
-    const int k = tid / L, q = tid % L;
-    float w2r[CP], acc[CP];
-#pragma unroll
-    for (int c = 0; c < CP; ++c) { acc[c] = 0.f; w2r[c] = 0.f; }
+    const int warp = tid >> 5;
+    const int r = lane >> 2, j = lane & 3;
+    for (int k0 = warp * 8; k0 < H; k0 += (nt >> 5) * 8) {
+      const int k = k0 + r;
+      const int kk = k < H ? k : 0;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+      for (int b = 0; b < B; ++b) {
+        const float hv = s_h[b * HP + kk];
+        const float4 d = *reinterpret_cast<const float4*>(s_dl + b * DS + 4 * j);
+        a0 = fmaf(hv, d.x, a0);
+        a1 = fmaf(hv, d.y, a1);
+        a2 = fmaf(hv, d.z, a2);
+        a3 = fmaf(hv, d.w, a3);
+      }
+      if (k < H) {
+        float* gw = p.gw2 + (long long)k * p.ldgw2 + 4 * j;      // NVLink stores straight into the ps slot
+        if (4 * j < C) gw[0] = a0;
+        if (4 * j + 1 < C) gw[1] = a1;
+        if (4 * j + 2 < C) gw[2] = a2;
+        if (4 * j + 3 < C) gw[3] = a3;
+      }
+    }
+  }
+  // ---- dh[b][k] = (h[b][k] > 0) * dl[b][:] . W2[k][:] ; db1[k] = sum_b dh[b][k] : a thread owns hidden unit k (its W2
+  //      row lives in registers) for a quarter of the rows; per row one scalar LDS (32 consecutive k: conflict-free)
+  //      and four broadcast LDS.128 (the dl row).  dh rows are written 64 contiguous bytes per warp. -------------------
+  {
+    const int QR = (nt / ((H + 31) / 32 * 32)) > 0 ? (nt / ((H + 31) / 32 * 32)) : 1;    // row groups
+    const int HPAD = (H + 31) / 32 * 32;
+    const int k = tid % HPAD, g = tid / HPAD;
     float db1 = 0.f;
-    if (k < H) {
+    if (g < QR && k < H) {
+      float w2r[CP];
       const float4* wr = reinterpret_cast<const float4*>(s_w2 + k * CP);
 #pragma unroll
-      for (int j = 0; j < CP / 4; ++j) {
-        const float4 w = wr[j];
-        w2r[4 * j] = w.x; w2r[4 * j + 1] = w.y; w2r[4 * j + 2] = w.z; w2r[4 * j + 3] = w.w;
+      for (int jj = 0; jj < CP / 4; ++jj) {
+        const float4 w = wr[jj];
+        w2r[4 * jj] = w.x; w2r[4 * jj + 1] = w.y; w2r[4 * jj + 2] = w.z; w2r[4 * jj + 3] = w.w;
       }
-      for (int b = q; b < B; b += L) {
+      for (int b = g; b < B; b += QR) {
         const float hv = s_h[b * HP + k];
         const float4* dr = reinterpret_cast<const float4*>(s_dl + b * DS);
         float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < CP / 4; ++j) {
-          const float4 dl = dr[j];
-          acc[4 * j] = fmaf(hv, dl.x, acc[4 * j]);
-          acc[4 * j + 1] = fmaf(hv, dl.y, acc[4 * j + 1]);
-          acc[4 * j + 2] = fmaf(hv, dl.z, acc[4 * j + 2]);
-          acc[4 * j + 3] = fmaf(hv, dl.w, acc[4 * j + 3]);
-          d0 = fmaf(dl.x, w2r[4 * j], d0);
-          d1 = fmaf(dl.y, w2r[4 * j + 1], d1);
-          d0 = fmaf(dl.z, w2r[4 * j + 2], d0);
-          d1 = fmaf(dl.w, w2r[4 * j + 3], d1);
+        for (int jj = 0; jj < CP / 4; ++jj) {
+          const float4 dl = dr[jj];
+          d0 = fmaf(dl.x, w2r[4 * jj], d0);
+          d1 = fmaf(dl.y, w2r[4 * jj + 1], d1);
+          d0 = fmaf(dl.z, w2r[4 * jj + 2], d0);
+          d1 = fmaf(dl.w, w2r[4 * jj + 3], d1);
         }
         const float d = hv > 0.f ? (d0 + d1) : 0.f;
         p.dh[(long long)b * p.lddh + k] = __float2bfloat16(d);
         db1 += d;
       }
     }
-#pragma unroll
-    for (int c = 0; c < CP; ++c) {
-      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
-      if (L == 4) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
-    }
-    db1 += __shfl_xor_sync(0xffffffffu, db1, 1);
-    if (L == 4) db1 += __shfl_xor_sync(0xffffffffu, db1, 2);
-    if (k < H && q == 0) {
-      // NVLink stores straight into the ps gradient slot
-      float* gw = p.gw2 + (long long)k * p.ldgw2;
-#pragma unroll
-      for (int c = 0; c < CP; ++c)
-        if (c < C) gw[c] = acc[c];
-      p.gb1[k] = db1;
+    // combine the row groups through shared memory (the logits tile rows >= ... are free: use s_lab as scratch)
+    __syncthreads();
+    float* s_part = s_red + 32;              // [QR][HPAD] <= 512 floats, reserved by the launcher
+    if (g < QR && k < HPAD) s_part[g * HPAD + k] = db1;
+    __syncthreads();
+    if (tid < H) {
+      float a = 0.f;
+      for (int gg = 0; gg < QR; ++gg) a += s_part[gg * HPAD + tid];
+      p.gb1[tid] = a;
     }
   }
   if (tid >= nt - 32 && tid - (nt - 32) < C) {
@@ -790,7 +796,7 @@ int dtf_mlp_head(const DtfMlpHeadArgs* a, cudaStream_t s) {
   p.mailbox = reinterpret_cast<const WorkerMailbox*>(a->mailbox); p.ctl = reinterpret_cast<PsControl*>(a->ctl);
   p.rank = a->rank; p.stamp_from_version = a->stamp_from_version; p.phase_trace = a->phase_trace;
   p.h_acc = a->h_acc; p.ld_acc = a->ld_acc; p.b1 = a->b1; p.sys_scope = a->sys_scope;
-  const size_t smem = sizeof(float) * ((size_t)a->B * (a->H + 1) + (size_t)a->H * 16 + (size_t)a->B * 40 + 16 + 32);
+  const size_t smem = sizeof(float) * ((size_t)a->B * (a->H + 1) + (size_t)a->H * 16 + (size_t)a->B * 40 + 16 + 32 + 512);
   if (a->B > 512 || a->H > 512) return -2;
   if ((a->ldh % 8) || (a->ldw2 % 8) || a->ldh > 8 * 8 * 512 / a->B) return -3;
   static size_t configured = 0;

@@ -58,6 +58,7 @@ class EngineConfig:
     clip_min: float = 1e-10
     publish_replicas: bool = False        # True: ps stores new params into every worker's replica (push-publish)
     colocated: bool = False               # single GPU: ps shard 0 and worker 0 share device + stream
+    f1_splits: int = 1                    # split-K CTAs for the first GEMM (fp32 atomic partials, bias+ReLU in the head)
     timeout_ns: int = 5_000_000_000
     loss_hist: int = 4096
     trace_cap: int = 4096
@@ -175,7 +176,7 @@ class PSTrainEngine:
                 names = [("mailbox_w%d" % w, self.mb_bytes * cfg.num_ps),
                          ("x16_w%d" % w, 128 * spec.in_dim * 2), ("labels_w%d" % w, 128 * 16 * 4),
                          ("xf32_w%d" % w, 128 * spec.in_dim * 4),
-                         ("h_w%d" % w, 128 * ldh * 2), ("dh_w%d" % w, 128 * ldh * 2),
+                         ("h_w%d" % w, 128 * ldh * 2), ("dh_w%d" % w, 128 * ldh * 2), ("hacc_w%d" % w, 128 * ldh * 4),
                          ("misc_w%d" % w, 4096 + cfg.loss_hist * 4)]
                 for s in range(cfg.num_ps):
                     names.append(("replica%d_w%d" % (s, w), self.shard_elems[s] * 2))
@@ -260,7 +261,7 @@ class PSTrainEngine:
                 w = self.worker_ranks.index(r)
                 with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
                     for name in ("mailbox_w%d" % w, "misc_w%d" % w, "x16_w%d" % w, "h_w%d" % w, "dh_w%d" % w,
-                                 "labels_w%d" % w):
+                                 "labels_w%d" % w, "hacc_w%d" % w):
                         rk.bufs[name].tensor(torch.uint8).zero_()
                 rk.stream.synchronize()
             rk.step = 0
@@ -343,6 +344,11 @@ class PSTrainEngine:
             g1.wait_flag = mb.ptr + lay["hid_w"].shard * self.mb_bytes      # token of the shard that owns W1
             g1.err, g1.timeout_ns = d["err_ptr"], cfg.timeout_ns
             g1.block_n_override = self.block_n_w1
+            if cfg.f1_splits > 1:
+                # split-K: several CTAs stream disjoint K ranges of x / W1 and red.add fp32 partials; bias + ReLU
+                # move into the head, which also clears the accumulator for the next step
+                g1.c, g1.ldc, g1.c_bf16 = rk.bufs["hacc_w%d" % w].ptr, ldh, 0
+                g1.bias, g1.relu, g1.splits = None, 0, cfg.f1_splits
             d["g1"] = g1
             # ---- head ---------------------------------------------------------------------------------
             hd = MlpHeadArgs()
@@ -358,6 +364,8 @@ class PSTrainEngine:
             hd.mailbox = mb.ptr
             hd.rank, hd.stamp_from_version = w, 0 if cfg.sync else 1
             hd.sys_scope = 0 if cfg.colocated else 1
+            if cfg.f1_splits > 1:
+                hd.h_acc, hd.ld_acc, hd.b1 = rk.bufs["hacc_w%d" % w].ptr, ldh, src("master", lay["hid_b"], 4)
             d["head"] = hd
             # Shards the head pushes to.  The dW1 GEMM (same stream, later) signals the shard that owns hid_w
             # on behalf of the whole push: kernel-boundary ordering makes the head's stores visible first.
