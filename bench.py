@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--publish", action="store_true", help="ps stores params into worker replicas (push-publish)")
     ap.add_argument("--num-train", type=int, default=55000)
     ap.add_argument("--f1-splits", type=int, default=1, help="split-K CTAs for the first GEMM")
+    ap.add_argument("--in-graph", action="store_true", help="ONE process drives all --gpus devices (in-graph replication)")
+    ap.add_argument("--num-ps", type=int, default=1, help="ps shards (variables placed round-robin)")
     return ap.parse_args()
 
 
@@ -122,6 +124,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if args.in_graph and world > 1:
+        raise SystemExit("--in-graph runs as ONE process (do not launch it with torchrun)")
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -146,12 +150,16 @@ def main():
     if args.lr is None:
         args.lr = 0.01 if args.optimizer == "adam" else 0.001
     opt = {"kind": args.optimizer, "lr": args.lr, "momentum": 0.9}
-    if N == 1:
+    if args.in_graph and N > 1:
+        cfg = EngineConfig(num_ps=args.num_ps, num_workers=N - args.num_ps, sync=args.mode == "sync", optimizer=opt,
+                           publish_replicas=args.publish, f1_splits=args.f1_splits)
+        fabric = Fabric(N, {r: r for r in range(N)})
+    elif N == 1:
         cfg = EngineConfig(num_ps=1, num_workers=1, colocated=True, sync=args.mode == "sync", optimizer=opt,
                            publish_replicas=args.publish, f1_splits=args.f1_splits)
         fabric = Fabric(1, {0: local_rank})
     else:
-        cfg = EngineConfig(num_ps=1, num_workers=N - 1, sync=args.mode == "sync", optimizer=opt,
+        cfg = EngineConfig(num_ps=args.num_ps, num_workers=N - args.num_ps, sync=args.mode == "sync", optimizer=opt,
                            publish_replicas=args.publish, f1_splits=args.f1_splits)
         fabric = Fabric.from_torch_distributed()
     eng = PSTrainEngine(spec, cfg, fabric)
@@ -224,7 +232,12 @@ def main():
         ms, launches_total = ms_local, launches
     value = num_workers * spec.batch * K / (ms / 1e3)
     loss = eng.read_loss() if is_worker else None
+    if world > 1:
+        lt = torch.tensor([loss if loss is not None else -1e30], dtype=torch.float64, device="cuda")
+        dist.all_reduce(lt, op=dist.ReduceOp.MAX)
+        loss = float(lt[0])
     gstep = eng.read_ctl(0, "global_step") if 0 in eng.ranks else None
+    stale = eng.staleness() if (args.mode == "async" and 0 in eng.ranks) else None
 
     # ---- end-to-end: public API step(x, y) with H2D of the batch and D2H of the loss every step -----------------
     e2e = None
@@ -282,14 +295,15 @@ def main():
             "impl": "ours",
             "config": {"model": "MNIST MLP 784-%d-10, clipped batch-sum xent" % spec.hidden,
                        "global_batch": num_workers * spec.batch, "per_worker_batch": spec.batch,
-                       "parallelism": ("ps1+worker1 colocated on one GPU" if N == 1 else "ps1+worker%d between-graph" % (N - 1)),
+                       "parallelism": ("ps1+worker1 colocated on one GPU" if N == 1 else "ps%d+worker%d %s" % (
+                           cfg.num_ps, cfg.num_workers, "in-graph (one client process)" if args.in_graph else "between-graph")),
                        "mode": args.mode, "optimizer": args.optimizer, "lr": args.lr,
                        "l2": "inputs larger than L2: 172 MB fp32 train split cycled in HBM",
                        "cuda_graph_unroll": unroll if use_graph else 0,
                        "pull": "publish-replicas" if args.publish else "peer-pull fused in GEMM",
                        "f1_splits": args.f1_splits},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total,
-            "final_loss": loss, "global_step": gstep,
+            "final_loss": loss, "global_step": gstep, "staleness": stale,
         }
         print(json.dumps(out))
     eng.close()

@@ -60,6 +60,9 @@ DTF_DEVICE uint64_t ld_relaxed_sys_u64(const uint64_t* p) {
 DTF_DEVICE void st_release_sys_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+DTF_DEVICE void st_relaxed_sys_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 DTF_DEVICE void st_release_sys_u64(uint64_t* p, uint64_t v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -82,14 +85,20 @@ DTF_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.share
 // Spin until *flag >= target (acquire, system scope) with a wall-clock bailout.
 // Returns false on timeout (the caller records an error instead of hanging the GPU).
 DTF_DEVICE bool wait_flag_ge_u64(const uint64_t* flag, uint64_t target, uint64_t timeout_ns) {
-  if (ld_acquire_sys_u64(flag) >= target) return true;
-  const uint64_t t0 = globaltimer_ns();
-  uint32_t spins = 0;
-  while (true) {
-    if (ld_acquire_sys_u64(flag) >= target) return true;
-    if ((++spins & 0x3FF) == 0 && (globaltimer_ns() - t0) > timeout_ns) return false;
-    __nanosleep(20);
+  // Poll with RELAXED system-scope loads and issue ONE acquire fence once the condition holds: an
+  // ld.acquire.sys per poll costs a system membar each time (SASS: LDG.STRONG.SYS + MEMBAR.ALL.SYS).
+  bool ok = ld_relaxed_sys_u64(flag) >= target;
+  if (!ok) {
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (true) {
+      if (ld_relaxed_sys_u64(flag) >= target) { ok = true; break; }
+      if ((++spins & 0x3FF) == 0 && (globaltimer_ns() - t0) > timeout_ns) break;
+      if (spins > 2048) __nanosleep(32);
+    }
   }
+  fence_acq_rel_sys();
+  return ok;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -471,12 +471,15 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
   if (rc) return rc < 0 ? -7 : 1000 + rc;
 
   const size_t smem = (size_t)stages * stage_bytes + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
+  // the opt-in shared-memory limit is a per-device function attribute (one process may drive all 8 GPUs)
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(224 * 1024));   // 227 KB minus static barriers + bias stage
     if (e != cudaSuccess) return 2000 + (int)e;
-    configured = 224 * 1024;
+    configured[dev] = true;
   }
   dim3 grid((unsigned)((g->M + kBlockM - 1) / kBlockM), (unsigned)((g->N + bn - 1) / bn), (unsigned)splits);
   gemm_bf16_tcgen05_kernel<<<grid, kThreads, smem, stream>>>(ma, mb, p);

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
         count = 0;
         if (p.mode == 0) {
           for (int w = 0; w < p.num_workers; ++w) {
-            const unsigned long long arr = ld_acquire_sys_u64(reinterpret_cast<const uint64_t*>(&ctl->w[w].arrivals));
+            const unsigned long long arr = ld_relaxed_sys_u64(reinterpret_cast<const uint64_t*>(&ctl->w[w].arrivals));
             if (arr >= ctl->consumed[w] + p.ctas_per_push) {
               const unsigned long long stamp = ld_relaxed_sys_u64(reinterpret_cast<const uint64_t*>(&ctl->w[w].stamp));
               if (stamp >= gs) {
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
           const int start = (int)((ctl->last_async_worker + 1) % (unsigned)p.num_workers);
           for (int i = 0; i < p.num_workers; ++i) {
             const int w = (start + i) % p.num_workers;
-            const unsigned long long arr = ld_acquire_sys_u64(reinterpret_cast<const uint64_t*>(&ctl->w[w].arrivals));
+            const unsigned long long arr = ld_relaxed_sys_u64(reinterpret_cast<const uint64_t*>(&ctl->w[w].arrivals));
             if (arr >= ctl->consumed[w] + p.ctas_per_push) {
               mask = 1u << w;
               count = 1;
@@ -128,6 +128,8 @@ __global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
         }
         if (spins > 4096) __nanosleep(64);
       }
+      // relaxed polling above, ONE acquire fence here: the gradient slots of the chosen workers are now visible
+      if (p.system_scope) fence_acq_rel_sys(); else __threadfence();
       ctl->decision_mask = mask;
       ctl->decision_count = count ? count : 1u;
       ctl->decision_ok = ok;
@@ -240,18 +242,20 @@ __global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
           ctl->beta2_power *= p.beta2;
         }
         if (p.system_scope) __threadfence_system(); else __threadfence();
-        // tokens: every replica gets one carrying the NEW global step (sync); the pusher only (async)
+        // tokens: every replica gets one carrying the NEW global step (sync); the pusher only (async).
+        // One fence, then RELAXED system-scope stores (fence + relaxed store == release): a st.release.sys per
+        // mailbox would issue a system membar per worker.
         for (int w = 0; w < p.num_workers; ++w) {
           if (p.mailbox[w] == nullptr) continue;
           if (p.mode == 1 && !(mask & (1u << w))) continue;
-          if (p.mode == 1) {
-            // async ack: count of this worker's applied pushes + the step it may stamp next
-            st_release_sys_u64(reinterpret_cast<uint64_t*>(&p.mailbox[w]->version), ngs);
-            red_release_sys_add_u64(reinterpret_cast<uint64_t*>(&p.mailbox[w]->token), 1ull);
-          } else {
-            st_release_sys_u64(reinterpret_cast<uint64_t*>(&p.mailbox[w]->version), ngs);
-            st_release_sys_u64(reinterpret_cast<uint64_t*>(&p.mailbox[w]->token), ngs);
-          }
+          st_relaxed_sys_u64(reinterpret_cast<uint64_t*>(&p.mailbox[w]->version), ngs);
+        }
+        if (p.system_scope) __threadfence_system(); else __threadfence();
+        for (int w = 0; w < p.num_workers; ++w) {
+          if (p.mailbox[w] == nullptr) continue;
+          if (p.mode == 1 && !(mask & (1u << w))) continue;
+          if (p.mode == 1) asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(&p.mailbox[w]->token), "l"(1ull) : "memory");
+          else st_relaxed_sys_u64(reinterpret_cast<uint64_t*>(&p.mailbox[w]->token), ngs);
         }
       }
       if (p.trace && p.trace_cap > 0) {
@@ -799,11 +803,13 @@ int dtf_mlp_head(const DtfMlpHeadArgs* a, cudaStream_t s) {
   const size_t smem = sizeof(float) * ((size_t)a->B * (a->H + 1) + (size_t)a->H * 16 + (size_t)a->B * 40 + 16 + 32 + 512);
   if (a->B > 512 || a->H > 512) return -2;
   if ((a->ldh % 8) || (a->ldw2 % 8) || a->ldh > 8 * 8 * 512 / a->B) return -3;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > 48 * 1024 && dev >= 0 && dev < 64 && !configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(mlp_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
-    configured = 200 * 1024;
+    configured[dev] = true;
   }
   mlp_head_kernel<<<1, 512, smem, s>>>(p);
   return (int)cudaGetLastError();

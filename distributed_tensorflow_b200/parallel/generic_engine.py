@@ -1,0 +1,261 @@
+"""Model-agnostic fabric parameter server: any set of named parameters, any loss.
+
+Same device-resident protocol as :mod:`parallel.ps_engine` (gradient slots + stamps + arrival counters in ps
+HBM, one fused ``ps_apply`` kernel per aggregate, tokens in worker mailboxes, sync or async) but the worker's
+compute is arbitrary: the caller supplies ``loss_fn(params, *batch) -> loss`` written with the framework's ops
+(``ops/native.py``: tcgen05 GEMM / conv-as-GEMM / fused xent, autograd-wrapped).  Per step a worker runs
+
+    wait_token (+ pull_shadow: peer loads of the ps's fp32 parameters into the local replica)
+    -> forward/backward (our kernels + autograd glue) -> gradients packed into one flat buffer
+    -> push_grad (vectorised NVLink stores into its slot on the ps + stamp + arrivals)
+
+and the ps runs ``ps_apply`` (N-way reduce + mean + SGD/Momentum/Adam + publish + tokens).  This is what runs
+ResNet-18 under the ps API (BASELINE.json config 5): see ``models/resnet.py``.
+
+Variables are sharded across ps ranks round-robin in creation order, exactly like ``replica_device_setter``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from ..ops import cuda_lib
+from ..ops.cuda_lib import MAX_WORKERS, PsApplyArgs, round_up
+from .fabric import Fabric, FabricBuffer
+from .ps_engine import EngineConfig, _KIND, _Rank
+
+__all__ = ["GenericPSEngine"]
+
+_PUSH_CTAS = 64
+
+
+class GenericPSEngine:
+    def __init__(self, param_shapes: Sequence[Tuple[str, Tuple[int, ...]]], cfg: EngineConfig, fabric: Fabric):
+        self.cfg, self.fabric = cfg, fabric
+        self.lib = cuda_lib.load()
+        self.world = fabric.world_size
+        if cfg.colocated:
+            assert self.world == 1 and cfg.num_ps == 1 and cfg.num_workers == 1
+            self.ps_ranks, self.worker_ranks = [0], [0]
+        else:
+            assert self.world == cfg.num_ps + cfg.num_workers
+            self.ps_ranks = list(range(cfg.num_ps))
+            self.worker_ranks = list(range(cfg.num_ps, self.world))
+        if cfg.num_workers > MAX_WORKERS:
+            raise ValueError("at most %d workers" % MAX_WORKERS)
+        # layout: (shard, offset, numel) per variable, round-robin in creation order, 64-element aligned
+        self.layout: Dict[str, Tuple[int, int, Tuple[int, ...]]] = {}
+        sizes = [0] * cfg.num_ps
+        for i, (name, shape) in enumerate(param_shapes):
+            shard = i % cfg.num_ps
+            off = round_up(sizes[shard], 64)
+            n = 1
+            for d in shape:
+                n *= int(d)
+            self.layout[name] = (shard, off, tuple(int(d) for d in shape))
+            sizes[shard] = off + n
+        self.shard_elems = [round_up(max(s, 64), 64) for s in sizes]
+        self.names = [n for n, _ in param_shapes]
+        self.R = cfg.replicas_to_aggregate or cfg.num_workers
+        self.opt = dict(cfg.optimizer)
+        self.kind = _KIND[self.opt["kind"]]
+        self.ctl_bytes = self.lib.dtf_sizeof_ps_control()
+        self.mb_bytes = self.lib.dtf_sizeof_mailbox()
+        self.off = {k: self.lib.dtf_offsetof_ctl(i) for i, k in enumerate(
+            ["global_step", "param_version", "beta1_power", "beta2_power", "dropped_stale", "applied_total",
+             "staleness_hist", "staleness_sum", "err", "w", "w_stride", "consumed"])}
+        self.ranks: Dict[int, _Rank] = {r: _Rank(r, d) for r, d in fabric.local_ranks.items()}
+        for rk in self.ranks.values():
+            with torch.cuda.device(rk.device):
+                rk.stream = torch.cuda.Stream(rk.device)
+        W = cfg.num_workers
+        for r, rk in self.ranks.items():
+            if r in self.ps_ranks:
+                s = self.ps_ranks.index(r)
+                n = self.shard_elems[s]
+                for name, nbytes in (("gctl%d" % s, self.ctl_bytes), ("gmaster%d" % s, n * 4), ("ggrads%d" % s, n * 4 * W),
+                                     ("gslot_m%d" % s, n * 4), ("gslot_v%d" % s, n * 4), ("gshadow%d" % s, n * 2)):
+                    rk.bufs[name] = fabric.alloc(r, name, nbytes)
+                for name in ("gctl%d" % s, "gmaster%d" % s, "ggrads%d" % s):
+                    fabric.publish(r, name)
+            if r in self.worker_ranks:
+                w = self.worker_ranks.index(r)
+                rk.bufs["gmailbox_w%d" % w] = fabric.alloc(r, "gmailbox_w%d" % w, self.mb_bytes * cfg.num_ps)
+                rk.bufs["gmisc_w%d" % w] = fabric.alloc(r, "gmisc_w%d" % w, 256)
+                fabric.publish(r, "gmailbox_w%d" % w)
+                for s in range(cfg.num_ps):
+                    rk.bufs["greplica%d_w%d" % (s, w)] = fabric.alloc(r, "greplica%d_w%d" % (s, w), self.shard_elems[s] * 4)
+                    rk.bufs["glocalgrad%d_w%d" % (s, w)] = fabric.alloc(r, "glocalgrad%d_w%d" % (s, w), self.shard_elems[s] * 4)
+        self.peer: Dict[Tuple[int, str], FabricBuffer] = {}
+        for r in self.ranks:
+            if r in self.worker_ranks:
+                for s, pr in enumerate(self.ps_ranks):
+                    for base in ("gctl", "gmaster", "ggrads"):
+                        self.peer[(r, "%s%d" % (base, s))] = fabric.peer(r, pr, "%s%d" % (base, s))
+            if r in self.ps_ranks:
+                for w, wr in enumerate(self.worker_ranks):
+                    self.peer[(r, "gmailbox_w%d" % w)] = fabric.peer(r, wr, "gmailbox_w%d" % w)
+        self._p: Dict[int, PsApplyArgs] = {}
+        for r, rk in self.ranks.items():
+            if r not in self.ps_ranks:
+                continue
+            s = self.ps_ranks.index(r)
+            n = self.shard_elems[s]
+            a = PsApplyArgs()
+            a.ctl, a.master = rk.bufs["gctl%d" % s].ptr, rk.bufs["gmaster%d" % s].ptr
+            a.slot_m, a.slot_v, a.shadow = rk.bufs["gslot_m%d" % s].ptr, rk.bufs["gslot_v%d" % s].ptr, rk.bufs["gshadow%d" % s].ptr
+            for w in range(W):
+                a.grad[w] = rk.bufs["ggrads%d" % s].ptr + w * n * 4
+                a.mailbox[w] = self.peer[(r, "gmailbox_w%d" % w)].ptr + s * self.mb_bytes
+            a.n, a.num_workers, a.replicas_to_aggregate = n, W, self.R
+            a.ctas_per_push = _PUSH_CTAS
+            a.mode, a.kind = (0 if cfg.sync else 1), self.kind
+            a.lr, a.momentum = float(self.opt["lr"]), float(self.opt.get("momentum", 0.0))
+            a.beta1, a.beta2 = float(self.opt.get("beta1", 0.9)), float(self.opt.get("beta2", 0.999))
+            a.eps = float(self.opt.get("eps", self.opt.get("epsilon", 1e-8)))
+            a.nesterov, a.publish_replicas, a.num_zero = int(bool(self.opt.get("nesterov", False))), 0, 0
+            a.timeout_ns, a.grid = cfg.timeout_ns, 0
+            a.system_scope = 0 if cfg.colocated else 1
+            self._p[r] = a
+
+    # -- parameters ------------------------------------------------------------------------------------------
+    def _view(self, buf: FabricBuffer, name: str) -> torch.Tensor:
+        shard, off, shape = self.layout[name]
+        n = 1
+        for d in shape:
+            n *= d
+        return buf.tensor(torch.float32, off * 4, n).view(shape)
+
+    def init_params(self, values: Dict[str, torch.Tensor]) -> None:
+        for r, rk in self.ranks.items():
+            if r in self.ps_ranks:
+                s = self.ps_ranks.index(r)
+                with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
+                    for base in ("gctl", "gmaster", "ggrads", "gslot_m", "gslot_v"):
+                        rk.bufs["%s%d" % (base, s)].tensor(torch.uint8).zero_()
+                    for name in self.names:
+                        if self.layout[name][0] == s:
+                            self._view(rk.bufs["gmaster%d" % s], name).copy_(values[name].to(rk.device).float())
+                    b = rk.bufs["gctl%d" % s].tensor(torch.float32, self.off["beta1_power"], 2)
+                    b[0] = float(self.opt.get("beta1", 0.9))
+                    b[1] = float(self.opt.get("beta2", 0.999))
+                rk.stream.synchronize()
+            if r in self.worker_ranks:
+                w = self.worker_ranks.index(r)
+                with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
+                    rk.bufs["gmailbox_w%d" % w].tensor(torch.uint8).zero_()
+                    rk.bufs["gmisc_w%d" % w].tensor(torch.uint8).zero_()
+                rk.stream.synchronize()
+            rk.step = 0
+        self.fabric.barrier()
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        out = {}
+        for r, rk in self.ranks.items():
+            if r in self.ps_ranks:
+                s = self.ps_ranks.index(r)
+                rk.stream.synchronize()
+                for name in self.names:
+                    if self.layout[name][0] == s:
+                        out[name] = self._view(rk.bufs["gmaster%d" % s], name).detach().cpu().clone()
+                if s == 0:
+                    out["global_step"] = torch.tensor(self.read_ctl(0, "global_step"), dtype=torch.int64)
+        return out
+
+    def read_ctl(self, shard: int, fld: str, count: int = 1):
+        rk = self.ranks[self.ps_ranks[shard]]
+        t = rk.bufs["gctl%d" % shard].tensor(torch.int64, self.off[fld], count).cpu()
+        return int(t[0]) if count == 1 else t.tolist()
+
+    # -- worker side -------------------------------------------------------------------------------------------
+    def pull(self, rank: int) -> Dict[str, torch.Tensor]:
+        """Wait for this step's token, then copy the ps's fp32 parameters into the local replica (peer loads)."""
+        rk = self.ranks[rank]
+        w = self.worker_ranks.index(rank)
+        st = rk.stream.cuda_stream
+        params = {}
+        with torch.cuda.device(rk.device):
+            for s in range(self.cfg.num_ps):
+                rc = self.lib.dtf_wait_token(rk.bufs["gmailbox_w%d" % w].ptr + s * self.mb_bytes, rk.step, None,
+                                             self.cfg.timeout_ns, rk.bufs["gmisc_w%d" % w].ptr + 16, st)
+                assert rc == 0, rc
+                rep = rk.bufs["greplica%d_w%d" % (s, w)]
+                rc = self.lib.dtf_pull_shadow(self.peer[(rank, "gmaster%d" % s)].ptr, rep.ptr, self.shard_elems[s] * 4, 148, st)
+                assert rc == 0, rc
+            cuda_lib._bump(2 * self.cfg.num_ps)
+            for name in self.names:
+                s = self.layout[name][0]
+                params[name] = self._view(rk.bufs["greplica%d_w%d" % (s, w)], name)
+        return params
+
+    def push(self, rank: int, grads: Dict[str, torch.Tensor]) -> None:
+        rk = self.ranks[rank]
+        w = self.worker_ranks.index(rank)
+        st = rk.stream.cuda_stream
+        with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
+            for name, g in grads.items():
+                s = self.layout[name][0]
+                self._view(rk.bufs["glocalgrad%d_w%d" % (s, w)], name).copy_(g)
+            for s in range(self.cfg.num_ps):
+                n = self.shard_elems[s]
+                dst = self.peer[(rank, "ggrads%d" % s)].ptr + w * n * 4
+                rc = self.lib.dtf_push_grad(rk.bufs["glocalgrad%d_w%d" % (s, w)].ptr, dst, n, self.peer[(rank, "gctl%d" % s)].ptr,
+                                            rk.bufs["gmailbox_w%d" % w].ptr + s * self.mb_bytes, w,
+                                            0 if self.cfg.sync else 1, 1, _PUSH_CTAS, st)
+                assert rc == 0, rc
+            cuda_lib._bump(self.cfg.num_ps)
+        rk.step += 1
+
+    def worker_step(self, rank: int, loss_fn: Callable[..., torch.Tensor], *batch) -> torch.Tensor:
+        rk = self.ranks[rank]
+        params = self.pull(rank)
+        with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
+            leaves = {k: v.detach().requires_grad_(True) for k, v in params.items()}
+            loss = loss_fn(leaves, *batch)
+            gl = torch.autograd.grad(loss, [leaves[k] for k in self.names], allow_unused=True)
+            grads = {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(self.names, gl)}
+        self.push(rank, grads)
+        return loss.detach()
+
+    def ps_apply(self, rank: int) -> None:
+        rk = self.ranks[rank]
+        with torch.cuda.device(rk.device):
+            rc = self.lib.dtf_ps_apply(ctypes.byref(self._p[rank]), rk.stream.cuda_stream)
+        assert rc == 0, rc
+        cuda_lib._bump()
+
+    def step(self, loss_fn: Callable[..., torch.Tensor], batches: Dict[int, Tuple]) -> Dict[int, torch.Tensor]:
+        """One step for every local rank; ``batches[rank]`` is the worker's batch tuple."""
+        losses = {}
+        for r in self.worker_ranks:
+            if r in self.ranks:
+                losses[r] = self.worker_step(r, loss_fn, *batches[r])
+        for r in self.ps_ranks:
+            if r in self.ranks:
+                for _ in range(1 if self.cfg.sync else self.cfg.num_workers):
+                    self.ps_apply(r)
+        return losses
+
+    def check_errors(self) -> None:
+        for r, rk in self.ranks.items():
+            rk.stream.synchronize()
+            if r in self.worker_ranks:
+                w = self.worker_ranks.index(r)
+                e = int(rk.bufs["gmisc_w%d" % w].tensor(torch.int32, 16, 1).cpu()[0])
+                if e:
+                    raise RuntimeError("worker %d: device-side wait timed out (code %d)" % (w, e))
+            if r in self.ps_ranks:
+                s = self.ps_ranks.index(r)
+                e = int(rk.bufs["gctl%d" % s].tensor(torch.int32, self.off["err"], 1).cpu()[0])
+                if e:
+                    raise RuntimeError("ps shard %d: device-side wait timed out (code %d)" % (s, e))
+
+    def synchronize(self) -> None:
+        for rk in self.ranks.values():
+            rk.stream.synchronize()
+
+    def close(self) -> None:
+        self.synchronize()
+        self.fabric.close()
