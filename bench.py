@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--publish", action="store_true", help="ps stores params into worker replicas (push-publish)")
     ap.add_argument("--num-train", type=int, default=55000)
     ap.add_argument("--f1-splits", type=int, default=1, help="split-K CTAs for the first GEMM")
+    ap.add_argument("--head-ctas", type=int, default=8, help="row-parallel CTAs of the fused MLP head")
+    ap.add_argument("--f1-block-n", type=int, default=64)
+    ap.add_argument("--b3-block-n", type=int, default=64)
     ap.add_argument("--in-graph", action="store_true", help="ONE process drives all --gpus devices (in-graph replication)")
     ap.add_argument("--num-ps", type=int, default=1, help="ps shards (variables placed round-robin)")
     return ap.parse_args()
@@ -152,15 +155,18 @@ def main():
     opt = {"kind": args.optimizer, "lr": args.lr, "momentum": 0.9}
     if args.in_graph and N > 1:
         cfg = EngineConfig(num_ps=args.num_ps, num_workers=N - args.num_ps, sync=args.mode == "sync", optimizer=opt,
-                           publish_replicas=args.publish, f1_splits=args.f1_splits)
+                           publish_replicas=args.publish, f1_splits=args.f1_splits, head_ctas=args.head_ctas,
+                           f1_block_n=args.f1_block_n, b3_block_n=args.b3_block_n)
         fabric = Fabric(N, {r: r for r in range(N)})
     elif N == 1:
         cfg = EngineConfig(num_ps=1, num_workers=1, colocated=True, sync=args.mode == "sync", optimizer=opt,
-                           publish_replicas=args.publish, f1_splits=args.f1_splits)
+                           publish_replicas=args.publish, f1_splits=args.f1_splits, head_ctas=args.head_ctas,
+                           f1_block_n=args.f1_block_n, b3_block_n=args.b3_block_n)
         fabric = Fabric(1, {0: local_rank})
     else:
         cfg = EngineConfig(num_ps=args.num_ps, num_workers=N - args.num_ps, sync=args.mode == "sync", optimizer=opt,
-                           publish_replicas=args.publish, f1_splits=args.f1_splits)
+                           publish_replicas=args.publish, f1_splits=args.f1_splits, head_ctas=args.head_ctas,
+                           f1_block_n=args.f1_block_n, b3_block_n=args.b3_block_n)
         fabric = Fabric.from_torch_distributed()
     eng = PSTrainEngine(spec, cfg, fabric)
     eng.init_params()
@@ -301,7 +307,8 @@ def main():
                        "l2": "inputs larger than L2: 172 MB fp32 train split cycled in HBM",
                        "cuda_graph_unroll": unroll if use_graph else 0,
                        "pull": "publish-replicas" if args.publish else "peer-pull fused in GEMM",
-                       "f1_splits": args.f1_splits},
+                       "f1_splits": args.f1_splits, "head_ctas": args.head_ctas, "f1_block_n": args.f1_block_n,
+                       "b3_block_n": args.b3_block_n},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total,
             "final_loss": loss, "global_step": gstep, "staleness": stale,
         }

@@ -85,20 +85,19 @@ DTF_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.share
 // Spin until *flag >= target (acquire, system scope) with a wall-clock bailout.
 // Returns false on timeout (the caller records an error instead of hanging the GPU).
 DTF_DEVICE bool wait_flag_ge_u64(const uint64_t* flag, uint64_t target, uint64_t timeout_ns) {
-  // Poll with RELAXED system-scope loads and issue ONE acquire fence once the condition holds: an
-  // ld.acquire.sys per poll costs a system membar each time (SASS: LDG.STRONG.SYS + MEMBAR.ALL.SYS).
-  bool ok = ld_relaxed_sys_u64(flag) >= target;
-  if (!ok) {
-    const uint64_t t0 = globaltimer_ns();
-    uint32_t spins = 0;
-    while (true) {
-      if (ld_relaxed_sys_u64(flag) >= target) { ok = true; break; }
-      if ((++spins & 0x3FF) == 0 && (globaltimer_ns() - t0) > timeout_ns) break;
-      if (spins > 2048) __nanosleep(32);
-    }
+  // Fast path: one acquire load.  Slow path: poll with RELAXED system-scope loads (an ld.acquire.sys per poll
+  // costs a system membar each time), then re-read once with acquire semantics -- the acquire load that observes
+  // the released value is what orders the subsequent parameter reads (cheaper than fence.acq_rel.sys: measured
+  // ~1.4K vs ~4.8K cycles on the critical path of every step).
+  if (ld_acquire_sys_u64(flag) >= target) return true;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (true) {
+    if (ld_relaxed_sys_u64(flag) >= target) break;
+    if ((++spins & 0x3FF) == 0 && (globaltimer_ns() - t0) > timeout_ns) return false;
+    if (spins > 2048) __nanosleep(32);
   }
-  fence_acq_rel_sys();
-  return ok;
+  return ld_acquire_sys_u64(flag) >= target;
 }
 
 // ------------------------------------------------------------------------------------------------

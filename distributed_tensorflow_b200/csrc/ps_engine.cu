@@ -319,11 +319,19 @@ struct MlpHeadParams {
   long long ld_acc;
   const float* b1;              // hidden bias (used with h_acc)
   int sys_scope;                // 1: ps is another GPU (system-scope fence before the arrival)
+  int rows_per_cta;             // batch rows per CTA (grid = ceil(B / rows_per_cta))
 };
 
 __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p) {
   extern __shared__ float sm[];
-  const int B = p.B, H = p.H, C = p.C;
+  // Row-parallel: CTA i owns batch rows [i*rows_per_cta, ...).  Row-owned work (logits, softmax, dh) is disjoint;
+  // the batch reductions (dW2, db2, db1, loss) are combined with fp32 atomics -- into the ps slot over NVLink
+  // for the gradients (the ps clears those ranges after reading them).
+  const int row_lo = blockIdx.x * p.rows_per_cta;
+  const int B = min(p.rows_per_cta, p.B - row_lo);
+  const int H = p.H, C = p.C;
+  const bool multi = gridDim.x > 1;
+  if (B <= 0) return;
   constexpr int CP = 16;                    // classes padded to 16 (4 x float4)
   constexpr int DS = 20;                    // row stride of the [B][16] tiles: 80 B keeps float4 rows conflict-free
   const int HP = H + 1;                     // padded activation row (bank-conflict-free column walks)
@@ -353,7 +361,7 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int i = tid + u * nt;
-      lreg[u] = (i < B * C) ? p.labels[(long long)(i / C) * p.ldl + (i % C)] : 0.f;
+      lreg[u] = (i < B * C) ? p.labels[(long long)(row_lo + i / C) * p.ldl + (i % C)] : 0.f;
     }
     const float b2v = (tid < C) ? p.b2[tid] : 0.f;
     if (p.h_acc == nullptr) {
@@ -364,7 +372,7 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int i = tid + u * nt;
-        hreg[u] = (i < nvec) ? reinterpret_cast<const uint4*>(p.h)[i] : make_uint4(0, 0, 0, 0);
+        hreg[u] = (i < nvec) ? reinterpret_cast<const uint4*>(p.h + (long long)row_lo * p.ldh)[i] : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -389,7 +397,7 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int i = tid + u * nt;
-        areg[u] = (i < nvec) ? reinterpret_cast<const float4*>(p.h_acc)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        areg[u] = (i < nvec) ? reinterpret_cast<const float4*>(p.h_acc + (long long)row_lo * p.ld_acc)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       float* s_b1 = s_h + (size_t)B * HP - 0;       // staged below through s_w2 region? no: use registers
       (void)s_b1;
@@ -397,7 +405,7 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
       for (int u = 0; u < 8; ++u) {
         const int i = tid + u * nt;
         if (i < nvec) {
-          reinterpret_cast<float4*>(p.h_acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          reinterpret_cast<float4*>(p.h_acc + (long long)row_lo * p.ld_acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           const int b = i / hv4, k0 = (i - b * hv4) * 4;
           const float v[4] = {areg[u].x, areg[u].y, areg[u].z, areg[u].w};
 #pragma unroll
@@ -462,7 +470,7 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
   __syncthreads();
   HSTAMP(2);          // logits done
   if (p.logits_out)
-    for (int i = tid; i < B * C; i += nt) p.logits_out[i] = s_dl[(i / C) * DS + (i % C)];
+    for (int i = tid; i < B * C; i += nt) p.logits_out[(long long)row_lo * C + i] = s_dl[(i / C) * DS + (i % C)];
 
   // ---- softmax + clipped xent + dlogits, one thread per row (rows read/written as float4) ---------------------------
   float my_loss = 0.f;
@@ -522,10 +530,12 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
   if (tid == 0) {
     float t = 0.f;
     for (int i = 0; i < (nt >> 5); ++i) t += s_red[i];
-    *p.loss_out = t;
-    unsigned long long step = 0;
-    if (p.step_counter) { step = *p.step_counter; *p.step_counter = step + 1; }
-    if (p.loss_hist && p.hist_cap > 0) p.loss_hist[step % (unsigned long long)p.hist_cap] = t;
+    p.loss_out[blockIdx.x] = t;            // per-CTA partial of the batch-sum loss (the reader adds them up)
+    if (blockIdx.x == 0) {
+      unsigned long long step = 0;
+      if (p.step_counter) { step = *p.step_counter; *p.step_counter = step + 1; }
+      if (!multi && p.loss_hist && p.hist_cap > 0) p.loss_hist[step % (unsigned long long)p.hist_cap] = t;
+    }
   }
   HSTAMP(3);          // softmax/xent/dlogits done
 
@@ -549,10 +559,17 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
       }
       if (k < H) {
         float* gw = p.gw2 + (long long)k * p.ldgw2 + 4 * j;      // NVLink stores straight into the ps slot
-        if (4 * j < C) gw[0] = a0;
-        if (4 * j + 1 < C) gw[1] = a1;
-        if (4 * j + 2 < C) gw[2] = a2;
-        if (4 * j + 3 < C) gw[3] = a3;
+        if (multi) {
+          if (4 * j < C) atomicAdd(gw, a0);
+          if (4 * j + 1 < C) atomicAdd(gw + 1, a1);
+          if (4 * j + 2 < C) atomicAdd(gw + 2, a2);
+          if (4 * j + 3 < C) atomicAdd(gw + 3, a3);
+        } else {
+          if (4 * j < C) gw[0] = a0;
+          if (4 * j + 1 < C) gw[1] = a1;
+          if (4 * j + 2 < C) gw[2] = a2;
+          if (4 * j + 3 < C) gw[3] = a3;
+        }
       }
     }
   }
@@ -585,7 +602,7 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
           d1 = fmaf(dl.w, w2r[4 * jj + 3], d1);
         }
         const float d = hv > 0.f ? (d0 + d1) : 0.f;
-        p.dh[(long long)b * p.lddh + k] = __float2bfloat16(d);
+        p.dh[(long long)(row_lo + b) * p.lddh + k] = __float2bfloat16(d);
         db1 += d;
       }
     }
@@ -597,7 +614,7 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
     if (tid < H) {
       float a = 0.f;
       for (int gg = 0; gg < QR; ++gg) a += s_part[gg * HPAD + tid];
-      p.gb1[tid] = a;
+      if (multi) atomicAdd(p.gb1 + tid, a); else p.gb1[tid] = a;
     }
   }
   if (tid >= nt - 32 && tid - (nt - 32) < C) {
@@ -606,7 +623,7 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
     int b = 0;
     for (; b + 2 <= B; b += 2) { a0 += s_dl[b * DS + c]; a1 += s_dl[(b + 1) * DS + c]; }
     if (b < B) a0 += s_dl[b * DS + c];
-    p.gb2[c] = a0 + a1;
+    if (multi) atomicAdd(p.gb2 + c, a0 + a1); else p.gb2[c] = a0 + a1;
   }
   HSTAMP(4);          // dW2/dh/db1 done and stored
   // ---- stamp + arrival (optional: a later kernel of the same step may signal for the whole push instead) --------
@@ -786,6 +803,7 @@ struct DtfMlpHeadArgs {
   int rank; int stamp_from_version;
   long long* phase_trace;
   float* h_acc; long long ld_acc; const float* b1; int sys_scope;
+  int ctas;
 };
 
 int dtf_mlp_head(const DtfMlpHeadArgs* a, cudaStream_t s) {
@@ -800,6 +818,10 @@ int dtf_mlp_head(const DtfMlpHeadArgs* a, cudaStream_t s) {
   p.mailbox = reinterpret_cast<const WorkerMailbox*>(a->mailbox); p.ctl = reinterpret_cast<PsControl*>(a->ctl);
   p.rank = a->rank; p.stamp_from_version = a->stamp_from_version; p.phase_trace = a->phase_trace;
   p.h_acc = a->h_acc; p.ld_acc = a->ld_acc; p.b1 = a->b1; p.sys_scope = a->sys_scope;
+  int ctas = a->ctas > 1 ? a->ctas : 1;
+  p.rows_per_cta = (a->B + ctas - 1) / ctas;
+  p.rows_per_cta = (p.rows_per_cta + 7) / 8 * 8;            // whole 8-row warp groups
+  ctas = (a->B + p.rows_per_cta - 1) / p.rows_per_cta;
   const size_t smem = sizeof(float) * ((size_t)a->B * (a->H + 1) + (size_t)a->H * 16 + (size_t)a->B * 40 + 16 + 32 + 512);
   if (a->B > 512 || a->H > 512) return -2;
   if ((a->ldh % 8) || (a->ldw2 % 8) || a->ldh > 8 * 8 * 512 / a->B) return -3;
@@ -811,7 +833,7 @@ int dtf_mlp_head(const DtfMlpHeadArgs* a, cudaStream_t s) {
     if (e != cudaSuccess) return (int)e;
     configured[dev] = true;
   }
-  mlp_head_kernel<<<1, 512, smem, s>>>(p);
+  mlp_head_kernel<<<ctas, 512, smem, s>>>(p);
   return (int)cudaGetLastError();
 }
 

@@ -62,7 +62,7 @@ class MlpHeadArgs(Structure):
                 ("gb2", c_void_p), ("gb1", c_void_p), ("logits_out", c_void_p),
                 ("mailbox", c_void_p), ("ctl", c_void_p), ("rank", c_int), ("stamp_from_version", c_int),
                 ("phase_trace", c_void_p), ("h_acc", c_void_p), ("ld_acc", c_longlong), ("b1", c_void_p),
-                ("sys_scope", c_int)]
+                ("sys_scope", c_int), ("ctas", c_int)]
 
 
 def available() -> bool:

@@ -59,6 +59,9 @@ class EngineConfig:
     publish_replicas: bool = False        # True: ps stores new params into every worker's replica (push-publish)
     colocated: bool = False               # single GPU: ps shard 0 and worker 0 share device + stream
     f1_splits: int = 1                    # split-K CTAs for the first GEMM (fp32 atomic partials, bias+ReLU in the head)
+    head_ctas: int = 8                    # row-parallel CTAs of the fused head (batch reductions via fp32 atomics)
+    f1_block_n: int = 64                  # N tile of the forward GEMM (0: one tile covering `hidden`)
+    b3_block_n: int = 64                  # N tile of the dW1 GEMM (0: one tile covering `hidden`)
     timeout_ns: int = 5_000_000_000
     loss_hist: int = 4096
     trace_cap: int = 4096
@@ -145,11 +148,17 @@ class PSTrainEngine:
         self.m_tiles_w1 = (spec.in_dim + 127) // 128
         self.ctas_per_push = [0] * cfg.num_ps
         head_shards = {lw["sm_w"].shard, lw["sm_b"].shard, lw["hid_b"].shard} - {lw["hid_w"].shard}
+        self.head_ctas = max(1, min(int(cfg.head_ctas), 16))
+        rows = (spec.batch + self.head_ctas - 1) // self.head_ctas
+        rows = (rows + 7) // 8 * 8
+        self.head_ctas = (spec.batch + rows - 1) // rows                 # what the launcher will actually use
         for s in head_shards:
-            self.ctas_per_push[s] += 1
+            self.ctas_per_push[s] += self.head_ctas
         bn = 64 if spec.hidden <= 64 else (128 if spec.hidden <= 128 else (192 if spec.hidden <= 192 else 256))
         self.block_n_w1 = bn
-        self.ctas_per_push[lw["hid_w"].shard] += self.m_tiles_w1 * ((spec.hidden + bn - 1) // bn)
+        self.block_n_f1 = cfg.f1_block_n or bn
+        self.block_n_b3 = cfg.b3_block_n or bn
+        self.ctas_per_push[lw["hid_w"].shard] += self.m_tiles_w1 * ((spec.hidden + self.block_n_b3 - 1) // self.block_n_b3)
         self._allocate()
         self._exchange()
         self._build_launches()
@@ -314,8 +323,8 @@ class PSTrainEngine:
             w = self.worker_ranks.index(r)
             ldh = round_up(H, 8)
             misc = rk.bufs["misc_w%d" % w]
-            # misc layout: [0] loss f32 | [8] step counter u64 | [16] err u32 | [64..] unused | [4096..] loss ring
-            d: Dict[str, Any] = {"ldh": ldh, "loss_ptr": misc.ptr, "stepctr_ptr": misc.ptr + 8, "err_ptr": misc.ptr + 16,
+            # misc layout: [0..64) per-CTA loss partials f32 | [64] step counter u64 | [72] err u32 | [4096..] loss ring
+            d: Dict[str, Any] = {"ldh": ldh, "loss_ptr": misc.ptr, "stepctr_ptr": misc.ptr + 64, "err_ptr": misc.ptr + 72,
                                  "hist_ptr": misc.ptr + 4096}
             mb = rk.bufs["mailbox_w%d" % w]
             d["mb0"] = mb.ptr
@@ -343,7 +352,7 @@ class PSTrainEngine:
             g1.alpha, g1.splits = 1.0, 1
             g1.wait_flag = mb.ptr + lay["hid_w"].shard * self.mb_bytes      # token of the shard that owns W1
             g1.err, g1.timeout_ns = d["err_ptr"], cfg.timeout_ns
-            g1.block_n_override = self.block_n_w1
+            g1.block_n_override = self.block_n_f1
             if cfg.f1_splits > 1:
                 # split-K: several CTAs stream disjoint K ranges of x / W1 and red.add fp32 partials; bias + ReLU
                 # move into the head, which also clears the accumulator for the next step
@@ -364,6 +373,7 @@ class PSTrainEngine:
             hd.mailbox = mb.ptr
             hd.rank, hd.stamp_from_version = w, 0 if cfg.sync else 1
             hd.sys_scope = 0 if cfg.colocated else 1
+            hd.ctas = self.head_ctas
             if cfg.f1_splits > 1:
                 hd.h_acc, hd.ld_acc, hd.b1 = rk.bufs["hacc_w%d" % w].ptr, ldh, src("master", lay["hid_b"], 4)
             d["head"] = hd
@@ -385,7 +395,7 @@ class PSTrainEngine:
             # the GEMM's first CTA also publishes the stamp (local_step / pulled version) for this push
             g3.stamp_src = mb.ptr + lay["hid_w"].shard * self.mb_bytes + (0 if cfg.sync else 8)
             g3.stamp_dst = ctl_arrivals(lay["hid_w"].shard) + 8
-            g3.block_n_override = self.block_n_w1
+            g3.block_n_override = self.block_n_b3
             d["g3"] = g3
             d["extra_wait_shards"] = [s for s in range(cfg.num_ps) if s != lay["hid_w"].shard]
             self._w[r] = d
@@ -414,6 +424,13 @@ class PSTrainEngine:
             a.nesterov = int(bool(self.opt.get("nesterov", False)))
             a.publish_replicas = int(cfg.publish_replicas)
             a.num_zero = 0
+            if self.head_ctas > 1:
+                # the row-parallel head accumulates dW2 / db2 / db1 with atomics: clear those slot ranges after reading
+                for vn in ("sm_w", "sm_b", "hid_b"):
+                    l = lay[vn]
+                    if l.shard == s:
+                        a.zero_begin[a.num_zero], a.zero_end[a.num_zero] = l.offset, l.offset + l.numel_padded
+                        a.num_zero += 1
             a.timeout_ns = cfg.timeout_ns
             a.trace, a.trace_cap = rk.bufs["trace%d" % s].ptr, cfg.trace_cap
             a.grid = 0
@@ -580,7 +597,8 @@ class PSTrainEngine:
                 rk = self.ranks[r]
                 w = self.worker_ranks.index(r)
                 rk.stream.synchronize()
-                return float(rk.bufs["misc_w%d" % w].tensor(torch.float32, 0, 1).cpu()[0])
+                # misc[0 : head_ctas] hold the per-CTA partials of the batch-sum loss
+                return float(rk.bufs["misc_w%d" % w].tensor(torch.float32, 0, self.head_ctas).cpu().sum())
         return None
 
     def check_errors(self) -> None:
@@ -588,7 +606,7 @@ class PSTrainEngine:
             rk.stream.synchronize()
             if r in self.worker_ranks:
                 w = self.worker_ranks.index(r)
-                e = int(rk.bufs["misc_w%d" % w].tensor(torch.int32, 16, 1).cpu()[0])
+                e = int(rk.bufs["misc_w%d" % w].tensor(torch.int32, 72, 1).cpu()[0])
                 if e:
                     raise RuntimeError("worker %d: device-side wait timed out (code %d)" % (w, e))
             if r in self.ps_ranks:

@@ -1,0 +1,112 @@
+"""MNIST MLP on the fabric parameter-server engine (the B200 fast path), between-graph or in-graph.
+
+between-graph (one process per GPU; rank 0..num_ps-1 are ps shards, the rest workers):
+
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 examples/fabric_mnist.py --num_ps 1 --issync
+
+in-graph (ONE client process drives every GPU, like reference example_in_graph.py but with parameters sharded
+over `--num_ps` ps GPUs and one training replica per remaining GPU):
+
+    python examples/fabric_mnist.py --in_graph --gpus 8 --num_ps 2 --issync --optimizer adam
+
+Same flags as distributed_mnist.py where they make sense; checkpoints are written by the chief (ps shard 0's
+process) in the SAME name-keyed format, so examples/distributed_mnist_predict.py restores them.
+"""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import distributed_tensorflow_b200 as dtf
+from distributed_tensorflow_b200.parallel.fabric import Fabric
+from distributed_tensorflow_b200.parallel.ps_engine import EngineConfig, MLPSpec, PSTrainEngine
+from distributed_tensorflow_b200.train.saver import update_checkpoint_state, write_bundle
+from distributed_tensorflow_b200.utils.mnist_data import synthetic_mnist
+
+flags = dtf.app.flags
+flags.DEFINE_integer("hidden_units", 100, "hidden layer width")
+flags.DEFINE_integer("train_steps", 2000, "global steps to run (sync: aggregates; async: applies / num_workers)")
+flags.DEFINE_integer("batch_size", 100, "per-worker batch")
+flags.DEFINE_float("learning_rate", 0.01, "learning rate")
+flags.DEFINE_string("optimizer", "adam", "sgd | momentum | adam")
+flags.DEFINE_bool("issync", True, "synchronous replicas")
+flags.DEFINE_integer("num_ps", 1, "ps shards")
+flags.DEFINE_bool("in_graph", False, "one process drives all GPUs")
+flags.DEFINE_integer("gpus", 0, "GPUs to use in in-graph mode (0: all)")
+flags.DEFINE_string("train_dir", "/tmp/dtf_ckpt/fabric_mnist", "checkpoint directory")
+flags.DEFINE_integer("num_train", 55000, "synthetic train-set size")
+FLAGS = flags.FLAGS
+
+
+def main():
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if FLAGS.in_graph or world == 1:
+        n = FLAGS.gpus or torch.cuda.device_count()
+        fabric = Fabric(n, {r: r for r in range(n)})
+        rank = 0
+    else:
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+        fabric = Fabric.from_torch_distributed()
+        n, rank = world, dist.get_rank()
+    colocated = n == 1
+    cfg = EngineConfig(num_ps=1 if colocated else FLAGS.num_ps, num_workers=1 if colocated else n - FLAGS.num_ps,
+                       sync=FLAGS.issync, colocated=colocated,
+                       optimizer={"kind": FLAGS.optimizer, "lr": FLAGS.learning_rate, "momentum": 0.9})
+    eng = PSTrainEngine(MLPSpec(hidden=FLAGS.hidden_units, batch=FLAGS.batch_size), cfg, fabric)
+    eng.init_params()
+    print("rank %d: ps shards %s, workers %s, placement %s" % (rank, eng.ps_ranks, eng.worker_ranks,
+                                                               {k: v.shard for k, v in eng.layout.items()}), flush=True)
+    xs, ys = synthetic_mnist(FLAGS.num_train, seed=1)
+    for r in eng.ranks:
+        if r in eng.worker_ranks:
+            eng.attach_dataset(r, xs, ys)
+    t0 = time.time()
+    steps = FLAGS.train_steps
+    done = 0
+    while done < steps:
+        k = min(200, steps - done)
+        eng.enqueue_local_steps(k, "dataset")
+        done += k
+        eng.synchronize()
+        loss = eng.read_loss()
+        if loss is not None:
+            print("time: %.2fs | rank: %d | local step: %d | loss: %f" % (time.time() - t0, rank, done, loss), flush=True)
+    eng.check_errors()
+    if not fabric.single_process:
+        dist.barrier()
+    sd = eng.state_dict()
+    if 0 in eng.ranks:
+        gs = int(sd["global_step"])
+        print("global_step %d after %.2fs  (%.0f samples/s)" % (gs, time.time() - t0,
+              cfg.num_workers * FLAGS.batch_size * steps / (time.time() - t0)))
+        if not cfg.sync:
+            print("staleness:", eng.staleness())
+    # name-keyed checkpoint, compatible with distributed_mnist_predict.py (every ps process adds its shard's variables)
+    if any(r in eng.ps_ranks for r in eng.ranks):
+        if fabric.single_process:
+            allsd = sd
+        else:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, sd)
+            allsd = {}
+            for g in gathered:
+                allsd.update(g or {})
+        if rank == 0:
+            prefix = os.path.join(FLAGS.train_dir, "model.ckpt-%d" % int(allsd["global_step"]))
+            write_bundle(prefix, allsd, {"engine": "fabric"})
+            update_checkpoint_state(FLAGS.train_dir, prefix)
+            print("checkpoint:", prefix)
+    elif not fabric.single_process:
+        dist.all_gather_object([None] * world, {})
+    eng.close()
+    if not fabric.single_process:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -34,8 +34,8 @@ def _oracle_step(p, x, y, opt, state, t):
     return float(loss)
 
 
-@pytest.mark.parametrize("kind,splits", [("sgd", 1), ("adam", 1), ("sgd", 4)])
-def test_colocated_engine_matches_oracle(kind, splits):
+@pytest.mark.parametrize("kind,splits,hctas", [("sgd", 1, 1), ("adam", 1, 4), ("sgd", 4, 4), ("sgd", 1, 8)])
+def test_colocated_engine_matches_oracle(kind, splits, hctas):
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
     from distributed_tensorflow_b200.parallel.fabric import Fabric
@@ -43,7 +43,7 @@ def test_colocated_engine_matches_oracle(kind, splits):
     from distributed_tensorflow_b200.utils.mnist_data import synthetic_mnist
     torch.cuda.set_device(0)
     opt = {"kind": kind, "lr": 0.01 if kind == "adam" else 0.002}
-    eng = PSTrainEngine(MLPSpec(), EngineConfig(colocated=True, optimizer=opt, seed=3, f1_splits=splits), Fabric(1, {0: 0}))
+    eng = PSTrainEngine(MLPSpec(), EngineConfig(colocated=True, optimizer=opt, seed=3, f1_splits=splits, head_ctas=hctas), Fabric(1, {0: 0}))
     eng.init_params()
     p = {k: v.clone() for k, v in eng.state_dict().items() if k in ("hid_w", "hid_b", "sm_w", "sm_b")}
     xs, ys = synthetic_mnist(1000, seed=5)
