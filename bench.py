@@ -152,6 +152,8 @@ def main():
     spec = MLPSpec(hidden=args.hidden, batch=args.batch)
     if args.lr is None:
         args.lr = 0.01 if args.optimizer == "adam" else 0.001
+        if args.mode == "async" and args.optimizer != "adam":
+            args.lr /= max(1, args.gpus - args.num_ps)       # every push is applied alone: keep the effective rate
     opt = {"kind": args.optimizer, "lr": args.lr, "momentum": 0.9}
     if args.in_graph and N > 1:
         cfg = EngineConfig(num_ps=args.num_ps, num_workers=N - args.num_ps, sync=args.mode == "sync", optimizer=opt,
