@@ -78,6 +78,23 @@ nn = _types.SimpleNamespace(
     clipped_softmax_xent_sum=_ops.clipped_softmax_xent_sum,
 )
 
+# -- dtf.fabric: NVLink parameter-server engines + the graph-API strategy -------------------------------
+def _fabric_ns():
+    from .parallel.fabric import Fabric
+    from .parallel.generic_engine import GenericPSEngine
+    from .parallel.ps_engine import EngineConfig, MLPSpec, PSTrainEngine
+    from .parallel.strategy import FabricPSStrategy
+    return _types.SimpleNamespace(Fabric=Fabric, GenericPSEngine=GenericPSEngine, EngineConfig=EngineConfig,
+                                  MLPSpec=MLPSpec, PSTrainEngine=PSTrainEngine, FabricPSStrategy=FabricPSStrategy)
+
+
+class _LazyFabric:
+    def __getattr__(self, name):
+        return getattr(_fabric_ns(), name)
+
+
+fabric = _LazyFabric()
+
 # -- tf.train -----------------------------------------------------------------------------------------
 from . import train  # noqa: E402
 from .python_compat import input_data, timeline  # noqa: E402,F401

@@ -46,6 +46,7 @@ struct PsApplyParams {
   unsigned long long* trace;     // optional ring: {kind, t0, t1, step} per launch
   int trace_cap;
   long long* phase_trace;        // optional [16] clock64 stamps of block 0 / the last block
+  int idle_ok;                   // 1: a timeout is not an error (host-driven service loop polls)
 };
 
 DTF_DEVICE unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
         }
         if ((++spins & 0xFF) == 0 && (globaltimer_ns() - t0) > p.timeout_ns) {
           ok = 0;
-          atomicExch(&ctl->err, 2u);
+          if (!p.idle_ok) atomicExch(&ctl->err, 2u);
           break;
         }
         if (spins > 4096) __nanosleep(64);
@@ -750,6 +751,7 @@ struct DtfPsApplyArgs {
   int grid;
   int system_scope;
   long long* phase_trace;
+  int idle_ok;
 };
 
 int dtf_ps_apply(const DtfPsApplyArgs* a, cudaStream_t s) {
@@ -770,7 +772,7 @@ int dtf_ps_apply(const DtfPsApplyArgs* a, cudaStream_t s) {
   for (int z = 0; z < 4; ++z) { p.zero_begin[z] = a->zero_begin[z]; p.zero_end[z] = a->zero_end[z]; }
   p.num_zero = a->num_zero;
   p.timeout_ns = a->timeout_ns ? a->timeout_ns : 2000000000ull;
-  p.trace = a->trace; p.trace_cap = a->trace_cap; p.phase_trace = a->phase_trace;
+  p.trace = a->trace; p.trace_cap = a->trace_cap; p.phase_trace = a->phase_trace; p.idle_ok = a->idle_ok;
   int grid = a->grid;
   if (grid <= 0) {
     long long want = (a->n / 4 + 255) / 256;                       // one float4 per thread: a single load round trip

@@ -32,23 +32,32 @@ class ResourceStore:
         self._vars: Dict[str, torch.Tensor] = {}
         self._lock = threading.RLock()
         self.resources: Dict[str, Any] = {}       # accumulators, queues, engine handles
+        self._uninit: Set[str] = set()            # bound (externally owned) storage that has not been assigned yet
+        self._bound: Set[str] = set()
         self.incarnation = time.time_ns()
 
     # -- variables ---------------------------------------------------------------
     def read(self, name: str) -> torch.Tensor:
         try:
+            if name in self._uninit:
+                raise KeyError(name)
             return self._vars[name]
         except KeyError:
             raise FailedPreconditionError("Attempting to use uninitialized value %s" % name) from None
 
     def is_initialized(self, name: str) -> bool:
-        return name in self._vars
+        return name in self._vars and name not in self._uninit
 
     def assign(self, name: str, value: torch.Tensor, device=None) -> torch.Tensor:
         with self._lock:
             cur = self._vars.get(name)
             if cur is not None and cur.shape == value.shape and cur.dtype == value.dtype:
                 cur.copy_(value)            # keep storage identity (peer-mapped buffers stay valid)
+                self._uninit.discard(name)
+                return cur
+            if cur is not None and name in self._bound:
+                cur.copy_(value.to(cur.dtype).reshape(cur.shape))     # bound storage never gets replaced
+                self._uninit.discard(name)
                 return cur
             t = value.detach().clone()
             if device is not None and t.device != torch.device(device):
@@ -62,10 +71,20 @@ class ResourceStore:
             cur.add_(delta.to(device=cur.device, dtype=cur.dtype))
             return cur.clone() if cur.dim() == 0 else cur
 
-    def bind(self, name: str, tensor: torch.Tensor) -> None:
-        """Adopt externally-owned storage (e.g. a slice of a fabric shard) as the variable."""
+    def bind(self, name: str, tensor: torch.Tensor, initialized: bool = True) -> None:
+        """Adopt externally-owned storage (e.g. a slice of a fabric ps shard) as the variable.  A value that was
+        already assigned under this name (the chief may have initialised before the fabric came up) is carried over."""
         with self._lock:
+            old = self._vars.get(name)
+            had = old is not None and name not in self._uninit
+            if had:
+                tensor.copy_(old.to(device=tensor.device, dtype=tensor.dtype).reshape(tensor.shape))
             self._vars[name] = tensor
+            self._bound.add(name)
+            if initialized or had:
+                self._uninit.discard(name)
+            else:
+                self._uninit.add(name)
 
     def variable_names(self) -> List[str]:
         with self._lock:
@@ -79,6 +98,8 @@ class ResourceStore:
     def clear(self) -> None:
         with self._lock:
             self._vars.clear()
+            self._uninit.clear()
+            self._bound.clear()
             for r in self.resources.values():
                 close = getattr(r, "close", None)
                 if close:
@@ -110,8 +131,11 @@ class ExecContext:
         self._gen: Optional[torch.Generator] = None
         self._seed = seed
         self._dev_cache: Dict[str, torch.device] = {}
+        self.force_device: Optional[torch.device] = None      # fabric strategy: run the whole sub-graph on the task's GPU
 
     def torch_device(self, node: Tensor) -> torch.device:
+        if self.force_device is not None:
+            return self.force_device
         key = node.device
         dev = self._dev_cache.get(key)
         if dev is None:

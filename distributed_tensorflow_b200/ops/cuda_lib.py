@@ -50,7 +50,7 @@ class PsApplyArgs(Structure):
                 ("nesterov", c_int), ("publish_replicas", c_int),
                 ("zero_begin", c_longlong * 4), ("zero_end", c_longlong * 4), ("num_zero", c_int),
                 ("timeout_ns", c_ulonglong), ("trace", c_void_p), ("trace_cap", c_int), ("grid", c_int),
-                ("system_scope", c_int), ("phase_trace", c_void_p)]
+                ("system_scope", c_int), ("phase_trace", c_void_p), ("idle_ok", c_int)]
 
 
 class MlpHeadArgs(Structure):

@@ -32,7 +32,8 @@ _PUSH_CTAS = 64
 
 
 class GenericPSEngine:
-    def __init__(self, param_shapes: Sequence[Tuple[str, Tuple[int, ...]]], cfg: EngineConfig, fabric: Fabric):
+    def __init__(self, param_shapes: Sequence[Tuple[str, Tuple[int, ...]]], cfg: EngineConfig, fabric: Fabric,
+                 shards: Optional[Sequence[int]] = None):
         self.cfg, self.fabric = cfg, fabric
         self.lib = cuda_lib.load()
         self.world = fabric.world_size
@@ -49,7 +50,7 @@ class GenericPSEngine:
         self.layout: Dict[str, Tuple[int, int, Tuple[int, ...]]] = {}
         sizes = [0] * cfg.num_ps
         for i, (name, shape) in enumerate(param_shapes):
-            shard = i % cfg.num_ps
+            shard = (i % cfg.num_ps) if shards is None else int(shards[i])      # explicit placement (device strings)
             off = round_up(sizes[shard], 64)
             n = 1
             for d in shape:
@@ -128,6 +129,26 @@ class GenericPSEngine:
             n *= d
         return buf.tensor(torch.float32, off * 4, n).view(shape)
 
+    def prepare(self) -> None:
+        """Zero the buffers and publish beta powers WITHOUT parameter values (they arrive through bound variables)."""
+        self.init_params({})
+
+    def adopt_global_step(self, rank: int) -> int:
+        """Worker: take the ps's current global_step as the base of its token / stamp sequence (fresh start or
+        restore from a checkpoint) and reset its local step count."""
+        rk = self.ranks[rank]
+        w = self.worker_ranks.index(rank)
+        rk.stream.synchronize()
+        gs = int(self.peer[(rank, "gctl0")].tensor(torch.int64, self.off["global_step"], 1).cpu()[0])
+        mb = rk.bufs["gmailbox_w%d" % w].tensor(torch.int64)
+        per = self.mb_bytes // 8
+        for s in range(self.cfg.num_ps):
+            mb[s * per] = gs
+            mb[s * per + 1] = gs
+        torch.cuda.synchronize(rk.device)
+        rk.base, rk.step = gs, 0
+        return gs
+
     def init_params(self, values: Dict[str, torch.Tensor]) -> None:
         for r, rk in self.ranks.items():
             if r in self.ps_ranks:
@@ -136,7 +157,7 @@ class GenericPSEngine:
                     for base in ("gctl", "gmaster", "ggrads", "gslot_m", "gslot_v"):
                         rk.bufs["%s%d" % (base, s)].tensor(torch.uint8).zero_()
                     for name in self.names:
-                        if self.layout[name][0] == s:
+                        if self.layout[name][0] == s and name in values:
                             self._view(rk.bufs["gmaster%d" % s], name).copy_(values[name].to(rk.device).float())
                     b = rk.bufs["gctl%d" % s].tensor(torch.float32, self.off["beta1_power"], 2)
                     b[0] = float(self.opt.get("beta1", 0.9))
@@ -149,6 +170,7 @@ class GenericPSEngine:
                     rk.bufs["gmisc_w%d" % w].tensor(torch.uint8).zero_()
                 rk.stream.synchronize()
             rk.step = 0
+            rk.base = 0
         self.fabric.barrier()
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
@@ -178,7 +200,7 @@ class GenericPSEngine:
         params = {}
         with torch.cuda.device(rk.device):
             for s in range(self.cfg.num_ps):
-                rc = self.lib.dtf_wait_token(rk.bufs["gmailbox_w%d" % w].ptr + s * self.mb_bytes, rk.step, None,
+                rc = self.lib.dtf_wait_token(rk.bufs["gmailbox_w%d" % w].ptr + s * self.mb_bytes, getattr(rk, "base", 0) + rk.step, None,
                                              self.cfg.timeout_ns, rk.bufs["gmisc_w%d" % w].ptr + 16, st)
                 assert rc == 0, rc
                 rep = rk.bufs["greplica%d_w%d" % (s, w)]
@@ -219,10 +241,14 @@ class GenericPSEngine:
         self.push(rank, grads)
         return loss.detach()
 
-    def ps_apply(self, rank: int) -> None:
+    def ps_apply(self, rank: int, idle_ok: bool = False) -> None:
         rk = self.ranks[rank]
+        a = self._p[rank]
+        a.idle_ok = int(idle_ok)
+        if idle_ok:
+            a.timeout_ns = 20_000_000          # service loop: come back to the host every 20 ms when nothing arrives
         with torch.cuda.device(rk.device):
-            rc = self.lib.dtf_ps_apply(ctypes.byref(self._p[rank]), rk.stream.cuda_stream)
+            rc = self.lib.dtf_ps_apply(ctypes.byref(a), rk.stream.cuda_stream)
         assert rc == 0, rc
         cuda_lib._bump()
 

@@ -255,6 +255,10 @@ class Server:
             self.store.assign(k, v if dev is None else v.to(dev), device=dev)
         return sorted(values)
 
+    def rpc_fabric_setup(self, spec):
+        from .strategy import ps_fabric_setup
+        return ps_fabric_setup(self, spec)
+
     def rpc_reset(self):
         self.store.clear()
         return True

@@ -44,6 +44,7 @@ flags.DEFINE_integer('validate_every', 1000, 'Validate when (global_step+1) is a
 flags.DEFINE_integer('num_train', 55000, 'Synthetic train-set size')
 flags.DEFINE_integer('log_every', 1, 'Print the per-step line every N local steps')
 flags.DEFINE_bool('measure_staleness', False, 'Async mode: record pull->apply staleness per step')
+flags.DEFINE_string('engine', 'graph', "'graph': control-plane tier (RPC); 'fabric': parameters/gradients/tokens over NVLink peer memory")
 FLAGS = flags.FLAGS
 
 
@@ -93,8 +94,9 @@ def main():
     cluster = dtf.train.ClusterSpec({'ps': ps_spec, 'worker': worker_spec})
     server = dtf.train.Server(cluster, job_name=FLAGS.job_name, task_index=FLAGS.task_index)
     if FLAGS.job_name == 'ps':
-        server.join()        # the ps only owns variables / accumulators / queues; blocks forever
+        server.join()        # the ps only owns variables / accumulators / queues (fabric: + the apply service); blocks
         return
+    strategy = dtf.fabric.FabricPSStrategy(server) if FLAGS.engine == 'fabric' else None
 
     mnist = input_data.read_data_sets(FLAGS.data_dir, one_hot=True, num_train=FLAGS.num_train)
     print("len of train images: ", len(mnist.train.images))
@@ -108,11 +110,16 @@ def main():
             print("is_sync:true")
             opt = dtf.train.SyncReplicasOptimizer(opt, replicas_to_aggregate=num_workers,
                                                   total_num_replicas=num_workers)
-            hooks.append(opt.make_session_run_hook(FLAGS.task_index == 0))
-        elif FLAGS.measure_staleness:
+            if strategy is None:
+                hooks.append(opt.make_session_run_hook(FLAGS.task_index == 0))
+        elif FLAGS.measure_staleness and strategy is None:
             staleness = dtf.train.StalenessHook()
             hooks.append(staleness)
-        train_step = opt.minimize(cross_entropy, global_step=global_step)
+        if strategy is not None:
+            # same program, but pull / push / aggregate / tokens run on the GPUs over NVLink
+            train_step, loss_fetch = strategy.minimize(opt, cross_entropy, global_step)
+        else:
+            train_step, loss_fetch = opt.minimize(cross_entropy, global_step=global_step), cross_entropy
 
         is_chief = (FLAGS.task_index == 0)
         if is_chief:
@@ -128,7 +135,7 @@ def main():
                                                 checkpoint_dir=FLAGS.train_dir, hooks=hooks) as mon_sess:
             while not mon_sess.should_stop():
                 batch_xs, batch_ys = mnist.train.next_batch(FLAGS.batch_size)
-                _, step, loss = mon_sess.run([train_step, global_step, cross_entropy],
+                _, step, loss = mon_sess.run([train_step, global_step, loss_fetch],
                                              feed_dict={x: batch_xs, y_: batch_ys})
                 local_step += 1
                 if local_step % FLAGS.log_every == 0:

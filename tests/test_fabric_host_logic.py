@@ -1,0 +1,74 @@
+"""Host-side logic of the fabric tier that does not need a GPU: store binding, rank mapping, strategy graph
+construction, engine layouts (SURVEY A5 placement carried into the fabric)."""
+import pytest
+import torch
+
+import distributed_tensorflow_b200 as dtf
+from distributed_tensorflow_b200.framework.executor import ResourceStore
+from distributed_tensorflow_b200.parallel.ps_engine import MLPSpec, _layout
+from distributed_tensorflow_b200.parallel.strategy import fabric_rank_of
+
+
+def test_store_bind_keeps_storage_and_tracks_initialisation():
+    st = ResourceStore()
+    buf = torch.zeros(8)
+    view = buf[2:6].view(2, 2)
+    st.bind("w", view, initialized=False)
+    assert not st.is_initialized("w")
+    with pytest.raises(dtf.errors.FailedPreconditionError):
+        st.read("w")
+    st.assign("w", torch.tensor([[1.0, 2.0], [3.0, 4.0]]))
+    assert st.is_initialized("w") and buf.tolist() == [0, 0, 1, 2, 3, 4, 0, 0]     # written THROUGH the binding
+    # a value assigned before the fabric came up is carried into the bound storage
+    st.assign("b", torch.tensor([7.0, 8.0]))
+    buf2 = torch.zeros(2)
+    st.bind("b", buf2, initialized=False)
+    assert st.is_initialized("b") and buf2.tolist() == [7.0, 8.0]
+    st.assign("b", torch.tensor([1.0, 1.0]))
+    assert buf2.tolist() == [1.0, 1.0] and st.read("b") is buf2
+    # 0-d int64 (global_step living in a control block)
+    ctl = torch.zeros(4, dtype=torch.int64)
+    st.bind("global_step", ctl[1:2].view(()), initialized=False)
+    st.assign("global_step", torch.tensor(41))
+    assert int(ctl[1]) == 41
+
+
+def test_fabric_rank_mapping_ps_first():
+    c = dtf.train.ClusterSpec({"worker": ["h:3", "h:4"], "ps": ["h:1", "h:2"]})
+    assert [fabric_rank_of(c, j, t)[0] for j, t in (("ps", 0), ("ps", 1), ("worker", 0), ("worker", 1))] == [0, 1, 2, 3]
+    assert fabric_rank_of(c, "worker", 1)[1] == 4
+
+
+def test_mlp_engine_layout_follows_round_robin_placement():
+    lay, sizes = _layout(MLPSpec(), 2)
+    # creation order global_step, hid_w, hid_b, sm_w, sm_b over 2 ps -> ps0, ps1, ps0, ps1, ps0
+    assert {k: v.shard for k, v in lay.items()} == {"hid_w": 1, "hid_b": 0, "sm_w": 1, "sm_b": 0}
+    assert lay["hid_w"].pitch % 8 == 0 and lay["hid_w"].pitch >= 100          # 16-byte bf16 rows for TMA
+    assert all(v.offset % 64 == 0 for v in lay.values())
+    lay1, sizes1 = _layout(MLPSpec(hidden=64), 1)
+    assert sizes1[0] >= 784 * 64 + 64 + 64 * 16 + 16
+
+
+def test_strategy_minimize_builds_fabric_train_step(ports):
+    p = ports(3)
+    cluster = dtf.train.ClusterSpec({"ps": ["127.0.0.1:%d" % p[0], "127.0.0.1:%d" % p[1]], "worker": ["127.0.0.1:%d" % p[2]]})
+    server = dtf.train.Server(cluster, "worker", 0)
+    try:
+        strategy = dtf.fabric.FabricPSStrategy(server)
+        with dtf.device(dtf.train.replica_device_setter(cluster=cluster, worker_device="/job:worker/task:0/cpu:0")):
+            gs = dtf.train.get_or_create_global_step()
+            w = dtf.Variable(dtf.zeros([4, 3]), name="w")
+            b = dtf.Variable(dtf.zeros([3]), name="b")
+            x = dtf.placeholder(dtf.float32, [None, 4])
+            loss = dtf.reduce_sum(dtf.square(dtf.nn.xw_plus_b(x, w, b)))
+            opt = dtf.train.SyncReplicasOptimizer(dtf.train.MomentumOptimizer(0.1, 0.9), 1, 1)
+            train_op, floss = strategy.minimize(opt, loss, gs)
+        spec = strategy._spec
+        assert [(n, s, sh) for n, s, sh in spec["params"]] == [("w", [4, 3], 1), ("b", [3], 0)]   # w->ps1, b->ps0
+        assert spec["optimizer"]["kind"] == "momentum" and spec["optimizer"]["sync"] and spec["global_step"] == "global_step"
+        assert train_op.op_type == "FabricTrainStep" and [i.op_type for i in train_op.inputs] == ["Placeholder"]
+        assert train_op.device == "/job:worker/task:0/device:CPU:0"
+        with pytest.raises(RuntimeError):
+            dtf.fabric.FabricPSStrategy(dtf.train.Server.create_local_server()).minimize(opt, loss, gs)
+    finally:
+        server.stop()
