@@ -327,7 +327,8 @@ class Session:
                 else:
                     sent = self._sent.get(task, 0)
                     all_nodes = self.graph.nodes
-                    new_defs = serialize_nodes(all_nodes[sent:]) if sent < len(all_nodes) else []
+                    new_defs = serialize_nodes(all_nodes[sent:], lambda n, t=task: self._task_of(n) == t) \
+                        if sent < len(all_nodes) else []
                     out = self._client(task).call("run_segment", run_id, self._graph_key, new_defs,
                                                   [n.id for n in nodes], inputs, want, opts)
                     self._sent[task] = len(all_nodes)

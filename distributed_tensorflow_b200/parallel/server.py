@@ -64,11 +64,14 @@ class NodeView:
         self.graph = graph
 
 
-def serialize_nodes(nodes: Sequence[Any]) -> List[Dict[str, Any]]:
+def serialize_nodes(nodes: Sequence[Any], runs_here=None) -> List[Dict[str, Any]]:
+    """Wire form of graph nodes for one remote task.  Attributes travel only for nodes that task will execute
+    (``runs_here(node)``); the others are structure-only stubs (their attrs may hold client-side objects)."""
     out = []
     for n in nodes:
+        keep = runs_here is None or runs_here(n)
         out.append({"id": n.id, "name": n.name, "op_type": n.op_type, "inputs": [i.id for i in n.inputs],
-                    "control_inputs": [c.id for c in n.control_inputs], "attrs": to_wire(n.attrs),
+                    "control_inputs": [c.id for c in n.control_inputs], "attrs": to_wire(n.attrs) if keep else {},
                     "device": n.device, "dtype": n.dtype, "shape": n.shape})
     return out
 

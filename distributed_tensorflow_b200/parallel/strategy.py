@@ -49,6 +49,12 @@ from .cluster import ClusterSpec
 __all__ = ["FabricPSStrategy", "fabric_rank_of", "init_fabric_process_group"]
 
 _PG_LOCK = threading.Lock()
+_DEBUG = os.environ.get("DTF_DEBUG", "0") == "1"
+
+
+def _dbg(msg: str) -> None:
+    if _DEBUG:
+        print("[dtf.fabric %.3f pid %d] %s" % (time.time() % 1000, os.getpid(), msg), flush=True)
 
 
 def fabric_rank_of(cluster: ClusterSpec, job: str, task: int) -> Tuple[int, int]:
@@ -66,7 +72,11 @@ def init_fabric_process_group(cluster: ClusterSpec, job: str, task: int) -> Tupl
             if host in ("localhost", "", "0.0.0.0"):
                 host = "127.0.0.1"
             port = int(port) + int(os.environ.get("DTF_FABRIC_PORT_OFFSET", "1000"))
-            dist.init_process_group("gloo", init_method="tcp://%s:%d" % (host, port), rank=rank, world_size=world)
+            import datetime
+            _dbg("joining process group rank %d/%d at %s:%d" % (rank, world, host, port))
+            dist.init_process_group("gloo", init_method="tcp://%s:%d" % (host, port), rank=rank, world_size=world,
+                                    timeout=datetime.timedelta(seconds=float(os.environ.get("DTF_FABRIC_TIMEOUT", "300"))))
+            _dbg("process group up")
     return rank, world
 
 
@@ -89,9 +99,12 @@ def build_engine(cluster: ClusterSpec, job: str, task: int, spec: Dict[str, Any]
                     prefix="dtf_fabric/%s" % spec["key"])
     num_ps = cluster.num_tasks("ps")
     cfg = _engine_cfg(spec, num_ps, world - num_ps)
+    _dbg("building engine (rank %d, device %d)" % (rank, dev))
     eng = GenericPSEngine([(n, tuple(s)) for n, s, _ in spec["params"]], cfg, fabric,
                           shards=[sh for _, _, sh in spec["params"]])
+    _dbg("engine built; preparing")
     eng.prepare()
+    _dbg("engine ready")
     return eng
 
 
@@ -124,6 +137,7 @@ class _PsService:
                 gs = rk.bufs["gctl0"].tensor(torch.int64, eng.off["global_step"], 1).view(())
                 srv.store.bind(self.spec["global_step"], gs, initialized=False)
             self.ready.set()
+            _dbg("ps service loop starts")
             per_round = 1 if eng.cfg.sync else eng.cfg.num_workers
             while not self._stop.is_set() and srv.is_running:
                 for _ in range(per_round):
@@ -131,6 +145,8 @@ class _PsService:
                 rk.stream.synchronize()
                 self.applies += per_round
         except BaseException as e:  # noqa: BLE001
+            import traceback
+            traceback.print_exc()
             self.error = e
             self.ready.set()
 
@@ -172,7 +188,11 @@ class FabricPSStrategy:
                                  "replica_device_setter" % (v.var_name, v.device))
             params.append((v.var_name, [int(d) for d in v.shape], int(spec.task or 0)))
         fs = dict(optimizer.fused_spec())
-        self._spec = {"key": "g%d" % id(g), "params": params, "optimizer": fs, "global_step": global_step.var_name}
+        import hashlib
+        import json
+        # the key must be identical in every worker process (it names the fabric buffers and the ps-side service)
+        key = hashlib.md5(json.dumps([params, sorted((k, str(v)) for k, v in fs.items())]).encode()).hexdigest()[:12]
+        self._spec = {"key": "f" + key, "params": params, "optimizer": fs, "global_step": global_step.var_name}
         loss_t = convert_to_tensor(loss)
         order = needed_nodes([loss_t], set())
         placeholders = [n for n in order if n.op_type == "Placeholder"]
@@ -216,10 +236,12 @@ class FabricPSStrategy:
         """First step after (re)initialisation: adopt the ps's global_step as this worker's token base."""
         eng = self.engine
         rank = next(iter(eng.ranks))
-        eng.adopt_global_step(rank)
+        gs = eng.adopt_global_step(rank)
+        _dbg("worker primed at global_step %d" % gs)
         self._primed = True
 
     def train_step(self, ctx, node, feeds: Sequence[torch.Tensor]) -> torch.Tensor:
+        _dbg("train_step enter") if self.engine is None else None
         self._ensure_engine()
         if not self._primed:
             self._prime()

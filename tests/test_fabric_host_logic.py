@@ -66,6 +66,7 @@ def test_strategy_minimize_builds_fabric_train_step(ports):
         spec = strategy._spec
         assert [(n, s, sh) for n, s, sh in spec["params"]] == [("w", [4, 3], 1), ("b", [3], 0)]   # w->ps1, b->ps0
         assert spec["optimizer"]["kind"] == "momentum" and spec["optimizer"]["sync"] and spec["global_step"] == "global_step"
+        assert spec["key"].startswith("f") and len(spec["key"]) == 13      # content hash: same in every worker process
         assert train_op.op_type == "FabricTrainStep" and [i.op_type for i in train_op.inputs] == ["Placeholder"]
         assert train_op.device == "/job:worker/task:0/device:CPU:0"
         with pytest.raises(RuntimeError):
