@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--b3-block-n", type=int, default=64)
     ap.add_argument("--in-graph", action="store_true", help="ONE process drives all --gpus devices (in-graph replication)")
     ap.add_argument("--num-ps", type=int, default=1, help="ps shards (variables placed round-robin)")
+    ap.add_argument("--nvls", default="off", choices=["off", "on", "auto"],
+                    help="symmetric buffers + NVLS multicast: gradients reduced in the switch (multimem.ld_reduce), "
+                         "parameters published with multimem.st")
     return ap.parse_args()
 
 
@@ -155,19 +158,20 @@ def main():
         if args.mode == "async" and args.optimizer != "adam":
             args.lr /= max(1, args.gpus - args.num_ps)       # every push is applied alone: keep the effective rate
     opt = {"kind": args.optimizer, "lr": args.lr, "momentum": 0.9}
+    NVLS = {"off": False, "on": True, "auto": "auto"}[args.nvls]
     if args.in_graph and N > 1:
         cfg = EngineConfig(num_ps=args.num_ps, num_workers=N - args.num_ps, sync=args.mode == "sync", optimizer=opt,
-                           publish_replicas=args.publish, f1_splits=args.f1_splits, head_ctas=args.head_ctas,
+                           publish_replicas=args.publish, nvls=NVLS, f1_splits=args.f1_splits, head_ctas=args.head_ctas,
                            f1_block_n=args.f1_block_n, b3_block_n=args.b3_block_n)
         fabric = Fabric(N, {r: r for r in range(N)})
     elif N == 1:
         cfg = EngineConfig(num_ps=1, num_workers=1, colocated=True, sync=args.mode == "sync", optimizer=opt,
-                           publish_replicas=args.publish, f1_splits=args.f1_splits, head_ctas=args.head_ctas,
+                           publish_replicas=args.publish, nvls=NVLS, f1_splits=args.f1_splits, head_ctas=args.head_ctas,
                            f1_block_n=args.f1_block_n, b3_block_n=args.b3_block_n)
         fabric = Fabric(1, {0: local_rank})
     else:
         cfg = EngineConfig(num_ps=args.num_ps, num_workers=N - args.num_ps, sync=args.mode == "sync", optimizer=opt,
-                           publish_replicas=args.publish, f1_splits=args.f1_splits, head_ctas=args.head_ctas,
+                           publish_replicas=args.publish, nvls=NVLS, f1_splits=args.f1_splits, head_ctas=args.head_ctas,
                            f1_block_n=args.f1_block_n, b3_block_n=args.b3_block_n)
         fabric = Fabric.from_torch_distributed()
     eng = PSTrainEngine(spec, cfg, fabric)
@@ -308,7 +312,11 @@ def main():
                        "mode": args.mode, "optimizer": args.optimizer, "lr": args.lr,
                        "l2": "inputs larger than L2: 172 MB fp32 train split cycled in HBM",
                        "cuda_graph_unroll": unroll if use_graph else 0,
-                       "pull": "publish-replicas" if args.publish else "peer-pull fused in GEMM",
+                       "pull": ("nvls multimem.st publish" if getattr(eng, "nvls", False) and getattr(eng, "nvls_multicast", False)
+                                else "publish-replicas" if (args.publish or getattr(eng, "nvls", False)) else "peer-pull fused in GEMM"),
+                       "push": ("local store + nvls multimem.ld_reduce on the ps" if getattr(eng, "nvls", False) and
+                                getattr(eng, "nvls_multicast", False) else
+                                "local store + ps peer loads" if getattr(eng, "nvls", False) else "peer stores fused in GEMM epilogue"),
                        "f1_splits": args.f1_splits, "head_ctas": args.head_ctas, "f1_block_n": args.f1_block_n,
                        "b3_block_n": args.b3_block_n},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total,

@@ -82,6 +82,37 @@ DTF_DEVICE void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "mem
 DTF_DEVICE void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 DTF_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------------
+// NVLS multicast (multimem.*): the address is the mapping of a multicast object bound to one allocation per GPU.
+// A multimem store is replicated by the NVSwitch into every GPU's copy; a multimem ld_reduce makes the switch
+// read every GPU's copy and return the element-wise sum.  Both are weak accesses: order them against flags with
+// the same fence.acq_rel.sys / release-acquire protocol as ordinary peer accesses.
+// ------------------------------------------------------------------------------------------------
+DTF_DEVICE float4 multimem_ld_reduce_add_f32x4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+DTF_DEVICE void multimem_st_f32x4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+// 8 bytes (four bf16 packed in two b32 words), bit-exact copy into every GPU's replica
+DTF_DEVICE void multimem_st_b64(void* mc, uint32_t lo, uint32_t hi) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc), "f"(__uint_as_float(lo)),
+               "f"(__uint_as_float(hi))
+               : "memory");
+}
+DTF_DEVICE void multimem_st_b128(void* mc, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
+
 // Spin until *flag >= target (acquire, system scope) with a wall-clock bailout.
 // Returns false on timeout (the caller records an error instead of hanging the GPU).
 DTF_DEVICE bool wait_flag_ge_u64(const uint64_t* flag, uint64_t target, uint64_t timeout_ns) {

@@ -47,6 +47,13 @@ struct PsApplyParams {
   int trace_cap;
   long long* phase_trace;        // optional [16] clock64 stamps of block 0 / the last block
   int idle_ok;                   // 1: a timeout is not an error (host-driven service loop polls)
+  // NVLS mode (symmetric buffers, csrc/fabric_vmm.cu): the gradient slots live in the WORKERS' memories
+  // (grad[w] = unicast peer pointer to worker w's copy) and the parameter replica is one symmetric buffer.
+  const float* grad_mc;          // multicast mapping of the gradient buffer: multimem.ld_reduce = in-switch N-way sum
+  float* grad_mc_rw;             // same mapping, writable (zero-after-read of atomically accumulated ranges)
+  __nv_bfloat16* shadow_mc;      // multicast mapping of the bf16 replica: ONE multimem.st updates every GPU's copy
+  float* master_mc;              // optional multicast mapping of an fp32 replica (models that consume fp32 parameters)
+  unsigned int full_mask;        // all workers: the ld_reduce path needs every copy to hold a fresh gradient
 };
 
 DTF_DEVICE unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
@@ -63,7 +70,7 @@ DTF_DEVICE void st_release_gpu_u64(unsigned long long* p, unsigned long long v) 
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
+__global__ void __launch_bounds__(256, 4) ps_apply_kernel(const PsApplyParams p) {
   __shared__ unsigned int s_mask, s_count, s_ok;
   __shared__ unsigned long long s_seq;
   __shared__ float s_lr;
@@ -160,17 +167,26 @@ __global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
 
   if (ok) {
     // ---------------- fused reduce + mean + apply + publish ----------------
+    // NVLS: when every worker contributed, ONE multimem.ld_reduce per 16 bytes makes the switch sum the workers'
+    // copies (the ps ingests n floats instead of N*n); otherwise (backup workers, stale drops, async) the chosen
+    // workers' copies are read one by one through their unicast peer mappings.
+    const bool mc_reduce = p.grad_mc != nullptr && mask == p.full_mask;
     const long long stride = (long long)gridDim.x * blockDim.x * 4;
     for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < p.n; i0 += stride) {
       float g[4] = {0.f, 0.f, 0.f, 0.f};
       const bool vec = (i0 + 4 <= p.n);
-      for (int w = 0; w < p.num_workers; ++w) {
-        if (!(mask & (1u << w))) continue;
-        if (vec) {
-          const float4 t = *reinterpret_cast<const float4*>(p.grad[w] + i0);
-          g[0] += t.x; g[1] += t.y; g[2] += t.z; g[3] += t.w;
-        } else {
-          for (int j = 0; j < 4 && i0 + j < p.n; ++j) g[j] += p.grad[w][i0 + j];
+      if (mc_reduce && vec) {
+        const float4 t = multimem_ld_reduce_add_f32x4(p.grad_mc + i0);
+        g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+      } else {
+        for (int w = 0; w < p.num_workers; ++w) {
+          if (!(mask & (1u << w))) continue;
+          if (vec) {
+            const float4 t = *reinterpret_cast<const float4*>(p.grad[w] + i0);
+            g[0] += t.x; g[1] += t.y; g[2] += t.z; g[3] += t.w;
+          } else {
+            for (int j = 0; j < 4 && i0 + j < p.n; ++j) g[j] += p.grad[w][i0 + j];
+          }
         }
       }
       float wv[4];
@@ -196,10 +212,15 @@ __global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
       }
       if (vec) {
         const uint2 packed = make_uint2(pack_bf16x2(wv[0], wv[1]), pack_bf16x2(wv[2], wv[3]));
-        if (p.shadow) *reinterpret_cast<uint2*>(p.shadow + i0) = packed;
-        if (p.publish_replicas)
-          for (int w = 0; w < p.num_workers; ++w)
-            if (p.replica[w]) *reinterpret_cast<uint2*>(p.replica[w] + i0) = packed;     // NVLink store
+        if (p.master_mc) multimem_st_f32x4(p.master_mc + i0, make_float4(wv[0], wv[1], wv[2], wv[3]));
+        if (p.shadow_mc) {
+          multimem_st_b64(p.shadow_mc + i0, packed.x, packed.y);      // the switch writes every GPU's replica (ours too)
+        } else {
+          if (p.shadow) *reinterpret_cast<uint2*>(p.shadow + i0) = packed;
+          if (p.publish_replicas)
+            for (int w = 0; w < p.num_workers; ++w)
+              if (p.replica[w]) *reinterpret_cast<uint2*>(p.replica[w] + i0) = packed;     // NVLink store
+        }
       } else {
         for (int j = 0; j < 4 && i0 + j < p.n; ++j) {
           const __nv_bfloat16 b = __float2bfloat16(wv[j]);
@@ -211,6 +232,10 @@ __global__ void __launch_bounds__(256) ps_apply_kernel(const PsApplyParams p) {
       }
       for (int z = 0; z < p.num_zero; ++z) {
         if (i0 + 4 > p.zero_begin[z] && i0 < p.zero_end[z]) {
+          if (mc_reduce && vec && i0 >= p.zero_begin[z] && i0 + 4 <= p.zero_end[z]) {
+            multimem_st_f32x4(p.grad_mc_rw + i0, make_float4(0.f, 0.f, 0.f, 0.f));     // clears every worker's copy
+            continue;
+          }
           for (int w = 0; w < p.num_workers; ++w) {
             if (!(mask & (1u << w))) continue;
             for (int j = 0; j < 4; ++j) {
@@ -703,10 +728,93 @@ __global__ void pull_shadow_kernel(const uint4* __restrict__ src_peer, uint4* __
     dst[i] = src_peer[i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fabric collectives as plain kernels (generic models, fabric tests, push/pull bandwidth measurements):
+//   broadcast: one source buffer -> every GPU's copy.   NVLS: one multimem.st per 16 bytes (the switch fans out);
+//              unicast: one peer store per destination (npeers x the egress bytes).
+//   reduce:    element-wise sum of every GPU's copy.     NVLS: one multimem.ld_reduce per 16 bytes (in-switch add);
+//              unicast: one peer load per source (npeers x the ingress bytes).
+// ---------------------------------------------------------------------------------------------
+struct PeerList {
+  void* p[DTF_MAX_WORKERS];
+};
+
+// Each thread keeps four 16-byte accesses in flight (independent loads first, then the stores / adds): a single
+// multimem round trip through the switch is microseconds, so bandwidth comes from memory-level parallelism.
+__global__ void __launch_bounds__(256) fabric_bcast_kernel(const uint4* __restrict__ src, uint4* mc_dst, PeerList peers, int npeers,
+                                                           long long n16) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * stride < n16) v[u] = src[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long j = i + u * stride;
+      if (j >= n16) break;
+      if (mc_dst != nullptr) {
+        multimem_st_b128(mc_dst + j, v[u]);
+      } else {
+        for (int k = 0; k < npeers; ++k) reinterpret_cast<uint4*>(peers.p[k])[j] = v[u];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) fabric_reduce_kernel(const float* mc_src, PeerList peers, int npeers, float* __restrict__ dst,
+                                                            long long n4) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 4 * stride) {
+    float4 acc[4];
+    if (mc_src != nullptr) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * stride < n4) acc[u] = multimem_ld_reduce_add_f32x4(mc_src + 4 * (i + u * stride));
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < npeers; ++k) {
+        float4 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i + u * stride < n4) t[u] = reinterpret_cast<const float4*>(peers.p[k])[i + u * stride];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i + u * stride < n4) { acc[u].x += t[u].x; acc[u].y += t[u].y; acc[u].z += t[u].z; acc[u].w += t[u].w; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * stride < n4) reinterpret_cast<float4*>(dst)[i + u * stride] = acc[u];
+  }
+}
+
 }  // namespace dtf
 
 extern "C" {
 using namespace dtf;
+
+int dtf_fabric_bcast(const void* src, void* mc_dst, void* const* peer_dst, int npeers, long long nbytes, int grid,
+                     cudaStream_t s) {
+  if (nbytes % 16 || npeers > DTF_MAX_WORKERS) return -2;
+  PeerList pl;
+  memset(&pl, 0, sizeof(pl));
+  for (int k = 0; k < npeers; ++k) pl.p[k] = peer_dst[k];
+  fabric_bcast_kernel<<<grid > 0 ? grid : 296, 256, 0, s>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(mc_dst), pl,
+                                                           npeers, nbytes / 16);
+  return (int)cudaGetLastError();
+}
+
+int dtf_fabric_reduce(const void* mc_src, void* const* peer_src, int npeers, float* dst, long long nfloats, int grid,
+                      cudaStream_t s) {
+  if (nfloats % 4 || npeers > DTF_MAX_WORKERS) return -2;
+  PeerList pl;
+  memset(&pl, 0, sizeof(pl));
+  for (int k = 0; k < npeers; ++k) pl.p[k] = peer_src[k];
+  fabric_reduce_kernel<<<grid > 0 ? grid : 296, 256, 0, s>>>(reinterpret_cast<const float*>(mc_src), pl, npeers, dst, nfloats / 4);
+  return (int)cudaGetLastError();
+}
 
 int dtf_sizeof_ps_control() { return (int)sizeof(PsControl); }
 int dtf_sizeof_mailbox() { return (int)sizeof(WorkerMailbox); }
@@ -752,6 +860,9 @@ struct DtfPsApplyArgs {
   int system_scope;
   long long* phase_trace;
   int idle_ok;
+  const float* grad_mc;
+  void* shadow_mc;
+  float* master_mc;
 };
 
 int dtf_ps_apply(const DtfPsApplyArgs* a, cudaStream_t s) {
@@ -773,10 +884,14 @@ int dtf_ps_apply(const DtfPsApplyArgs* a, cudaStream_t s) {
   p.num_zero = a->num_zero;
   p.timeout_ns = a->timeout_ns ? a->timeout_ns : 2000000000ull;
   p.trace = a->trace; p.trace_cap = a->trace_cap; p.phase_trace = a->phase_trace; p.idle_ok = a->idle_ok;
+  p.grad_mc = a->grad_mc; p.grad_mc_rw = const_cast<float*>(a->grad_mc);
+  p.shadow_mc = reinterpret_cast<__nv_bfloat16*>(a->shadow_mc);
+  p.master_mc = a->master_mc;
+  p.full_mask = a->num_workers >= 32 ? 0xFFFFFFFFu : ((1u << a->num_workers) - 1u);
   int grid = a->grid;
   if (grid <= 0) {
     long long want = (a->n / 4 + 255) / 256;                       // one float4 per thread: a single load round trip
-    grid = (int)(want < 1 ? 1 : (want > 148 ? 148 : want));      // all CTAs must be co-resident
+    grid = (int)(want < 1 ? 1 : (want > 592 ? 592 : want));      // all CTAs must be co-resident (4 per SM by launch bounds)
   }
   ps_apply_kernel<<<grid, 256, 0, s>>>(p);
   return (int)cudaGetLastError();

@@ -1,0 +1,168 @@
+// Native step executor: one C call enqueues a whole training step (host->device copies of the batch, every kernel
+// of the step, the device->host read of the loss) and -- optionally -- waits for it.
+//
+// The Python engines build an op list ONCE per rank (pointers into their ctypes launch descriptors); per step only
+// the host source pointers of the H2D ops change.  This is the host half of the "launch-bound inner loop" story:
+// the device half is CUDA-graph replay (bench kernel-only number), this is the end-to-end path a user's
+// `engine.step(x_pinned, y_pinned) -> loss` call takes (SURVEY A8 feed_dict + fetch of the loss, C7).
+//
+// Role in the reference: the per-step `mon_sess.run([train_step, global_step, loss], feed_dict=...)` round trip
+// (distributed_mnist.py:152) -- feed copied to the device, the step executed, the fetched loss copied back.
+#include <cstdio>
+#include <cstring>
+
+#include <cuda_runtime.h>
+
+extern "C" {
+
+// entry points of the other translation units (same shared object)
+struct DtfGemmArgs;
+struct DtfMlpHeadArgs;
+struct DtfPsApplyArgs;
+int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream);
+int dtf_mlp_head(const DtfMlpHeadArgs* a, cudaStream_t s);
+int dtf_ps_apply(const DtfPsApplyArgs* a, cudaStream_t s);
+int dtf_convert_f32_bf16(const float* in, long long ld_in, void* out, long long ld_out, long long rows, long long cols,
+                         long long cols_pad, cudaStream_t s);
+int dtf_wait_token(const void* mailbox, unsigned long long target, const unsigned long long* target_ptr,
+                   unsigned long long timeout_ns, unsigned int* err, cudaStream_t s);
+int dtf_push_grad(const float* src, float* dst_peer, long long n, void* ctl, const void* mailbox, int rank,
+                  int stamp_from_version, int write_stamp, int grid, cudaStream_t s);
+int dtf_stage_from_dataset(const float* images, const float* labels, long long nbatches, int B, int D, int C,
+                           long long stride, long long offset, const unsigned long long* step_counter, void* x16,
+                           float* lab_out, cudaStream_t s);
+
+enum DtfOpKind {
+  DTF_OP_H2D = 1,         // p0 = dst (device), p1 = src (pinned host), i0 = bytes
+  DTF_OP_D2H = 2,         // p0 = dst (pinned host), p1 = src (device), i0 = bytes
+  DTF_OP_CONVERT = 3,     // p0 = in f32, p1 = out bf16, i0 = ld_in, i1 = ld_out, i2 = rows, i3 = cols, i4 = cols_pad
+  DTF_OP_GEMM = 4,        // p0 = DtfGemmArgs*
+  DTF_OP_HEAD = 5,        // p0 = DtfMlpHeadArgs*
+  DTF_OP_PS_APPLY = 6,    // p0 = DtfPsApplyArgs*
+  DTF_OP_WAIT_TOKEN = 7,  // p0 = mailbox, p1 = target_ptr, p2 = err, i0 = target, u0 = timeout_ns
+  DTF_OP_SIGNAL = 8,      // p0 = ctl, p1 = mailbox, i0 = worker index, i1 = stamp_from_version
+  DTF_OP_STAGE = 9,       // p0 = images, p1 = labels, p2 = step counter, p3 = x16, p4 = labels out, i0 = nbatches, i1 = B,
+                          // i2 = D, i3 = C, i4 = stride, i5 = offset
+  DTF_OP_SYNC = 10,       // cudaStreamSynchronize
+  DTF_OP_EVENT_RECORD = 11,   // p0 = cudaEvent_t
+  DTF_OP_EVENT_WAIT = 12,     // p0 = cudaEvent_t (cross-stream dependency)
+  DTF_OP_GRAPH = 13           // p0 = cudaGraphExec_t captured from a kernel-only op range (dtf_capture_ops)
+};
+
+struct DtfStepOp {
+  int kind;
+  int is_kernel;          // counted by the launch counter (filled by the executor's caller for bookkeeping only)
+  void* p0;
+  void* p1;
+  void* p2;
+  void* p3;
+  void* p4;
+  long long i0, i1, i2, i3, i4, i5;
+  unsigned long long u0;
+};
+
+// Runs ops[0..n) on `stream` of `device` (>= 0: made current for the call and restored afterwards).
+// Returns 0, or (index + 1) * 100000 + |code| of the first failing op.  *kernels_out += kernels launched.
+int dtf_run_ops(const DtfStepOp* ops, int n, int device, cudaStream_t stream, int* kernels_out) {
+  int prev = -1;
+  if (device >= 0) {
+    cudaGetDevice(&prev);
+    if (prev != device) cudaSetDevice(device); else prev = -1;
+  }
+  int rc = 0, kernels = 0, i = 0;
+  for (; i < n && rc == 0; ++i) {
+    const DtfStepOp& o = ops[i];
+    switch (o.kind) {
+      case DTF_OP_H2D:
+        rc = (int)cudaMemcpyAsync(o.p0, o.p1, (size_t)o.i0, cudaMemcpyHostToDevice, stream);
+        break;
+      case DTF_OP_D2H:
+        rc = (int)cudaMemcpyAsync(o.p0, o.p1, (size_t)o.i0, cudaMemcpyDeviceToHost, stream);
+        break;
+      case DTF_OP_CONVERT:
+        rc = dtf_convert_f32_bf16(reinterpret_cast<const float*>(o.p0), o.i0, o.p1, o.i1, o.i2, o.i3, o.i4, stream);
+        ++kernels;
+        break;
+      case DTF_OP_GEMM:
+        rc = dtf_gemm_bf16(reinterpret_cast<const DtfGemmArgs*>(o.p0), stream);
+        ++kernels;
+        break;
+      case DTF_OP_HEAD:
+        rc = dtf_mlp_head(reinterpret_cast<const DtfMlpHeadArgs*>(o.p0), stream);
+        ++kernels;
+        break;
+      case DTF_OP_PS_APPLY:
+        rc = dtf_ps_apply(reinterpret_cast<const DtfPsApplyArgs*>(o.p0), stream);
+        ++kernels;
+        break;
+      case DTF_OP_WAIT_TOKEN:
+        rc = dtf_wait_token(o.p0, (unsigned long long)o.i0, reinterpret_cast<const unsigned long long*>(o.p1), o.u0,
+                            reinterpret_cast<unsigned int*>(o.p2), stream);
+        ++kernels;
+        break;
+      case DTF_OP_SIGNAL:
+        rc = dtf_push_grad(nullptr, nullptr, 0, o.p0, o.p1, (int)o.i0, (int)o.i1, 1, 1, stream);
+        ++kernels;
+        break;
+      case DTF_OP_STAGE:
+        rc = dtf_stage_from_dataset(reinterpret_cast<const float*>(o.p0), reinterpret_cast<const float*>(o.p1), o.i0, (int)o.i1,
+                                    (int)o.i2, (int)o.i3, o.i4, o.i5, reinterpret_cast<const unsigned long long*>(o.p2), o.p3,
+                                    reinterpret_cast<float*>(o.p4), stream);
+        ++kernels;
+        break;
+      case DTF_OP_SYNC:
+        rc = (int)cudaStreamSynchronize(stream);
+        break;
+      case DTF_OP_EVENT_RECORD:
+        rc = (int)cudaEventRecord(reinterpret_cast<cudaEvent_t>(o.p0), stream);
+        break;
+      case DTF_OP_EVENT_WAIT:
+        rc = (int)cudaStreamWaitEvent(stream, reinterpret_cast<cudaEvent_t>(o.p0), 0);
+        break;
+      case DTF_OP_GRAPH:
+        rc = (int)cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(o.p0), stream);
+        kernels += (int)o.i0;       // kernels inside the graph (recorded at capture time)
+        break;
+      default:
+        rc = -99;
+    }
+  }
+  if (kernels_out) *kernels_out += kernels;
+  if (prev >= 0) cudaSetDevice(prev);
+  if (rc != 0) return i * 100000 + (rc < 0 ? -rc : rc);
+  return 0;
+}
+
+// Capture ops[0..n) (kernel launches whose step-dependent inputs all come from device memory: wait targets and
+// batch indices are read from device counters, never from launch arguments) into an executable CUDA graph.
+// Every kernel must have been launched eagerly once before (first-launch attribute setup is not capturable).
+int dtf_capture_ops(const DtfStepOp* ops, int n, int device, cudaStream_t stream, void** exec_out, int* kernels_out) {
+  int prev = -1;
+  if (device >= 0) {
+    cudaGetDevice(&prev);
+    if (prev != device) cudaSetDevice(device); else prev = -1;
+  }
+  int rc = (int)cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+  int kernels = 0;
+  if (rc == 0) {
+    rc = dtf_run_ops(ops, n, -1, stream, &kernels);
+    cudaGraph_t graph = nullptr;
+    const int rc2 = (int)cudaStreamEndCapture(stream, &graph);
+    if (rc == 0) rc = rc2;
+    if (rc == 0) {
+      cudaGraphExec_t exec = nullptr;
+      rc = (int)cudaGraphInstantiate(&exec, graph, 0);
+      if (rc == 0) *exec_out = exec;
+    }
+    if (graph) cudaGraphDestroy(graph);
+  }
+  if (kernels_out) *kernels_out = kernels;
+  if (prev >= 0) cudaSetDevice(prev);
+  return rc;
+}
+
+int dtf_graph_destroy(void* exec) { return (int)cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(exec)); }
+
+int dtf_sizeof_step_op() { return (int)sizeof(DtfStepOp); }
+
+}  // extern "C"

@@ -50,7 +50,8 @@ class PsApplyArgs(Structure):
                 ("nesterov", c_int), ("publish_replicas", c_int),
                 ("zero_begin", c_longlong * 4), ("zero_end", c_longlong * 4), ("num_zero", c_int),
                 ("timeout_ns", c_ulonglong), ("trace", c_void_p), ("trace_cap", c_int), ("grid", c_int),
-                ("system_scope", c_int), ("phase_trace", c_void_p), ("idle_ok", c_int)]
+                ("system_scope", c_int), ("phase_trace", c_void_p), ("idle_ok", c_int),
+                ("grad_mc", c_void_p), ("shadow_mc", c_void_p), ("master_mc", c_void_p)]
 
 
 class MlpHeadArgs(Structure):
@@ -63,6 +64,61 @@ class MlpHeadArgs(Structure):
                 ("mailbox", c_void_p), ("ctl", c_void_p), ("rank", c_int), ("stamp_from_version", c_int),
                 ("phase_trace", c_void_p), ("h_acc", c_void_p), ("ld_acc", c_longlong), ("b1", c_void_p),
                 ("sys_scope", c_int), ("ctas", c_int)]
+
+
+class StepOp(Structure):
+    """One entry of a native step plan (``csrc/step_exec.cu``: ``DtfStepOp``)."""
+    _fields_ = [("kind", c_int), ("is_kernel", c_int), ("p0", c_void_p), ("p1", c_void_p), ("p2", c_void_p),
+                ("p3", c_void_p), ("p4", c_void_p), ("i0", c_longlong), ("i1", c_longlong), ("i2", c_longlong),
+                ("i3", c_longlong), ("i4", c_longlong), ("i5", c_longlong), ("u0", c_ulonglong)]
+
+
+OP_H2D, OP_D2H, OP_CONVERT, OP_GEMM, OP_HEAD, OP_PS_APPLY, OP_WAIT_TOKEN, OP_SIGNAL, OP_STAGE, OP_SYNC = range(1, 11)
+OP_GRAPH = 13
+_KERNEL_OPS = (OP_CONVERT, OP_GEMM, OP_HEAD, OP_PS_APPLY, OP_WAIT_TOKEN, OP_SIGNAL, OP_STAGE)
+
+
+class StepPlan:
+    """A fixed op sequence executed by ONE native call (memcpys, kernel launches, optional stream sync)."""
+
+    def __init__(self, ops: Sequence[StepOp], device: int, stream: int, keep=()):
+        self.n = len(ops)
+        self.ops = (StepOp * self.n)(*ops)
+        self.device, self.stream = int(device), stream
+        self.keep = list(keep)            # objects whose memory the ops point into
+        self._kernels = c_int(0)
+
+    def run(self) -> int:
+        self._kernels.value = 0
+        rc = load().dtf_run_ops(self.ops, self.n, self.device, self.stream, byref(self._kernels))
+        if rc:
+            raise RuntimeError("native step plan failed at op %d (kind %d) with code %d" % (
+                rc // 100000 - 1, self.ops[rc // 100000 - 1].kind, rc % 100000))
+        _bump(self._kernels.value)
+        return self._kernels.value
+
+    def graphed(self) -> "StepPlan":
+        """Same plan with every maximal run of kernel ops replaced by ONE CUDA-graph launch.  Call after the plan
+        has run eagerly at least once (first-launch attribute setup cannot be captured)."""
+        lib = load()
+        out, i, keep = [], 0, list(self.keep) + [self]
+        while i < self.n:
+            if self.ops[i].kind not in _KERNEL_OPS:
+                out.append(self.ops[i])
+                i += 1
+                continue
+            j = i
+            while j < self.n and self.ops[j].kind in _KERNEL_OPS:
+                j += 1
+            sub = (StepOp * (j - i))(*[self.ops[k] for k in range(i, j)])
+            ex, nk = c_void_p(), c_int(0)
+            rc = lib.dtf_capture_ops(sub, j - i, self.device, self.stream, byref(ex), byref(nk))
+            if rc or not ex.value:
+                raise RuntimeError("CUDA-graph capture of ops [%d, %d) failed with code %d" % (i, j, rc))
+            out.append(StepOp(kind=OP_GRAPH, p0=ex.value, i0=nk.value))
+            keep.append(sub)
+            i = j
+        return StepPlan(out, self.device, self.stream, keep=keep)
 
 
 def available() -> bool:
@@ -127,6 +183,32 @@ def load() -> ctypes.CDLL:
                      "dtf_ipc_handle_size"):
             getattr(lib, name).restype = c_int
         lib.dtf_offsetof_ctl.argtypes = [c_int]
+        lib.dtf_fabric_bcast.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_int, c_void_p]
+        lib.dtf_fabric_reduce.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_longlong, c_int, c_void_p]
+        lib.dtf_vmm_support.argtypes = [c_int]
+        lib.dtf_vmm_granularity.argtypes = [c_int, c_int, POINTER(c_longlong)]
+        lib.dtf_vmm_create.argtypes = [c_int, c_longlong, POINTER(c_ulonglong)]
+        lib.dtf_vmm_map.argtypes = [c_ulonglong, c_longlong, c_int, POINTER(c_void_p)]
+        lib.dtf_vmm_unmap.argtypes = [c_void_p, c_longlong]
+        lib.dtf_vmm_release.argtypes = [c_ulonglong]
+        lib.dtf_vmm_export_fd.argtypes = [c_ulonglong, POINTER(c_int)]
+        lib.dtf_vmm_import_fd.argtypes = [c_int, POINTER(c_ulonglong)]
+        lib.dtf_mc_create.argtypes = [c_int, c_longlong, POINTER(c_ulonglong)]
+        lib.dtf_mc_add_device.argtypes = [c_ulonglong, c_int]
+        lib.dtf_mc_bind.argtypes = [c_ulonglong, c_ulonglong, c_longlong]
+        lib.dtf_mc_unbind.argtypes = [c_ulonglong, c_int, c_longlong]
+        for name in ("dtf_fabric_bcast", "dtf_fabric_reduce", "dtf_vmm_support", "dtf_vmm_granularity", "dtf_vmm_create",
+                     "dtf_vmm_map", "dtf_vmm_unmap", "dtf_vmm_release", "dtf_vmm_export_fd", "dtf_vmm_import_fd",
+                     "dtf_mc_create", "dtf_mc_add_device", "dtf_mc_bind", "dtf_mc_unbind"):
+            getattr(lib, name).restype = c_int
+        lib.dtf_run_ops.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
+        lib.dtf_run_ops.restype = c_int
+        lib.dtf_capture_ops.argtypes = [c_void_p, c_int, c_int, c_void_p, POINTER(c_void_p), POINTER(c_int)]
+        lib.dtf_capture_ops.restype = c_int
+        lib.dtf_graph_destroy.argtypes = [c_void_p]
+        lib.dtf_graph_destroy.restype = c_int
+        lib.dtf_sizeof_step_op.restype = c_int
+        assert lib.dtf_sizeof_step_op() == ctypes.sizeof(StepOp), "StepOp layout mismatch"
         _LIB = lib
         return lib
 

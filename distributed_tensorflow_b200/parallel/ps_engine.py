@@ -58,6 +58,9 @@ class EngineConfig:
     clip_min: float = 1e-10
     publish_replicas: bool = False        # True: ps stores new params into every worker's replica (push-publish)
     colocated: bool = False               # single GPU: ps shard 0 and worker 0 share device + stream
+    nvls: Any = False                     # True/"auto": symmetric VMM buffers -- gradients stay in the WORKERS' HBM and the
+                                          # ps sums them with multimem.ld_reduce (in-switch), parameters are published with
+                                          # ONE multimem.st stream into every GPU's replica ("auto": only if the box has NVLS)
     f1_splits: int = 1                    # split-K CTAs for the first GEMM (fp32 atomic partials, bias+ReLU in the head)
     head_ctas: int = 8                    # row-parallel CTAs of the fused head (batch reductions via fp32 atomics)
     f1_block_n: int = 64                  # N tile of the forward GEMM (0: one tile covering `hidden`)
@@ -169,6 +172,23 @@ class PSTrainEngine:
     def _allocate(self) -> None:
         f, cfg, spec = self.fabric, self.cfg, self.spec
         W = cfg.num_workers
+        # ---- NVLS mode: one symmetric gradient buffer and one symmetric bf16 replica per shard (collective allocs) ----
+        want = cfg.nvls
+        self.nvls = False
+        self.sym_grads: List[Any] = []
+        self.sym_repl: List[Any] = []
+        if want and self.world > 1:
+            level = f.nvls_level()
+            if want == "auto" and level < 2:
+                want = False
+            elif level == 0:
+                raise RuntimeError("nvls=True needs CUDA VMM (POSIX fd export); not available on this machine")
+        if want and self.world > 1:
+            self.nvls = True
+            for s in range(cfg.num_ps):
+                self.sym_grads.append(f.alloc_symmetric("sgrads%d" % s, self.shard_elems[s] * 4))
+                self.sym_repl.append(f.alloc_symmetric("srepl%d" % s, self.shard_elems[s] * 2))
+            self.nvls_multicast = self.sym_grads[0].multicast
         for r, rk in self.ranks.items():
             if r in self.ps_ranks:
                 s = self.ps_ranks.index(r)
@@ -176,8 +196,13 @@ class PSTrainEngine:
                 for name, nbytes in (("ctl%d" % s, self.ctl_bytes), ("master%d" % s, n * 4), ("shadow%d" % s, n * 2),
                                      ("grads%d" % s, n * 4 * W), ("slot_m%d" % s, n * 4), ("slot_v%d" % s, n * 4),
                                      ("trace%d" % s, cfg.trace_cap * 32)):
-                    rk.bufs[name] = f.alloc(r, name, nbytes)
-                for name in ("ctl%d" % s, "master%d" % s, "shadow%d" % s, "grads%d" % s):
+                    if self.nvls and name.startswith("shadow"):
+                        rk.bufs[name] = self.sym_repl[s].local(r)           # the ps's own copy of the replica
+                    elif self.nvls and name.startswith("grads"):
+                        rk.bufs[name] = self.sym_grads[s].local(r)          # stays zero: the ps contributes nothing
+                    else:
+                        rk.bufs[name] = f.alloc(r, name, nbytes)
+                for name in ("ctl%d" % s, "master%d" % s) + (() if self.nvls else ("shadow%d" % s, "grads%d" % s)):
                     f.publish(r, name)
             if r in self.worker_ranks:
                 w = self.worker_ranks.index(r)
@@ -188,11 +213,14 @@ class PSTrainEngine:
                          ("h_w%d" % w, 128 * ldh * 2), ("dh_w%d" % w, 128 * ldh * 2), ("hacc_w%d" % w, 128 * ldh * 4),
                          ("misc_w%d" % w, 4096 + cfg.loss_hist * 4)]
                 for s in range(cfg.num_ps):
-                    names.append(("replica%d_w%d" % (s, w), self.shard_elems[s] * 2))
+                    if self.nvls:
+                        rk.bufs["replica%d_w%d" % (s, w)] = self.sym_repl[s].local(r)
+                    else:
+                        names.append(("replica%d_w%d" % (s, w), self.shard_elems[s] * 2))
                 for name, nbytes in names:
                     rk.bufs[name] = f.alloc(r, name, nbytes)
                 f.publish(r, "mailbox_w%d" % w)
-                if cfg.publish_replicas:
+                if cfg.publish_replicas and not self.nvls:
                     for s in range(cfg.num_ps):
                         f.publish(r, "replica%d_w%d" % (s, w))
 
@@ -202,13 +230,17 @@ class PSTrainEngine:
         for r in self.ranks:
             if r in self.worker_ranks:
                 for s, pr in enumerate(self.ps_ranks):
-                    for base in ("ctl", "master", "shadow", "grads"):
+                    for base in ("ctl", "master") + (() if self.nvls else ("shadow", "grads")):
                         self.peer[(r, "%s%d" % (base, s))] = f.peer(r, pr, "%s%d" % (base, s))
             if r in self.ps_ranks:
+                s = self.ps_ranks.index(r)
                 for w, wr in enumerate(self.worker_ranks):
                     self.peer[(r, "mailbox_w%d" % w)] = f.peer(r, wr, "mailbox_w%d" % w)
-                    if cfg.publish_replicas:
-                        s = self.ps_ranks.index(r)
+                    if self.nvls:
+                        # unicast views of every worker's copies: async / backup-worker reads, replica stores without NVLS
+                        self.peer[(r, "sgrads%d_w%d" % (s, w))] = self.sym_grads[s].peer(r, wr)
+                        self.peer[(r, "replica%d_w%d" % (s, w))] = self.sym_repl[s].peer(r, wr)
+                    elif cfg.publish_replicas:
                         self.peer[(r, "replica%d_w%d" % (s, w))] = f.peer(r, wr, "replica%d_w%d" % (s, w))
 
     # ------------------------------------------------------------------------------------------------
@@ -260,10 +292,10 @@ class PSTrainEngine:
                 rc = self.lib.dtf_ps_publish(rk.bufs["master%d" % s].ptr, rk.bufs["shadow%d" % s].ptr, n,
                                              rk.stream.cuda_stream)
                 assert rc == 0, rc
-                if cfg.publish_replicas:
-                    sh = rk.bufs["shadow%d" % s].tensor(torch.bfloat16)
+                if cfg.publish_replicas or self.nvls:
+                    sh = rk.bufs["shadow%d" % s].tensor(torch.bfloat16, 0, n)
                     for w in range(cfg.num_workers):
-                        self.peer[(r, "replica%d_w%d" % (s, w))].tensor(torch.bfloat16).copy_(sh)
+                        self.peer[(r, "replica%d_w%d" % (s, w))].tensor(torch.bfloat16, 0, n).copy_(sh)
             rk.stream.synchronize()
         for r, rk in self.ranks.items():
             if r in self.worker_ranks:
@@ -272,6 +304,8 @@ class PSTrainEngine:
                     for name in ("mailbox_w%d" % w, "misc_w%d" % w, "x16_w%d" % w, "h_w%d" % w, "dh_w%d" % w,
                                  "labels_w%d" % w, "hacc_w%d" % w):
                         rk.bufs[name].tensor(torch.uint8).zero_()
+                    for sg in self.sym_grads:
+                        sg.local(r).tensor(torch.uint8).zero_()
                 rk.stream.synchronize()
             rk.step = 0
         self.fabric.barrier()
@@ -330,11 +364,13 @@ class PSTrainEngine:
             d["mb0"] = mb.ptr
 
             def src(base: str, l: VarLayout, es: int) -> int:
-                if cfg.publish_replicas and base == "shadow":
-                    return rk.bufs["replica%d_w%d" % (l.shard, w)].ptr + l.offset * es
+                if (cfg.publish_replicas or self.nvls) and base == "shadow":
+                    return rk.bufs["replica%d_w%d" % (l.shard, w)].ptr + l.offset * es      # local copy
                 return self.peer[(r, "%s%d" % (base, l.shard))].ptr + l.offset * es
 
             def slot(l: VarLayout) -> int:
+                if self.nvls:
+                    return self.sym_grads[l.shard].local(r).ptr + l.offset * 4              # gradients stay local
                 return self.peer[(r, "grads%d" % l.shard)].ptr + (w * self.shard_elems[l.shard] + l.offset) * 4
 
             def ctl_arrivals(shard: int) -> int:
@@ -410,10 +446,13 @@ class PSTrainEngine:
             a.slot_m, a.slot_v = rk.bufs["slot_m%d" % s].ptr, rk.bufs["slot_v%d" % s].ptr
             a.shadow = rk.bufs["shadow%d" % s].ptr
             for w in range(cfg.num_workers):
-                a.grad[w] = rk.bufs["grads%d" % s].ptr + w * n * 4
+                a.grad[w] = self.peer[(r, "sgrads%d_w%d" % (s, w))].ptr if self.nvls else rk.bufs["grads%d" % s].ptr + w * n * 4
                 a.mailbox[w] = self.peer[(r, "mailbox_w%d" % w)].ptr + s * self.mb_bytes
-                if cfg.publish_replicas:
+                if cfg.publish_replicas or (self.nvls and not self.nvls_multicast):
                     a.replica[w] = self.peer[(r, "replica%d_w%d" % (s, w))].ptr
+            if self.nvls and self.nvls_multicast:
+                a.grad_mc = self.sym_grads[s].mc(r)
+                a.shadow_mc = self.sym_repl[s].mc(r)
             a.n, a.num_workers, a.replicas_to_aggregate = n, cfg.num_workers, self.R
             a.ctas_per_push = self.ctas_per_push[s]
             a.mode, a.kind = (0 if cfg.sync else 1), self.kind
@@ -422,7 +461,7 @@ class PSTrainEngine:
             a.beta1, a.beta2, a.eps = float(self.opt.get("beta1", 0.9)), float(self.opt.get("beta2", 0.999)), \
                 float(self.opt.get("eps", self.opt.get("epsilon", 1e-8)))
             a.nesterov = int(bool(self.opt.get("nesterov", False)))
-            a.publish_replicas = int(cfg.publish_replicas)
+            a.publish_replicas = int(cfg.publish_replicas or (self.nvls and not self.nvls_multicast))
             a.num_zero = 0
             if self.head_ctas > 1:
                 # the row-parallel head accumulates dW2 / db2 / db1 with atomics: clear those slot ranges after reading
@@ -531,16 +570,117 @@ class PSTrainEngine:
             assert rc == 0, rc
         cuda_lib._bump()
 
+    # ------------------------------------------------------------------------------------------------
+    # native step plans (end-to-end path: one C call per rank per step, see csrc/step_exec.cu)
+    # ------------------------------------------------------------------------------------------------
+    def _plans(self) -> Dict[str, Any]:
+        """Per-rank op sequences for ``step(x_pinned, y_pinned)``: H2D x, H2D y, fp32->bf16 staging, the worker's
+        kernels / the ps's apply kernels, and -- for the rank whose loss is returned -- D2H of the loss partials
+        into pinned host memory + a stream sync.  Built once; per step only the H2D source pointers change."""
+        got = getattr(self, "_native_plans", None)
+        if got is not None:
+            return got
+        from ..ops.cuda_lib import (OP_CONVERT, OP_D2H, OP_GEMM, OP_H2D, OP_HEAD, OP_PS_APPLY, OP_SIGNAL, OP_SYNC,
+                                    OP_WAIT_TOKEN, StepOp, StepPlan)
+        B, D, C = self.spec.batch, self.spec.in_dim, self.spec.classes
+        plans: Dict[str, Any] = {"worker": {}, "ps": {}, "loss": {}}
+        for r, rk in self.ranks.items():
+            st = rk.stream.cuda_stream
+            if r in self.worker_ranks:
+                w = self.worker_ranks.index(r)
+                d = self._w[r]
+                xf, lab, x16 = rk.bufs["xf32_w%d" % w].ptr, rk.bufs["labels_w%d" % w].ptr, rk.bufs["x16_w%d" % w].ptr
+                ops = [StepOp(kind=OP_H2D, p0=xf, p1=None, i0=B * D * 4), StepOp(kind=OP_H2D, p0=lab, p1=None, i0=B * C * 4),
+                       StepOp(kind=OP_CONVERT, p0=xf, p1=x16, i0=D, i1=D, i2=B, i3=D, i4=D)]
+                for s_ in d["extra_wait_shards"]:
+                    ops.append(StepOp(kind=OP_WAIT_TOKEN, p0=rk.bufs["mailbox_w%d" % w].ptr + s_ * self.mb_bytes,
+                                      p1=d["stepctr_ptr"], p2=d["err_ptr"], i0=0, u0=self.cfg.timeout_ns))
+                g1, hd, g3 = d["g1"], d["head"], d["g3"]
+                g1.wait_target, g1.wait_target_ptr = 0, d["stepctr_ptr"]
+                if d["head_ctls"]:
+                    hd.ctl, hd.mailbox = d["head_ctls"][0], d["head_mailboxes"][0]
+                else:
+                    hd.ctl, hd.mailbox = None, d["mb0"]
+                ops.append(StepOp(kind=OP_GEMM, p0=ctypes.addressof(g1)))
+                ops.append(StepOp(kind=OP_HEAD, p0=ctypes.addressof(hd)))
+                for ctl_ptr, mbp in zip(d["head_ctls"][1:], d["head_mailboxes"][1:]):
+                    ops.append(StepOp(kind=OP_SIGNAL, p0=ctl_ptr, p1=mbp, i0=w, i1=hd.stamp_from_version))
+                ops.append(StepOp(kind=OP_GEMM, p0=ctypes.addressof(g3)))
+                keep = [g1, hd, g3]
+                if self.cfg.colocated:
+                    # ps and worker share the GPU and the stream: the apply joins the worker's plan (one graph)
+                    ops += [StepOp(kind=OP_PS_APPLY, p0=ctypes.addressof(self._p[r]))
+                            for _ in range(1 if self.cfg.sync else self.cfg.num_workers)]
+                    keep.append(self._p[r])
+                plans["worker"][r] = StepPlan(ops, rk.device.index, st, keep=keep)
+                host = torch.zeros(16, dtype=torch.float32).pin_memory()
+                plans["loss"][r] = (StepPlan([StepOp(kind=OP_D2H, p0=host.data_ptr(), p1=d["loss_ptr"], i0=self.head_ctas * 4),
+                                              StepOp(kind=OP_SYNC)], rk.device.index, st), host)
+            if r in self.ps_ranks and not self.cfg.colocated:
+                k = 1 if self.cfg.sync else self.cfg.num_workers
+                plans["ps"][r] = StepPlan([StepOp(kind=OP_PS_APPLY, p0=ctypes.addressof(self._p[r])) for _ in range(k)],
+                                          rk.device.index, st, keep=[self._p[r]])
+        plans["runs"] = 0
+        self._native_plans = plans
+        return plans
+
+    def _graph_plans(self) -> None:
+        """After the first eager pass: every kernel run of every plan becomes ONE CUDA-graph launch, so a step costs
+        the host two memcpy enqueues + one graph launch per worker (+ the loss read-back)."""
+        plans = self._native_plans
+        self.synchronize()
+        for kind in ("worker", "ps"):
+            for r in list(plans[kind]):
+                plans[kind][r] = plans[kind][r].graphed()
+        plans["graphed"] = True
+
+    @staticmethod
+    def _is_pinned_f32(t) -> bool:
+        return isinstance(t, torch.Tensor) and (not t.is_cuda) and t.dtype == torch.float32 and t.is_contiguous() \
+            and t.is_pinned()
+
     def step(self, x=None, y=None, sync_loss: bool = True, source: str = "dataset") -> Optional[float]:
         """One training step for every LOCAL rank.  Workers: (optional staging of the host batch) +
         3 kernels; ps shards: one ps_apply per aggregate (sync) or per worker push (async).
-        Returns the local worker's loss when ``sync_loss`` (a device->host read)."""
+        Returns the local worker's loss when ``sync_loss`` (a device->host read).
+
+        ``x``/``y``: one batch ``[B, in_dim]`` / ``[B, classes]`` (every local worker trains on it) or, with several
+        local workers (in-graph replication), ``[W_local * B, ...]`` split across them in worker order -- the
+        scatter of ``example_in_graph.py:38``.  Pinned fp32 host tensors take the native path: ONE C call per rank
+        enqueues the H2D copies, the staging kernel and the step's kernels (``csrc/step_exec.cu``)."""
         cfg = self.cfg
-        for r in self.worker_ranks:
-            if r in self.ranks:
-                if x is not None:
+        local_workers = [r for r in self.worker_ranks if r in self.ranks]
+        if x is not None and self._is_pinned_f32(x) and self._is_pinned_f32(y):
+            plans = self._plans()
+            B = self.spec.batch
+            split = len(local_workers) > 1 and x.shape[0] == B * len(local_workers)
+            xp, yp = x.data_ptr(), y.data_ptr()
+            xs, ys = B * self.spec.in_dim * 4, B * self.spec.classes * 4
+            for i, r in enumerate(local_workers):
+                pl = plans["worker"][r]
+                pl.ops[0].p1 = xp + (i * xs if split else 0)
+                pl.ops[1].p1 = yp + (i * ys if split else 0)
+                pl.run()
+                self.ranks[r].step += 1
+            for r in self.ps_ranks:
+                if r in plans["ps"]:
+                    plans["ps"][r].run()
+            plans["runs"] += 1
+            if plans["runs"] == 2 and not plans.get("graphed") and os.environ.get("DTF_E2E_GRAPH", "1") == "1":
+                self._graph_plans()
+            if sync_loss and local_workers:
+                pl, host = plans["loss"][local_workers[0]]
+                pl.run()
+                return float(host[:self.head_ctas].sum())
+            return None
+        for i, r in enumerate(local_workers):
+            if x is not None:
+                B = self.spec.batch
+                if len(local_workers) > 1 and x.shape[0] == B * len(local_workers):
+                    self.stage_batch(r, x[i * B:(i + 1) * B], y[i * B:(i + 1) * B])
+                else:
                     self.stage_batch(r, x, y)
-                self.enqueue_worker_step(r, "staged" if x is not None else source)
+            self.enqueue_worker_step(r, "staged" if x is not None else source)
         for r in self.ps_ranks:
             if r in self.ranks:
                 for _ in range(1 if cfg.sync else cfg.num_workers):

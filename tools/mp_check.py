@@ -37,12 +37,14 @@ def main():
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     num_ps = int(os.environ.get("DTF_NUM_PS", "1"))
+    nvls = os.environ.get("DTF_NVLS", "0")
+    nvls = {"0": False, "1": True}.get(nvls, nvls)
     W = world - num_ps
     xs, ys = synthetic_mnist(100 * W * 8, seed=11)
     report = {}
     for mode in ("sync", "async"):
         cfg = EngineConfig(num_ps=num_ps, num_workers=W, sync=(mode == "sync"), optimizer={"kind": "sgd", "lr": 0.001},
-                           seed=2)
+                           seed=2, nvls=nvls)
         eng = PSTrainEngine(MLPSpec(), cfg, Fabric.from_torch_distributed())
         eng.init_params()
         p0 = None
@@ -94,9 +96,10 @@ def main():
     if rank == 0:
         report["world"] = world
         report["num_ps"] = num_ps
+        report["nvls"] = str(nvls)
         print("MP_CHECK " + json.dumps(report))
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", "mp_check_%d.json" % world), "w") as f:
+        with open(os.path.join(ROOT, "gpurun_out", "mp_check_%d%s.json" % (world, "_nvls" if nvls else "")), "w") as f:
             json.dump(report, f, indent=1)
     dist.destroy_process_group()
 
