@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--unroll", type=int, default=0, help="steps per CUDA graph (0: auto)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="-1: min(steps, 1000); 0: skip")
+    ap.add_argument("--e2e-prefetch", type=int, default=1, help="1: step t+1's H2D overlaps step t (double-buffered staging)")
     ap.add_argument("--publish", action="store_true", help="ps stores params into worker replicas (push-publish)")
     ap.add_argument("--num-train", type=int, default=55000)
     ap.add_argument("--f1-splits", type=int, default=1, help="split-K CTAs for the first GEMM")
@@ -54,6 +55,8 @@ def parse_args():
     ap.add_argument("--b3-block-n", type=int, default=64)
     ap.add_argument("--in-graph", action="store_true", help="ONE process drives all --gpus devices (in-graph replication)")
     ap.add_argument("--num-ps", type=int, default=1, help="ps shards (variables placed round-robin)")
+    ap.add_argument("--model", default="mnist_mlp", choices=["mnist_mlp", "resnet18"],
+                    help="resnet18: BASELINE.json config 5 (conv model under the same ps API; bandwidth-relevant: 44.7 MB per push)")
     ap.add_argument("--nvls", default="off", choices=["off", "on", "auto"],
                     help="symmetric buffers + NVLS multicast: gradients reduced in the switch (multimem.ld_reduce), "
                          "parameters published with multimem.st")
@@ -117,6 +120,108 @@ def reference_arm(args):
     print(json.dumps({"impl": "reference", "unavailable": why, "metric": "MNIST MLP samples/sec", "n_gpus": args.gpus}))
 
 
+def run_resnet18(args, rank, world, local_rank):
+    """ResNet-18 (CIFAR stem, 11.2 M parameters) under the same fabric ps protocol: conv-as-tcgen05-GEMM workers,
+    fused ps_apply (momentum), sync replicas.  Timed exactly like the headline: CUDA events, barrier + synchronize on
+    both sides, max over ranks; every step copies its batch from pinned host memory and reads the loss back."""
+    import torch
+    import torch.distributed as dist
+    from distributed_tensorflow_b200.models import resnet18_init, resnet18_loss, resnet18_param_shapes
+    from distributed_tensorflow_b200.ops import cuda_lib
+    from distributed_tensorflow_b200.parallel.fabric import Fabric
+    from distributed_tensorflow_b200.parallel.generic_engine import GenericPSEngine
+    from distributed_tensorflow_b200.parallel.ps_engine import EngineConfig
+    N = args.gpus
+    B = args.batch if args.batch != 100 else 64
+    nvls = {"off": False, "on": True, "auto": "auto"}[args.nvls]
+    opt = {"kind": "momentum", "lr": args.lr or 0.05, "momentum": 0.9}
+    if N == 1:
+        cfg = EngineConfig(num_ps=1, num_workers=1, colocated=True, optimizer=opt)
+        fabric = Fabric(1, {0: local_rank})
+    else:
+        cfg = EngineConfig(num_ps=args.num_ps, num_workers=N - args.num_ps, optimizer=opt, nvls=nvls)
+        fabric = Fabric.from_torch_distributed()
+    shapes = resnet18_param_shapes(10, "cifar")
+    eng = GenericPSEngine(shapes, cfg, fabric)
+    eng.init_params(resnet18_init(10, "cifar", seed=2))
+    nparams = sum(eng.shard_elems)
+    is_worker = any(r in eng.worker_ranks for r in eng.ranks)
+    my = next(iter(eng.ranks))
+    rk = eng.ranks[my]
+    nb = 64                                   # 64 pinned batches x B x 32x32x3 fp32 (50 MB at B=64), cycled
+    g = torch.Generator().manual_seed(5 + rank)
+    hx = torch.randn(nb, B, 32, 32, 3, generator=g).pin_memory() if is_worker else None
+    hy = torch.eye(10)[torch.randint(0, 10, (nb, B), generator=g)].pin_memory() if is_worker else None
+
+    def barrier():
+        eng.synchronize()
+        if world > 1:
+            dist.barrier()
+        eng.synchronize()
+
+    losses = []
+
+    def step(i):
+        if is_worker:
+            with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
+                x = hx[i % nb].to(rk.device, non_blocking=True)
+                y = hy[i % nb].to(rk.device, non_blocking=True)
+            loss = eng.worker_step(my, resnet18_loss, x, y)
+            if my in eng.ps_ranks:
+                eng.ps_apply(my)
+            losses.append(float(loss))        # D2H read of the step's loss
+        else:
+            eng.ps_apply(my)
+    K, W = args.steps if args.steps != 2000 else 20, max(3, min(args.warmup, 5))
+    for i in range(W):
+        step(i)
+    barrier()
+    eng.check_errors()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    n0 = cuda_lib.launch_count()
+    t0 = time.time()
+    with torch.cuda.device(rk.device):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(rk.stream)
+    for i in range(K):
+        step(W + i)
+    e1.record(rk.stream)
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    ms_local = e0.elapsed_time(e1)
+    stats = torch.tensor([ms_local, float(cuda_lib.launch_count() - n0)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx, sm = stats.clone(), stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, launches = float(mx[0]), int(sm[1])
+    else:
+        ms, launches = ms_local, int(stats[1])
+    eng.check_errors()
+    value = cfg.num_workers * B * K / (ms / 1e3)
+    out = {"metric": "ResNet-18 samples/sec (whole box, device-timed, max over ranks), sync-replica PS", "value": value,
+           "unit": "samples/sec", "n_gpus": N, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "impl": "ours",
+           "data": "synthetic CIFAR-shaped 32x32x3 from pinned host memory (H2D every step), random-init weights",
+           "config": {"model": "ResNet-18 (CIFAR stem), %d parameters" % nparams, "per_worker_batch": B,
+                      "global_batch": cfg.num_workers * B, "optimizer": "momentum", "mode": "sync",
+                      "parallelism": "ps1+worker1 colocated" if N == 1 else "ps%d+worker%d between-graph" % (cfg.num_ps, cfg.num_workers),
+                      "grad_bytes_per_push": nparams * 4, "param_bytes_per_pull": nparams * 4,
+                      "fabric": ("nvls: multimem.ld_reduce push / multimem.st pull" if getattr(eng, "nvls_multicast", False)
+                                 else "symmetric buffers, unicast" if getattr(eng, "nvls", False) else "unicast peer stores / loads"),
+                      "l2": "64 distinct batches cycled; activations + 45 MB of parameters + gradients exceed L2 per step"},
+           "clocks": clocks, "gpu_launches": launches,
+           "e2e": {"value": value, "unit": "samples/sec", "h2d_bytes_per_step": B * (32 * 32 * 3 + 10) * 4, "d2h_bytes_per_step": 4,
+                   "note": "the timed loop itself copies every batch from pinned host memory and reads the loss back"},
+           "first_loss": losses[0] if losses else None, "final_loss": losses[-1] if losses else None}
+    eng.close()
+    return out
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -150,6 +255,15 @@ def main():
     from distributed_tensorflow_b200.parallel.fabric import Fabric
     from distributed_tensorflow_b200.parallel.ps_engine import EngineConfig, MLPSpec, PSTrainEngine
     from distributed_tensorflow_b200.utils.mnist_data import synthetic_mnist
+
+    if args.model == "resnet18":
+        out = run_resnet18(args, rank, world, local_rank)
+        if rank == 0:
+            print(json.dumps(out))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
 
     N = args.gpus
     spec = MLPSpec(hidden=args.hidden, batch=args.batch)
@@ -264,13 +378,20 @@ def main():
         wl = [r for r in eng.ranks if r in eng.worker_ranks]
         woff = eng.worker_ranks.index(wl[0]) if wl else 0
 
+        views = [(hx[b * spec.batch:(b + 1) * spec.batch], hy[b * spec.batch:(b + 1) * spec.batch]) for b in range(nb)] \
+            if is_worker else []
+
+        def batch_of(i):
+            return views[(i * num_workers + woff) % nb]
+
         def e2e_loop(n, start):
+            # every step: H2D of THIS step's batch from pinned host memory (issued one step ahead on the copy stream
+            # = input double buffering, overlapping the previous step's kernels) + D2H read of this step's loss
             last = None
             for i in range(n):
                 if is_worker:
-                    b = ((start + i) * num_workers + woff) % nb
-                    last = eng.step(hx[b * spec.batch:(b + 1) * spec.batch], hy[b * spec.batch:(b + 1) * spec.batch],
-                                    sync_loss=True)
+                    x, y = batch_of(start + i)
+                    last = eng.step(x, y, sync_loss=True, prefetch=batch_of(start + i + 1) if args.e2e_prefetch else None)
                 else:
                     eng.step(sync_loss=False)
             return last
@@ -296,7 +417,9 @@ def main():
         e2e = {"value": num_workers * spec.batch * Ke / (ems / 1e3), "unit": "samples/sec", "steps": Ke,
                "ms_per_step": ems / Ke, "wall_ms_per_step": float(t[1]) / Ke,
                "h2d_bytes_per_step": spec.batch * (spec.in_dim + spec.classes) * 4, "d2h_bytes_per_step": 4,
-               "api": "PSTrainEngine.step(x_pinned, y_pinned) -> loss", "last_loss": last_loss}
+               "api": "PSTrainEngine.step(x_pinned, y_pinned, prefetch=next) -> loss" if args.e2e_prefetch
+               else "PSTrainEngine.step(x_pinned, y_pinned) -> loss",
+               "input_double_buffering": bool(args.e2e_prefetch), "last_loss": last_loss}
 
     if rank == 0:
         out = {

@@ -217,6 +217,57 @@ DTF_DEVICE void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// ---- cta_group::2 (CTA pair: two SMs of one TPC cooperate on one M=256 tile) -----------------------------------
+// The pair is a 2-CTA cluster; CTA rank 0 (the "leader") issues the MMAs, both CTAs load operands and run epilogues.
+// A shared::cta address with bit 24 cleared names the same offset in the EVEN CTA of the pair (cluster window).
+static constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+DTF_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+DTF_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+DTF_DEVICE void tmem_alloc_2cta(uint32_t* smem_holder, uint32_t ncols) {     // one warp in EACH CTA, same holder offset
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)), "r"(ncols)
+               : "memory");
+}
+DTF_DEVICE void tmem_relinquish_2cta() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+DTF_DEVICE void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both CTAs: 128 rows each] * B[smem of both CTAs: N/2 rows each]; leader thread only.
+DTF_DEVICE void umma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive (once all previously issued MMAs completed) on the barrier at this offset in BOTH CTAs of the pair.
+DTF_DEVICE void umma_commit_2cta_mc(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are counted on the LEADER CTA's barrier.
+DTF_DEVICE void tma_load_2d_2cta(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// Plain arrive on the LEADER CTA's copy of a barrier (from either CTA of the pair).
+DTF_DEVICE void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
 // TMEM -> registers: each thread of the warp reads 32 consecutive fp32 columns of ITS lane
 // (warp w%4 owns lanes [32*(w%4), 32*(w%4)+32)).
 DTF_DEVICE void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {

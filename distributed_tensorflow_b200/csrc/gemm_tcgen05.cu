@@ -325,6 +325,204 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 }
 
 // =================================================================================================
+// Persistent variant for compute-sized problems (plain GEMMs: conv-as-GEMM, dense layers at scale).
+//
+// One CTA (or CTA PAIR) per SM loops over output tiles (static round-robin, M fastest so concurrently running
+// CTAs share B panels in L2).  The accumulator is DOUBLE-BUFFERED in tensor memory (2 x BLOCK_N columns <= 512):
+// while the epilogue warps drain tile i out of TMEM buffer i%2, the MMA thread is already accumulating tile i+1
+// into the other buffer and the TMA producer is prefetching its operands -- the epilogue, the kernel prologue
+// (barrier init, TMEM alloc, descriptor prefetch) and the pipeline fill are paid once per SM instead of once per
+// tile.  Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), the tile loop.
+//
+// CTAS == 2 (tcgen05 cta_group::2): the two SMs of a TPC form a 2-CTA cluster working on ONE 256 x BLOCK_N tile.
+// Each CTA loads its own 128 rows of A and only HALF of the B tile (BLOCK_N/2 rows); the leader CTA's single
+// MMA thread issues M=256 instructions that read both CTAs' shared memory and write both CTAs' tensor memory.
+// Per output element this moves 1.5x fewer operand bytes from L2 into the SMs than the 1-CTA 128 x 256 tile --
+// measured: the 1-CTA kernel saturates the L2 -> SM fabric (~12 TB/s) at ~1.15 PFLOP/s.
+// Barrier topology (pair): full[s] lives in the leader (one arrive.expect_tx for BOTH CTAs' bytes; each CTA's TMA
+// counts its bytes there), empty[s] / tmem_full[a] live in both CTAs (multicast tcgen05.commit), tmem_empty[a]
+// lives in the leader (epilogue warps of both CTAs arrive, the peer's remotely).
+// =================================================================================================
+template <int CTAS>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                    const GemmParams p, const int tiles_m, const int tiles_n) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ __align__(8) uint64_t empty_bar[8];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_holder;
+  __shared__ float s_bias[2][256];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int bn_cta = p.block_n / CTAS;                         // rows of the B tile THIS CTA loads
+  const int b_bytes = bn_cta * kBlockK * 2;
+  const int stage_bytes = kABytes + b_bytes;                    // per CTA
+  uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint32_t acc_cols = 32;                       // columns of ONE accumulator buffer (power of two >= BLOCK_N)
+  while (acc_cols < (uint32_t)p.block_n) acc_cols <<= 1;
+  const uint32_t tmem_cols = 2 * acc_cols;
+  const int num_tiles = tiles_m * tiles_n;                      // tiles of (CTAS * 128) x BLOCK_N
+  const int worker = blockIdx.x / CTAS, num_workers = gridDim.x / CTAS;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], CTAS * kEpilogueWarps);      // one arrival per epilogue warp (of both CTAs)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1) {
+    if (CTAS == 2) { tmem_alloc_2cta(&tmem_holder, tmem_cols); tmem_relinquish_2cta(); }
+    else { tmem_alloc(&tmem_holder, tmem_cols); tmem_relinquish(); }
+  }
+  tc_fence_before();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs of a pair) =====================
+    if (elect_one()) {
+      int it = 0;
+      for (int t = worker; t < num_tiles; t += num_workers) {
+        const int m0 = (t % tiles_m) * (kBlockM * CTAS) + (int)cta_rank * kBlockM;
+        const int n0 = (t / tiles_m) * p.block_n + (int)cta_rank * bn_cta;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], stage_bytes * CTAS);
+          uint8_t* a_dst = tiles + s * stage_bytes;
+          uint8_t* b_dst = a_dst + kABytes;
+          const int k0 = kb * kBlockK;
+          if (CTAS == 2) {
+            if (!p.a_mn) {
+              tma_load_2d_2cta(a_dst, &map_a, &full_bar[s], k0, m0);
+            } else {
+              tma_load_2d_2cta(a_dst, &map_a, &full_bar[s], m0, k0);
+              tma_load_2d_2cta(a_dst + 8192, &map_a, &full_bar[s], m0 + 64, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d_2cta(b_dst, &map_b, &full_bar[s], k0, n0);
+            } else {
+              for (int j = 0; j < bn_cta / 64; ++j)
+                tma_load_2d_2cta(b_dst + j * 8192, &map_b, &full_bar[s], n0 + 64 * j, k0);
+            }
+          } else {
+            if (!p.a_mn) {
+              tma_load_2d(a_dst, &map_a, &full_bar[s], k0, m0);
+            } else {
+              tma_load_2d(a_dst, &map_a, &full_bar[s], m0, k0);
+              tma_load_2d(a_dst + 8192, &map_a, &full_bar[s], m0 + 64, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(b_dst, &map_b, &full_bar[s], k0, n0);
+            } else {
+              for (int j = 0; j < bn_cta / 64; ++j)
+                tma_load_2d(b_dst + j * 8192, &map_b, &full_bar[s], n0 + 64 * j, k0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(kBlockM * CTAS, p.block_n, p.a_mn, p.b_mn);
+      const uint32_t a_step = p.a_mn ? (2048u >> 4) : (32u >> 4);
+      const uint32_t b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
+      int it = 0, ti = 0;
+      for (int t = worker; t < num_tiles; t += num_workers, ++ti) {
+        const int acc = ti & 1;
+        const uint32_t acc_ph = (ti >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);        // the epilogues have drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + s * stage_bytes);
+          const uint32_t b_addr = a_addr + kABytes;
+          const uint64_t a_desc = p.a_mn ? make_smem_desc_sw128(a_addr, 8192, 1024) : make_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t b_desc = p.b_mn ? make_smem_desc_sw128(b_addr, 8192, 1024) : make_smem_desc_sw128(b_addr, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            if (CTAS == 2)
+              umma_bf16_2cta(d_tmem, a_desc + (uint64_t)(a_step * k), b_desc + (uint64_t)(b_step * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_bf16(d_tmem, a_desc + (uint64_t)(a_step * k), b_desc + (uint64_t)(b_step * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          if (CTAS == 2) umma_commit_2cta_mc(&empty_bar[s]); else umma_commit(&empty_bar[s]);
+        }
+        if (CTAS == 2) umma_commit_2cta_mc(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs: each drains its own 128 accumulator rows) =====================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const bool split_cols = (p.block_n % 32) == 0;
+    const int c_begin = split_cols ? half * (p.block_n / 2) : 0;
+    const int c_end = split_cols ? c_begin + p.block_n / 2 : (half == 0 ? p.block_n : 0);
+    const bool add_bias = p.bias != nullptr;
+    int ti = 0;
+    for (int t = worker; t < num_tiles; t += num_workers, ++ti) {
+      const int acc = ti & 1;
+      const uint32_t acc_ph = (ti >> 1) & 1;
+      const int m0 = (t % tiles_m) * (kBlockM * CTAS) + (int)cta_rank * kBlockM;
+      const int n0 = (t / tiles_m) * p.block_n;
+      const long long grow = (long long)m0 + q * 32 + lane;
+      const bool row_ok = grow < p.M;
+      if (add_bias) {
+        // bias slice of this tile (double-buffered with the accumulator: the previous tile may still be read)
+        for (int i = threadIdx.x - 64; i < p.block_n; i += 32 * kEpilogueWarps) s_bias[acc][i] = (n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(q * 32) << 16);
+      bool released = false;
+      for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_addr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (c0 + 16 >= c_end) {
+          // all of this warp's TMEM reads of the buffer have completed: hand it back to the MMA thread BEFORE the
+          // last slice's global stores, so the next-but-one tile's accumulation can start as early as possible
+          tc_fence_before();
+          if (lane == 0) { if (CTAS == 2) mbar_arrive_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
+          released = true;
+        }
+        epilogue_chunk16(p, r, c0, n0, grow, row_ok, add_bias, s_bias[acc], lane);
+      }
+      if (!released) {               // (BLOCK_N % 32 != 0: the upper half-warps own no columns but still arrive)
+        tc_fence_before();
+        if (lane == 0) { if (CTAS == 2) mbar_arrive_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
+      }
+    }
+  }
+  __syncwarp();                    // role branches leave warps 0/1 diverged; the cluster barrier is warp-aligned
+  tc_fence_before();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) { if (CTAS == 2) tmem_dealloc_2cta(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// =================================================================================================
 // host side
 // =================================================================================================
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -418,6 +616,8 @@ struct DtfGemmArgs {
   int signal_gpu_scope;
   const unsigned long long* stamp_src;
   unsigned long long* stamp_dst;
+  int persistent;        // 0: auto (persistent kernel when tiles > SMs), 1: force persistent 1-CTA, 2: force CTA pairs, -1: never
+  int cta_pair;          // -1: never use cta_group::2 in auto mode
 };
 
 // Returns 0 on success, <0 for argument errors, >0 for CUDA errors.
@@ -473,15 +673,70 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   // the opt-in shared-memory limit is a per-device function attribute (one process may drive all 8 GPUs)
   static bool configured[64] = {false};
+  static int sm_count[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(224 * 1024));   // 227 KB minus static barriers + bias stage
     if (e != cudaSuccess) return 2000 + (int)e;
+    e = cudaFuncSetAttribute(gemm_bf16_tcgen05_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(220 * 1024));               // more static shared memory (double-buffered bias)
+    if (e != cudaSuccess) return 2000 + (int)e;
+    e = cudaFuncSetAttribute(gemm_bf16_tcgen05_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(220 * 1024));
+    if (e != cudaSuccess) return 2000 + (int)e;
+    cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
     configured[dev] = true;
   }
-  dim3 grid((unsigned)((g->M + kBlockM - 1) / kBlockM), (unsigned)((g->N + bn - 1) / bn), (unsigned)splits);
+  const unsigned tiles_m = (unsigned)((g->M + kBlockM - 1) / kBlockM), tiles_n = (unsigned)((g->N + bn - 1) / bn);
+  const int sms = (dev >= 0 && dev < 64 && sm_count[dev] > 0) ? sm_count[dev] : 148;
+  // Persistent path: plain GEMMs with more tiles than SMs (no split-K, no fused wait/signal, no phase stamps).
+  const bool plain = splits == 1 && !p.atomic && p.wait_flag == nullptr && p.signal == nullptr && p.phase_trace == nullptr;
+  if (plain && g->persistent >= 0 && (g->persistent > 0 || (long long)tiles_m * tiles_n > sms)) {
+    // CTA pairs (cta_group::2, 256 x BLOCK_N tiles) when the tile shape allows it: BLOCK_N a multiple of 32 (each
+    // CTA loads BLOCK_N/2 rows of B; 128 when B is MN-major) and at least two 128-row blocks of M.
+    int ctas = 1;
+    const bool pair_ok = (bn % 32 == 0) && (!g->b_mn || bn % 128 == 0) && g->M > kBlockM;
+    // measured (tools/gemm_perf.py): pairs win only with the widest tile (BLOCK_N = 256: 1292 vs 1144 TFLOP/s at 4096^3);
+    // with narrower tiles the B half-tile is too small to matter and the 1-CTA kernel's finer tile granularity wins
+    if (g->persistent == 2 || (g->persistent != 1 && pair_ok && g->cta_pair >= 0 && bn >= 192)) ctas = pair_ok ? 2 : 1;
+    if (ctas == 2 && !g->b_mn) {
+      // K-major B: the TMA box of one CTA covers only ITS half of the tile's N rows
+      rc = cached_map(&mb, g->b, g->N, g->K, g->ldb, 64, bn / 2);
+      if (rc) return rc < 0 ? -7 : 1000 + rc;
+    }
+    const int st_bytes = kABytes + (bn / ctas) * kBlockK * 2;
+    int pst = (int)((216 * 1024 - 1024) / st_bytes);
+    if (pst > 8) pst = 8;
+    if (pst > p.num_kb) pst = p.num_kb < 2 ? 2 : p.num_kb;
+    p.stages = pst;
+    const size_t psmem = (size_t)pst * st_bytes + 1024;
+    const unsigned tm = (unsigned)((g->M + kBlockM * ctas - 1) / (kBlockM * ctas));
+    long long nt = (long long)tm * tiles_n;
+    if (ctas == 2) {
+      const unsigned pairs = (unsigned)(nt < sms / 2 ? nt : sms / 2);
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(2 * pairs, 1, 1);
+      cfg.blockDim = dim3(kThreads, 1, 1);
+      cfg.dynamicSmemBytes = psmem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_persistent_kernel<2>, ma, mb, p, (int)tm, (int)tiles_n);
+      return (int)e;
+    }
+    const unsigned pgrid = (unsigned)(nt < sms ? nt : sms);
+    gemm_bf16_tcgen05_persistent_kernel<1><<<pgrid, kThreads, psmem, stream>>>(ma, mb, p, (int)tm, (int)tiles_n);
+    return (int)cudaGetLastError();
+  }
+  dim3 grid(tiles_m, tiles_n, (unsigned)splits);
   gemm_bf16_tcgen05_kernel<<<grid, kThreads, smem, stream>>>(ma, mb, p);
   return (int)cudaGetLastError();
 }

@@ -37,7 +37,7 @@ class GemmArgs(Structure):
                 ("wait_flag", c_void_p), ("wait_target", c_ulonglong),
                 ("signal", c_void_p), ("err", c_void_p), ("timeout_ns", c_ulonglong),
                 ("block_n_override", c_int), ("wait_target_ptr", c_void_p), ("phase_trace", c_void_p),
-                ("signal_gpu_scope", c_int), ("stamp_src", c_void_p), ("stamp_dst", c_void_p)]
+                ("signal_gpu_scope", c_int), ("stamp_src", c_void_p), ("stamp_dst", c_void_p), ("persistent", c_int), ("cta_pair", c_int)]
 
 
 class PsApplyArgs(Structure):
@@ -284,7 +284,7 @@ def gemm_raw(a: torch.Tensor, lda: int, b: torch.Tensor, ldb: int, c: torch.Tens
              accumulate: bool = False, colsum: Optional[torch.Tensor] = None, wait_flag: int = 0, wait_target: int = 0,
              signal: int = 0, err: int = 0, timeout_ns: int = 0, block_n: int = 0, stream: Optional[int] = None,
              a_ptr: Optional[int] = None, b_ptr: Optional[int] = None, c_ptr: Optional[int] = None,
-             bias_ptr: Optional[int] = None, c_bf16: Optional[bool] = None) -> None:
+             bias_ptr: Optional[int] = None, c_bf16: Optional[bool] = None, persistent: int = 0) -> None:
     """Launch the tcgen05 GEMM on raw buffers (pointers may be peer memory)."""
     g = GemmArgs()
     g.a = a_ptr if a_ptr is not None else a.data_ptr()
@@ -301,6 +301,7 @@ def gemm_raw(a: torch.Tensor, lda: int, b: torch.Tensor, ldb: int, c: torch.Tens
     g.wait_flag, g.wait_target = wait_flag or None, wait_target
     g.signal, g.err, g.timeout_ns = signal or None, err or None, timeout_ns
     g.block_n_override = block_n
+    g.persistent = persistent
     lib = load()
     st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
     _check(lib.dtf_gemm_bf16(byref(g), st), "gemm_bf16_tcgen05")
@@ -308,7 +309,8 @@ def gemm_raw(a: torch.Tensor, lda: int, b: torch.Tensor, ldb: int, c: torch.Tens
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, ta: bool = False, tb: bool = False, bias: Optional[torch.Tensor] = None,
-         relu: bool = False, out_dtype: torch.dtype = torch.float32, splits: int = 1) -> torch.Tensor:
+         relu: bool = False, out_dtype: torch.dtype = torch.float32, splits: int = 1, persistent: int = 0,
+         block_n: int = 0) -> torch.Tensor:
     """``op(a) @ op(b)`` (+bias, ReLU) on the tensor cores; inputs fp32 or bf16, bf16 compute, fp32 accumulate."""
     assert a.is_cuda and b.is_cuda and a.dim() == 2 and b.dim() == 2
     M, K = (a.shape[1], a.shape[0]) if ta else (a.shape[0], a.shape[1])
@@ -322,7 +324,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, ta: bool = False, tb: bool = False, b
         c = (torch.zeros if splits > 1 else torch.empty)((M, ldc), dtype=out_dtype, device=a.device)
         if bias is not None:
             bias = bias.float().contiguous()
-        gemm_raw(a16, lda, b16, ldb, c, ldc, M, N, K, a_mn=ta, b_mn=not tb, bias=bias, relu=relu, splits=splits)
+        gemm_raw(a16, lda, b16, ldb, c, ldc, M, N, K, a_mn=ta, b_mn=not tb, bias=bias, relu=relu, splits=splits,
+                 persistent=persistent, block_n=block_n)
     return c if ldc == N else c[:, :N]
 
 

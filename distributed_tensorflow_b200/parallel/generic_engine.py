@@ -17,6 +17,7 @@ Variables are sharded across ps ranks round-robin in creation order, exactly lik
 from __future__ import annotations
 
 import ctypes
+import ctypes as _ct
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -72,14 +73,37 @@ class GenericPSEngine:
             with torch.cuda.device(rk.device):
                 rk.stream = torch.cuda.Stream(rk.device)
         W = cfg.num_workers
+        # ---- NVLS mode (cfg.nvls): symmetric buffers.  Gradients stay in the WORKERS' HBM and the ps sums them in the
+        # switch (multimem.ld_reduce): it ingests n floats per step instead of W*n.  The fp32 parameters are published
+        # with ONE multimem.st stream into every GPU's replica: the ps emits n floats instead of W*n. ----
+        want = cfg.nvls
+        self.nvls, self.nvls_multicast = False, False
+        self.sym_grads: List[Any] = []
+        self.sym_repl: List[Any] = []
+        if want and self.world > 1:
+            level = fabric.nvls_level()
+            if want == "auto" and level < 2:
+                want = False
+            elif level == 0:
+                raise RuntimeError("nvls=True needs CUDA VMM (POSIX fd export); not available on this machine")
+        if want and self.world > 1:
+            self.nvls = True
+            for s in range(cfg.num_ps):
+                self.sym_grads.append(fabric.alloc_symmetric("gsgrads%d" % s, self.shard_elems[s] * 4))
+                self.sym_repl.append(fabric.alloc_symmetric("gsrepl%d" % s, self.shard_elems[s] * 4))
+            self.nvls_multicast = self.sym_grads[0].multicast
+        self.push_ctas = 1 if self.nvls else _PUSH_CTAS
         for r, rk in self.ranks.items():
             if r in self.ps_ranks:
                 s = self.ps_ranks.index(r)
                 n = self.shard_elems[s]
                 for name, nbytes in (("gctl%d" % s, self.ctl_bytes), ("gmaster%d" % s, n * 4), ("ggrads%d" % s, n * 4 * W),
                                      ("gslot_m%d" % s, n * 4), ("gslot_v%d" % s, n * 4), ("gshadow%d" % s, n * 2)):
-                    rk.bufs[name] = fabric.alloc(r, name, nbytes)
-                for name in ("gctl%d" % s, "gmaster%d" % s, "ggrads%d" % s):
+                    if self.nvls and name.startswith("ggrads"):
+                        rk.bufs[name] = self.sym_grads[s].local(r)       # stays zero: the ps contributes nothing
+                    else:
+                        rk.bufs[name] = fabric.alloc(r, name, nbytes)
+                for name in ("gctl%d" % s, "gmaster%d" % s) + (() if self.nvls else ("ggrads%d" % s,)):
                     fabric.publish(r, name)
             if r in self.worker_ranks:
                 w = self.worker_ranks.index(r)
@@ -87,17 +111,25 @@ class GenericPSEngine:
                 rk.bufs["gmisc_w%d" % w] = fabric.alloc(r, "gmisc_w%d" % w, 256)
                 fabric.publish(r, "gmailbox_w%d" % w)
                 for s in range(cfg.num_ps):
-                    rk.bufs["greplica%d_w%d" % (s, w)] = fabric.alloc(r, "greplica%d_w%d" % (s, w), self.shard_elems[s] * 4)
-                    rk.bufs["glocalgrad%d_w%d" % (s, w)] = fabric.alloc(r, "glocalgrad%d_w%d" % (s, w), self.shard_elems[s] * 4)
+                    if self.nvls:
+                        rk.bufs["greplica%d_w%d" % (s, w)] = self.sym_repl[s].local(r)
+                        rk.bufs["glocalgrad%d_w%d" % (s, w)] = self.sym_grads[s].local(r)
+                    else:
+                        rk.bufs["greplica%d_w%d" % (s, w)] = fabric.alloc(r, "greplica%d_w%d" % (s, w), self.shard_elems[s] * 4)
+                        rk.bufs["glocalgrad%d_w%d" % (s, w)] = fabric.alloc(r, "glocalgrad%d_w%d" % (s, w), self.shard_elems[s] * 4)
         self.peer: Dict[Tuple[int, str], FabricBuffer] = {}
         for r in self.ranks:
             if r in self.worker_ranks:
                 for s, pr in enumerate(self.ps_ranks):
-                    for base in ("gctl", "gmaster", "ggrads"):
+                    for base in ("gctl", "gmaster") + (() if self.nvls else ("ggrads",)):
                         self.peer[(r, "%s%d" % (base, s))] = fabric.peer(r, pr, "%s%d" % (base, s))
             if r in self.ps_ranks:
+                s = self.ps_ranks.index(r)
                 for w, wr in enumerate(self.worker_ranks):
                     self.peer[(r, "gmailbox_w%d" % w)] = fabric.peer(r, wr, "gmailbox_w%d" % w)
+                    if self.nvls:
+                        self.peer[(r, "gsgrads%d_w%d" % (s, w))] = self.sym_grads[s].peer(r, wr)
+                        self.peer[(r, "gsrepl%d_w%d" % (s, w))] = self.sym_repl[s].peer(r, wr)
         self._p: Dict[int, PsApplyArgs] = {}
         for r, rk in self.ranks.items():
             if r not in self.ps_ranks:
@@ -108,10 +140,13 @@ class GenericPSEngine:
             a.ctl, a.master = rk.bufs["gctl%d" % s].ptr, rk.bufs["gmaster%d" % s].ptr
             a.slot_m, a.slot_v, a.shadow = rk.bufs["gslot_m%d" % s].ptr, rk.bufs["gslot_v%d" % s].ptr, rk.bufs["gshadow%d" % s].ptr
             for w in range(W):
-                a.grad[w] = rk.bufs["ggrads%d" % s].ptr + w * n * 4
+                a.grad[w] = self.peer[(r, "gsgrads%d_w%d" % (s, w))].ptr if self.nvls else rk.bufs["ggrads%d" % s].ptr + w * n * 4
                 a.mailbox[w] = self.peer[(r, "gmailbox_w%d" % w)].ptr + s * self.mb_bytes
+            if self.nvls and self.nvls_multicast:
+                a.grad_mc = self.sym_grads[s].mc(r)
+                a.master_mc = self.sym_repl[s].mc(r)
             a.n, a.num_workers, a.replicas_to_aggregate = n, W, self.R
-            a.ctas_per_push = _PUSH_CTAS
+            a.ctas_per_push = self.push_ctas
             a.mode, a.kind = (0 if cfg.sync else 1), self.kind
             a.lr, a.momentum = float(self.opt["lr"]), float(self.opt.get("momentum", 0.0))
             a.beta1, a.beta2 = float(self.opt.get("beta1", 0.9)), float(self.opt.get("beta2", 0.999))
@@ -162,6 +197,8 @@ class GenericPSEngine:
                     b = rk.bufs["gctl%d" % s].tensor(torch.float32, self.off["beta1_power"], 2)
                     b[0] = float(self.opt.get("beta1", 0.9))
                     b[1] = float(self.opt.get("beta2", 0.999))
+                    if self.nvls:
+                        self.publish_params(r)
                 rk.stream.synchronize()
             if r in self.worker_ranks:
                 w = self.worker_ranks.index(r)
@@ -172,6 +209,20 @@ class GenericPSEngine:
             rk.step = 0
             rk.base = 0
         self.fabric.barrier()
+
+    def publish_params(self, rank: int) -> None:
+        """NVLS mode, ps side: copy the fp32 master into every worker's replica -- one multimem.st stream when the box
+        has NVLS (the switch fans out), otherwise one peer store per worker (``fabric_bcast`` kernel)."""
+        rk = self.ranks[rank]
+        s = self.ps_ranks.index(rank)
+        n = self.shard_elems[s]
+        W = self.cfg.num_workers
+        peers = (_ct.c_void_p * 16)(*[self.peer[(rank, "gsrepl%d_w%d" % (s, w))].ptr for w in range(W)])
+        mc = self.sym_repl[s].mc(rank) if self.nvls_multicast else None
+        with torch.cuda.device(rk.device):
+            rc = self.lib.dtf_fabric_bcast(rk.bufs["gmaster%d" % s].ptr, mc, peers, W, n * 4, 0, rk.stream.cuda_stream)
+        assert rc == 0, rc
+        cuda_lib._bump()
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         out = {}
@@ -203,10 +254,11 @@ class GenericPSEngine:
                 rc = self.lib.dtf_wait_token(rk.bufs["gmailbox_w%d" % w].ptr + s * self.mb_bytes, getattr(rk, "base", 0) + rk.step, None,
                                              self.cfg.timeout_ns, rk.bufs["gmisc_w%d" % w].ptr + 16, st)
                 assert rc == 0, rc
-                rep = rk.bufs["greplica%d_w%d" % (s, w)]
-                rc = self.lib.dtf_pull_shadow(self.peer[(rank, "gmaster%d" % s)].ptr, rep.ptr, self.shard_elems[s] * 4, 148, st)
-                assert rc == 0, rc
-            cuda_lib._bump(2 * self.cfg.num_ps)
+                if not self.nvls:        # NVLS mode: the ps already stored the new parameters into this replica
+                    rep = rk.bufs["greplica%d_w%d" % (s, w)]
+                    rc = self.lib.dtf_pull_shadow(self.peer[(rank, "gmaster%d" % s)].ptr, rep.ptr, self.shard_elems[s] * 4, 148, st)
+                    assert rc == 0, rc
+            cuda_lib._bump((1 if self.nvls else 2) * self.cfg.num_ps)
             for name in self.names:
                 s = self.layout[name][0]
                 params[name] = self._view(rk.bufs["greplica%d_w%d" % (s, w)], name)
@@ -222,10 +274,16 @@ class GenericPSEngine:
                 self._view(rk.bufs["glocalgrad%d_w%d" % (s, w)], name).copy_(g)
             for s in range(self.cfg.num_ps):
                 n = self.shard_elems[s]
-                dst = self.peer[(rank, "ggrads%d" % s)].ptr + w * n * 4
-                rc = self.lib.dtf_push_grad(rk.bufs["glocalgrad%d_w%d" % (s, w)].ptr, dst, n, self.peer[(rank, "gctl%d" % s)].ptr,
-                                            rk.bufs["gmailbox_w%d" % w].ptr + s * self.mb_bytes, w,
-                                            0 if self.cfg.sync else 1, 1, _PUSH_CTAS, st)
+                if self.nvls:
+                    # the gradient already sits in this worker's copy of the symmetric buffer: stamp + arrival only
+                    rc = self.lib.dtf_push_grad(None, None, 0, self.peer[(rank, "gctl%d" % s)].ptr,
+                                                rk.bufs["gmailbox_w%d" % w].ptr + s * self.mb_bytes, w,
+                                                0 if self.cfg.sync else 1, 1, 1, st)
+                else:
+                    dst = self.peer[(rank, "ggrads%d" % s)].ptr + w * n * 4
+                    rc = self.lib.dtf_push_grad(rk.bufs["glocalgrad%d_w%d" % (s, w)].ptr, dst, n, self.peer[(rank, "gctl%d" % s)].ptr,
+                                                rk.bufs["gmailbox_w%d" % w].ptr + s * self.mb_bytes, w,
+                                                0 if self.cfg.sync else 1, 1, _PUSH_CTAS, st)
                 assert rc == 0, rc
             cuda_lib._bump(self.cfg.num_ps)
         rk.step += 1

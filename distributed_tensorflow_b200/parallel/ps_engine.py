@@ -574,72 +574,128 @@ class PSTrainEngine:
     # native step plans (end-to-end path: one C call per rank per step, see csrc/step_exec.cu)
     # ------------------------------------------------------------------------------------------------
     def _plans(self) -> Dict[str, Any]:
-        """Per-rank op sequences for ``step(x_pinned, y_pinned)``: H2D x, H2D y, fp32->bf16 staging, the worker's
-        kernels / the ps's apply kernels, and -- for the rank whose loss is returned -- D2H of the loss partials
-        into pinned host memory + a stream sync.  Built once; per step only the H2D source pointers change."""
+        """Per-rank op sequences for ``step(x_pinned, y_pinned)``.  Input staging is DOUBLE-BUFFERED and runs on a
+        copy stream: ``copy[p]`` = wait until the compute stream is done with buffer set ``p`` -> H2D x -> H2D y ->
+        fp32->bf16 staging kernel -> record ``ready[p]``; ``compute[p]`` = wait ``ready[p]`` -> the worker's
+        kernels on buffer set ``p`` (-> the ps's apply kernels when colocated) -> record ``done[p]``.  A step
+        alternates ``p``; ``step(..., prefetch=(x_next, y_next))`` issues ``copy[p^1]`` for the NEXT batch right
+        after launching this step's kernels, so the PCIe transfer overlaps the step's compute.  The rank whose loss
+        is returned adds D2H of the loss partials into pinned host memory + a stream sync.  Built once; per step
+        only the H2D source pointers change."""
         got = getattr(self, "_native_plans", None)
         if got is not None:
             return got
         from ..ops.cuda_lib import (OP_CONVERT, OP_D2H, OP_GEMM, OP_H2D, OP_HEAD, OP_PS_APPLY, OP_SIGNAL, OP_SYNC,
                                     OP_WAIT_TOKEN, StepOp, StepPlan)
+        OP_EVENT_RECORD, OP_EVENT_WAIT = 11, 12
         B, D, C = self.spec.batch, self.spec.in_dim, self.spec.classes
-        plans: Dict[str, Any] = {"worker": {}, "ps": {}, "loss": {}}
+        plans: Dict[str, Any] = {"copy": {}, "compute": {}, "ps": {}, "loss": {}, "keep": []}
         for r, rk in self.ranks.items():
             st = rk.stream.cuda_stream
             if r in self.worker_ranks:
                 w = self.worker_ranks.index(r)
                 d = self._w[r]
-                xf, lab, x16 = rk.bufs["xf32_w%d" % w].ptr, rk.bufs["labels_w%d" % w].ptr, rk.bufs["x16_w%d" % w].ptr
-                ops = [StepOp(kind=OP_H2D, p0=xf, p1=None, i0=B * D * 4), StepOp(kind=OP_H2D, p0=lab, p1=None, i0=B * C * 4),
-                       StepOp(kind=OP_CONVERT, p0=xf, p1=x16, i0=D, i1=D, i2=B, i3=D, i4=D)]
-                for s_ in d["extra_wait_shards"]:
-                    ops.append(StepOp(kind=OP_WAIT_TOKEN, p0=rk.bufs["mailbox_w%d" % w].ptr + s_ * self.mb_bytes,
-                                      p1=d["stepctr_ptr"], p2=d["err_ptr"], i0=0, u0=self.cfg.timeout_ns))
+                with torch.cuda.device(rk.device):
+                    copy_stream = torch.cuda.Stream(rk.device)
+                    events = []
+                    for _ in range(4):                       # ready[0], ready[1], done[0], done[1]
+                        ev = torch.cuda.Event()
+                        ev.record(rk.stream)                 # materialises the cudaEvent_t (and makes the first wait a no-op)
+                        events.append(ev)
+                plans["keep"] += [copy_stream] + events
+                ready, done = events[:2], events[2:]
                 g1, hd, g3 = d["g1"], d["head"], d["g3"]
                 g1.wait_target, g1.wait_target_ptr = 0, d["stepctr_ptr"]
                 if d["head_ctls"]:
                     hd.ctl, hd.mailbox = d["head_ctls"][0], d["head_mailboxes"][0]
                 else:
                     hd.ctl, hd.mailbox = None, d["mb0"]
-                ops.append(StepOp(kind=OP_GEMM, p0=ctypes.addressof(g1)))
-                ops.append(StepOp(kind=OP_HEAD, p0=ctypes.addressof(hd)))
-                for ctl_ptr, mbp in zip(d["head_ctls"][1:], d["head_mailboxes"][1:]):
-                    ops.append(StepOp(kind=OP_SIGNAL, p0=ctl_ptr, p1=mbp, i0=w, i1=hd.stamp_from_version))
-                ops.append(StepOp(kind=OP_GEMM, p0=ctypes.addressof(g3)))
-                keep = [g1, hd, g3]
-                if self.cfg.colocated:
-                    # ps and worker share the GPU and the stream: the apply joins the worker's plan (one graph)
-                    ops += [StepOp(kind=OP_PS_APPLY, p0=ctypes.addressof(self._p[r]))
-                            for _ in range(1 if self.cfg.sync else self.cfg.num_workers)]
-                    keep.append(self._p[r])
-                plans["worker"][r] = StepPlan(ops, rk.device.index, st, keep=keep)
+                plans["copy"][r], plans["compute"][r] = [], []
+                for par in range(2):
+                    sfx = "" if par == 0 else "b"
+                    if par == 1:
+                        for base, nbytes in (("xf32", 128 * D * 4), ("labels", 128 * 16 * 4), ("x16", 128 * D * 2)):
+                            name = "%sb_w%d" % (base, w)
+                            if name not in rk.bufs:
+                                rk.bufs[name] = self.fabric.alloc(r, name, nbytes)
+                    xf = rk.bufs["xf32%s_w%d" % (sfx, w)].ptr
+                    lab = rk.bufs["labels%s_w%d" % (sfx, w)].ptr
+                    x16 = rk.bufs["x16%s_w%d" % (sfx, w)].ptr
+                    if par == 0:
+                        g1p, hdp, g3p = g1, hd, g3
+                    else:
+                        g1p, hdp, g3p = type(g1).from_buffer_copy(g1), type(hd).from_buffer_copy(hd), type(g3).from_buffer_copy(g3)
+                        g1p.a, g3p.a, hdp.labels = x16, x16, lab
+                    cops = [StepOp(kind=OP_EVENT_WAIT, p0=done[par].cuda_event),
+                            StepOp(kind=OP_H2D, p0=xf, p1=None, i0=B * D * 4), StepOp(kind=OP_H2D, p0=lab, p1=None, i0=B * C * 4),
+                            StepOp(kind=OP_CONVERT, p0=xf, p1=x16, i0=D, i1=D, i2=B, i3=D, i4=D),
+                            StepOp(kind=OP_EVENT_RECORD, p0=ready[par].cuda_event)]
+                    plans["copy"][r].append(StepPlan(cops, rk.device.index, copy_stream.cuda_stream))
+                    ops = [StepOp(kind=OP_EVENT_WAIT, p0=ready[par].cuda_event)]
+                    for s_ in d["extra_wait_shards"]:
+                        ops.append(StepOp(kind=OP_WAIT_TOKEN, p0=rk.bufs["mailbox_w%d" % w].ptr + s_ * self.mb_bytes,
+                                          p1=d["stepctr_ptr"], p2=d["err_ptr"], i0=0, u0=self.cfg.timeout_ns))
+                    ops.append(StepOp(kind=OP_GEMM, p0=ctypes.addressof(g1p)))
+                    ops.append(StepOp(kind=OP_HEAD, p0=ctypes.addressof(hdp)))
+                    for ctl_ptr, mbp in zip(d["head_ctls"][1:], d["head_mailboxes"][1:]):
+                        ops.append(StepOp(kind=OP_SIGNAL, p0=ctl_ptr, p1=mbp, i0=w, i1=hd.stamp_from_version))
+                    ops.append(StepOp(kind=OP_GEMM, p0=ctypes.addressof(g3p)))
+                    keep = [g1p, hdp, g3p]
+                    if self.cfg.colocated:
+                        # ps and worker share the GPU and the stream: the apply joins the worker's plan (one graph)
+                        ops += [StepOp(kind=OP_PS_APPLY, p0=ctypes.addressof(self._p[r]))
+                                for _ in range(1 if self.cfg.sync else self.cfg.num_workers)]
+                        keep.append(self._p[r])
+                    ops.append(StepOp(kind=OP_EVENT_RECORD, p0=done[par].cuda_event))
+                    plans["compute"][r].append(StepPlan(ops, rk.device.index, st, keep=keep))
                 host = torch.zeros(16, dtype=torch.float32).pin_memory()
                 plans["loss"][r] = (StepPlan([StepOp(kind=OP_D2H, p0=host.data_ptr(), p1=d["loss_ptr"], i0=self.head_ctas * 4),
-                                              StepOp(kind=OP_SYNC)], rk.device.index, st), host)
+                                              StepOp(kind=OP_SYNC)], rk.device.index, st), host.numpy(), host)
             if r in self.ps_ranks and not self.cfg.colocated:
                 k = 1 if self.cfg.sync else self.cfg.num_workers
                 plans["ps"][r] = StepPlan([StepOp(kind=OP_PS_APPLY, p0=ctypes.addressof(self._p[r])) for _ in range(k)],
                                           rk.device.index, st, keep=[self._p[r]])
-        plans["runs"] = 0
+        plans["runs"], plans["parity"], plans["prefetched"] = 0, 0, None
         self._native_plans = plans
         return plans
 
     def _graph_plans(self) -> None:
-        """After the first eager pass: every kernel run of every plan becomes ONE CUDA-graph launch, so a step costs
-        the host two memcpy enqueues + one graph launch per worker (+ the loss read-back)."""
+        """After both buffer sets have run eagerly once: every kernel run of every compute / ps plan becomes ONE
+        CUDA-graph launch, so a step costs the host two memcpy enqueues + a staging launch (copy stream) and one
+        graph launch per worker (+ the loss read-back)."""
         plans = self._native_plans
         self.synchronize()
-        for kind in ("worker", "ps"):
-            for r in list(plans[kind]):
-                plans[kind][r] = plans[kind][r].graphed()
+        for r in list(plans["compute"]):
+            plans["compute"][r] = [pl.graphed() for pl in plans["compute"][r]]
+        for r in list(plans["ps"]):
+            plans["ps"][r] = plans["ps"][r].graphed()
         plans["graphed"] = True
 
-    @staticmethod
-    def _is_pinned_f32(t) -> bool:
-        return isinstance(t, torch.Tensor) and (not t.is_cuda) and t.dtype == torch.float32 and t.is_contiguous() \
-            and t.is_pinned()
+    def _is_pinned_f32(self, t) -> bool:
+        """Pinned contiguous fp32 host tensor?  (``is_pinned`` asks the driver: cache the answer per storage range.)"""
+        if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            return False
+        cache = self.__dict__.setdefault("_pinned_cache", {})
+        key = (t.data_ptr(), t.numel())
+        ok = cache.get(key)
+        if ok is None:
+            if len(cache) > 65536:
+                cache.clear()
+            ok = cache[key] = bool(t.is_pinned())
+        return ok
 
-    def step(self, x=None, y=None, sync_loss: bool = True, source: str = "dataset") -> Optional[float]:
+    def _issue_copy(self, plans, local_workers, par: int, x: torch.Tensor, y: torch.Tensor) -> None:
+        B = self.spec.batch
+        split = len(local_workers) > 1 and x.shape[0] == B * len(local_workers)
+        xp, yp = x.data_ptr(), y.data_ptr()
+        xs, ys = B * self.spec.in_dim * 4, B * self.spec.classes * 4
+        for i, r in enumerate(local_workers):
+            pl = plans["copy"][r][par]
+            pl.ops[1].p1 = xp + (i * xs if split else 0)
+            pl.ops[2].p1 = yp + (i * ys if split else 0)
+            pl.run()
+
+    def step(self, x=None, y=None, sync_loss: bool = True, source: str = "dataset", prefetch=None) -> Optional[float]:
         """One training step for every LOCAL rank.  Workers: (optional staging of the host batch) +
         3 kernels; ps shards: one ps_apply per aggregate (sync) or per worker push (async).
         Returns the local worker's loss when ``sync_loss`` (a device->host read).
@@ -647,31 +703,34 @@ class PSTrainEngine:
         ``x``/``y``: one batch ``[B, in_dim]`` / ``[B, classes]`` (every local worker trains on it) or, with several
         local workers (in-graph replication), ``[W_local * B, ...]`` split across them in worker order -- the
         scatter of ``example_in_graph.py:38``.  Pinned fp32 host tensors take the native path: ONE C call per rank
-        enqueues the H2D copies, the staging kernel and the step's kernels (``csrc/step_exec.cu``)."""
+        and stream enqueues the H2D copies + staging kernel (copy stream) and the step's kernels, CUDA-graphed
+        (``csrc/step_exec.cu``).  ``prefetch=(x_next, y_next)``: start the next step's host->device copy now, so it
+        overlaps this step's kernels (input double buffering; the next ``step`` must be called with those tensors)."""
         cfg = self.cfg
         local_workers = [r for r in self.worker_ranks if r in self.ranks]
         if x is not None and self._is_pinned_f32(x) and self._is_pinned_f32(y):
             plans = self._plans()
-            B = self.spec.batch
-            split = len(local_workers) > 1 and x.shape[0] == B * len(local_workers)
-            xp, yp = x.data_ptr(), y.data_ptr()
-            xs, ys = B * self.spec.in_dim * 4, B * self.spec.classes * 4
-            for i, r in enumerate(local_workers):
-                pl = plans["worker"][r]
-                pl.ops[0].p1 = xp + (i * xs if split else 0)
-                pl.ops[1].p1 = yp + (i * ys if split else 0)
-                pl.run()
+            par = plans["parity"]
+            if plans["prefetched"] != (x.data_ptr(), y.data_ptr(), par):
+                self._issue_copy(plans, local_workers, par, x, y)
+            plans["prefetched"] = None
+            for r in local_workers:
+                plans["compute"][r][par].run()
                 self.ranks[r].step += 1
             for r in self.ps_ranks:
                 if r in plans["ps"]:
                     plans["ps"][r].run()
+            if prefetch is not None and self._is_pinned_f32(prefetch[0]) and self._is_pinned_f32(prefetch[1]):
+                self._issue_copy(plans, local_workers, par ^ 1, prefetch[0], prefetch[1])
+                plans["prefetched"] = (prefetch[0].data_ptr(), prefetch[1].data_ptr(), par ^ 1)
+            plans["parity"] = par ^ 1
             plans["runs"] += 1
-            if plans["runs"] == 2 and not plans.get("graphed") and os.environ.get("DTF_E2E_GRAPH", "1") == "1":
+            if plans["runs"] == 4 and not plans.get("graphed") and os.environ.get("DTF_E2E_GRAPH", "1") == "1":
                 self._graph_plans()
             if sync_loss and local_workers:
-                pl, host = plans["loss"][local_workers[0]]
+                pl, host_np, _ = plans["loss"][local_workers[0]]
                 pl.run()
-                return float(host[:self.head_ctas].sum())
+                return float(host_np[:self.head_ctas].sum())
             return None
         for i, r in enumerate(local_workers):
             if x is not None:

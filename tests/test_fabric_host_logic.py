@@ -73,3 +73,43 @@ def test_strategy_minimize_builds_fabric_train_step(ports):
             dtf.fabric.FabricPSStrategy(dtf.train.Server.create_local_server()).minimize(opt, loss, gs)
     finally:
         server.stop()
+
+
+def test_fd_passing_between_processes():
+    """VMM / multicast handles travel between task processes as POSIX fds over a unix socket (parallel/fdshare.py)."""
+    import multiprocessing as mp
+    import os
+    from distributed_tensorflow_b200.parallel.fdshare import FdServer, fetch_fd
+    srv = FdServer()
+    r, w = os.pipe()
+    os.write(w, b"sym-buffer")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_fd_child, args=(srv.path, q))
+    p.start()
+    srv.register("srepl0/mem/1", r)            # registered AFTER the client connected: the server waits for it
+    assert q.get(timeout=60) == b"sym-buffer"
+    p.join(timeout=30)
+    with pytest.raises(Exception):
+        fetch_fd(srv.path + ".nope", "x", timeout=0.3)
+    srv.close()
+
+
+def _fd_child(path, q):
+    import os
+    from distributed_tensorflow_b200.parallel.fdshare import fetch_fd
+    fd = fetch_fd(path, "srepl0/mem/1")
+    q.put(os.read(fd, 10))
+
+
+def test_native_step_plan_layout_and_host_ops():
+    """The ctypes mirror of DtfStepOp matches the C struct, and a plan of host-side ops reports failures by index."""
+    import ctypes
+    from distributed_tensorflow_b200.ops import cuda_lib
+    if not cuda_lib.available():
+        pytest.skip("kernel library not built")
+    lib = cuda_lib.load()
+    assert lib.dtf_sizeof_step_op() == ctypes.sizeof(cuda_lib.StepOp)
+    bad = cuda_lib.StepPlan([cuda_lib.StepOp(kind=99)], -1, None)
+    with pytest.raises(RuntimeError, match="op 0"):
+        bad.run()

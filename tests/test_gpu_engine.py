@@ -136,3 +136,36 @@ def test_generic_engine_resnet18_trains_on_fabric_ps():
     assert abs(losses[0] - ref) < 0.05 * abs(ref)
     assert not torch.equal(sd["stem/conv"], init["stem/conv"])
     eng.close()
+
+
+def test_native_step_prefetch_matches_plain_steps():
+    """Double-buffered input staging (copy stream + prefetch of the next batch) and the CUDA-graphed native plans
+    produce exactly the parameters of the same steps issued one by one."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from distributed_tensorflow_b200.parallel.fabric import Fabric
+    from distributed_tensorflow_b200.parallel.ps_engine import EngineConfig, MLPSpec, PSTrainEngine
+    from distributed_tensorflow_b200.utils.mnist_data import synthetic_mnist
+    torch.cuda.set_device(0)
+    xs, ys = synthetic_mnist(1200, seed=9)
+    hx, hy = torch.from_numpy(xs).pin_memory(), torch.from_numpy(ys).pin_memory()
+    batches = [(hx[i * 100:(i + 1) * 100], hy[i * 100:(i + 1) * 100]) for i in range(12)]
+
+    def run(prefetch):
+        eng = PSTrainEngine(MLPSpec(), EngineConfig(colocated=True, optimizer={"kind": "momentum", "lr": 0.001, "momentum": 0.9},
+                                                    seed=4, head_ctas=1), Fabric(1, {0: 0}))     # one head CTA: no fp32 atomics, bit-exact
+        eng.init_params()
+        losses = []
+        for i in range(11):
+            losses.append(eng.step(*batches[i], prefetch=batches[i + 1] if prefetch else None))
+        eng.check_errors()
+        sd = eng.state_dict()
+        eng.close()
+        return losses, sd
+    l0, s0 = run(False)
+    l1, s1 = run(True)
+    assert int(s0["global_step"]) == 11 and int(s1["global_step"]) == 11
+    np.testing.assert_allclose(l0, l1, rtol=1e-6)
+    for k in ("hid_w", "hid_b", "sm_w", "sm_b"):
+        torch.testing.assert_close(s0[k], s1[k], rtol=0, atol=0)
+    assert l0[-1] < l0[0]

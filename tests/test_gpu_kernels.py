@@ -34,6 +34,28 @@ def test_tcgen05_gemm_all_operand_majors(lib, M, N, K, ta, tb):
     torch.testing.assert_close(got, ref, rtol=2e-4, atol=2e-3)
 
 
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("M,N,K,bn", [(1000, 520, 200, 0), (2048, 1536, 512, 256), (4100, 96, 72, 0), (512, 512, 2048, 128)])
+def test_persistent_gemm_double_buffered_tmem(lib, M, N, K, bn, ta, tb, mode):
+    """Persistent kernel (tile loop per SM, two TMEM accumulator buffers, epilogue overlapped with the next tile's
+    mainloop), forced on so that small grids exercise several tiles per CTA as well.  mode 2 = CTA pairs
+    (tcgen05 cta_group::2: 256-row tiles, each CTA loads half of B; falls back to 1-CTA when the tile shape
+    does not split)."""
+    if tb is False and bn == 0 and N % 64:
+        bn = 0                                       # MN-major B picks a multiple of 64 itself
+    torch.manual_seed(M + N + K)
+    a = torch.randn((K, M) if ta else (M, K), device="cuda")
+    b = torch.randn((N, K) if tb else (K, N), device="cuda")
+    bias = torch.randn(N, device="cuda")
+    got = lib.gemm(a, b, ta, tb, bias=bias, relu=True, persistent=mode, block_n=bn)
+    ref = torch.relu(_ref_mm(a, b, ta, tb) + bias)
+    torch.testing.assert_close(got, ref, rtol=3e-4, atol=4e-3)
+    # auto-dispatch (persistent when tiles > SMs) agrees with the single-tile-per-CTA kernel
+    plain = lib.gemm(a, b, ta, tb, bias=bias, relu=True, persistent=-1, block_n=bn)
+    torch.testing.assert_close(got, plain, rtol=0, atol=0)
+
+
 def test_gemm_fused_bias_relu_and_bf16_out(lib):
     torch.manual_seed(0)
     a, b, bias = torch.randn(100, 784, device="cuda"), torch.randn(784, 100, device="cuda"), torch.randn(100, device="cuda")
