@@ -57,40 +57,124 @@ def parse_args():
     ap.add_argument("--num-ps", type=int, default=1, help="ps shards (variables placed round-robin)")
     ap.add_argument("--model", default="mnist_mlp", choices=["mnist_mlp", "resnet18"],
                     help="resnet18: BASELINE.json config 5 (conv model under the same ps API; bandwidth-relevant: 44.7 MB per push)")
-    ap.add_argument("--nvls", default="off", choices=["off", "on", "auto"],
+    ap.add_argument("--nvls", default="auto", choices=["off", "on", "auto"],
                     help="symmetric buffers + NVLS multicast: gradients reduced in the switch (multimem.ld_reduce), "
                          "parameters published with multimem.st")
     return ap.parse_args()
 
 
 class ClockSampler:
-    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock / throttle-reason sampler running DURING the timed region (B200_PROFILING.md clocks line).
+
+    In-process NVML polling (2 ms period) of THIS rank's GPU, so even a timed region of a few tens of milliseconds
+    gets samples; falls back to an ``nvidia-smi -i <gpu> -lms`` subprocess when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int, period_ms: int = 50):
+    def __init__(self, gpu_index: int, period_ms: int = 2):
         self.gpu, self.rows, self.proc = gpu_index, [], None
         self.period = period_ms
+        self.nvml = None
+        self._stop = False
+        self.thread = None
+
+    # -- NVML path ------------------------------------------------------------------------------------------------
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = None
+        if h is None:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(t.strip().isdigit() for t in vis.split(",")) and self.gpu < len(vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        return pynvml, h
+
+    def _poll_nvml(self):
+        pynvml, h = self.nvml
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop:
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                rs = int(get_reasons(h))
+                try:
+                    pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = None
+                self.rows.append((time.time(), float(sm), rs, pw))
+            except Exception:
+                pass
+            time.sleep(self.period / 1000.0)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", str(self.period)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                                         text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.nvml = self._nvml_handle()
+            pynvml, h = self.nvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.smi_period = 50
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", str(self.smi_period)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
+            self.thread.start()
+            t_end = time.time() + 5.0
+            while not self.rows and time.time() < t_end:     # the first nvidia-smi sample can take a second
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
-    def _read(self):
+    def _read_smi(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0: float, t1: float):
+        if self.nvml is not None:
+            time.sleep(self.period / 1000.0 * 2)
+            self._stop = True
+            self.thread.join(timeout=1.0)
+            inside = [r for r in self.rows if t0 <= r[0] <= t1]
+            note = None
+            if not inside:
+                inside = sorted(self.rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[:2]
+                note = "timed region shorter than the sampling period: nearest samples"
+            if not inside:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "source": "nvml"}
+            pynvml = self.nvml[0]
+            bits = 0
+            for r in inside:
+                bits |= r[2]
+            names = (("hw_slowdown", "HwSlowdown", 0x8), ("hw_thermal_slowdown", "HwThermalSlowdown", 0x40),
+                     ("sw_thermal_slowdown", "SwThermalSlowdown", 0x20), ("sw_power_cap", "SwPowerCap", 0x4),
+                     ("hw_power_brake_slowdown", "HwPowerBrakeSlowdown", 0x80))
+            reasons = []
+            for out_name, nv, default in names:
+                mask = getattr(pynvml, "nvmlClocksEventReason" + nv, getattr(pynvml, "nvmlClocksThrottleReason" + nv, default))
+                if bits & int(mask):
+                    reasons.append(out_name)
+            pws = [r[3] for r in inside if r[3] is not None]
+            out = {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                   "samples": len(inside), "power_w_max": max(pws) if pws else None, "source": "nvml"}
+            if note:
+                out["note"] = note
+            return out
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(self.period / 1000.0 * 1.5)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi and NVML unavailable"]}
+        time.sleep(self.smi_period / 1000.0 * 1.5)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -99,18 +183,18 @@ class ClockSampler:
         mine = []
         for ts, line in self.rows:
             f = [x.strip() for x in line.split(",")]
-            if len(f) >= 8 and f[0] == str(self.gpu):
+            if len(f) >= 8:
                 mine.append((ts, f))
-        inside = [f for ts, f in mine if t0 <= ts <= t1 + self.period / 1000.0] or [f for _, f in mine[-3:]]
+        inside = [f for ts, f in mine if t0 <= ts <= t1 + self.smi_period / 1000.0] or [f for _, f in mine[-3:]]
         if not inside:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "source": "nvidia-smi"}
         sm = [float(f[1]) for f in inside]
         reasons = []
         for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
             if any(f[col].lower().startswith("active") for f in inside):
                 reasons.append(name)
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(inside[0][2]), "reasons": reasons,
-                "samples": len(inside), "power_w_max": max(float(f[3]) for f in inside if f[3].replace(".", "").isdigit())
+                "samples": len(inside), "source": "nvidia-smi", "power_w_max": max(float(f[3]) for f in inside if f[3].replace(".", "").isdigit())
                 if any(f[3].replace(".", "").isdigit() for f in inside) else None}
 
 
@@ -203,6 +287,10 @@ def run_resnet18(args, rank, world, local_rank):
         ms, launches = ms_local, int(stats[1])
     eng.check_errors()
     value = cfg.num_workers * B * K / (ms / 1e3)
+    lt = torch.tensor([losses[W] if len(losses) > W else -1e30, losses[-1] if losses else -1e30], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(lt, op=dist.ReduceOp.MAX)           # the ps ranks have no loss: take a worker's
+    losses = [float(lt[0]), float(lt[1])]
     out = {"metric": "ResNet-18 samples/sec (whole box, device-timed, max over ranks), sync-replica PS", "value": value,
            "unit": "samples/sec", "n_gpus": N, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "impl": "ours",
@@ -273,6 +361,8 @@ def main():
             args.lr /= max(1, args.gpus - args.num_ps)       # every push is applied alone: keep the effective rate
     opt = {"kind": args.optimizer, "lr": args.lr, "momentum": 0.9}
     NVLS = {"off": False, "on": True, "auto": "auto"}[args.nvls]
+    if args.in_graph and args.nvls == "auto":
+        NVLS = False            # one-process topology: opt in with --nvls on
     if args.in_graph and N > 1:
         cfg = EngineConfig(num_ps=args.num_ps, num_workers=N - args.num_ps, sync=args.mode == "sync", optimizer=opt,
                            publish_replicas=args.publish, nvls=NVLS, f1_splits=args.f1_splits, head_ctas=args.head_ctas,

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 200 python -m pytest tests/test_gpu_kernels.py -x -q -k "persistent" > gpurun_out/t_persist.log 2>&1; echo "persist rc=$?"; tail -6 gpurun_out/t_persist.log
-timeout 200 python tools/gemm_perf.py > gpurun_out/gemm_perf.log 2>&1; echo "perf rc=$?"; tail -8 gpurun_out/gemm_perf.log
-timeout 200 python -m pytest tests/test_gpu_engine.py -x -q > gpurun_out/t_engine.log 2>&1; echo "engine rc=$?"; tail -6 gpurun_out/t_engine.log
-timeout 120 python bench.py --gpus 1 --steps 1000 --warmup 10 --e2e-steps 500 > gpurun_out/b1.log 2>&1; echo "b1 rc=$?"; tail -1 gpurun_out/b1.log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
+timeout 70 $TR bench.py --gpus 8 --steps 2000 --warmup 10 --e2e-steps 400 --nvls on > gpurun_out/b8_nvls.log 2>&1; echo "b8_nvls rc=$?"; tail -1 gpurun_out/b8_nvls.log
+timeout 70 $TR bench.py --gpus 8 --steps 2000 --warmup 10 --e2e-steps 400 > gpurun_out/b8_off.log 2>&1; echo "b8_off rc=$?"; tail -1 gpurun_out/b8_off.log
+timeout 50 $TR tools/nvls_check.py --iters 10 > gpurun_out/nvls8_mp.log 2>&1; echo "nvls8 rc=$?"; tail -1 gpurun_out/nvls8_mp.log
