@@ -143,6 +143,12 @@ class ClockSampler:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0: float, t1: float):
+        try:
+            return self._stop_impl(t0, t1)
+        except Exception as e:      # a sampling problem must never cost the measurement itself
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler error: %r" % (e,)]}
+
+    def _stop_impl(self, t0: float, t1: float):
         if self.nvml is not None:
             time.sleep(self.period / 1000.0 * 2)
             self._stop = True

@@ -174,7 +174,7 @@ class PSTrainEngine:
         W = cfg.num_workers
         # ---- NVLS mode: one symmetric gradient buffer and one symmetric bf16 replica per shard (collective allocs) ----
         want = cfg.nvls
-        self.nvls = False
+        self.nvls, self.nvls_multicast = False, False
         self.sym_grads: List[Any] = []
         self.sym_repl: List[Any] = []
         if want and self.world > 1:

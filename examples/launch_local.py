@@ -4,10 +4,12 @@
 
 Each task gets ``--job_name/--task_index/--ps_hosts/--worker_hosts``; with GPUs present
 task n is bound to GPU ``n % num_gpus`` through ``DTF_GPU_INDEX`` (ps tasks first).
-Workers' exit ends the run; ps processes are then terminated (they ``join()`` forever).
+Workers' exit ends the run; ps processes are then terminated (they ``join()`` forever).  In-graph programs
+(``example_in_graph.py``, ``example_distributed_server.py``) have ONE client, worker 0: run them with ``--wait first``.
 """
 import argparse
 import os
+import signal
 import socket
 import subprocess
 import sys
@@ -33,9 +35,16 @@ def main():
     ap.add_argument("--num_workers", type=int, default=2)
     ap.add_argument("--timeout", type=float, default=600)
     ap.add_argument("--gpus", type=int, default=-1, help="GPUs to spread tasks over (-1: all visible, 0: none)")
-    ap.add_argument("rest", nargs=argparse.REMAINDER)
-    a = ap.parse_args()
-    extra = [x for x in a.rest if x != "--"]
+    ap.add_argument("--wait", default="all", choices=["all", "first"],
+                    help="all: the run ends when every worker exits (between-graph); first: when worker 0 exits "
+                         "(in-graph replication: worker 0 is the only client, the other workers just serve)")
+    # launcher options may come before or after the script; everything after a literal "--" goes to the script
+    argv = sys.argv[1:]
+    extra = []
+    if "--" in argv:
+        k = argv.index("--")
+        argv, extra = argv[:k], argv[k + 1:]
+    a = ap.parse_args(argv)
     ports = free_ports(a.num_ps + a.num_workers)
     ps_hosts = ",".join("127.0.0.1:%d" % p for p in ports[:a.num_ps])
     wk_hosts = ",".join("127.0.0.1:%d" % p for p in ports[a.num_ps:])
@@ -59,9 +68,10 @@ def main():
             n += 1
     rc = 0
     deadline = time.time() + a.timeout
+    signal.signal(signal.SIGTERM, lambda *_: sys.exit(143))      # killed launcher still reaps its tasks (finally below)
     try:
         for job, i, p in procs:
-            if job != "worker":
+            if job != "worker" or (a.wait == "first" and i != 0):
                 continue
             left = max(1.0, deadline - time.time())
             try:

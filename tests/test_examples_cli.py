@@ -1,0 +1,93 @@
+"""Example programs run the way a user of the reference runs them: one ``python X.py --job_name ... --task_index ...``
+process per task on localhost ports (the only no-cluster technique the reference has).
+CPU tier -- every script mirrors one reference script (S1-S20)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EX = os.path.join(ROOT, "examples")
+ENV = dict(os.environ, CUDA_VISIBLE_DEVICES="", DTF_FABRIC="0")
+
+
+def _run(args, timeout=240, cwd=None):
+    r = subprocess.run([sys.executable] + args, capture_output=True, text=True, timeout=timeout, env=ENV, cwd=cwd or ROOT)
+    assert r.returncode == 0, "exit %d\nSTDOUT:\n%s\nSTDERR:\n%s" % (r.returncode, r.stdout[-3000:], r.stderr[-3000:])
+    return r.stdout
+
+
+def test_standalone_one_gpu_golden_values():
+    out = _run([os.path.join(EX, "standalone.py"), "--one_gpu"])
+    flat = out.replace("\n", " ")
+    assert "2." in flat and "7." in flat and "14." in flat            # [[2,3],[6,7]] and [[5],[14]]
+
+
+def test_standalone_towers_train_and_report_time():
+    out = _run([os.path.join(EX, "standalone.py"), "--iters", "30", "--batch_size", "200", "--num_gpu", "2"])
+    assert "2 towers:" in out and "for 30 iterations" in out and "final tower loss" in out
+    assert "affine_last/w" in out                                      # variables allocated once, shared by both towers
+
+
+def test_between_graph_linear_regression_cluster_async(tmp_path):
+    """example_between_graph.py: 1 ps + 2 workers, async SGD on y = 2x + 10, checkpoints in ckpt_dir."""
+    out = _run([os.path.join(EX, "launch_local.py"), os.path.join(EX, "example_between_graph.py"), "--num_ps", "1",
+                "--num_workers", "2", "--gpus", "0", "--timeout", "200", "--", "--num_steps=400", "--steps_to_validate=100",
+                "--ckpt_dir=%s" % (tmp_path / "ckpt"), "--save_checkpoint_secs=1"], timeout=300)
+    assert "weight" in out.lower() or "step" in out.lower()
+    assert (tmp_path / "ckpt" / "checkpoint").exists()
+
+
+def test_in_graph_example_golden_result_and_timeline(tmp_path):
+    """example_in_graph.py on 1 ps + 2 workers: scatter on the ps, one matmul per worker, gather -> [[9],[21],[33],[45]]."""
+    out = _run([os.path.join(EX, "launch_local.py"), os.path.join(EX, "example_in_graph.py"), "--num_ps", "1",
+                "--num_workers", "2", "--gpus", "0", "--timeout", "120", "--wait", "first", "--", "--out_dir=%s" % tmp_path], timeout=200)
+    flat = out.replace("\n", " ")
+    for v in ("9.", "21.", "33.", "45."):
+        assert v in flat, out
+    tl = tmp_path / "timeline_client.json"
+    assert tl.exists()
+    ev = json.load(open(tl))["traceEvents"]
+    assert any(e.get("ph") == "X" for e in ev)
+    assert (tmp_path / "logs").exists() and os.listdir(tmp_path / "logs")
+
+
+def test_distributed_server_plus_pure_client(tmp_path):
+    """example_distributed_server.py x3 (ps, worker 0, worker 1 only serve) + example_distributed_client.py: a pure
+    client with no ClusterSpec connects to worker 0's master and gets the same golden result."""
+    import socket
+    import time
+    socks, ports = [], []
+    for _ in range(3):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        ports.append(s.getsockname()[1])
+        socks.append(s)
+    for s in socks:
+        s.close()
+    hosts = ["--ps_hosts=127.0.0.1:%d" % ports[0], "--worker_hosts=127.0.0.1:%d,127.0.0.1:%d" % (ports[1], ports[2])]
+    servers = []
+    try:
+        for job, idx in (("ps", 0), ("worker", 0), ("worker", 1)):
+            servers.append(subprocess.Popen([sys.executable, "-u", os.path.join(EX, "example_distributed_server.py"),
+                                             "--job_name=%s" % job, "--task_index=%d" % idx] + hosts, env=ENV,
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        for p in servers:                           # each prints one "serving ..." line when it is up
+            line = p.stdout.readline()
+            assert "serving" in line, line
+        out = _run([os.path.join(EX, "example_distributed_client.py"), "--master=grpc://127.0.0.1:%d" % ports[1],
+                    "--out_dir=%s" % tmp_path], timeout=120)
+        flat = out.replace("\n", " ")
+        for v in ("9.", "21.", "33.", "45."):
+            assert v in flat, out
+        assert (tmp_path / "timeline_client.json").exists()
+    finally:
+        for p in servers:
+            p.terminate()
+        for p in servers:
+            try:
+                p.wait(timeout=10)
+            except subprocess.TimeoutExpired:
+                p.kill()
