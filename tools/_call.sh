@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
-timeout 70 $TR bench.py --gpus 8 --steps 2000 --warmup 10 --e2e-steps 400 --nvls on > gpurun_out/b8_nvls.log 2>&1; echo "b8_nvls rc=$?"; tail -1 gpurun_out/b8_nvls.log
-timeout 70 $TR bench.py --gpus 8 --steps 2000 --warmup 10 --e2e-steps 400 > gpurun_out/b8_off.log 2>&1; echo "b8_off rc=$?"; tail -1 gpurun_out/b8_off.log
-timeout 50 $TR tools/nvls_check.py --iters 10 > gpurun_out/nvls8_mp.log 2>&1; echo "nvls8 rc=$?"; tail -1 gpurun_out/nvls8_mp.log
+timeout 80 python -m pytest tests -x -q -m gpu > gpurun_out/t_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -2 gpurun_out/t_gpu.log
+timeout 60 python bench.py > gpurun_out/b1_default.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/b1_default.log
+timeout 60 ncu --set full --clock-control none --import-source on -k regex:persistent --launch-skip 2 -c 1 -f -o gpurun_out/prof_gemm_pair python tools/ncu_gemm.py > gpurun_out/ncu_pair.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/ncu_pair.log
