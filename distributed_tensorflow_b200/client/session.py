@@ -63,13 +63,18 @@ class GPUOptions:
 class ConfigProto:
     def __init__(self, gpu_options: Optional[GPUOptions] = None, allow_soft_placement: bool = True,
                  log_device_placement: bool = False, device_filters: Optional[Sequence[str]] = None,
-                 operation_timeout_in_ms: int = 0):
+                 operation_timeout_in_ms: int = 0, intra_op_parallelism_threads: int = 0,
+                 inter_op_parallelism_threads: int = 0):
+        self.intra_op_parallelism_threads = int(intra_op_parallelism_threads)     # 0: the task's default budget
+        self.inter_op_parallelism_threads = int(inter_op_parallelism_threads)     # accepted for parity (one executor thread)
         self.gpu_options = gpu_options or GPUOptions()
         self.allow_soft_placement, self.log_device_placement = allow_soft_placement, log_device_placement
         self.device_filters = list(device_filters or [])
         self.operation_timeout_in_ms = operation_timeout_in_ms
 
     def apply(self) -> None:
+        if self.intra_op_parallelism_threads > 0:
+            torch.set_num_threads(self.intra_op_parallelism_threads)
         frac = self.gpu_options.per_process_gpu_memory_fraction
         if frac and torch.cuda.is_available():
             for d in range(torch.cuda.device_count()):

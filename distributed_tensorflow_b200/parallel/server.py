@@ -16,6 +16,7 @@ task between segments of the same run, so forward and backward of one
 from __future__ import annotations
 
 import os
+import socket
 import threading
 import time
 import weakref
@@ -103,6 +104,7 @@ class Server:
             if env is not None and env != "":
                 gpu_index = int(env)
         self.gpu_index = gpu_index if (gpu_index is not None and gpu_index >= 0 and torch.cuda.is_available()) else None
+        self._set_intra_op_threads(config)
         self._graphs: Dict[str, Dict[int, NodeView]] = {}
         self._runs: Dict[str, _RunState] = {}
         self._cancel: Dict[str, threading.Event] = {}
@@ -112,6 +114,33 @@ class Server:
         self._peers: Dict[Tuple[str, int], RpcClient] = {}
         if start:
             self.start()
+
+    def _set_intra_op_threads(self, config) -> None:
+        """CPU thread budget of this task's kernels.  Several tasks of a cluster usually share one machine (the
+        reference's localhost ps/worker layout, ``distributed_mnist.py:27-29``); if each of them ran the default
+        one-thread-per-core pool the pools would thrash (measured: 18 vs 77 sync steps/s for 1 ps + 2 workers on
+        8 cores).  Default: cores / tasks-on-this-host, at most 4 (the per-step tensors are small);
+        ``ConfigProto(intra_op_parallelism_threads=n)`` or ``DTF_INTRA_OP_THREADS`` override it."""
+        n = int(getattr(config, "intra_op_parallelism_threads", 0) or 0) if config is not None else 0
+        if n <= 0:
+            n = int(os.environ.get("DTF_INTRA_OP_THREADS", "0") or 0)
+        if n <= 0:
+            if os.environ.get("OMP_NUM_THREADS"):
+                return                       # the user already chose
+            local = {"127.0.0.1", "localhost", "0.0.0.0", "", socket.gethostname()}
+            mine = parse_address(self.address)[0]
+            tasks = 0
+            for job in self.cluster.jobs:
+                for t in self.cluster.task_indices(job):
+                    host = parse_address(self.cluster.task_address(job, t))[0]
+                    if host == mine or (host in local and mine in local):
+                        tasks += 1
+            n = max(1, min(4, (os.cpu_count() or 1) // max(tasks, 1)))
+        try:
+            torch.set_num_threads(n)
+        except RuntimeError:
+            pass
+        self.intra_op_threads = n
 
     # -- lifecycle ----------------------------------------------------------------------
     def start(self) -> None:

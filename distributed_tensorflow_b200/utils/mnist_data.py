@@ -100,8 +100,49 @@ class DataSet:
         return self._dev_images[s:s + batch_size], self._dev_labels[s:s + batch_size]
 
 
+def _cache_path(num: int, seed: int, noise: float) -> Optional[str]:
+    root = os.environ.get("DTF_DATA_CACHE", "/tmp/dtf_data_cache")
+    if root in ("", "0"):
+        return None
+    return os.path.join(root, "synth_mnist_n%d_s%d_z%g.npz" % (num, seed, noise))
+
+
 def synthetic_mnist(num: int, seed: int = 0, one_hot: bool = True, noise: float = 0.25) -> Tuple[np.ndarray, np.ndarray]:
-    """``num`` MNIST-shaped examples drawn around ten fixed prototypes."""
+    """``num`` MNIST-shaped examples drawn around ten fixed prototypes.  Pixels are 8-bit like real MNIST, so a
+    split is cached on disk as uint8 (``DTF_DATA_CACHE``, default ``/tmp/dtf_data_cache``; ``0`` disables) -- every
+    task process of a cluster asks for the same split, and generating 55 000 images takes seconds."""
+    cache = _cache_path(num, seed, noise) if num >= 2000 else None
+    if cache is not None and os.path.exists(cache):
+        try:
+            with np.load(cache) as z:
+                u8, labels = z["images"], z["labels"]
+            if u8.shape == (num, 784) and labels.shape == (num,):
+                return _finish_synthetic(u8.astype(np.float32) / np.float32(255.0), labels.astype(np.int64), one_hot)
+        except Exception:
+            pass                                     # unreadable / half-written cache: regenerate
+    images, labels = _generate_synthetic(num, seed, noise)
+    if cache is not None:
+        try:
+            os.makedirs(os.path.dirname(cache), exist_ok=True)
+            tmp = "%s.%d.tmp.npz" % (cache, os.getpid())
+            np.savez(tmp, images=np.round(images * 255.0).astype(np.uint8), labels=labels.astype(np.int16))
+            os.replace(tmp, cache)
+        except OSError:
+            pass
+    return _finish_synthetic(images, labels, one_hot)
+
+
+def _finish_synthetic(images: np.ndarray, labels: np.ndarray, one_hot: bool) -> Tuple[np.ndarray, np.ndarray]:
+    num = images.shape[0]
+    if one_hot:
+        lab = np.zeros((num, 10), np.float32)
+        lab[np.arange(num), labels] = 1.0
+    else:
+        lab = labels.astype(np.int64)
+    return images, lab
+
+
+def _generate_synthetic(num: int, seed: int, noise: float) -> Tuple[np.ndarray, np.ndarray]:
     proto_rng = np.random.RandomState(1234)          # prototypes are the same for every split
     yy, xx = np.mgrid[0:28, 0:28].astype(np.float32)
     protos = np.zeros((10, 28, 28), np.float32)
@@ -126,13 +167,7 @@ def synthetic_mnist(num: int, seed: int = 0, one_hot: bool = True, noise: float 
     np.clip(out, 0.0, 1.0, out=out)
     # quantise to 8 bits like real MNIST pixels (exactly representable in bf16: 8-bit significand)
     out = np.round(out * 255.0) / 255.0
-    images = out.reshape(num, 784).astype(np.float32)
-    if one_hot:
-        lab = np.zeros((num, 10), np.float32)
-        lab[np.arange(num), labels] = 1.0
-    else:
-        lab = labels.astype(np.int64)
-    return images, lab
+    return out.reshape(num, 784).astype(np.float32), labels.astype(np.int64)
 
 
 def _read_idx(path: str) -> np.ndarray:
