@@ -1,160 +1,103 @@
-"""Between-graph parameter-server training of the MNIST MLP, async or sync.
+"""MNIST MLP on a parameter-server cluster: between-graph replication, asynchronous or synchronous replicas.
 
-Capability mirror of reference ``distributed_mnist.py`` (S1-S8): same flags, same
-model (784 -> hidden_units ReLU -> 10 softmax, batch-sum clipped cross-entropy),
-Adam, ``replica_device_setter`` placement, optional ``SyncReplicasOptimizer``,
-``MonitoredTrainingSession`` with a custom stop hook, per-step log line,
-validation every 1000 global steps, final summary.
+What the reference's ``distributed_mnist.py`` does (S1-S8), written against this framework's helpers: the model
+comes from ``dtf.models.build_mnist_mlp`` (784 -> hidden ReLU -> 10, clipped batch-SUM cross-entropy, variables
+``hid_w, hid_b, sm_w, sm_b`` placed round-robin on the ps tasks by ``replica_device_setter``), Adam, optional
+``SyncReplicasOptimizer``, ``MonitoredTrainingSession`` (chief initialises / restores and checkpoints, the others
+wait), a stop hook on the shared global step, validation every ``--validate_every`` global steps.
 
-Run one process per task, e.g. on one box::
+    python examples/launch_local.py examples/distributed_mnist.py --num_ps 1 --num_workers 2 -- --issync=True --train_steps=2000
 
-    python examples/distributed_mnist.py --job_name=ps     --task_index=0 --ps_hosts=127.0.0.1:22221 --worker_hosts=127.0.0.1:22222,127.0.0.1:22223 &
-    python examples/distributed_mnist.py --job_name=worker --task_index=0 ... --issync=True &
-    python examples/distributed_mnist.py --job_name=worker --task_index=1 ... --issync=True
-
-Differences from the reference, on purpose: ``--train_steps`` is honoured
-(the reference hard-codes 10000), the checkpoint dir is a flag, data is synthetic
-MNIST-shaped when no IDX files are present, and GPUs are used when visible
-(``DTF_GPU_INDEX`` binds a task to one B200) instead of being hidden.
+or one process per task by hand (``--job_name=ps|worker --task_index=N --ps_hosts=... --worker_hosts=...``).
+``--engine=fabric`` keeps the same program but moves pull / push / aggregation / tokens onto the GPUs (NVLink).
+Unlike the reference: ``--train_steps`` is honoured, the checkpoint directory is a flag, GPUs are used when visible.
 """
-import math
-import os
-import sys
 import time
+
 from datetime import datetime
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import distributed_tensorflow_b200 as dtf
+from _common import bring_up, define_cluster_flags, dtf
 from distributed_tensorflow_b200 import input_data
+from distributed_tensorflow_b200.models import build_mnist_mlp
 
 flags = dtf.app.flags
-IMAGE_PIXELS = 28
-flags.DEFINE_string('data_dir', '/tmp/mnist-data', 'Directory for storing mnist data (IDX files); synthetic if absent')
-flags.DEFINE_integer('hidden_units', 100, 'Number of units in the hidden layer of the NN')
-flags.DEFINE_integer('train_steps', 10000, 'Global step at which training stops')
-flags.DEFINE_integer('batch_size', 100, 'Training batch size')
-flags.DEFINE_float('learning_rate', 0.01, 'Learning rate')
-flags.DEFINE_string('ps_hosts', '127.0.0.1:22221', 'Comma-separated list of hostname:port pairs')
-flags.DEFINE_string('worker_hosts', '127.0.0.1:22222,127.0.0.1:22223', 'Comma-separated list of hostname:port pairs')
-flags.DEFINE_string('job_name', 'worker', 'job name: worker or ps')
-flags.DEFINE_integer('task_index', 0, 'Index of task within the job')
-flags.DEFINE_bool('issync', False, 'Use synchronous replicas (SyncReplicasOptimizer)')
-flags.DEFINE_string('train_dir', '/tmp/dtf_ckpt/mnist', 'Checkpoint directory (shared filesystem)')
-flags.DEFINE_integer('validate_every', 1000, 'Validate when (global_step+1) is a multiple of this')
-flags.DEFINE_integer('num_train', 55000, 'Synthetic train-set size')
-flags.DEFINE_integer('log_every', 1, 'Print the per-step line every N local steps')
-flags.DEFINE_bool('measure_staleness', False, 'Async mode: record pull->apply staleness per step')
-flags.DEFINE_string('engine', 'graph', "'graph': control-plane tier (RPC); 'fabric': parameters/gradients/tokens over NVLink peer memory")
-FLAGS = flags.FLAGS
+FLAGS = define_cluster_flags("127.0.0.1:22221", "127.0.0.1:22222,127.0.0.1:22223")
+flags.DEFINE_string("data_dir", "/tmp/mnist-data", "MNIST IDX files; a synthetic MNIST-shaped split is used if absent")
+flags.DEFINE_integer("hidden_units", 100, "width of the hidden layer")
+flags.DEFINE_integer("train_steps", 10000, "global step at which every worker stops")
+flags.DEFINE_integer("batch_size", 100, "examples per worker step")
+flags.DEFINE_float("learning_rate", 0.01, "Adam step size")
+flags.DEFINE_bool("issync", False, "aggregate the workers' gradients (SyncReplicasOptimizer) instead of applying each alone")
+flags.DEFINE_string("train_dir", "/tmp/dtf_ckpt/mnist", "checkpoint directory on a filesystem every task can reach")
+flags.DEFINE_integer("validate_every", 1000, "validate when global_step + 1 is a multiple of this")
+flags.DEFINE_integer("num_train", 55000, "size of the synthetic training split")
+flags.DEFINE_integer("log_every", 1, "print the step line every N local steps")
+flags.DEFINE_bool("measure_staleness", False, "async mode: histogram of (global step at apply) - (global step at pull)")
+flags.DEFINE_string("engine", "graph", "'graph' = control-plane tier over RPC, 'fabric' = NVLink peer-memory tier")
 
 
-class MyStopAtStepHook(dtf.train.StopAtStepHook):
-    """Stop hook that reports where it started and where it stops."""
+class AnnouncedStop(dtf.train.StopAtStepHook):
+    """``StopAtStepHook`` that says where it will stop and when it did (cf. reference ``distributed_mnist.py:41-54``)."""
 
     def after_create_session(self, session, coord):
-        if self._last_step is None:
-            global_step = session.run(self._global_step_tensor)
-            self._last_step = global_step + self._num_steps
-            print("now global_step is %d after create session, num_steps: %d, last_step:%d :"
-                  % (global_step, self._num_steps, self._last_step))
+        super().after_create_session(session, coord)
+        print("stop hook armed: last_step=%s" % self._last_step, flush=True)
 
     def after_run(self, run_context, run_values):
-        global_step = run_values.results
-        if global_step >= self._last_step:
-            print("global_step is %d when stop." % global_step)
+        if run_values.results >= self._last_step:
+            print("global_step is %d when stop." % run_values.results, flush=True)
             run_context.request_stop()
 
 
-def build_model(hidden_units):
-    global_step = dtf.train.get_or_create_global_step()
-    hid_w = dtf.Variable(dtf.truncated_normal([IMAGE_PIXELS * IMAGE_PIXELS, hidden_units],
-                                              stddev=1.0 / IMAGE_PIXELS), name='hid_w')
-    hid_b = dtf.Variable(dtf.zeros([hidden_units]), name='hid_b')
-    sm_w = dtf.Variable(dtf.truncated_normal([hidden_units, 10], stddev=1.0 / math.sqrt(hidden_units)), name='sm_w')
-    sm_b = dtf.Variable(dtf.zeros([10]), name='sm_b')
-    x = dtf.placeholder(dtf.float32, [None, IMAGE_PIXELS * IMAGE_PIXELS])
-    y_ = dtf.placeholder(dtf.float32, [None, 10])
-    hid = dtf.nn.relu(dtf.nn.xw_plus_b(x, hid_w, hid_b))
-    y = dtf.nn.softmax(dtf.nn.xw_plus_b(hid, sm_w, sm_b))
-    cross_entropy = -dtf.reduce_sum(y_ * dtf.log(dtf.clip_by_value(y, 1e-10, 1.0)))
-    return global_step, x, y_, y, cross_entropy
-
-
 def main():
-    if FLAGS.job_name is None or FLAGS.job_name == '':
-        raise ValueError('Must specify an explicit job_name !')
-    print('job_name : %s' % FLAGS.job_name)
-    if FLAGS.task_index is None or FLAGS.task_index == '':
-        raise ValueError('Must specify an explicit task_index!')
-    print('task_index : %d' % FLAGS.task_index)
+    cluster, server, num_workers = bring_up(FLAGS)
+    me, chief = FLAGS.task_index, FLAGS.task_index == 0
+    fabric = dtf.fabric.FabricPSStrategy(server) if FLAGS.engine == "fabric" else None
+    data = input_data.read_data_sets(FLAGS.data_dir, one_hot=True, num_train=FLAGS.num_train)
+    print("len of train images: ", len(data.train.images))
 
-    ps_spec = [h.strip() for h in FLAGS.ps_hosts.split(',')]
-    worker_spec = [h.strip() for h in FLAGS.worker_hosts.split(',')]
-    num_workers = len(worker_spec)
-    cluster = dtf.train.ClusterSpec({'ps': ps_spec, 'worker': worker_spec})
-    server = dtf.train.Server(cluster, job_name=FLAGS.job_name, task_index=FLAGS.task_index)
-    if FLAGS.job_name == 'ps':
-        server.join()        # the ps only owns variables / accumulators / queues (fabric: + the apply service); blocks
-        return
-    strategy = dtf.fabric.FabricPSStrategy(server) if FLAGS.engine == 'fabric' else None
-
-    mnist = input_data.read_data_sets(FLAGS.data_dir, one_hot=True, num_train=FLAGS.num_train)
-    print("len of train images: ", len(mnist.train.images))
-    worker_device = '/job:worker/task:%d/cpu:0' % FLAGS.task_index
-    with dtf.device(dtf.train.replica_device_setter(cluster=cluster, worker_device=worker_device)):
-        global_step, x, y_, y, cross_entropy = build_model(FLAGS.hidden_units)
+    with dtf.device(dtf.train.replica_device_setter(cluster=cluster, worker_device="/job:worker/task:%d/cpu:0" % me)):
+        net = build_mnist_mlp(hidden=FLAGS.hidden_units)
+        gstep, loss = net["global_step"], net["loss"]
         opt = dtf.train.AdamOptimizer(FLAGS.learning_rate)
-        hooks = [MyStopAtStepHook(last_step=FLAGS.train_steps)]
-        staleness = None
+        hooks, stale = [AnnouncedStop(last_step=FLAGS.train_steps)], None
         if FLAGS.issync:
             print("is_sync:true")
-            opt = dtf.train.SyncReplicasOptimizer(opt, replicas_to_aggregate=num_workers,
-                                                  total_num_replicas=num_workers)
-            if strategy is None:
-                hooks.append(opt.make_session_run_hook(FLAGS.task_index == 0))
-        elif FLAGS.measure_staleness and strategy is None:
-            staleness = dtf.train.StalenessHook()
-            hooks.append(staleness)
-        if strategy is not None:
-            # same program, but pull / push / aggregate / tokens run on the GPUs over NVLink
-            train_step, loss_fetch = strategy.minimize(opt, cross_entropy, global_step)
+            opt = dtf.train.SyncReplicasOptimizer(opt, replicas_to_aggregate=num_workers, total_num_replicas=num_workers)
+            if fabric is None:
+                hooks.append(opt.make_session_run_hook(chief))
+        elif FLAGS.measure_staleness and fabric is None:
+            stale = dtf.train.StalenessHook()
+            hooks.append(stale)
+        if fabric is None:
+            train_op, loss_fetch = opt.minimize(loss, global_step=gstep), loss
         else:
-            train_step, loss_fetch = opt.minimize(cross_entropy, global_step=global_step), cross_entropy
+            train_op, loss_fetch = fabric.minimize(opt, loss, gstep)       # same semantics, executed by the GPUs
 
-        is_chief = (FLAGS.task_index == 0)
-        if is_chief:
-            print('Worker %d: Initializing session...' % FLAGS.task_index)
-        else:
-            print('Worker %d: Waiting for session to be initialized...' % FLAGS.task_index)
-
-        local_step = 0
-        best_val_loss = 10000.0
-        time_begin = time.time()
-        print('Training begins @ %f' % time_begin)
-        with dtf.train.MonitoredTrainingSession(master=server.target, is_chief=is_chief,
-                                                checkpoint_dir=FLAGS.train_dir, hooks=hooks) as mon_sess:
-            while not mon_sess.should_stop():
-                batch_xs, batch_ys = mnist.train.next_batch(FLAGS.batch_size)
-                _, step, loss = mon_sess.run([train_step, global_step, loss_fetch],
-                                             feed_dict={x: batch_xs, y_: batch_ys})
-                local_step += 1
-                if local_step % FLAGS.log_every == 0:
-                    print('time: %s | worker: %d | training step:%d | global step:%d | loss: %f' % (
-                        str(datetime.now()), FLAGS.task_index, local_step, step, loss))
-                if (step + 1) % FLAGS.validate_every == 0 and not mon_sess.should_stop():
-                    val_feed = {x: mnist.validation.images, y_: mnist.validation.labels}
-                    val_xent = mon_sess.run(cross_entropy, feed_dict=val_feed) / len(mnist.validation.images)
-                    best_val_loss = min(best_val_loss, val_xent)
-                    print('At global step: %d, validation cross entropy = %g (best %g)' % (step, val_xent, best_val_loss))
-        time_end = time.time()
-        print('Training ends @ %f' % time_end)
-        print('Worker %d | Training elapsed time: %f s | Train step: %d | best val loss: %f' %
-              (FLAGS.task_index, time_end - time_begin, local_step, best_val_loss))
-        if staleness is not None:
-            print('Worker %d | staleness mean %.3f histogram %s' % (FLAGS.task_index, staleness.mean(),
-                                                                   staleness.histogram()))
+    print("Worker %d: %s" % (me, "Initializing session..." if chief else "Waiting for session to be initialized..."))
+    best, local_step, t0 = 10000.0, 0, time.time()
+    print("Training begins @ %f" % t0)
+    with dtf.train.MonitoredTrainingSession(master=server.target, is_chief=chief, checkpoint_dir=FLAGS.train_dir,
+                                            hooks=hooks) as sess:
+        while not sess.should_stop():
+            xs, ys = data.train.next_batch(FLAGS.batch_size)
+            _, step, batch_loss = sess.run([train_op, gstep, loss_fetch], feed_dict={net["x"]: xs, net["y_"]: ys})
+            local_step += 1
+            if local_step % FLAGS.log_every == 0:
+                print("time: %s | worker: %d | training step:%d | global step:%d | loss: %f"
+                      % (datetime.now(), me, local_step, step, batch_loss))
+            if (step + 1) % FLAGS.validate_every == 0 and not sess.should_stop():
+                val = sess.run(loss, feed_dict={net["x"]: data.validation.images, net["y_"]: data.validation.labels})
+                val /= len(data.validation.images)
+                best = min(best, val)
+                print("At global step: %d, validation cross entropy = %g (best %g)" % (step, val, best))
+    t1 = time.time()
+    print("Training ends @ %f" % t1)
+    print("Worker %d | Training elapsed time: %f s | Train step: %d | best val loss: %f" % (me, t1 - t0, local_step, best))
+    if stale is not None:
+        print("Worker %d | staleness mean %.3f histogram %s" % (me, stale.mean(), stale.histogram()))
     server.stop()
 
 
-if __name__ == '__main__':
+if __name__ == "__main__":
     main()

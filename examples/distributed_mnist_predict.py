@@ -1,53 +1,41 @@
-"""Single-process inference from a training checkpoint (reference ``distributed_mnist_predict.py``, S14).
+"""Inference from a training checkpoint, in one process (what the reference's ``distributed_mnist_predict.py`` does, S14).
 
-Rebuilds the four MLP variables **by name** (``hid_w, hid_b, sm_w, sm_b``), restores just
-those from the newest checkpoint in ``--checkpoint_dir`` (the file also holds ``global_step``,
-Adam slots and beta powers: partial, name-keyed restore), and counts correct predictions on
-the validation split.  Unlike the reference it stops with a clear message when there is no
-checkpoint instead of crashing in ``restore``.
+The model is rebuilt with the SAME variable names the trainer used (``build_mnist_mlp``: ``hid_w, hid_b, sm_w,
+sm_b``); ``Saver.restore`` is name-keyed and partial, so the optimizer slots, beta powers and ``global_step`` that
+are also in the file are simply not read (the topology that wrote the checkpoint -- n ps tasks, m workers -- does
+not matter).  Prints the number of predictions, the number of correct ones and the accuracy on the validation split.
+With no checkpoint in ``--checkpoint_dir`` it says so and exits 1 (the reference would crash inside ``restore``).
 """
-import math
-import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import distributed_tensorflow_b200 as dtf
+from _common import dtf
 from distributed_tensorflow_b200 import input_data
+from distributed_tensorflow_b200.models import build_mnist_mlp
 
-dtf.app.flags.DEFINE_string("data_dir", "/tmp/mnist-data", "MNIST IDX directory (synthetic if absent)")
-dtf.app.flags.DEFINE_string("checkpoint_dir", "/tmp/dtf_ckpt/mnist", "directory written by distributed_mnist.py")
-dtf.app.flags.DEFINE_integer("hidden_units", 100, "hidden layer width used in training")
+dtf.app.flags.DEFINE_string("data_dir", "/tmp/mnist-data", "MNIST IDX directory (synthetic split if absent)")
+dtf.app.flags.DEFINE_string("checkpoint_dir", "/tmp/dtf_ckpt/mnist", "directory distributed_mnist.py checkpointed into")
+dtf.app.flags.DEFINE_integer("hidden_units", 100, "hidden width the checkpoint was trained with")
 FLAGS = dtf.app.flags.FLAGS
-IMAGE_PIXELS = 28
 
 
 def main():
-    mnist = input_data.read_data_sets(FLAGS.data_dir, one_hot=True, num_train=1000)
-    print("len of validation images: ", len(mnist.validation.images))
-    H = FLAGS.hidden_units
-    hid_w = dtf.Variable(dtf.truncated_normal([IMAGE_PIXELS * IMAGE_PIXELS, H], stddev=1.0 / IMAGE_PIXELS), name='hid_w')
-    hid_b = dtf.Variable(dtf.zeros([H]), name='hid_b')
-    sm_w = dtf.Variable(dtf.truncated_normal([H, 10], stddev=1.0 / math.sqrt(H)), name='sm_w')
-    sm_b = dtf.Variable(dtf.zeros([10]), name='sm_b')
-    x = dtf.placeholder(dtf.float32, [None, IMAGE_PIXELS * IMAGE_PIXELS])
-    hid = dtf.nn.relu(dtf.nn.xw_plus_b(x, hid_w, hid_b))
-    y = dtf.nn.softmax(dtf.nn.xw_plus_b(hid, sm_w, sm_b))
-    pre = dtf.arg_max(y, dimension=1)
-
+    val = input_data.read_data_sets(FLAGS.data_dir, one_hot=True, num_train=1000).validation
+    print("len of validation images: ", len(val.images))
+    net = build_mnist_mlp(hidden=FLAGS.hidden_units)
+    predicted_class = dtf.arg_max(net["y"], dimension=1)
+    state = dtf.train.get_checkpoint_state(FLAGS.checkpoint_dir)
+    if not state:
+        print("ckpt is none.")
+        return 1
     with dtf.Session() as sess:
-        restorer = dtf.train.Saver()
-        check_point = dtf.train.get_checkpoint_state(FLAGS.checkpoint_dir)
-        if not check_point:
-            print("ckpt is none.")
-            return 1
-        restorer.restore(sess, check_point.model_checkpoint_path)
-        pre_ = sess.run(pre, feed_dict={x: mnist.validation.images})
-        print("predict: ", len(pre_))
-        correct = int(np.sum(pre_ == np.argmax(mnist.validation.labels, axis=1)))
-        print(correct)
-        print("accuracy: %.4f" % (correct / float(len(pre_))))
+        dtf.train.Saver(var_list=list(net["vars"])).restore(sess, state.model_checkpoint_path)
+        guess = sess.run(predicted_class, feed_dict={net["x"]: val.images})
+    hits = int(np.sum(guess == np.argmax(val.labels, axis=1)))
+    print("predict: ", len(guess))
+    print(hits)
+    print("accuracy: %.4f" % (hits / float(len(guess))))
     return 0
 
 

@@ -1,64 +1,50 @@
-"""In-graph replication: ONE client graph spanning a ps and two workers, with a Timeline trace.
+"""In-graph replication: ONE client builds ONE graph that spans the ps and every worker.
 
-Capability mirror of reference ``example_in_graph.py`` (S11) and its twin
-``example_distributed_server.py`` (S12): every task starts a Server; worker 0 is the only
-client; variables are pinned to ``/job:ps/task:0``, the input is split on the ps, each half is
-multiplied on a different worker, the results are concatenated on the ps; the last ``run`` is
-traced (``FULL_TRACE``) and written as ``timeline_client.json``; the graph is dumped with
-``summary.FileWriter``.  Expected output: ``[[9],[21],[33],[45]]``.
-Fixes vs the reference: the master address comes from ``--worker_hosts`` instead of a
-hard-coded ``grpc://localhost:2223``; ``/gpu:0`` placements fall back to CPU when the task
-has no GPU (soft placement) instead of failing.
+Counterpart of the reference's ``example_in_graph.py`` (S11).  A [4,3] table and a [3,1] column live on
+``/job:ps/task:0``; the table is split row-wise, shard ``k`` is multiplied by the column on ``/job:worker/task:k``
+and the partial products are concatenated back on the ps -- scatter, parallel compute, gather.  Expected output
+``[[9],[21],[33],[45]]``.  Worker 0 is the client (it connects to its own server, which acts as master); the ps and
+the other workers only serve.  The final run is traced (``RunOptions.FULL_TRACE`` -> ``timeline_client.json``, one
+chrome-trace process per device) and the graph is dumped for TensorBoard under ``logs/``.
+
+    python examples/launch_local.py examples/example_in_graph.py --num_ps 1 --num_workers 2 --wait first
 """
 import os
-import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import distributed_tensorflow_b200 as dtf
+from _common import bring_up, define_cluster_flags, dtf
 from distributed_tensorflow_b200 import timeline
 
-dtf.app.flags.DEFINE_string("ps_hosts", "localhost:2222", "ps hosts")
-dtf.app.flags.DEFINE_string("worker_hosts", "localhost:2223,localhost:2224", "worker hosts")
-dtf.app.flags.DEFINE_string("job_name", "worker", "'ps' or 'worker'")
-dtf.app.flags.DEFINE_integer("task_index", 0, "Index of task within the job")
-dtf.app.flags.DEFINE_string("out_dir", ".", "where logs/ and timeline_client.json go")
-FLAGS = dtf.app.flags.FLAGS
+FLAGS = define_cluster_flags("localhost:2222", "localhost:2223,localhost:2224")
+dtf.app.flags.DEFINE_string("out_dir", ".", "where logs/ and timeline_client.json are written")
+PS0 = "/job:ps/task:0/cpu:0"
+
+
+def scatter_compute_gather(num_workers):
+    with dtf.device(PS0):
+        table = dtf.Variable([[1., 2., 3.], [4., 5., 6.], [7., 8., 9.], [10., 11., 12.]], name="input_data")
+        column = dtf.Variable([[1.], [1.], [2.]], name="w")
+    shards = dtf.split(table, num_workers)
+    partial = []
+    for k, shard in enumerate(shards):
+        with dtf.device("/job:worker/task:%d/gpu:0" % k):        # falls back to the task's CPU when it has no GPU
+            partial.append(dtf.matmul(shard, column))
+    with dtf.device(PS0):
+        return shards, dtf.concat(partial, axis=0)
 
 
 def main():
-    ps_hosts = FLAGS.ps_hosts.split(",")
-    worker_hosts = FLAGS.worker_hosts.split(",")
-    # identical on every node
-    cluster = dtf.train.ClusterSpec({"ps": ps_hosts, "worker": worker_hosts})
-    server = dtf.train.Server(cluster, job_name=FLAGS.job_name, task_index=FLAGS.task_index)
-
-    with dtf.device('/job:ps/task:0/cpu:0'):
-        input_data = dtf.Variable([[1., 2., 3.], [4., 5., 6.], [7., 8., 9.], [10., 11., 12.]], name="input_data")
-        b = dtf.Variable([[1.], [1.], [2.]], name="w")
-    inputs = dtf.split(input_data, 2)
-    outputs = []
-
-    run_options = dtf.RunOptions(trace_level=dtf.RunOptions.FULL_TRACE)
-    run_metadata = dtf.RunMetadata()
-
-    if FLAGS.job_name == 'ps' or FLAGS.task_index != 0:
-        server.join()      # ps and non-client workers only serve
-        return
-    # in-graph replication: only worker 0 creates a client
-    with dtf.Session("grpc://" + worker_hosts[0]) as sess:
+    _, server, num_workers = bring_up(FLAGS, serve_only=lambda job, idx: job == "ps" or idx != 0)
+    shards, gathered = scatter_compute_gather(num_workers)
+    meta = dtf.RunMetadata()
+    with dtf.Session(server.target) as sess:
         sess.run(dtf.global_variables_initializer())
-        for i in range(len(worker_hosts)):
-            with dtf.device("/job:worker/task:%d/gpu:0" % i):
-                print("now is worker %d: " % i)
-                print(sess.run(inputs[i % 2]))
-                outputs.append(dtf.matmul(inputs[i % 2], b))
-        with dtf.device('/job:ps/task:0/cpu:0'):
-            output = dtf.concat(outputs[:2], axis=0)
-            print(sess.run(output, options=run_options, run_metadata=run_metadata))
+        for k, shard in enumerate(shards):
+            print("now is worker %d: " % k)
+            print(sess.run(shard))
+        print(sess.run(gathered, options=dtf.RunOptions(trace_level=dtf.RunOptions.FULL_TRACE), run_metadata=meta))
         dtf.summary.FileWriter(os.path.join(FLAGS.out_dir, "logs/"), sess.graph).close()
-        tl = timeline.Timeline(step_stats=run_metadata.step_stats)
-        with open(os.path.join(FLAGS.out_dir, 'timeline_client.json'), 'w') as f:
-            f.write(tl.generate_chrome_trace_format())
+    with open(os.path.join(FLAGS.out_dir, "timeline_client.json"), "w") as f:
+        f.write(timeline.Timeline(step_stats=meta.step_stats).generate_chrome_trace_format())
     server.stop()
 
 
