@@ -339,6 +339,23 @@ class PSTrainEngine:
         t = rk.bufs["ctl%d" % shard].tensor(torch.int64, self.off[fld], count).cpu()
         return int(t[0]) if count == 1 else t.tolist()
 
+    def step_stats(self) -> List[Dict[str, Any]]:
+        """Device-side trace of the LOCAL ps shards (SURVEY A19 on the fabric tier): every ``ps_apply`` launch stamps
+        ``(kind, %globaltimer at entry, %globaltimer when the tokens were released, global_step)`` into a ring in ps
+        HBM (``trace_cap`` entries).  Returns timeline events -- feed them to ``dtf.timeline.Timeline(step_stats=...)``
+        for a chrome trace with one process per ``/job:ps/task:k`` GPU."""
+        from ..utils.timeline import events_from_ring
+        events: List[Dict[str, Any]] = []
+        for r, rk in self.ranks.items():
+            if r not in self.ps_ranks:
+                continue
+            s = self.ps_ranks.index(r)
+            rk.stream.synchronize()
+            ring = rk.bufs["trace%d" % s].tensor(torch.int64, 0, self.cfg.trace_cap * 4).view(-1, 4).cpu().tolist()
+            events += events_from_ring("/job:ps/task:%d" % s, [row for row in ring if row[0] != 0], {1: "ps_apply"},
+                                       gpu_index=rk.device.index or 0)
+        return sorted(events, key=lambda e: e["start_us"])
+
     def staleness(self, shard: int = 0) -> Dict[str, Any]:
         hist = self.read_ctl(shard, "staleness_hist", 16)
         tot = sum(hist)
