@@ -169,3 +169,40 @@ def test_native_step_prefetch_matches_plain_steps():
     for k in ("hid_w", "hid_b", "sm_w", "sm_b"):
         torch.testing.assert_close(s0[k], s1[k], rtol=0, atol=0)
     assert l0[-1] < l0[0]
+
+
+def test_symmetric_buffers_and_nvls_collectives_two_gpus():
+    """Fabric collectives on symmetric VMM buffers with ONE process driving two GPUs (in-graph topology): unicast peer
+    loads/stores always, multimem.ld_reduce / multimem.st when the box has NVLS.  Needs >= 2 GPUs."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import ctypes
+    from distributed_tensorflow_b200.ops import cuda_lib
+    from distributed_tensorflow_b200.parallel.fabric import Fabric
+    lib = cuda_lib.load()
+    fabric = Fabric(2, {0: 0, 1: 1})
+    if fabric.nvls_level() == 0:
+        pytest.skip("CUDA VMM with POSIX fd export is not available here")
+    n = 256 * 1024
+    grads = fabric.alloc_symmetric("t_grads", n * 4)
+    repl = fabric.alloc_symmetric("t_repl", n * 4)
+    grads.local(1).tensor(torch.float32, 0, n).fill_(3.0)        # the worker's gradient; rank 0 (ps) contributes zeros
+    torch.cuda.synchronize(1)
+    with torch.cuda.device(0):
+        dst = torch.zeros(n, device="cuda:0")
+        src = torch.arange(n, dtype=torch.float32, device="cuda:0")
+        st = torch.cuda.current_stream().cuda_stream
+        peers_g = (ctypes.c_void_p * 16)(grads.peer(0, 1).ptr)
+        peers_r = (ctypes.c_void_p * 16)(repl.peer(0, 1).ptr)
+        modes = [None] + ([True] if grads.multicast else [])
+        for use_mc in modes:
+            dst.zero_()
+            assert lib.dtf_fabric_reduce(grads.mc(0) if use_mc else None, peers_g, 1, dst.data_ptr(), n, 0, st) == 0
+            torch.cuda.synchronize(0)
+            assert bool(torch.all(dst == 3.0))
+            repl.local(1).tensor(torch.float32, 0, n).zero_()
+            torch.cuda.synchronize(1)
+            assert lib.dtf_fabric_bcast(src.data_ptr(), repl.mc(0) if use_mc else None, peers_r, 1, n * 4, 0, st) == 0
+            torch.cuda.synchronize(0)
+            assert torch.equal(repl.local(1).tensor(torch.float32, 0, n).cpu(), src.cpu())
+    fabric.close()
