@@ -315,6 +315,7 @@ class Session:
                 "session_id": self.session_id, "graph_seed": self.graph.seed}
         master_values: Dict[int, Any] = dict(feeds)
         touched: List[Tuple[str, int]] = []
+        last_segment = {task: si for si, (task, _) in enumerate(plan.segments)}     # where each task's run state can go
         try:
             for si, (task, nodes) in enumerate(plan.segments):
                 if task not in touched:
@@ -334,9 +335,15 @@ class Session:
                     all_nodes = self.graph.nodes
                     new_defs = serialize_nodes(all_nodes[sent:], lambda n, t=task: self._task_of(n) == t) \
                         if sent < len(all_nodes) else []
+                    finish = last_segment[task] == si
                     out = self._client(task).call("run_segment", run_id, self._graph_key, new_defs,
-                                                  [n.id for n in nodes], inputs, want, opts)
+                                                  [n.id for n in nodes], inputs, want, opts, finish)
                     self._sent[task] = len(all_nodes)
+                    if finish:                       # the task released the run state in the same round trip
+                        touched.remove(task)
+                        if trace and run_metadata is not None and out["events"]:
+                            run_metadata.step_stats.extend(out["events"])
+                        out = out["values"]
                 master_values.update(out)
         finally:
             for task in touched:

@@ -22,7 +22,7 @@ import torch
 
 from ..framework import errors
 
-__all__ = ["RpcServer", "RpcClient", "parse_address", "to_wire"]
+__all__ = ["RpcServer", "RpcClient", "parse_address", "to_wire", "from_wire"]
 
 _AUTHKEY = b"dtf-b200-control-plane"
 
@@ -43,15 +43,47 @@ def parse_address(addr: str) -> Tuple[str, int]:
     return host, int(port)
 
 
+_TENSOR_TAG = "__dtf_tensor__"
+_VIEW_AS = {torch.bfloat16: torch.int16}            # dtypes numpy cannot represent travel as same-width integers
+
+
 def to_wire(value: Any) -> Any:
-    """Detach + move tensors to host memory, recursively."""
+    """Detach + move tensors to host memory, recursively, and encode them as ``(tag, dtype, ndarray)``: a numpy array
+    pickles with one memcpy (protocol 5), a torch tensor goes through ``torch.save`` machinery (~10x slower for the
+    small tensors of a parameter-server step -- measured 116 us vs 10 us for a 10-element vector)."""
     if isinstance(value, torch.Tensor):
         t = value.detach()
-        return t.cpu() if t.device.type != "cpu" else t
+        if t.device.type != "cpu":
+            t = t.cpu()
+        if not t.is_contiguous():
+            t = t.contiguous()
+        carrier = _VIEW_AS.get(t.dtype)
+        if carrier is not None:
+            return (_TENSOR_TAG, str(t.dtype), t.view(carrier).numpy())
+        try:
+            return (_TENSOR_TAG, None, t.numpy())
+        except (TypeError, RuntimeError):            # exotic dtype: let torch pickle it
+            return t
     if isinstance(value, dict):
         return {k: to_wire(v) for k, v in value.items()}
     if isinstance(value, (list, tuple)):
+        if len(value) == 3 and isinstance(value[0], str) and value[0] == _TENSOR_TAG:
+            return value                                 # already encoded
         return type(value)(to_wire(v) for v in value)
+    return value
+
+
+def from_wire(value: Any) -> Any:
+    """Inverse of :func:`to_wire` on the receiving side."""
+    if isinstance(value, tuple):
+        if len(value) == 3 and isinstance(value[0], str) and value[0] == _TENSOR_TAG:
+            t = torch.from_numpy(value[2])
+            return t if value[1] is None else t.view(getattr(torch, value[1].split(".")[-1]))
+        return tuple(from_wire(v) for v in value)
+    if isinstance(value, list):
+        return [from_wire(v) for v in value]
+    if isinstance(value, dict):
+        return {k: from_wire(v) for k, v in value.items()}
     return value
 
 
@@ -80,7 +112,7 @@ class RpcServer:
         try:
             while not self._closed.is_set():
                 try:
-                    method, args, kwargs = pickle.loads(conn.recv_bytes())
+                    method, args, kwargs = from_wire(pickle.loads(conn.recv_bytes()))
                 except (EOFError, OSError, ConnectionError):
                     return
                 try:
@@ -152,7 +184,7 @@ class RpcClient:
         try:
             c = self._conn()
             c.send_bytes(pickle.dumps((method, to_wire(args), to_wire(kwargs)), protocol=pickle.HIGHEST_PROTOCOL))
-            reply = pickle.loads(c.recv_bytes())
+            reply = from_wire(pickle.loads(c.recv_bytes()))
         except (EOFError, ConnectionError, BrokenPipeError, OSError) as e:
             self._drop()
             raise errors.UnavailableError("task at %s:%d went away during %s: %s" % (self.host, self.port, method, e))

@@ -72,7 +72,7 @@ def serialize_nodes(nodes: Sequence[Any], runs_here=None) -> List[Dict[str, Any]
     for n in nodes:
         keep = runs_here is None or runs_here(n)
         out.append({"id": n.id, "name": n.name, "op_type": n.op_type, "inputs": [i.id for i in n.inputs],
-                    "control_inputs": [c.id for c in n.control_inputs], "attrs": to_wire(n.attrs) if keep else {},
+                    "control_inputs": [c.id for c in n.control_inputs], "attrs": dict(n.attrs) if keep else {},      # tensors inside are encoded by RpcClient.call
                     "device": n.device, "dtype": n.dtype, "shape": n.shape})
     return out
 
@@ -243,7 +243,9 @@ class Server:
     def rpc_get_cluster(self):
         return {"cluster": self.cluster.as_dict(), "task": self.task}
 
-    def rpc_run_segment(self, run_id, graph_key, new_nodedefs, node_ids, inputs, want_ids, opts):
+    def rpc_run_segment(self, run_id, graph_key, new_nodedefs, node_ids, inputs, want_ids, opts, finish=False):
+        """``finish``: this is the run's last segment on this task -- release the run state in the same round trip
+        (the reply then is ``{"values": ..., "events": trace events or None}``), saving one RPC per step per task."""
         with self._lock:
             g = self._graphs.setdefault(graph_key, {})
             stub = _GraphStub(opts.get("graph_seed"))
@@ -257,7 +259,14 @@ class Server:
                 nv.inputs = [g[i] for i in nv.inputs]
                 nv.control_inputs = [g[i] for i in nv.control_inputs if i in g]
             nodes = [g[i] for i in node_ids]
-        return self.run_segment_local(run_id, nodes, inputs, want_ids, opts)
+        if not finish:
+            return self.run_segment_local(run_id, nodes, inputs, want_ids, opts)
+        try:
+            values = self.run_segment_local(run_id, nodes, inputs, want_ids, opts)
+        except BaseException:
+            self.end_run_local(run_id)
+            raise
+        return {"values": values, "events": self.end_run_local(run_id)}
 
     def rpc_end_run(self, run_id):
         return self.end_run_local(run_id)

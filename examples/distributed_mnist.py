@@ -12,6 +12,10 @@ or one process per task by hand (``--job_name=ps|worker --task_index=N --ps_host
 ``--engine=fabric`` keeps the same program but moves pull / push / aggregation / tokens onto the GPUs (NVLink).
 Unlike the reference: ``--train_steps`` is honoured, the checkpoint directory is a flag, GPUs are used when visible.
 """
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))      # examples/_common.py
 import time
 
 from datetime import datetime

@@ -6,7 +6,10 @@ are also in the file are simply not read (the topology that wrote the checkpoint
 not matter).  Prints the number of predictions, the number of correct ones and the accuracy on the validation split.
 With no checkpoint in ``--checkpoint_dir`` it says so and exits 1 (the reference would crash inside ``restore``).
 """
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))      # examples/_common.py
 
 import numpy as np
 

@@ -9,6 +9,10 @@ checkpoints into ``--ckpt_dir`` every ``--save_checkpoint_secs``; restart the jo
 
     python examples/launch_local.py examples/example_between_graph.py --num_ps 1 --num_workers 2 -- --is_sync=True
 """
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))      # examples/_common.py
 from datetime import datetime
 
 import numpy as np

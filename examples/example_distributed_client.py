@@ -5,6 +5,9 @@ reach worker 0.  The master tells the client the cluster layout; the program is 
 gather graph of ``example_in_graph.py`` with the matmuls pinned to each worker's CPU.
 """
 import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))      # examples/_common.py
 
 from _common import dtf
 from distributed_tensorflow_b200 import timeline

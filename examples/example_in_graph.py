@@ -10,6 +10,9 @@ chrome-trace process per device) and the graph is dumped for TensorBoard under `
     python examples/launch_local.py examples/example_in_graph.py --num_ps 1 --num_workers 2 --wait first
 """
 import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))      # examples/_common.py
 
 from _common import bring_up, define_cluster_flags, dtf
 from distributed_tensorflow_b200 import timeline

@@ -10,6 +10,10 @@ Counterpart of the reference's ``standalone.py`` (S15-S20), restructured around 
   ``i`` runs on ``/gpu:i`` when that GPU exists and on the CPU otherwise; each tower computes its own gradients,
   they are averaged per variable (``expand_dims`` + ``concat`` + ``reduce_mean``) and applied once by SGD.
 """
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))      # examples/_common.py
 import argparse
 import time
 
