@@ -1,0 +1,17 @@
+#!/bin/bash
+# Sanitizer tier: run the single-GPU kernel tests under compute-sanitizer.
+#   gpurun --timeout 900 -- 'bash tools/sanitize.sh'        -> gpurun_out/sanitize_<tool>.log (+ a one-line summary each)
+# memcheck: out-of-bounds / misaligned accesses (TMA boxes, epilogue tails); racecheck: shared-memory hazards between
+# the producer / MMA / epilogue warps; synccheck: barrier misuse.  tcgen05/TMA traffic goes through the async proxy,
+# which the tools only partly model: a clean run is necessary, not sufficient.
+set -u
+mkdir -p gpurun_out
+TESTS="tests/test_gpu_kernels.py -k 'gemm or xent or optimizer or small or conv'"
+for tool in memcheck racecheck synccheck; do
+  log=gpurun_out/sanitize_${tool}.log
+  timeout 280 compute-sanitizer --tool ${tool} --error-exitcode 3 --launch-timeout 60 \
+      python -m pytest ${TESTS} -x -q > ${log} 2>&1
+  rc=$?
+  errs=$(grep -c "========= .*error\|========= Invalid\|========= Race" ${log} || true)
+  echo "${tool}: rc=${rc} reported=${errs} $(tail -1 ${log})" | tee -a gpurun_out/sanitize_summary.txt
+done
