@@ -91,3 +91,12 @@ def test_distributed_server_plus_pure_client(tmp_path):
                 p.wait(timeout=10)
             except subprocess.TimeoutExpired:
                 p.kill()
+
+
+def test_mnist_standalone_single_process_cpu(tmp_path):
+    """BASELINE.json config 1: MNIST MLP, one process, CPU, world_size 1 -- trains and checkpoints."""
+    out = _run([os.path.join(EX, "mnist_standalone.py"), "--train_steps=120", "--num_train=2000", "--train_dir=%s" % (tmp_path / "ck")])
+    line = [l for l in out.splitlines() if l.startswith("standalone:")][-1]
+    assert "120 steps" in line and "steps/s" in line
+    assert float(line.rsplit(" ", 1)[1]) < 60.0                 # batch-sum loss of 100 examples starts near 230
+    assert (tmp_path / "ck" / "checkpoint").exists()
