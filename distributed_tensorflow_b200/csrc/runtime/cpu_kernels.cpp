@@ -1,0 +1,67 @@
+// Host (CPU-tier) optimizer apply kernels: one fused pass per variable, the role of TF's C++ ApplyGradientDescent /
+// ApplyMomentum / ApplyAdam kernels on a /cpu:0 parameter server (the apply op runs on the variable's
+// device, i.e. inside the ps task; reference distributed_mnist.py:115,126 and example_between_graph.py:61,73).
+// The GPU tier's equivalents are optimizer_apply_kernel / ps_apply_kernel (csrc/elementwise.cu, csrc/ps_engine.cu).
+//
+// Semantics are TF-1.x's: momentum  accum = momentum*accum + g ; var -= lr*accum  (nesterov: var -= lr*g + lr*momentum*accum)
+//                         adam      m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; var -= lr_t * m / (sqrt(v) + eps)
+// with lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller (epsilon is NOT bias-corrected: unlike torch.optim.Adam).
+#include <cmath>
+#include <cstdint>
+
+// The loops are compiled twice (AVX2+FMA and baseline x86-64) and dispatched at load time (GCC function
+// multi-versioning): the library is built on one machine and shipped to others, so -march=native is not an option.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define DTF_CPU_CLONES __attribute__((target_clones("avx2,fma", "default")))
+#else
+#define DTF_CPU_CLONES
+#endif
+
+extern "C" {
+
+// kind: 0 sgd, 1 momentum, 2 adam.  All buffers fp32, contiguous, n elements, NOT overlapping.  Returns 0, or -1 on bad
+// arguments.
+DTF_CPU_CLONES
+int dtf_cpu_optimizer_apply(int kind, float* __restrict__ var, float* __restrict__ m, float* __restrict__ v,
+                            const float* __restrict__ g, long long n, float lr, float momentum, int nesterov, float beta1,
+                            float beta2, float eps) {
+  if (n < 0 || var == nullptr || g == nullptr) return -1;
+  if (kind == 0) {
+    for (long long i = 0; i < n; ++i) var[i] -= lr * g[i];
+    return 0;
+  }
+  if (kind == 1) {
+    if (m == nullptr) return -1;
+    if (nesterov) {
+      const float lm = lr * momentum;
+      for (long long i = 0; i < n; ++i) {
+        const float acc = momentum * m[i] + g[i];
+        m[i] = acc;
+        var[i] -= lr * g[i] + lm * acc;
+      }
+    } else {
+      for (long long i = 0; i < n; ++i) {
+        const float acc = momentum * m[i] + g[i];
+        m[i] = acc;
+        var[i] -= lr * acc;
+      }
+    }
+    return 0;
+  }
+  if (kind == 2) {
+    if (m == nullptr || v == nullptr) return -1;
+    const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+    for (long long i = 0; i < n; ++i) {
+      const float gi = g[i];
+      const float mi = beta1 * m[i] + omb1 * gi;
+      const float vi = beta2 * v[i] + omb2 * gi * gi;
+      m[i] = mi;
+      v[i] = vi;
+      var[i] -= lr * mi / (std::sqrt(vi) + eps);
+    }
+    return 0;
+  }
+  return -1;
+}
+
+}  // extern "C"

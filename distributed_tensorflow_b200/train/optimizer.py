@@ -26,6 +26,7 @@ from ..framework import ops as _ops
 from ..framework.graph import GraphKeys, Tensor, convert_to_tensor, get_default_graph
 from ..framework.ops import register_kernel
 from ..framework.variables import Variable, assign, assign_add, trainable_variables
+from ..utils import native_runtime
 
 __all__ = ["Optimizer", "GradientDescentOptimizer", "MomentumOptimizer", "AdamOptimizer", "adam_reference_step"]
 
@@ -201,11 +202,12 @@ def _k_apply_momentum(ctx, node, grad):
         cuda_lib.apply_momentum_(var, acc, g, a["lr"], a["momentum"], a["nesterov"])
     else:
         g = g.to(var.dtype)
-        acc.mul_(a["momentum"]).add_(g)                       # accum = momentum*accum + grad (TF)
-        if a["nesterov"]:
-            var.sub_(g * a["lr"] + acc * (a["momentum"] * a["lr"]))
-        else:
-            var.sub_(acc, alpha=a["lr"])
+        if not native_runtime.cpu_optimizer_apply(1, var, acc, None, g, a["lr"], momentum=a["momentum"], nesterov=a["nesterov"]):
+            acc.mul_(a["momentum"]).add_(g)                       # accum = momentum*accum + grad (TF)
+            if a["nesterov"]:
+                var.sub_(g * a["lr"] + acc * (a["momentum"] * a["lr"]))
+            else:
+                var.sub_(acc, alpha=a["lr"])
     return None
 
 
@@ -262,9 +264,10 @@ def _k_apply_adam(ctx, node, grad, b1p, b2p):
         cuda_lib.apply_adam_(var, m, v, g, lr_t, a["beta1"], a["beta2"], a["eps"])
     else:
         g = g.to(var.dtype)
-        m.mul_(a["beta1"]).add_(g, alpha=1.0 - a["beta1"])
-        v.mul_(a["beta2"]).addcmul_(g, g, value=1.0 - a["beta2"])
-        var.sub_(lr_t * m / (v.sqrt() + a["eps"]))
+        if not native_runtime.cpu_optimizer_apply(2, var, m, v, g, lr_t, beta1=a["beta1"], beta2=a["beta2"], eps=a["eps"]):
+            m.mul_(a["beta1"]).add_(g, alpha=1.0 - a["beta1"])
+            v.mul_(a["beta2"]).addcmul_(g, g, value=1.0 - a["beta2"])
+            var.sub_(lr_t * m / (v.sqrt() + a["eps"]))
     return None
 
 

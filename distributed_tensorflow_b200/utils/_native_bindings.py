@@ -15,6 +15,11 @@ _OK, _CANCELLED, _DEADLINE, _CLOSED, _BAD = 0, 1, 2, 3, 4
 
 
 def declare(lib: ctypes.CDLL) -> None:
+    if hasattr(lib, "dtf_cpu_optimizer_apply"):
+        lib.dtf_cpu_optimizer_apply.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong,
+                                                ctypes.c_float, ctypes.c_float, c_int, ctypes.c_float, ctypes.c_float,
+                                                ctypes.c_float]
+        lib.dtf_cpu_optimizer_apply.restype = c_int
     lib.dtf_acc_create.restype = c_void_p
     lib.dtf_acc_destroy.argtypes = [c_void_p]
     lib.dtf_acc_apply_grad.argtypes = [c_void_p, c_void_p, c_int64, c_int64]

@@ -62,3 +62,23 @@ def make_queue(name: str):
         return NativeQueue(lib, name)
     from ..parallel.ps_state import FIFOQueue
     return FIFOQueue(name=name)
+
+
+def cpu_optimizer_apply(kind: int, var, m, v, g, lr: float, momentum: float = 0.0, nesterov: bool = False,
+                        beta1: float = 0.0, beta2: float = 0.0, eps: float = 0.0) -> bool:
+    """Fused in-place apply on contiguous fp32 CPU tensors through ``csrc/runtime/cpu_kernels.cpp`` (kind 0 sgd,
+    1 momentum, 2 TF-Adam with ``lr`` = the bias-corrected ``lr_t``).  Returns False when the native library or the
+    layout does not allow it -- the caller then runs the equivalent torch ops."""
+    import torch
+    lib = load()
+    if lib is None or not hasattr(lib, "dtf_cpu_optimizer_apply"):
+        return False
+    for t in (var, m, v, g):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.device.type != "cpu"):
+            return False
+    if g.numel() != var.numel():
+        return False
+    rc = lib.dtf_cpu_optimizer_apply(kind, var.data_ptr(), None if m is None else m.data_ptr(),
+                                     None if v is None else v.data_ptr(), g.data_ptr(), var.numel(), lr, momentum,
+                                     int(bool(nesterov)), beta1, beta2, eps)
+    return rc == 0
