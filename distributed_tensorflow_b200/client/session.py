@@ -161,10 +161,7 @@ class Session:
         self._closed = True
         if self.cluster is not None:
             for task in list(self._sent) + ([self.master_task] if self.master_task else []):
-                try:
-                    self._call(task, "release_session", self.session_id, self._graph_key)
-                except Exception:
-                    pass
+                self._call_best_effort(task, "release_session", self.session_id, self._graph_key)
         for c in self._clients.values():
             c.close()
         self._clients.clear()
@@ -174,10 +171,22 @@ class Session:
         if self.cluster is None:
             return
         for job, idx, _ in self.cluster.all_tasks():
-            try:
-                self._call((job, idx), "cancel", self.session_id)
-            except Exception:
-                pass
+            self._call_best_effort((job, idx), "cancel", self.session_id)
+
+    def _call_best_effort(self, task, method, *args) -> None:
+        """Clean-up broadcast (cancel / release): never waits for a task that is gone.  A normal call retries the
+        connection for 30 s (tasks may still be starting); at shutdown a dead peer -- e.g. a killed backup worker --
+        must not hold the survivors up."""
+        try:
+            srv = self._server(task)
+            if srv is not None:
+                getattr(srv, "rpc_" + method)(*args)
+                return
+            if task not in self._clients and not RpcClient(self.cluster.task_address(*task)).try_connect(timeout=0.3):
+                return
+            self._client(task).call(method, *args)
+        except Exception:
+            pass
 
     # -- task plumbing ------------------------------------------------------------------------------
     def _task_of(self, node: Tensor):

@@ -136,6 +136,10 @@ class FIFOQueue:
         with self._cv:
             return len(self._q)
 
+    def is_closed(self) -> bool:
+        with self._cv:
+            return self._closed
+
     def close(self, cancel_pending_enqueues: bool = False) -> None:
         with self._cv:
             self._closed = True

@@ -11,6 +11,7 @@ memory from inside the kernels (``parallel/fabric.py`` + ``ops/``).
 from __future__ import annotations
 
 import pickle
+import select
 import socket
 import threading
 import time
@@ -22,7 +23,8 @@ import torch
 
 from ..framework import errors
 
-__all__ = ["RpcServer", "RpcClient", "parse_address", "to_wire", "from_wire"]
+__all__ = ["RpcServer", "RpcClient", "parse_address", "to_wire", "from_wire", "PeerAwareCancel", "current_connection",
+           "peer_closed"]
 
 _AUTHKEY = b"dtf-b200-control-plane"
 
@@ -87,6 +89,45 @@ def from_wire(value: Any) -> Any:
     return value
 
 
+_current = threading.local()          # the connection whose request the calling thread is serving
+
+
+def peer_closed(conn: Optional[Connection]) -> bool:
+    """True once the client end of ``conn`` is gone (process killed, socket closed): the kernel reports a hang-up
+    on the descriptor even while a handler thread is blocked inside a long-running request."""
+    if conn is None:
+        return False
+    try:
+        p = select.poll()
+        p.register(conn.fileno(), select.POLLRDHUP | select.POLLHUP | select.POLLERR)
+        return any(ev & (select.POLLRDHUP | select.POLLHUP | select.POLLERR | select.POLLNVAL) for _, ev in p.poll(0))
+    except (OSError, ValueError):
+        return True
+
+
+class PeerAwareCancel:
+    """Duck-typed ``threading.Event`` handed to blocking kernels (token dequeue, ``take_grad``) that run on behalf
+    of a remote client: it fires when the session is cancelled OR the requesting client has died.  Without it a
+    worker killed while it waits for a sync token would still consume the token when it arrives -- the reply goes
+    nowhere, the token is lost and the surviving replicas starve (backup-worker tolerance)."""
+
+    def __init__(self, event: threading.Event, conn: Optional[Connection]):
+        self._event, self._conn = event, conn
+
+    def is_set(self) -> bool:
+        return self._event.is_set() or peer_closed(self._conn)
+
+    def wait(self, timeout: Optional[float] = None) -> bool:
+        if self._event.wait(timeout):
+            return True
+        return peer_closed(self._conn)
+
+
+def current_connection() -> Optional[Connection]:
+    """The RPC connection being served by this thread (None for in-process calls)."""
+    return getattr(_current, "conn", None)
+
+
 class RpcServer:
     def __init__(self, address: str, service: Any):
         self.host, self.port = parse_address(address)
@@ -115,11 +156,14 @@ class RpcServer:
                     method, args, kwargs = from_wire(pickle.loads(conn.recv_bytes()))
                 except (EOFError, OSError, ConnectionError):
                     return
+                _current.conn = conn
                 try:
                     fn = getattr(self._service, "rpc_" + method)
                     result = ("ok", to_wire(fn(*args, **kwargs)))
                 except BaseException as e:  # noqa: BLE001 - errors travel to the caller
                     result = ("err", type(e).__name__, str(e), traceback.format_exc())
+                finally:
+                    _current.conn = None
                 try:
                     conn.send_bytes(pickle.dumps(result, protocol=pickle.HIGHEST_PROTOCOL))
                 except (OSError, ConnectionError, BrokenPipeError):

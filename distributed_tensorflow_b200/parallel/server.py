@@ -27,7 +27,7 @@ import torch
 from ..framework import errors
 from ..framework.executor import ExecContext, ResourceStore, execute
 from .cluster import ClusterSpec
-from .rpc import RpcClient, RpcServer, parse_address, to_wire
+from .rpc import PeerAwareCancel, RpcClient, RpcServer, current_connection, parse_address
 
 __all__ = ["Server", "NodeView", "serialize_nodes", "local_server_for"]
 
@@ -216,6 +216,9 @@ class Server:
             raise errors.AbortedError("server %s was stopped" % self.address)
         st = self._run_state(run_id, opts)
         ctx = st.ctx
+        conn = current_connection()
+        if conn is not None:         # remote client: blocking kernels also give up when that client dies
+            ctx.cancel_event = PeerAwareCancel(self.cancel_event(opts.get("session_id", "")), conn)
         dev_default = None
         for nid, v in inputs.items():
             if isinstance(v, torch.Tensor):

@@ -74,10 +74,18 @@ class Coordinator:
 
 
 class QueueRunner:
-    def __init__(self, queue=None, enqueue_ops: Optional[Sequence[Any]] = None):
+    def __init__(self, queue=None, enqueue_ops: Optional[Sequence[Any]] = None, close_op=None):
         self.queue = queue
         self.enqueue_ops = list(enqueue_ops or [])
+        self.close_op = close_op          # run once when the coordinator stops (closes the queue for its consumers)
         self.exceptions_raised: List[BaseException] = []
+
+    def _close_on_stop(self, sess, coord: Coordinator) -> None:
+        coord.wait_for_stop()
+        try:
+            sess.run(self.close_op)
+        except Exception:                 # noqa: BLE001 - the session / ps may already be gone at shutdown
+            pass
 
     def _run(self, sess, op, coord: Optional[Coordinator]) -> None:
         try:
@@ -110,6 +118,9 @@ class QueueRunner:
             if coord is not None:
                 coord.register_thread(t)
             threads.append(t)
+        if self.close_op is not None and coord is not None:
+            t = threading.Thread(target=self._close_on_stop, args=(sess, coord), name="dtf-queue-closer", daemon=True)
+            threads.append(t)             # not registered with the coordinator: it only starts working once that stops
         if start:
             for t in threads:
                 t.start()

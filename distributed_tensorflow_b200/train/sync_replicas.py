@@ -106,6 +106,18 @@ def _k_q_close(ctx, node):
     return None
 
 
+@register_kernel("QueueRenew", stateful=True)
+def _k_q_renew(ctx, node):
+    """Chief start-up: replace a CLOSED queue of this name (left behind by a previous chief on a long-lived ps) with
+    a fresh one; an open queue is kept (its tokens belong to replicas that are still running)."""
+    name = node.attrs["queue_name"]
+    with ctx.store._lock:
+        q = ctx.store.resources.get(name)
+        if q is not None and getattr(q, "is_closed", lambda: False)():
+            ctx.store.resources[name] = _make_queue(name)
+    return None
+
+
 class SyncReplicasOptimizer(Optimizer):
     def __init__(self, opt: Optimizer, replicas_to_aggregate: int, total_num_replicas: Optional[int] = None,
                  variable_averages=None, variables_to_average=None, use_locking: bool = False,
@@ -207,7 +219,15 @@ class SyncReplicasOptimizer(Optimizer):
                                                  {"queue_name": self._sync_token_queue_name,
                                                   "count": self._tokens_per_step}, "sync_token_q_EnqueueMany",
                                                  device=qdev)
-            self._chief_queue_runner = QueueRunner(self._sync_token_queue_name, [self.sync_op])
+            with _device.device(None), _device.device(qdev or None):
+                # when the chief's coordinator stops, the token queue is closed (TF's QueueRunner does the same with
+                # cancel_pending_enqueues): replicas still blocked in the dequeue get OutOfRangeError = a clean end of
+                # training, instead of waiting for tokens nobody will produce any more
+                close_op = g.create_node("QueueClose", [], {"queue_name": self._sync_token_queue_name},
+                                         "sync_token_q_Close", device=qdev)
+                chief_init_ops.append(g.create_node("QueueRenew", [], {"queue_name": self._sync_token_queue_name},
+                                                    "sync_token_q_Renew", device=qdev))
+            self._chief_queue_runner = QueueRunner(self._sync_token_queue_name, [self.sync_op], close_op=close_op)
             self.chief_init_op = _ops.group(*chief_init_ops, name="chief_init")
             self.ready_for_local_init_op = report_uninitialized_variables(global_variables())
             self._gradients_applied = True
@@ -269,4 +289,11 @@ class SyncReplicasOptimizerHook(SessionRunHook):
             self._threads = self._q_runner.create_threads(raw, coord=coord, daemon=True, start=True)
 
     def end(self, session):
-        pass
+        # Clean end of the chief's training loop: close the token queue NOW, while the session is still open (the
+        # queue runner's close-on-stop thread races with the session teardown).  Replicas that are still running drain
+        # the remaining tokens and then get OutOfRangeError from the dequeue = a clean end of their loop.
+        if self._is_chief and self._q_runner is not None and self._q_runner.close_op is not None:
+            try:
+                getattr(session, "raw_session", lambda: session)().run(self._q_runner.close_op)
+            except Exception:      # noqa: BLE001 - the ps may already be gone
+                pass

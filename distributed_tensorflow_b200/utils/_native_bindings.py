@@ -183,7 +183,11 @@ class NativeQueue:
         return int(self._lib.dtf_queue_size(self._h))
 
     def close(self, cancel_pending_enqueues: bool = False) -> None:
+        self._closed = True
         self._lib.dtf_queue_close(self._h)
+
+    def is_closed(self) -> bool:
+        return getattr(self, "_closed", False)
 
     def __del__(self):
         try:

@@ -24,7 +24,9 @@ FLAGS = define_cluster_flags("127.0.0.1:2222", "127.0.0.1:2223,127.0.0.1:2224")
 F.DEFINE_float("learning_rate", 0.03, "SGD step size")
 F.DEFINE_integer("steps_to_validate", 1, "print the fitted line every N global steps")
 F.DEFINE_bool("is_sync", False, "synchronous replicas")
-F.DEFINE_integer("num_workers", 0, "replicas to aggregate in sync mode (0 = all workers of the cluster)")
+F.DEFINE_integer("num_workers", 0, "total_num_replicas in sync mode (0 = all workers of the cluster)")
+F.DEFINE_integer("replicas_to_aggregate", 0, "gradients averaged per update (0 = num_workers); fewer than num_workers "
+                                             "= backup workers: the slowest / dead replicas are not waited for")
 F.DEFINE_integer("num_steps", 2000, "global steps to run, counted from the step found at session creation")
 F.DEFINE_string("ckpt_dir", "/tmp/dtf_ckpt/linear", "checkpoint directory every task can reach")
 F.DEFINE_integer("save_checkpoint_secs", 60, "seconds between checkpoints")
@@ -51,7 +53,8 @@ def main():
         hooks = [dtf.train.StopAtStepHook(num_steps=FLAGS.num_steps)]
         if FLAGS.is_sync:
             n = FLAGS.num_workers or n_workers
-            sgd = dtf.train.SyncReplicasOptimizer(sgd, replicas_to_aggregate=n, total_num_replicas=n)
+            sgd = dtf.train.SyncReplicasOptimizer(sgd, replicas_to_aggregate=FLAGS.replicas_to_aggregate or n,
+                                                  total_num_replicas=n)
             hooks.append(sgd.make_session_run_hook(chief))
         update = sgd.minimize(mse, global_step=step)
     session_config = dtf.ConfigProto(gpu_options=dtf.GPUOptions(per_process_gpu_memory_fraction=0.1))

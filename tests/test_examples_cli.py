@@ -100,3 +100,53 @@ def test_mnist_standalone_single_process_cpu(tmp_path):
     assert "120 steps" in line and "steps/s" in line
     assert float(line.rsplit(" ", 1)[1]) < 60.0                 # batch-sum loss of 100 examples starts near 230
     assert (tmp_path / "ck" / "checkpoint").exists()
+
+
+def test_backup_worker_survives_a_killed_replica(tmp_path):
+    """Fault injection (SURVEY section 5): 1 ps + 3 sync workers with replicas_to_aggregate=2 (one backup replica);
+    worker 2 is SIGKILLed mid-run.  The survivors keep training to the stop step and exit promptly: the dead
+    client's pending token dequeue is cancelled on the ps (no token is lost) and shutdown does not wait for it."""
+    import signal
+    import socket
+    import time
+    socks, ports = [], []
+    for _ in range(4):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        ports.append(s.getsockname()[1])
+        socks.append(s)
+    for s in socks:
+        s.close()
+    script = os.path.join(EX, "example_between_graph.py")
+    hosts = ["--ps_hosts=127.0.0.1:%d" % ports[0], "--worker_hosts=" + ",".join("127.0.0.1:%d" % p for p in ports[1:])]
+    args = hosts + ["--is_sync=True", "--replicas_to_aggregate=2", "--num_steps=1200", "--steps_to_validate=400",
+                    "--ckpt_dir=%s" % (tmp_path / "ck")]
+
+    def task(job, idx, out):
+        return subprocess.Popen([sys.executable, "-u", script, "--job_name=%s" % job, "--task_index=%d" % idx] + args, env=ENV,
+                                stdout=out, stderr=subprocess.STDOUT, text=True)
+    logs = [open(tmp_path / ("w%d.log" % i), "w") for i in range(3)]
+    ps = task("ps", 0, subprocess.DEVNULL)
+    workers = [task("worker", i, logs[i]) for i in range(3)]
+    try:
+        deadline = time.time() + 120
+        while time.time() < deadline:                      # wait until training is under way, then kill worker 2
+            if "step: 400" in open(tmp_path / "w0.log").read():
+                break
+            time.sleep(0.2)
+        workers[2].send_signal(signal.SIGKILL)
+        t_kill = time.time()
+        assert workers[0].wait(timeout=120) == 0 and workers[1].wait(timeout=60) == 0
+        assert time.time() - t_kill < 60                   # no 30 s connect retries towards the dead task at shutdown
+        out0 = open(tmp_path / "w0.log").read()
+        last = [l for l in out0.splitlines() if "weight:" in l][-1]
+        assert int(last.split("step:")[1].split(",")[0]) >= 800            # progress continued after the kill at ~400
+        assert abs(float(last.split("weight:")[1].split(",")[0]) - 2.0) < 0.3
+        final = [int(f.split("-")[1].split(".")[0]) for f in os.listdir(tmp_path / "ck") if f.startswith("model.ckpt-") and f.endswith(".index")]
+        assert max(final) >= 1200                                          # the chief's final checkpoint is at the stop step
+    finally:
+        for p in workers + [ps]:
+            if p.poll() is None:
+                p.kill()
+        for f in logs:
+            f.close()
