@@ -150,3 +150,20 @@ def test_backup_worker_survives_a_killed_replica(tmp_path):
                 p.kill()
         for f in logs:
             f.close()
+
+
+def test_job_restart_resumes_from_checkpoint(tmp_path):
+    """Checkpoint / resume at job level: the same cluster program is run twice with the same
+    checkpoint directory; the second run's chief restores variables + global_step and ``StopAtStepHook(num_steps)``
+    counts from the restored step."""
+    def run():
+        return _run([os.path.join(EX, "launch_local.py"), os.path.join(EX, "example_between_graph.py"), "--num_ps", "1",
+                     "--num_workers", "1", "--gpus", "0", "--timeout", "200", "--", "--num_steps=300", "--steps_to_validate=100",
+                     "--ckpt_dir=%s" % (tmp_path / "ck")], timeout=300)
+
+    def steps(out):
+        return [int(l.split("step:")[1].split(",")[0]) for l in out.splitlines() if "weight:" in l]
+    first, second = steps(run()), steps(run())
+    assert max(first) <= 300 and min(second) >= 300 and max(second) >= 500, (first, second)     # 0..300, then 301..601
+    saved = [int(f.split("-")[1].split(".")[0]) for f in os.listdir(tmp_path / "ck") if f.endswith(".index")]
+    assert max(saved) >= 600
