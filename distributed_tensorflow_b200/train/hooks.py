@@ -99,9 +99,13 @@ class StopAtStepHook(SessionRunHook):
         return SessionRunArgs(self._global_step_tensor)
 
     def after_run(self, run_context, run_values):
-        global_step = run_values.results
+        # The fetched value is the global step BEFORE this run's update (TF-1.12 semantics): assume the run
+        # incremented it, and confirm with a fresh read so that training stops AT last_step, not one step past it.
+        global_step = int(run_values.results) + 1
         if global_step >= self._last_step:
-            run_context.request_stop()
+            step = int(run_context.session.run(self._global_step_tensor))
+            if step >= self._last_step:
+                run_context.request_stop()
 
 
 class SecondOrStepTimer:
