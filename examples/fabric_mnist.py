@@ -37,6 +37,8 @@ flags.DEFINE_bool("in_graph", False, "one process drives all GPUs")
 flags.DEFINE_integer("gpus", 0, "GPUs to use in in-graph mode (0: all)")
 flags.DEFINE_string("train_dir", "/tmp/dtf_ckpt/fabric_mnist", "checkpoint directory")
 flags.DEFINE_integer("num_train", 55000, "synthetic train-set size")
+flags.DEFINE_string("nvls", "auto", "NVLS multicast fabric: off | on | auto (auto = on when the box has NVLS and one process "
+                                    "per GPU is used; the one-process topology opts in with 'on')")
 FLAGS = flags.FLAGS
 
 
@@ -55,6 +57,7 @@ def main():
     colocated = n == 1
     cfg = EngineConfig(num_ps=1 if colocated else FLAGS.num_ps, num_workers=1 if colocated else n - FLAGS.num_ps,
                        sync=FLAGS.issync, colocated=colocated,
+                       nvls={"off": False, "on": True}.get(FLAGS.nvls, False if (FLAGS.in_graph or world == 1) else "auto"),
                        optimizer={"kind": FLAGS.optimizer, "lr": FLAGS.learning_rate, "momentum": 0.9})
     eng = PSTrainEngine(MLPSpec(hidden=FLAGS.hidden_units, batch=FLAGS.batch_size), cfg, fabric)
     eng.init_params()
