@@ -52,9 +52,60 @@ int pread_all(int fd, uint8_t* p, int64_t n, int64_t off) {
   return 0;
 }
 
+// ---- CRC32C (Castagnoli): the checksum of TensorFlow's checkpoint (tensor bundle) and event-file formats ----------
+uint32_t crc32c_table[256];
+std::atomic<bool> crc32c_ready{false};
+
+void crc32c_init() {
+  if (crc32c_ready.load()) return;
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c & 1) ? (0x82F63B78u ^ (c >> 1)) : (c >> 1);
+    crc32c_table[i] = c;
+  }
+  crc32c_ready.store(true);
+}
+
+uint32_t crc32c_sw(uint32_t c, const uint8_t* p, int64_t n) {
+  crc32c_init();
+  for (int64_t i = 0; i < n; ++i) c = crc32c_table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+  return c;
+}
+
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("sse4.2"))) uint32_t crc32c_hw(uint32_t c, const uint8_t* p, int64_t n) {
+  uint64_t c64 = c;
+  while (n >= 8) {
+    uint64_t v;
+    memcpy(&v, p, 8);
+    c64 = __builtin_ia32_crc32di(c64, v);
+    p += 8; n -= 8;
+  }
+  c = (uint32_t)c64;
+  while (n > 0) {
+    c = __builtin_ia32_crc32qi(c, *p);
+    ++p; --n;
+  }
+  return c;
+}
+bool have_sse42() { return __builtin_cpu_supports("sse4.2"); }
+#else
+uint32_t crc32c_hw(uint32_t c, const uint8_t* p, int64_t n) { return crc32c_sw(c, p, n); }
+bool have_sse42() { return false; }
+#endif
+
 }  // namespace
 
 extern "C" {
+
+// Plain (unmasked) CRC32C of a buffer; `seed` = a previous result to continue a running checksum (0 to start).
+uint32_t dtf_crc32c(const void* data, int64_t n, uint32_t seed) {
+  static const bool hw = have_sse42();
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = seed ^ 0xFFFFFFFFu;
+  c = hw ? crc32c_hw(c, p, n) : crc32c_sw(c, p, n);
+  return c ^ 0xFFFFFFFFu;
+}
 
 uint32_t dtf_crc32(const void* data, int64_t n) {
   crc_init();

@@ -1,14 +1,17 @@
 """Name-keyed checkpoints: ``Saver``, ``get_checkpoint_state``, ``latest_checkpoint``.
 
-On-disk layout (a "tensor bundle" of this framework's own design):
+On-disk layout = TensorFlow's checkpoint V2 ("tensor bundle"):
 
 * ``<dir>/checkpoint`` -- text state file: ``model_checkpoint_path: "model.ckpt-1200"`` plus one
   ``all_model_checkpoint_paths`` line per retained checkpoint (``max_to_keep=5``);
-* ``<prefix>.index`` -- JSON: tensor name -> {dtype, shape, offset, nbytes, crc32};
+* ``<prefix>.index`` -- a LevelDB-format table: tensor name -> ``BundleEntryProto`` {dtype, shape, shard, offset,
+  size, masked CRC32C}, key ``""`` -> ``BundleHeaderProto`` (``train/tensor_bundle.py``);
 * ``<prefix>.data-00000-of-00001`` -- the raw little-endian tensor bytes, 64-byte aligned
   (written by ``csrc/runtime/bundle_io.cpp`` with positional writes when the native runtime
-  is built, by Python otherwise);
-* ``<prefix>.meta`` -- JSON graph description (for inspection / TensorBoard-style tools).
+  is built, by Python otherwise; CRC32C by the SSE4.2 instruction);
+* ``<prefix>.meta`` -- JSON graph description (TF writes a MetaGraphDef proto here; this one is for inspection).
+
+Checkpoints written by earlier versions of this framework (JSON ``.index``) are still readable.
 
 Tensors are keyed **by variable name**, and restore is **partial**: a Saver only
 looks up the names of *its* variables, so the predict program can pull
@@ -36,6 +39,7 @@ from ..framework import errors
 from ..framework import ops as _ops
 from ..framework.graph import get_default_graph
 from ..framework.variables import Variable, assign, global_variables
+from . import tensor_bundle
 
 __all__ = ["Saver", "CheckpointState", "get_checkpoint_state", "latest_checkpoint", "update_checkpoint_state",
            "checkpoint_exists", "load_checkpoint", "list_variables", "resolve_path", "NewCheckpointReader"]
@@ -149,8 +153,8 @@ def write_bundle(prefix: str, tensors: Dict[str, torch.Tensor], meta: Optional[D
         if not isinstance(t, torch.Tensor):
             t = torch.as_tensor(t)
         b = _tensor_bytes(t)
-        index[name] = {"dtype": _dtype_name(t.dtype), "shape": list(t.shape), "offset": offset,
-                       "nbytes": len(b), "crc32": zlib.crc32(b) & 0xFFFFFFFF}
+        index[name] = tensor_bundle.entry_proto(_dtype_name(t.dtype), list(t.shape), offset, len(b),
+                                                tensor_bundle.masked_crc32c(b))
         blobs.append((offset, b))
         offset += (len(b) + _ALIGN - 1) // _ALIGN * _ALIGN
     data_path = prefix + ".data-00000-of-00001"
@@ -167,9 +171,7 @@ def write_bundle(prefix: str, tensors: Dict[str, torch.Tensor], meta: Optional[D
                 f.write(b)
             f.truncate(offset)
     os.replace(tmp, data_path)
-    with open(prefix + ".index.tmp", "w") as f:
-        json.dump({"format": "dtf-bundle-v1", "total_bytes": offset, "tensors": index}, f)
-    os.replace(prefix + ".index.tmp", prefix + ".index")
+    tensor_bundle.write_index(prefix + ".index", index)
     if meta is not None:
         with open(prefix + ".meta", "w") as f:
             json.dump(meta, f)
@@ -181,8 +183,18 @@ class CheckpointReader:
         idx = self.prefix + ".index"
         if not os.path.exists(idx):
             raise errors.NotFoundError("checkpoint %r not found (no %s)" % (prefix, idx))
-        with open(idx) as f:
-            self._index = json.load(f)["tensors"]
+        with open(idx, "rb") as f:
+            legacy = f.read(1) == b"{"
+        if legacy:                                   # JSON index of earlier versions of this framework
+            with open(idx) as f:
+                self._index = json.load(f)["tensors"]
+        else:
+            header, entries = tensor_bundle.read_index(idx)
+            if header.get("endianness", 0) != 0:
+                raise errors.OpError("checkpoint %s was written big-endian" % self.prefix)
+            self._index = {k: {"dtype": e["dtype"], "shape": e["shape"], "offset": e["offset"], "nbytes": e["size"],
+                               "crc32c": e["crc32c"], "shard": e["shard_id"]} for k, e in entries.items()}
+            self._num_shards = int(header.get("num_shards", 1))
         self._data = self.prefix + ".data-00000-of-00001"
 
     def has_tensor(self, name: str) -> bool:
@@ -199,13 +211,19 @@ class CheckpointReader:
             e = self._index[name]
         except KeyError:
             raise errors.NotFoundError("Key %s not found in checkpoint %s" % (name, self.prefix)) from None
-        with open(self._data, "rb") as f:
+        data = self._data
+        if e.get("shard"):                           # multi-shard bundles (written by TensorFlow with sharded savers)
+            data = "%s.data-%05d-of-%05d" % (self.prefix, e["shard"], getattr(self, "_num_shards", 1))
+        with open(data, "rb") as f:
             f.seek(e["offset"])
             b = f.read(e["nbytes"])
         if len(b) != e["nbytes"]:
             raise errors.OpError("checkpoint %s is truncated at tensor %s" % (self.prefix, name))
-        if verify and (zlib.crc32(b) & 0xFFFFFFFF) != e["crc32"]:
-            raise errors.OpError("checksum mismatch for tensor %s in %s" % (name, self.prefix))
+        if verify:
+            bad = (tensor_bundle.masked_crc32c(b) != e["crc32c"]) if "crc32c" in e \
+                else ((zlib.crc32(b) & 0xFFFFFFFF) != e["crc32"])
+            if bad:
+                raise errors.OpError("checksum mismatch for tensor %s in %s" % (name, self.prefix))
         dt = _DTYPES[e["dtype"]]
         if dt == torch.bfloat16:
             t = torch.from_numpy(np.frombuffer(b, dtype=np.int16).copy()).view(torch.bfloat16)
