@@ -95,6 +95,43 @@ class _LazyFabric:
 
 fabric = _LazyFabric()
 
+# -- tf.logging ----------------------------------------------------------------------------------------
+def _make_logging():
+    import logging as _pylog
+    log = _pylog.getLogger("dtf")
+    if not log.handlers and not _pylog.getLogger().handlers:
+        _pylog.basicConfig(format="%(levelname)s:%(name)s:%(message)s")
+    ns = _types.SimpleNamespace(DEBUG=_pylog.DEBUG, INFO=_pylog.INFO, WARN=_pylog.WARNING, ERROR=_pylog.ERROR,
+                                FATAL=_pylog.CRITICAL, debug=log.debug, info=log.info, warn=log.warning,
+                                warning=log.warning, error=log.error, fatal=log.critical,
+                                set_verbosity=log.setLevel, get_verbosity=log.getEffectiveLevel)
+    return ns
+
+
+logging = _make_logging()
+
+
+# -- tf.layers (the one everybody uses) -----------------------------------------------------------------
+def _dense(inputs, units, activation=None, use_bias=True, kernel_initializer=None, bias_initializer=None, name=None,
+           reuse=None, trainable=True):
+    """``tf.layers.dense``: ``activation(inputs . kernel + bias)`` with variables ``<name>/kernel`` and ``<name>/bias``
+    (glorot-uniform / zeros by default) created through ``get_variable``, so scopes, reuse and
+    ``replica_device_setter`` placement behave as for hand-made variables."""
+    x = convert_to_tensor(inputs)
+    in_dim = int(x.get_shape()[-1])
+    with variable_scope(name or "dense", reuse=reuse):
+        kernel = get_variable("kernel", [in_dim, int(units)], initializer=kernel_initializer or glorot_uniform_initializer(),
+                              trainable=trainable)
+        if use_bias:
+            bias = get_variable("bias", [int(units)], initializer=bias_initializer or zeros_initializer(), trainable=trainable)
+            y = _ops.xw_plus_b(x, kernel, bias)
+        else:
+            y = _ops.matmul(x, kernel)
+    return activation(y) if activation is not None else y
+
+
+layers = _types.SimpleNamespace(dense=_dense)
+
 # -- tf.train -----------------------------------------------------------------------------------------
 from . import train  # noqa: E402
 from .python_compat import input_data, timeline  # noqa: E402,F401

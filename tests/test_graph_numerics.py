@@ -228,3 +228,27 @@ def test_conv_bn_pool_shapes_and_grads():
     ref = torch.nn.functional.conv2d(torch.from_numpy(xin).permute(0, 3, 1, 2), torch.from_numpy(wv).permute(3, 2, 0, 1),
                                      padding=1).permute(0, 2, 3, 1).numpy()
     np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-5)
+
+
+def test_layers_dense_and_logging_conveniences():
+    """``tf.layers.dense`` creates ``<name>/kernel`` / ``<name>/bias`` through get_variable (scopes + reuse work) and trains;
+    ``tf.logging`` mirrors the TF-1.x module."""
+    x = dtf.placeholder(dtf.float32, [None, 4])
+    h = dtf.layers.dense(x, 8, activation=dtf.nn.relu, name="fc1")
+    y = dtf.layers.dense(h, 1, name="out")
+    again = dtf.layers.dense(x, 8, name="fc1", reuse=True)                # shares fc1's variables
+    assert [v.var_name for v in dtf.trainable_variables()] == ["fc1/kernel", "fc1/bias", "out/kernel", "out/bias"]
+    loss = dtf.reduce_mean(dtf.square(y - 1.0))
+    step = dtf.train.GradientDescentOptimizer(0.1).minimize(loss)
+    xs = np.random.RandomState(0).rand(16, 4).astype(np.float32)
+    with dtf.Session() as sess:
+        sess.run(dtf.global_variables_initializer())
+        first = sess.run(loss, {x: xs})
+        for _ in range(60):
+            sess.run(step, {x: xs})
+        assert sess.run(loss, {x: xs}) < 0.1 * first
+        a, b = sess.run([h, dtf.nn.relu(again)], {x: xs})
+        np.testing.assert_allclose(a, b, rtol=1e-6)
+    dtf.logging.set_verbosity(dtf.logging.INFO)
+    assert dtf.logging.get_verbosity() == dtf.logging.INFO
+    dtf.logging.info("step %d", 3)
