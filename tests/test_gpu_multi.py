@@ -1,0 +1,37 @@
+"""Distributed GPU tier: the fabric engine on TWO GPUs, one process per GPU (torchrun), against the CPU
+oracle that replays the same batches -- sync (mean of the workers' gradients, tokens) and async (every push applied,
+staleness counted).  Runs ``tools/mp_check.py``; skipped on boxes with fewer than two GPUs."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("nvls", ["0", "auto"])
+def test_two_gpu_engine_matches_cpu_oracle(nvls, tmp_path):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    env = dict(os.environ, DTF_NVLS=nvls, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "mp_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("MP_CHECK ")][-1]
+    rep = json.loads(line[len("MP_CHECK "):])
+    assert rep["sync"]["ok"] and rep["sync"]["global_step"] == 6 and rep["sync"]["max_rel_err_vs_oracle"] < 3e-2
+    assert rep["async"]["ok"] and rep["async"]["staleness"]["count"] == 6
