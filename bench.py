@@ -331,6 +331,9 @@ def main():
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     if args.in_graph and world > 1:
         raise SystemExit("--in-graph runs as ONE process (do not launch it with torchrun)")
+    if args.gpus > 1 and world == 1 and not args.in_graph:
+        # `python bench.py --gpus N` without torchrun: one client process drives all N GPUs (in-graph replication)
+        args.in_graph = True
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
