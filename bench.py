@@ -222,6 +222,8 @@ def run_resnet18(args, rank, world, local_rank):
     from distributed_tensorflow_b200.parallel.generic_engine import GenericPSEngine
     from distributed_tensorflow_b200.parallel.ps_engine import EngineConfig
     N = args.gpus
+    if N > 1 and world == 1:
+        raise SystemExit("--model resnet18 with --gpus %d: launch one process per GPU with torch.distributed.run" % N)
     B = args.batch if args.batch != 100 else 64
     nvls = {"off": False, "on": True, "auto": "auto"}[args.nvls]
     opt = {"kind": "momentum", "lr": args.lr or 0.05, "momentum": 0.9}
