@@ -13,3 +13,4 @@ from .optimizer import AdamOptimizer, GradientDescentOptimizer, MomentumOptimize
 from .saver import (CheckpointState, NewCheckpointReader, Saver, checkpoint_exists, get_checkpoint_state,
                     latest_checkpoint, list_variables, load_checkpoint, update_checkpoint_state)
 from .sync_replicas import SyncReplicasOptimizer, SyncReplicasOptimizerHook
+from .supervisor import Supervisor

@@ -228,7 +228,9 @@ class SyncReplicasOptimizer(Optimizer):
                 chief_init_ops.append(g.create_node("QueueRenew", [], {"queue_name": self._sync_token_queue_name},
                                                     "sync_token_q_Renew", device=qdev))
             self._chief_queue_runner = QueueRunner(self._sync_token_queue_name, [self.sync_op], close_op=close_op)
-            self.chief_init_op = _ops.group(*chief_init_ops, name="chief_init")
+            # like TF: the chief's init op also initialises ITS local_step (mnist_replica.py passes chief_init_op as the
+            # chief's local_init_op and local_step_init_op as everybody else's)
+            self.chief_init_op = _ops.group(self.local_step_init_op, *chief_init_ops, name="chief_init")
             self.ready_for_local_init_op = report_uninitialized_variables(global_variables())
             self._gradients_applied = True
             return train_op

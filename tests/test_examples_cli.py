@@ -167,3 +167,16 @@ def test_job_restart_resumes_from_checkpoint(tmp_path):
     assert max(first) <= 300 and min(second) >= 300 and max(second) >= 500, (first, second)     # 0..300, then 301..601
     saved = [int(f.split("-")[1].split(".")[0]) for f in os.listdir(tmp_path / "ck") if f.endswith(".index")]
     assert max(saved) >= 600
+
+
+@pytest.mark.parametrize("sync", ["False", "True"])
+def test_supervisor_style_mnist_job(tmp_path, sync):
+    """examples/mnist_supervisor.py: the mnist_replica.py generation of ps programs (tf.train.Supervisor, chief queue
+    runner + init tokens in sync mode) on 1 ps + 2 workers."""
+    out = _run([os.path.join(EX, "launch_local.py"), os.path.join(EX, "mnist_supervisor.py"), "--num_ps", "1", "--num_workers", "2",
+                "--gpus", "0", "--timeout", "200", "--", "--sync_replicas=%s" % sync, "--train_steps=150", "--num_train=2000",
+                "--train_dir=%s" % (tmp_path / "sv")], timeout=300)
+    assert out.count("Session initialization complete.") == 2
+    vals = [float(l.rsplit("=", 1)[1]) for l in out.splitlines() if "validation cross entropy" in l]
+    assert len(vals) == 2 and max(vals) < 2000.0                # 5000 validation images, batch-sum loss: ~11500 untrained
+    assert (tmp_path / "sv" / "checkpoint").exists()

@@ -393,3 +393,60 @@ def test_multiprocess_distributed_mnist_then_predict(tmp_path, mode):
     assert r2.returncode == 0, r2.stdout + r2.stderr
     acc = float(r2.stdout.strip().splitlines()[-1].split()[-1])
     assert acc > 0.3        # chance is 0.1
+
+
+# ---------------------------------------------------------------- tf.train.Supervisor (the mnist_replica.py generation)
+@pytest.mark.parametrize("sync", [False, True])
+def test_supervisor_driven_ps_training(cluster3, tmp_path, sync):
+    """The protocol of TF r1.3's mnist_replica.py (the reference's ancestor, distributed_mnist.py:57): Supervisor chief
+    initialises, the other worker waits; with SyncReplicasOptimizer the chief runs the init-tokens op and starts the
+    optimizer's queue runner through ``sv.start_queue_runners``; the chief checkpoints into ``logdir``."""
+    cluster, servers = cluster3
+    results, errs = {}, []
+    xs = np.random.RandomState(0).rand(64).astype(np.float32)
+    ys = 3.0 * xs - 1.0
+
+    def worker(task):
+        try:
+            g = dtf.Graph()
+            with g.as_default():
+                with dtf.device(dtf.train.replica_device_setter(cluster=cluster, worker_device="/job:worker/task:%d" % task)):
+                    gs = dtf.train.get_or_create_global_step()
+                    w = dtf.get_variable("w", [1], initializer=dtf.zeros_initializer())
+                    b = dtf.get_variable("b", [1], initializer=dtf.zeros_initializer())
+                    x, y = dtf.placeholder(dtf.float32), dtf.placeholder(dtf.float32)
+                    loss = dtf.reduce_mean(dtf.square(y - (x * w + b)))
+                    opt = dtf.train.GradientDescentOptimizer(0.2)
+                    if sync:
+                        opt = dtf.train.SyncReplicasOptimizer(opt, replicas_to_aggregate=2, total_num_replicas=2)
+                    train_op = opt.minimize(loss, global_step=gs)
+                    init_op = dtf.global_variables_initializer()
+                chief = task == 0
+                kw = {}
+                if sync:
+                    kw = {"local_init_op": opt.local_step_init_op, "ready_for_local_init_op": opt.ready_for_local_init_op}
+                    if chief:
+                        kw["local_init_op"] = opt.chief_init_op
+                sv = dtf.train.Supervisor(is_chief=chief, logdir=str(tmp_path / "sv"), init_op=init_op, recovery_wait_secs=0.2,
+                                          global_step=gs, save_model_secs=1, **kw)
+                sess = sv.prepare_or_wait_for_session(servers[1 + task].target)
+                if sync and chief:
+                    sess.run(opt.get_init_tokens_op())
+                    sv.start_queue_runners(sess, [opt.get_chief_queue_runner()])
+                step = 0
+                while not sv.should_stop() and step < 150:
+                    _, step = sess.run([train_op, gs], feed_dict={x: xs, y: ys})
+                results[task] = (int(step), sess.run([w, b]))
+                sv.stop()
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+    ts = [threading.Thread(target=worker, args=(t,)) for t in (0, 1)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(120)
+    assert not errs, errs
+    assert not any(t.is_alive() for t in ts)
+    step, (wv, bv) = results[0]
+    assert step >= 150 and abs(float(wv[0]) - 3.0) < 0.3 and abs(float(bv[0]) + 1.0) < 0.2
+    assert dtf.train.latest_checkpoint(str(tmp_path / "sv")) is not None
