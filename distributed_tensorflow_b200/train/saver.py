@@ -9,7 +9,7 @@ On-disk layout = TensorFlow's checkpoint V2 ("tensor bundle"):
 * ``<prefix>.data-00000-of-00001`` -- the raw little-endian tensor bytes, 64-byte aligned
   (written by ``csrc/runtime/bundle_io.cpp`` with positional writes when the native runtime
   is built, by Python otherwise; CRC32C by the SSE4.2 instruction);
-* ``<prefix>.meta`` -- JSON graph description (TF writes a MetaGraphDef proto here; this one is for inspection).
+* ``<prefix>.meta`` -- a ``MetaGraphDef`` proto: the graph (``NodeDef`` per node, as in the event files) + ``saver_def``.
 
 Checkpoints written by earlier versions of this framework (JSON ``.index``) are still readable.
 
@@ -173,8 +173,18 @@ def write_bundle(prefix: str, tensors: Dict[str, torch.Tensor], meta: Optional[D
     os.replace(tmp, data_path)
     tensor_bundle.write_index(prefix + ".index", index)
     if meta is not None:
-        with open(prefix + ".meta", "w") as f:
-            json.dump(meta, f)
+        with open(prefix + ".meta", "wb") as f:
+            f.write(_meta_graph_def(meta))
+
+
+def _meta_graph_def(meta: Dict[str, Any]) -> bytes:
+    """``<prefix>.meta`` as a ``tensorflow.MetaGraphDef``: ``meta_info_def`` {tensorflow_version, tags}, ``graph_def`` (the same
+    GraphDef encoding the event files use) and a ``saver_def`` {restore_op_name, max_to_keep, version = V2}."""
+    from ..utils.summary import _f_bytes, _f_float, _f_str, _f_varint, _graph_def
+    info = _f_str(4, "train") + _f_str(5, "1.12.0-dtf_b200")                 # MetaInfoDef.tags / tensorflow_version
+    saver = (_f_str(1, "save/Const:0") + _f_str(2, "save/control_dependency:0") + _f_str(3, "save/restore_all")
+             + _f_varint(4, int(meta.get("saver", {}).get("max_to_keep", 5))) + _f_float(6, 10000.0) + _f_varint(7, 2))
+    return _f_bytes(1, info) + _f_bytes(2, _graph_def(meta["graph_def"])) + _f_bytes(3, saver)
 
 
 class CheckpointReader:
@@ -305,7 +315,7 @@ class Saver:
                 tensors[k] = tensors[k].to(want)
         meta = None
         if write_meta_graph:
-            meta = {"graph_def": raw.graph.as_graph_def(), "saver": {"variables": keys},
+            meta = {"graph_def": raw.graph.as_graph_def(), "saver": {"variables": keys, "max_to_keep": self._max_to_keep},
                     "written": time.time()}
         write_bundle(prefix, tensors, meta)
         full = resolve_path(prefix)
@@ -343,8 +353,8 @@ class Saver:
     def export_meta_graph(self, filename: Optional[str] = None):
         meta = {"graph_def": get_default_graph().as_graph_def(), "saver": {"variables": list(self._vars)}}
         if filename:
-            with open(resolve_path(filename), "w") as f:
-                json.dump(meta, f)
+            with open(resolve_path(filename), "wb") as f:
+                f.write(_meta_graph_def(meta))
         return meta
 
 

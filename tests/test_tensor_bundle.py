@@ -160,3 +160,40 @@ def test_corruption_is_detected_and_legacy_json_index_still_reads(tmp_path):
         "w": {"dtype": "float32", "shape": [2, 3], "offset": 0, "nbytes": len(b), "crc32": zlib.crc32(b) & 0xFFFFFFFF}}},
         open(p2 + ".index", "w"))
     assert torch.equal(saver_mod.CheckpointReader(p2).get_tensor("w"), torch.arange(6, dtype=torch.float32).reshape(2, 3))
+
+
+def test_meta_file_is_a_meta_graph_def(tmp_path):
+    """``model.ckpt-N.meta`` parses as MetaGraphDef {meta_info_def, graph_def, saver_def} with the protobuf runtime."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    F = descriptor_pb2.FieldDescriptorProto
+    fd = descriptor_pb2.FileDescriptorProto(name="dtf_meta_min.proto", package="tensorflow", syntax="proto3")
+
+    def msg(name, fields):
+        m = fd.message_type.add(name=name)
+        for fname, num, typ, label, tname in fields:
+            f = m.field.add(name=fname, number=num, type=typ, label=label)
+            if tname:
+                f.type_name = tname
+    O, R = F.LABEL_OPTIONAL, F.LABEL_REPEATED
+    msg("NodeDef", [("name", 1, F.TYPE_STRING, O, None), ("op", 2, F.TYPE_STRING, O, None), ("input", 3, F.TYPE_STRING, R, None),
+                    ("device", 4, F.TYPE_STRING, O, None)])
+    msg("GraphDef", [("node", 1, F.TYPE_MESSAGE, R, ".tensorflow.NodeDef")])
+    msg("MetaInfoDef", [("tags", 4, F.TYPE_STRING, R, None), ("tensorflow_version", 5, F.TYPE_STRING, O, None)])
+    msg("SaverDef", [("filename_tensor_name", 1, F.TYPE_STRING, O, None), ("save_tensor_name", 2, F.TYPE_STRING, O, None),
+                     ("restore_op_name", 3, F.TYPE_STRING, O, None), ("max_to_keep", 4, F.TYPE_INT32, O, None),
+                     ("keep_checkpoint_every_n_hours", 6, F.TYPE_FLOAT, O, None), ("version", 7, F.TYPE_INT32, O, None)])
+    msg("MetaGraphDef", [("meta_info_def", 1, F.TYPE_MESSAGE, O, ".tensorflow.MetaInfoDef"), ("graph_def", 2, F.TYPE_MESSAGE, O, ".tensorflow.GraphDef"),
+                         ("saver_def", 3, F.TYPE_MESSAGE, O, ".tensorflow.SaverDef")])
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    Meta = message_factory.GetMessageClass(pool.FindMessageTypeByName("tensorflow.MetaGraphDef"))
+    w = dtf.Variable(dtf.zeros([2, 2]), name="w")
+    gs = dtf.train.get_or_create_global_step()
+    with dtf.Session() as sess:
+        sess.run(dtf.global_variables_initializer())
+        path = dtf.train.Saver(max_to_keep=3).save(sess, str(tmp_path / "model.ckpt"), global_step=7)
+    m = Meta()
+    m.ParseFromString(open(path + ".meta", "rb").read())
+    assert m.meta_info_def.tensorflow_version.startswith("1.12") and list(m.meta_info_def.tags) == ["train"]
+    assert {"w", "global_step"} <= {n.name for n in m.graph_def.node}
+    assert m.saver_def.max_to_keep == 3 and m.saver_def.version == 2 and m.saver_def.restore_op_name == "save/restore_all"
