@@ -28,7 +28,8 @@ from ..framework.ops import register_kernel
 from ..framework.variables import Variable, assign, assign_add, trainable_variables
 from ..utils import native_runtime
 
-__all__ = ["Optimizer", "GradientDescentOptimizer", "MomentumOptimizer", "AdamOptimizer", "adam_reference_step"]
+__all__ = ["Optimizer", "GradientDescentOptimizer", "MomentumOptimizer", "AdamOptimizer", "adam_reference_step",
+           "exponential_decay", "piecewise_constant"]
 
 
 class Optimizer:
@@ -139,8 +140,28 @@ class Optimizer:
         raise NotImplementedError
 
 
+def _is_dynamic(lr) -> bool:
+    return isinstance(lr, (Tensor, Variable))
+
+
 def _lr_value(lr) -> float:
+    if _is_dynamic(lr):
+        raise ValueError("this path needs a constant learning rate; got the tensor %r (a schedule such as "
+                         "tf.train.exponential_decay works with the graph optimizers, not with the fused fabric engines)"
+                         % getattr(lr, "name", lr))
     return float(lr)
+
+
+def _lr_inputs(lr):
+    """(extra input nodes, attr value): a tensor-valued learning rate (``exponential_decay`` ...) is a run-time INPUT
+    of the apply op -- evaluated wherever it was placed, shipped to the variable's task like any other tensor."""
+    if _is_dynamic(lr):
+        return [convert_to_tensor(lr)], None
+    return [], float(lr)
+
+
+def _lr_at_run_time(node, extra) -> float:
+    return float(extra[-1]) if node.attrs.get("lr") is None else node.attrs["lr"]
 
 
 class GradientDescentOptimizer(Optimizer):
@@ -149,8 +170,9 @@ class GradientDescentOptimizer(Optimizer):
         self._lr = learning_rate
 
     def _apply_dense(self, grad, var, prep):
+        extra, lr = _lr_inputs(self._lr)
         return get_default_graph().create_node(
-            "ApplyGradientDescent", [grad], {"var_name": var.var_name, "lr": _lr_value(self._lr)},
+            "ApplyGradientDescent", [grad] + extra, {"var_name": var.var_name, "lr": lr},
             "update_%s/ApplyGradientDescent" % var.var_name.replace("/", "_"), device=var.device)
 
     def fused_spec(self):
@@ -158,14 +180,15 @@ class GradientDescentOptimizer(Optimizer):
 
 
 @register_kernel("ApplyGradientDescent", stateful=True)
-def _k_apply_sgd(ctx, node, grad):
+def _k_apply_sgd(ctx, node, grad, *extra):
     var = ctx.store.read(node.attrs["var_name"])
     g = grad.to(device=var.device)
+    lr = _lr_at_run_time(node, extra)
     if var.is_cuda:
         from ..ops import cuda_lib
-        cuda_lib.apply_sgd_(var, g, node.attrs["lr"])
+        cuda_lib.apply_sgd_(var, g, lr)
     else:
-        var.sub_(g.to(var.dtype), alpha=node.attrs["lr"])
+        var.sub_(g.to(var.dtype), alpha=lr)
     return None
 
 
@@ -181,10 +204,11 @@ class MomentumOptimizer(Optimizer):
 
     def _apply_dense(self, grad, var, prep):
         slot = self.get_slot(var, "momentum")
+        extra, lr = _lr_inputs(self._lr)
         return get_default_graph().create_node(
-            "ApplyMomentum", [grad], {"var_name": var.var_name, "accum_name": slot.var_name,
-                                      "lr": _lr_value(self._lr), "momentum": float(self._momentum),
-                                      "nesterov": bool(self._nesterov)},
+            "ApplyMomentum", [grad] + extra, {"var_name": var.var_name, "accum_name": slot.var_name,
+                                              "lr": lr, "momentum": float(self._momentum),
+                                              "nesterov": bool(self._nesterov)},
             "update_%s/ApplyMomentum" % var.var_name.replace("/", "_"), device=var.device)
 
     def fused_spec(self):
@@ -193,8 +217,8 @@ class MomentumOptimizer(Optimizer):
 
 
 @register_kernel("ApplyMomentum", stateful=True)
-def _k_apply_momentum(ctx, node, grad):
-    a = node.attrs
+def _k_apply_momentum(ctx, node, grad, *extra):
+    a = dict(node.attrs, lr=_lr_at_run_time(node, extra))
     var, acc = ctx.store.read(a["var_name"]), ctx.store.read(a["accum_name"])
     g = grad.to(device=var.device)
     if var.is_cuda:
@@ -233,9 +257,10 @@ class AdamOptimizer(Optimizer):
 
     def _apply_dense(self, grad, var, prep):
         m, v = self.get_slot(var, "m"), self.get_slot(var, "v")
+        extra, lr = _lr_inputs(self._lr)
         return get_default_graph().create_node(
-            "ApplyAdam", [grad, self._beta1_power._node, self._beta2_power._node],
-            {"var_name": var.var_name, "m_name": m.var_name, "v_name": v.var_name, "lr": _lr_value(self._lr),
+            "ApplyAdam", [grad, self._beta1_power._node, self._beta2_power._node] + extra,
+            {"var_name": var.var_name, "m_name": m.var_name, "v_name": v.var_name, "lr": lr,
              "beta1": float(self._beta1), "beta2": float(self._beta2), "eps": float(self._eps)},
             "update_%s/ApplyAdam" % var.var_name.replace("/", "_"), device=var.device)
 
@@ -253,8 +278,8 @@ class AdamOptimizer(Optimizer):
 
 
 @register_kernel("ApplyAdam", stateful=True)
-def _k_apply_adam(ctx, node, grad, b1p, b2p):
-    a = node.attrs
+def _k_apply_adam(ctx, node, grad, b1p, b2p, *extra):
+    a = dict(node.attrs, lr=_lr_at_run_time(node, extra))
     var, m, v = ctx.store.read(a["var_name"]), ctx.store.read(a["m_name"]), ctx.store.read(a["v_name"])
     g = grad.to(device=var.device)
     b1p, b2p = float(b1p), float(b2p)
@@ -278,3 +303,42 @@ def adam_reference_step(var, m, v, g, t: int, lr=0.001, beta1=0.9, beta2=0.999, 
     v = beta2 * v + (1 - beta2) * g * g
     var = var - lr_t * m / (v.sqrt() + eps)
     return var, m, v
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# learning-rate schedules: scalar tensors computed from the global step
+# ---------------------------------------------------------------------------------------------------------------
+def exponential_decay(learning_rate, global_step, decay_steps, decay_rate, staircase: bool = False, name=None) -> Tensor:
+    """``learning_rate * decay_rate ^ (global_step / decay_steps)`` (integer division when ``staircase``)."""
+    gs = convert_to_tensor(global_step)
+    with _device.device(None), _device.device(gs.device or None):
+        return get_default_graph().create_node(
+            "LearningRateSchedule", [gs], {"kind": "exponential", "lr": float(learning_rate), "decay_steps": float(decay_steps),
+                                           "decay_rate": float(decay_rate), "staircase": bool(staircase)},
+            name or "ExponentialDecay", torch.float32, (), device=gs.device)
+
+
+def piecewise_constant(x, boundaries: Sequence[float], values: Sequence[float], name=None) -> Tensor:
+    """``values[0]`` while ``x <= boundaries[0]``, ``values[1]`` while ``x <= boundaries[1]``, ..., ``values[-1]`` after."""
+    if len(values) != len(boundaries) + 1:
+        raise ValueError("The length of boundaries should be 1 less than the length of values")
+    xs = convert_to_tensor(x)
+    with _device.device(None), _device.device(xs.device or None):
+        return get_default_graph().create_node(
+            "LearningRateSchedule", [xs], {"kind": "piecewise", "boundaries": [float(b) for b in boundaries],
+                                           "values": [float(v) for v in values]},
+            name or "PiecewiseConstant", torch.float32, (), device=xs.device)
+
+
+@register_kernel("LearningRateSchedule")
+def _k_lr_schedule(ctx, node, step):
+    a, s = node.attrs, float(step)
+    if a["kind"] == "exponential":
+        p = s / a["decay_steps"]
+        if a["staircase"]:
+            p = float(int(p))
+        return torch.tensor(a["lr"] * a["decay_rate"] ** p, dtype=torch.float32)
+    for b, v in zip(a["boundaries"], a["values"]):
+        if s <= b:
+            return torch.tensor(v, dtype=torch.float32)
+    return torch.tensor(a["values"][-1], dtype=torch.float32)
