@@ -450,3 +450,21 @@ def test_supervisor_driven_ps_training(cluster3, tmp_path, sync):
     step, (wv, bv) = results[0]
     assert step >= 150 and abs(float(wv[0]) - 3.0) < 0.3 and abs(float(bv[0]) + 1.0) < 0.2
     assert dtf.train.latest_checkpoint(str(tmp_path / "sv")) is not None
+
+
+def test_learning_rate_schedule_across_tasks(cluster3):
+    """The schedule is computed where global_step lives (ps 0) and consumed by apply ops on the variable's ps task."""
+    cluster, servers = cluster3
+    with dtf.device(dtf.train.replica_device_setter(cluster=cluster, worker_device="/job:worker/task:0")):
+        gs = dtf.train.get_or_create_global_step()
+        w = dtf.Variable([4.0], name="w")
+        lr = dtf.train.piecewise_constant(gs, [1], [0.5, 0.25])
+        train = dtf.train.GradientDescentOptimizer(lr).minimize(dtf.reduce_sum(w * 1.0), global_step=gs)
+    assert "/job:ps" in lr.device and "/job:ps" in w.device
+    with dtf.Session(servers[1].target) as sess:
+        sess.run(dtf.global_variables_initializer())
+        vals = []
+        for _ in range(4):
+            sess.run(train)
+            vals.append(float(sess.run(w)[0]))
+    np.testing.assert_allclose(vals, [3.5, 3.0, 2.75, 2.5], rtol=1e-6)      # steps 0,1 use 0.5; later ones 0.25
