@@ -124,3 +124,36 @@ def test_reference_distributed_mnist_then_predict_py(tmp_path):
     pred = _run(tmp_path, "distributed_mnist_predict.py", timeout=300)
     nums = [int(x) for x in pred.split() if x.isdigit()]
     assert nums and nums[-1] > 4500, pred            # > 90 % of the 5 000 validation images
+
+
+@pytest.mark.parametrize("sync", ["False", "True"])
+def test_tf_style_supervisor_program_through_the_shim(tmp_path, sync):
+    """A ``tf.app.run`` / ``tf.train.Supervisor`` / chief-queue-runner program in TF spelling (tests/fixtures) on
+    1 ps + 2 workers: the generation of scripts the reference descends from (``distributed_mnist.py:57``)."""
+    import re
+    script = os.path.join(ROOT, "tests", "fixtures", "tf_style_replica.py")
+    hosts = ["--ps_hosts=127.0.0.1:22281", "--worker_hosts=127.0.0.1:22282,127.0.0.1:22283", "--sync_replicas=%s" % sync]
+
+    def cmd(job, idx):
+        return [sys.executable, "-u", "-m", "distributed_tensorflow_b200.compat.run", script, "--job_name=%s" % job,
+                "--task_index=%d" % idx] + hosts
+    procs = [subprocess.Popen(cmd("ps", 0), env=_env(tmp_path), cwd=str(tmp_path), stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)]
+    logs = []
+    try:
+        for i in (0, 1):
+            f = open(tmp_path / ("w%d.log" % i), "w")
+            logs.append(f)
+            procs.append(subprocess.Popen(cmd("worker", i), env=_env(tmp_path), cwd=str(tmp_path), stdout=f, stderr=subprocess.STDOUT))
+        for p in procs[1:]:
+            assert p.wait(timeout=300) == 0, open(tmp_path / "w0.log").read()[-2000:] + open(tmp_path / "w1.log").read()[-2000:]
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        for f in logs:
+            f.close()
+    for i in (0, 1):
+        out = open(tmp_path / ("w%d.log" % i)).read()
+        assert "Session initialization complete." in out
+        val = float(re.findall(r"validation cross entropy = ([0-9][0-9.eE+-]*)", out)[-1])
+        assert val < 2000.0                                         # ~11500 for the untrained model (5000 images, batch sum)
