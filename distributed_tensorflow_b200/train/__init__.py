@@ -4,7 +4,7 @@ from ..framework.variables import create_global_step, get_global_step, get_or_cr
 from ..parallel.cluster import ClusterSpec
 from ..parallel.server import Server
 from .coordinator import Coordinator, QueueRunner
-from .hooks import (CheckpointSaverHook, FinalOpsHook, GlobalStepWaiterHook, LoggingTensorHook, NanTensorHook,
+from .hooks import (CheckpointSaverHook, FinalOpsHook, GlobalStepWaiterHook, LoggingTensorHook, NanTensorHook, ProfilerHook,
                     SecondOrStepTimer, SessionRunArgs, SessionRunContext, SessionRunHook, SessionRunValues,
                     StalenessHook, StepCounterHook, StopAtStepHook, SummarySaverHook)
 from .monitored_session import (ChiefSessionCreator, MonitoredSession, MonitoredTrainingSession, Scaffold,

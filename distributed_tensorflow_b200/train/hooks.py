@@ -24,7 +24,7 @@ from ..framework.variables import get_global_step
 
 __all__ = ["SessionRunHook", "SessionRunArgs", "SessionRunContext", "SessionRunValues", "StopAtStepHook",
            "CheckpointSaverHook", "StepCounterHook", "LoggingTensorHook", "NanTensorHook", "FinalOpsHook",
-           "SummarySaverHook", "SecondOrStepTimer", "GlobalStepWaiterHook", "StalenessHook"]
+           "SummarySaverHook", "SecondOrStepTimer", "GlobalStepWaiterHook", "StalenessHook", "ProfilerHook"]
 
 
 class SessionRunArgs:
@@ -354,3 +354,45 @@ class StalenessHook(SessionRunHook):
 
     def mean(self) -> float:
         return float(np.mean(self.samples)) if self.samples else 0.0
+
+
+class ProfilerHook(SessionRunHook):
+    """``tf.train.ProfilerHook``: every ``save_steps`` global steps (or ``save_secs`` seconds) run ONE step with
+    ``RunOptions(trace_level=FULL_TRACE)`` and write its chrome trace to ``<output_dir>/timeline-<step>.json`` (one
+    process per ``/job/task`` device) -- the per-run tracing of the reference's in-graph examples
+    (``example_in_graph.py:42-43,65-68``) made available inside a training loop."""
+
+    def __init__(self, save_steps: Optional[int] = None, save_secs: Optional[float] = None, output_dir: str = "",
+                 show_dataflow: bool = True, show_memory: bool = False):
+        self._timer = SecondOrStepTimer(every_secs=save_secs, every_steps=save_steps)
+        self._dir, self._show_dataflow, self._show_memory = output_dir, show_dataflow, show_memory
+        self._global_step_tensor = None
+        self._next_step = None
+        self._tracing = False
+        self.files: List[str] = []
+
+    def begin(self):
+        self._global_step_tensor = get_global_step()
+        if self._global_step_tensor is None:
+            raise RuntimeError("Global step should be created to use ProfilerHook.")
+
+    def before_run(self, run_context):
+        self._tracing = self._next_step is None or self._timer.should_trigger_for_step(self._next_step)
+        opts = None
+        if self._tracing:
+            from ..client.session import RunOptions
+            opts = RunOptions(trace_level=RunOptions.FULL_TRACE)
+        return SessionRunArgs(self._global_step_tensor, options=opts)
+
+    def after_run(self, run_context, run_values):
+        step = int(run_values.results) + 1
+        if self._tracing and run_values.run_metadata is not None:
+            from ..utils.timeline import Timeline
+            self._timer.update_last_triggered_step(step)
+            os.makedirs(self._dir or ".", exist_ok=True)
+            path = os.path.join(self._dir or ".", "timeline-%d.json" % step)
+            with open(path, "w") as f:
+                f.write(Timeline(run_values.run_metadata.step_stats).generate_chrome_trace_format(
+                    show_dataflow=self._show_dataflow, show_memory=self._show_memory))
+            self.files.append(path)
+        self._next_step = step + 1

@@ -238,6 +238,9 @@ class MonitoredSession:
                     merged_feed.update(req.feed_dict)
                 if req.options is not None and options is None:
                     options = req.options
+        if options is not None and run_metadata is None and getattr(options, "trace_level", 0):
+            from ..client.session import RunMetadata
+            run_metadata = RunMetadata()          # a hook asked for a trace: give after_run something to read
         out = self._sess.run({"caller": fetches, "hooks": hook_fetches}, feed_dict=merged_feed or None,
                              options=options, run_metadata=run_metadata)
         for i, h in enumerate(self._hooks):

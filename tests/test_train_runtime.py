@@ -468,3 +468,25 @@ def test_learning_rate_schedule_across_tasks(cluster3):
             sess.run(train)
             vals.append(float(sess.run(w)[0]))
     np.testing.assert_allclose(vals, [3.5, 3.0, 2.75, 2.5], rtol=1e-6)      # steps 0,1 use 0.5; later ones 0.25
+
+
+def test_profiler_hook_traces_steps_inside_a_training_loop(cluster3, tmp_path):
+    """ProfilerHook: a FULL_TRACE step every N global steps, chrome trace per traced step with one process per device
+    (ps and worker tasks both appear)."""
+    cluster, servers = cluster3
+    with dtf.device(dtf.train.replica_device_setter(cluster=cluster, worker_device="/job:worker/task:0")):
+        gs = dtf.train.get_or_create_global_step()
+        w = dtf.Variable([[1.0], [2.0]], name="w")
+        x = dtf.placeholder(dtf.float32, [None, 2])
+        loss = dtf.reduce_mean(dtf.square(dtf.matmul(x, w)))
+        train = dtf.train.GradientDescentOptimizer(0.01).minimize(loss, global_step=gs)
+    prof = dtf.train.ProfilerHook(save_steps=4, output_dir=str(tmp_path / "prof"))
+    with dtf.train.MonitoredTrainingSession(master=servers[1].target, is_chief=True,
+                                            hooks=[dtf.train.StopAtStepHook(last_step=10), prof]) as sess:
+        while not sess.should_stop():
+            sess.run(train, feed_dict={x: np.ones((4, 2), np.float32)})
+    assert len(prof.files) >= 2 and all(os.path.exists(f) for f in prof.files)
+    ev = json.load(open(prof.files[0]))["traceEvents"]
+    names = {e["args"]["name"] for e in ev if e.get("ph") == "M"}
+    assert any("/job:ps" in n for n in names) and any("/job:worker" in n for n in names)
+    assert any(e.get("ph") == "X" and e["args"]["op"] == "ApplyGradientDescent" for e in ev)
