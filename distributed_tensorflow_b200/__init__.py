@@ -136,4 +136,5 @@ layers = _types.SimpleNamespace(dense=_dense)
 from . import train  # noqa: E402
 from .python_compat import input_data, timeline  # noqa: E402,F401
 
-__all__ = [n for n in dir() if not n.startswith("_")]
+__all__ = [n for n in dir() if not n.startswith("_") and n not in {
+    "Any", "Callable", "Dict", "List", "Optional", "Sequence", "Union", "annotations", "np", "torch", "F"}]
