@@ -490,3 +490,39 @@ def test_profiler_hook_traces_steps_inside_a_training_loop(cluster3, tmp_path):
     names = {e["args"]["name"] for e in ev if e.get("ph") == "M"}
     assert any("/job:ps" in n for n in names) and any("/job:worker" in n for n in names)
     assert any(e.get("ph") == "X" and e["args"]["op"] == "ApplyGradientDescent" for e in ev)
+
+
+def test_recoverable_session_in_sync_mode_survives_ps_restart(ports, tmp_path):
+    """A15 + A12: with SyncReplicasOptimizer the ps also owns the accumulators and the token queue; after it is
+    restarted empty, the recovered chief session re-creates them (chief_init_op: accumulator steps, a fresh token
+    queue, initial tokens, a new queue-runner thread) and training continues from the last checkpoint."""
+    p = ports(2)
+    cluster = dtf.train.ClusterSpec({"ps": ["127.0.0.1:%d" % p[0]], "worker": ["127.0.0.1:%d" % p[1]]})
+    ps = dtf.train.Server(cluster, "ps", 0)
+    wk = dtf.train.Server(cluster, "worker", 0)
+    try:
+        with dtf.device(dtf.train.replica_device_setter(cluster=cluster, worker_device="/job:worker/task:0")):
+            gs = dtf.train.get_or_create_global_step()
+            w = dtf.Variable(dtf.constant([5.0]), name="w")
+            opt = dtf.train.SyncReplicasOptimizer(dtf.train.GradientDescentOptimizer(0.1), replicas_to_aggregate=1,
+                                                  total_num_replicas=1)
+            train = opt.minimize(dtf.reduce_sum(dtf.square(w)), global_step=gs)
+        seen, killed = [], False
+        with dtf.train.MonitoredTrainingSession(master=wk.target, is_chief=True, checkpoint_dir=str(tmp_path / "ck"),
+                                                save_checkpoint_secs=None, save_checkpoint_steps=1, log_step_count_steps=None,
+                                                hooks=[opt.make_session_run_hook(True), dtf.train.StopAtStepHook(last_step=9)]) as sess:
+            while not sess.should_stop():
+                _, step = sess.run([train, gs])
+                seen.append(int(step))
+                if step >= 4 and not killed:
+                    killed = True
+                    ps.stop()
+                    ps = dtf.train.Server(cluster, "ps", 0)
+            assert sess.num_recoveries >= 1
+        assert killed and max(seen) >= 9 and seen[0] <= 1
+        final = dtf.train.NewCheckpointReader(dtf.train.latest_checkpoint(str(tmp_path / "ck")))
+        assert int(final.get_tensor("global_step")) >= 9
+        assert abs(float(final.get_tensor("w")[0])) < 5.0 * 0.8 ** 8 * 1.5       # w shrinks by 0.8 per applied step
+    finally:
+        ps.stop()
+        wk.stop()
