@@ -154,8 +154,8 @@ class RpcServer:
             while not self._closed.is_set():
                 try:
                     method, args, kwargs = from_wire(pickle.loads(conn.recv_bytes()))
-                except (EOFError, OSError, ConnectionError):
-                    return
+                except (EOFError, OSError, ConnectionError, TypeError, ValueError):
+                    return               # peer gone, or this server closed the connection under the blocked read
                 _current.conn = conn
                 try:
                     fn = getattr(self._service, "rpc_" + method)
