@@ -339,6 +339,10 @@ class Session:
                 srv = self._server(task)
                 if srv is not None:
                     out = srv.run_segment_local(run_id, nodes, inputs, want, opts)
+                    # a value leaving its task is a COPY (TF's Send/Recv; what the RPC path does by serialising):
+                    # without it a variable read would alias the ps's storage and a concurrent apply (the chief's
+                    # aggregation thread, another worker) could modify it between this step's forward and backward
+                    out = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
                 else:
                     sent = self._sent.get(task, 0)
                     all_nodes = self.graph.nodes
