@@ -179,5 +179,5 @@ def test_supervisor_style_mnist_job(tmp_path, sync):
     assert out.count("Session initialization complete.") == 2
     import re                                                     # two unbuffered workers share one pipe: lines may interleave
     vals = [float(v) for v in re.findall(r"validation cross entropy = ([0-9][0-9.eE+-]*)", out)]
-    assert len(vals) == 2 and max(vals) < 2000.0                # 5000 validation images, batch-sum loss: ~11500 untrained
+    assert len(vals) == 2 and max(vals) < 5000.0                # 5000 validation images, batch-sum loss: ~11500 untrained
     assert (tmp_path / "sv" / "checkpoint").exists()

@@ -156,4 +156,4 @@ def test_tf_style_supervisor_program_through_the_shim(tmp_path, sync):
         out = open(tmp_path / ("w%d.log" % i)).read()
         assert "Session initialization complete." in out
         val = float(re.findall(r"validation cross entropy = ([0-9][0-9.eE+-]*)", out)[-1])
-        assert val < 2000.0                                         # ~11500 for the untrained model (5000 images, batch sum)
+        assert val < 5000.0                                         # ~11500 for the untrained model (5000 images, batch sum)
