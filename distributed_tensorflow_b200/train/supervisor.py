@@ -53,6 +53,7 @@ class Supervisor:
         self._coord = Coordinator()
         self._session_manager = session_manager
         self._threads: List[threading.Thread] = []
+        self._queue_runners: List[QueueRunner] = []
         self._sess = None
 
     # -- properties TF programs read --------------------------------------------------------------------------
@@ -134,6 +135,7 @@ class Supervisor:
         threads: List[threading.Thread] = []
         for qr in (queue_runners or []):
             threads += qr.create_threads(sess, coord=self._coord, daemon=True, start=True)
+            self._queue_runners.append(qr)
         self._threads += threads
         return threads
 
@@ -161,6 +163,15 @@ class Supervisor:
         self._coord.request_stop()
         sess = self._sess
         if sess is not None:
+            # close the queues this supervisor's runners feed while the session is still usable (their close-on-stop
+            # thread races with the session teardown below): consumers on other tasks then drain what is left and end
+            # with OutOfRangeError instead of waiting for tokens nobody produces any more
+            for qr in self._queue_runners:
+                if qr.close_op is not None:
+                    try:
+                        sess.run(qr.close_op)
+                    except Exception:     # noqa: BLE001
+                        pass
             try:
                 sess.cancel()         # unblock take_grad / token dequeues of this session's queue runners
             except Exception:         # noqa: BLE001

@@ -57,7 +57,11 @@ def main():
         sess.run(opt.get_init_tokens_op())                         # lets the first step through
         sv.start_queue_runners(sess, [opt.get_chief_queue_runner()])
     t0, local_step, step = time.time(), 0, 0
-    while not sv.should_stop() and step < FLAGS.train_steps:
+    # sync mode: replicas can be a step apart, so only the chief decides when training ends -- the others keep feeding
+    # gradients until its sv.stop() closes the token queue (OutOfRangeError below); stopping them on their own view of
+    # global_step could leave the chief waiting for a gradient nobody sends
+    follower = FLAGS.sync_replicas and not chief
+    while not sv.should_stop() and (follower or step < FLAGS.train_steps):
         xs, ys = data.train.next_batch(FLAGS.batch_size)
         try:
             _, step = sess.run([train_op, net["global_step"]], feed_dict={net["x"]: xs, net["y_"]: ys})

@@ -435,8 +435,15 @@ def test_supervisor_driven_ps_training(cluster3, tmp_path, sync):
                     sess.run(opt.get_init_tokens_op())
                     sv.start_queue_runners(sess, [opt.get_chief_queue_runner()])
                 step = 0
-                while not sv.should_stop() and step < 150:
-                    _, step = sess.run([train_op, gs], feed_dict={x: xs, y: ys})
+                # sync mode: the replicas may be a step apart (the init tokens let one run ahead), so only the chief
+                # decides when training ends; its sv.stop() closes the token queue and the other worker's blocked
+                # train_op ends with OutOfRangeError -- the clean end-of-training signal, as in TF
+                while not sv.should_stop() and (step < 150 or (sync and not chief)):
+                    try:
+                        _, step = sess.run([train_op, gs], feed_dict={x: xs, y: ys})
+                    except dtf.errors.OutOfRangeError:
+                        assert sync and not chief
+                        break
                 results[task] = (int(step), sess.run([w, b]))
                 sv.stop()
         except BaseException as e:  # noqa: BLE001
