@@ -37,7 +37,35 @@ from ..ops import cuda_lib
 from ..ops.cuda_lib import MAX_WORKERS, GemmArgs, MlpHeadArgs, PsApplyArgs, round_up
 from .fabric import Fabric, FabricBuffer, view_tensor
 
-__all__ = ["MLPSpec", "EngineConfig", "PSTrainEngine", "smoke_step", "VarLayout"]
+__all__ = ["MLPSpec", "EngineConfig", "PSTrainEngine", "PendingLoss", "smoke_step", "VarLayout"]
+
+
+class PendingLoss:
+    """The loss of a step whose device->host copy may still be in flight (``step(..., sync_loss="deferred")``).
+
+    ``result()`` waits for THAT step's copy only (an event recorded right behind it on the compute stream) and
+    returns the batch-sum loss; the host is free to enqueue the next step first, so the GPU never idles while
+    Python comes back around the loop.  The equivalent in the reference's world is fetching ``loss`` one ``run``
+    late; every step's loss is still read back (4 * head_ctas bytes) exactly once."""
+    __slots__ = ("_event", "_host", "_n", "_value")
+
+    def __init__(self, event, host, n: int, value: Optional[float] = None):
+        self._event, self._host, self._n, self._value = event, host, int(n), value
+
+    def done(self) -> bool:
+        return self._value is not None or bool(self._event.query())
+
+    def result(self) -> float:
+        if self._value is None:
+            self._event.synchronize()
+            self._value = float(self._host[:self._n].sum())
+            self._event = self._host = None
+        return self._value
+
+    __float__ = result
+
+    def __repr__(self) -> str:
+        return "PendingLoss(%s)" % ("%g" % self._value if self._value is not None else "in flight")
 
 
 @dataclass
@@ -606,7 +634,7 @@ class PSTrainEngine:
                                     OP_WAIT_TOKEN, StepOp, StepPlan)
         OP_EVENT_RECORD, OP_EVENT_WAIT = 11, 12
         B, D, C = self.spec.batch, self.spec.in_dim, self.spec.classes
-        plans: Dict[str, Any] = {"copy": {}, "compute": {}, "ps": {}, "loss": {}, "keep": []}
+        plans: Dict[str, Any] = {"copy": {}, "compute": {}, "ps": {}, "loss": {}, "loss_async": {}, "pending": {}, "keep": []}
         for r, rk in self.ranks.items():
             st = rk.stream.cuda_stream
             if r in self.worker_ranks:
@@ -676,6 +704,28 @@ class PSTrainEngine:
         self._native_plans = plans
         return plans
 
+    def _loss_async_plans(self, r: int):
+        """Deferred read-back of worker ``r``'s loss (built on first use): one pinned landing buffer + event per parity;
+        the plan copies the head's loss partials D2H right behind the step's kernels and records the event behind the
+        copy -- ``PendingLoss.result()`` waits on that event only."""
+        plans = self._native_plans
+        got = plans["loss_async"].get(r)
+        if got is None:
+            from ..ops.cuda_lib import OP_D2H, StepOp, StepPlan
+            OP_EVENT_RECORD = 11
+            rk, d = self.ranks[r], self._w[r]
+            got = []
+            for _ in range(2):
+                hostp = torch.zeros(16, dtype=torch.float32).pin_memory()
+                with torch.cuda.device(rk.device):
+                    lev = torch.cuda.Event()
+                    lev.record(rk.stream)        # materialises the cudaEvent_t
+                lpl = StepPlan([StepOp(kind=OP_D2H, p0=hostp.data_ptr(), p1=d["loss_ptr"], i0=self.head_ctas * 4),
+                                StepOp(kind=OP_EVENT_RECORD, p0=lev.cuda_event)], rk.device.index, rk.stream.cuda_stream)
+                got.append((lpl, hostp.numpy(), hostp, lev))
+            plans["loss_async"][r] = got
+        return got
+
     def _graph_plans(self) -> None:
         """After both buffer sets have run eagerly once: every kernel run of every compute / ps plan becomes ONE
         CUDA-graph launch, so a step costs the host two memcpy enqueues + a staging launch (copy stream) and one
@@ -712,10 +762,12 @@ class PSTrainEngine:
             pl.ops[2].p1 = yp + (i * ys if split else 0)
             pl.run()
 
-    def step(self, x=None, y=None, sync_loss: bool = True, source: str = "dataset", prefetch=None) -> Optional[float]:
+    def step(self, x=None, y=None, sync_loss=True, source: str = "dataset", prefetch=None):
         """One training step for every LOCAL rank.  Workers: (optional staging of the host batch) +
         3 kernels; ps shards: one ps_apply per aggregate (sync) or per worker push (async).
-        Returns the local worker's loss when ``sync_loss`` (a device->host read).
+        Returns the local worker's loss when ``sync_loss`` (a device->host read).  ``sync_loss="deferred"`` returns a
+        :class:`PendingLoss` instead: the read-back is enqueued behind the step's kernels and ``.result()`` waits for
+        it later -- call ``step`` for batch t+1 first and the host's turnaround overlaps step t on the GPU.
 
         ``x``/``y``: one batch ``[B, in_dim]`` / ``[B, classes]`` (every local worker trains on it) or, with several
         local workers (in-graph replication), ``[W_local * B, ...]`` split across them in worker order -- the
@@ -744,6 +796,14 @@ class PSTrainEngine:
             plans["runs"] += 1
             if plans["runs"] == 4 and not plans.get("graphed") and os.environ.get("DTF_E2E_GRAPH", "1") == "1":
                 self._graph_plans()
+            if sync_loss == "deferred" and local_workers:
+                lpl, host_np, _, lev = self._loss_async_plans(local_workers[0])[par]
+                old = plans["pending"].get(par)
+                if old is not None:
+                    old.result()              # its landing buffer and event are about to be reused
+                lpl.run()
+                plans["pending"][par] = pending = PendingLoss(lev, host_np, self.head_ctas)
+                return pending
             if sync_loss and local_workers:
                 pl, host_np, _ = plans["loss"][local_workers[0]]
                 pl.run()
@@ -761,6 +821,8 @@ class PSTrainEngine:
             if r in self.ranks:
                 for _ in range(1 if cfg.sync else cfg.num_workers):
                     self.enqueue_ps_apply(r)
+        if sync_loss == "deferred":
+            return PendingLoss(None, None, 0, value=self.read_loss())
         if sync_loss:
             return self.read_loss()
         return None

@@ -113,3 +113,63 @@ def test_native_step_plan_layout_and_host_ops():
     bad = cuda_lib.StepPlan([cuda_lib.StepOp(kind=99)], -1, None)
     with pytest.raises(RuntimeError, match="op 0"):
         bad.run()
+
+
+def test_deferred_loss_step_ordering_with_fake_plans():
+    """``step(..., sync_loss="deferred")`` host logic without a GPU: plans are replaced by recorders.  Per step: the copy
+    plan of this parity (unless prefetched), the compute plan, the prefetch copy of the other parity, then the loss
+    read-back plan of this parity; a handle that was never read is resolved before its landing buffer is reused."""
+    import numpy as np
+    from types import SimpleNamespace
+    from distributed_tensorflow_b200.parallel.ps_engine import PendingLoss, PSTrainEngine
+
+    log = []
+
+    class Plan:
+        def __init__(self, name):
+            self.name, self.ops = name, [SimpleNamespace(p1=None) for _ in range(3)]
+
+        def run(self):
+            log.append(self.name)
+
+    class Event:
+        def __init__(self, name):
+            self.name, self.syncs = name, 0
+
+        def query(self):
+            return False
+
+        def synchronize(self):
+            self.syncs += 1
+            log.append("sync:" + self.name)
+
+    eng = PSTrainEngine.__new__(PSTrainEngine)
+    eng.cfg = SimpleNamespace(sync=True, num_workers=1, colocated=True)
+    eng.spec = SimpleNamespace(batch=4, in_dim=8, classes=2)
+    eng.worker_ranks, eng.ps_ranks, eng.head_ctas = [0], [0], 2
+    eng.ranks = {0: SimpleNamespace(step=0)}
+    eng._is_pinned_f32 = lambda t: True
+    hosts = [np.array([1.0, 2.0, 50.0], dtype=np.float32), np.array([10.0, 20.0, 50.0], dtype=np.float32)]
+    events = [Event("l0"), Event("l1")]
+    eng._native_plans = {"copy": {0: [Plan("copy0"), Plan("copy1")]}, "compute": {0: [Plan("compute0"), Plan("compute1")]},
+                         "ps": {}, "loss": {}, "pending": {}, "keep": [], "runs": 10, "parity": 0, "prefetched": None, "graphed": True,
+                         "loss_async": {0: [(Plan("loss0"), hosts[0], None, events[0]), (Plan("loss1"), hosts[1], None, events[1])]}}
+    import torch
+    xs = [torch.zeros(4, 8) + i for i in range(4)]
+    ys = [torch.zeros(4, 2) for _ in range(4)]
+    h0 = eng.step(xs[0], ys[0], sync_loss="deferred", prefetch=(xs[1], ys[1]))
+    assert isinstance(h0, PendingLoss) and not h0.done()
+    assert log == ["copy0", "compute0", "copy1", "loss0"]
+    h1 = eng.step(xs[1], ys[1], sync_loss="deferred", prefetch=(xs[2], ys[2]))          # batch 1 was prefetched: no second copy
+    assert log[4:] == ["compute1", "copy0", "loss1"]
+    assert h0.result() == 3.0 and log[-1] == "sync:l0" and float(h0) == 3.0 and events[0].syncs == 1
+    del log[:]
+    h2 = eng.step(xs[2], ys[2], sync_loss="deferred")                                    # parity 0 again; h0 already read
+    assert log == ["compute0", "loss0"]
+    del log[:]
+    hosts[1][:2] = [7.0, 8.0]
+    h3 = eng.step(xs[3], ys[3], sync_loss="deferred")          # parity 1: h1 was never read -> resolved before reuse
+    assert log == ["copy1", "compute1", "sync:l1", "loss1"]
+    assert h1.result() == 15.0 and h1.done()
+    assert h2.result() == 3.0 and h3.result() == 15.0
+    assert eng.ranks[0].step == 4
