@@ -1,0 +1,249 @@
+// Fused training-mode batch normalisation for NHWC activations (the BN / ReLU / residual glue between the
+// convolutions of ResNet-18).  The activation tensor is viewed as fp32 [rows, C] with rows = N*H*W, C % 4 == 0.
+//
+//   forward   bn_reduce<0>  : per-channel sum(x), sum(x^2) -> mean, rstd          (one pass over x)
+//             bn_apply      : y = relu?( (x - mean) * rstd * scale + offset (+ residual) )   (one pass, float4)
+//   backward  bn_reduce<1>  : g = dy * [y > 0]?;  doffset = sum(g), dscale = sum(g * xhat)   (one pass over dy, x, y)
+//             bn_bwd_apply  : dx = scale * rstd * (g - doffset/rows - xhat * dscale/rows);  dresidual = g
+//
+// i.e. 2 launches forward + 2 backward per BN layer instead of ~25 element-wise / reduction launches of the eager
+// formulation, and x is read twice + written once instead of ~10 round trips through HBM.
+//
+// Reduction layout: block (32, 8) -- x-threads own one float4 channel group each (a warp reads 512 contiguous bytes of a
+// row), y-threads stride over rows; grid (ceil(C/128), G).  Every block writes its partial sums to a workspace
+// [G][2][C]; the LAST block to finish a channel column (ticket counter, threadfence pattern) folds the G partials in
+// double precision and writes the per-channel results, then resets the ticket so the kernel is CUDA-graph replayable.
+// Deterministic: no floating-point atomics.
+//
+// STATUS: written at the end of round 1 after the GPU budget was spent.  Compiled (ptxas: no spills), formulas checked
+// on CPU against autograd (tests/test_nn_fused_reference.py); first hardware run is tests/test_gpu_nn_fused.py.
+// Off by default (DTF_FUSED_BN=1 turns it on in ops/native.py).
+#include <cstdint>
+
+// DTF_HOST_EMU: the same source compiled by g++ against tests/emu/host_emu.h (threads + barriers stand in for a thread
+// block, blocks run one after another) so that indexing / reduction / ticket logic is checked on machines without a GPU.
+#ifdef DTF_HOST_EMU
+#include "host_emu.h"
+#define DTF_LAUNCH(kernel, grid, block, stream, ...) dtf_emu::launch((grid), (block), [&]() { kernel(__VA_ARGS__); })
+#else
+#include "common.cuh"
+#define DTF_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+
+namespace dtf {
+
+constexpr int kBnTX = 32;          // float4 channel groups per block (128 channels)
+constexpr int kBnTY = 8;           // row lanes per block
+constexpr int kBnCh = kBnTX * 4;   // channels per block column
+
+// MODE 0: a = x,              s1 += a,  s2 += a * a
+// MODE 1: g = dy * mask(y),   s1 += g,  s2 += g * (x - mean) * rstd
+template <int MODE>
+__global__ void __launch_bounds__(kBnTX* kBnTY)
+bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y_mask,
+                 const float* __restrict__ mean, const float* __restrict__ rstd, long long rows, int C,
+                 float* __restrict__ partial, unsigned int* __restrict__ tickets, float* __restrict__ r1,
+                 float* __restrict__ r2, float eps) {
+  __shared__ float sm[2][kBnTY][kBnCh];
+  __shared__ double smd[2][kBnCh];
+  __shared__ int is_last;
+  const int tx = threadIdx.x, ty = threadIdx.y, t = ty * kBnTX + tx;
+  const int cbase = blockIdx.x * kBnCh;
+  const int c = cbase + tx * 4;
+  const bool live = c < C;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (live) {
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f), rs = m;
+    if (MODE == 1) {
+      m = *reinterpret_cast<const float4*>(mean + c);
+      rs = *reinterpret_cast<const float4*>(rstd + c);
+    }
+    for (long long r = (long long)blockIdx.y * kBnTY + ty; r < rows; r += (long long)gridDim.y * kBnTY) {
+      const long long off = r * C + c;
+      const float4 v = *reinterpret_cast<const float4*>(x + off);
+      if (MODE == 0) {
+        s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+        s2[0] += v.x * v.x; s2[1] += v.y * v.y; s2[2] += v.z * v.z; s2[3] += v.w * v.w;
+      } else {
+        float4 g = *reinterpret_cast<const float4*>(dy + off);
+        if (y_mask != nullptr) {
+          const float4 o = *reinterpret_cast<const float4*>(y_mask + off);
+          g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
+          g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+        }
+        s1[0] += g.x; s1[1] += g.y; s1[2] += g.z; s1[3] += g.w;
+        s2[0] += g.x * (v.x - m.x) * rs.x; s2[1] += g.y * (v.y - m.y) * rs.y;
+        s2[2] += g.z * (v.z - m.z) * rs.z; s2[3] += g.w * (v.w - m.w) * rs.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sm[0][ty][tx * 4 + j] = s1[j];
+    sm[1][ty][tx * 4 + j] = s2[j];
+  }
+  __syncthreads();
+  // 256 threads = 2 quantities x 128 channels: fold the 8 row lanes, publish this block's partial
+  const int q = t / kBnCh, ch = t % kBnCh;
+  {
+    float acc = 0.f;
+#pragma unroll
+    for (int yy = 0; yy < kBnTY; ++yy) acc += sm[q][yy][ch];
+    if (cbase + ch < C) partial[((long long)blockIdx.y * 2 + q) * C + cbase + ch] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    const unsigned int ticket = atomicAdd(&tickets[blockIdx.x], 1u);
+    is_last = (ticket == gridDim.y - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  {
+    double acc = 0.0;
+    if (cbase + ch < C)
+      for (unsigned int g = 0; g < gridDim.y; ++g) acc += (double)__ldcg(partial + ((long long)g * 2 + q) * C + cbase + ch);
+    smd[q][ch] = acc;
+  }
+  __syncthreads();
+  if (q == 0 && cbase + ch < C) {
+    const double S1 = smd[0][ch], S2 = smd[1][ch];
+    if (MODE == 0) {
+      const double mu = S1 / (double)rows;
+      double var = S2 / (double)rows - mu * mu;
+      if (var < 0.0) var = 0.0;
+      r1[cbase + ch] = (float)mu;
+      r2[cbase + ch] = (float)(1.0 / sqrt(var + (double)eps));
+    } else {
+      r1[cbase + ch] = (float)S1;      // d offset
+      r2[cbase + ch] = (float)S2;      // d scale
+    }
+  }
+  if (t == 0) tickets[blockIdx.x] = 0u;     // replayable: the next launch starts from a clean ticket
+}
+
+__global__ void bn_apply_kernel(const float4* __restrict__ x, const float4* __restrict__ res, float4* __restrict__ y,
+                                const float4* __restrict__ mean, const float4* __restrict__ rstd,
+                                const float4* __restrict__ scale, const float4* __restrict__ offset, long long n4, int c4n,
+                                int relu) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % c4n);
+    const float4 m = __ldg(mean + c4), rs = __ldg(rstd + c4), sc = __ldg(scale + c4), of = __ldg(offset + c4);
+    const float4 v = x[i];
+    float4 o;
+    o.x = (v.x - m.x) * rs.x * sc.x + of.x;
+    o.y = (v.y - m.y) * rs.y * sc.y + of.y;
+    o.z = (v.z - m.z) * rs.z * sc.z + of.z;
+    o.w = (v.w - m.w) * rs.w * sc.w + of.w;
+    if (res != nullptr) {
+      const float4 r = res[i];
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    if (relu) {
+      o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+    }
+    y[i] = o;
+  }
+}
+
+__global__ void bn_bwd_apply_kernel(const float4* __restrict__ dy, const float4* __restrict__ y_mask,
+                                    const float4* __restrict__ x, const float4* __restrict__ mean,
+                                    const float4* __restrict__ rstd, const float4* __restrict__ scale,
+                                    const float4* __restrict__ doffset, const float4* __restrict__ dscale,
+                                    float4* __restrict__ dx, float4* __restrict__ dres, long long n4, int c4n,
+                                    float inv_rows) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % c4n);
+    const float4 m = __ldg(mean + c4), rs = __ldg(rstd + c4), sc = __ldg(scale + c4);
+    const float4 s1 = __ldg(doffset + c4), s2 = __ldg(dscale + c4);
+    float4 g = dy[i];
+    if (y_mask != nullptr) {
+      const float4 o = y_mask[i];
+      g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
+      g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+    }
+    const float4 v = x[i];
+    float4 d;
+    d.x = sc.x * rs.x * (g.x - s1.x * inv_rows - (v.x - m.x) * rs.x * s2.x * inv_rows);
+    d.y = sc.y * rs.y * (g.y - s1.y * inv_rows - (v.y - m.y) * rs.y * s2.y * inv_rows);
+    d.z = sc.z * rs.z * (g.z - s1.z * inv_rows - (v.z - m.z) * rs.z * s2.z * inv_rows);
+    d.w = sc.w * rs.w * (g.w - s1.w * inv_rows - (v.w - m.w) * rs.w * s2.w * inv_rows);
+    dx[i] = d;
+    if (dres != nullptr) dres[i] = g;
+  }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static inline int bn_grid_for(long long n, int block = 256) {
+  long long g = (n + block - 1) / block;
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace dtf
+
+extern "C" {
+using namespace dtf;
+
+// Row-split factor G the launchers use for [rows, C]: enough blocks to fill 148 SMs a few times over, at least 64 rows
+// per block.  The workspace must hold dtf_bn_workspace_floats(rows, C) floats, tickets ceil(C/128) zeroed uint32.
+int dtf_bn_row_splits(long long rows, int C) {
+  const int gx = (C + kBnCh - 1) / kBnCh;
+  long long g = (148 * 4 + gx - 1) / gx;
+  const long long by_rows = (rows + 63) / 64;
+  if (g > by_rows) g = by_rows;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+long long dtf_bn_workspace_floats(long long rows, int C) { return (long long)dtf_bn_row_splits(rows, C) * 2 * C; }
+
+// mode 0: (x) -> r1 = mean, r2 = rstd.   mode 1: (x, dy, y_mask?, mean, rstd) -> r1 = doffset, r2 = dscale.
+int dtf_bn_reduce(int mode, const float* x, const float* dy, const float* y_mask, const float* mean, const float* rstd,
+                  long long rows, int C, float* workspace, unsigned int* tickets, float* r1, float* r2, float eps,
+                  cudaStream_t s) {
+  if (C % 4 != 0 || rows <= 0 || !aligned16(x) || (mode == 1 && (!aligned16(dy) || !aligned16(mean) || !aligned16(rstd))) ||
+      (y_mask != nullptr && !aligned16(y_mask)))
+    return -1;
+  dim3 block(kBnTX, kBnTY), grid((C + kBnCh - 1) / kBnCh, dtf_bn_row_splits(rows, C));
+  const float* none = nullptr;
+  if (mode == 0)
+    DTF_LAUNCH(bn_reduce_kernel<0>, grid, block, s, x, none, none, none, none, rows, C, workspace, tickets, r1, r2, eps);
+  else
+    DTF_LAUNCH(bn_reduce_kernel<1>, grid, block, s, x, dy, y_mask, mean, rstd, rows, C, workspace, tickets, r1, r2, eps);
+  return (int)cudaGetLastError();
+}
+
+int dtf_bn_apply(const float* x, const float* residual, float* y, const float* mean, const float* rstd, const float* scale,
+                 const float* offset, long long rows, int C, int relu, cudaStream_t s) {
+  if (C % 4 != 0 || !aligned16(x) || !aligned16(y) || !aligned16(mean) || !aligned16(rstd) || !aligned16(scale) ||
+      !aligned16(offset) || (residual != nullptr && !aligned16(residual)))
+    return -1;
+  const long long n4 = rows * C / 4;
+  DTF_LAUNCH(bn_apply_kernel, bn_grid_for(n4), 256, s, reinterpret_cast<const float4*>(x),
+             reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(mean),
+             reinterpret_cast<const float4*>(rstd), reinterpret_cast<const float4*>(scale),
+             reinterpret_cast<const float4*>(offset), n4, C / 4, relu);
+  return (int)cudaGetLastError();
+}
+
+int dtf_bn_bwd_apply(const float* dy, const float* y_mask, const float* x, const float* mean, const float* rstd,
+                     const float* scale, const float* doffset, const float* dscale, float* dx, float* dres, long long rows,
+                     int C, cudaStream_t s) {
+  if (C % 4 != 0 || !aligned16(dy) || !aligned16(x) || !aligned16(dx) || !aligned16(mean) || !aligned16(rstd) ||
+      !aligned16(scale) || !aligned16(doffset) || !aligned16(dscale) || (y_mask != nullptr && !aligned16(y_mask)) ||
+      (dres != nullptr && !aligned16(dres)))
+    return -1;
+  const long long n4 = rows * C / 4;
+  DTF_LAUNCH(bn_bwd_apply_kernel, bn_grid_for(n4), 256, s, reinterpret_cast<const float4*>(dy),
+             reinterpret_cast<const float4*>(y_mask), reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(mean),
+             reinterpret_cast<const float4*>(rstd), reinterpret_cast<const float4*>(scale),
+             reinterpret_cast<const float4*>(doffset), reinterpret_cast<const float4*>(dscale), reinterpret_cast<float4*>(dx),
+             reinterpret_cast<float4*>(dres), n4, C / 4, 1.0f / (float)rows);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -3,7 +3,8 @@
 NHWC activations, HWIO filters (channels-last is the tensor-core layout).  Every convolution and the final
 dense layer lower to the tcgen05 GEMM through ``ops.native`` (im2col gather kernel + ``gemm_bf16_tcgen05``;
 backward = two more GEMMs + col2im), the loss is the fused softmax-cross-entropy kernel; batch-norm
-(training mode, batch statistics), ReLU and pooling are element-wise glue.  On CPU the same functions run
+(training mode, batch statistics) + residual add + ReLU go through ``native.batch_norm_train`` (fused kernels
+of ``csrc/nn_kernels.cu`` behind ``DTF_FUSED_BN=1``, element-wise PyTorch glue otherwise); pooling is glue.  On CPU the same functions run
 plain PyTorch, which is the oracle in the tests.
 
 ``resnet18_param_shapes(num_classes, stem)`` lists the variables in creation order (what the ps shards
@@ -58,12 +59,10 @@ def resnet18_init(num_classes: int = 10, stem: str = "cifar", seed: int = 0, in_
     return out
 
 
-def _bn(x: torch.Tensor, scale: torch.Tensor, offset: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
-    dims = (0, 1, 2)
-    xf = x.float()
-    mean = xf.mean(dim=dims, keepdim=True)
-    var = (xf - mean).pow(2).mean(dim=dims, keepdim=True)
-    return (xf - mean) * torch.rsqrt(var + eps) * scale + offset
+def _bn(x: torch.Tensor, scale: torch.Tensor, offset: torch.Tensor, residual=None, relu: bool = False) -> torch.Tensor:
+    """Training-mode BN (+ residual add + ReLU): ``native.batch_norm_train`` -- the fused kernels of
+    ``csrc/nn_kernels.cu`` when enabled (``DTF_FUSED_BN=1``), the plain PyTorch formulation otherwise."""
+    return native.batch_norm_train(x, scale, offset, residual=residual, relu=relu)
 
 
 def resnet18_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, stem: str = "cifar") -> torch.Tensor:
@@ -72,7 +71,7 @@ def resnet18_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, stem: str = "c
         h = native.conv2d_nhwc(x, p["stem/conv"], (1, 1, 1, 1), "SAME")
     else:
         h = native.conv2d_nhwc(x, p["stem/conv"], (1, 2, 2, 1), "SAME")
-    h = torch.relu(_bn(h, p["stem/bn_scale"], p["stem/bn_offset"]))
+    h = _bn(h, p["stem/bn_scale"], p["stem/bn_offset"], relu=True)
     if stem != "cifar":
         h = F.max_pool2d(h.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
     cin = 64
@@ -81,15 +80,14 @@ def resnet18_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, stem: str = "c
             pre = "stage%d/block%d" % (si, bi)
             s = stride if bi == 0 else 1
             y = native.conv2d_nhwc(h, p[pre + "/conv1"], (1, s, s, 1), "SAME")
-            y = torch.relu(_bn(y, p[pre + "/bn1_scale"], p[pre + "/bn1_offset"]))
+            y = _bn(y, p[pre + "/bn1_scale"], p[pre + "/bn1_offset"], relu=True)
             y = native.conv2d_nhwc(y, p[pre + "/conv2"], (1, 1, 1, 1), "SAME")
-            y = _bn(y, p[pre + "/bn2_scale"], p[pre + "/bn2_offset"])
             if (pre + "/down_conv") in p:
                 sc = native.conv2d_nhwc(h, p[pre + "/down_conv"], (1, s, s, 1), "SAME")
                 sc = _bn(sc, p[pre + "/down_bn_scale"], p[pre + "/down_bn_offset"])
             else:
                 sc = h
-            h = torch.relu(y + sc)
+            h = _bn(y, p[pre + "/bn2_scale"], p[pre + "/bn2_offset"], residual=sc, relu=True)      # relu(bn(y) + shortcut)
             cin = c
     pooled = h.mean(dim=(1, 2))
     return native.linear(pooled.contiguous(), p["fc/w"], p["fc/b"])

@@ -209,6 +209,17 @@ def load() -> ctypes.CDLL:
         lib.dtf_graph_destroy.restype = c_int
         lib.dtf_sizeof_step_op.restype = c_int
         assert lib.dtf_sizeof_step_op() == ctypes.sizeof(StepOp), "StepOp layout mismatch"
+        if hasattr(lib, "dtf_bn_reduce"):                  # csrc/nn_kernels.cu (fused batch norm)
+            lib.dtf_bn_row_splits.argtypes = [c_longlong, c_int]
+            lib.dtf_bn_row_splits.restype = c_int
+            lib.dtf_bn_workspace_floats.argtypes = [c_longlong, c_int]
+            lib.dtf_bn_workspace_floats.restype = c_longlong
+            lib.dtf_bn_reduce.argtypes = [c_int] + [c_void_p] * 5 + [c_longlong, c_int] + [c_void_p] * 4 + [c_float, c_void_p]
+            lib.dtf_bn_reduce.restype = c_int
+            lib.dtf_bn_apply.argtypes = [c_void_p] * 7 + [c_longlong, c_int, c_int, c_void_p]
+            lib.dtf_bn_apply.restype = c_int
+            lib.dtf_bn_bwd_apply.argtypes = [c_void_p] * 10 + [c_longlong, c_int, c_void_p]
+            lib.dtf_bn_bwd_apply.restype = c_int
         _LIB = lib
         return lib
 
@@ -456,3 +467,73 @@ def col2im_nhwc(gcols: torch.Tensor, xshape, kh: int, kw: int, strides, pads) ->
                                       ho, wo, _stream(gcols)), "col2im_nhwc")
     _bump()
     return gx
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused training-mode batch norm over [rows, C] fp32 (csrc/nn_kernels.cu); all launches on the current stream
+# ---------------------------------------------------------------------------------------------------
+_BN_WS: dict = {}
+
+
+def _bn_workspace(dev: torch.device, floats: int):
+    """Per-device scratch: partial sums (grown on demand) + the ticket counters (zeroed once; the kernel resets them).
+    One workspace per device = calls must be stream-ordered, which they are (everything runs on the current stream)."""
+    ws = _BN_WS.get(dev)
+    if ws is None or ws[0].numel() < floats:
+        tickets = ws[1] if ws is not None else torch.zeros(64, dtype=torch.int32, device=dev)
+        ws = _BN_WS[dev] = (torch.empty(max(floats, 1 << 16), dtype=torch.float32, device=dev), tickets)
+    return ws
+
+
+def _aligned16(t: torch.Tensor) -> torch.Tensor:
+    """Views into flat parameter buffers can start at any element: the float4 kernels need 16-byte alignment."""
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
+def bn_forward(x2d: torch.Tensor, scale: torch.Tensor, offset: torch.Tensor, residual: Optional[torch.Tensor], relu: bool,
+               eps: float):
+    """x2d: [rows, C] fp32 contiguous, C % 4 == 0, C <= 8192 -> (y, mean, rstd)."""
+    lib = load()
+    rows, C = x2d.shape
+    assert x2d.dtype == torch.float32 and x2d.is_contiguous() and C % 4 == 0 and C <= 64 * 128
+    dev = x2d.device
+    mean = torch.empty(C, dtype=torch.float32, device=dev)
+    rstd = torch.empty(C, dtype=torch.float32, device=dev)
+    y = torch.empty_like(x2d)
+    scale, offset = _aligned16(scale.float().contiguous()), _aligned16(offset.float().contiguous())
+    if residual is not None:
+        residual = _aligned16(residual.float().contiguous())
+    with torch.cuda.device(dev):
+        ws, tickets = _bn_workspace(dev, int(lib.dtf_bn_workspace_floats(rows, C)))
+        st = _stream(x2d)
+        _check(lib.dtf_bn_reduce(0, x2d.data_ptr(), None, None, None, None, rows, C, ws.data_ptr(), tickets.data_ptr(),
+                                 mean.data_ptr(), rstd.data_ptr(), float(eps), st), "bn_reduce(stats)")
+        _check(lib.dtf_bn_apply(x2d.data_ptr(), _ptr(residual), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                scale.data_ptr(), offset.data_ptr(), rows, C, int(relu), st), "bn_apply")
+    _bump(2)
+    return y, mean, rstd
+
+
+def bn_backward(dy: torch.Tensor, y_mask: Optional[torch.Tensor], x2d: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor,
+                scale: torch.Tensor, want_dres: bool):
+    """-> (dx, dscale, doffset, dres or None).  ``y_mask``: the forward output when ReLU was fused (gradient gate)."""
+    lib = load()
+    rows, C = x2d.shape
+    dev = x2d.device
+    dy = _aligned16(dy.float().contiguous())
+    scale = _aligned16(scale.float().contiguous())
+    doffset = torch.empty(C, dtype=torch.float32, device=dev)
+    dscale = torch.empty(C, dtype=torch.float32, device=dev)
+    dx = torch.empty_like(x2d)
+    dres = torch.empty_like(x2d) if want_dres else None
+    with torch.cuda.device(dev):
+        ws, tickets = _bn_workspace(dev, int(lib.dtf_bn_workspace_floats(rows, C)))
+        st = _stream(x2d)
+        _check(lib.dtf_bn_reduce(1, x2d.data_ptr(), dy.data_ptr(), _ptr(y_mask), mean.data_ptr(), rstd.data_ptr(), rows, C,
+                                 ws.data_ptr(), tickets.data_ptr(), doffset.data_ptr(), dscale.data_ptr(), 0.0, st),
+               "bn_reduce(backward)")
+        _check(lib.dtf_bn_bwd_apply(dy.data_ptr(), _ptr(y_mask), x2d.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                    scale.data_ptr(), doffset.data_ptr(), dscale.data_ptr(), dx.data_ptr(), _ptr(dres),
+                                    rows, C, st), "bn_bwd_apply")
+    _bump(2)
+    return dx, dscale, doffset, dres

@@ -151,6 +151,71 @@ def softmax_xent(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------
+# batch normalisation (training mode, batch statistics) + residual add + ReLU
+# ---------------------------------------------------------------------------
+_FUSED_BN = os.environ.get("DTF_FUSED_BN", "0") == "1"      # csrc/nn_kernels.cu: first hardware validation pending
+
+
+def bn_train_reference(x, scale, offset, residual=None, relu=False, eps: float = 1e-5):
+    """Plain PyTorch formulation (CPU oracle; CUDA path while DTF_FUSED_BN is off): statistics over every axis but
+    the last, biased variance."""
+    dims = tuple(range(x.dim() - 1))
+    xf = x.float()
+    mean = xf.mean(dim=dims, keepdim=True)
+    var = (xf - mean).pow(2).mean(dim=dims, keepdim=True)
+    y = (xf - mean) * torch.rsqrt(var + eps) * scale + offset
+    if residual is not None:
+        y = y + residual
+    return torch.relu(y) if relu else y
+
+
+def bn_backward_reference(dy, y, x2d, mean, rstd, scale, relu: bool):
+    """The closed form the fused backward kernels implement, in PyTorch (tested against autograd on CPU):
+    g = dy * [y > 0] (when ReLU was fused); doffset = sum g; dscale = sum g * xhat;
+    dx = scale * rstd * (g - doffset / rows - xhat * dscale / rows); dresidual = g."""
+    g = dy * (y > 0) if relu else dy
+    xhat = (x2d - mean) * rstd
+    doffset = g.sum(0)
+    dscale = (g * xhat).sum(0)
+    rows = x2d.shape[0]
+    dx = scale * rstd * (g - doffset / rows - xhat * dscale / rows)
+    return dx, dscale, doffset, g
+
+
+class _FusedBNFn(torch.autograd.Function):
+    """y = relu?(BN_train(x) (+ residual)) as two launches forward (statistics, apply) and two backward (sums, apply)."""
+
+    @staticmethod
+    def forward(ctx, x, scale, offset, residual, relu: bool, eps: float):
+        lib = _lib()
+        shape = x.shape
+        x2 = x.float().contiguous().view(-1, shape[-1])
+        r2 = residual.float().contiguous().view(-1, shape[-1]) if residual is not None else None
+        y, mean, rstd = lib.bn_forward(x2, scale, offset, r2, relu, eps)
+        ctx.save_for_backward(x2, mean, rstd, scale, y if relu else None)
+        ctx.relu, ctx.has_res, ctx.shape = relu, residual is not None, shape
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib()
+        x2, mean, rstd, scale, y = ctx.saved_tensors
+        g2 = g.contiguous().view(-1, ctx.shape[-1])
+        want_res = ctx.has_res and ctx.needs_input_grad[3]
+        dx, dscale, doffset, dres = lib.bn_backward(g2, y if ctx.relu else None, x2, mean, rstd, scale, want_res)
+        return (dx.view(ctx.shape), dscale.view_as(scale), doffset.view_as(scale),
+                dres.view(ctx.shape) if dres is not None else None, None, None)
+
+
+def batch_norm_train(x: torch.Tensor, scale: torch.Tensor, offset: torch.Tensor, residual: Optional[torch.Tensor] = None,
+                     relu: bool = False, eps: float = 1e-5) -> torch.Tensor:
+    """Training-mode batch norm over the last (channel) axis, optionally fused with a residual add and ReLU."""
+    if _use_native(x) and _FUSED_BN and x.shape[-1] % 4 == 0 and scale.dim() == 1:
+        return _FusedBNFn.apply(x, scale, offset, residual, relu, float(eps))
+    return bn_train_reference(x, scale, offset, residual, relu, eps)
+
+
+# ---------------------------------------------------------------------------
 # convolution (NHWC data, HWIO filter)
 # ---------------------------------------------------------------------------
 def _same_pad(size: int, k: int, s: int):
