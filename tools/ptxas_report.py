@@ -8,7 +8,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "distributed_tensorflow_b200", "csrc")
-FILES = ["gemm_tcgen05.cu", "ps_engine.cu", "elementwise.cu", "step_exec.cu", "fabric_vmm.cu"]
+FILES = ["gemm_tcgen05.cu", "ps_engine.cu", "elementwise.cu", "step_exec.cu", "fabric_vmm.cu", "nn_kernels.cu"]
 
 
 def main():
