@@ -561,6 +561,19 @@ def main():
             except Exception as e:      # noqa: BLE001 - keep the validated synchronous measurement
                 e2e["pipelined_error"] = repr(e)[:300]
 
+    # ---- ps traffic implied by the measured step time (BASELINE metric: push/pull GB/s vs 900 GB/s/dir) -----------
+    # true-shape bytes: gradients travel as fp32, parameters as the bf16 replica; every worker moves both every step.
+    n_params = spec.in_dim * spec.hidden + spec.hidden + spec.hidden * spec.classes + spec.classes
+    step_s = ms / K / 1e3
+    push_b, pull_b = 4 * n_params, 2 * n_params
+    traffic = {"params": n_params, "push_bytes_per_worker_step": push_b, "pull_bytes_per_worker_step": pull_b,
+               "ps_ingest_gbps": num_workers * push_b / step_s / 1e9 / max(1, cfg.num_ps),
+               "ps_egress_gbps": num_workers * pull_b / step_s / 1e9 / max(1, cfg.num_ps),
+               "note": "effective rate per ps shard over the whole step (latency-bound at this model size: 0.3 MB per push); "
+                       "link-rate measurements of the same kernels at large payloads: profiles/nvls_check_*.json"}
+    traffic["ps_ingest_fraction_of_900"] = traffic["ps_ingest_gbps"] / 900.0
+    traffic["ps_egress_fraction_of_900"] = traffic["ps_egress_gbps"] / 900.0
+
     if rank == 0:
         out = {
             "metric": "MNIST MLP samples/sec (whole box, device-timed, max over ranks), sync-replica PS",
@@ -582,7 +595,7 @@ def main():
                                 "local store + ps peer loads" if getattr(eng, "nvls", False) else "peer stores fused in GEMM epilogue"),
                        "f1_splits": args.f1_splits, "head_ctas": args.head_ctas, "f1_block_n": args.f1_block_n,
                        "b3_block_n": args.b3_block_n},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total, "ps_traffic": traffic,
             "final_loss": loss, "global_step": gstep, "staleness": stale,
         }
         print(json.dumps(out))
