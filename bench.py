@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="-1: min(steps, 1000); 0: skip")
     ap.add_argument("--e2e-prefetch", type=int, default=1, help="1: step t+1's H2D overlaps step t (double-buffered staging)")
+    ap.add_argument("--ps-on-workers", type=int, default=0,
+                    help="1: N workers on N GPUs, ps shard s shares worker s's GPU and stream (no ps-only GPU); "
+                         "0: ranks 0..num_ps-1 are ps-only tasks (the validated topology)")
     ap.add_argument("--e2e-pipeline", type=int, default=1,
                     help="1 (one-GPU runs): also time step(..., sync_loss='deferred') -- the loss of step t is read after "
                          "step t+1 was enqueued -- and report the better arm, both kept under e2e.synchronous/.pipelined")
@@ -373,13 +376,15 @@ def main():
     if args.lr is None:
         args.lr = 0.01 if args.optimizer == "adam" else 0.001
         if args.mode == "async" and args.optimizer != "adam":
-            args.lr /= max(1, args.gpus - args.num_ps)       # every push is applied alone: keep the effective rate
+            args.lr /= max(1, args.gpus - (0 if args.ps_on_workers else args.num_ps))   # every push is applied alone: keep the effective rate
     opt = {"kind": args.optimizer, "lr": args.lr, "momentum": 0.9}
+    pow_ = bool(args.ps_on_workers) and N > 1
+    nw = N if pow_ else N - args.num_ps
     NVLS = {"off": False, "on": True, "auto": "auto"}[args.nvls]
     if args.in_graph and args.nvls == "auto":
         NVLS = False            # one-process topology: opt in with --nvls on
     if args.in_graph and N > 1:
-        cfg = EngineConfig(num_ps=args.num_ps, num_workers=N - args.num_ps, sync=args.mode == "sync", optimizer=opt,
+        cfg = EngineConfig(num_ps=args.num_ps, num_workers=nw, sync=args.mode == "sync", optimizer=opt, ps_on_workers=pow_,
                            publish_replicas=args.publish, nvls=NVLS, f1_splits=args.f1_splits, head_ctas=args.head_ctas,
                            f1_block_n=args.f1_block_n, b3_block_n=args.b3_block_n)
         fabric = Fabric(N, {r: r for r in range(N)})
@@ -389,7 +394,7 @@ def main():
                            f1_block_n=args.f1_block_n, b3_block_n=args.b3_block_n)
         fabric = Fabric(1, {0: local_rank})
     else:
-        cfg = EngineConfig(num_ps=args.num_ps, num_workers=N - args.num_ps, sync=args.mode == "sync", optimizer=opt,
+        cfg = EngineConfig(num_ps=args.num_ps, num_workers=nw, sync=args.mode == "sync", optimizer=opt, ps_on_workers=pow_,
                            publish_replicas=args.publish, nvls=NVLS, f1_splits=args.f1_splits, head_ctas=args.head_ctas,
                            f1_block_n=args.f1_block_n, b3_block_n=args.b3_block_n)
         fabric = Fabric.from_torch_distributed()
@@ -583,8 +588,9 @@ def main():
             "impl": "ours",
             "config": {"model": "MNIST MLP 784-%d-10, clipped batch-sum xent" % spec.hidden,
                        "global_batch": num_workers * spec.batch, "per_worker_batch": spec.batch,
-                       "parallelism": ("ps1+worker1 colocated on one GPU" if N == 1 else "ps%d+worker%d %s" % (
-                           cfg.num_ps, cfg.num_workers, "in-graph (one client process)" if args.in_graph else "between-graph")),
+                       "parallelism": ("ps1+worker1 colocated on one GPU" if N == 1 else "ps%d+worker%d %s%s" % (
+                           cfg.num_ps, cfg.num_workers, "in-graph (one client process)" if args.in_graph else "between-graph",
+                           ", ps shards on the first workers' GPUs" if cfg.ps_on_workers else "")),
                        "mode": args.mode, "optimizer": args.optimizer, "lr": args.lr,
                        "l2": "inputs larger than L2: 172 MB fp32 train split cycled in HBM",
                        "cuda_graph_unroll": unroll if use_graph else 0,

@@ -86,6 +86,8 @@ class EngineConfig:
     clip_min: float = 1e-10
     publish_replicas: bool = False        # True: ps stores new params into every worker's replica (push-publish)
     colocated: bool = False               # single GPU: ps shard 0 and worker 0 share device + stream
+    ps_on_workers: bool = False           # N GPUs, N workers: ps shard s lives on worker s's GPU and shares its stream (no GPU is
+                                          # spent on a ps-only task; world == num_workers).  First hardware run pending.
     nvls: Any = False                     # True/"auto": symmetric VMM buffers -- gradients stay in the WORKERS' HBM and the
                                           # ps sums them with multimem.ld_reduce (in-switch), parameters are published with
                                           # ONE multimem.st stream into every GPU's replica ("auto": only if the box has NVLS)
@@ -157,6 +159,14 @@ class PSTrainEngine:
         if cfg.colocated:
             assert self.world == 1 and cfg.num_ps == 1 and cfg.num_workers == 1
             self.ps_ranks, self.worker_ranks = [0], [0]
+        elif cfg.ps_on_workers:
+            # every rank is a worker; ranks 0..num_ps-1 additionally host a ps shard.  On such a rank the stream runs
+            # [worker step t][ps_apply t][worker step t+1]...: the apply waits for the OTHER workers' arrivals while this
+            # GPU's own step-t work is already done, and the next step needs the apply's token anyway, so sharing the
+            # stream adds nothing to the critical path.
+            assert self.world == cfg.num_workers and 1 <= cfg.num_ps <= self.world, "ps_on_workers: world = num_workers >= num_ps"
+            self.ps_ranks = list(range(cfg.num_ps))
+            self.worker_ranks = list(range(self.world))
         else:
             assert self.world == cfg.num_ps + cfg.num_workers, "world = num_ps + num_workers"
             self.ps_ranks = list(range(cfg.num_ps))
@@ -686,7 +696,7 @@ class PSTrainEngine:
                         ops.append(StepOp(kind=OP_SIGNAL, p0=ctl_ptr, p1=mbp, i0=w, i1=hd.stamp_from_version))
                     ops.append(StepOp(kind=OP_GEMM, p0=ctypes.addressof(g3p)))
                     keep = [g1p, hdp, g3p]
-                    if self.cfg.colocated:
+                    if r in self.ps_ranks:
                         # ps and worker share the GPU and the stream: the apply joins the worker's plan (one graph)
                         ops += [StepOp(kind=OP_PS_APPLY, p0=ctypes.addressof(self._p[r]))
                                 for _ in range(1 if self.cfg.sync else self.cfg.num_workers)]
@@ -696,7 +706,7 @@ class PSTrainEngine:
                 host = torch.zeros(16, dtype=torch.float32).pin_memory()
                 plans["loss"][r] = (StepPlan([StepOp(kind=OP_D2H, p0=host.data_ptr(), p1=d["loss_ptr"], i0=self.head_ctas * 4),
                                               StepOp(kind=OP_SYNC)], rk.device.index, st), host.numpy(), host)
-            if r in self.ps_ranks and not self.cfg.colocated:
+            if r in self.ps_ranks and r not in self.worker_ranks:
                 k = 1 if self.cfg.sync else self.cfg.num_workers
                 plans["ps"][r] = StepPlan([StepOp(kind=OP_PS_APPLY, p0=ctypes.addressof(self._p[r])) for _ in range(k)],
                                           rk.device.index, st, keep=[self._p[r]])

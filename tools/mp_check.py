@@ -39,12 +39,13 @@ def main():
     num_ps = int(os.environ.get("DTF_NUM_PS", "1"))
     nvls = os.environ.get("DTF_NVLS", "0")
     nvls = {"0": False, "1": True}.get(nvls, nvls)
-    W = world - num_ps
+    pow_ = os.environ.get("DTF_PS_ON_WORKERS", "0") == "1"      # every rank a worker, ps shards on the first ranks' GPUs
+    W = world if pow_ else world - num_ps
     xs, ys = synthetic_mnist(100 * W * 8, seed=11)
     report = {}
     for mode in ("sync", "async"):
         cfg = EngineConfig(num_ps=num_ps, num_workers=W, sync=(mode == "sync"), optimizer={"kind": "sgd", "lr": 0.001},
-                           seed=2, nvls=nvls)
+                           seed=2, nvls=nvls, ps_on_workers=pow_)
         eng = PSTrainEngine(MLPSpec(), cfg, Fabric.from_torch_distributed())
         eng.init_params()
         p0 = None
@@ -63,7 +64,7 @@ def main():
         dist.all_gather_object(gathered, {k: v for k, v in sd.items()})
         p0s = [None] * world
         dist.all_gather_object(p0s, p0)
-        loss = eng.read_loss() if rank >= num_ps else None
+        loss = eng.read_loss() if rank in eng.worker_ranks else None
         if rank == 0:
             final = {}
             for g in gathered[:num_ps]:
@@ -97,6 +98,7 @@ def main():
         report["world"] = world
         report["num_ps"] = num_ps
         report["nvls"] = str(nvls)
+        report["ps_on_workers"] = pow_
         print("MP_CHECK " + json.dumps(report))
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "mp_check_%d%s.json" % (world, "_nvls" if nvls else "")), "w") as f:
