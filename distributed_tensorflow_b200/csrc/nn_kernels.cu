@@ -15,6 +15,11 @@
 // double precision and writes the per-channel results, then resets the ticket so the kernel is CUDA-graph replayable.
 // Deterministic: no floating-point atomics.
 //
+// Also here: channel-vectorised convolution lowering for C % 8 == 0 (every ResNet layer but the 3-channel stem):
+//   im2col_nhwc_vec8 : one thread = one (output pixel, filter tap, 8-channel group): 2 x 16-byte loads of fp32, one
+//                      16-byte store of 8 bf16 -- 8x fewer index computations than the scalar kernel in elementwise.cu
+//   col2im_nhwc_vec4 : one thread = one (input pixel, 4-channel group), gathers its <= kh*kw contributions as float4
+//
 // STATUS: written at the end of round 1 after the GPU budget was spent.  Compiled (ptxas: no spills), formulas checked
 // on CPU against autograd (tests/test_nn_fused_reference.py); first hardware run is tests/test_gpu_nn_fused.py.
 // Off by default (DTF_FUSED_BN=1 turns it on in ops/native.py).
@@ -174,6 +179,64 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ dy, const float4*
   }
 }
 
+// cols[row, (ky*kw + kx)*c + ci] = bf16(x[b, oy*sh - pt + ky, ox*sw - pl + kx, ci]) (0 outside), row = (b*ho + oy)*wo + ox
+__global__ void im2col_nhwc_vec8_kernel(const float* __restrict__ x, uint4* __restrict__ cols, int n, int h, int w, int c,
+                                        int kh, int kw, int sh, int sw, int pt, int pl, int ho, int wo, long long ldc8) {
+  const int c8n = c / 8, taps = kh * kw;
+  const long long per_row = (long long)taps * c8n;
+  const long long total = (long long)n * ho * wo * per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / per_row;
+    const int rem = (int)(i - row * per_row);
+    const int tap = rem / c8n, c8 = rem - tap * c8n;
+    const int ky = tap / kw, kx = tap - ky * kw;
+    const int ox = (int)(row % wo);
+    const int oy = (int)((row / wo) % ho);
+    const int b = (int)(row / ((long long)wo * ho));
+    const int iy = oy * sh - pt + ky, ix = ox * sw - pl + kx;
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+      const float4* src = reinterpret_cast<const float4*>(x + (((long long)b * h + iy) * w + ix) * c + c8 * 8);
+      const float4 a = src[0], bq = src[1];
+      out.x = pack_bf16x2(a.x, a.y); out.y = pack_bf16x2(a.z, a.w);
+      out.z = pack_bf16x2(bq.x, bq.y); out.w = pack_bf16x2(bq.z, bq.w);
+    }
+    cols[row * ldc8 + (long long)tap * c8n + c8] = out;
+  }
+}
+
+// gx[b, iy, ix, ci] = sum over taps (ky, kx) with (iy + pt - ky) % sh == 0, (ix + pl - kx) % sw == 0 and the output
+// pixel in range of gcols[row(b, oy, ox), (ky*kw + kx)*c + ci]
+__global__ void col2im_nhwc_vec4_kernel(const float* __restrict__ gcols, long long ldg, float4* __restrict__ gx, int n, int h,
+                                        int w, int c, int kh, int kw, int sh, int sw, int pt, int pl, int ho, int wo) {
+  const int c4n = c / 4;
+  const long long total = (long long)n * h * w * c4n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % c4n);
+    const long long pix = i / c4n;
+    const int ix = (int)(pix % w);
+    const int iy = (int)((pix / w) % h);
+    const int b = (int)(pix / ((long long)w * h));
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ky = 0; ky < kh; ++ky) {
+      const int ty = iy + pt - ky;
+      if (ty < 0 || ty % sh) continue;
+      const int oy = ty / sh;
+      if (oy >= ho) continue;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int tx = ix + pl - kx;
+        if (tx < 0 || tx % sw) continue;
+        const int ox = tx / sw;
+        if (ox >= wo) continue;
+        const long long row = ((long long)b * ho + oy) * wo + ox;
+        const float4 v = *reinterpret_cast<const float4*>(gcols + row * ldg + ((long long)ky * kw + kx) * c + c4 * 4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+    }
+    gx[i] = s;
+  }
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static inline int bn_grid_for(long long n, int block = 256) {
@@ -243,6 +306,25 @@ int dtf_bn_bwd_apply(const float* dy, const float* y_mask, const float* x, const
              reinterpret_cast<const float4*>(rstd), reinterpret_cast<const float4*>(scale),
              reinterpret_cast<const float4*>(doffset), reinterpret_cast<const float4*>(dscale), reinterpret_cast<float4*>(dx),
              reinterpret_cast<float4*>(dres), n4, C / 4, 1.0f / (float)rows);
+  return (int)cudaGetLastError();
+}
+
+// -1: shape / alignment not eligible (the caller falls back to the scalar kernels of elementwise.cu)
+int dtf_im2col_nhwc_vec8(const float* x, void* cols, int n, int h, int w, int c, int kh, int kw, int sh, int sw, int pt, int pl,
+                         int ho, int wo, long long ldc, cudaStream_t s) {
+  if (c % 8 != 0 || ldc % 8 != 0 || ldc != (long long)kh * kw * c || !aligned16(x) || !aligned16(cols)) return -1;
+  const long long total = (long long)n * ho * wo * kh * kw * (c / 8);
+  DTF_LAUNCH(im2col_nhwc_vec8_kernel, bn_grid_for(total), 256, s, x, reinterpret_cast<uint4*>(cols), n, h, w, c, kh, kw, sh, sw,
+             pt, pl, ho, wo, ldc / 8);
+  return (int)cudaGetLastError();
+}
+
+int dtf_col2im_nhwc_vec4(const float* gcols, long long ldg, float* gx, int n, int h, int w, int c, int kh, int kw, int sh, int sw,
+                         int pt, int pl, int ho, int wo, cudaStream_t s) {
+  if (c % 4 != 0 || ldg % 4 != 0 || !aligned16(gcols) || !aligned16(gx)) return -1;
+  const long long total = (long long)n * h * w * (c / 4);
+  DTF_LAUNCH(col2im_nhwc_vec4_kernel, bn_grid_for(total), 256, s, gcols, ldg, reinterpret_cast<float4*>(gx), n, h, w, c, kh, kw,
+             sh, sw, pt, pl, ho, wo);
   return (int)cudaGetLastError();
 }
 

@@ -153,7 +153,7 @@ def softmax_xent(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 # batch normalisation (training mode, batch statistics) + residual add + ReLU
 # ---------------------------------------------------------------------------
-_FUSED_BN = os.environ.get("DTF_FUSED_BN", "0") == "1"      # csrc/nn_kernels.cu: first hardware validation pending
+_FUSED_BN = os.environ.get("DTF_FUSED_NN", os.environ.get("DTF_FUSED_BN", "0")) == "1"      # csrc/nn_kernels.cu: opt-in until its first hardware run
 
 
 def bn_train_reference(x, scale, offset, residual=None, relu=False, eps: float = 1e-5):

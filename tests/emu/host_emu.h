@@ -22,6 +22,22 @@ struct alignas(16) float4 {
 };
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 
+struct alignas(16) uint4 {
+  unsigned x, y, z, w;
+};
+static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
+
+// fp32 -> bf16 round-to-nearest-even (what cvt.rn.bf16x2.f32 does), NaN kept quiet
+static inline unsigned dtf_emu_bf16(float f) {
+  unsigned u;
+  __builtin_memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (u >> 16) | 0x40u;
+  return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+}
+namespace dtf {
+static inline unsigned pack_bf16x2(float lo, float hi) { return dtf_emu_bf16(lo) | (dtf_emu_bf16(hi) << 16); }
+}  // namespace dtf
+
 typedef void* cudaStream_t;
 static inline int cudaGetLastError() { return 0; }
 

@@ -56,8 +56,11 @@ def test_resnet18_loss_and_grads_with_fused_bn(monkeypatch):
     x = torch.randn(8, 32, 32, 3, generator=g).cuda()
     y = torch.nn.functional.one_hot(torch.randint(0, 10, (8,), generator=g), 10).float().cuda()
 
+    from distributed_tensorflow_b200.ops import cuda_lib
+
     def run(fused):
         monkeypatch.setattr(native, "_FUSED_BN", fused)
+        monkeypatch.setattr(cuda_lib, "FUSED_NN", fused)
         loss = resnet18_loss(init, x, y)
         grads = torch.autograd.grad(loss, list(init.values()))
         return float(loss), grads
@@ -67,3 +70,22 @@ def test_resnet18_loss_and_grads_with_fused_bn(monkeypatch):
     for (k, _), a, b in zip(init.items(), g0, g1):
         denom = float(a.abs().max()) + 1e-6
         assert float((a - b).abs().max()) / denom < 2e-2, k
+
+
+@pytest.mark.parametrize("shape,k,stride", [((8, 32, 32, 64), 3, 1), ((4, 16, 16, 128), 3, 2), ((2, 9, 7, 256), 1, 2), ((3, 8, 8, 8), 3, 1)])
+def test_vector_im2col_col2im_match_scalar_kernels(shape, k, stride, monkeypatch):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from distributed_tensorflow_b200.ops import cuda_lib
+    g = torch.Generator().manual_seed(k + stride)
+    x = torch.randn(*shape, generator=g).cuda()
+    pads = (1, 1, 1, 1) if k == 3 else (0, 0, 0, 0)
+    outs = []
+    for fused in (False, True):
+        monkeypatch.setattr(cuda_lib, "FUSED_NN", fused)
+        cols, (n, ho, wo) = cuda_lib.im2col_nhwc(x, k, k, (stride, stride), pads)
+        gc = torch.randn(cols.shape, generator=torch.Generator().manual_seed(1)).cuda()
+        gx = cuda_lib.col2im_nhwc(gc, x.shape, k, k, (stride, stride), pads)
+        outs.append((cols, gx))
+    assert torch.equal(outs[0][0], outs[1][0])
+    torch.testing.assert_close(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-5)

@@ -82,3 +82,42 @@ def test_emulated_launchers_reject_bad_arguments(emu):
     x = torch.zeros(9, 8)
     off = x.view(-1)[1:65].view(8, 8)                                                                       # 4-byte offset
     assert emu.dtf_bn_apply(_p(off), None, _p(x), None, None, None, None, 8, 8, 0, None) == -1
+
+
+def _im2col_ref(x, kh, kw, sh, sw, pt, pb, pl, pr):
+    n, h, w, c = x.shape
+    xp = torch.nn.functional.pad(x, (0, 0, pl, pr, pt, pb))
+    ho, wo = (h + pt + pb - kh) // sh + 1, (w + pl + pr - kw) // sw + 1
+    cols = torch.empty(n, ho, wo, kh * kw * c)
+    for ky in range(kh):
+        for kx in range(kw):
+            cols[..., (ky * kw + kx) * c:(ky * kw + kx + 1) * c] = xp[:, ky:ky + (ho - 1) * sh + 1:sh, kx:kx + (wo - 1) * sw + 1:sw, :]
+    return cols.reshape(n * ho * wo, kh * kw * c), ho, wo
+
+
+@pytest.mark.parametrize("shape,k,stride,pads", [((2, 6, 6, 8), 3, 1, (1, 1, 1, 1)), ((1, 7, 5, 16), 3, 2, (1, 1, 1, 1)),
+                                                 ((2, 4, 4, 8), 1, 2, (0, 0, 0, 0)), ((1, 8, 8, 8), 3, 2, (0, 1, 0, 1))])
+def test_emulated_vector_im2col_col2im(emu, shape, k, stride, pads):
+    vp, ll, i = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+    emu.dtf_im2col_nhwc_vec8.argtypes = [vp, vp] + [i] * 12 + [ll, vp]
+    emu.dtf_col2im_nhwc_vec4.argtypes = [vp, ll, vp] + [i] * 12 + [vp]
+    g = torch.Generator().manual_seed(sum(shape) + k)
+    x = torch.randn(*shape, generator=g)
+    n, h, w, c = shape
+    pt, pb, pl, pr = pads
+    want, ho, wo = _im2col_ref(x, k, k, stride, stride, pt, pb, pl, pr)
+    ld = k * k * c
+    cols = torch.full((n * ho * wo, ld), 7.0, dtype=torch.bfloat16)
+    assert emu.dtf_im2col_nhwc_vec8(_p(x), _p(cols), n, h, w, c, k, k, stride, stride, pt, pl, ho, wo, ld, None) == 0
+    assert torch.equal(cols, want.bfloat16())              # same round-to-nearest-even as the hardware conversion
+    # col2im is the adjoint of im2col: <im2col(x), G> == <x, col2im(G)>; and equals autograd's gradient
+    gcols = torch.randn(n * ho * wo, ld, generator=g)
+    gx = torch.full(shape, float("nan"))
+    assert emu.dtf_col2im_nhwc_vec4(_p(gcols), ld, _p(gx), n, h, w, c, k, k, stride, stride, pt, pl, ho, wo, None) == 0
+    xr = x.clone().requires_grad_()
+    ref, _, _ = _im2col_ref(xr, k, k, stride, stride, pt, pb, pl, pr)
+    (gref,) = torch.autograd.grad(ref, xr, gcols)
+    torch.testing.assert_close(gx, gref, rtol=1e-5, atol=1e-5)
+    # ineligible shapes are refused (the caller falls back to the scalar kernels)
+    x3 = torch.zeros(1, 4, 4, 3)
+    assert emu.dtf_im2col_nhwc_vec8(_p(x3), _p(cols), 1, 4, 4, 3, 3, 3, 1, 1, 1, 1, 4, 4, 32, None) == -1
