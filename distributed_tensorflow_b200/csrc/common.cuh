@@ -13,6 +13,8 @@
 #include <stdio.h>
 
 #define DTF_DEVICE __device__ __forceinline__
+// Kernel launch (no dynamic shared memory).  tests/emu/host_emu.h defines the same macro for the g++ emulation build.
+#define DTF_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 
 namespace dtf {
 

@@ -29,10 +29,8 @@
 // block, blocks run one after another) so that indexing / reduction / ticket logic is checked on machines without a GPU.
 #ifdef DTF_HOST_EMU
 #include "host_emu.h"
-#define DTF_LAUNCH(kernel, grid, block, stream, ...) dtf_emu::launch((grid), (block), [&]() { kernel(__VA_ARGS__); })
 #else
 #include "common.cuh"
-#define DTF_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #endif
 
 namespace dtf {

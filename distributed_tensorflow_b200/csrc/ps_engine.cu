@@ -15,7 +15,15 @@
 #include <cstdio>
 #include <cstring>
 
+// DTF_HOST_EMU: the ps-side kernels of this file (ps_apply, publish, push/pull, token wait, fabric collectives) also
+// compile with g++ against tests/emu/host_emu.h -- threads + barriers stand in for a thread block, plain atomics for the
+// scoped PTX accesses, a registry of member buffers for multimem -- so the protocol (fresh/stale decision, mean, apply,
+// tokens, staleness) is exercised by the CPU test tier from the SAME source.  The tensor-core-side kernels are excluded.
+#ifdef DTF_HOST_EMU
+#include "host_emu.h"
+#else
 #include "common.cuh"
+#endif
 #include "ps_control.h"
 
 namespace dtf {
@@ -56,6 +64,7 @@ struct PsApplyParams {
   unsigned int full_mask;        // all workers: the ld_reduce path needs every copy to hold a fresh gradient
 };
 
+#ifndef DTF_HOST_EMU
 DTF_DEVICE unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -69,6 +78,13 @@ DTF_DEVICE unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
 DTF_DEVICE void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+DTF_DEVICE void red_relaxed_sys_add_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+DTF_DEVICE void st_relaxed_sys_ull(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+#endif
 
 __global__ void __launch_bounds__(256, 4) ps_apply_kernel(const PsApplyParams p) {
   __shared__ unsigned int s_mask, s_count, s_ok;
@@ -280,7 +296,7 @@ __global__ void __launch_bounds__(256, 4) ps_apply_kernel(const PsApplyParams p)
         for (int w = 0; w < p.num_workers; ++w) {
           if (p.mailbox[w] == nullptr) continue;
           if (p.mode == 1 && !(mask & (1u << w))) continue;
-          if (p.mode == 1) asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(&p.mailbox[w]->token), "l"(1ull) : "memory");
+          if (p.mode == 1) red_relaxed_sys_add_u64(&p.mailbox[w]->token, 1ull);
           else st_relaxed_sys_u64(reinterpret_cast<uint64_t*>(&p.mailbox[w]->token), ngs);
         }
       }
@@ -307,6 +323,7 @@ __global__ void ps_publish_kernel(const float* __restrict__ master, __nv_bfloat1
     shadow[i] = __float2bfloat16(master[i]);
 }
 
+#ifndef DTF_HOST_EMU   // tensor-core-side kernel (warp shuffles, dynamic shared memory): hardware tier only
 // ---------------------------------------------------------------------------------------------
 // Fused MLP head (SURVEY K2+K3+K4 small parts), ONE CTA:
 //   logits = h.W2 + b2 ; softmax ; clipped cross-entropy (batch SUM) ; dlogits ;
@@ -667,6 +684,8 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
   HSTAMP(6);          // fenced + signalled
 }
 
+#endif  // !DTF_HOST_EMU
+
 // Input-pipeline stage for the device-resident dataset: batch index = (step * stride + offset) % nbatches,
 // where step is the worker's DEVICE step counter (so the launch is CUDA-graph replayable).  Converts the
 // fp32 images of that batch to the bf16 staging tile consumed by both GEMMs and copies the labels.
@@ -715,7 +734,7 @@ __global__ void push_grad_kernel(const float* __restrict__ src, float* __restric
     __threadfence_system();
     if (write_stamp && blockIdx.x == 0) {
       const unsigned long long stamp = stamp_from_version ? mb->version : mb->token;
-      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&ctl->w[rank].stamp), "l"(stamp) : "memory");
+      st_relaxed_sys_ull(&ctl->w[rank].stamp, stamp);
       __threadfence_system();
     }
     red_release_sys_add_u64(reinterpret_cast<uint64_t*>(&ctl->w[rank].arrivals), 1ull);
@@ -801,8 +820,8 @@ int dtf_fabric_bcast(const void* src, void* mc_dst, void* const* peer_dst, int n
   PeerList pl;
   memset(&pl, 0, sizeof(pl));
   for (int k = 0; k < npeers; ++k) pl.p[k] = peer_dst[k];
-  fabric_bcast_kernel<<<grid > 0 ? grid : 296, 256, 0, s>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(mc_dst), pl,
-                                                           npeers, nbytes / 16);
+  DTF_LAUNCH(fabric_bcast_kernel, grid > 0 ? grid : 296, 256, s, reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(mc_dst),
+             pl, npeers, nbytes / 16);
   return (int)cudaGetLastError();
 }
 
@@ -812,7 +831,7 @@ int dtf_fabric_reduce(const void* mc_src, void* const* peer_src, int npeers, flo
   PeerList pl;
   memset(&pl, 0, sizeof(pl));
   for (int k = 0; k < npeers; ++k) pl.p[k] = peer_src[k];
-  fabric_reduce_kernel<<<grid > 0 ? grid : 296, 256, 0, s>>>(reinterpret_cast<const float*>(mc_src), pl, npeers, dst, nfloats / 4);
+  DTF_LAUNCH(fabric_reduce_kernel, grid > 0 ? grid : 296, 256, s, reinterpret_cast<const float*>(mc_src), pl, npeers, dst, nfloats / 4);
   return (int)cudaGetLastError();
 }
 
@@ -893,17 +912,18 @@ int dtf_ps_apply(const DtfPsApplyArgs* a, cudaStream_t s) {
     long long want = (a->n / 4 + 255) / 256;                       // one float4 per thread: a single load round trip
     grid = (int)(want < 1 ? 1 : (want > 592 ? 592 : want));      // all CTAs must be co-resident (4 per SM by launch bounds)
   }
-  ps_apply_kernel<<<grid, 256, 0, s>>>(p);
+  DTF_LAUNCH(ps_apply_kernel, grid, 256, s, p);
   return (int)cudaGetLastError();
 }
 
 int dtf_ps_publish(const float* master, void* shadow, long long n, cudaStream_t s) {
   long long g = (n + 255) / 256;
   if (g > 1184) g = 1184;
-  ps_publish_kernel<<<(int)g, 256, 0, s>>>(master, reinterpret_cast<__nv_bfloat16*>(shadow), n);
+  DTF_LAUNCH(ps_publish_kernel, (int)g, 256, s, master, reinterpret_cast<__nv_bfloat16*>(shadow), n);
   return (int)cudaGetLastError();
 }
 
+#ifndef DTF_HOST_EMU
 struct DtfMlpHeadArgs {
   const void* h; long long ldh;
   const void* w2; long long ldw2;
@@ -954,36 +974,37 @@ int dtf_mlp_head(const DtfMlpHeadArgs* a, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
+#endif  // !DTF_HOST_EMU
+
 int dtf_stage_from_dataset(const float* images, const float* labels, long long nbatches, int B, int D, int C,
                            long long stride, long long offset, const unsigned long long* step_counter, void* x16,
                            float* lab_out, cudaStream_t s) {
   if (((long long)B * D) % 4) return -2;
-  stage_from_dataset_kernel<<<40, 256, 0, s>>>(images, labels, nbatches, B, D, C, stride, offset, step_counter,
-                                               reinterpret_cast<__nv_bfloat16*>(x16), lab_out);
+  DTF_LAUNCH(stage_from_dataset_kernel, 40, 256, s, images, labels, nbatches, B, D, C, stride, offset, step_counter,
+             reinterpret_cast<__nv_bfloat16*>(x16), lab_out);
   return (int)cudaGetLastError();
 }
 
 int dtf_wait_token(const void* mailbox, unsigned long long target, const unsigned long long* target_ptr,
                    unsigned long long timeout_ns, unsigned int* err, cudaStream_t s) {
-  wait_token_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const WorkerMailbox*>(mailbox), target, target_ptr,
-                                     timeout_ns ? timeout_ns : 2000000000ull, err);
+  DTF_LAUNCH(wait_token_kernel, 1, 32, s, reinterpret_cast<const WorkerMailbox*>(mailbox), target, target_ptr,
+             timeout_ns ? timeout_ns : 2000000000ull, err);
   return (int)cudaGetLastError();
 }
 
 int dtf_push_grad(const float* src, float* dst_peer, long long n, void* ctl, const void* mailbox, int rank,
                   int stamp_from_version, int write_stamp, int grid, cudaStream_t s) {
-  push_grad_kernel<<<grid, 256, 0, s>>>(src, dst_peer, n, reinterpret_cast<PsControl*>(ctl),
-                                        reinterpret_cast<const WorkerMailbox*>(mailbox), rank, stamp_from_version,
-                                        write_stamp);
+  DTF_LAUNCH(push_grad_kernel, grid, 256, s, src, dst_peer, n, reinterpret_cast<PsControl*>(ctl),
+             reinterpret_cast<const WorkerMailbox*>(mailbox), rank, stamp_from_version, write_stamp);
   return (int)cudaGetLastError();
 }
 
 int dtf_pull_shadow(const void* src_peer, void* dst, long long nbytes, int grid, cudaStream_t s) {
-  pull_shadow_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(src_peer), reinterpret_cast<uint4*>(dst),
-                                          nbytes / 16);
+  DTF_LAUNCH(pull_shadow_kernel, grid, 256, s, reinterpret_cast<const uint4*>(src_peer), reinterpret_cast<uint4*>(dst), nbytes / 16);
   return (int)cudaGetLastError();
 }
 
+#ifndef DTF_HOST_EMU
 // ---------------------------------------------------------------------------------------------
 // fabric: IPC-exportable device allocations + peer access
 // ---------------------------------------------------------------------------------------------
@@ -1020,5 +1041,7 @@ int dtf_ipc_handle_size() { return (int)sizeof(cudaIpcMemHandle_t); }
 int dtf_memcpy_d2h(void* dst, const void* src, long long n) { return (int)cudaMemcpy(dst, src, (size_t)n, cudaMemcpyDeviceToHost); }
 int dtf_memcpy_h2d(void* dst, const void* src, long long n) { return (int)cudaMemcpy(dst, src, (size_t)n, cudaMemcpyHostToDevice); }
 int dtf_memset(void* p, int v, long long n, cudaStream_t s) { return (int)cudaMemsetAsync(p, v, (size_t)n, s); }
+
+#endif  // !DTF_HOST_EMU
 
 }  // extern "C"

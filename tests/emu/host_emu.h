@@ -7,9 +7,13 @@
 #include <pthread.h>
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -37,6 +41,20 @@ static inline unsigned dtf_emu_bf16(float f) {
 namespace dtf {
 static inline unsigned pack_bf16x2(float lo, float hi) { return dtf_emu_bf16(lo) | (dtf_emu_bf16(hi) << 16); }
 }  // namespace dtf
+
+struct alignas(8) uint2 {
+  unsigned x, y;
+};
+static inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
+
+struct __nv_bfloat16 {
+  uint16_t v;
+};
+static inline __nv_bfloat16 __float2bfloat16(float f) { return __nv_bfloat16{(uint16_t)dtf_emu_bf16(f)}; }
+
+#define __align__(n) alignas(n)
+#define DTF_DEVICE static inline
+#define DTF_LAUNCH(kernel, grid, block, stream, ...) dtf_emu::launch((grid), (block), [&]() { kernel(__VA_ARGS__); })
 
 typedef void* cudaStream_t;
 static inline int cudaGetLastError() { return 0; }
@@ -90,3 +108,80 @@ static inline T __ldg(const T* p) { return *p; }
 template <class T>
 static inline T __ldcg(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
 static inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+
+static inline unsigned int atomicExch(unsigned int* p, unsigned int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+static inline long long clock64() { return (long long)std::chrono::steady_clock::now().time_since_epoch().count(); }
+static inline void __nanosleep(unsigned ns) { std::this_thread::sleep_for(std::chrono::nanoseconds(ns)); }
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+
+// ---- multimem emulation: a "multicast address range" is a registered placeholder range plus its member buffers -------------
+namespace dtf_emu {
+struct McRange {
+  char* base;
+  size_t bytes;
+  std::vector<char*> members;
+};
+inline std::vector<McRange> mc_ranges;
+inline std::mutex mc_mu;
+static inline const McRange& mc_find(const void* p) {
+  const char* c = reinterpret_cast<const char*>(p);
+  for (const auto& r : mc_ranges)
+    if (c >= r.base && c < r.base + r.bytes) return r;
+  std::terminate();            // a multimem access outside every registered range is a test bug
+}
+}  // namespace dtf_emu
+
+extern "C" __attribute__((weak)) void dtf_emu_mc_register(void* base, long long bytes, void* const* members, int n) {
+  std::lock_guard<std::mutex> g(dtf_emu::mc_mu);
+  dtf_emu::McRange r{reinterpret_cast<char*>(base), (size_t)bytes, {}};
+  for (int i = 0; i < n; ++i) r.members.push_back(reinterpret_cast<char*>(members[i]));
+  dtf_emu::mc_ranges.push_back(r);
+}
+extern "C" __attribute__((weak)) void dtf_emu_mc_clear() {
+  std::lock_guard<std::mutex> g(dtf_emu::mc_mu);
+  dtf_emu::mc_ranges.clear();
+}
+
+// ---- the scoped / ordered accesses of common.cuh as sequentially consistent host atomics -----------------------------------
+namespace dtf {
+static inline uint64_t globaltimer_ns() {
+  return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static inline uint64_t ld_relaxed_sys_u64(const uint64_t* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+static inline uint64_t ld_acquire_sys_u64(const uint64_t* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+static inline void st_relaxed_sys_u64(uint64_t* p, uint64_t v) { __atomic_store_n(p, v, __ATOMIC_SEQ_CST); }
+static inline void red_release_sys_add_u64(uint64_t* p, uint64_t v) { __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline void fence_acq_rel_sys() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline unsigned int ld_acquire_gpu_u32(const unsigned int* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+static inline unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+static inline void st_release_gpu_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_SEQ_CST); }
+static inline void red_relaxed_sys_add_u64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline void st_relaxed_sys_ull(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_SEQ_CST); }
+static inline bool wait_flag_ge_u64(const uint64_t* flag, uint64_t target, uint64_t timeout_ns) {
+  const uint64_t t0 = globaltimer_ns();
+  while (__atomic_load_n(flag, __ATOMIC_SEQ_CST) < target) {
+    if (globaltimer_ns() - t0 > timeout_ns) return false;
+    std::this_thread::yield();
+  }
+  return true;
+}
+static inline float4 multimem_ld_reduce_add_f32x4(const float* mc) {
+  const auto& r = dtf_emu::mc_find(mc);
+  const size_t off = reinterpret_cast<const char*>(mc) - r.base;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (char* m : r.members) {
+    const float4 v = *reinterpret_cast<const float4*>(m + off);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  return acc;
+}
+template <class T>
+static inline void dtf_emu_mc_store(void* mc, const T& v) {
+  const auto& r = dtf_emu::mc_find(mc);
+  const size_t off = reinterpret_cast<char*>(mc) - r.base;
+  for (char* m : r.members) *reinterpret_cast<T*>(m + off) = v;
+}
+static inline void multimem_st_f32x4(float* mc, float4 v) { dtf_emu_mc_store(mc, v); }
+static inline void multimem_st_b64(void* mc, uint32_t lo, uint32_t hi) { dtf_emu_mc_store(mc, uint2{lo, hi}); }
+static inline void multimem_st_b128(void* mc, uint4 v) { dtf_emu_mc_store(mc, v); }
+}  // namespace dtf

@@ -1,0 +1,333 @@
+"""The device-side parameter-server protocol (csrc/ps_engine.cu: ps_apply, push_grad, wait_token, publish, fabric
+collectives) executed on the CPU: the SAME kernel source compiled by g++ against tests/emu/host_emu.h (threads + barriers
+= a thread block, blocks one after another, sequentially consistent atomics for the scoped PTX accesses, a registry of
+member buffers for multimem).  Covers what SURVEY A11/A12 specify for the ps: fresh / stale decision, backup workers,
+gradient MEAN, SGD / Momentum / TF-Adam, bf16 publication (unicast replicas and multicast), zero-after-read ranges,
+tokens and versions, async round-robin + staleness histogram, bounded waits.  Memory-model races between concurrently
+running blocks/GPUs are outside what an emulation can show: that is the hardware tier (tests/test_gpu_*.py, tools/mp_check.py).
+"""
+import ctypes
+import math
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from distributed_tensorflow_b200.ops.cuda_lib import MAX_WORKERS, PsApplyArgs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "distributed_tensorflow_b200", "csrc")
+CTL_FIELDS = ["global_step", "param_version", "beta1_power", "beta2_power", "dropped_stale", "applied_total",
+              "staleness_hist", "staleness_sum", "err", "w", "w_stride", "consumed"]
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    so = str(tmp_path_factory.mktemp("emu") / "libps_emu.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-DDTF_HOST_EMU", "-I" + os.path.join(ROOT, "tests", "emu"), "-I" + CSRC,
+                    "-x", "c++", "-shared", "-fPIC", "-pthread", "-o", so, os.path.join(CSRC, "ps_engine.cu")], check=True)
+    lib = ctypes.CDLL(so)
+    vp, ll, i, ull = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_ulonglong
+    lib.dtf_ps_apply.argtypes = [ctypes.POINTER(PsApplyArgs), vp]
+    lib.dtf_ps_publish.argtypes = [vp, vp, ll, vp]
+    lib.dtf_wait_token.argtypes = [vp, ull, vp, ull, vp, vp]
+    lib.dtf_push_grad.argtypes = [vp, vp, ll, vp, vp, i, i, i, i, vp]
+    lib.dtf_pull_shadow.argtypes = [vp, vp, ll, i, vp]
+    lib.dtf_fabric_bcast.argtypes = [vp, vp, vp, i, ll, i, vp]
+    lib.dtf_fabric_reduce.argtypes = [vp, vp, i, vp, ll, i, vp]
+    lib.dtf_offsetof_ctl.argtypes = [i]
+    lib.dtf_emu_mc_register.argtypes = [vp, ll, vp, i]
+    lib.off = {k: lib.dtf_offsetof_ctl(j) for j, k in enumerate(CTL_FIELDS)}
+    return lib
+
+
+def _aligned_bytes(nbytes, align=128):
+    """Zeroed host buffer whose data pointer is ``align``-byte aligned (the control structs are __align__(128))."""
+    raw = torch.zeros(nbytes + align, dtype=torch.uint8)
+    off = (-raw.data_ptr()) % align
+    return raw[off:off + nbytes], raw
+
+
+class World:
+    """Host-memory stand-in for one ps shard and its workers (what PSTrainEngine allocates on the GPUs)."""
+
+    def __init__(self, lib, n=1280, workers=3, kind=0, sync=True, R=None, ctas_per_push=2, lr=0.1, **opt):
+        self.lib, self.n, self.W, self.cpp = lib, n, workers, ctas_per_push
+        self.ctl, self._k0 = _aligned_bytes(lib.dtf_sizeof_ps_control())
+        self.mb_bytes = lib.dtf_sizeof_mailbox()
+        self.mb, self._k1 = _aligned_bytes(self.mb_bytes * workers)
+        g = torch.Generator().manual_seed(n + workers)
+        self.master = torch.randn(n, generator=g)
+        self.master0 = self.master.clone()
+        self.slot_m, self.slot_v = torch.zeros(n), torch.zeros(n)
+        self.shadow = torch.zeros(n, dtype=torch.bfloat16)
+        self.grads = [torch.zeros(n) for _ in range(workers)]              # separate allocations: 16-byte aligned slots
+        self.replicas = [torch.zeros(n, dtype=torch.bfloat16) for _ in range(workers)]
+        a = PsApplyArgs()
+        a.ctl, a.master, a.slot_m, a.slot_v = self.ctl.data_ptr(), self.master.data_ptr(), self.slot_m.data_ptr(), self.slot_v.data_ptr()
+        a.shadow = self.shadow.data_ptr()
+        for w in range(workers):
+            a.grad[w] = self.grads[w].data_ptr()
+            a.mailbox[w] = self.mb.data_ptr() + w * self.mb_bytes
+        a.n, a.num_workers, a.replicas_to_aggregate, a.ctas_per_push = n, workers, R or workers, ctas_per_push
+        a.mode, a.kind, a.lr = (0 if sync else 1), kind, lr
+        a.momentum, a.nesterov = opt.get("momentum", 0.0), int(opt.get("nesterov", False))
+        a.beta1, a.beta2, a.eps = opt.get("beta1", 0.9), opt.get("beta2", 0.999), opt.get("eps", 1e-8)
+        a.timeout_ns, a.system_scope = 200_000_000, 1
+        self.a = a
+        self.f32("beta1_power", 2)[:] = torch.tensor([a.beta1, a.beta2])
+
+    # -- typed views into the control block / mailboxes -------------------------------------------------
+    def u64(self, field, count=1, extra=0):
+        o = self.lib.off[field] + extra
+        return self.ctl[o:o + 8 * count].view(torch.int64)
+
+    def u32(self, field):
+        o = self.lib.off[field]
+        return self.ctl[o:o + 4].view(torch.int32)
+
+    def f32(self, field, count=1):
+        o = self.lib.off[field]
+        return self.ctl[o:o + 4 * count].view(torch.float32)
+
+    def slot(self, w):          # (arrivals, stamp) of worker w
+        return self.u64("w", 2, w * self.lib.off["w_stride"])
+
+    def mailbox(self, w):       # (token, version)
+        return self.mb[w * self.mb_bytes:w * self.mb_bytes + 16].view(torch.int64)
+
+    def push(self, w, grad, stamp):
+        """What a worker's kernels do: gradient into its slot, stamp, then the arrivals of all its pushing CTAs."""
+        self.grads[w].copy_(grad)
+        s = self.slot(w)
+        s[1] = stamp
+        s[0] += self.cpp
+
+    def apply(self):
+        assert self.lib.dtf_ps_apply(ctypes.byref(self.a), None) == 0
+
+
+def _bf16(t):
+    return t.bfloat16()
+
+
+def test_sync_sgd_mean_tokens_and_shadow(emu):
+    wd = World(emu, n=1280, workers=3, kind=0, lr=0.1)
+    gs = [torch.randn(1280) for _ in range(3)]
+    for w in range(3):
+        wd.push(w, gs[w], stamp=0)
+    wd.apply()
+    want = wd.master0 - 0.1 * (gs[0] + gs[1] + gs[2]) / 3
+    torch.testing.assert_close(wd.master, want, rtol=1e-6, atol=1e-6)
+    assert torch.equal(wd.shadow, _bf16(wd.master))
+    assert int(wd.u64("global_step")) == 1 and int(wd.u64("param_version")) == 1 and int(wd.u64("applied_total")) == 3
+    for w in range(3):
+        assert wd.mailbox(w).tolist() == [1, 1]                 # token and version carry the NEW global step
+        assert int(wd.u64("consumed", 1, 8 * w)) == wd.cpp
+    assert int(wd.u32("err")) == 0
+    # second aggregate: stamps must be >= the current global step (1) to count
+    for w in range(3):
+        wd.push(w, gs[w], stamp=1)
+    wd.apply()
+    torch.testing.assert_close(wd.master, want - 0.1 * (gs[0] + gs[1] + gs[2]) / 3, rtol=1e-6, atol=1e-6)
+    assert int(wd.u64("global_step")) == 2 and wd.mailbox(2).tolist() == [2, 2]
+
+
+def test_incomplete_push_is_not_consumed_until_all_its_ctas_arrived(emu):
+    wd = World(emu, workers=2, ctas_per_push=4)
+    wd.a.timeout_ns = 2_000_000
+    wd.push(0, torch.ones(wd.n), 0)
+    wd.grads[1].fill_(1.0)
+    wd.slot(1)[0] += 3                                           # 3 of 4 CTAs of worker 1 have arrived
+    wd.apply()
+    assert int(wd.u32("err")) == 2 and int(wd.u64("global_step")) == 0 and torch.equal(wd.master, wd.master0)
+    wd.u32("err")[0] = 0
+    wd.slot(1)[0] += 1                                           # the last CTA
+    wd.apply()
+    assert int(wd.u32("err")) == 0 and int(wd.u64("global_step")) == 1
+    torch.testing.assert_close(wd.master, wd.master0 - 0.1 * torch.ones(wd.n))
+
+
+def test_backup_workers_and_stale_drop(emu):
+    """replicas_to_aggregate=2 of 3: the aggregate goes ahead with two fresh gradients; the straggler's push, stamped
+    with the old step, is dropped by the next aggregate, which then waits for fresh ones."""
+    wd = World(emu, workers=3, R=2, lr=0.5)
+    g = [torch.full((wd.n,), float(w + 1)) for w in range(3)]
+    wd.push(0, g[0], 0)
+    wd.push(1, g[1], 0)
+    wd.apply()
+    torch.testing.assert_close(wd.master, wd.master0 - 0.5 * (g[0] + g[1]) / 2)
+    assert int(wd.u64("global_step")) == 1 and int(wd.u64("dropped_stale")) == 0
+    assert [wd.mailbox(w)[0].item() for w in range(3)] == [1, 1, 1]        # every replica gets a token, pushers or not
+    m1 = wd.master.clone()
+    wd.push(2, g[2], 0)          # straggler: computed against step 0
+    wd.push(0, g[0], 1)
+    wd.push(1, g[1], 1)
+    wd.apply()
+    assert int(wd.u64("dropped_stale")) == 1 and int(wd.u64("global_step")) == 2
+    torch.testing.assert_close(wd.master, m1 - 0.5 * (g[0] + g[1]) / 2)    # the stale gradient did not contribute
+    assert int(wd.u64("consumed", 1, 16)) == wd.cpp                          # ...but its arrivals were consumed
+
+
+def test_timeout_sets_error_unless_idle_polling(emu):
+    wd = World(emu, workers=2)
+    wd.a.timeout_ns = 1_000_000
+    wd.a.idle_ok = 1
+    wd.apply()
+    assert int(wd.u32("err")) == 0 and int(wd.u64("global_step")) == 0 and int(wd.u64("param_version")) == 1
+    wd.a.idle_ok = 0
+    wd.apply()
+    assert int(wd.u32("err")) == 2 and wd.mailbox(0).tolist() == [0, 0]
+
+
+def test_async_applies_each_push_alone_round_robin_with_staleness(emu):
+    wd = World(emu, workers=3, sync=False, lr=0.1)
+    g = [torch.full((wd.n,), float(w + 1)) for w in range(3)]
+    for w in (2, 0):                     # two pushes pending, both computed from version 0
+        wd.push(w, g[w], stamp=0)
+    wd.apply()                           # round robin starts after last_async_worker (0) -> worker 2? no: 1 is empty -> 2
+    wd.apply()
+    torch.testing.assert_close(wd.master, wd.master0 - 0.1 * g[2] - 0.1 * g[0])       # no mean: each push applied alone
+    assert int(wd.u64("global_step")) == 2
+    hist = wd.u64("staleness_hist", 16).tolist()
+    assert hist[0] == 1 and hist[1] == 1 and sum(hist) == 2 and int(wd.u64("staleness_sum")) == 1
+    assert wd.mailbox(2).tolist() == [1, 1] and wd.mailbox(0).tolist() == [1, 2]      # acks only to the pusher; version = gs
+    assert wd.mailbox(1).tolist() == [0, 0]
+
+
+def test_momentum_and_nesterov(emu):
+    for nesterov in (False, True):
+        wd = World(emu, workers=1, kind=1, lr=0.1, momentum=0.9, nesterov=nesterov)
+        p, acc = wd.master0.clone(), torch.zeros(wd.n)
+        for t in range(3):
+            g = torch.randn(wd.n, generator=torch.Generator().manual_seed(t))
+            wd.push(0, g, t)
+            wd.apply()
+            acc = 0.9 * acc + g
+            p = p - (0.1 * g + 0.1 * 0.9 * acc if nesterov else 0.1 * acc)
+        torch.testing.assert_close(wd.master, p, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(wd.slot_m, acc, rtol=1e-5, atol=1e-5)
+
+
+def test_tf_adam_formulation_and_beta_powers(emu):
+    wd = World(emu, workers=2, kind=2, lr=0.01)
+    p, m, v = wd.master0.double(), torch.zeros(wd.n).double(), torch.zeros(wd.n).double()
+    for t in range(1, 4):
+        gs = [torch.randn(wd.n, generator=torch.Generator().manual_seed(10 * t + w)) for w in range(2)]
+        for w in range(2):
+            wd.push(w, gs[w], t - 1)
+        wd.apply()
+        g = ((gs[0] + gs[1]) / 2).double()
+        lr_t = 0.01 * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)        # epsilon OUTSIDE the bias correction (TF)
+        m = 0.9 * m + 0.1 * g
+        v = 0.999 * v + 0.001 * g * g
+        p = p - lr_t * m / (v.sqrt() + 1e-8)
+    torch.testing.assert_close(wd.master.double(), p, rtol=2e-4, atol=2e-5)
+    b = wd.f32("beta1_power", 2)
+    assert abs(float(b[0]) - 0.9 ** 4) < 1e-6 and abs(float(b[1]) - 0.999 ** 4) < 1e-6
+
+
+def test_zero_after_read_ranges_and_unicast_replica_publish(emu):
+    wd = World(emu, workers=2)
+    wd.a.publish_replicas = 1
+    for w in range(2):
+        wd.a.replica[w] = wd.replicas[w].data_ptr()
+    wd.a.num_zero = 1
+    wd.a.zero_begin[0], wd.a.zero_end[0] = 64, 130              # not float4-aligned at the end on purpose
+    for w in range(2):
+        wd.push(w, torch.ones(wd.n), 0)
+    wd.apply()
+    for w in range(2):
+        assert torch.equal(wd.replicas[w], _bf16(wd.master))
+        assert float(wd.grads[w][64:130].abs().sum()) == 0.0 and float(wd.grads[w][:64].min()) == 1.0
+        assert float(wd.grads[w][130:].min()) == 1.0
+
+
+@pytest.mark.parametrize("n", [1280, 1030])
+def test_multicast_reduce_and_publish_match_the_unicast_path(emu, n):
+    """NVLS mode: gradients stay in the workers' copies of a symmetric buffer (the ps's own copy holds zeros),
+    multimem.ld_reduce sums them, ONE multimem.st updates every replica, zero-after-read clears every copy."""
+    W = 3
+    uni, mc = World(emu, n=n, workers=W), World(emu, n=n, workers=W)
+    g = [torch.randn(n, generator=torch.Generator().manual_seed(w)) for w in range(W)]
+    ps_copy = torch.zeros(n)                                       # the ps GPU's own copy of the symmetric gradient buffer
+    fake_g, fake_r = torch.zeros(n), torch.zeros(n, dtype=torch.bfloat16)          # placeholder "multicast" address ranges
+    members_g = (ctypes.c_void_p * (W + 1))(ps_copy.data_ptr(), *[mc.grads[w].data_ptr() for w in range(W)])
+    ps_repl = torch.zeros(n, dtype=torch.bfloat16)
+    members_r = (ctypes.c_void_p * (W + 1))(ps_repl.data_ptr(), *[mc.replicas[w].data_ptr() for w in range(W)])
+    emu.dtf_emu_mc_register(fake_g.data_ptr(), n * 4, members_g, W + 1)
+    emu.dtf_emu_mc_register(fake_r.data_ptr(), n * 2, members_r, W + 1)
+    mc.a.grad_mc, mc.a.shadow_mc = fake_g.data_ptr(), fake_r.data_ptr()
+    mc.a.shadow = ps_repl.data_ptr()
+    for wd in (uni, mc):
+        wd.a.num_zero = 1
+        wd.a.zero_begin[0], wd.a.zero_end[0] = 128, 256
+        for w in range(W):
+            wd.push(w, g[w], 0)
+        wd.apply()
+    torch.testing.assert_close(mc.master, uni.master, rtol=1e-6, atol=1e-6)
+    nv = n // 4 * 4                                               # the scalar tail is written through `shadow` only
+    for w in range(W):
+        assert torch.equal(mc.replicas[w][:nv], _bf16(mc.master)[:nv])
+        assert float(mc.grads[w][128:256].abs().sum()) == 0.0 and float(mc.grads[w][:128].abs().sum()) > 0
+    assert torch.equal(ps_repl, _bf16(mc.master))
+    # a missing push (backup workers) falls back to unicast reads of the chosen workers' copies
+    mc.a.replicas_to_aggregate = 2
+    m1 = mc.master.clone()
+    mc.push(0, g[0], 1)
+    mc.push(2, g[2], 1)
+    mc.apply()
+    want = m1 - 0.1 * (g[0] + g[2]) / 2
+    want[128:256] = m1[128:256] - 0.1 * (g[0] + g[2])[128:256] / 2
+    torch.testing.assert_close(mc.master, want, rtol=1e-6, atol=1e-6)
+    emu.dtf_emu_mc_clear()
+
+
+def test_push_grad_wait_token_publish_and_pull(emu):
+    wd = World(emu, n=1030, workers=2)
+    src = torch.randn(1030)
+    wd.mailbox(1)[0], wd.mailbox(1)[1] = 7, 9                    # token 7, version 9
+    mbp = wd.mb.data_ptr() + wd.mb_bytes
+    slot1 = torch.zeros(1030)                      # 16-byte aligned like the engine's slots (1030: exercises the scalar tail)
+    assert emu.dtf_push_grad(src.data_ptr(), slot1.data_ptr(), 1030, wd.ctl.data_ptr(), mbp, 1, 0, 1, 3, None) == 0
+    assert torch.equal(slot1, src) and wd.slot(1).tolist() == [3, 7]                  # 3 CTAs arrived, stamp = token (sync)
+    assert emu.dtf_push_grad(None, None, 0, wd.ctl.data_ptr(), mbp, 1, 1, 1, 1, None) == 0     # signal-only, async stamp
+    assert wd.slot(1).tolist() == [4, 9]
+    err = torch.zeros(1, dtype=torch.int32)
+    assert emu.dtf_wait_token(mbp, 7, None, 1_000_000, err.data_ptr(), None) == 0 and int(err) == 0
+    base = torch.tensor([3], dtype=torch.int64)                                        # target = 5 + *ptr = 8 > token 7
+    assert emu.dtf_wait_token(mbp, 5, base.data_ptr(), 1_000_000, err.data_ptr(), None) == 0 and int(err) == 3
+    shadow = torch.zeros(1030, dtype=torch.bfloat16)
+    assert emu.dtf_ps_publish(wd.master.data_ptr(), shadow.data_ptr(), 1030, None) == 0
+    assert torch.equal(shadow, _bf16(wd.master))
+    dst = torch.zeros(1024, dtype=torch.bfloat16)
+    assert emu.dtf_pull_shadow(shadow.data_ptr(), dst.data_ptr(), 2048, 2, None) == 0
+    assert torch.equal(dst, shadow[:1024])
+
+
+def test_fabric_broadcast_and_reduce_unicast_and_multicast(emu):
+    n = 4096 + 8
+    src = torch.arange(n, dtype=torch.float32)
+    copies = [torch.zeros(n) for _ in range(3)]
+    peers = (ctypes.c_void_p * MAX_WORKERS)(*[c.data_ptr() for c in copies])
+    assert emu.dtf_fabric_bcast(src.data_ptr(), None, peers, 3, n * 4, 2, None) == 0
+    assert all(torch.equal(c, src) for c in copies)
+    out = torch.zeros(n)
+    assert emu.dtf_fabric_reduce(None, peers, 3, out.data_ptr(), n, 2, None) == 0
+    assert torch.equal(out, 3 * src)
+    fake = torch.zeros(n)
+    emu.dtf_emu_mc_register(fake.data_ptr(), n * 4, peers, 3)
+    for c in copies:
+        c.zero_()
+    assert emu.dtf_fabric_bcast(src.data_ptr(), fake.data_ptr(), peers, 0, n * 4, 3, None) == 0
+    assert all(torch.equal(c, src) for c in copies)
+    out.zero_()
+    assert emu.dtf_fabric_reduce(fake.data_ptr(), peers, 0, out.data_ptr(), n, 3, None) == 0
+    assert torch.equal(out, 3 * src)
+    assert emu.dtf_fabric_reduce(None, peers, 3, out.data_ptr(), n - 2, 1, None) == -2        # not a multiple of 4 floats
+    emu.dtf_emu_mc_clear()
