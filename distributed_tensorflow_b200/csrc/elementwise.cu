@@ -8,7 +8,13 @@
 #include <cstdio>
 #include <cstring>
 
+// DTF_HOST_EMU: this file also compiles with g++ against tests/emu/host_emu.h, so the CPU test tier runs these kernels
+// from the same source (docs/TESTING.md, "Host emulation of the CUDA block model").
+#ifdef DTF_HOST_EMU
+#include "host_emu.h"
+#else
 #include "common.cuh"
+#endif
 
 namespace dtf {
 
@@ -297,17 +303,17 @@ int dtf_convert_f32_bf16(const float* in, long long ld_in, void* out, long long 
   if (ld_in == cols && ld_out == cols && cols_pad == cols && (rows * cols) % 4 == 0 &&
       (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
     const long long n4 = rows * cols / 4;
-    convert_f32_bf16_vec_kernel<<<grid_for(n4), 256, 0, s>>>(reinterpret_cast<const float4*>(in),
+    DTF_LAUNCH(convert_f32_bf16_vec_kernel, grid_for(n4), 256, s, reinterpret_cast<const float4*>(in),
                                                              reinterpret_cast<uint2*>(out), n4);
   } else {
-    convert_f32_bf16_kernel<<<grid_for(rows * cols_pad), 256, 0, s>>>(in, ld_in, reinterpret_cast<__nv_bfloat16*>(out),
+    DTF_LAUNCH(convert_f32_bf16_kernel, grid_for(rows * cols_pad), 256, s, in, ld_in, reinterpret_cast<__nv_bfloat16*>(out),
                                                                       ld_out, rows, cols, cols_pad);
   }
   return (int)cudaGetLastError();
 }
 
 int dtf_convert_u8_bf16(const void* in, void* out, long long n, float scale, cudaStream_t s) {
-  convert_u8_bf16_kernel<<<grid_for(n), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(in),
+  DTF_LAUNCH(convert_u8_bf16_kernel, grid_for(n), 256, s, reinterpret_cast<const uint8_t*>(in),
                                                      reinterpret_cast<__nv_bfloat16*>(out), n, scale);
   return (int)cudaGetLastError();
 }
@@ -317,29 +323,29 @@ int dtf_softmax_xent(const float* logits, long long ld_logits, const float* labe
                      void* dlogits_bf16, long long ld_db, int cols_pad_bf16, float* probs, long long ld_p, float grad_scale,
                      cudaStream_t s) {
   const int wpb = 4;
-  softmax_xent_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, s>>>(
+  DTF_LAUNCH(softmax_xent_kernel, (rows + wpb - 1) / wpb, wpb * 32, s,
       logits, ld_logits, labels, ld_labels, rows, cols, clip_min, loss_sum, loss_rows, dlogits, ld_d,
       reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ld_db, cols_pad_bf16, probs, ld_p, grad_scale);
   return (int)cudaGetLastError();
 }
 
 int dtf_relu_grad(const float* g, const float* y, float* out, long long n, cudaStream_t s) {
-  relu_grad_kernel<<<grid_for(n), 256, 0, s>>>(g, y, out, n);
+  DTF_LAUNCH(relu_grad_kernel, grid_for(n), 256, s, g, y, out, n);
   return (int)cudaGetLastError();
 }
 
 int dtf_colsum(const float* in, long long ld, int rows, int cols, float* out, cudaStream_t s) {
-  colsum_kernel<<<(cols + 31) / 32, 256, 0, s>>>(in, ld, rows, cols, out);
+  DTF_LAUNCH(colsum_kernel, (cols + 31) / 32, 256, s, in, ld, rows, cols, out);
   return (int)cudaGetLastError();
 }
 
 int dtf_argmax_rows(const float* in, long long ld, int rows, int cols, long long* out, cudaStream_t s) {
-  argmax_rows_kernel<<<(rows + 3) / 4, 128, 0, s>>>(in, ld, rows, cols, out);
+  DTF_LAUNCH(argmax_rows_kernel, (rows + 3) / 4, 128, s, in, ld, rows, cols, out);
   return (int)cudaGetLastError();
 }
 
 int dtf_mean_of_n(const float* const* ins_dev, int n_in, float* out, long long n, cudaStream_t s) {
-  mean_of_n_kernel<<<grid_for(n), 256, 0, s>>>(ins_dev, n_in, out, n);
+  DTF_LAUNCH(mean_of_n_kernel, grid_for(n), 256, s, ins_dev, n_in, out, n);
   return (int)cudaGetLastError();
 }
 
@@ -350,20 +356,20 @@ int dtf_optimizer_apply(float* var, float* m, float* v, const float* g, void* sh
   a.var = var; a.m = m; a.v = v; a.g = g; a.shadow = reinterpret_cast<__nv_bfloat16*>(shadow_bf16); a.n = n;
   a.kind = kind; a.lr = lr; a.momentum = momentum; a.nesterov = nesterov; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
   a.grad_scale = grad_scale;
-  optimizer_apply_kernel<<<grid_for(n), 256, 0, s>>>(a);
+  DTF_LAUNCH(optimizer_apply_kernel, grid_for(n), 256, s, a);
   return (int)cudaGetLastError();
 }
 
 int dtf_im2col_nhwc(const float* x, void* cols, int n, int h, int w, int c, int kh, int kw, int sh, int sw, int pt, int pl,
                     int ho, int wo, long long ldc, cudaStream_t s) {
-  im2col_nhwc_kernel<<<grid_for((long long)n * ho * wo * ldc), 256, 0, s>>>(
+  DTF_LAUNCH(im2col_nhwc_kernel, grid_for((long long)n * ho * wo * ldc), 256, s,
       x, reinterpret_cast<__nv_bfloat16*>(cols), n, h, w, c, kh, kw, sh, sw, pt, pl, ho, wo, ldc);
   return (int)cudaGetLastError();
 }
 
 int dtf_col2im_nhwc(const float* gcols, long long ldg, float* gx, int n, int h, int w, int c, int kh, int kw, int sh, int sw,
                     int pt, int pl, int ho, int wo, cudaStream_t s) {
-  col2im_nhwc_kernel<<<grid_for((long long)n * h * w * c), 256, 0, s>>>(gcols, ldg, gx, n, h, w, c, kh, kw, sh, sw, pt,
+  DTF_LAUNCH(col2im_nhwc_kernel, grid_for((long long)n * h * w * c), 256, s, gcols, ldg, gx, n, h, w, c, kh, kw, sh, sw, pt,
                                                                        pl, ho, wo);
   return (int)cudaGetLastError();
 }
@@ -371,7 +377,7 @@ int dtf_col2im_nhwc(const float* gcols, long long ldg, float* gx, int n, int h, 
 int dtf_gemm_ref(const void* a, const void* b, float* c, int M, int N, int K, long long lda, long long ldb, long long ldc,
                  int a_mn, int b_mn, const float* bias, int relu, float alpha, cudaStream_t s) {
   dim3 block(32, 8), grid((N + 31) / 32, (M + 7) / 8);
-  gemm_ref_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b),
+  DTF_LAUNCH(gemm_ref_kernel, grid, block, s, reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b),
                                          c, M, N, K, lda, ldb, ldc, a_mn, b_mn, bias, relu, alpha);
   return (int)cudaGetLastError();
 }

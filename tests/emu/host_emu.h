@@ -6,6 +6,7 @@
 #pragma once
 #include <pthread.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -61,8 +62,11 @@ static inline int cudaGetLastError() { return 0; }
 
 namespace dtf_emu {
 inline thread_local dim3 t_idx;
+inline thread_local unsigned lin_tid;                 // x + y * dim.x + z * dim.x * dim.y: warps are 32 consecutive ids
 inline dim3 b_idx, b_dim, g_dim;
 inline pthread_barrier_t* barrier = nullptr;
+inline pthread_barrier_t* warp_bars = nullptr;        // one barrier + one exchange row per warp (warp shuffles)
+inline uint64_t (*warp_slots)[32] = nullptr;
 
 static inline void sync() { pthread_barrier_wait(barrier); }
 
@@ -71,6 +75,12 @@ static inline void launch(dim3 grid, dim3 block, const std::function<void()>& bo
   pthread_barrier_t bar;
   pthread_barrier_init(&bar, nullptr, nthreads);
   barrier = &bar;
+  const unsigned nwarps = (nthreads + 31) / 32;
+  std::vector<pthread_barrier_t> wb(nwarps);
+  for (unsigned wi = 0; wi < nwarps; ++wi) pthread_barrier_init(&wb[wi], nullptr, std::min(32u, nthreads - 32 * wi));
+  std::vector<uint64_t> slots((size_t)nwarps * 32);
+  warp_bars = wb.data();
+  warp_slots = reinterpret_cast<uint64_t(*)[32]>(slots.data());
   g_dim = grid;
   b_dim = block;
   for (unsigned bz = 0; bz < grid.z; ++bz)
@@ -84,12 +94,16 @@ static inline void launch(dim3 grid, dim3 block, const std::function<void()>& bo
             for (unsigned tx = 0; tx < block.x; ++tx)
               ts.emplace_back([&, tx, ty, tz]() {
                 t_idx = dim3(tx, ty, tz);
+                lin_tid = tx + ty * block.x + tz * block.x * block.y;
                 body();
               });
         for (auto& t : ts) t.join();
       }
   pthread_barrier_destroy(&bar);
+  for (auto& b : wb) pthread_barrier_destroy(&b);
   barrier = nullptr;
+  warp_bars = nullptr;
+  warp_slots = nullptr;
 }
 }  // namespace dtf_emu
 
@@ -185,3 +199,33 @@ static inline void multimem_st_f32x4(float* mc, float4 v) { dtf_emu_mc_store(mc,
 static inline void multimem_st_b64(void* mc, uint32_t lo, uint32_t hi) { dtf_emu_mc_store(mc, uint2{lo, hi}); }
 static inline void multimem_st_b128(void* mc, uint4 v) { dtf_emu_mc_store(mc, v); }
 }  // namespace dtf
+
+// ---- warp shuffles (full-mask, all lanes of the warp call it -- which is how the kernels use them) --------------------------
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+  const unsigned warp = dtf_emu::lin_tid / 32, lane = dtf_emu::lin_tid % 32;
+  uint64_t bits = 0;
+  std::memcpy(&bits, &v, sizeof(T));
+  dtf_emu::warp_slots[warp][lane] = bits;
+  pthread_barrier_wait(&dtf_emu::warp_bars[warp]);
+  const uint64_t other = dtf_emu::warp_slots[warp][lane ^ (unsigned)lane_mask];
+  pthread_barrier_wait(&dtf_emu::warp_bars[warp]);
+  T r;
+  std::memcpy(&r, &other, sizeof(T));
+  return r;
+}
+#define __expf(x) std::exp((float)(x))       // glibc declares __expf / __logf itself: map the CUDA fast-math names by macro
+#define __logf(x) std::log((float)(x))
+static inline float __bfloat162float(__nv_bfloat16 b) {
+  const unsigned u = (unsigned)b.v << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+static inline float atomicAdd(float* p, float v) {
+  static std::mutex mu;                  // blocks run one after another; threads of a block contend rarely
+  std::lock_guard<std::mutex> g(mu);
+  const float old = *p;
+  *p = old + v;
+  return old;
+}
