@@ -15,6 +15,8 @@
 #define DTF_DEVICE __device__ __forceinline__
 // Kernel launch (no dynamic shared memory).  tests/emu/host_emu.h defines the same macro for the g++ emulation build.
 #define DTF_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define DTF_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define DTF_DYN_SMEM(type, name) extern __shared__ type name[]
 
 namespace dtf {
 

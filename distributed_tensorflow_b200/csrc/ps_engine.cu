@@ -18,7 +18,7 @@
 // DTF_HOST_EMU: the ps-side kernels of this file (ps_apply, publish, push/pull, token wait, fabric collectives) also
 // compile with g++ against tests/emu/host_emu.h -- threads + barriers stand in for a thread block, plain atomics for the
 // scoped PTX accesses, a registry of member buffers for multimem -- so the protocol (fresh/stale decision, mean, apply,
-// tokens, staleness) is exercised by the CPU test tier from the SAME source.  The tensor-core-side kernels are excluded.
+// tokens, staleness) and the fused MLP head are exercised by the CPU test tier from the SAME source.
 #ifdef DTF_HOST_EMU
 #include "host_emu.h"
 #else
@@ -323,7 +323,6 @@ __global__ void ps_publish_kernel(const float* __restrict__ master, __nv_bfloat1
     shadow[i] = __float2bfloat16(master[i]);
 }
 
-#ifndef DTF_HOST_EMU   // tensor-core-side kernel (warp shuffles, dynamic shared memory): hardware tier only
 // ---------------------------------------------------------------------------------------------
 // Fused MLP head (SURVEY K2+K3+K4 small parts), ONE CTA:
 //   logits = h.W2 + b2 ; softmax ; clipped cross-entropy (batch SUM) ; dlogits ;
@@ -366,7 +365,7 @@ struct MlpHeadParams {
 };
 
 __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p) {
-  extern __shared__ float sm[];
+  DTF_DYN_SMEM(float, sm);
   // Row-parallel: CTA i owns batch rows [i*rows_per_cta, ...).  Row-owned work (logits, softmax, dh) is disjoint;
   // the batch reductions (dW2, db2, db1, loss) are combined with fp32 atomics -- into the ps slot over NVLink
   // for the gradients (the ps clears those ranges after reading them).
@@ -512,8 +511,11 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
   }
   __syncthreads();
   HSTAMP(2);          // logits done
-  if (p.logits_out)
+  if (p.logits_out) {
     for (int i = tid; i < B * C; i += nt) p.logits_out[(long long)row_lo * C + i] = s_dl[(i / C) * DS + (i % C)];
+    __syncthreads();    // the softmax below rewrites s_dl in place (uniform branch: logits_out is a kernel argument);
+                        // found by the host-emulation tier -- without it the optional copy raced with the row owners
+  }
 
   // ---- softmax + clipped xent + dlogits, one thread per row (rows read/written as float4) ---------------------------
   float my_loss = 0.f;
@@ -677,14 +679,12 @@ __global__ void __launch_bounds__(512, 1) mlp_head_kernel(const MlpHeadParams p)
       // thread serialises for tens of microseconds
       if (p.sys_scope) __threadfence_system(); else __threadfence();
       const unsigned long long stamp = p.stamp_from_version ? p.mailbox->version : p.mailbox->token;
-      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&p.ctl->w[p.rank].stamp), "l"(stamp) : "memory");
+      st_relaxed_sys_ull(&p.ctl->w[p.rank].stamp, stamp);
       red_release_sys_add_u64(reinterpret_cast<uint64_t*>(&p.ctl->w[p.rank].arrivals), 1ull);
     }
   }
   HSTAMP(6);          // fenced + signalled
 }
-
-#endif  // !DTF_HOST_EMU
 
 // Input-pipeline stage for the device-resident dataset: batch index = (step * stride + offset) % nbatches,
 // where step is the worker's DEVICE step counter (so the launch is CUDA-graph replayable).  Converts the
@@ -923,7 +923,6 @@ int dtf_ps_publish(const float* master, void* shadow, long long n, cudaStream_t 
   return (int)cudaGetLastError();
 }
 
-#ifndef DTF_HOST_EMU
 struct DtfMlpHeadArgs {
   const void* h; long long ldh;
   const void* w2; long long ldw2;
@@ -962,6 +961,7 @@ int dtf_mlp_head(const DtfMlpHeadArgs* a, cudaStream_t s) {
   const size_t smem = sizeof(float) * ((size_t)a->B * (a->H + 1) + (size_t)a->H * 16 + (size_t)a->B * 40 + 16 + 32 + 512);
   if (a->B > 512 || a->H > 512) return -2;
   if ((a->ldh % 8) || (a->ldw2 % 8) || a->ldh > 8 * 8 * 512 / a->B) return -3;
+#ifndef DTF_HOST_EMU
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -970,11 +970,10 @@ int dtf_mlp_head(const DtfMlpHeadArgs* a, cudaStream_t s) {
     if (e != cudaSuccess) return (int)e;
     configured[dev] = true;
   }
-  mlp_head_kernel<<<ctas, 512, smem, s>>>(p);
+#endif
+  DTF_LAUNCH_SMEM(mlp_head_kernel, ctas, 512, smem, s, p);
   return (int)cudaGetLastError();
 }
-
-#endif  // !DTF_HOST_EMU
 
 int dtf_stage_from_dataset(const float* images, const float* labels, long long nbatches, int B, int D, int C,
                            long long stride, long long offset, const unsigned long long* step_counter, void* x16,

@@ -56,6 +56,9 @@ static inline __nv_bfloat16 __float2bfloat16(float f) { return __nv_bfloat16{(ui
 #define __align__(n) alignas(n)
 #define DTF_DEVICE static inline
 #define DTF_LAUNCH(kernel, grid, block, stream, ...) dtf_emu::launch((grid), (block), [&]() { kernel(__VA_ARGS__); })
+#define DTF_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
+  dtf_emu::launch((grid), (block), [&]() { kernel(__VA_ARGS__); }, (size_t)(smem))
+#define DTF_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(dtf_emu::dyn_smem)
 
 typedef void* cudaStream_t;
 static inline int cudaGetLastError() { return 0; }
@@ -67,11 +70,14 @@ inline dim3 b_idx, b_dim, g_dim;
 inline pthread_barrier_t* barrier = nullptr;
 inline pthread_barrier_t* warp_bars = nullptr;        // one barrier + one exchange row per warp (warp shuffles)
 inline uint64_t (*warp_slots)[32] = nullptr;
+inline void* dyn_smem = nullptr;                      // dynamic shared memory of the block being executed
 
 static inline void sync() { pthread_barrier_wait(barrier); }
 
-static inline void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
+static inline void launch(dim3 grid, dim3 block, const std::function<void()>& body, size_t smem_bytes = 0) {
   const unsigned nthreads = block.x * block.y * block.z;
+  std::vector<float4> smem_buf((smem_bytes + 15) / 16 + 1);        // 16-byte aligned like the hardware's
+  dyn_smem = smem_buf.data();
   pthread_barrier_t bar;
   pthread_barrier_init(&bar, nullptr, nthreads);
   barrier = &bar;
@@ -104,6 +110,7 @@ static inline void launch(dim3 grid, dim3 block, const std::function<void()>& bo
   barrier = nullptr;
   warp_bars = nullptr;
   warp_slots = nullptr;
+  dyn_smem = nullptr;
 }
 }  // namespace dtf_emu
 
@@ -229,3 +236,11 @@ static inline float atomicAdd(float* p, float v) {
   *p = old + v;
   return old;
 }
+
+static inline float __uint_as_float(unsigned u) {
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+using std::max;
+using std::min;

@@ -331,3 +331,74 @@ def test_fabric_broadcast_and_reduce_unicast_and_multicast(emu):
     assert torch.equal(out, 3 * src)
     assert emu.dtf_fabric_reduce(None, peers, 3, out.data_ptr(), n - 2, 1, None) == -2        # not a multiple of 4 floats
     emu.dtf_emu_mc_clear()
+
+
+@pytest.mark.parametrize("ctas,split_k", [(1, False), (8, False), (4, True)])
+def test_fused_mlp_head_matches_pytorch(emu, ctas, split_k):
+    """mlp_head_kernel (K2 + K3 + the small parts of K4, fused with the push of dW2 / db2 / db1 and the arrival signal):
+    logits, softmax, the reference's clipped batch-SUM cross-entropy, dlogits with the clip gate, dW2, db2, dh (bf16, feeds
+    the dW1 GEMM), db1 -- one CTA (plain stores) and row-parallel CTAs (fp32 atomics into the zeroed ps slot)."""
+    from distributed_tensorflow_b200.ops.cuda_lib import MlpHeadArgs
+    emu.dtf_mlp_head.argtypes = [ctypes.POINTER(MlpHeadArgs), ctypes.c_void_p]
+    B, H, C, ldh, ldw = 100, 100, 10, 104, 16
+    g = torch.Generator().manual_seed(ctas)
+    b1 = torch.randn(H, generator=g) * 0.1
+    acc = torch.randn(B, ldh, generator=g)
+    acc[:, H:] = 0
+    hf = torch.relu(acc[:, :H] + b1) if split_k else torch.relu(torch.randn(B, H, generator=g))
+    h16 = torch.zeros(B, ldh, dtype=torch.bfloat16)
+    h16[:, :H] = hf.bfloat16()
+    hq = hf if split_k else h16[:, :H].float()              # what the kernel sees: fp32 (split-K) or bf16-rounded h
+    w2 = torch.zeros(H, ldw, dtype=torch.bfloat16)
+    w2[:, :C] = (torch.randn(H, C, generator=g) * 0.3).bfloat16()
+    b2 = torch.randn(C, generator=g) * 0.1
+    labels = torch.nn.functional.one_hot(torch.randint(0, C, (B,), generator=g), C).float()
+    hq[0] = 0.0                                              # row 0: logits = b2; push class 3 far below the clip
+    if split_k:
+        acc[0] = -10.0
+    else:
+        h16[0] = 0
+    b2c = b2.clone()
+    b2c[3] = -70.0
+    labels[0] = 0.0
+    labels[0, 3] = 1.0
+
+    wd = World(emu, workers=2)
+    wd.mailbox(1)[0], wd.mailbox(1)[1] = 5, 6
+    loss = torch.zeros(16)
+    stepctr = torch.tensor([41], dtype=torch.int64)
+    dh = torch.full((B, ldh), 7.0, dtype=torch.bfloat16)
+    gw2, gb2, gb1 = torch.zeros(H, ldw), torch.zeros(C), torch.zeros(H)
+    logits = torch.zeros(B, C)
+    a = MlpHeadArgs()
+    a.h, a.ldh, a.w2, a.ldw2, a.b2 = h16.data_ptr(), ldh, w2.data_ptr(), ldw, b2c.data_ptr()
+    a.labels, a.ldl, a.B, a.H, a.C, a.clip_min = labels.data_ptr(), C, B, H, C, 1e-10
+    a.loss_out, a.step_counter = loss.data_ptr(), stepctr.data_ptr()
+    a.dh, a.lddh, a.gw2, a.ldgw2, a.gb2, a.gb1 = dh.data_ptr(), ldh, gw2.data_ptr(), ldw, gb2.data_ptr(), gb1.data_ptr()
+    a.logits_out = logits.data_ptr()
+    a.mailbox, a.ctl, a.rank, a.stamp_from_version = wd.mb.data_ptr() + wd.mb_bytes, wd.ctl.data_ptr(), 1, 0
+    a.sys_scope, a.ctas = 1, ctas
+    if split_k:
+        a.h_acc, a.ld_acc, a.b1 = acc.data_ptr(), ldh, b1.data_ptr()
+    assert emu.dtf_mlp_head(ctypes.byref(a), None) == 0
+
+    W = w2[:, :C].float()
+    z = (hq.double() @ W.double() + b2c.double()).requires_grad_()
+    y = torch.softmax(z, -1)
+    want_loss = -(labels.double() * torch.log(torch.clamp(y, 1e-10, 1.0))).sum()
+    (dl,) = torch.autograd.grad(want_loss, z)
+    n_ctas = (B + ((B + ctas - 1) // ctas + 7) // 8 * 8 - 1) // (((B + ctas - 1) // ctas + 7) // 8 * 8)
+    torch.testing.assert_close(loss[:n_ctas].double().sum(), want_loss.detach(), rtol=1e-5, atol=1e-3)
+    assert float(loss[n_ctas:].abs().sum()) == 0.0
+    torch.testing.assert_close(logits.double(), z.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(gw2[:, :C].double(), hq.double().t() @ dl, rtol=1e-4, atol=1e-4)
+    assert float(gw2[:, C:].abs().sum()) == 0.0
+    torch.testing.assert_close(gb2.double(), dl.sum(0), rtol=1e-4, atol=1e-4)
+    dhf = (dl @ W.double().t()) * (hq.double() > 0)
+    torch.testing.assert_close(gb1.double(), dhf.sum(0), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dh[:, :H].float().double(), dhf, rtol=1e-2, atol=1e-3)           # bf16 output
+    assert float(dl[0].abs().max()) == 0.0 and float(dh[0, :H].float().abs().max()) == 0.0       # the clipped row
+    assert int(stepctr) == 42                                                                      # device step counter
+    assert wd.slot(1).tolist() == [n_ctas, 5]                      # one arrival per CTA, stamp = the token (sync)
+    if split_k:
+        assert float(acc[:, :H].abs().sum()) == 0.0               # accumulator cleared for the next step
