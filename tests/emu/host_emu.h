@@ -58,47 +58,56 @@ static inline __nv_bfloat16 __float2bfloat16(float f) { return __nv_bfloat16{(ui
 #define DTF_LAUNCH(kernel, grid, block, stream, ...) dtf_emu::launch((grid), (block), [&]() { kernel(__VA_ARGS__); })
 #define DTF_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
   dtf_emu::launch((grid), (block), [&]() { kernel(__VA_ARGS__); }, (size_t)(smem))
-#define DTF_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(dtf_emu::dyn_smem)
+#define DTF_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(dtf_emu::ctx->dyn_smem)
 
 typedef void* cudaStream_t;
 static inline int cudaGetLastError() { return 0; }
 
 namespace dtf_emu {
+// Everything a running block needs lives in a per-launch context, reached through a thread_local pointer: several host
+// threads can launch kernels at the same time (the multi-"GPU" protocol simulations do: one host thread per emulated
+// stream).  `__shared__` variables are function statics, so two launches of the SAME kernel must not overlap unless that
+// kernel declares no static shared memory.
+struct LaunchCtx {
+  dim3 b_idx, b_dim, g_dim;
+  pthread_barrier_t* barrier = nullptr;
+  pthread_barrier_t* warp_bars = nullptr;        // one barrier + one exchange row per warp (warp shuffles)
+  uint64_t (*warp_slots)[32] = nullptr;
+  void* dyn_smem = nullptr;                      // dynamic shared memory of the block being executed
+};
+inline thread_local LaunchCtx* ctx = nullptr;
 inline thread_local dim3 t_idx;
-inline thread_local unsigned lin_tid;                 // x + y * dim.x + z * dim.x * dim.y: warps are 32 consecutive ids
-inline dim3 b_idx, b_dim, g_dim;
-inline pthread_barrier_t* barrier = nullptr;
-inline pthread_barrier_t* warp_bars = nullptr;        // one barrier + one exchange row per warp (warp shuffles)
-inline uint64_t (*warp_slots)[32] = nullptr;
-inline void* dyn_smem = nullptr;                      // dynamic shared memory of the block being executed
+inline thread_local unsigned lin_tid;            // x + y * dim.x + z * dim.x * dim.y: warps are 32 consecutive ids
 
-static inline void sync() { pthread_barrier_wait(barrier); }
+static inline void sync() { pthread_barrier_wait(ctx->barrier); }
 
 static inline void launch(dim3 grid, dim3 block, const std::function<void()>& body, size_t smem_bytes = 0) {
   const unsigned nthreads = block.x * block.y * block.z;
+  LaunchCtx c;
   std::vector<float4> smem_buf((smem_bytes + 15) / 16 + 1);        // 16-byte aligned like the hardware's
-  dyn_smem = smem_buf.data();
+  c.dyn_smem = smem_buf.data();
   pthread_barrier_t bar;
   pthread_barrier_init(&bar, nullptr, nthreads);
-  barrier = &bar;
+  c.barrier = &bar;
   const unsigned nwarps = (nthreads + 31) / 32;
   std::vector<pthread_barrier_t> wb(nwarps);
   for (unsigned wi = 0; wi < nwarps; ++wi) pthread_barrier_init(&wb[wi], nullptr, std::min(32u, nthreads - 32 * wi));
   std::vector<uint64_t> slots((size_t)nwarps * 32);
-  warp_bars = wb.data();
-  warp_slots = reinterpret_cast<uint64_t(*)[32]>(slots.data());
-  g_dim = grid;
-  b_dim = block;
+  c.warp_bars = wb.data();
+  c.warp_slots = reinterpret_cast<uint64_t(*)[32]>(slots.data());
+  c.g_dim = grid;
+  c.b_dim = block;
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
-        b_idx = dim3(bx, by, bz);
+        c.b_idx = dim3(bx, by, bz);
         std::vector<std::thread> ts;
         ts.reserve(nthreads);
         for (unsigned tz = 0; tz < block.z; ++tz)
           for (unsigned ty = 0; ty < block.y; ++ty)
             for (unsigned tx = 0; tx < block.x; ++tx)
               ts.emplace_back([&, tx, ty, tz]() {
+                ctx = &c;
                 t_idx = dim3(tx, ty, tz);
                 lin_tid = tx + ty * block.x + tz * block.x * block.y;
                 body();
@@ -107,17 +116,13 @@ static inline void launch(dim3 grid, dim3 block, const std::function<void()>& bo
       }
   pthread_barrier_destroy(&bar);
   for (auto& b : wb) pthread_barrier_destroy(&b);
-  barrier = nullptr;
-  warp_bars = nullptr;
-  warp_slots = nullptr;
-  dyn_smem = nullptr;
 }
 }  // namespace dtf_emu
 
 #define threadIdx (dtf_emu::t_idx)
-#define blockIdx (dtf_emu::b_idx)
-#define blockDim (dtf_emu::b_dim)
-#define gridDim (dtf_emu::g_dim)
+#define blockIdx (dtf_emu::ctx->b_idx)
+#define blockDim (dtf_emu::ctx->b_dim)
+#define gridDim (dtf_emu::ctx->g_dim)
 #define __global__
 #define __shared__ static
 #define __launch_bounds__(...)
@@ -213,10 +218,10 @@ static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   const unsigned warp = dtf_emu::lin_tid / 32, lane = dtf_emu::lin_tid % 32;
   uint64_t bits = 0;
   std::memcpy(&bits, &v, sizeof(T));
-  dtf_emu::warp_slots[warp][lane] = bits;
-  pthread_barrier_wait(&dtf_emu::warp_bars[warp]);
-  const uint64_t other = dtf_emu::warp_slots[warp][lane ^ (unsigned)lane_mask];
-  pthread_barrier_wait(&dtf_emu::warp_bars[warp]);
+  dtf_emu::ctx->warp_slots[warp][lane] = bits;
+  pthread_barrier_wait(&dtf_emu::ctx->warp_bars[warp]);
+  const uint64_t other = dtf_emu::ctx->warp_slots[warp][lane ^ (unsigned)lane_mask];
+  pthread_barrier_wait(&dtf_emu::ctx->warp_bars[warp]);
   T r;
   std::memcpy(&r, &other, sizeof(T));
   return r;

@@ -402,3 +402,68 @@ def test_fused_mlp_head_matches_pytorch(emu, ctas, split_k):
     assert wd.slot(1).tolist() == [n_ctas, 5]                      # one arrival per CTA, stamp = the token (sync)
     if split_k:
         assert float(acc[:, :H].abs().sum()) == 0.0               # accumulator cleared for the next step
+
+
+@pytest.mark.parametrize("sync", [True, False])
+@pytest.mark.parametrize("ps_on_workers", [False, True])
+def test_concurrent_protocol_simulation(emu, sync, ps_on_workers):
+    """Liveness + result of the whole protocol with REAL concurrency: one host thread per emulated GPU stream runs the
+    kernels a rank enqueues -- workers: wait_token -> (gradient) -> push_grad; ps: ps_apply -- against shared host memory.
+    ``ps_on_workers``: the ps shard shares worker 0's stream, i.e. thread 0 runs [wait, push, apply...] per step
+    (EngineConfig.ps_on_workers); otherwise a dedicated ps thread.  Sync: K aggregates of the mean of W gradients;
+    async: W*K single-push applies.  No thread may time out, every token must arrive, the parameters must match."""
+    import threading
+    W, K, n, lr = 3, 5, 1024, 0.1
+    wd = World(emu, n=n, workers=W, sync=sync, ctas_per_push=1, lr=lr)
+    wd.a.timeout_ns = 20_000_000_000
+    errs = [torch.zeros(1, dtype=torch.int32) for _ in range(W)]
+    srcs = [torch.zeros(n) for _ in range(W)]
+    failures = []
+
+    def grad(w, t):
+        return torch.full((n,), float(1 + w + 10 * t))
+
+    def apply_once():
+        assert emu.dtf_ps_apply(ctypes.byref(wd.a), None) == 0
+
+    def worker(w):
+        try:
+            mbp = wd.mb.data_ptr() + w * wd.mb_bytes
+            for t in range(K):
+                assert emu.dtf_wait_token(mbp, t, None, 20_000_000_000, errs[w].data_ptr(), None) == 0
+                assert int(errs[w]) == 0, "worker %d timed out waiting for token %d" % (w, t)
+                srcs[w].copy_(grad(w, t))
+                assert emu.dtf_push_grad(srcs[w].data_ptr(), wd.grads[w].data_ptr(), n, wd.ctl.data_ptr(), mbp, w,
+                                         0 if sync else 1, 1, 1, None) == 0
+                if ps_on_workers and w == 0:
+                    for _ in range(1 if sync else W):
+                        apply_once()
+        except BaseException as e:      # noqa: BLE001
+            failures.append(e)
+
+    def ps():
+        try:
+            for _ in range(K if sync else K * W):
+                apply_once()
+        except BaseException as e:      # noqa: BLE001
+            failures.append(e)
+
+    threads = [threading.Thread(target=worker, args=(w,)) for w in range(W)]
+    if not ps_on_workers:
+        threads.append(threading.Thread(target=ps))
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not failures, failures
+    assert not any(t.is_alive() for t in threads)
+    assert int(wd.u32("err")) == 0
+    total = sum(grad(w, t) for w in range(W) for t in range(K))
+    if sync:
+        assert int(wd.u64("global_step")) == K and int(wd.u64("dropped_stale")) == 0
+        torch.testing.assert_close(wd.master, wd.master0 - lr * total / W, rtol=1e-5, atol=1e-4)
+        assert [int(wd.mailbox(w)[0]) for w in range(W)] == [K] * W
+    else:
+        assert int(wd.u64("global_step")) == K * W and sum(wd.u64("staleness_hist", 16).tolist()) == K * W
+        torch.testing.assert_close(wd.master, wd.master0 - lr * total, rtol=1e-5, atol=1e-4)      # every push applied alone
+        assert [int(wd.mailbox(w)[0]) for w in range(W)] == [K] * W                                # one ack per push
