@@ -2,6 +2,8 @@
 # Standard measurement battery for one gpurun call; everything lands in gpurun_out/ (copy what matters to profiles/).
 #   gpurun --timeout 900 -- 'bash tools/gpu_battery.sh single'            # 1 GPU : tests, bench, GEMM table, ncu of the pair GEMM
 #   gpurun --gpus 2 --timeout 600 -- 'bash tools/gpu_battery.sh multi 2'  # N GPUs: engine vs oracle, fabric GB/s, bench (NVLS + unicast)
+#   gpurun --timeout 600 -- 'bash tools/gpu_battery.sh pending'           # 1 GPU : first hardware run of everything written blind
+#   gpurun --gpus 2 --timeout 600 -- 'bash tools/gpu_battery.sh pending-multi 2'   # N GPUs: ps_on_workers topology vs the oracle + bench
 # Each step has its own timeout and logs to its own file, so one failure does not hide the others.
 set -u
 mode=${1:-single}
@@ -15,6 +17,21 @@ if [ "$mode" = "single" ]; then
   step phase_trace 120 python tools/phase_trace.py
   step ncu_pair 120 ncu --set full --clock-control none --import-source on -k regex:persistent --launch-skip 2 -c 1 -f \
       -o gpurun_out/prof_gemm_pair python tools/ncu_gemm.py
+elif [ "$mode" = "pending" ]; then
+  # kernels / paths written after round 1's GPU budget was spent (validated under the host emulation only)
+  DTF_TEST_UNVALIDATED=1 step t_nn_fused 300 python -m pytest tests/test_gpu_nn_fused.py -q -m gpu
+  step t_pipeline 120 python -m pytest tests/test_gpu_pipeline.py -q -m gpu
+  step t_gpu 300 python -m pytest tests -x -q -m gpu
+  step bench_n1 180 python bench.py
+  step resnet18_eager 200 python bench.py --model resnet18 --steps 10 --warmup 3
+  DTF_FUSED_NN=1 step resnet18_fused 200 python bench.py --model resnet18 --steps 10 --warmup 3
+elif [ "$mode" = "pending-multi" ]; then
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
+  DTF_PS_ON_WORKERS=1 step mp_check_pow 120 $TR tools/mp_check.py
+  DTF_PS_ON_WORKERS=1 DTF_NVLS=1 step mp_check_pow_nvls 120 $TR tools/mp_check.py
+  step bench_pow_nvls 150 $TR bench.py --gpus $N --nvls on --ps-on-workers 1
+  step bench_pow_unicast 150 $TR bench.py --gpus $N --nvls off --ps-on-workers 1
+  step bench_ref 150 $TR bench.py --gpus $N
 else
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
   DTF_NVLS=1 step mp_check_nvls 120 $TR tools/mp_check.py
