@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="-1: min(steps, 1000); 0: skip")
     ap.add_argument("--e2e-prefetch", type=int, default=1, help="1: step t+1's H2D overlaps step t (double-buffered staging)")
+    ap.add_argument("--graph-step", type=int, default=0,
+                    help="resnet18: 1 = capture the worker's forward/backward into a CUDA graph after two eager steps")
     ap.add_argument("--ps-on-workers", type=int, default=0,
                     help="1: N workers on N GPUs, ps shard s shares worker s's GPU and stream (no ps-only GPU); "
                          "0: ranks 0..num_ps-1 are ps-only tasks (the validated topology)")
@@ -265,7 +267,7 @@ def run_resnet18(args, rank, world, local_rank):
             with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
                 x = hx[i % nb].to(rk.device, non_blocking=True)
                 y = hy[i % nb].to(rk.device, non_blocking=True)
-            loss = eng.worker_step(my, resnet18_loss, x, y)
+            loss = eng.worker_step(my, resnet18_loss, x, y, graph=bool(args.graph_step))
             if my in eng.ps_ranks:
                 eng.ps_apply(my)
             losses.append(float(loss))        # D2H read of the step's loss

@@ -25,6 +25,8 @@ elif [ "$mode" = "pending" ]; then
   step bench_n1 180 python bench.py
   step resnet18_eager 200 python bench.py --model resnet18 --steps 10 --warmup 3
   DTF_FUSED_NN=1 step resnet18_fused 200 python bench.py --model resnet18 --steps 10 --warmup 3
+  step resnet18_graph 200 python bench.py --model resnet18 --steps 10 --warmup 4 --graph-step 1
+  DTF_FUSED_NN=1 step resnet18_fused_graph 200 python bench.py --model resnet18 --steps 10 --warmup 4 --graph-step 1
 elif [ "$mode" = "pending-multi" ]; then
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
   DTF_PS_ON_WORKERS=1 step mp_check_pow 120 $TR tools/mp_check.py
