@@ -7,6 +7,7 @@ there is no silent eager fallback (DESIGN.md "no compatibility layers").
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
 import threading
@@ -125,6 +126,120 @@ def available() -> bool:
     return os.path.exists(lib_path())
 
 
+class _Missing:
+    """Stand-in for an entry point the loaded library does not have (the emulation build has no tcgen05 GEMM, VMM, step
+    executor): declaring its signature is a no-op, calling it is an error."""
+
+    def __call__(self, *a, **k):
+        raise RuntimeError("this entry point is not part of the loaded kernel library (kernel-emulation build?)")
+
+
+class _Tolerant:
+    def __init__(self, lib):
+        object.__setattr__(self, "_lib", lib)
+
+    def __getattr__(self, name):
+        try:
+            return getattr(object.__getattribute__(self, "_lib"), name)
+        except AttributeError:
+            return _Missing()
+
+
+def _declare(lib) -> None:
+    """argtypes / restype of every entry point (``lib``: the CDLL, or a ``_Tolerant`` view of a partial library)."""
+    lib.dtf_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
+    lib.dtf_gemm_bf16.restype = c_int
+    lib.dtf_ps_apply.argtypes = [POINTER(PsApplyArgs), c_void_p]
+    lib.dtf_ps_apply.restype = c_int
+    lib.dtf_mlp_head.argtypes = [POINTER(MlpHeadArgs), c_void_p]
+    lib.dtf_mlp_head.restype = c_int
+    lib.dtf_convert_f32_bf16.argtypes = [c_void_p, c_longlong, c_void_p, c_longlong, c_longlong, c_longlong,
+                                         c_longlong, c_void_p]
+    lib.dtf_convert_u8_bf16.argtypes = [c_void_p, c_void_p, c_longlong, c_float, c_void_p]
+    lib.dtf_softmax_xent.argtypes = [c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_float, c_void_p,
+                                     c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p,
+                                     c_longlong, c_float, c_void_p]
+    lib.dtf_relu_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
+    lib.dtf_colsum.argtypes = [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]
+    lib.dtf_argmax_rows.argtypes = [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]
+    lib.dtf_mean_of_n.argtypes = [c_void_p, c_int, c_void_p, c_longlong, c_void_p]
+    lib.dtf_optimizer_apply.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float,
+                                        c_float, c_int, c_float, c_float, c_float, c_float, c_void_p]
+    lib.dtf_im2col_nhwc.argtypes = [c_void_p, c_void_p] + [c_int] * 12 + [c_longlong, c_void_p]
+    lib.dtf_col2im_nhwc.argtypes = [c_void_p, c_longlong, c_void_p] + [c_int] * 12 + [c_void_p]
+    lib.dtf_gemm_ref.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_longlong,
+                                 c_longlong, c_int, c_int, c_void_p, c_int, c_float, c_void_p]
+    lib.dtf_ps_publish.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p]
+    lib.dtf_wait_token.argtypes = [c_void_p, c_ulonglong, c_void_p, c_ulonglong, c_void_p, c_void_p]
+    lib.dtf_stage_from_dataset.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_longlong, c_longlong,
+                                           c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.dtf_stage_from_dataset.restype = c_int
+    lib.dtf_push_grad.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                  c_void_p]
+    lib.dtf_pull_shadow.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_void_p]
+    lib.dtf_fabric_alloc.argtypes = [POINTER(c_void_p), c_longlong]
+    lib.dtf_fabric_free.argtypes = [c_void_p]
+    lib.dtf_fabric_export.argtypes = [c_void_p, c_void_p]
+    lib.dtf_fabric_import.argtypes = [c_void_p, POINTER(c_void_p)]
+    lib.dtf_fabric_close.argtypes = [c_void_p]
+    lib.dtf_enable_peer.argtypes = [c_int]
+    lib.dtf_can_access_peer.argtypes = [c_int, c_int]
+    lib.dtf_memcpy_d2h.argtypes = [c_void_p, c_void_p, c_longlong]
+    lib.dtf_memcpy_h2d.argtypes = [c_void_p, c_void_p, c_longlong]
+    lib.dtf_memset.argtypes = [c_void_p, c_int, c_longlong, c_void_p]
+    for name in ("dtf_convert_f32_bf16", "dtf_convert_u8_bf16", "dtf_softmax_xent", "dtf_relu_grad", "dtf_colsum",
+                 "dtf_argmax_rows", "dtf_mean_of_n", "dtf_optimizer_apply", "dtf_im2col_nhwc", "dtf_col2im_nhwc",
+                 "dtf_gemm_ref", "dtf_ps_publish", "dtf_wait_token", "dtf_push_grad", "dtf_pull_shadow",
+                 "dtf_fabric_alloc", "dtf_fabric_free", "dtf_fabric_export", "dtf_fabric_import",
+                 "dtf_fabric_close", "dtf_enable_peer", "dtf_can_access_peer", "dtf_memcpy_d2h", "dtf_memcpy_h2d",
+                 "dtf_memset", "dtf_sizeof_ps_control", "dtf_sizeof_mailbox", "dtf_offsetof_ctl",
+                 "dtf_ipc_handle_size"):
+        getattr(lib, name).restype = c_int
+    lib.dtf_offsetof_ctl.argtypes = [c_int]
+    lib.dtf_fabric_bcast.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_int, c_void_p]
+    lib.dtf_fabric_reduce.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_longlong, c_int, c_void_p]
+    lib.dtf_vmm_support.argtypes = [c_int]
+    lib.dtf_vmm_granularity.argtypes = [c_int, c_int, POINTER(c_longlong)]
+    lib.dtf_vmm_create.argtypes = [c_int, c_longlong, POINTER(c_ulonglong)]
+    lib.dtf_vmm_map.argtypes = [c_ulonglong, c_longlong, c_int, POINTER(c_void_p)]
+    lib.dtf_vmm_unmap.argtypes = [c_void_p, c_longlong]
+    lib.dtf_vmm_release.argtypes = [c_ulonglong]
+    lib.dtf_vmm_export_fd.argtypes = [c_ulonglong, POINTER(c_int)]
+    lib.dtf_vmm_import_fd.argtypes = [c_int, POINTER(c_ulonglong)]
+    lib.dtf_mc_create.argtypes = [c_int, c_longlong, POINTER(c_ulonglong)]
+    lib.dtf_mc_add_device.argtypes = [c_ulonglong, c_int]
+    lib.dtf_mc_bind.argtypes = [c_ulonglong, c_ulonglong, c_longlong]
+    lib.dtf_mc_unbind.argtypes = [c_ulonglong, c_int, c_longlong]
+    for name in ("dtf_fabric_bcast", "dtf_fabric_reduce", "dtf_vmm_support", "dtf_vmm_granularity", "dtf_vmm_create",
+                 "dtf_vmm_map", "dtf_vmm_unmap", "dtf_vmm_release", "dtf_vmm_export_fd", "dtf_vmm_import_fd",
+                 "dtf_mc_create", "dtf_mc_add_device", "dtf_mc_bind", "dtf_mc_unbind"):
+        getattr(lib, name).restype = c_int
+    lib.dtf_run_ops.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
+    lib.dtf_run_ops.restype = c_int
+    lib.dtf_capture_ops.argtypes = [c_void_p, c_int, c_int, c_void_p, POINTER(c_void_p), POINTER(c_int)]
+    lib.dtf_capture_ops.restype = c_int
+    lib.dtf_graph_destroy.argtypes = [c_void_p]
+    lib.dtf_graph_destroy.restype = c_int
+    lib.dtf_sizeof_step_op.restype = c_int
+    if not isinstance(lib.dtf_sizeof_step_op, _Missing):
+        assert lib.dtf_sizeof_step_op() == ctypes.sizeof(StepOp), "StepOp layout mismatch"
+    if not isinstance(getattr(lib, "dtf_bn_reduce", _Missing()), _Missing):    # csrc/nn_kernels.cu (a stale build lacks it)
+        lib.dtf_bn_row_splits.argtypes = [c_longlong, c_int]
+        lib.dtf_bn_row_splits.restype = c_int
+        lib.dtf_bn_workspace_floats.argtypes = [c_longlong, c_int]
+        lib.dtf_bn_workspace_floats.restype = c_longlong
+        lib.dtf_bn_reduce.argtypes = [c_int] + [c_void_p] * 5 + [c_longlong, c_int] + [c_void_p] * 4 + [c_float, c_void_p]
+        lib.dtf_bn_reduce.restype = c_int
+        lib.dtf_bn_apply.argtypes = [c_void_p] * 7 + [c_longlong, c_int, c_int, c_void_p]
+        lib.dtf_bn_apply.restype = c_int
+        lib.dtf_bn_bwd_apply.argtypes = [c_void_p] * 10 + [c_longlong, c_int, c_void_p]
+        lib.dtf_bn_bwd_apply.restype = c_int
+        lib.dtf_im2col_nhwc_vec8.argtypes = [c_void_p, c_void_p] + [c_int] * 12 + [c_longlong, c_void_p]
+        lib.dtf_im2col_nhwc_vec8.restype = c_int
+        lib.dtf_col2im_nhwc_vec4.argtypes = [c_void_p, c_longlong, c_void_p] + [c_int] * 12 + [c_void_p]
+        lib.dtf_col2im_nhwc_vec4.restype = c_int
+
+
 def load() -> ctypes.CDLL:
     global _LIB
     with _LOCK:
@@ -134,98 +249,51 @@ def load() -> ctypes.CDLL:
         if not os.path.exists(p):
             raise RuntimeError("sm_100a kernel library %s is missing: run `python __graft_entry__.py build`" % p)
         lib = ctypes.CDLL(p)
-        lib.dtf_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
-        lib.dtf_gemm_bf16.restype = c_int
-        lib.dtf_ps_apply.argtypes = [POINTER(PsApplyArgs), c_void_p]
-        lib.dtf_ps_apply.restype = c_int
-        lib.dtf_mlp_head.argtypes = [POINTER(MlpHeadArgs), c_void_p]
-        lib.dtf_mlp_head.restype = c_int
-        lib.dtf_convert_f32_bf16.argtypes = [c_void_p, c_longlong, c_void_p, c_longlong, c_longlong, c_longlong,
-                                             c_longlong, c_void_p]
-        lib.dtf_convert_u8_bf16.argtypes = [c_void_p, c_void_p, c_longlong, c_float, c_void_p]
-        lib.dtf_softmax_xent.argtypes = [c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_float, c_void_p,
-                                         c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p,
-                                         c_longlong, c_float, c_void_p]
-        lib.dtf_relu_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
-        lib.dtf_colsum.argtypes = [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]
-        lib.dtf_argmax_rows.argtypes = [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]
-        lib.dtf_mean_of_n.argtypes = [c_void_p, c_int, c_void_p, c_longlong, c_void_p]
-        lib.dtf_optimizer_apply.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float,
-                                            c_float, c_int, c_float, c_float, c_float, c_float, c_void_p]
-        lib.dtf_im2col_nhwc.argtypes = [c_void_p, c_void_p] + [c_int] * 12 + [c_longlong, c_void_p]
-        lib.dtf_col2im_nhwc.argtypes = [c_void_p, c_longlong, c_void_p] + [c_int] * 12 + [c_void_p]
-        lib.dtf_gemm_ref.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_longlong,
-                                     c_longlong, c_int, c_int, c_void_p, c_int, c_float, c_void_p]
-        lib.dtf_ps_publish.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p]
-        lib.dtf_wait_token.argtypes = [c_void_p, c_ulonglong, c_void_p, c_ulonglong, c_void_p, c_void_p]
-        lib.dtf_stage_from_dataset.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_longlong, c_longlong,
-                                               c_void_p, c_void_p, c_void_p, c_void_p]
-        lib.dtf_stage_from_dataset.restype = c_int
-        lib.dtf_push_grad.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                      c_void_p]
-        lib.dtf_pull_shadow.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_void_p]
-        lib.dtf_fabric_alloc.argtypes = [POINTER(c_void_p), c_longlong]
-        lib.dtf_fabric_free.argtypes = [c_void_p]
-        lib.dtf_fabric_export.argtypes = [c_void_p, c_void_p]
-        lib.dtf_fabric_import.argtypes = [c_void_p, POINTER(c_void_p)]
-        lib.dtf_fabric_close.argtypes = [c_void_p]
-        lib.dtf_enable_peer.argtypes = [c_int]
-        lib.dtf_can_access_peer.argtypes = [c_int, c_int]
-        lib.dtf_memcpy_d2h.argtypes = [c_void_p, c_void_p, c_longlong]
-        lib.dtf_memcpy_h2d.argtypes = [c_void_p, c_void_p, c_longlong]
-        lib.dtf_memset.argtypes = [c_void_p, c_int, c_longlong, c_void_p]
-        for name in ("dtf_convert_f32_bf16", "dtf_convert_u8_bf16", "dtf_softmax_xent", "dtf_relu_grad", "dtf_colsum",
-                     "dtf_argmax_rows", "dtf_mean_of_n", "dtf_optimizer_apply", "dtf_im2col_nhwc", "dtf_col2im_nhwc",
-                     "dtf_gemm_ref", "dtf_ps_publish", "dtf_wait_token", "dtf_push_grad", "dtf_pull_shadow",
-                     "dtf_fabric_alloc", "dtf_fabric_free", "dtf_fabric_export", "dtf_fabric_import",
-                     "dtf_fabric_close", "dtf_enable_peer", "dtf_can_access_peer", "dtf_memcpy_d2h", "dtf_memcpy_h2d",
-                     "dtf_memset", "dtf_sizeof_ps_control", "dtf_sizeof_mailbox", "dtf_offsetof_ctl",
-                     "dtf_ipc_handle_size"):
-            getattr(lib, name).restype = c_int
-        lib.dtf_offsetof_ctl.argtypes = [c_int]
-        lib.dtf_fabric_bcast.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_int, c_void_p]
-        lib.dtf_fabric_reduce.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_longlong, c_int, c_void_p]
-        lib.dtf_vmm_support.argtypes = [c_int]
-        lib.dtf_vmm_granularity.argtypes = [c_int, c_int, POINTER(c_longlong)]
-        lib.dtf_vmm_create.argtypes = [c_int, c_longlong, POINTER(c_ulonglong)]
-        lib.dtf_vmm_map.argtypes = [c_ulonglong, c_longlong, c_int, POINTER(c_void_p)]
-        lib.dtf_vmm_unmap.argtypes = [c_void_p, c_longlong]
-        lib.dtf_vmm_release.argtypes = [c_ulonglong]
-        lib.dtf_vmm_export_fd.argtypes = [c_ulonglong, POINTER(c_int)]
-        lib.dtf_vmm_import_fd.argtypes = [c_int, POINTER(c_ulonglong)]
-        lib.dtf_mc_create.argtypes = [c_int, c_longlong, POINTER(c_ulonglong)]
-        lib.dtf_mc_add_device.argtypes = [c_ulonglong, c_int]
-        lib.dtf_mc_bind.argtypes = [c_ulonglong, c_ulonglong, c_longlong]
-        lib.dtf_mc_unbind.argtypes = [c_ulonglong, c_int, c_longlong]
-        for name in ("dtf_fabric_bcast", "dtf_fabric_reduce", "dtf_vmm_support", "dtf_vmm_granularity", "dtf_vmm_create",
-                     "dtf_vmm_map", "dtf_vmm_unmap", "dtf_vmm_release", "dtf_vmm_export_fd", "dtf_vmm_import_fd",
-                     "dtf_mc_create", "dtf_mc_add_device", "dtf_mc_bind", "dtf_mc_unbind"):
-            getattr(lib, name).restype = c_int
-        lib.dtf_run_ops.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
-        lib.dtf_run_ops.restype = c_int
-        lib.dtf_capture_ops.argtypes = [c_void_p, c_int, c_int, c_void_p, POINTER(c_void_p), POINTER(c_int)]
-        lib.dtf_capture_ops.restype = c_int
-        lib.dtf_graph_destroy.argtypes = [c_void_p]
-        lib.dtf_graph_destroy.restype = c_int
-        lib.dtf_sizeof_step_op.restype = c_int
-        assert lib.dtf_sizeof_step_op() == ctypes.sizeof(StepOp), "StepOp layout mismatch"
-        if hasattr(lib, "dtf_bn_reduce"):                  # csrc/nn_kernels.cu (fused batch norm)
-            lib.dtf_bn_row_splits.argtypes = [c_longlong, c_int]
-            lib.dtf_bn_row_splits.restype = c_int
-            lib.dtf_bn_workspace_floats.argtypes = [c_longlong, c_int]
-            lib.dtf_bn_workspace_floats.restype = c_longlong
-            lib.dtf_bn_reduce.argtypes = [c_int] + [c_void_p] * 5 + [c_longlong, c_int] + [c_void_p] * 4 + [c_float, c_void_p]
-            lib.dtf_bn_reduce.restype = c_int
-            lib.dtf_bn_apply.argtypes = [c_void_p] * 7 + [c_longlong, c_int, c_int, c_void_p]
-            lib.dtf_bn_apply.restype = c_int
-            lib.dtf_bn_bwd_apply.argtypes = [c_void_p] * 10 + [c_longlong, c_int, c_void_p]
-            lib.dtf_bn_bwd_apply.restype = c_int
-            lib.dtf_im2col_nhwc_vec8.argtypes = [c_void_p, c_void_p] + [c_int] * 12 + [c_longlong, c_void_p]
-            lib.dtf_im2col_nhwc_vec8.restype = c_int
-            lib.dtf_col2im_nhwc_vec4.argtypes = [c_void_p, c_longlong, c_void_p] + [c_int] * 12 + [c_void_p]
-            lib.dtf_col2im_nhwc_vec4.restype = c_int
+        _declare(lib)
         _LIB = lib
         return lib
+
+
+# ---------------------------------------------------------------------------------------------------
+# kernel emulation: the op layer on HOST tensors (tests without a GPU)
+# ---------------------------------------------------------------------------------------------------
+EMULATION = False
+_EMU_SOURCES = ("elementwise.cu", "ps_engine.cu", "nn_kernels.cu")
+
+
+def enable_emulation(build_dir: Optional[str] = None) -> ctypes.CDLL:
+    """Swap the kernel library for a g++ build of the SAME ``.cu`` sources against ``tests/emu/host_emu.h`` (threads +
+    barriers emulate a thread block; docs/TESTING.md) and let the wrappers of this module -- and the autograd functions of
+    ``ops/native.py`` on top -- accept host tensors.  The tcgen05 / TMA GEMM is hardware-only: ``gemm`` runs the CUDA-core
+    reference GEMM kernel (same bf16-rounded operands, fp32 accumulate) instead.  Test tier only."""
+    global _LIB, EMULATION
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
+    emu_dir = os.path.join(root, "tests", "emu")
+    out_dir = build_dir or tempfile.mkdtemp(prefix="dtf_emu_")
+    so = os.path.join(out_dir, "libdtf_kernels_emu.so")
+    if not os.path.exists(so):
+        objs = []
+        for src in _EMU_SOURCES:
+            obj = os.path.join(out_dir, src + ".o")
+            subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-DDTF_HOST_EMU", "-I" + emu_dir, "-I" + csrc, "-x", "c++", "-fPIC",
+                            "-pthread", "-c", os.path.join(csrc, src), "-o", obj], check=True)
+            objs.append(obj)
+        subprocess.run(["g++", "-shared", "-pthread", "-o", so] + objs, check=True)
+    with _LOCK:
+        lib = ctypes.CDLL(so)
+        _declare(_Tolerant(lib))
+        enable_emulation._saved = _LIB
+        _LIB, EMULATION = lib, True
+    return lib
+
+
+def disable_emulation() -> None:
+    global _LIB, EMULATION
+    with _LOCK:
+        _LIB, EMULATION = getattr(enable_emulation, "_saved", None), False
 
 
 # csrc/nn_kernels.cu (fused batch norm, channel-vectorised im2col / col2im): checked under host emulation, first hardware
@@ -260,9 +328,22 @@ def _cuda_err(rc: int) -> str:
     return " (cudaError %d)" % rc
 
 
-def _stream(t: Optional[torch.Tensor] = None) -> int:
+def _stream(t: Optional[torch.Tensor] = None) -> Optional[int]:
+    if EMULATION:
+        return None                       # host emulation: kernels run synchronously inside the call
     dev = t.device if t is not None else None
     return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _on(dev):
+    """``torch.cuda.device(dev)`` for CUDA tensors; a no-op for the host tensors of the kernel-emulation mode."""
+    dev = torch.device(dev) if not isinstance(dev, torch.device) else dev
+    return torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()
+
+
+def _on_device(t: torch.Tensor) -> bool:
+    """May our kernels touch this tensor?  CUDA tensors always; host tensors only under the kernel emulation."""
+    return t.is_cuda or EMULATION
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -278,7 +359,7 @@ def round_up(x: int, m: int) -> int:
 # ---------------------------------------------------------------------------------------------------
 def to_bf16_padded(x: torch.Tensor) -> Tuple[torch.Tensor, int]:
     """Row-major 2-D tensor -> (bf16 tensor whose row pitch is a multiple of 8 elements, pitch)."""
-    assert x.dim() == 2 and x.is_cuda
+    assert x.dim() == 2 and _on_device(x)
     rows, cols = x.shape
     if x.dtype == torch.bfloat16 and x.stride(1) == 1 and x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0:
         return x, x.stride(0)
@@ -287,7 +368,7 @@ def to_bf16_padded(x: torch.Tensor) -> Tuple[torch.Tensor, int]:
         x = x.float().contiguous()
     out = torch.empty((rows, ld), dtype=torch.bfloat16, device=x.device)
     lib = load()
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _check(lib.dtf_convert_f32_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), ld, rows, cols, ld, _stream(x)),
                "convert_f32_bf16")
     _bump()
@@ -331,12 +412,29 @@ def gemm(a: torch.Tensor, b: torch.Tensor, ta: bool = False, tb: bool = False, b
          relu: bool = False, out_dtype: torch.dtype = torch.float32, splits: int = 1, persistent: int = 0,
          block_n: int = 0) -> torch.Tensor:
     """``op(a) @ op(b)`` (+bias, ReLU) on the tensor cores; inputs fp32 or bf16, bf16 compute, fp32 accumulate."""
-    assert a.is_cuda and b.is_cuda and a.dim() == 2 and b.dim() == 2
+    assert _on_device(a) and _on_device(b) and a.dim() == 2 and b.dim() == 2
+    if EMULATION:
+        # the tcgen05 / TMA kernel is hardware-only.  Same contract (bf16-rounded operands, fp32 accumulate, fused bias /
+        # ReLU) from the CUDA-core reference GEMM kernel while one emulated thread per output element is affordable,
+        # from a plain matmul beyond that.
+        Mo = a.shape[1] if ta else a.shape[0]
+        No = b.shape[0] if tb else b.shape[1]
+        if Mo * No <= 1 << 14:
+            out = gemm_ref(a, b, ta, tb, bias=bias, relu=relu)
+        else:
+            x = (a.t() if ta else a).bfloat16().float()
+            y = (b.t() if tb else b).bfloat16().float()
+            out = x @ y
+            if bias is not None:
+                out = out + bias.float()
+            if relu:
+                out = torch.relu(out)
+        return out if out_dtype == torch.float32 else out.to(out_dtype)
     M, K = (a.shape[1], a.shape[0]) if ta else (a.shape[0], a.shape[1])
     Kb, N = (b.shape[1], b.shape[0]) if tb else (b.shape[0], b.shape[1])
     if K != Kb:
         raise ValueError("gemm: inner dimensions differ (%d vs %d)" % (K, Kb))
-    with torch.cuda.device(a.device):
+    with _on(a.device):
         a16, lda = to_bf16_padded(a)
         b16, ldb = to_bf16_padded(b)
         ldc = N if out_dtype == torch.float32 else round_up(N, 8)
@@ -352,7 +450,7 @@ def gemm_ref(a: torch.Tensor, b: torch.Tensor, ta: bool = False, tb: bool = Fals
     """CUDA-core reference over the same bf16-rounded operands (tests)."""
     M, K = (a.shape[1], a.shape[0]) if ta else (a.shape[0], a.shape[1])
     N = b.shape[0] if tb else b.shape[1]
-    with torch.cuda.device(a.device):
+    with _on(a.device):
         a16, lda = to_bf16_padded(a)
         b16, ldb = to_bf16_padded(b)
         c = torch.empty((M, N), dtype=torch.float32, device=a.device)
@@ -372,7 +470,7 @@ def softmax_xent_fwd_bwd(logits: torch.Tensor, labels: torch.Tensor, clip_min: f
     labels = labels.float().contiguous()
     rows, cols = logits.shape
     dl = torch.empty_like(logits)
-    with torch.cuda.device(logits.device):
+    with _on(logits.device):
         if reduce_sum:
             loss = torch.zeros((), dtype=torch.float32, device=logits.device)
             lsum, lrows = loss.data_ptr(), None
@@ -390,7 +488,7 @@ def relu_grad(g: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     g = g.float().contiguous()
     y = y.float().contiguous()
     out = torch.empty_like(g)
-    with torch.cuda.device(g.device):
+    with _on(g.device):
         _check(load().dtf_relu_grad(g.data_ptr(), y.data_ptr(), out.data_ptr(), g.numel(), _stream(g)), "relu_grad")
     _bump()
     return out
@@ -400,7 +498,7 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
     x = x.float().contiguous()
     rows, cols = x.shape
     out = torch.empty((cols,), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _check(load().dtf_colsum(x.data_ptr(), cols, rows, cols, out.data_ptr(), _stream(x)), "colsum")
     _bump()
     return out
@@ -410,7 +508,7 @@ def argmax_rows(x: torch.Tensor) -> torch.Tensor:
     x = x.float().contiguous()
     rows, cols = x.shape
     out = torch.empty((rows,), dtype=torch.int64, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _check(load().dtf_argmax_rows(x.data_ptr(), cols, rows, cols, out.data_ptr(), _stream(x)), "argmax_rows")
     _bump()
     return out
@@ -423,7 +521,7 @@ def _apply(var, m, v, g, kind, lr, momentum=0.0, nesterov=False, beta1=0.0, beta
            grad_scale=1.0):
     assert var.is_contiguous() and var.dtype == torch.float32
     g = g.to(dtype=torch.float32).contiguous()
-    with torch.cuda.device(var.device):
+    with _on(var.device):
         _check(load().dtf_optimizer_apply(var.data_ptr(), _ptr(m), _ptr(v), g.data_ptr(), _ptr(shadow), var.numel(), kind,
                                           lr, momentum, int(nesterov), beta1, beta2, eps, grad_scale, _stream(var)),
                "optimizer_apply")
@@ -455,7 +553,7 @@ def im2col_nhwc(x: torch.Tensor, kh: int, kw: int, strides: Sequence[int], pads:
     kdim = kh * kw * c
     ld = round_up(kdim, 8)
     cols = torch.empty((n * ho * wo, ld), dtype=torch.bfloat16, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         rc = load().dtf_im2col_nhwc_vec8(x.data_ptr(), cols.data_ptr(), n, h, w, c, kh, kw, sh, sw, pt, pl, ho, wo, ld,
                                          _stream(x)) if FUSED_NN and c % 8 == 0 else -1
         if rc >= 0:                       # -1: not eligible -> scalar kernel below
@@ -476,7 +574,7 @@ def col2im_nhwc(gcols: torch.Tensor, xshape, kh: int, kw: int, strides, pads) ->
     ho = (h + pt + pb - kh) // sh + 1
     wo = (w + pl + pr - kw) // sw + 1
     gx = torch.empty(tuple(xshape), dtype=torch.float32, device=gcols.device)
-    with torch.cuda.device(gcols.device):
+    with _on(gcols.device):
         rc = load().dtf_col2im_nhwc_vec4(gcols.data_ptr(), gcols.shape[1], gx.data_ptr(), n, h, w, c, kh, kw, sh, sw, pt, pl,
                                          ho, wo, _stream(gcols)) if FUSED_NN and c % 4 == 0 else -1
         if rc >= 0:
@@ -523,7 +621,7 @@ def bn_forward(x2d: torch.Tensor, scale: torch.Tensor, offset: torch.Tensor, res
     scale, offset = _aligned16(scale.float().contiguous()), _aligned16(offset.float().contiguous())
     if residual is not None:
         residual = _aligned16(residual.float().contiguous())
-    with torch.cuda.device(dev):
+    with _on(dev):
         ws, tickets = _bn_workspace(dev, int(lib.dtf_bn_workspace_floats(rows, C)))
         st = _stream(x2d)
         _check(lib.dtf_bn_reduce(0, x2d.data_ptr(), None, None, None, None, rows, C, ws.data_ptr(), tickets.data_ptr(),
@@ -546,7 +644,7 @@ def bn_backward(dy: torch.Tensor, y_mask: Optional[torch.Tensor], x2d: torch.Ten
     dscale = torch.empty(C, dtype=torch.float32, device=dev)
     dx = torch.empty_like(x2d)
     dres = torch.empty_like(x2d) if want_dres else None
-    with torch.cuda.device(dev):
+    with _on(dev):
         ws, tickets = _bn_workspace(dev, int(lib.dtf_bn_workspace_floats(rows, C)))
         st = _stream(x2d)
         _check(lib.dtf_bn_reduce(1, x2d.data_ptr(), dy.data_ptr(), _ptr(y_mask), mean.data_ptr(), rstd.data_ptr(), rows, C,

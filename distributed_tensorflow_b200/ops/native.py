@@ -27,7 +27,13 @@ _FORCE_EAGER = os.environ.get("DTF_FORCE_EAGER", "0") == "1"
 
 
 def _use_native(t: torch.Tensor) -> bool:
-    return t.is_cuda and not _FORCE_EAGER
+    if _FORCE_EAGER:
+        return False
+    if t.is_cuda:
+        return True
+    import sys
+    mod = sys.modules.get(__package__ + ".cuda_lib")       # host tensors: only under the kernel emulation (tests)
+    return bool(mod is not None and mod.EMULATION)
 
 
 def _lib():

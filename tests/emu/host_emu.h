@@ -69,25 +69,29 @@ namespace dtf_emu {
 // stream).  `__shared__` variables are function statics, so two launches of the SAME kernel must not overlap unless that
 // kernel declares no static shared memory.
 struct LaunchCtx {
-  dim3 b_idx, b_dim, g_dim;
-  pthread_barrier_t* barrier = nullptr;
+  dim3 b_dim, g_dim;
+  pthread_barrier_t* barrier = nullptr;          // __syncthreads()
   pthread_barrier_t* warp_bars = nullptr;        // one barrier + one exchange row per warp (warp shuffles)
   uint64_t (*warp_slots)[32] = nullptr;
   void* dyn_smem = nullptr;                      // dynamic shared memory of the block being executed
 };
 inline thread_local LaunchCtx* ctx = nullptr;
-inline thread_local dim3 t_idx;
+inline thread_local dim3 t_idx, t_bidx;          // threadIdx / blockIdx of the calling emulated thread
 inline thread_local unsigned lin_tid;            // x + y * dim.x + z * dim.x * dim.y: warps are 32 consecutive ids
 
 static inline void sync() { pthread_barrier_wait(ctx->barrier); }
 
+// One host thread per CUDA thread of a block, created ONCE per launch; every thread walks the grid block by block with a
+// barrier between blocks, so blocks still run strictly one after another (block 0 first) without paying a thread
+// creation per block.
 static inline void launch(dim3 grid, dim3 block, const std::function<void()>& body, size_t smem_bytes = 0) {
   const unsigned nthreads = block.x * block.y * block.z;
   LaunchCtx c;
   std::vector<float4> smem_buf((smem_bytes + 15) / 16 + 1);        // 16-byte aligned like the hardware's
   c.dyn_smem = smem_buf.data();
-  pthread_barrier_t bar;
+  pthread_barrier_t bar, block_bar;
   pthread_barrier_init(&bar, nullptr, nthreads);
+  pthread_barrier_init(&block_bar, nullptr, nthreads);
   c.barrier = &bar;
   const unsigned nwarps = (nthreads + 31) / 32;
   std::vector<pthread_barrier_t> wb(nwarps);
@@ -97,30 +101,32 @@ static inline void launch(dim3 grid, dim3 block, const std::function<void()>& bo
   c.warp_slots = reinterpret_cast<uint64_t(*)[32]>(slots.data());
   c.g_dim = grid;
   c.b_dim = block;
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        c.b_idx = dim3(bx, by, bz);
-        std::vector<std::thread> ts;
-        ts.reserve(nthreads);
-        for (unsigned tz = 0; tz < block.z; ++tz)
-          for (unsigned ty = 0; ty < block.y; ++ty)
-            for (unsigned tx = 0; tx < block.x; ++tx)
-              ts.emplace_back([&, tx, ty, tz]() {
-                ctx = &c;
-                t_idx = dim3(tx, ty, tz);
-                lin_tid = tx + ty * block.x + tz * block.x * block.y;
+  std::vector<std::thread> ts;
+  ts.reserve(nthreads);
+  for (unsigned tz = 0; tz < block.z; ++tz)
+    for (unsigned ty = 0; ty < block.y; ++ty)
+      for (unsigned tx = 0; tx < block.x; ++tx)
+        ts.emplace_back([&, tx, ty, tz]() {
+          ctx = &c;
+          t_idx = dim3(tx, ty, tz);
+          lin_tid = tx + ty * block.x + tz * block.x * block.y;
+          for (unsigned bz = 0; bz < grid.z; ++bz)
+            for (unsigned by = 0; by < grid.y; ++by)
+              for (unsigned bx = 0; bx < grid.x; ++bx) {
+                t_bidx = dim3(bx, by, bz);
                 body();
-              });
-        for (auto& t : ts) t.join();
-      }
+                pthread_barrier_wait(&block_bar);        // the whole block is done before the next one starts
+              }
+        });
+  for (auto& t : ts) t.join();
   pthread_barrier_destroy(&bar);
+  pthread_barrier_destroy(&block_bar);
   for (auto& b : wb) pthread_barrier_destroy(&b);
 }
 }  // namespace dtf_emu
 
 #define threadIdx (dtf_emu::t_idx)
-#define blockIdx (dtf_emu::ctx->b_idx)
+#define blockIdx (dtf_emu::t_bidx)
 #define blockDim (dtf_emu::ctx->b_dim)
 #define gridDim (dtf_emu::ctx->g_dim)
 #define __global__
