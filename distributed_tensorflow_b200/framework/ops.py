@@ -689,11 +689,9 @@ def fused_batch_norm_train(x, scale, offset, eps=1e-5, name="FusedBatchNorm"):
 
 @register_kernel("FusedBatchNormTrain")
 def _k_fbn(ctx, node, x, scale, offset):
-    xf = x.float()
-    dims = tuple(range(x.dim() - 1))
-    mean = xf.mean(dim=dims, keepdim=True)
-    var = ((xf - mean) ** 2).mean(dim=dims, keepdim=True)
-    return ((xf - mean) * torch.rsqrt(var + node.attrs["eps"]) * scale.float() + offset.float()).to(x.dtype)
+    # ops/native.py: the fused statistics + apply kernels on /gpu when enabled (DTF_FUSED_NN=1), the plain formulation otherwise
+    from ..ops import native
+    return native.batch_norm_train(x, scale.float(), offset.float(), eps=node.attrs["eps"]).to(x.dtype)
 
 
 def dropout(x, keep_prob=None, rate=None, name="dropout"):
