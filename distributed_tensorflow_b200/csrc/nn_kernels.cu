@@ -20,6 +20,12 @@
 //                      16-byte store of 8 bf16 -- 8x fewer index computations than the scalar kernel in elementwise.cu
 //   col2im_nhwc_vec4 : one thread = one (input pixel, 4-channel group), gathers its <= kh*kw contributions as float4
 //
+// And the pooling of the model family (K14 "pool"), NHWC, 4 channels per thread:
+//   maxpool_nhwc_fwd / _bwd : window max with the argmax (position inside the window) kept as one byte per element; the
+//                            backward GATHERS -- every input element sums dy of the windows whose argmax it is -- so it is
+//                            deterministic and needs no atomics.  Padding behaves like -inf (TF SAME semantics).
+//   global_avgpool_nhwc_fwd / _bwd : mean over H*W per (image, channel) and its broadcast gradient.
+//
 // STATUS: written at the end of round 1 after the GPU budget was spent.  Compiled (ptxas: no spills), formulas checked
 // on CPU against autograd (tests/test_nn_fused_reference.py); first hardware run is tests/test_gpu_nn_fused.py.
 // Off by default (DTF_FUSED_BN=1 turns it on in ops/native.py).
@@ -235,6 +241,101 @@ __global__ void col2im_nhwc_vec4_kernel(const float* __restrict__ gcols, long lo
   }
 }
 
+// y[b, oy, ox, c] = max over the window; arg = ky * kw + kx of the (first) maximum
+__global__ void maxpool_nhwc_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, uchar4* __restrict__ arg, int n,
+                                        int h, int w, int c4n, int kh, int kw, int sh, int sw, int pt, int pl, int ho, int wo) {
+  const long long total = (long long)n * ho * wo * c4n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % c4n);
+    const long long pix = i / c4n;
+    const int ox = (int)(pix % wo);
+    const int oy = (int)((pix / wo) % ho);
+    const int b = (int)(pix / ((long long)wo * ho));
+    float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    uchar4 bi = make_uchar4(0, 0, 0, 0);
+    for (int ky = 0; ky < kh; ++ky) {
+      const int iy = oy * sh - pt + ky;
+      if (iy < 0 || iy >= h) continue;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int ix = ox * sw - pl + kx;
+        if (ix < 0 || ix >= w) continue;
+        const float4 v = x[(((long long)b * h + iy) * w + ix) * c4n + c4];
+        const unsigned char t = (unsigned char)(ky * kw + kx);
+        if (v.x > best.x) { best.x = v.x; bi.x = t; }
+        if (v.y > best.y) { best.y = v.y; bi.y = t; }
+        if (v.z > best.z) { best.z = v.z; bi.z = t; }
+        if (v.w > best.w) { best.w = v.w; bi.w = t; }
+      }
+    }
+    y[i] = best;
+    arg[i] = bi;
+  }
+}
+
+// dx[b, iy, ix, c] = sum of dy over the windows that cover (iy, ix) AND whose argmax is this position
+__global__ void maxpool_nhwc_bwd_kernel(const float4* __restrict__ dy, const uchar4* __restrict__ arg, float4* __restrict__ dx,
+                                        int n, int h, int w, int c4n, int kh, int kw, int sh, int sw, int pt, int pl, int ho,
+                                        int wo) {
+  const long long total = (long long)n * h * w * c4n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % c4n);
+    const long long pix = i / c4n;
+    const int ix = (int)(pix % w);
+    const int iy = (int)((pix / w) % h);
+    const int b = (int)(pix / ((long long)w * h));
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ky = 0; ky < kh; ++ky) {
+      const int ty = iy + pt - ky;
+      if (ty < 0 || ty % sh) continue;
+      const int oy = ty / sh;
+      if (oy >= ho) continue;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int tx = ix + pl - kx;
+        if (tx < 0 || tx % sw) continue;
+        const int ox = tx / sw;
+        if (ox >= wo) continue;
+        const long long o = (((long long)b * ho + oy) * wo + ox) * c4n + c4;
+        const uchar4 a = arg[o];
+        const float4 g = dy[o];
+        const unsigned char t = (unsigned char)(ky * kw + kx);
+        if (a.x == t) s.x += g.x;
+        if (a.y == t) s.y += g.y;
+        if (a.z == t) s.z += g.z;
+        if (a.w == t) s.w += g.w;
+      }
+    }
+    dx[i] = s;
+  }
+}
+
+// out[b, c] = mean over h*w of x[b, :, :, c]; one thread per (image, 4 channels): consecutive threads read consecutive
+// channel groups, so every row of the walk is one coalesced segment
+__global__ void global_avgpool_nhwc_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ out, int n, int hw, int c4n) {
+  const long long total = (long long)n * c4n;
+  const float inv = 1.0f / (float)hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % c4n);
+    const long long b = i / c4n;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < hw; ++p) {
+      const float4 v = x[(b * hw + p) * c4n + c4];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    out[i] = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+  }
+}
+
+__global__ void global_avgpool_nhwc_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dx, int n, int hw, int c4n) {
+  const long long total = (long long)n * hw * c4n;
+  const float inv = 1.0f / (float)hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % c4n);
+    const long long b = i / ((long long)hw * c4n);
+    const float4 g = dy[b * c4n + c4];
+    dx[i] = make_float4(g.x * inv, g.y * inv, g.z * inv, g.w * inv);
+  }
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static inline int bn_grid_for(long long n, int block = 256) {
@@ -323,6 +424,36 @@ int dtf_col2im_nhwc_vec4(const float* gcols, long long ldg, float* gx, int n, in
   const long long total = (long long)n * h * w * (c / 4);
   DTF_LAUNCH(col2im_nhwc_vec4_kernel, bn_grid_for(total), 256, s, gcols, ldg, reinterpret_cast<float4*>(gx), n, h, w, c, kh, kw,
              sh, sw, pt, pl, ho, wo);
+  return (int)cudaGetLastError();
+}
+
+// pooling: -1 = not eligible (C % 4, alignment, window of more than 255 positions)
+int dtf_maxpool_nhwc_fwd(const float* x, float* y, void* arg, int n, int h, int w, int c, int kh, int kw, int sh, int sw, int pt,
+                         int pl, int ho, int wo, cudaStream_t s) {
+  if (c % 4 != 0 || kh * kw > 255 || !aligned16(x) || !aligned16(y) || (reinterpret_cast<uintptr_t>(arg) & 3)) return -1;
+  const long long total = (long long)n * ho * wo * (c / 4);
+  DTF_LAUNCH(maxpool_nhwc_fwd_kernel, bn_grid_for(total), 256, s, reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y),
+             reinterpret_cast<uchar4*>(arg), n, h, w, c / 4, kh, kw, sh, sw, pt, pl, ho, wo);
+  return (int)cudaGetLastError();
+}
+
+int dtf_maxpool_nhwc_bwd(const float* dy, const void* arg, float* dx, int n, int h, int w, int c, int kh, int kw, int sh, int sw,
+                         int pt, int pl, int ho, int wo, cudaStream_t s) {
+  if (c % 4 != 0 || kh * kw > 255 || !aligned16(dy) || !aligned16(dx) || (reinterpret_cast<uintptr_t>(arg) & 3)) return -1;
+  const long long total = (long long)n * h * w * (c / 4);
+  DTF_LAUNCH(maxpool_nhwc_bwd_kernel, bn_grid_for(total), 256, s, reinterpret_cast<const float4*>(dy),
+             reinterpret_cast<const uchar4*>(arg), reinterpret_cast<float4*>(dx), n, h, w, c / 4, kh, kw, sh, sw, pt, pl, ho, wo);
+  return (int)cudaGetLastError();
+}
+
+int dtf_global_avgpool_nhwc(const float* in, float* out, int n, int hw, int c, int backward, cudaStream_t s) {
+  if (c % 4 != 0 || hw <= 0 || !aligned16(in) || !aligned16(out)) return -1;
+  if (!backward)
+    DTF_LAUNCH(global_avgpool_nhwc_fwd_kernel, bn_grid_for((long long)n * (c / 4)), 256, s, reinterpret_cast<const float4*>(in),
+               reinterpret_cast<float4*>(out), n, hw, c / 4);
+  else
+    DTF_LAUNCH(global_avgpool_nhwc_bwd_kernel, bn_grid_for((long long)n * hw * (c / 4)), 256, s,
+               reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), n, hw, c / 4);
   return (int)cudaGetLastError();
 }
 

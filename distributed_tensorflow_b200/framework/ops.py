@@ -658,7 +658,12 @@ def _pool(x, attrs, mode):
     return out.permute(0, 2, 3, 1)
 
 
-register_kernel("MaxPool")(lambda ctx, n, x: _pool(x, n.attrs, "max"))
+def _k_maxpool(ctx, n, x):
+    from ..ops import native                       # our NHWC kernels on /gpu when enabled, F.max_pool2d otherwise
+    return native.max_pool_nhwc(x, n.attrs["ksize"], n.attrs["strides"], n.attrs["padding"])
+
+
+register_kernel("MaxPool")(_k_maxpool)
 register_kernel("AvgPool")(lambda ctx, n, x: _pool(x, n.attrs, "avg"))
 
 

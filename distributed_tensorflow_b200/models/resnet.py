@@ -73,7 +73,7 @@ def resnet18_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, stem: str = "c
         h = native.conv2d_nhwc(x, p["stem/conv"], (1, 2, 2, 1), "SAME")
     h = _bn(h, p["stem/bn_scale"], p["stem/bn_offset"], relu=True)
     if stem != "cifar":
-        h = F.max_pool2d(h.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
+        h = native.max_pool_nhwc(h, (1, 3, 3, 1), (1, 2, 2, 1), "SAME").contiguous()
     cin = 64
     for si, (c, stride) in enumerate(_STAGES):
         for bi in range(2):
@@ -89,7 +89,7 @@ def resnet18_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, stem: str = "c
                 sc = h
             h = _bn(y, p[pre + "/bn2_scale"], p[pre + "/bn2_offset"], residual=sc, relu=True)      # relu(bn(y) + shortcut)
             cin = c
-    pooled = h.mean(dim=(1, 2))
+    pooled = native.global_avg_pool(h)
     return native.linear(pooled.contiguous(), p["fc/w"], p["fc/b"])
 
 

@@ -238,6 +238,12 @@ def _declare(lib) -> None:
         lib.dtf_im2col_nhwc_vec8.restype = c_int
         lib.dtf_col2im_nhwc_vec4.argtypes = [c_void_p, c_longlong, c_void_p] + [c_int] * 12 + [c_void_p]
         lib.dtf_col2im_nhwc_vec4.restype = c_int
+        lib.dtf_maxpool_nhwc_fwd.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int] * 12 + [c_void_p]
+        lib.dtf_maxpool_nhwc_fwd.restype = c_int
+        lib.dtf_maxpool_nhwc_bwd.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int] * 12 + [c_void_p]
+        lib.dtf_maxpool_nhwc_bwd.restype = c_int
+        lib.dtf_global_avgpool_nhwc.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+        lib.dtf_global_avgpool_nhwc.restype = c_int
 
 
 def load() -> ctypes.CDLL:
@@ -655,3 +661,57 @@ def bn_backward(dy: torch.Tensor, y_mask: Optional[torch.Tensor], x2d: torch.Ten
                                     rows, C, st), "bn_bwd_apply")
     _bump(2)
     return dx, dscale, doffset, dres
+
+
+# ---------------------------------------------------------------------------------------------------
+# pooling (csrc/nn_kernels.cu), NHWC fp32, C % 4 == 0
+# ---------------------------------------------------------------------------------------------------
+def maxpool_nhwc(x: torch.Tensor, kh: int, kw: int, strides: Sequence[int], pads: Sequence[int]):
+    """-> (y [n, ho, wo, c], argmax bytes [n, ho, wo, c]: position inside the window, consumed by the backward)."""
+    x = _aligned16(x.float().contiguous())
+    n, h, w, c = x.shape
+    sh, sw = strides
+    pt, pb, pl, pr = pads
+    ho = (h + pt + pb - kh) // sh + 1
+    wo = (w + pl + pr - kw) // sw + 1
+    y = torch.empty((n, ho, wo, c), dtype=torch.float32, device=x.device)
+    arg = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device)
+    with _on(x.device):
+        _check(load().dtf_maxpool_nhwc_fwd(x.data_ptr(), y.data_ptr(), arg.data_ptr(), n, h, w, c, kh, kw, sh, sw, pt, pl, ho, wo,
+                                           _stream(x)), "maxpool_nhwc_fwd")
+    _bump()
+    return y, arg
+
+
+def maxpool_nhwc_bwd(dy: torch.Tensor, arg: torch.Tensor, xshape, kh: int, kw: int, strides, pads) -> torch.Tensor:
+    dy = _aligned16(dy.float().contiguous())
+    n, h, w, c = xshape
+    sh, sw = strides
+    pt, pb, pl, pr = pads
+    ho, wo = dy.shape[1], dy.shape[2]
+    dx = torch.empty(tuple(xshape), dtype=torch.float32, device=dy.device)
+    with _on(dy.device):
+        _check(load().dtf_maxpool_nhwc_bwd(dy.data_ptr(), arg.data_ptr(), dx.data_ptr(), n, h, w, c, kh, kw, sh, sw, pt, pl, ho,
+                                           wo, _stream(dy)), "maxpool_nhwc_bwd")
+    _bump()
+    return dx
+
+
+def global_avgpool_nhwc(x: torch.Tensor) -> torch.Tensor:
+    x = _aligned16(x.float().contiguous())
+    n, h, w, c = x.shape
+    out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    with _on(x.device):
+        _check(load().dtf_global_avgpool_nhwc(x.data_ptr(), out.data_ptr(), n, h * w, c, 0, _stream(x)), "global_avgpool_nhwc")
+    _bump()
+    return out
+
+
+def global_avgpool_nhwc_bwd(dy: torch.Tensor, xshape) -> torch.Tensor:
+    dy = _aligned16(dy.float().contiguous())
+    n, h, w, c = xshape
+    dx = torch.empty(tuple(xshape), dtype=torch.float32, device=dy.device)
+    with _on(dy.device):
+        _check(load().dtf_global_avgpool_nhwc(dy.data_ptr(), dx.data_ptr(), n, h * w, c, 1, _stream(dy)), "global_avgpool_nhwc_bwd")
+    _bump()
+    return dx

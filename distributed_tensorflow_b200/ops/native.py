@@ -222,6 +222,65 @@ def batch_norm_train(x: torch.Tensor, scale: torch.Tensor, offset: torch.Tensor,
 
 
 # ---------------------------------------------------------------------------
+# pooling (NHWC)
+# ---------------------------------------------------------------------------
+def _fused_nn() -> bool:
+    return bool(_lib().FUSED_NN)
+
+
+class _MaxPoolFn(torch.autograd.Function):
+    """Window max with a byte argmax per element; the backward gathers (deterministic, no atomics)."""
+
+    @staticmethod
+    def forward(ctx, x, kh, kw, strides, pads):
+        y, arg = _lib().maxpool_nhwc(x, kh, kw, strides, pads)
+        ctx.save_for_backward(arg)
+        ctx.meta = (tuple(x.shape), kh, kw, strides, pads)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        xshape, kh, kw, strides, pads = ctx.meta
+        return _lib().maxpool_nhwc_bwd(g, arg, xshape, kh, kw, strides, pads), None, None, None, None
+
+
+def max_pool_nhwc(x: torch.Tensor, ksize: Sequence[int], strides: Sequence[int], padding: str) -> torch.Tensor:
+    """``tf.nn.max_pool`` on NHWC data (padding counts as -inf)."""
+    kh, kw = int(ksize[1]), int(ksize[2])
+    sh, sw = int(strides[1]), int(strides[2])
+    if padding.upper() == "SAME":
+        pt, pb = _same_pad(x.shape[1], kh, sh)
+        pl, pr = _same_pad(x.shape[2], kw, sw)
+    else:
+        pt = pb = pl = pr = 0
+    if _use_native(x) and _fused_nn() and x.shape[-1] % 4 == 0 and kh * kw <= 255:
+        return _MaxPoolFn.apply(x, kh, kw, (sh, sw), (pt, pb, pl, pr))
+    xn = x.permute(0, 3, 1, 2)
+    if pt or pb or pl or pr:
+        xn = F.pad(xn, (pl, pr, pt, pb), value=float("-inf"))
+    return F.max_pool2d(xn, (kh, kw), (sh, sw)).permute(0, 2, 3, 1)
+
+
+class _GlobalAvgPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.xshape = tuple(x.shape)
+        return _lib().global_avgpool_nhwc(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _lib().global_avgpool_nhwc_bwd(g, ctx.xshape)
+
+
+def global_avg_pool(x: torch.Tensor) -> torch.Tensor:
+    """[N, H, W, C] -> [N, C] mean over the spatial axes (the pooling in front of ResNet's classifier)."""
+    if _use_native(x) and _fused_nn() and x.dim() == 4 and x.shape[-1] % 4 == 0:
+        return _GlobalAvgPoolFn.apply(x)
+    return x.mean(dim=(1, 2))
+
+
+# ---------------------------------------------------------------------------
 # convolution (NHWC data, HWIO filter)
 # ---------------------------------------------------------------------------
 def _same_pad(size: int, k: int, s: int):

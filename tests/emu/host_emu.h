@@ -43,6 +43,11 @@ namespace dtf {
 static inline unsigned pack_bf16x2(float lo, float hi) { return dtf_emu_bf16(lo) | (dtf_emu_bf16(hi) << 16); }
 }  // namespace dtf
 
+struct alignas(4) uchar4 {
+  unsigned char x, y, z, w;
+};
+static inline uchar4 make_uchar4(unsigned char a, unsigned char b, unsigned char c, unsigned char d) { return uchar4{a, b, c, d}; }
+
 struct alignas(8) uint2 {
   unsigned x, y;
 };

@@ -89,3 +89,29 @@ def test_vector_im2col_col2im_match_scalar_kernels(shape, k, stride, monkeypatch
         outs.append((cols, gx))
     assert torch.equal(outs[0][0], outs[1][0])
     torch.testing.assert_close(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape,k,stride", [((8, 32, 32, 64), 3, 2), ((4, 16, 16, 128), 2, 2), ((2, 7, 9, 8), 3, 1)])
+def test_pooling_kernels_match_pytorch(shape, k, stride, monkeypatch):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from distributed_tensorflow_b200.ops import cuda_lib, native
+    monkeypatch.setattr(cuda_lib, "FUSED_NN", True)
+    g = torch.Generator().manual_seed(k)
+    x = torch.randn(*shape, generator=g).cuda()
+
+    def both(fn):
+        outs = []
+        for fused in (True, False):
+            monkeypatch.setattr(cuda_lib, "FUSED_NN", fused)
+            leaf = x.clone().requires_grad_()
+            y = fn(leaf)
+            (gx,) = torch.autograd.grad((y * y).sum(), leaf)
+            outs.append((y.detach(), gx))
+        return outs
+    (y1, g1), (y0, g0) = both(lambda t: native.max_pool_nhwc(t, (1, k, k, 1), (1, stride, stride, 1), "SAME"))
+    assert torch.equal(y1, y0)
+    torch.testing.assert_close(g1, g0, rtol=1e-6, atol=1e-6)
+    (y1, g1), (y0, g0) = both(native.global_avg_pool)
+    torch.testing.assert_close(y1, y0, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(g1, g0, rtol=1e-5, atol=1e-7)

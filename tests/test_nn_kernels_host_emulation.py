@@ -121,3 +121,38 @@ def test_emulated_vector_im2col_col2im(emu, shape, k, stride, pads):
     # ineligible shapes are refused (the caller falls back to the scalar kernels)
     x3 = torch.zeros(1, 4, 4, 3)
     assert emu.dtf_im2col_nhwc_vec8(_p(x3), _p(cols), 1, 4, 4, 3, 3, 3, 1, 1, 1, 1, 4, 4, 32, None) == -1
+
+
+@pytest.mark.parametrize("shape,k,stride,pads", [((2, 8, 8, 8), 3, 2, (0, 1, 0, 1)), ((1, 7, 5, 4), 2, 2, (0, 1, 0, 1)),
+                                                 ((2, 6, 6, 12), 3, 1, (1, 1, 1, 1))])
+def test_emulated_pooling_kernels(emu, shape, k, stride, pads):
+    vp, i = ctypes.c_void_p, ctypes.c_int
+    emu.dtf_maxpool_nhwc_fwd.argtypes = [vp, vp, vp] + [i] * 12 + [vp]
+    emu.dtf_maxpool_nhwc_bwd.argtypes = [vp, vp, vp] + [i] * 12 + [vp]
+    emu.dtf_global_avgpool_nhwc.argtypes = [vp, vp, i, i, i, i, vp]
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    n, h, w, c = shape
+    pt, pb, pl, pr = pads
+    ho, wo = (h + pt + pb - k) // stride + 1, (w + pl + pr - k) // stride + 1
+    y = torch.empty(n, ho, wo, c)
+    arg = torch.empty(n, ho, wo, c, dtype=torch.uint8)
+    assert emu.dtf_maxpool_nhwc_fwd(_p(x), _p(y), _p(arg), n, h, w, c, k, k, stride, stride, pt, pl, ho, wo, None) == 0
+    xr = x.clone().requires_grad_()
+    xp = torch.nn.functional.pad(xr.permute(0, 3, 1, 2), (pl, pr, pt, pb), value=float("-inf"))
+    ref = torch.nn.functional.max_pool2d(xp, k, stride).permute(0, 2, 3, 1)
+    assert torch.equal(y, ref.detach())
+    dy = torch.randn(n, ho, wo, c, generator=g)
+    dx = torch.full(shape, float("nan"))
+    assert emu.dtf_maxpool_nhwc_bwd(_p(dy), _p(arg), _p(dx), n, h, w, c, k, k, stride, stride, pt, pl, ho, wo, None) == 0
+    (gref,) = torch.autograd.grad(ref, xr, dy)
+    torch.testing.assert_close(dx, gref, rtol=1e-6, atol=1e-6)
+    # global average pooling and its gradient
+    out = torch.empty(n, c)
+    assert emu.dtf_global_avgpool_nhwc(_p(x), _p(out), n, h * w, c, 0, None) == 0
+    torch.testing.assert_close(out, x.mean(dim=(1, 2)), rtol=1e-5, atol=1e-6)
+    gd = torch.randn(n, c, generator=g)
+    gx = torch.empty(shape)
+    assert emu.dtf_global_avgpool_nhwc(_p(gd), _p(gx), n, h * w, c, 1, None) == 0
+    torch.testing.assert_close(gx, (gd / (h * w))[:, None, None, :].expand(shape), rtol=1e-6, atol=1e-7)
+    assert emu.dtf_maxpool_nhwc_fwd(_p(x), _p(y), _p(arg), n, h, w, 6, k, k, stride, stride, pt, pl, ho, wo, None) == -1   # C % 4

@@ -100,6 +100,24 @@ def test_fused_batch_norm_autograd_function(emulated, monkeypatch, relu, with_re
         torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-3)
 
 
+def test_pooling_autograd_functions(emulated, monkeypatch):
+    monkeypatch.setattr(cuda_lib, "FUSED_NN", True)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 9, 8, 8, generator=g)
+    wgt = torch.randn(2, 5, 4, 8, generator=g)
+    n0 = cuda_lib.launch_count()
+    out, grads = _grads(lambda a: native.max_pool_nhwc(a, (1, 3, 3, 1), (1, 2, 2, 1), "SAME") * wgt, [x])
+    pooled, pg = _grads(lambda a: native.global_avg_pool(a) * wgt[:, 0, 0, :], [x])
+    assert cuda_lib.launch_count() - n0 == 4
+    monkeypatch.setattr(cuda_lib, "EMULATION", False)
+    ref_out, ref = _grads(lambda a: native.max_pool_nhwc(a, (1, 3, 3, 1), (1, 2, 2, 1), "SAME") * wgt, [x])
+    ref_pooled, rpg = _grads(lambda a: native.global_avg_pool(a) * wgt[:, 0, 0, :], [x])
+    assert torch.equal(out, ref_out)
+    torch.testing.assert_close(grads[0], ref[0], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(pooled, ref_pooled, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(pg[0], rpg[0], rtol=1e-6, atol=1e-7)
+
+
 def test_resnet18_loss_and_every_gradient_through_the_fused_path(emulated, monkeypatch):
     """ResNet-18 (CIFAR stem) on an 8 x 4 x 4 x 3 batch, three ways: (a) our kernels with the fused BN + residual + ReLU and
     the vectorised im2col / col2im, (b) our kernels with the element-wise BN glue and the scalar lowering, (c) plain
