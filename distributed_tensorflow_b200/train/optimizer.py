@@ -179,12 +179,21 @@ class GradientDescentOptimizer(Optimizer):
         return {"kind": "sgd", "lr": _lr_value(self._lr)}
 
 
+def _our_kernels_apply(var: torch.Tensor) -> bool:
+    """CUDA variables are updated by ``optimizer_apply_kernel``; host variables too under the kernel emulation (tests)."""
+    if var.is_cuda:
+        return True
+    import sys
+    mod = sys.modules.get("distributed_tensorflow_b200.ops.cuda_lib")
+    return bool(mod is not None and mod.EMULATION and var.dtype == torch.float32 and var.is_contiguous())
+
+
 @register_kernel("ApplyGradientDescent", stateful=True)
 def _k_apply_sgd(ctx, node, grad, *extra):
     var = ctx.store.read(node.attrs["var_name"])
     g = grad.to(device=var.device)
     lr = _lr_at_run_time(node, extra)
-    if var.is_cuda:
+    if _our_kernels_apply(var):
         from ..ops import cuda_lib
         cuda_lib.apply_sgd_(var, g, lr)
     else:
@@ -221,7 +230,7 @@ def _k_apply_momentum(ctx, node, grad, *extra):
     a = dict(node.attrs, lr=_lr_at_run_time(node, extra))
     var, acc = ctx.store.read(a["var_name"]), ctx.store.read(a["accum_name"])
     g = grad.to(device=var.device)
-    if var.is_cuda:
+    if _our_kernels_apply(var):
         from ..ops import cuda_lib
         cuda_lib.apply_momentum_(var, acc, g, a["lr"], a["momentum"], a["nesterov"])
     else:
@@ -284,7 +293,7 @@ def _k_apply_adam(ctx, node, grad, b1p, b2p, *extra):
     g = grad.to(device=var.device)
     b1p, b2p = float(b1p), float(b2p)
     lr_t = a["lr"] * (1.0 - b2p) ** 0.5 / (1.0 - b1p)
-    if var.is_cuda:
+    if _our_kernels_apply(var):
         from ..ops import cuda_lib
         cuda_lib.apply_adam_(var, m, v, g, lr_t, a["beta1"], a["beta2"], a["eps"])
     else:
