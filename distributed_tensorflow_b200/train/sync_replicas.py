@@ -228,6 +228,17 @@ class SyncReplicasOptimizer(Optimizer):
                 chief_init_ops.append(g.create_node("QueueRenew", [], {"queue_name": self._sync_token_queue_name},
                                                     "sync_token_q_Renew", device=qdev))
             self._chief_queue_runner = QueueRunner(self._sync_token_queue_name, [self.sync_op], close_op=close_op)
+            # A replica whose training loop ends cleanly (StopAtStepHook saw the last step) while another replica is still
+            # inside a step would leave that one waiting for a token whose aggregate needs the departed replica's
+            # gradient -- the init tokens let replicas run a step apart, and stale drops at the start use the spare
+            # tokens up.  The departing replica therefore leaves one "farewell" token per other replica: whoever is
+            # blocked finishes its run, sees the same global step and stops too.  (TF has this end-of-training hazard.)
+            self._farewell_op = None
+            if self._total_num_replicas > 1:
+                self._farewell_op = g.create_node("QueueEnqueueMany", [self._global_step._node],
+                                                  {"queue_name": self._sync_token_queue_name,
+                                                   "count": int(self._total_num_replicas - 1)},
+                                                  "sync_token_q_farewell", device=qdev)
             # like TF: the chief's init op also initialises ITS local_step (mnist_replica.py passes chief_init_op as the
             # chief's local_init_op and local_step_init_op as everybody else's)
             self.chief_init_op = _ops.group(self.local_step_init_op, *chief_init_ops, name="chief_init")
@@ -294,8 +305,14 @@ class SyncReplicasOptimizerHook(SessionRunHook):
         # Clean end of the chief's training loop: close the token queue NOW, while the session is still open (the
         # queue runner's close-on-stop thread races with the session teardown).  Replicas that are still running drain
         # the remaining tokens and then get OutOfRangeError from the dequeue = a clean end of their loop.
+        raw = getattr(session, "raw_session", lambda: session)()
         if self._is_chief and self._q_runner is not None and self._q_runner.close_op is not None:
             try:
-                getattr(session, "raw_session", lambda: session)().run(self._q_runner.close_op)
+                raw.run(self._q_runner.close_op)
             except Exception:      # noqa: BLE001 - the ps may already be gone
+                pass
+        elif not self._is_chief and getattr(self._sync_optimizer, "_farewell_op", None) is not None:
+            try:
+                raw.run(self._sync_optimizer._farewell_op)       # see apply_gradients: nobody waits for our gradient
+            except Exception:      # noqa: BLE001 - queue already closed by the chief / ps gone: nothing to release
                 pass

@@ -534,3 +534,31 @@ def test_recoverable_session_in_sync_mode_survives_ps_restart(ports, tmp_path):
     finally:
         ps.stop()
         wk.stop()
+
+
+def test_departing_sync_replica_leaves_farewell_tokens(cluster3):
+    """End-of-training hazard of SyncReplicasOptimizer (present in TF): replicas run up to a step apart, so one can finish
+    (StopAtStepHook) while another is inside a step whose aggregate needs the finished replica's gradient.  A non-chief
+    replica that ends cleanly therefore enqueues ``total_num_replicas - 1`` tokens in its hook's ``end()``; a replica
+    blocked on the token queue proceeds, sees the same global step and stops."""
+    cluster, servers = cluster3
+    g = dtf.Graph()
+    with g.as_default():
+        with dtf.device(dtf.train.replica_device_setter(cluster=cluster, worker_device="/job:worker/task:1")):
+            gs = dtf.train.get_or_create_global_step()
+            w = dtf.get_variable("w", [1], initializer=dtf.zeros_initializer())
+            opt = dtf.train.SyncReplicasOptimizer(dtf.train.GradientDescentOptimizer(0.1), replicas_to_aggregate=3, total_num_replicas=3)
+            opt.minimize(dtf.reduce_sum(w * w), global_step=gs)
+            size = g.create_node("QueueSize", [], {"queue_name": opt._sync_token_queue_name}, "q_size", device=gs.device)
+        chief_hook, hook = opt.make_session_run_hook(True), opt.make_session_run_hook(False)
+        chief_hook.begin()
+        hook.begin()
+        with dtf.Session(servers[2].target) as sess:
+            sess.run(dtf.global_variables_initializer())
+            sess.run(opt.chief_init_op)                       # creates the accumulators / token queue on the ps
+            assert int(sess.run(size)) == 0
+            hook.end(sess)                                    # a non-chief replica leaves cleanly
+            assert int(sess.run(size)) == 2                   # one token for each of the two other replicas
+            chief_hook._q_runner = opt.get_chief_queue_runner()
+            chief_hook.end(sess)                              # the chief leaves: queue closed ...
+            hook.end(sess)                                    # ... a later farewell is refused quietly
