@@ -467,3 +467,50 @@ def test_concurrent_protocol_simulation(emu, sync, ps_on_workers):
         assert int(wd.u64("global_step")) == K * W and sum(wd.u64("staleness_hist", 16).tolist()) == K * W
         torch.testing.assert_close(wd.master, wd.master0 - lr * total, rtol=1e-5, atol=1e-4)      # every push applied alone
         assert [int(wd.mailbox(w)[0]) for w in range(W)] == [K] * W                                # one ack per push
+
+
+def test_concurrent_backup_worker_with_a_straggler(emu):
+    """replicas_to_aggregate = 3 of 4 with one slow replica, real concurrency: the job never waits for the straggler, its
+    late pushes are either aggregated (stamped with the then-current step) or dropped as stale, every replica keeps
+    receiving tokens, and the counters add up."""
+    import threading
+    import time
+    W, R, K, n = 4, 3, 8, 1024
+    wd = World(emu, n=n, workers=W, R=R, ctas_per_push=1, lr=0.01)
+    wd.a.timeout_ns = 20_000_000_000
+    errs = [torch.zeros(1, dtype=torch.int32) for _ in range(W)]
+    srcs = [torch.ones(n) for _ in range(W)]
+    failures = []
+
+    def worker(w):
+        try:
+            mbp = wd.mb.data_ptr() + w * wd.mb_bytes
+            for t in range(K):
+                assert emu.dtf_wait_token(mbp, t if w < 3 else 0, None, 20_000_000_000, errs[w].data_ptr(), None) == 0
+                assert int(errs[w]) == 0
+                if w == 3:
+                    time.sleep(0.03)                     # the straggler
+                assert emu.dtf_push_grad(srcs[w].data_ptr(), wd.grads[w].data_ptr(), n, wd.ctl.data_ptr(), mbp, w, 0, 1, 1, None) == 0
+        except BaseException as e:      # noqa: BLE001
+            failures.append(e)
+
+    def ps():
+        try:
+            for _ in range(K):
+                assert emu.dtf_ps_apply(ctypes.byref(wd.a), None) == 0
+        except BaseException as e:      # noqa: BLE001
+            failures.append(e)
+
+    threads = [threading.Thread(target=worker, args=(w,)) for w in range(W)] + [threading.Thread(target=ps)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not failures, failures
+    assert not any(t.is_alive() for t in threads)
+    assert int(wd.u32("err")) == 0 and int(wd.u64("global_step")) == K
+    applied, dropped = int(wd.u64("applied_total")), int(wd.u64("dropped_stale"))
+    assert 3 * K <= applied <= 4 * K and 0 <= dropped <= K and applied + dropped <= 4 * K
+    assert all(int(wd.mailbox(w)[0]) == K for w in range(W))              # the straggler got every token too
+    # all gradients are ones: every aggregate is a mean of ones whatever its size, so the result is exact
+    torch.testing.assert_close(wd.master, wd.master0 - 0.01 * K, rtol=1e-5, atol=1e-5)
