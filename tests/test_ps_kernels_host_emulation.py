@@ -514,3 +514,21 @@ def test_concurrent_backup_worker_with_a_straggler(emu):
     assert all(int(wd.mailbox(w)[0]) == K for w in range(W))              # the straggler got every token too
     # all gradients are ones: every aggregate is a mean of ones whatever its size, so the result is exact
     torch.testing.assert_close(wd.master, wd.master0 - 0.01 * K, rtol=1e-5, atol=1e-5)
+
+
+def test_stage_from_dataset_walks_batches_by_device_step_counter(emu):
+    """Input pipeline stage of the device-resident dataset: batch index = (step * stride + offset) % nbatches with the step
+    read from the worker's device counter (CUDA-graph replayable), fp32 images -> bf16 staging tile, labels copied."""
+    vp, ll, i = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+    emu.dtf_stage_from_dataset.argtypes = [vp, vp, ll, i, i, i, ll, ll, vp, vp, vp, vp]
+    nb, B, D, C = 5, 8, 16, 4
+    g = torch.Generator().manual_seed(3)
+    images, labels = torch.randn(nb, B, D, generator=g), torch.rand(nb, B, C, generator=g)
+    x16, lab = torch.zeros(B, D, dtype=torch.bfloat16), torch.zeros(B, C)
+    for step, stride, offset in [(0, 3, 1), (4, 3, 1), (7, 1, 0)]:
+        ctr = torch.tensor([step], dtype=torch.int64)
+        assert emu.dtf_stage_from_dataset(images.data_ptr(), labels.data_ptr(), nb, B, D, C, stride, offset, ctr.data_ptr(),
+                                          x16.data_ptr(), lab.data_ptr(), None) == 0
+        bi = (step * stride + offset) % nb
+        assert torch.equal(x16, images[bi].bfloat16()) and torch.equal(lab, labels[bi])
+    assert emu.dtf_stage_from_dataset(images.data_ptr(), labels.data_ptr(), nb, 3, 5, C, 1, 0, None, x16.data_ptr(), lab.data_ptr(), None) == -2
