@@ -25,6 +25,9 @@ elif [ "$mode" = "pending" ]; then
   step bench_n1 180 python bench.py
   step resnet18_eager 200 python bench.py --model resnet18 --steps 10 --warmup 3
   DTF_FUSED_NN=1 step resnet18_fused 200 python bench.py --model resnet18 --steps 10 --warmup 3
+  step nn_perf 200 python tools/nn_perf.py
+  step ncu_nn 240 ncu --set full --clock-control none --import-source on -k "regex:bn_|im2col_nhwc_vec8|col2im_nhwc_vec4|pool" -c 12 -f \
+      -o gpurun_out/prof_nn python tools/nn_perf.py --ncu
   step resnet18_graph 200 python bench.py --model resnet18 --steps 10 --warmup 4 --graph-step 1
   DTF_FUSED_NN=1 step resnet18_fused_graph 200 python bench.py --model resnet18 --steps 10 --warmup 4 --graph-step 1
 elif [ "$mode" = "pending-multi" ]; then
