@@ -35,6 +35,7 @@ flags.DEFINE_bool("issync", True, "synchronous replicas")
 flags.DEFINE_integer("num_ps", 1, "ps shards")
 flags.DEFINE_bool("in_graph", False, "one process drives all GPUs")
 flags.DEFINE_integer("gpus", 0, "GPUs to use in in-graph mode (0: all)")
+flags.DEFINE_bool("ps_on_workers", False, "every GPU runs a worker; ps shard s shares worker s's GPU and stream (no ps-only GPU)")
 flags.DEFINE_string("train_dir", "/tmp/dtf_ckpt/fabric_mnist", "checkpoint directory")
 flags.DEFINE_integer("num_train", 55000, "synthetic train-set size")
 flags.DEFINE_string("nvls", "auto", "NVLS multicast fabric: off | on | auto (auto = on when the box has NVLS and one process "
@@ -55,8 +56,9 @@ def main():
         fabric = Fabric.from_torch_distributed()
         n, rank = world, dist.get_rank()
     colocated = n == 1
-    cfg = EngineConfig(num_ps=1 if colocated else FLAGS.num_ps, num_workers=1 if colocated else n - FLAGS.num_ps,
-                       sync=FLAGS.issync, colocated=colocated,
+    pow_ = FLAGS.ps_on_workers and not colocated
+    cfg = EngineConfig(num_ps=1 if colocated else FLAGS.num_ps, num_workers=1 if colocated else (n if pow_ else n - FLAGS.num_ps),
+                       sync=FLAGS.issync, colocated=colocated, ps_on_workers=pow_,
                        nvls={"off": False, "on": True}.get(FLAGS.nvls, False if (FLAGS.in_graph or world == 1) else "auto"),
                        optimizer={"kind": FLAGS.optimizer, "lr": FLAGS.learning_rate, "momentum": 0.9})
     eng = PSTrainEngine(MLPSpec(hidden=FLAGS.hidden_units, batch=FLAGS.batch_size), cfg, fabric)
