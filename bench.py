@@ -55,7 +55,8 @@ def parse_args():
                          "0: ranks 0..num_ps-1 are ps-only tasks (the validated topology)")
     ap.add_argument("--e2e-pipeline", type=int, default=1,
                     help="1 (one-GPU runs): also time step(..., sync_loss='deferred') -- the loss of step t is read after "
-                         "step t+1 was enqueued -- and report the better arm, both kept under e2e.synchronous/.pipelined")
+                         "step t+1 was enqueued -- and report the better arm, both kept under e2e.synchronous/.pipelined; "
+                         "2: do so on every topology (multi-rank: no fallback, first hardware run pending); 0: off")
     ap.add_argument("--publish", action="store_true", help="ps stores params into worker replicas (push-publish)")
     ap.add_argument("--num-train", type=int, default=55000)
     ap.add_argument("--f1-splits", type=int, default=1, help="split-K CTAs for the first GEMM")
@@ -512,6 +513,9 @@ def main():
             # host's turnaround overlaps the GPU's work on step t; every loss is still read back, one step late
             pending = last = None
             for i in range(n):
+                if not is_worker:
+                    eng.step(sync_loss=False)          # ps-only rank: one apply per aggregate, as in the synchronous loop
+                    continue
                 x, y = batch_of(start + i)
                 h = eng.step(x, y, sync_loss="deferred", prefetch=batch_of(start + i + 1))
                 if pending is not None:
@@ -550,7 +554,7 @@ def main():
                else "PSTrainEngine.step(x_pinned, y_pinned) -> loss",
                "input_double_buffering": bool(args.e2e_prefetch), "loss_read": "synchronous, every step",
                "last_loss": last_loss}
-        if args.e2e_pipeline and world == 1 and N == 1 and is_worker:
+        if (args.e2e_pipeline == 1 and world == 1 and N == 1 and is_worker) or args.e2e_pipeline == 2:
             # second arm of the same API: loss handles read one step late.  One process / one GPU only for now (no
             # cross-rank protocol to disturb if it fails); a failure keeps the synchronous number above.
             try:
@@ -566,6 +570,8 @@ def main():
                     e2e["api"] = "PSTrainEngine.step(x_pinned, y_pinned, sync_loss='deferred', prefetch=next) -> PendingLoss; .result()"
                     e2e["loss_read"] = "every step's loss is copied D2H behind its kernels and read by the host one step late"
             except Exception as e:      # noqa: BLE001 - keep the validated synchronous measurement
+                if world > 1:
+                    raise                # ranks must not diverge: --e2e-pipeline 2 is an explicit opt-in without a fallback
                 e2e["pipelined_error"] = repr(e)[:300]
 
     # ---- ps traffic implied by the measured step time (BASELINE metric: push/pull GB/s vs 900 GB/s/dir) -----------
