@@ -37,6 +37,7 @@ elif [ "$mode" = "pending-multi" ]; then
   step bench_pow_nvls 150 $TR bench.py --gpus $N --nvls on --ps-on-workers 1
   step bench_pow_unicast 150 $TR bench.py --gpus $N --nvls off --ps-on-workers 1
   step bench_ref 150 $TR bench.py --gpus $N
+  step bench_e2e_pipe 150 $TR bench.py --gpus $N --e2e-pipeline 2
 else
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
   DTF_NVLS=1 step mp_check_nvls 120 $TR tools/mp_check.py
