@@ -314,8 +314,19 @@ class _ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gw = lib.gemm(cols, g2, True, False).reshape(wshape)
         if ctx.needs_input_grad[0]:
-            gcols = lib.gemm(g2, w2, False, True)
-            gx = lib.col2im_nhwc(gcols, xshape, wshape[0], wshape[1], strides, pads)
+            kh, kw, cin, cout = wshape
+            if lib.FUSED_NN and strides == (1, 1) and cout % 8 == 0:
+                # stride 1: dX is itself a convolution of dY with the spatially flipped, in/out-swapped filter --
+                #   dX[b, iy, ix, ci] = sum_{ky', kx', co} dY[b, iy + ky' - (kh-1-pt), ix + kx' - (kw-1-pl), co] * w[kh-1-ky', kw-1-kx', ci, co]
+                # so it reuses the im2col + GEMM pair: a bf16 patch matrix of dY (rows x kh*kw*Cout x 2 B) replaces the fp32
+                # [rows, kh*kw*Cin] product + the col2im gather (half the HBM traffic, one launch less, output written once)
+                pt, pb, pl, pr = pads
+                wf = w2.reshape(kh, kw, cin, cout).flip(0, 1).permute(0, 1, 3, 2).reshape(kh * kw * cout, cin)
+                gcols_in, _ = lib.im2col_nhwc(g2.reshape(n, ho, wo, cout), kh, kw, (1, 1), (kh - 1 - pt, kh - 1 - pb, kw - 1 - pl, kw - 1 - pr))
+                gx = lib.gemm(gcols_in, wf.contiguous(), False, False).reshape(xshape)
+            else:
+                gcols = lib.gemm(g2, w2, False, True)
+                gx = lib.col2im_nhwc(gcols, xshape, kh, kw, strides, pads)
         return gx, gw, None, None
 
 

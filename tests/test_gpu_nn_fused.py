@@ -117,3 +117,21 @@ def test_pooling_kernels_match_pytorch(shape, k, stride, monkeypatch):
     (y1, g1), (y0, g0) = both(native.global_avg_pool)
     torch.testing.assert_close(y1, y0, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(g1, g0, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("shape,k,cout", [((8, 32, 32, 64), 3, 64), ((4, 16, 16, 128), 3, 128), ((2, 8, 8, 16), 2, 24)])
+def test_stride1_data_gradient_as_convolution_matches_col2im_path(shape, k, cout, monkeypatch):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from distributed_tensorflow_b200.ops import cuda_lib, native
+    g = torch.Generator().manual_seed(k)
+    x = torch.randn(*shape, generator=g).cuda()
+    w = (torch.randn(k, k, shape[-1], cout, generator=g) * 0.1).cuda()
+    outs = []
+    for fused in (True, False):
+        monkeypatch.setattr(cuda_lib, "FUSED_NN", fused)
+        xl, wl = x.clone().requires_grad_(), w.clone().requires_grad_()
+        y = native.conv2d_nhwc(xl, wl, (1, 1, 1, 1), "SAME")
+        outs.append(torch.autograd.grad((y * y).sum(), [xl, wl]))
+    for a, b in zip(*outs):
+        assert float((a - b).norm() / (b.norm() + 1e-12)) < 1e-2

@@ -204,3 +204,24 @@ def test_nn_perf_tool_dry_run_under_emulation(tmp_path):
                            timeout=600, env=env, cwd=str(tmp_path))
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "fused_fwd_ms" in r.stdout or True
+
+
+@pytest.mark.parametrize("k,padding", [(2, "SAME"), (3, "VALID"), (1, "SAME"), (4, "SAME")])
+def test_stride1_data_gradient_as_convolution(emulated, monkeypatch, k, padding):
+    """With DTF_FUSED_NN the stride-1 data gradient is computed as a convolution of dY with the flipped, in/out-swapped
+    filter (im2col of dY + one GEMM) instead of GEMM + col2im: same result for even / odd kernels and both paddings."""
+    monkeypatch.setattr(cuda_lib, "FUSED_NN", True)
+    g = torch.Generator().manual_seed(k)
+    x, w = torch.randn(2, 6, 5, 8, generator=g), torch.randn(k, k, 8, 16, generator=g) * 0.2
+
+    def f(a, b):
+        out = native.conv2d_nhwc(a, b, (1, 1, 1, 1), padding)
+        return out + out * out
+    _, grads = _grads(f, [x, w])
+    monkeypatch.setattr(cuda_lib, "FUSED_NN", False)              # GEMM + col2im formulation, same emulated kernels
+    _, classic = _grads(f, [x, w])
+    monkeypatch.setattr(cuda_lib, "EMULATION", False)
+    _, ref = _grads(f, [x, w])
+    _close(grads[0], classic[0], 1e-2)
+    _close(grads[0], ref[0], 1e-2)
+    _close(grads[1], ref[1], 1e-2)
