@@ -58,8 +58,15 @@ bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
   __shared__ int is_last;
   const int tx = threadIdx.x, ty = threadIdx.y, t = ty * kBnTX + tx;
   const int cbase = blockIdx.x * kBnCh;
-  const int c = cbase + tx * 4;
+  // Narrow tensors (C < 128, one column block): the x-lanes beyond C/4 would idle, so a warp covers SUB consecutive rows
+  // instead -- lane = sub * (C/4) + channel group.  Wide tensors: SUB = 1, lane = channel group.
+  const int c4n = C / 4;
+  const int SUB = (gridDim.x == 1 && c4n < kBnTX && kBnTX % c4n == 0) ? kBnTX / c4n : 1;
+  const int sub = SUB > 1 ? tx / c4n : 0;
+  const int c = SUB > 1 ? (tx % c4n) * 4 : cbase + tx * 4;
   const bool live = c < C;
+  // independent rows in flight per thread: the reduction is latency-bound otherwise (one 16-byte load per thread per trip)
+  constexpr int UNR = MODE == 0 ? 4 : 2;
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   if (live) {
     float4 m = make_float4(0.f, 0.f, 0.f, 0.f), rs = m;
@@ -67,22 +74,37 @@ bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
       m = *reinterpret_cast<const float4*>(mean + c);
       rs = *reinterpret_cast<const float4*>(rstd + c);
     }
-    for (long long r = (long long)blockIdx.y * kBnTY + ty; r < rows; r += (long long)gridDim.y * kBnTY) {
-      const long long off = r * C + c;
-      const float4 v = *reinterpret_cast<const float4*>(x + off);
-      if (MODE == 0) {
-        s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
-        s2[0] += v.x * v.x; s2[1] += v.y * v.y; s2[2] += v.z * v.z; s2[3] += v.w * v.w;
-      } else {
-        float4 g = *reinterpret_cast<const float4*>(dy + off);
-        if (y_mask != nullptr) {
-          const float4 o = *reinterpret_cast<const float4*>(y_mask + off);
-          g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
-          g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+    const long long rstride = (long long)gridDim.y * kBnTY * SUB;
+    for (long long r0 = ((long long)blockIdx.y * kBnTY + ty) * SUB + sub; r0 < rows; r0 += rstride * UNR) {
+      float4 v[UNR], g[UNR], o[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const long long r = r0 + u * rstride;
+        if (r < rows) {
+          const long long off = r * C + c;
+          v[u] = *reinterpret_cast<const float4*>(x + off);
+          if (MODE == 1) {
+            g[u] = *reinterpret_cast<const float4*>(dy + off);
+            if (y_mask != nullptr) o[u] = *reinterpret_cast<const float4*>(y_mask + off);
+          }
         }
-        s1[0] += g.x; s1[1] += g.y; s1[2] += g.z; s1[3] += g.w;
-        s2[0] += g.x * (v.x - m.x) * rs.x; s2[1] += g.y * (v.y - m.y) * rs.y;
-        s2[2] += g.z * (v.z - m.z) * rs.z; s2[3] += g.w * (v.w - m.w) * rs.w;
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (r0 + u * rstride >= rows) break;
+        if (MODE == 0) {
+          s1[0] += v[u].x; s1[1] += v[u].y; s1[2] += v[u].z; s1[3] += v[u].w;
+          s2[0] += v[u].x * v[u].x; s2[1] += v[u].y * v[u].y; s2[2] += v[u].z * v[u].z; s2[3] += v[u].w * v[u].w;
+        } else {
+          float4 gg = g[u];
+          if (y_mask != nullptr) {
+            gg.x = o[u].x > 0.f ? gg.x : 0.f; gg.y = o[u].y > 0.f ? gg.y : 0.f;
+            gg.z = o[u].z > 0.f ? gg.z : 0.f; gg.w = o[u].w > 0.f ? gg.w : 0.f;
+          }
+          s1[0] += gg.x; s1[1] += gg.y; s1[2] += gg.z; s1[3] += gg.w;
+          s2[0] += gg.x * (v[u].x - m.x) * rs.x; s2[1] += gg.y * (v[u].y - m.y) * rs.y;
+          s2[2] += gg.z * (v[u].z - m.z) * rs.z; s2[3] += gg.w * (v[u].w - m.w) * rs.w;
+        }
       }
     }
   }
@@ -92,14 +114,21 @@ bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
     sm[1][ty][tx * 4 + j] = s2[j];
   }
   __syncthreads();
-  // 256 threads = 2 quantities x 128 channels: fold the 8 row lanes, publish this block's partial
+  // 256 threads = 2 quantities x 128 lane-slots: fold the 8 row lanes ...
   const int q = t / kBnCh, ch = t % kBnCh;
-  {
-    float acc = 0.f;
+  float acc = 0.f;
 #pragma unroll
-    for (int yy = 0; yy < kBnTY; ++yy) acc += sm[q][yy][ch];
-    if (cbase + ch < C) partial[((long long)blockIdx.y * 2 + q) * C + cbase + ch] = acc;
+  for (int yy = 0; yy < kBnTY; ++yy) acc += sm[q][yy][ch];
+  if (SUB > 1) {
+    // ... and, for narrow tensors, the SUB row groups that share a channel: slot = sub * C + channel
+    __syncthreads();
+    sm[q][0][ch] = acc;
+    __syncthreads();
+    acc = 0.f;
+    if (ch < C)
+      for (int sidx = 0; sidx < SUB; ++sidx) acc += sm[q][0][sidx * C + ch];
   }
+  if (cbase + ch < C) partial[((long long)blockIdx.y * 2 + q) * C + cbase + ch] = acc;
   __threadfence();
   __syncthreads();
   if (t == 0) {
@@ -110,10 +139,10 @@ bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
   if (!is_last) return;
   __threadfence();
   {
-    double acc = 0.0;
+    double dacc = 0.0;
     if (cbase + ch < C)
-      for (unsigned int g = 0; g < gridDim.y; ++g) acc += (double)__ldcg(partial + ((long long)g * 2 + q) * C + cbase + ch);
-    smd[q][ch] = acc;
+      for (unsigned int g = 0; g < gridDim.y; ++g) dacc += (double)__ldcg(partial + ((long long)g * 2 + q) * C + cbase + ch);
+    smd[q][ch] = dacc;
   }
   __syncthreads();
   if (q == 0 && cbase + ch < C) {
