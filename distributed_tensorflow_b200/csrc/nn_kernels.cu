@@ -10,7 +10,8 @@
 // formulation, and x is read twice + written once instead of ~10 round trips through HBM.
 //
 // Reduction layout: block (32, 8) -- x-threads own one float4 channel group each (a warp reads 512 contiguous bytes of a
-// row), y-threads stride over rows; grid (ceil(C/128), G).  Every block writes its partial sums to a workspace
+// row; for C < 128 the spare lanes take further rows so the warp still covers 512 contiguous bytes), y-threads stride over
+// rows with 4 (statistics) / 2 (backward) independent rows in flight per thread; grid (ceil(C/128), G).  Every block writes its partial sums to a workspace
 // [G][2][C]; the LAST block to finish a channel column (ticket counter, threadfence pattern) folds the G partials in
 // double precision and writes the per-channel results, then resets the ticket so the kernel is CUDA-graph replayable.
 // Deterministic: no floating-point atomics.
