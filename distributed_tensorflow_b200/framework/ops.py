@@ -376,7 +376,16 @@ def _red(fn_all, fn_dim):
 
 
 register_kernel("Sum")(_red(lambda x: x.sum(), lambda x, a, k: x.sum(dim=a, keepdim=k)))
-register_kernel("Mean")(_red(lambda x: x.mean(), lambda x, a, k: x.mean(dim=a, keepdim=k)))
+def _mean_over(x, a, k):
+    # NHWC global average pooling (mean over H, W of a 4-D tensor, ResNet's classifier input): our pooling kernel on /gpu
+    # when the fused NN kernels are enabled; plain mean otherwise
+    if x.dim() == 4 and not k and sorted(int(i) % 4 for i in (a if isinstance(a, (list, tuple)) else [a])) == [1, 2]:
+        from ..ops import native
+        return native.global_avg_pool(x).to(x.dtype)
+    return x.mean(dim=a, keepdim=k)
+
+
+register_kernel("Mean")(_red(lambda x: x.mean(), _mean_over))
 register_kernel("Max")(_red(lambda x: x.max(), lambda x, a, k: x.amax(dim=a, keepdim=k)))
 register_kernel("Min")(_red(lambda x: x.min(), lambda x, a, k: x.amin(dim=a, keepdim=k)))
 
