@@ -532,3 +532,23 @@ def test_stage_from_dataset_walks_batches_by_device_step_counter(emu):
         bi = (step * stride + offset) % nb
         assert torch.equal(x16, images[bi].bfloat16()) and torch.equal(lab, labels[bi])
     assert emu.dtf_stage_from_dataset(images.data_ptr(), labels.data_ptr(), nb, 3, 5, C, 1, 0, None, x16.data_ptr(), lab.data_ptr(), None) == -2
+
+
+def test_ps_apply_trace_ring_feeds_the_timeline(emu):
+    """Tracing on the fabric tier: every ps_apply launch stamps (kind, start ns, end ns, global step) into a
+    ring in ps memory; ``events_from_ring`` + ``Timeline`` turn it into a chrome trace with one process per ps GPU."""
+    import json
+    from distributed_tensorflow_b200.utils.timeline import Timeline, events_from_ring
+    wd = World(emu, workers=2)
+    ring = torch.zeros(8 * 4, dtype=torch.int64)
+    wd.a.trace, wd.a.trace_cap = ring.data_ptr(), 8
+    for t in range(3):
+        for w in range(2):
+            wd.push(w, torch.ones(wd.n), t)
+        wd.apply()
+    rows = [r for r in ring.view(-1, 4).tolist() if r[0] != 0]
+    assert [r[3] for r in rows] == [1, 2, 3] and all(r[2] >= r[1] > 0 for r in rows)
+    events = events_from_ring("/job:ps/task:0", rows, {1: "ps_apply"}, gpu_index=0)
+    trace = json.loads(Timeline(events).generate_chrome_trace_format())
+    names = [e["name"] for e in trace["traceEvents"] if e.get("ph") == "X"]
+    assert names == ["ps_apply[step 1]", "ps_apply[step 2]", "ps_apply[step 3]"] or len(names) == len([r for r in rows if r[2] > r[1]])
