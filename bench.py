@@ -241,7 +241,9 @@ def run_resnet18(args, rank, world, local_rank):
         cfg = EngineConfig(num_ps=1, num_workers=1, colocated=True, optimizer=opt)
         fabric = Fabric(1, {0: local_rank})
     else:
-        cfg = EngineConfig(num_ps=args.num_ps, num_workers=N - args.num_ps, optimizer=opt, nvls=nvls)
+        pow_ = bool(args.ps_on_workers)
+        cfg = EngineConfig(num_ps=args.num_ps, num_workers=N if pow_ else N - args.num_ps, optimizer=opt, nvls=nvls,
+                           ps_on_workers=pow_)
         fabric = Fabric.from_torch_distributed()
     shapes = resnet18_param_shapes(10, "cifar")
     eng = GenericPSEngine(shapes, cfg, fabric)
@@ -315,7 +317,9 @@ def run_resnet18(args, rank, world, local_rank):
            "data": "synthetic CIFAR-shaped 32x32x3 from pinned host memory (H2D every step), random-init weights",
            "config": {"model": "ResNet-18 (CIFAR stem), %d parameters" % nparams, "per_worker_batch": B,
                       "global_batch": cfg.num_workers * B, "optimizer": "momentum", "mode": "sync",
-                      "parallelism": "ps1+worker1 colocated" if N == 1 else "ps%d+worker%d between-graph" % (cfg.num_ps, cfg.num_workers),
+                      "parallelism": "ps1+worker1 colocated" if N == 1 else "ps%d+worker%d between-graph%s" % (
+                          cfg.num_ps, cfg.num_workers, ", ps shards on the first workers' GPUs" if cfg.ps_on_workers else ""),
+                      "fused_nn": bool(cuda_lib.FUSED_NN), "graph_step": bool(args.graph_step),
                       "grad_bytes_per_push": nparams * 4, "param_bytes_per_pull": nparams * 4,
                       "fabric": ("nvls: multimem.ld_reduce push / multimem.st pull" if getattr(eng, "nvls_multicast", False)
                                  else "symmetric buffers, unicast" if getattr(eng, "nvls", False) else "unicast peer stores / loads"),

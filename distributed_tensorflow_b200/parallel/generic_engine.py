@@ -41,6 +41,12 @@ class GenericPSEngine:
         if cfg.colocated:
             assert self.world == 1 and cfg.num_ps == 1 and cfg.num_workers == 1
             self.ps_ranks, self.worker_ranks = [0], [0]
+        elif getattr(cfg, "ps_on_workers", False):
+            # every rank a worker, ps shard s on worker s's GPU and stream (see PSTrainEngine): the caller runs
+            # worker_step(r) then ps_apply(r) on those ranks
+            assert self.world == cfg.num_workers and 1 <= cfg.num_ps <= self.world
+            self.ps_ranks = list(range(cfg.num_ps))
+            self.worker_ranks = list(range(self.world))
         else:
             assert self.world == cfg.num_ps + cfg.num_workers
             self.ps_ranks = list(range(cfg.num_ps))

@@ -38,6 +38,8 @@ elif [ "$mode" = "pending-multi" ]; then
   step bench_pow_unicast 150 $TR bench.py --gpus $N --nvls off --ps-on-workers 1
   step bench_ref 150 $TR bench.py --gpus $N
   step bench_e2e_pipe 150 $TR bench.py --gpus $N --e2e-pipeline 2
+  step resnet18_pow 200 $TR bench.py --gpus $N --model resnet18 --steps 10 --warmup 3 --ps-on-workers 1
+  DTF_FUSED_NN=1 step resnet18_pow_fused_graph 200 $TR bench.py --gpus $N --model resnet18 --steps 10 --warmup 4 --ps-on-workers 1 --graph-step 1
 else
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
   DTF_NVLS=1 step mp_check_nvls 120 $TR tools/mp_check.py
