@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -91,6 +92,9 @@ static inline void sync() { pthread_barrier_wait(ctx->barrier); }
 // creation per block.
 static inline void launch(dim3 grid, dim3 block, const std::function<void()>& body, size_t smem_bytes = 0) {
   const unsigned nthreads = block.x * block.y * block.z;
+  // DTF_EMU_BLOCK_ORDER=reverse walks the grid from the last block to the first: a kernel whose result depends on the order
+  // in which blocks run (other than by design, like ps_apply's "block 0 decides") has a bug the hardware will find too
+  static const bool reverse = [] { const char* e = std::getenv("DTF_EMU_BLOCK_ORDER"); return e && std::strcmp(e, "reverse") == 0; }();
   LaunchCtx c;
   std::vector<float4> smem_buf((smem_bytes + 15) / 16 + 1);        // 16-byte aligned like the hardware's
   c.dyn_smem = smem_buf.data();
@@ -115,13 +119,13 @@ static inline void launch(dim3 grid, dim3 block, const std::function<void()>& bo
           ctx = &c;
           t_idx = dim3(tx, ty, tz);
           lin_tid = tx + ty * block.x + tz * block.x * block.y;
-          for (unsigned bz = 0; bz < grid.z; ++bz)
-            for (unsigned by = 0; by < grid.y; ++by)
-              for (unsigned bx = 0; bx < grid.x; ++bx) {
-                t_bidx = dim3(bx, by, bz);
-                body();
-                pthread_barrier_wait(&block_bar);        // the whole block is done before the next one starts
-              }
+          const unsigned long long total = (unsigned long long)grid.x * grid.y * grid.z;
+          for (unsigned long long i = 0; i < total; ++i) {
+            const unsigned long long idx = reverse ? total - 1 - i : i;      // x fastest, like the hardware's linear block id
+            t_bidx = dim3((unsigned)(idx % grid.x), (unsigned)((idx / grid.x) % grid.y), (unsigned)(idx / ((unsigned long long)grid.x * grid.y)));
+            body();
+            pthread_barrier_wait(&block_bar);        // the whole block is done before the next one starts
+          }
         });
   for (auto& t : ts) t.join();
   pthread_barrier_destroy(&bar);

@@ -156,3 +156,20 @@ def test_emulated_pooling_kernels(emu, shape, k, stride, pads):
     assert emu.dtf_global_avgpool_nhwc(_p(gd), _p(gx), n, h * w, c, 1, None) == 0
     torch.testing.assert_close(gx, (gd / (h * w))[:, None, None, :].expand(shape), rtol=1e-6, atol=1e-7)
     assert emu.dtf_maxpool_nhwc_fwd(_p(x), _p(y), _p(arg), n, h, w, 6, k, k, stride, stride, pt, pl, ho, wo, None) == -1   # C % 4
+
+
+def test_kernels_do_not_depend_on_block_order():
+    """The emulator runs blocks one after another; ``DTF_EMU_BLOCK_ORDER=reverse`` walks the grid backwards.  Everything
+    except ps_apply (where block 0 deciding first is the design, and all CTAs are co-resident on the hardware) must give the
+    same answers: the nn / element-wise suites and the head / push / fabric / staging tests are re-run in reverse order."""
+    import sys
+    env = dict(os.environ, DTF_EMU_BLOCK_ORDER="reverse")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider",
+                        os.path.join(here, "test_nn_kernels_host_emulation.py"),
+                        os.path.join(here, "test_elementwise_kernels_host_emulation.py"),
+                        os.path.join(here, "test_ps_kernels_host_emulation.py"),
+                        "-k", "(emulated or softmax or colsum or optimizer or conversions or head or push_grad or fabric or stage) and not block_order"],
+                       capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
