@@ -35,3 +35,19 @@ def test_two_gpu_engine_matches_cpu_oracle(nvls, tmp_path):
     rep = json.loads(line[len("MP_CHECK "):])
     assert rep["sync"]["ok"] and rep["sync"]["global_step"] == 6 and rep["sync"]["max_rel_err_vs_oracle"] < 3e-2
     assert rep["async"]["ok"] and rep["async"]["staleness"]["count"] == 6
+
+
+@pytest.mark.skipif(os.environ.get("DTF_TEST_UNVALIDATED") != "1", reason="first hardware validation pending: set DTF_TEST_UNVALIDATED=1")
+@pytest.mark.parametrize("nvls", ["0", "auto"])
+def test_two_gpu_ps_on_workers_matches_cpu_oracle(nvls):
+    """Same check with every rank a worker and the ps shard on worker 0's GPU / stream (EngineConfig.ps_on_workers)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    env = dict(os.environ, DTF_NVLS=nvls, DTF_PS_ON_WORKERS="1", MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "mp_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    rep = json.loads([l for l in r.stdout.splitlines() if l.startswith("MP_CHECK ")][-1][len("MP_CHECK "):])
+    assert rep["ps_on_workers"] and rep["sync"]["ok"] and rep["sync"]["global_step"] == 6
+    assert rep["async"]["ok"] and rep["async"]["staleness"]["count"] == 12          # 2 workers x 6 steps
