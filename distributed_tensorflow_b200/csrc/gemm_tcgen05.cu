@@ -21,7 +21,14 @@
 #include <mutex>
 #include <tuple>
 
+// DTF_HOST_EMU: only the HOST half of this file (argument checks, tile / stage / kernel selection, tensor-map boxes, grid
+// and shared-memory sizes) is compiled by g++, against tests/emu/gemm_host_stubs.h which records what would have been
+// encoded and launched -- the dispatch logic is unit-tested on machines without a GPU.  The kernels are hardware-only.
+#ifdef DTF_HOST_EMU
+#include "gemm_host_stubs.h"
+#else
 #include "common.cuh"
+#endif
 
 namespace dtf {
 
@@ -61,6 +68,7 @@ struct GemmParams {
 };
 
 
+#ifndef DTF_HOST_EMU   // ---- device code (tcgen05 / TMEM / TMA): hardware only ----
 // One 16-column slice of the epilogue: alpha, bias, ReLU, ReLU-backward mask, bias-gradient column sums, store
 // (fp32 / bf16 / atomic accumulate).  `r` holds the fp32 accumulators of this thread's row.
 DTF_DEVICE void epilogue_chunk16(const GemmParams& p, const uint32_t* r, int c0, int n0, long long grow, bool row_ok,
@@ -522,9 +530,12 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap map_a, c
   if (warp == 1) { if (CTAS == 2) tmem_dealloc_2cta(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols); }
 }
 
+#endif  // !DTF_HOST_EMU
+
 // =================================================================================================
 // host side
 // =================================================================================================
+#ifndef DTF_HOST_EMU
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -557,6 +568,7 @@ static int make_map(CUtensorMap* out, const void* ptr, long long rows, long long
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
+#endif  // !DTF_HOST_EMU (the emulation stubs provide make_map: it records the requested tensor map)
 
 struct MapKey {
   const void* ptr;
@@ -677,6 +689,7 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
+#ifndef DTF_HOST_EMU
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(224 * 1024));   // 227 KB minus static barriers + bias stage
     if (e != cudaSuccess) return 2000 + (int)e;
@@ -686,6 +699,7 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
     e = cudaFuncSetAttribute(gemm_bf16_tcgen05_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(220 * 1024));
     if (e != cudaSuccess) return 2000 + (int)e;
+#endif
     cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
     configured[dev] = true;
   }
@@ -729,16 +743,28 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
+#ifdef DTF_HOST_EMU
+      return dtf_emu_record_gemm_launch(2, cfg.gridDim, cfg.dynamicSmemBytes, (int)attr[0].val.clusterDim.x, ma, mb, p, (int)tm, (int)tiles_n);
+#else
       cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_persistent_kernel<2>, ma, mb, p, (int)tm, (int)tiles_n);
       return (int)e;
+#endif
     }
     const unsigned pgrid = (unsigned)(nt < sms ? nt : sms);
+#ifdef DTF_HOST_EMU
+    return dtf_emu_record_gemm_launch(1, dim3(pgrid, 1, 1), psmem, 1, ma, mb, p, (int)tm, (int)tiles_n);
+#else
     gemm_bf16_tcgen05_persistent_kernel<1><<<pgrid, kThreads, psmem, stream>>>(ma, mb, p, (int)tm, (int)tiles_n);
     return (int)cudaGetLastError();
+#endif
   }
   dim3 grid(tiles_m, tiles_n, (unsigned)splits);
+#ifdef DTF_HOST_EMU
+  return dtf_emu_record_gemm_launch(0, grid, smem, 1, ma, mb, p, (int)tiles_m, (int)tiles_n);
+#else
   gemm_bf16_tcgen05_kernel<<<grid, kThreads, smem, stream>>>(ma, mb, p);
   return (int)cudaGetLastError();
+#endif
 }
 
 void dtf_gemm_clear_map_cache() {
