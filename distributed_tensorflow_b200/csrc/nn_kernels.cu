@@ -162,19 +162,38 @@ bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
   if (t == 0) tickets[blockIdx.x] = 0u;     // replayable: the next launch starts from a clean ticket
 }
 
+// The grid stride (gridDim.x * blockDim.x float4 elements) is a multiple of C/4 for every power-of-two channel count, so a
+// thread keeps ONE channel group for its whole walk and loads the per-channel coefficients once; otherwise they are
+// re-read per element (they sit in L1).
 __global__ void bn_apply_kernel(const float4* __restrict__ x, const float4* __restrict__ res, float4* __restrict__ y,
                                 const float4* __restrict__ mean, const float4* __restrict__ rstd,
                                 const float4* __restrict__ scale, const float4* __restrict__ offset, long long n4, int c4n,
                                 int relu) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % c4n);
-    const float4 m = __ldg(mean + c4), rs = __ldg(rstd + c4), sc = __ldg(scale + c4), of = __ldg(offset + c4);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool fixed = stride % c4n == 0;
+  float4 m = make_float4(0.f, 0.f, 0.f, 0.f), a = m, of = m;
+  if (fixed && i0 < n4) {
+    const int c4 = (int)(i0 % c4n);
+    const float4 rs = __ldg(rstd + c4), sc = __ldg(scale + c4);
+    m = __ldg(mean + c4);
+    of = __ldg(offset + c4);
+    a = make_float4(rs.x * sc.x, rs.y * sc.y, rs.z * sc.z, rs.w * sc.w);
+  }
+  for (long long i = i0; i < n4; i += stride) {
+    if (!fixed) {
+      const int c4 = (int)(i % c4n);
+      const float4 rs = __ldg(rstd + c4), sc = __ldg(scale + c4);
+      m = __ldg(mean + c4);
+      of = __ldg(offset + c4);
+      a = make_float4(rs.x * sc.x, rs.y * sc.y, rs.z * sc.z, rs.w * sc.w);
+    }
     const float4 v = x[i];
     float4 o;
-    o.x = (v.x - m.x) * rs.x * sc.x + of.x;
-    o.y = (v.y - m.y) * rs.y * sc.y + of.y;
-    o.z = (v.z - m.z) * rs.z * sc.z + of.z;
-    o.w = (v.w - m.w) * rs.w * sc.w + of.w;
+    o.x = (v.x - m.x) * a.x + of.x;
+    o.y = (v.y - m.y) * a.y + of.y;
+    o.z = (v.z - m.z) * a.z + of.z;
+    o.w = (v.w - m.w) * a.w + of.w;
     if (res != nullptr) {
       const float4 r = res[i];
       o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
@@ -192,10 +211,22 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ dy, const float4*
                                     const float4* __restrict__ doffset, const float4* __restrict__ dscale,
                                     float4* __restrict__ dx, float4* __restrict__ dres, long long n4, int c4n,
                                     float inv_rows) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % c4n);
-    const float4 m = __ldg(mean + c4), rs = __ldg(rstd + c4), sc = __ldg(scale + c4);
-    const float4 s1 = __ldg(doffset + c4), s2 = __ldg(dscale + c4);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool fixed = stride % c4n == 0;
+  // dx = k1 * (g - k2 - (x - m) * k3) with k1 = scale * rstd, k2 = doffset / rows, k3 = rstd * dscale / rows
+  float4 m = make_float4(0.f, 0.f, 0.f, 0.f), rs = m, k1 = m, k2 = m, k3 = m;
+  auto coeffs = [&](int c4) {
+    const float4 sc = __ldg(scale + c4), s1 = __ldg(doffset + c4), s2 = __ldg(dscale + c4);
+    m = __ldg(mean + c4);
+    rs = __ldg(rstd + c4);
+    k1 = make_float4(sc.x * rs.x, sc.y * rs.y, sc.z * rs.z, sc.w * rs.w);
+    k2 = make_float4(s1.x * inv_rows, s1.y * inv_rows, s1.z * inv_rows, s1.w * inv_rows);
+    k3 = make_float4(rs.x * s2.x * inv_rows, rs.y * s2.y * inv_rows, rs.z * s2.z * inv_rows, rs.w * s2.w * inv_rows);
+  };
+  if (fixed && i0 < n4) coeffs((int)(i0 % c4n));
+  for (long long i = i0; i < n4; i += stride) {
+    if (!fixed) coeffs((int)(i % c4n));
     float4 g = dy[i];
     if (y_mask != nullptr) {
       const float4 o = y_mask[i];
@@ -204,10 +235,10 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ dy, const float4*
     }
     const float4 v = x[i];
     float4 d;
-    d.x = sc.x * rs.x * (g.x - s1.x * inv_rows - (v.x - m.x) * rs.x * s2.x * inv_rows);
-    d.y = sc.y * rs.y * (g.y - s1.y * inv_rows - (v.y - m.y) * rs.y * s2.y * inv_rows);
-    d.z = sc.z * rs.z * (g.z - s1.z * inv_rows - (v.z - m.z) * rs.z * s2.z * inv_rows);
-    d.w = sc.w * rs.w * (g.w - s1.w * inv_rows - (v.w - m.w) * rs.w * s2.w * inv_rows);
+    d.x = k1.x * (g.x - k2.x - (v.x - m.x) * k3.x);
+    d.y = k1.y * (g.y - k2.y - (v.y - m.y) * k3.y);
+    d.z = k1.z * (g.z - k2.z - (v.z - m.z) * k3.z);
+    d.w = k1.w * (g.w - k2.w - (v.w - m.w) * k3.w);
     dx[i] = d;
     if (dres != nullptr) dres[i] = g;
   }
