@@ -11,10 +11,17 @@
 #include <cstdio>
 #include <cstring>
 
+// DTF_HOST_EMU: compiled by g++ against tests/emu/step_exec_stubs.h, where the CUDA runtime calls and the kernel launchers
+// record a trace instead of running -- the op dispatch below is unit-tested without a GPU (tests/test_step_exec_host.py).
+#ifdef DTF_HOST_EMU
+#include "step_exec_stubs.h"
+#else
 #include <cuda_runtime.h>
+#endif
 
 extern "C" {
 
+#ifndef DTF_HOST_EMU
 // entry points of the other translation units (same shared object)
 struct DtfGemmArgs;
 struct DtfMlpHeadArgs;
@@ -31,6 +38,7 @@ int dtf_push_grad(const float* src, float* dst_peer, long long n, void* ctl, con
 int dtf_stage_from_dataset(const float* images, const float* labels, long long nbatches, int B, int D, int C,
                            long long stride, long long offset, const unsigned long long* step_counter, void* x16,
                            float* lab_out, cudaStream_t s);
+#endif
 
 enum DtfOpKind {
   DTF_OP_H2D = 1,         // p0 = dst (device), p1 = src (pinned host), i0 = bytes

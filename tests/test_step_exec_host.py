@@ -1,0 +1,83 @@
+"""csrc/step_exec.cu (the native step executor behind ``engine.step(x_pinned, y_pinned)``) compiled by g++ against
+tests/emu/step_exec_stubs.h: the CUDA runtime calls and kernel launchers record a trace.  Pins the argument mapping of every
+op kind, the kernel count, the error index, device switching and the graph-capture sequence."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from distributed_tensorflow_b200.ops.cuda_lib import (OP_CONVERT, OP_D2H, OP_GEMM, OP_GRAPH, OP_H2D, OP_HEAD, OP_PS_APPLY, OP_SIGNAL, OP_STAGE,
+                                                     OP_SYNC, OP_WAIT_TOKEN, StepOp)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OP_EVENT_RECORD, OP_EVENT_WAIT = 11, 12
+
+
+@pytest.fixture(scope="module")
+def host(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    so = str(tmp_path_factory.mktemp("emu") / "libstep_host.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-DDTF_HOST_EMU", "-I" + os.path.join(ROOT, "tests", "emu"), "-x", "c++", "-shared",
+                    "-fPIC", "-o", so, os.path.join(ROOT, "distributed_tensorflow_b200", "csrc", "step_exec.cu")], check=True)
+    lib = ctypes.CDLL(so)
+    lib.dtf_run_ops.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lib.dtf_capture_ops.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                    ctypes.POINTER(ctypes.c_int)]
+    lib.step_emu_trace.restype = ctypes.c_char_p
+    lib.step_emu_reset.argtypes = [ctypes.c_int, ctypes.c_int]
+    return lib
+
+
+def _run(host, ops, device=-1, stream=0x57):
+    arr = (StepOp * len(ops))(*ops)
+    k = ctypes.c_int(0)
+    rc = host.dtf_run_ops(arr, len(ops), device, stream, ctypes.byref(k))
+    return rc, k.value, host.step_emu_trace().decode().splitlines()
+
+
+def test_every_op_kind_maps_its_arguments(host):
+    assert host.dtf_sizeof_step_op() == ctypes.sizeof(StepOp)
+    host.step_emu_reset(0, 0)
+    ops = [StepOp(kind=OP_EVENT_WAIT, p0=0xe0),
+           StepOp(kind=OP_H2D, p0=0xd0, p1=0xa0, i0=313600),
+           StepOp(kind=OP_CONVERT, p0=0xd0, p1=0xd1, i0=784, i1=784, i2=100, i3=784, i4=784),
+           StepOp(kind=OP_EVENT_RECORD, p0=0xe1),
+           StepOp(kind=OP_WAIT_TOKEN, p0=0xb0, p1=0xb1, p2=0xb2, i0=3, u0=5000),
+           StepOp(kind=OP_GEMM, p0=0x100), StepOp(kind=OP_HEAD, p0=0x200),
+           StepOp(kind=OP_SIGNAL, p0=0xc0, p1=0xc1, i0=4, i1=1),
+           StepOp(kind=OP_STAGE, p0=0x1, p1=0x2, p2=0x3, p3=0x4, p4=0x5, i0=550, i1=100, i2=784, i3=10, i4=7, i5=2),
+           StepOp(kind=OP_PS_APPLY, p0=0x300),
+           StepOp(kind=OP_D2H, p0=0xa1, p1=0xd2, i0=32), StepOp(kind=OP_GRAPH, p0=0x900, i0=5), StepOp(kind=OP_SYNC)]
+    rc, kernels, trace = _run(host, ops)
+    assert rc == 0 and kernels == 7 + 5                       # convert, wait, gemm, head, signal, stage, apply + 5 inside the graph
+    assert trace == [
+        "event_wait ev=0xe0 stream=0x57",
+        "memcpy h2d dst=0xd0 src=0xa0 n=313600 stream=0x57",
+        "convert in=0xd0 ld_in=784 out=0xd1 ld_out=784 rows=100 cols=784 pad=784",
+        "event_record ev=0xe1 stream=0x57",
+        "wait_token mb=0xb0 target=3 ptr=0xb1 timeout=5000 err=0xb2",
+        "gemm args=0x100 stream=0x57", "head args=0x200 stream=0x57",
+        "push_grad src=(nil) dst=(nil) n=0 ctl=0xc0 mb=0xc1 rank=4 from_version=1 write_stamp=1 grid=1",
+        "stage images=0x1 labels=0x2 nb=550 B=100 D=784 C=10 stride=7 offset=2 ctr=0x3 x16=0x4 lab=0x5",
+        "ps_apply args=0x300 stream=0x57",
+        "memcpy d2h dst=0xa1 src=0xd2 n=32 stream=0x57",
+        "graph_launch exec=0x900 stream=0x57", "sync stream=0x57"]
+
+
+def test_error_index_device_switch_and_capture(host):
+    host.step_emu_reset(4, 77)                                # the GEMM launcher fails with code 77
+    rc, kernels, trace = _run(host, [StepOp(kind=OP_HEAD, p0=1), StepOp(kind=OP_GEMM, p0=2), StepOp(kind=OP_PS_APPLY, p0=3)], device=3)
+    assert rc == 2 * 100000 + 77 and kernels == 2             # (index + 1) * 100000 + code; nothing after the failure runs
+    assert trace[0] == "setdevice 3" and trace[-1] == "setdevice 0" and not any(l.startswith("ps_apply") for l in trace)
+    host.step_emu_reset(0, 0)
+    assert _run(host, [StepOp(kind=99)])[0] == 100000 + 99
+    host.step_emu_reset(0, 0)
+    ops = (StepOp * 2)(StepOp(kind=OP_GEMM, p0=1), StepOp(kind=OP_HEAD, p0=2))
+    ex, nk = ctypes.c_void_p(), ctypes.c_int(0)
+    assert host.dtf_capture_ops(ops, 2, -1, 0x57, ctypes.byref(ex), ctypes.byref(nk)) == 0
+    assert ex.value == 0xe1 and nk.value == 2
+    assert host.step_emu_trace().decode().splitlines() == ["begin_capture stream=0x57", "gemm args=0x1 stream=0x57", "head args=0x2 stream=0x57",
+                                                           "end_capture stream=0x57", "instantiate graph=0x6a", "graph_destroy 0x6a"]
