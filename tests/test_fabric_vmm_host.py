@@ -19,7 +19,9 @@ def vmm(tmp_path_factory):
     if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda.h")):
         pytest.skip("needs g++ and the CUDA toolkit headers")
     so = str(tmp_path_factory.mktemp("emu") / "libvmm_host.so")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-I" + CUDA_INC, "-x", "c++", "-shared", "-fPIC", "-o", so,
+    subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-I" + CUDA_INC, "-x", "c++", "-shared", "-fPIC",
+                    "-Wl,-Bsymbolic",        # bind fabric_vmm.cu's cudaGetDriverEntryPoint / cudaFree calls to THIS library's fakes even
+                    "-o", so,                # when a real libcudart is already loaded globally in the test process (torch)
                     os.path.join(ROOT, "distributed_tensorflow_b200", "csrc", "fabric_vmm.cu"),
                     os.path.join(ROOT, "tests", "emu", "fake_cuda_driver.cpp")], check=True)
     lib = ctypes.CDLL(so)
