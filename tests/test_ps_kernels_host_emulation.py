@@ -552,3 +552,22 @@ def test_ps_apply_trace_ring_feeds_the_timeline(emu):
     trace = json.loads(Timeline(events).generate_chrome_trace_format())
     names = [e["name"] for e in trace["traceEvents"] if e.get("ph") == "X"]
     assert names == ["ps_apply[step 1]", "ps_apply[step 2]", "ps_apply[step 3]"] or len(names) == len([r for r in rows if r[2] > r[1]])
+
+
+def test_fp32_parameter_replicas_published_through_multicast(emu):
+    """Generic models consume fp32 parameters: with ``master_mc`` the ps publishes the updated master through one
+    multimem.st stream into every GPU's fp32 replica (GenericPSEngine, NVLS mode)."""
+    n, W = 1024, 2
+    wd = World(emu, n=n, workers=W)
+    replicas = [torch.zeros(n) for _ in range(W + 1)]
+    fake = torch.zeros(n)
+    members = (ctypes.c_void_p * (W + 1))(*[r.data_ptr() for r in replicas])
+    emu.dtf_emu_mc_register(fake.data_ptr(), n * 4, members, W + 1)
+    wd.a.master_mc = fake.data_ptr()
+    for w in range(W):
+        wd.push(w, torch.full((n,), float(w + 1)), 0)
+    wd.apply()
+    torch.testing.assert_close(wd.master, wd.master0 - 0.1 * 1.5)
+    for r in replicas:
+        assert torch.equal(r, wd.master)
+    emu.dtf_emu_mc_clear()
