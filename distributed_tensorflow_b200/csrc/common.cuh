@@ -215,6 +215,17 @@ DTF_DEVICE void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uin
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// fp32 operands in shared memory multiplied as TF32 (K = 8 per instruction), fp32 accumulate.
+DTF_DEVICE void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier when all previously issued MMAs of this thread have completed
 // (implicitly performs tcgen05.fence::before_thread_sync).
 DTF_DEVICE void umma_commit(uint64_t* bar) {
@@ -249,6 +260,16 @@ DTF_DEVICE void umma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+DTF_DEVICE void umma_tf32_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -317,6 +338,18 @@ DTF_DEVICE uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
   return d;
 }
 
+// Same with the layout type given: 2 = SWIZZLE_128B; 1 = SWIZZLE_128B_BASE32B (MN-major 32-bit operands: 128-byte rows,
+// 32-byte chunks XORed with row % 4, atoms of 4 K-rows -> SBO = 512 when the K-rows are dense).
+DTF_DEVICE uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout_type & 7u) << 61;
+  return d;
+}
+
 // Instruction descriptor (32-bit) for kind::f16 with bf16 A/B and fp32 accumulate:
 //   [4,6) D format (1 = F32)  [7,10) A format (1 = BF16)  [10,13) B format (1 = BF16)
 //   [15] A major (0 = K, 1 = MN)  [16] B major  [17,23) N >> 3  [24,29) M >> 4
@@ -329,6 +362,13 @@ DTF_DEVICE uint32_t make_idesc_bf16(uint32_t m, uint32_t n, uint32_t a_mn_major,
   d |= (b_mn_major & 1u) << 16;
   d |= ((n >> 3) & 0x3Fu) << 17;
   d |= ((m >> 4) & 0x1Fu) << 24;
+  return d;
+}
+
+// same with the operand format selected at run time: bf16 (format 1, kind::f16) or tf32 (format 2, kind::tf32)
+DTF_DEVICE uint32_t make_idesc(uint32_t m, uint32_t n, uint32_t a_mn_major, uint32_t b_mn_major, int tf32) {
+  uint32_t d = make_idesc_bf16(m, n, a_mn_major, b_mn_major);
+  if (tf32) d = (d & ~((7u << 7) | (7u << 10))) | (2u << 7) | (2u << 10);
   return d;
 }
 

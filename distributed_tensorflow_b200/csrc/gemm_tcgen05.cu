@@ -1,6 +1,10 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a with fused epilogues and fused NVLink push/pull.
 //
-//   C[M,N] = alpha * op(A)[M,K] . op(B)[K,N]  (+ bias[N]) (ReLU) (* relu-mask) ; bf16 operands, fp32 accumulate.
+//   C[M,N] = alpha * op(A)[M,K] . op(B)[K,N]  (+ bias[N]) (ReLU) (* relu-mask) ; fp32 accumulate in tensor memory.
+//   Operand precision: bf16 (tcgen05.mma.kind::f16) or fp32 storage consumed as TF32 (tcgen05.mma.kind::tf32: the
+//   reference model is fp32 end to end, /root/reference/distributed_mnist.py:98-113 -- fp32 tensors stay fp32 in HBM,
+//   TMA moves them untouched and the tensor core reads the top 19 bits).  One shared-memory stage is 128 bytes of K
+//   per row for both: 64 bf16 or 32 fp32 elements, four MMAs (K = 16 / K = 8) per stage.
 //
 // * Operands are loaded by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into a multi-stage
 //   shared-memory ring; one elected thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) with the
@@ -33,8 +37,7 @@
 namespace dtf {
 
 static constexpr int kBlockM = 128;
-static constexpr int kBlockK = 64;            // bf16 elements per stage along K = one 128-byte swizzle row
-static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
+static constexpr int kABytes = kBlockM * 128;   // 16 KB: 128 rows x one 128-byte swizzle row (64 bf16 / 32 fp32 of K)
 static constexpr int kEpilogueWarps = 8;
 static constexpr int kThreads = 64 + 32 * kEpilogueWarps;   // TMA warp + MMA warp + epilogue warps
 
@@ -65,10 +68,26 @@ struct GemmParams {
   int signal_gpu_scope;                  // 1: consumer is on the same GPU (gpu-scope fence suffices)
   const unsigned long long* stamp_src;   // optional: *stamp_dst = *stamp_src before the arrival (block 0,0,0 only)
   unsigned long long* stamp_dst;
+  // operand precision (host-filled): bf16 -> {0, 64, 8192, 128};  fp32-as-tf32 -> {1, 32, 4096, 64}
+  int tf32;              // 1: fp32 operands, tcgen05.mma.kind::tf32
+  int kbk;               // K elements per shared-memory stage (= one 128-byte swizzle row)
+  int mn_lbo;            // MN-major tiles: bytes between adjacent 128-byte-wide MN chunks (= kbk rows x 128 B)
+  int mn_kstep16;        // MN-major tiles: descriptor advance (>> 4) per MMA = K-per-MMA rows x 128 B
+  int mn_sbo;            // MN-major tiles: bytes between swizzle atoms along K (8 rows x 128 B; fp32: 4 rows x 128 B)
+  int mn_type;           // MN-major tiles: descriptor layout type (2 = SWIZZLE_128B; fp32: 1 = SWIZZLE_128B_BASE32B)
 };
 
 
 #ifndef DTF_HOST_EMU   // ---- device code (tcgen05 / TMEM / TMA): hardware only ----
+// One MMA of the stage: bf16 (K = 16) or tf32 (K = 8); CTAS == 2 -> cta_group::2 (leader thread of the pair).
+template <int CTAS>
+DTF_DEVICE void umma_any(const GemmParams& p, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  if (p.tf32) {
+    if (CTAS == 2) umma_tf32_2cta(d_tmem, a_desc, b_desc, idesc, acc); else umma_tf32(d_tmem, a_desc, b_desc, idesc, acc);
+  } else {
+    if (CTAS == 2) umma_bf16_2cta(d_tmem, a_desc, b_desc, idesc, acc); else umma_bf16(d_tmem, a_desc, b_desc, idesc, acc);
+  }
+}
 // One 16-column slice of the epilogue: alpha, bias, ReLU, ReLU-backward mask, bias-gradient column sums, store
 // (fp32 / bf16 / atomic accumulate).  `r` holds the fp32 accumulators of this thread's row.
 DTF_DEVICE void epilogue_chunk16(const GemmParams& p, const uint32_t* r, int c0, int n0, long long grow, bool row_ok,
@@ -182,8 +201,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   const int n0 = blockIdx.y * p.block_n;
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
-  const int b_bytes = p.block_n * kBlockK * 2;
+  const int b_bytes = p.block_n * 128;                 // 128 bytes of K per row: 64 bf16 / 32 fp32
   const int stage_bytes = kABytes + b_bytes;
+  const int mnc = p.kbk;                               // elements per 128-byte MN chunk (== K elements per stage)
   // 128B-swizzled tiles must start on 1024-byte boundaries
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint32_t tmem_cols = 32;
@@ -231,18 +251,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
         uint8_t* a_dst = tiles + s * stage_bytes;
         uint8_t* b_dst = a_dst + kABytes;
-        const int k0 = kb * kBlockK;
+        const int k0 = kb * p.kbk;
         if (!p.a_mn) {
-          tma_load_2d(a_dst, &map_a, &full_bar[s], k0, m0);                 // box {64 k, 128 m}
+          tma_load_2d(a_dst, &map_a, &full_bar[s], k0, m0);                 // box {128 B of k, 128 m}
         } else {
-          tma_load_2d(a_dst, &map_a, &full_bar[s], m0, k0);                 // box {64 m, 64 k} x2
-          tma_load_2d(a_dst + 8192, &map_a, &full_bar[s], m0 + 64, k0);
+          for (int j = 0; j < kBlockM / mnc; ++j)                           // box {128 B of m, kbk k} x (2 | 4)
+            tma_load_2d(a_dst + j * p.mn_lbo, &map_a, &full_bar[s], m0 + mnc * j, k0);
         }
         if (!p.b_mn) {
-          tma_load_2d(b_dst, &map_b, &full_bar[s], k0, n0);                 // box {64 k, block_n}
+          tma_load_2d(b_dst, &map_b, &full_bar[s], k0, n0);                 // box {128 B of k, block_n}
         } else {
-          for (int j = 0; j < p.block_n / 64; ++j)
-            tma_load_2d(b_dst + j * 8192, &map_b, &full_bar[s], n0 + 64 * j, k0);   // box {64 n, 64 k}
+          for (int j = 0; j < p.block_n / mnc; ++j)
+            tma_load_2d(b_dst + j * p.mn_lbo, &map_b, &full_bar[s], n0 + mnc * j, k0);   // box {128 B of n, kbk k}
         }
       }
       DTF_STAMP(3);                              // last TMA issued
@@ -250,7 +270,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, p.a_mn, p.b_mn);
+      const uint32_t idesc = make_idesc(kBlockM, p.block_n, p.a_mn, p.b_mn, p.tf32);
       int it = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
         const int s = it % p.stages;
@@ -260,14 +280,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         tc_fence_after();
         const uint32_t a_addr = smem_u32(tiles + s * stage_bytes);
         const uint32_t b_addr = a_addr + kABytes;
-        const uint64_t a_desc = p.a_mn ? make_smem_desc_sw128(a_addr, 8192, 1024) : make_smem_desc_sw128(a_addr, 16, 1024);
-        const uint64_t b_desc = p.b_mn ? make_smem_desc_sw128(b_addr, 8192, 1024) : make_smem_desc_sw128(b_addr, 16, 1024);
-        const uint32_t a_step = p.a_mn ? (2048u >> 4) : (32u >> 4);   // advance 16 K-elements
-        const uint32_t b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
+        const uint64_t a_desc = p.a_mn ? make_smem_desc(a_addr, p.mn_lbo, p.mn_sbo, p.mn_type) : make_smem_desc_sw128(a_addr, 16, 1024);
+        const uint64_t b_desc = p.b_mn ? make_smem_desc(b_addr, p.mn_lbo, p.mn_sbo, p.mn_type) : make_smem_desc_sw128(b_addr, 16, 1024);
+        const uint32_t a_step = p.a_mn ? (uint32_t)p.mn_kstep16 : (32u >> 4);   // advance one MMA of K (32 bytes K-major)
+        const uint32_t b_step = p.b_mn ? (uint32_t)p.mn_kstep16 : (32u >> 4);
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          umma_bf16(tmem_base, a_desc + (uint64_t)(a_step * k), b_desc + (uint64_t)(b_step * k), idesc,
-                    (it > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) {                                           // 4 MMAs per 128-byte stage
+          umma_any<1>(p, tmem_base, a_desc + (uint64_t)(a_step * k), b_desc + (uint64_t)(b_step * k), idesc,
+                      (it > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);      // frees the smem slot once these MMAs have consumed it
       }
@@ -368,8 +388,9 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap map_a, c
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   const int bn_cta = p.block_n / CTAS;                         // rows of the B tile THIS CTA loads
-  const int b_bytes = bn_cta * kBlockK * 2;
+  const int b_bytes = bn_cta * 128;
   const int stage_bytes = kABytes + b_bytes;                    // per CTA
+  const int mnc = p.kbk;
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint32_t acc_cols = 32;                       // columns of ONE accumulator buffer (power of two >= BLOCK_N)
   while (acc_cols < (uint32_t)p.block_n) acc_cols <<= 1;
@@ -415,32 +436,32 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap map_a, c
           if (leader) mbar_arrive_expect_tx(&full_bar[s], stage_bytes * CTAS);
           uint8_t* a_dst = tiles + s * stage_bytes;
           uint8_t* b_dst = a_dst + kABytes;
-          const int k0 = kb * kBlockK;
+          const int k0 = kb * p.kbk;
           if (CTAS == 2) {
             if (!p.a_mn) {
               tma_load_2d_2cta(a_dst, &map_a, &full_bar[s], k0, m0);
             } else {
-              tma_load_2d_2cta(a_dst, &map_a, &full_bar[s], m0, k0);
-              tma_load_2d_2cta(a_dst + 8192, &map_a, &full_bar[s], m0 + 64, k0);
+              for (int j = 0; j < kBlockM / mnc; ++j)
+                tma_load_2d_2cta(a_dst + j * p.mn_lbo, &map_a, &full_bar[s], m0 + mnc * j, k0);
             }
             if (!p.b_mn) {
               tma_load_2d_2cta(b_dst, &map_b, &full_bar[s], k0, n0);
             } else {
-              for (int j = 0; j < bn_cta / 64; ++j)
-                tma_load_2d_2cta(b_dst + j * 8192, &map_b, &full_bar[s], n0 + 64 * j, k0);
+              for (int j = 0; j < bn_cta / mnc; ++j)
+                tma_load_2d_2cta(b_dst + j * p.mn_lbo, &map_b, &full_bar[s], n0 + mnc * j, k0);
             }
           } else {
             if (!p.a_mn) {
               tma_load_2d(a_dst, &map_a, &full_bar[s], k0, m0);
             } else {
-              tma_load_2d(a_dst, &map_a, &full_bar[s], m0, k0);
-              tma_load_2d(a_dst + 8192, &map_a, &full_bar[s], m0 + 64, k0);
+              for (int j = 0; j < kBlockM / mnc; ++j)
+                tma_load_2d(a_dst + j * p.mn_lbo, &map_a, &full_bar[s], m0 + mnc * j, k0);
             }
             if (!p.b_mn) {
               tma_load_2d(b_dst, &map_b, &full_bar[s], k0, n0);
             } else {
-              for (int j = 0; j < bn_cta / 64; ++j)
-                tma_load_2d(b_dst + j * 8192, &map_b, &full_bar[s], n0 + 64 * j, k0);
+              for (int j = 0; j < bn_cta / mnc; ++j)
+                tma_load_2d(b_dst + j * p.mn_lbo, &map_b, &full_bar[s], n0 + mnc * j, k0);
             }
           }
         }
@@ -449,9 +470,9 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap map_a, c
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(kBlockM * CTAS, p.block_n, p.a_mn, p.b_mn);
-      const uint32_t a_step = p.a_mn ? (2048u >> 4) : (32u >> 4);
-      const uint32_t b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
+      const uint32_t idesc = make_idesc(kBlockM * CTAS, p.block_n, p.a_mn, p.b_mn, p.tf32);
+      const uint32_t a_step = p.a_mn ? (uint32_t)p.mn_kstep16 : (32u >> 4);
+      const uint32_t b_step = p.b_mn ? (uint32_t)p.mn_kstep16 : (32u >> 4);
       int it = 0, ti = 0;
       for (int t = worker; t < num_tiles; t += num_workers, ++ti) {
         const int acc = ti & 1;
@@ -466,15 +487,11 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap map_a, c
           tc_fence_after();
           const uint32_t a_addr = smem_u32(tiles + s * stage_bytes);
           const uint32_t b_addr = a_addr + kABytes;
-          const uint64_t a_desc = p.a_mn ? make_smem_desc_sw128(a_addr, 8192, 1024) : make_smem_desc_sw128(a_addr, 16, 1024);
-          const uint64_t b_desc = p.b_mn ? make_smem_desc_sw128(b_addr, 8192, 1024) : make_smem_desc_sw128(b_addr, 16, 1024);
+          const uint64_t a_desc = p.a_mn ? make_smem_desc(a_addr, p.mn_lbo, p.mn_sbo, p.mn_type) : make_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t b_desc = p.b_mn ? make_smem_desc(b_addr, p.mn_lbo, p.mn_sbo, p.mn_type) : make_smem_desc_sw128(b_addr, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            if (CTAS == 2)
-              umma_bf16_2cta(d_tmem, a_desc + (uint64_t)(a_step * k), b_desc + (uint64_t)(b_step * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            else
-              umma_bf16(d_tmem, a_desc + (uint64_t)(a_step * k), b_desc + (uint64_t)(b_step * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_any<CTAS>(p, d_tmem, a_desc + (uint64_t)(a_step * k), b_desc + (uint64_t)(b_step * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           if (CTAS == 2) umma_commit_2cta_mc(&empty_bar[s]); else umma_commit(&empty_bar[s]);
         }
         if (CTAS == 2) umma_commit_2cta_mc(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
@@ -553,18 +570,21 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements),
-// box = {box_cols (<= 64 -> 128 bytes), box_rows}, 128-byte swizzle, zero fill out of bounds.
+// 2-D bf16 / fp32 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements),
+// box = {box_cols (x esize = 128 bytes), box_rows}, 128-byte swizzle, zero fill out of bounds.
+// sw32 = 1: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (32-byte chunks XOR row % 4) -- the only layout tcgen05 accepts for MN-major
+// 32-bit operands (descriptor layout type SWIZZLE_128B_BASE32B).
 static int make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_cols,
-                    int box_rows) {
+                    int box_rows, int esize, int sw32) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return -1;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)esize};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  CUresult r = enc(out, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
@@ -573,23 +593,30 @@ static int make_map(CUtensorMap* out, const void* ptr, long long rows, long long
 struct MapKey {
   const void* ptr;
   long long rows, cols, ld;
-  int bc, br;
+  int bc, br, es, sw32;
   bool operator<(const MapKey& o) const {
-    return std::tie(ptr, rows, cols, ld, bc, br) < std::tie(o.ptr, o.rows, o.cols, o.ld, o.bc, o.br);
+    return std::tie(ptr, rows, cols, ld, bc, br, es, sw32) < std::tie(o.ptr, o.rows, o.cols, o.ld, o.bc, o.br, o.es, o.sw32);
   }
 };
 static std::map<MapKey, CUtensorMap> g_maps;
 static std::mutex g_maps_mu;
+static int cached_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int bc, int br, int es, int sw32);
+// fp32 maps for the other translation units (csrc/mlp_step.cu)
+int cached_map_f32(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows,
+                   int sw32) {
+  return cached_map(out, ptr, rows, cols, ld, box_cols, box_rows, 4, sw32);
+}
 
-static int cached_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int bc, int br) {
-  MapKey k{ptr, rows, cols, ld, bc, br};
+static int cached_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int bc, int br,
+                      int es, int sw32) {
+  MapKey k{ptr, rows, cols, ld, bc, br, es, sw32};
   std::lock_guard<std::mutex> g(g_maps_mu);
   auto it = g_maps.find(k);
   if (it != g_maps.end()) {
     *out = it->second;
     return 0;
   }
-  int rc = make_map(out, ptr, rows, cols, ld, bc, br);
+  int rc = make_map(out, ptr, rows, cols, ld, bc, br, es, sw32);
   if (rc == 0) {
     if (g_maps.size() > 4096) g_maps.clear();
     g_maps[k] = *out;
@@ -630,13 +657,16 @@ struct DtfGemmArgs {
   unsigned long long* stamp_dst;
   int persistent;        // 0: auto (persistent kernel when tiles > SMs), 1: force persistent 1-CTA, 2: force CTA pairs, -1: never
   int cta_pair;          // -1: never use cta_group::2 in auto mode
+  int tf32;              // 1: A and B are fp32 in memory, multiplied as TF32 (tcgen05.mma.kind::tf32); lda/ldb % 4 == 0
 };
 
 // Returns 0 on success, <0 for argument errors, >0 for CUDA errors.
 int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
   using namespace dtf;
   if (g->M <= 0 || g->N <= 0 || g->K <= 0) return -2;
-  if ((g->lda % 8) || (g->ldb % 8)) return -3;                                  // TMA: 16-byte row pitch
+  const int es = g->tf32 ? 4 : 2;                                               // operand element size
+  const int kbk = 128 / es;                                                     // K elements per stage (128-byte rows)
+  if ((g->lda % (16 / es)) || (g->ldb % (16 / es))) return -3;                  // TMA: 16-byte row pitch
   if ((reinterpret_cast<uintptr_t>(g->a) & 15) || (reinterpret_cast<uintptr_t>(g->b) & 15)) return -4;
   if (g->splits > 1 && (g->relu || g->c_bf16)) return -5;
   GemmParams p;
@@ -647,15 +677,18 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
   if (g->block_n_override > 0) bn = g->block_n_override;
   else if (g->b_mn) bn = g->N <= 64 ? 64 : (g->N <= 128 ? 128 : (g->N <= 192 ? 192 : 256));
   else { bn = (int)((g->N + 15) / 16 * 16); if (bn > 256) bn = (g->N % 256 == 0 || g->N > 1024) ? 256 : 128; }
-  if (g->b_mn && (bn % 64)) return -6;
+  if (g->b_mn && (bn % kbk)) return -6;                                         // whole 128-byte MN chunks
   if (bn % 16 || bn > 256 || bn < 16) return -6;
   p.block_n = bn;
-  p.num_kb = (int)((g->K + kBlockK - 1) / kBlockK);
+  p.tf32 = g->tf32 ? 1 : 0; p.kbk = kbk; p.mn_lbo = kbk * 128; p.mn_kstep16 = ((g->tf32 ? 8 : 16) * 128) >> 4;
+  p.mn_sbo = g->tf32 ? 512 : 1024; p.mn_type = g->tf32 ? 1 : 2;
+  const int sw32 = g->tf32 ? 1 : 0;                                             // MN-major fp32 tiles: 32-byte-chunk swizzle
+  p.num_kb = (int)((g->K + kbk - 1) / kbk);
   int splits = g->splits > 1 ? g->splits : 1;
   if (splits > p.num_kb) splits = p.num_kb;
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
   splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
-  const int stage_bytes = kABytes + bn * kBlockK * 2;
+  const int stage_bytes = kABytes + bn * 128;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > p.kb_per_split) stages = p.kb_per_split < 2 ? 2 : p.kb_per_split;
@@ -675,11 +708,11 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
 
   CUtensorMap ma, mb;
   int rc;
-  if (!g->a_mn) rc = cached_map(&ma, g->a, g->M, g->K, g->lda, 64, kBlockM);      // [M rows, K cols]
-  else          rc = cached_map(&ma, g->a, g->K, g->M, g->lda, 64, 64);           // [K rows, M cols]
+  if (!g->a_mn) rc = cached_map(&ma, g->a, g->M, g->K, g->lda, kbk, kBlockM, es, 0);  // [M rows, K cols]
+  else          rc = cached_map(&ma, g->a, g->K, g->M, g->lda, kbk, kbk, es, sw32);   // [K rows, M cols]
   if (rc) return rc < 0 ? -7 : 1000 + rc;
-  if (!g->b_mn) rc = cached_map(&mb, g->b, g->N, g->K, g->ldb, 64, bn);           // [N rows, K cols]
-  else          rc = cached_map(&mb, g->b, g->K, g->N, g->ldb, 64, 64);           // [K rows, N cols]
+  if (!g->b_mn) rc = cached_map(&mb, g->b, g->N, g->K, g->ldb, kbk, bn, es, 0);       // [N rows, K cols]
+  else          rc = cached_map(&mb, g->b, g->K, g->N, g->ldb, kbk, kbk, es, sw32);   // [K rows, N cols]
   if (rc) return rc < 0 ? -7 : 1000 + rc;
 
   const size_t smem = (size_t)stages * stage_bytes + 1024;
@@ -711,16 +744,16 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
     // CTA pairs (cta_group::2, 256 x BLOCK_N tiles) when the tile shape allows it: BLOCK_N a multiple of 32 (each
     // CTA loads BLOCK_N/2 rows of B; 128 when B is MN-major) and at least two 128-row blocks of M.
     int ctas = 1;
-    const bool pair_ok = (bn % 32 == 0) && (!g->b_mn || bn % 128 == 0) && g->M > kBlockM;
+    const bool pair_ok = (bn % 32 == 0) && (!g->b_mn || (bn / 2) % kbk == 0) && g->M > kBlockM;
     // measured (tools/gemm_perf.py): pairs win only with the widest tile (BLOCK_N = 256: 1292 vs 1144 TFLOP/s at 4096^3);
     // with narrower tiles the B half-tile is too small to matter and the 1-CTA kernel's finer tile granularity wins
     if (g->persistent == 2 || (g->persistent != 1 && pair_ok && g->cta_pair >= 0 && bn >= 192)) ctas = pair_ok ? 2 : 1;
     if (ctas == 2 && !g->b_mn) {
       // K-major B: the TMA box of one CTA covers only ITS half of the tile's N rows
-      rc = cached_map(&mb, g->b, g->N, g->K, g->ldb, 64, bn / 2);
+      rc = cached_map(&mb, g->b, g->N, g->K, g->ldb, kbk, bn / 2, es, 0);
       if (rc) return rc < 0 ? -7 : 1000 + rc;
     }
-    const int st_bytes = kABytes + (bn / ctas) * kBlockK * 2;
+    const int st_bytes = kABytes + (bn / ctas) * 128;
     int pst = (int)((216 * 1024 - 1024) / st_bytes);
     if (pst > 8) pst = 8;
     if (pst > p.num_kb) pst = p.num_kb < 2 ? 2 : p.num_kb;

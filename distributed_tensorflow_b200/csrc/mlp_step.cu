@@ -1,0 +1,679 @@
+// One worker training step of the reference MLP as ONE kernel (SURVEY 7.4 #1, K1-K4 + C1 + C2 + C5 fused):
+//
+//   token wait -> h = relu(x.W1 + b1) -> logits, softmax, clipped batch-SUM cross-entropy, dlogits -> dW2, db2, db1,
+//   dh -> dW1 = x^T.dh -> gradients pushed to the ps slots -> stamp + arrival
+//   (/root/reference/distributed_mnist.py:109-113,126 = one `mon_sess.run(train_step)` of a worker, :152)
+//
+// fp32 end to end in memory like the reference model (:98-107); the two large GEMMs run on the tensor cores as TF32
+// (tcgen05.mma.kind::tf32, fp32 accumulate in TMEM), everything else in fp32 on the CUDA cores.
+//
+// Decomposition: G CTAs, CTA c owns the input-feature slice [c*ds, c*ds + ds) (ds a multiple of 8; 784 = 7 x 112).
+//   phase 1  TMA-loads its slice of x ([128, ds], issued BEFORE the token wait: the batch does not depend on the
+//            parameters) and -- after acquiring the ps token -- its ds rows of W1 straight from the parameter
+//            replica / the ps GPU's memory (the pull is the B operand of the first GEMM); ds/8 MMAs give the partial
+//            pre-activation [128, H] of the slice in TMEM; it is written to a scratch buffer in L2.
+//   phase 2  (after a device-scope counter says all G partials landed) CTA c finalises batch rows [c*R, c*R + R):
+//            h = relu(sum of partials + b1), logits, softmax, loss, dlogits, dh rows (-> scratch), and its partial
+//            sums of dW2 / db2 / db1, which go into the gradient slot with fp32 atomics (the ps clears those ranges
+//            after reading them).
+//   phase 3  (after a second counter) TMA-loads all of dh; dW1^T[H, slice] = dh^T . x_slice with the SAME slice of the
+//            batch, re-fetched from L2 into the same shared-memory buffer while phase 2 runs (tcgen05 wants 32-bit
+//            MN-major operands in the SWIZZLE_128B_BASE32B arrangement, the K-major A of phase 1 in SWIZZLE_128B: same
+//            bytes, different swizzle, so TMA writes them twice); the epilogue stores the slice's rows of dW1 from TMEM
+//            into the gradient slot (local symmetric memory under NVLS, the ps GPU's HBM over NVLink otherwise), then
+//            ONE system-scope fence + release-increment of the arrival counter per CTA.
+// The split of F1 along K is the split of dW1 along M: CTA c pulls and pushes the SAME rows of W1 / dW1 and reads only
+// its slice of the batch from HBM.  Cross-CTA exchange goes through L2 (two counters, ~57 KB written / read per CTA): measured
+// DSMEM bandwidth (~20 B/clk/SM) makes a cluster exchange no faster, and a plain grid has no cluster-shape constraint.
+//
+// DTF_HOST_EMU: compiled by g++ against tests/emu/host_emu.h with the TMA / tcgen05 parts replaced by scalar loops
+// (the accumulator rows are recomputed from global memory where the hardware reads TMEM); the three phases are then
+// launched one after another (phase_mask), because emulated blocks run sequentially.  The same phase-by-phase mode
+// exists on hardware (debugging aid: it removes the inter-CTA waits from the picture).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#ifdef DTF_HOST_EMU
+#include "host_emu.h"
+#else
+#include "common.cuh"
+#endif
+#include "ps_control.h"
+
+namespace dtf {
+
+static constexpr int kStepThreads = 256;
+static constexpr int kXChunkBytes = 128 * 128;     // one 32-feature-wide chunk of the batch tile: 128 rows x 128 bytes
+
+struct MlpStepParams {
+  int B, D, H, C;              // batch <= 128, input features, hidden <= 128, classes <= 16
+  int G, ds;                   // CTAs (= slices) and slice width (multiple of 8; G * ds >= D)
+  int rows_per_cta;            // batch rows finalised per CTA in phase 2 (<= 16)
+  int phase_mask;              // bit 0 / 1 / 2: run phase 1 / 2 / 3 (7 = fused; anything else = one phase per launch)
+  int n1, n2, kb;              // MMA N of F1 (H rounded to 16), MMA N of B3 (ds rounded to 16), batch rounded to 8
+  // ---- inputs: a device-resident dataset walked by the device step counter, or a staged batch (nbatches == 0)
+  const float* x;              // [rows, ldx] fp32 (also described by map_x)
+  long long ldx;
+  const float* labels;         // [rows, ldl] fp32 one-hot
+  long long ldl;
+  long long nbatches, bstride, boffset;
+  // ---- parameters (fp32): the worker's replica, or the ps GPU's master buffers (peer pointers)
+  const float* w1;             // [D, ldw1] (also described by map_w1)
+  long long ldw1;
+  const float* b1;
+  const float* w2;             // [H, ldw2]
+  long long ldw2;
+  const float* b2;
+  // ---- scratch (worker-local, L2 resident)
+  float* hpart;                // [G][128][n1] partial pre-activations
+  float* dh;                   // [128][lddh] (rows >= B and columns >= H stay zero)
+  long long lddh;
+  unsigned int* flags;         // [0]: partials written, [1]: dh rows written, [2]: CTAs finished (monotonic: G per step)
+  // ---- gradient slots
+  float* gw1;                  // [D, ldgw1]
+  long long ldgw1;
+  float* gb1;
+  float* gw2;                  // [H, ldgw2]
+  long long ldgw2;
+  float* gb2;
+  // ---- loss / bookkeeping
+  float clip_min;
+  float* loss_out;             // [G] per-CTA partials of the batch-sum loss
+  float* logits_out;           // optional [B, C] (forward-only launches: validation / predict)
+  unsigned long long* step_counter;     // device step counter (read at entry, incremented by CTA 0 at exit)
+  int forward_only;            // 1: stop after the loss / logits (no gradients, no arrival)
+  // ---- ps protocol
+  int num_tokens;
+  const unsigned long long* token[2];   // mailbox token words: wait until >= step (per ps shard holding a parameter)
+  int num_signals;
+  unsigned long long* arrivals[2];      // ps arrival counters (+1 per CTA per push)
+  unsigned long long* stamp_dst[2];
+  const unsigned long long* stamp_src[2];
+  int sys_scope;               // 0: the ps shares this GPU (gpu-scope fences suffice)
+  unsigned long long timeout_ns;
+  unsigned int* err;
+  unsigned long long* trace;   // optional [G][16] %globaltimer stamps (profiling / Timeline)
+};
+
+#ifndef DTF_HOST_EMU
+DTF_DEVICE unsigned int ld_acquire_gpu_u32_(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+DTF_DEVICE unsigned int ld_relaxed_gpu_u32_(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+DTF_DEVICE void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+#else
+static inline unsigned int ld_acquire_gpu_u32_(const unsigned int* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+static inline unsigned int ld_relaxed_gpu_u32_(const unsigned int* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+#endif
+
+// wait until a device-scope counter reaches `target` (bounded); one thread calls it
+DTF_DEVICE bool wait_counter_ge(const unsigned int* ctr, unsigned int target, unsigned long long timeout_ns) {
+  if ((int)(ld_acquire_gpu_u32_(ctr) - target) >= 0) return true;
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned int spins = 0;
+  while ((int)(ld_relaxed_gpu_u32_(ctr) - target) < 0) {
+    if ((++spins & 0x3FF) == 0 && (globaltimer_ns() - t0) > timeout_ns) return false;
+  }
+  return (int)(ld_acquire_gpu_u32_(ctr) - target) >= 0;
+}
+
+#ifndef DTF_HOST_EMU
+#define DTF_STEP_MAPS const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_x2, \
+                      const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_dh,
+#else
+#define DTF_STEP_MAPS
+#endif
+
+__global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS const MlpStepParams p) {
+  DTF_DYN_SMEM(unsigned char, smem_raw);
+  __shared__ unsigned long long bars[8];               // mbarriers (8-byte aligned by type)
+  __shared__ unsigned int tmem_holder;
+  __shared__ unsigned long long s_step;
+  __shared__ float s_red[16];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x;
+  const int d0 = cta * p.ds;
+  const bool fused = p.phase_mask == 7;
+  unsigned long long* tr = p.trace ? p.trace + 16 * cta : nullptr;
+#define STAMP(slot) do { if (tr && tid == 0) tr[slot] = globaltimer_ns(); } while (0)
+  STAMP(0);
+
+  // ---- shared memory carve-up: [x tile | W1 slice / dh tile | head scratch]
+#ifndef DTF_HOST_EMU
+  unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+#else
+  unsigned char* tiles = smem_raw;
+#endif
+  const int nqx = (p.ds + 31) / 32;                       // 32-feature chunks of the batch tile
+  const int nq1 = (p.n1 + 31) / 32;                       // 32-unit chunks of the W1 slice
+  const int w_chunk = p.ds * 128;                         // bytes of one W1 chunk ([ds rows] x 128 B)
+  const int dh_chunk = p.kb * 128;                        // bytes of one dh chunk ([kb rows] x 128 B)
+  unsigned char* x_sm = tiles;
+  unsigned char* w_sm = x_sm + nqx * kXChunkBytes;
+  const int w_region = max(nq1 * w_chunk, 4 * dh_chunk);
+  float* hs = reinterpret_cast<float*>(w_sm + ((w_region + 1023) & ~1023));
+  constexpr int HP = 132;                                 // padded row of the [16][128] activation tiles
+  float* s_h = hs;                                        // [16][HP]
+  float* s_dh = s_h + 16 * HP;                            // [16][HP]
+  float* s_w2 = s_dh + 16 * HP;                           // [128][16]
+  float* s_b1 = s_w2 + 128 * 16;                          // [128]
+  float* s_dl = s_b1 + 128;                               // [16][16]
+  float* s_lab = s_dl + 256;                              // [16][16]
+  float* s_b2 = s_lab + 256;                              // [16]
+
+  if (tid == 0) s_step = p.step_counter ? *p.step_counter : 0ull;
+#ifndef DTF_HOST_EMU
+  uint64_t* bar_x = reinterpret_cast<uint64_t*>(&bars[0]);
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(&bars[1]);
+  uint64_t* bar_m1 = reinterpret_cast<uint64_t*>(&bars[2]);
+  uint64_t* bar_dh = reinterpret_cast<uint64_t*>(&bars[3]);
+  uint64_t* bar_m2 = reinterpret_cast<uint64_t*>(&bars[4]);
+  uint64_t* bar_x2 = reinterpret_cast<uint64_t*>(&bars[5]);
+  if (tid == 0) {
+    for (int i = 0; i < 6; ++i) mbar_init(reinterpret_cast<uint64_t*>(&bars[i]), 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_x2);
+    tma_prefetch_desc(&map_w1);
+    tma_prefetch_desc(&map_dh);
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_holder, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+#endif
+  __syncthreads();
+#ifndef DTF_HOST_EMU
+  tc_fence_after();
+  const uint32_t tmem_d1 = tmem_holder;                   // F1 accumulator: columns [0, n1)
+  const uint32_t tmem_d2 = tmem_holder + 128;             // B3 accumulator: columns [128, 128 + n2)
+#endif
+  const unsigned long long step = s_step;
+  const long long row0 = p.nbatches > 0
+      ? (long long)((step * (unsigned long long)p.bstride + (unsigned long long)p.boffset) % (unsigned long long)p.nbatches) * p.B
+      : 0ll;
+  const int r_lo = cta * p.rows_per_cta;                  // batch rows this CTA finalises in phase 2
+  const int nrows = max(0, min(p.rows_per_cta, p.B - r_lo));
+  STAMP(1);
+
+  // =====================================================================================================
+  // phase 1: partial pre-activation of this feature slice
+  // =====================================================================================================
+  if (p.phase_mask & 3) {
+    if (tid == 0) {
+#ifndef DTF_HOST_EMU
+      if (p.phase_mask & 1) {
+        mbar_arrive_expect_tx(bar_x, (uint32_t)(nqx * kXChunkBytes));
+        for (int q = 0; q < nqx; ++q) tma_load_2d(x_sm + q * kXChunkBytes, &map_x, bar_x, d0 + 32 * q, (int32_t)row0);
+      }
+#endif
+      // the parameters behind every later read were published by the ps: acquire its token(s) for this step
+      for (int i = 0; i < p.num_tokens; ++i)
+        if (!wait_flag_ge_u64(reinterpret_cast<const uint64_t*>(p.token[i]), step, p.timeout_ns) && p.err) atomicExch(p.err, 1u);
+#ifndef DTF_HOST_EMU
+      fence_proxy_async();
+      if (p.phase_mask & 1) {
+        mbar_arrive_expect_tx(bar_w, (uint32_t)(nq1 * w_chunk));
+        for (int q = 0; q < nq1; ++q) tma_load_2d(w_sm + q * w_chunk, &map_w1, bar_w, 32 * q, d0);   // box {32 units, ds rows}
+      }
+#endif
+    }
+    __syncthreads();                                       // token acquired (thread 0's acquire + barrier)
+    STAMP(2);
+  }
+  if (p.phase_mask & 1) {
+#ifndef DTF_HOST_EMU
+    if (tid == 0) {
+      mbar_wait(bar_x, 0);
+      mbar_wait(bar_w, 0);
+      tc_fence_after();
+      const uint32_t idesc = make_idesc(128, (uint32_t)p.n1, 0, 1, 1);       // A = x: K-major; B = W1[i][j]: MN-major
+      const uint32_t xa = smem_u32(x_sm), wa = smem_u32(w_sm);
+      for (int s = 0; s < p.ds / 8; ++s) {
+        const uint64_t a_desc = make_smem_desc_sw128(xa + (s >> 2) * kXChunkBytes + (s & 3) * 32, 16, 1024);
+        const uint64_t b_desc = make_smem_desc(wa + s * 1024, (uint32_t)w_chunk, 512, 1);      // 32-bit MN-major: BASE32B atoms
+        umma_tf32(tmem_d1, a_desc, b_desc, idesc, s > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_m1);
+      if (fused && !p.forward_only) {
+        // the tensor core is done with the K-major copy of the batch slice: fetch the MN-major arrangement for phase 3
+        // into the same buffer now, under the shadow of phase 2
+        mbar_wait(bar_m1, 0);
+        mbar_arrive_expect_tx(bar_x2, (uint32_t)(nqx * kXChunkBytes));
+        for (int q = 0; q < nqx; ++q) tma_load_2d(x_sm + q * kXChunkBytes, &map_x2, bar_x2, d0 + 32 * q, (int32_t)row0);
+      }
+    }
+#endif
+  }
+  // small parameters and this CTA's label rows -> shared memory (overlaps the MMAs above)
+  if (p.phase_mask & 2) {
+    for (int i = tid; i < 128 * 16; i += kStepThreads) {
+      const int j = i >> 4, c = i & 15;
+      s_w2[i] = (j < p.H && c < p.C) ? p.w2[(long long)j * p.ldw2 + c] : 0.f;
+    }
+    if (tid < 128) s_b1[tid] = tid < p.H ? p.b1[tid] : 0.f;
+    if (tid < 16) s_b2[tid] = tid < p.C ? p.b2[tid] : 0.f;
+    {
+      const int r = tid >> 4, c = tid & 15;
+      s_lab[tid] = (r < nrows && c < p.C) ? p.labels[(row0 + r_lo + r) * p.ldl + c] : 0.f;
+    }
+  }
+  if (p.phase_mask & 1) {
+#ifndef DTF_HOST_EMU
+    mbar_wait(bar_m1, 0);
+    tc_fence_after();
+#endif
+    STAMP(3);
+    // epilogue 1: TMEM (lane = batch row, column = hidden unit) -> hpart[cta][row][0..n1)
+    const int q = warp & 3, half = warp >> 2;
+    const int b = q * 32 + lane;
+    const int nchunks = p.n1 / 8;
+    const int c_lo = half * ((nchunks + 1) / 2), c_hi = half ? nchunks : (nchunks + 1) / 2;
+    float* dst = p.hpart + ((long long)cta * 128 + b) * p.n1;
+    for (int ch = c_lo; ch < c_hi; ++ch) {
+      float v[8];
+#ifndef DTF_HOST_EMU
+      uint32_t r[8];
+      tmem_ld_32x32b_x8(tmem_d1 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 8), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[u]);
+#else
+      for (int u = 0; u < 8; ++u) {
+        const int j = ch * 8 + u;
+        float a = 0.f;
+        if (b < p.B && j < p.H)
+          for (int i = d0; i < min(d0 + p.ds, p.D); ++i) a += p.x[(row0 + b) * p.ldx + i] * p.w1[(long long)i * p.ldw1 + j];
+        v[u] = a;
+      }
+#endif
+      if (b < p.B) {
+        reinterpret_cast<float4*>(dst + ch * 8)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(dst + ch * 8)[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(&p.flags[0], 1u);
+    }
+    STAMP(4);
+  }
+
+  // =====================================================================================================
+  // phase 2: finalise this CTA's batch rows -- h, logits, softmax / loss / dlogits, dh, dW2 / db2 / db1 partials
+  // =====================================================================================================
+  if (p.phase_mask & 2) {
+    if (fused) {
+      if (tid == 0 && !wait_counter_ge(&p.flags[0], (unsigned int)(p.G * (step + 1ull)), p.timeout_ns) && p.err) atomicExch(p.err, 4u);
+    }
+    __syncthreads();
+    STAMP(5);
+    // h[r][j] = relu(sum_c hpart[c][r_lo + r][j] + b1[j])
+    const int n1v = p.n1 / 4;
+    for (int idx = tid; idx < 16 * n1v; idx += kStepThreads) {
+      const int r = idx / n1v, j4 = idx - r * n1v;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nrows) {
+        for (int c = 0; c < p.G; ++c) {
+          const float4 t = __ldcg(reinterpret_cast<const float4*>(p.hpart + ((long long)c * 128 + r_lo + r) * p.n1) + j4);
+          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        a.x = fmaxf(a.x + s_b1[4 * j4], 0.f);
+        a.y = fmaxf(a.y + s_b1[4 * j4 + 1], 0.f);
+        a.z = fmaxf(a.z + s_b1[4 * j4 + 2], 0.f);
+        a.w = fmaxf(a.w + s_b1[4 * j4 + 3], 0.f);
+      }
+      float* o = s_h + r * HP + 4 * j4;
+      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+    }
+    __syncthreads();
+    // logits / softmax / loss / dlogits: warp w owns rows 2w and 2w + 1, lane = (row parity, class)
+    float my_loss = 0.f;
+    {
+      const int r = 2 * warp + (lane >> 4), c = lane & 15;
+      const float* hr = s_h + r * HP;
+      float z0 = 0.f, z1 = 0.f;
+      for (int j = 0; j < p.H; j += 2) {
+        z0 = fmaf(hr[j], s_w2[j * 16 + c], z0);
+        if (j + 1 < p.H) z1 = fmaf(hr[j + 1], s_w2[(j + 1) * 16 + c], z1);
+      }
+      const bool live = c < p.C;
+      float z = live ? (z0 + z1 + s_b2[c]) : -INFINITY;
+      if (p.logits_out && live && r < nrows) p.logits_out[(long long)(r_lo + r) * p.C + c] = z;
+      float mx = z;
+      for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float e = live ? __expf(z - mx) : 0.f;
+      float se = e;
+      for (int o = 8; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+      const float y = e / se;
+      const float lse = mx + __logf(se);
+      const float lab = s_lab[r * 16 + c];
+      float t = 0.f, lterm = 0.f;
+      if (live) {
+        if (p.clip_min > 0.f) {
+          lterm = -lab * fmaxf(z - lse, __logf(p.clip_min));   // log(clamp(y, clip, 1)) = max(log y, log clip) for y <= 1
+          t = (y >= p.clip_min) ? lab : 0.f;
+        } else {
+          lterm = -lab * (z - lse);
+          t = lab;
+        }
+      }
+      float tsum = t;
+      for (int o = 8; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+      const float g = (live && r < nrows) ? (y * tsum - t) : 0.f;
+      s_dl[r * 16 + c] = g;
+      my_loss = (r < nrows) ? lterm : 0.f;
+      for (int o = 16; o > 0; o >>= 1) my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
+      if (lane == 0) s_red[warp] = my_loss;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+      for (int i = 0; i < kStepThreads / 32; ++i) t += s_red[i];
+      p.loss_out[cta] = t;
+    }
+    if (!p.forward_only) {
+      // dh[r][j] = (h > 0) * dl[r][:] . W2[j][:]   (-> shared memory for db1, -> L2 scratch for every CTA's dW1 GEMM)
+      for (int idx = tid; idx < 16 * p.n1; idx += kStepThreads) {
+        const int r = idx / p.n1, j = idx - r * p.n1;
+        float d = 0.f;
+        if (r < nrows) {
+          const float* dl = s_dl + r * 16;
+          const float* w = s_w2 + j * 16;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) d = fmaf(dl[c], w[c], d);
+          d = s_h[r * HP + j] > 0.f ? d : 0.f;
+          p.dh[(long long)(r_lo + r) * p.lddh + j] = d;
+        }
+        s_dh[r * HP + j] = d;
+      }
+      // dW2[j][c] += sum_r h[r][j] * dl[r][c]
+      for (int idx = tid; idx < p.H * 16; idx += kStepThreads) {
+        const int j = idx >> 4, c = idx & 15;
+        if (c < p.C) {
+          float a = 0.f;
+          for (int r = 0; r < nrows; ++r) a = fmaf(s_h[r * HP + j], s_dl[r * 16 + c], a);
+          atomicAdd(p.gw2 + (long long)j * p.ldgw2 + c, a);
+        }
+      }
+      if (tid < p.C) {
+        float a = 0.f;
+        for (int r = 0; r < nrows; ++r) a += s_dl[r * 16 + tid];
+        atomicAdd(p.gb2 + tid, a);
+      }
+      __syncthreads();
+      if (tid < p.H) {
+        float a = 0.f;
+        for (int r = 0; r < nrows; ++r) a += s_dh[r * HP + tid];
+        atomicAdd(p.gb1 + tid, a);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(&p.flags[1], 1u);
+      }
+    }
+    STAMP(6);
+  }
+
+  // =====================================================================================================
+  // phase 3: dW1 rows of this slice = x_slice^T . dh, pushed from TMEM into the gradient slot; arrival
+  // =====================================================================================================
+  if ((p.phase_mask & 4) && !p.forward_only) {
+#ifndef DTF_HOST_EMU
+    if (tid == 0) {
+      if (fused && !wait_counter_ge(&p.flags[1], (unsigned int)(p.G * (step + 1ull)), p.timeout_ns) && p.err) atomicExch(p.err, 5u);
+      fence_proxy_async();
+      mbar_arrive_expect_tx(bar_dh, (uint32_t)(4 * dh_chunk));
+      for (int q = 0; q < 4; ++q) tma_load_2d(w_sm + q * dh_chunk, &map_dh, bar_dh, 32 * q, 0);      // box {32 units, kb rows}
+      if (!fused) {
+        mbar_arrive_expect_tx(bar_x2, (uint32_t)(nqx * kXChunkBytes));
+        for (int q = 0; q < nqx; ++q) tma_load_2d(x_sm + q * kXChunkBytes, &map_x2, bar_x2, d0 + 32 * q, (int32_t)row0);
+      }
+      mbar_wait(bar_x2, 0);
+      mbar_wait(bar_dh, 0);
+      tc_fence_after();
+      const uint32_t idesc = make_idesc(128, (uint32_t)p.n2, 1, 1, 1);       // A = dh[b][j]: MN-major; B = x[b][i]: MN-major
+      const uint32_t xa = smem_u32(x_sm), da = smem_u32(w_sm);
+      for (int s = 0; s < p.kb / 8; ++s) {
+        const uint64_t a_desc = make_smem_desc(da + s * 1024, (uint32_t)dh_chunk, 512, 1);
+        const uint64_t b_desc = make_smem_desc(xa + s * 1024, (uint32_t)kXChunkBytes, 512, 1);
+        umma_tf32(tmem_d2, a_desc, b_desc, idesc, s > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_m2);
+    }
+    mbar_wait(bar_m2, 0);
+    tc_fence_after();
+#else
+    if (fused) { /* emulated blocks run one after another: the fused mode is hardware-only */ }
+#endif
+    STAMP(7);
+    // epilogue 2: TMEM (lane = hidden unit j, column = feature i of the slice) -> gw1[d0 + i][j]: a warp stores 32
+    // consecutive j per feature = one 128-byte line per instruction
+    {
+      const int q = warp & 3, half = warp >> 2;
+      const int j = q * 32 + lane;
+      const int nchunks = p.n2 / 8;
+      const int c_lo = half * ((nchunks + 1) / 2), c_hi = half ? nchunks : (nchunks + 1) / 2;
+      for (int ch = c_lo; ch < c_hi; ++ch) {
+        float v[8];
+#ifndef DTF_HOST_EMU
+        uint32_t r[8];
+        tmem_ld_32x32b_x8(tmem_d2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 8), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[u]);
+#else
+        for (int u = 0; u < 8; ++u) {
+          const int i = d0 + ch * 8 + u;
+          float a = 0.f;
+          if (j < p.H && i < p.D)
+            for (int b = 0; b < p.B; ++b) a += p.x[(row0 + b) * p.ldx + i] * p.dh[(long long)b * p.lddh + j];
+          v[u] = a;
+        }
+#endif
+        if (j < p.H) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int il = ch * 8 + u;
+            if (il < p.ds && d0 + il < p.D) p.gw1[(long long)(d0 + il) * p.ldgw1 + j] = v[u];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    STAMP(8);
+    if (tid == 0) {
+      // ONE fence by one thread after the CTA barrier (release is cumulative), then the arrival(s)
+      if (p.sys_scope) fence_acq_rel_sys(); else __threadfence();
+      for (int i = 0; i < p.num_signals; ++i) {
+        if (cta == 0 && p.stamp_dst[i]) st_relaxed_sys_u64(reinterpret_cast<uint64_t*>(p.stamp_dst[i]), *p.stamp_src[i]);
+      }
+      if (cta == 0 && p.num_signals && p.sys_scope) fence_acq_rel_sys();
+      for (int i = 0; i < p.num_signals; ++i) red_release_sys_add_u64(reinterpret_cast<uint64_t*>(p.arrivals[i]), 1ull);
+    }
+    STAMP(9);
+  }
+  // step counter: advanced by the LAST CTA to get here (ticket), i.e. after every CTA of this launch has read it
+  const bool last_phase = (p.phase_mask & 4) != 0;
+  if (last_phase && tid == 0 && p.step_counter && !p.forward_only) {
+    const unsigned int ticket = atomicAdd(&p.flags[2], 1u);
+    if (ticket + 1u == (unsigned int)(p.G * (step + 1ull))) *p.step_counter = step + 1ull;
+  }
+#ifndef DTF_HOST_EMU
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_holder, 256);
+#endif
+  STAMP(10);
+#undef STAMP
+}
+
+}  // namespace dtf
+
+#ifndef DTF_HOST_EMU
+namespace dtf {
+// tensor-map cache of csrc/gemm_tcgen05.cu
+int cached_map_f32(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows,
+                   int sw32);
+}
+#endif
+
+extern "C" {
+using namespace dtf;
+
+struct DtfMlpStepArgs {
+  int B, D, H, C;
+  int G;                       // 0: auto
+  int phase_mask;              // 0 -> 7 (fused)
+  const float* x; long long ldx; long long x_rows;
+  const float* labels; long long ldl;
+  long long nbatches, bstride, boffset;
+  const float* w1; long long ldw1;
+  const float* b1;
+  const float* w2; long long ldw2;
+  const float* b2;
+  float* hpart; float* dh; long long lddh; unsigned int* flags;
+  float* gw1; long long ldgw1; float* gb1; float* gw2; long long ldgw2; float* gb2;
+  float clip_min;
+  float* loss_out; float* logits_out;
+  unsigned long long* step_counter;
+  int forward_only;
+  int num_tokens; const unsigned long long* token[2];
+  int num_signals; unsigned long long* arrivals[2]; unsigned long long* stamp_dst[2]; const unsigned long long* stamp_src[2];
+  int sys_scope;
+  unsigned long long timeout_ns;
+  unsigned int* err;
+  unsigned long long* trace;
+};
+
+// Slices: at least ceil(B / 16) CTAs (phase 2 finalises <= 16 batch rows per CTA), at most 16; among those the widest
+// slice (a multiple of 8, <= 128) that divides D evenly, else the widest.  784 features, batch 100 -> 7 x 112.
+int dtf_mlp_step_slices(int D, int B, int* ds_out) {
+  const int g_min = (B + 15) / 16;
+  int g_any = 0, ds_any = 0;
+  for (int ds = 128; ds >= 8; ds -= 8) {
+    const int g = (D + ds - 1) / ds;
+    if (g > 16) break;
+    if (g < g_min) continue;
+    if (D % ds == 0) {
+      if (ds_out) *ds_out = ds;
+      return g;
+    }
+    if (!g_any) { g_any = g; ds_any = ds; }
+  }
+  if (!g_any) {            // few features: more CTAs than slices (the extra ones own empty slices and only do phase 2)
+    g_any = g_min;
+    ds_any = ((D + g_min - 1) / g_min + 7) / 8 * 8;
+  }
+  if (ds_out) *ds_out = ds_any;
+  return g_any;
+}
+
+// scratch sizes (floats): hpart = G * 128 * n1, dh = 128 * 128
+long long dtf_mlp_step_scratch_floats(int D, int B, int H) {
+  int ds = 0;
+  const int g = dtf_mlp_step_slices(D, B, &ds);
+  const int n1 = (H + 15) / 16 * 16;
+  return (long long)g * 128 * n1 + 128 * 128 + 64;
+}
+
+int dtf_mlp_step(const DtfMlpStepArgs* a, cudaStream_t s) {
+  if (a->B < 1 || a->B > 128 || a->H < 1 || a->H > 128 || a->C < 1 || a->C > 16 || a->D < 8) return -2;
+  if ((a->ldx % 4) || (a->ldw1 % 4) || (a->lddh % 4) || a->lddh < 128) return -3;
+  MlpStepParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = a->B; p.D = a->D; p.H = a->H; p.C = a->C;
+  int ds = 0;
+  int g = dtf_mlp_step_slices(a->D, a->B, &ds);
+  if (a->G > 0) { g = a->G; ds = ((a->D + g - 1) / g + 7) / 8 * 8; }
+  if (ds > 128 || ds < 8 || g > 64) return -2;
+  p.G = g; p.ds = ds;
+  p.rows_per_cta = (a->B + g - 1) / g;
+  if (p.rows_per_cta > 16) return -2;
+  p.phase_mask = a->phase_mask ? a->phase_mask : 7;
+  p.n1 = (a->H + 15) / 16 * 16;
+  p.n2 = (ds + 15) / 16 * 16;
+  p.kb = (a->B + 7) / 8 * 8;
+  p.x = a->x; p.ldx = a->ldx; p.labels = a->labels; p.ldl = a->ldl;
+  p.nbatches = a->nbatches; p.bstride = a->bstride; p.boffset = a->boffset;
+  p.w1 = a->w1; p.ldw1 = a->ldw1; p.b1 = a->b1; p.w2 = a->w2; p.ldw2 = a->ldw2; p.b2 = a->b2;
+  p.hpart = a->hpart; p.dh = a->dh; p.lddh = a->lddh; p.flags = a->flags;
+  p.gw1 = a->gw1; p.ldgw1 = a->ldgw1; p.gb1 = a->gb1; p.gw2 = a->gw2; p.ldgw2 = a->ldgw2; p.gb2 = a->gb2;
+  p.clip_min = a->clip_min; p.loss_out = a->loss_out; p.logits_out = a->logits_out;
+  p.step_counter = a->step_counter; p.forward_only = a->forward_only;
+  p.num_tokens = a->num_tokens > 2 ? 2 : a->num_tokens;
+  p.num_signals = a->num_signals > 2 ? 2 : a->num_signals;
+  for (int i = 0; i < 2; ++i) {
+    p.token[i] = a->token[i]; p.arrivals[i] = a->arrivals[i]; p.stamp_dst[i] = a->stamp_dst[i]; p.stamp_src[i] = a->stamp_src[i];
+  }
+  p.sys_scope = a->sys_scope;
+  p.timeout_ns = a->timeout_ns ? a->timeout_ns : 2000000000ull;
+  p.err = a->err; p.trace = a->trace;
+  const int nqx = (ds + 31) / 32, nq1 = (p.n1 + 31) / 32;
+  const int w_region = (std::max(nq1 * ds * 128, 4 * p.kb * 128) + 1023) & ~1023;
+  const size_t head_floats = 2 * 16 * 132 + 128 * 16 + 128 + 256 + 256 + 16;
+  const size_t smem = 1024 + (size_t)nqx * kXChunkBytes + w_region + head_floats * 4;
+#ifdef DTF_HOST_EMU
+  const int masks[3] = {1, 2, 4};
+  for (int ph = 0; ph < 3; ++ph) {
+    if (!(p.phase_mask & masks[ph])) continue;
+    MlpStepParams q = p;
+    q.phase_mask = masks[ph];
+    DTF_LAUNCH_SMEM(mlp_step_kernel, g, kStepThreads, smem, s, q);
+  }
+  return 0;
+#else
+  CUtensorMap mx, mx2, mw, md;
+  // x: [rows, D] box {32 features, 128 rows}, once per swizzle (K-major A of F1 / MN-major B of B3);
+  // W1: [D, H] box {32 units, ds rows}; dh: [128, 128] box {32 units, kb rows} -- both MN-major operands
+  int rc = cached_map_f32(&mx, a->x, a->x_rows, a->D, a->ldx, 32, 128, 0);
+  if (rc) return rc < 0 ? -7 : 1000 + rc;
+  rc = cached_map_f32(&mx2, a->x, a->x_rows, a->D, a->ldx, 32, 128, 1);
+  if (rc) return rc < 0 ? -7 : 1000 + rc;
+  rc = cached_map_f32(&mw, a->w1, a->D, a->H, a->ldw1, 32, ds, 1);
+  if (rc) return rc < 0 ? -7 : 1000 + rc;
+  rc = cached_map_f32(&md, a->dh, 128, 128, a->lddh, 32, p.kb, 1);
+  if (rc) return rc < 0 ? -7 : 1000 + rc;
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return 2000 + (int)e;
+    configured[dev] = true;
+  }
+  if (smem > 200 * 1024) return -2;
+  if (p.phase_mask == 7) {
+    mlp_step_kernel<<<g, kStepThreads, smem, s>>>(mx, mx2, mw, md, p);
+  } else {
+    const int masks[3] = {1, 2, 4};
+    for (int ph = 0; ph < 3; ++ph) {
+      if (!(p.phase_mask & masks[ph])) continue;
+      MlpStepParams q = p;
+      q.phase_mask = masks[ph];
+      // phase-by-phase launches leave the step counter to the last phase
+      mlp_step_kernel<<<g, kStepThreads, smem, s>>>(mx, mx2, mw, md, q);
+    }
+  }
+  return (int)cudaGetLastError();
+#endif
+}
+
+int dtf_sizeof_mlp_step_args() { return (int)sizeof(DtfMlpStepArgs); }
+
+}  // extern "C"

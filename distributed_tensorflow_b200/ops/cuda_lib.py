@@ -38,7 +38,8 @@ class GemmArgs(Structure):
                 ("wait_flag", c_void_p), ("wait_target", c_ulonglong),
                 ("signal", c_void_p), ("err", c_void_p), ("timeout_ns", c_ulonglong),
                 ("block_n_override", c_int), ("wait_target_ptr", c_void_p), ("phase_trace", c_void_p),
-                ("signal_gpu_scope", c_int), ("stamp_src", c_void_p), ("stamp_dst", c_void_p), ("persistent", c_int), ("cta_pair", c_int)]
+                ("signal_gpu_scope", c_int), ("stamp_src", c_void_p), ("stamp_dst", c_void_p), ("persistent", c_int), ("cta_pair", c_int),
+                ("tf32", c_int)]
 
 
 class PsApplyArgs(Structure):
@@ -65,6 +66,23 @@ class MlpHeadArgs(Structure):
                 ("mailbox", c_void_p), ("ctl", c_void_p), ("rank", c_int), ("stamp_from_version", c_int),
                 ("phase_trace", c_void_p), ("h_acc", c_void_p), ("ld_acc", c_longlong), ("b1", c_void_p),
                 ("sys_scope", c_int), ("ctas", c_int)]
+
+
+class MlpStepArgs(Structure):
+    """``csrc/mlp_step.cu: DtfMlpStepArgs`` -- one whole worker step of the MLP as one kernel (fp32 storage, TF32 MMAs)."""
+    _fields_ = [("B", c_int), ("D", c_int), ("H", c_int), ("C", c_int), ("G", c_int), ("phase_mask", c_int),
+                ("x", c_void_p), ("ldx", c_longlong), ("x_rows", c_longlong),
+                ("labels", c_void_p), ("ldl", c_longlong),
+                ("nbatches", c_longlong), ("bstride", c_longlong), ("boffset", c_longlong),
+                ("w1", c_void_p), ("ldw1", c_longlong), ("b1", c_void_p), ("w2", c_void_p), ("ldw2", c_longlong),
+                ("b2", c_void_p),
+                ("hpart", c_void_p), ("dh", c_void_p), ("lddh", c_longlong), ("flags", c_void_p),
+                ("gw1", c_void_p), ("ldgw1", c_longlong), ("gb1", c_void_p), ("gw2", c_void_p), ("ldgw2", c_longlong),
+                ("gb2", c_void_p),
+                ("clip_min", c_float), ("loss_out", c_void_p), ("logits_out", c_void_p), ("step_counter", c_void_p),
+                ("forward_only", c_int), ("num_tokens", c_int), ("token", c_void_p * 2),
+                ("num_signals", c_int), ("arrivals", c_void_p * 2), ("stamp_dst", c_void_p * 2), ("stamp_src", c_void_p * 2),
+                ("sys_scope", c_int), ("timeout_ns", c_ulonglong), ("err", c_void_p), ("trace", c_void_p)]
 
 
 class StepOp(Structure):
@@ -214,6 +232,15 @@ def _declare(lib) -> None:
                  "dtf_vmm_map", "dtf_vmm_unmap", "dtf_vmm_release", "dtf_vmm_export_fd", "dtf_vmm_import_fd",
                  "dtf_mc_create", "dtf_mc_add_device", "dtf_mc_bind", "dtf_mc_unbind"):
         getattr(lib, name).restype = c_int
+    if not isinstance(getattr(lib, "dtf_mlp_step", _Missing()), _Missing):
+        lib.dtf_mlp_step.argtypes = [POINTER(MlpStepArgs), c_void_p]
+        lib.dtf_mlp_step.restype = c_int
+        lib.dtf_mlp_step_slices.argtypes = [c_int, c_int, POINTER(c_int)]
+        lib.dtf_mlp_step_slices.restype = c_int
+        lib.dtf_mlp_step_scratch_floats.argtypes = [c_int, c_int, c_int]
+        lib.dtf_mlp_step_scratch_floats.restype = c_longlong
+        lib.dtf_sizeof_mlp_step_args.restype = c_int
+        assert lib.dtf_sizeof_mlp_step_args() == ctypes.sizeof(MlpStepArgs), "MlpStepArgs layout mismatch"
     lib.dtf_run_ops.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
     lib.dtf_run_ops.restype = c_int
     lib.dtf_capture_ops.argtypes = [c_void_p, c_int, c_int, c_void_p, POINTER(c_void_p), POINTER(c_int)]
@@ -264,7 +291,7 @@ def load() -> ctypes.CDLL:
 # kernel emulation: the op layer on HOST tensors (tests without a GPU)
 # ---------------------------------------------------------------------------------------------------
 EMULATION = False
-_EMU_SOURCES = ("elementwise.cu", "ps_engine.cu", "nn_kernels.cu")
+_EMU_SOURCES = ("elementwise.cu", "ps_engine.cu", "nn_kernels.cu", "mlp_step.cu")
 
 
 def enable_emulation(build_dir: Optional[str] = None) -> ctypes.CDLL:
@@ -381,6 +408,33 @@ def to_bf16_padded(x: torch.Tensor) -> Tuple[torch.Tensor, int]:
     return out, ld
 
 
+def to_f32_padded(x: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """Row-major 2-D tensor -> (fp32 tensor with a 16-byte row pitch and base, pitch): the TF32 GEMM's TMA reads fp32
+    tensors in place; only odd pitches / other dtypes are copied."""
+    assert x.dim() == 2 and _on_device(x)
+    rows, cols = x.shape
+    if x.dtype == torch.float32 and x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.stride(0) >= cols and x.data_ptr() % 16 == 0:
+        return x, x.stride(0)
+    ld = round_up(cols, 4)
+    out = torch.zeros((rows, ld), dtype=torch.float32, device=x.device) if ld != cols else \
+        torch.empty((rows, ld), dtype=torch.float32, device=x.device)
+    out[:, :cols].copy_(x)
+    return out, ld
+
+
+# Operand precision of fp32 matmuls on /gpu devices.  "tf32": fp32 tensors stay fp32 in memory and are multiplied by
+# tcgen05.mma.kind::tf32 (the reference model is fp32: /root/reference/distributed_mnist.py:98-113); "bf16": operands
+# are rounded to bf16 first (kind::f16, twice the tensor throughput).  Accumulation is fp32 either way.
+MATMUL_PRECISION = os.environ.get("DTF_MATMUL_PRECISION", "tf32")
+
+
+def set_matmul_precision(p: str) -> str:
+    global MATMUL_PRECISION
+    assert p in ("tf32", "bf16"), p
+    old, MATMUL_PRECISION = MATMUL_PRECISION, p
+    return old
+
+
 # ---------------------------------------------------------------------------------------------------
 # GEMM
 # ---------------------------------------------------------------------------------------------------
@@ -390,8 +444,8 @@ def gemm_raw(a: torch.Tensor, lda: int, b: torch.Tensor, ldb: int, c: torch.Tens
              accumulate: bool = False, colsum: Optional[torch.Tensor] = None, wait_flag: int = 0, wait_target: int = 0,
              signal: int = 0, err: int = 0, timeout_ns: int = 0, block_n: int = 0, stream: Optional[int] = None,
              a_ptr: Optional[int] = None, b_ptr: Optional[int] = None, c_ptr: Optional[int] = None,
-             bias_ptr: Optional[int] = None, c_bf16: Optional[bool] = None, persistent: int = 0) -> None:
-    """Launch the tcgen05 GEMM on raw buffers (pointers may be peer memory)."""
+             bias_ptr: Optional[int] = None, c_bf16: Optional[bool] = None, persistent: int = 0, tf32: bool = False) -> None:
+    """Launch the tcgen05 GEMM on raw buffers (pointers may be peer memory).  ``tf32``: A and B are fp32."""
     g = GemmArgs()
     g.a = a_ptr if a_ptr is not None else a.data_ptr()
     g.b = b_ptr if b_ptr is not None else b.data_ptr()
@@ -408,6 +462,7 @@ def gemm_raw(a: torch.Tensor, lda: int, b: torch.Tensor, ldb: int, c: torch.Tens
     g.signal, g.err, g.timeout_ns = signal or None, err or None, timeout_ns
     g.block_n_override = block_n
     g.persistent = persistent
+    g.tf32 = int(tf32)
     lib = load()
     st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
     _check(lib.dtf_gemm_bf16(byref(g), st), "gemm_bf16_tcgen05")
@@ -416,20 +471,26 @@ def gemm_raw(a: torch.Tensor, lda: int, b: torch.Tensor, ldb: int, c: torch.Tens
 
 def gemm(a: torch.Tensor, b: torch.Tensor, ta: bool = False, tb: bool = False, bias: Optional[torch.Tensor] = None,
          relu: bool = False, out_dtype: torch.dtype = torch.float32, splits: int = 1, persistent: int = 0,
-         block_n: int = 0) -> torch.Tensor:
-    """``op(a) @ op(b)`` (+bias, ReLU) on the tensor cores; inputs fp32 or bf16, bf16 compute, fp32 accumulate."""
+         block_n: int = 0, precision: Optional[str] = None) -> torch.Tensor:
+    """``op(a) @ op(b)`` (+bias, ReLU) on the tensor cores, fp32 accumulate.  ``precision``: "bf16" (operands rounded to
+    bf16) or "tf32" (fp32 operands read in place, TF32 multiply); default: bf16 inputs -> "bf16", otherwise
+    ``MATMUL_PRECISION``."""
     assert _on_device(a) and _on_device(b) and a.dim() == 2 and b.dim() == 2
+    if precision is None:
+        precision = "bf16" if (a.dtype == torch.bfloat16 or b.dtype == torch.bfloat16) else MATMUL_PRECISION
+    tf32 = precision == "tf32"
     if EMULATION:
         # the tcgen05 / TMA kernel is hardware-only.  Same contract (bf16-rounded operands, fp32 accumulate, fused bias /
         # ReLU) from the CUDA-core reference GEMM kernel while one emulated thread per output element is affordable,
         # from a plain matmul beyond that.
         Mo = a.shape[1] if ta else a.shape[0]
         No = b.shape[0] if tb else b.shape[1]
-        if Mo * No <= 1 << 14:
+        if Mo * No <= 1 << 14 and not tf32:
             out = gemm_ref(a, b, ta, tb, bias=bias, relu=relu)
         else:
-            x = (a.t() if ta else a).bfloat16().float()
-            y = (b.t() if tb else b).bfloat16().float()
+            rnd = (lambda t: t.float()) if tf32 else (lambda t: t.bfloat16().float())
+            x = rnd(a.t() if ta else a)
+            y = rnd(b.t() if tb else b)
             out = x @ y
             if bias is not None:
                 out = out + bias.float()
@@ -441,14 +502,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, ta: bool = False, tb: bool = False, b
     if K != Kb:
         raise ValueError("gemm: inner dimensions differ (%d vs %d)" % (K, Kb))
     with _on(a.device):
-        a16, lda = to_bf16_padded(a)
-        b16, ldb = to_bf16_padded(b)
+        a16, lda = to_f32_padded(a) if tf32 else to_bf16_padded(a)
+        b16, ldb = to_f32_padded(b) if tf32 else to_bf16_padded(b)
         ldc = N if out_dtype == torch.float32 else round_up(N, 8)
         c = (torch.zeros if splits > 1 else torch.empty)((M, ldc), dtype=out_dtype, device=a.device)
         if bias is not None:
             bias = bias.float().contiguous()
         gemm_raw(a16, lda, b16, ldb, c, ldc, M, N, K, a_mn=ta, b_mn=not tb, bias=bias, relu=relu, splits=splits,
-                 persistent=persistent, block_n=block_n)
+                 persistent=persistent, block_n=block_n, tf32=tf32)
     return c if ldc == N else c[:, :N]
 
 

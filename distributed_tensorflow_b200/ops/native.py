@@ -299,7 +299,7 @@ class _ConvFn(torch.autograd.Function):
         kh, kw, cin, cout = w.shape
         cols, (n, ho, wo) = lib.im2col_nhwc(x, kh, kw, strides, pads)
         w2 = w.reshape(kh * kw * cin, cout)
-        y = lib.gemm(cols, w2, False, False)
+        y = lib.gemm(cols, w2, False, False, precision="bf16")      # conv model family: bf16 operands (BASELINE config 5)
         ctx.save_for_backward(cols, w2)
         ctx.meta = (x.shape, w.shape, strides, pads, (n, ho, wo))
         return y.reshape(n, ho, wo, cout)
@@ -312,7 +312,7 @@ class _ConvFn(torch.autograd.Function):
         g2 = g.reshape(n * ho * wo, wshape[3]).contiguous()
         gx = gw = None
         if ctx.needs_input_grad[1]:
-            gw = lib.gemm(cols, g2, True, False).reshape(wshape)
+            gw = lib.gemm(cols, g2, True, False, precision="bf16").reshape(wshape)
         if ctx.needs_input_grad[0]:
             kh, kw, cin, cout = wshape
             if lib.FUSED_NN and strides == (1, 1) and cout % 8 == 0:
@@ -323,9 +323,9 @@ class _ConvFn(torch.autograd.Function):
                 pt, pb, pl, pr = pads
                 wf = w2.reshape(kh, kw, cin, cout).flip(0, 1).permute(0, 1, 3, 2).reshape(kh * kw * cout, cin)
                 gcols_in, _ = lib.im2col_nhwc(g2.reshape(n, ho, wo, cout), kh, kw, (1, 1), (kh - 1 - pt, kh - 1 - pb, kw - 1 - pl, kw - 1 - pr))
-                gx = lib.gemm(gcols_in, wf.contiguous(), False, False).reshape(xshape)
+                gx = lib.gemm(gcols_in, wf.contiguous(), False, False, precision="bf16").reshape(xshape)
             else:
-                gcols = lib.gemm(g2, w2, False, True)
+                gcols = lib.gemm(g2, w2, False, True, precision="bf16")
                 gx = lib.col2im_nhwc(gcols, xshape, kh, kw, strides, pads)
         return gx, gw, None, None
 

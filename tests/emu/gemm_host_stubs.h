@@ -69,7 +69,7 @@ static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) {
 }
 
 namespace dtf {
-static int make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows) {
+static int make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows, int /*esize*/ = 2, int /*sw32*/ = 0) {
   *out = CUtensorMap{ptr, rows, cols, ld, box_cols, box_rows};
   return 0;
 }

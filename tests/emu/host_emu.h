@@ -147,7 +147,11 @@ static inline void launch(dim3 grid, dim3 block, const std::function<void()>& bo
 template <class T>
 static inline T __ldg(const T* p) { return *p; }
 template <class T>
-static inline T __ldcg(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
+static inline T __ldcg(const T* p) {       // cache-global load: a plain read here (aggregates have no volatile copy)
+  T v;
+  std::memcpy(&v, p, sizeof(T));
+  return v;
+}
 static inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 
 static inline unsigned int atomicExch(unsigned int* p, unsigned int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }

@@ -14,7 +14,9 @@ def lib():
         pytest.skip("needs a GPU")
     from distributed_tensorflow_b200.ops import cuda_lib
     cuda_lib.load()          # must load on a GPU box: no silent fallback
-    return cuda_lib
+    old = cuda_lib.set_matmul_precision("bf16")      # the bf16-rounded references below; the tf32 tests pass precision=
+    yield cuda_lib
+    cuda_lib.set_matmul_precision(old)
 
 
 def _ref_mm(a, b, ta, tb):
@@ -32,6 +34,38 @@ def test_tcgen05_gemm_all_operand_majors(lib, M, N, K, ta, tb):
     got = lib.gemm(a, b, ta, tb)
     ref = _ref_mm(a, b, ta, tb)
     torch.testing.assert_close(got, ref, rtol=2e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (100, 100, 784), (784, 100, 100), (100, 10, 100), (300, 520, 200),
+                                   (1, 8, 24), (256, 96, 36)])
+def test_tcgen05_gemm_tf32_all_operand_majors_vs_pure_fp32(lib, M, N, K, ta, tb):
+    """fp32 operands read in place by TMA and multiplied as TF32 (tcgen05.mma.kind::tf32), all four operand-major
+    combinations, against a float64 matmul of the UNROUNDED fp32 inputs: the only error is TF32's 10-bit mantissa
+    (2^-11 per operand), i.e. ~1e-3 norm-wise -- an order of magnitude closer to the fp32 reference model than bf16."""
+    torch.manual_seed(M * 5 + N * 3 + K)
+    a = torch.randn((K, M) if ta else (M, K), device="cuda")
+    b = torch.randn((N, K) if tb else (K, N), device="cuda")
+    got = lib.gemm(a, b, ta, tb, precision="tf32")
+    ref = ((a.double().t() if ta else a.double()) @ (b.double().t() if tb else b.double()))
+    rel = float((got.double() - ref).norm() / ref.norm())
+    assert rel < 1.5e-3, rel
+    bf = lib.gemm(a, b, ta, tb, precision="bf16")
+    rel_bf = float((bf.double() - ref).norm() / ref.norm())
+    assert rel < rel_bf, (rel, rel_bf)               # and it IS closer to fp32 than the bf16 path
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_tcgen05_gemm_tf32_persistent_and_epilogues(lib, mode):
+    torch.manual_seed(11)
+    M, N, K = 2048, 512, 320
+    a, b, bias = torch.randn(M, K, device="cuda"), torch.randn(K, N, device="cuda"), torch.randn(N, device="cuda")
+    got = lib.gemm(a, b, bias=bias, relu=True, precision="tf32", persistent=mode, block_n=256 if mode == 2 else 0)
+    ref = torch.relu(a.double() @ b.double() + bias.double())
+    assert float((got.double() - ref).norm() / ref.norm()) < 1.5e-3
+    got_t = lib.gemm(a.t().contiguous(), b.t().contiguous(), True, True, precision="tf32", persistent=mode)
+    ref_t = a.double() @ b.double()
+    assert float((got_t.double() - ref_t).norm() / ref_t.norm()) < 1.5e-3
 
 
 @pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])

@@ -41,6 +41,7 @@ def test_mnist_mlp_ops_forward_backward(emulated, monkeypatch):
     def model(w1, b1, w2, b2):
         h = native.linear(x, w1, b1, relu=True)
         return native.clipped_softmax_xent_sum(native.linear(h, w2, b2), y)
+    monkeypatch.setattr(cuda_lib, "MATMUL_PRECISION", "bf16")
     n0 = cuda_lib.launch_count()
     loss, grads = _grads(model, [w1, b1, w2, b2])
     assert cuda_lib.launch_count() - n0 >= 10                      # GEMMs, conversions, xent, relu_grad, colsum really ran
@@ -61,6 +62,31 @@ def test_mnist_mlp_ops_forward_backward(emulated, monkeypatch):
     assert abs(float(loss) - float(eager_loss)) < 2e-2 * abs(float(eager_loss))
     for a, b in zip(grads, eager):
         _close(a, b, 1e-1)
+
+
+def test_mnist_mlp_ops_tf32_precision_matches_pure_fp32_oracle(emulated, monkeypatch):
+    """Default precision of fp32 graph tensors on /gpu: fp32 storage, TF32 multiply (emulated: plain fp32 matmul).  The
+    oracle is the float64 network with NO operand rounding (the reference model is fp32: distributed_mnist.py:98-113)."""
+    monkeypatch.setattr(cuda_lib, "MATMUL_PRECISION", "tf32")
+    g = torch.Generator().manual_seed(1)
+    x, w1, b1 = torch.rand(100, 784, generator=g), torch.randn(784, 100, generator=g) / 28, torch.zeros(100)
+    w2, b2 = torch.randn(100, 10, generator=g) / 10, torch.zeros(10)
+    y = torch.nn.functional.one_hot(torch.randint(0, 10, (100,), generator=g), 10).float()
+
+    def model(w1, b1, w2, b2):
+        h = native.linear(x, w1, b1, relu=True)
+        return native.clipped_softmax_xent_sum(native.linear(h, w2, b2), y)
+    loss, grads = _grads(model, [w1, b1, w2, b2])
+    d = lambda t: t.double()
+    h = torch.relu(d(x) @ d(w1) + d(b1))
+    p = torch.softmax(h @ d(w2) + d(b2), -1)
+    ref_loss = -(d(y) * torch.log(torch.clamp(p, 1e-10, 1.0))).sum()
+    dl = p - d(y)
+    dh = (dl @ d(w2).t()) * (h > 0)
+    ref = [d(x).t() @ dh, dh.sum(0), h.t() @ dl, dl.sum(0)]
+    assert abs(float(loss) - float(ref_loss)) < 1e-5 * abs(float(ref_loss))
+    for a, b in zip(grads, ref):
+        _close(a.double(), b, 1e-5)
 
 
 @pytest.mark.parametrize("cin,fused", [(3, False), (8, True), (16, True)])
