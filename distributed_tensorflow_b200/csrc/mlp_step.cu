@@ -69,7 +69,8 @@ struct MlpStepParams {
   float* hpart;                // [G][128][n1] partial pre-activations
   float* dh;                   // [128][lddh] (rows >= B and columns >= H stay zero)
   long long lddh;
-  unsigned int* flags;         // [0]: partials written, [1]: dh rows written, [2]: CTAs finished (monotonic: G per step)
+  unsigned int* flags;         // [8]: {partials written, dh rows written, CTAs finished (all monotonic: G per launch), launch
+                               //       epoch} for training launches, the same four again for forward-only launches
   // ---- gradient slots
   float* gw1;                  // [D, ldgw1]
   long long ldgw1;
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
   __shared__ unsigned long long bars[8];               // mbarriers (8-byte aligned by type)
   __shared__ unsigned int tmem_holder;
   __shared__ unsigned long long s_step;
+  __shared__ unsigned int s_epoch;
   __shared__ float s_red[16];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x;
@@ -173,7 +175,11 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
   float* s_lab = s_dl + 256;                              // [16][16]
   float* s_b2 = s_lab + 256;                              // [16]
 
-  if (tid == 0) s_step = p.step_counter ? *p.step_counter : 0ull;
+  unsigned int* fl = p.flags + (p.forward_only ? 4 : 0);
+  if (tid == 0) {
+    s_step = p.step_counter ? *p.step_counter : 0ull;
+    s_epoch = ld_relaxed_gpu_u32_(&fl[3]);
+  }
 #ifndef DTF_HOST_EMU
   uint64_t* bar_x = reinterpret_cast<uint64_t*>(&bars[0]);
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(&bars[1]);
@@ -202,6 +208,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
   const uint32_t tmem_d2 = tmem_holder + 128;             // B3 accumulator: columns [128, 128 + n2)
 #endif
   const unsigned long long step = s_step;
+  const unsigned int sync_target = (unsigned int)p.G * (s_epoch + 1u);      // what the monotonic counters reach in THIS launch
   const long long row0 = p.nbatches > 0
       ? (long long)((step * (unsigned long long)p.bstride + (unsigned long long)p.boffset) % (unsigned long long)p.nbatches) * p.B
       : 0ll;
@@ -308,7 +315,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
     __syncthreads();
     if (tid == 0) {
       __threadfence();
-      atomicAdd(&p.flags[0], 1u);
+      atomicAdd(&fl[0], 1u);
     }
     STAMP(4);
   }
@@ -318,7 +325,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
   // =====================================================================================================
   if (p.phase_mask & 2) {
     if (fused) {
-      if (tid == 0 && !wait_counter_ge(&p.flags[0], (unsigned int)(p.G * (step + 1ull)), p.timeout_ns) && p.err) atomicExch(p.err, 4u);
+      if (tid == 0 && !wait_counter_ge(&fl[0], sync_target, p.timeout_ns) && p.err) atomicExch(p.err, 4u);
     }
     __syncthreads();
     STAMP(5);
@@ -424,7 +431,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
       __syncthreads();
       if (tid == 0) {
         __threadfence();
-        atomicAdd(&p.flags[1], 1u);
+        atomicAdd(&fl[1], 1u);
       }
     }
     STAMP(6);
@@ -436,7 +443,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
   if ((p.phase_mask & 4) && !p.forward_only) {
 #ifndef DTF_HOST_EMU
     if (tid == 0) {
-      if (fused && !wait_counter_ge(&p.flags[1], (unsigned int)(p.G * (step + 1ull)), p.timeout_ns) && p.err) atomicExch(p.err, 5u);
+      if (fused && !wait_counter_ge(&fl[1], sync_target, p.timeout_ns) && p.err) atomicExch(p.err, 5u);
       fence_proxy_async();
       mbar_arrive_expect_tx(bar_dh, (uint32_t)(4 * dh_chunk));
       for (int q = 0; q < 4; ++q) tma_load_2d(w_sm + q * dh_chunk, &map_dh, bar_dh, 32 * q, 0);      // box {32 units, kb rows}
@@ -508,11 +515,15 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
     }
     STAMP(9);
   }
-  // step counter: advanced by the LAST CTA to get here (ticket), i.e. after every CTA of this launch has read it
-  const bool last_phase = (p.phase_mask & 4) != 0;
-  if (last_phase && tid == 0 && p.step_counter && !p.forward_only) {
-    const unsigned int ticket = atomicAdd(&p.flags[2], 1u);
-    if (ticket + 1u == (unsigned int)(p.G * (step + 1ull))) *p.step_counter = step + 1ull;
+  // launch epoch (+ the device step counter of training launches): advanced by the LAST CTA to get here (ticket), i.e.
+  // after every CTA of this launch has read them
+  const bool last_phase = p.forward_only ? (p.phase_mask & 2) != 0 : (p.phase_mask & 4) != 0;
+  if (last_phase && tid == 0) {
+    const unsigned int ticket = atomicAdd(&fl[2], 1u);
+    if (ticket + 1u == sync_target) {
+      fl[3] = s_epoch + 1u;
+      if (p.step_counter && !p.forward_only) *p.step_counter = step + 1ull;
+    }
   }
 #ifndef DTF_HOST_EMU
   tc_fence_before();

@@ -49,13 +49,14 @@ def test_step_kernel_matches_float64_model(B, D, H, C, nbatches, mask):
     n1 = (H + 15) // 16 * 16
     hpart = torch.zeros(G * 128 * n1, device=dev)
     dh = torch.zeros(128, 128, device=dev)
-    flags = torch.zeros(4, dtype=torch.int32, device=dev)
+    flags = torch.zeros(8, dtype=torch.int32, device=dev)
     gw1, gb1 = torch.full((D, ldw1), 7.0, device=dev), torch.zeros(H, device=dev)
     gw2, gb2 = torch.zeros(H, ldw2, device=dev), torch.zeros(C, device=dev)
     loss, logits = torch.zeros(16, device=dev), torch.zeros(B, C, device=dev)
     step0 = 1 if nbatches else 0
     stepctr = torch.tensor([step0], dtype=torch.int64, device=dev)
-    flags[:3] = G * step0
+    flags[:3] = G * 3
+    flags[3] = 3
     token = torch.tensor([5, 9], dtype=torch.int64, device=dev)
     arrivals = torch.zeros(2, dtype=torch.int64, device=dev)
     err = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -88,7 +89,7 @@ def test_step_kernel_matches_float64_model(B, D, H, C, nbatches, mask):
     assert _rel(gb1, ref["b1"]) < 3e-3 and _rel(gw2[:, :C], ref["w2"]) < 3e-3 and _rel(gb2, ref["b2"]) < 3e-3
     assert int(stepctr[0]) == step0 + 1
     assert int(arrivals[0]) == G and int(arrivals[1]) == 5
-    assert flags[:3].tolist() == [G * (step0 + 1)] * 3
+    assert flags[:4].tolist() == [G * 4] * 3 + [4] and flags[4:].tolist() == [0] * 4
     if mask == 7:
         t = trace.view(16, 16)[:G].cpu()
         assert bool((t[:, 10] > t[:, 0]).all())                    # every CTA stamped entry and exit
@@ -112,7 +113,7 @@ def test_step_kernel_two_consecutive_steps_and_forward_only():
     b1, b2 = torch.zeros(H, device=dev), torch.zeros(C, device=dev)
     G = lib.dtf_mlp_step_slices(D, B, None)
     hpart, dh = torch.zeros(G * 128 * 112, device=dev), torch.zeros(128, 128, device=dev)
-    flags = torch.zeros(4, dtype=torch.int32, device=dev)
+    flags = torch.zeros(8, dtype=torch.int32, device=dev)
     gw1, gb1, gw2, gb2 = (torch.zeros(s, device=dev) for s in ((D, 104), (H,), (H, 16), (C,)))
     loss, logits = torch.zeros(16, device=dev), torch.zeros(B, C, device=dev)
     stepctr = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -149,3 +150,4 @@ def test_step_kernel_two_consecutive_steps_and_forward_only():
     assert _rel(logits, ref_z) < 2e-3
     assert abs(float(loss[:G].sum()) - float(ref_loss)) < 2e-3 * abs(float(ref_loss))
     assert torch.equal(before[0], gw1) and int(arrivals[0]) == before[1] and int(stepctr[0]) == 2
+    assert flags.tolist() == [2 * G, 2 * G, 2 * G, 2, G, 0, G, 1]

@@ -56,7 +56,7 @@ def test_step_kernel_matches_float64_model(emu, B, D, H, C, nbatches):
     n1 = (H + 15) // 16 * 16
     hpart = torch.zeros(G * 128 * n1)
     dh = torch.zeros(128, 128)
-    flags = torch.zeros(4, dtype=torch.int32)
+    flags = torch.zeros(8, dtype=torch.int32)
     gw1, gb1 = torch.full((D, ldw1), 7.0), torch.zeros(H)          # dW1 is STORED (stale content must be overwritten) ...
     gw2, gb2 = torch.zeros(H, ldw2), torch.zeros(C)                # ... the head's sums are ACCUMULATED (the ps clears them)
     loss = torch.zeros(16)
@@ -78,7 +78,8 @@ def test_step_kernel_matches_float64_model(emu, B, D, H, C, nbatches):
     a.num_signals, a.arrivals[0], a.stamp_dst[0], a.stamp_src[0] = 1, _ptr(arrivals), _ptr(arrivals) + 8, _ptr(token)
     a.sys_scope, a.timeout_ns, a.err = 1, 10**9, _ptr(err)
     step0 = int(stepctr[0])
-    flags[:3] = G * step0                                          # counters are monotonic: G per step already run
+    flags[:3] = G * 3                                              # counters are monotonic: as if three launches ran before
+    flags[3] = 3
     assert emu.dtf_mlp_step(ctypes.byref(a), None) == 0
     bi = ((step0 * 2 + 1) % nbatches) if nbatches else 0
     x, y = xs[bi * B:(bi + 1) * B], ys[bi * B:(bi + 1) * B]
@@ -94,7 +95,7 @@ def test_step_kernel_matches_float64_model(emu, B, D, H, C, nbatches):
     torch.testing.assert_close(gb2.double(), ref["b2"], rtol=1e-4, atol=1e-5)
     assert int(stepctr[0]) == step0 + 1                            # CTA 0 advanced the device step counter once
     assert int(arrivals[0]) == G and int(arrivals[1]) == 5         # one arrival per CTA, stamp = the token
-    assert flags[:3].tolist() == [G * (step0 + 1)] * 3
+    assert flags[:4].tolist() == [G * 4] * 3 + [4] and flags[4:].tolist() == [0] * 4
 
 
 def test_forward_only_leaves_gradients_and_protocol_untouched(emu):
@@ -105,7 +106,7 @@ def test_forward_only_leaves_gradients_and_protocol_untouched(emu):
     w1, w2 = torch.randn(D, 104, generator=g) / 28, torch.randn(H, 16, generator=g) / 10
     b1, b2 = torch.zeros(H), torch.zeros(C)
     G = emu.dtf_mlp_step_slices(D, B, None)
-    hpart, dh, flags = torch.zeros(G * 128 * 112), torch.zeros(128, 128), torch.zeros(4, dtype=torch.int32)
+    hpart, dh, flags = torch.zeros(G * 128 * 112), torch.zeros(128, 128), torch.zeros(8, dtype=torch.int32)
     loss, logits = torch.zeros(16), torch.zeros(B, C)
     stepctr, token = torch.zeros(1, dtype=torch.int64), torch.zeros(2, dtype=torch.int64)
     arrivals = torch.zeros(2, dtype=torch.int64)
@@ -123,3 +124,4 @@ def test_forward_only_leaves_gradients_and_protocol_untouched(emu):
     assert abs(float(loss[:G].sum()) - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
     torch.testing.assert_close(logits.double(), ref_z, rtol=1e-4, atol=1e-5)
     assert int(stepctr[0]) == 0 and int(arrivals[0]) == 0 and float(dh.abs().max()) == 0.0
+    assert flags.tolist() == [0, 0, 0, 0, G, 0, G, 1]              # forward-only launches keep their own counters
