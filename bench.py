@@ -3,15 +3,20 @@
 Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` (N>1: launched with
 ``python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...``).  Rank 0 prints ONE
 JSON line.  Config named by BASELINE.json: between-graph parameter server, 784-100-10 MLP, batch 100
-per worker, clipped batch-sum cross-entropy, sync replicas (``replicas_to_aggregate = num_workers``).
-Topology: N GPUs = 1 ps + (N-1) workers (8 GPUs -> 1 ps + 7 workers); 1 GPU = ps and worker share it.
+per worker, clipped batch-sum cross-entropy, sync replicas (``replicas_to_aggregate = num_workers``),
+fp32 storage with TF32 tensor-core multiplies (the reference model is fp32; ``--precision bf16`` = config 3).
+Topology: every listed worker trains (/root/reference/distributed_mnist.py:27-29,120-122): N GPUs = N workers,
+ps shard s shares worker s's GPU; ``--ps-only-task 1`` gives the ps its own GPU (1 ps + (N-1) workers).
 
-* ``value``: whole-job samples/sec from the device-timed region (CUDA events on every rank's stream,
-  barrier + synchronize on both sides, MAX over ranks).  The step loop is captured in CUDA graphs.
+* ``value``: whole-job samples/sec.  A repetition = EXACTLY K steps (one CUDA-graph replay chain) between CUDA events on
+  every rank's stream, after a barrier + synchronize and two untimed alignment steps; MAX over ranks per repetition;
+  repetitions continue until >= 100 ms of timed region were collected; the MEDIAN repetition is reported (``reps``).
 * inputs: a 55 000 x 784 fp32 synthetic MNIST-shaped training set resident in each worker's HBM
-  (172 MB > the 126 MB L2), batches walked in order; fp32 -> bf16 staging is part of every step.
+  (172 MB > the 126 MB L2), batches walked in order; the step kernel's TMA reads them in place.
 * ``e2e``: the same metric through ``PSTrainEngine.step(x, y)`` with, every step, the host->device copy
-  of that step's batch from pinned host memory and a device->host read of the loss.
+  of that step's batch from pinned host memory and a device->host read of the loss (same repetition protocol).
+* ``vs_baseline``: value / the in-repo torch + NCCL + cuBLAS (CUDA-graphed) arm measured in the SAME invocation with the
+  same steps, repetitions and precision (``baseline``: its value, e2e and clocks).  The reference itself cannot run.
 * ``--impl reference``: the reference is TensorFlow-1.x example scripts; TF is not installable in this
   image (no wheel for Python 3.12, no network), so this arm reports ``unavailable``.
 * ``--impl nccl``: the in-repo torch + NCCL + cuBLAS emulation of the same workflow (``baseline/``),
@@ -50,9 +55,14 @@ def parse_args():
     ap.add_argument("--e2e-prefetch", type=int, default=1, help="1: step t+1's H2D overlaps step t (double-buffered staging)")
     ap.add_argument("--graph-step", type=int, default=0,
                     help="resnet18: 1 = capture the worker's forward/backward into a CUDA graph after two eager steps")
-    ap.add_argument("--ps-on-workers", type=int, default=0,
-                    help="1: N workers on N GPUs, ps shard s shares worker s's GPU and stream (no ps-only GPU); "
-                         "0: ranks 0..num_ps-1 are ps-only tasks (the validated topology)")
+    ap.add_argument("--ps-on-workers", type=int, default=1,
+                    help="1 (default): N workers on N GPUs, ps shard s shares worker s's GPU and stream; 0 = --ps-only-task 1")
+    ap.add_argument("--ps-only-task", type=int, default=0, help="1: ranks 0..num_ps-1 are ps-only tasks (1 ps + (N-1) workers)")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16"],
+                    help="tf32: fp32 storage, TF32 MMAs, one-kernel worker step (reference precision); bf16: config 3")
+    ap.add_argument("--min-ms", type=float, default=100.0, help="collect at least this much timed region (repetitions of K steps)")
+    ap.add_argument("--max-reps", type=int, default=400)
+    ap.add_argument("--baseline", type=int, default=1, help="1: also time the torch+NCCL+cuBLAS arm in this invocation -> vs_baseline")
     ap.add_argument("--e2e-pipeline", type=int, default=1,
                     help="1 (one-GPU runs): also time step(..., sync_loss='deferred') -- the loss of step t is read after "
                          "step t+1 was enqueued -- and report the better arm, both kept under e2e.synchronous/.pipelined; "
@@ -383,27 +393,23 @@ def main():
     if args.lr is None:
         args.lr = 0.01 if args.optimizer == "adam" else 0.001
         if args.mode == "async" and args.optimizer != "adam":
-            args.lr /= max(1, args.gpus - (0 if args.ps_on_workers else args.num_ps))   # every push is applied alone: keep the effective rate
+            args.lr /= max(1, args.gpus - (0 if (args.ps_on_workers and not args.ps_only_task) else args.num_ps))   # every push is applied alone
     opt = {"kind": args.optimizer, "lr": args.lr, "momentum": 0.9}
-    pow_ = bool(args.ps_on_workers) and N > 1
+    pow_ = bool(args.ps_on_workers) and not bool(args.ps_only_task) and N > 1
     nw = N if pow_ else N - args.num_ps
     NVLS = {"off": False, "on": True, "auto": "auto"}[args.nvls]
     if args.in_graph and args.nvls == "auto":
         NVLS = False            # one-process topology: opt in with --nvls on
+    common = dict(sync=args.mode == "sync", optimizer=opt, publish_replicas=args.publish, nvls=NVLS, f1_splits=args.f1_splits,
+                  head_ctas=args.head_ctas, f1_block_n=args.f1_block_n, b3_block_n=args.b3_block_n, precision=args.precision)
     if args.in_graph and N > 1:
-        cfg = EngineConfig(num_ps=args.num_ps, num_workers=nw, sync=args.mode == "sync", optimizer=opt, ps_on_workers=pow_,
-                           publish_replicas=args.publish, nvls=NVLS, f1_splits=args.f1_splits, head_ctas=args.head_ctas,
-                           f1_block_n=args.f1_block_n, b3_block_n=args.b3_block_n)
+        cfg = EngineConfig(num_ps=args.num_ps, num_workers=nw, ps_on_workers=pow_, **common)
         fabric = Fabric(N, {r: r for r in range(N)})
     elif N == 1:
-        cfg = EngineConfig(num_ps=1, num_workers=1, colocated=True, sync=args.mode == "sync", optimizer=opt,
-                           publish_replicas=args.publish, nvls=NVLS, f1_splits=args.f1_splits, head_ctas=args.head_ctas,
-                           f1_block_n=args.f1_block_n, b3_block_n=args.b3_block_n)
+        cfg = EngineConfig(num_ps=1, num_workers=1, colocated=True, **common)
         fabric = Fabric(1, {0: local_rank})
     else:
-        cfg = EngineConfig(num_ps=args.num_ps, num_workers=nw, sync=args.mode == "sync", optimizer=opt, ps_on_workers=pow_,
-                           publish_replicas=args.publish, nvls=NVLS, f1_splits=args.f1_splits, head_ctas=args.head_ctas,
-                           f1_block_n=args.f1_block_n, b3_block_n=args.b3_block_n)
+        cfg = EngineConfig(num_ps=args.num_ps, num_workers=nw, ps_on_workers=pow_, **common)
         fabric = Fabric.from_torch_distributed()
     eng = PSTrainEngine(spec, cfg, fabric)
     eng.init_params()
@@ -424,6 +430,12 @@ def main():
             dist.barrier()
         eng.synchronize()
 
+    def allmax(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
     K, W = args.steps, max(args.warmup, 3)
     use_graph = not args.no_graph
     unroll = args.unroll or next(u for u in (50, 40, 32, 25, 20, 16, 10, 8, 5, 4, 2, 1) if K % u == 0)
@@ -433,59 +445,84 @@ def main():
     eng.check_errors()
     if use_graph:
         eng.capture_graphs(unroll, "dataset")
+        k_graphs = eng._graphs
+        eng.capture_graphs(2, "dataset")          # two untimed alignment steps in front of every timed repetition
+        align_graphs = eng._graphs
+        eng._graphs = k_graphs
         eng.replay_graphs(1)
         barrier()
         eng.check_errors()
+
+    def align_steps():
+        if use_graph:
+            eng._graphs = align_graphs
+            eng.replay_graphs(1)
+            eng._graphs = k_graphs
+        else:
+            eng.enqueue_local_steps(2, "dataset")
+
+    def k_steps():
+        if use_graph:
+            eng.replay_graphs(K // unroll)
+            if K % unroll:
+                eng.enqueue_local_steps(K % unroll, "dataset")
+        else:
+            eng.enqueue_local_steps(K, "dataset")
+
+    def measure(body):
+        """Repetitions of EXACTLY K steps: barrier + synchronize, two untimed alignment steps (the sync protocol itself lines
+        the ranks up, so the start skew of the barrier release is not part of the measurement), CUDA events on every local
+        stream around the K steps, MAX over ranks; until >= --min-ms of timed region (at least 3, at most --max-reps)."""
+        times, total = [], 0.0
+        while len(times) < 3 or (total < args.min_ms and len(times) < args.max_reps):
+            barrier()
+            align_steps()
+            evs = []
+            for r, rk in eng.ranks.items():
+                with torch.cuda.device(rk.device):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(rk.stream)
+                    evs.append((e0, e1, rk))
+            body()
+            for e0, e1, rk in evs:
+                e1.record(rk.stream)
+            eng.synchronize()
+            times.append(allmax([max(e0.elapsed_time(e1) for e0, e1, _ in evs)])[0])
+            total += times[-1]
+        return times
 
     # ---- timed region ---------------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
     barrier()
-    evs = {}
     launches0 = cuda_lib.launch_count()
     t0 = time.time()
-    for r, rk in eng.ranks.items():
-        with torch.cuda.device(rk.device):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(rk.stream)
-            evs[r] = (e0, e1)
-    if use_graph:
-        eng.replay_graphs(K // unroll)
-        if K % unroll:
-            eng.enqueue_local_steps(K % unroll, "dataset")
-    else:
-        eng.enqueue_local_steps(K, "dataset")
-    for r, rk in eng.ranks.items():
-        evs[r][1].record(rk.stream)
+    times = measure(k_steps)
     barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
-    launches = cuda_lib.launch_count() - launches0
-    ms_local = max(e0.elapsed_time(e1) for e0, e1 in evs.values())
+    reps = len(times)
+    # kernels launched by the timed K-step regions only (the alignment steps are untimed and not counted)
+    per_rep = (cuda_lib.launch_count() - launches0) // reps
+    per_align = 2 * sum((eng.launches_per_worker_step("dataset") if r in eng.worker_ranks else 0) +
+                        ((1 if cfg.sync else num_workers) if r in eng.ps_ranks else 0) for r in eng.ranks)
+    launches = per_rep - per_align
     eng.check_errors()
-    stats = torch.tensor([ms_local, float(launches)], dtype=torch.float64, device="cuda")
+    ms = statistics.median(times)
+    st = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
-        mx = stats.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = stats.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms, launches_total = float(mx[0]), int(sm[1])
-    else:
-        ms, launches_total = ms_local, launches
+        dist.all_reduce(st, op=dist.ReduceOp.SUM)
+    launches_total = int(st[0])
     value = num_workers * spec.batch * K / (ms / 1e3)
     loss = eng.read_loss() if is_worker else None
-    if world > 1:
-        lt = torch.tensor([loss if loss is not None else -1e30], dtype=torch.float64, device="cuda")
-        dist.all_reduce(lt, op=dist.ReduceOp.MAX)
-        loss = float(lt[0])
+    loss = allmax([loss if loss is not None else -1e30])[0]
     gstep = eng.read_ctl(0, "global_step") if 0 in eng.ranks else None
     stale = eng.staleness() if (args.mode == "async" and 0 in eng.ranks) else None
 
     # ---- end-to-end: public API step(x, y) with H2D of the batch and D2H of the loss every step -----------------
     e2e = None
-    Ke = min(K, 1000) if args.e2e_steps < 0 else args.e2e_steps
-    if Ke > 0:
+    if args.e2e_steps != 0:
         hx = hy = None
         if is_worker:
             n_use = min(args.num_train, 20000)
@@ -494,95 +531,114 @@ def main():
             nb = n_use // spec.batch
         wl = [r for r in eng.ranks if r in eng.worker_ranks]
         woff = eng.worker_ranks.index(wl[0]) if wl else 0
-
         views = [(hx[b * spec.batch:(b + 1) * spec.batch], hy[b * spec.batch:(b + 1) * spec.batch]) for b in range(nb)] \
             if is_worker else []
+        ctr = [0]
+        last = [None]
 
         def batch_of(i):
             return views[(i * num_workers + woff) % nb]
 
-        def e2e_loop(n, start):
+        def e2e_k_steps():
             # every step: H2D of THIS step's batch from pinned host memory (issued one step ahead on the copy stream
             # = input double buffering, overlapping the previous step's kernels) + D2H read of this step's loss
-            last = None
-            for i in range(n):
+            for _ in range(K):
+                i = ctr[0]
                 if is_worker:
-                    x, y = batch_of(start + i)
-                    last = eng.step(x, y, sync_loss=True, prefetch=batch_of(start + i + 1) if args.e2e_prefetch else None)
+                    x, y = batch_of(i)
+                    last[0] = eng.step(x, y, sync_loss=True, prefetch=batch_of(i + 1) if args.e2e_prefetch else None)
                 else:
                     eng.step(sync_loss=False)
-            return last
-        def e2e_loop_pipelined(n, start):
+                ctr[0] += 1
+
+        def e2e_k_steps_pipelined():
             # same copies every step, but step t+1 is enqueued BEFORE step t's loss is waited for (PendingLoss): the
             # host's turnaround overlaps the GPU's work on step t; every loss is still read back, one step late
-            pending = last = None
-            for i in range(n):
+            pending = None
+            for _ in range(K):
+                i = ctr[0]
                 if not is_worker:
-                    eng.step(sync_loss=False)          # ps-only rank: one apply per aggregate, as in the synchronous loop
-                    continue
-                x, y = batch_of(start + i)
-                h = eng.step(x, y, sync_loss="deferred", prefetch=batch_of(start + i + 1))
-                if pending is not None:
-                    last = pending.result()
-                pending = h
-            return pending.result() if pending is not None else last
+                    eng.step(sync_loss=False)
+                else:
+                    x, y = batch_of(i)
+                    h = eng.step(x, y, sync_loss="deferred", prefetch=batch_of(i + 1))
+                    if pending is not None:
+                        last[0] = pending.result()
+                    pending = h
+                ctr[0] += 1
+            if pending is not None:
+                last[0] = pending.result()
 
-        def time_e2e(loop, start):
-            loop(5, start)
-            barrier()
-            te0 = time.time()
-            ee = {}
-            for r, rk in eng.ranks.items():
-                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(rk.stream)
-                ee[r] = (a, b_)
-            last = loop(Ke, start + 5)
-            for r, rk in eng.ranks.items():
-                ee[r][1].record(rk.stream)
-            barrier()
-            ems_local = max(a.elapsed_time(b_) for a, b_ in ee.values())
-            wall_ms = (time.time() - te0) * 1e3
-            t = torch.tensor([max(ems_local, 0.0), wall_ms], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        def align_e2e():
+            for _ in range(2):
+                if is_worker:
+                    x, y = batch_of(ctr[0])
+                    eng.step(x, y, sync_loss=False)
+                else:
+                    eng.step(sync_loss=False)
+                ctr[0] += 1
+
+        def measure_e2e(body):
+            for _ in range(6):           # both staging parities + the CUDA-graphed plans are built by the first steps
+                align_e2e()
+            times, total = [], 0.0
+            while len(times) < 3 or (total < args.min_ms and len(times) < args.max_reps):
+                barrier()
+                align_e2e()
+                evs = []
+                for r, rk in eng.ranks.items():
+                    with torch.cuda.device(rk.device):
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(rk.stream)
+                        evs.append((e0, e1, rk))
+                w0 = time.time()
+                body()
+                for e0, e1, rk in evs:
+                    e1.record(rk.stream)
+                eng.synchronize()
+                wall = (time.time() - w0) * 1e3
+                times.append(allmax([max(max(e0.elapsed_time(e1) for e0, e1, _ in evs), 0.0), wall]))
+                total += times[-1][0]
             eng.check_errors()
-            return float(t[0]), float(t[1]), last
+            return times
 
-        ems, wall, last_loss = time_e2e(e2e_loop, 0)
-        per_step = num_workers * spec.batch * Ke
-        e2e = {"value": per_step / (ems / 1e3), "unit": "samples/sec", "steps": Ke,
-               "ms_per_step": ems / Ke, "wall_ms_per_step": wall / Ke,
+        et = measure_e2e(e2e_k_steps)
+        ems = statistics.median(t[0] for t in et)
+        per_step = num_workers * spec.batch * K
+        e2e = {"value": per_step / (ems / 1e3), "unit": "samples/sec", "steps": K, "reps": len(et),
+               "ms_per_step": ems / K, "wall_ms_per_step": statistics.median(t[1] for t in et) / K,
                "h2d_bytes_per_step": spec.batch * (spec.in_dim + spec.classes) * 4,
-               "d2h_bytes_per_step": 4 * eng.head_ctas,          # the loss partials of the head's CTAs
+               "d2h_bytes_per_step": 4 * eng.head_ctas,          # the loss partials of the step kernel's / head's CTAs
                "api": "PSTrainEngine.step(x_pinned, y_pinned, prefetch=next) -> loss" if args.e2e_prefetch
                else "PSTrainEngine.step(x_pinned, y_pinned) -> loss",
                "input_double_buffering": bool(args.e2e_prefetch), "loss_read": "synchronous, every step",
-               "last_loss": last_loss}
-        if (args.e2e_pipeline == 1 and world == 1 and N == 1 and is_worker) or args.e2e_pipeline == 2:
-            # second arm of the same API: loss handles read one step late.  One process / one GPU only for now (no
-            # cross-rank protocol to disturb if it fails); a failure keeps the synchronous number above.
+               "last_loss": allmax([last[0] if last[0] is not None else -1e30])[0]}
+        if args.e2e_pipeline and ((world == 1 and is_worker) or args.e2e_pipeline == 2 or pow_):
+            # second arm of the same API: loss handles read one step late
             try:
-                pems, pwall, plast = time_e2e(e2e_loop_pipelined, Ke + 5)
-                if is_worker and not (plast is not None and math.isfinite(plast)):
+                pt = measure_e2e(e2e_k_steps_pipelined)
+                pems = statistics.median(t[0] for t in pt)
+                plast = allmax([last[0] if last[0] is not None else -1e30])[0]
+                if not math.isfinite(plast):
                     raise RuntimeError("pipelined loop returned loss %r" % (plast,))
                 sync_part = {k: e2e[k] for k in ("value", "ms_per_step", "wall_ms_per_step", "last_loss")}
-                pipe_part = {"value": per_step / (pems / 1e3), "ms_per_step": pems / Ke, "wall_ms_per_step": pwall / Ke,
-                             "last_loss": plast}
+                pipe_part = {"value": per_step / (pems / 1e3), "ms_per_step": pems / K,
+                             "wall_ms_per_step": statistics.median(t[1] for t in pt) / K, "last_loss": plast}
                 e2e["synchronous"], e2e["pipelined"] = sync_part, pipe_part
                 if pipe_part["value"] > e2e["value"]:
                     e2e.update(pipe_part)
                     e2e["api"] = "PSTrainEngine.step(x_pinned, y_pinned, sync_loss='deferred', prefetch=next) -> PendingLoss; .result()"
                     e2e["loss_read"] = "every step's loss is copied D2H behind its kernels and read by the host one step late"
-            except Exception as e:      # noqa: BLE001 - keep the validated synchronous measurement
+            except Exception as e:      # noqa: BLE001 - keep the synchronous measurement
                 if world > 1:
-                    raise                # ranks must not diverge: --e2e-pipeline 2 is an explicit opt-in without a fallback
+                    raise                # ranks must not diverge
                 e2e["pipelined_error"] = repr(e)[:300]
 
     # ---- ps traffic implied by the measured step time (BASELINE metric: push/pull GB/s vs 900 GB/s/dir) -----------
-    # true-shape bytes: gradients travel as fp32, parameters as the bf16 replica; every worker moves both every step.
+    # true-shape bytes: gradients travel as fp32, parameters as fp32 (tf32 engines) / bf16 replicas; every worker moves both every step.
     n_params = spec.in_dim * spec.hidden + spec.hidden + spec.hidden * spec.classes + spec.classes
     step_s = ms / K / 1e3
-    push_b, pull_b = 4 * n_params, 2 * n_params
+    push_b, pull_b = 4 * n_params, (4 if args.precision == "tf32" else 2) * n_params
     traffic = {"params": n_params, "push_bytes_per_worker_step": push_b, "pull_bytes_per_worker_step": pull_b,
                "ps_ingest_gbps": num_workers * push_b / step_s / 1e9 / max(1, cfg.num_ps),
                "ps_egress_gbps": num_workers * pull_b / step_s / 1e9 / max(1, cfg.num_ps),
@@ -590,34 +646,57 @@ def main():
                        "link-rate measurements of the same kernels at large payloads: profiles/nvls_check_*.json"}
     traffic["ps_ingest_fraction_of_900"] = traffic["ps_ingest_gbps"] / 900.0
     traffic["ps_egress_fraction_of_900"] = traffic["ps_egress_gbps"] / 900.0
+    nvls_on, mc_on = bool(getattr(eng, "nvls", False)), bool(getattr(eng, "nvls_multicast", False))
+    eng.close()
+
+    # ---- the divisor: torch + NCCL + cuBLAS (CUDA-graphed) arm, same invocation / steps / repetitions / precision --------
+    base = None
+    if args.baseline and not args.in_graph:
+        try:
+            from baseline.nccl_ps import run_nccl_baseline
+            bargs = argparse.Namespace(**vars(args))
+            bargs.ps_on_workers, bargs.ps_only_task = int(pow_ or N == 1), int(not pow_ and N > 1)
+            base = run_nccl_baseline(bargs, rank, world, local_rank, sampler_cls=ClockSampler, images=images, labels=labels)
+        except Exception as e:          # noqa: BLE001 - the measured arm must survive a baseline problem
+            if world > 1:
+                raise
+            base = {"error": repr(e)[:300]}
 
     if rank == 0:
         out = {
             "metric": "MNIST MLP samples/sec (whole box, device-timed, max over ranks), sync-replica PS",
             "value": value, "unit": "samples/sec", "n_gpus": N, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic MNIST-shaped 28x28 (55000x784 fp32 in HBM), random-init weights",
-            "impl": "ours",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": (value / base["value"]) if base and base.get("value") else None,
+            "dtype": args.precision,
+            "data": "synthetic MNIST-shaped 28x28 (55000x784 fp32 in HBM), random-init weights",
+            "impl": "ours", "reps": reps, "timed_ms_total": sum(times),
+            "ms_per_step_min_max": [min(times) / K, max(times) / K],
             "config": {"model": "MNIST MLP 784-%d-10, clipped batch-sum xent" % spec.hidden,
                        "global_batch": num_workers * spec.batch, "per_worker_batch": spec.batch,
                        "parallelism": ("ps1+worker1 colocated on one GPU" if N == 1 else "ps%d+worker%d %s%s" % (
                            cfg.num_ps, cfg.num_workers, "in-graph (one client process)" if args.in_graph else "between-graph",
                            ", ps shards on the first workers' GPUs" if cfg.ps_on_workers else "")),
                        "mode": args.mode, "optimizer": args.optimizer, "lr": args.lr,
+                       "precision": ("fp32 storage, TF32 tensor-core multiply, fp32 accumulate" if args.precision == "tf32"
+                                     else "bf16 operands, fp32 accumulate"),
+                       "worker_step": ("one kernel (csrc/mlp_step.cu)" if args.precision == "tf32" else "stage + GEMM + head + GEMM"),
                        "l2": "inputs larger than L2: 172 MB fp32 train split cycled in HBM",
+                       "timing": "median of %d repetitions of exactly %d steps, each after barrier + 2 untimed alignment steps" % (reps, K),
                        "cuda_graph_unroll": unroll if use_graph else 0,
-                       "pull": ("nvls multimem.st publish" if getattr(eng, "nvls", False) and getattr(eng, "nvls_multicast", False)
-                                else "publish-replicas" if (args.publish or getattr(eng, "nvls", False)) else "peer-pull fused in GEMM"),
-                       "push": ("local store + nvls multimem.ld_reduce on the ps" if getattr(eng, "nvls", False) and
-                                getattr(eng, "nvls_multicast", False) else
-                                "local store + ps peer loads" if getattr(eng, "nvls", False) else "peer stores fused in GEMM epilogue"),
-                       "f1_splits": args.f1_splits, "head_ctas": args.head_ctas, "f1_block_n": args.f1_block_n,
-                       "b3_block_n": args.b3_block_n},
+                       "pull": ("nvls multimem.st publish into fp32/bf16 replicas" if nvls_on and mc_on
+                                else "publish-replicas" if (args.publish or nvls_on) else "peer-pull by TMA inside the step / GEMM kernel"),
+                       "push": ("local store + nvls multimem.ld_reduce on the ps" if nvls_on and mc_on else
+                                "local store + ps peer loads" if nvls_on else "peer stores from the TMEM epilogue")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total, "ps_traffic": traffic,
             "final_loss": loss, "global_step": gstep, "staleness": stale,
         }
+        if base is not None:
+            out["baseline"] = {k: base.get(k) for k in ("impl", "value", "ms_per_step", "reps", "clocks", "e2e", "error", "config")
+                               if base.get(k) is not None}
+            if e2e and base.get("e2e") and base["e2e"].get("value"):
+                out["vs_baseline_e2e"] = e2e["value"] / base["e2e"]["value"]
         print(json.dumps(out))
-    eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

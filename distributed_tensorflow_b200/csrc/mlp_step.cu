@@ -86,11 +86,11 @@ struct MlpStepParams {
   int forward_only;            // 1: stop after the loss / logits (no gradients, no arrival)
   // ---- ps protocol
   int num_tokens;
-  const unsigned long long* token[2];   // mailbox token words: wait until >= step (per ps shard holding a parameter)
+  const unsigned long long* token[4];   // mailbox token words: wait until >= step (per ps shard holding a parameter)
   int num_signals;
-  unsigned long long* arrivals[2];      // ps arrival counters (+1 per CTA per push)
-  unsigned long long* stamp_dst[2];
-  const unsigned long long* stamp_src[2];
+  unsigned long long* arrivals[4];      // ps arrival counters (+1 per CTA per push)
+  unsigned long long* stamp_dst[4];
+  const unsigned long long* stamp_src[4];
   int sys_scope;               // 0: the ps shares this GPU (gpu-scope fences suffice)
   unsigned long long timeout_ns;
   unsigned int* err;
@@ -564,8 +564,8 @@ struct DtfMlpStepArgs {
   float* loss_out; float* logits_out;
   unsigned long long* step_counter;
   int forward_only;
-  int num_tokens; const unsigned long long* token[2];
-  int num_signals; unsigned long long* arrivals[2]; unsigned long long* stamp_dst[2]; const unsigned long long* stamp_src[2];
+  int num_tokens; const unsigned long long* token[4];
+  int num_signals; unsigned long long* arrivals[4]; unsigned long long* stamp_dst[4]; const unsigned long long* stamp_src[4];
   int sys_scope;
   unsigned long long timeout_ns;
   unsigned int* err;
@@ -627,9 +627,10 @@ int dtf_mlp_step(const DtfMlpStepArgs* a, cudaStream_t s) {
   p.gw1 = a->gw1; p.ldgw1 = a->ldgw1; p.gb1 = a->gb1; p.gw2 = a->gw2; p.ldgw2 = a->ldgw2; p.gb2 = a->gb2;
   p.clip_min = a->clip_min; p.loss_out = a->loss_out; p.logits_out = a->logits_out;
   p.step_counter = a->step_counter; p.forward_only = a->forward_only;
-  p.num_tokens = a->num_tokens > 2 ? 2 : a->num_tokens;
-  p.num_signals = a->num_signals > 2 ? 2 : a->num_signals;
-  for (int i = 0; i < 2; ++i) {
+  if (a->num_tokens > 4 || a->num_signals > 4) return -2;
+  p.num_tokens = a->num_tokens;
+  p.num_signals = a->num_signals;
+  for (int i = 0; i < 4; ++i) {
     p.token[i] = a->token[i]; p.arrivals[i] = a->arrivals[i]; p.stamp_dst[i] = a->stamp_dst[i]; p.stamp_src[i] = a->stamp_src[i];
   }
   p.sys_scope = a->sys_scope;

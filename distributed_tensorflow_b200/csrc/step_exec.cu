@@ -26,9 +26,11 @@ extern "C" {
 struct DtfGemmArgs;
 struct DtfMlpHeadArgs;
 struct DtfPsApplyArgs;
+struct DtfMlpStepArgs;
 int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream);
 int dtf_mlp_head(const DtfMlpHeadArgs* a, cudaStream_t s);
 int dtf_ps_apply(const DtfPsApplyArgs* a, cudaStream_t s);
+int dtf_mlp_step(const DtfMlpStepArgs* a, cudaStream_t s);
 int dtf_convert_f32_bf16(const float* in, long long ld_in, void* out, long long ld_out, long long rows, long long cols,
                          long long cols_pad, cudaStream_t s);
 int dtf_wait_token(const void* mailbox, unsigned long long target, const unsigned long long* target_ptr,
@@ -54,7 +56,8 @@ enum DtfOpKind {
   DTF_OP_SYNC = 10,       // cudaStreamSynchronize
   DTF_OP_EVENT_RECORD = 11,   // p0 = cudaEvent_t
   DTF_OP_EVENT_WAIT = 12,     // p0 = cudaEvent_t (cross-stream dependency)
-  DTF_OP_GRAPH = 13           // p0 = cudaGraphExec_t captured from a kernel-only op range (dtf_capture_ops)
+  DTF_OP_GRAPH = 13,          // p0 = cudaGraphExec_t captured from a kernel-only op range (dtf_capture_ops)
+  DTF_OP_MLP_STEP = 14        // p0 = DtfMlpStepArgs*: the whole worker step of the MLP as one kernel (csrc/mlp_step.cu)
 };
 
 struct DtfStepOp {
@@ -101,6 +104,10 @@ int dtf_run_ops(const DtfStepOp* ops, int n, int device, cudaStream_t stream, in
         break;
       case DTF_OP_PS_APPLY:
         rc = dtf_ps_apply(reinterpret_cast<const DtfPsApplyArgs*>(o.p0), stream);
+        ++kernels;
+        break;
+      case DTF_OP_MLP_STEP:
+        rc = dtf_mlp_step(reinterpret_cast<const DtfMlpStepArgs*>(o.p0), stream);
         ++kernels;
         break;
       case DTF_OP_WAIT_TOKEN:

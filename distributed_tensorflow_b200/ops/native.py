@@ -159,7 +159,7 @@ def softmax_xent(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 # batch normalisation (training mode, batch statistics) + residual add + ReLU
 # ---------------------------------------------------------------------------
-_FUSED_BN = os.environ.get("DTF_FUSED_NN", os.environ.get("DTF_FUSED_BN", "0")) == "1"      # csrc/nn_kernels.cu: opt-in until its first hardware run
+_FUSED_BN = os.environ.get("DTF_FUSED_NN", os.environ.get("DTF_FUSED_BN", "1")) == "1"      # csrc/nn_kernels.cu (validated on hardware in round 2)
 
 
 def bn_train_reference(x, scale, offset, residual=None, relu=False, eps: float = 1e-5):

@@ -15,6 +15,12 @@ mode applies every push immediately and measures staleness -- but all of it runs
 * the ps step is one kernel: ``ps_apply`` (wait for arrivals -> N-way reduce -> mean -> apply ->
   publish bf16 shadow -> release tokens).
 
+``EngineConfig.precision`` selects the worker's arithmetic: ``"tf32"`` (default; the reference model is fp32,
+/root/reference/distributed_mnist.py:98-113): parameters, activations and gradients stay fp32 in memory, the two large
+GEMMs run as TF32 on the tensor cores, and the WHOLE worker step is ONE kernel (``csrc/mlp_step.cu``: token wait, W1
+pulled by TMA as the B operand, fused head, dW1 pushed from TMEM, arrival) -- a step is two launches, worker + ps;
+``"bf16"`` (BASELINE config 3): bf16 parameter replica and activations, the three-kernel chain described above.
+
 No NCCL, cuBLAS or host round trip is on the step path.  ``torch.distributed`` is used once, to
 exchange IPC handles, and by the benchmark for barriers.
 
@@ -34,7 +40,7 @@ import numpy as np
 import torch
 
 from ..ops import cuda_lib
-from ..ops.cuda_lib import MAX_WORKERS, GemmArgs, MlpHeadArgs, PsApplyArgs, round_up
+from ..ops.cuda_lib import MAX_WORKERS, GemmArgs, MlpHeadArgs, MlpStepArgs, PsApplyArgs, round_up
 from .fabric import Fabric, FabricBuffer, view_tensor
 
 __all__ = ["MLPSpec", "EngineConfig", "PSTrainEngine", "PendingLoss", "smoke_step", "VarLayout"]
@@ -91,6 +97,8 @@ class EngineConfig:
     nvls: Any = False                     # True/"auto": symmetric VMM buffers -- gradients stay in the WORKERS' HBM and the
                                           # ps sums them with multimem.ld_reduce (in-switch), parameters are published with
                                           # ONE multimem.st stream into every GPU's replica ("auto": only if the box has NVLS)
+    precision: str = "tf32"               # "tf32": fp32 storage, TF32 tensor-core GEMMs, one-kernel worker step (mlp_step.cu);
+                                          # "bf16": bf16 replica / activations, GEMM + head + GEMM kernels
     f1_splits: int = 1                    # split-K CTAs for the first GEMM (fp32 atomic partials, bias+ReLU in the head)
     head_ctas: int = 8                    # row-parallel CTAs of the fused head (batch reductions via fp32 atomics)
     f1_block_n: int = 64                  # N tile of the forward GEMM (0: one tile covering `hidden`)
@@ -155,6 +163,11 @@ class PSTrainEngine:
             raise ValueError("at most %d workers" % MAX_WORKERS)
         if spec.batch > 128 or spec.hidden > 256 or spec.classes > 16:
             raise ValueError("the fused MLP head handles batch<=128, hidden<=256, classes<=16")
+        if cfg.precision not in ("tf32", "bf16"):
+            raise ValueError("precision must be 'tf32' or 'bf16'")
+        self.tf32 = cfg.precision == "tf32"
+        if self.tf32 and (spec.hidden > 128 or cfg.num_ps > 4):
+            raise ValueError("the one-kernel tf32 step handles hidden<=128 and <=4 ps shards; use precision='bf16'")
         self.world = fabric.world_size
         if cfg.colocated:
             assert self.world == 1 and cfg.num_ps == 1 and cfg.num_workers == 1
@@ -200,6 +213,14 @@ class PSTrainEngine:
         self.block_n_f1 = cfg.f1_block_n or bn
         self.block_n_b3 = cfg.b3_block_n or bn
         self.ctas_per_push[lw["hid_w"].shard] += self.m_tiles_w1 * ((spec.hidden + self.block_n_b3 - 1) // self.block_n_b3)
+        if self.tf32:
+            # one kernel of G CTAs does the whole step; every CTA signals every shard that holds one of the four variables
+            ds = ctypes.c_int(0)
+            self.step_ctas = int(self.lib.dtf_mlp_step_slices(spec.in_dim, spec.batch, ctypes.byref(ds)))
+            self.step_slice = int(ds.value)
+            self.head_ctas = self.step_ctas                        # loss partials per step
+            self.var_shards = sorted({lw[v].shard for v in ("hid_w", "hid_b", "sm_w", "sm_b")})
+            self.ctas_per_push = [self.step_ctas if s in self.var_shards else 0 for s in range(cfg.num_ps)]
         self._allocate()
         self._exchange()
         self._build_launches()
@@ -221,11 +242,13 @@ class PSTrainEngine:
                 want = False
             elif level == 0:
                 raise RuntimeError("nvls=True needs CUDA VMM (POSIX fd export); not available on this machine")
+            elif self.tf32 and level < 2:
+                want = False            # fp32 replicas are published with multimem.st only: no multicast -> unicast fabric
         if want and self.world > 1:
             self.nvls = True
             for s in range(cfg.num_ps):
                 self.sym_grads.append(f.alloc_symmetric("sgrads%d" % s, self.shard_elems[s] * 4))
-                self.sym_repl.append(f.alloc_symmetric("srepl%d" % s, self.shard_elems[s] * 2))
+                self.sym_repl.append(f.alloc_symmetric("srepl%d" % s, self.shard_elems[s] * (4 if self.tf32 else 2)))
             self.nvls_multicast = self.sym_grads[0].multicast
         for r, rk in self.ranks.items():
             if r in self.ps_ranks:
@@ -250,6 +273,10 @@ class PSTrainEngine:
                          ("xf32_w%d" % w, 128 * spec.in_dim * 4),
                          ("h_w%d" % w, 128 * ldh * 2), ("dh_w%d" % w, 128 * ldh * 2), ("hacc_w%d" % w, 128 * ldh * 4),
                          ("misc_w%d" % w, 4096 + cfg.loss_hist * 4)]
+                if self.tf32:
+                    # scratch of the one-kernel step: partial pre-activations + dh (L2 resident), 8 sync counters, phase stamps
+                    nfl = int(self.lib.dtf_mlp_step_scratch_floats(spec.in_dim, spec.batch, spec.hidden))
+                    names += [("stepscr_w%d" % w, nfl * 4), ("stepflags_w%d" % w, 256), ("steptrace_w%d" % w, 16 * 16 * 8)]
                 for s in range(cfg.num_ps):
                     if self.nvls:
                         rk.bufs["replica%d_w%d" % (s, w)] = self.sym_repl[s].local(r)
@@ -327,20 +354,30 @@ class PSTrainEngine:
                 b[0] = float(self.opt.get("beta1", 0.9))
                 b[1] = float(self.opt.get("beta2", 0.999))
                 n = self.shard_elems[s]
-                rc = self.lib.dtf_ps_publish(rk.bufs["master%d" % s].ptr, rk.bufs["shadow%d" % s].ptr, n,
-                                             rk.stream.cuda_stream)
-                assert rc == 0, rc
-                if cfg.publish_replicas or self.nvls:
-                    sh = rk.bufs["shadow%d" % s].tensor(torch.bfloat16, 0, n)
-                    for w in range(cfg.num_workers):
-                        self.peer[(r, "replica%d_w%d" % (s, w))].tensor(torch.bfloat16, 0, n).copy_(sh)
+                if self.tf32:
+                    # fp32 end to end: workers read the master itself (same GPU / NVLink peer loads by TMA) or, under
+                    # NVLS, their fp32 replica of it
+                    if self.nvls:
+                        m = rk.bufs["master%d" % s].tensor(torch.float32, 0, n)
+                        rk.bufs["shadow%d" % s].tensor(torch.float32, 0, n).copy_(m)
+                        for w in range(cfg.num_workers):
+                            self.peer[(r, "replica%d_w%d" % (s, w))].tensor(torch.float32, 0, n).copy_(m)
+                else:
+                    rc = self.lib.dtf_ps_publish(rk.bufs["master%d" % s].ptr, rk.bufs["shadow%d" % s].ptr, n,
+                                                 rk.stream.cuda_stream)
+                    assert rc == 0, rc
+                    if cfg.publish_replicas or self.nvls:
+                        sh = rk.bufs["shadow%d" % s].tensor(torch.bfloat16, 0, n)
+                        for w in range(cfg.num_workers):
+                            self.peer[(r, "replica%d_w%d" % (s, w))].tensor(torch.bfloat16, 0, n).copy_(sh)
             rk.stream.synchronize()
         for r, rk in self.ranks.items():
             if r in self.worker_ranks:
                 w = self.worker_ranks.index(r)
                 with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
                     for name in ("mailbox_w%d" % w, "misc_w%d" % w, "x16_w%d" % w, "h_w%d" % w, "dh_w%d" % w,
-                                 "labels_w%d" % w, "hacc_w%d" % w):
+                                 "labels_w%d" % w, "hacc_w%d" % w, "xf32_w%d" % w) + \
+                            (("stepscr_w%d" % w, "stepflags_w%d" % w, "steptrace_w%d" % w) if self.tf32 else ()):
                         rk.bufs[name].tensor(torch.uint8).zero_()
                     for sg in self.sym_grads:
                         sg.local(r).tensor(torch.uint8).zero_()
@@ -489,6 +526,40 @@ class PSTrainEngine:
             g3.block_n_override = self.block_n_b3
             d["g3"] = g3
             d["extra_wait_shards"] = [s for s in range(cfg.num_ps) if s != lay["hid_w"].shard]
+            if self.tf32:
+                # ---- the whole step as one kernel (csrc/mlp_step.cu): fp32 parameters read in place ------------------
+                def psrc(l: VarLayout) -> int:
+                    if self.nvls:
+                        return rk.bufs["replica%d_w%d" % (l.shard, w)].ptr + l.offset * 4       # local fp32 replica
+                    return self.peer[(r, "master%d" % l.shard)].ptr + l.offset * 4              # the ps's master (same GPU / NVLink)
+
+                scr = rk.bufs["stepscr_w%d" % w]
+                n1 = round_up(H, 16)
+
+                def step_args(x_ptr: int, x_rows: int, lab_ptr: int, nbatches: int = 0, rows: int = B) -> MlpStepArgs:
+                    a = MlpStepArgs()
+                    a.B, a.D, a.H, a.C, a.G, a.phase_mask = rows, D, H, C, self.step_ctas, 7
+                    a.x, a.ldx, a.x_rows = x_ptr, D, x_rows
+                    a.labels, a.ldl = lab_ptr, C
+                    a.nbatches, a.bstride, a.boffset = nbatches, cfg.num_workers, w
+                    a.w1, a.ldw1, a.b1 = psrc(lay["hid_w"]), lay["hid_w"].pitch, psrc(lay["hid_b"])
+                    a.w2, a.ldw2, a.b2 = psrc(lay["sm_w"]), lay["sm_w"].pitch, psrc(lay["sm_b"])
+                    a.hpart, a.dh, a.lddh = scr.ptr, scr.ptr + self.step_ctas * 128 * n1 * 4, 128
+                    a.flags = rk.bufs["stepflags_w%d" % w].ptr
+                    a.gw1, a.ldgw1, a.gb1 = slot(lay["hid_w"]), lay["hid_w"].pitch, slot(lay["hid_b"])
+                    a.gw2, a.ldgw2, a.gb2 = slot(lay["sm_w"]), lay["sm_w"].pitch, slot(lay["sm_b"])
+                    a.clip_min, a.loss_out, a.step_counter = cfg.clip_min, d["loss_ptr"], d["stepctr_ptr"]
+                    a.num_tokens = a.num_signals = len(self.var_shards)
+                    for i, sh in enumerate(self.var_shards):
+                        a.token[i] = mb.ptr + sh * self.mb_bytes
+                        a.arrivals[i] = ctl_arrivals(sh)
+                        a.stamp_dst[i] = ctl_arrivals(sh) + 8
+                        a.stamp_src[i] = mb.ptr + sh * self.mb_bytes + (0 if cfg.sync else 8)
+                    a.sys_scope = 0 if cfg.colocated else 1
+                    a.timeout_ns, a.err = cfg.timeout_ns, d["err_ptr"]
+                    return a
+                d["step_args"] = step_args
+                d["step_staged"] = step_args(rk.bufs["xf32_w%d" % w].ptr, 128, rk.bufs["labels_w%d" % w].ptr)
             self._w[r] = d
         self._p: Dict[int, PsApplyArgs] = {}
         for r, rk in self.ranks.items():
@@ -503,11 +574,16 @@ class PSTrainEngine:
             for w in range(cfg.num_workers):
                 a.grad[w] = self.peer[(r, "sgrads%d_w%d" % (s, w))].ptr if self.nvls else rk.bufs["grads%d" % s].ptr + w * n * 4
                 a.mailbox[w] = self.peer[(r, "mailbox_w%d" % w)].ptr + s * self.mb_bytes
-                if cfg.publish_replicas or (self.nvls and not self.nvls_multicast):
+                if (cfg.publish_replicas or (self.nvls and not self.nvls_multicast)) and not self.tf32:
                     a.replica[w] = self.peer[(r, "replica%d_w%d" % (s, w))].ptr
+            if self.tf32:
+                a.shadow = None                                  # no bf16 copy: the fp32 master (or its multicast replica) is the pull source
             if self.nvls and self.nvls_multicast:
                 a.grad_mc = self.sym_grads[s].mc(r)
-                a.shadow_mc = self.sym_repl[s].mc(r)
+                if self.tf32:
+                    a.master_mc = self.sym_repl[s].mc(r)         # ONE multimem.st of fp32 parameters into every GPU's replica
+                else:
+                    a.shadow_mc = self.sym_repl[s].mc(r)
             a.n, a.num_workers, a.replicas_to_aggregate = n, cfg.num_workers, self.R
             a.ctas_per_push = self.ctas_per_push[s]
             a.mode, a.kind = (0 if cfg.sync else 1), self.kind
@@ -516,9 +592,9 @@ class PSTrainEngine:
             a.beta1, a.beta2, a.eps = float(self.opt.get("beta1", 0.9)), float(self.opt.get("beta2", 0.999)), \
                 float(self.opt.get("eps", self.opt.get("epsilon", 1e-8)))
             a.nesterov = int(bool(self.opt.get("nesterov", False)))
-            a.publish_replicas = int(cfg.publish_replicas or (self.nvls and not self.nvls_multicast))
+            a.publish_replicas = int((cfg.publish_replicas or (self.nvls and not self.nvls_multicast)) and not self.tf32)
             a.num_zero = 0
-            if self.head_ctas > 1:
+            if self.head_ctas > 1 or self.tf32:
                 # the row-parallel head accumulates dW2 / db2 / db1 with atomics: clear those slot ranges after reading
                 for vn in ("sm_w", "sm_b", "hid_b"):
                     l = lay[vn]
@@ -535,6 +611,8 @@ class PSTrainEngine:
     # stepping
     # ------------------------------------------------------------------------------------------------
     def launches_per_worker_step(self, source: str = "staged") -> int:
+        if self.tf32:
+            return 1
         any_w = next(iter(self._w.values()), None)
         extra = len(any_w["extra_wait_shards"]) if any_w else 0
         nhead = len(any_w["head_ctls"]) if any_w else 0
@@ -551,6 +629,10 @@ class PSTrainEngine:
             lab = torch.as_tensor(labels, dtype=torch.float32).contiguous().to(rk.device)
         d["ds_images"], d["ds_labels"], d["ds_nbatches"] = img, lab, img.shape[0] // B
         assert d["ds_nbatches"] >= 1
+        if self.tf32:
+            # the step kernel's TMA reads the batch straight out of the dataset (row = batch index x B, from the device step
+            # counter): no staging pass at all
+            d["step_ds"] = d["step_args"](img.data_ptr(), img.shape[0], lab.data_ptr(), d["ds_nbatches"])
 
     def enqueue_worker_step(self, rank: int, source: str = "staged") -> None:
         """Enqueue one worker step on the rank's stream.  ``source='staged'``: the batch is already in the
@@ -561,6 +643,15 @@ class PSTrainEngine:
         lib = self.lib
         w = self.worker_ranks.index(rank)
         n = 0
+        if self.tf32:
+            a = d["step_ds"] if source == "dataset" else d["step_staged"]
+            with torch.cuda.device(rk.device):
+                rc = lib.dtf_mlp_step(ctypes.byref(a), st)
+            assert rc == 0, "mlp_step rc=%d" % rc
+            cuda_lib._bump(1)
+            rk.step += 1
+            self._last_step_launches = 1
+            return
         with torch.cuda.device(rk.device):
             def stage_next():
                 rc_ = lib.dtf_stage_from_dataset(d["ds_images"].data_ptr(), d["ds_labels"].data_ptr(), d["ds_nbatches"],
@@ -620,6 +711,8 @@ class PSTrainEngine:
             xf = rk.bufs["xf32_w%d" % w].tensor(torch.float32, 0, B * D).view(B, D)
             xf.copy_(x, non_blocking=True)
             rk.bufs["labels_w%d" % w].tensor(torch.float32, 0, B * C).view(B, C).copy_(y, non_blocking=True)
+            if self.tf32:
+                return                    # the step kernel reads the fp32 staging buffer in place
             rc = self.lib.dtf_convert_f32_bf16(xf.data_ptr(), D, rk.bufs["x16_w%d" % w].ptr, D, B, D, D,
                                                rk.stream.cuda_stream)
             assert rc == 0, rc
@@ -640,7 +733,7 @@ class PSTrainEngine:
         got = getattr(self, "_native_plans", None)
         if got is not None:
             return got
-        from ..ops.cuda_lib import (OP_CONVERT, OP_D2H, OP_GEMM, OP_H2D, OP_HEAD, OP_PS_APPLY, OP_SIGNAL, OP_SYNC,
+        from ..ops.cuda_lib import (OP_CONVERT, OP_D2H, OP_GEMM, OP_H2D, OP_HEAD, OP_MLP_STEP, OP_PS_APPLY, OP_SIGNAL, OP_SYNC,
                                     OP_WAIT_TOKEN, StepOp, StepPlan)
         OP_EVENT_RECORD, OP_EVENT_WAIT = 11, 12
         B, D, C = self.spec.batch, self.spec.in_dim, self.spec.classes
@@ -682,20 +775,27 @@ class PSTrainEngine:
                         g1p, hdp, g3p = type(g1).from_buffer_copy(g1), type(hd).from_buffer_copy(hd), type(g3).from_buffer_copy(g3)
                         g1p.a, g3p.a, hdp.labels = x16, x16, lab
                     cops = [StepOp(kind=OP_EVENT_WAIT, p0=done[par].cuda_event),
-                            StepOp(kind=OP_H2D, p0=xf, p1=None, i0=B * D * 4), StepOp(kind=OP_H2D, p0=lab, p1=None, i0=B * C * 4),
-                            StepOp(kind=OP_CONVERT, p0=xf, p1=x16, i0=D, i1=D, i2=B, i3=D, i4=D),
-                            StepOp(kind=OP_EVENT_RECORD, p0=ready[par].cuda_event)]
+                            StepOp(kind=OP_H2D, p0=xf, p1=None, i0=B * D * 4), StepOp(kind=OP_H2D, p0=lab, p1=None, i0=B * C * 4)]
+                    if not self.tf32:
+                        cops.append(StepOp(kind=OP_CONVERT, p0=xf, p1=x16, i0=D, i1=D, i2=B, i3=D, i4=D))
+                    cops.append(StepOp(kind=OP_EVENT_RECORD, p0=ready[par].cuda_event))
                     plans["copy"][r].append(StepPlan(cops, rk.device.index, copy_stream.cuda_stream))
                     ops = [StepOp(kind=OP_EVENT_WAIT, p0=ready[par].cuda_event)]
-                    for s_ in d["extra_wait_shards"]:
-                        ops.append(StepOp(kind=OP_WAIT_TOKEN, p0=rk.bufs["mailbox_w%d" % w].ptr + s_ * self.mb_bytes,
-                                          p1=d["stepctr_ptr"], p2=d["err_ptr"], i0=0, u0=self.cfg.timeout_ns))
-                    ops.append(StepOp(kind=OP_GEMM, p0=ctypes.addressof(g1p)))
-                    ops.append(StepOp(kind=OP_HEAD, p0=ctypes.addressof(hdp)))
-                    for ctl_ptr, mbp in zip(d["head_ctls"][1:], d["head_mailboxes"][1:]):
-                        ops.append(StepOp(kind=OP_SIGNAL, p0=ctl_ptr, p1=mbp, i0=w, i1=hd.stamp_from_version))
-                    ops.append(StepOp(kind=OP_GEMM, p0=ctypes.addressof(g3p)))
-                    keep = [g1p, hdp, g3p]
+                    if self.tf32:
+                        # fp32 staging buffer read in place by the step kernel's TMA: H2D -> ONE kernel -> (ps apply)
+                        sp = d["step_staged"] if par == 0 else d["step_args"](xf, 128, lab)
+                        ops.append(StepOp(kind=OP_MLP_STEP, p0=ctypes.addressof(sp)))
+                        keep = [sp]
+                    else:
+                        for s_ in d["extra_wait_shards"]:
+                            ops.append(StepOp(kind=OP_WAIT_TOKEN, p0=rk.bufs["mailbox_w%d" % w].ptr + s_ * self.mb_bytes,
+                                              p1=d["stepctr_ptr"], p2=d["err_ptr"], i0=0, u0=self.cfg.timeout_ns))
+                        ops.append(StepOp(kind=OP_GEMM, p0=ctypes.addressof(g1p)))
+                        ops.append(StepOp(kind=OP_HEAD, p0=ctypes.addressof(hdp)))
+                        for ctl_ptr, mbp in zip(d["head_ctls"][1:], d["head_mailboxes"][1:]):
+                            ops.append(StepOp(kind=OP_SIGNAL, p0=ctl_ptr, p1=mbp, i0=w, i1=hd.stamp_from_version))
+                        ops.append(StepOp(kind=OP_GEMM, p0=ctypes.addressof(g3p)))
+                        keep = [g1p, hdp, g3p]
                     if r in self.ps_ranks:
                         # ps and worker share the GPU and the stream: the apply joins the worker's plan (one graph)
                         ops += [StepOp(kind=OP_PS_APPLY, p0=ctypes.addressof(self._p[r]))
@@ -878,6 +978,73 @@ class PSTrainEngine:
                 n += k
         cuda_lib._bump(n)
         return n
+
+    # ------------------------------------------------------------------------------------------------
+    # forward only: validation / prediction on the fabric (reference distributed_mnist.py:160-165, distributed_mnist_predict.py:28-43)
+    # ------------------------------------------------------------------------------------------------
+    def evaluate(self, x, y=None, rank: Optional[int] = None) -> Dict[str, Any]:
+        """Forward pass of the CURRENT parameters over ``x`` ([N, in_dim], any N; host or device fp32) on a local worker GPU,
+        enqueued behind that worker's training steps: returns ``{"logits": [N, classes] (device), "loss": batch-SUM clipped
+        cross-entropy (if ``y`` one-hot [N, classes] is given), "accuracy", "correct"}``.  Nothing is pushed, no token is
+        consumed, the step counter does not move.  tf32 engines run the step kernel in forward-only mode over 128-row
+        tiles (TMA-fed TF32 MMAs, parameters read from the worker's replica / the ps); bf16 engines run the bf16 GEMM +
+        softmax kernels of the op layer on the ps's published parameters."""
+        r = rank if rank is not None else next(q for q in self.worker_ranks if q in self.ranks)
+        rk, d = self.ranks[r], self._w[r]
+        spec = self.spec
+        C, D = spec.classes, spec.in_dim
+        with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
+            xd = torch.as_tensor(x, dtype=torch.float32).to(rk.device, non_blocking=True).contiguous()
+            N = xd.shape[0]
+            yd = None if y is None else torch.as_tensor(y, dtype=torch.float32).to(rk.device, non_blocking=True).contiguous()
+            lab = yd if yd is not None else torch.zeros((N, C), dtype=torch.float32, device=rk.device)
+            logits = torch.empty((N, C), dtype=torch.float32, device=rk.device)
+            if self.tf32:
+                nch = (N + 127) // 128
+                lossbuf = torch.zeros((nch, 16), dtype=torch.float32, device=rk.device)
+                for i in range(nch):
+                    rows = min(128, N - i * 128)
+                    a = d["step_args"](xd.data_ptr() + i * 128 * D * 4, rows, lab.data_ptr() + i * 128 * C * 4, 0, rows)
+                    a.forward_only, a.num_signals = 1, 0
+                    a.logits_out, a.loss_out = logits.data_ptr() + i * 128 * C * 4, lossbuf.data_ptr() + i * 64
+                    rc = self.lib.dtf_mlp_step(ctypes.byref(a), rk.stream.cuda_stream)
+                    assert rc == 0, "mlp_step(forward_only) rc=%d" % rc
+                cuda_lib._bump(nch)
+                loss = lossbuf.sum() if yd is not None else None
+            else:
+                lay = self.layout
+                if rk.rank in self.ps_ranks or self.world == 1:
+                    pv = {k: self._var_view(rk, "master", lay[k]) for k in ("hid_w", "hid_b", "sm_w", "sm_b")}
+                else:
+                    pv = {k: self._peer_var_view(r, lay[k]) for k in ("hid_w", "hid_b", "sm_w", "sm_b")}
+                # wait for the apply that follows this worker's last step (same acquire the next training step would do)
+                for s_ in range(self.cfg.num_ps):
+                    rc = self.lib.dtf_wait_token(rk.bufs["mailbox_w%d" % self.worker_ranks.index(r)].ptr + s_ * self.mb_bytes, 0,
+                                                 d["stepctr_ptr"], self.cfg.timeout_ns, d["err_ptr"], rk.stream.cuda_stream)
+                    assert rc == 0, rc
+                h = cuda_lib.gemm(xd, pv["hid_w"].contiguous(), bias=pv["hid_b"].contiguous(), relu=True, precision="bf16")
+                logits = cuda_lib.gemm(h, pv["sm_w"].contiguous(), bias=pv["sm_b"].contiguous(), precision="bf16")
+                loss = None
+                if yd is not None:
+                    loss, _ = cuda_lib.softmax_xent_fwd_bwd(logits, yd, self.cfg.clip_min, reduce_sum=True)
+            out: Dict[str, Any] = {"logits": logits}
+            if yd is not None:
+                pred = cuda_lib.argmax_rows(logits)
+                correct = int((pred == yd.argmax(dim=1)).sum())
+                out.update(loss=float(loss), correct=correct, accuracy=correct / max(N, 1), count=N)
+        return out
+
+    def predict(self, x, rank: Optional[int] = None) -> torch.Tensor:
+        """argmax of the forward pass (reference distributed_mnist_predict.py:33,41) as an int64 device tensor."""
+        r = rank if rank is not None else next(q for q in self.worker_ranks if q in self.ranks)
+        rk = self.ranks[r]
+        logits = self.evaluate(x, None, rank=r)["logits"]
+        with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
+            return cuda_lib.argmax_rows(logits)
+
+    def _peer_var_view(self, r: int, lay: VarLayout) -> torch.Tensor:
+        buf = self.peer[(r, "master%d" % lay.shard)]
+        return buf.tensor(torch.float32, lay.offset * 4, lay.numel_padded).view(lay.rows, lay.pitch)[:, :lay.cols]
 
     def read_loss(self, rank: Optional[int] = None) -> Optional[float]:
         for r in ([rank] if rank is not None else self.worker_ranks):

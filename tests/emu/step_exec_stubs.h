@@ -48,9 +48,11 @@ extern "C" {
 struct DtfGemmArgs;
 struct DtfMlpHeadArgs;
 struct DtfPsApplyArgs;
+struct DtfMlpStepArgs;
 __attribute__((weak)) int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t s) { step_emu::log("gemm args=%p stream=%p", (const void*)g, s); return step_emu::fail_kind == 4 ? step_emu::fail_code : 0; }
 __attribute__((weak)) int dtf_mlp_head(const DtfMlpHeadArgs* a, cudaStream_t s) { step_emu::log("head args=%p stream=%p", (const void*)a, s); return 0; }
 __attribute__((weak)) int dtf_ps_apply(const DtfPsApplyArgs* a, cudaStream_t s) { step_emu::log("ps_apply args=%p stream=%p", (const void*)a, s); return 0; }
+__attribute__((weak)) int dtf_mlp_step(const DtfMlpStepArgs* a, cudaStream_t s) { step_emu::log("mlp_step args=%p stream=%p", (const void*)a, s); return 0; }
 __attribute__((weak)) int dtf_convert_f32_bf16(const float* in, long long ld_in, void* out, long long ld_out, long long rows, long long cols,
                                                long long cols_pad, cudaStream_t s) {
   step_emu::log("convert in=%p ld_in=%lld out=%p ld_out=%lld rows=%lld cols=%lld pad=%lld", (const void*)in, ld_in, out, ld_out, rows, cols, cols_pad);

@@ -37,7 +37,6 @@ def test_two_gpu_engine_matches_cpu_oracle(nvls, tmp_path):
     assert rep["async"]["ok"] and rep["async"]["staleness"]["count"] == 6
 
 
-@pytest.mark.skipif(os.environ.get("DTF_TEST_UNVALIDATED") != "1", reason="first hardware validation pending: set DTF_TEST_UNVALIDATED=1")
 @pytest.mark.parametrize("nvls", ["0", "auto"])
 def test_two_gpu_ps_on_workers_matches_cpu_oracle(nvls):
     """Same check with every rank a worker and the ps shard on worker 0's GPU / stream (EngineConfig.ps_on_workers)."""

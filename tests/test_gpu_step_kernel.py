@@ -27,6 +27,21 @@ def _rel(a, b):
     return float((a.double().cpu() - b).norm() / (b.norm() + 1e-30))
 
 
+def _check_backward(x, w1, b1, dh_k, gw1_k, gb1_k, ref, B, H):
+    """dh carries the ReLU gate (h > 0): a pre-activation within TF32 rounding of zero may legitimately land on the other
+    side, which flips that ONE element between d and 0 (a few per step; each is a full-magnitude difference).  So: dh is
+    compared where the gate is unambiguous, and the two quantities computed FROM dh (dW1 = x^T.dh on the tensor cores,
+    db1 = column sums) are checked against the kernel's own dh -- that isolates the GEMM / reduction being tested."""
+    pre = x.double() @ w1.double() + b1.double()
+    sure = pre.abs() > 4e-3 * (x.double().abs() @ w1.double().abs() + b1.double().abs())
+    dh_k = dh_k[:B, :H].double().cpu()
+    assert float(sure.double().mean()) > 0.97
+    assert float(((dh_k - ref["dh"]) * sure).norm() / ref["dh"].norm()) < 3e-3
+    assert int(((dh_k != 0) != (ref["dh"] != 0))[sure].sum()) == 0      # the gate itself agrees wherever it is unambiguous
+    assert _rel(gw1_k, x.double().t() @ dh_k) < 2e-3
+    assert _rel(gb1_k, dh_k.sum(0)) < 1e-5
+
+
 @pytest.mark.parametrize("mask", [15, 7])            # 15: one launch per phase (no inter-CTA waits); 7: the fused kernel
 @pytest.mark.parametrize("B,D,H,C,nbatches", [(100, 784, 100, 10, 3), (37, 200, 64, 7, 0), (128, 96, 128, 16, 2)])
 def test_step_kernel_matches_float64_model(B, D, H, C, nbatches, mask):
@@ -83,10 +98,9 @@ def test_step_kernel_matches_float64_model(B, D, H, C, nbatches, mask):
     ref_loss, ref_z, ref = _reference(x, y, w1_h[:, :H], b1_h, w2_h[:, :C], b2_h)
     assert _rel(logits, ref_z) < 2e-3
     assert abs(float(loss[:G].sum()) - float(ref_loss)) < 2e-3 * abs(float(ref_loss))
-    assert _rel(dh[:B, :H], ref["dh"]) < 3e-3
+    _check_backward(x, w1_h[:, :H], b1_h, dh, gw1[:, :H], gb1, ref, B, H)
     assert float(dh[B:].abs().sum()) == 0.0 and float(dh[:, H:].abs().sum()) == 0.0
-    assert _rel(gw1[:, :H], ref["w1"]) < 3e-3
-    assert _rel(gb1, ref["b1"]) < 3e-3 and _rel(gw2[:, :C], ref["w2"]) < 3e-3 and _rel(gb2, ref["b2"]) < 3e-3
+    assert _rel(gw2[:, :C], ref["w2"]) < 3e-3 and _rel(gb2, ref["b2"]) < 3e-3
     assert int(stepctr[0]) == step0 + 1
     assert int(arrivals[0]) == G and int(arrivals[1]) == 5
     assert flags[:4].tolist() == [G * 4] * 3 + [4] and flags[4:].tolist() == [0] * 4
@@ -139,7 +153,7 @@ def test_step_kernel_two_consecutive_steps_and_forward_only():
         torch.cuda.synchronize()
         ref_loss, _, ref = _reference(xs_h[t * B:(t + 1) * B], ys_h[t * B:(t + 1) * B], w1_h[:, :H], b1.cpu(), w2_h[:, :C], b2.cpu())
         assert abs(float(loss[:G].sum()) - float(ref_loss)) < 2e-3 * abs(float(ref_loss))
-        assert _rel(gw1[:, :H], ref["w1"]) < 3e-3
+        _check_backward(xs_h[t * B:(t + 1) * B], w1_h[:, :H], b1.cpu(), dh, gw1[:, :H], gb1, ref, B, H)
     assert int(stepctr[0]) == 2 and int(arrivals[0]) == 2 * G and int(err[0]) == 0
     # forward-only on batch 2 (the step counter selects it and is NOT advanced)
     before = (gw1.clone(), int(arrivals[0]))
