@@ -94,7 +94,7 @@ struct MlpStepParams {
   int sys_scope;               // 0: the ps shares this GPU (gpu-scope fences suffice)
   unsigned long long timeout_ns;
   unsigned int* err;
-  unsigned long long* trace;   // optional [G][16] %globaltimer stamps (profiling / Timeline)
+  unsigned long long* trace;   // optional [G][32] %globaltimer stamps (profiling / Timeline)
 };
 
 #ifndef DTF_HOST_EMU
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
   const int cta = blockIdx.x;
   const int d0 = cta * p.ds;
   const bool fused = p.phase_mask == 7;
-  unsigned long long* tr = p.trace ? p.trace + 16 * cta : nullptr;
+  unsigned long long* tr = p.trace ? p.trace + 32 * cta : nullptr;
 #define STAMP(slot) do { if (tr && tid == 0) tr[slot] = globaltimer_ns(); } while (0)
   STAMP(0);
 
@@ -169,8 +169,10 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
   constexpr int HP = 132;                                 // padded row of the [16][128] activation tiles
   float* s_h = hs;                                        // [16][HP]
   float* s_dh = s_h + 16 * HP;                            // [16][HP]
-  float* s_w2 = s_dh + 16 * HP;                           // [128][16]
-  float* s_b1 = s_w2 + 128 * 16;                          // [128]
+  constexpr int WS = 20;                                  // row stride of the [128][16] W2 tile: 80 B keeps float4 rows of
+                                                          // consecutive hidden units on distinct banks
+  float* s_w2 = s_dh + 16 * HP;                           // [128][WS]
+  float* s_b1 = s_w2 + 128 * WS;                          // [128]
   float* s_dl = s_b1 + 128;                               // [16][16]
   float* s_lab = s_dl + 256;                              // [16][16]
   float* s_b2 = s_lab + 256;                              // [16]
@@ -241,11 +243,27 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
     __syncthreads();                                       // token acquired (thread 0's acquire + barrier)
     STAMP(2);
   }
+  // small parameters and this CTA's label rows -> shared memory: every thread (thread 0 included) issues its loads NOW, so
+  // they fly while the TMA tiles land; thread 0 then walks the TMA -> MMA chain without further global loads
+  if (p.phase_mask & 2) {
+    for (int i = tid; i < 128 * 16; i += kStepThreads) {
+      const int j = i >> 4, c = i & 15;
+      s_w2[j * WS + c] = (j < p.H && c < p.C) ? p.w2[(long long)j * p.ldw2 + c] : 0.f;
+    }
+    if (tid < 128) s_b1[tid] = tid < p.H ? p.b1[tid] : 0.f;
+    if (tid < 16) s_b2[tid] = tid < p.C ? p.b2[tid] : 0.f;
+    {
+      const int r = tid >> 4, c = tid & 15;
+      s_lab[tid] = (r < nrows && c < p.C) ? p.labels[(row0 + r_lo + r) * p.ldl + c] : 0.f;
+    }
+  }
   if (p.phase_mask & 1) {
 #ifndef DTF_HOST_EMU
     if (tid == 0) {
       mbar_wait(bar_x, 0);
+      STAMP(11);
       mbar_wait(bar_w, 0);
+      STAMP(12);
       tc_fence_after();
       const uint32_t idesc = make_idesc(128, (uint32_t)p.n1, 0, 1, 1);       // A = x: K-major; B = W1[i][j]: MN-major
       const uint32_t xa = smem_u32(x_sm), wa = smem_u32(w_sm);
@@ -255,28 +273,17 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
         umma_tf32(tmem_d1, a_desc, b_desc, idesc, s > 0 ? 1u : 0u);
       }
       umma_commit(bar_m1);
+      STAMP(13);
       if (fused && !p.forward_only) {
         // the tensor core is done with the K-major copy of the batch slice: fetch the MN-major arrangement for phase 3
         // into the same buffer now, under the shadow of phase 2
         mbar_wait(bar_m1, 0);
         mbar_arrive_expect_tx(bar_x2, (uint32_t)(nqx * kXChunkBytes));
         for (int q = 0; q < nqx; ++q) tma_load_2d(x_sm + q * kXChunkBytes, &map_x2, bar_x2, d0 + 32 * q, (int32_t)row0);
+        STAMP(14);
       }
     }
 #endif
-  }
-  // small parameters and this CTA's label rows -> shared memory (overlaps the MMAs above)
-  if (p.phase_mask & 2) {
-    for (int i = tid; i < 128 * 16; i += kStepThreads) {
-      const int j = i >> 4, c = i & 15;
-      s_w2[i] = (j < p.H && c < p.C) ? p.w2[(long long)j * p.ldw2 + c] : 0.f;
-    }
-    if (tid < 128) s_b1[tid] = tid < p.H ? p.b1[tid] : 0.f;
-    if (tid < 16) s_b2[tid] = tid < p.C ? p.b2[tid] : 0.f;
-    {
-      const int r = tid >> 4, c = tid & 15;
-      s_lab[tid] = (r < nrows && c < p.C) ? p.labels[(row0 + r_lo + r) * p.ldl + c] : 0.f;
-    }
   }
   if (p.phase_mask & 1) {
 #ifndef DTF_HOST_EMU
@@ -290,15 +297,27 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
     const int nchunks = p.n1 / 8;
     const int c_lo = half * ((nchunks + 1) / 2), c_hi = half ? nchunks : (nchunks + 1) / 2;
     float* dst = p.hpart + ((long long)cta * 128 + b) * p.n1;
+#ifndef DTF_HOST_EMU
+    {
+      // all of this warp's TMEM loads in flight at once (<= 8 chunks of 8 columns), ONE wait, then the stores
+      uint32_t r[8][8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (c_lo + u < c_hi) tmem_ld_32x32b_x8(tmem_d1 + ((uint32_t)(q * 32) << 16) + (uint32_t)((c_lo + u) * 8), r[u]);
+      tmem_ld_wait();
+      if (b < p.B) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (c_lo + u < c_hi) {
+            float4* o = reinterpret_cast<float4*>(dst + (c_lo + u) * 8);
+            o[0] = make_float4(__uint_as_float(r[u][0]), __uint_as_float(r[u][1]), __uint_as_float(r[u][2]), __uint_as_float(r[u][3]));
+            o[1] = make_float4(__uint_as_float(r[u][4]), __uint_as_float(r[u][5]), __uint_as_float(r[u][6]), __uint_as_float(r[u][7]));
+          }
+      }
+    }
+#else
     for (int ch = c_lo; ch < c_hi; ++ch) {
       float v[8];
-#ifndef DTF_HOST_EMU
-      uint32_t r[8];
-      tmem_ld_32x32b_x8(tmem_d1 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 8), r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[u]);
-#else
       for (int u = 0; u < 8; ++u) {
         const int j = ch * 8 + u;
         float a = 0.f;
@@ -306,12 +325,12 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
           for (int i = d0; i < min(d0 + p.ds, p.D); ++i) a += p.x[(row0 + b) * p.ldx + i] * p.w1[(long long)i * p.ldw1 + j];
         v[u] = a;
       }
-#endif
       if (b < p.B) {
         reinterpret_cast<float4*>(dst + ch * 8)[0] = make_float4(v[0], v[1], v[2], v[3]);
         reinterpret_cast<float4*>(dst + ch * 8)[1] = make_float4(v[4], v[5], v[6], v[7]);
       }
     }
+#endif
     __syncthreads();
     if (tid == 0) {
       __threadfence();
@@ -329,15 +348,21 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
     }
     __syncthreads();
     STAMP(5);
-    // h[r][j] = relu(sum_c hpart[c][r_lo + r][j] + b1[j])
+    // h[r][j] = relu(sum_c hpart[c][r_lo + r][j] + b1[j]); the G partials of a position are loaded as ONE batch of
+    // independent L2 requests (a serial loop would pay G round trips)
     const int n1v = p.n1 / 4;
     for (int idx = tid; idx < 16 * n1v; idx += kStepThreads) {
       const int r = idx / n1v, j4 = idx - r * n1v;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < nrows) {
-        for (int c = 0; c < p.G; ++c) {
-          const float4 t = __ldcg(reinterpret_cast<const float4*>(p.hpart + ((long long)c * 128 + r_lo + r) * p.n1) + j4);
-          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        const float4* base = reinterpret_cast<const float4*>(p.hpart + (long long)(r_lo + r) * p.n1) + j4;
+        const long long cstride = (long long)128 * p.n1 / 4;
+        for (int c0 = 0; c0 < p.G; c0 += 8) {
+          float4 t[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t[u] = (c0 + u < p.G) ? __ldcg(base + (c0 + u) * cstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { a.x += t[u].x; a.y += t[u].y; a.z += t[u].z; a.w += t[u].w; }
         }
         a.x = fmaxf(a.x + s_b1[4 * j4], 0.f);
         a.y = fmaxf(a.y + s_b1[4 * j4 + 1], 0.f);
@@ -348,16 +373,22 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
       o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
     }
     __syncthreads();
+    STAMP(15);
     // logits / softmax / loss / dlogits: warp w owns rows 2w and 2w + 1, lane = (row parity, class)
     float my_loss = 0.f;
     {
       const int r = 2 * warp + (lane >> 4), c = lane & 15;
       const float* hr = s_h + r * HP;
-      float z0 = 0.f, z1 = 0.f;
-      for (int j = 0; j < p.H; j += 2) {
-        z0 = fmaf(hr[j], s_w2[j * 16 + c], z0);
-        if (j + 1 < p.H) z1 = fmaf(hr[j + 1], s_w2[(j + 1) * 16 + c], z1);
+      float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
+      // rows of s_h / s_w2 beyond H are zero: walk whole groups of four hidden units, four independent chains
+#pragma unroll 4
+      for (int j = 0; j < p.n1; j += 4) {
+        z0 = fmaf(hr[j], s_w2[j * WS + c], z0);
+        z1 = fmaf(hr[j + 1], s_w2[(j + 1) * WS + c], z1);
+        z2 = fmaf(hr[j + 2], s_w2[(j + 2) * WS + c], z2);
+        z3 = fmaf(hr[j + 3], s_w2[(j + 3) * WS + c], z3);
       }
+      z0 += z2; z1 += z3;
       const bool live = c < p.C;
       float z = live ? (z0 + z1 + s_b2[c]) : -INFINITY;
       if (p.logits_out && live && r < nrows) p.logits_out[(long long)(r_lo + r) * p.C + c] = z;
@@ -388,6 +419,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
       if (lane == 0) s_red[warp] = my_loss;
     }
     __syncthreads();
+    STAMP(16);
     if (tid == 0) {
       float t = 0.f;
       for (int i = 0; i < kStepThreads / 32; ++i) t += s_red[i];
@@ -399,36 +431,51 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
         const int r = idx / p.n1, j = idx - r * p.n1;
         float d = 0.f;
         if (r < nrows) {
-          const float* dl = s_dl + r * 16;
-          const float* w = s_w2 + j * 16;
+          const float4* dl = reinterpret_cast<const float4*>(s_dl + r * 16);
+          const float4* w = reinterpret_cast<const float4*>(s_w2 + j * WS);
+          float d1 = 0.f;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) d = fmaf(dl[c], w[c], d);
+          for (int c = 0; c < 4; ++c) {
+            const float4 a4 = dl[c], w4 = w[c];
+            d = fmaf(a4.x, w4.x, d); d1 = fmaf(a4.y, w4.y, d1);
+            d = fmaf(a4.z, w4.z, d); d1 = fmaf(a4.w, w4.w, d1);
+          }
+          d += d1;
           d = s_h[r * HP + j] > 0.f ? d : 0.f;
           p.dh[(long long)(r_lo + r) * p.lddh + j] = d;
         }
         s_dh[r * HP + j] = d;
       }
+      STAMP(17);
       // dW2[j][c] += sum_r h[r][j] * dl[r][c]
       for (int idx = tid; idx < p.H * 16; idx += kStepThreads) {
         const int j = idx >> 4, c = idx & 15;
         if (c < p.C) {
-          float a = 0.f;
-          for (int r = 0; r < nrows; ++r) a = fmaf(s_h[r * HP + j], s_dl[r * 16 + c], a);
-          atomicAdd(p.gw2 + (long long)j * p.ldgw2 + c, a);
+          float a = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int r = 0; r < 16; r += 2) {                  // row slots beyond nrows hold zeros in s_h and s_dl
+            a = fmaf(s_h[r * HP + j], s_dl[r * 16 + c], a);
+            a1 = fmaf(s_h[(r + 1) * HP + j], s_dl[(r + 1) * 16 + c], a1);
+          }
+          atomicAdd(p.gw2 + (long long)j * p.ldgw2 + c, a + a1);
         }
       }
       if (tid < p.C) {
         float a = 0.f;
-        for (int r = 0; r < nrows; ++r) a += s_dl[r * 16 + tid];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) a += s_dl[r * 16 + tid];
         atomicAdd(p.gb2 + tid, a);
       }
       __syncthreads();
+      STAMP(18);
       if (tid < p.H) {
         float a = 0.f;
-        for (int r = 0; r < nrows; ++r) a += s_dh[r * HP + tid];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) a += s_dh[r * HP + tid];
         atomicAdd(p.gb1 + tid, a);
       }
       __syncthreads();
+      STAMP(19);
       if (tid == 0) {
         __threadfence();
         atomicAdd(&fl[1], 1u);
@@ -451,8 +498,10 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
         mbar_arrive_expect_tx(bar_x2, (uint32_t)(nqx * kXChunkBytes));
         for (int q = 0; q < nqx; ++q) tma_load_2d(x_sm + q * kXChunkBytes, &map_x2, bar_x2, d0 + 32 * q, (int32_t)row0);
       }
+      STAMP(20);
       mbar_wait(bar_x2, 0);
       mbar_wait(bar_dh, 0);
+      STAMP(21);
       tc_fence_after();
       const uint32_t idesc = make_idesc(128, (uint32_t)p.n2, 1, 1, 1);       // A = dh[b][j]: MN-major; B = x[b][i]: MN-major
       const uint32_t xa = smem_u32(x_sm), da = smem_u32(w_sm);
@@ -476,15 +525,28 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
       const int j = q * 32 + lane;
       const int nchunks = p.n2 / 8;
       const int c_lo = half * ((nchunks + 1) / 2), c_hi = half ? nchunks : (nchunks + 1) / 2;
+#ifndef DTF_HOST_EMU
+      {
+        uint32_t r[8][8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (c_lo + u < c_hi) tmem_ld_32x32b_x8(tmem_d2 + ((uint32_t)(q * 32) << 16) + (uint32_t)((c_lo + u) * 8), r[u]);
+        tmem_ld_wait();
+        if (j < p.H) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (c_lo + u < c_hi) {
+#pragma unroll
+              for (int v = 0; v < 8; ++v) {
+                const int il = (c_lo + u) * 8 + v;
+                if (il < p.ds && d0 + il < p.D) p.gw1[(long long)(d0 + il) * p.ldgw1 + j] = __uint_as_float(r[u][v]);
+              }
+            }
+        }
+      }
+#else
       for (int ch = c_lo; ch < c_hi; ++ch) {
         float v[8];
-#ifndef DTF_HOST_EMU
-        uint32_t r[8];
-        tmem_ld_32x32b_x8(tmem_d2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 8), r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[u]);
-#else
         for (int u = 0; u < 8; ++u) {
           const int i = d0 + ch * 8 + u;
           float a = 0.f;
@@ -492,15 +554,14 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
             for (int b = 0; b < p.B; ++b) a += p.x[(row0 + b) * p.ldx + i] * p.dh[(long long)b * p.lddh + j];
           v[u] = a;
         }
-#endif
         if (j < p.H) {
-#pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int il = ch * 8 + u;
             if (il < p.ds && d0 + il < p.D) p.gw1[(long long)(d0 + il) * p.ldgw1 + j] = v[u];
           }
         }
       }
+#endif
     }
     __syncthreads();
     STAMP(8);
@@ -638,7 +699,7 @@ int dtf_mlp_step(const DtfMlpStepArgs* a, cudaStream_t s) {
   p.err = a->err; p.trace = a->trace;
   const int nqx = (ds + 31) / 32, nq1 = (p.n1 + 31) / 32;
   const int w_region = (std::max(nq1 * ds * 128, 4 * p.kb * 128) + 1023) & ~1023;
-  const size_t head_floats = 2 * 16 * 132 + 128 * 16 + 128 + 256 + 256 + 16;
+  const size_t head_floats = 2 * 16 * 132 + 128 * 20 + 128 + 256 + 256 + 16;
   const size_t smem = 1024 + (size_t)nqx * kXChunkBytes + w_region + head_floats * 4;
 #ifdef DTF_HOST_EMU
   const int masks[3] = {1, 2, 4};
@@ -657,7 +718,10 @@ int dtf_mlp_step(const DtfMlpStepArgs* a, cudaStream_t s) {
   if (rc) return rc < 0 ? -7 : 1000 + rc;
   rc = cached_map_f32(&mx2, a->x, a->x_rows, a->D, a->ldx, 32, 128, 1);
   if (rc) return rc < 0 ? -7 : 1000 + rc;
-  rc = cached_map_f32(&mw, a->w1, a->D, a->H, a->ldw1, 32, ds, 1);
+  // W1 rows padded to whole 32-unit chunks (the engine's tf32 layout: zero padding that no update ever changes): describe
+  // the padded width, so that every box row is one aligned, fully in-bounds 128-byte line
+  const long long wcols = (a->ldw1 >= 32 * nq1) ? 32 * nq1 : a->H;
+  rc = cached_map_f32(&mw, a->w1, a->D, wcols, a->ldw1, 32, ds, 1);
   if (rc) return rc < 0 ? -7 : 1000 + rc;
   rc = cached_map_f32(&md, a->dh, 128, 128, a->lddh, 32, p.kb, 1);
   if (rc) return rc < 0 ? -7 : 1000 + rc;

@@ -127,8 +127,10 @@ class VarLayout:
 _KIND = {"sgd": 0, "momentum": 1, "adam": 2}
 
 
-def _layout(spec: MLPSpec, num_ps: int) -> Tuple[Dict[str, VarLayout], List[int]]:
-    """Round-robin placement in creation order (global_step, hid_w, hid_b, sm_w, sm_b), SURVEY A5."""
+def _layout(spec: MLPSpec, num_ps: int, wide_pitch: bool = False) -> Tuple[Dict[str, VarLayout], List[int]]:
+    """Round-robin placement in creation order (global_step, hid_w, hid_b, sm_w, sm_b), SURVEY A5.
+    ``wide_pitch`` (fp32 / tf32 engines): rows of the large matrix are padded to whole 128-byte chunks (32 floats), so every
+    row of a TMA box is one aligned line; the padding is zero and stays zero (its gradient is never written)."""
     order = [("global_step", ()), ("hid_w", (spec.in_dim, spec.hidden)), ("hid_b", (spec.hidden,)),
              ("sm_w", (spec.hidden, spec.classes)), ("sm_b", (spec.classes,))]
     sizes = [0] * num_ps
@@ -138,7 +140,7 @@ def _layout(spec: MLPSpec, num_ps: int) -> Tuple[Dict[str, VarLayout], List[int]
         if name == "global_step":
             continue                      # lives in the shard-0 control block (K7)
         rows, cols = (shape[0], shape[1]) if len(shape) == 2 else (1, shape[0])
-        pitch = round_up(cols, 8)
+        pitch = round_up(cols, 32) if (wide_pitch and len(shape) == 2 and cols > 16) else round_up(cols, 8)
         off = round_up(sizes[shard], 64)
         out[name] = VarLayout(name, tuple(shape), shard, off, rows, cols, pitch)
         sizes[shard] = off + rows * pitch
@@ -184,7 +186,7 @@ class PSTrainEngine:
             assert self.world == cfg.num_ps + cfg.num_workers, "world = num_ps + num_workers"
             self.ps_ranks = list(range(cfg.num_ps))
             self.worker_ranks = list(range(cfg.num_ps, self.world))
-        self.layout, self.shard_elems = _layout(spec, cfg.num_ps)
+        self.layout, self.shard_elems = _layout(spec, cfg.num_ps, wide_pitch=self.tf32)
         self.R = cfg.replicas_to_aggregate or cfg.num_workers
         self.opt = dict(cfg.optimizer)
         self.kind = _KIND[self.opt["kind"]]
@@ -276,7 +278,7 @@ class PSTrainEngine:
                 if self.tf32:
                     # scratch of the one-kernel step: partial pre-activations + dh (L2 resident), 8 sync counters, phase stamps
                     nfl = int(self.lib.dtf_mlp_step_scratch_floats(spec.in_dim, spec.batch, spec.hidden))
-                    names += [("stepscr_w%d" % w, nfl * 4), ("stepflags_w%d" % w, 256), ("steptrace_w%d" % w, 16 * 16 * 8)]
+                    names += [("stepscr_w%d" % w, nfl * 4), ("stepflags_w%d" % w, 256), ("steptrace_w%d" % w, 16 * 32 * 8)]
                 for s in range(cfg.num_ps):
                     if self.nvls:
                         rk.bufs["replica%d_w%d" % (s, w)] = self.sym_repl[s].local(r)

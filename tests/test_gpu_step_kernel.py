@@ -75,7 +75,7 @@ def test_step_kernel_matches_float64_model(B, D, H, C, nbatches, mask):
     token = torch.tensor([5, 9], dtype=torch.int64, device=dev)
     arrivals = torch.zeros(2, dtype=torch.int64, device=dev)
     err = torch.zeros(1, dtype=torch.int32, device=dev)
-    trace = torch.zeros(16 * 16, dtype=torch.int64, device=dev)
+    trace = torch.zeros(16 * 32, dtype=torch.int64, device=dev)
     p = lambda t: t.data_ptr()
     a = cuda_lib.MlpStepArgs()
     a.B, a.D, a.H, a.C, a.G, a.phase_mask = B, D, H, C, 0, mask
@@ -105,7 +105,7 @@ def test_step_kernel_matches_float64_model(B, D, H, C, nbatches, mask):
     assert int(arrivals[0]) == G and int(arrivals[1]) == 5
     assert flags[:4].tolist() == [G * 4] * 3 + [4] and flags[4:].tolist() == [0] * 4
     if mask == 7:
-        t = trace.view(16, 16)[:G].cpu()
+        t = trace.view(16, 32)[:G].cpu()
         assert bool((t[:, 10] > t[:, 0]).all())                    # every CTA stamped entry and exit
 
 
