@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--ps-only-task", type=int, default=0, help="1: ranks 0..num_ps-1 are ps-only tasks (1 ps + (N-1) workers)")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16"],
                     help="tf32: fp32 storage, TF32 MMAs, one-kernel worker step (reference precision); bf16: config 3")
+    ap.add_argument("--step-ctas", type=int, default=0, help="tf32: CTAs of the step kernel (0: widest even split of the features)")
     ap.add_argument("--min-ms", type=float, default=100.0, help="collect at least this much timed region (repetitions of K steps)")
     ap.add_argument("--max-reps", type=int, default=400)
     ap.add_argument("--baseline", type=int, default=1, help="1: also time the torch+NCCL+cuBLAS arm in this invocation -> vs_baseline")
@@ -401,7 +402,7 @@ def main():
     if args.in_graph and args.nvls == "auto":
         NVLS = False            # one-process topology: opt in with --nvls on
     common = dict(sync=args.mode == "sync", optimizer=opt, publish_replicas=args.publish, nvls=NVLS, f1_splits=args.f1_splits,
-                  head_ctas=args.head_ctas, f1_block_n=args.f1_block_n, b3_block_n=args.b3_block_n, precision=args.precision)
+                  head_ctas=args.head_ctas, f1_block_n=args.f1_block_n, b3_block_n=args.b3_block_n, precision=args.precision, step_ctas=args.step_ctas)
     if args.in_graph and N > 1:
         cfg = EngineConfig(num_ps=args.num_ps, num_workers=nw, ps_on_workers=pow_, **common)
         fabric = Fabric(N, {r: r for r in range(N)})

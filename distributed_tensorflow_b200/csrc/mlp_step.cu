@@ -108,6 +108,11 @@ DTF_DEVICE unsigned int ld_relaxed_gpu_u32_(const unsigned int* p) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// bring a tile into L2 only (no shared-memory destination, no completion tracking): next step's batch slice
+DTF_DEVICE void tma_prefetch_l2_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+               : "memory");
+}
 DTF_DEVICE void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -214,6 +219,15 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
   const long long row0 = p.nbatches > 0
       ? (long long)((step * (unsigned long long)p.bstride + (unsigned long long)p.boffset) % (unsigned long long)p.nbatches) * p.B
       : 0ll;
+#ifndef DTF_HOST_EMU
+  if (fused && !p.forward_only && p.nbatches > 0 && warp == 2 && lane == 0) {
+    // the dataset is larger than L2 (172 MB): start pulling the NEXT step's slice of the batch into L2 now, a whole step
+    // ahead, so that step's TMA finds it there instead of paying HBM latency on 128-byte pieces
+    const long long row_next = (long long)(((step + 1ull) * (unsigned long long)p.bstride + (unsigned long long)p.boffset) %
+                                           (unsigned long long)p.nbatches) * p.B;
+    for (int q = 0; q < nqx; ++q) tma_prefetch_l2_2d(&map_x, d0 + 32 * q, (int32_t)row_next);
+  }
+#endif
   const int r_lo = cta * p.rows_per_cta;                  // batch rows this CTA finalises in phase 2
   const int nrows = max(0, min(p.rows_per_cta, p.B - r_lo));
   STAMP(1);
@@ -232,6 +246,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
       // the parameters behind every later read were published by the ps: acquire its token(s) for this step
       for (int i = 0; i < p.num_tokens; ++i)
         if (!wait_flag_ge_u64(reinterpret_cast<const uint64_t*>(p.token[i]), step, p.timeout_ns) && p.err) atomicExch(p.err, 1u);
+      // (colocated: the ps kernel that released this token finished before this kernel started -- stream order -- so the
+      //  acquire's fast path is a single already-satisfied load)
 #ifndef DTF_HOST_EMU
       fence_proxy_async();
       if (p.phase_mask & 1) {
@@ -243,18 +259,37 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
     __syncthreads();                                       // token acquired (thread 0's acquire + barrier)
     STAMP(2);
   }
-  // small parameters and this CTA's label rows -> shared memory: every thread (thread 0 included) issues its loads NOW, so
-  // they fly while the TMA tiles land; thread 0 then walks the TMA -> MMA chain without further global loads
-  if (p.phase_mask & 2) {
-    for (int i = tid; i < 128 * 16; i += kStepThreads) {
+  // small parameters and this CTA's label rows -> shared memory, by warps 1..7 (warp 0's elected thread walks the
+  // TMA -> MMA chain and must not wait on global loads); each thread's loads are issued as one independent batch
+  if ((p.phase_mask & 2) && warp > 0) {
+    const int t = tid - 32, nt = kStepThreads - 32;
+    float v[10];
+#pragma unroll
+    for (int u = 0; u < 10; ++u) {
+      const int i = t + u * nt;                             // 2048 (j, c) pairs over 224 threads
       const int j = i >> 4, c = i & 15;
-      s_w2[j * WS + c] = (j < p.H && c < p.C) ? p.w2[(long long)j * p.ldw2 + c] : 0.f;
+      v[u] = (i < 128 * 16 && j < p.H && c < p.C) ? p.w2[(long long)j * p.ldw2 + c] : 0.f;
     }
-    if (tid < 128) s_b1[tid] = tid < p.H ? p.b1[tid] : 0.f;
-    if (tid < 16) s_b2[tid] = tid < p.C ? p.b2[tid] : 0.f;
-    {
-      const int r = tid >> 4, c = tid & 15;
-      s_lab[tid] = (r < nrows && c < p.C) ? p.labels[(row0 + r_lo + r) * p.ldl + c] : 0.f;
+    const float vb1 = t < p.H ? p.b1[t] : 0.f;
+    const float vb2 = t < p.C ? p.b2[t] : 0.f;
+    float vl[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = t + u * nt;
+      const int r = i >> 4, c = i & 15;
+      vl[u] = (i < 256 && r < nrows && c < p.C) ? p.labels[(row0 + r_lo + r) * p.ldl + c] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 10; ++u) {
+      const int i = t + u * nt;
+      if (i < 128 * 16) s_w2[(i >> 4) * WS + (i & 15)] = v[u];
+    }
+    if (t < 128) s_b1[t] = vb1;
+    if (t < 16) s_b2[t] = vb2;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = t + u * nt;
+      if (i < 256) s_lab[i] = vl[u];
     }
   }
   if (p.phase_mask & 1) {
@@ -566,13 +601,18 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
     __syncthreads();
     STAMP(8);
     if (tid == 0) {
-      // ONE fence by one thread after the CTA barrier (release is cumulative), then the arrival(s)
-      if (p.sys_scope) fence_acq_rel_sys(); else __threadfence();
+      // ONE fence by one thread after the CTA barrier (release is cumulative), then the arrival(s).  When the ps shares
+      // this GPU AND this stream (colocated), its kernel starts after this one has completed: the kernel boundary orders
+      // the gradient stores, the arrival is a plain count
+      if (p.sys_scope) fence_acq_rel_sys();
       for (int i = 0; i < p.num_signals; ++i) {
         if (cta == 0 && p.stamp_dst[i]) st_relaxed_sys_u64(reinterpret_cast<uint64_t*>(p.stamp_dst[i]), *p.stamp_src[i]);
       }
       if (cta == 0 && p.num_signals && p.sys_scope) fence_acq_rel_sys();
-      for (int i = 0; i < p.num_signals; ++i) red_release_sys_add_u64(reinterpret_cast<uint64_t*>(p.arrivals[i]), 1ull);
+      for (int i = 0; i < p.num_signals; ++i) {
+        if (p.sys_scope) red_release_sys_add_u64(reinterpret_cast<uint64_t*>(p.arrivals[i]), 1ull);
+        else atomicAdd(reinterpret_cast<unsigned long long*>(p.arrivals[i]), 1ull);
+      }
     }
     STAMP(9);
   }

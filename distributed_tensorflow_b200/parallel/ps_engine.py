@@ -97,6 +97,7 @@ class EngineConfig:
     nvls: Any = False                     # True/"auto": symmetric VMM buffers -- gradients stay in the WORKERS' HBM and the
                                           # ps sums them with multimem.ld_reduce (in-switch), parameters are published with
                                           # ONE multimem.st stream into every GPU's replica ("auto": only if the box has NVLS)
+    step_ctas: int = 0                    # tf32: CTAs (= input-feature slices) of the step kernel; 0 = widest even split (784 -> 7 x 112)
     precision: str = "tf32"               # "tf32": fp32 storage, TF32 tensor-core GEMMs, one-kernel worker step (mlp_step.cu);
                                           # "bf16": bf16 replica / activations, GEMM + head + GEMM kernels
     f1_splits: int = 1                    # split-K CTAs for the first GEMM (fp32 atomic partials, bias+ReLU in the head)
@@ -220,6 +221,10 @@ class PSTrainEngine:
             ds = ctypes.c_int(0)
             self.step_ctas = int(self.lib.dtf_mlp_step_slices(spec.in_dim, spec.batch, ctypes.byref(ds)))
             self.step_slice = int(ds.value)
+            if cfg.step_ctas:
+                self.step_ctas = int(cfg.step_ctas)
+                self.step_slice = round_up((spec.in_dim + self.step_ctas - 1) // self.step_ctas, 8)
+                assert self.step_ctas <= 16 and self.step_slice <= 128 and (spec.batch + self.step_ctas - 1) // self.step_ctas <= 16
             self.head_ctas = self.step_ctas                        # loss partials per step
             self.var_shards = sorted({lw[v].shard for v in ("hid_w", "hid_b", "sm_w", "sm_b")})
             self.ctas_per_push = [self.step_ctas if s in self.var_shards else 0 for s in range(cfg.num_ps)]
@@ -277,7 +282,7 @@ class PSTrainEngine:
                          ("misc_w%d" % w, 4096 + cfg.loss_hist * 4)]
                 if self.tf32:
                     # scratch of the one-kernel step: partial pre-activations + dh (L2 resident), 8 sync counters, phase stamps
-                    nfl = int(self.lib.dtf_mlp_step_scratch_floats(spec.in_dim, spec.batch, spec.hidden))
+                    nfl = self.step_ctas * 128 * round_up(spec.hidden, 16) + 128 * 128 + 64
                     names += [("stepscr_w%d" % w, nfl * 4), ("stepflags_w%d" % w, 256), ("steptrace_w%d" % w, 16 * 32 * 8)]
                 for s in range(cfg.num_ps):
                     if self.nvls:

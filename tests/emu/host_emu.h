@@ -154,6 +154,7 @@ static inline T __ldcg(const T* p) {       // cache-global load: a plain read he
 }
 static inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned int atomicExch(unsigned int* p, unsigned int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 static inline long long clock64() { return (long long)std::chrono::steady_clock::now().time_since_epoch().count(); }
 static inline void __nanosleep(unsigned ns) { std::this_thread::sleep_for(std::chrono::nanoseconds(ns)); }

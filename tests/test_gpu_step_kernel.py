@@ -33,9 +33,9 @@ def _check_backward(x, w1, b1, dh_k, gw1_k, gb1_k, ref, B, H):
     compared where the gate is unambiguous, and the two quantities computed FROM dh (dW1 = x^T.dh on the tensor cores,
     db1 = column sums) are checked against the kernel's own dh -- that isolates the GEMM / reduction being tested."""
     pre = x.double() @ w1.double() + b1.double()
-    sure = pre.abs() > 4e-3 * (x.double().abs() @ w1.double().abs() + b1.double().abs())
+    sure = pre.abs() > 1e-3 * (x.double().abs() @ w1.double().abs() + b1.double().abs())     # worst-case TF32 error of pre
     dh_k = dh_k[:B, :H].double().cpu()
-    assert float(sure.double().mean()) > 0.97
+    assert float(sure.double().mean()) > 0.9
     assert float(((dh_k - ref["dh"]) * sure).norm() / ref["dh"].norm()) < 3e-3
     assert int(((dh_k != 0) != (ref["dh"] != 0))[sure].sum()) == 0      # the gate itself agrees wherever it is unambiguous
     assert _rel(gw1_k, x.double().t() @ dh_k) < 2e-3

@@ -26,7 +26,8 @@ ORDER = [0, 1, 2, 11, 12, 13, 14, 3, 4, 5, 15, 16, 17, 18, 19, 6, 20, 21, 7, 8, 
 def main():
     torch.cuda.set_device(0)
     xs, ys = synthetic_mnist(20000, seed=1)
-    eng = PSTrainEngine(MLPSpec(), EngineConfig(colocated=True, optimizer={"kind": "sgd", "lr": 0.001}), Fabric(1, {0: 0}))
+    eng = PSTrainEngine(MLPSpec(), EngineConfig(colocated=True, optimizer={"kind": "sgd", "lr": 0.001},
+                                           step_ctas=int(os.environ.get("DTF_STEP_CTAS", "0"))), Fabric(1, {0: 0}))
     eng.init_params()
     eng.attach_dataset(0, xs, ys)
     d = eng._w[0]
