@@ -485,6 +485,7 @@ def main():
                     e0.record(rk.stream)
                     evs.append((e0, e1, rk))
             body()
+            eng.join_streams()
             for e0, e1, rk in evs:
                 e1.record(rk.stream)
             eng.synchronize()
@@ -594,6 +595,7 @@ def main():
                         evs.append((e0, e1, rk))
                 w0 = time.time()
                 body()
+                eng.join_streams()
                 for e0, e1, rk in evs:
                     e1.record(rk.stream)
                 eng.synchronize()

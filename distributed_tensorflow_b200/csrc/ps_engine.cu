@@ -84,6 +84,10 @@ DTF_DEVICE void red_relaxed_sys_add_u64(unsigned long long* p, unsigned long lon
 DTF_DEVICE void st_relaxed_sys_ull(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// {token, version} of a worker mailbox as ONE 16-byte store (the pair shares an aligned 16-byte slot of the 128-byte line)
+DTF_DEVICE void st_relaxed_sys_v2_u64(unsigned long long* p, unsigned long long a, unsigned long long b) {
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
 #endif
 
 __global__ void __launch_bounds__(256, 4) ps_apply_kernel(const PsApplyParams p) {
@@ -96,7 +100,41 @@ __global__ void __launch_bounds__(256, 4) ps_apply_kernel(const PsApplyParams p)
   PSTAMP(0);
   const unsigned long long t_start = (blockIdx.x == 0 && threadIdx.x == 0) ? globaltimer_ns() : 0ull;
 
-  if (threadIdx.x == 0) {
+  // Sync mode with replicas_to_aggregate == total_num_replicas (the reference's setting, distributed_mnist.py:120-122): the
+  // only possible decision is "all W pushes, all fresh" (a worker cannot run ahead of an aggregate it is part of, so no
+  // stamp can be stale) -- every CTA waits for it BY ITSELF, no block-0 decision + broadcast round trip.
+  const bool all_fresh_only = p.mode == 0 && p.replicas_to_aggregate == p.num_workers;
+  if (threadIdx.x == 0 && all_fresh_only) {
+    const unsigned long long seq = ld_acquire_gpu_u64(&ctl->param_version) + 1ull;
+    s_seq = seq;
+    unsigned int ok = 1, spins = 0;
+    const unsigned long long t0 = globaltimer_ns();
+    while (true) {
+      unsigned long long arr[DTF_MAX_WORKERS];
+#pragma unroll
+      for (int w = 0; w < DTF_MAX_WORKERS; ++w)                // one batch of independent loads per poll
+        arr[w] = w < p.num_workers ? ld_relaxed_sys_u64(reinterpret_cast<const uint64_t*>(&ctl->w[w].arrivals)) : ~0ull;
+      bool all = true;
+#pragma unroll
+      for (int w = 0; w < DTF_MAX_WORKERS; ++w)
+        if (w < p.num_workers && arr[w] < ctl->consumed[w] + p.ctas_per_push) all = false;
+      if (all) break;
+      if ((++spins & 0xFF) == 0 && (globaltimer_ns() - t0) > p.timeout_ns) {
+        ok = 0;
+        if (!p.idle_ok && blockIdx.x == 0) atomicExch(&ctl->err, 2u);
+        break;
+      }
+      if (spins > 4096) __nanosleep(64);
+    }
+    if (p.system_scope) fence_acq_rel_sys(); else __threadfence();     // the gradient slots of all workers are now visible
+    s_mask = p.full_mask;
+    s_count = (unsigned int)p.num_workers;
+    s_ok = ok;
+    float lr = p.lr;
+    if (p.kind == 2) lr = p.lr * sqrtf(1.0f - ctl->beta2_power) / (1.0f - ctl->beta1_power);
+    s_lr = lr;
+  }
+  if (threadIdx.x == 0 && !all_fresh_only) {
     const unsigned long long seq = ld_acquire_gpu_u64(&ctl->param_version) + 1ull;
     s_seq = seq;
     unsigned int ok = 1;
@@ -271,7 +309,9 @@ __global__ void __launch_bounds__(256, 4) ps_apply_kernel(const PsApplyParams p)
     if (p.system_scope) __threadfence_system(); else __threadfence();      // one fence per CTA, after the barrier
     const unsigned int prev = atomicAdd(&ctl->done_ctas, 1u);
     if (prev == gridDim.x - 1) {
-      __threadfence();
+      // the ticket observed every CTA's fence + increment: ONE fence here makes all their parameter stores (local, peer,
+      // multicast) precede the token stores below; the bookkeeping is ps-private (next launch = kernel boundary)
+      if (p.system_scope) __threadfence_system(); else __threadfence();
       ctl->done_ctas = 0;
       if (ok) {
         for (int w = 0; w < p.num_workers; ++w)
@@ -283,21 +323,23 @@ __global__ void __launch_bounds__(256, 4) ps_apply_kernel(const PsApplyParams p)
           ctl->beta1_power *= p.beta1;
           ctl->beta2_power *= p.beta2;
         }
-        if (p.system_scope) __threadfence_system(); else __threadfence();
-        // tokens: every replica gets one carrying the NEW global step (sync); the pusher only (async).
-        // One fence, then RELAXED system-scope stores (fence + relaxed store == release): a st.release.sys per
-        // mailbox would issue a system membar per worker.
-        for (int w = 0; w < p.num_workers; ++w) {
-          if (p.mailbox[w] == nullptr) continue;
-          if (p.mode == 1 && !(mask & (1u << w))) continue;
-          st_relaxed_sys_u64(reinterpret_cast<uint64_t*>(&p.mailbox[w]->version), ngs);
-        }
-        if (p.system_scope) __threadfence_system(); else __threadfence();
-        for (int w = 0; w < p.num_workers; ++w) {
-          if (p.mailbox[w] == nullptr) continue;
-          if (p.mode == 1 && !(mask & (1u << w))) continue;
-          if (p.mode == 1) red_relaxed_sys_add_u64(&p.mailbox[w]->token, 1ull);
-          else st_relaxed_sys_u64(reinterpret_cast<uint64_t*>(&p.mailbox[w]->token), ngs);
+        if (p.mode == 0) {
+          // tokens (sync): every replica gets one carrying the NEW global step.  The fence above (after the ticket that
+          // observed every CTA's release) + RELAXED system-scope stores = release; {token, version} travel as ONE
+          // 16-byte store per mailbox, so no second fence is needed to order the pair
+          for (int w = 0; w < p.num_workers; ++w)
+            if (p.mailbox[w] != nullptr) st_relaxed_sys_v2_u64(&p.mailbox[w]->token, ngs, ngs);
+        } else {
+          // async: the pusher only; its token is a COUNT (red.add), so version and token are two accesses
+          for (int w = 0; w < p.num_workers; ++w) {
+            if (p.mailbox[w] == nullptr || !(mask & (1u << w))) continue;
+            st_relaxed_sys_u64(reinterpret_cast<uint64_t*>(&p.mailbox[w]->version), ngs);
+          }
+          if (p.system_scope) __threadfence_system(); else __threadfence();
+          for (int w = 0; w < p.num_workers; ++w) {
+            if (p.mailbox[w] == nullptr || !(mask & (1u << w))) continue;
+            red_relaxed_sys_add_u64(&p.mailbox[w]->token, 1ull);
+          }
         }
       }
       if (p.trace && p.trace_cap > 0) {

@@ -151,9 +151,15 @@ def _layout(spec: MLPSpec, num_ps: int, wide_pitch: bool = False) -> Tuple[Dict[
 class _Rank:
     """Per-rank device state (buffers, stream, cached launch descriptors)."""
 
+    def sync(self) -> None:
+        self.stream.synchronize()
+        if self.ps_stream is not None:
+            self.ps_stream.synchronize()
+
     def __init__(self, rank: int, device: int):
         self.rank, self.device = rank, torch.device("cuda", device)
         self.stream: Optional[torch.cuda.Stream] = None
+        self.ps_stream: Optional[torch.cuda.Stream] = None     # ps shard hosted next to a worker on another GPU's fabric: own stream
         self.step = 0                    # steps enqueued so far (worker) / applies enqueued (ps)
         self.bufs: Dict[str, FabricBuffer] = {}
 
@@ -200,6 +206,12 @@ class PSTrainEngine:
         for rk in self.ranks.values():
             with torch.cuda.device(rk.device):
                 rk.stream = torch.cuda.Stream(rk.device)
+                if cfg.ps_on_workers and rk.rank in self.ps_ranks and os.environ.get("DTF_PS_STREAM", "1") == "1":
+                    # The shard's apply kernels run NEXT TO this GPU's worker kernels, not between them: everything they
+                    # exchange goes through the same system-scope flags as with a remote worker, so no stream order is
+                    # needed -- and the worker's next step (setup, batch prefetch, token wait) no longer queues behind
+                    # the apply's launch + completion.
+                    rk.ps_stream = torch.cuda.Stream(rk.device)
         # arrivals a complete push adds on each shard: 1 for the head (if it pushes there) + dW1 tiles
         lw = self.layout
         self.m_tiles_w1 = (spec.in_dim + 127) // 128
@@ -399,7 +411,7 @@ class PSTrainEngine:
             if r not in self.ps_ranks:
                 continue
             s = self.ps_ranks.index(r)
-            rk.stream.synchronize()
+            rk.sync()
             for name, lay in self.layout.items():
                 if lay.shard == s:
                     out[name] = self._var_view(rk, "master", lay).reshape(lay.shape).detach().cpu().clone()
@@ -418,6 +430,7 @@ class PSTrainEngine:
     def read_ctl(self, shard: int, fld: str, count: int = 1):
         r = self.ps_ranks[shard]
         rk = self.ranks[r]
+        rk.sync()
         t = rk.bufs["ctl%d" % shard].tensor(torch.int64, self.off[fld], count).cpu()
         return int(t[0]) if count == 1 else t.tolist()
 
@@ -535,38 +548,21 @@ class PSTrainEngine:
             d["extra_wait_shards"] = [s for s in range(cfg.num_ps) if s != lay["hid_w"].shard]
             if self.tf32:
                 # ---- the whole step as one kernel (csrc/mlp_step.cu): fp32 parameters read in place ------------------
-                def psrc(l: VarLayout) -> int:
+                def psrc(l: VarLayout, r=r, rk=rk, w=w) -> int:
                     if self.nvls:
                         return rk.bufs["replica%d_w%d" % (l.shard, w)].ptr + l.offset * 4       # local fp32 replica
                     return self.peer[(r, "master%d" % l.shard)].ptr + l.offset * 4              # the ps's master (same GPU / NVLink)
 
-                scr = rk.bufs["stepscr_w%d" % w]
-                n1 = round_up(H, 16)
-
-                def step_args(x_ptr: int, x_rows: int, lab_ptr: int, nbatches: int = 0, rows: int = B) -> MlpStepArgs:
-                    a = MlpStepArgs()
-                    a.B, a.D, a.H, a.C, a.G, a.phase_mask = rows, D, H, C, self.step_ctas, 7
-                    a.x, a.ldx, a.x_rows = x_ptr, D, x_rows
-                    a.labels, a.ldl = lab_ptr, C
-                    a.nbatches, a.bstride, a.boffset = nbatches, cfg.num_workers, w
-                    a.w1, a.ldw1, a.b1 = psrc(lay["hid_w"]), lay["hid_w"].pitch, psrc(lay["hid_b"])
-                    a.w2, a.ldw2, a.b2 = psrc(lay["sm_w"]), lay["sm_w"].pitch, psrc(lay["sm_b"])
-                    a.hpart, a.dh, a.lddh = scr.ptr, scr.ptr + self.step_ctas * 128 * n1 * 4, 128
-                    a.flags = rk.bufs["stepflags_w%d" % w].ptr
-                    a.gw1, a.ldgw1, a.gb1 = slot(lay["hid_w"]), lay["hid_w"].pitch, slot(lay["hid_b"])
-                    a.gw2, a.ldgw2, a.gb2 = slot(lay["sm_w"]), lay["sm_w"].pitch, slot(lay["sm_b"])
-                    a.clip_min, a.loss_out, a.step_counter = cfg.clip_min, d["loss_ptr"], d["stepctr_ptr"]
-                    a.num_tokens = a.num_signals = len(self.var_shards)
-                    for i, sh in enumerate(self.var_shards):
-                        a.token[i] = mb.ptr + sh * self.mb_bytes
-                        a.arrivals[i] = ctl_arrivals(sh)
-                        a.stamp_dst[i] = ctl_arrivals(sh) + 8
-                        a.stamp_src[i] = mb.ptr + sh * self.mb_bytes + (0 if cfg.sync else 8)
-                    a.sys_scope = 0 if cfg.colocated else 1
-                    a.timeout_ns, a.err = cfg.timeout_ns, d["err_ptr"]
-                    return a
-                d["step_args"] = step_args
-                d["step_staged"] = step_args(rk.bufs["xf32_w%d" % w].ptr, 128, rk.bufs["labels_w%d" % w].ptr)
+                # everything the argument block points at, resolved NOW (the builder below is called later, from
+                # attach_dataset / evaluate / the plan builder, when this loop's variables have moved on)
+                d["step_const"] = dict(
+                    w=w, w1=psrc(lay["hid_w"]), ldw1=lay["hid_w"].pitch, b1=psrc(lay["hid_b"]),
+                    w2=psrc(lay["sm_w"]), ldw2=lay["sm_w"].pitch, b2=psrc(lay["sm_b"]),
+                    scr=rk.bufs["stepscr_w%d" % w].ptr, flags=rk.bufs["stepflags_w%d" % w].ptr,
+                    gw1=slot(lay["hid_w"]), gb1=slot(lay["hid_b"]), gw2=slot(lay["sm_w"]), gb2=slot(lay["sm_b"]),
+                    tokens=[mb.ptr + sh * self.mb_bytes for sh in self.var_shards],
+                    arrivals=[ctl_arrivals(sh) for sh in self.var_shards])
+                d["step_staged"] = self._step_args(d, rk.bufs["xf32_w%d" % w].ptr, 128, rk.bufs["labels_w%d" % w].ptr)
             self._w[r] = d
         self._p: Dict[int, PsApplyArgs] = {}
         for r, rk in self.ranks.items():
@@ -614,6 +610,33 @@ class PSTrainEngine:
             a.system_scope = 0 if cfg.colocated else 1
             self._p[r] = a
 
+    def _step_args(self, d: Dict[str, Any], x_ptr: int, x_rows: int, lab_ptr: int, nbatches: int = 0,
+                   rows: Optional[int] = None) -> MlpStepArgs:
+        """Argument block of ``dtf_mlp_step`` for one worker: ``x`` / labels = a staged batch (``nbatches == 0``) or a
+        device-resident dataset walked by the device step counter."""
+        spec, cfg, lay, k = self.spec, self.cfg, self.layout, d["step_const"]
+        a = MlpStepArgs()
+        a.B, a.D, a.H, a.C, a.G, a.phase_mask = (rows or spec.batch), spec.in_dim, spec.hidden, spec.classes, self.step_ctas, 7
+        a.x, a.ldx, a.x_rows = x_ptr, spec.in_dim, x_rows
+        a.labels, a.ldl = lab_ptr, spec.classes
+        a.nbatches, a.bstride, a.boffset = nbatches, cfg.num_workers, k["w"]
+        a.w1, a.ldw1, a.b1 = k["w1"], k["ldw1"], k["b1"]
+        a.w2, a.ldw2, a.b2 = k["w2"], k["ldw2"], k["b2"]
+        a.hpart, a.dh, a.lddh = k["scr"], k["scr"] + self.step_ctas * 128 * round_up(spec.hidden, 16) * 4, 128
+        a.flags = k["flags"]
+        a.gw1, a.ldgw1, a.gb1 = k["gw1"], lay["hid_w"].pitch, k["gb1"]
+        a.gw2, a.ldgw2, a.gb2 = k["gw2"], lay["sm_w"].pitch, k["gb2"]
+        a.clip_min, a.loss_out, a.step_counter = cfg.clip_min, d["loss_ptr"], d["stepctr_ptr"]
+        a.num_tokens = a.num_signals = len(self.var_shards)
+        for i in range(len(self.var_shards)):
+            a.token[i] = k["tokens"][i]
+            a.arrivals[i] = k["arrivals"][i]
+            a.stamp_dst[i] = k["arrivals"][i] + 8
+            a.stamp_src[i] = k["tokens"][i] + (0 if cfg.sync else 8)
+        a.sys_scope = 0 if cfg.colocated else 1
+        a.timeout_ns, a.err = cfg.timeout_ns, d["err_ptr"]
+        return a
+
     # ------------------------------------------------------------------------------------------------
     # stepping
     # ------------------------------------------------------------------------------------------------
@@ -639,7 +662,7 @@ class PSTrainEngine:
         if self.tf32:
             # the step kernel's TMA reads the batch straight out of the dataset (row = batch index x B, from the device step
             # counter): no staging pass at all
-            d["step_ds"] = d["step_args"](img.data_ptr(), img.shape[0], lab.data_ptr(), d["ds_nbatches"])
+            d["step_ds"] = self._step_args(d, img.data_ptr(), img.shape[0], lab.data_ptr(), d["ds_nbatches"])
 
     def enqueue_worker_step(self, rank: int, source: str = "staged") -> None:
         """Enqueue one worker step on the rank's stream.  ``source='staged'``: the batch is already in the
@@ -705,7 +728,7 @@ class PSTrainEngine:
     def enqueue_ps_apply(self, rank: int) -> None:
         rk = self.ranks[rank]
         with torch.cuda.device(rk.device):
-            rc = self.lib.dtf_ps_apply(ctypes.byref(self._p[rank]), rk.stream.cuda_stream)
+            rc = self.lib.dtf_ps_apply(ctypes.byref(self._p[rank]), (rk.ps_stream or rk.stream).cuda_stream)
         assert rc == 0, "ps_apply rc=%d" % rc
         cuda_lib._bump()
 
@@ -790,7 +813,7 @@ class PSTrainEngine:
                     ops = [StepOp(kind=OP_EVENT_WAIT, p0=ready[par].cuda_event)]
                     if self.tf32:
                         # fp32 staging buffer read in place by the step kernel's TMA: H2D -> ONE kernel -> (ps apply)
-                        sp = d["step_staged"] if par == 0 else d["step_args"](xf, 128, lab)
+                        sp = d["step_staged"] if par == 0 else self._step_args(d, xf, 128, lab)
                         ops.append(StepOp(kind=OP_MLP_STEP, p0=ctypes.addressof(sp)))
                         keep = [sp]
                     else:
@@ -803,7 +826,7 @@ class PSTrainEngine:
                             ops.append(StepOp(kind=OP_SIGNAL, p0=ctl_ptr, p1=mbp, i0=w, i1=hd.stamp_from_version))
                         ops.append(StepOp(kind=OP_GEMM, p0=ctypes.addressof(g3p)))
                         keep = [g1p, hdp, g3p]
-                    if r in self.ps_ranks:
+                    if r in self.ps_ranks and rk.ps_stream is None:
                         # ps and worker share the GPU and the stream: the apply joins the worker's plan (one graph)
                         ops += [StepOp(kind=OP_PS_APPLY, p0=ctypes.addressof(self._p[r]))
                                 for _ in range(1 if self.cfg.sync else self.cfg.num_workers)]
@@ -813,10 +836,10 @@ class PSTrainEngine:
                 host = torch.zeros(16, dtype=torch.float32).pin_memory()
                 plans["loss"][r] = (StepPlan([StepOp(kind=OP_D2H, p0=host.data_ptr(), p1=d["loss_ptr"], i0=self.head_ctas * 4),
                                               StepOp(kind=OP_SYNC)], rk.device.index, st), host.numpy(), host)
-            if r in self.ps_ranks and r not in self.worker_ranks:
+            if r in self.ps_ranks and (r not in self.worker_ranks or rk.ps_stream is not None):
                 k = 1 if self.cfg.sync else self.cfg.num_workers
                 plans["ps"][r] = StepPlan([StepOp(kind=OP_PS_APPLY, p0=ctypes.addressof(self._p[r])) for _ in range(k)],
-                                          rk.device.index, st, keep=[self._p[r]])
+                                          rk.device.index, (rk.ps_stream or rk.stream).cuda_stream, keep=[self._p[r]])
         plans["runs"], plans["parity"], plans["prefetched"] = 0, 0, None
         self._native_plans = plans
         return plans
@@ -962,12 +985,20 @@ class PSTrainEngine:
                 g = torch.cuda.CUDAGraph()
                 before = cuda_lib.launch_count()
                 with torch.cuda.graph(g, stream=rk.stream, capture_error_mode="thread_local"):
+                    if rk.ps_stream is not None:             # fork: the shard's applies form a parallel branch of the graph
+                        fork = torch.cuda.Event()
+                        fork.record(rk.stream)
+                        rk.ps_stream.wait_event(fork)
                     for _ in range(unroll):
                         if r in self.worker_ranks:
                             self.enqueue_worker_step(r, source)
                         if r in self.ps_ranks:
                             for _k in range(1 if self.cfg.sync else self.cfg.num_workers):
                                 self.enqueue_ps_apply(r)
+                    if rk.ps_stream is not None:             # join
+                        join = torch.cuda.Event()
+                        join.record(rk.ps_stream)
+                        rk.stream.wait_event(join)
                 graphs[r] = (g, cuda_lib.launch_count() - before)
                 cuda_lib._bump(-(cuda_lib.launch_count() - before))      # capture launched nothing
         self._graphs = graphs
@@ -1011,7 +1042,7 @@ class PSTrainEngine:
                 lossbuf = torch.zeros((nch, 16), dtype=torch.float32, device=rk.device)
                 for i in range(nch):
                     rows = min(128, N - i * 128)
-                    a = d["step_args"](xd.data_ptr() + i * 128 * D * 4, rows, lab.data_ptr() + i * 128 * C * 4, 0, rows)
+                    a = self._step_args(d, xd.data_ptr() + i * 128 * D * 4, rows, lab.data_ptr() + i * 128 * C * 4, 0, rows)
                     a.forward_only, a.num_signals = 1, 0
                     a.logits_out, a.loss_out = logits.data_ptr() + i * 128 * C * 4, lossbuf.data_ptr() + i * 64
                     rc = self.lib.dtf_mlp_step(ctypes.byref(a), rk.stream.cuda_stream)
@@ -1065,7 +1096,7 @@ class PSTrainEngine:
 
     def check_errors(self) -> None:
         for r, rk in self.ranks.items():
-            rk.stream.synchronize()
+            rk.sync()
             if r in self.worker_ranks:
                 w = self.worker_ranks.index(r)
                 e = int(rk.bufs["misc_w%d" % w].tensor(torch.int32, 72, 1).cpu()[0])
@@ -1079,7 +1110,14 @@ class PSTrainEngine:
 
     def synchronize(self) -> None:
         for rk in self.ranks.values():
-            rk.stream.synchronize()
+            rk.sync()
+
+    def join_streams(self) -> None:
+        """Make every local worker stream wait for the work enqueued so far on its GPU's ps stream (so that an event
+        recorded next on the worker stream covers both)."""
+        for rk in self.ranks.values():
+            if rk.ps_stream is not None:
+                rk.stream.wait_stream(rk.ps_stream)
 
     def close(self) -> None:
         self.synchronize()

@@ -203,6 +203,10 @@ static inline unsigned long long ld_acquire_gpu_u64(const unsigned long long* p)
 static inline void st_release_gpu_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_SEQ_CST); }
 static inline void red_relaxed_sys_add_u64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline void st_relaxed_sys_ull(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_SEQ_CST); }
+static inline void st_relaxed_sys_v2_u64(unsigned long long* p, unsigned long long a, unsigned long long b) {
+  __atomic_store_n(p + 1, b, __ATOMIC_SEQ_CST);      // version first, token last: a reader that sees the token sees the version
+  __atomic_store_n(p, a, __ATOMIC_SEQ_CST);
+}
 static inline bool wait_flag_ge_u64(const uint64_t* flag, uint64_t target, uint64_t timeout_ns) {
   const uint64_t t0 = globaltimer_ns();
   while (__atomic_load_n(flag, __ATOMIC_SEQ_CST) < target) {

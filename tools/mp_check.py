@@ -86,8 +86,11 @@ def main():
                         acc = g if acc is None else {k: acc[k] + g[k] for k in g}
                     for k in p:
                         p[k] = p[k] - 0.001 * acc[k] / W
-                err = max(float((final[k] - p[k]).abs().max() / (p[k].abs().max() + 1e-6)) for k in p)
-                report[mode] = {"global_step": int(final["global_step"]), "max_rel_err_vs_oracle": err,
+                errs = {k: float((final[k] - p[k]).abs().max() / (p[k].abs().max() + 1e-6)) for k in p}
+                nerrs = {k: float((final[k].double() - p[k].double()).norm() / (p[k].double() - init[k].double()).norm()) for k in p}
+                err = max(errs.values())
+                report[mode] = {"global_step": int(final["global_step"]), "max_rel_err_vs_oracle": err, "per_var": errs,
+                                "update_norm_rel_err": nerrs,
                                 "ok": int(final["global_step"]) == steps and err < (3e-2 if PRECISION == "bf16" else 5e-3)}
             else:
                 st = eng.staleness()
