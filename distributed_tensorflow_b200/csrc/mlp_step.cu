@@ -66,7 +66,7 @@ struct MlpStepParams {
   long long ldw2;
   const float* b2;
   // ---- scratch (worker-local, L2 resident)
-  float* hpart;                // [G][128][n1] partial pre-activations
+  float* hpart;                // [G][128][n1 + 4] partial pre-activations (row pitch n1 + 4: conflict-free staging rows)
   float* dh;                   // [128][lddh] (rows >= B and columns >= H stay zero)
   long long lddh;
   unsigned int* flags;         // [8]: {partials written, dh rows written, CTAs finished (all monotonic: G per launch), launch
@@ -95,6 +95,9 @@ struct MlpStepParams {
   unsigned long long timeout_ns;
   unsigned int* err;
   unsigned long long* trace;   // optional [G][32] %globaltimer stamps (profiling / Timeline)
+  int clustered;               // 1: the G CTAs are ONE thread-block cluster: the two exchanges are ordered by barrier.cluster
+                               //    (release / acquire at cluster scope, ~0.2 us) instead of fence + counter + poll through L2
+  int dbg;                     // debugging knobs: bit 0 skip the dW1 stores, bit 1 skip their TMEM loads
 };
 
 #ifndef DTF_HOST_EMU
@@ -112,6 +115,15 @@ DTF_DEVICE unsigned int ld_relaxed_gpu_u32_(const unsigned int* p) {
 DTF_DEVICE void tma_prefetch_l2_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
                : "memory");
+}
+// bulk (TMA) store of a contiguous shared-memory tile to global memory: one instruction by one thread, the copy engine
+// streams it out (the destination may be peer memory: the unicast fabric's gradient slot in the ps GPU's HBM)
+DTF_DEVICE void bulk_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+DTF_DEVICE void bulk_commit_and_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 DTF_DEVICE void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -169,7 +181,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
   const int dh_chunk = p.kb * 128;                        // bytes of one dh chunk ([kb rows] x 128 B)
   unsigned char* x_sm = tiles;
   unsigned char* w_sm = x_sm + nqx * kXChunkBytes;
-  const int w_region = max(nq1 * w_chunk, 4 * dh_chunk);
+  const int hpp = p.n1 + 4;                               // row pitch of the partial-pre-activation tile (smem staging == global)
+  const int w_region = max(max(nq1 * w_chunk, 4 * dh_chunk), 128 * hpp * 4);
   float* hs = reinterpret_cast<float*>(w_sm + ((w_region + 1023) & ~1023));
   constexpr int HP = 132;                                 // padded row of the [16][128] activation tiles
   float* s_h = hs;                                        // [16][HP]
@@ -331,23 +344,30 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
     const int b = q * 32 + lane;
     const int nchunks = p.n1 / 8;
     const int c_lo = half * ((nchunks + 1) / 2), c_hi = half ? nchunks : (nchunks + 1) / 2;
-    float* dst = p.hpart + ((long long)cta * 128 + b) * p.n1;
+    float* dst = p.hpart + ((long long)cta * 128 + b) * hpp;
 #ifndef DTF_HOST_EMU
     {
-      // all of this warp's TMEM loads in flight at once (<= 8 chunks of 8 columns), ONE wait, then the stores
+      // all of this warp's TMEM loads in flight at once (<= 8 chunks of 8 columns), ONE wait; the rows are parked in shared
+      // memory (the W1 tile is dead: its MMAs completed) and leave as ONE bulk store -- hpart[cta] is that same [rows][hpp]
+      // block in global memory
+      float* stage = reinterpret_cast<float*>(w_sm) + b * hpp;
       uint32_t r[8][8];
 #pragma unroll
       for (int u = 0; u < 8; ++u)
         if (c_lo + u < c_hi) tmem_ld_32x32b_x8(tmem_d1 + ((uint32_t)(q * 32) << 16) + (uint32_t)((c_lo + u) * 8), r[u]);
       tmem_ld_wait();
-      if (b < p.B) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (c_lo + u < c_hi) {
-            float4* o = reinterpret_cast<float4*>(dst + (c_lo + u) * 8);
-            o[0] = make_float4(__uint_as_float(r[u][0]), __uint_as_float(r[u][1]), __uint_as_float(r[u][2]), __uint_as_float(r[u][3]));
-            o[1] = make_float4(__uint_as_float(r[u][4]), __uint_as_float(r[u][5]), __uint_as_float(r[u][6]), __uint_as_float(r[u][7]));
-          }
+      for (int u = 0; u < 8; ++u)
+        if (c_lo + u < c_hi) {
+          float4* o = reinterpret_cast<float4*>(stage + (c_lo + u) * 8);
+          o[0] = make_float4(__uint_as_float(r[u][0]), __uint_as_float(r[u][1]), __uint_as_float(r[u][2]), __uint_as_float(r[u][3]));
+          o[1] = make_float4(__uint_as_float(r[u][4]), __uint_as_float(r[u][5]), __uint_as_float(r[u][6]), __uint_as_float(r[u][7]));
+        }
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        bulk_store_1d(p.hpart + (long long)cta * 128 * hpp, w_sm, (uint32_t)(p.B * hpp * 4));
+        bulk_commit_and_wait();
       }
     }
 #else
@@ -365,11 +385,19 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
         reinterpret_cast<float4*>(dst + ch * 8)[1] = make_float4(v[4], v[5], v[6], v[7]);
       }
     }
+    (void)dst;
 #endif
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      atomicAdd(&fl[0], 1u);
+#ifndef DTF_HOST_EMU
+    if (fused && p.clustered) {
+      cluster_sync_all();            // every CTA's partials are written and visible to every CTA of the cluster
+    } else
+#endif
+    {
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(&fl[0], 1u);
+      }
     }
     STAMP(4);
   }
@@ -378,7 +406,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
   // phase 2: finalise this CTA's batch rows -- h, logits, softmax / loss / dlogits, dh, dW2 / db2 / db1 partials
   // =====================================================================================================
   if (p.phase_mask & 2) {
-    if (fused) {
+    if (fused && !p.clustered) {
       if (tid == 0 && !wait_counter_ge(&fl[0], sync_target, p.timeout_ns) && p.err) atomicExch(p.err, 4u);
     }
     __syncthreads();
@@ -390,8 +418,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
       const int r = idx / n1v, j4 = idx - r * n1v;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < nrows) {
-        const float4* base = reinterpret_cast<const float4*>(p.hpart + (long long)(r_lo + r) * p.n1) + j4;
-        const long long cstride = (long long)128 * p.n1 / 4;
+        const float4* base = reinterpret_cast<const float4*>(p.hpart + (long long)(r_lo + r) * hpp) + j4;
+        const long long cstride = (long long)128 * hpp / 4;
         for (int c0 = 0; c0 < p.G; c0 += 8) {
           float4 t[8];
 #pragma unroll
@@ -509,11 +537,19 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
         for (int r = 0; r < 16; ++r) a += s_dh[r * HP + tid];
         atomicAdd(p.gb1 + tid, a);
       }
-      __syncthreads();
-      STAMP(19);
-      if (tid == 0) {
-        __threadfence();
-        atomicAdd(&fl[1], 1u);
+#ifndef DTF_HOST_EMU
+      if (fused && p.clustered) {
+        STAMP(19);
+        cluster_sync_all();          // every CTA's dh rows are in L2 and visible to the cluster
+      } else
+#endif
+      {
+        __syncthreads();
+        STAMP(19);
+        if (tid == 0) {
+          __threadfence();
+          atomicAdd(&fl[1], 1u);
+        }
       }
     }
     STAMP(6);
@@ -525,7 +561,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
   if ((p.phase_mask & 4) && !p.forward_only) {
 #ifndef DTF_HOST_EMU
     if (tid == 0) {
-      if (fused && !wait_counter_ge(&fl[1], sync_target, p.timeout_ns) && p.err) atomicExch(p.err, 5u);
+      if (fused && !p.clustered && !wait_counter_ge(&fl[1], sync_target, p.timeout_ns) && p.err) atomicExch(p.err, 5u);
       fence_proxy_async();
       mbar_arrive_expect_tx(bar_dh, (uint32_t)(4 * dh_chunk));
       for (int q = 0; q < 4; ++q) tma_load_2d(w_sm + q * dh_chunk, &map_dh, bar_dh, 32 * q, 0);      // box {32 units, kb rows}
@@ -565,17 +601,34 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
         uint32_t r[8][8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          if (c_lo + u < c_hi) tmem_ld_32x32b_x8(tmem_d2 + ((uint32_t)(q * 32) << 16) + (uint32_t)((c_lo + u) * 8), r[u]);
+          if (c_lo + u < c_hi && !(p.dbg & 2)) tmem_ld_32x32b_x8(tmem_d2 + ((uint32_t)(q * 32) << 16) + (uint32_t)((c_lo + u) * 8), r[u]);
         tmem_ld_wait();
-        if (j < p.H) {
+        const int ncols = min(p.ds, p.D - d0);                 // features of this slice that exist
+        if (p.ldgw1 == 128) {
+          // the slot's rows are 128 floats: the slice's rows form ONE contiguous block [ncols][128] -- park the tile in
+          // shared memory (the batch tile is dead: the B3 MMAs completed; lanes = consecutive j -> conflict-free) and
+          // push it with one bulk store.  Hidden units >= H are rows of exact zeros (dh's padding), like the slot's padding.
+          float* stage = reinterpret_cast<float*>(x_sm);
 #pragma unroll
           for (int u = 0; u < 8; ++u)
             if (c_lo + u < c_hi) {
 #pragma unroll
-              for (int v = 0; v < 8; ++v) {
-                const int il = (c_lo + u) * 8 + v;
-                if (il < p.ds && d0 + il < p.D) p.gw1[(long long)(d0 + il) * p.ldgw1 + j] = __uint_as_float(r[u][v]);
-              }
+              for (int v = 0; v < 8; ++v) stage[((c_lo + u) * 8 + v) * 128 + j] = __uint_as_float(r[u][v]);
+            }
+          fence_proxy_async_smem();
+          __syncthreads();
+          if (tid == 0 && ncols > 0 && !(p.dbg & 1)) {
+            bulk_store_1d(p.gw1 + (long long)d0 * 128, x_sm, (uint32_t)(ncols * 512));
+            bulk_commit_and_wait();
+          }
+        } else if (j < p.H && !(p.dbg & 1)) {
+          float* g = p.gw1 + (long long)(d0 + c_lo * 8) * p.ldgw1 + j;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (c_lo + u < c_hi) {
+#pragma unroll
+              for (int v = 0; v < 8; ++v)
+                if ((c_lo + u) * 8 + v < ncols) g[(long long)(u * 8 + v) * p.ldgw1] = __uint_as_float(r[u][v]);
             }
         }
       }
@@ -671,6 +724,8 @@ struct DtfMlpStepArgs {
   unsigned long long timeout_ns;
   unsigned int* err;
   unsigned long long* trace;
+  int no_cluster;              // 1: plain grid + L2 counters even when the CTAs would fit one cluster
+  int dbg;
 };
 
 // Slices: at least ceil(B / 16) CTAs (phase 2 finalises <= 16 batch rows per CTA), at most 16; among those the widest
@@ -696,12 +751,12 @@ int dtf_mlp_step_slices(int D, int B, int* ds_out) {
   return g_any;
 }
 
-// scratch sizes (floats): hpart = G * 128 * n1, dh = 128 * 128
+// scratch sizes (floats): hpart = G * 128 * (n1 + 4), dh = 128 * 128
 long long dtf_mlp_step_scratch_floats(int D, int B, int H) {
   int ds = 0;
   const int g = dtf_mlp_step_slices(D, B, &ds);
   const int n1 = (H + 15) / 16 * 16;
-  return (long long)g * 128 * n1 + 128 * 128 + 64;
+  return (long long)g * 128 * (n1 + 4) + 128 * 128 + 64;
 }
 
 int dtf_mlp_step(const DtfMlpStepArgs* a, cudaStream_t s) {
@@ -736,9 +791,9 @@ int dtf_mlp_step(const DtfMlpStepArgs* a, cudaStream_t s) {
   }
   p.sys_scope = a->sys_scope;
   p.timeout_ns = a->timeout_ns ? a->timeout_ns : 2000000000ull;
-  p.err = a->err; p.trace = a->trace;
+  p.err = a->err; p.trace = a->trace; p.dbg = a->dbg;
   const int nqx = (ds + 31) / 32, nq1 = (p.n1 + 31) / 32;
-  const int w_region = (std::max(nq1 * ds * 128, 4 * p.kb * 128) + 1023) & ~1023;
+  const int w_region = (std::max(std::max(nq1 * ds * 128, 4 * p.kb * 128), 128 * (p.n1 + 4) * 4) + 1023) & ~1023;
   const size_t head_floats = 2 * 16 * 132 + 128 * 20 + 128 + 256 + 256 + 16;
   const size_t smem = 1024 + (size_t)nqx * kXChunkBytes + w_region + head_floats * 4;
 #ifdef DTF_HOST_EMU
@@ -774,7 +829,24 @@ int dtf_mlp_step(const DtfMlpStepArgs* a, cudaStream_t s) {
     configured[dev] = true;
   }
   if (smem > 200 * 1024) return -2;
-  if (p.phase_mask == 7) {
+  if (p.phase_mask == 7 && g <= 8 && !a->no_cluster) {
+    // the G CTAs as ONE cluster (co-scheduled on one GPC): barrier.cluster orders the two exchanges
+    p.clustered = 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(g, 1, 1);
+    cfg.blockDim = dim3(kStepThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = g;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, mlp_step_kernel, mx, mx2, mw, md, p);
+  } else if (p.phase_mask == 7) {
     mlp_step_kernel<<<g, kStepThreads, smem, s>>>(mx, mx2, mw, md, p);
   } else {
     const int masks[3] = {1, 2, 4};

@@ -294,7 +294,7 @@ class PSTrainEngine:
                          ("misc_w%d" % w, 4096 + cfg.loss_hist * 4)]
                 if self.tf32:
                     # scratch of the one-kernel step: partial pre-activations + dh (L2 resident), 8 sync counters, phase stamps
-                    nfl = self.step_ctas * 128 * round_up(spec.hidden, 16) + 128 * 128 + 64
+                    nfl = self.step_ctas * 128 * (round_up(spec.hidden, 16) + 4) + 128 * 128 + 64
                     names += [("stepscr_w%d" % w, nfl * 4), ("stepflags_w%d" % w, 256), ("steptrace_w%d" % w, 16 * 32 * 8)]
                 for s in range(cfg.num_ps):
                     if self.nvls:
@@ -622,7 +622,7 @@ class PSTrainEngine:
         a.nbatches, a.bstride, a.boffset = nbatches, cfg.num_workers, k["w"]
         a.w1, a.ldw1, a.b1 = k["w1"], k["ldw1"], k["b1"]
         a.w2, a.ldw2, a.b2 = k["w2"], k["ldw2"], k["b2"]
-        a.hpart, a.dh, a.lddh = k["scr"], k["scr"] + self.step_ctas * 128 * round_up(spec.hidden, 16) * 4, 128
+        a.hpart, a.dh, a.lddh = k["scr"], k["scr"] + self.step_ctas * 128 * (round_up(spec.hidden, 16) + 4) * 4, 128
         a.flags = k["flags"]
         a.gw1, a.ldgw1, a.gb1 = k["gw1"], lay["hid_w"].pitch, k["gb1"]
         a.gw2, a.ldgw2, a.gb2 = k["gw2"], lay["sm_w"].pitch, k["gb2"]
@@ -635,6 +635,8 @@ class PSTrainEngine:
             a.stamp_src[i] = k["tokens"][i] + (0 if cfg.sync else 8)
         a.sys_scope = 0 if cfg.colocated else 1
         a.timeout_ns, a.err = cfg.timeout_ns, d["err_ptr"]
+        a.no_cluster = int(os.environ.get("DTF_STEP_NO_CLUSTER", "0") == "1")
+        a.dbg = int(os.environ.get("DTF_STEP_DBG", "0"))
         return a
 
     # ------------------------------------------------------------------------------------------------

@@ -43,8 +43,9 @@ def _check_backward(x, w1, b1, dh_k, gw1_k, gb1_k, ref, B, H):
 
 
 @pytest.mark.parametrize("mask", [15, 7])            # 15: one launch per phase (no inter-CTA waits); 7: the fused kernel
-@pytest.mark.parametrize("B,D,H,C,nbatches", [(100, 784, 100, 10, 3), (37, 200, 64, 7, 0), (128, 96, 128, 16, 2)])
-def test_step_kernel_matches_float64_model(B, D, H, C, nbatches, mask):
+@pytest.mark.parametrize("B,D,H,C,nbatches,wide", [(100, 784, 100, 10, 3, True), (100, 784, 100, 10, 3, False), (37, 200, 64, 7, 0, False),
+                                                   (128, 96, 128, 16, 2, True)])
+def test_step_kernel_matches_float64_model(B, D, H, C, nbatches, wide, mask):
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
     from distributed_tensorflow_b200.ops import cuda_lib
@@ -54,7 +55,8 @@ def test_step_kernel_matches_float64_model(B, D, H, C, nbatches, mask):
     rows = max(nbatches, 1) * B
     xs_h = torch.rand(rows + 64, D, generator=g)                    # + slack rows: the 128-row box of the last batch
     ys_h = torch.nn.functional.one_hot(torch.randint(0, C, (rows,), generator=g), C).float()
-    ldw1, ldw2 = (H + 7) // 8 * 8, (C + 7) // 8 * 8
+    # wide: 128-float rows (the engine's tf32 layout: in-bounds TMA boxes, dW1 leaves as ONE bulk store per CTA)
+    ldw1, ldw2 = (128 if wide else (H + 7) // 8 * 8), (C + 7) // 8 * 8
     w1_h = torch.zeros(D, ldw1); w1_h[:, :H] = torch.randn(D, H, generator=g) / np.sqrt(D)
     w2_h = torch.zeros(H, ldw2); w2_h[:, :C] = torch.randn(H, C, generator=g) / np.sqrt(H)
     b1_h, b2_h = torch.randn(H, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1
@@ -62,7 +64,7 @@ def test_step_kernel_matches_float64_model(B, D, H, C, nbatches, mask):
     ds = ctypes.c_int(0)
     G = lib.dtf_mlp_step_slices(D, B, ctypes.byref(ds))
     n1 = (H + 15) // 16 * 16
-    hpart = torch.zeros(G * 128 * n1, device=dev)
+    hpart = torch.zeros(G * 128 * (n1 + 4), device=dev)
     dh = torch.zeros(128, 128, device=dev)
     flags = torch.zeros(8, dtype=torch.int32, device=dev)
     gw1, gb1 = torch.full((D, ldw1), 7.0, device=dev), torch.zeros(H, device=dev)
@@ -103,7 +105,10 @@ def test_step_kernel_matches_float64_model(B, D, H, C, nbatches, mask):
     assert _rel(gw2[:, :C], ref["w2"]) < 3e-3 and _rel(gb2, ref["b2"]) < 3e-3
     assert int(stepctr[0]) == step0 + 1
     assert int(arrivals[0]) == G and int(arrivals[1]) == 5
-    assert flags[:4].tolist() == [G * 4] * 3 + [4] and flags[4:].tolist() == [0] * 4
+    clustered = mask == 7 and G <= 8                               # one cluster: barrier.cluster instead of the two L2 counters
+    assert flags[:4].tolist() == [G * (3 if clustered else 4)] * 2 + [G * 4, 4] and flags[4:].tolist() == [0] * 4
+    if wide:
+        assert float(gw1[:, H:].abs().sum()) == 0.0                # padding columns of the slot receive exact zeros
     if mask == 7:
         t = trace.view(16, 32)[:G].cpu()
         assert bool((t[:, 10] > t[:, 0]).all())                    # every CTA stamped entry and exit
@@ -126,7 +131,7 @@ def test_step_kernel_two_consecutive_steps_and_forward_only():
     xs, ys, w1, w2 = xs_h.to(dev), ys_h.to(dev), w1_h.to(dev), w2_h.to(dev)
     b1, b2 = torch.zeros(H, device=dev), torch.zeros(C, device=dev)
     G = lib.dtf_mlp_step_slices(D, B, None)
-    hpart, dh = torch.zeros(G * 128 * 112, device=dev), torch.zeros(128, 128, device=dev)
+    hpart, dh = torch.zeros(G * 128 * 116, device=dev), torch.zeros(128, 128, device=dev)
     flags = torch.zeros(8, dtype=torch.int32, device=dev)
     gw1, gb1, gw2, gb2 = (torch.zeros(s, device=dev) for s in ((D, 104), (H,), (H, 16), (C,)))
     loss, logits = torch.zeros(16, device=dev), torch.zeros(B, C, device=dev)
@@ -164,4 +169,4 @@ def test_step_kernel_two_consecutive_steps_and_forward_only():
     assert _rel(logits, ref_z) < 2e-3
     assert abs(float(loss[:G].sum()) - float(ref_loss)) < 2e-3 * abs(float(ref_loss))
     assert torch.equal(before[0], gw1) and int(arrivals[0]) == before[1] and int(stepctr[0]) == 2
-    assert flags.tolist() == [2 * G, 2 * G, 2 * G, 2, G, 0, G, 1]
+    assert flags.tolist() == [0, 0, 2 * G, 2, 0, 0, G, 1]           # clustered launches: only the ticket + epoch counters move

@@ -54,7 +54,7 @@ def test_step_kernel_matches_float64_model(emu, B, D, H, C, nbatches):
     if D == 784:
         assert (G, ds.value) == (7, 112)
     n1 = (H + 15) // 16 * 16
-    hpart = torch.zeros(G * 128 * n1)
+    hpart = torch.zeros(G * 128 * (n1 + 4))
     dh = torch.zeros(128, 128)
     flags = torch.zeros(8, dtype=torch.int32)
     gw1, gb1 = torch.full((D, ldw1), 7.0), torch.zeros(H)          # dW1 is STORED (stale content must be overwritten) ...
@@ -106,7 +106,7 @@ def test_forward_only_leaves_gradients_and_protocol_untouched(emu):
     w1, w2 = torch.randn(D, 104, generator=g) / 28, torch.randn(H, 16, generator=g) / 10
     b1, b2 = torch.zeros(H), torch.zeros(C)
     G = emu.dtf_mlp_step_slices(D, B, None)
-    hpart, dh, flags = torch.zeros(G * 128 * 112), torch.zeros(128, 128), torch.zeros(8, dtype=torch.int32)
+    hpart, dh, flags = torch.zeros(G * 128 * 116), torch.zeros(128, 128), torch.zeros(8, dtype=torch.int32)
     loss, logits = torch.zeros(16), torch.zeros(B, C)
     stepctr, token = torch.zeros(1, dtype=torch.int64), torch.zeros(2, dtype=torch.int64)
     arrivals = torch.zeros(2, dtype=torch.int64)

@@ -1,10 +1,10 @@
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517"
-step() { local name=$1 t=$2; shift 2; timeout "$t" "$@" > "gpurun_out/${name}.log" 2>&1; echo "${name}: rc=$? $(tail -1 gpurun_out/${name}.log | cut -c1-420)"; }
+N=${1:-2}
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
+step() { local name=$1 t=$2; shift 2; timeout "$t" "$@" > "gpurun_out/${name}.log" 2>&1; echo "${name}: rc=$? $(tail -1 gpurun_out/${name}.log | cut -c1-330)"; }
 DTF_PS_ON_WORKERS=1 DTF_NVLS=1 step mp_pow_nvls_tf32 120 $TR tools/mp_check.py
 DTF_PS_ON_WORKERS=1 DTF_NVLS=0 step mp_pow_uni_tf32 120 $TR tools/mp_check.py
 DTF_PS_ON_WORKERS=0 DTF_NVLS=1 step mp_ref_nvls_tf32 120 $TR tools/mp_check.py
-DTF_PS_ON_WORKERS=0 DTF_NVLS=0 step mp_ref_uni_tf32 120 $TR tools/mp_check.py
 DTF_PS_ON_WORKERS=1 DTF_NVLS=1 DTF_PRECISION=bf16 step mp_pow_nvls_bf16 120 $TR tools/mp_check.py
-step bench2_nvls 200 $TR bench.py --gpus 2 --nvls on
-step bench2_uni 200 $TR bench.py --gpus 2 --nvls off --baseline 0
-step bench2_k20 200 $TR bench.py --gpus 2 --steps 20 --warmup 3 --baseline 0
+step bench${N}_nvls 200 $TR bench.py --gpus $N --nvls on
+DTF_PS_STREAM=0 step bench${N}_nvls_1stream 200 $TR bench.py --gpus $N --nvls on --baseline 0 --e2e-steps 0
+step bench${N}_psonly 200 $TR bench.py --gpus $N --ps-only-task 1 --baseline 0 --e2e-steps 0
