@@ -437,47 +437,80 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
     }
     __syncthreads();
     STAMP(15);
-    // logits / softmax / loss / dlogits: warp w owns rows 2w and 2w + 1, lane = (row parity, class)
+    // logits / softmax / loss / dlogits.  Thread = (row r, quarter jq of the hidden units, class quad cq): one scalar + one
+    // 16-byte shared-memory load per 4 FMAs; the four jq partials meet by shuffles, the 16 classes of a row = 4 lanes x 4.
     float my_loss = 0.f;
     {
-      const int r = 2 * warp + (lane >> 4), c = lane & 15;
-      const float* hr = s_h + r * HP;
-      float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
-      // rows of s_h / s_w2 beyond H are zero: walk whole groups of four hidden units, four independent chains
+      const int r = tid >> 4, jq = (tid >> 2) & 3, cq = tid & 3;
+      const int jn = p.n1 >> 2;                                  // n1 is a multiple of 16
+      const float* hr = s_h + r * HP + jq * jn;
+      const float* wr = s_w2 + (jq * jn) * WS + 4 * cq;
+      float z[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
-      for (int j = 0; j < p.n1; j += 4) {
-        z0 = fmaf(hr[j], s_w2[j * WS + c], z0);
-        z1 = fmaf(hr[j + 1], s_w2[(j + 1) * WS + c], z1);
-        z2 = fmaf(hr[j + 2], s_w2[(j + 2) * WS + c], z2);
-        z3 = fmaf(hr[j + 3], s_w2[(j + 3) * WS + c], z3);
+      for (int j = 0; j < jn; ++j) {                             // rows of s_h / s_w2 beyond H are zero
+        const float hv = hr[j];
+        const float4 w = *reinterpret_cast<const float4*>(wr + j * WS);
+        z[0] = fmaf(hv, w.x, z[0]); z[1] = fmaf(hv, w.y, z[1]); z[2] = fmaf(hv, w.z, z[2]); z[3] = fmaf(hv, w.w, z[3]);
       }
-      z0 += z2; z1 += z3;
-      const bool live = c < p.C;
-      float z = live ? (z0 + z1 + s_b2[c]) : -INFINITY;
-      if (p.logits_out && live && r < nrows) p.logits_out[(long long)(r_lo + r) * p.C + c] = z;
-      float mx = z;
-      for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float e = live ? __expf(z - mx) : 0.f;
-      float se = e;
-      for (int o = 8; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-      const float y = e / se;
-      const float lse = mx + __logf(se);
-      const float lab = s_lab[r * 16 + c];
-      float t = 0.f, lterm = 0.f;
-      if (live) {
-        if (p.clip_min > 0.f) {
-          lterm = -lab * fmaxf(z - lse, __logf(p.clip_min));   // log(clamp(y, clip, 1)) = max(log y, log clip) for y <= 1
-          t = (y >= p.clip_min) ? lab : 0.f;
-        } else {
-          lterm = -lab * (z - lse);
-          t = lab;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        z[k] += __shfl_xor_sync(0xffffffffu, z[k], 4);
+        z[k] += __shfl_xor_sync(0xffffffffu, z[k], 8);
+      }
+      bool live[4];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        live[k] = 4 * cq + k < p.C;
+        z[k] = live[k] ? z[k] + s_b2[4 * cq + k] : -INFINITY;
+        mx = fmaxf(mx, z[k]);
+      }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float e[4], se = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        e[k] = live[k] ? __expf(z[k] - mx) : 0.f;
+        se += e[k];
+      }
+      se += __shfl_xor_sync(0xffffffffu, se, 1);
+      se += __shfl_xor_sync(0xffffffffu, se, 2);
+      const float inv = 1.f / se, lse = mx + __logf(se);
+      const float4 lab4 = *reinterpret_cast<const float4*>(s_lab + r * 16 + 4 * cq);
+      const float lab[4] = {lab4.x, lab4.y, lab4.z, lab4.w};
+      float t[4], y[4], tsum = 0.f, lterm = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        y[k] = e[k] * inv;
+        t[k] = 0.f;
+        if (live[k]) {
+          if (p.clip_min > 0.f) {
+            lterm -= lab[k] * fmaxf(z[k] - lse, __logf(p.clip_min));   // log(clamp(y, clip, 1)) = max(log y, log clip), y <= 1
+            t[k] = (y[k] >= p.clip_min) ? lab[k] : 0.f;
+          } else {
+            lterm -= lab[k] * (z[k] - lse);
+            t[k] = lab[k];
+          }
+        }
+        tsum += t[k];
+      }
+      tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
+      tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
+      const bool rlive = r < nrows;
+      if (jq == 0) {                                             // one writer per (row, quad)
+        float4 g4;
+        g4.x = (live[0] && rlive) ? y[0] * tsum - t[0] : 0.f;
+        g4.y = (live[1] && rlive) ? y[1] * tsum - t[1] : 0.f;
+        g4.z = (live[2] && rlive) ? y[2] * tsum - t[2] : 0.f;
+        g4.w = (live[3] && rlive) ? y[3] * tsum - t[3] : 0.f;
+        *reinterpret_cast<float4*>(s_dl + r * 16 + 4 * cq) = g4;
+        if (p.logits_out && rlive) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (live[k]) p.logits_out[(long long)(r_lo + r) * p.C + 4 * cq + k] = z[k];
         }
       }
-      float tsum = t;
-      for (int o = 8; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
-      const float g = (live && r < nrows) ? (y * tsum - t) : 0.f;
-      s_dl[r * 16 + c] = g;
-      my_loss = (r < nrows) ? lterm : 0.f;
+      my_loss = (jq == 0 && rlive) ? lterm : 0.f;
       for (int o = 16; o > 0; o >>= 1) my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
       if (lane == 0) s_red[warp] = my_loss;
     }
@@ -489,38 +522,47 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
       p.loss_out[cta] = t;
     }
     if (!p.forward_only) {
-      // dh[r][j] = (h > 0) * dl[r][:] . W2[j][:]   (-> shared memory for db1, -> L2 scratch for every CTA's dW1 GEMM)
-      for (int idx = tid; idx < 16 * p.n1; idx += kStepThreads) {
-        const int r = idx / p.n1, j = idx - r * p.n1;
-        float d = 0.f;
-        if (r < nrows) {
+      // dh[r][j] = (h > 0) * dl[r][:] . W2[j][:] and db1[j] = sum_r dh[r][j].  Thread = (hidden unit j, row group): the W2 row
+      // stays in registers across the group's 8 rows, the dl row is a broadcast; dh rows go to the L2 scratch (coalesced over j)
+      {
+        const int j = tid & 127, rg = tid >> 7;
+        float4 w[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) w[c] = *reinterpret_cast<const float4*>(s_w2 + j * WS + 4 * c);
+        float db1 = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int r = rg * 8 + rr;
           const float4* dl = reinterpret_cast<const float4*>(s_dl + r * 16);
-          const float4* w = reinterpret_cast<const float4*>(s_w2 + j * WS);
-          float d1 = 0.f;
+          float d = 0.f, d1 = 0.f;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const float4 a4 = dl[c], w4 = w[c];
-            d = fmaf(a4.x, w4.x, d); d1 = fmaf(a4.y, w4.y, d1);
-            d = fmaf(a4.z, w4.z, d); d1 = fmaf(a4.w, w4.w, d1);
+            const float4 a4 = dl[c];
+            d = fmaf(a4.x, w[c].x, d); d1 = fmaf(a4.y, w[c].y, d1);
+            d = fmaf(a4.z, w[c].z, d); d1 = fmaf(a4.w, w[c].w, d1);
           }
-          d += d1;
-          d = s_h[r * HP + j] > 0.f ? d : 0.f;
-          p.dh[(long long)(r_lo + r) * p.lddh + j] = d;
+          d = (j < p.n1 && s_h[r * HP + j] > 0.f) ? d + d1 : 0.f;   // rows >= nrows / units >= H: h == 0 -> 0
+          if (r < nrows && j < p.n1) p.dh[(long long)(r_lo + r) * p.lddh + j] = d;
+          db1 += d;
         }
-        s_dh[r * HP + j] = d;
+        s_dh[rg * 128 + j] = db1;                                // combine the two row groups below
       }
       STAMP(17);
-      // dW2[j][c] += sum_r h[r][j] * dl[r][c]
-      for (int idx = tid; idx < p.H * 16; idx += kStepThreads) {
-        const int j = idx >> 4, c = idx & 15;
-        if (c < p.C) {
-          float a = 0.f, a1 = 0.f;
+      // dW2[j][4cq .. 4cq+3] += sum_r h[r][j] * dl[r][4cq .. 4cq+3]: one scalar + one 16-byte load per 4 FMAs
+      for (int it = tid; it < 128 * 4; it += kStepThreads) {
+        const int j = it >> 2, cq = it & 3;
+        if (j < p.H && 4 * cq < p.C) {
+          float a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int r = 0; r < 16; r += 2) {                  // row slots beyond nrows hold zeros in s_h and s_dl
-            a = fmaf(s_h[r * HP + j], s_dl[r * 16 + c], a);
-            a1 = fmaf(s_h[(r + 1) * HP + j], s_dl[(r + 1) * 16 + c], a1);
+          for (int r = 0; r < 16; ++r) {                         // row slots beyond nrows hold zeros in s_h and s_dl
+            const float hv = s_h[r * HP + j];
+            const float4 d4 = *reinterpret_cast<const float4*>(s_dl + r * 16 + 4 * cq);
+            a[0] = fmaf(hv, d4.x, a[0]); a[1] = fmaf(hv, d4.y, a[1]); a[2] = fmaf(hv, d4.z, a[2]); a[3] = fmaf(hv, d4.w, a[3]);
           }
-          atomicAdd(p.gw2 + (long long)j * p.ldgw2 + c, a + a1);
+          float* gw = p.gw2 + (long long)j * p.ldgw2 + 4 * cq;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (4 * cq + k < p.C) atomicAdd(gw + k, a[k]);
         }
       }
       if (tid < p.C) {
@@ -531,12 +573,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
       }
       __syncthreads();
       STAMP(18);
-      if (tid < p.H) {
-        float a = 0.f;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) a += s_dh[r * HP + tid];
-        atomicAdd(p.gb1 + tid, a);
-      }
+      if (tid < p.H) atomicAdd(p.gb1 + tid, s_dh[tid] + s_dh[128 + tid]);
 #ifndef DTF_HOST_EMU
       if (fused && p.clustered) {
         STAMP(19);

@@ -1040,13 +1040,14 @@ class PSTrainEngine:
             lab = yd if yd is not None else torch.zeros((N, C), dtype=torch.float32, device=rk.device)
             logits = torch.empty((N, C), dtype=torch.float32, device=rk.device)
             if self.tf32:
-                nch = (N + 127) // 128
+                ch = min(128, 16 * self.step_ctas)        # phase 2 finalises <= 16 rows per CTA
+                nch = (N + ch - 1) // ch
                 lossbuf = torch.zeros((nch, 16), dtype=torch.float32, device=rk.device)
                 for i in range(nch):
-                    rows = min(128, N - i * 128)
-                    a = self._step_args(d, xd.data_ptr() + i * 128 * D * 4, rows, lab.data_ptr() + i * 128 * C * 4, 0, rows)
+                    rows = min(ch, N - i * ch)
+                    a = self._step_args(d, xd.data_ptr() + i * ch * D * 4, rows, lab.data_ptr() + i * ch * C * 4, 0, rows)
                     a.forward_only, a.num_signals = 1, 0
-                    a.logits_out, a.loss_out = logits.data_ptr() + i * 128 * C * 4, lossbuf.data_ptr() + i * 64
+                    a.logits_out, a.loss_out = logits.data_ptr() + i * ch * C * 4, lossbuf.data_ptr() + i * 64
                     rc = self.lib.dtf_mlp_step(ctypes.byref(a), rk.stream.cuda_stream)
                     assert rc == 0, "mlp_step(forward_only) rc=%d" % rc
                 cuda_lib._bump(nch)
