@@ -105,6 +105,10 @@ DTF_DEVICE void multimem_st_f32x4(float* mc, float4 v) {
                "f"(v.w)
                : "memory");
 }
+// one add replicated by the switch into every GPU's copy of a 64-bit counter
+DTF_DEVICE void multimem_red_add_u64(unsigned long long* mc, unsigned long long v) {
+  asm volatile("multimem.red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(mc), "l"(v) : "memory");
+}
 // 8 bytes (four bf16 packed in two b32 words), bit-exact copy into every GPU's replica
 DTF_DEVICE void multimem_st_b64(void* mc, uint32_t lo, uint32_t hi) {
   asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc), "f"(__uint_as_float(lo)),

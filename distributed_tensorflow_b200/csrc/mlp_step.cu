@@ -86,7 +86,9 @@ struct MlpStepParams {
   int forward_only;            // 1: stop after the loss / logits (no gradients, no arrival)
   // ---- ps protocol
   int num_tokens;
-  const unsigned long long* token[4];   // mailbox token words: wait until >= step (per ps shard holding a parameter)
+  const unsigned long long* token[4];   // per ps shard holding a parameter: wait until *token >= step * token_scale
+  unsigned long long token_scale[4];    // 1: mailbox token (= global step); G_ps: counter bumped once per ps_apply CTA
+  int stamp_step;                       // 1 (sync): the push is stamped with the step; 0 (async): with *stamp_src (version)
   int num_signals;
   unsigned long long* arrivals[4];      // ps arrival counters (+1 per CTA per push)
   unsigned long long* stamp_dst[4];
@@ -101,6 +103,9 @@ struct MlpStepParams {
 };
 
 #ifndef DTF_HOST_EMU
+DTF_DEVICE void red_relaxed_sys_add_u64_(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 DTF_DEVICE unsigned int ld_acquire_gpu_u32_(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -132,6 +137,7 @@ DTF_DEVICE void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
                : "memory");
 }
 #else
+static inline void red_relaxed_sys_add_u64_(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned int ld_acquire_gpu_u32_(const unsigned int* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
 static inline unsigned int ld_relaxed_gpu_u32_(const unsigned int* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
 #endif
@@ -258,7 +264,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
 #endif
       // the parameters behind every later read were published by the ps: acquire its token(s) for this step
       for (int i = 0; i < p.num_tokens; ++i)
-        if (!wait_flag_ge_u64(reinterpret_cast<const uint64_t*>(p.token[i]), step, p.timeout_ns) && p.err) atomicExch(p.err, 1u);
+        if (!wait_flag_ge_u64(reinterpret_cast<const uint64_t*>(p.token[i]), step * p.token_scale[i], p.timeout_ns) && p.err)
+          atomicExch(p.err, 1u);
       // (colocated: the ps kernel that released this token finished before this kernel started -- stream order -- so the
       //  acquire's fast path is a single already-satisfied load)
 #ifndef DTF_HOST_EMU
@@ -691,16 +698,16 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
     __syncthreads();
     STAMP(8);
     if (tid == 0) {
-      // ONE fence by one thread after the CTA barrier (release is cumulative), then the arrival(s).  When the ps shares
-      // this GPU AND this stream (colocated), its kernel starts after this one has completed: the kernel boundary orders
-      // the gradient stores, the arrival is a plain count
+      // CTA 0 stamps the push FIRST; then ONE fence by one thread per CTA after the CTA barrier (release is cumulative: it
+      // covers the bulk store waited for above, the head's atomics and the stamp), then a RELAXED arrival.  The ps acts on
+      // the push only once all G arrivals are in, CTA 0's included, so the stamp is visible by then.  When the ps shares this
+      // GPU AND this stream (colocated), its kernel starts after this one has completed: no fence at all.
+      if (cta == 0)
+        for (int i = 0; i < p.num_signals; ++i)
+          if (p.stamp_dst[i]) st_relaxed_sys_u64(reinterpret_cast<uint64_t*>(p.stamp_dst[i]), p.stamp_step ? step : *p.stamp_src[i]);
       if (p.sys_scope) fence_acq_rel_sys();
       for (int i = 0; i < p.num_signals; ++i) {
-        if (cta == 0 && p.stamp_dst[i]) st_relaxed_sys_u64(reinterpret_cast<uint64_t*>(p.stamp_dst[i]), *p.stamp_src[i]);
-      }
-      if (cta == 0 && p.num_signals && p.sys_scope) fence_acq_rel_sys();
-      for (int i = 0; i < p.num_signals; ++i) {
-        if (p.sys_scope) red_release_sys_add_u64(reinterpret_cast<uint64_t*>(p.arrivals[i]), 1ull);
+        if (p.sys_scope) red_relaxed_sys_add_u64_(p.arrivals[i], 1ull);
         else atomicAdd(reinterpret_cast<unsigned long long*>(p.arrivals[i]), 1ull);
       }
     }
@@ -755,7 +762,7 @@ struct DtfMlpStepArgs {
   float* loss_out; float* logits_out;
   unsigned long long* step_counter;
   int forward_only;
-  int num_tokens; const unsigned long long* token[4];
+  int num_tokens; const unsigned long long* token[4]; unsigned long long token_scale[4]; int stamp_step;
   int num_signals; unsigned long long* arrivals[4]; unsigned long long* stamp_dst[4]; const unsigned long long* stamp_src[4];
   int sys_scope;
   unsigned long long timeout_ns;
@@ -824,9 +831,9 @@ int dtf_mlp_step(const DtfMlpStepArgs* a, cudaStream_t s) {
   p.num_tokens = a->num_tokens;
   p.num_signals = a->num_signals;
   for (int i = 0; i < 4; ++i) {
-    p.token[i] = a->token[i]; p.arrivals[i] = a->arrivals[i]; p.stamp_dst[i] = a->stamp_dst[i]; p.stamp_src[i] = a->stamp_src[i];
+    p.token[i] = a->token[i]; p.token_scale[i] = a->token_scale[i] ? a->token_scale[i] : 1ull; p.arrivals[i] = a->arrivals[i]; p.stamp_dst[i] = a->stamp_dst[i]; p.stamp_src[i] = a->stamp_src[i];
   }
-  p.sys_scope = a->sys_scope;
+  p.sys_scope = a->sys_scope; p.stamp_step = a->stamp_step;
   p.timeout_ns = a->timeout_ns ? a->timeout_ns : 2000000000ull;
   p.err = a->err; p.trace = a->trace; p.dbg = a->dbg;
   const int nqx = (ds + 31) / 32, nq1 = (p.n1 + 31) / 32;

@@ -62,6 +62,8 @@ struct PsApplyParams {
   __nv_bfloat16* shadow_mc;      // multicast mapping of the bf16 replica: ONE multimem.st updates every GPU's copy
   float* master_mc;              // optional multicast mapping of an fp32 replica (models that consume fp32 parameters)
   unsigned int full_mask;        // all workers: the ld_reduce path needs every copy to hold a fresh gradient
+  unsigned long long* token_mc;  // optional multicast address of a counter in every worker's replica buffer: each CTA bumps it once
+                                 // (multimem.red) right after its own release fence -- the workers need no last-block round
 };
 
 #ifndef DTF_HOST_EMU
@@ -307,6 +309,9 @@ __global__ void __launch_bounds__(256, 4) ps_apply_kernel(const PsApplyParams p)
   PSTAMP(2);          // block 0 finished its slice
   if (threadIdx.x == 0) {
     if (p.system_scope) __threadfence_system(); else __threadfence();      // one fence per CTA, after the barrier
+    // NVLS: tell EVERY worker "this slice is published" with one switch-replicated add; a worker's step starts when all
+    // gridDim.x slices of this aggregate have said so (sync, all-fresh aggregates only: a token for every replica)
+    if (p.token_mc != nullptr && all_fresh_only && ok) multimem_red_add_u64(p.token_mc, 1ull);
     const unsigned int prev = atomicAdd(&ctl->done_ctas, 1u);
     if (prev == gridDim.x - 1) {
       // the ticket observed every CTA's fence + increment: ONE fence here makes all their parameter stores (local, peer,
@@ -924,7 +929,14 @@ struct DtfPsApplyArgs {
   const float* grad_mc;
   void* shadow_mc;
   float* master_mc;
+  unsigned long long* token_mc;
 };
+
+// default grid: one float4 per thread (a single load round trip); all CTAs must be co-resident (4 per SM by launch bounds)
+int dtf_ps_apply_grid(long long n) {
+  long long want = (n / 4 + 255) / 256;
+  return (int)(want < 1 ? 1 : (want > 592 ? 592 : want));
+}
 
 int dtf_ps_apply(const DtfPsApplyArgs* a, cudaStream_t s) {
   PsApplyParams p;
@@ -948,12 +960,10 @@ int dtf_ps_apply(const DtfPsApplyArgs* a, cudaStream_t s) {
   p.grad_mc = a->grad_mc; p.grad_mc_rw = const_cast<float*>(a->grad_mc);
   p.shadow_mc = reinterpret_cast<__nv_bfloat16*>(a->shadow_mc);
   p.master_mc = a->master_mc;
+  p.token_mc = a->token_mc;
   p.full_mask = a->num_workers >= 32 ? 0xFFFFFFFFu : ((1u << a->num_workers) - 1u);
   int grid = a->grid;
-  if (grid <= 0) {
-    long long want = (a->n / 4 + 255) / 256;                       // one float4 per thread: a single load round trip
-    grid = (int)(want < 1 ? 1 : (want > 592 ? 592 : want));      // all CTAs must be co-resident (4 per SM by launch bounds)
-  }
+  if (grid <= 0) grid = dtf_ps_apply_grid(a->n);
   DTF_LAUNCH(ps_apply_kernel, grid, 256, s, p);
   return (int)cudaGetLastError();
 }

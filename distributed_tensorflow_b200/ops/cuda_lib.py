@@ -53,7 +53,7 @@ class PsApplyArgs(Structure):
                 ("zero_begin", c_longlong * 4), ("zero_end", c_longlong * 4), ("num_zero", c_int),
                 ("timeout_ns", c_ulonglong), ("trace", c_void_p), ("trace_cap", c_int), ("grid", c_int),
                 ("system_scope", c_int), ("phase_trace", c_void_p), ("idle_ok", c_int),
-                ("grad_mc", c_void_p), ("shadow_mc", c_void_p), ("master_mc", c_void_p)]
+                ("grad_mc", c_void_p), ("shadow_mc", c_void_p), ("master_mc", c_void_p), ("token_mc", c_void_p)]
 
 
 class MlpHeadArgs(Structure):
@@ -80,7 +80,8 @@ class MlpStepArgs(Structure):
                 ("gw1", c_void_p), ("ldgw1", c_longlong), ("gb1", c_void_p), ("gw2", c_void_p), ("ldgw2", c_longlong),
                 ("gb2", c_void_p),
                 ("clip_min", c_float), ("loss_out", c_void_p), ("logits_out", c_void_p), ("step_counter", c_void_p),
-                ("forward_only", c_int), ("num_tokens", c_int), ("token", c_void_p * 4),
+                ("forward_only", c_int), ("num_tokens", c_int), ("token", c_void_p * 4), ("token_scale", c_ulonglong * 4),
+                ("stamp_step", c_int),
                 ("num_signals", c_int), ("arrivals", c_void_p * 4), ("stamp_dst", c_void_p * 4), ("stamp_src", c_void_p * 4),
                 ("sys_scope", c_int), ("timeout_ns", c_ulonglong), ("err", c_void_p), ("trace", c_void_p),
                 ("no_cluster", c_int), ("dbg", c_int)]
@@ -171,6 +172,9 @@ def _declare(lib) -> None:
     lib.dtf_gemm_bf16.restype = c_int
     lib.dtf_ps_apply.argtypes = [POINTER(PsApplyArgs), c_void_p]
     lib.dtf_ps_apply.restype = c_int
+    if not isinstance(getattr(lib, "dtf_ps_apply_grid", _Missing()), _Missing):
+        lib.dtf_ps_apply_grid.argtypes = [c_longlong]
+        lib.dtf_ps_apply_grid.restype = c_int
     lib.dtf_mlp_head.argtypes = [POINTER(MlpHeadArgs), c_void_p]
     lib.dtf_mlp_head.restype = c_int
     lib.dtf_convert_f32_bf16.argtypes = [c_void_p, c_longlong, c_void_p, c_longlong, c_longlong, c_longlong,

@@ -267,7 +267,8 @@ class PSTrainEngine:
             self.nvls = True
             for s in range(cfg.num_ps):
                 self.sym_grads.append(f.alloc_symmetric("sgrads%d" % s, self.shard_elems[s] * 4))
-                self.sym_repl.append(f.alloc_symmetric("srepl%d" % s, self.shard_elems[s] * (4 if self.tf32 else 2)))
+                # (+ 256 bytes behind the replica: the multicast token counter of the tf32 path, bumped by multimem.red)
+                self.sym_repl.append(f.alloc_symmetric("srepl%d" % s, self.shard_elems[s] * (4 if self.tf32 else 2) + 256))
             self.nvls_multicast = self.sym_grads[0].multicast
         for r, rk in self.ranks.items():
             if r in self.ps_ranks:
@@ -400,6 +401,8 @@ class PSTrainEngine:
                         rk.bufs[name].tensor(torch.uint8).zero_()
                     for sg in self.sym_grads:
                         sg.local(r).tensor(torch.uint8).zero_()
+                    for s_, sr in enumerate(self.sym_repl):       # the token counter behind the replica (multimem.red target)
+                        sr.local(r).tensor(torch.uint8, self.shard_elems[s_] * (4 if self.tf32 else 2), 256).zero_()
                 rk.stream.synchronize()
             rk.step = 0
         self.fabric.barrier()
@@ -560,7 +563,11 @@ class PSTrainEngine:
                     w2=psrc(lay["sm_w"]), ldw2=lay["sm_w"].pitch, b2=psrc(lay["sm_b"]),
                     scr=rk.bufs["stepscr_w%d" % w].ptr, flags=rk.bufs["stepflags_w%d" % w].ptr,
                     gw1=slot(lay["hid_w"]), gb1=slot(lay["hid_b"]), gw2=slot(lay["sm_w"]), gb2=slot(lay["sm_b"]),
-                    tokens=[mb.ptr + sh * self.mb_bytes for sh in self.var_shards],
+                    tokens=[(rk.bufs["replica%d_w%d" % (sh, w)].ptr + self.shard_elems[sh] * 4) if self._mc_tokens()
+                            else (mb.ptr + sh * self.mb_bytes) for sh in self.var_shards],
+                    token_scale=[int(self.lib.dtf_ps_apply_grid(self.shard_elems[sh])) if self._mc_tokens() else 1
+                                 for sh in self.var_shards],
+                    mb_tokens=[mb.ptr + sh * self.mb_bytes for sh in self.var_shards],
                     arrivals=[ctl_arrivals(sh) for sh in self.var_shards])
                 d["step_staged"] = self._step_args(d, rk.bufs["xf32_w%d" % w].ptr, 128, rk.bufs["labels_w%d" % w].ptr)
             self._w[r] = d
@@ -585,6 +592,8 @@ class PSTrainEngine:
                 a.grad_mc = self.sym_grads[s].mc(r)
                 if self.tf32:
                     a.master_mc = self.sym_repl[s].mc(r)         # ONE multimem.st of fp32 parameters into every GPU's replica
+                    if self._mc_tokens():
+                        a.token_mc = self.sym_repl[s].mc(r) + n * 4
                 else:
                     a.shadow_mc = self.sym_repl[s].mc(r)
             a.n, a.num_workers, a.replicas_to_aggregate = n, cfg.num_workers, self.R
@@ -610,6 +619,13 @@ class PSTrainEngine:
             a.system_scope = 0 if cfg.colocated else 1
             self._p[r] = a
 
+    def _mc_tokens(self) -> bool:
+        """Workers wait on a counter in their own replica buffer that every ps_apply CTA bumps through the switch
+        (multimem.red) right after its release fence -- no last-block round -- when: tf32 engine, NVLS multicast, sync with
+        replicas_to_aggregate == total replicas (a token for every replica after every aggregate)."""
+        return bool(self.tf32 and self.nvls and self.nvls_multicast and self.cfg.sync and self.R == self.cfg.num_workers
+                    and os.environ.get("DTF_MC_TOKENS", "1") == "1")
+
     def _step_args(self, d: Dict[str, Any], x_ptr: int, x_rows: int, lab_ptr: int, nbatches: int = 0,
                    rows: Optional[int] = None) -> MlpStepArgs:
         """Argument block of ``dtf_mlp_step`` for one worker: ``x`` / labels = a staged batch (``nbatches == 0``) or a
@@ -630,9 +646,11 @@ class PSTrainEngine:
         a.num_tokens = a.num_signals = len(self.var_shards)
         for i in range(len(self.var_shards)):
             a.token[i] = k["tokens"][i]
+            a.token_scale[i] = k["token_scale"][i]
             a.arrivals[i] = k["arrivals"][i]
             a.stamp_dst[i] = k["arrivals"][i] + 8
-            a.stamp_src[i] = k["tokens"][i] + (0 if cfg.sync else 8)
+            a.stamp_src[i] = k["mb_tokens"][i] + 8             # async: the version the parameters were pulled at
+        a.stamp_step = 1 if cfg.sync else 0                    # sync: local step == global step at the pull
         a.sys_scope = 0 if cfg.colocated else 1
         a.timeout_ns, a.err = cfg.timeout_ns, d["err_ptr"]
         a.no_cluster = int(os.environ.get("DTF_STEP_NO_CLUSTER", "0") == "1")

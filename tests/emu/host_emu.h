@@ -231,6 +231,11 @@ static inline void dtf_emu_mc_store(void* mc, const T& v) {
   const size_t off = reinterpret_cast<char*>(mc) - r.base;
   for (char* m : r.members) *reinterpret_cast<T*>(m + off) = v;
 }
+static inline void multimem_red_add_u64(unsigned long long* mc, unsigned long long v) {
+  const auto& r = dtf_emu::mc_find(mc);
+  const size_t off = reinterpret_cast<char*>(mc) - r.base;
+  for (char* m : r.members) __atomic_fetch_add(reinterpret_cast<unsigned long long*>(m + off), v, __ATOMIC_SEQ_CST);
+}
 static inline void multimem_st_f32x4(float* mc, float4 v) { dtf_emu_mc_store(mc, v); }
 static inline void multimem_st_b64(void* mc, uint32_t lo, uint32_t hi) { dtf_emu_mc_store(mc, uint2{lo, hi}); }
 static inline void multimem_st_b128(void* mc, uint4 v) { dtf_emu_mc_store(mc, v); }

@@ -1,0 +1,7 @@
+N=${1:-8}
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
+step() { local name=$1 t=$2; shift 2; timeout "$t" "$@" > "gpurun_out/${name}.log" 2>&1; echo "${name}: rc=$? $(tail -1 gpurun_out/${name}.log | cut -c1-330)"; }
+DTF_PS_ON_WORKERS=1 DTF_NVLS=1 step mp${N}_pow_nvls_tf32 150 $TR tools/mp_check.py
+step bench${N}_nvls 240 $TR bench.py --gpus $N --nvls on
+step bench${N}_k20 200 $TR bench.py --gpus $N --steps 20 --warmup 3 --baseline 0 --e2e-steps 0
+step mp_trace${N} 150 $TR tools/mp_trace.py
