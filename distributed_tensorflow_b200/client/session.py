@@ -293,10 +293,34 @@ class Session:
                             raise ValueError("Cannot feed value of shape %s for Tensor %r, which has shape %s"
                                              % (tuple(t.shape), node.name, node.shape))
                 feeds[node.id] = t
-        plan = self._plan(flat, set(feeds))
         trace = options is not None and options.trace_level != RunOptions.NO_TRACE
-        results = self._execute_plan(plan, feeds, trace, run_metadata)
-        values = [_to_numpy(results.get(n.id)) for n in flat]
+        # Fetch overrides (parallel/auto_fabric.py): a tensor whose value a fused engine step already produced -- the loss
+        # of a FabricTrainStep fetched in the same run, or fetched alone for validation -- is answered by the engine instead
+        # of being recomputed through the graph.  An override returns NotImplemented to decline.
+        overrides = getattr(self.graph, "_fetch_overrides", None)
+        taken: Dict[int, Any] = {}
+        normal = flat
+        if overrides:
+            normal = [n for n in flat if n.id not in overrides]
+        results: Dict[int, Any] = {}
+        if normal or not flat:
+            plan = self._plan(normal, set(feeds))
+            results = self._execute_plan(plan, feeds, trace, run_metadata)
+        if overrides and len(normal) != len(flat):
+            fetch_ids = {n.id for n in flat}
+            declined = []
+            for n in flat:
+                if n.id in overrides and n.id not in taken:
+                    v = overrides[n.id](self, feeds, fetch_ids)
+                    if v is NotImplemented:
+                        declined.append(n)
+                    else:
+                        taken[n.id] = v
+            if declined:
+                plan2 = self._plan(declined, set(feeds))
+                results = dict(results)
+                results.update(self._execute_plan(plan2, feeds, trace, run_metadata))
+        values = [_to_numpy(taken[n.id] if n.id in taken else results.get(n.id)) for n in flat]
         return _unflatten(structure, values)
 
     def _execute_plan(self, plan: _Plan, feeds: Dict[int, torch.Tensor], trace: bool,

@@ -97,6 +97,8 @@ class EngineConfig:
     nvls: Any = False                     # True/"auto": symmetric VMM buffers -- gradients stay in the WORKERS' HBM and the
                                           # ps sums them with multimem.ld_reduce (in-switch), parameters are published with
                                           # ONE multimem.st stream into every GPU's replica ("auto": only if the box has NVLS)
+    shards: Optional[Dict[str, int]] = None   # explicit ps shard of hid_w / hid_b / sm_w / sm_b (graph programs: from the variables'
+                                          # device strings); default = round-robin in the reference's creation order
     step_ctas: int = 0                    # tf32: CTAs (= input-feature slices) of the step kernel; 0 = widest even split (784 -> 7 x 112)
     precision: str = "tf32"               # "tf32": fp32 storage, TF32 tensor-core GEMMs, one-kernel worker step (mlp_step.cu);
                                           # "bf16": bf16 replica / activations, GEMM + head + GEMM kernels
@@ -128,7 +130,8 @@ class VarLayout:
 _KIND = {"sgd": 0, "momentum": 1, "adam": 2}
 
 
-def _layout(spec: MLPSpec, num_ps: int, wide_pitch: bool = False) -> Tuple[Dict[str, VarLayout], List[int]]:
+def _layout(spec: MLPSpec, num_ps: int, wide_pitch: bool = False, shards: Optional[Dict[str, int]] = None
+            ) -> Tuple[Dict[str, VarLayout], List[int]]:
     """Round-robin placement in creation order (global_step, hid_w, hid_b, sm_w, sm_b), SURVEY A5.
     ``wide_pitch`` (fp32 / tf32 engines): rows of the large matrix are padded to whole 128-byte chunks (32 floats), so every
     row of a TMA box is one aligned line; the padding is zero and stays zero (its gradient is never written)."""
@@ -137,7 +140,7 @@ def _layout(spec: MLPSpec, num_ps: int, wide_pitch: bool = False) -> Tuple[Dict[
     sizes = [0] * num_ps
     out: Dict[str, VarLayout] = {}
     for i, (name, shape) in enumerate(order):
-        shard = i % num_ps
+        shard = (shards[name] if shards and name in shards else i) % num_ps
         if name == "global_step":
             continue                      # lives in the shard-0 control block (K7)
         rows, cols = (shape[0], shape[1]) if len(shape) == 2 else (1, shape[0])
@@ -193,7 +196,7 @@ class PSTrainEngine:
             assert self.world == cfg.num_ps + cfg.num_workers, "world = num_ps + num_workers"
             self.ps_ranks = list(range(cfg.num_ps))
             self.worker_ranks = list(range(cfg.num_ps, self.world))
-        self.layout, self.shard_elems = _layout(spec, cfg.num_ps, wide_pitch=self.tf32)
+        self.layout, self.shard_elems = _layout(spec, cfg.num_ps, wide_pitch=self.tf32, shards=cfg.shards)
         self.R = cfg.replicas_to_aggregate or cfg.num_workers
         self.opt = dict(cfg.optimizer)
         self.kind = _KIND[self.opt["kind"]]
@@ -649,8 +652,10 @@ class PSTrainEngine:
             a.token_scale[i] = k["token_scale"][i]
             a.arrivals[i] = k["arrivals"][i]
             a.stamp_dst[i] = k["arrivals"][i] + 8
-            a.stamp_src[i] = k["mb_tokens"][i] + 8             # async: the version the parameters were pulled at
-        a.stamp_step = 1 if cfg.sync else 0                    # sync: local step == global step at the pull
+            a.stamp_src[i] = k["mb_tokens"][i] + (0 if cfg.sync else 8)   # token (sync) / pulled version (async)
+        # sync: the push is stamped with the token the worker holds (= global step at the pull); with the multicast counter
+        # tokens the mailbox token may lag one aggregate, and step == global step there (all-fresh aggregates only)
+        a.stamp_step = 1 if (cfg.sync and self._mc_tokens()) else 0
         a.sys_scope = 0 if cfg.colocated else 1
         a.timeout_ns, a.err = cfg.timeout_ns, d["err_ptr"]
         a.no_cluster = int(os.environ.get("DTF_STEP_NO_CLUSTER", "0") == "1")
@@ -744,6 +749,22 @@ class PSTrainEngine:
         cuda_lib._bump(n)
         rk.step += 1
         self._last_step_launches = n
+
+    # -- the interface the graph-API strategy drives (same shape as GenericPSEngine's) ------------------------------------
+    def prepare(self) -> None:
+        self.init_params()
+
+    def ps_apply(self, rank: int, idle_ok: bool = False) -> None:
+        """One apply launch of the local ps shard; ``idle_ok``: a timed-out wait for pushes is not an error (service loop)."""
+        self._p[rank].idle_ok = int(idle_ok)
+        self.enqueue_ps_apply(rank)
+
+    def var_tensor(self, rank: int, name: str) -> torch.Tensor:
+        """True-shape fp32 view of variable ``name`` in the LOCAL ps shard's master buffer (graph variables are bound to it)."""
+        return self._var_view(self.ranks[rank], "master", self.layout[name])
+
+    def global_step_tensor(self, rank: int) -> torch.Tensor:
+        return self.ranks[rank].bufs["ctl0"].tensor(torch.int64, self.off["global_step"], 1).view(())
 
     def enqueue_ps_apply(self, rank: int) -> None:
         rk = self.ranks[rank]
@@ -1091,6 +1112,8 @@ class PSTrainEngine:
                 pred = cuda_lib.argmax_rows(logits)
                 correct = int((pred == yd.argmax(dim=1)).sum())
                 out.update(loss=float(loss), correct=correct, accuracy=correct / max(N, 1), count=N)
+        # the returned device tensors were produced on the worker's stream: whatever stream the caller works on waits for it
+        torch.cuda.current_stream(rk.device).wait_stream(rk.stream)
         return out
 
     def predict(self, x, rank: Optional[int] = None) -> torch.Tensor:
@@ -1099,7 +1122,9 @@ class PSTrainEngine:
         rk = self.ranks[r]
         logits = self.evaluate(x, None, rank=r)["logits"]
         with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
-            return cuda_lib.argmax_rows(logits)
+            pred = cuda_lib.argmax_rows(logits)
+        torch.cuda.current_stream(rk.device).wait_stream(rk.stream)
+        return pred
 
     def _peer_var_view(self, r: int, lay: VarLayout) -> torch.Tensor:
         buf = self.peer[(r, "master%d" % lay.shard)]

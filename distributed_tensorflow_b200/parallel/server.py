@@ -29,7 +29,7 @@ from ..framework.executor import ExecContext, ResourceStore, execute
 from .cluster import ClusterSpec
 from .rpc import PeerAwareCancel, RpcClient, RpcServer, current_connection, parse_address
 
-__all__ = ["Server", "NodeView", "serialize_nodes", "local_server_for"]
+__all__ = ["Server", "NodeView", "serialize_nodes", "local_server_for", "local_servers"]
 
 _LOCAL_SERVERS: Dict[Tuple[str, int], "weakref.ReferenceType[Server]"] = {}
 _LOCAL_LOCK = threading.Lock()
@@ -44,6 +44,18 @@ def local_server_for(address: str) -> Optional["Server"]:
         ref = _LOCAL_SERVERS.get(key)
     srv = ref() if ref is not None else None
     return srv if srv is not None and srv.is_running else None
+
+
+def local_servers() -> List["Server"]:
+    """Every running Server of this process (a between-graph task normally has exactly one)."""
+    with _LOCAL_LOCK:
+        refs = list(_LOCAL_SERVERS.values())
+    out = []
+    for ref in refs:
+        srv = ref()
+        if srv is not None and srv.is_running:
+            out.append(srv)
+    return out
 
 
 class _GraphStub:

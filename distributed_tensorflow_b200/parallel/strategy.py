@@ -100,6 +100,18 @@ def build_engine(cluster: ClusterSpec, job: str, task: int, spec: Dict[str, Any]
     num_ps = cluster.num_tasks("ps")
     cfg = _engine_cfg(spec, num_ps, world - num_ps)
     _dbg("building engine (rank %d, device %d)" % (rank, dev))
+    if spec.get("mlp"):
+        # the reference network: ONE fused step kernel per worker step, ONE apply kernel per aggregate (ps_engine.py)
+        from .ps_engine import MLPSpec, PSTrainEngine
+        m = spec["mlp"]
+        shard_of = {n: sh for n, _, sh in spec["params"]}
+        cfg.shards = {role: shard_of[m["roles"][role]] for role in ("hid_w", "hid_b", "sm_w", "sm_b")}
+        cfg.precision, cfg.nvls, cfg.clip_min = "tf32", False, float(m["clip_min"])
+        eng = PSTrainEngine(MLPSpec(in_dim=m["in_dim"], hidden=m["hidden"], classes=m["classes"], batch=m["batch"]), cfg, fabric)
+        eng.names = [m["roles"][r] for r in ("hid_w", "hid_b", "sm_w", "sm_b")]
+        _dbg("fused MLP engine built; preparing")
+        eng.prepare()
+        return eng
     eng = GenericPSEngine([(n, tuple(s)) for n, s, _ in spec["params"]], cfg, fabric,
                           shards=[sh for _, _, sh in spec["params"]])
     _dbg("engine built; preparing")
@@ -130,12 +142,19 @@ class _PsService:
             s = eng.ps_ranks.index(rank)
             rk = eng.ranks[rank]
             # graph variables on this task live in the engine's master buffer from now on
-            for name in eng.names:
-                if eng.layout[name][0] == s:
-                    srv.store.bind(name, eng._view(rk.bufs["gmaster%d" % s], name), initialized=False)
-            if s == 0:
-                gs = rk.bufs["gctl0"].tensor(torch.int64, eng.off["global_step"], 1).view(())
-                srv.store.bind(self.spec["global_step"], gs, initialized=False)
+            if self.spec.get("mlp"):
+                for role, gname in self.spec["mlp"]["roles"].items():
+                    if eng.layout[role].shard == s:
+                        srv.store.bind(gname, eng.var_tensor(rank, role), initialized=False)
+                if s == 0:
+                    srv.store.bind(self.spec["global_step"], eng.global_step_tensor(rank), initialized=False)
+            else:
+                for name in eng.names:
+                    if eng.layout[name][0] == s:
+                        srv.store.bind(name, eng._view(rk.bufs["gmaster%d" % s], name), initialized=False)
+                if s == 0:
+                    gs = rk.bufs["gctl0"].tensor(torch.int64, eng.off["global_step"], 1).view(())
+                    srv.store.bind(self.spec["global_step"], gs, initialized=False)
             self.ready.set()
             _dbg("ps service loop starts")
             per_round = 1 if eng.cfg.sync else eng.cfg.num_workers
@@ -172,6 +191,10 @@ class FabricPSStrategy:
         self.loss: Optional[Tensor] = None
         self._spec: Optional[Dict[str, Any]] = None
         self._primed = False
+        self.mlp: Optional[Dict[str, Any]] = None         # the reference network recognised in the loss sub-graph (auto_fabric)
+        self._last_loss: Optional[float] = None
+        self._step_node_id: Optional[int] = None
+        self._pinned: List[Any] = []
 
     # -- graph construction ---------------------------------------------------------------------------------------
     def minimize(self, optimizer, loss, global_step: Variable, var_list: Optional[Sequence[Variable]] = None
@@ -194,6 +217,10 @@ class FabricPSStrategy:
         key = hashlib.md5(json.dumps([params, sorted((k, str(v)) for k, v in fs.items())]).encode()).hexdigest()[:12]
         self._spec = {"key": "f" + key, "params": params, "optimizer": fs, "global_step": global_step.var_name}
         loss_t = convert_to_tensor(loss)
+        from .auto_fabric import match_reference_mlp
+        m = match_reference_mlp(loss_t, vars_)
+        if m is not None and m["hidden"] <= 128 and m["classes"] <= 16 and len({sh for _, _, sh in params}) <= 4:
+            self.mlp = m          # the batch size is only known at the first run: the engine spec is completed there
         order = needed_nodes([loss_t], set())
         placeholders = [n for n in order if n.op_type == "Placeholder"]
         with _device.device(None), _device.device(loss_t.device or None):
@@ -201,12 +228,36 @@ class FabricPSStrategy:
                                  {"strategy": self, "loss": loss_t, "var_nodes": [v._node for v in vars_],
                                   "order": order}, "fabric_train_step", loss_t.dtype, ())
             self.loss = _ops.identity(step, name="fabric_loss")
+        self._step_node_id = step.id
+        # the user's own loss tensor, fetched next to the train op (or alone, for validation), is answered by the engine
+        overrides = g.__dict__.setdefault("_fetch_overrides", {})
+        overrides[loss_t.id] = self._loss_fetch
+        self._loss_t = loss_t
         return step, self.loss
 
+    def _loss_fetch(self, session, feeds: Dict[int, Any], fetch_ids) -> Any:
+        """Session fetch override of the loss tensor: the value the fused step of THIS run computed, or -- fetched without
+        the train op (validation, reference distributed_mnist.py:160-165) -- the engine's forward-only kernel."""
+        if self._step_node_id in fetch_ids and self._last_loss is not None:
+            return torch.tensor(self._last_loss, dtype=torch.float32)
+        if self.mlp is not None and self.engine is not None and self.mlp["x"].id in feeds and self.mlp["y_"].id in feeds:
+            ev = self.engine.evaluate(feeds[self.mlp["x"].id].float(), feeds[self.mlp["y_"].id].float())
+            return torch.tensor(ev["loss"], dtype=torch.float32)
+        return NotImplemented
+
     # -- runtime ---------------------------------------------------------------------------------------------------
-    def _ensure_engine(self) -> None:
+    def _ensure_engine(self, batch: Optional[int] = None) -> None:
         if self.engine is not None:
             return
+        if self.mlp is not None:
+            if batch is None or batch > 128:
+                self.mlp = None       # the fused step handles <= 128 rows per worker step: generic engine instead
+            else:
+                m = self.mlp
+                self._spec["mlp"] = {"roles": {r: m[r].var_name for r in ("hid_w", "hid_b", "sm_w", "sm_b")},
+                                     "in_dim": m["in_dim"], "hidden": m["hidden"], "classes": m["classes"],
+                                     "batch": int(batch), "clip_min": m["clip_min"]}
+                self._spec["key"] += "m%d" % int(batch)
         # (1) every ps task joins the fabric (control-plane RPC; blocks until its buffers are exported)
         threads, errs = [], []
         for t in range(self.cluster.num_tasks("ps")):
@@ -231,6 +282,18 @@ class FabricPSStrategy:
             th.join(180.0)
         if errs:
             raise errs[0]
+        import atexit
+        atexit.register(self._report)
+
+    def _report(self) -> None:
+        """One line at process exit: which engine ran this worker's steps and how many kernels of ours it launched."""
+        try:
+            from ..ops import cuda_lib
+            kind = "fused MLP step (mlp_step_kernel + ps_apply_kernel)" if self.mlp is not None else "generic fabric engine"
+            print("dtf.fabric: worker %d ran %d steps on the %s; %d kernel launches of ours in this process" % (
+                self.server.task_index, getattr(self, "_steps", 0), kind, cuda_lib.launch_count()), flush=True)
+        except Exception:      # noqa: BLE001
+            pass
 
     def _prime(self) -> None:
         """First step after (re)initialisation: adopt the ps's global_step as this worker's token base."""
@@ -242,6 +305,13 @@ class FabricPSStrategy:
 
     def train_step(self, ctx, node, feeds: Sequence[torch.Tensor]) -> torch.Tensor:
         _dbg("train_step enter") if self.engine is None else None
+        if self.mlp is not None:
+            ph_ids = [p.id for p in node.inputs]
+            x = feeds[ph_ids.index(self.mlp["x"].id)]
+            y = feeds[ph_ids.index(self.mlp["y_"].id)]
+            self._ensure_engine(int(x.shape[0]))
+            if self.mlp is not None:
+                return self._mlp_step(x, y)
         self._ensure_engine()
         if not self._primed:
             self._prime()
@@ -263,6 +333,31 @@ class FabricPSStrategy:
             return sub.values[a["loss"].id]
         loss = eng.worker_step(rank, loss_fn)
         return loss
+
+
+def _mlp_step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """One fused worker step (mlp_step_kernel): the fed batch goes through pinned staging (H2D on the copy stream), the
+    loss comes back with the step; push / aggregate / apply / token are the engine's device-side protocol."""
+    eng = self.engine
+    if int(x.shape[0]) != eng.spec.batch:
+        raise ValueError("the fused MLP step was built for batches of %d rows, got %d (feed a constant batch size, or set "
+                         "DTF_FABRIC=0)" % (eng.spec.batch, int(x.shape[0])))
+    if not self._pinned:
+        for _ in range(2):
+            self._pinned.append((torch.empty((eng.spec.batch, eng.spec.in_dim), dtype=torch.float32).pin_memory(),
+                                 torch.empty((eng.spec.batch, eng.spec.classes), dtype=torch.float32).pin_memory()))
+        self._pin_i = 0
+    px, py = self._pinned[self._pin_i]
+    self._pin_i ^= 1
+    px.copy_(x)
+    py.copy_(y)
+    loss = eng.step(px, py, sync_loss=True)
+    self._steps = getattr(self, "_steps", 0) + 1
+    self._last_loss = float(loss)
+    return torch.tensor(self._last_loss, dtype=torch.float32)
+
+
+FabricPSStrategy._mlp_step = _mlp_step
 
 
 @register_kernel("FabricTrainStep", stateful=True)

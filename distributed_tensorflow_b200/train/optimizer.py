@@ -81,6 +81,13 @@ class Optimizer:
 
     def minimize(self, loss, global_step: Optional[Variable] = None, var_list=None, gate_gradients=None,
                  aggregation_method=None, colocate_gradients_with_ops=False, name=None, grad_loss=None) -> Tensor:
+        # a ps/worker program whose worker task is bound to a B200 runs its step on the NVLink fabric (fused kernels, device-side
+        # accumulate / apply / tokens) without being told to: parallel/auto_fabric.py
+        from ..parallel.auto_fabric import maybe_route_minimize
+        routed = maybe_route_minimize(self, loss, global_step, var_list)
+        if routed is not None:
+            self._gradients_applied = True
+            return routed
         gv = self.compute_gradients(loss, var_list)
         if all(g is None for g, _ in gv):
             raise ValueError("No gradients provided for any variable, check your graph.")

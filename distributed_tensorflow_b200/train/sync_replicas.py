@@ -284,9 +284,15 @@ class SyncReplicasOptimizerHook(SessionRunHook):
         self._local_init_op = None
         self._threads: List[threading.Thread] = []
 
+    def _on_fabric(self) -> bool:
+        # accumulators, token queue and the chief's aggregate loop are the fabric engine's device-side protocol there
+        return getattr(self._sync_optimizer, "_fabric_strategy", None) is not None
+
     def begin(self):
         if not self._sync_optimizer._gradients_applied:
             raise ValueError("SyncReplicasOptimizer.apply_gradients should be called before using the hook.")
+        if self._on_fabric():
+            return
         self._local_init_op = self._sync_optimizer.local_step_init_op
         if self._is_chief:
             self._q_runner = self._sync_optimizer.get_chief_queue_runner()
@@ -294,6 +300,8 @@ class SyncReplicasOptimizerHook(SessionRunHook):
             self._chief_init_op = self._sync_optimizer.chief_init_op
 
     def after_create_session(self, session, coord):
+        if self._on_fabric():
+            return
         raw = getattr(session, "raw_session", lambda: session)()
         raw.run(self._local_init_op)
         if self._is_chief:
@@ -305,6 +313,8 @@ class SyncReplicasOptimizerHook(SessionRunHook):
         # Clean end of the chief's training loop: close the token queue NOW, while the session is still open (the
         # queue runner's close-on-stop thread races with the session teardown).  Replicas that are still running drain
         # the remaining tokens and then get OutOfRangeError from the dequeue = a clean end of their loop.
+        if self._on_fabric():
+            return
         raw = getattr(session, "raw_session", lambda: session)()
         if self._is_chief and self._q_runner is not None and self._q_runner.close_op is not None:
             try:

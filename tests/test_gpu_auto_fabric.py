@@ -1,0 +1,58 @@
+"""The reference's OWN ``distributed_mnist.py``, byte for byte, through the ``tensorflow`` shim with its tasks bound to a
+B200 (``DTF_GPU_INDEX``): ``opt.minimize`` routes itself onto the fabric (parallel/auto_fabric.py), every worker step is ONE
+``mlp_step_kernel`` launch and every aggregate ONE ``ps_apply_kernel`` launch, the validation every 1000 steps
+(/root/reference/distributed_mnist.py:160-165) runs the engine's forward-only kernel, and training still converges.
+1 ps + 2 workers, sync replicas, all three processes share GPU 0 (the driver's GPU box has one)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+REF = os.environ.get("DTF_REFERENCE_DIR", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("sync", ["True", "False"])
+def test_unmodified_reference_mnist_trains_on_the_fused_fabric_path(tmp_path, sync):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    if not os.path.exists(os.path.join(REF, "distributed_mnist.py")):
+        pytest.skip("reference checkout not available")
+    base = 22400 + (0 if sync == "True" else 10)
+    hosts = ["--ps_hosts=127.0.0.1:%d" % base, "--worker_hosts=127.0.0.1:%d,127.0.0.1:%d" % (base + 1, base + 2)]
+    env = dict(os.environ, DTF_GPU_INDEX="0", DTF_FABRIC="1", DTF_HDFS_ROOT=str(tmp_path / "hdfs"),
+               DTF_FABRIC_PORT_OFFSET="1500")
+    env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
+
+    def cmd(job, idx):
+        return [sys.executable, "-u", "-m", "distributed_tensorflow_b200.compat.run", os.path.join(REF, "distributed_mnist.py"),
+                "--job_name=%s" % job, "--task_index=%d" % idx, "--issync=%s" % sync] + hosts
+    logs = [open(tmp_path / ("%s.log" % n), "w") for n in ("ps", "w0", "w1")]
+    procs = [subprocess.Popen(cmd(j, i), env=env, cwd=str(tmp_path), stdout=f, stderr=subprocess.STDOUT)
+             for (j, i), f in zip((("ps", 0), ("worker", 0), ("worker", 1)), logs)]
+    try:
+        for p in procs[1:]:
+            assert p.wait(timeout=420) == 0, "".join(open(tmp_path / ("%s.log" % n)).read()[-2500:] for n in ("ps", "w0", "w1"))
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        for f in logs:
+            f.close()
+    steps = 0
+    for n in ("w0", "w1"):
+        out = open(tmp_path / ("%s.log" % n)).read()
+        assert "routed onto the NVLink fabric (fused MLP step" in out, out[-2000:]
+        m = re.search(r"dtf.fabric: worker \d ran (\d+) steps on the fused MLP step \(mlp_step_kernel \+ ps_apply_kernel\); (\d+) kernel", out)
+        assert m, out[-2000:]
+        steps += int(m.group(1))
+        assert int(m.group(2)) >= int(m.group(1))                   # at least one kernel of ours per step in that process
+        assert "Training elapsed time" in out
+        losses = [float(v) for v in re.findall(r"loss: ([0-9.eE+-]+)", out)]
+        assert len(losses) > 1000 and sum(losses[-50:]) / 50 < 0.5 * sum(losses[:50]) / 50      # it trains
+        assert re.search(r"validation cross entropy = ", out)       # the 1000-step validation ran (forward-only kernel)
+    assert steps >= 9000                                            # the two workers shared ~10 000 global steps

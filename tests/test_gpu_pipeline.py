@@ -11,7 +11,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_deferred_loss_pipeline_matches_synchronous_steps():
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_deferred_loss_pipeline_matches_synchronous_steps(precision):
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
     from distributed_tensorflow_b200.parallel.fabric import Fabric
@@ -24,7 +25,8 @@ def test_deferred_loss_pipeline_matches_synchronous_steps():
 
     def run(deferred):
         eng = PSTrainEngine(MLPSpec(), EngineConfig(colocated=True, optimizer={"kind": "momentum", "lr": 0.001, "momentum": 0.9},
-                                                    seed=4, head_ctas=1), Fabric(1, {0: 0}))     # one head CTA: bit-exact
+                                                    seed=4, head_ctas=1, precision=precision), Fabric(1, {0: 0}))
+        # bf16 with ONE head CTA is bit-exact; the tf32 step kernel sums its CTAs' dW2 / db partials with fp32 atomics
         eng.init_params()
         losses, pending = [], None
         for i in range(13):
@@ -46,6 +48,7 @@ def test_deferred_loss_pipeline_matches_synchronous_steps():
     l0, s0 = run(False)
     l1, s1 = run(True)
     assert len(l0) == len(l1) == 13 and int(s0["global_step"]) == 13 and int(s1["global_step"]) == 13
-    np.testing.assert_allclose(l0, l1, rtol=1e-6)
+    exact = precision == "bf16"
+    np.testing.assert_allclose(l0, l1, rtol=1e-6 if exact else 5e-5)
     for k in ("hid_w", "hid_b", "sm_w", "sm_b"):
-        torch.testing.assert_close(s0[k], s1[k], rtol=0, atol=0)
+        torch.testing.assert_close(s0[k], s1[k], rtol=0 if exact else 1e-4, atol=0 if exact else 1e-5)

@@ -5,6 +5,6 @@ DTF_PS_ON_WORKERS=1 DTF_NVLS=1 step mp_pow_nvls_tf32 120 $TR tools/mp_check.py
 DTF_PS_ON_WORKERS=1 DTF_NVLS=0 step mp_pow_uni_tf32 120 $TR tools/mp_check.py
 DTF_PS_ON_WORKERS=0 DTF_NVLS=1 step mp_ref_nvls_tf32 120 $TR tools/mp_check.py
 DTF_PS_ON_WORKERS=1 DTF_NVLS=1 DTF_PRECISION=bf16 step mp_pow_nvls_bf16 120 $TR tools/mp_check.py
-step bench${N}_nvls 200 $TR bench.py --gpus $N --nvls on
-DTF_PS_STREAM=0 step bench${N}_nvls_1stream 200 $TR bench.py --gpus $N --nvls on --baseline 0 --e2e-steps 0
-step bench${N}_psonly 200 $TR bench.py --gpus $N --ps-only-task 1 --baseline 0 --e2e-steps 0
+step bench${N}_nvls 200 $TR bench.py --gpus $N --nvls on --baseline 0 --e2e-steps 0
+DTF_MC_TOKENS=0 step bench${N}_nvls_mbtok 200 $TR bench.py --gpus $N --nvls on --baseline 0 --e2e-steps 0
+step mp_trace${N} 150 $TR tools/mp_trace.py

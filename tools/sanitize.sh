@@ -1,22 +1,23 @@
 #!/bin/bash
-# Sanitizer tier: run the single-GPU kernel tests under compute-sanitizer.
-#   gpurun --timeout 900 -- 'bash tools/sanitize.sh'        -> gpurun_out/sanitize_<tool>.log (+ a one-line summary each)
-# memcheck: out-of-bounds / misaligned accesses (TMA boxes, epilogue tails); racecheck: shared-memory hazards between
-# the producer / MMA / epilogue warps; synccheck: barrier misuse.  tcgen05/TMA traffic goes through the async proxy,
-# which the tools only partly model: a clean run is necessary, not sufficient.
+# Sanitizer tier: the single-GPU kernel tests under compute-sanitizer.
+#   gpurun --timeout 1200 -- 'bash tools/sanitize.sh'        -> gpurun_out/sanitize_<tool>_<suite>.log + sanitize_summary.txt
+# memcheck: out-of-bounds / misaligned accesses (TMA boxes, epilogue tails, bulk stores); racecheck: shared-memory hazards
+# between the producer / MMA / epilogue warps and inside the fused head; synccheck: barrier misuse.  tcgen05 / TMA traffic
+# goes through the async proxy, which the tools only partly model: a clean run is necessary, not sufficient.
 set -u
 mkdir -p gpurun_out
-TESTS=(tests/test_gpu_kernels.py -k "gemm or xent or optimizer or small or conv")
-# the fused NN kernels (plain bandwidth kernels: the tools model them fully) -- their hardware tests are still gated
-NN_TESTS=(tests/test_gpu_nn_fused.py -k "fused_bn or pooling or im2col")
+: > gpurun_out/sanitize_summary.txt
+run() {  # tool suite timeout pytest-args...
+  local tool=$1 suite=$2 t=$3; shift 3
+  local log=gpurun_out/sanitize_${tool}_${suite}.log
+  timeout "$t" compute-sanitizer --tool "${tool}" --error-exitcode 3 --launch-timeout 60 python -m pytest "$@" -x -q > "${log}" 2>&1
+  local rc=$?
+  local errs=$(grep -c "========= .*[Ee]rror\|========= Invalid\|========= Race\|========= Hazard" "${log}" || true)
+  echo "${tool} ${suite}: rc=${rc} reported=${errs} | $(grep -E "passed|failed" "${log}" | tail -1) | $(grep "ERROR SUMMARY\|RACECHECK SUMMARY" "${log}" | tail -1)" | tee -a gpurun_out/sanitize_summary.txt
+}
 for tool in memcheck racecheck synccheck; do
-  DTF_TEST_UNVALIDATED=1 timeout 200 compute-sanitizer --tool ${tool} --error-exitcode 3 --launch-timeout 60 \
-      python -m pytest "${NN_TESTS[@]}" -x -q > gpurun_out/sanitize_nn_${tool}.log 2>&1
-  echo "nn ${tool}: rc=$? $(tail -1 gpurun_out/sanitize_nn_${tool}.log)" | tee -a gpurun_out/sanitize_summary.txt
-  log=gpurun_out/sanitize_${tool}.log
-  timeout 280 compute-sanitizer --tool ${tool} --error-exitcode 3 --launch-timeout 60 \
-      python -m pytest "${TESTS[@]}" -x -q > ${log} 2>&1
-  rc=$?
-  errs=$(grep -c "========= .*error\|========= Invalid\|========= Race" ${log} || true)
-  echo "${tool}: rc=${rc} reported=${errs} $(tail -1 ${log})" | tee -a gpurun_out/sanitize_summary.txt
+  run ${tool} step 240 tests/test_gpu_step_kernel.py -m gpu -k "100-784 or two_consecutive"
+  run ${tool} gemm 240 tests/test_gpu_kernels.py -m gpu -k "(all_operand_majors and 100-100-784) or xent or optimizer or tf32_persistent"
+  run ${tool} nn 200 tests/test_gpu_nn_fused.py -m gpu -k "fused_bn and 1000 or pooling"
 done
+run memcheck engine 240 tests/test_gpu_engine.py -m gpu -k "tf32 and sgd"
