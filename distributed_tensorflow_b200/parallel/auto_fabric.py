@@ -51,39 +51,40 @@ def match_reference_mlp(loss: Tensor, variables: Sequence[Variable]) -> Optional
     """Recognise the reference network (``distributed_mnist.py:106-113``).  Returns ``{"x", "y_": placeholders,
     "hid_w", "hid_b", "sm_w", "sm_b": variables, "clip_min": float}`` or ``None``."""
     by_node = {v._node.id: v for v in variables}
-    neg = _producer(loss, "Neg")
-    if neg is None:
-        return None
-    red = _producer(neg.inputs[0], "Sum")
-    if red is None or red.attrs.get("axis") is not None:
-        return None
-    mul = _producer(red.inputs[0], "Mul")
-    if mul is None:
-        return None
-    a, b = mul.inputs
-    log = _producer(a, "Log") or _producer(b, "Log")
-    if log is None:
-        return None
-    labels = b if _producer(a, "Log") is not None else a
-    labels = _producer(labels, "Placeholder")
-    clip = _producer(log.inputs[0], "ClipByValue")
-    if labels is None or clip is None:
-        return None
-    lo = clip.attrs.get("clip_value_min", clip.attrs.get("lo"))
-    hi = clip.attrs.get("clip_value_max", clip.attrs.get("hi"))
-    if lo is None and len(clip.inputs) == 3:              # bounds as Const inputs
-        c_lo, c_hi = _producer(clip.inputs[1], "Const"), _producer(clip.inputs[2], "Const")
-        if c_lo is None or c_hi is None:
+    fused = _producer(loss, "ClippedSoftmaxXentSum")       # the same loss as ONE node (dtf.nn.clipped_softmax_xent_sum)
+    if fused is not None:
+        labels, lo = _producer(fused.inputs[1], "Placeholder"), fused.attrs.get("clip_min", 1e-10)
+        l2 = _producer(fused.inputs[0], "XwPlusB")
+        if labels is None or l2 is None or not (0.0 <= float(lo) < 1e-3):
             return None
-        lo, hi = float(c_lo.attrs["value"]), float(c_hi.attrs["value"])
-    if lo is None or hi is None or float(hi) != 1.0 or not (0.0 <= float(lo) < 1e-3):
-        return None
-    sm = _producer(clip.inputs[0], "Softmax")
-    if sm is None:
-        return None
-    l2 = _producer(sm.inputs[0], "XwPlusB")
-    if l2 is None:
-        return None
+    else:
+        neg = _producer(loss, "Neg")
+        if neg is None:
+            return None
+        red = _producer(neg.inputs[0], "Sum")
+        if red is None or red.attrs.get("axis") is not None:
+            return None
+        mul = _producer(red.inputs[0], "Mul")
+        if mul is None:
+            return None
+        a, b = mul.inputs
+        log = _producer(a, "Log") or _producer(b, "Log")
+        if log is None:
+            return None
+        labels = b if _producer(a, "Log") is not None else a
+        labels = _producer(labels, "Placeholder")
+        clip = _producer(log.inputs[0], "ClipByValue")
+        if labels is None or clip is None:
+            return None
+        lo, hi = clip.attrs.get("lo"), clip.attrs.get("hi")
+        if lo is None or hi is None or float(hi) != 1.0 or not (0.0 <= float(lo) < 1e-3):
+            return None
+        sm = _producer(clip.inputs[0], "Softmax")
+        if sm is None:
+            return None
+        l2 = _producer(sm.inputs[0], "XwPlusB")
+        if l2 is None:
+            return None
     relu = _producer(l2.inputs[0], "Relu")
     if relu is None:
         return None

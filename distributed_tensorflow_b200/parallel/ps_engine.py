@@ -756,8 +756,23 @@ class PSTrainEngine:
 
     def ps_apply(self, rank: int, idle_ok: bool = False) -> None:
         """One apply launch of the local ps shard; ``idle_ok``: a timed-out wait for pushes is not an error (service loop)."""
-        self._p[rank].idle_ok = int(idle_ok)
+        a = self._p[rank]
+        a.idle_ok = int(idle_ok)
+        # a service loop polls: short waits (no push yet = not an error), so that host-side requests -- stop, farewell -- are
+        # seen within milliseconds
+        a.timeout_ns = min(int(self.cfg.timeout_ns), 50_000_000) if idle_ok else int(self.cfg.timeout_ns)
         self.enqueue_ps_apply(rank)
+
+    def release_all_tokens(self, rank: int) -> None:
+        """End of training (a sync replica left): write a token no step will ever exceed into every worker's mailbox for the
+        LOCAL ps shard, so a replica blocked in its device-side token wait completes the step it is in."""
+        rk = self.ranks[rank]
+        s = self.ps_ranks.index(rank)
+        rk.sync()
+        with torch.cuda.device(rk.device):
+            for w in range(self.cfg.num_workers):
+                self.peer[(rank, "mailbox_w%d" % w)].tensor(torch.int64, s * self.mb_bytes, 2).fill_(1 << 62)
+            torch.cuda.synchronize(rk.device)
 
     def var_tensor(self, rank: int, name: str) -> torch.Tensor:
         """True-shape fp32 view of variable ``name`` in the LOCAL ps shard's master buffer (graph variables are bound to it)."""

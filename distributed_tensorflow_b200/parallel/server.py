@@ -315,6 +315,15 @@ class Server:
         from .strategy import ps_fabric_setup
         return ps_fabric_setup(self, spec)
 
+    def rpc_fabric_farewell(self, key):
+        """A sync replica finished its training loop: release every worker's device-side token wait for good, so a replica
+        still inside a step (whose aggregate would need the departed one's gradient) completes it, reads the final
+        global step and stops too (the control-plane tier's farewell tokens, train/sync_replicas.py)."""
+        svc = self.store.resources.get("fabric_service/" + key)
+        if svc is not None:
+            svc.farewell()
+        return True
+
     def rpc_reset(self):
         self.store.clear()
         return True

@@ -129,6 +129,8 @@ class _PsService:
         self.ready = threading.Event()
         self.error: Optional[BaseException] = None
         self.applies = 0
+        self._farewell = threading.Event()
+        self._farewell_done = False
         self._stop = threading.Event()
         self.thread = threading.Thread(target=self._run, name="dtf-fabric-ps", daemon=True)
         self.thread.start()
@@ -163,6 +165,9 @@ class _PsService:
                     eng.ps_apply(rank, idle_ok=True)
                 rk.stream.synchronize()
                 self.applies += per_round
+                if self._farewell.is_set() and not self._farewell_done and hasattr(eng, "release_all_tokens"):
+                    eng.release_all_tokens(rank)
+                    self._farewell_done = True
         except BaseException as e:  # noqa: BLE001
             import traceback
             traceback.print_exc()
@@ -171,6 +176,9 @@ class _PsService:
 
     def stop(self):
         self._stop.set()
+
+    def farewell(self):
+        self._farewell.set()
 
 
 def ps_fabric_setup(server, spec: Dict[str, Any]) -> bool:
@@ -285,8 +293,26 @@ class FabricPSStrategy:
         import atexit
         atexit.register(self._report)
 
+    def farewell(self) -> None:
+        """This replica's training loop is over (sync mode): ask every ps shard to release the device-side token waits of
+        the replicas that are still inside a step (see ``Server.rpc_fabric_farewell``).  Idempotent, best effort."""
+        if self.engine is None or getattr(self, "_farewell_sent", False) or not self._spec["optimizer"].get("sync"):
+            return
+        self._farewell_sent = True
+        for t in range(self.cluster.num_tasks("ps")):
+            try:
+                from .server import local_server_for
+                srv = local_server_for(self.cluster.task_address("ps", t))
+                if srv is not None:
+                    srv.rpc_fabric_farewell(self._spec["key"])
+                else:
+                    self.server.peer("ps", t).call("fabric_farewell", self._spec["key"])
+            except Exception:      # noqa: BLE001 - the ps may already be gone
+                pass
+
     def _report(self) -> None:
         """One line at process exit: which engine ran this worker's steps and how many kernels of ours it launched."""
+        self.farewell()
         try:
             from ..ops import cuda_lib
             kind = "fused MLP step (mlp_step_kernel + ps_apply_kernel)" if self.mlp is not None else "generic fabric engine"

@@ -314,6 +314,7 @@ class SyncReplicasOptimizerHook(SessionRunHook):
         # queue runner's close-on-stop thread races with the session teardown).  Replicas that are still running drain
         # the remaining tokens and then get OutOfRangeError from the dequeue = a clean end of their loop.
         if self._on_fabric():
+            self._sync_optimizer._fabric_strategy.farewell()     # nobody will wait for this replica's gradient any more
             return
         raw = getattr(session, "raw_session", lambda: session)()
         if self._is_chief and self._q_runner is not None and self._q_runner.close_op is not None:

@@ -32,6 +32,15 @@ def test_matcher_recognises_the_reference_network():
     assert (m["in_dim"], m["hidden"], m["classes"], m["clip_min"]) == (784, 64, 7, 1e-10)
 
 
+def test_matcher_recognises_the_fused_loss_node_too():
+    from distributed_tensorflow_b200.models import build_mnist_mlp
+    for fused in (False, True):
+        dtf.reset_default_graph()
+        net = build_mnist_mlp(hidden=32, fused=fused)
+        m = match_reference_mlp(dtf.convert_to_tensor(net["loss"]), dtf.trainable_variables())
+        assert m is not None and (m["hidden"], m["classes"]) == (32, 10) and m["hid_w"] is net["vars"][0]
+
+
 @pytest.mark.parametrize("kw", [dict(extra_var=True), dict(mean=True), dict(clip=0.1)])
 def test_matcher_declines_anything_else(kw):
     loss, _ = _reference_model(**kw)

@@ -1,8 +1,10 @@
-"""The reference's OWN ``distributed_mnist.py``, byte for byte, through the ``tensorflow`` shim with its tasks bound to a
-B200 (``DTF_GPU_INDEX``): ``opt.minimize`` routes itself onto the fabric (parallel/auto_fabric.py), every worker step is ONE
-``mlp_step_kernel`` launch and every aggregate ONE ``ps_apply_kernel`` launch, the validation every 1000 steps
+"""A ps/worker program that only says ``opt.minimize(loss, global_step)`` -- the reference's OWN ``distributed_mnist.py``, byte
+for byte, through the ``tensorflow`` shim where the checkout exists (/root/reference is not shipped to the GPU boxes), and
+this repo's twin of it (``examples/distributed_mnist.py``, same program in ``dtf`` spelling) everywhere -- with its tasks
+bound to a B200 (``DTF_GPU_INDEX``): ``minimize`` routes itself onto the fabric (parallel/auto_fabric.py), every worker step is
+ONE ``mlp_step_kernel`` launch and every aggregate ONE ``ps_apply_kernel`` launch, the validation every 1000 steps
 (/root/reference/distributed_mnist.py:160-165) runs the engine's forward-only kernel, and training still converges.
-1 ps + 2 workers, sync replicas, all three processes share GPU 0 (the driver's GPU box has one)."""
+1 ps + 2 workers, sync and async, all three processes share GPU 0 (the driver's GPU box has one)."""
 import os
 import re
 import subprocess
@@ -16,21 +18,26 @@ REF = os.environ.get("DTF_REFERENCE_DIR", "/root/reference")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("program", ["reference", "twin"])
 @pytest.mark.parametrize("sync", ["True", "False"])
-def test_unmodified_reference_mnist_trains_on_the_fused_fabric_path(tmp_path, sync):
+def test_minimize_routes_itself_onto_the_fused_fabric_path(tmp_path, sync, program):
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
-    if not os.path.exists(os.path.join(REF, "distributed_mnist.py")):
-        pytest.skip("reference checkout not available")
-    base = 22400 + (0 if sync == "True" else 10)
+    if program == "reference" and not os.path.exists(os.path.join(REF, "distributed_mnist.py")):
+        pytest.skip("reference checkout not available on this box")
+    base = 22400 + (0 if sync == "True" else 10) + (0 if program == "reference" else 20)
     hosts = ["--ps_hosts=127.0.0.1:%d" % base, "--worker_hosts=127.0.0.1:%d,127.0.0.1:%d" % (base + 1, base + 2)]
     env = dict(os.environ, DTF_GPU_INDEX="0", DTF_FABRIC="1", DTF_HDFS_ROOT=str(tmp_path / "hdfs"),
                DTF_FABRIC_PORT_OFFSET="1500")
     env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
 
     def cmd(job, idx):
-        return [sys.executable, "-u", "-m", "distributed_tensorflow_b200.compat.run", os.path.join(REF, "distributed_mnist.py"),
-                "--job_name=%s" % job, "--task_index=%d" % idx, "--issync=%s" % sync] + hosts
+        if program == "reference":
+            head = [sys.executable, "-u", "-m", "distributed_tensorflow_b200.compat.run", os.path.join(REF, "distributed_mnist.py")]
+        else:
+            head = [sys.executable, "-u", os.path.join(ROOT, "examples", "distributed_mnist.py"), "--train_steps=10000",
+                    "--train_dir=%s" % (tmp_path / "ckpt")]
+        return head + ["--job_name=%s" % job, "--task_index=%d" % idx, "--issync=%s" % sync] + hosts
     logs = [open(tmp_path / ("%s.log" % n), "w") for n in ("ps", "w0", "w1")]
     procs = [subprocess.Popen(cmd(j, i), env=env, cwd=str(tmp_path), stdout=f, stderr=subprocess.STDOUT)
              for (j, i), f in zip((("ps", 0), ("worker", 0), ("worker", 1)), logs)]
