@@ -260,6 +260,15 @@ class GenericPSEngine:
                 rc = self.lib.dtf_wait_token(rk.bufs["gmailbox_w%d" % w].ptr + s * self.mb_bytes, getattr(rk, "base", 0) + rk.step, None,
                                              self.cfg.timeout_ns, rk.bufs["gmisc_w%d" % w].ptr + 16, st)
                 assert rc == 0, rc
+                if self.cfg.sync and self.R < self.cfg.num_workers:
+                    # backup workers: this worker's previous push may still be waiting in its slot (a straggler holds the
+                    # next token already); the slot / local gradient buffer is rewritten only once the ps folded it in or
+                    # dropped it as stale (TF's ConditionalAccumulator copies under a lock instead)
+                    per_push = 1 if self.nvls else _PUSH_CTAS
+                    rc = self.lib.dtf_wait_token(self.peer[(rank, "gctl%d" % s)].ptr + self.off["consumed"] + w * 8,
+                                                 rk.step * per_push, None, self.cfg.timeout_ns,
+                                                 rk.bufs["gmisc_w%d" % w].ptr + 16, st)
+                    assert rc == 0, rc
                 if not self.nvls:        # NVLS mode: the ps already stored the new parameters into this replica
                     rep = rk.bufs["greplica%d_w%d" % (s, w)]
                     rc = self.lib.dtf_pull_shadow(self.peer[(rank, "gmaster%d" % s)].ptr, rep.ptr, self.shard_elems[s] * 4, 148, st)

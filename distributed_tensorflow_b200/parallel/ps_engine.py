@@ -571,7 +571,8 @@ class PSTrainEngine:
                     token_scale=[int(self.lib.dtf_ps_apply_grid(self.shard_elems[sh])) if self._mc_tokens() else 1
                                  for sh in self.var_shards],
                     mb_tokens=[mb.ptr + sh * self.mb_bytes for sh in self.var_shards],
-                    arrivals=[ctl_arrivals(sh) for sh in self.var_shards])
+                    arrivals=[ctl_arrivals(sh) for sh in self.var_shards],
+                    consumed=[self.peer[(r, "ctl%d" % sh)].ptr + self.off["consumed"] + w * 8 for sh in self.var_shards])
                 d["step_staged"] = self._step_args(d, rk.bufs["xf32_w%d" % w].ptr, 128, rk.bufs["labels_w%d" % w].ptr)
             self._w[r] = d
         self._p: Dict[int, PsApplyArgs] = {}
@@ -650,6 +651,8 @@ class PSTrainEngine:
         for i in range(len(self.var_shards)):
             a.token[i] = k["tokens"][i]
             a.token_scale[i] = k["token_scale"][i]
+            if cfg.sync and self.R < cfg.num_workers:
+                a.consumed[i] = k["consumed"][i]           # backup workers: never overwrite a push the ps has not consumed / dropped
             a.arrivals[i] = k["arrivals"][i]
             a.stamp_dst[i] = k["arrivals"][i] + 8
             a.stamp_src[i] = k["mb_tokens"][i] + (0 if cfg.sync else 8)   # token (sync) / pulled version (async)
@@ -723,6 +726,14 @@ class PSTrainEngine:
                                         self.cfg.timeout_ns, d["err_ptr"], st)
                 assert rc == 0, rc
                 n += 1
+            if self.cfg.sync and self.R < self.cfg.num_workers:
+                # backup workers: the slot is rewritten only once the ps consumed or dropped this worker's previous push
+                for s in range(self.cfg.num_ps):
+                    if self.ctas_per_push[s]:
+                        rc = lib.dtf_wait_token(self.peer[(rank, "ctl%d" % s)].ptr + self.off["consumed"] + w * 8,
+                                                rk.step * self.ctas_per_push[s], None, self.cfg.timeout_ns, d["err_ptr"], st)
+                        assert rc == 0, rc
+                        n += 1
             g1, hd, g3 = d["g1"], d["head"], d["g3"]
             g1.wait_target, g1.wait_target_ptr = 0, d["stepctr_ptr"]
             rc = lib.dtf_gemm_bf16(ctypes.byref(g1), st)
@@ -1034,6 +1045,9 @@ class PSTrainEngine:
         """Capture ``unroll`` steps of every local rank's stream into a CUDA graph (launch-bound inner loop).
         Everything step-dependent (wait targets, batch index) is read from device counters, so a graph can be
         replayed any number of times.  Call after at least one eager step (first-launch attribute setup)."""
+        if not self.tf32 and self.cfg.sync and self.R < self.cfg.num_workers:
+            raise NotImplementedError("bf16 engine with backup workers (replicas_to_aggregate < replicas): the consumed-push wait "
+                                      "takes a host-side step number -- run eagerly, or use precision='tf32'")
         graphs: Dict[int, Any] = {}
         self.synchronize()
         for r, rk in self.ranks.items():

@@ -10,13 +10,17 @@ memory from inside the kernels (``parallel/fabric.py`` + ``ops/``).
 """
 from __future__ import annotations
 
+import hashlib
+import io
+import os
 import pickle
 import select
 import socket
 import threading
 import time
 import traceback
-from multiprocessing.connection import Client, Connection, Listener
+from multiprocessing import AuthenticationError
+from multiprocessing.connection import Client, Connection, Listener, answer_challenge, deliver_challenge
 from typing import Any, Callable, Dict, Optional, Tuple
 
 import torch
@@ -26,7 +30,76 @@ from ..framework import errors
 __all__ = ["RpcServer", "RpcClient", "parse_address", "to_wire", "from_wire", "PeerAwareCancel", "current_connection",
            "peer_closed"]
 
-_AUTHKEY = b"dtf-b200-control-plane"
+_LOOPBACK = ("127.0.0.1", "::1", "localhost")
+_HANDSHAKE_TIMEOUT = 10.0
+
+
+def cluster_authkey(host: str) -> bytes:
+    """The shared secret both ends of a control-plane connection must prove (HMAC challenge, both directions).
+
+    * ``DTF_CLUSTER_SECRET`` (the secret itself) or ``DTF_CLUSTER_SECRET_FILE`` (a file holding it): REQUIRED as soon as a
+      task binds or dials a non-loopback address -- a multi-host cluster ships the same secret to every task, like an ssh
+      key; without one such a bind is refused (anyone who can reach the port could otherwise drive the task).
+    * loopback only (the reference's localhost layout, every test): a per-user random secret created on first use in
+      ``~/.dtf_b200/cluster_secret`` (mode 0600), so other local users cannot connect either."""
+    env = os.environ.get("DTF_CLUSTER_SECRET")
+    if env:
+        return hashlib.sha256(env.encode()).digest()
+    path = os.environ.get("DTF_CLUSTER_SECRET_FILE")
+    if path:
+        with open(path, "rb") as f:
+            return hashlib.sha256(f.read().strip()).digest()
+    if host not in _LOOPBACK:
+        raise PermissionError("refusing a control-plane endpoint on non-loopback address %r without a cluster secret: set "
+                              "DTF_CLUSTER_SECRET or DTF_CLUSTER_SECRET_FILE to the same value on every task" % host)
+    d = os.path.join(os.path.expanduser("~"), ".dtf_b200")
+    f = os.path.join(d, "cluster_secret")
+    try:
+        with open(f, "rb") as fh:
+            key = fh.read()
+        if len(key) >= 32:
+            return key[:64]
+    except OSError:
+        pass
+    os.makedirs(d, mode=0o700, exist_ok=True)
+    key = os.urandom(48)
+    tmp = "%s.%d" % (f, os.getpid())
+    fd = os.open(tmp, os.O_WRONLY | os.O_CREAT | os.O_EXCL, 0o600)
+    with os.fdopen(fd, "wb") as fh:
+        fh.write(key)
+    try:
+        os.link(tmp, f)                      # first writer wins; everybody then reads the same file
+    except OSError:
+        pass
+    os.unlink(tmp)
+    with open(f, "rb") as fh:
+        return fh.read()[:64]
+
+
+# ---- wire format: pickle, but only of a closed set of types ---------------------------------------------------------------
+_SAFE_BUILTINS = {"set", "frozenset", "slice", "range", "complex", "bytearray", "tuple", "list", "dict", "int", "float", "str",
+                  "bytes", "bool", "object", "NoneType", "Ellipsis"}
+_SAFE_MODULE_PREFIXES = ("numpy", "torch", "collections", "distributed_tensorflow_b200")
+_DENY_NAMES = {"eval", "exec", "compile", "open", "__import__", "getattr", "setattr", "delattr", "system", "popen", "Popen",
+               "load", "loads", "load_state_dict", "run", "call", "check_output", "spawn", "fork", "execv", "execve"}
+
+
+class _RestrictedUnpickler(pickle.Unpickler):
+    """Requests and replies carry python scalars / containers, numpy arrays (tensors), torch dtypes and this package's own
+    small value classes -- nothing else is allowed to be named by a pickle arriving over the network (the classic
+    ``os.system`` / ``subprocess`` gadgets are not importable through it)."""
+
+    def find_class(self, module: str, name: str):
+        root = module.split(".")[0]
+        ok = (module == "builtins" and name in _SAFE_BUILTINS) or \
+             (root in _SAFE_MODULE_PREFIXES and name.split(".")[-1] not in _DENY_NAMES and not name.startswith("_import"))
+        if not ok:
+            raise pickle.UnpicklingError("control-plane message names %s.%s, which is not an allowed wire type" % (module, name))
+        return super().find_class(module, name)
+
+
+def _loads(data: bytes) -> Any:
+    return _RestrictedUnpickler(io.BytesIO(data)).load()
 
 _ERRORS = {c.__name__: c for c in (
     errors.OpError, errors.FailedPreconditionError, errors.AbortedError, errors.UnavailableError,
@@ -132,7 +205,8 @@ class RpcServer:
     def __init__(self, address: str, service: Any):
         self.host, self.port = parse_address(address)
         self._service = service
-        self._listener = Listener((self.host, self.port), authkey=_AUTHKEY, backlog=64)
+        self._authkey = cluster_authkey(self.host)
+        self._listener = Listener((self.host, self.port), backlog=64)      # handshake: per connection, below
         self._closed = threading.Event()
         self._conns = []
         self._thread = threading.Thread(target=self._accept_loop, name="dtf-rpc-accept-%d" % self.port, daemon=True)
@@ -149,13 +223,30 @@ class RpcServer:
             self._conns.append(conn)
             threading.Thread(target=self._serve, args=(conn,), name="dtf-rpc-conn", daemon=True).start()
 
+    def _handshake(self, conn: Connection) -> bool:
+        """Mutual HMAC challenge in THIS connection's thread (the accept loop never waits on a client), bounded by a
+        watchdog that closes a connection which does not complete it in time."""
+        dog = threading.Timer(_HANDSHAKE_TIMEOUT, conn.close)
+        dog.daemon = True
+        dog.start()
+        try:
+            deliver_challenge(conn, self._authkey)
+            answer_challenge(conn, self._authkey)
+            return True
+        except (AuthenticationError, EOFError, OSError, ValueError, TypeError):
+            return False
+        finally:
+            dog.cancel()
+
     def _serve(self, conn: Connection) -> None:
         try:
+            if not self._handshake(conn):
+                return
             while not self._closed.is_set():
                 try:
-                    method, args, kwargs = from_wire(pickle.loads(conn.recv_bytes()))
-                except (EOFError, OSError, ConnectionError, TypeError, ValueError):
-                    return               # peer gone, or this server closed the connection under the blocked read
+                    method, args, kwargs = from_wire(_loads(conn.recv_bytes()))
+                except (EOFError, OSError, ConnectionError, TypeError, ValueError, pickle.UnpicklingError):
+                    return               # peer gone, this server closed the connection, or a message outside the wire types
                 _current.conn = conn
                 try:
                     fn = getattr(self._service, "rpc_" + method)
@@ -212,7 +303,15 @@ class RpcClient:
             delay = 0.02
             while True:
                 try:
-                    c = Client((self.host, self.port), authkey=_AUTHKEY)
+                    c = Client((self.host, self.port))
+                    try:
+                        key = cluster_authkey(self.host)
+                        answer_challenge(c, key)
+                        deliver_challenge(c, key)
+                    except (AuthenticationError, EOFError) as e:
+                        c.close()
+                        raise errors.UnavailableError("task at %s:%d rejected the cluster secret (%s): every task needs the same "
+                                                      "DTF_CLUSTER_SECRET" % (self.host, self.port, e))
                     break
                 except (ConnectionRefusedError, FileNotFoundError, OSError) as e:
                     if time.time() > deadline:
@@ -228,7 +327,7 @@ class RpcClient:
         try:
             c = self._conn()
             c.send_bytes(pickle.dumps((method, to_wire(args), to_wire(kwargs)), protocol=pickle.HIGHEST_PROTOCOL))
-            reply = from_wire(pickle.loads(c.recv_bytes()))
+            reply = from_wire(_loads(c.recv_bytes()))
         except (EOFError, ConnectionError, BrokenPipeError, OSError) as e:
             self._drop()
             raise errors.UnavailableError("task at %s:%d went away during %s: %s" % (self.host, self.port, method, e))
