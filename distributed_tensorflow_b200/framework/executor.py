@@ -97,6 +97,7 @@ class ResourceStore:
 
     def clear(self) -> None:
         with self._lock:
+            self.__dict__.pop("_rng_streams", None)
             self._vars.clear()
             self._uninit.clear()
             self._bound.clear()

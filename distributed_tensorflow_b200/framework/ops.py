@@ -183,11 +183,28 @@ def random_uniform(shape, minval=0.0, maxval=1.0, dtype=float32, seed=None, name
 
 
 def _gen(ctx, node):
-    seed = node.attrs.get("seed")
-    if seed is None:
-        return ctx.generator(node)
-    g = torch.Generator(device="cpu")
-    g.manual_seed(int(seed))
+    """The random stream of ONE op, TF style: seeded from (graph-level seed, op-level seed, the op's identity) and STATEFUL --
+    it lives in the executing task's resource store, so every execution of the op continues it (a seeded op does not
+    return the same tensor every step), two same-shaped initialisers draw different values even when they sit on
+    different tasks, and a fresh store (a new local Session, a restarted ps) replays the same sequence.  With neither
+    seed the stream is seeded from entropy."""
+    import zlib
+    op_seed = node.attrs.get("seed")
+    graph_seed = ctx._seed if getattr(ctx, "_seed", None) is not None else getattr(node.graph, "seed", None)
+    store = ctx.store
+    with store._lock:
+        gens = store.__dict__.setdefault("_rng_streams", {})
+        key = node.name if node.name else "node%d" % node.id
+        g = gens.get(key)
+        if g is None:
+            g = torch.Generator(device="cpu")
+            if op_seed is None and graph_seed is None:
+                g.seed()
+            else:
+                mix = (int(graph_seed or 0) * 1000003) ^ (int(op_seed or 0) * 7919 + (1 if op_seed is not None else 0)) \
+                    ^ (zlib.crc32(key.encode()) << 17)
+                g.manual_seed(mix & ((1 << 63) - 1))
+            gens[key] = g
     return g
 
 
@@ -708,13 +725,21 @@ def _k_fbn(ctx, node, x, scale, offset):
     return native.batch_norm_train(x, scale.float(), offset.float(), eps=node.attrs["eps"]).to(x.dtype)
 
 
-def dropout(x, keep_prob=None, rate=None, name="dropout"):
+def dropout(x, keep_prob=None, rate=None, name="dropout", seed=None, noise_shape=None):
     x = convert_to_tensor(x)
     r = float(rate) if rate is not None else 1.0 - float(keep_prob)
-    return _node("Dropout", (x,), {"rate": r}, name, x.dtype, x.shape)
+    return _node("Dropout", (x,), {"rate": r, "seed": seed}, name, x.dtype, x.shape)
 
 
-register_kernel("Dropout")(lambda ctx, n, x: F.dropout(x, n.attrs["rate"], training=True))
+@register_kernel("Dropout")
+def _k_dropout(ctx, n, x):
+    r = n.attrs["rate"]
+    seeded = n.attrs.get("seed") is not None or getattr(ctx, "_seed", None) is not None or getattr(n.graph, "seed", None) is not None
+    if not seeded or r <= 0.0:
+        return F.dropout(x, r, training=True)
+    # reproducible mask from the op's own stream (drawn on the host so CPU and GPU tasks agree), inverted-dropout scaling
+    keep = (torch.rand(x.shape, generator=_gen(ctx, n)) >= r).to(device=x.device, dtype=x.dtype)
+    return x * keep / (1.0 - r)
 
 
 # ---------------------------------------------------------------------------

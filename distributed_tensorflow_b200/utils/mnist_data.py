@@ -31,7 +31,9 @@ import torch
 
 __all__ = ["DataSet", "Datasets", "read_data_sets", "synthetic_mnist", "PinnedBatchPipe"]
 
-Datasets = namedtuple("Datasets", ["train", "validation", "test"])
+class Datasets(namedtuple("Datasets", ["train", "validation", "test"])):
+    """``(train, validation, test)`` + ``source``: "mnist-idx:<dir>" or "synthetic" (what the numbers were measured on)."""
+    source = "unknown"
 
 
 class DataSet:
@@ -101,7 +103,7 @@ class DataSet:
 
 
 def _cache_path(num: int, seed: int, noise: float) -> Optional[str]:
-    root = os.environ.get("DTF_DATA_CACHE", "/tmp/dtf_data_cache")
+    root = os.environ.get("DTF_DATA_CACHE", "/tmp/dtf_data_cache_%d" % os.getuid())      # per user: not a shared, guessable path
     if root in ("", "0"):
         return None
     return os.path.join(root, "synth_mnist_n%d_s%d_z%g.npz" % (num, seed, noise))
@@ -109,7 +111,7 @@ def _cache_path(num: int, seed: int, noise: float) -> Optional[str]:
 
 def synthetic_mnist(num: int, seed: int = 0, one_hot: bool = True, noise: float = 0.25) -> Tuple[np.ndarray, np.ndarray]:
     """``num`` MNIST-shaped examples drawn around ten fixed prototypes.  Pixels are 8-bit like real MNIST, so a
-    split is cached on disk as uint8 (``DTF_DATA_CACHE``, default ``/tmp/dtf_data_cache``; ``0`` disables) -- every
+    split is cached on disk as uint8 (``DTF_DATA_CACHE``, default ``/tmp/dtf_data_cache_<uid>``; ``0`` disables) -- every
     task process of a cluster asks for the same split, and generating 55 000 images takes seconds."""
     cache = _cache_path(num, seed, noise) if num >= 2000 else None
     if cache is not None and os.path.exists(cache):
@@ -209,11 +211,25 @@ def read_data_sets(train_dir: Optional[str] = None, fake_data: bool = False, one
         va_i, va_l = tr_i[:validation_size], tr_l[:validation_size]
         tr_i, tr_l = tr_i[validation_size:], tr_l[validation_size:]
     else:
+        # The reference downloads MNIST or fails; there is no network here, so the splits are SYNTHETIC -- say so loudly:
+        # accuracies printed by a script that asked for a data directory are not MNIST accuracies.
+        import warnings
+        msg = ("read_data_sets(%r): no MNIST IDX files there -- using the synthetic MNIST-shaped prototype dataset (%d train / "
+               "%d validation / %d test); reported losses / accuracies are NOT MNIST numbers" % (train_dir, num_train,
+                                                                                              validation_size, num_test))
+        if not fake_data:
+            warnings.warn(msg, RuntimeWarning, stacklevel=2)
+            print("WARNING: " + msg, flush=True)
         tr_i, tr_l = synthetic_mnist(num_train, seed=seed + 1, one_hot=one_hot)
         va_i, va_l = synthetic_mnist(validation_size, seed=seed + 2, one_hot=one_hot)
         te_i, te_l = synthetic_mnist(num_test, seed=seed + 3, one_hot=one_hot)
-    return Datasets(DataSet(tr_i, tr_l, one_hot, seed), DataSet(va_i, va_l, one_hot, seed + 1),
-                    DataSet(te_i, te_l, one_hot, seed + 2))
+    ds = Datasets(DataSet(tr_i, tr_l, one_hot, seed), DataSet(va_i, va_l, one_hot, seed + 1),
+                  DataSet(te_i, te_l, one_hot, seed + 2))
+    try:
+        ds.source = "mnist-idx:%s" % train_dir if files else "synthetic"       # recorded by benches / profiles
+    except AttributeError:
+        pass
+    return ds
 
 
 class PinnedBatchPipe:

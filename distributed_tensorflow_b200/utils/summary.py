@@ -40,11 +40,37 @@ def _crc_table() -> List[int]:
 
 
 def crc32c(data: bytes) -> int:
+    """CRC-32C (Castagnoli).  Small inputs: the byte loop.  Large inputs (checkpoint tensors when the native runtime library
+    is missing): the CRC register update is linear over GF(2), so the buffer is cut into equal chunks whose registers are
+    advanced TOGETHER, one numpy table lookup per byte position for all chunks at once, and then folded left to right
+    with the "append L zero bytes" operator -- ~0.3 s for a 45 MB tensor instead of tens of seconds."""
     t = _crc_table()
-    c = 0xFFFFFFFF
-    for b in data:
-        c = t[(c ^ b) & 0xFF] ^ (c >> 8)
-    return c ^ 0xFFFFFFFF
+    n = len(data)
+    if n < (1 << 15):
+        c = 0xFFFFFFFF
+        for b in data:
+            c = t[(c ^ b) & 0xFF] ^ (c >> 8)
+        return c ^ 0xFFFFFFFF
+    import numpy as np
+    L = 4096
+    K = n // L
+    tab = np.asarray(t, dtype=np.uint32)
+    body = np.frombuffer(data, dtype=np.uint8, count=K * L).reshape(K, L).T.copy()       # [L, K]: one row per byte position
+    state = np.zeros(K, dtype=np.uint32)
+    state[0] = 0xFFFFFFFF
+    # the zero-byte operator rides along: 4 x 256 basis registers (one set byte each) advanced by the same L steps
+    basis = (np.arange(256, dtype=np.uint32)[None, :] << (8 * np.arange(4, dtype=np.uint32))[:, None]).reshape(-1)
+    for j in range(L):
+        state = tab[(state ^ body[j]) & 0xFF] ^ (state >> 8)
+        basis = tab[basis & 0xFF] ^ (basis >> 8)
+    T0, T1, T2, T3 = (basis[i * 256:(i + 1) * 256].tolist() for i in range(4))
+    regs = state.tolist()
+    r = regs[0]
+    for i in range(1, K):
+        r = T0[r & 0xFF] ^ T1[(r >> 8) & 0xFF] ^ T2[(r >> 16) & 0xFF] ^ T3[r >> 24] ^ regs[i]
+    for b in bytes(data[K * L:]):
+        r = t[(r ^ b) & 0xFF] ^ (r >> 8)
+    return r ^ 0xFFFFFFFF
 
 
 def masked_crc32c(data: bytes) -> int:

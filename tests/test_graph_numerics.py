@@ -201,7 +201,10 @@ def test_truncated_normal_within_two_sigma_and_seeded():
         a = sess.run(t)
         b = sess.run(t)
     assert np.abs(a).max() <= 1.0 + 1e-6 and 0.3 < a.std() < 0.5
-    np.testing.assert_array_equal(a, b)
+    assert not np.array_equal(a, b)                # TF: an op-level seed fixes the SEQUENCE; every run advances it ...
+    with dtf.Session() as sess:
+        np.testing.assert_array_equal(a, sess.run(t))      # ... and a new session replays it from the start
+        np.testing.assert_array_equal(b, sess.run(t))
 
 
 def test_conv_bn_pool_shapes_and_grads():
@@ -291,3 +294,48 @@ def test_learning_rate_schedules_feed_the_apply_ops():
             for _ in range(20):
                 sess.run(tr)
             assert float(np.abs(sess.run(v)).sum()) < before
+
+
+def test_random_ops_are_stateful_per_op_streams():
+    """with set_random_seed, (1) two same-shaped initialisers differ, also across tasks, (2) a seeded random op
+    advances between runs, (3) a fresh session replays the same sequence, (4) dropout honours seeds."""
+    import distributed_tensorflow_b200 as dtf
+    dtf.set_random_seed(7)
+    a = dtf.Variable(dtf.truncated_normal([64], stddev=1.0), name="a")
+    b = dtf.Variable(dtf.truncated_normal([64], stddev=1.0), name="b")
+    r = dtf.random_normal([8], seed=3)
+    d = dtf.nn.dropout(dtf.ones([1000]), keep_prob=0.5, seed=11)
+    runs = []
+    for _ in range(2):
+        with dtf.Session() as sess:
+            sess.run(dtf.global_variables_initializer())
+            av, bv = sess.run([a, b])
+            r1, r2 = sess.run(r), sess.run(r)
+            d1, d2 = sess.run(d), sess.run(d)
+        assert not np.allclose(av, bv)
+        assert not np.allclose(r1, r2) and not np.array_equal(d1, d2)
+        assert set(np.unique(d1)) <= {0.0, 2.0} and 350 < (d1 > 0).sum() < 650
+        runs.append((av, bv, r1, r2, d1))
+    for x, y in zip(*runs):
+        np.testing.assert_array_equal(x, y)
+
+
+def test_same_shaped_initialisers_on_two_ps_tasks_differ(ports):
+    """The placement case from the advisory: variables that are each the FIRST random draw on their own ps task."""
+    import distributed_tensorflow_b200 as dtf
+    p = ports(3)
+    cluster = dtf.train.ClusterSpec({"ps": ["127.0.0.1:%d" % p[0], "127.0.0.1:%d" % p[1]], "worker": ["127.0.0.1:%d" % p[2]]})
+    servers = [dtf.train.Server(cluster, "ps", 0), dtf.train.Server(cluster, "ps", 1), dtf.train.Server(cluster, "worker", 0)]
+    try:
+        dtf.set_random_seed(5)
+        with dtf.device("/job:ps/task:0"):
+            v0 = dtf.Variable(dtf.truncated_normal([32]), name="v0")
+        with dtf.device("/job:ps/task:1"):
+            v1 = dtf.Variable(dtf.truncated_normal([32]), name="v1")
+        with dtf.Session(servers[2].target) as sess:
+            sess.run(dtf.global_variables_initializer())
+            a, b = sess.run([v0, v1])
+        assert not np.allclose(a, b)
+    finally:
+        for s in servers:
+            s.stop()
