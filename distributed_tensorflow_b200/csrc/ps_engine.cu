@@ -92,7 +92,7 @@ DTF_DEVICE void st_relaxed_sys_v2_u64(unsigned long long* p, unsigned long long 
 }
 #endif
 
-__global__ void __launch_bounds__(256, 4) ps_apply_kernel(const PsApplyParams p) {
+__global__ void __launch_bounds__(256, 2) ps_apply_kernel(const PsApplyParams p) {
   __shared__ unsigned int s_mask, s_count, s_ok;
   __shared__ unsigned long long s_seq;
   __shared__ float s_lr;
@@ -228,75 +228,114 @@ __global__ void __launch_bounds__(256, 4) ps_apply_kernel(const PsApplyParams p)
     // workers' copies are read one by one through their unicast peer mappings.
     const bool mc_reduce = p.grad_mc != nullptr && mask == p.full_mask;
     const long long stride = (long long)gridDim.x * blockDim.x * 4;
-    for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < p.n; i0 += stride) {
-      float g[4] = {0.f, 0.f, 0.f, 0.f};
-      const bool vec = (i0 + 4 <= p.n);
-      if (mc_reduce && vec) {
-        const float4 t = multimem_ld_reduce_add_f32x4(p.grad_mc + i0);
-        g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
-      } else {
-        for (int w = 0; w < p.num_workers; ++w) {
-          if (!(mask & (1u << w))) continue;
-          if (vec) {
-            const float4 t = *reinterpret_cast<const float4*>(p.grad[w] + i0);
-            g[0] += t.x; g[1] += t.y; g[2] += t.z; g[3] += t.w;
-          } else {
-            for (int j = 0; j < 4 && i0 + j < p.n; ++j) g[j] += p.grad[w][i0 + j];
-          }
-        }
-      }
-      float wv[4];
-      for (int j = 0; j < 4 && i0 + j < p.n; ++j) {
-        const long long i = i0 + j;
-        const float gj = g[j] * inv;
-        float x = p.master[i];
-        if (p.kind == 0) {
-          x -= lr * gj;
-        } else if (p.kind == 1) {
-          const float acc = p.momentum * p.slot_m[i] + gj;
-          p.slot_m[i] = acc;
-          x -= p.nesterov ? (lr * gj + lr * p.momentum * acc) : (lr * acc);
+    // Up to PU float4 positions per thread per pass: ALL their gradient loads (multimem.ld_reduce round trips through the
+    // switch, or the chosen workers' peer loads) and master / slot loads are issued before the first one is consumed, so a
+    // large shard (ResNet-18: 11 M parameters) keeps PU x 16 B per thread in flight instead of one; the
+    // MNIST-sized shards still take one position per thread (grid = n / 1024).
+    constexpr int PU = 4;
+    for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; base < p.n; base += PU * stride) {
+      float g[PU][4], xm[PU][4], sm[PU][4], sv[PU][4];
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        const long long i0 = base + u * stride;
+        g[u][0] = g[u][1] = g[u][2] = g[u][3] = 0.f;
+        if (i0 >= p.n) continue;
+        const bool vec = (i0 + 4 <= p.n);
+        if (mc_reduce && vec) {
+          const float4 t = multimem_ld_reduce_add_f32x4(p.grad_mc + i0);
+          g[u][0] = t.x; g[u][1] = t.y; g[u][2] = t.z; g[u][3] = t.w;
         } else {
-          const float m = p.beta1 * p.slot_m[i] + (1.0f - p.beta1) * gj;
-          const float v = p.beta2 * p.slot_v[i] + (1.0f - p.beta2) * gj * gj;
-          p.slot_m[i] = m;
-          p.slot_v[i] = v;
-          x -= lr * m / (sqrtf(v) + p.eps);
-        }
-        p.master[i] = x;
-        wv[j] = x;
-      }
-      if (vec) {
-        const uint2 packed = make_uint2(pack_bf16x2(wv[0], wv[1]), pack_bf16x2(wv[2], wv[3]));
-        if (p.master_mc) multimem_st_f32x4(p.master_mc + i0, make_float4(wv[0], wv[1], wv[2], wv[3]));
-        if (p.shadow_mc) {
-          multimem_st_b64(p.shadow_mc + i0, packed.x, packed.y);      // the switch writes every GPU's replica (ours too)
-        } else {
-          if (p.shadow) *reinterpret_cast<uint2*>(p.shadow + i0) = packed;
-          if (p.publish_replicas)
-            for (int w = 0; w < p.num_workers; ++w)
-              if (p.replica[w]) *reinterpret_cast<uint2*>(p.replica[w] + i0) = packed;     // NVLink store
-        }
-      } else {
-        for (int j = 0; j < 4 && i0 + j < p.n; ++j) {
-          const __nv_bfloat16 b = __float2bfloat16(wv[j]);
-          if (p.shadow) p.shadow[i0 + j] = b;
-          if (p.publish_replicas)
-            for (int w = 0; w < p.num_workers; ++w)
-              if (p.replica[w]) p.replica[w][i0 + j] = b;
-        }
-      }
-      for (int z = 0; z < p.num_zero; ++z) {
-        if (i0 + 4 > p.zero_begin[z] && i0 < p.zero_end[z]) {
-          if (mc_reduce && vec && i0 >= p.zero_begin[z] && i0 + 4 <= p.zero_end[z]) {
-            multimem_st_f32x4(p.grad_mc_rw + i0, make_float4(0.f, 0.f, 0.f, 0.f));     // clears every worker's copy
-            continue;
-          }
           for (int w = 0; w < p.num_workers; ++w) {
             if (!(mask & (1u << w))) continue;
-            for (int j = 0; j < 4; ++j) {
-              const long long i = i0 + j;
-              if (i >= p.zero_begin[z] && i < p.zero_end[z] && i < p.n) p.grad_rw[w][i] = 0.f;
+            if (vec) {
+              const float4 t = *reinterpret_cast<const float4*>(p.grad[w] + i0);
+              g[u][0] += t.x; g[u][1] += t.y; g[u][2] += t.z; g[u][3] += t.w;
+            } else {
+              for (int j = 0; j < 4 && i0 + j < p.n; ++j) g[u][j] += p.grad[w][i0 + j];
+            }
+          }
+        }
+        if (vec) {
+          const float4 t = *reinterpret_cast<const float4*>(p.master + i0);
+          xm[u][0] = t.x; xm[u][1] = t.y; xm[u][2] = t.z; xm[u][3] = t.w;
+          if (p.kind >= 1) {
+            const float4 m4 = *reinterpret_cast<const float4*>(p.slot_m + i0);
+            sm[u][0] = m4.x; sm[u][1] = m4.y; sm[u][2] = m4.z; sm[u][3] = m4.w;
+          }
+          if (p.kind == 2) {
+            const float4 v4 = *reinterpret_cast<const float4*>(p.slot_v + i0);
+            sv[u][0] = v4.x; sv[u][1] = v4.y; sv[u][2] = v4.z; sv[u][3] = v4.w;
+          }
+        } else {
+          for (int j = 0; j < 4 && i0 + j < p.n; ++j) {
+            xm[u][j] = p.master[i0 + j];
+            if (p.kind >= 1) sm[u][j] = p.slot_m[i0 + j];
+            if (p.kind == 2) sv[u][j] = p.slot_v[i0 + j];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        const long long i0 = base + u * stride;
+        if (i0 >= p.n) continue;
+        const bool vec = (i0 + 4 <= p.n);
+        float wv[4];
+        for (int j = 0; j < 4 && i0 + j < p.n; ++j) {
+          const float gj = g[u][j] * inv;
+          float x = xm[u][j];
+          if (p.kind == 0) {
+            x -= lr * gj;
+          } else if (p.kind == 1) {
+            const float acc = p.momentum * sm[u][j] + gj;
+            sm[u][j] = acc;
+            x -= p.nesterov ? (lr * gj + lr * p.momentum * acc) : (lr * acc);
+          } else {
+            const float m = p.beta1 * sm[u][j] + (1.0f - p.beta1) * gj;
+            const float v = p.beta2 * sv[u][j] + (1.0f - p.beta2) * gj * gj;
+            sm[u][j] = m;
+            sv[u][j] = v;
+            x -= lr * m / (sqrtf(v) + p.eps);
+          }
+          wv[j] = x;
+        }
+        if (vec) {
+          *reinterpret_cast<float4*>(p.master + i0) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+          if (p.kind >= 1) *reinterpret_cast<float4*>(p.slot_m + i0) = make_float4(sm[u][0], sm[u][1], sm[u][2], sm[u][3]);
+          if (p.kind == 2) *reinterpret_cast<float4*>(p.slot_v + i0) = make_float4(sv[u][0], sv[u][1], sv[u][2], sv[u][3]);
+          const uint2 packed = make_uint2(pack_bf16x2(wv[0], wv[1]), pack_bf16x2(wv[2], wv[3]));
+          if (p.master_mc) multimem_st_f32x4(p.master_mc + i0, make_float4(wv[0], wv[1], wv[2], wv[3]));
+          if (p.shadow_mc) {
+            multimem_st_b64(p.shadow_mc + i0, packed.x, packed.y);      // the switch writes every GPU's replica (ours too)
+          } else {
+            if (p.shadow) *reinterpret_cast<uint2*>(p.shadow + i0) = packed;
+            if (p.publish_replicas)
+              for (int w = 0; w < p.num_workers; ++w)
+                if (p.replica[w]) *reinterpret_cast<uint2*>(p.replica[w] + i0) = packed;     // NVLink store
+          }
+        } else {
+          for (int j = 0; j < 4 && i0 + j < p.n; ++j) {
+            p.master[i0 + j] = wv[j];
+            if (p.kind >= 1) p.slot_m[i0 + j] = sm[u][j];
+            if (p.kind == 2) p.slot_v[i0 + j] = sv[u][j];
+            const __nv_bfloat16 b = __float2bfloat16(wv[j]);
+            if (p.shadow) p.shadow[i0 + j] = b;
+            if (p.publish_replicas)
+              for (int w = 0; w < p.num_workers; ++w)
+                if (p.replica[w]) p.replica[w][i0 + j] = b;
+          }
+        }
+        for (int z = 0; z < p.num_zero; ++z) {
+          if (i0 + 4 > p.zero_begin[z] && i0 < p.zero_end[z]) {
+            if (mc_reduce && vec && i0 >= p.zero_begin[z] && i0 + 4 <= p.zero_end[z]) {
+              multimem_st_f32x4(p.grad_mc_rw + i0, make_float4(0.f, 0.f, 0.f, 0.f));     // clears every worker's copy
+              continue;
+            }
+            for (int w = 0; w < p.num_workers; ++w) {
+              if (!(mask & (1u << w))) continue;
+              for (int j = 0; j < 4; ++j) {
+                const long long i = i0 + j;
+                if (i >= p.zero_begin[z] && i < p.zero_end[z] && i < p.n) p.grad_rw[w][i] = 0.f;
+              }
             }
           }
         }
@@ -805,18 +844,20 @@ struct PeerList {
   void* p[DTF_MAX_WORKERS];
 };
 
-// Each thread keeps four 16-byte accesses in flight (independent loads first, then the stores / adds): a single
-// multimem round trip through the switch is microseconds, so bandwidth comes from memory-level parallelism.
+// Each thread keeps U 16-byte accesses in flight (independent loads first, then the stores / adds): a single multimem
+// round trip through the switch is microseconds, so bandwidth comes from memory-level parallelism -- U x 16 B per thread
+// x 256 threads x the resident CTAs must cover (link rate x round-trip time) ~ 900 GB/s x 3 us ~ 2.7 MB.
+template <int U>
 __global__ void __launch_bounds__(256) fabric_bcast_kernel(const uint4* __restrict__ src, uint4* mc_dst, PeerList peers, int npeers,
                                                            long long n16) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += 4 * stride) {
-    uint4 v[4];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += U * stride) {
+    uint4 v[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < U; ++u)
       if (i + u * stride < n16) v[u] = src[i + u * stride];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const long long j = i + u * stride;
       if (j >= n16) break;
       if (mc_dst != nullptr) {
@@ -828,30 +869,31 @@ __global__ void __launch_bounds__(256) fabric_bcast_kernel(const uint4* __restri
   }
 }
 
+template <int U>
 __global__ void __launch_bounds__(256) fabric_reduce_kernel(const float* mc_src, PeerList peers, int npeers, float* __restrict__ dst,
                                                             long long n4) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 4 * stride) {
-    float4 acc[4];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += U * stride) {
+    float4 acc[U];
     if (mc_src != nullptr) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < U; ++u)
         if (i + u * stride < n4) acc[u] = multimem_ld_reduce_add_f32x4(mc_src + 4 * (i + u * stride));
     } else {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int k = 0; k < npeers; ++k) {
-        float4 t[4];
+        float4 t[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < U; ++u)
           if (i + u * stride < n4) t[u] = reinterpret_cast<const float4*>(peers.p[k])[i + u * stride];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < U; ++u)
           if (i + u * stride < n4) { acc[u].x += t[u].x; acc[u].y += t[u].y; acc[u].z += t[u].z; acc[u].w += t[u].w; }
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < U; ++u)
       if (i + u * stride < n4) reinterpret_cast<float4*>(dst)[i + u * stride] = acc[u];
   }
 }
@@ -861,25 +903,42 @@ __global__ void __launch_bounds__(256) fabric_reduce_kernel(const float* mc_src,
 extern "C" {
 using namespace dtf;
 
-int dtf_fabric_bcast(const void* src, void* mc_dst, void* const* peer_dst, int npeers, long long nbytes, int grid,
-                     cudaStream_t s) {
+// grid <= 0 / unroll <= 0: defaults tuned on 8 x B200 (tools/nvls_check.py sweep): 8 accesses in flight per thread, 4 CTAs / SM
+int dtf_fabric_bcast_ex(const void* src, void* mc_dst, void* const* peer_dst, int npeers, long long nbytes, int grid, int unroll,
+                        cudaStream_t s) {
   if (nbytes % 16 || npeers > DTF_MAX_WORKERS) return -2;
   PeerList pl;
   memset(&pl, 0, sizeof(pl));
   for (int k = 0; k < npeers; ++k) pl.p[k] = peer_dst[k];
-  DTF_LAUNCH(fabric_bcast_kernel, grid > 0 ? grid : 296, 256, s, reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(mc_dst),
-             pl, npeers, nbytes / 16);
+  const int g = grid > 0 ? grid : 592;
+  const uint4* sp = reinterpret_cast<const uint4*>(src);
+  uint4* mp = reinterpret_cast<uint4*>(mc_dst);
+  if (unroll >= 16) { DTF_LAUNCH(fabric_bcast_kernel<16>, g, 256, s, sp, mp, pl, npeers, nbytes / 16); }
+  else if (unroll == 4) { DTF_LAUNCH(fabric_bcast_kernel<4>, g, 256, s, sp, mp, pl, npeers, nbytes / 16); }
+  else { DTF_LAUNCH(fabric_bcast_kernel<8>, g, 256, s, sp, mp, pl, npeers, nbytes / 16); }
   return (int)cudaGetLastError();
 }
 
-int dtf_fabric_reduce(const void* mc_src, void* const* peer_src, int npeers, float* dst, long long nfloats, int grid,
-                      cudaStream_t s) {
+int dtf_fabric_reduce_ex(const void* mc_src, void* const* peer_src, int npeers, float* dst, long long nfloats, int grid, int unroll,
+                         cudaStream_t s) {
   if (nfloats % 4 || npeers > DTF_MAX_WORKERS) return -2;
   PeerList pl;
   memset(&pl, 0, sizeof(pl));
   for (int k = 0; k < npeers; ++k) pl.p[k] = peer_src[k];
-  DTF_LAUNCH(fabric_reduce_kernel, grid > 0 ? grid : 296, 256, s, reinterpret_cast<const float*>(mc_src), pl, npeers, dst, nfloats / 4);
+  const int g = grid > 0 ? grid : 592;
+  const float* mp = reinterpret_cast<const float*>(mc_src);
+  if (unroll >= 16) { DTF_LAUNCH(fabric_reduce_kernel<16>, g, 256, s, mp, pl, npeers, dst, nfloats / 4); }
+  else if (unroll == 4) { DTF_LAUNCH(fabric_reduce_kernel<4>, g, 256, s, mp, pl, npeers, dst, nfloats / 4); }
+  else { DTF_LAUNCH(fabric_reduce_kernel<8>, g, 256, s, mp, pl, npeers, dst, nfloats / 4); }
   return (int)cudaGetLastError();
+}
+
+int dtf_fabric_bcast(const void* src, void* mc_dst, void* const* peer_dst, int npeers, long long nbytes, int grid, cudaStream_t s) {
+  return dtf_fabric_bcast_ex(src, mc_dst, peer_dst, npeers, nbytes, grid, 0, s);
+}
+
+int dtf_fabric_reduce(const void* mc_src, void* const* peer_src, int npeers, float* dst, long long nfloats, int grid, cudaStream_t s) {
+  return dtf_fabric_reduce_ex(mc_src, peer_src, npeers, dst, nfloats, grid, 0, s);
 }
 
 int dtf_sizeof_ps_control() { return (int)sizeof(PsControl); }
@@ -932,10 +991,11 @@ struct DtfPsApplyArgs {
   unsigned long long* token_mc;
 };
 
-// default grid: one float4 per thread (a single load round trip); all CTAs must be co-resident (4 per SM by launch bounds)
+// default grid: one float4 per thread (a single load round trip) for small shards, up to 4 per thread per pass for large
+// ones; all CTAs must be co-resident (blocks other than the decider spin): 2 per SM by launch bounds -> at most 296
 int dtf_ps_apply_grid(long long n) {
   long long want = (n / 4 + 255) / 256;
-  return (int)(want < 1 ? 1 : (want > 592 ? 592 : want));
+  return (int)(want < 1 ? 1 : (want > 296 ? 296 : want));
 }
 
 int dtf_ps_apply(const DtfPsApplyArgs* a, cudaStream_t s) {

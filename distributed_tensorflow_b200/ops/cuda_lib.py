@@ -222,6 +222,10 @@ def _declare(lib) -> None:
     lib.dtf_offsetof_ctl.argtypes = [c_int]
     lib.dtf_fabric_bcast.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_int, c_void_p]
     lib.dtf_fabric_reduce.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_longlong, c_int, c_void_p]
+    if not isinstance(getattr(lib, "dtf_fabric_reduce_ex", _Missing()), _Missing):
+        lib.dtf_fabric_bcast_ex.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_void_p]
+        lib.dtf_fabric_reduce_ex.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_longlong, c_int, c_int, c_void_p]
+        lib.dtf_fabric_bcast_ex.restype = lib.dtf_fabric_reduce_ex.restype = c_int
     lib.dtf_vmm_support.argtypes = [c_int]
     lib.dtf_vmm_granularity.argtypes = [c_int, c_int, POINTER(c_longlong)]
     lib.dtf_vmm_create.argtypes = [c_int, c_longlong, POINTER(c_ulonglong)]

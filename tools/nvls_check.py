@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=0)
     ap.add_argument("--mbytes", type=float, default=44.7, help="payload (default: ResNet-18 fp32 gradient, 44.7 MB)")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--sweep", type=int, default=1, help="1: try several (CTAs, 16-byte accesses in flight per thread) and keep the best")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     lib = cuda_lib.load()
@@ -70,8 +71,15 @@ def main():
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / args.iters * 1e-3
 
+    sampler = None
     if rank0_local:
         dev = fabric.local_ranks[0]
+        sys.path.insert(0, ROOT)
+        from bench import ClockSampler
+        import time
+        sampler = ClockSampler(dev)
+        sampler.start()
+        t_start = time.time()
         with torch.cuda.device(dev):
             dst = torch.zeros(nfl, dtype=torch.float32, device="cuda")
             src = torch.arange(nfl, dtype=torch.float32, device="cuda")
@@ -82,16 +90,33 @@ def main():
         for mode in (["nvls", "unicast"] if grads.multicast else ["unicast"]):
             mc_g = grads.mc(0) if mode == "nvls" else None
             mc_r = repl.mc(0) if mode == "nvls" else None
+            shapes = [(296, 4), (592, 8), (1184, 8), (592, 16), (1184, 16), (2368, 16)] if args.sweep else [(0, 0)]
             # ---- push/reduce ----
-            dst.zero_()
-            t = timed(lambda: lib.dtf_fabric_reduce(mc_g, peers_g, N - 1, dst.data_ptr(), nfl, 0, st()), dev)
-            ok = bool(torch.all(dst == expect).item())
-            res["push_" + mode] = {"ok": ok, "seconds": t, "payload_GBps": (N - 1) * nbytes / t / 1e9,
-                                   "ps_port_GBps": (nbytes if mode == "nvls" else (N - 1) * nbytes) / t / 1e9}
+            best, tried = None, {}
+            for grid, unroll in shapes:
+                dst.zero_()
+                t = timed(lambda: lib.dtf_fabric_reduce_ex(mc_g, peers_g, N - 1, dst.data_ptr(), nfl, grid, unroll, st()), dev)
+                ok = bool(torch.all(dst == expect).item())
+                tried["%dx%d" % (grid, unroll)] = round((nbytes if mode == "nvls" else (N - 1) * nbytes) / t / 1e9, 1)
+                if ok and (best is None or t < best[0]):
+                    best = (t, grid, unroll)
+            t = best[0]
+            res["push_" + mode] = {"ok": best is not None, "seconds": t, "payload_GBps": (N - 1) * nbytes / t / 1e9,
+                                   "ps_port_GBps": (nbytes if mode == "nvls" else (N - 1) * nbytes) / t / 1e9,
+                                   "ctas_x_in_flight": [best[1], best[2]], "ps_port_GBps_by_shape": tried}
             # ---- pull/broadcast ----
-            t = timed(lambda: lib.dtf_fabric_bcast(src.data_ptr(), mc_r, peers_r, N - 1, nbytes, 0, st()), dev)
+            best, tried = None, {}
+            for grid, unroll in shapes:
+                t = timed(lambda: lib.dtf_fabric_bcast_ex(src.data_ptr(), mc_r, peers_r, N - 1, nbytes, grid, unroll, st()), dev)
+                tried["%dx%d" % (grid, unroll)] = round((nbytes if mode == "nvls" else (N - 1) * nbytes) / t / 1e9, 1)
+                if best is None or t < best[0]:
+                    best = (t, grid, unroll)
+            t = best[0]
             res["pull_" + mode] = {"seconds": t, "payload_GBps": (N - 1) * nbytes / t / 1e9,
-                                   "ps_port_GBps": (nbytes if mode == "nvls" else (N - 1) * nbytes) / t / 1e9}
+                                   "ps_port_GBps": (nbytes if mode == "nvls" else (N - 1) * nbytes) / t / 1e9,
+                                   "ctas_x_in_flight": [best[1], best[2]], "ps_port_GBps_by_shape": tried}
+            for k in ("push_" + mode, "pull_" + mode):
+                res[k]["ps_port_fraction_of_900"] = res[k]["ps_port_GBps"] / 900.0
             torch.cuda.synchronize(dev)
             fabric.barrier() if world == 1 else None
             if world == 1:
@@ -102,6 +127,7 @@ def main():
                     tr.zero_()
                 res["pull_" + mode]["ok"] = all(oks)
         out["results"] = res
+        out["clocks"] = sampler.stop(t_start, time.time())
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
