@@ -340,6 +340,17 @@ def run_resnet18(args, rank, world, local_rank):
                    "note": "the timed loop itself copies every batch from pinned host memory and reads the loss back"},
            "first_loss": losses[0] if losses else None, "final_loss": losses[-1] if losses else None}
     eng.close()
+    if getattr(args, "baseline", 0):
+        # the divisor for config 5: cuDNN + autograd + NCCL arm, same invocation / batch / topology
+        try:
+            from baseline.nccl_resnet import run_nccl_resnet
+            base = run_nccl_resnet(args, rank, world, local_rank, sampler_cls=ClockSampler)
+            out["baseline"] = base
+            out["vs_baseline"] = value / base["value"] if base.get("value") else None
+        except Exception as e:          # noqa: BLE001
+            if world > 1:
+                raise
+            out["baseline"] = {"error": repr(e)[:300]}
     return out
 
 
