@@ -418,7 +418,9 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap map_a, c
     else { tmem_alloc(&tmem_holder, tmem_cols); tmem_relinquish(); }
   }
   tc_fence_before();
-  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
+  // (pair: barrier.cluster orders the allocator's write of the holder in BOTH CTAs; the CTA barrier behind it is free here
+  //  -- once per kernel -- and is the ordering compute-sanitizer's racecheck models for shared memory)
+  if (CTAS == 2) { cluster_sync_all(); __syncthreads(); } else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
 

@@ -103,6 +103,8 @@ struct MlpStepParams {
   int clustered;               // 1: the G CTAs are ONE thread-block cluster: the two exchanges are ordered by barrier.cluster
                                //    (release / acquire at cluster scope, ~0.2 us) instead of fence + counter + poll through L2
   int dbg;                     // debugging knobs: bit 0 skip the dW1 stores, bit 1 skip their TMEM loads
+  unsigned long long* ring;    // optional worker ring [ring_cap][8] u64 (always-on tracing for the Timeline): CTA 0 writes
+  int ring_cap;                //   {kind 2|3, t_entry, t_token, t_forward_end, t_head_end, t_exit, step, G} per launch
 };
 
 #ifndef DTF_HOST_EMU
@@ -177,6 +179,10 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
   unsigned long long* tr = p.trace ? p.trace + 32 * cta : nullptr;
 #define STAMP(slot) do { if (tr && tid == 0) tr[slot] = globaltimer_ns(); } while (0)
   STAMP(0);
+  // worker ring: thread 0 of CTA 0 keeps five %globaltimer reads in registers and writes ONE 64-byte row at exit
+  const bool ringer = p.ring != nullptr && cta == 0 && tid == 0;
+  unsigned long long rt_entry = 0, rt_token = 0, rt_fwd = 0, rt_head = 0;
+  if (ringer) rt_entry = globaltimer_ns();
 
   // ---- shared memory carve-up: [x tile | W1 slice / dh tile | head scratch]
 #ifndef DTF_HOST_EMU
@@ -285,6 +291,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
       }
 #endif
     }
+    if (ringer) rt_token = globaltimer_ns();
     __syncthreads();                                       // token acquired (thread 0's acquire + barrier)
     STAMP(2);
   }
@@ -355,6 +362,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
     tc_fence_after();
 #endif
     STAMP(3);
+    if (ringer) rt_fwd = globaltimer_ns();
     // epilogue 1: TMEM (lane = batch row, column = hidden unit) -> hpart[cta][row][0..n1)
     const int q = warp & 3, half = warp >> 2;
     const int b = q * 32 + lane;
@@ -606,6 +614,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
       }
     }
     STAMP(6);
+    if (ringer) rt_head = globaltimer_ns();
   }
 
   // =====================================================================================================
@@ -738,6 +747,13 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
   if (warp == 1) tmem_dealloc(tmem_holder, 256);
 #endif
   STAMP(10);
+  if (ringer && last_phase) {
+    unsigned long long* row = p.ring + (step % (unsigned long long)p.ring_cap) * 8ull;
+    if (p.forward_only) row = p.ring + (unsigned long long)p.ring_cap * 8ull;      // one extra row: the last forward-only launch
+    row[1] = rt_entry; row[2] = rt_token; row[3] = rt_fwd; row[4] = rt_head; row[5] = globaltimer_ns();
+    row[6] = step; row[7] = (unsigned long long)p.G;
+    row[0] = p.forward_only ? 3ull : 2ull;
+  }
 #undef STAMP
 }
 
@@ -780,6 +796,7 @@ struct DtfMlpStepArgs {
   unsigned long long* trace;
   int no_cluster;              // 1: plain grid + L2 counters even when the CTAs would fit one cluster
   int dbg;
+  unsigned long long* ring; int ring_cap;      // optional worker trace ring: (ring_cap + 1) rows of 8 u64
 };
 
 // Slices: at least ceil(B / 16) CTAs (phase 2 finalises <= 16 batch rows per CTA), at most 16; among those the widest
@@ -847,6 +864,7 @@ int dtf_mlp_step(const DtfMlpStepArgs* a, cudaStream_t s) {
   p.sys_scope = a->sys_scope; p.stamp_step = a->stamp_step;
   p.timeout_ns = a->timeout_ns ? a->timeout_ns : 2000000000ull;
   p.err = a->err; p.trace = a->trace; p.dbg = a->dbg;
+  p.ring = a->ring_cap > 0 ? a->ring : nullptr; p.ring_cap = a->ring_cap;
   const int nqx = (ds + 31) / 32, nq1 = (p.n1 + 31) / 32;
   const int w_region = (std::max(std::max(nq1 * ds * 128, 4 * p.kb * 128), 128 * (p.n1 + 4) * 4) + 1023) & ~1023;
   const size_t head_floats = 2 * 16 * 132 + 128 * 20 + 128 + 256 + 256 + 16;

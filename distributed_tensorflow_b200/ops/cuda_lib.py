@@ -84,7 +84,7 @@ class MlpStepArgs(Structure):
                 ("stamp_step", c_int), ("consumed", c_void_p * 4),
                 ("num_signals", c_int), ("arrivals", c_void_p * 4), ("stamp_dst", c_void_p * 4), ("stamp_src", c_void_p * 4),
                 ("sys_scope", c_int), ("timeout_ns", c_ulonglong), ("err", c_void_p), ("trace", c_void_p),
-                ("no_cluster", c_int), ("dbg", c_int)]
+                ("no_cluster", c_int), ("dbg", c_int), ("ring", c_void_p), ("ring_cap", c_int)]
 
 
 class StepOp(Structure):

@@ -109,6 +109,7 @@ class EngineConfig:
     timeout_ns: int = 5_000_000_000
     loss_hist: int = 4096
     trace_cap: int = 4096
+    worker_trace_cap: int = 1024     # rows of the per-worker step ring (mlp_step_kernel stamps one 64-byte row per launch)
     seed: int = 0
 
 
@@ -299,7 +300,8 @@ class PSTrainEngine:
                 if self.tf32:
                     # scratch of the one-kernel step: partial pre-activations + dh (L2 resident), 8 sync counters, phase stamps
                     nfl = self.step_ctas * 128 * (round_up(spec.hidden, 16) + 4) + 128 * 128 + 64
-                    names += [("stepscr_w%d" % w, nfl * 4), ("stepflags_w%d" % w, 256), ("steptrace_w%d" % w, 16 * 32 * 8)]
+                    names += [("stepscr_w%d" % w, nfl * 4), ("stepflags_w%d" % w, 256), ("steptrace_w%d" % w, 16 * 32 * 8),
+                              ("stepring_w%d" % w, (cfg.worker_trace_cap + 1) * 64)]
                 for s in range(cfg.num_ps):
                     if self.nvls:
                         rk.bufs["replica%d_w%d" % (s, w)] = self.sym_repl[s].local(r)
@@ -400,7 +402,7 @@ class PSTrainEngine:
                 with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
                     for name in ("mailbox_w%d" % w, "misc_w%d" % w, "x16_w%d" % w, "h_w%d" % w, "dh_w%d" % w,
                                  "labels_w%d" % w, "hacc_w%d" % w, "xf32_w%d" % w) + \
-                            (("stepscr_w%d" % w, "stepflags_w%d" % w, "steptrace_w%d" % w) if self.tf32 else ()):
+                            (("stepscr_w%d" % w, "stepflags_w%d" % w, "steptrace_w%d" % w, "stepring_w%d" % w) if self.tf32 else ()):
                         rk.bufs[name].tensor(torch.uint8).zero_()
                     for sg in self.sym_grads:
                         sg.local(r).tensor(torch.uint8).zero_()
@@ -441,13 +443,31 @@ class PSTrainEngine:
         return int(t[0]) if count == 1 else t.tolist()
 
     def step_stats(self) -> List[Dict[str, Any]]:
-        """Device-side trace of the LOCAL ps shards (SURVEY A19 on the fabric tier): every ``ps_apply`` launch stamps
-        ``(kind, %globaltimer at entry, %globaltimer when the tokens were released, global_step)`` into a ring in ps
-        HBM (``trace_cap`` entries).  Returns timeline events -- feed them to ``dtf.timeline.Timeline(step_stats=...)``
-        for a chrome trace with one process per ``/job:ps/task:k`` GPU."""
+        """Device-side trace of the LOCAL ranks (SURVEY A19 on the fabric tier; the reference traces the whole step per task,
+        example_in_graph.py:65-68).  ps shards: every ``ps_apply`` launch stamps ``(kind, %globaltimer at entry, %globaltimer
+        when the tokens were released, global_step)`` into a ring in ps HBM (``trace_cap`` entries).  Workers (one-kernel
+        step): CTA 0 of every ``mlp_step_kernel`` launch writes ``(kind, entry, token acquired, forward GEMM done, head done,
+        exit, step, G)`` into the worker's ring (``worker_trace_cap`` rows) -- four phases per step.  Returns timeline events
+        -- feed them to ``dtf.timeline.Timeline(step_stats=...)`` for a chrome trace with one process per
+        ``/job:ps/task:k`` and ``/job:worker/task:i`` GPU; %globaltimer is one clock per GPU, synchronised across the box
+        well enough (sub-microsecond) to read the ps and worker rows against each other."""
         from ..utils.timeline import events_from_ring
         events: List[Dict[str, Any]] = []
         for r, rk in self.ranks.items():
+            if r in self.worker_ranks and self.tf32:
+                w = self.worker_ranks.index(r)
+                rk.stream.synchronize()
+                rows = rk.bufs["stepring_w%d" % w].tensor(torch.int64, 0, (self.cfg.worker_trace_cap + 1) * 8).view(-1, 8).cpu().tolist()
+                task = "/job:worker/task:%d" % w
+                for kind, t_in, t_tok, t_fwd, t_head, t_out, step, _g in rows:
+                    if kind == 0:
+                        continue
+                    name = {2: "mlp_step", 3: "mlp_forward"}.get(int(kind), "k%d" % kind)
+                    phases = [(name + "/wait_token", t_in, t_tok), (name + "/forward_gemm", t_tok, t_fwd),
+                              (name + "/head_softmax_xent", t_fwd, t_head), (name + "/backward_gemm_push", t_head, t_out)]
+                    ring = [(10 + i, a, b, step) for i, (_, a, b) in enumerate(phases) if a and b]
+                    events += events_from_ring(task, ring, {10 + i: ph[0] for i, ph in enumerate(phases)},
+                                               gpu_index=rk.device.index or 0)
             if r not in self.ps_ranks:
                 continue
             s = self.ps_ranks.index(r)
@@ -565,6 +585,7 @@ class PSTrainEngine:
                     w=w, w1=psrc(lay["hid_w"]), ldw1=lay["hid_w"].pitch, b1=psrc(lay["hid_b"]),
                     w2=psrc(lay["sm_w"]), ldw2=lay["sm_w"].pitch, b2=psrc(lay["sm_b"]),
                     scr=rk.bufs["stepscr_w%d" % w].ptr, flags=rk.bufs["stepflags_w%d" % w].ptr,
+                    ring=rk.bufs["stepring_w%d" % w].ptr,
                     gw1=slot(lay["hid_w"]), gb1=slot(lay["hid_b"]), gw2=slot(lay["sm_w"]), gb2=slot(lay["sm_b"]),
                     tokens=[(rk.bufs["replica%d_w%d" % (sh, w)].ptr + self.shard_elems[sh] * 4) if self._mc_tokens()
                             else (mb.ptr + sh * self.mb_bytes) for sh in self.var_shards],
@@ -654,7 +675,12 @@ class PSTrainEngine:
             if cfg.sync and self.R < cfg.num_workers:
                 a.consumed[i] = k["consumed"][i]           # backup workers: never overwrite a push the ps has not consumed / dropped
             a.arrivals[i] = k["arrivals"][i]
-            a.stamp_dst[i] = k["arrivals"][i] + 8
+            # the stamp (which parameters this push was computed from) is what the ps's staleness / stale-gradient logic
+            # reads; with replicas_to_aggregate == replicas every aggregate is all-fresh by construction and the ps never
+            # looks at it (ps_engine.cu all_fresh_only) -- skipping the remote store there also takes a pending NVLink
+            # write out from under the step kernel's release fence
+            a.stamp_dst[i] = 0 if (cfg.sync and self.R == cfg.num_workers and os.environ.get("DTF_STAMP_ALWAYS", "0") != "1") \
+                else k["arrivals"][i] + 8
             a.stamp_src[i] = k["mb_tokens"][i] + (0 if cfg.sync else 8)   # token (sync) / pulled version (async)
         # sync: the push is stamped with the token the worker holds (= global step at the pull); with the multicast counter
         # tokens the mailbox token may lag one aggregate, and step == global step there (all-fresh aggregates only)
@@ -663,6 +689,7 @@ class PSTrainEngine:
         a.timeout_ns, a.err = cfg.timeout_ns, d["err_ptr"]
         a.no_cluster = int(os.environ.get("DTF_STEP_NO_CLUSTER", "0") == "1")
         a.dbg = int(os.environ.get("DTF_STEP_DBG", "0"))
+        a.ring, a.ring_cap = k["ring"], cfg.worker_trace_cap
         return a
 
     # ------------------------------------------------------------------------------------------------

@@ -324,6 +324,14 @@ class Server:
             svc.farewell()
         return True
 
+    def rpc_fabric_step_stats(self, key):
+        """Timeline events of this ps task's fabric engine (device-side ``ps_apply`` ring): what a traced ``Session.run`` on
+        a worker merges into ``RunMetadata.step_stats`` next to its own step-kernel phases."""
+        svc = self.store.resources.get("fabric_service/" + key)
+        if svc is None or svc.engine is None or not hasattr(svc.engine, "step_stats"):
+            return []
+        return svc.engine.step_stats()
+
     def rpc_reset(self):
         self.store.clear()
         return True

@@ -310,6 +310,27 @@ class FabricPSStrategy:
             except Exception:      # noqa: BLE001 - the ps may already be gone
                 pass
 
+    def _trace_into(self, tracer) -> None:
+        """FULL_TRACE run on the fused path: the device-side rings (this worker's step-kernel phases, every ps shard's
+        ``ps_apply`` launches) become timeline events of the run, one process row per task -- the whole step per
+        ``/job:worker/task:i`` and ``/job:ps/task:k`` (reference example_in_graph.py:65-68)."""
+        events = list(self.engine.step_stats()) if hasattr(self.engine, "step_stats") else []
+        for t in range(self.cluster.num_tasks("ps")):
+            try:
+                from .server import local_server_for
+                srv = local_server_for(self.cluster.task_address("ps", t))
+                ev = srv.rpc_fabric_step_stats(self._spec["key"]) if srv is not None else \
+                    self.server.peer("ps", t).call("fabric_step_stats", self._spec["key"])
+                events += ev
+            except Exception:      # noqa: BLE001 - tracing is best effort
+                pass
+        seen = self.__dict__.setdefault("_traced", set())
+        for e in events:
+            k = (e["task"], e["name"], e["start_us"])
+            if k not in seen:
+                seen.add(k)
+                tracer.add_event(e)
+
     def _report(self) -> None:
         """One line at process exit: which engine ran this worker's steps and how many kernels of ours it launched."""
         self.farewell()
@@ -337,7 +358,10 @@ class FabricPSStrategy:
             y = feeds[ph_ids.index(self.mlp["y_"].id)]
             self._ensure_engine(int(x.shape[0]))
             if self.mlp is not None:
-                return self._mlp_step(x, y)
+                out = self._mlp_step(x, y)
+                if ctx.tracer is not None:
+                    self._trace_into(ctx.tracer)
+                return out
         self._ensure_engine()
         if not self._primed:
             self._prime()

@@ -168,6 +168,42 @@ def test_device_dataset_and_cuda_graph_replay_are_step_exact(precision):
     torch.testing.assert_close(s0["hid_w"], s1["hid_w"], rtol=1e-4, atol=1e-5)
 
 
+def test_step_stats_trace_the_whole_step_per_task():
+    """Timeline on the fabric tier (reference example_in_graph.py:65-68 traces the step per task): the ps ring has one
+    ``ps_apply`` row per aggregate, the worker ring four phases per ``mlp_step_kernel`` launch, in device-clock order."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import json
+    from distributed_tensorflow_b200.parallel.fabric import Fabric
+    from distributed_tensorflow_b200.parallel.ps_engine import EngineConfig, MLPSpec, PSTrainEngine
+    from distributed_tensorflow_b200.utils.mnist_data import synthetic_mnist
+    from distributed_tensorflow_b200.utils.timeline import Timeline
+    torch.cuda.set_device(0)
+    xs, ys = synthetic_mnist(1200, seed=6)
+    eng = PSTrainEngine(MLPSpec(), EngineConfig(colocated=True, optimizer={"kind": "sgd", "lr": 0.002}, seed=1), Fabric(1, {0: 0}))
+    eng.init_params()
+    eng.attach_dataset(0, xs, ys)
+    eng.enqueue_local_steps(5, "dataset")
+    eng.evaluate(torch.from_numpy(xs[:200]), torch.from_numpy(ys[:200]))
+    ev = eng.step_stats()
+    eng.check_errors()
+    eng.close()
+    ps = [e for e in ev if e["task"] == "/job:ps/task:0"]
+    wk = [e for e in ev if e["task"] == "/job:worker/task:0"]
+    assert len(ps) == 5
+    for step in range(5):
+        mine = sorted((e for e in wk if e["name"].startswith("mlp_step/") and e["name"].endswith("[step %d]" % step)),
+                      key=lambda e: e["start_us"])
+        assert [e["op"].split("/")[1] for e in mine] == ["wait_token", "forward_gemm", "head_softmax_xent", "backward_gemm_push"]
+        for a, b in zip(mine, mine[1:]):
+            assert b["start_us"] >= a["start_us"] + a["dur_us"] - 1e-3
+        assert sum(e["dur_us"] for e in mine) < 1000.0               # a step is tens of microseconds, not a wrapped clock
+    assert any(e["name"].startswith("mlp_forward/") for e in wk)         # the forward-only (validation) launch is traced too
+    trace = json.loads(Timeline(ev).generate_chrome_trace_format())
+    names = {t["args"]["name"] for t in trace["traceEvents"] if t.get("ph") == "M"}
+    assert any("/job:worker/task:0" in n for n in names) and any("/job:ps/task:0" in n for n in names)
+
+
 def test_smoke_entry_point():
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")

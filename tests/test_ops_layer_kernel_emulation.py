@@ -207,7 +207,8 @@ def test_graph_tier_training_step_dispatches_to_our_kernels(emulated, monkeypatc
         return losses, weights, launched
     l1, w1, launched = train(True)
     l0, w0, none = train(False)
-    assert launched >= 3 * 12 and none == 0, (launched, none)
+    # per step: 3 GEMMs (forward with fused bias+ReLU, dW, dX) + the fused head + the optimizer applies
+    assert launched >= 3 * 7 and none == 0, (launched, none)
     np.testing.assert_allclose(l1, l0, rtol=2e-2)
     for a, b in zip(w1, w0):
         # Adam normalises every coordinate's step to ~lr: a gradient whose sign flips under bf16 rounding moves by up to

@@ -23,12 +23,18 @@ def main():
     sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
     per = collections.OrderedDict()
     cur = None
+    full = collections.OrderedDict()            # kernel -> its complete SASS listing (profiles/sass/<kernel>.sass)
+    cur_lines = None
     for line in sass.splitlines():
         m = re.search(r"Function : (\S+)", line)
         if m:
             name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
             cur = per.setdefault(name, collections.Counter())
+            cur_lines = full.setdefault(name, [])
+            cur_lines.append(line)
             continue
+        if cur_lines is not None:
+            cur_lines.append(line)
         m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Za-z0-9_.]*)", line)
         if m and cur is not None:
             op = m.group(1)
@@ -47,6 +53,17 @@ def main():
             continue
         out.append(name)
         out.append("   " + ", ".join("%s x%d" % (k, v) for k, v in sorted(c.items())))
+    sdir = os.path.join(ROOT, "profiles", "sass")
+    os.makedirs(sdir, exist_ok=True)
+    for old in os.listdir(sdir):
+        os.unlink(os.path.join(sdir, old))
+    for name, lines in full.items():
+        fn = re.sub(r"[^A-Za-z0-9_]+", "_", name.replace("dtf::", "")).strip("_")[:120] + ".sass"
+        # instruction text only (the /*hex encoding*/ columns double the size and carry no extra evidence)
+        body = [re.sub(r"\s*/\* 0x[0-9a-f]{16} \*/\s*$", "", l) for l in lines if not re.match(r"^\s*/\* 0x[0-9a-f]{16} \*/\s*$", l)]
+        with open(os.path.join(sdir, fn), "a") as f:
+            f.write("\n".join(body) + "\n")
+    print("wrote %d full listings to profiles/sass/" % len(full))
     path = os.path.join(ROOT, "profiles", "sass_mnemonics.txt")
     open(path, "w").write("\n".join(out) + "\n")
     print("\n".join(out[:6]))
