@@ -480,12 +480,35 @@ def gemm_raw(a: torch.Tensor, lda: int, b: torch.Tensor, ldb: int, c: torch.Tens
     _bump()
 
 
+AUTO_SPLIT_K = os.environ.get("DTF_AUTO_SPLIT_K", "1") == "1"
+
+
+def auto_splits(M: int, N: int, K: int, b_mn: bool, tf32: bool, sms: int = 148) -> int:
+    """Split-K factor for a GEMM whose output tiles do not fill the GPU (the weight-gradient GEMMs of a convolution are the
+    extreme: [9*Cin, pixels] x [pixels, Cout] is a handful of tiles with K in the tens of thousands -- 5 CTAs walking
+    K = 65536 measured 469 us; the same work over 150 CTAs is ~20 us).  Mirrors the tile choice of ``dtf_gemm_bf16``:
+    at least 8 K-blocks per split, at most one wave of CTAs, and the fp32 red.add traffic (splits x output) bounded."""
+    kbk = 32 if tf32 else 64
+    if b_mn:
+        bn = 64 if N <= 64 else (128 if N <= 128 else (192 if N <= 192 else 256))
+    else:
+        bn = round_up(N, 16)
+        if bn > 256:
+            bn = 256 if (N % 256 == 0 or N > 1024) else 128
+    tiles = -(-M // 128) * -(-N // bn)
+    num_kb = -(-K // kbk)
+    if tiles * 2 > sms or num_kb < 16:
+        return 1
+    s = min(sms // tiles, num_kb // 8, max(1, (64 << 20) // (M * N * 4)))
+    return max(int(s), 1)
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, ta: bool = False, tb: bool = False, bias: Optional[torch.Tensor] = None,
-         relu: bool = False, out_dtype: torch.dtype = torch.float32, splits: int = 1, persistent: int = 0,
+         relu: bool = False, out_dtype: torch.dtype = torch.float32, splits: int = 0, persistent: int = 0,
          block_n: int = 0, precision: Optional[str] = None) -> torch.Tensor:
     """``op(a) @ op(b)`` (+bias, ReLU) on the tensor cores, fp32 accumulate.  ``precision``: "bf16" (operands rounded to
     bf16) or "tf32" (fp32 operands read in place, TF32 multiply); default: bf16 inputs -> "bf16", otherwise
-    ``MATMUL_PRECISION``."""
+    ``MATMUL_PRECISION``.  ``splits``: split-K factor (fp32 output, no ReLU); 0 = :func:`auto_splits`."""
     assert _on_device(a) and _on_device(b) and a.dim() == 2 and b.dim() == 2
     if precision is None:
         precision = "bf16" if (a.dtype == torch.bfloat16 or b.dtype == torch.bfloat16) else MATMUL_PRECISION
@@ -512,6 +535,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, ta: bool = False, tb: bool = False, b
     Kb, N = (b.shape[1], b.shape[0]) if tb else (b.shape[0], b.shape[1])
     if K != Kb:
         raise ValueError("gemm: inner dimensions differ (%d vs %d)" % (K, Kb))
+    if splits <= 0:
+        splits = auto_splits(M, N, K, not tb, tf32) if (out_dtype == torch.float32 and not relu and block_n == 0
+                                                        and AUTO_SPLIT_K) else 1
     with _on(a.device):
         a16, lda = to_f32_padded(a) if tf32 else to_bf16_padded(a)
         b16, ldb = to_f32_padded(b) if tf32 else to_bf16_padded(b)

@@ -50,7 +50,7 @@ def test_minimize_routes_itself_onto_the_fused_fabric_path(tmp_path, sync, progr
                 p.kill()
         for f in logs:
             f.close()
-    steps = 0
+    steps, validated = 0, []
     for n in ("w0", "w1"):
         out = open(tmp_path / ("%s.log" % n)).read()
         assert "routed onto the NVLink fabric (fused MLP step" in out, out[-2000:]
@@ -59,7 +59,11 @@ def test_minimize_routes_itself_onto_the_fused_fabric_path(tmp_path, sync, progr
         steps += int(m.group(1))
         assert int(m.group(2)) >= int(m.group(1))                   # at least one kernel of ours per step in that process
         assert "Training elapsed time" in out
-        losses = [float(v) for v in re.findall(r"loss: ([0-9.eE+-]+)", out)]
+        losses = [float(v) for v in re.findall(r"\| loss: ([0-9.eE+-]+)", out)]
         assert len(losses) > 1000 and sum(losses[-50:]) / 50 < 0.5 * sum(losses[:50]) / 50      # it trains
-        assert re.search(r"validation cross entropy = ", out)       # the 1000-step validation ran (forward-only kernel)
+        validated.append(bool(re.search(r"validation cross entropy = ", out)))
+    # the 1000-step validation ran (forward-only kernel).  Sync: every replica sees every global step.  Async: a replica
+    # validates when ITS fetch of the global step lands on 999 mod 1000 (reference distributed_mnist.py:160), which with
+    # two workers bumping the counter concurrently need not happen on both
+    assert all(validated) if sync == "True" else any(validated), validated
     assert steps >= 9000                                            # the two workers shared ~10 000 global steps
