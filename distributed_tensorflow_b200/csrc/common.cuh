@@ -193,6 +193,15 @@ DTF_DEVICE void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* ba
       : "memory");
 }
 
+// 4-D tile (implicit-GEMM convolution: {channels, w, h, image} of an NHWC activation; coordinates may be negative or run past
+// the tensor -- the out-of-bounds part of the box is ZERO-filled, which is exactly the convolution's padding)
+DTF_DEVICE void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // tcgen05: tensor memory + 5th-gen tensor-core MMA
 // ------------------------------------------------------------------------------------------------

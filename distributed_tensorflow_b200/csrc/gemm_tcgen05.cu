@@ -75,6 +75,17 @@ struct GemmParams {
   int mn_kstep16;        // MN-major tiles: descriptor advance (>> 4) per MMA = K-per-MMA rows x 128 B
   int mn_sbo;            // MN-major tiles: bytes between swizzle atoms along K (8 rows x 128 B; fp32: 4 rows x 128 B)
   int mn_type;           // MN-major tiles: descriptor layout type (2 = SWIZZLE_128B; fp32: 1 = SWIZZLE_128B_BASE32B)
+  // implicit-GEMM convolution (bf16, stride 1): map_a is a 4-D map {C, W, H, images} over the NHWC activation and the
+  // A operand is its patch matrix, never materialised -- one shifted box per (tap, 64-channel chunk); the zero fill of the
+  // out-of-bounds part of a box IS the padding.
+  //   conv == 1: A = patches [pixels, taps*C] (K-major: fprop, and dgrad on dY with the flipped filter); box = 128 pixels
+  //   conv == 2: A = patches^T [taps*C, pixels] (MN-major: wgrad, K = pixels); box = 64 pixels, one per 64-channel M chunk
+  int conv;
+  int cv_w, cv_hw;       // W and H*W of the activation (pixels are ordered image, row, column)
+  int cv_cpt;            // 64-channel chunks per tap (C / 64)
+  int cv_kw, cv_taps;    // filter width, kh*kw
+  int cv_pt, cv_pl;      // top / left padding
+  int cv_n;              // images (coordinate of an all-out-of-bounds box: the M tail of wgrad)
 };
 
 
@@ -252,7 +263,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         uint8_t* a_dst = tiles + s * stage_bytes;
         uint8_t* b_dst = a_dst + kABytes;
         const int k0 = kb * p.kbk;
-        if (!p.a_mn) {
+        if (p.conv == 1) {
+          const int tap = kb / p.cv_cpt, c0 = (kb - tap * p.cv_cpt) * 64;
+          const int ky = tap / p.cv_kw, kx = tap - ky * p.cv_kw;
+          const int img = m0 / p.cv_hw, h0 = (m0 - img * p.cv_hw) / p.cv_w;
+          tma_load_4d(a_dst, &map_a, &full_bar[s], c0, kx - p.cv_pl, h0 + ky - p.cv_pt, img);   // box {64 ch, W, rows, images} = 128 pixels
+        } else if (p.conv == 2) {
+          const int img = k0 / p.cv_hw, h0 = (k0 - img * p.cv_hw) / p.cv_w;                     // k0 = first of 64 pixels
+          for (int j = 0; j < 2; ++j) {
+            const int mc = m0 / 64 + j, tap = mc / p.cv_cpt, c0 = (mc - tap * p.cv_cpt) * 64;
+            const int ky = tap / p.cv_kw, kx = tap - ky * p.cv_kw;
+            tma_load_4d(a_dst + j * p.mn_lbo, &map_a, &full_bar[s], c0, kx - p.cv_pl, h0 + ky - p.cv_pt,
+                        tap < p.cv_taps ? img : p.cv_n);
+          }
+        } else if (!p.a_mn) {
           tma_load_2d(a_dst, &map_a, &full_bar[s], k0, m0);                 // box {128 B of k, 128 m}
         } else {
           for (int j = 0; j < kBlockM / mnc; ++j)                           // box {128 B of m, kbk k} x (2 | 4)
@@ -590,7 +614,22 @@ static int make_map(CUtensorMap* out, const void* ptr, long long rows, long long
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
-#endif  // !DTF_HOST_EMU (the emulation stubs provide make_map: it records the requested tensor map)
+// 4-D bf16 map over a dense NHWC activation: dims {C, W, H, images}, box {64 channels (128 B), bw, bh, bn}, 128-byte swizzle,
+// zero fill outside the tensor.  A box lands in shared memory as [bn*bh*bw pixel rows] x 128 B -- the same image as the 2-D
+// box {64, rows} of a materialised patch matrix, so the UMMA descriptors do not change.
+static int make_map4(CUtensorMap* out, const void* ptr, int n, int h, int w, int c, int bw, int bh, int bn) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2ull, (cuuint64_t)w * c * 2ull, (cuuint64_t)h * w * c * 2ull};
+  cuuint32_t box[4] = {64u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+#endif  // !DTF_HOST_EMU (the emulation stubs provide make_map / make_map4: they record the requested tensor map)
 
 struct MapKey {
   const void* ptr;
@@ -603,6 +642,7 @@ struct MapKey {
 static std::map<MapKey, CUtensorMap> g_maps;
 static std::mutex g_maps_mu;
 static int cached_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int bc, int br, int es, int sw32);
+static int cached_map4(CUtensorMap* out, const void* ptr, int n, int h, int w, int c, int bw, int bh, int bn);
 // fp32 maps for the other translation units (csrc/mlp_step.cu)
 int cached_map_f32(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows,
                    int sw32) {
@@ -619,6 +659,23 @@ static int cached_map(CUtensorMap* out, const void* ptr, long long rows, long lo
     return 0;
   }
   int rc = make_map(out, ptr, rows, cols, ld, bc, br, es, sw32);
+  if (rc == 0) {
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps[k] = *out;
+  }
+  return rc;
+}
+
+// 4-D activation maps share the cache: the key packs the geometry into the 2-D fields (es = 0 marks a 4-D entry)
+static int cached_map4(CUtensorMap* out, const void* ptr, int n, int h, int w, int c, int bw, int bh, int bn) {
+  MapKey k{ptr, ((long long)n << 32) | (unsigned)h, ((long long)w << 32) | (unsigned)c, (long long)bn, bw, bh, 0, 0};
+  std::lock_guard<std::mutex> g(g_maps_mu);
+  auto it = g_maps.find(k);
+  if (it != g_maps.end()) {
+    *out = it->second;
+    return 0;
+  }
+  int rc = make_map4(out, ptr, n, h, w, c, bw, bh, bn);
   if (rc == 0) {
     if (g_maps.size() > 4096) g_maps.clear();
     g_maps[k] = *out;
@@ -660,6 +717,9 @@ struct DtfGemmArgs {
   int persistent;        // 0: auto (persistent kernel when tiles > SMs), 1: force persistent 1-CTA, 2: force CTA pairs, -1: never
   int cta_pair;          // -1: never use cta_group::2 in auto mode
   int tf32;              // 1: A and B are fp32 in memory, multiplied as TF32 (tcgen05.mma.kind::tf32); lda/ldb % 4 == 0
+  // implicit-GEMM convolution: a = bf16 NHWC activation [cv_n, cv_h, cv_w, cv_c] (dense), M/K describe the patch matrix
+  int conv;              // 0 plain, 1 A = patches (M = pixels, K = taps*C), 2 A = patches^T (M = taps*C, K = pixels)
+  int cv_n, cv_h, cv_w, cv_c, cv_kh, cv_kw, cv_pt, cv_pl;
 };
 
 // Returns 0 on success, <0 for argument errors, >0 for CUDA errors.
@@ -671,6 +731,21 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
   if ((g->lda % (16 / es)) || (g->ldb % (16 / es))) return -3;                  // TMA: 16-byte row pitch
   if ((reinterpret_cast<uintptr_t>(g->a) & 15) || (reinterpret_cast<uintptr_t>(g->b) & 15)) return -4;
   if (g->splits > 1 && (g->relu || g->c_bf16)) return -5;
+  int cv_bw = 0, cv_bh = 0, cv_bn = 0;
+  if (g->conv) {
+    // implicit-GEMM convolution: bf16, stride 1, whole 64-channel chunks, and a tile's pixels = one box of whole rows /
+    // whole images (W | tile, tile | H*W or H*W | tile)
+    const int tile = g->conv == 1 ? kBlockM : 64;
+    const long long hw = (long long)g->cv_h * g->cv_w, pixels = (long long)g->cv_n * hw, taps = (long long)g->cv_kh * g->cv_kw;
+    if (g->tf32 || (g->conv != 1 && g->conv != 2) || g->cv_c % 64 || g->cv_w > tile || tile % g->cv_w) return -8;
+    if (!((hw % tile) == 0 || (tile % hw) == 0) || pixels % tile) return -8;
+    if (g->conv == 1 && (g->a_mn || g->M != pixels || g->K != taps * g->cv_c)) return -8;
+    if (g->conv == 2 && (!g->a_mn || g->K != pixels || g->M != taps * g->cv_c)) return -8;
+    cv_bw = g->cv_w;
+    cv_bh = (int)(hw >= tile ? tile / g->cv_w : g->cv_h);
+    cv_bn = (int)(hw >= tile ? 1 : tile / hw);
+    if (cv_bh > 256 || cv_bn > 256) return -8;
+  }
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = (int)g->M; p.N = (int)g->N; p.K = (int)g->K;
@@ -693,6 +768,13 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
   const int stage_bytes = kABytes + bn * 128;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
+  if (g->conv) {
+    // short K loops (taps x chunks) under many tiles: two CTAs per SM, so one tile's epilogue runs under the other's mainloop
+    p.conv = g->conv; p.cv_w = g->cv_w; p.cv_hw = g->cv_h * g->cv_w; p.cv_cpt = g->cv_c / 64;
+    p.cv_kw = g->cv_kw; p.cv_taps = g->cv_kh * g->cv_kw; p.cv_pt = g->cv_pt; p.cv_pl = g->cv_pl; p.cv_n = g->cv_n;
+    const int two = (100 * 1024) / stage_bytes;
+    if (two >= 3 && stages > two) stages = two;
+  }
   if (stages > p.kb_per_split) stages = p.kb_per_split < 2 ? 2 : p.kb_per_split;
   if (stages < 2) stages = 2;
   p.stages = stages;
@@ -710,8 +792,9 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
 
   CUtensorMap ma, mb;
   int rc;
-  if (!g->a_mn) rc = cached_map(&ma, g->a, g->M, g->K, g->lda, kbk, kBlockM, es, 0);  // [M rows, K cols]
-  else          rc = cached_map(&ma, g->a, g->K, g->M, g->lda, kbk, kbk, es, sw32);   // [K rows, M cols]
+  if (g->conv)       rc = cached_map4(&ma, g->a, g->cv_n, g->cv_h, g->cv_w, g->cv_c, cv_bw, cv_bh, cv_bn);
+  else if (!g->a_mn) rc = cached_map(&ma, g->a, g->M, g->K, g->lda, kbk, kBlockM, es, 0);  // [M rows, K cols]
+  else               rc = cached_map(&ma, g->a, g->K, g->M, g->lda, kbk, kbk, es, sw32);   // [K rows, M cols]
   if (rc) return rc < 0 ? -7 : 1000 + rc;
   if (!g->b_mn) rc = cached_map(&mb, g->b, g->N, g->K, g->ldb, kbk, bn, es, 0);       // [N rows, K cols]
   else          rc = cached_map(&mb, g->b, g->K, g->N, g->ldb, kbk, kbk, es, sw32);   // [K rows, N cols]
@@ -741,7 +824,8 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
   const unsigned tiles_m = (unsigned)((g->M + kBlockM - 1) / kBlockM), tiles_n = (unsigned)((g->N + bn - 1) / bn);
   const int sms = (dev >= 0 && dev < 64 && sm_count[dev] > 0) ? sm_count[dev] : 148;
   // Persistent path: plain GEMMs with more tiles than SMs (no split-K, no fused wait/signal, no phase stamps).
-  const bool plain = splits == 1 && !p.atomic && p.wait_flag == nullptr && p.signal == nullptr && p.phase_trace == nullptr;
+  const bool plain = splits == 1 && !p.atomic && p.wait_flag == nullptr && p.signal == nullptr && p.phase_trace == nullptr &&
+                     !g->conv;
   if (plain && g->persistent >= 0 && (g->persistent > 0 || (long long)tiles_m * tiles_n > sms)) {
     // CTA pairs (cta_group::2, 256 x BLOCK_N tiles) when the tile shape allows it: BLOCK_N a multiple of 32 (each
     // CTA loads BLOCK_N/2 rows of B; 128 when B is MN-major) and at least two 128-row blocks of M.

@@ -39,7 +39,9 @@ class GemmArgs(Structure):
                 ("signal", c_void_p), ("err", c_void_p), ("timeout_ns", c_ulonglong),
                 ("block_n_override", c_int), ("wait_target_ptr", c_void_p), ("phase_trace", c_void_p),
                 ("signal_gpu_scope", c_int), ("stamp_src", c_void_p), ("stamp_dst", c_void_p), ("persistent", c_int), ("cta_pair", c_int),
-                ("tf32", c_int)]
+                ("tf32", c_int),
+                ("conv", c_int), ("cv_n", c_int), ("cv_h", c_int), ("cv_w", c_int), ("cv_c", c_int), ("cv_kh", c_int),
+                ("cv_kw", c_int), ("cv_pt", c_int), ("cv_pl", c_int)]
 
 
 class PsApplyArgs(Structure):
@@ -481,6 +483,55 @@ def gemm_raw(a: torch.Tensor, lda: int, b: torch.Tensor, ldb: int, c: torch.Tens
 
 
 AUTO_SPLIT_K = os.environ.get("DTF_AUTO_SPLIT_K", "1") == "1"
+# implicit-GEMM convolution (4-D TMA boxes over the NHWC activation instead of a materialised patch matrix)
+IMPLICIT_CONV = os.environ.get("DTF_IMPLICIT_CONV", "1") == "1"
+
+
+def implicit_conv_ok(n: int, h: int, w: int, c: int, strides=(1, 1)) -> bool:
+    """Shapes the implicit-GEMM path of ``dtf_gemm_bf16`` takes (csrc/gemm_tcgen05.cu, ``conv``): stride 1, whole
+    64-channel chunks, and both tile sizes (128 pixels for fprop / dgrad, 64 for wgrad) made of whole rows / whole images."""
+    if tuple(strides) != (1, 1) or c % 64 or w > 64 or 64 % w:
+        return False
+    hw = h * w
+    for tile in (128, 64):
+        if not (hw % tile == 0 or tile % hw == 0) or (n * hw) % tile:
+            return False
+    return (h if hw < 128 else 128 // w) <= 256
+
+
+def conv_igemm(x16: torch.Tensor, b: torch.Tensor, kh: int, kw: int, pt: int, pl: int, wgrad: bool = False,
+               splits: int = 0) -> torch.Tensor:
+    """Implicit-GEMM convolution product on the tcgen05 GEMM; ``x16``: bf16 NHWC activation [n, h, w, c] (dense).
+
+    ``wgrad=False``: ``patches(x16) @ b`` with ``b`` = filter matrix [kh*kw*c, cout] -> fp32 [n*h*w, cout] (the forward
+    convolution; with dY as ``x16`` and the flipped, in/out-swapped filter, the data gradient).
+    ``wgrad=True``: ``patches(x16)^T @ b`` with ``b`` = dY [n*h*w, cout] -> fp32 [kh*kw*c, cout] (split-K over the pixels).
+    The patch matrix is never written: the kernel's TMA producer loads one shifted 4-D box per (tap, 64-channel chunk) and
+    the box's out-of-bounds zero fill is the padding."""
+    assert x16.dtype == torch.bfloat16 and x16.is_contiguous() and x16.dim() == 4
+    n, h, w, c = x16.shape
+    pixels, kdim = n * h * w, kh * kw * c
+    with _on(x16.device):
+        b16, ldb = to_bf16_padded(b)
+        cout = b.shape[1]
+        g = GemmArgs()
+        g.a, g.b, g.lda, g.ldb = x16.data_ptr(), b16.data_ptr(), c, ldb
+        if not wgrad:
+            M, N, K = pixels, cout, kdim
+            g.a_mn, g.conv = 0, 1
+        else:
+            M, N, K = kdim, cout, pixels
+            g.a_mn, g.conv = 1, 2
+        assert b.shape[0] == K, (tuple(b.shape), K)
+        if splits <= 0:
+            splits = auto_splits(M, N, K, True, False) if AUTO_SPLIT_K else 1
+        out = (torch.zeros if splits > 1 else torch.empty)((M, N), dtype=torch.float32, device=x16.device)
+        g.c, g.ldc, g.M, g.N, g.K = out.data_ptr(), N, M, N, K
+        g.b_mn, g.alpha, g.splits = 1, 1.0, splits
+        g.cv_n, g.cv_h, g.cv_w, g.cv_c, g.cv_kh, g.cv_kw, g.cv_pt, g.cv_pl = n, h, w, c, kh, kw, pt, pl
+        _check(load().dtf_gemm_bf16(byref(g), torch.cuda.current_stream().cuda_stream), "conv_igemm")
+        _bump()
+    return out
 
 
 def auto_splits(M: int, N: int, K: int, b_mn: bool, tf32: bool, sms: int = 148) -> int:

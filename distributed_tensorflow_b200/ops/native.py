@@ -290,37 +290,63 @@ def _same_pad(size: int, k: int, s: int):
 
 
 class _ConvFn(torch.autograd.Function):
-    """Implicit-GEMM convolution: NHWC patches gathered to a [N*Ho*Wo, kh*kw*Cin] bf16 matrix by a
-    hand-written gather kernel, then the tcgen05 GEMM against the [kh*kw*Cin, Cout] filter."""
+    """Convolution on the tcgen05 GEMM.
+
+    Stride 1 with whole 64-channel chunks (every 3x3 convolution of a ResNet stage after its first): IMPLICIT GEMM -- the
+    activation is rounded to bf16 once ([N, H, W, C], 2 B / element) and the GEMM's TMA producer reads shifted 4-D boxes of
+    it, one per (tap, channel chunk); the patch matrix (kh*kw times larger) is never written or read, and the box's
+    out-of-bounds zero fill is the padding.  dX = the same kernel over dY with the flipped, in/out-swapped filter; dW =
+    patches(x)^T . dY with the pixels as the (split) K dimension.
+    Otherwise (strided, 3-channel stem): NHWC patches gathered to a [N*Ho*Wo, kh*kw*Cin] bf16 matrix by a hand-written gather
+    kernel, then the plain GEMM against the [kh*kw*Cin, Cout] filter."""
 
     @staticmethod
     def forward(ctx, x, w, strides, pads):
         lib = _lib()
         kh, kw, cin, cout = w.shape
-        cols, (n, ho, wo) = lib.im2col_nhwc(x, kh, kw, strides, pads)
         w2 = w.reshape(kh * kw * cin, cout)
+        n, h, wd = x.shape[0], x.shape[1], x.shape[2]
+        pt, pb, pl, pr = pads
+        same = (h + pt + pb - kh + 1 == h) and (wd + pl + pr - kw + 1 == wd)
+        if lib.IMPLICIT_CONV and not lib.EMULATION and same and lib.implicit_conv_ok(n, h, wd, cin, strides) \
+                and lib.implicit_conv_ok(n, h, wd, cout) and cout % 8 == 0:
+            x16 = lib.to_bf16_padded(x.reshape(n * h * wd, cin))[0].view(n, h, wd, cin)
+            y = lib.conv_igemm(x16, w2, kh, kw, pt, pl)
+            ctx.save_for_backward(x16, w2)
+            ctx.meta = (x.shape, w.shape, strides, pads, (n, h, wd), True)
+            return y.reshape(n, h, wd, cout)
+        cols, (n, ho, wo) = lib.im2col_nhwc(x, kh, kw, strides, pads)
         y = lib.gemm(cols, w2, False, False, precision="bf16")      # conv model family: bf16 operands (BASELINE config 5)
         ctx.save_for_backward(cols, w2)
-        ctx.meta = (x.shape, w.shape, strides, pads, (n, ho, wo))
+        ctx.meta = (x.shape, w.shape, strides, pads, (n, ho, wo), False)
         return y.reshape(n, ho, wo, cout)
 
     @staticmethod
     def backward(ctx, g):
         lib = _lib()
         cols, w2 = ctx.saved_tensors
-        xshape, wshape, strides, pads, (n, ho, wo) = ctx.meta
-        g2 = g.reshape(n * ho * wo, wshape[3]).contiguous()
+        xshape, wshape, strides, pads, (n, ho, wo), implicit = ctx.meta
+        kh, kw, cin, cout = wshape
+        pt, pb, pl, pr = pads
+        g2 = g.reshape(n * ho * wo, cout).contiguous()
         gx = gw = None
+        if implicit:
+            x16 = cols
+            g16 = lib.to_bf16_padded(g2)[0]                      # one rounding of dY serves both products
+            if ctx.needs_input_grad[1]:
+                gw = lib.conv_igemm(x16, g16, kh, kw, pt, pl, wgrad=True).reshape(wshape)
+            if ctx.needs_input_grad[0]:
+                wf = w2.reshape(kh, kw, cin, cout).flip(0, 1).permute(0, 1, 3, 2).reshape(kh * kw * cout, cin)
+                gx = lib.conv_igemm(g16.view(n, ho, wo, cout), wf.contiguous(), kh, kw, kh - 1 - pt, kw - 1 - pl).reshape(xshape)
+            return gx, gw, None, None
         if ctx.needs_input_grad[1]:
             gw = lib.gemm(cols, g2, True, False, precision="bf16").reshape(wshape)
         if ctx.needs_input_grad[0]:
-            kh, kw, cin, cout = wshape
             if lib.FUSED_NN and strides == (1, 1) and cout % 8 == 0:
                 # stride 1: dX is itself a convolution of dY with the spatially flipped, in/out-swapped filter --
                 #   dX[b, iy, ix, ci] = sum_{ky', kx', co} dY[b, iy + ky' - (kh-1-pt), ix + kx' - (kw-1-pl), co] * w[kh-1-ky', kw-1-kx', ci, co]
                 # so it reuses the im2col + GEMM pair: a bf16 patch matrix of dY (rows x kh*kw*Cout x 2 B) replaces the fp32
                 # [rows, kh*kw*Cin] product + the col2im gather (half the HBM traffic, one launch less, output written once)
-                pt, pb, pl, pr = pads
                 wf = w2.reshape(kh, kw, cin, cout).flip(0, 1).permute(0, 1, 3, 2).reshape(kh * kw * cout, cin)
                 gcols_in, _ = lib.im2col_nhwc(g2.reshape(n, ho, wo, cout), kh, kw, (1, 1), (kh - 1 - pt, kh - 1 - pb, kw - 1 - pl, kw - 1 - pr))
                 gx = lib.gemm(gcols_in, wf.contiguous(), False, False, precision="bf16").reshape(xshape)

@@ -73,6 +73,10 @@ static int make_map(CUtensorMap* out, const void* ptr, long long rows, long long
   *out = CUtensorMap{ptr, rows, cols, ld, box_cols, box_rows};
   return 0;
 }
+static int make_map4(CUtensorMap* out, const void* ptr, int n, int h, int w, int c, int bw, int bh, int bn) {
+  *out = CUtensorMap{ptr, (long long)n * h * w, (long long)c, (long long)c, 64, bw * bh * bn};     // pixels x channels, box = pixels of one tile
+  return 0;
+}
 }  // namespace dtf
 
 template <class P>

@@ -115,3 +115,37 @@ def test_split_k_fused_signals_and_argument_errors(host):
     assert _run(host, g)[0] == -4                                                      # 16-byte alignment
     assert _run(host, _args(64, 64, 256, splits=2, relu=1))[0] == -5
     assert _run(host, _args(64, 96, 64, b_mn=1, ldb=96, block_n_override=48))[0] == -6  # MN-major B needs BLOCK_N % 64 == 0
+
+
+def _conv(mode, n, h, w, c, cout, k=3, splits=1):
+    pixels, kdim = n * h * w, k * k * c
+    M, K = (pixels, kdim) if mode == 1 else (kdim, pixels)
+    return _args(M, cout, K, a_mn=int(mode == 2), b_mn=1, lda=c, ldb=cout, splits=splits, conv=mode, cv_n=n, cv_h=h, cv_w=w,
+                 cv_c=c, cv_kh=k, cv_kw=k, cv_pt=k // 2, cv_pl=k // 2)
+
+
+def test_implicit_conv_dispatch_boxes_stages_and_grid(host):
+    # fprop of a ResNet stage-0 convolution: 128-pixel boxes (4 rows of one 32-wide image), one K block per tap, tile kernel
+    # (never the persistent one), 4 x 24 KB stages so two CTAs share an SM
+    rc, r = _run(host, _conv(1, 64, 32, 32, 64, 64))
+    assert rc == 0 and r.kind == 0 and (r.gx, r.gy, r.gz) == (512, 1, 1) and (r.block_n, r.num_kb, r.stages) == (64, 9, 4)
+    assert r.smem == 4 * (16384 + 8192) + 1024
+    assert (r.a_rows, r.a_cols, r.a_box_cols, r.a_box_rows) == (65536, 64, 64, 128)
+    assert (r.b_rows, r.b_cols, r.b_box_cols, r.b_box_rows) == (576, 64, 64, 64)
+    # 4x4 feature maps: a box spans 8 whole images; 512 channels = 8 chunks per tap; split-K over the taps x chunks
+    rc, r = _run(host, _conv(1, 64, 4, 4, 512, 512, splits=9))
+    assert rc == 0 and (r.gx, r.gy, r.gz) == (8, 2, 9) and (r.num_kb, r.kb_per_split, r.atomic) == (72, 8, 1) and r.a_box_rows == 128
+    # wgrad: M = taps x channels (the 10th 64-channel chunk of the last tile is an all-out-of-bounds box), K = pixels in
+    # 64-pixel boxes, split over the CTAs
+    rc, r = _run(host, _conv(2, 64, 32, 32, 64, 64, splits=29))
+    assert rc == 0 and r.kind == 0 and (r.gx, r.gy) == (5, 1) and r.num_kb == 1024 and r.a_box_rows == 64 and r.atomic == 1
+    assert r.gz * r.kb_per_split >= 1024 and (r.gz - 1) * r.kb_per_split < 1024
+    # rejected: 3 input channels, widths that do not tile, pixel counts that leave a partial box, fp32 operands
+    assert _run(host, _conv(1, 64, 32, 32, 3, 64))[0] == -3           # (a 6-byte pixel pitch is not even a legal TMA stride)
+    assert _run(host, _conv(1, 64, 32, 32, 32, 64))[0] == -8
+    assert _run(host, _conv(1, 4, 24, 24, 64, 64))[0] == -8
+    assert _run(host, _conv(1, 2, 4, 4, 512, 512))[0] == -8
+    g = _conv(1, 64, 32, 32, 64, 64)
+    g.tf32 = 1
+    g.lda = g.ldb = 64
+    assert _run(host, g)[0] == -8
