@@ -75,7 +75,12 @@ def parse_args():
     ap.add_argument("--f1-block-n", type=int, default=64)
     ap.add_argument("--b3-block-n", type=int, default=64)
     ap.add_argument("--in-graph", action="store_true", help="ONE process drives all --gpus devices (in-graph replication)")
-    ap.add_argument("--num-ps", type=int, default=1, help="ps shards (variables placed round-robin)")
+    ap.add_argument("--num-ps", type=int, default=0,
+                    help="ps shards; 0 = auto: 1 for the MNIST MLP (0.3 MB of parameters: one apply kernel is the latency floor), "
+                         "one per GPU for ResNet-18 with the shards on the workers' GPUs (45 MB: every GPU reduces / publishes 1/N)")
+    ap.add_argument("--placement", default="greedy", choices=["round_robin", "greedy"],
+                    help="ResNet-18 variables -> ps shards: replica_device_setter's round robin, or its GreedyLoadBalancingStrategy "
+                         "by bytes (creation order, least-loaded shard)")
     ap.add_argument("--model", default="mnist_mlp", choices=["mnist_mlp", "resnet18"],
                     help="resnet18: BASELINE.json config 5 (conv model under the same ps API; bandwidth-relevant: 44.7 MB per push)")
     ap.add_argument("--nvls", default="auto", choices=["off", "on", "auto"],
@@ -257,7 +262,16 @@ def run_resnet18(args, rank, world, local_rank):
                            ps_on_workers=pow_)
         fabric = Fabric.from_torch_distributed()
     shapes = resnet18_param_shapes(10, "cifar")
-    eng = GenericPSEngine(shapes, cfg, fabric)
+    shards = None
+    if cfg.num_ps > 1 and args.placement == "greedy":
+        # tf.contrib.training.GreedyLoadBalancingStrategy(num_ps, byte_size_load_fn) under replica_device_setter
+        load = [0] * cfg.num_ps
+        shards = []
+        for _, shp in shapes:
+            t = min(range(cfg.num_ps), key=load.__getitem__)
+            load[t] += 4 * int(torch.tensor(shp).prod())
+            shards.append(t)
+    eng = GenericPSEngine(shapes, cfg, fabric, shards=shards)
     eng.init_params(resnet18_init(10, "cifar", seed=2))
     nparams = sum(eng.shard_elems)
     is_worker = any(r in eng.worker_ranks for r in eng.ranks)
@@ -391,6 +405,8 @@ def main():
     from distributed_tensorflow_b200.parallel.ps_engine import EngineConfig, MLPSpec, PSTrainEngine
     from distributed_tensorflow_b200.utils.mnist_data import synthetic_mnist
 
+    if args.num_ps <= 0:
+        args.num_ps = args.gpus if (args.model == "resnet18" and args.ps_on_workers and not args.ps_only_task) else 1
     if args.model == "resnet18":
         out = run_resnet18(args, rank, world, local_rank)
         if rank == 0:

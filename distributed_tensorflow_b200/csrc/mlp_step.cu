@@ -88,6 +88,8 @@ struct MlpStepParams {
   int num_tokens;
   const unsigned long long* token[4];   // per ps shard holding a parameter: wait until *token >= step * token_scale
   unsigned long long token_scale[4];    // 1: mailbox token (= global step); G_ps: counter bumped once per ps_apply CTA
+  unsigned long long token_base[4];     // the shard's global step when this worker adopted it (checkpoint restore / fabric
+                                        // re-formation): step k waits for token >= k * scale + base
   int stamp_step;                       // 1 (sync): the push is stamped with the step; 0 (async): with *stamp_src (version)
   const unsigned long long* consumed[4]; // optional (backup workers, replicas_to_aggregate < replicas): the ps's count of this
                                         // worker's arrivals it has consumed OR dropped -- the slot is rewritten only once the
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
 #endif
       // the parameters behind every later read were published by the ps: acquire its token(s) for this step
       for (int i = 0; i < p.num_tokens; ++i)
-        if (!wait_flag_ge_u64(reinterpret_cast<const uint64_t*>(p.token[i]), step * p.token_scale[i], p.timeout_ns) && p.err)
+        if (!wait_flag_ge_u64(reinterpret_cast<const uint64_t*>(p.token[i]), step * p.token_scale[i] + p.token_base[i], p.timeout_ns) && p.err)
           atomicExch(p.err, 1u);
       // backup workers: a straggler holds the next token while its late push still waits in the slot for the ps to fold it
       // in or drop it as stale -- do not overwrite a gradient the ps may be reading (TF's accumulator copies under a lock)
@@ -787,7 +789,8 @@ struct DtfMlpStepArgs {
   float* loss_out; float* logits_out;
   unsigned long long* step_counter;
   int forward_only;
-  int num_tokens; const unsigned long long* token[4]; unsigned long long token_scale[4]; int stamp_step;
+  int num_tokens; const unsigned long long* token[4]; unsigned long long token_scale[4]; unsigned long long token_base[4];
+  int stamp_step;
   const unsigned long long* consumed[4];
   int num_signals; unsigned long long* arrivals[4]; unsigned long long* stamp_dst[4]; const unsigned long long* stamp_src[4];
   int sys_scope;
@@ -859,7 +862,7 @@ int dtf_mlp_step(const DtfMlpStepArgs* a, cudaStream_t s) {
   p.num_signals = a->num_signals;
   for (int i = 0; i < 4; ++i) {
     p.consumed[i] = a->consumed[i];
-    p.token[i] = a->token[i]; p.token_scale[i] = a->token_scale[i] ? a->token_scale[i] : 1ull; p.arrivals[i] = a->arrivals[i]; p.stamp_dst[i] = a->stamp_dst[i]; p.stamp_src[i] = a->stamp_src[i];
+    p.token[i] = a->token[i]; p.token_scale[i] = a->token_scale[i] ? a->token_scale[i] : 1ull; p.token_base[i] = a->token_base[i]; p.arrivals[i] = a->arrivals[i]; p.stamp_dst[i] = a->stamp_dst[i]; p.stamp_src[i] = a->stamp_src[i];
   }
   p.sys_scope = a->sys_scope; p.stamp_step = a->stamp_step;
   p.timeout_ns = a->timeout_ns ? a->timeout_ns : 2000000000ull;

@@ -86,6 +86,14 @@ class ResourceStore:
             else:
                 self._uninit.add(name)
 
+    def unbind(self, name: str) -> None:
+        """Give up externally-owned storage (the fabric engine behind it is being torn down): the variable keeps its current
+        value and initialisation state in storage of its own, so a later ``bind`` carries the value into the new engine."""
+        with self._lock:
+            if name in self._bound and name in self._vars:
+                self._vars[name] = self._vars[name].detach().clone()
+                self._bound.discard(name)
+
     def variable_names(self) -> List[str]:
         with self._lock:
             return sorted(self._vars)

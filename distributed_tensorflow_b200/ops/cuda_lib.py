@@ -83,7 +83,7 @@ class MlpStepArgs(Structure):
                 ("gb2", c_void_p),
                 ("clip_min", c_float), ("loss_out", c_void_p), ("logits_out", c_void_p), ("step_counter", c_void_p),
                 ("forward_only", c_int), ("num_tokens", c_int), ("token", c_void_p * 4), ("token_scale", c_ulonglong * 4),
-                ("stamp_step", c_int), ("consumed", c_void_p * 4),
+                ("token_base", c_ulonglong * 4), ("stamp_step", c_int), ("consumed", c_void_p * 4),
                 ("num_signals", c_int), ("arrivals", c_void_p * 4), ("stamp_dst", c_void_p * 4), ("stamp_src", c_void_p * 4),
                 ("sys_scope", c_int), ("timeout_ns", c_ulonglong), ("err", c_void_p), ("trace", c_void_p),
                 ("no_cluster", c_int), ("dbg", c_int), ("ring", c_void_p), ("ring_cap", c_int)]

@@ -672,6 +672,7 @@ class PSTrainEngine:
         for i in range(len(self.var_shards)):
             a.token[i] = k["tokens"][i]
             a.token_scale[i] = k["token_scale"][i]
+            a.token_base[i] = d.get("token_base", [0, 0, 0, 0])[i]
             if cfg.sync and self.R < cfg.num_workers:
                 a.consumed[i] = k["consumed"][i]           # backup workers: never overwrite a push the ps has not consumed / dropped
             a.arrivals[i] = k["arrivals"][i]
@@ -811,6 +812,33 @@ class PSTrainEngine:
             for w in range(self.cfg.num_workers):
                 self.peer[(rank, "mailbox_w%d" % w)].tensor(torch.int64, s * self.mb_bytes, 2).fill_(1 << 62)
             torch.cuda.synchronize(rk.device)
+
+    def adopt_global_step(self, rank: int) -> int:
+        """Worker ``rank``: take each ps shard's CURRENT global step as the base of its token sequence -- a run restored from
+        a checkpoint, or a fabric re-formed after a task failure, starts with ``global_step`` = g on the ps while this
+        worker's device step counter starts at 0.  Sync: its mailbox token / version become g (as if the ps had just handed
+        it the token of step g) and step k waits for token >= g + k; async tokens are push COUNTS and need no base.  Call
+        before the first step (the step plans copy the argument block).  Returns shard 0's global step."""
+        rk, d = self.ranks[rank], self._w[rank]
+        w = self.worker_ranks.index(rank)
+        rk.sync()
+        base, mb = [0, 0, 0, 0], rk.bufs["mailbox_w%d" % w]
+        out = 0
+        with torch.cuda.device(rk.device):
+            for i, sh in enumerate(self.var_shards):
+                gs = int(self.peer[(rank, "ctl%d" % sh)].tensor(torch.int64, self.off["global_step"], 1).cpu()[0])
+                if i == 0 or sh == 0:
+                    out = gs                                                         # shard 0 owns the graph's global_step
+                mb.tensor(torch.int64, sh * self.mb_bytes, 2).fill_(gs)             # {token, version}
+                if self.cfg.sync and not self._mc_tokens():
+                    base[i] = gs
+                elif not self.cfg.sync:
+                    mb.tensor(torch.int64, sh * self.mb_bytes, 1).fill_(0)          # async: token = applied-push count
+            torch.cuda.synchronize(rk.device)
+        d["token_base"] = base
+        if self.tf32:
+            d["step_staged"] = self._step_args(d, rk.bufs["xf32_w%d" % w].ptr, 128, rk.bufs["labels_w%d" % w].ptr)
+        return out
 
     def var_tensor(self, rank: int, name: str) -> torch.Tensor:
         """True-shape fp32 view of variable ``name`` in the LOCAL ps shard's master buffer (graph variables are bound to it)."""

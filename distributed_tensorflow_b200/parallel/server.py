@@ -124,6 +124,8 @@ class Server:
         self._rpc: Optional[RpcServer] = None
         self._stopped = threading.Event()
         self._peers: Dict[Tuple[str, int], RpcClient] = {}
+        self._fabric_gen: Dict[str, Dict[str, Any]] = {}      # fabric incarnations (rpc_fabric_generation); ps task 0 is asked
+        self._fabric_gen_lock = threading.Lock()
         if start:
             self.start()
 
@@ -323,6 +325,33 @@ class Server:
         if svc is not None:
             svc.farewell()
         return True
+
+    def rpc_fabric_generation(self, base_key, at_least=0, rank=None):
+        """Which incarnation of the fabric (buffers, rendezvous, apply service) the tasks of the job ``base_key`` should be
+        in.  ps task 0 is the authority.  ``at_least``: a task that saw a failure at generation g asks for g + 1; every
+        survivor of the same failure asks for the same number.  ``rank``: a task that asks to join a generation it is ALREADY
+        a member of is a restarted process (its old incarnation's mappings are gone) -> the generation moves on and the
+        surviving members learn it from their periodic liveness call."""
+        with self._fabric_gen_lock:
+            st = self._fabric_gen.setdefault(base_key, {"gen": 0, "members": set()})
+            if int(at_least) > st["gen"]:
+                st["gen"], st["members"] = int(at_least), set()
+            elif rank is not None and rank in st["members"]:
+                st["gen"], st["members"] = st["gen"] + 1, set()
+            if rank is not None:
+                st["members"].add(rank)
+            return st["gen"]
+
+    def rpc_fabric_current_generation(self, base_key):
+        with self._fabric_gen_lock:
+            st = self._fabric_gen.get(base_key)
+            return st["gen"] if st else 0
+
+    def rpc_fabric_teardown(self, base_key):
+        """Stop this task's apply service(s) of the job ``base_key``: the graph variables keep their values in storage of
+        their own (``VariableStore.unbind``), the engine's HBM and peer mappings are released."""
+        from .strategy import ps_fabric_teardown
+        return ps_fabric_teardown(self, base_key)
 
     def rpc_fabric_step_stats(self, key):
         """Timeline events of this ps task's fabric engine (device-side ``ps_apply`` ring): what a traced ``Session.run`` on

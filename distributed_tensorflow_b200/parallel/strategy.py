@@ -62,20 +62,33 @@ def fabric_rank_of(cluster: ClusterSpec, job: str, task: int) -> Tuple[int, int]
     return tasks.index((job, int(task))), len(tasks)
 
 
-def init_fabric_process_group(cluster: ClusterSpec, job: str, task: int) -> Tuple[int, int]:
-    """Join the fabric's torch.distributed group (idempotent).  gloo: only a store + barriers are needed."""
+_PG_GEN: List[Optional[int]] = [None]       # generation of the process group THIS module created (None: not ours / none)
+
+
+def init_fabric_process_group(cluster: ClusterSpec, job: str, task: int, generation: int = 0) -> Tuple[int, int]:
+    """Join the fabric's torch.distributed group of ``generation`` (idempotent).  gloo: only a store + barriers are needed.
+    A new generation (the fabric re-forms after a task failure, ``FabricPSStrategy._abort``) leaves the old group -- it has
+    a dead member -- and rendezvouses on its own port (``+ generation``) with whoever is alive or restarted by then."""
     import torch.distributed as dist
     rank, world = fabric_rank_of(cluster, job, task)
     with _PG_LOCK:
+        if dist.is_initialized() and _PG_GEN[0] is not None and _PG_GEN[0] != generation:
+            _dbg("leaving process group of generation %d" % _PG_GEN[0])
+            try:
+                dist.destroy_process_group()
+            except Exception:      # noqa: BLE001 - peers of the old group may be gone
+                pass
+            _PG_GEN[0] = None
         if not dist.is_initialized():
             host, _, port = cluster.all_tasks()[0][2].rpartition(":")
             if host in ("localhost", "", "0.0.0.0"):
                 host = "127.0.0.1"
-            port = int(port) + int(os.environ.get("DTF_FABRIC_PORT_OFFSET", "1000"))
+            port = int(port) + int(os.environ.get("DTF_FABRIC_PORT_OFFSET", "1000")) + int(generation)
             import datetime
-            _dbg("joining process group rank %d/%d at %s:%d" % (rank, world, host, port))
+            _dbg("joining process group rank %d/%d at %s:%d (generation %d)" % (rank, world, host, port, generation))
             dist.init_process_group("gloo", init_method="tcp://%s:%d" % (host, port), rank=rank, world_size=world,
                                     timeout=datetime.timedelta(seconds=float(os.environ.get("DTF_FABRIC_TIMEOUT", "300"))))
+            _PG_GEN[0] = generation
             _dbg("process group up")
     return rank, world
 
@@ -85,13 +98,14 @@ def _engine_cfg(spec: Dict[str, Any], num_ps: int, num_workers: int):
     opt = dict(spec["optimizer"])
     return EngineConfig(num_ps=num_ps, num_workers=num_workers, sync=bool(opt.get("sync", False)),
                         replicas_to_aggregate=opt.get("replicas_to_aggregate"), optimizer=opt,
-                        timeout_ns=int(spec.get("timeout_ns", 20_000_000_000)))
+                        timeout_ns=int(spec.get("timeout_ns") or
+                                       float(os.environ.get("DTF_FABRIC_STEP_TIMEOUT", "20")) * 1e9))
 
 
 def build_engine(cluster: ClusterSpec, job: str, task: int, spec: Dict[str, Any], gpu_index: Optional[int]):
     from .fabric import Fabric
     from .generic_engine import GenericPSEngine
-    rank, world = init_fabric_process_group(cluster, job, task)
+    rank, world = init_fabric_process_group(cluster, job, task, int(spec.get("generation", 0)))
     dev = gpu_index if gpu_index is not None else 0
     torch.cuda.set_device(dev)
     import torch.distributed as dist
@@ -132,6 +146,7 @@ class _PsService:
         self._farewell = threading.Event()
         self._farewell_done = False
         self._stop = threading.Event()
+        self._bound_names: List[str] = []
         self.thread = threading.Thread(target=self._run, name="dtf-fabric-ps", daemon=True)
         self.thread.start()
 
@@ -144,19 +159,21 @@ class _PsService:
             s = eng.ps_ranks.index(rank)
             rk = eng.ranks[rank]
             # graph variables on this task live in the engine's master buffer from now on
+            def bind(gname, tensor):
+                srv.store.bind(gname, tensor, initialized=False)        # (a value assigned earlier is carried over)
+                self._bound_names.append(gname)
             if self.spec.get("mlp"):
                 for role, gname in self.spec["mlp"]["roles"].items():
                     if eng.layout[role].shard == s:
-                        srv.store.bind(gname, eng.var_tensor(rank, role), initialized=False)
+                        bind(gname, eng.var_tensor(rank, role))
                 if s == 0:
-                    srv.store.bind(self.spec["global_step"], eng.global_step_tensor(rank), initialized=False)
+                    bind(self.spec["global_step"], eng.global_step_tensor(rank))
             else:
                 for name in eng.names:
                     if eng.layout[name][0] == s:
-                        srv.store.bind(name, eng._view(rk.bufs["gmaster%d" % s], name), initialized=False)
+                        bind(name, eng._view(rk.bufs["gmaster%d" % s], name))
                 if s == 0:
-                    gs = rk.bufs["gctl0"].tensor(torch.int64, eng.off["global_step"], 1).view(())
-                    srv.store.bind(self.spec["global_step"], gs, initialized=False)
+                    bind(self.spec["global_step"], rk.bufs["gctl0"].tensor(torch.int64, eng.off["global_step"], 1).view(()))
             self.ready.set()
             _dbg("ps service loop starts")
             per_round = 1 if eng.cfg.sync else eng.cfg.num_workers
@@ -177,12 +194,44 @@ class _PsService:
     def stop(self):
         self._stop.set()
 
+    close = stop           # VariableStore.clear() closes its resources
+
     def farewell(self):
         self._farewell.set()
 
+    def teardown(self) -> None:
+        """The fabric re-forms (a task failed or restarted): stop the apply loop, move the graph variables out of the engine's
+        HBM (they keep their values), release the buffers and the peer mappings.  Idempotent."""
+        self._stop.set()
+        if self.thread is not threading.current_thread():
+            self.thread.join(15.0)
+        eng, self.engine = self.engine, None
+        for name in self._bound_names:
+            self.server.store.unbind(name)
+        self._bound_names = []
+        if eng is not None:
+            try:
+                eng.close()
+            except Exception:      # noqa: BLE001
+                import traceback
+                traceback.print_exc()
+        _dbg("ps service %s torn down" % self.spec["key"])
+
+
+def ps_fabric_teardown(server, base_key: str, keep: Optional[str] = None) -> bool:
+    """Tear down this task's services of the job ``base_key`` (all generations but ``keep``)."""
+    for k, svc in list(server.store.resources.items()):
+        if k.startswith("fabric_service/") and isinstance(svc, _PsService) and \
+                svc.spec.get("base_key", svc.spec["key"]) == base_key and svc.spec["key"] != keep:
+            svc.teardown()
+            server.store.resources.pop(k, None)
+    return True
+
 
 def ps_fabric_setup(server, spec: Dict[str, Any]) -> bool:
-    """Called through ``Server.rpc_fabric_setup`` on every ps task (idempotent per spec key)."""
+    """Called through ``Server.rpc_fabric_setup`` on every ps task (idempotent per spec key).  A spec of a NEW generation of
+    the same job first retires the older generations' services on this task."""
+    ps_fabric_teardown(server, spec.get("base_key", spec["key"]), keep=spec["key"])
     svc = server.store.get_resource("fabric_service/" + spec["key"], lambda: _PsService(server, spec))
     if not svc.ready.wait(120.0):
         raise RuntimeError("ps task %s did not join the fabric within 120 s" % (server.task,))
@@ -203,6 +252,11 @@ class FabricPSStrategy:
         self._last_loss: Optional[float] = None
         self._step_node_id: Optional[int] = None
         self._pinned: List[Any] = []
+        self._spec_base: Optional[Dict[str, Any]] = None
+        self._gen: Optional[int] = None          # fabric incarnation this worker is in
+        self._min_gen = 0                         # ... and the least one it will join next (bumped by _abort)
+        self._last_live = 0.0
+        self._live_every = float(os.environ.get("DTF_FABRIC_LIVENESS_SECS", "2.0"))
 
     # -- graph construction ---------------------------------------------------------------------------------------
     def minimize(self, optimizer, loss, global_step: Variable, var_list: Optional[Sequence[Variable]] = None
@@ -223,7 +277,10 @@ class FabricPSStrategy:
         import json
         # the key must be identical in every worker process (it names the fabric buffers and the ps-side service)
         key = hashlib.md5(json.dumps([params, sorted((k, str(v)) for k, v in fs.items())]).encode()).hexdigest()[:12]
-        self._spec = {"key": "f" + key, "params": params, "optimizer": fs, "global_step": global_step.var_name}
+        # the job's identity; the spec of one fabric INCARNATION (generation, batch-specialised engine) is derived from it in
+        # _ensure_engine
+        self._spec_base = {"key": "f" + key, "params": params, "optimizer": fs, "global_step": global_step.var_name}
+        self._spec = dict(self._spec_base)
         loss_t = convert_to_tensor(loss)
         from .auto_fabric import match_reference_mlp
         m = match_reference_mlp(loss_t, vars_)
@@ -254,44 +311,122 @@ class FabricPSStrategy:
         return NotImplemented
 
     # -- runtime ---------------------------------------------------------------------------------------------------
+    def _ps_call(self, t: int, method: str, *args):
+        """Control-plane call to ps task ``t`` (in-process server: direct call)."""
+        from .server import local_server_for
+        srv = local_server_for(self.cluster.task_address("ps", t))
+        if srv is not None:
+            return getattr(srv, "rpc_" + method)(*args)
+        return self.server.peer("ps", t).call(method, *args)
+
     def _ensure_engine(self, batch: Optional[int] = None) -> None:
         if self.engine is not None:
             return
+        from ..framework import errors
+        base = self._spec_base["key"]
+        rank, _ = fabric_rank_of(self.cluster, self.server.job_name, self.server.task_index)
+        try:
+            gen = int(self._ps_call(0, "fabric_generation", base, self._min_gen, rank))
+        except (OSError, EOFError, ConnectionError) as e:
+            raise errors.UnavailableError("ps task 0 is unreachable (%s: %s)" % (type(e).__name__, e))
+        spec = dict(self._spec_base)
+        spec["base_key"], spec["generation"] = base, gen
+        spec["key"] = base + ("g%d" % gen if gen else "")
         if self.mlp is not None:
             if batch is None or batch > 128:
                 self.mlp = None       # the fused step handles <= 128 rows per worker step: generic engine instead
             else:
                 m = self.mlp
-                self._spec["mlp"] = {"roles": {r: m[r].var_name for r in ("hid_w", "hid_b", "sm_w", "sm_b")},
-                                     "in_dim": m["in_dim"], "hidden": m["hidden"], "classes": m["classes"],
-                                     "batch": int(batch), "clip_min": m["clip_min"]}
-                self._spec["key"] += "m%d" % int(batch)
+                spec["mlp"] = {"roles": {r: m[r].var_name for r in ("hid_w", "hid_b", "sm_w", "sm_b")},
+                               "in_dim": m["in_dim"], "hidden": m["hidden"], "classes": m["classes"],
+                               "batch": int(batch), "clip_min": m["clip_min"]}
+                spec["key"] += "m%d" % int(batch)
+        self._spec, self._gen = spec, gen
+        self._farewell_sent = False
         # (1) every ps task joins the fabric (control-plane RPC; blocks until its buffers are exported)
         threads, errs = [], []
         for t in range(self.cluster.num_tasks("ps")):
             def call(t=t):
                 try:
-                    from .server import local_server_for
-                    addr = self.cluster.task_address("ps", t)
-                    srv = local_server_for(addr)
-                    if srv is not None:
-                        srv.rpc_fabric_setup(self._spec)
-                    else:
-                        self.server.peer("ps", t).call("fabric_setup", self._spec)
+                    self._ps_call(t, "fabric_setup", spec)
                 except BaseException as e:  # noqa: BLE001
                     errs.append(e)
             th = threading.Thread(target=call, daemon=True)
             th.start()
             threads.append(th)
         # (2) this worker joins too (the handle exchange needs all ranks)
-        self.engine = build_engine(self.cluster, self.server.job_name, self.server.task_index, self._spec,
-                                   self.server.gpu_index)
-        for th in threads:
-            th.join(180.0)
-        if errs:
-            raise errs[0]
-        import atexit
-        atexit.register(self._report)
+        try:
+            self.engine = build_engine(self.cluster, self.server.job_name, self.server.task_index, spec, self.server.gpu_index)
+            for th in threads:
+                th.join(180.0)
+            if errs:
+                raise errs[0]
+            if self.mlp is not None:
+                me = next(iter(self.engine.ranks))
+                gs = self.engine.adopt_global_step(me)      # restored checkpoint / re-formed fabric: tokens continue from gs
+                _dbg("fused MLP worker adopted global_step %d" % gs)
+            self._primed = False
+        except BaseException as e:  # noqa: BLE001 - a rendezvous that never completed, a ps that went away mid-setup, ...
+            if isinstance(e, (KeyboardInterrupt, SystemExit)):
+                raise
+            self._abort("building generation %d of the fabric failed: %s: %s" % (gen, type(e).__name__, e))
+        self._last_live = time.time()
+        if not getattr(self, "_atexit", False):
+            import atexit
+            atexit.register(self._report)
+            self._atexit = True
+
+    # -- failure handling (reference example_between_graph.py:99: MonitoredTrainingSession recovers from AbortedError) -----
+    def _abort(self, why: str) -> None:
+        """A peer of this fabric incarnation is gone (a device-side wait timed out, the rendezvous failed, ps task 0 reports
+        a newer generation): leave it -- release this worker's engine, ask the reachable ps tasks to retire their services
+        (the graph variables keep their values) -- and raise the error ``MonitoredTrainingSession`` recovers from:
+        ``UnavailableError`` when a ps task does not answer on the control plane, ``AbortedError`` otherwise.  The next
+        ``train_step`` forms generation + 1 with whoever is alive or restarted by then."""
+        from ..framework import errors
+        eng, self.engine = self.engine, None
+        self._min_gen = max(self._min_gen, (self._gen if self._gen is not None else -1) + 1)
+        self._primed = False
+        if eng is not None:
+            try:
+                eng.close()
+            except Exception:      # noqa: BLE001
+                pass
+        down = []
+        for t in range(self.cluster.num_tasks("ps")):
+            try:
+                self._ps_call(t, "fabric_teardown", self._spec_base["key"])
+            except Exception:      # noqa: BLE001
+                down.append(t)
+        self.aborts = getattr(self, "aborts", 0) + 1
+        msg = "fabric generation %s of job %s aborted on worker %d: %s" % (self._gen, self._spec_base["key"],
+                                                                           self.server.task_index, why)
+        print("dtf.fabric: " + msg, flush=True)
+        if down:
+            raise errors.UnavailableError(msg + " (ps task(s) %s unreachable)" % down)
+        raise errors.AbortedError(msg)
+
+    def _after_step(self, t0: float) -> None:
+        """Failure detection without a per-step cost: a step that took long had a device-side wait run into its timeout (a
+        peer stopped pushing / applying) -> read the error words; every ``DTF_FABRIC_LIVENESS_SECS`` ask ps task 0 whether
+        the fabric has moved on to a newer generation (a restarted task re-joined)."""
+        now = time.time()
+        eng = self.engine
+        timeout_s = eng.cfg.timeout_ns / 1e9
+        if now - t0 > min(1.0, timeout_s / 4):
+            try:
+                eng.check_errors()
+            except RuntimeError as e:
+                if not getattr(self, "_farewell_sent", False):
+                    self._abort(str(e))
+        if now - self._last_live > self._live_every:
+            self._last_live = now
+            try:
+                cur = int(self._ps_call(0, "fabric_current_generation", self._spec_base["key"]))
+            except Exception as e:      # noqa: BLE001
+                self._abort("ps task 0 does not answer (%s)" % type(e).__name__)
+            if cur > self._gen:
+                self._abort("the job moved on to fabric generation %d (a task restarted)" % cur)
 
     def farewell(self) -> None:
         """This replica's training loop is over (sync mode): ask every ps shard to release the device-side token waits of
@@ -358,7 +493,9 @@ class FabricPSStrategy:
             y = feeds[ph_ids.index(self.mlp["y_"].id)]
             self._ensure_engine(int(x.shape[0]))
             if self.mlp is not None:
+                t0 = time.time()
                 out = self._mlp_step(x, y)
+                self._after_step(t0)
                 if ctx.tracer is not None:
                     self._trace_into(ctx.tracer)
                 return out
@@ -381,7 +518,11 @@ class FabricPSStrategy:
                 sub.values[vn.id] = leaves[vn.attrs["var_name"]]
             execute([n for n in a["order"] if n.id not in sub.values], sub, True)
             return sub.values[a["loss"].id]
+        t0 = time.time()
         loss = eng.worker_step(rank, loss_fn)
+        if time.time() - t0 > 0.5 or time.time() - self._last_live > self._live_every:
+            float(loss)                      # the step's kernels have run (a timed-out wait has set its error word by now)
+            self._after_step(t0)
         return loss
 
 
