@@ -193,6 +193,17 @@ DTF_DEVICE void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* ba
       : "memory");
 }
 
+// Programmatic dependent launch (kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization; both are no-ops
+// otherwise).  launch_dependents: the NEXT kernel in the stream may start its prologue now.  wait: block until the PREVIOUS
+// kernel has completed and its memory is visible -- nothing a prior kernel wrote may be read before it.
+DTF_DEVICE void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+DTF_DEVICE void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// 1 when DTF_PDL=1 (default; read once): step / apply kernels are launched with the programmatic-serialization attribute
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("DTF_PDL"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
+
 // 4-D tile (implicit-GEMM convolution: {channels, w, h, image} of an NHWC activation; coordinates may be negative or run past
 // the tensor -- the out-of-bounds part of the box is ZERO-filled, which is exactly the convolution's padding)
 DTF_DEVICE void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {

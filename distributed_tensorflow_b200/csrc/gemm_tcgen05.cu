@@ -161,9 +161,20 @@ DTF_DEVICE void epilogue_chunk16(const GemmParams& p, const uint32_t* r, int c0,
   if (row_ok) {
     const bool full = gc0 + 16 <= p.N;
     if (p.atomic) {
+      float* dst = cf + grow * p.ldc + gc0;
+      if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        // split-K partials: one 16-byte reduction per four columns (REDG.E.ADD.F32x4) -- the scalar form made the L2 atomic
+        // units the bottleneck of every split GEMM (conv wgrad / small-M fprop: ~16 M scalar atomics = ~60 us per layer)
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (gc0 + j < p.N) atomicAdd(cf + grow * p.ldc + gc0 + j, v[j]);
+        for (int j = 0; j < 4; ++j)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                       "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                       : "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (gc0 + j < p.N) atomicAdd(dst + j, v[j]);
+      }
     } else if (p.c_bf16) {
       __nv_bfloat16* dst = cb + grow * p.ldc + gc0;
       if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -477,7 +488,13 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap map_a, c
                 tma_load_2d_2cta(b_dst + j * p.mn_lbo, &map_b, &full_bar[s], n0 + mnc * j, k0);
             }
           } else {
-            if (!p.a_mn) {
+            if (p.conv == 1) {
+              // implicit-GEMM fprop / dgrad (see gemm_bf16_tcgen05_kernel): one shifted 4-D box of the activation per K block
+              const int tap = kb / p.cv_cpt, c0 = (kb - tap * p.cv_cpt) * 64;
+              const int ky = tap / p.cv_kw, kx = tap - ky * p.cv_kw;
+              const int img = m0 / p.cv_hw, h0 = (m0 - img * p.cv_hw) / p.cv_w;
+              tma_load_4d(a_dst, &map_a, &full_bar[s], c0, kx - p.cv_pl, h0 + ky - p.cv_pt, img);
+            } else if (!p.a_mn) {
               tma_load_2d(a_dst, &map_a, &full_bar[s], k0, m0);
             } else {
               for (int j = 0; j < kBlockM / mnc; ++j)
@@ -772,8 +789,11 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
     // short K loops (taps x chunks) under many tiles: two CTAs per SM, so one tile's epilogue runs under the other's mainloop
     p.conv = g->conv; p.cv_w = g->cv_w; p.cv_hw = g->cv_h * g->cv_w; p.cv_cpt = g->cv_c / 64;
     p.cv_kw = g->cv_kw; p.cv_taps = g->cv_kh * g->cv_kw; p.cv_pt = g->cv_pt; p.cv_pl = g->cv_pl; p.cv_n = g->cv_n;
+    // ... when there ARE two CTAs' worth of tiles per SM; a grid of at most one CTA per SM keeps the deep pipeline (it is
+    // TMA-latency bound: 3 stages in flight measured 30 us for 18 K blocks)
+    const long long ctas_total = ((g->M + kBlockM - 1) / kBlockM) * ((g->N + bn - 1) / bn) * splits;
     const int two = (100 * 1024) / stage_bytes;
-    if (two >= 3 && stages > two) stages = two;
+    if (ctas_total > 148 && two >= 3 && stages > two) stages = two;
   }
   if (stages > p.kb_per_split) stages = p.kb_per_split < 2 ? 2 : p.kb_per_split;
   if (stages < 2) stages = 2;
@@ -824,13 +844,15 @@ int dtf_gemm_bf16(const DtfGemmArgs* g, cudaStream_t stream) {
   const unsigned tiles_m = (unsigned)((g->M + kBlockM - 1) / kBlockM), tiles_n = (unsigned)((g->N + bn - 1) / bn);
   const int sms = (dev >= 0 && dev < 64 && sm_count[dev] > 0) ? sm_count[dev] : 148;
   // Persistent path: plain GEMMs with more tiles than SMs (no split-K, no fused wait/signal, no phase stamps).
+  // (implicit-GEMM fprop / dgrad with more tiles than SMs takes the persistent 1-CTA kernel too: per-tile prologue / epilogue of
+  //  a 9-K-block tile is most of its time -- measured 26 us for 512 tiles of 128 x 64 x 576 in the tile kernel)
   const bool plain = splits == 1 && !p.atomic && p.wait_flag == nullptr && p.signal == nullptr && p.phase_trace == nullptr &&
-                     !g->conv;
+                     g->conv != 2;
   if (plain && g->persistent >= 0 && (g->persistent > 0 || (long long)tiles_m * tiles_n > sms)) {
     // CTA pairs (cta_group::2, 256 x BLOCK_N tiles) when the tile shape allows it: BLOCK_N a multiple of 32 (each
     // CTA loads BLOCK_N/2 rows of B; 128 when B is MN-major) and at least two 128-row blocks of M.
     int ctas = 1;
-    const bool pair_ok = (bn % 32 == 0) && (!g->b_mn || (bn / 2) % kbk == 0) && g->M > kBlockM;
+    const bool pair_ok = (bn % 32 == 0) && (!g->b_mn || (bn / 2) % kbk == 0) && g->M > kBlockM && !g->conv;
     // measured (tools/gemm_perf.py): pairs win only with the widest tile (BLOCK_N = 256: 1292 vs 1144 TFLOP/s at 4096^3);
     // with narrower tiles the B half-tile is too small to matter and the 1-CTA kernel's finer tile granularity wins
     if (g->persistent == 2 || (g->persistent != 1 && pair_ok && g->cta_pair >= 0 && bn >= 192)) ctas = pair_ok ? 2 : 1;

@@ -213,10 +213,11 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
   float* s_b2 = s_lab + 256;                              // [16]
 
   unsigned int* fl = p.flags + (p.forward_only ? 4 : 0);
-  if (tid == 0) {
-    s_step = p.step_counter ? *p.step_counter : 0ull;
-    s_epoch = ld_relaxed_gpu_u32_(&fl[3]);
-  }
+  // programmatic dependent launch: the kernel behind this one in the stream (the ps's apply when it shares the GPU, the next
+  // step otherwise) may start ITS prologue now; ours -- barriers, tensor memory, descriptor prefetch -- runs under the tail of
+  // the kernel in front of us, and nothing that kernel wrote (step counter, launch epoch, tokens, parameters) is read before
+  // griddep_wait() below
+  griddep_launch_dependents();
 #ifndef DTF_HOST_EMU
   uint64_t* bar_x = reinterpret_cast<uint64_t*>(&bars[0]);
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(&bars[1]);
@@ -238,6 +239,11 @@ __global__ void __launch_bounds__(kStepThreads, 1) mlp_step_kernel(DTF_STEP_MAPS
   }
   tc_fence_before();
 #endif
+  griddep_wait();
+  if (tid == 0) {
+    s_step = p.step_counter ? *p.step_counter : 0ull;
+    s_epoch = ld_relaxed_gpu_u32_(&fl[3]);
+  }
   __syncthreads();
 #ifndef DTF_HOST_EMU
   tc_fence_after();
@@ -914,13 +920,15 @@ int dtf_mlp_step(const DtfMlpStepArgs* a, cudaStream_t s) {
     cfg.blockDim = dim3(kStepThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = g;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     return (int)cudaLaunchKernelEx(&cfg, mlp_step_kernel, mx, mx2, mw, md, p);
   } else if (p.phase_mask == 7) {
     mlp_step_kernel<<<g, kStepThreads, smem, s>>>(mx, mx2, mw, md, p);

@@ -99,8 +99,13 @@ __global__ void __launch_bounds__(256, 2) ps_apply_kernel(const PsApplyParams p)
   PsControl* ctl = p.ctl;
   long long* tr = p.phase_trace;
 #define PSTAMP(slot) do { if (tr && threadIdx.x == 0 && blockIdx.x == 0) tr[slot] = clock64(); } while (0)
+  // programmatic dependent launch: this grid may have been started under the tail of the worker's step kernel (same GPU, same
+  // stream) -- wait for it to complete before anything it wrote is read; only THEN let the next step kernel start its prologue
+  // (it must not run beside the step kernel before it: it reads the device step counter that one advances at exit)
+  griddep_wait();
+  griddep_launch_dependents();
   PSTAMP(0);
-  const unsigned long long t_start = (blockIdx.x == 0 && threadIdx.x == 0) ? globaltimer_ns() : 0ull;
+  const unsigned long long t_start = threadIdx.x == 0 ? globaltimer_ns() : 0ull;     // (the LAST CTA to finish writes the ring row)
 
   // Sync mode with replicas_to_aggregate == total_num_replicas (the reference's setting, distributed_mnist.py:120-122): the
   // only possible decision is "all W pushes, all fresh" (a worker cannot run ahead of an aggregate it is part of, so no
@@ -1024,6 +1029,21 @@ int dtf_ps_apply(const DtfPsApplyArgs* a, cudaStream_t s) {
   p.full_mask = a->num_workers >= 32 ? 0xFFFFFFFFu : ((1u << a->num_workers) - 1u);
   int grid = a->grid;
   if (grid <= 0) grid = dtf_ps_apply_grid(a->n);
+#ifndef DTF_HOST_EMU
+  if (pdl_enabled()) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, ps_apply_kernel, p);
+  }
+#endif
   DTF_LAUNCH(ps_apply_kernel, grid, 256, s, p);
   return (int)cudaGetLastError();
 }

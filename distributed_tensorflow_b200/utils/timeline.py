@@ -65,11 +65,11 @@ def events_from_ring(task_name: str, ring: Iterable, names: Dict[int, str], gpu_
     """Convert (kind, t_start_ns, t_end_ns, step) device records into timeline events."""
     out = []
     for kind, t0, t1, step in ring:
-        if t1 <= t0:
+        if t1 < t0 or not t0:
             continue
         out.append({"task": task_name, "device": "%s/device:GPU:%d (kernels)" % (task_name, gpu_index),
                     "name": "%s[step %d]" % (names.get(int(kind), "k%d" % kind), step), "op": names.get(int(kind), "kernel"),
-                    "inputs": [], "start_us": t0 / 1e3, "dur_us": (t1 - t0) / 1e3, "bytes": 0, "shape": None,
+                    "inputs": [], "start_us": t0 / 1e3, "dur_us": max((t1 - t0) / 1e3, 0.001), "bytes": 0, "shape": None,
                     "thread": 0})
     return out
 

@@ -190,6 +190,8 @@ extern "C" __attribute__((weak)) void dtf_emu_mc_clear() {
 
 // ---- the scoped / ordered accesses of common.cuh as sequentially consistent host atomics -----------------------------------
 namespace dtf {
+static inline void griddep_launch_dependents() {}
+static inline void griddep_wait() {}
 static inline uint64_t globaltimer_ns() {
   return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }

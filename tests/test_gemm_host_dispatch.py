@@ -125,13 +125,19 @@ def _conv(mode, n, h, w, c, cout, k=3, splits=1):
 
 
 def test_implicit_conv_dispatch_boxes_stages_and_grid(host):
-    # fprop of a ResNet stage-0 convolution: 128-pixel boxes (4 rows of one 32-wide image), one K block per tap, tile kernel
-    # (never the persistent one), 4 x 24 KB stages so two CTAs share an SM
+    # fprop of a ResNet stage-0 convolution: 128-pixel boxes (4 rows of one 32-wide image), one K block per tap.  512 tiles of
+    # 9 K blocks: the PERSISTENT 1-CTA kernel (never CTA pairs), one CTA per SM, 8 x 24 KB stages
     rc, r = _run(host, _conv(1, 64, 32, 32, 64, 64))
-    assert rc == 0 and r.kind == 0 and (r.gx, r.gy, r.gz) == (512, 1, 1) and (r.block_n, r.num_kb, r.stages) == (64, 9, 4)
-    assert r.smem == 4 * (16384 + 8192) + 1024
+    assert rc == 0 and r.kind == 1 and (r.gx, r.gy, r.gz) == (148, 1, 1) and (r.block_n, r.num_kb, r.stages) == (64, 9, 8)
+    assert (r.tiles_m, r.tiles_n) == (512, 1) and r.smem == 8 * (16384 + 8192) + 1024
     assert (r.a_rows, r.a_cols, r.a_box_cols, r.a_box_rows) == (65536, 64, 64, 128)
     assert (r.b_rows, r.b_cols, r.b_box_cols, r.b_box_rows) == (576, 64, 64, 64)
+    # the same product split in two (tile kernel, 1024 CTAs): 4 x 24 KB stages so two CTAs share an SM
+    rc, r = _run(host, _conv(1, 64, 32, 32, 64, 64, splits=2))
+    assert rc == 0 and r.kind == 0 and (r.gx, r.gy, r.gz) == (512, 1, 2) and r.stages == 4 and r.smem == 4 * (16384 + 8192) + 1024
+    # one wave or less (128 tiles): the deep pipeline stays (TMA-latency bound)
+    rc, r = _run(host, _conv(1, 64, 16, 16, 128, 128))
+    assert rc == 0 and r.kind == 0 and (r.gx, r.gy, r.gz) == (128, 1, 1) and (r.block_n, r.num_kb, r.stages) == (128, 18, 6)
     # 4x4 feature maps: a box spans 8 whole images; 512 channels = 8 chunks per tap; split-K over the taps x chunks
     rc, r = _run(host, _conv(1, 64, 4, 4, 512, 512, splits=9))
     assert rc == 0 and (r.gx, r.gy, r.gz) == (8, 2, 9) and (r.num_kb, r.kb_per_split, r.atomic) == (72, 8, 1) and r.a_box_rows == 128

@@ -140,6 +140,42 @@ def main():
         flag = torch.tensor([1 if ok else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         out["pull_verified_on_workers"] = bool(flag.item())
+        if grads.multicast:
+            # ---- sharded ps (one shard per GPU, what `bench.py --model resnet18` runs at N > 1): EVERY rank reduces its 1/N
+            # slice of the gradient with multimem.ld_reduce and publishes its 1/N slice of the parameters with multimem.st, all
+            # at once -- the switch-side reduce-scatter + all-gather.  Per GPU: egress = the (N-1)/N of its gradient copy the
+            # other shards pull, ingress = 1/N; the time is the max over ranks.
+            me = dist.get_rank()
+            dev = fabric.local_ranks[me]
+            sl = nfl // N // 1024 * 1024
+            off = me * sl
+            with torch.cuda.device(dev):
+                dst_s = torch.zeros(sl, dtype=torch.float32, device="cuda")
+                src_s = torch.arange(off, off + sl, dtype=torch.float32, device="cuda")
+            none = (ctypes.c_void_p * 16)()
+            stc = lambda: torch.cuda.current_stream().cuda_stream
+            sh = {}
+            repl.local(me).tensor(torch.float32, 0, nfl).zero_()        # (the single-ps pull above left the expected values)
+            for name, fn in (("push", lambda: lib.dtf_fabric_reduce_ex(grads.mc(me) + off * 4, none, 0, dst_s.data_ptr(), sl, 0, 0, stc())),
+                             ("pull", lambda: lib.dtf_fabric_bcast_ex(src_s.data_ptr(), repl.mc(me) + off * 4, none, 0, sl * 4, 0, 0, stc()))):
+                torch.cuda.synchronize(dev)
+                dist.barrier()
+                t = timed(fn, dev)
+                tt = torch.tensor([t], device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t = float(tt.item())
+                sh[name] = {"seconds": t, "gradient_GBps": N * sl * 4 / t / 1e9,
+                            "per_gpu_egress_GBps" if name == "push" else "per_gpu_ingress_GBps": (N - 1) * sl * 4 / t / 1e9,
+                            "fraction_of_900": (N - 1) * sl * 4 / t / 1e9 / 900.0}
+            okp = bool(torch.all(dst_s == expect).item())
+            dist.barrier()
+            tr = repl.local(me).tensor(torch.float32, 0, N * sl)
+            okl = bool(torch.equal(tr.cpu(), torch.arange(N * sl, dtype=torch.float32)))
+            flag = torch.tensor([1 if (okp and okl) else 0], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            sh["ok"] = bool(flag.item())
+            sh["slice_bytes"] = sl * 4
+            out["sharded_nvls"] = sh
     if rank0_local:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "nvls_check_%d_%s.json" % (N, "mp" if world > 1 else "sp")), "w") as f:
