@@ -928,7 +928,9 @@ int dtf_mlp_step(const DtfMlpStepArgs* a, cudaStream_t s) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    // programmatic launch only where it was measured to pay: ps and worker on ONE GPU and stream (N = 1: 25.9 -> 24.6 us per
+    // step).  Across GPUs the next step's prologue already hides under its token wait, so the launch path stays the plain one
+    cfg.numAttrs = (pdl_enabled() && !a->sys_scope) ? 2 : 1;
     return (int)cudaLaunchKernelEx(&cfg, mlp_step_kernel, mx, mx2, mw, md, p);
   } else if (p.phase_mask == 7) {
     mlp_step_kernel<<<g, kStepThreads, smem, s>>>(mx, mx2, mw, md, p);

@@ -1030,7 +1030,7 @@ int dtf_ps_apply(const DtfPsApplyArgs* a, cudaStream_t s) {
   int grid = a->grid;
   if (grid <= 0) grid = dtf_ps_apply_grid(a->n);
 #ifndef DTF_HOST_EMU
-  if (pdl_enabled()) {
+  if (pdl_enabled() && !a->system_scope) {      // colocated ps (same GPU and stream as the worker): see csrc/mlp_step.cu
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid, 1, 1);
