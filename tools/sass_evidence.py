@@ -15,7 +15,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "distributed_tensorflow_b200", "_lib", "libdtf_kernels.so")
-KEEP = re.compile(r"^(UTCHMMA|UTCBAR|UTMALDG|UTMAPF|LDTM|LDGMC|SYNCS|MEMBAR|REDG|ATOMG|NANOSLEEP|HMMA|UCGABAR|UTCATOMSWS|"
+KEEP = re.compile(r"^(UTCHMMA|UTCBAR|UTMALDG|UTMAPF|UTMASTG|UBLKCP|LDTM|LDGMC|SYNCS|MEMBAR|REDG|ATOMG|NANOSLEEP|HMMA|UCGABAR|UTCATOMSWS|"
+                  r"ACQBULK|PREEXIT|"
                   r"LDG\.E\.[0-9.]*STRONG\.SYS|STG\.E\.[0-9.]*STRONG\.SYS|LD\.E\.[0-9.]*STRONG\.SYS|ST\.E\.[0-9.]*STRONG\.SYS)")
 
 
