@@ -93,12 +93,31 @@ def _raise(rc: int, what: str):
 
 
 class NativeAccumulator:
+    """Conditional accumulator in the native runtime (fp32 sums on the host: the common case of the control-plane tier).
+    Gradients of another dtype (float64, bf16) or living on a GPU keep their dtype and device instead: the first such
+    ``apply_grad`` hands this accumulator over to the tensor-based implementation (no D2H round trip per push, no silent
+    cast), carrying the accumulator's time step along."""
+
     def __init__(self, lib: ctypes.CDLL, name: str = "accumulator"):
         self._lib, self.name = lib, name
         self._h = lib.dtf_acc_create()
         self._shape, self._dtype, self._device = None, torch.float32, torch.device("cpu")
+        self._py = None
+        self._used = False
+
+    def _delegate(self):
+        from ..parallel.ps_state import ConditionalAccumulator
+        py = ConditionalAccumulator(name=self.name)
+        py.set_global_step(int(self._lib.dtf_acc_global_step(self._h)))
+        self._py = py
+        return py
 
     def apply_grad(self, grad: torch.Tensor, local_step: int) -> bool:
+        if self._py is None and not self._used and (grad.dtype != torch.float32 or grad.device.type != "cpu"):
+            self._delegate()
+        if self._py is not None:
+            return self._py.apply_grad(grad, local_step)
+        self._used = True
         self._shape, self._device = tuple(grad.shape), grad.device
         g = grad.detach().to(device="cpu", dtype=torch.float32).contiguous()
         rc = self._lib.dtf_acc_apply_grad(self._h, g.data_ptr(), g.numel(), int(local_step))
@@ -108,8 +127,13 @@ class NativeAccumulator:
 
     def take_grad(self, num_required: int, cancel: Optional[threading.Event] = None,
                   timeout: Optional[float] = None) -> torch.Tensor:
+        if self._py is not None:
+            return self._py.take_grad(num_required, cancel, timeout)
         what = "take_grad on %s" % self.name
-        _blocking(lambda t: self._lib.dtf_acc_wait_count(self._h, int(num_required), None, t), cancel, timeout, what)
+        _blocking(lambda t: _OK if self._py is not None else self._lib.dtf_acc_wait_count(self._h, int(num_required), None, t),
+                  cancel, timeout, what)
+        if self._py is not None:             # handed over while this consumer was waiting
+            return self._py.take_grad(num_required, cancel, timeout)
         n = self._lib.dtf_acc_size(self._h)
         out = torch.empty(n, dtype=torch.float32)
         rc = self._lib.dtf_acc_take_grad(self._h, int(num_required), out.data_ptr(), n, None, 0.0)
@@ -120,20 +144,30 @@ class NativeAccumulator:
         return out.to(self._device) if self._device.type != "cpu" else out
 
     def set_global_step(self, s: int) -> None:
+        if self._py is not None:
+            return self._py.set_global_step(s)
         self._lib.dtf_acc_set_global_step(self._h, int(s))
 
     def num_accumulated(self) -> int:
+        if self._py is not None:
+            return self._py.num_accumulated()
         return int(self._lib.dtf_acc_num_accumulated(self._h))
 
     @property
     def global_step(self) -> int:
+        if self._py is not None:
+            return self._py.global_step
         return int(self._lib.dtf_acc_global_step(self._h))
 
     @property
     def num_dropped(self) -> int:
+        if self._py is not None:
+            return self._py.num_dropped
         return int(self._lib.dtf_acc_dropped(self._h))
 
     def close(self) -> None:
+        if self._py is not None:
+            self._py.close()
         self._lib.dtf_acc_close(self._h)
 
     def __del__(self):

@@ -17,6 +17,29 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 # ---------------------------------------------------------------- accumulators / queues (A12 oracle)
+def test_native_accumulator_keeps_dtype_of_non_fp32_gradients():
+    """float64 / bf16 variables: the accumulated mean keeps the gradient's dtype (the native fp32 sum is bypassed), the stale
+    drop and the accumulator's time step behave the same, a consumer already waiting is served."""
+    from distributed_tensorflow_b200.utils import native_runtime
+    if not native_runtime.available():
+        pytest.skip("native runtime not built")
+    acc = native_runtime.make_accumulator("acc64")
+    acc.set_global_step(3)
+    got = []
+    t = threading.Thread(target=lambda: got.append(acc.take_grad(2, timeout=10.0)))
+    t.start()
+    time.sleep(0.1)
+    big = torch.tensor([1.0 + 2.0 ** -40, 2.0], dtype=torch.float64)          # not representable in fp32
+    assert not acc.apply_grad(big, 2)                                          # stamped before the carried time step: stale
+    assert acc.apply_grad(big, 3) and acc.apply_grad(big, 3)
+    t.join(10.0)
+    assert got and got[0].dtype == torch.float64 and torch.equal(got[0], big)
+    assert acc.global_step == 4 and acc.num_dropped == 1
+    b = native_runtime.make_accumulator("acc16")
+    assert b.apply_grad(torch.ones(4, dtype=torch.bfloat16), 0)
+    assert b.take_grad(1).dtype == torch.bfloat16
+
+
 @pytest.mark.parametrize("native", [False, True])
 def test_accumulator_mean_stale_drop_and_backup_workers(native):
     if native:
