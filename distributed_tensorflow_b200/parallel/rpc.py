@@ -26,6 +26,7 @@ from typing import Any, Callable, Dict, Optional, Tuple
 import torch
 
 from ..framework import errors
+from . import transport as _transport
 
 __all__ = ["RpcServer", "RpcClient", "parse_address", "to_wire", "from_wire", "PeerAwareCancel", "current_connection",
            "peer_closed"]
@@ -98,8 +99,24 @@ class _RestrictedUnpickler(pickle.Unpickler):
         return super().find_class(module, name)
 
 
-def _loads(data: bytes) -> Any:
-    return _RestrictedUnpickler(io.BytesIO(data)).load()
+def _loads(data, buffers=None) -> Any:
+    """``buffers``: the out-of-band tensor segments of a native-transport frame (pickle protocol 5)."""
+    return _RestrictedUnpickler(io.BytesIO(data), buffers=buffers).load()
+
+
+def _send_obj(conn, obj: Any) -> None:
+    """One message: a native-transport frame (envelope + one segment per tensor, gathered from the tensors' memory) or a
+    length-prefixed pickle on a ``multiprocessing.connection`` connection."""
+    if isinstance(conn, _transport.NativeConnection):
+        conn.send_message(obj)
+    else:
+        conn.send_bytes(pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL))
+
+
+def _recv_obj(conn) -> Any:
+    if isinstance(conn, _transport.NativeConnection):
+        return conn.recv_message(_loads)
+    return _loads(conn.recv_bytes())
 
 _ERRORS = {c.__name__: c for c in (
     errors.OpError, errors.FailedPreconditionError, errors.AbortedError, errors.UnavailableError,
@@ -206,7 +223,10 @@ class RpcServer:
         self.host, self.port = parse_address(address)
         self._service = service
         self._authkey = cluster_authkey(self.host)
-        self._listener = Listener((self.host, self.port), backlog=64)      # handshake: per connection, below
+        self.native = _transport.available()
+        # handshake: per connection, below
+        self._listener = _transport.NativeListener(self.host, self.port, backlog=64) if self.native else \
+            Listener((self.host, self.port), backlog=64)
         self._closed = threading.Event()
         self._conns = []
         self._thread = threading.Thread(target=self._accept_loop, name="dtf-rpc-accept-%d" % self.port, daemon=True)
@@ -220,6 +240,9 @@ class RpcServer:
                 if self._closed.is_set():
                     return
                 continue
+            if conn is None:                 # native accept woke up on its timeout: look at the closed flag again
+                continue
+            self._conns = [c for c in self._conns if not getattr(c, "closed", False)]
             self._conns.append(conn)
             threading.Thread(target=self._serve, args=(conn,), name="dtf-rpc-conn", daemon=True).start()
 
@@ -233,7 +256,7 @@ class RpcServer:
             deliver_challenge(conn, self._authkey)
             answer_challenge(conn, self._authkey)
             return True
-        except (AuthenticationError, EOFError, OSError, ValueError, TypeError):
+        except (AuthenticationError, EOFError, OSError, ValueError, TypeError, ConnectionError):
             return False
         finally:
             dog.cancel()
@@ -244,7 +267,7 @@ class RpcServer:
                 return
             while not self._closed.is_set():
                 try:
-                    method, args, kwargs = from_wire(_loads(conn.recv_bytes()))
+                    method, args, kwargs = from_wire(_recv_obj(conn))
                 except (EOFError, OSError, ConnectionError, TypeError, ValueError, pickle.UnpicklingError):
                     return               # peer gone, this server closed the connection, or a message outside the wire types
                 _current.conn = conn
@@ -256,8 +279,8 @@ class RpcServer:
                 finally:
                     _current.conn = None
                 try:
-                    conn.send_bytes(pickle.dumps(result, protocol=pickle.HIGHEST_PROTOCOL))
-                except (OSError, ConnectionError, BrokenPipeError):
+                    _send_obj(conn, result)
+                except (OSError, ConnectionError, BrokenPipeError, EOFError):
                     return
         finally:
             try:
@@ -303,12 +326,13 @@ class RpcClient:
             delay = 0.02
             while True:
                 try:
-                    c = Client((self.host, self.port))
+                    c = _transport.connect(self.host, self.port, timeout=5.0) if _transport.available() else \
+                        Client((self.host, self.port))
                     try:
                         key = cluster_authkey(self.host)
                         answer_challenge(c, key)
                         deliver_challenge(c, key)
-                    except (AuthenticationError, EOFError) as e:
+                    except (AuthenticationError, EOFError, ConnectionError) as e:
                         c.close()
                         raise errors.UnavailableError("task at %s:%d rejected the cluster secret (%s): every task needs the same "
                                                       "DTF_CLUSTER_SECRET" % (self.host, self.port, e))
@@ -326,8 +350,8 @@ class RpcClient:
     def call(self, method: str, *args, **kwargs) -> Any:
         try:
             c = self._conn()
-            c.send_bytes(pickle.dumps((method, to_wire(args), to_wire(kwargs)), protocol=pickle.HIGHEST_PROTOCOL))
-            reply = from_wire(_loads(c.recv_bytes()))
+            _send_obj(c, (method, to_wire(args), to_wire(kwargs)))
+            reply = from_wire(_recv_obj(c))
         except (EOFError, ConnectionError, BrokenPipeError, OSError) as e:
             self._drop()
             raise errors.UnavailableError("task at %s:%d went away during %s: %s" % (self.host, self.port, method, e))
