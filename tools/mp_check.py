@@ -3,6 +3,11 @@ sync (mean of N worker gradients per step, tokens) and async (every push applied
 against a CPU oracle that replays the same batches.
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/mp_check.py
+
+``DTF_RTA=R`` (replicas_to_aggregate, R < workers): the backup-worker protocol instead -- no oracle (which replicas make an
+aggregate is a race by design), the invariants: no device-side wait times out (the ``consumed`` handshake that keeps a straggler
+from overwriting a push the ps may still read does not deadlock), exactly one global step per aggregate, R gradients folded per
+aggregate, every other push dropped as stale or still pending, parameters finite and moved.
 """
 import json
 import math
@@ -46,6 +51,45 @@ def main():
     W = world if pow_ else world - num_ps
     xs, ys = synthetic_mnist(100 * W * 8, seed=11)
     report = {}
+    rta = int(os.environ.get("DTF_RTA", "0"))
+    if rta:
+        assert 0 < rta < W, "DTF_RTA must be below the number of workers (%d)" % W
+        cfg = EngineConfig(num_ps=num_ps, num_workers=W, sync=True, replicas_to_aggregate=rta, optimizer={"kind": "sgd", "lr": 0.001},
+                           seed=2, nvls=nvls, ps_on_workers=pow_, precision=PRECISION, timeout_ns=10_000_000_000)
+        eng = PSTrainEngine(MLPSpec(), cfg, Fabric.from_torch_distributed())
+        eng.init_params()
+        p0 = eng.state_dict() if rank < num_ps else None
+        for r in eng.ranks:
+            if r in eng.worker_ranks:
+                eng.attach_dataset(r, xs, ys)
+        steps = 12
+        eng.enqueue_local_steps(steps, "dataset")
+        eng.synchronize()
+        dist.barrier()
+        err = None
+        try:
+            eng.check_errors()
+        except RuntimeError as e:
+            err = str(e)
+        errs = [None] * world
+        dist.all_gather_object(errs, err)
+        if rank == 0:
+            sd = eng.state_dict()
+            applied, dropped = eng.read_ctl(0, "applied_total"), eng.read_ctl(0, "dropped_stale")
+            moved = max(float((sd[k] - p0[k]).abs().max()) for k in ("hid_w", "hid_b", "sm_w", "sm_b"))
+            finite = all(bool(torch.isfinite(sd[k]).all()) for k in ("hid_w", "hid_b", "sm_w", "sm_b"))
+            report["backup_workers"] = {
+                "replicas_to_aggregate": rta, "workers": W, "global_step": int(sd["global_step"]), "applied_total": int(applied),
+                "dropped_stale": int(dropped), "errors": [e for e in errs if e], "moved": moved,
+                "ok": (not any(errs)) and int(sd["global_step"]) == steps and int(applied) == steps * rta
+                and int(dropped) <= steps * (W - rta) and finite and moved > 0}
+            report.update(world=world, num_ps=num_ps, nvls=str(nvls), ps_on_workers=pow_, precision=PRECISION)
+            print("MP_CHECK " + json.dumps(report))
+        dist.barrier()
+        eng.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     for mode in ("sync", "async"):
         cfg = EngineConfig(num_ps=num_ps, num_workers=W, sync=(mode == "sync"), optimizer={"kind": "sgd", "lr": 0.001},
                            seed=2, nvls=nvls, ps_on_workers=pow_, precision=PRECISION)
