@@ -236,6 +236,20 @@ def reference_arm(args):
     print(json.dumps({"impl": "reference", "unavailable": why, "metric": "MNIST MLP samples/sec", "n_gpus": args.gpus}))
 
 
+def greedy_shards(shapes, num_ps: int):
+    """``tf.contrib.training.GreedyLoadBalancingStrategy(num_ps, byte_size_load_fn)`` under ``replica_device_setter``: variables in
+    creation order, each to the ps task carrying the fewest bytes so far (ties: the lowest task)."""
+    load, out = [0] * num_ps, []
+    for _, shp in shapes:
+        t = min(range(num_ps), key=load.__getitem__)
+        n = 4
+        for d in shp:
+            n *= int(d)
+        load[t] += n
+        out.append(t)
+    return out
+
+
 def run_resnet18(args, rank, world, local_rank):
     """ResNet-18 (CIFAR stem, 11.2 M parameters) under the same fabric ps protocol: conv-as-tcgen05-GEMM workers,
     fused ps_apply (momentum), sync replicas.  Timed exactly like the headline: CUDA events, barrier + synchronize on
@@ -262,15 +276,7 @@ def run_resnet18(args, rank, world, local_rank):
                            ps_on_workers=pow_)
         fabric = Fabric.from_torch_distributed()
     shapes = resnet18_param_shapes(10, "cifar")
-    shards = None
-    if cfg.num_ps > 1 and args.placement == "greedy":
-        # tf.contrib.training.GreedyLoadBalancingStrategy(num_ps, byte_size_load_fn) under replica_device_setter
-        load = [0] * cfg.num_ps
-        shards = []
-        for _, shp in shapes:
-            t = min(range(cfg.num_ps), key=load.__getitem__)
-            load[t] += 4 * int(torch.tensor(shp).prod())
-            shards.append(t)
+    shards = greedy_shards(shapes, cfg.num_ps) if (cfg.num_ps > 1 and args.placement == "greedy") else None
     eng = GenericPSEngine(shapes, cfg, fabric, shards=shards)
     eng.init_params(resnet18_init(10, "cifar", seed=2))
     nparams = sum(eng.shard_elems)
