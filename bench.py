@@ -65,9 +65,9 @@ def parse_args():
     ap.add_argument("--max-reps", type=int, default=400)
     ap.add_argument("--baseline", type=int, default=1, help="1: also time the torch+NCCL+cuBLAS arm in this invocation -> vs_baseline")
     ap.add_argument("--e2e-pipeline", type=int, default=1,
-                    help="1 (one-GPU runs): also time step(..., sync_loss='deferred') -- the loss of step t is read after "
+                    help="1 (one-GPU runs and every-rank-a-worker topologies): also time step(..., sync_loss='deferred') -- the loss of step t is read after "
                          "step t+1 was enqueued -- and report the better arm, both kept under e2e.synchronous/.pipelined; "
-                         "2: do so on every topology (multi-rank: no fallback, first hardware run pending); 0: off")
+                         "2: do so on every topology without the fallback to the synchronous number; 0: off")
     ap.add_argument("--publish", action="store_true", help="ps stores params into worker replicas (push-publish)")
     ap.add_argument("--num-train", type=int, default=55000)
     ap.add_argument("--f1-splits", type=int, default=1, help="split-K CTAs for the first GEMM")

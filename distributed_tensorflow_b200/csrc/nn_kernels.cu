@@ -27,9 +27,10 @@
 //                            deterministic and needs no atomics.  Padding behaves like -inf (TF SAME semantics).
 //   global_avgpool_nhwc_fwd / _bwd : mean over H*W per (image, channel) and its broadcast gradient.
 //
-// STATUS: written at the end of round 1 after the GPU budget was spent.  Compiled (ptxas: no spills), formulas checked
-// on CPU against autograd (tests/test_nn_fused_reference.py); first hardware run is tests/test_gpu_nn_fused.py.
-// Off by default (DTF_FUSED_BN=1 turns it on in ops/native.py).
+// STATUS: validated on hardware in round 2 (tests/test_gpu_nn_fused.py, memcheck / racecheck / synccheck clean, ncu summaries in
+// profiles/prof_nn.ncu-summary.txt); formulas also checked on CPU against autograd (tests/test_nn_fused_reference.py) and the
+// source runs under the host emulation (tests/test_nn_kernels_host_emulation.py).  Default on (DTF_FUSED_NN=0 / DTF_FUSED_BN=0
+// switch back to the element-wise PyTorch formulation in ops/native.py).
 #include <cstdint>
 
 // DTF_HOST_EMU: the same source compiled by g++ against tests/emu/host_emu.h (threads + barriers stand in for a thread

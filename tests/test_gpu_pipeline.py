@@ -1,9 +1,8 @@
 """Deferred loss read-back (``step(..., sync_loss="deferred")`` -> ``PendingLoss``) on one GPU: the pipelined loop -- step
 t+1 enqueued before step t's loss is waited for -- computes exactly what the synchronous loop computes.
 
-First written at the end of round 1 after the GPU budget was spent: its host logic is covered on CPU
-(``test_fabric_host_logic.py::test_deferred_loss_step_ordering_with_fake_plans``), this file is its first hardware run
-(sorted after the other GPU files on purpose)."""
+The host logic is also covered on CPU (``test_fabric_host_logic.py::test_deferred_loss_step_ordering_with_fake_plans``); on
+hardware since round 2, both precisions."""
 import numpy as np
 import pytest
 import torch
