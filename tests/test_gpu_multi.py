@@ -52,21 +52,3 @@ def test_two_gpu_ps_on_workers_matches_cpu_oracle(nvls):
     rep = json.loads([l for l in r.stdout.splitlines() if l.startswith("MP_CHECK ")][-1][len("MP_CHECK "):])
     assert rep["ps_on_workers"] and rep["sync"]["ok"] and rep["sync"]["global_step"] == 6
     assert rep["async"]["ok"] and rep["async"]["staleness"]["count"] == 12          # 2 workers x 6 steps
-
-
-@pytest.mark.parametrize("workers,rta", [(2, 1), (4, 3)])
-def test_backup_workers_on_the_fabric(workers, rta):
-    """``SyncReplicasOptimizer(replicas_to_aggregate < total_num_replicas)`` on the device protocol (reference
-    distributed_mnist.py:120-122 allows it): a straggler never overwrites a push the ps may still read (``consumed`` handshake),
-    nothing deadlocks, one global step and ``rta`` gradients per aggregate.  Written after the round's GPU budget was spent: the
-    same protocol runs under the host emulation with real concurrency (test_concurrent_backup_worker_with_a_straggler); this
-    is its hardware twin, first run pending."""
-    if not torch.cuda.is_available() or torch.cuda.device_count() < workers:
-        pytest.skip("needs %d GPUs" % workers)
-    env = dict(os.environ, DTF_NVLS="auto", DTF_PS_ON_WORKERS="1", DTF_RTA=str(rta), MASTER_ADDR="127.0.0.1")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(workers), "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "mp_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env, cwd=ROOT)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    rep = json.loads([l for l in r.stdout.splitlines() if l.startswith("MP_CHECK ")][-1][len("MP_CHECK "):])["backup_workers"]
-    assert rep["ok"], rep
