@@ -129,6 +129,8 @@ class NativeConnection:
     def send_message(self, obj: Any) -> None:
         oob: List[pickle.PickleBuffer] = []
         env = pickle.dumps(obj, protocol=5, buffer_callback=oob.append)
+        if len(oob) >= _MAX_SEG:                  # thousands of tensors in one message: keep them inside the envelope
+            oob, env = [], pickle.dumps(obj, protocol=5)
         self.send_segments([env] + [b.raw() for b in oob])
 
     def recv_message(self, loads: Callable[..., Any], timeout: Optional[float] = None) -> Any:

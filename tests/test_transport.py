@@ -1,0 +1,114 @@
+"""Native control-plane transport (csrc/runtime/transport.cpp + parallel/transport.py): frames of segments, out-of-band
+tensors, deadlines, hang-up detection, close() waking a blocked reader."""
+import pickle
+import threading
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from distributed_tensorflow_b200.parallel import rpc, transport
+
+pytestmark = pytest.mark.skipif(not transport.available(), reason="native runtime not built")
+
+
+@pytest.fixture
+def pair():
+    lst = transport.NativeListener("127.0.0.1", 0)
+    got = []
+    t = threading.Thread(target=lambda: got.append(lst.accept(timeout=5.0)))
+    t.start()
+    c = transport.connect("127.0.0.1", lst.port)
+    t.join(5.0)
+    s = got[0]
+    assert s is not None
+    yield c, s
+    c.close()
+    s.close()
+    lst.close()
+
+
+def test_segments_roundtrip_without_copies_into_one_buffer(pair):
+    c, s = pair
+    a = np.arange(1 << 20, dtype=np.float32)
+    b = bytearray(b"xyz" * 1000)
+    t = threading.Thread(target=lambda: c.send_segments([b"envelope", a, b, b""]))      # 4 MB: more than the socket buffers hold
+    t.start()
+    segs = s.recv_segments(timeout=5.0)
+    t.join(5.0)
+    assert [m.nbytes for m in segs] == [8, a.nbytes, 3000, 0]
+    assert bytes(segs[0]) == b"envelope" and np.array_equal(np.frombuffer(segs[1], dtype=np.float32), a) and bytes(segs[2]) == bytes(b)
+    assert np.frombuffer(segs[1], dtype=np.uint8).ctypes.data % 16 == 0          # aligned landing buffers
+    with pytest.raises(ValueError):
+        c.send_segments([])
+
+
+def test_messages_carry_tensors_out_of_band(pair):
+    c, s = pair
+    x = torch.randn(300, 200)
+    msg = ("call", rpc.to_wire({"x": x, "h": torch.ones(5, dtype=torch.bfloat16), "nc": torch.arange(12.0).view(3, 4).t()}), 7)
+    c.send_message(msg)
+    segs = s.recv_segments(timeout=5.0)
+    assert len(segs) >= 3 and segs[0].nbytes < 1000 and any(m.nbytes == x.numel() * 4 for m in segs[1:])
+    out = rpc.from_wire(rpc._loads(segs[0], segs[1:]))
+    assert out[0] == "call" and out[2] == 7 and torch.equal(out[1]["x"], x) and out[1]["h"].dtype == torch.bfloat16
+    assert torch.equal(out[1]["nc"], torch.arange(12.0).view(3, 4).t())
+    # the restricted unpickler still guards the envelope
+    class Evil:
+        def __reduce__(self):
+            import os
+            return (os.system, ("true",))
+    c.send_message(Evil())
+    with pytest.raises(pickle.UnpicklingError):
+        s.recv_message(rpc._loads, timeout=5.0)
+
+
+def test_deadline_applies_to_the_start_of_a_frame_only(pair):
+    c, s = pair
+    t0 = time.time()
+    with pytest.raises(transport.TransportTimeout):
+        s.recv_segments(timeout=0.15)
+    assert 0.1 < time.time() - t0 < 2.0
+    c.send_bytes(b"late")                                   # the stream is still in sync after a timeout
+    assert s.recv_bytes() == b"late"
+    with pytest.raises(OSError):
+        c.send_bytes(b"x" * 300)
+        s.recv_bytes(maxlength=256)
+
+
+def test_hang_up_is_visible_and_close_wakes_a_blocked_reader(pair):
+    c, s = pair
+    assert not s.peer_closed()
+    c.close()
+    deadline = time.time() + 5.0
+    while not s.peer_closed() and time.time() < deadline:
+        time.sleep(0.01)
+    assert s.peer_closed()
+    with pytest.raises(EOFError):
+        s.recv_segments(timeout=2.0)
+    # a reader blocked without a deadline is released by close() from another thread
+    lst = transport.NativeListener("127.0.0.1", 0)
+    acc = []
+    t = threading.Thread(target=lambda: acc.append(lst.accept(timeout=5.0)))
+    t.start()
+    c2 = transport.connect("127.0.0.1", lst.port)
+    t.join(5.0)
+    s2, res = acc[0], []
+
+    def reader():
+        try:
+            s2.recv_segments()
+            res.append("data")
+        except (EOFError, OSError) as e:
+            res.append(type(e).__name__)
+    rt = threading.Thread(target=reader)
+    rt.start()
+    time.sleep(0.1)
+    s2.close()
+    rt.join(5.0)
+    assert res and res[0] in ("EOFError", "OSError", "ConnectionError")
+    c2.close()
+    lst.close()
+    with pytest.raises((ConnectionRefusedError, OSError)):
+        transport.connect("127.0.0.1", lst.port, timeout=0.5)
