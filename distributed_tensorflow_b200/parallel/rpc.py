@@ -187,6 +187,8 @@ def peer_closed(conn: Optional[Connection]) -> bool:
     on the descriptor even while a handler thread is blocked inside a long-running request."""
     if conn is None:
         return False
+    if isinstance(conn, _transport.NativeConnection):
+        return conn.peer_closed()
     try:
         p = select.poll()
         p.register(conn.fileno(), select.POLLRDHUP | select.POLLHUP | select.POLLERR)

@@ -77,7 +77,11 @@ def _raise(rc: int, what: str):
 
 
 class NativeConnection:
-    """One TCP connection; not thread-safe (the RPC layer uses one per calling thread / one handler thread per peer)."""
+    """One TCP connection.  One reader and one writer at a time (the RPC layer uses one connection per calling thread / one
+    handler thread per peer); ``close()`` may come from ANY thread: it shuts the socket down at once -- a thread blocked in
+    ``recv`` wakes up with EOF, later sends fail -- but the descriptor itself is released only when no native call is using it
+    any more, so a handler thread that finishes its request after the server was stopped can never write into whatever
+    socket the kernel gave the same descriptor number next."""
 
     def __init__(self, fd: int):
         self._fd = fd
@@ -85,6 +89,8 @@ class NativeConnection:
         self.timeout: Optional[float] = None          # seconds recv waits for the START of a frame (None: forever)
         self._lens = (ctypes.c_uint64 * _MAX_SEG)()
         self._closed = False
+        self._busy = 0
+        self._state = threading.Lock()
 
     def fileno(self) -> int:
         return self._fd
@@ -92,6 +98,20 @@ class NativeConnection:
     @property
     def closed(self) -> bool:
         return self._closed
+
+    def _enter(self) -> int:
+        with self._state:
+            if self._closed:
+                raise OSError("connection is closed")
+            self._busy += 1
+            return self._fd
+
+    def _exit(self) -> None:
+        with self._state:
+            self._busy -= 1
+            if self._closed and self._busy == 0 and self._fd >= 0:
+                self._lib.dtf_net_close(self._fd)
+                self._fd = -1
 
     # -- frames ------------------------------------------------------------------------------------------------------------
     def send_segments(self, segments: List[Any]) -> None:
@@ -107,20 +127,28 @@ class NativeConnection:
             keep.append(a)
             lens[i] = a.size
             ptrs[i] = a.ctypes.data if a.size else None
-        rc = self._lib.dtf_net_send(self._fd, ptrs, lens, n)
+        fd = self._enter()
+        try:
+            rc = self._lib.dtf_net_send(fd, ptrs, lens, n)
+        finally:
+            self._exit()
         del keep
         if rc != _OK:
             _raise(rc, "send")
 
     def recv_segments(self, timeout: Optional[float] = None) -> List[memoryview]:
-        """Next frame; segment 0 as ``bytes``-like, the others as writable, 64-byte aligned buffers."""
+        """Next frame; every segment in a writable, aligned buffer of its own."""
         t = self.timeout if timeout is None else timeout
-        n = self._lib.dtf_net_recv_header(self._fd, self._lens, _MAX_SEG, -1.0 if t is None else float(t))
-        if n <= 0:
-            _raise(n if n < 0 else _BAD, "recv")
-        bufs = [np.empty(int(self._lens[i]), dtype=np.uint8) for i in range(n)]
-        ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data if b.size else None for b in bufs])
-        rc = self._lib.dtf_net_recv_body(self._fd, ptrs, self._lens, n)
+        fd = self._enter()
+        try:
+            n = self._lib.dtf_net_recv_header(fd, self._lens, _MAX_SEG, -1.0 if t is None else float(t))
+            if n <= 0:
+                _raise(n if n < 0 else _BAD, "recv")
+            bufs = [np.empty(int(self._lens[i]), dtype=np.uint8) for i in range(n)]
+            ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data if b.size else None for b in bufs])
+            rc = self._lib.dtf_net_recv_body(fd, ptrs, self._lens, n)
+        finally:
+            self._exit()
         if rc != _OK:
             _raise(rc, "recv")
         return [memoryview(b) for b in bufs]
@@ -149,13 +177,21 @@ class NativeConnection:
         return segs[0].tobytes()
 
     def peer_closed(self) -> bool:
-        return self._closed or bool(self._lib.dtf_net_peer_closed(self._fd))
+        with self._state:
+            if self._closed or self._fd < 0:
+                return True
+            return bool(self._lib.dtf_net_peer_closed(self._fd))
 
     def close(self) -> None:
-        if not self._closed:
+        with self._state:
+            if self._closed:
+                return
             self._closed = True
-            self._lib.dtf_net_shutdown(self._fd)      # wakes a thread blocked in recv on this connection
-            self._lib.dtf_net_close(self._fd)
+            if self._fd >= 0:
+                self._lib.dtf_net_shutdown(self._fd)      # wakes a thread blocked in recv on this connection
+                if self._busy == 0:
+                    self._lib.dtf_net_close(self._fd)
+                    self._fd = -1
 
     def __del__(self):
         try:
