@@ -64,6 +64,10 @@ def parse_args():
     ap.add_argument("--min-ms", type=float, default=100.0, help="collect at least this much timed region (repetitions of K steps)")
     ap.add_argument("--max-reps", type=int, default=400)
     ap.add_argument("--baseline", type=int, default=1, help="1: also time the torch+NCCL+cuBLAS arm in this invocation -> vs_baseline")
+    ap.add_argument("--e2e-native-loop", type=int, default=1,
+                    help="1: third e2e arm = PSTrainEngine.train_loop(x_batches_pinned, y_batches_pinned, steps): the same per-step "
+                         "H2D copy / kernels / D2H loss read, K steps enqueued by one native call (csrc/step_exec.cu dtf_run_loop)")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="native loop: steps the host may run ahead of the landed losses")
     ap.add_argument("--e2e-pipeline", type=int, default=1,
                     help="1 (one-GPU runs and every-rank-a-worker topologies): also time step(..., sync_loss='deferred') -- the loss of step t is read after "
                          "step t+1 was enqueued -- and report the better arm, both kept under e2e.synchronous/.pipelined; "
@@ -604,6 +608,23 @@ def main():
             if pending is not None:
                 last[0] = pending.result()
 
+        hx3 = hx[:nb * spec.batch].view(nb, spec.batch, spec.in_dim) if is_worker else None
+        hy3 = hy[:nb * spec.batch].view(nb, spec.batch, spec.classes) if is_worker else None
+
+        def e2e_k_steps_native():
+            # same per-step work (H2D of THIS step's batch one step ahead on the copy stream, the step's kernels, D2H of the
+            # step's loss row), but the K steps are enqueued by ONE native call; the host reads every loss, at most
+            # --e2e-depth steps late
+            if is_worker:
+                ls = eng.train_loop(hx3, hy3, K, first=(ctr[0] * num_workers + woff) % nb, stride=num_workers, depth=args.e2e_depth)
+                last[0] = float(ls[-1])
+                if not all(math.isfinite(float(v)) for v in ls):
+                    raise RuntimeError("native loop returned a non-finite loss")
+            else:
+                for _ in range(K):
+                    eng.step(sync_loss=False)
+            ctr[0] += K
+
         def align_e2e():
             for _ in range(2):
                 if is_worker:
@@ -669,6 +690,30 @@ def main():
                 if world > 1:
                     raise                # ranks must not diverge
                 e2e["pipelined_error"] = repr(e)[:300]
+        if args.e2e_native_loop and ((world == 1 and is_worker) or pow_):
+            # third arm: the framework's own training loop (one native call per K steps)
+            try:
+                nt = measure_e2e(e2e_k_steps_native)
+                nems = statistics.median(t[0] for t in nt)
+                nlast = allmax([last[0] if last[0] is not None else -1e30])[0]
+                if not math.isfinite(nlast):
+                    raise RuntimeError("native loop returned loss %r" % (nlast,))
+                if "synchronous" not in e2e:
+                    e2e["synchronous"] = {k: e2e[k] for k in ("value", "ms_per_step", "wall_ms_per_step", "last_loss")}
+                nat_part = {"value": per_step / (nems / 1e3), "ms_per_step": nems / K,
+                            "wall_ms_per_step": statistics.median(t[1] for t in nt) / K, "last_loss": nlast}
+                e2e["native_loop"] = dict(nat_part, depth=args.e2e_depth)
+                if nat_part["value"] > e2e["value"]:
+                    e2e.update(nat_part)
+                    e2e["reps"] = len(nt)
+                    e2e["api"] = "PSTrainEngine.train_loop(x_batches_pinned, y_batches_pinned, steps=K) -> losses[K]"
+                    e2e["loss_read"] = ("every step's loss is copied D2H behind its kernels into its own pinned row; the host waits "
+                                        "for row i-%d before enqueuing step i and reads all K rows" % args.e2e_depth)
+                    e2e["input_double_buffering"] = True
+            except Exception as e:      # noqa: BLE001 - keep the measurements of the other arms
+                if world > 1:
+                    raise                # ranks must not diverge
+                e2e["native_loop_error"] = repr(e)[:300]
 
     # ---- ps traffic implied by the measured step time (BASELINE metric: push/pull GB/s vs 900 GB/s/dir) -----------
     # true-shape bytes: gradients travel as fp32, parameters as fp32 (tf32 engines) / bf16 replicas; every worker moves both every step.

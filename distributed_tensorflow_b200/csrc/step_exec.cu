@@ -176,6 +176,94 @@ int dtf_capture_ops(const DtfStepOp* ops, int n, int device, cudaStream_t stream
   return rc;
 }
 
+// ---- native multi-step loop: the end-to-end inner loop without the interpreter between steps -----------------------------
+// One call runs `steps` training steps of ONE local worker: per step the H2D copy of THAT step's batch from pinned host memory
+// (copy stream, double-buffered: issued one step ahead so it overlaps the previous step's kernels), the step's kernels (the
+// CUDA-graphed compute plan of the buffer parity), the ps shard's apply when it runs on its own stream, and the D2H copy of
+// the step's loss partials into row i of a pinned host array.  The host keeps at most `depth` steps in flight (it waits for
+// the loss of step i - depth to have LANDED before enqueuing step i).  Exactly what `PSTrainEngine.step(x, y,
+// sync_loss="deferred", prefetch=next)` does per step, minus the Python between the calls.
+// Reference role: the `while` loop around `mon_sess.run([train_step, global_step, loss], feed_dict=...)`
+// (distributed_mnist.py:148-152), i.e. next_batch -> feed -> step -> fetched loss, K times.
+struct DtfLoopArgs {
+  int device;               // made current for the call (>= 0)
+  int steps;
+  int depth;                // >= 1
+  int parity;               // buffer set of the first step; on return: of the next step
+  int prefetched;           // in: copy[parity] was already issued for the first batch.  out: 0
+  int x_op, y_op;           // index of the H2D ops (x, labels) inside both copy plans
+  int n_copy[2], n_compute[2], n_ps;
+  DtfStepOp* copy_ops[2];   // per parity: wait done[p] -> H2D x -> H2D y -> (convert) -> record ready[p]
+  DtfStepOp* compute_ops[2];// per parity: wait ready[p] -> kernels / graph -> record done[p]
+  DtfStepOp* ps_ops;        // optional: the ps shard's applies on its own stream
+  cudaStream_t copy_stream, stream, ps_stream;
+  const char* x_base;       // pinned host batches: batch b at x_base + b * x_stride (bytes)
+  const char* y_base;
+  long long x_stride, y_stride;
+  long long nbatches, first, batch_step;   // step i trains on batch (first + i * batch_step) % nbatches
+  const void* loss_src;     // device: the step's loss partials
+  long long loss_bytes;
+  char* loss_host;          // pinned host: row i (loss_row_bytes apart) receives step i's partials
+  long long loss_row_bytes;
+  long long kernels;        // out: kernels launched
+  long long waited;         // out: event waits the host issued (run-ahead bound + the final one)
+};
+
+int dtf_run_loop(DtfLoopArgs* a) {
+  if (!a || a->steps < 0 || a->depth < 1 || a->depth > 64 || a->nbatches < 1) return -1;
+  if (a->x_op < 0 || a->y_op < 0 || a->x_op >= a->n_copy[0] || a->y_op >= a->n_copy[0] || a->x_op >= a->n_copy[1] ||
+      a->y_op >= a->n_copy[1]) return -2;
+  int prev = -1;
+  if (a->device >= 0) {
+    cudaGetDevice(&prev);
+    if (prev != a->device) cudaSetDevice(a->device); else prev = -1;
+  }
+  cudaEvent_t landed[64];
+  int made = 0, rc = 0, kernels = 0;
+  for (; made < a->depth && made < a->steps && rc == 0; ++made)
+    rc = (int)cudaEventCreateWithFlags(&landed[made], cudaEventDisableTiming);
+  if (rc != 0) --made;
+  auto issue_copy = [&](int par, long long step) -> int {
+    long long b = (a->first + step * a->batch_step) % a->nbatches;
+    if (b < 0) b += a->nbatches;
+    a->copy_ops[par][a->x_op].p1 = const_cast<char*>(a->x_base) + b * a->x_stride;
+    a->copy_ops[par][a->y_op].p1 = const_cast<char*>(a->y_base) + b * a->y_stride;
+    return dtf_run_ops(a->copy_ops[par], a->n_copy[par], -1, a->copy_stream, &kernels);
+  };
+  int par = a->parity & 1;
+  long long waits = 0;
+  if (rc == 0 && a->steps > 0 && !a->prefetched) rc = issue_copy(par, 0);
+  for (int i = 0; i < a->steps && rc == 0; ++i) {
+    const int slot = i % a->depth;
+    if (i >= a->depth) {                       // the loss of step i - depth has landed: its event slot is free again
+      rc = (int)cudaEventSynchronize(landed[slot]);
+      ++waits;
+      if (rc != 0) break;
+    }
+    rc = dtf_run_ops(a->compute_ops[par], a->n_compute[par], -1, a->stream, &kernels);
+    if (rc == 0 && a->n_ps > 0) rc = dtf_run_ops(a->ps_ops, a->n_ps, -1, a->ps_stream, &kernels);
+    if (rc == 0 && i + 1 < a->steps) rc = issue_copy(par ^ 1, i + 1);          // next batch travels under this step's kernels
+    if (rc == 0 && a->loss_bytes > 0)
+      rc = (int)cudaMemcpyAsync(a->loss_host + (long long)i * a->loss_row_bytes, a->loss_src, (size_t)a->loss_bytes,
+                                cudaMemcpyDeviceToHost, a->stream);
+    if (rc == 0) rc = (int)cudaEventRecord(landed[slot], a->stream);
+    par ^= 1;
+  }
+  if (rc == 0 && a->steps > 0) {               // every loss row is on the host when the call returns
+    rc = (int)cudaEventSynchronize(landed[(a->steps - 1) % a->depth]);
+    ++waits;
+  }
+  for (int e = 0; e < made; ++e) cudaEventDestroy(landed[e]);
+  a->parity = par;
+  a->prefetched = 0;
+  a->kernels = kernels;
+  a->waited = waits;
+  if (prev >= 0) cudaSetDevice(prev);
+  return rc;
+}
+
+int dtf_sizeof_loop_args() { return (int)sizeof(DtfLoopArgs); }
+
 int dtf_graph_destroy(void* exec) { return (int)cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(exec)); }
 
 int dtf_sizeof_step_op() { return (int)sizeof(DtfStepOp); }

@@ -96,6 +96,19 @@ class StepOp(Structure):
                 ("i3", c_longlong), ("i4", c_longlong), ("i5", c_longlong), ("u0", c_ulonglong)]
 
 
+class LoopArgs(Structure):
+    """``csrc/step_exec.cu: DtfLoopArgs`` -- ``steps`` end-to-end training steps of one local worker in ONE native call
+    (per step: H2D of that step's pinned batch one step ahead, the step's plan, the ps shard's plan, D2H of the loss row)."""
+    _fields_ = [("device", c_int), ("steps", c_int), ("depth", c_int), ("parity", c_int), ("prefetched", c_int),
+                ("x_op", c_int), ("y_op", c_int), ("n_copy", c_int * 2), ("n_compute", c_int * 2), ("n_ps", c_int),
+                ("copy_ops", c_void_p * 2), ("compute_ops", c_void_p * 2), ("ps_ops", c_void_p),
+                ("copy_stream", c_void_p), ("stream", c_void_p), ("ps_stream", c_void_p),
+                ("x_base", c_void_p), ("y_base", c_void_p), ("x_stride", c_longlong), ("y_stride", c_longlong),
+                ("nbatches", c_longlong), ("first", c_longlong), ("batch_step", c_longlong),
+                ("loss_src", c_void_p), ("loss_bytes", c_longlong), ("loss_host", c_void_p), ("loss_row_bytes", c_longlong),
+                ("kernels", c_longlong), ("waited", c_longlong)]
+
+
 OP_H2D, OP_D2H, OP_CONVERT, OP_GEMM, OP_HEAD, OP_PS_APPLY, OP_WAIT_TOKEN, OP_SIGNAL, OP_STAGE, OP_SYNC = range(1, 11)
 OP_GRAPH = 13
 OP_MLP_STEP = 14
@@ -260,6 +273,11 @@ def _declare(lib) -> None:
     lib.dtf_graph_destroy.argtypes = [c_void_p]
     lib.dtf_graph_destroy.restype = c_int
     lib.dtf_sizeof_step_op.restype = c_int
+    lib.dtf_run_loop.argtypes = [POINTER(LoopArgs)]
+    lib.dtf_run_loop.restype = c_int
+    lib.dtf_sizeof_loop_args.restype = c_int
+    if not isinstance(lib.dtf_sizeof_loop_args, _Missing):
+        assert lib.dtf_sizeof_loop_args() == ctypes.sizeof(LoopArgs), "LoopArgs layout mismatch"
     if not isinstance(lib.dtf_sizeof_step_op, _Missing):
         assert lib.dtf_sizeof_step_op() == ctypes.sizeof(StepOp), "StepOp layout mismatch"
     if not isinstance(getattr(lib, "dtf_bn_reduce", _Missing()), _Missing):    # csrc/nn_kernels.cu (a stale build lacks it)

@@ -1089,6 +1089,94 @@ class PSTrainEngine:
             return self.read_loss()
         return None
 
+    def train_loop(self, x_batches, y_batches, steps: int, first: int = 0, stride: int = 1, depth: int = 2):
+        """``steps`` end-to-end training steps in ONE native call (``csrc/step_exec.cu: dtf_run_loop``) -- the reference's
+        ``while`` loop around ``mon_sess.run([train_step, global_step, loss], feed_dict=...)``
+        (``/root/reference/distributed_mnist.py:148-152``) without the interpreter between the steps.
+
+        ``x_batches`` ``[nb, B, in_dim]`` / ``y_batches`` ``[nb, B, classes]``: pinned contiguous fp32 HOST tensors.  Step i
+        trains on batch ``(first + i * stride) % nb``: every step its batch is copied host->device (copy stream, one step
+        ahead of the kernels that consume it), the step runs (the same CUDA-graphed plans ``step()`` uses), and the step's
+        loss partials are copied device->host into row i of a pinned array; the host stays at most ``depth`` steps ahead
+        of the landed losses.  Returns the ``steps`` losses (numpy fp32).  One local worker per process (between-graph
+        replication); other topologies, and a process whose plans are not built yet, take ``step()`` per step."""
+        import numpy as np
+        from ..ops.cuda_lib import LoopArgs
+        B, D, C = self.spec.batch, self.spec.in_dim, self.spec.classes
+        steps = int(steps)
+        local_workers = [r for r in self.worker_ranks if r in self.ranks]
+        shaped = (isinstance(x_batches, torch.Tensor) and isinstance(y_batches, torch.Tensor) and x_batches.dim() == 3
+                  and tuple(x_batches.shape[1:]) == (B, D) and tuple(y_batches.shape[1:]) == (B, C)
+                  and y_batches.shape[0] == x_batches.shape[0] and x_batches.shape[0] > 0)
+        nb = int(x_batches.shape[0]) if shaped else 0
+        ok = (shaped and len(local_workers) == 1 and steps > 0 and self._is_pinned_f32(x_batches) and self._is_pinned_f32(y_batches)
+              and os.environ.get("DTF_NATIVE_LOOP", "1") == "1")
+        losses = np.zeros(max(steps, 0), np.float32)
+        i = 0
+        if ok:
+            # the first steps of a process build the plans eagerly (both buffer parities) and graph them
+            plans = self._plans()
+            while i < steps and not plans.get("graphed"):
+                b = (first + i * stride) % nb
+                losses[i] = self.step(x_batches[b], y_batches[b], sync_loss=True)
+                i += 1
+                if plans["runs"] >= 4 and not plans.get("graphed"):
+                    ok = False                     # graphing is switched off (DTF_E2E_GRAPH=0): stay on step()
+                    break
+        if not ok:
+            while i < steps:
+                b = (first + i * stride) % max(nb, 1)
+                if local_workers and nb:
+                    out = self.step(x_batches[b], y_batches[b], sync_loss=True)
+                    losses[i] = out if out is not None else 0.0
+                elif local_workers:
+                    raise ValueError("train_loop needs pinned fp32 host batches [nb, %d, %d] / [nb, %d, %d]" % (B, D, B, C))
+                else:
+                    self.step(sync_loss=False)
+                i += 1
+            return losses
+        if i == steps:
+            return losses
+        r = local_workers[0]
+        rk, d = self.ranks[r], self._w[r]
+        for old in list(plans["pending"].values()):      # deferred read-backs of step(): let them land first
+            old.result()
+        plans["pending"].clear()
+        n = steps - i
+        st = plans.get("loop_state")
+        if st is None or st["rows"] < n:
+            rows = max(n, 256)
+            host = torch.zeros(rows, 16, dtype=torch.float32)
+            if torch.cuda.is_available():
+                host = host.pin_memory()
+            st = plans["loop_state"] = {"rows": rows, "host": host, "np": host.numpy(), "args": LoopArgs()}
+        a = st["args"]
+        cp, cm = plans["copy"][r], plans["compute"][r]
+        a.device, a.steps, a.depth, a.parity = rk.device.index, n, max(1, min(int(depth), 64)), plans["parity"]
+        b0 = (first + i * stride) % nb
+        a.prefetched = int(plans["prefetched"] == (x_batches[b0].data_ptr(), y_batches[b0].data_ptr(), plans["parity"]))
+        a.x_op, a.y_op = 1, 2
+        for p_ in range(2):
+            a.n_copy[p_], a.n_compute[p_] = cp[p_].n, cm[p_].n
+            a.copy_ops[p_], a.compute_ops[p_] = ctypes.addressof(cp[p_].ops), ctypes.addressof(cm[p_].ops)
+        psp = plans["ps"].get(r)
+        a.n_ps, a.ps_ops, a.ps_stream = (psp.n, ctypes.addressof(psp.ops), psp.stream) if psp is not None else (0, None, None)
+        a.copy_stream, a.stream = cp[0].stream, cm[0].stream
+        a.x_base, a.y_base = x_batches.data_ptr(), y_batches.data_ptr()
+        a.x_stride, a.y_stride = B * D * 4, B * C * 4
+        a.nbatches, a.first, a.batch_step = nb, b0, stride % nb
+        a.loss_src, a.loss_bytes = d["loss_ptr"], self.head_ctas * 4
+        a.loss_host, a.loss_row_bytes = st["host"].data_ptr(), 64
+        rc = self.lib.dtf_run_loop(ctypes.byref(a))
+        if rc:
+            raise RuntimeError("native training loop failed with code %d (op %d of a plan, code %d)" % (rc, rc // 100000 - 1, rc % 100000))
+        cuda_lib._bump(int(a.kernels))
+        plans["parity"], plans["prefetched"] = int(a.parity), None
+        plans["runs"] += n
+        rk.step += n
+        losses[i:] = st["np"][:n, :self.head_ctas].sum(axis=1)
+        return losses
+
     def enqueue_local_steps(self, n: int = 1, source: str = "dataset") -> int:
         """Enqueue ``n`` steps for every local rank (no host sync).  Returns the kernels launched."""
         before = cuda_lib.launch_count()

@@ -37,6 +37,16 @@ static inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, 
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t s) { step_emu::log("sync stream=%p", s); return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) { step_emu::log("event_record ev=%p stream=%p", e, s); return 0; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned) { step_emu::log("event_wait ev=%p stream=%p", e, s); return 0; }
+enum { cudaEventDisableTiming = 2 };
+namespace step_emu { inline long long next_event = 0xe000; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned flags) {
+  if (step_emu::fail_kind == 100) return step_emu::fail_code;
+  *e = (void*)(step_emu::next_event++);
+  step_emu::log("event_create ev=%p flags=%u", *e, flags);
+  return 0;
+}
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t e) { step_emu::log("event_sync ev=%p", e); return 0; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { step_emu::log("event_destroy ev=%p", e); return 0; }
 static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t g, cudaStream_t s) { step_emu::log("graph_launch exec=%p stream=%p", g, s); return 0; }
 static inline cudaError_t cudaStreamBeginCapture(cudaStream_t s, cudaStreamCaptureMode) { step_emu::log("begin_capture stream=%p", s); return 0; }
 static inline cudaError_t cudaStreamEndCapture(cudaStream_t s, cudaGraph_t* g) { step_emu::log("end_capture stream=%p", s); *g = (void*)0x6a; return 0; }
@@ -82,5 +92,6 @@ __attribute__((weak)) void step_emu_reset(int fail_kind, int fail_code) {
   step_emu::fail_kind = fail_kind;
   step_emu::fail_code = fail_code;
   step_emu::current_device = 0;
+  step_emu::next_event = 0xe000;
 }
 }

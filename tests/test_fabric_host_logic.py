@@ -173,3 +173,79 @@ def test_deferred_loss_step_ordering_with_fake_plans():
     assert h1.result() == 15.0 and h1.done()
     assert h2.result() == 3.0 and h3.result() == 15.0
     assert eng.ranks[0].step == 4
+
+
+def test_train_loop_host_logic_with_a_fake_native_loop():
+    """``PSTrainEngine.train_loop`` without a GPU: the first steps of a process go through ``step()`` until the plans are
+    graphed, the rest is ONE ``dtf_run_loop`` call whose arguments (plans, streams, batch walk, parity, prefetch state, loss
+    rows) are checked here; the loss rows the native loop fills come back summed per step."""
+    import ctypes
+    import numpy as np
+    import torch
+    from types import SimpleNamespace
+    from distributed_tensorflow_b200.ops.cuda_lib import LoopArgs, StepOp
+    from distributed_tensorflow_b200.parallel.ps_engine import PSTrainEngine
+
+    calls = []
+
+    class Plan:
+        def __init__(self, n, stream):
+            self.n, self.ops, self.stream = n, (StepOp * n)(), stream
+
+    class Lib:
+        def dtf_run_loop(self, ref):
+            a = ctypes.cast(ref, ctypes.POINTER(LoopArgs)).contents
+            calls.append({k: getattr(a, k) for k in ("device", "steps", "depth", "parity", "prefetched", "x_op", "y_op", "n_ps", "copy_stream",
+                                                     "stream", "ps_stream", "x_base", "y_base", "x_stride", "y_stride", "nbatches", "first",
+                                                     "batch_step", "loss_src", "loss_bytes", "loss_row_bytes")})
+            calls[-1]["n_copy"], calls[-1]["copy_ops"] = list(a.n_copy), list(a.copy_ops)
+            rows = np.ctypeslib.as_array(ctypes.cast(a.loss_host, ctypes.POINTER(ctypes.c_float)), shape=(a.steps, 16))
+            for i in range(a.steps):
+                rows[i, :] = 100.0                       # beyond head_ctas: must not be summed
+                rows[i, :2] = [i, 0.5]
+            a.kernels, a.parity = 2 * a.steps, (a.parity + a.steps) & 1
+            return 0
+
+    eng = PSTrainEngine.__new__(PSTrainEngine)
+    eng.cfg = SimpleNamespace(sync=True, num_workers=2, colocated=False)
+    eng.spec = SimpleNamespace(batch=4, in_dim=8, classes=2)
+    eng.worker_ranks, eng.ps_ranks, eng.head_ctas, eng.lib = [0, 1], [0], 2, Lib()
+    eng.ranks = {1: SimpleNamespace(step=0, device=SimpleNamespace(index=3))}
+    eng._w = {1: {"loss_ptr": 0xbeef}}
+    eng._is_pinned_f32 = lambda t: isinstance(t, torch.Tensor)
+    cp, cm, ps = [Plan(4, 0x58), Plan(4, 0x58)], [Plan(3, 0x57), Plan(3, 0x57)], Plan(1, 0x59)
+    stepped = []
+    eng._native_plans = plans = {"copy": {1: cp}, "compute": {1: cm}, "ps": {1: ps}, "loss": {}, "pending": {}, "keep": [], "runs": 2,
+                                 "parity": 0, "prefetched": None, "loss_async": {}}
+
+    def fake_step(x, y, sync_loss=True, **kw):
+        stepped.append(int(x[0, 0]))
+        plans["runs"] += 1
+        plans["parity"] ^= 1
+        if plans["runs"] == 4:
+            plans["graphed"] = True
+        return 7.0
+    eng.step = fake_step
+    xb = torch.arange(5, dtype=torch.float32).view(5, 1, 1).expand(5, 4, 8).contiguous()
+    yb = torch.zeros(5, 4, 2)
+    out = eng.train_loop(xb, yb, steps=6, first=3, stride=2, depth=3)
+    assert stepped == [3, 0]                              # batches (3 + 2 i) % 5 of the two eager steps
+    assert len(calls) == 1
+    c = calls[0]
+    assert (c["device"], c["steps"], c["depth"], c["parity"], c["prefetched"], c["x_op"], c["y_op"]) == (3, 4, 3, 0, 0, 1, 2)
+    assert (c["n_ps"], c["copy_stream"], c["stream"], c["ps_stream"]) == (1, 0x58, 0x57, 0x59)
+    assert (c["x_base"], c["y_base"], c["x_stride"], c["y_stride"]) == (xb.data_ptr(), yb.data_ptr(), 4 * 8 * 4, 4 * 2 * 4)
+    assert (c["nbatches"], c["first"], c["batch_step"]) == (5, (3 + 2 * 2) % 5, 2)
+    assert (c["loss_src"], c["loss_bytes"], c["loss_row_bytes"]) == (0xbeef, 8, 64)
+    assert c["n_copy"] == [4, 4] and c["copy_ops"] == [ctypes.addressof(cp[0].ops), ctypes.addressof(cp[1].ops)]
+    np.testing.assert_allclose(out, [7.0, 7.0, 0.5, 1.5, 2.5, 3.5])
+    assert eng.ranks[1].step == 4 and plans["runs"] == 8 and plans["parity"] == 0 and plans["prefetched"] is None
+    # a batch that step() prefetched for exactly this parity is not copied again
+    plans["prefetched"] = (xb[1].data_ptr(), yb[1].data_ptr(), 0)
+    eng.train_loop(xb, yb, steps=1, first=1)
+    assert calls[-1]["prefetched"] == 1 and calls[-1]["steps"] == 1
+    # several local workers (in-graph replication) or unpinned inputs: step() per step
+    eng.ranks[0] = SimpleNamespace(step=0, device=SimpleNamespace(index=2))
+    n = len(calls)
+    out = eng.train_loop(xb, yb, steps=3)
+    assert len(calls) == n and list(out) == [7.0] * 3

@@ -81,3 +81,86 @@ def test_error_index_device_switch_and_capture(host):
     assert ex.value == 0xe1 and nk.value == 2
     assert host.step_emu_trace().decode().splitlines() == ["begin_capture stream=0x57", "gemm args=0x1 stream=0x57", "head args=0x2 stream=0x57",
                                                            "end_capture stream=0x57", "instantiate graph=0x6a", "graph_destroy 0x6a"]
+
+
+def _loop_args(host, steps, depth, prefetched=0, ps=True, parity=0, first=3, batch_step=2, nb=5):
+    from distributed_tensorflow_b200.ops.cuda_lib import LoopArgs
+    assert host.dtf_sizeof_loop_args() == ctypes.sizeof(LoopArgs)
+    host.dtf_run_loop.argtypes = [ctypes.POINTER(LoopArgs)]
+    keep = []
+    a = LoopArgs()
+    a.device, a.steps, a.depth, a.parity, a.prefetched, a.x_op, a.y_op = 2, steps, depth, parity, prefetched, 1, 2
+    for p in range(2):
+        cops = (StepOp * 4)(StepOp(kind=OP_EVENT_WAIT, p0=0xd0 + p), StepOp(kind=OP_H2D, p0=0x1000 + p, i0=400),
+                            StepOp(kind=OP_H2D, p0=0x2000 + p, i0=40), StepOp(kind=OP_EVENT_RECORD, p0=0xa0 + p))
+        mops = (StepOp * 3)(StepOp(kind=OP_EVENT_WAIT, p0=0xa0 + p), StepOp(kind=OP_GRAPH, p0=0x900 + p, i0=2),
+                            StepOp(kind=OP_EVENT_RECORD, p0=0xd0 + p))
+        keep += [cops, mops]
+        a.n_copy[p], a.n_compute[p] = 4, 3
+        a.copy_ops[p], a.compute_ops[p] = ctypes.addressof(cops), ctypes.addressof(mops)
+    if ps:
+        pops = (StepOp * 1)(StepOp(kind=OP_PS_APPLY, p0=0x300))
+        keep.append(pops)
+        a.n_ps, a.ps_ops, a.ps_stream = 1, ctypes.addressof(pops), 0x59
+    a.copy_stream, a.stream = 0x58, 0x57
+    a.x_base, a.y_base, a.x_stride, a.y_stride = 0x100000, 0x200000, 0x1000, 0x100
+    a.nbatches, a.first, a.batch_step = nb, first, batch_step
+    a.loss_src, a.loss_bytes, a.loss_host, a.loss_row_bytes = 0xbeef, 28, 0x300000, 64
+    return a, keep
+
+
+def test_native_loop_orders_copies_kernels_loss_reads_and_bounds_the_run_ahead(host):
+    host.step_emu_reset(0, 0)
+    a, keep = _loop_args(host, steps=4, depth=2)
+    assert host.dtf_run_loop(ctypes.byref(a)) == 0
+    t = host.step_emu_trace().decode().splitlines()
+    batches = [(3 + 2 * i) % 5 for i in range(4)]                     # 3, 0, 2, 4
+
+    def copy(par, b):
+        return ["event_wait ev=0x%x stream=0x58" % (0xd0 + par),
+                "memcpy h2d dst=0x%x src=0x%x n=400 stream=0x58" % (0x1000 + par, 0x100000 + b * 0x1000),
+                "memcpy h2d dst=0x%x src=0x%x n=40 stream=0x58" % (0x2000 + par, 0x200000 + b * 0x100),
+                "event_record ev=0x%x stream=0x58" % (0xa0 + par)]
+
+    def compute(par):
+        return ["event_wait ev=0x%x stream=0x57" % (0xa0 + par), "graph_launch exec=0x%x stream=0x57" % (0x900 + par),
+                "event_record ev=0x%x stream=0x57" % (0xd0 + par), "ps_apply args=0x300 stream=0x59"]
+
+    def loss(i, ev):
+        return ["memcpy d2h dst=0x%x src=0xbeef n=28 stream=0x57" % (0x300000 + 64 * i), "event_record ev=0x%x stream=0x57" % ev]
+
+    want = ["setdevice 2", "event_create ev=0xe000 flags=2", "event_create ev=0xe001 flags=2"]
+    want += copy(0, batches[0])
+    want += compute(0) + copy(1, batches[1]) + loss(0, 0xe000)
+    want += compute(1) + copy(0, batches[2]) + loss(1, 0xe001)
+    want += ["event_sync ev=0xe000"] + compute(0) + copy(1, batches[3]) + loss(2, 0xe000)     # step 2 waits for the loss of step 0
+    want += ["event_sync ev=0xe001"] + compute(1) + loss(3, 0xe001)                            # no copy after the last step
+    want += ["event_sync ev=0xe001", "event_destroy ev=0xe000", "event_destroy ev=0xe001", "setdevice 0"]
+    assert t == want
+    assert (a.parity, a.prefetched, a.kernels, a.waited) == (0, 0, 4 * 3, 3)
+
+
+def test_native_loop_prefetched_first_batch_odd_parity_short_runs_and_errors(host):
+    host.step_emu_reset(0, 0)
+    a, keep = _loop_args(host, steps=1, depth=4, prefetched=1, ps=False, parity=1)
+    assert host.dtf_run_loop(ctypes.byref(a)) == 0
+    t = host.step_emu_trace().decode().splitlines()
+    assert t == ["setdevice 2", "event_create ev=0xe000 flags=2",
+                 "event_wait ev=0xa1 stream=0x57", "graph_launch exec=0x901 stream=0x57", "event_record ev=0xd1 stream=0x57",
+                 "memcpy d2h dst=0x300000 src=0xbeef n=28 stream=0x57", "event_record ev=0xe000 stream=0x57",
+                 "event_sync ev=0xe000", "event_destroy ev=0xe000", "setdevice 0"]
+    assert (a.parity, a.kernels) == (0, 2)
+    host.step_emu_reset(0, 0)
+    a, keep = _loop_args(host, steps=0, depth=2)
+    assert host.dtf_run_loop(ctypes.byref(a)) == 0 and a.kernels == 0
+    assert not any(l.startswith(("memcpy", "graph")) for l in host.step_emu_trace().decode().splitlines())
+    for bad in (dict(depth=0), dict(depth=65), dict(nb=0)):
+        a, keep = _loop_args(host, steps=2, **{"depth": 2, **bad})
+        assert host.dtf_run_loop(ctypes.byref(a)) == -1
+    a, keep = _loop_args(host, steps=2, depth=2)
+    a.x_op = 9
+    assert host.dtf_run_loop(ctypes.byref(a)) == -2
+    host.step_emu_reset(100, 2)                                        # event creation fails: nothing is enqueued
+    a, keep = _loop_args(host, steps=3, depth=2)
+    assert host.dtf_run_loop(ctypes.byref(a)) == 2
+    assert not any(l.startswith(("memcpy", "graph", "event_destroy")) for l in host.step_emu_trace().decode().splitlines())
