@@ -691,13 +691,19 @@ def main():
                     raise                # ranks must not diverge
                 e2e["pipelined_error"] = repr(e)[:300]
         if args.e2e_native_loop and ((world == 1 and is_worker) or pow_):
-            # third arm: the framework's own training loop (one native call per K steps)
+            # third arm: the framework's own training loop (one native call per K steps).  A failure on any rank drops the
+            # arm on every rank (the flag is agreed on before anything is recorded); the other arms' numbers stand.
+            nt, nerr = None, None
             try:
                 nt = measure_e2e(e2e_k_steps_native)
+            except Exception as e:      # noqa: BLE001
+                nerr = repr(e)[:300]
+            nlast = allmax([last[0] if (last[0] is not None and nerr is None) else -1e30])[0]
+            failed = allmax([1.0 if (nerr is not None or not math.isfinite(nlast)) else 0.0])[0] > 0
+            if failed:
+                e2e["native_loop_error"] = nerr or "non-finite loss %r or a failure on another rank" % (nlast,)
+            else:
                 nems = statistics.median(t[0] for t in nt)
-                nlast = allmax([last[0] if last[0] is not None else -1e30])[0]
-                if not math.isfinite(nlast):
-                    raise RuntimeError("native loop returned loss %r" % (nlast,))
                 if "synchronous" not in e2e:
                     e2e["synchronous"] = {k: e2e[k] for k in ("value", "ms_per_step", "wall_ms_per_step", "last_loss")}
                 nat_part = {"value": per_step / (nems / 1e3), "ms_per_step": nems / K,
@@ -710,10 +716,6 @@ def main():
                     e2e["loss_read"] = ("every step's loss is copied D2H behind its kernels into its own pinned row; the host waits "
                                         "for row i-%d before enqueuing step i and reads all K rows" % args.e2e_depth)
                     e2e["input_double_buffering"] = True
-            except Exception as e:      # noqa: BLE001 - keep the measurements of the other arms
-                if world > 1:
-                    raise                # ranks must not diverge
-                e2e["native_loop_error"] = repr(e)[:300]
 
     # ---- ps traffic implied by the measured step time (BASELINE metric: push/pull GB/s vs 900 GB/s/dir) -----------
     # true-shape bytes: gradients travel as fp32, parameters as fp32 (tf32 engines) / bf16 replicas; every worker moves both every step.
