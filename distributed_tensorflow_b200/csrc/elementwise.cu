@@ -15,6 +15,7 @@
 #else
 #include "common.cuh"
 #endif
+#include "philox.h"
 
 namespace dtf {
 
@@ -53,6 +54,104 @@ __global__ void convert_u8_bf16_kernel(const uint8_t* __restrict__ in, __nv_bflo
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16((float)in[i] * scale);
 }
+
+// ---------------------------------------------------------------------------------------------
+// K13: random initialisers.  One thread per Philox block of four values (csrc/philox.h defines the stream; the CPU tier
+// draws the same values from the same definition).  out[i], i in [0, n): word i % 4 of block `offset + i / 4`.
+// ---------------------------------------------------------------------------------------------
+__global__ void philox_fill_kernel(float* __restrict__ out, long long n, unsigned long long key, unsigned long long offset,
+                                   unsigned long long stream_id, int kind, float p0, float p1) {
+  const long long nblk = (n + 3) / 4;
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
+    const dtf_rng::Block blk = dtf_rng::philox4x32_10(offset + (unsigned long long)b, stream_id, key);
+    float v[4];
+    dtf_rng::block_values(blk, kind, p0, p1, v);
+    const long long i = b * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (i + j < n) out[i + j] = v[j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K9: element-wise graph ops (the linear-regression programs: example_between_graph.py:55-60 `y = weight * x + biase`,
+// `tf.square(y_ - y)`, tf.reduce_mean; the in-graph example's matmul results added up).  fp32, contiguous.
+//   binary: out[i] = f(a[ia], b[ib]);  an operand is indexed by i (full), 0 (scalar) or i % inner (a trailing-dims vector
+//   broadcast over the leading dims) -- the broadcasts these programs use.
+// ---------------------------------------------------------------------------------------------
+enum { EW_ADD = 0, EW_SUB = 1, EW_MUL = 2, EW_DIV = 3, EW_MAX = 4, EW_MIN = 5, EW_SQDIFF = 6 };
+enum { EW_NEG = 0, EW_SQUARE = 1, EW_SQRT = 2, EW_RSQRT = 3, EW_EXP = 4, EW_LOG = 5, EW_ABS = 6, EW_SIGMOID = 7, EW_TANH = 8,
+       EW_RELU = 9 };
+enum { EW_FULL = 0, EW_SCALAR = 1, EW_INNER = 2 };
+
+DTF_DEVICE float ew_binary(int op, float x, float y) {
+  switch (op) {
+    case EW_ADD: return x + y;
+    case EW_SUB: return x - y;
+    case EW_MUL: return x * y;
+    case EW_DIV: return x / y;
+    case EW_MAX: return fmaxf(x, y);
+    case EW_MIN: return fminf(x, y);
+    default: { const float d = x - y; return d * d; }
+  }
+}
+
+DTF_DEVICE float ew_unary(int op, float x) {
+  switch (op) {
+    case EW_NEG: return -x;
+    case EW_SQUARE: return x * x;
+    case EW_SQRT: return sqrtf(x);
+    case EW_RSQRT: return 1.0f / sqrtf(x);
+    case EW_EXP: return expf(x);
+    case EW_LOG: return logf(x);
+    case EW_ABS: return fabsf(x);
+    case EW_SIGMOID: return 1.0f / (1.0f + expf(-x));
+    case EW_TANH: return tanhf(x);
+    default: return x > 0.0f ? x : 0.0f;
+  }
+}
+
+__global__ void ew_binary_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n,
+                                 int op, int mode_a, int mode_b, long long inner) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = a[mode_a == EW_FULL ? i : (mode_a == EW_SCALAR ? 0 : i % inner)];
+    const float y = b[mode_b == EW_FULL ? i : (mode_b == EW_SCALAR ? 0 : i % inner)];
+    out[i] = ew_binary(op, x, y);
+  }
+}
+
+__global__ void ew_unary_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, int op) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = ew_unary(op, x[i]);
+}
+
+// out[i] = alpha * x[i or 0] + beta: scalings, negation, and the broadcast of a scalar gradient (the backward of a full reduction)
+__global__ void ew_affine_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, int mode, float alpha, float beta) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = alpha * x[mode == EW_FULL ? i : 0] + beta;
+}
+
+// out[0] += scale * sum(x) (out zeroed by the launcher): warp shuffles -> one shared-memory row per block -> one atomic per
+// block.  `square`: sum of squares (the mean-squared-error reduction in one pass).
+__global__ void ew_reduce_sum_kernel(const float* __restrict__ x, long long n, float scale, int square, float* __restrict__ out) {
+  __shared__ float part[8];
+  float acc = 0.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    acc += square ? v * v : v;
+  }
+  acc = warp_sum(acc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) part[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float v = lane < (int)(blockDim.x >> 5) ? part[lane] : 0.0f;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(out, v * scale);
+  }
+}
+
+// element-wise binary / unary kernels above walk fp32; everything else stays with the op layer
 
 // ---------------------------------------------------------------------------------------------
 // fused softmax + cross-entropy, forward and backward in one pass (one warp per row)
@@ -326,6 +425,48 @@ int dtf_softmax_xent(const float* logits, long long ld_logits, const float* labe
   DTF_LAUNCH(softmax_xent_kernel, (rows + wpb - 1) / wpb, wpb * 32, s,
       logits, ld_logits, labels, ld_labels, rows, cols, clip_min, loss_sum, loss_rows, dlogits, ld_d,
       reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ld_db, cols_pad_bf16, probs, ld_p, grad_scale);
+  return (int)cudaGetLastError();
+}
+
+int dtf_philox_fill(float* out, long long n, unsigned long long key, unsigned long long offset, unsigned long long stream_id,
+                    int kind, float p0, float p1, cudaStream_t s) {
+  if (n < 0 || kind < 0 || kind > 2 || (n > 0 && out == nullptr)) return -1;
+  if (n == 0) return 0;
+  DTF_LAUNCH(philox_fill_kernel, grid_for((n + 3) / 4), 256, s, out, n, key, offset, stream_id, kind, p0, p1);
+  return (int)cudaGetLastError();
+}
+
+int dtf_ew_binary(const float* a, const float* b, float* out, long long n, int op, int mode_a, int mode_b, long long inner,
+                  cudaStream_t s) {
+  if (n < 0 || op < 0 || op > 6 || mode_a < 0 || mode_a > 2 || mode_b < 0 || mode_b > 2) return -1;
+  if ((mode_a == 2 || mode_b == 2) && inner < 1) return -1;
+  if (n == 0) return 0;
+  DTF_LAUNCH(ew_binary_kernel, grid_for(n), 256, s, a, b, out, n, op, mode_a, mode_b, inner);
+  return (int)cudaGetLastError();
+}
+
+int dtf_ew_unary(const float* x, float* out, long long n, int op, cudaStream_t s) {
+  if (n < 0 || op < 0 || op > 9) return -1;
+  if (n == 0) return 0;
+  DTF_LAUNCH(ew_unary_kernel, grid_for(n), 256, s, x, out, n, op);
+  return (int)cudaGetLastError();
+}
+
+int dtf_ew_affine(const float* x, float* out, long long n, int mode, float alpha, float beta, cudaStream_t s) {
+  if (n < 0 || mode < 0 || mode > 1) return -1;
+  if (n == 0) return 0;
+  DTF_LAUNCH(ew_affine_kernel, grid_for(n), 256, s, x, out, n, mode, alpha, beta);
+  return (int)cudaGetLastError();
+}
+
+// out[0] = scale * sum(x) or scale * sum(x^2).  `out` must not alias x.
+int dtf_ew_reduce_sum(const float* x, long long n, float scale, int square, float* out, cudaStream_t s) {
+  if (n < 0 || out == nullptr) return -1;
+  int rc = (int)cudaMemsetAsync(out, 0, sizeof(float), s);
+  if (rc != 0 || n == 0) return rc;
+  long long blocks = (n + 256 * 8 - 1) / (256 * 8);           // >= 8 elements per thread before another block is worth an atomic
+  if (blocks > 592) blocks = 592;
+  DTF_LAUNCH(ew_reduce_sum_kernel, (int)blocks, 256, s, x, n, scale, square, out);
   return (int)cudaGetLastError();
 }
 

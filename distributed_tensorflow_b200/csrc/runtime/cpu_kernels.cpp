@@ -9,6 +9,8 @@
 #include <cmath>
 #include <cstdint>
 
+#include "../philox.h"
+
 // The loops are compiled twice (AVX2+FMA and baseline x86-64) and dispatched at load time (GCC function
 // multi-versioning): the library is built on one machine and shipped to others, so -march=native is not an option.
 #if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
@@ -62,6 +64,32 @@ int dtf_cpu_optimizer_apply(int kind, float* __restrict__ var, float* __restrict
     return 0;
   }
   return -1;
+}
+
+// Random fill of the CPU tier (initialisers of variables living on a /cpu:0 parameter server): the stream defined in
+// csrc/philox.h, i.e. the values the GPU kernel philox_fill_kernel (csrc/elementwise.cu) draws for the same (key, offset).
+// kind: 0 uniform [p0, p1), 1 normal(mean p0, stddev p1), 2 truncated normal (|z| <= 2).  Returns 0, or -1 on bad arguments.
+int dtf_cpu_philox_fill(float* out, long long n, unsigned long long key, unsigned long long offset, unsigned long long stream_id,
+                        int kind, float p0, float p1) {
+  if (n < 0 || kind < 0 || kind > 2 || (n > 0 && out == nullptr)) return -1;
+  const long long nblk = (n + 3) / 4;
+  for (long long b = 0; b < nblk; ++b) {
+    const dtf_rng::Block blk = dtf_rng::philox4x32_10(offset + (unsigned long long)b, stream_id, key);
+    float v[4];
+    dtf_rng::block_values(blk, kind, p0, p1, v);
+    for (int j = 0; j < 4 && b * 4 + j < n; ++j) out[b * 4 + j] = v[j];
+  }
+  return 0;
+}
+
+// The raw 32-bit words of `nblk` blocks (known-answer tests of the generator itself).
+int dtf_cpu_philox_words(unsigned int* out, long long nblk, unsigned long long key, unsigned long long ctr_lo, unsigned long long ctr_hi) {
+  if (nblk < 0 || (nblk > 0 && out == nullptr)) return -1;
+  for (long long b = 0; b < nblk; ++b) {
+    const dtf_rng::Block blk = dtf_rng::philox4x32_10(ctr_lo + (unsigned long long)b, ctr_hi, key);
+    for (int j = 0; j < 4; ++j) out[b * 4 + j] = blk.w[j];
+  }
+  return 0;
 }
 
 }  // extern "C"

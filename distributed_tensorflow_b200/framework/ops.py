@@ -182,54 +182,72 @@ def random_uniform(shape, minval=0.0, maxval=1.0, dtype=float32, seed=None, name
     return _fill("RandomUniform", shape, dtype, name, minval=float(minval), maxval=float(maxval), seed=seed)
 
 
-def _gen(ctx, node):
-    """The random stream of ONE op, TF style: seeded from (graph-level seed, op-level seed, the op's identity) and STATEFUL --
-    it lives in the executing task's resource store, so every execution of the op continues it (a seeded op does not
-    return the same tensor every step), two same-shaped initialisers draw different values even when they sit on
-    different tasks, and a fresh store (a new local Session, a restarted ps) replays the same sequence.  With neither
-    seed the stream is seeded from entropy."""
+class _OpStream:
+    """The random stream of ONE op: a Philox key + the next unused block (``csrc/philox.h``)."""
+    __slots__ = ("key", "offset", "lock")
+
+    def __init__(self, key: int):
+        import threading
+        self.key, self.offset, self.lock = key & (2 ** 64 - 1), 0, threading.Lock()
+
+    def take(self, blocks: int) -> int:
+        with self.lock:
+            at = self.offset
+            self.offset += int(blocks)
+            return at
+
+
+def _op_stream(ctx, node) -> _OpStream:
+    """TF-style per-op stream: keyed by (graph-level seed, op-level seed, the op's identity) and STATEFUL -- it lives in the
+    executing task's resource store, so every execution of the op continues it (a seeded op does not return the same tensor
+    every step), two same-shaped initialisers draw different values even when they sit on different tasks, and a fresh
+    store (a new local Session, a restarted ps) replays the same sequence.  With neither seed the key comes from entropy.
+    The stream is counter-based (Philox4x32-10): the same (key, offset) yields the same values on a CPU task and on a GPU
+    task (``ops/random_ops.py``)."""
+    import os as _os
     import zlib
     op_seed = node.attrs.get("seed")
     graph_seed = ctx._seed if getattr(ctx, "_seed", None) is not None else getattr(node.graph, "seed", None)
     store = ctx.store
     with store._lock:
-        gens = store.__dict__.setdefault("_rng_streams", {})
+        streams = store.__dict__.setdefault("_rng_streams", {})
         key = node.name if node.name else "node%d" % node.id
-        g = gens.get(key)
-        if g is None:
-            g = torch.Generator(device="cpu")
+        st = streams.get(key)
+        if st is None:
             if op_seed is None and graph_seed is None:
-                g.seed()
+                k = int.from_bytes(_os.urandom(8), "little")
             else:
-                mix = (int(graph_seed or 0) * 1000003) ^ (int(op_seed or 0) * 7919 + (1 if op_seed is not None else 0)) \
+                k = (int(graph_seed or 0) * 1000003) ^ (int(op_seed or 0) * 7919 + (1 if op_seed is not None else 0)) \
                     ^ (zlib.crc32(key.encode()) << 17)
-                g.manual_seed(mix & ((1 << 63) - 1))
-            gens[key] = g
-    return g
+                k = (k * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019) & (2 ** 64 - 1)      # spread small seeds over the key bits
+            st = streams[key] = _OpStream(k)
+    return st
+
+
+def _random_fill(ctx, node, kind: int, p0: float, p1: float, shape=None, device=None) -> torch.Tensor:
+    from ..ops import random_ops
+    shape = tuple(node.attrs["shape"]) if shape is None else tuple(shape)
+    st = _op_stream(ctx, node)
+    at = st.take(random_ops.blocks_used(shape))
+    return random_ops.philox_fill(shape, kind, p0, p1, st.key, at, device if device is not None else ctx.torch_device(node))
 
 
 @register_kernel("TruncatedNormal")
 def _k_tn(ctx, node):
-    # resample-beyond-2-sigma semantics (SURVEY A7); drawn on host so CPU and GPU tasks agree bit-for-bit
     a = node.attrs
-    t = torch.empty(a["shape"], dtype=torch.float32)
-    torch.nn.init.trunc_normal_(t, mean=a["mean"], std=a["stddev"], a=a["mean"] - 2 * a["stddev"],
-                                b=a["mean"] + 2 * a["stddev"], generator=_gen(ctx, node))
-    return t.to(device=ctx.torch_device(node), dtype=a["dtype"])
+    return _random_fill(ctx, node, 2, a["mean"], a["stddev"]).to(dtype=a["dtype"])
 
 
 @register_kernel("RandomNormal")
 def _k_rn(ctx, node):
     a = node.attrs
-    t = torch.empty(a["shape"], dtype=torch.float32).normal_(a["mean"], a["stddev"], generator=_gen(ctx, node))
-    return t.to(device=ctx.torch_device(node), dtype=a["dtype"])
+    return _random_fill(ctx, node, 1, a["mean"], a["stddev"]).to(dtype=a["dtype"])
 
 
 @register_kernel("RandomUniform")
 def _k_ru(ctx, node):
     a = node.attrs
-    t = torch.empty(a["shape"], dtype=torch.float32).uniform_(a["minval"], a["maxval"], generator=_gen(ctx, node))
-    return t.to(device=ctx.torch_device(node), dtype=a["dtype"])
+    return _random_fill(ctx, node, 0, a["minval"], a["maxval"]).to(dtype=a["dtype"])
 
 
 # ---------------------------------------------------------------------------
@@ -269,24 +287,30 @@ def stop_gradient(x, name="StopGradient"): return _unary("StopGradient", x, name
 
 sub, mul, div, neg = subtract, multiply, divide, negative
 
-register_kernel("Add")(lambda ctx, n, a, b: a + b)
-register_kernel("Sub")(lambda ctx, n, a, b: a - b)
-register_kernel("Mul")(lambda ctx, n, a, b: a * b)
-register_kernel("RealDiv")(lambda ctx, n, a, b: a / b)
+
+def _native_ew():
+    """K9: fp32 tensors on /gpu run the ew_* kernels of csrc/elementwise.cu (forward and backward), see ops/native.py."""
+    from ..ops import native
+    return native
+
+register_kernel("Add")(lambda ctx, n, a, b: _native_ew().binary("add", a, b))
+register_kernel("Sub")(lambda ctx, n, a, b: _native_ew().binary("sub", a, b))
+register_kernel("Mul")(lambda ctx, n, a, b: _native_ew().binary("mul", a, b))
+register_kernel("RealDiv")(lambda ctx, n, a, b: _native_ew().binary("div", a, b))
 register_kernel("Maximum")(lambda ctx, n, a, b: torch.maximum(a, b))
 register_kernel("Minimum")(lambda ctx, n, a, b: torch.minimum(a, b))
 register_kernel("Pow")(lambda ctx, n, a, b: torch.pow(a, b))
-register_kernel("SquaredDifference")(lambda ctx, n, a, b: (a - b) * (a - b))
-register_kernel("Neg")(lambda ctx, n, x: -x)
-register_kernel("Square")(lambda ctx, n, x: x * x)
-register_kernel("Sqrt")(lambda ctx, n, x: torch.sqrt(x))
+register_kernel("SquaredDifference")(lambda ctx, n, a, b: _native_ew().binary("sqdiff", a, b))
+register_kernel("Neg")(lambda ctx, n, x: _native_ew().unary("neg", x))
+register_kernel("Square")(lambda ctx, n, x: _native_ew().unary("square", x))
+register_kernel("Sqrt")(lambda ctx, n, x: _native_ew().unary("sqrt", x))
 register_kernel("Rsqrt")(lambda ctx, n, x: torch.rsqrt(x))
-register_kernel("Exp")(lambda ctx, n, x: torch.exp(x))
-register_kernel("Log")(lambda ctx, n, x: torch.log(x))
+register_kernel("Exp")(lambda ctx, n, x: _native_ew().unary("exp", x))
+register_kernel("Log")(lambda ctx, n, x: _native_ew().unary("log", x))
 register_kernel("Abs")(lambda ctx, n, x: torch.abs(x))
-register_kernel("Sigmoid")(lambda ctx, n, x: torch.sigmoid(x))
-register_kernel("Tanh")(lambda ctx, n, x: torch.tanh(x))
-register_kernel("Relu")(lambda ctx, n, x: torch.relu(x))
+register_kernel("Sigmoid")(lambda ctx, n, x: _native_ew().unary("sigmoid", x))
+register_kernel("Tanh")(lambda ctx, n, x: _native_ew().unary("tanh", x))
+register_kernel("Relu")(lambda ctx, n, x: _native_ew().unary("relu", x))
 register_kernel("Identity")(lambda ctx, n, x: x)
 register_kernel("StopGradient")(lambda ctx, n, x: x.detach())
 
@@ -392,7 +416,7 @@ def _red(fn_all, fn_dim):
     return k
 
 
-register_kernel("Sum")(_red(lambda x: x.sum(), lambda x, a, k: x.sum(dim=a, keepdim=k)))
+register_kernel("Sum")(_red(lambda x: _native_ew().reduce_all(x, False), lambda x, a, k: x.sum(dim=a, keepdim=k)))
 def _mean_over(x, a, k):
     # NHWC global average pooling (mean over H, W of a 4-D tensor, ResNet's classifier input): our pooling kernel on /gpu
     # when the fused NN kernels are enabled; plain mean otherwise
@@ -402,7 +426,7 @@ def _mean_over(x, a, k):
     return x.mean(dim=a, keepdim=k)
 
 
-register_kernel("Mean")(_red(lambda x: x.mean(), _mean_over))
+register_kernel("Mean")(_red(lambda x: _native_ew().reduce_all(x, True), _mean_over))
 register_kernel("Max")(_red(lambda x: x.max(), lambda x, a, k: x.amax(dim=a, keepdim=k)))
 register_kernel("Min")(_red(lambda x: x.min(), lambda x, a, k: x.amin(dim=a, keepdim=k)))
 
@@ -737,8 +761,8 @@ def _k_dropout(ctx, n, x):
     seeded = n.attrs.get("seed") is not None or getattr(ctx, "_seed", None) is not None or getattr(n.graph, "seed", None) is not None
     if not seeded or r <= 0.0:
         return F.dropout(x, r, training=True)
-    # reproducible mask from the op's own stream (drawn on the host so CPU and GPU tasks agree), inverted-dropout scaling
-    keep = (torch.rand(x.shape, generator=_gen(ctx, n)) >= r).to(device=x.device, dtype=x.dtype)
+    # reproducible mask from the op's own counter-based stream (CPU and GPU tasks draw the same mask), inverted-dropout scaling
+    keep = (_random_fill(ctx, n, 0, 0.0, 1.0, shape=x.shape, device=x.device) >= r).to(dtype=x.dtype)
     return x * keep / (1.0 - r)
 
 

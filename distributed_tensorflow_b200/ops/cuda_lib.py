@@ -280,6 +280,17 @@ def _declare(lib) -> None:
         assert lib.dtf_sizeof_loop_args() == ctypes.sizeof(LoopArgs), "LoopArgs layout mismatch"
     if not isinstance(lib.dtf_sizeof_step_op, _Missing):
         assert lib.dtf_sizeof_step_op() == ctypes.sizeof(StepOp), "StepOp layout mismatch"
+    if not isinstance(getattr(lib, "dtf_philox_fill", _Missing()), _Missing):    # random fills + element-wise graph ops (K13, K9)
+        lib.dtf_philox_fill.argtypes = [c_void_p, c_longlong, c_ulonglong, c_ulonglong, c_ulonglong, c_int, c_float, c_float, c_void_p]
+        lib.dtf_philox_fill.restype = c_int
+        lib.dtf_ew_binary.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_longlong, c_void_p]
+        lib.dtf_ew_binary.restype = c_int
+        lib.dtf_ew_unary.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_void_p]
+        lib.dtf_ew_unary.restype = c_int
+        lib.dtf_ew_affine.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_float, c_float, c_void_p]
+        lib.dtf_ew_affine.restype = c_int
+        lib.dtf_ew_reduce_sum.argtypes = [c_void_p, c_longlong, c_float, c_int, c_void_p, c_void_p]
+        lib.dtf_ew_reduce_sum.restype = c_int
     if not isinstance(getattr(lib, "dtf_bn_reduce", _Missing()), _Missing):    # csrc/nn_kernels.cu (a stale build lacks it)
         lib.dtf_bn_row_splits.argtypes = [c_longlong, c_int]
         lib.dtf_bn_row_splits.restype = c_int
@@ -655,6 +666,102 @@ def softmax_xent_fwd_bwd(logits: torch.Tensor, labels: torch.Tensor, clip_min: f
                                     dl.data_ptr(), cols, None, 0, 0, None, 0, 1.0, _stream(logits)), "softmax_xent")
     _bump()
     return loss, dl
+
+
+# ---------------------------------------------------------------------------------------------------
+# random fills (K13) and element-wise graph ops (K9): csrc/elementwise.cu
+# ---------------------------------------------------------------------------------------------------
+PHILOX_UNIFORM, PHILOX_NORMAL, PHILOX_TRUNCATED_NORMAL = 0, 1, 2
+EW_BINARY = {"add": 0, "sub": 1, "mul": 2, "div": 3, "max": 4, "min": 5, "sqdiff": 6}
+EW_UNARY = {"neg": 0, "square": 1, "sqrt": 2, "rsqrt": 3, "exp": 4, "log": 5, "abs": 6, "sigmoid": 7, "tanh": 8, "relu": 9}
+_EW_FULL, _EW_SCALAR, _EW_INNER = 0, 1, 2
+
+
+def philox_fill(out: torch.Tensor, kind: int, p0: float, p1: float, key: int, offset: int, stream_id: int = 0) -> torch.Tensor:
+    """Fill the contiguous fp32 tensor ``out`` from the Philox stream ``(key, stream_id)`` starting at block ``offset``
+    (``csrc/philox.h``: element i = word i % 4 of block offset + i // 4).  Returns ``out``."""
+    assert out.dtype == torch.float32 and out.is_contiguous() and _on_device(out)
+    with _on(out.device):
+        _check(load().dtf_philox_fill(out.data_ptr(), out.numel(), key & (2 ** 64 - 1), offset & (2 ** 64 - 1),
+                                      stream_id & (2 ** 64 - 1), int(kind), float(p0), float(p1), _stream(out)), "philox_fill")
+    _bump()
+    return out
+
+
+def ew_broadcast_mode(shape: Sequence[int], other: Sequence[int], out_shape: Sequence[int]) -> Optional[Tuple[int, int]]:
+    """How the kernel indexes an operand of ``shape`` against the broadcast result ``out_shape``: (mode, inner) with mode
+    full / scalar / trailing-dims vector, or None when the pattern needs a general broadcast (the op layer then uses torch)."""
+    shape, out_shape = tuple(shape), tuple(out_shape)
+    n = 1
+    for d in shape:
+        n *= d
+    if shape == out_shape:
+        return (_EW_FULL, 1)
+    if n == 1:
+        return (_EW_SCALAR, 1)
+    core = shape
+    while core and core[0] == 1:
+        core = core[1:]
+    if core and len(core) <= len(out_shape) and tuple(out_shape[len(out_shape) - len(core):]) == core:
+        return (_EW_INNER, n)
+    return None
+
+
+def ew_binary(op: str, a: torch.Tensor, b: torch.Tensor) -> Optional[torch.Tensor]:
+    """``a (op) b`` with numpy broadcasting for the patterns the kernel indexes directly; None = not handled."""
+    if a.dtype != torch.float32 or b.dtype != torch.float32 or a.device != b.device:
+        return None
+    try:
+        out_shape = torch.broadcast_shapes(a.shape, b.shape)
+    except RuntimeError:
+        return None
+    ma, mb = ew_broadcast_mode(a.shape, b.shape, out_shape), ew_broadcast_mode(b.shape, a.shape, out_shape)
+    if ma is None or mb is None:
+        return None
+    a, b = a.contiguous(), b.contiguous()
+    out = torch.empty(out_shape, dtype=torch.float32, device=a.device)
+    inner = ma[1] if ma[0] == _EW_INNER else mb[1]
+    if ma[0] == _EW_INNER and mb[0] == _EW_INNER and ma[1] != mb[1]:
+        return None
+    with _on(a.device):
+        _check(load().dtf_ew_binary(a.data_ptr(), b.data_ptr(), out.data_ptr(), out.numel(), EW_BINARY[op], ma[0], mb[0], inner,
+                                    _stream(a)), "ew_binary(%s)" % op)
+    _bump()
+    return out
+
+
+def ew_unary(op: str, x: torch.Tensor) -> torch.Tensor:
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    with _on(x.device):
+        _check(load().dtf_ew_unary(x.data_ptr(), out.data_ptr(), x.numel(), EW_UNARY[op], _stream(x)), "ew_unary(%s)" % op)
+    _bump()
+    return out
+
+
+def ew_affine(x: torch.Tensor, alpha: float, beta: float = 0.0, out_shape: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """``alpha * x + beta``; with ``out_shape`` the one-element ``x`` is broadcast to that shape."""
+    x = x.contiguous()
+    if out_shape is None:
+        out, mode = torch.empty_like(x), _EW_FULL
+    else:
+        assert x.numel() == 1
+        out, mode = torch.empty(tuple(out_shape), dtype=torch.float32, device=x.device), _EW_SCALAR
+    with _on(x.device):
+        _check(load().dtf_ew_affine(x.data_ptr(), out.data_ptr(), out.numel(), mode, float(alpha), float(beta), _stream(x)), "ew_affine")
+    _bump()
+    return out
+
+
+def ew_reduce_sum(x: torch.Tensor, scale: float = 1.0, square: bool = False) -> torch.Tensor:
+    """0-d tensor ``scale * sum(x)`` (``square``: of the squares) over every element."""
+    x = x.contiguous()
+    out = torch.empty((), dtype=torch.float32, device=x.device)
+    with _on(x.device):
+        _check(load().dtf_ew_reduce_sum(x.data_ptr(), x.numel(), float(scale), int(bool(square)), out.data_ptr(), _stream(x)),
+               "ew_reduce_sum")
+    _bump()
+    return out
 
 
 def relu_grad(g: torch.Tensor, y: torch.Tensor) -> torch.Tensor:

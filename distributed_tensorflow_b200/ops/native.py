@@ -374,3 +374,187 @@ def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, strides: Sequence[int], paddin
         xn = F.pad(xn, (pl, pr, pt, pb))
     y = F.conv2d(xn, w.permute(3, 2, 0, 1), stride=(sh, sw))
     return y.permute(0, 2, 3, 1)
+
+
+# ---------------------------------------------------------------------------
+# element-wise graph ops and full reductions (K9): csrc/elementwise.cu ew_* kernels
+# ---------------------------------------------------------------------------
+# Reference programs: `y = weight * x + biase`, `tf.square(y_ - y)`, `tf.reduce_mean(...)` (example_between_graph.py:55-60),
+# `tf.reduce_sum(y_ * tf.log(...))` (distributed_mnist.py:113).  fp32 tensors on a CUDA device (or host tensors under the
+# kernel emulation) run our kernels forward AND backward; other dtypes / general broadcasts stay with torch.
+_TORCH_BINARY = {"add": torch.add, "sub": torch.sub, "mul": torch.mul, "div": torch.div,
+                 "sqdiff": lambda a, b: (a - b) * (a - b)}
+_TORCH_UNARY = {"neg": torch.neg, "square": lambda x: x * x, "sqrt": torch.sqrt, "exp": torch.exp, "log": torch.log,
+                "sigmoid": torch.sigmoid, "tanh": torch.tanh, "relu": torch.relu}
+EW_SELF_TEST = {"state": "not run"}
+_EW_ENABLED = os.environ.get("DTF_NATIVE_ELEMENTWISE", "1") == "1"
+
+
+def _ew_self_test(device: torch.device) -> bool:
+    """First CUDA use in a process: every ew_* kernel against torch on small tensors (full, scalar and trailing-vector
+    operands, a reduction longer than one block).  A mismatch is logged, recorded in ``EW_SELF_TEST`` and switches these ops
+    back to torch for the process -- a wrong kernel must not silently train a wrong model."""
+    if EW_SELF_TEST["state"] != "not run":
+        return EW_SELF_TEST["state"] == "passed"
+    lib = _lib()
+    EW_SELF_TEST["state"] = "running"
+    try:
+        g = torch.Generator().manual_seed(3)
+        a = (torch.rand(37, 29, generator=g) + 0.5).to(device)
+        b = (torch.rand(37, 29, generator=g) + 0.5).to(device)
+        v = (torch.rand(29, generator=g) + 0.5).to(device)
+        s = (torch.rand(1, generator=g) + 0.5).to(device)
+        worst = 0.0
+        for op, fn in _TORCH_BINARY.items():
+            for x, y in ((a, b), (a, v), (v, a), (a, s), (s, a)):
+                worst = max(worst, float((lib.ew_binary(op, x, y) - fn(x, y)).abs().max()))
+        for op, fn in _TORCH_UNARY.items():
+            worst = max(worst, float((lib.ew_unary(op, a) - fn(a)).abs().max()))
+        big = (torch.rand(70001, generator=g) - 0.5).to(device)
+        worst = max(worst, float((lib.ew_reduce_sum(big, 0.5) - 0.5 * big.double().sum().float()).abs()))
+        worst = max(worst, float((lib.ew_reduce_sum(big, 1.0, square=True) - (big.double() ** 2).sum().float()).abs()))
+        worst = max(worst, float((lib.ew_affine(a, -2.0, 0.25) - (-2.0 * a + 0.25)).abs().max()))
+        worst = max(worst, float((lib.ew_affine(s, 3.0, out_shape=(5, 7)) - (3.0 * s).expand(5, 7)).abs().max()))
+        ok = worst <= 2e-3 and worst == worst
+        EW_SELF_TEST.update(state="passed" if ok else "failed", max_abs_diff=worst)
+    except Exception as e:          # noqa: BLE001
+        ok = False
+        EW_SELF_TEST.update(state="failed", error=repr(e)[:300])
+    if not ok:
+        import logging
+        logging.getLogger("dtf").error("element-wise kernels failed their self-test (%s): these graph ops run on torch in this "
+                                       "process", EW_SELF_TEST)
+    return ok
+
+
+def _ew_ok(*ts) -> bool:
+    if not _EW_ENABLED:
+        return False
+    dev = None
+    for t in ts:
+        if not isinstance(t, torch.Tensor) or t.dtype != torch.float32 or not _use_native(t):
+            return False
+        if dev is not None and t.device != dev:
+            return False
+        dev = t.device
+    if _lib().EMULATION:
+        return True
+    if EW_SELF_TEST["state"] == "running":
+        return False
+    return _ew_self_test(dev)
+
+
+def _unbroadcast(g: torch.Tensor, shape, out_shape) -> torch.Tensor:
+    """Sum the gradient of a broadcast operand back to the operand's shape (full / scalar / trailing-dims vector)."""
+    lib = _lib()
+    mode = lib.ew_broadcast_mode(shape, out_shape, out_shape)
+    if mode[0] == 0:
+        return g.reshape(shape)
+    if mode[0] == 1:
+        return lib.ew_reduce_sum(g).reshape(shape)
+    return lib.colsum(g.reshape(-1, mode[1])).reshape(shape)
+
+
+class _EwBinaryFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, op: str):
+        out = _lib().ew_binary(op, a, b)
+        ctx.op = op
+        ctx.save_for_backward(a, b, out if op == "div" else a.new_empty(0))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib()
+        a, b, out = ctx.saved_tensors
+        op = ctx.op
+        g = g.contiguous()
+        oshape = tuple(g.shape)
+        ga = gb = None
+        if op == "add":
+            ga, gb = g, g
+        elif op == "sub":
+            ga, gb = g, (lib.ew_affine(g, -1.0) if ctx.needs_input_grad[1] else None)
+        elif op == "mul":
+            ga = lib.ew_binary("mul", g, b) if ctx.needs_input_grad[0] else None
+            gb = lib.ew_binary("mul", g, a) if ctx.needs_input_grad[1] else None
+        elif op == "div":
+            q = lib.ew_binary("div", g, b)
+            ga = q
+            gb = lib.ew_affine(lib.ew_binary("mul", q, out), -1.0) if ctx.needs_input_grad[1] else None
+        else:                                   # sqdiff: d/da (a - b)^2 = 2 (a - b)
+            ga = lib.ew_affine(lib.ew_binary("mul", g, lib.ew_binary("sub", a, b)), 2.0)
+            gb = lib.ew_affine(ga, -1.0) if ctx.needs_input_grad[1] else None
+        ga = _unbroadcast(ga, tuple(a.shape), oshape) if (ga is not None and ctx.needs_input_grad[0]) else None
+        gb = _unbroadcast(gb, tuple(b.shape), oshape) if (gb is not None and ctx.needs_input_grad[1]) else None
+        return ga, gb, None
+
+
+def binary(op: str, a, b):
+    """Graph kernels Add / Sub / Mul / RealDiv / SquaredDifference."""
+    if _ew_ok(a, b):
+        lib = _lib()
+        try:
+            oshape = torch.broadcast_shapes(a.shape, b.shape)
+        except RuntimeError:
+            oshape = None
+        if oshape is not None and lib.ew_broadcast_mode(a.shape, b.shape, oshape) is not None \
+                and lib.ew_broadcast_mode(b.shape, a.shape, oshape) is not None and len(oshape) > 0:
+            return _EwBinaryFn.apply(a, b, op)
+    return _TORCH_BINARY[op](a, b)
+
+
+class _EwUnaryFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, op: str):
+        y = _lib().ew_unary(op, x)
+        ctx.op = op
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib()
+        x, y = ctx.saved_tensors
+        op = ctx.op
+        g = g.contiguous()
+        if op == "neg":
+            return lib.ew_affine(g, -1.0), None
+        if op == "square":
+            return lib.ew_affine(lib.ew_binary("mul", g, x), 2.0), None
+        if op == "sqrt":
+            return lib.ew_affine(lib.ew_binary("div", g, y), 0.5), None
+        if op == "exp":
+            return lib.ew_binary("mul", g, y), None
+        if op == "log":
+            return lib.ew_binary("div", g, x), None
+        if op == "sigmoid":
+            return lib.ew_binary("mul", lib.ew_binary("mul", g, y), lib.ew_affine(y, -1.0, 1.0)), None
+        if op == "tanh":
+            return lib.ew_binary("mul", g, lib.ew_affine(lib.ew_unary("square", y), -1.0, 1.0)), None
+        return lib.relu_grad(g, y), None
+
+
+def unary(op: str, x):
+    """Graph kernels Neg / Square / Sqrt / Exp / Log / Sigmoid / Tanh / Relu."""
+    if _ew_ok(x) and x.dim() > 0:
+        return _EwUnaryFn.apply(x, op)
+    return _TORCH_UNARY[op](x)
+
+
+class _EwReduceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale: float):
+        ctx.scale, ctx.shape = scale, tuple(x.shape)
+        return _lib().ew_reduce_sum(x, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _lib().ew_affine(g.reshape(1).contiguous(), ctx.scale, out_shape=ctx.shape), None
+
+
+def reduce_all(x, mean: bool):
+    """``tf.reduce_sum(x)`` / ``tf.reduce_mean(x)`` over every element -> 0-d tensor."""
+    if _ew_ok(x) and x.numel() > 0 and x.dim() > 0:
+        return _EwReduceFn.apply(x, (1.0 / x.numel()) if mean else 1.0)
+    return x.mean() if mean else x.sum()

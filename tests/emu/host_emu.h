@@ -68,6 +68,7 @@ static inline __nv_bfloat16 __float2bfloat16(float f) { return __nv_bfloat16{(ui
 
 typedef void* cudaStream_t;
 static inline int cudaGetLastError() { return 0; }
+static inline int cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return 0; }
 
 namespace dtf_emu {
 // Everything a running block needs lives in a per-launch context, reached through a thread_local pointer: several host

@@ -1,0 +1,81 @@
+"""K13 / K9 kernels on hardware (written after the round's GPU budget was spent: the first hardware run is the driver's; the
+file sorts last).  CPU coverage of the same sources: tests/test_random_and_elementwise_kernels.py (host emulation)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    torch.cuda.set_device(0)
+
+
+@pytest.mark.parametrize("kind,p0,p1", [(0, -1.0, 2.0), (1, 0.5, 2.0), (2, 0.0, 0.1)])
+def test_philox_fill_kernel_matches_the_host_stream(kind, p0, p1):
+    _need_gpu()
+    from distributed_tensorflow_b200.ops import cuda_lib, random_ops
+    n, key, off, sid = 1_000_003, 0x9e3779b97f4a7c15, 12345678901, 2
+    n0 = cuda_lib.launch_count()
+    dev = cuda_lib.philox_fill(torch.empty(n, device="cuda"), kind, p0, p1, key, off, sid)
+    assert cuda_lib.launch_count() == n0 + 1
+    ref = random_ops.philox_fill_numpy(n, kind, p0, p1, key, off, sid)
+    assert np.abs(dev.cpu().numpy() - ref).max() < 1e-5 * max(1.0, abs(p0) + 4 * abs(p1))
+    t = random_ops.philox_fill((1000, 17), kind, p0, p1, key, off, torch.device("cuda", 0), sid)
+    assert t.is_cuda and random_ops.SELF_TEST["state"] == "passed", random_ops.SELF_TEST
+    assert np.abs(t.cpu().numpy().reshape(-1) - ref[:17000]).max() < 1e-5 * max(1.0, abs(p0) + 4 * abs(p1))
+
+
+def test_elementwise_kernels_match_torch_on_device():
+    _need_gpu()
+    from distributed_tensorflow_b200.ops import cuda_lib, native
+    g = torch.Generator().manual_seed(1)
+    a, b = (torch.rand(64, 50, 70, generator=g) + 0.5).cuda(), (torch.rand(64, 50, 70, generator=g) + 0.5).cuda()
+    v, s = (torch.rand(70, generator=g) + 0.5).cuda(), (torch.rand(1, generator=g) + 0.5).cuda()
+    n0 = cuda_lib.launch_count()
+    for op, fn in native._TORCH_BINARY.items():
+        for x, y in ((a, b), (a, v), (v, a), (a, s), (s, a)):
+            xs, ys = x.clone().requires_grad_(), y.clone().requires_grad_()
+            out = native.binary(op, xs, ys)
+            w = torch.rand(out.shape, generator=g).cuda()
+            gx, gy = torch.autograd.grad((out * w).sum(), (xs, ys))
+            xr, yr = x.clone().requires_grad_(), y.clone().requires_grad_()
+            ref = fn(xr, yr)
+            rx, ry = torch.autograd.grad((ref * w).sum(), (xr, yr))
+            torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(gx, rx, rtol=2e-4, atol=1e-3)
+            torch.testing.assert_close(gy, ry, rtol=2e-4, atol=1e-3)
+    for op, fn in native._TORCH_UNARY.items():
+        x = (a - 1.0) if op in ("relu", "tanh", "sigmoid", "neg", "square") else a
+        xs, xr = x.clone().requires_grad_(), x.clone().requires_grad_()
+        out, ref = native.unary(op, xs), fn(xr)
+        torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(torch.autograd.grad(out.sum(), xs)[0], torch.autograd.grad(ref.sum(), xr)[0], rtol=1e-4, atol=1e-5)
+    big = (torch.rand(3000, 257, generator=g) - 0.5).cuda()
+    for mean in (False, True):
+        xs, xr = big.clone().requires_grad_(), big.clone().requires_grad_()
+        out, ref = native.reduce_all(xs, mean), (xr.double().mean() if mean else xr.double().sum()).float()
+        torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-3)
+        torch.testing.assert_close(torch.autograd.grad(out * 3.0, xs)[0], torch.full_like(big, 3.0 / big.numel() if mean else 3.0))
+    assert native.EW_SELF_TEST["state"] == "passed", native.EW_SELF_TEST
+    assert cuda_lib.launch_count() - n0 > 100                          # the kernels ran (no torch fallback)
+
+
+def test_seeded_initialisers_draw_the_same_values_on_gpu_and_cpu():
+    _need_gpu()
+    import distributed_tensorflow_b200 as tf
+
+    def run(dev):
+        g = tf.Graph()
+        with g.as_default(), tf.device(dev):
+            tf.set_random_seed(11)
+            w = tf.get_variable("w", [784, 100], initializer=tf.truncated_normal_initializer(stddev=1.0 / 28))
+            u = tf.get_variable("u", [100, 10], initializer=tf.random_uniform_initializer(-1, 1))
+            with tf.Session() as sess:
+                sess.run(tf.global_variables_initializer())
+                return sess.run([w, u])
+    (w0, u0), (w1, u1) = run("/cpu:0"), run("/gpu:0")
+    np.testing.assert_allclose(w0, w1, atol=2e-6)
+    np.testing.assert_allclose(u0, u1, atol=2e-6)
