@@ -154,6 +154,33 @@ __global__ void ew_reduce_sum_kernel(const float* __restrict__ x, long long n, f
 // element-wise binary / unary kernels above walk fp32; everything else stays with the op layer
 
 // ---------------------------------------------------------------------------------------------
+// K10: split / concat as ONE gather-scatter kernel over up to 16 parts.  Part p is `outer` rows of `row_len[p]` contiguous
+// floats; source and destination rows are `*_stride[p]` apart and start at `*_off[p]`.  concat along an axis = every part
+// reads its own tensor and writes a column band of the result; the scatter of a global batch = every part reads a row band
+// and writes its own destination -- which may live on a PEER GPU (in-graph replication: example_in_graph.py:38 splits the
+// batch across workers, :58 concatenates their results; with peer access enabled the stores / loads travel over NVLink).
+// ---------------------------------------------------------------------------------------------
+struct CopyParts {
+  const float* src[16];
+  float* dst[16];
+  long long src_stride[16], dst_stride[16], src_off[16], dst_off[16], row_len[16];
+  long long cum[17];            // cum[p] = elements of parts 0..p-1 (outer * row_len each)
+  long long outer;
+  int nparts;
+};
+
+__global__ void copy_parts_kernel(const CopyParts t) {
+  const long long total = t.cum[t.nparts];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int p = 0;
+    while (p + 1 < t.nparts && i >= t.cum[p + 1]) ++p;
+    const long long j = i - t.cum[p];
+    const long long o = j / t.row_len[p], c = j - o * t.row_len[p];
+    t.dst[p][o * t.dst_stride[p] + t.dst_off[p] + c] = t.src[p][o * t.src_stride[p] + t.src_off[p] + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // fused softmax + cross-entropy, forward and backward in one pass (one warp per row)
 //   y = softmax(logits);  t_j = labels_j * [y_j >= clip_min]
 //   loss_row = -sum_j labels_j * log(clamp(y_j, clip_min, 1))          (clip_min = 0: -sum labels*log_softmax)
@@ -467,6 +494,32 @@ int dtf_ew_reduce_sum(const float* x, long long n, float scale, int square, floa
   long long blocks = (n + 256 * 8 - 1) / (256 * 8);           // >= 8 elements per thread before another block is worth an atomic
   if (blocks > 592) blocks = 592;
   DTF_LAUNCH(ew_reduce_sum_kernel, (int)blocks, 256, s, x, n, scale, square, out);
+  return (int)cudaGetLastError();
+}
+
+// parts: nparts <= 16; arrays of nparts entries (host memory).  See copy_parts_kernel.
+int dtf_copy_parts(int nparts, long long outer, const void* const* src, void* const* dst, const long long* src_stride,
+                   const long long* dst_stride, const long long* src_off, const long long* dst_off, const long long* row_len,
+                   cudaStream_t s) {
+  if (nparts < 1 || nparts > 16 || outer < 0) return -1;
+  CopyParts t;
+  memset(&t, 0, sizeof(t));
+  t.nparts = nparts;
+  t.outer = outer;
+  t.cum[0] = 0;
+  for (int p = 0; p < nparts; ++p) {
+    if (row_len[p] < 0 || src_stride[p] < 0 || dst_stride[p] < 0 || src_off[p] < 0 || dst_off[p] < 0) return -1;
+    t.src[p] = reinterpret_cast<const float*>(src[p]);
+    t.dst[p] = reinterpret_cast<float*>(dst[p]);
+    t.src_stride[p] = src_stride[p];
+    t.dst_stride[p] = dst_stride[p];
+    t.src_off[p] = src_off[p];
+    t.dst_off[p] = dst_off[p];
+    t.row_len[p] = row_len[p] > 0 ? row_len[p] : 1;          // an empty part contributes no element; keep the divisor sane
+    t.cum[p + 1] = t.cum[p] + outer * row_len[p];
+  }
+  if (t.cum[nparts] == 0) return 0;
+  DTF_LAUNCH(copy_parts_kernel, grid_for(t.cum[nparts]), 256, s, t);
   return (int)cudaGetLastError();
 }
 

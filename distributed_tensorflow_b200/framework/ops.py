@@ -507,7 +507,7 @@ def concat(values, axis=0, name="concat"):
     return _node("ConcatV2", ins, {"axis": int(axis)}, name, ins[0].dtype, shp)
 
 
-register_kernel("ConcatV2")(lambda ctx, n, *xs: torch.cat(xs, dim=n.attrs["axis"]))
+register_kernel("ConcatV2")(lambda ctx, n, *xs: _native_ew().concat(xs, n.attrs["axis"]))
 
 
 def stack(values, axis=0, name="stack"):

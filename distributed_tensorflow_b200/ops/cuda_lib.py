@@ -287,6 +287,8 @@ def _declare(lib) -> None:
         lib.dtf_ew_binary.restype = c_int
         lib.dtf_ew_unary.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_void_p]
         lib.dtf_ew_unary.restype = c_int
+        lib.dtf_copy_parts.argtypes = [c_int, c_longlong] + [c_void_p] * 7 + [c_void_p]
+        lib.dtf_copy_parts.restype = c_int
         lib.dtf_ew_affine.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_float, c_float, c_void_p]
         lib.dtf_ew_affine.restype = c_int
         lib.dtf_ew_reduce_sum.argtypes = [c_void_p, c_longlong, c_float, c_int, c_void_p, c_void_p]
@@ -737,6 +739,64 @@ def ew_unary(op: str, x: torch.Tensor) -> torch.Tensor:
         _check(load().dtf_ew_unary(x.data_ptr(), out.data_ptr(), x.numel(), EW_UNARY[op], _stream(x)), "ew_unary(%s)" % op)
     _bump()
     return out
+
+
+def _copy_parts(outer: int, srcs, dsts, src_stride, dst_stride, src_off, dst_off, row_len, device: torch.device) -> None:
+    n = len(srcs)
+    LL, VP = c_longlong * n, c_void_p * n
+    with _on(device):
+        _check(load().dtf_copy_parts(n, int(outer), VP(*srcs), VP(*dsts), LL(*src_stride), LL(*dst_stride), LL(*src_off), LL(*dst_off),
+                                     LL(*row_len), None if EMULATION else torch.cuda.current_stream(device).cuda_stream),
+               "copy_parts")
+    _bump()
+
+
+def concat(xs: Sequence[torch.Tensor], axis: int) -> Optional[torch.Tensor]:
+    """``torch.cat(xs, axis)`` of 2..16 contiguous fp32 tensors in ONE gather kernel; None = not handled."""
+    xs = list(xs)
+    if not (2 <= len(xs) <= 16) or any(x.dtype != torch.float32 or x.device != xs[0].device or x.dim() != xs[0].dim() or x.dim() == 0
+                                       for x in xs):
+        return None
+    nd = xs[0].dim()
+    ax = axis % nd
+    base = list(xs[0].shape)
+    for x in xs:
+        if [d for i, d in enumerate(x.shape) if i != ax] != [d for i, d in enumerate(base) if i != ax]:
+            return None
+    outer, inner = 1, 1
+    for d in base[:ax]:
+        outer *= d
+    for d in base[ax + 1:]:
+        inner *= d
+    lens = [x.shape[ax] for x in xs]
+    total = sum(lens)
+    shape = base[:ax] + [total] + base[ax + 1:]
+    out = torch.empty(shape, dtype=torch.float32, device=xs[0].device)
+    xs = [x.contiguous() for x in xs]
+    offs, acc = [], 0
+    for l in lens:
+        offs.append(acc * inner)
+        acc += l
+    _copy_parts(outer, [x.data_ptr() for x in xs], [out.data_ptr()] * len(xs), [l * inner for l in lens], [total * inner] * len(xs),
+                [0] * len(xs), offs, [l * inner for l in lens], out.device)
+    return out
+
+
+def scatter_rows(x: torch.Tensor, outs: Sequence[torch.Tensor]) -> None:
+    """Split the leading dimension of the contiguous fp32 ``x`` across ``outs`` (contiguous fp32, rows summing to x's) with ONE
+    kernel launched on x's device; an ``out`` on another GPU is written through its peer mapping (peer access must be on)."""
+    outs = list(outs)
+    assert 1 <= len(outs) <= 16 and x.dtype == torch.float32 and x.is_contiguous() and x.dim() >= 1
+    inner = x[0].numel() if x.shape[0] else 1
+    rows = [o.shape[0] for o in outs]
+    assert sum(rows) == x.shape[0] and all(o.dtype == torch.float32 and o.is_contiguous() and (o[0].numel() if o.shape[0] else inner) == inner
+                                             for o in outs)
+    offs, acc = [], 0
+    for r in rows:
+        offs.append(acc * inner)
+        acc += r
+    _copy_parts(1, [x.data_ptr()] * len(outs), [o.data_ptr() for o in outs], [0] * len(outs), [0] * len(outs), offs, [0] * len(outs),
+                [r * inner for r in rows], x.device)
 
 
 def ew_affine(x: torch.Tensor, alpha: float, beta: float = 0.0, out_shape: Optional[Sequence[int]] = None) -> torch.Tensor:

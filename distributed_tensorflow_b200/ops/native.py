@@ -415,6 +415,12 @@ def _ew_self_test(device: torch.device) -> bool:
         worst = max(worst, float((lib.ew_reduce_sum(big, 1.0, square=True) - (big.double() ** 2).sum().float()).abs()))
         worst = max(worst, float((lib.ew_affine(a, -2.0, 0.25) - (-2.0 * a + 0.25)).abs().max()))
         worst = max(worst, float((lib.ew_affine(s, 3.0, out_shape=(5, 7)) - (3.0 * s).expand(5, 7)).abs().max()))
+        parts = [a[:, :11].contiguous(), a[:, 11:12].contiguous(), a[:, 12:].contiguous()]
+        worst = max(worst, float((lib.concat(parts, 1) - a).abs().max()))
+        worst = max(worst, float((lib.concat([a, b], 0) - torch.cat([a, b], 0)).abs().max()))
+        o1, o2 = torch.empty(30, 29, device=device), torch.empty(7, 29, device=device)
+        lib.scatter_rows(a, [o1, o2])
+        worst = max(worst, float((torch.cat([o1, o2], 0) - a).abs().max()))
         ok = worst <= 2e-3 and worst == worst
         EW_SELF_TEST.update(state="passed" if ok else "failed", max_abs_diff=worst)
     except Exception as e:          # noqa: BLE001
@@ -558,3 +564,31 @@ def reduce_all(x, mean: bool):
     if _ew_ok(x) and x.numel() > 0 and x.dim() > 0:
         return _EwReduceFn.apply(x, (1.0 / x.numel()) if mean else 1.0)
     return x.mean() if mean else x.sum()
+
+
+class _ConcatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, axis: int, *xs):
+        ctx.axis, ctx.lens = axis, [x.shape[axis] for x in xs]
+        return _lib().concat(xs, axis)
+
+    @staticmethod
+    def backward(ctx, g):
+        outs, off = [], 0
+        for l in ctx.lens:                       # the gradient of a concat is a split: views, no copy
+            outs.append(g.narrow(ctx.axis, off, l))
+            off += l
+        return (None,) + tuple(outs)
+
+
+def concat(xs, axis: int):
+    """Graph kernel ConcatV2 (K10): one gather kernel for 2..16 fp32 parts on /gpu (``example_in_graph.py:58``,
+    ``standalone.py:86``); anything else is ``torch.cat``."""
+    xs = list(xs)
+    if 2 <= len(xs) <= 16 and _ew_ok(*xs) and all(x.dim() == xs[0].dim() and x.dim() > 0 for x in xs):
+        nd = xs[0].dim()
+        ax = axis % nd
+        ref = [d for i, d in enumerate(xs[0].shape) if i != ax]
+        if all([d for i, d in enumerate(x.shape) if i != ax] == ref for x in xs):
+            return _ConcatFn.apply(ax, *xs)
+    return torch.cat(xs, dim=axis)

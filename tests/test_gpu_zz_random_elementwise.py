@@ -79,3 +79,33 @@ def test_seeded_initialisers_draw_the_same_values_on_gpu_and_cpu():
     (w0, u0), (w1, u1) = run("/cpu:0"), run("/gpu:0")
     np.testing.assert_allclose(w0, w1, atol=2e-6)
     np.testing.assert_allclose(u0, u1, atol=2e-6)
+
+
+def test_concat_and_scatter_kernel_on_device_and_across_peers():
+    _need_gpu()
+    from distributed_tensorflow_b200.ops import cuda_lib, native
+    g = torch.Generator().manual_seed(2)
+    for shapes, axis in (([(400, 30), (200, 30)], 0), ([(30, 20, 50), (30, 70, 50), (30, 1, 50)], 1), ([(3, 4, 2), (3, 4, 6)], -1)):
+        xs = [torch.rand(s, generator=g).cuda().requires_grad_() for s in shapes]
+        n0 = cuda_lib.launch_count()
+        out = native.concat(xs, axis)
+        ref = torch.cat([x.detach() for x in xs], dim=axis)
+        torch.testing.assert_close(out, ref, rtol=0, atol=0)
+        grads = torch.autograd.grad(out.sum(), xs)
+        assert all(float(gr.min()) == 1.0 == float(gr.max()) for gr in grads)
+    assert native.EW_SELF_TEST["state"] == "passed" and cuda_lib.launch_count() > n0
+    x = torch.rand(1000, 784, generator=g).cuda()
+    outs = [torch.zeros(300, 784, device="cuda"), torch.zeros(700, 784, device="cuda")]
+    cuda_lib.scatter_rows(x, outs)
+    torch.testing.assert_close(torch.cat(outs, 0), x, rtol=0, atol=0)
+    if torch.cuda.device_count() >= 2 and torch.cuda.can_device_access_peer(0, 1):
+        lib = cuda_lib.load()
+        with torch.cuda.device(0):
+            lib.dtf_enable_peer(1)
+        far = torch.zeros(700, 784, device="cuda:1")
+        near = torch.zeros(300, 784, device="cuda:0")
+        torch.cuda.synchronize(1)
+        cuda_lib.scatter_rows(x, [near, far])                      # the second part is written over NVLink by GPU 0's kernel
+        torch.cuda.synchronize(0)
+        torch.testing.assert_close(far.cpu(), x[300:].cpu(), rtol=0, atol=0)
+        torch.testing.assert_close(near, x[:300], rtol=0, atol=0)

@@ -169,3 +169,39 @@ def test_linear_regression_program_trains_on_the_kernels(emulated):
     for (l1, w1, b1), (l2, w2, b2) in zip(emu, ref):
         np.testing.assert_allclose([l1, w1[0], b1[0]], [l2, w2[0], b2[0]], rtol=2e-4, atol=1e-5)
     assert emu[-1][0] < emu[0][0] * 0.05
+
+
+def test_concat_and_scatter_kernel(emulated):
+    """K10: the gather-scatter kernel (copy_parts_kernel) behind ConcatV2 on /gpu and behind the one-launch scatter of a batch."""
+    g = torch.Generator().manual_seed(2)
+    for shapes, axis in (([(4, 3), (2, 3)], 0), ([(2, 1), (2, 1)], 0), ([(3, 2, 5), (3, 7, 5), (3, 1, 5)], 1), ([(3, 4, 2), (3, 4, 6)], -1),
+                         ([(5,), (1,), (9,)], 0)):
+        xs = [torch.rand(s, generator=g).requires_grad_() for s in shapes]
+        rs = [x.detach().clone().requires_grad_() for x in xs]
+        n0 = cuda_lib.launch_count()
+        out, ref = native.concat(xs, axis), torch.cat(rs, dim=axis)
+        assert cuda_lib.launch_count() == n0 + 1
+        torch.testing.assert_close(out, ref, rtol=0, atol=0)
+        w = torch.rand(ref.shape, generator=g)
+        for a, b in zip(torch.autograd.grad((out * w).sum(), xs), torch.autograd.grad((ref * w).sum(), rs)):
+            torch.testing.assert_close(a, b, rtol=0, atol=0)
+    # 17 parts, mixed dtypes, mismatched shapes: torch
+    many = [torch.rand(1, 2) for _ in range(17)]
+    n0 = cuda_lib.launch_count()
+    assert native.concat(many, 0).shape == (17, 2) and cuda_lib.launch_count() == n0
+    assert native.concat([torch.ones(2, dtype=torch.int64), torch.ones(3, dtype=torch.int64)], 0).dtype == torch.int64
+    # scatter of a global batch across per-worker staging buffers (in-graph replication), one launch
+    x = torch.rand(10, 3, 4, generator=g)
+    outs = [torch.zeros(2, 3, 4), torch.zeros(5, 3, 4), torch.zeros(3, 3, 4)]
+    n0 = cuda_lib.launch_count()
+    cuda_lib.scatter_rows(x, outs)
+    assert cuda_lib.launch_count() == n0 + 1
+    torch.testing.assert_close(torch.cat(outs, 0), x, rtol=0, atol=0)
+    # the graph op: the in-graph example's split -> per-part work -> concat
+    gr = tf.Graph()
+    with gr.as_default():
+        a = tf.constant(np.arange(12, dtype=np.float32).reshape(4, 3))
+        parts = tf.split(a, 2)
+        y = tf.concat([tf.matmul(p, tf.constant([[1.0], [1.0], [1.0]])) for p in parts], 0)
+        with tf.Session() as sess:
+            assert sess.run(y).tolist() == [[3.0], [12.0], [21.0], [30.0]]
