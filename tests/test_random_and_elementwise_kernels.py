@@ -205,3 +205,24 @@ def test_concat_and_scatter_kernel(emulated):
         y = tf.concat([tf.matmul(p, tf.constant([[1.0], [1.0], [1.0]])) for p in parts], 0)
         with tf.Session() as sess:
             assert sess.run(y).tolist() == [[3.0], [12.0], [21.0], [30.0]]
+
+
+def test_first_use_self_tests_run_clean_under_the_emulation(emulated, monkeypatch):
+    """The checks a process runs before it trusts the new kernels on hardware, executed here against the emulated kernels;
+    and their failure path: a wrong kernel is reported, recorded and the ops fall back to torch."""
+    monkeypatch.setitem(native.EW_SELF_TEST, "state", "not run")
+    assert native._ew_self_test(torch.device("cpu")) and native.EW_SELF_TEST["state"] == "passed"
+    assert native.EW_SELF_TEST["max_abs_diff"] < 1e-4
+    monkeypatch.setitem(random_ops.SELF_TEST, "state", "not run")
+    assert random_ops._device_fill_checked(torch.device("cpu")) and random_ops.SELF_TEST["state"] == "passed"
+    # failure path
+    monkeypatch.setitem(native.EW_SELF_TEST, "state", "not run")
+    monkeypatch.setattr(cuda_lib, "ew_affine", lambda x, alpha, beta=0.0, out_shape=None: torch.zeros_like(x))
+    assert not native._ew_self_test(torch.device("cpu")) and native.EW_SELF_TEST["state"] == "failed"
+    monkeypatch.setattr(cuda_lib, "EMULATION", False)
+    assert not native._ew_ok(torch.ones(3))
+    monkeypatch.setitem(random_ops.SELF_TEST, "state", "not run")
+    monkeypatch.setattr(cuda_lib, "philox_fill", lambda out, *a, **k: out.zero_())
+    assert not random_ops._device_fill_checked(torch.device("cpu")) and random_ops.SELF_TEST["state"] == "failed"
+    monkeypatch.setitem(native.EW_SELF_TEST, "state", "passed")
+    monkeypatch.setitem(random_ops.SELF_TEST, "state", "not run")
