@@ -616,7 +616,8 @@ def main():
             # step's loss row), but the K steps are enqueued by ONE native call; the host reads every loss, at most
             # --e2e-depth steps late
             if is_worker:
-                ls = eng.train_loop(hx3, hy3, K, first=(ctr[0] * num_workers + woff) % nb, stride=num_workers, depth=args.e2e_depth)
+                ls = eng.train_loop(hx3, hy3, K, first=(ctr[0] * num_workers + woff) % nb, stride=num_workers, depth=args.e2e_depth,
+                                    prefetch_next=bool(args.e2e_prefetch))
                 last[0] = float(ls[-1])
                 if not all(math.isfinite(float(v)) for v in ls):
                     raise RuntimeError("native loop returned a non-finite loss")
@@ -629,7 +630,9 @@ def main():
             for _ in range(2):
                 if is_worker:
                     x, y = batch_of(ctr[0])
-                    eng.step(x, y, sync_loss=False)
+                    # the loop is continuous across the untimed / timed boundary: the batch of the next step is already
+                    # travelling (every timed step still issues one H2D copy: the one of the step after it)
+                    eng.step(x, y, sync_loss=False, prefetch=batch_of(ctr[0] + 1) if args.e2e_prefetch else None)
                 else:
                     eng.step(sync_loss=False)
                 ctr[0] += 1

@@ -190,7 +190,8 @@ struct DtfLoopArgs {
   int steps;
   int depth;                // >= 1
   int parity;               // buffer set of the first step; on return: of the next step
-  int prefetched;           // in: copy[parity] was already issued for the first batch.  out: 0
+  int prefetched;           // in: copy[parity] was already issued for the first batch.  out: prefetch_next
+  int prefetch_next;        // also issue the copy of the batch FOLLOWING the last step (a continuous loop across calls)
   int x_op, y_op;           // index of the H2D ops (x, labels) inside both copy plans
   int n_copy[2], n_compute[2], n_ps;
   DtfStepOp* copy_ops[2];   // per parity: wait done[p] -> H2D x -> H2D y -> (convert) -> record ready[p]
@@ -242,7 +243,8 @@ int dtf_run_loop(DtfLoopArgs* a) {
     }
     rc = dtf_run_ops(a->compute_ops[par], a->n_compute[par], -1, a->stream, &kernels);
     if (rc == 0 && a->n_ps > 0) rc = dtf_run_ops(a->ps_ops, a->n_ps, -1, a->ps_stream, &kernels);
-    if (rc == 0 && i + 1 < a->steps) rc = issue_copy(par ^ 1, i + 1);          // next batch travels under this step's kernels
+    if (rc == 0 && (i + 1 < a->steps || a->prefetch_next))
+      rc = issue_copy(par ^ 1, i + 1);                                           // next batch travels under this step's kernels
     if (rc == 0 && a->loss_bytes > 0)
       rc = (int)cudaMemcpyAsync(a->loss_host + (long long)i * a->loss_row_bytes, a->loss_src, (size_t)a->loss_bytes,
                                 cudaMemcpyDeviceToHost, a->stream);
@@ -255,7 +257,7 @@ int dtf_run_loop(DtfLoopArgs* a) {
   }
   for (int e = 0; e < made; ++e) cudaEventDestroy(landed[e]);
   a->parity = par;
-  a->prefetched = 0;
+  a->prefetched = (rc == 0 && a->steps > 0 && a->prefetch_next) ? 1 : 0;
   a->kernels = kernels;
   a->waited = waits;
   if (prev >= 0) cudaSetDevice(prev);

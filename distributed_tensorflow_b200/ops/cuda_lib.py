@@ -100,7 +100,7 @@ class LoopArgs(Structure):
     """``csrc/step_exec.cu: DtfLoopArgs`` -- ``steps`` end-to-end training steps of one local worker in ONE native call
     (per step: H2D of that step's pinned batch one step ahead, the step's plan, the ps shard's plan, D2H of the loss row)."""
     _fields_ = [("device", c_int), ("steps", c_int), ("depth", c_int), ("parity", c_int), ("prefetched", c_int),
-                ("x_op", c_int), ("y_op", c_int), ("n_copy", c_int * 2), ("n_compute", c_int * 2), ("n_ps", c_int),
+                ("prefetch_next", c_int), ("x_op", c_int), ("y_op", c_int), ("n_copy", c_int * 2), ("n_compute", c_int * 2), ("n_ps", c_int),
                 ("copy_ops", c_void_p * 2), ("compute_ops", c_void_p * 2), ("ps_ops", c_void_p),
                 ("copy_stream", c_void_p), ("stream", c_void_p), ("ps_stream", c_void_p),
                 ("x_base", c_void_p), ("y_base", c_void_p), ("x_stride", c_longlong), ("y_stride", c_longlong),

@@ -1089,7 +1089,7 @@ class PSTrainEngine:
             return self.read_loss()
         return None
 
-    def train_loop(self, x_batches, y_batches, steps: int, first: int = 0, stride: int = 1, depth: int = 2):
+    def train_loop(self, x_batches, y_batches, steps: int, first: int = 0, stride: int = 1, depth: int = 2, prefetch_next: bool = False):
         """``steps`` end-to-end training steps in ONE native call (``csrc/step_exec.cu: dtf_run_loop``) -- the reference's
         ``while`` loop around ``mon_sess.run([train_step, global_step, loss], feed_dict=...)``
         (``/root/reference/distributed_mnist.py:148-152``) without the interpreter between the steps.
@@ -1098,7 +1098,9 @@ class PSTrainEngine:
         trains on batch ``(first + i * stride) % nb``: every step its batch is copied host->device (copy stream, one step
         ahead of the kernels that consume it), the step runs (the same CUDA-graphed plans ``step()`` uses), and the step's
         loss partials are copied device->host into row i of a pinned array; the host stays at most ``depth`` steps ahead
-        of the landed losses.  Returns the ``steps`` losses (numpy fp32).  One local worker per process (between-graph
+        of the landed losses.  ``prefetch_next``: also start the copy of the batch after the last step, so that a following
+        ``train_loop`` / ``step`` on that batch finds it on the device (one continuous loop across calls).  Returns the
+        ``steps`` losses (numpy fp32).  One local worker per process (between-graph
         replication); other topologies, and a process whose plans are not built yet, take ``step()`` per step."""
         import numpy as np
         from ..ops.cuda_lib import LoopArgs
@@ -1155,7 +1157,7 @@ class PSTrainEngine:
         a.device, a.steps, a.depth, a.parity = rk.device.index, n, max(1, min(int(depth), 64)), plans["parity"]
         b0 = (first + i * stride) % nb
         a.prefetched = int(plans["prefetched"] == (x_batches[b0].data_ptr(), y_batches[b0].data_ptr(), plans["parity"]))
-        a.x_op, a.y_op = 1, 2
+        a.x_op, a.y_op, a.prefetch_next = 1, 2, int(bool(prefetch_next))
         for p_ in range(2):
             a.n_copy[p_], a.n_compute[p_] = cp[p_].n, cm[p_].n
             a.copy_ops[p_], a.compute_ops[p_] = ctypes.addressof(cp[p_].ops), ctypes.addressof(cm[p_].ops)
@@ -1172,6 +1174,9 @@ class PSTrainEngine:
             raise RuntimeError("native training loop failed with code %d (op %d of a plan, code %d)" % (rc, rc // 100000 - 1, rc % 100000))
         cuda_lib._bump(int(a.kernels))
         plans["parity"], plans["prefetched"] = int(a.parity), None
+        if a.prefetched:
+            bn = (first + steps * stride) % nb
+            plans["prefetched"] = (x_batches[bn].data_ptr(), y_batches[bn].data_ptr(), int(a.parity))
         plans["runs"] += n
         rk.step += n
         losses[i:] = st["np"][:n, :self.head_ctas].sum(axis=1)

@@ -244,6 +244,20 @@ def test_train_loop_host_logic_with_a_fake_native_loop():
     plans["prefetched"] = (xb[1].data_ptr(), yb[1].data_ptr(), 0)
     eng.train_loop(xb, yb, steps=1, first=1)
     assert calls[-1]["prefetched"] == 1 and calls[-1]["steps"] == 1
+    # prefetch_next: the native loop reports that the batch after the last step is travelling; step() must recognise it
+    class Lib2(Lib):
+        def dtf_run_loop(self, ref):
+            rc = Lib.dtf_run_loop(self, ref)
+            a = ctypes.cast(ref, ctypes.POINTER(LoopArgs)).contents
+            a.prefetched = a.prefetch_next
+            return rc
+    eng.lib = Lib2()
+    par0 = plans["parity"]
+    eng.train_loop(xb, yb, steps=3, first=4, stride=2, prefetch_next=True)
+    bn = (4 + 3 * 2) % 5
+    assert plans["prefetched"] == (xb[bn].data_ptr(), yb[bn].data_ptr(), (par0 + 3) & 1)
+    eng.lib = Lib()
+    plans["prefetched"] = None
     # several local workers (in-graph replication) or unpinned inputs: step() per step
     eng.ranks[0] = SimpleNamespace(step=0, device=SimpleNamespace(index=2))
     n = len(calls)

@@ -30,7 +30,7 @@ def test_native_train_loop_matches_synchronous_steps(precision):
         eng.init_params()
         if native:
             before = cuda_lib.launch_count()
-            a = eng.train_loop(hx, hy, 9, first=2, stride=3, depth=2)                 # 4 eager steps + 5 in the native loop
+            a = eng.train_loop(hx, hy, 9, first=2, stride=3, depth=2, prefetch_next=True)     # 4 eager steps + 5 in the native loop; the batch of step 9 is prefetched
             extra = eng.step(hx[(2 + 9 * 3) % 7], hy[(2 + 9 * 3) % 7], prefetch=(hx[(2 + 10 * 3) % 7], hy[(2 + 10 * 3) % 7]))
             b = eng.train_loop(hx, hy, K - 10, first=2 + 10 * 3, stride=3, depth=4)    # enters with its first batch prefetched
             losses = list(a) + [extra] + list(b)

@@ -164,3 +164,18 @@ def test_native_loop_prefetched_first_batch_odd_parity_short_runs_and_errors(hos
     a, keep = _loop_args(host, steps=3, depth=2)
     assert host.dtf_run_loop(ctypes.byref(a)) == 2
     assert not any(l.startswith(("memcpy", "graph", "event_destroy")) for l in host.step_emu_trace().decode().splitlines())
+
+
+def test_native_loop_prefetch_next_copies_the_batch_after_the_last_step(host):
+    host.step_emu_reset(0, 0)
+    a, keep = _loop_args(host, steps=2, depth=2, ps=False)
+    a.prefetch_next = 1
+    assert host.dtf_run_loop(ctypes.byref(a)) == 0
+    t = host.step_emu_trace().decode().splitlines()
+    h2d = [l for l in t if l.startswith("memcpy h2d") and "n=400" in l]
+    batches = [(3 + 2 * i) % 5 for i in range(3)]
+    assert [int(l.split("src=")[1].split()[0], 16) for l in h2d] == [0x100000 + b * 0x1000 for b in batches]     # steps 0, 1 and the one after
+    assert h2d[2].split("dst=")[1].split()[0] == "0x1000"                 # ... into the buffer set the next step will use (parity 0)
+    assert (a.parity, a.prefetched) == (0, 1)
+    last_graph = max(i for i, l in enumerate(t) if l.startswith("graph_launch"))
+    assert t.index(h2d[2]) > last_graph                                   # issued behind the last step's kernels
