@@ -38,6 +38,9 @@ flags.DEFINE_integer("gpus", 0, "GPUs to use in in-graph mode (0: all)")
 flags.DEFINE_bool("ps_on_workers", False, "every GPU runs a worker; ps shard s shares worker s's GPU and stream (no ps-only GPU)")
 flags.DEFINE_string("train_dir", "/tmp/dtf_ckpt/fabric_mnist", "checkpoint directory")
 flags.DEFINE_integer("num_train", 55000, "synthetic train-set size")
+flags.DEFINE_string("input", "device", "device: the train split lives in every worker's HBM; host: every step's batch is copied from "
+                                        "pinned host memory and every step's loss is read back (PSTrainEngine.train_loop: the reference's "
+                                        "feed_dict loop, K steps per native call)")
 flags.DEFINE_string("nvls", "auto", "NVLS multicast fabric: off | on | auto (auto = on when the box has NVLS and one process "
                                     "per GPU is used; the one-process topology opts in with 'on')")
 FLAGS = flags.FLAGS
@@ -66,18 +69,35 @@ def main():
     print("rank %d: ps shards %s, workers %s, placement %s" % (rank, eng.ps_ranks, eng.worker_ranks,
                                                                {k: v.shard for k, v in eng.layout.items()}), flush=True)
     xs, ys = synthetic_mnist(FLAGS.num_train, seed=1)
-    for r in eng.ranks:
-        if r in eng.worker_ranks:
+    local_workers = [r for r in eng.ranks if r in eng.worker_ranks]
+    host_feed = FLAGS.input == "host" and len(local_workers) <= 1
+    hx = hy = None
+    if host_feed and local_workers:
+        B = FLAGS.batch_size
+        nb = min(FLAGS.num_train, 20000) // B
+        hx = torch.from_numpy(xs[:nb * B]).pin_memory().view(nb, B, -1)
+        hy = torch.from_numpy(ys[:nb * B]).pin_memory().view(nb, B, -1)
+        woff = eng.worker_ranks.index(local_workers[0])
+    elif not host_feed:
+        for r in local_workers:
             eng.attach_dataset(r, xs, ys)
     t0 = time.time()
     steps = FLAGS.train_steps
     done = 0
     while done < steps:
         k = min(200, steps - done)
-        eng.enqueue_local_steps(k, "dataset")
+        if host_feed:
+            # worker w trains on batches w, w + W, w + 2W, ... like the reference's per-worker next_batch streams; a ps-only
+            # process just enqueues its applies (train_loop without batches)
+            if local_workers:
+                losses = eng.train_loop(hx, hy, k, first=done * cfg.num_workers + woff, stride=cfg.num_workers, depth=4, prefetch_next=True)
+            else:
+                eng.train_loop(None, None, k)
+        else:
+            eng.enqueue_local_steps(k, "dataset")
         done += k
         eng.synchronize()
-        loss = eng.read_loss()
+        loss = float(losses[-1]) if (host_feed and local_workers) else eng.read_loss()
         if loss is not None:
             print("time: %.2fs | rank: %d | local step: %d | loss: %f" % (time.time() - t0, rank, done, loss), flush=True)
     eng.check_errors()
