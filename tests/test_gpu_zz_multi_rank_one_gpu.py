@@ -1,0 +1,72 @@
+"""The multi-rank parameter-server protocol on a ONE-GPU box: every rank of a single-process fabric (the in-graph topology,
+``Fabric(world, {rank: device})``) is mapped to GPU 0, each on its own stream, so the sync aggregation over two workers (mean of
+the gradients, stamps, tokens), the async apply-per-push path and both role layouts (a ps-only rank; every rank a worker with the
+ps shard next to worker 0) run where the multi-GPU tiers (tests/test_gpu_multi.py, tools/mp_check.py) are skipped -- against the
+same CPU oracle that replays the batches.  The kernels of the ranks wait for each other on the device, so they must be
+co-resident: 2 x 7 CTAs of the step kernel + the apply grid fit one B200 many times over; every wait is bounded (a protocol bug
+is a failed check_errors(), not a hang).
+
+Written after the round's GPU budget was spent: first hardware run is the driver's (the file sorts last)."""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle_sync(init, xs, ys, steps, W, lr=0.001):
+    sys.path.insert(0, ROOT)
+    from tools.mp_check import grads
+    p = {k: v.clone() for k, v in init.items()}
+    nb = xs.shape[0] // 100
+    for t in range(steps):
+        acc = None
+        for w in range(W):
+            b = (t * W + w) % nb
+            g, _ = grads(p, torch.from_numpy(xs[b * 100:(b + 1) * 100]), torch.from_numpy(ys[b * 100:(b + 1) * 100]))
+            acc = g if acc is None else {k: acc[k] + g[k] for k in g}
+        for k in p:
+            p[k] = p[k] - lr * acc[k] / W
+    return p
+
+
+@pytest.mark.parametrize("ps_on_workers", [False, True])
+def test_two_workers_and_a_ps_on_one_gpu_match_the_cpu_oracle(ps_on_workers):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from distributed_tensorflow_b200.parallel.fabric import Fabric
+    from distributed_tensorflow_b200.parallel.ps_engine import EngineConfig, MLPSpec, PSTrainEngine
+    from distributed_tensorflow_b200.utils.mnist_data import synthetic_mnist
+    torch.cuda.set_device(0)
+    W = 2
+    world = W if ps_on_workers else W + 1
+    xs, ys = synthetic_mnist(100 * W * 8, seed=11)
+    steps = 6
+    for mode in ("sync", "async"):
+        cfg = EngineConfig(num_ps=1, num_workers=W, sync=(mode == "sync"), optimizer={"kind": "sgd", "lr": 0.001}, seed=2, nvls=False,
+                           ps_on_workers=ps_on_workers, precision="tf32", timeout_ns=15_000_000_000)
+        eng = PSTrainEngine(MLPSpec(), cfg, Fabric(world, {r: 0 for r in range(world)}))
+        try:
+            eng.init_params()
+            init = {k: v.clone() for k, v in eng.state_dict().items() if k in ("hid_w", "hid_b", "sm_w", "sm_b")}
+            for r in eng.worker_ranks:
+                eng.attach_dataset(r, xs, ys)
+            eng.enqueue_local_steps(steps, "dataset")
+            eng.synchronize()
+            eng.check_errors()
+            final = eng.state_dict()
+            if mode == "sync":
+                p = _oracle_sync(init, xs, ys, steps, W)
+                assert int(final["global_step"]) == steps
+                errs = {k: float((final[k].cpu() - p[k]).abs().max() / (p[k].abs().max() + 1e-6)) for k in p}
+                # the thresholds of tools/mp_check.py (TF32 multiply against the unrounded fp32 model)
+                assert errs["hid_w"] < 5e-3 and errs["sm_w"] < 5e-3 and max(errs.values()) < 5e-2, errs
+            else:
+                st = eng.staleness()
+                moved = max(float((final[k].cpu() - init[k].cpu()).abs().max()) for k in init)
+                assert int(final["global_step"]) == steps * W and st["count"] == steps * W and moved > 0, (final["global_step"], st)
+        finally:
+            eng.close()
