@@ -47,7 +47,7 @@ def test_two_workers_and_a_ps_on_one_gpu_match_the_cpu_oracle(ps_on_workers):
     steps = 6
     for mode in ("sync", "async"):
         cfg = EngineConfig(num_ps=1, num_workers=W, sync=(mode == "sync"), optimizer={"kind": "sgd", "lr": 0.001}, seed=2, nvls=False,
-                           ps_on_workers=ps_on_workers, precision="tf32", timeout_ns=15_000_000_000)
+                           ps_on_workers=ps_on_workers, precision="tf32", timeout_ns=5_000_000_000)
         eng = PSTrainEngine(MLPSpec(), cfg, Fabric(world, {r: 0 for r in range(world)}))
         try:
             eng.init_params()
