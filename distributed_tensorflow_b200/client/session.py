@@ -97,7 +97,7 @@ def get_default_session() -> Optional["Session"]:
 
 
 class _Plan:
-    __slots__ = ("fetch_nodes", "order", "segments", "leaves", "want_grad", "wanted", "consumers_task", "version")
+    __slots__ = ("fetch_nodes", "order", "segments", "leaves", "want_grad", "wanted", "consumers_task", "version", "fusions")
 
 
 class Session:
@@ -267,6 +267,9 @@ class Session:
                     if sj is not None and plan.segments[sj][0] != task:
                         wanted[sj].add(d.id)
         plan.wanted = wanted
+        from ..framework import fusion as _fusion
+        task_of_id = {nid: plan.segments[si][0] for nid, si in seg_of.items()}
+        plan.fusions = _fusion.plan_fusions(plan.order, {f.id for f in fetch_nodes}, plan.leaves, task_of_id, fed)
         if len(self._plans) > 256:
             self._plans.clear()
         self._plans[key] = plan
@@ -333,6 +336,9 @@ class Session:
                 tracer = StepTracer("/job:localhost/replica:0/task:0")
             ctx = ExecContext(self._local_store, None, None, tracer, None, self.config.allow_soft_placement)
             ctx.leaves = plan.leaves
+            if plan.fusions:
+                from ..framework.fusion import FusionState
+                ctx.fusions = FusionState(plan.fusions)
             ctx.cancel_event = threading.Event()
             for nid, v in feeds.items():
                 ctx.values[nid] = v.detach().requires_grad_(True) if (nid in plan.leaves and v.is_floating_point()) else v
@@ -345,7 +351,7 @@ class Session:
         # ---- distributed: master drives per-task segments ----
         run_id = "%s-%d" % (self.session_id, next(self._run_counter))
         opts = {"leaves": list(plan.leaves), "want_grad": plan.want_grad, "trace": trace,
-                "session_id": self.session_id, "graph_seed": self.graph.seed}
+                "session_id": self.session_id, "graph_seed": self.graph.seed, "fusions": plan.fusions}
         master_values: Dict[int, Any] = dict(feeds)
         touched: List[Tuple[str, int]] = []
         last_segment = {task: si for si, (task, _) in enumerate(plan.segments)}     # where each task's run state can go

@@ -16,6 +16,7 @@ from typing import Any, Dict, Iterable, List, Optional, Sequence, Set, Tuple
 
 import torch
 
+from . import fusion as _fusion
 from . import ops as _ops
 from .device import DeviceSpec
 from .errors import FailedPreconditionError
@@ -138,6 +139,7 @@ class ExecContext:
         self.leaves: Set[int] = set()         # node ids whose values must be autograd leaves
         self.allow_soft_placement = allow_soft_placement
         self._gen: Optional[torch.Generator] = None
+        self.fusions = None                   # framework/fusion.py FusionState of this run (None: nothing planned)
         self._seed = seed
         self._dev_cache: Dict[str, torch.device] = {}
         self.force_device: Optional[torch.device] = None      # fabric strategy: run the whole sub-graph on the task's GPU
@@ -262,9 +264,21 @@ def execute(nodes: Sequence[Tensor], ctx: ExecContext, want_grad: bool) -> None:
     """Evaluate ``nodes`` (already topologically ordered, inputs available in ``ctx.values``)."""
     values = ctx.values
     tracer = ctx.tracer
+    fus = getattr(ctx, "fusions", None)
     for node in nodes:
         if node.id in values:
             continue
+        if fus:
+            # plan-time rewrites (framework/fusion.py): bias + ReLU in the GEMM epilogue, the clipped softmax cross-entropy chain
+            # as one kernel; nodes interior to an active rewrite have no value of their own
+            t0 = time.perf_counter_ns() if tracer is not None else 0
+            handled, out = _fusion.try_execute(node, ctx, values, fus, ctx.torch_device(node), want_grad)
+            if handled:
+                if out is not None:
+                    values[node.id] = out
+                    if tracer is not None:
+                        tracer.record(node, ctx, t0, time.perf_counter_ns(), out)
+                continue
         kernel = _ops.KERNELS.get(node.op_type)
         if kernel is None:
             raise NotImplementedError("no kernel registered for op type %r (node %r)" % (node.op_type, node.name))

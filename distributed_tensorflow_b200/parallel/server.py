@@ -226,6 +226,9 @@ class Server:
                     tracer = StepTracer("/job:%s/task:%d" % self.task)
                 ctx = ExecContext(self.store, self.task, self.gpu_index, tracer, opts.get("seed"))
                 ctx.leaves = set(opts.get("leaves", ()))
+                if opts.get("fusions"):
+                    from ..framework.fusion import FusionState
+                    ctx.fusions = FusionState(opts["fusions"])
                 ctx.cancel_event = self.cancel_event(opts.get("session_id", ""))
                 ctx.server = self
                 st = self._runs[run_id] = _RunState(ctx, bool(opts.get("want_grad")))

@@ -38,6 +38,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import torch
 
 from ..framework import device as _device
+from ..framework import fusion as _fusion
 from ..framework import ops as _ops
 from ..framework.device import DeviceSpec
 from ..framework.executor import ExecContext, execute, needed_nodes
@@ -291,7 +292,11 @@ class FabricPSStrategy:
         with _device.device(None), _device.device(loss_t.device or None):
             step = g.create_node("FabricTrainStep", placeholders,
                                  {"strategy": self, "loss": loss_t, "var_nodes": [v._node for v in vars_],
-                                  "order": order}, "fabric_train_step", loss_t.dtype, ())
+                                  "order": order,
+                                  # plan-time rewrites of the worker sub-graph (framework/fusion.py): only the loss leaves it
+                                  "fusions": _fusion.plan_fusions(order, {loss_t.id}, {v._node.id for v in vars_},
+                                                                  {n.id: 0 for n in order}, set())},
+                                 "fabric_train_step", loss_t.dtype, ())
             self.loss = _ops.identity(step, name="fabric_loss")
         self._step_node_id = step.id
         # the user's own loss tensor, fetched next to the train op (or alone, for validation), is answered by the engine
@@ -516,6 +521,8 @@ class FabricPSStrategy:
                 sub.values[pnode.id] = val.to(rk.device, non_blocking=True)
             for vn in var_nodes:
                 sub.values[vn.id] = leaves[vn.attrs["var_name"]]
+            if a.get("fusions"):
+                sub.fusions = _fusion.FusionState(a["fusions"])
             execute([n for n in a["order"] if n.id not in sub.values], sub, True)
             return sub.values[a["loss"].id]
         t0 = time.time()

@@ -1,0 +1,148 @@
+"""Plan-time fusion of the graph tier (framework/fusion.py): which patterns are rewritten, when a rewrite is refused because it
+could be observed, and that a fused plan computes what the node-by-node plan computes -- on the torch path bit for bit, on the
+kernel path (host emulation) to rounding.  Reference program: /root/reference/distributed_mnist.py:106-126."""
+import shutil
+
+import numpy as np
+import pytest
+import torch
+
+import distributed_tensorflow_b200 as tf
+from distributed_tensorflow_b200.framework import fusion
+from distributed_tensorflow_b200.ops import cuda_lib
+from distributed_tensorflow_b200.utils.mnist_data import synthetic_mnist
+
+
+def _mnist_graph(hidden=32):
+    tf.set_random_seed(3)
+    x, y_ = tf.placeholder(tf.float32, [None, 784]), tf.placeholder(tf.float32, [None, 10])
+    w1 = tf.Variable(tf.truncated_normal([784, hidden], stddev=1.0 / 28), name="hid_w")
+    b1 = tf.Variable(tf.zeros([hidden]), name="hid_b")
+    w2 = tf.Variable(tf.truncated_normal([hidden, 10], stddev=1.0 / np.sqrt(hidden)), name="sm_w")
+    b2 = tf.Variable(tf.zeros([10]), name="sm_b")
+    hid_lin = tf.nn.xw_plus_b(x, w1, b1)
+    hid = tf.nn.relu(hid_lin)
+    y = tf.nn.softmax(tf.nn.xw_plus_b(hid, w2, b2))
+    loss = -tf.reduce_sum(y_ * tf.log(tf.clip_by_value(y, 1e-10, 1.0)))
+    gs = tf.train.get_or_create_global_step()
+    train = tf.train.GradientDescentOptimizer(0.001).minimize(loss, global_step=gs)
+    return dict(x=x, y_=y_, hid_lin=hid_lin, hid=hid, y=y, loss=loss, train=train, vars=[w1, b1, w2, b2])
+
+
+def test_patterns_are_planned_only_when_unobservable():
+    g = _mnist_graph()
+    with tf.Session() as sess:
+        feeds = {g["x"].id if hasattr(g["x"], "id") else 0}
+
+        def plan(fetches, fed=()):
+            nodes = [sess._resolve(f) for f in fetches]
+            return sess._plan(nodes, set(sess._resolve(f).id for f in fed)).fusions
+        p = plan([g["train"], g["loss"]])
+        assert p is not None and len(p["relu"]) == 1 and len(p["xent"]) == 1
+        neg, sm, logits, labels, lo, interior = p["xent"][0]
+        assert neg == g["loss"].id and sm == g["y"].id and labels == g["y_"].id and lo == 1e-10 and len(interior) == 5
+        assert p["relu"][0] == [g["hid_lin"].id, g["hid"].id]
+        assert plan([g["loss"], g["y"]])["xent"] == []                      # the softmax output is fetched: keep the chain
+        assert plan([g["loss"], g["hid_lin"]])["relu"] == []                # the pre-activation is fetched: keep XwPlusB + Relu
+        assert plan([g["loss"]], fed=[g["y"]]) is None or plan([g["loss"]], fed=[g["y"]])["xent"] == []     # y is fed
+        only_pred = plan([g["y"]])
+        assert only_pred is not None and only_pred["xent"] == [] and len(only_pred["relu"]) == 1
+        # a second consumer of the hidden pre-activation
+        extra = tf.reduce_sum(g["hid_lin"])
+        assert plan([g["loss"], extra])["relu"] == []
+        # gradients with respect to an interior value
+        gy = tf.gradients(g["loss"], [g["y"]])[0]
+        p2 = plan([gy])
+        assert p2 is None or p2["xent"] == []
+    # other clip bounds / axis reductions are not the pattern
+    tf.reset_default_graph()
+    x = tf.placeholder(tf.float32, [None, 10])
+    y_ = tf.placeholder(tf.float32, [None, 10])
+    with tf.Session() as sess:
+        for loss in (-tf.reduce_sum(y_ * tf.log(tf.clip_by_value(tf.nn.softmax(x), 1e-2, 1.0))),
+                     -tf.reduce_sum(y_ * tf.log(tf.clip_by_value(tf.nn.softmax(x), 1e-10, 0.9))),
+                     -tf.reduce_sum(y_ * tf.log(tf.clip_by_value(tf.nn.softmax(x), 1e-10, 1.0)), axis=1)):
+            assert sess._plan([sess._resolve(loss)], set()).fusions is None
+
+
+def _train(steps=5, fetch_extra=False):
+    tf.reset_default_graph()
+    g = _mnist_graph()
+    xs, ys = synthetic_mnist(100 * steps, seed=2)
+    out = []
+    with tf.Session() as sess:
+        sess.run(tf.global_variables_initializer())
+        for i in range(steps):
+            fetches = [g["train"], g["loss"]] + ([g["y"], g["hid_lin"]] if fetch_extra else [])
+            out.append(float(sess.run(fetches, {g["x"]: xs[i * 100:(i + 1) * 100], g["y_"]: ys[i * 100:(i + 1) * 100]})[1]))
+        ws = sess.run(g["vars"])
+        pred = sess.run(g["y"], {g["x"]: xs[:50]})                            # forward-only plan: ReLU fusion without the loss
+    return out, ws, pred
+
+
+def test_fused_plan_equals_node_by_node_plan_on_the_torch_path(monkeypatch):
+    fused = _train()
+    monkeypatch.setattr(fusion, "ENABLED", False)
+    plain = _train()
+    monkeypatch.setattr(fusion, "ENABLED", True)
+    observed = _train(fetch_extra=True)                                    # fetching interior values switches the rewrites off per plan
+    for other in (plain, observed):
+        assert fused[0] == other[0]
+        for a, b in zip(fused[1], other[1]):
+            assert np.array_equal(a, b)
+        assert np.array_equal(fused[2], other[2])
+    assert fused[0][-1] < fused[0][0]
+
+
+def test_fused_plan_runs_the_fused_kernels_under_the_emulation(tmp_path_factory, monkeypatch):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    cuda_lib.enable_emulation(str(tmp_path_factory.mktemp("emu_lib")))
+    try:
+        n0 = cuda_lib.launch_count()
+        fused = _train(steps=3)
+        n_fused = cuda_lib.launch_count() - n0
+        monkeypatch.setattr(fusion, "ENABLED", False)
+        n0 = cuda_lib.launch_count()
+        plain = _train(steps=3)
+        n_plain = cuda_lib.launch_count() - n0
+    finally:
+        cuda_lib.disable_emulation()
+    assert n_fused <= n_plain - 3 * 5                                      # our element-wise launches the rewrites remove, per training step
+    np.testing.assert_allclose(fused[0], plain[0], rtol=2e-4)
+    for a, b in zip(fused[1], plain[1]):
+        np.testing.assert_allclose(a, b, rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(fused[2], plain[2], rtol=1e-3, atol=1e-5)
+
+
+def test_fusions_travel_to_remote_tasks(ports):
+    """1 ps + 1 worker in this process: the worker's segment receives the planned rewrites through the run options."""
+    p = ports(2)
+    cluster = tf.train.ClusterSpec({"ps": ["127.0.0.1:%d" % p[0]], "worker": ["127.0.0.1:%d" % p[1]]})
+    ps = tf.train.Server(cluster, job_name="ps", task_index=0)
+    wk = tf.train.Server(cluster, job_name="worker", task_index=0)
+    try:
+        with tf.device(tf.train.replica_device_setter(cluster=cluster, worker_device="/job:worker/task:0")):
+            g = _mnist_graph()
+        xs, ys = synthetic_mnist(300, seed=2)
+        seen = []
+        orig = fusion.try_execute
+
+        def spy(node, ctx, values, st, dev, want_grad):
+            handled, out = orig(node, ctx, values, st, dev, want_grad)
+            if handled:
+                seen.append((ctx.task, node.op_type))
+            return handled, out
+        fusion.try_execute = spy
+        try:
+            with tf.Session(wk.target) as sess:
+                sess.run(tf.global_variables_initializer())
+                l0 = float(sess.run([g["train"], g["loss"]], {g["x"]: xs[:100], g["y_"]: ys[:100]})[1])
+                l1 = float(sess.run([g["train"], g["loss"]], {g["x"]: xs[:100], g["y_"]: ys[:100]})[1])
+        finally:
+            fusion.try_execute = orig
+        assert l1 < l0
+        assert (("worker", 0), "Neg") in seen and (("worker", 0), "XwPlusB") in seen and (("worker", 0), "Softmax") in seen
+    finally:
+        wk.stop()
+        ps.stop()
