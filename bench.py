@@ -693,7 +693,7 @@ def main():
                 if world > 1:
                     raise                # ranks must not diverge
                 e2e["pipelined_error"] = repr(e)[:300]
-        if args.e2e_native_loop and ((world == 1 and is_worker) or pow_):
+        if args.e2e_native_loop and len(wl) <= 1 and ((world == 1 and is_worker) or pow_):
             # third arm: the framework's own training loop (one native call per K steps).  A failure on any rank drops the
             # arm on every rank (the flag is agreed on before anything is recorded); the other arms' numbers stand.
             nt, nerr = None, None
