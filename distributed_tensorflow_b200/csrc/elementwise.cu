@@ -84,45 +84,48 @@ enum { EW_NEG = 0, EW_SQUARE = 1, EW_SQRT = 2, EW_RSQRT = 3, EW_EXP = 4, EW_LOG 
        EW_RELU = 9 };
 enum { EW_FULL = 0, EW_SCALAR = 1, EW_INNER = 2 };
 
-DTF_DEVICE float ew_binary(int op, float x, float y) {
-  switch (op) {
-    case EW_ADD: return x + y;
-    case EW_SUB: return x - y;
-    case EW_MUL: return x * y;
-    case EW_DIV: return x / y;
-    case EW_MAX: return fmaxf(x, y);
-    case EW_MIN: return fminf(x, y);
-    default: { const float d = x - y; return d * d; }
+template <int OP>
+DTF_DEVICE float ew_binary(float x, float y) {
+  if (OP == EW_ADD) return x + y;
+  if (OP == EW_SUB) return x - y;
+  if (OP == EW_MUL) return x * y;
+  if (OP == EW_DIV) return x / y;
+  if (OP == EW_MAX) return fmaxf(x, y);
+  if (OP == EW_MIN) return fminf(x, y);
+  const float d = x - y;
+  return d * d;
+}
+
+template <int OP>
+DTF_DEVICE float ew_unary(float x) {
+  if (OP == EW_NEG) return -x;
+  if (OP == EW_SQUARE) return x * x;
+  if (OP == EW_SQRT) return sqrtf(x);
+  if (OP == EW_RSQRT) return 1.0f / sqrtf(x);
+  if (OP == EW_EXP) return expf(x);
+  if (OP == EW_LOG) return logf(x);
+  if (OP == EW_ABS) return fabsf(x);
+  if (OP == EW_SIGMOID) return 1.0f / (1.0f + expf(-x));
+  if (OP == EW_TANH) return tanhf(x);
+  return x > 0.0f ? x : 0.0f;
+}
+
+// The op is a template parameter (one instantiation per op: no switch in the loop); indices are 32-bit (the launcher splits
+// larger tensors), so the trailing-vector broadcast costs one 32-bit remainder per element.
+template <int OP>
+__global__ void ew_binary_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, unsigned int n,
+                                 int mode_a, int mode_b, unsigned int inner) {
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned int r = (mode_a == EW_INNER || mode_b == EW_INNER) ? i % inner : 0u;
+    const float x = a[mode_a == EW_FULL ? i : (mode_a == EW_SCALAR ? 0u : r)];
+    const float y = b[mode_b == EW_FULL ? i : (mode_b == EW_SCALAR ? 0u : r)];
+    out[i] = ew_binary<OP>(x, y);
   }
 }
 
-DTF_DEVICE float ew_unary(int op, float x) {
-  switch (op) {
-    case EW_NEG: return -x;
-    case EW_SQUARE: return x * x;
-    case EW_SQRT: return sqrtf(x);
-    case EW_RSQRT: return 1.0f / sqrtf(x);
-    case EW_EXP: return expf(x);
-    case EW_LOG: return logf(x);
-    case EW_ABS: return fabsf(x);
-    case EW_SIGMOID: return 1.0f / (1.0f + expf(-x));
-    case EW_TANH: return tanhf(x);
-    default: return x > 0.0f ? x : 0.0f;
-  }
-}
-
-__global__ void ew_binary_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n,
-                                 int op, int mode_a, int mode_b, long long inner) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float x = a[mode_a == EW_FULL ? i : (mode_a == EW_SCALAR ? 0 : i % inner)];
-    const float y = b[mode_b == EW_FULL ? i : (mode_b == EW_SCALAR ? 0 : i % inner)];
-    out[i] = ew_binary(op, x, y);
-  }
-}
-
-__global__ void ew_unary_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, int op) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = ew_unary(op, x[i]);
+template <int OP>
+__global__ void ew_unary_kernel(const float* __restrict__ x, float* __restrict__ out, unsigned int n) {
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = ew_unary<OP>(x[i]);
 }
 
 // out[i] = alpha * x[i or 0] + beta: scalings, negation, and the broadcast of a scalar gradient (the backward of a full reduction)
@@ -419,6 +422,34 @@ static inline int grid_for(long long n, int block = 256) {
   return (int)g;
 }
 
+// Chunks of at most 2^30 elements per launch keep the kernels' index arithmetic in 32 bits; a chunk boundary is a multiple of
+// `inner`, so the trailing-vector broadcast stays aligned.
+template <int OP>
+static int ew_binary_launch(const float* a, const float* b, float* out, long long n, int mode_a, int mode_b, long long inner,
+                            cudaStream_t s) {
+  long long chunk = 1ll << 30;
+  if (mode_a == EW_INNER || mode_b == EW_INNER) {
+    if (inner >= (1ll << 31)) return -1;
+    chunk = inner > chunk ? inner : chunk / inner * inner;
+  }
+  for (long long off = 0; off < n; off += chunk) {
+    const long long m = n - off < chunk ? n - off : chunk;
+    DTF_LAUNCH(ew_binary_kernel<OP>, grid_for(m), 256, s, a + (mode_a == EW_FULL ? off : 0), b + (mode_b == EW_FULL ? off : 0), out + off,
+               (unsigned int)m, mode_a, mode_b, (unsigned int)(inner > 0 ? inner : 1));
+  }
+  return (int)cudaGetLastError();
+}
+
+template <int OP>
+static int ew_unary_launch(const float* x, float* out, long long n, cudaStream_t s) {
+  const long long chunk = 1ll << 30;
+  for (long long off = 0; off < n; off += chunk) {
+    const long long m = n - off < chunk ? n - off : chunk;
+    DTF_LAUNCH(ew_unary_kernel<OP>, grid_for(m), 256, s, x + off, out + off, (unsigned int)m);
+  }
+  return (int)cudaGetLastError();
+}
+
 }  // namespace dtf
 
 extern "C" {
@@ -468,15 +499,32 @@ int dtf_ew_binary(const float* a, const float* b, float* out, long long n, int o
   if (n < 0 || op < 0 || op > 6 || mode_a < 0 || mode_a > 2 || mode_b < 0 || mode_b > 2) return -1;
   if ((mode_a == 2 || mode_b == 2) && inner < 1) return -1;
   if (n == 0) return 0;
-  DTF_LAUNCH(ew_binary_kernel, grid_for(n), 256, s, a, b, out, n, op, mode_a, mode_b, inner);
-  return (int)cudaGetLastError();
+  switch (op) {
+    case EW_ADD: return ew_binary_launch<EW_ADD>(a, b, out, n, mode_a, mode_b, inner, s);
+    case EW_SUB: return ew_binary_launch<EW_SUB>(a, b, out, n, mode_a, mode_b, inner, s);
+    case EW_MUL: return ew_binary_launch<EW_MUL>(a, b, out, n, mode_a, mode_b, inner, s);
+    case EW_DIV: return ew_binary_launch<EW_DIV>(a, b, out, n, mode_a, mode_b, inner, s);
+    case EW_MAX: return ew_binary_launch<EW_MAX>(a, b, out, n, mode_a, mode_b, inner, s);
+    case EW_MIN: return ew_binary_launch<EW_MIN>(a, b, out, n, mode_a, mode_b, inner, s);
+    default: return ew_binary_launch<EW_SQDIFF>(a, b, out, n, mode_a, mode_b, inner, s);
+  }
 }
 
 int dtf_ew_unary(const float* x, float* out, long long n, int op, cudaStream_t s) {
   if (n < 0 || op < 0 || op > 9) return -1;
   if (n == 0) return 0;
-  DTF_LAUNCH(ew_unary_kernel, grid_for(n), 256, s, x, out, n, op);
-  return (int)cudaGetLastError();
+  switch (op) {
+    case EW_NEG: return ew_unary_launch<EW_NEG>(x, out, n, s);
+    case EW_SQUARE: return ew_unary_launch<EW_SQUARE>(x, out, n, s);
+    case EW_SQRT: return ew_unary_launch<EW_SQRT>(x, out, n, s);
+    case EW_RSQRT: return ew_unary_launch<EW_RSQRT>(x, out, n, s);
+    case EW_EXP: return ew_unary_launch<EW_EXP>(x, out, n, s);
+    case EW_LOG: return ew_unary_launch<EW_LOG>(x, out, n, s);
+    case EW_ABS: return ew_unary_launch<EW_ABS>(x, out, n, s);
+    case EW_SIGMOID: return ew_unary_launch<EW_SIGMOID>(x, out, n, s);
+    case EW_TANH: return ew_unary_launch<EW_TANH>(x, out, n, s);
+    default: return ew_unary_launch<EW_RELU>(x, out, n, s);
+  }
 }
 
 int dtf_ew_affine(const float* x, float* out, long long n, int mode, float alpha, float beta, cudaStream_t s) {
