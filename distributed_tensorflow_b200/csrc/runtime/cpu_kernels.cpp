@@ -8,6 +8,9 @@
 // with lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller (epsilon is NOT bias-corrected: unlike torch.optim.Adam).
 #include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
 
 #include "../philox.h"
 
@@ -89,6 +92,36 @@ int dtf_cpu_philox_words(unsigned int* out, long long nblk, unsigned long long k
     const dtf_rng::Block blk = dtf_rng::philox4x32_10(ctr_lo + (unsigned long long)b, ctr_hi, key);
     for (int j = 0; j < 4; ++j) out[b * 4 + j] = blk.w[j];
   }
+  return 0;
+}
+
+// Input pipeline: dst row i = src row idx[i] (rows of row_bytes bytes), split over up to `threads` host threads -- the gather
+// behind a shuffled epoch of batches laid out [batch, row] in (pinned) host memory, i.e. the role of `mnist.train.next_batch`
+// (distributed_mnist.py:149) done once per epoch, off the training thread and without the GIL.
+// Returns 0, -1 on bad arguments, -2 when an index is outside [0, n_src).
+int dtf_gather_rows(const void* src, long long n_src, const long long* idx, long long n, long long row_bytes, void* dst, int threads) {
+  if (n < 0 || n_src < 0 || row_bytes < 0 || (n > 0 && (src == nullptr || dst == nullptr || idx == nullptr))) return -1;
+  for (long long i = 0; i < n; ++i)
+    if (idx[i] < 0 || idx[i] >= n_src) return -2;
+  const char* s = static_cast<const char*>(src);
+  char* d = static_cast<char*>(dst);
+  auto work = [&](long long lo, long long hi) {
+    for (long long i = lo; i < hi; ++i) std::memcpy(d + i * row_bytes, s + idx[i] * row_bytes, (size_t)row_bytes);
+  };
+  long long t = threads < 1 ? 1 : threads;
+  if (n * row_bytes < (1ll << 20)) t = 1;                 // small gathers are not worth a thread start
+  if (t > n) t = n > 0 ? n : 1;
+  if (t == 1) {
+    work(0, n);
+    return 0;
+  }
+  std::vector<std::thread> pool;
+  const long long per = (n + t - 1) / t;
+  for (long long k = 0; k < t; ++k) {
+    const long long lo = k * per, hi = lo + per < n ? lo + per : n;
+    if (lo < hi) pool.emplace_back(work, lo, hi);
+  }
+  for (auto& th : pool) th.join();
   return 0;
 }
 

@@ -26,6 +26,9 @@ def declare(lib: ctypes.CDLL) -> None:
         lib.dtf_cpu_philox_fill.restype = c_int
         lib.dtf_cpu_philox_words.argtypes = [c_void_p, ctypes.c_longlong, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_ulonglong]
         lib.dtf_cpu_philox_words.restype = c_int
+    if hasattr(lib, "dtf_gather_rows"):
+        lib.dtf_gather_rows.argtypes = [c_void_p, ctypes.c_longlong, c_void_p, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_int]
+        lib.dtf_gather_rows.restype = c_int
     lib.dtf_acc_create.restype = c_void_p
     lib.dtf_acc_destroy.argtypes = [c_void_p]
     lib.dtf_acc_apply_grad.argtypes = [c_void_p, c_void_p, c_int64, c_int64]

@@ -73,11 +73,14 @@ def main():
     host_feed = FLAGS.input == "host" and len(local_workers) <= 1
     hx = hy = None
     if host_feed and local_workers:
-        B = FLAGS.batch_size
-        nb = min(FLAGS.num_train, 20000) // B
-        hx = torch.from_numpy(xs[:nb * B]).pin_memory().view(nb, B, -1)
-        hy = torch.from_numpy(ys[:nb * B]).pin_memory().view(nb, B, -1)
+        # shuffled epochs in pinned host memory, the next one gathered in the background (utils/input_pipeline.py); every
+        # process builds the same epochs (same seed) and worker w takes batches w, w + W, ... of each
+        from distributed_tensorflow_b200.utils.input_pipeline import EpochBatcher
+        batcher = EpochBatcher(xs, ys, FLAGS.batch_size, shuffle=True, seed=1)
+        hx, hy = batcher.next_epoch()
         woff = eng.worker_ranks.index(local_workers[0])
+        per_epoch = batcher.num_batches // cfg.num_workers           # steps this worker takes per epoch
+        in_epoch = 0
     elif not host_feed:
         for r in local_workers:
             eng.attach_dataset(r, xs, ys)
@@ -90,7 +93,13 @@ def main():
             # worker w trains on batches w, w + W, w + 2W, ... like the reference's per-worker next_batch streams; a ps-only
             # process just enqueues its applies (train_loop without batches)
             if local_workers:
-                losses = eng.train_loop(hx, hy, k, first=done * cfg.num_workers + woff, stride=cfg.num_workers, depth=4, prefetch_next=True)
+                k = min(k, per_epoch - in_epoch)
+                losses = eng.train_loop(hx, hy, k, first=in_epoch * cfg.num_workers + woff, stride=cfg.num_workers, depth=4,
+                                        prefetch_next=in_epoch + k < per_epoch)
+                in_epoch += k
+                if in_epoch == per_epoch:
+                    hx, hy = batcher.next_epoch()
+                    in_epoch = 0
             else:
                 eng.train_loop(None, None, k)
         else:
