@@ -346,17 +346,18 @@ class PSTrainEngine:
         """Chief-style initialisation on the ps shards (truncated normal / zeros like the reference model),
         then publish the bf16 shadow (+replicas) and the initial tokens."""
         spec, cfg = self.spec, self.cfg
-        # the framework's counter-based stream (csrc/philox.h; K13): key from the engine seed, one stream id per variable, truncated
-        # normal with |z| <= 2 like tf.truncated_normal (reference distributed_mnist.py:98-105).  Drawn by the host implementation
-        # and copied -- the same values philox_fill_kernel writes for a graph-tier initialiser placed on /gpu with this key.
-        from ..ops import random_ops
-        key = (int(cfg.seed) * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019) & (2 ** 64 - 1)
+        g = torch.Generator(device="cpu")
+        g.manual_seed(cfg.seed)
         init = {}
-        init["hid_w"] = random_ops._fill_host(spec.in_dim * spec.hidden, random_ops.TRUNCATED_NORMAL, 0.0, 1.0 / math.sqrt(spec.in_dim),
-                                              key, 0, 1).view(spec.in_dim, spec.hidden)
+        t = torch.empty(spec.in_dim, spec.hidden)
+        torch.nn.init.trunc_normal_(t, 0.0, 1.0 / math.sqrt(spec.in_dim), -2.0 / math.sqrt(spec.in_dim),
+                                    2.0 / math.sqrt(spec.in_dim), generator=g)
+        init["hid_w"] = t
         init["hid_b"] = torch.zeros(spec.hidden)
-        init["sm_w"] = random_ops._fill_host(spec.hidden * spec.classes, random_ops.TRUNCATED_NORMAL, 0.0, 1.0 / math.sqrt(spec.hidden),
-                                             key, 0, 2).view(spec.hidden, spec.classes)
+        t2 = torch.empty(spec.hidden, spec.classes)
+        sd = 1.0 / math.sqrt(spec.hidden)
+        torch.nn.init.trunc_normal_(t2, 0.0, sd, -2 * sd, 2 * sd, generator=g)
+        init["sm_w"] = t2
         init["sm_b"] = torch.zeros(spec.classes)
         if values:
             for k, v in values.items():
