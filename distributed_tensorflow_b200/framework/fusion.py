@@ -3,6 +3,8 @@ work into the producing kernel -- the B200 rule "fuse elementwise/activation wor
 
 * ``Relu(XwPlusB(x, W, b))`` (``/root/reference/distributed_mnist.py:109-110``) -> ONE GEMM with the bias + ReLU epilogue
   (``ops/native.linear(relu=True)``: out of TMEM on ``/gpu``), the ReLU mask applied in the backward GEMMs' producer;
+* ``Relu(MatMul(x, W) + b)`` / ``MatMul(x, W) + b`` with a vector or scalar ``b`` (``/root/reference/standalone.py:52-53,60``: the
+  tower spelling) -> the same GEMM epilogue;
 * ``-reduce_sum(y_ * log(clip_by_value(softmax(logits), eps, 1)))`` (``distributed_mnist.py:112-113``) -> ONE fused
   softmax + clipped cross-entropy forward/backward kernel (``ops/native.clipped_softmax_xent_sum``) instead of six node kernels
   forward and six backward.
@@ -29,7 +31,8 @@ def _through_identity(t):
 
 
 def plan_fusions(order: Sequence[Any], fetch_ids: Set[int], leaves: Set[int], task_of: Dict[int, Any], fed: Set[int]) -> Optional[Dict[str, list]]:
-    """Wire form ``{"relu": [[xwb_id, relu_id], ...], "xent": [[neg, softmax, logits, labels, clip_min, [interior ids]], ...]}``
+    """Wire form ``{"relu": [[xwb_id, relu_id], ...], "affine": [[matmul, add, relu or -1, x, w, b], ...],
+    "xent": [[neg, softmax, logits, labels, clip_min, [interior ids]], ...]}``
     (plain ints / floats: it travels to remote tasks inside the run options), or ``None``."""
     if not ENABLED:
         return None
@@ -46,10 +49,25 @@ def plan_fusions(order: Sequence[Any], fetch_ids: Set[int], leaves: Set[int], ta
         """``node`` is produced in this plan, seen by ``consumer`` only, and nobody outside can observe it."""
         return (node.id in pos and node.id not in protected and [u.id for u in users.get(node.id, ())] == [consumer.id]
                 and node.id in task_of and consumer.id in task_of and task_of[node.id] == task_of[consumer.id])
-    relu_pairs, xent = [], []
+    relu_pairs, affine, xent = [], [], []
     taken: Set[int] = set()
+    for n in order:                      # MatMul + Add (+ Relu): planned first, a Relu on top joins below
+        if n.id in fed or n.id not in task_of or n.op_type != "Add" or n.id in leaves or n.id in taken:
+            continue
+        a, b = n.inputs
+        mm, bias = (a, b) if a.op_type == "MatMul" else ((b, a) if b.op_type == "MatMul" else (None, None))
+        if mm is None or mm.attrs.get("ta") or mm.attrs.get("tb") or not private(mm, n) or mm.id in taken:
+            continue
+        if bias.id in pos and bias.id not in fed and pos[bias.id] > pos[mm.id]:
+            continue                     # the bias must exist when the MatMul node (the decision point) is reached
+        relu = -1
+        us = users.get(n.id, ())
+        if len(us) == 1 and us[0].op_type == "Relu" and private(n, us[0]) and us[0].id not in leaves and us[0].id not in taken:
+            relu = us[0].id
+        affine.append([mm.id, n.id, relu, mm.inputs[0].id, mm.inputs[1].id, bias.id])
+        taken.update((mm.id, n.id) + ((relu,) if relu >= 0 else ()))
     for n in order:
-        if n.id in fed or n.id not in task_of:
+        if n.id in fed or n.id not in task_of or n.id in taken:
             continue
         if n.op_type == "Relu" and n.id not in leaves:
             src = n.inputs[0]
@@ -85,14 +103,14 @@ def plan_fusions(order: Sequence[Any], fetch_ids: Set[int], leaves: Set[int], ta
                 continue
             xent.append([n.id, sm.id, logits.id, labels.id, float(lo), interior])
             taken.update(interior + [n.id])
-    if not relu_pairs and not xent:
+    if not relu_pairs and not xent and not affine:
         return None
-    return {"relu": relu_pairs, "xent": xent}
+    return {"relu": relu_pairs, "affine": affine, "xent": xent}
 
 
 class FusionState:
     """Runtime form of the planned rewrites for one run on one task."""
-    __slots__ = ("xwb", "relu", "softmax", "interior", "neg", "active")
+    __slots__ = ("xwb", "relu", "softmax", "interior", "neg", "active", "aff_first", "aff_interior", "aff_last")
 
     def __init__(self, wire: Optional[Dict[str, list]]):
         self.xwb: Dict[int, int] = {}
@@ -101,6 +119,17 @@ class FusionState:
         self.interior: Dict[int, int] = {}
         self.neg: Dict[int, tuple] = {}
         self.active: Dict[int, bool] = {}
+        self.aff_first: Dict[int, tuple] = {}        # MatMul id -> spec (the decision point)
+        self.aff_interior: Dict[int, int] = {}       # Add id (when a Relu closes the pattern) -> MatMul id
+        self.aff_last: Dict[int, tuple] = {}         # id of the node that receives the fused value -> spec
+        for mm, add, relu, x, w, b in (wire or {}).get("affine", ()):
+            spec = (int(mm), int(add), int(relu), int(x), int(w), int(b))
+            self.aff_first[int(mm)] = spec
+            if relu >= 0:
+                self.aff_interior[int(add)] = int(mm)
+                self.aff_last[int(relu)] = spec
+            else:
+                self.aff_last[int(add)] = spec
         for x, r in (wire or {}).get("relu", ()):
             self.xwb[int(x)] = int(r)
             self.relu[int(r)] = int(x)
@@ -112,7 +141,7 @@ class FusionState:
                 self.interior[int(i)] = int(sm)
 
     def __bool__(self) -> bool:
-        return bool(self.xwb or self.softmax)
+        return bool(self.xwb or self.softmax or self.aff_first)
 
 
 def try_execute(node, ctx, values: Dict[int, Any], st: FusionState, dev, want_grad: bool):
@@ -135,6 +164,27 @@ def try_execute(node, ctx, values: Dict[int, Any], st: FusionState, dev, want_gr
         if st.active.get(src):
             return True, values[src]                       # the producer's epilogue already applied the activation
         return False, None
+    if nid in st.aff_first:
+        mm, add, relu, xid, wid, bid = st.aff_first[nid]
+        x, w, b = values.get(xid), values.get(wid), values.get(bid)
+        ok = (isinstance(x, torch.Tensor) and isinstance(w, torch.Tensor) and isinstance(b, torch.Tensor) and x.dim() == 2 and w.dim() == 2
+              and x.dtype == torch.float32 and w.dtype == torch.float32 and b.dtype == torch.float32
+              and (b.numel() == 1 or tuple(b.shape) == (w.shape[1],)))
+        st.active[nid] = ok
+        return (True, None) if ok else (False, None)
+    if nid in st.aff_interior:
+        return (True, None) if st.active.get(st.aff_interior[nid]) else (False, None)
+    if nid in st.aff_last:
+        mm, add, relu, xid, wid, bid = st.aff_last[nid]
+        if not st.active.get(mm):
+            return False, None
+        x, w, b = values[xid], values[wid], values[bid]
+        if dev is not None:
+            x, w, b = (v.to(dev, non_blocking=True) if v.device != dev else v for v in (x, w, b))
+        with (torch.enable_grad() if want_grad else torch.no_grad()):
+            if b.numel() == 1 and tuple(b.shape) != (w.shape[1],):
+                b = b.reshape(1).expand(w.shape[1])              # a scalar bias: one value per output column (its gradient sums back)
+            return True, native.linear(x, w, b.contiguous(), relu=relu >= 0)
     if nid in st.softmax:
         _, _, lid, yid, _ = st.softmax[nid]
         logits, labels = values.get(lid), values.get(yid)

@@ -146,3 +146,60 @@ def test_fusions_travel_to_remote_tasks(ports):
     finally:
         wk.stop()
         ps.stop()
+
+
+def _tower_graph():
+    """The tower of /root/reference/standalone.py:46-63: matmul + scalar bias + relu per layer, mean squared error."""
+    tf.set_random_seed(4)
+    x, t = tf.placeholder(tf.float32, [None, 2]), tf.placeholder(tf.float32, [None, 1])
+    h, ws = x, []
+    for i, d in enumerate((16, 8)):
+        w = tf.get_variable("affine%d/w" % i, [h.get_shape()[1], d], initializer=tf.truncated_normal_initializer(0, 1))
+        b = tf.get_variable("affine%d/b" % i, [], initializer=tf.zeros_initializer)
+        h = tf.nn.relu(tf.matmul(h, w) + b)
+        ws += [w, b]
+    w = tf.get_variable("affine_last/w", [h.get_shape()[1], 1], initializer=tf.constant_initializer(value=1))
+    b = tf.get_variable("affine_last/b", [1], initializer=tf.zeros_initializer)          # a vector bias on the last layer
+    y = tf.matmul(h, w) + b
+    loss = tf.reduce_mean(tf.square(y - t))
+    train = tf.train.GradientDescentOptimizer(0.01).minimize(loss)
+    return dict(x=x, t=t, y=y, loss=loss, train=train, vars=ws + [w, b])
+
+
+def _train_tower(steps=8):
+    tf.reset_default_graph()
+    g = _tower_graph()
+    rng = np.random.RandomState(0)
+    out = []
+    with tf.Session() as sess:
+        sess.run(tf.global_variables_initializer())
+        plan = sess._plan([sess._resolve(g["train"]), sess._resolve(g["loss"])], {g["x"].id, g["t"].id}).fusions
+        for _ in range(steps):
+            xs = rng.rand(64, 2).astype(np.float32)
+            out.append(float(sess.run([g["train"], g["loss"]], {g["x"]: xs, g["t"]: xs.sum(1, keepdims=True)})[1]))
+        ws = sess.run(g["vars"])
+    return plan, out, ws
+
+
+def test_matmul_bias_relu_towers_fuse_into_the_gemm_epilogue(monkeypatch, tmp_path_factory):
+    plan, fused, fw = _train_tower()
+    assert plan is not None and len(plan["affine"]) == 3
+    assert [a[2] >= 0 for a in plan["affine"]] == [True, True, False]        # two layers end in a Relu, the last one does not
+    monkeypatch.setattr(fusion, "ENABLED", False)
+    plan0, plain, pw = _train_tower()
+    assert plan0 is None
+    np.testing.assert_allclose(fused, plain, rtol=1e-6)
+    for a, b in zip(fw, pw):
+        np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6)
+    assert fused[-1] < fused[0]
+    if shutil.which("g++") is None:
+        return
+    monkeypatch.setattr(fusion, "ENABLED", True)
+    cuda_lib.enable_emulation(str(tmp_path_factory.mktemp("emu_lib")))     # ... and on the kernel path
+    try:
+        _, emu, ew = _train_tower()
+    finally:
+        cuda_lib.disable_emulation()
+    np.testing.assert_allclose(emu, plain, rtol=2e-3)
+    for a, b in zip(ew, pw):
+        np.testing.assert_allclose(a, b, rtol=5e-3, atol=5e-4)
