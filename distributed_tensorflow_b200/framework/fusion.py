@@ -5,6 +5,8 @@ work into the producing kernel -- the B200 rule "fuse elementwise/activation wor
   (``ops/native.linear(relu=True)``: out of TMEM on ``/gpu``), the ReLU mask applied in the backward GEMMs' producer;
 * ``Relu(MatMul(x, W) + b)`` / ``MatMul(x, W) + b`` with a vector or scalar ``b`` (``/root/reference/standalone.py:52-53,60``: the
   tower spelling) -> the same GEMM epilogue;
+* ``reduce_mean(square(a - b))`` (``example_between_graph.py:59``, ``standalone.py:61``) -> one difference kernel + a
+  sum-of-squares reduction (``ops/native.mse``), three kernels instead of seven per training step;
 * ``-reduce_sum(y_ * log(clip_by_value(softmax(logits), eps, 1)))`` (``distributed_mnist.py:112-113``) -> ONE fused
   softmax + clipped cross-entropy forward/backward kernel (``ops/native.clipped_softmax_xent_sum``) instead of six node kernels
   forward and six backward.
@@ -32,7 +34,7 @@ def _through_identity(t):
 
 def plan_fusions(order: Sequence[Any], fetch_ids: Set[int], leaves: Set[int], task_of: Dict[int, Any], fed: Set[int]) -> Optional[Dict[str, list]]:
     """Wire form ``{"relu": [[xwb_id, relu_id], ...], "affine": [[matmul, add, relu or -1, x, w, b], ...],
-    "xent": [[neg, softmax, logits, labels, clip_min, [interior ids]], ...]}``
+    "mse": [[mean, square, sub, a, b], ...], "xent": [[neg, softmax, logits, labels, clip_min, [interior ids]], ...]}``
     (plain ints / floats: it travels to remote tasks inside the run options), or ``None``."""
     if not ENABLED:
         return None
@@ -66,6 +68,20 @@ def plan_fusions(order: Sequence[Any], fetch_ids: Set[int], leaves: Set[int], ta
             relu = us[0].id
         affine.append([mm.id, n.id, relu, mm.inputs[0].id, mm.inputs[1].id, bias.id])
         taken.update((mm.id, n.id) + ((relu,) if relu >= 0 else ()))
+    mse = []
+    for n in order:                      # Mean(Square(Sub(a, b))) over every element
+        if n.id in fed or n.id not in task_of or n.op_type != "Mean" or n.id in leaves or n.id in taken:
+            continue
+        if n.attrs.get("axis") is not None or n.attrs.get("keepdims"):
+            continue
+        sq = n.inputs[0]
+        if sq.op_type != "Square" or not private(sq, n) or sq.id in taken:
+            continue
+        sub = sq.inputs[0]
+        if sub.op_type != "Sub" or not private(sub, sq) or sub.id in taken:
+            continue
+        mse.append([n.id, sq.id, sub.id, sub.inputs[0].id, sub.inputs[1].id])
+        taken.update((n.id, sq.id, sub.id))
     for n in order:
         if n.id in fed or n.id not in task_of or n.id in taken:
             continue
@@ -103,14 +119,15 @@ def plan_fusions(order: Sequence[Any], fetch_ids: Set[int], leaves: Set[int], ta
                 continue
             xent.append([n.id, sm.id, logits.id, labels.id, float(lo), interior])
             taken.update(interior + [n.id])
-    if not relu_pairs and not xent and not affine:
+    if not relu_pairs and not xent and not affine and not mse:
         return None
-    return {"relu": relu_pairs, "affine": affine, "xent": xent}
+    return {"relu": relu_pairs, "affine": affine, "mse": mse, "xent": xent}
 
 
 class FusionState:
     """Runtime form of the planned rewrites for one run on one task."""
-    __slots__ = ("xwb", "relu", "softmax", "interior", "neg", "active", "aff_first", "aff_interior", "aff_last")
+    __slots__ = ("xwb", "relu", "softmax", "interior", "neg", "active", "aff_first", "aff_interior", "aff_last", "mse_first", "mse_interior",
+                 "mse_last")
 
     def __init__(self, wire: Optional[Dict[str, list]]):
         self.xwb: Dict[int, int] = {}
@@ -130,6 +147,14 @@ class FusionState:
                 self.aff_last[int(relu)] = spec
             else:
                 self.aff_last[int(add)] = spec
+        self.mse_first: Dict[int, tuple] = {}        # Sub id -> spec (the decision point)
+        self.mse_interior: Dict[int, int] = {}       # Square id -> Sub id
+        self.mse_last: Dict[int, tuple] = {}         # Mean id -> spec
+        for mean, sq, sub, a, b in (wire or {}).get("mse", ()):
+            spec = (int(mean), int(sq), int(sub), int(a), int(b))
+            self.mse_first[int(sub)] = spec
+            self.mse_interior[int(sq)] = int(sub)
+            self.mse_last[int(mean)] = spec
         for x, r in (wire or {}).get("relu", ()):
             self.xwb[int(x)] = int(r)
             self.relu[int(r)] = int(x)
@@ -141,7 +166,7 @@ class FusionState:
                 self.interior[int(i)] = int(sm)
 
     def __bool__(self) -> bool:
-        return bool(self.xwb or self.softmax or self.aff_first)
+        return bool(self.xwb or self.softmax or self.aff_first or self.mse_first)
 
 
 def try_execute(node, ctx, values: Dict[int, Any], st: FusionState, dev, want_grad: bool):
@@ -185,6 +210,24 @@ def try_execute(node, ctx, values: Dict[int, Any], st: FusionState, dev, want_gr
             if b.numel() == 1 and tuple(b.shape) != (w.shape[1],):
                 b = b.reshape(1).expand(w.shape[1])              # a scalar bias: one value per output column (its gradient sums back)
             return True, native.linear(x, w, b.contiguous(), relu=relu >= 0)
+    if nid in st.mse_first:
+        _, _, _, aid, bid = st.mse_first[nid]
+        a, b = values.get(aid), values.get(bid)
+        ok = (isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor) and a.dtype == torch.float32 and b.dtype == torch.float32
+              and a.dim() > 0 and b.dim() > 0 and a.numel() > 0 and b.numel() > 0)
+        st.active[nid] = ok
+        return (True, None) if ok else (False, None)
+    if nid in st.mse_interior:
+        return (True, None) if st.active.get(st.mse_interior[nid]) else (False, None)
+    if nid in st.mse_last:
+        _, _, sub, aid, bid = st.mse_last[nid]
+        if not st.active.get(sub):
+            return False, None
+        a, b = values[aid], values[bid]
+        if dev is not None:
+            a, b = (v.to(dev, non_blocking=True) if v.device != dev else v for v in (a, b))
+        with (torch.enable_grad() if want_grad else torch.no_grad()):
+            return True, native.mse(a, b)
     if nid in st.softmax:
         _, _, lid, yid, _ = st.softmax[nid]
         logits, labels = values.get(lid), values.get(yid)

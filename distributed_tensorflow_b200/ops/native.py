@@ -594,3 +594,40 @@ def concat(xs, axis: int):
         if all([d for i, d in enumerate(x.shape) if i != ax] == ref for x in xs):
             return _ConcatFn.apply(ax, *xs)
     return torch.cat(xs, dim=axis)
+
+
+class _MseFn(torch.autograd.Function):
+    """mean((a - b)^2) over every element: the difference is kept for the backward pass, the square is folded into the reduction."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        lib = _lib()
+        d = lib.ew_binary("sub", a, b)
+        ctx.save_for_backward(d)
+        ctx.shapes = (tuple(a.shape), tuple(b.shape))
+        return lib.ew_reduce_sum(d, 1.0 / d.numel(), square=True)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib()
+        (d,) = ctx.saved_tensors
+        gd = lib.ew_binary("mul", d, g.reshape(1).contiguous())            # d * dL (scalar operand)
+        oshape = tuple(d.shape)
+        ga = _unbroadcast(lib.ew_affine(gd, 2.0 / d.numel()), ctx.shapes[0], oshape) if ctx.needs_input_grad[0] else None
+        gb = _unbroadcast(lib.ew_affine(gd, -2.0 / d.numel()), ctx.shapes[1], oshape) if ctx.needs_input_grad[1] else None
+        return ga, gb
+
+
+def mse(a, b):
+    """``tf.reduce_mean(tf.square(a - b))`` (``example_between_graph.py:59``, ``standalone.py:61``) as one fused op."""
+    if _ew_ok(a, b):
+        lib = _lib()
+        try:
+            oshape = torch.broadcast_shapes(a.shape, b.shape)
+        except RuntimeError:
+            oshape = None
+        if oshape is not None and len(oshape) > 0 and lib.ew_broadcast_mode(a.shape, b.shape, oshape) is not None \
+                and lib.ew_broadcast_mode(b.shape, a.shape, oshape) is not None:
+            return _MseFn.apply(a, b)
+    d = a - b
+    return (d * d).mean()

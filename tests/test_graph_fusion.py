@@ -203,3 +203,54 @@ def test_matmul_bias_relu_towers_fuse_into_the_gemm_epilogue(monkeypatch, tmp_pa
     np.testing.assert_allclose(emu, plain, rtol=2e-3)
     for a, b in zip(ew, pw):
         np.testing.assert_allclose(a, b, rtol=5e-3, atol=5e-4)
+
+
+def test_mean_squared_error_chain_is_one_fused_op(monkeypatch, tmp_path_factory):
+    """example_between_graph.py:55-60: y = weight * x + biase; loss = reduce_mean(square(y_ - y))."""
+    def run(steps=20):
+        tf.reset_default_graph()
+        tf.set_random_seed(1)
+        x, y_ = tf.placeholder(tf.float32, [None]), tf.placeholder(tf.float32, [None])
+        weight = tf.get_variable("weight", [1], tf.float32, initializer=tf.random_normal_initializer())
+        biase = tf.get_variable("biase", [1], tf.float32, initializer=tf.random_normal_initializer())
+        loss = tf.reduce_mean(tf.square(y_ - (tf.multiply(weight, x) + biase)))
+        train = tf.train.GradientDescentOptimizer(0.1).minimize(loss)
+        rng = np.random.RandomState(0)
+        out = []
+        with tf.Session() as sess:
+            sess.run(tf.global_variables_initializer())
+            plan = sess._plan([sess._resolve(train), sess._resolve(loss)], {x.id, y_.id}).fusions
+            for _ in range(steps):
+                xs = rng.rand(16).astype(np.float32)
+                out.append(sess.run([train, loss, weight, biase], {x: xs, y_: 2 * xs + 10})[1:])
+        return plan, out
+    plan, fused = run()
+    assert plan is not None and len(plan["mse"]) == 1 and plan["affine"] == []
+    monkeypatch.setattr(fusion, "ENABLED", False)
+    _, plain = run()
+    for (l1, w1, b1), (l2, w2, b2) in zip(fused, plain):
+        np.testing.assert_allclose([l1, w1[0], b1[0]], [l2, w2[0], b2[0]], rtol=1e-6)
+    if shutil.which("g++") is None:
+        return
+    cuda_lib.enable_emulation(str(tmp_path_factory.mktemp("emu_lib")))
+    try:
+        n0 = cuda_lib.launch_count()
+        _, plain_emu = run()
+        n_plain = cuda_lib.launch_count() - n0
+        monkeypatch.setattr(fusion, "ENABLED", True)
+        n0 = cuda_lib.launch_count()
+        _, fused_emu = run()
+        n_fused = cuda_lib.launch_count() - n0
+    finally:
+        cuda_lib.disable_emulation()
+    assert n_fused <= n_plain - 20 * 2                                      # at least two launches fewer per step
+    for (l1, w1, b1), (l2, w2, b2) in zip(fused_emu, plain):
+        np.testing.assert_allclose([l1, w1[0], b1[0]], [l2, w2[0], b2[0]], rtol=2e-4, atol=1e-5)
+    # a reduction over an axis, or a second consumer of the difference, is not the pattern
+    tf.reset_default_graph()
+    a, b = tf.placeholder(tf.float32, [None, 3]), tf.placeholder(tf.float32, [None, 3])
+    with tf.Session() as sess:
+        assert sess._plan([sess._resolve(tf.reduce_mean(tf.square(a - b), axis=1))], {a.id, b.id}).fusions is None
+        d = a - b
+        both = [sess._resolve(tf.reduce_mean(tf.square(d))), sess._resolve(tf.reduce_sum(d))]
+        assert sess._plan(both, {a.id, b.id}).fusions is None
