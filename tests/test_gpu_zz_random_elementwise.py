@@ -109,3 +109,40 @@ def test_concat_and_scatter_kernel_on_device_and_across_peers():
         torch.cuda.synchronize(0)
         torch.testing.assert_close(far.cpu(), x[300:].cpu(), rtol=0, atol=0)
         torch.testing.assert_close(near, x[:300], rtol=0, atol=0)
+
+
+def test_fused_graph_plans_on_gpu_track_the_cpu_tier():
+    """The tower spelling (MatMul + scalar bias + ReLU, mean squared error) and the linear-regression program with the plan-time
+    rewrites (framework/fusion.py) on /gpu:0 against the same programs on /cpu:0."""
+    _need_gpu()
+    import distributed_tensorflow_b200 as tf
+    from distributed_tensorflow_b200.ops import cuda_lib
+
+    def tower(dev):
+        tf.reset_default_graph()
+        with tf.device(dev):
+            tf.set_random_seed(4)
+            x, t = tf.placeholder(tf.float32, [None, 2]), tf.placeholder(tf.float32, [None, 1])
+            h = x
+            for i, d in enumerate((64, 32)):
+                w = tf.get_variable("affine%d/w" % i, [h.get_shape()[1], d], initializer=tf.truncated_normal_initializer(0, 0.3))
+                b = tf.get_variable("affine%d/b" % i, [], initializer=tf.zeros_initializer)
+                h = tf.nn.relu(tf.matmul(h, w) + b)
+            w = tf.get_variable("affine_last/w", [h.get_shape()[1], 1], initializer=tf.constant_initializer(value=0.1))
+            b = tf.get_variable("affine_last/b", [], initializer=tf.zeros_initializer)
+            loss = tf.reduce_mean(tf.square(tf.matmul(h, w) + b - t))
+            train = tf.train.GradientDescentOptimizer(0.01).minimize(loss)
+        rng = np.random.RandomState(0)
+        out = []
+        with tf.Session() as sess:
+            sess.run(tf.global_variables_initializer())
+            for _ in range(10):
+                xs = rng.rand(1000, 2).astype(np.float32)
+                out.append(float(sess.run([train, loss], {x: xs, t: xs.sum(1, keepdims=True)})[1]))
+        return out
+    n0 = cuda_lib.launch_count()
+    gpu = tower("/gpu:0")
+    assert cuda_lib.launch_count() - n0 >= 10 * 6
+    cpu = tower("/cpu:0")
+    np.testing.assert_allclose(gpu, cpu, rtol=3e-2)
+    assert gpu[-1] < gpu[0]
