@@ -250,7 +250,10 @@ class Session:
                 plan.want_grad = True
                 ny = n.attrs["num_ys"]
                 plan.leaves.update(x.id for x in n.inputs[ny:])
-        plan.segments = schedule_segments(plan.order, self._task_of, fed)
+        if self.cluster is None:
+            plan.segments = [(None, [n for n in plan.order if n.id not in fed])]      # one process: the whole plan is one segment
+        else:
+            plan.segments = schedule_segments(plan.order, self._task_of, fed)
         # which node values must leave their producing task: fetches + cross-task consumers
         seg_of: Dict[int, int] = {}
         for si, (_, nodes) in enumerate(plan.segments):

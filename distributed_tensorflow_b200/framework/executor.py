@@ -265,10 +265,11 @@ def execute(nodes: Sequence[Tensor], ctx: ExecContext, want_grad: bool) -> None:
     values = ctx.values
     tracer = ctx.tracer
     fus = getattr(ctx, "fusions", None)
+    fus_ids = fus.ids if fus else ()
     for node in nodes:
         if node.id in values:
             continue
-        if fus:
+        if node.id in fus_ids:
             # plan-time rewrites (framework/fusion.py): bias + ReLU in the GEMM epilogue, the clipped softmax cross-entropy chain
             # as one kernel; nodes interior to an active rewrite have no value of their own
             t0 = time.perf_counter_ns() if tracer is not None else 0

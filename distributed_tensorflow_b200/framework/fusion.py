@@ -127,7 +127,7 @@ def plan_fusions(order: Sequence[Any], fetch_ids: Set[int], leaves: Set[int], ta
 class FusionState:
     """Runtime form of the planned rewrites for one run on one task."""
     __slots__ = ("xwb", "relu", "softmax", "interior", "neg", "active", "aff_first", "aff_interior", "aff_last", "mse_first", "mse_interior",
-                 "mse_last")
+                 "mse_last", "ids")
 
     def __init__(self, wire: Optional[Dict[str, list]]):
         self.xwb: Dict[int, int] = {}
@@ -164,6 +164,11 @@ class FusionState:
             self.neg[int(neg)] = spec
             for i in interior:
                 self.interior[int(i)] = int(sm)
+
+        # every node id a rewrite touches: the executor asks try_execute() only for these
+        self.ids = frozenset(list(self.xwb) + list(self.relu) + list(self.softmax) + list(self.interior) + list(self.neg)
+                             + list(self.aff_first) + list(self.aff_interior) + list(self.aff_last)
+                             + list(self.mse_first) + list(self.mse_interior) + list(self.mse_last))
 
     def __bool__(self) -> bool:
         return bool(self.xwb or self.softmax or self.aff_first or self.mse_first)
