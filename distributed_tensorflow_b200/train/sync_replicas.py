@@ -213,8 +213,10 @@ class SyncReplicasOptimizer(Optimizer):
             train_op = assign(self._local_step, token, name="set_local_step")
             # chief-side: once the update ran, hand out tokens carrying the NEW global step
             with g.control_dependencies([update_op]):
-                step_after = _ops.identity(global_step._node, name="global_step_after_update")
+                # everything between the aggregate and the tokens stays on the global step's device (TF colocates the sync op
+                # with the global step): the chief's loop is ONE ps segment -- take_grad, apply, enqueue in one round trip
                 with _device.device(None), _device.device(qdev or None):
+                    step_after = _ops.identity(global_step._node, name="global_step_after_update")
                     self.sync_op = g.create_node("QueueEnqueueMany", [step_after],
                                                  {"queue_name": self._sync_token_queue_name,
                                                   "count": self._tokens_per_step}, "sync_token_q_EnqueueMany",
