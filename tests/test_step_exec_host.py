@@ -179,3 +179,83 @@ def test_native_loop_prefetch_next_copies_the_batch_after_the_last_step(host):
     assert (a.parity, a.prefetched) == (0, 1)
     last_graph = max(i for i, l in enumerate(t) if l.startswith("graph_launch"))
     assert t.index(h2d[2]) > last_graph                                   # issued behind the last step's kernels
+
+
+def _happens_before(trace):
+    """CUDA ordering rules applied to a recorded trace: ops issued to one stream run in issue order; ``event_wait`` makes the
+    following ops of its stream depend on the LAST ``event_record`` of that event issued before the wait; ``event_sync`` makes
+    every later host call depend on that record.  Returns (ops, reach) with reach[i] = set of op indices that happen before i."""
+    ops, last_in_stream, last_record, host_dep = [], {}, {}, set()
+    deps = []
+    for line in trace:
+        kind = line.split()[0]
+        f = dict(kv.split("=") for kv in line.split()[1:] if "=" in kv)
+        if kind == "event_sync":
+            if f["ev"] in last_record:
+                host_dep = host_dep | {last_record[f["ev"]]}
+            continue
+        if kind not in ("memcpy", "graph_launch", "event_record", "event_wait", "ps_apply"):
+            continue
+        i = len(ops)
+        ops.append((kind, f, line))
+        d = set(host_dep)
+        s = f["stream"]
+        if s in last_in_stream:
+            d.add(last_in_stream[s])
+        if kind == "event_wait" and f["ev"] in last_record:
+            d.add(last_record[f["ev"]])
+        deps.append(d)
+        last_in_stream[s] = i
+        if kind == "event_record":
+            last_record[f["ev"]] = i
+    reach = []
+    for i, d in enumerate(deps):
+        r = set(d)
+        for j in d:
+            r |= reach[j]
+        reach.append(r)
+    return ops, reach
+
+
+@pytest.mark.parametrize("steps,depth,prefetched,prefetch_next", [(7, 2, 0, 0), (6, 4, 0, 1), (5, 1, 1, 1), (1, 3, 0, 0)])
+def test_native_loop_has_no_buffer_hazard_under_cuda_ordering_rules(host, steps, depth, prefetched, prefetch_next):
+    """The double-buffered staging is only safe if (a) the copy of step i's batch happens before step i's kernels, (b) the kernels
+    that read a buffer set happen before the NEXT copy into that set, (c) a loss row is copied after its step's kernels and before
+    the next step's kernels overwrite the device-side partials -- derived from the trace with CUDA's stream / event rules, not
+    from the order of the host calls."""
+    host.step_emu_reset(0, 0)
+    a, keep = _loop_args(host, steps=steps, depth=depth, prefetched=prefetched, ps=True)
+    a.prefetch_next = prefetch_next
+    pre = []
+    if prefetched:                                   # what step()'s prefetch would have issued before the call
+        pre = ["event_wait ev=0xd0 stream=0x58", "memcpy h2d dst=0x1000 src=0x103000 n=400 stream=0x58",
+               "memcpy h2d dst=0x2000 src=0x200300 n=40 stream=0x58", "event_record ev=0xa0 stream=0x58"]
+    assert host.dtf_run_loop(ctypes.byref(a)) == 0
+    ops, reach = _happens_before(pre + host.step_emu_trace().decode().splitlines())
+    computes = [i for i, (k, f, _) in enumerate(ops) if k == "graph_launch"]
+    copies_x = [i for i, (k, f, l) in enumerate(ops) if k == "memcpy" and "h2d" in l and f["n"] == "400"]
+    loss = [i for i, (k, f, l) in enumerate(ops) if k == "memcpy" and "d2h" in l]
+    assert len(computes) == steps and len(loss) == steps and len(copies_x) == steps + prefetch_next
+    for i, c in enumerate(computes):
+        par = i % 2
+        assert ops[c][1]["exec"] == "0x%x" % (0x900 + par)
+        assert copies_x[i] in reach[c], "step %d runs before its batch has landed" % i                       # (a)
+        assert ops[copies_x[i]][1]["dst"] == "0x%x" % (0x1000 + par)
+        if i + 2 < len(copies_x):
+            assert c in reach[copies_x[i + 2]], "batch %d overwrites the buffers step %d still reads" % (i + 2, i)   # (b)
+        assert c in reach[loss[i]]                                                                           # (c)
+        if i + 1 < steps:
+            assert loss[i] in reach[computes[i + 1]]
+        assert ops[loss[i]][1]["dst"] == "0x%x" % (0x300000 + 64 * i)
+
+
+def test_the_hazard_checker_notices_a_missing_dependency(host):
+    """Without the copy stream's wait on done[p] the rule (b) above must fail: the checker is not vacuous."""
+    host.step_emu_reset(0, 0)
+    a, keep = _loop_args(host, steps=5, depth=2, ps=False)
+    assert host.dtf_run_loop(ctypes.byref(a)) == 0
+    trace = [l for l in host.step_emu_trace().decode().splitlines() if not (l.startswith("event_wait") and "stream=0x58" in l)]
+    ops, reach = _happens_before(trace)
+    computes = [i for i, (k, f, _) in enumerate(ops) if k == "graph_launch"]
+    copies_x = [i for i, (k, f, l) in enumerate(ops) if k == "memcpy" and "h2d" in l and f["n"] == "400"]
+    assert any(computes[i] not in reach[copies_x[i + 2]] for i in range(3))
