@@ -16,6 +16,7 @@
 from __future__ import annotations
 
 import itertools
+import sys
 import threading
 import uuid
 from typing import Any, Dict, List, Optional, Sequence, Set, Tuple
@@ -273,6 +274,15 @@ class Session:
         from ..framework import fusion as _fusion
         task_of_id = {nid: plan.segments[si][0] for nid, si in seg_of.items()}
         plan.fusions = _fusion.plan_fusions(plan.order, {f.id for f in fetch_nodes}, plan.leaves, task_of_id, fed)
+        if getattr(self.config, "log_device_placement", False):
+            # TF logs the placement of every node the first time it is part of a run
+            logged = self.__dict__.setdefault("_placement_logged", set())
+            for n in plan.order:
+                if n.id not in logged:
+                    logged.add(n.id)
+                    task = self._task_of(n)
+                    where = n.device or ("/job:%s/task:%d" % task if task else "/job:localhost/replica:0/task:0/device:CPU:0")
+                    print("%s: (%s): %s" % (n.name, n.op_type, where), file=sys.stderr, flush=True)
         if len(self._plans) > 256:
             self._plans.clear()
         self._plans[key] = plan

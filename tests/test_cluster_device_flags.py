@@ -107,3 +107,15 @@ def test_flags_bool_spellings(monkeypatch):
     F.DEFINE_bool("c", False, "")
     monkeypatch.setattr("sys.argv", ["prog", "--noa", "--b=True", "--c", "false"])
     assert (F.FLAGS.a, F.FLAGS.b, F.FLAGS.c) == (False, True, False)
+
+
+def test_log_device_placement_prints_each_node_once(capsys):
+    import distributed_tensorflow_b200 as tf
+    a = tf.constant([1.0, 2.0], name="a")
+    with tf.device("/cpu:0"):
+        b = tf.add(a, a, name="b")
+    with tf.Session(config=tf.ConfigProto(log_device_placement=True)) as sess:
+        sess.run(b)
+        sess.run(b)
+    err = capsys.readouterr().err
+    assert err.count("a: (Const): ") == 1 and err.count("b: (Add): /device:CPU:0") == 1
