@@ -185,6 +185,8 @@ int dtf_capture_ops(const DtfStepOp* ops, int n, int device, cudaStream_t stream
 // sync_loss="deferred", prefetch=next)` does per step, minus the Python between the calls.
 // Reference role: the `while` loop around `mon_sess.run([train_step, global_step, loss], feed_dict=...)`
 // (distributed_mnist.py:148-152), i.e. next_batch -> feed -> step -> fetched loss, K times.
+#define DTF_LOOP_MAX_DEVICES 64
+
 struct DtfLoopArgs {
   int device;               // made current for the call (>= 0)
   int steps;
@@ -210,6 +212,23 @@ struct DtfLoopArgs {
   long long waited;         // out: event waits the host issued (run-ahead bound + the final one)
 };
 
+static cudaEvent_t loop_event_pool[DTF_LOOP_MAX_DEVICES][64];
+static int loop_events_made[DTF_LOOP_MAX_DEVICES];
+
+// Destroys the cached events of every device (tests; a process that wants its handles back).  Not while a loop is running.
+int dtf_loop_release_events() {
+  int n = 0, prev = -1;
+  cudaGetDevice(&prev);
+  for (int d = 0; d < DTF_LOOP_MAX_DEVICES; ++d) {
+    if (loop_events_made[d] == 0) continue;
+    cudaSetDevice(d);
+    for (int e = 0; e < loop_events_made[d]; ++e, ++n) cudaEventDestroy(loop_event_pool[d][e]);
+    loop_events_made[d] = 0;
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  return n;
+}
+
 int dtf_run_loop(DtfLoopArgs* a) {
   if (!a || a->steps < 0 || a->depth < 1 || a->depth > 64 || a->nbatches < 1) return -1;
   if (a->x_op < 0 || a->y_op < 0 || a->x_op >= a->n_copy[0] || a->y_op >= a->n_copy[0] || a->x_op >= a->n_copy[1] ||
@@ -219,11 +238,21 @@ int dtf_run_loop(DtfLoopArgs* a) {
     cudaGetDevice(&prev);
     if (prev != a->device) cudaSetDevice(a->device); else prev = -1;
   }
-  cudaEvent_t landed[64];
-  int made = 0, rc = 0, kernels = 0;
-  for (; made < a->depth && made < a->steps && rc == 0; ++made)
-    rc = (int)cudaEventCreateWithFlags(&landed[made], cudaEventDisableTiming);
-  if (rc != 0) --made;
+  // "loss row i has landed" events: created once per device and reused by later calls (a K = 20 step call should not pay
+  // for creating and destroying them every time); a loop of one process is driven by one thread at a time
+  int cur = 0;
+  if (a->device < 0) cudaGetDevice(&cur); else cur = a->device;
+  if (cur < 0 || cur >= DTF_LOOP_MAX_DEVICES) {
+    if (prev >= 0) cudaSetDevice(prev);
+    return -3;
+  }
+  cudaEvent_t* landed = loop_event_pool[cur];
+  int rc = 0, kernels = 0;
+  const int need = a->depth < a->steps ? a->depth : a->steps;
+  while (loop_events_made[cur] < need && rc == 0) {
+    rc = (int)cudaEventCreateWithFlags(&landed[loop_events_made[cur]], cudaEventDisableTiming);
+    if (rc == 0) ++loop_events_made[cur];
+  }
   auto issue_copy = [&](int par, long long step) -> int {
     long long b = (a->first + step * a->batch_step) % a->nbatches;
     if (b < 0) b += a->nbatches;
@@ -255,7 +284,6 @@ int dtf_run_loop(DtfLoopArgs* a) {
     rc = (int)cudaEventSynchronize(landed[(a->steps - 1) % a->depth]);
     ++waits;
   }
-  for (int e = 0; e < made; ++e) cudaEventDestroy(landed[e]);
   a->parity = par;
   a->prefetched = (rc == 0 && a->steps > 0 && a->prefetch_next) ? 1 : 0;
   a->kernels = kernels;

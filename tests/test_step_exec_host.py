@@ -86,6 +86,8 @@ def test_error_index_device_switch_and_capture(host):
 def _loop_args(host, steps, depth, prefetched=0, ps=True, parity=0, first=3, batch_step=2, nb=5):
     from distributed_tensorflow_b200.ops.cuda_lib import LoopArgs
     assert host.dtf_sizeof_loop_args() == ctypes.sizeof(LoopArgs)
+    host.dtf_loop_release_events()            # the loop caches its events per device across calls: every test starts without them
+    host.step_emu_reset(0, 0)
     host.dtf_run_loop.argtypes = [ctypes.POINTER(LoopArgs)]
     keep = []
     a = LoopArgs()
@@ -135,9 +137,14 @@ def test_native_loop_orders_copies_kernels_loss_reads_and_bounds_the_run_ahead(h
     want += compute(1) + copy(0, batches[2]) + loss(1, 0xe001)
     want += ["event_sync ev=0xe000"] + compute(0) + copy(1, batches[3]) + loss(2, 0xe000)     # step 2 waits for the loss of step 0
     want += ["event_sync ev=0xe001"] + compute(1) + loss(3, 0xe001)                            # no copy after the last step
-    want += ["event_sync ev=0xe001", "event_destroy ev=0xe000", "event_destroy ev=0xe001", "setdevice 0"]
+    want += ["event_sync ev=0xe001", "setdevice 0"]                      # the events stay cached for the next call
     assert t == want
     assert (a.parity, a.prefetched, a.kernels, a.waited) == (0, 0, 4 * 3, 3)
+    host.step_emu_reset(0, 0)                                           # a second call reuses the cached events
+    assert host.dtf_run_loop(ctypes.byref(a)) == 0
+    t2 = host.step_emu_trace().decode().splitlines()
+    assert not any(l.startswith(("event_create", "event_destroy")) for l in t2) and t2[1:] == want[3:]
+    assert host.dtf_loop_release_events() == 2
 
 
 def test_native_loop_prefetched_first_batch_odd_parity_short_runs_and_errors(host):
@@ -148,7 +155,7 @@ def test_native_loop_prefetched_first_batch_odd_parity_short_runs_and_errors(hos
     assert t == ["setdevice 2", "event_create ev=0xe000 flags=2",
                  "event_wait ev=0xa1 stream=0x57", "graph_launch exec=0x901 stream=0x57", "event_record ev=0xd1 stream=0x57",
                  "memcpy d2h dst=0x300000 src=0xbeef n=28 stream=0x57", "event_record ev=0xe000 stream=0x57",
-                 "event_sync ev=0xe000", "event_destroy ev=0xe000", "setdevice 0"]
+                 "event_sync ev=0xe000", "setdevice 0"]
     assert (a.parity, a.kernels) == (0, 2)
     host.step_emu_reset(0, 0)
     a, keep = _loop_args(host, steps=0, depth=2)
@@ -160,8 +167,8 @@ def test_native_loop_prefetched_first_batch_odd_parity_short_runs_and_errors(hos
     a, keep = _loop_args(host, steps=2, depth=2)
     a.x_op = 9
     assert host.dtf_run_loop(ctypes.byref(a)) == -2
-    host.step_emu_reset(100, 2)                                        # event creation fails: nothing is enqueued
     a, keep = _loop_args(host, steps=3, depth=2)
+    host.step_emu_reset(100, 2)                                        # event creation fails: nothing is enqueued
     assert host.dtf_run_loop(ctypes.byref(a)) == 2
     assert not any(l.startswith(("memcpy", "graph", "event_destroy")) for l in host.step_emu_trace().decode().splitlines())
 
