@@ -378,6 +378,187 @@ def run_resnet18(args, rank, world, local_rank):
     return out
 
 
+class CudaStreamTimer:
+    """Device time of a region: CUDA events on every local rank's stream (max over them), read after a synchronize."""
+
+    def start(self, eng):
+        import torch
+        evs = []
+        for r, rk in eng.ranks.items():
+            with torch.cuda.device(rk.device):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(rk.stream)
+                evs.append((e0, e1, rk))
+        return evs
+
+    def stop(self, evs, eng) -> float:
+        for e0, e1, rk in evs:
+            e1.record(rk.stream)
+        eng.synchronize()
+        return max(e0.elapsed_time(e1) for e0, e1, _ in evs)
+
+
+def run_e2e(eng, args, spec, K, num_workers, is_worker, world, pow_, images, labels, barrier, allmax, timer=None, pin=None):
+    """The end-to-end arms: the same metric through the public API with, every step, the H2D copy of that step's batch from
+    pinned host memory and a D2H read of the step's loss -- ``step()`` synchronous, ``step(sync_loss="deferred")`` pipelined,
+    ``train_loop()`` (K steps per native call); same repetition protocol as the device-timed number.  ``timer`` / ``pin`` are
+    injected so that this logic also runs against a stand-in engine on CPU (tests/test_bench_e2e_logic.py)."""
+    import torch
+    timer = timer or CudaStreamTimer()
+    pin = pin or (lambda a: torch.from_numpy(a).pin_memory())
+    hx = hy = None
+    if is_worker:
+        n_use = min(args.num_train, 20000)
+        hx = pin(images[:n_use])
+        hy = pin(labels[:n_use])
+        nb = n_use // spec.batch
+    wl = [r for r in eng.ranks if r in eng.worker_ranks]
+    woff = eng.worker_ranks.index(wl[0]) if wl else 0
+    views = [(hx[b * spec.batch:(b + 1) * spec.batch], hy[b * spec.batch:(b + 1) * spec.batch]) for b in range(nb)] \
+        if is_worker else []
+    ctr = [0]
+    last = [None]
+
+    def batch_of(i):
+        return views[(i * num_workers + woff) % nb]
+
+    def e2e_k_steps():
+        # every step: H2D of THIS step's batch from pinned host memory (issued one step ahead on the copy stream
+        # = input double buffering, overlapping the previous step's kernels) + D2H read of this step's loss
+        for _ in range(K):
+            i = ctr[0]
+            if is_worker:
+                x, y = batch_of(i)
+                last[0] = eng.step(x, y, sync_loss=True, prefetch=batch_of(i + 1) if args.e2e_prefetch else None)
+            else:
+                eng.step(sync_loss=False)
+            ctr[0] += 1
+
+    def e2e_k_steps_pipelined():
+        # same copies every step, but step t+1 is enqueued BEFORE step t's loss is waited for (PendingLoss): the
+        # host's turnaround overlaps the GPU's work on step t; every loss is still read back, one step late
+        pending = None
+        for _ in range(K):
+            i = ctr[0]
+            if not is_worker:
+                eng.step(sync_loss=False)
+            else:
+                x, y = batch_of(i)
+                h = eng.step(x, y, sync_loss="deferred", prefetch=batch_of(i + 1))
+                if pending is not None:
+                    last[0] = pending.result()
+                pending = h
+            ctr[0] += 1
+        if pending is not None:
+            last[0] = pending.result()
+
+    hx3 = hx[:nb * spec.batch].view(nb, spec.batch, spec.in_dim) if is_worker else None
+    hy3 = hy[:nb * spec.batch].view(nb, spec.batch, spec.classes) if is_worker else None
+
+    def e2e_k_steps_native():
+        # same per-step work (H2D of THIS step's batch one step ahead on the copy stream, the step's kernels, D2H of the
+        # step's loss row), but the K steps are enqueued by ONE native call; the host reads every loss, at most
+        # --e2e-depth steps late
+        if is_worker:
+            ls = eng.train_loop(hx3, hy3, K, first=(ctr[0] * num_workers + woff) % nb, stride=num_workers, depth=args.e2e_depth,
+                                prefetch_next=bool(args.e2e_prefetch))
+            last[0] = float(ls[-1])
+            if not all(math.isfinite(float(v)) for v in ls):
+                raise RuntimeError("native loop returned a non-finite loss")
+        else:
+            for _ in range(K):
+                eng.step(sync_loss=False)
+        ctr[0] += K
+
+    def align_e2e():
+        for _ in range(2):
+            if is_worker:
+                x, y = batch_of(ctr[0])
+                # the loop is continuous across the untimed / timed boundary: the batch of the next step is already
+                # travelling (every timed step still issues one H2D copy: the one of the step after it)
+                eng.step(x, y, sync_loss=False, prefetch=batch_of(ctr[0] + 1) if args.e2e_prefetch else None)
+            else:
+                eng.step(sync_loss=False)
+            ctr[0] += 1
+
+    def measure_e2e(body):
+        for _ in range(6):           # both staging parities + the CUDA-graphed plans are built by the first steps
+            align_e2e()
+        times, total = [], 0.0
+        while len(times) < 3 or (total < args.min_ms and len(times) < args.max_reps):
+            barrier()
+            align_e2e()
+            handle = timer.start(eng)
+            w0 = time.time()
+            body()
+            eng.join_streams()
+            dev_ms = timer.stop(handle, eng)             # records the end events, synchronizes, reads the device time
+            wall = (time.time() - w0) * 1e3
+            times.append(allmax([max(dev_ms, 0.0), wall]))
+            total += times[-1][0]
+        eng.check_errors()
+        return times
+
+    et = measure_e2e(e2e_k_steps)
+    ems = statistics.median(t[0] for t in et)
+    per_step = num_workers * spec.batch * K
+    e2e = {"value": per_step / (ems / 1e3), "unit": "samples/sec", "steps": K, "reps": len(et),
+           "ms_per_step": ems / K, "wall_ms_per_step": statistics.median(t[1] for t in et) / K,
+           "h2d_bytes_per_step": spec.batch * (spec.in_dim + spec.classes) * 4,
+           "d2h_bytes_per_step": 4 * eng.head_ctas,          # the loss partials of the step kernel's / head's CTAs
+           "api": "PSTrainEngine.step(x_pinned, y_pinned, prefetch=next) -> loss" if args.e2e_prefetch
+           else "PSTrainEngine.step(x_pinned, y_pinned) -> loss",
+           "input_double_buffering": bool(args.e2e_prefetch), "loss_read": "synchronous, every step",
+           "last_loss": allmax([last[0] if last[0] is not None else -1e30])[0]}
+    if args.e2e_pipeline and ((world == 1 and is_worker) or args.e2e_pipeline == 2 or pow_):
+        # second arm of the same API: loss handles read one step late
+        try:
+            pt = measure_e2e(e2e_k_steps_pipelined)
+            pems = statistics.median(t[0] for t in pt)
+            plast = allmax([last[0] if last[0] is not None else -1e30])[0]
+            if not math.isfinite(plast):
+                raise RuntimeError("pipelined loop returned loss %r" % (plast,))
+            sync_part = {k: e2e[k] for k in ("value", "ms_per_step", "wall_ms_per_step", "last_loss")}
+            pipe_part = {"value": per_step / (pems / 1e3), "ms_per_step": pems / K,
+                         "wall_ms_per_step": statistics.median(t[1] for t in pt) / K, "last_loss": plast}
+            e2e["synchronous"], e2e["pipelined"] = sync_part, pipe_part
+            if pipe_part["value"] > e2e["value"]:
+                e2e.update(pipe_part)
+                e2e["api"] = "PSTrainEngine.step(x_pinned, y_pinned, sync_loss='deferred', prefetch=next) -> PendingLoss; .result()"
+                e2e["loss_read"] = "every step's loss is copied D2H behind its kernels and read by the host one step late"
+        except Exception as e:      # noqa: BLE001 - keep the synchronous measurement
+            if world > 1:
+                raise                # ranks must not diverge
+            e2e["pipelined_error"] = repr(e)[:300]
+    if args.e2e_native_loop and len(wl) <= 1 and ((world == 1 and is_worker) or pow_):
+        # third arm: the framework's own training loop (one native call per K steps).  A failure on any rank drops the
+        # arm on every rank (the flag is agreed on before anything is recorded); the other arms' numbers stand.
+        nt, nerr = None, None
+        try:
+            nt = measure_e2e(e2e_k_steps_native)
+        except Exception as e:      # noqa: BLE001
+            nerr = repr(e)[:300]
+        nlast = allmax([last[0] if (last[0] is not None and nerr is None) else -1e30])[0]
+        failed = allmax([1.0 if (nerr is not None or not math.isfinite(nlast)) else 0.0])[0] > 0
+        if failed:
+            e2e["native_loop_error"] = nerr or "non-finite loss %r or a failure on another rank" % (nlast,)
+        else:
+            nems = statistics.median(t[0] for t in nt)
+            if "synchronous" not in e2e:
+                e2e["synchronous"] = {k: e2e[k] for k in ("value", "ms_per_step", "wall_ms_per_step", "last_loss")}
+            nat_part = {"value": per_step / (nems / 1e3), "ms_per_step": nems / K,
+                        "wall_ms_per_step": statistics.median(t[1] for t in nt) / K, "last_loss": nlast}
+            e2e["native_loop"] = dict(nat_part, depth=args.e2e_depth)
+            if nat_part["value"] > e2e["value"]:
+                e2e.update(nat_part)
+                e2e["reps"] = len(nt)
+                e2e["api"] = "PSTrainEngine.train_loop(x_batches_pinned, y_batches_pinned, steps=K) -> losses[K]"
+                e2e["loss_read"] = ("every step's loss is copied D2H behind its kernels into its own pinned row; the host waits "
+                                    "for row i-%d before enqueuing step i and reads all K rows" % args.e2e_depth)
+                e2e["input_double_buffering"] = True
+    return e2e
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -562,163 +743,7 @@ def main():
     # ---- end-to-end: public API step(x, y) with H2D of the batch and D2H of the loss every step -----------------
     e2e = None
     if args.e2e_steps != 0:
-        hx = hy = None
-        if is_worker:
-            n_use = min(args.num_train, 20000)
-            hx = torch.from_numpy(images[:n_use]).pin_memory()
-            hy = torch.from_numpy(labels[:n_use]).pin_memory()
-            nb = n_use // spec.batch
-        wl = [r for r in eng.ranks if r in eng.worker_ranks]
-        woff = eng.worker_ranks.index(wl[0]) if wl else 0
-        views = [(hx[b * spec.batch:(b + 1) * spec.batch], hy[b * spec.batch:(b + 1) * spec.batch]) for b in range(nb)] \
-            if is_worker else []
-        ctr = [0]
-        last = [None]
-
-        def batch_of(i):
-            return views[(i * num_workers + woff) % nb]
-
-        def e2e_k_steps():
-            # every step: H2D of THIS step's batch from pinned host memory (issued one step ahead on the copy stream
-            # = input double buffering, overlapping the previous step's kernels) + D2H read of this step's loss
-            for _ in range(K):
-                i = ctr[0]
-                if is_worker:
-                    x, y = batch_of(i)
-                    last[0] = eng.step(x, y, sync_loss=True, prefetch=batch_of(i + 1) if args.e2e_prefetch else None)
-                else:
-                    eng.step(sync_loss=False)
-                ctr[0] += 1
-
-        def e2e_k_steps_pipelined():
-            # same copies every step, but step t+1 is enqueued BEFORE step t's loss is waited for (PendingLoss): the
-            # host's turnaround overlaps the GPU's work on step t; every loss is still read back, one step late
-            pending = None
-            for _ in range(K):
-                i = ctr[0]
-                if not is_worker:
-                    eng.step(sync_loss=False)
-                else:
-                    x, y = batch_of(i)
-                    h = eng.step(x, y, sync_loss="deferred", prefetch=batch_of(i + 1))
-                    if pending is not None:
-                        last[0] = pending.result()
-                    pending = h
-                ctr[0] += 1
-            if pending is not None:
-                last[0] = pending.result()
-
-        hx3 = hx[:nb * spec.batch].view(nb, spec.batch, spec.in_dim) if is_worker else None
-        hy3 = hy[:nb * spec.batch].view(nb, spec.batch, spec.classes) if is_worker else None
-
-        def e2e_k_steps_native():
-            # same per-step work (H2D of THIS step's batch one step ahead on the copy stream, the step's kernels, D2H of the
-            # step's loss row), but the K steps are enqueued by ONE native call; the host reads every loss, at most
-            # --e2e-depth steps late
-            if is_worker:
-                ls = eng.train_loop(hx3, hy3, K, first=(ctr[0] * num_workers + woff) % nb, stride=num_workers, depth=args.e2e_depth,
-                                    prefetch_next=bool(args.e2e_prefetch))
-                last[0] = float(ls[-1])
-                if not all(math.isfinite(float(v)) for v in ls):
-                    raise RuntimeError("native loop returned a non-finite loss")
-            else:
-                for _ in range(K):
-                    eng.step(sync_loss=False)
-            ctr[0] += K
-
-        def align_e2e():
-            for _ in range(2):
-                if is_worker:
-                    x, y = batch_of(ctr[0])
-                    # the loop is continuous across the untimed / timed boundary: the batch of the next step is already
-                    # travelling (every timed step still issues one H2D copy: the one of the step after it)
-                    eng.step(x, y, sync_loss=False, prefetch=batch_of(ctr[0] + 1) if args.e2e_prefetch else None)
-                else:
-                    eng.step(sync_loss=False)
-                ctr[0] += 1
-
-        def measure_e2e(body):
-            for _ in range(6):           # both staging parities + the CUDA-graphed plans are built by the first steps
-                align_e2e()
-            times, total = [], 0.0
-            while len(times) < 3 or (total < args.min_ms and len(times) < args.max_reps):
-                barrier()
-                align_e2e()
-                evs = []
-                for r, rk in eng.ranks.items():
-                    with torch.cuda.device(rk.device):
-                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        e0.record(rk.stream)
-                        evs.append((e0, e1, rk))
-                w0 = time.time()
-                body()
-                eng.join_streams()
-                for e0, e1, rk in evs:
-                    e1.record(rk.stream)
-                eng.synchronize()
-                wall = (time.time() - w0) * 1e3
-                times.append(allmax([max(max(e0.elapsed_time(e1) for e0, e1, _ in evs), 0.0), wall]))
-                total += times[-1][0]
-            eng.check_errors()
-            return times
-
-        et = measure_e2e(e2e_k_steps)
-        ems = statistics.median(t[0] for t in et)
-        per_step = num_workers * spec.batch * K
-        e2e = {"value": per_step / (ems / 1e3), "unit": "samples/sec", "steps": K, "reps": len(et),
-               "ms_per_step": ems / K, "wall_ms_per_step": statistics.median(t[1] for t in et) / K,
-               "h2d_bytes_per_step": spec.batch * (spec.in_dim + spec.classes) * 4,
-               "d2h_bytes_per_step": 4 * eng.head_ctas,          # the loss partials of the step kernel's / head's CTAs
-               "api": "PSTrainEngine.step(x_pinned, y_pinned, prefetch=next) -> loss" if args.e2e_prefetch
-               else "PSTrainEngine.step(x_pinned, y_pinned) -> loss",
-               "input_double_buffering": bool(args.e2e_prefetch), "loss_read": "synchronous, every step",
-               "last_loss": allmax([last[0] if last[0] is not None else -1e30])[0]}
-        if args.e2e_pipeline and ((world == 1 and is_worker) or args.e2e_pipeline == 2 or pow_):
-            # second arm of the same API: loss handles read one step late
-            try:
-                pt = measure_e2e(e2e_k_steps_pipelined)
-                pems = statistics.median(t[0] for t in pt)
-                plast = allmax([last[0] if last[0] is not None else -1e30])[0]
-                if not math.isfinite(plast):
-                    raise RuntimeError("pipelined loop returned loss %r" % (plast,))
-                sync_part = {k: e2e[k] for k in ("value", "ms_per_step", "wall_ms_per_step", "last_loss")}
-                pipe_part = {"value": per_step / (pems / 1e3), "ms_per_step": pems / K,
-                             "wall_ms_per_step": statistics.median(t[1] for t in pt) / K, "last_loss": plast}
-                e2e["synchronous"], e2e["pipelined"] = sync_part, pipe_part
-                if pipe_part["value"] > e2e["value"]:
-                    e2e.update(pipe_part)
-                    e2e["api"] = "PSTrainEngine.step(x_pinned, y_pinned, sync_loss='deferred', prefetch=next) -> PendingLoss; .result()"
-                    e2e["loss_read"] = "every step's loss is copied D2H behind its kernels and read by the host one step late"
-            except Exception as e:      # noqa: BLE001 - keep the synchronous measurement
-                if world > 1:
-                    raise                # ranks must not diverge
-                e2e["pipelined_error"] = repr(e)[:300]
-        if args.e2e_native_loop and len(wl) <= 1 and ((world == 1 and is_worker) or pow_):
-            # third arm: the framework's own training loop (one native call per K steps).  A failure on any rank drops the
-            # arm on every rank (the flag is agreed on before anything is recorded); the other arms' numbers stand.
-            nt, nerr = None, None
-            try:
-                nt = measure_e2e(e2e_k_steps_native)
-            except Exception as e:      # noqa: BLE001
-                nerr = repr(e)[:300]
-            nlast = allmax([last[0] if (last[0] is not None and nerr is None) else -1e30])[0]
-            failed = allmax([1.0 if (nerr is not None or not math.isfinite(nlast)) else 0.0])[0] > 0
-            if failed:
-                e2e["native_loop_error"] = nerr or "non-finite loss %r or a failure on another rank" % (nlast,)
-            else:
-                nems = statistics.median(t[0] for t in nt)
-                if "synchronous" not in e2e:
-                    e2e["synchronous"] = {k: e2e[k] for k in ("value", "ms_per_step", "wall_ms_per_step", "last_loss")}
-                nat_part = {"value": per_step / (nems / 1e3), "ms_per_step": nems / K,
-                            "wall_ms_per_step": statistics.median(t[1] for t in nt) / K, "last_loss": nlast}
-                e2e["native_loop"] = dict(nat_part, depth=args.e2e_depth)
-                if nat_part["value"] > e2e["value"]:
-                    e2e.update(nat_part)
-                    e2e["reps"] = len(nt)
-                    e2e["api"] = "PSTrainEngine.train_loop(x_batches_pinned, y_batches_pinned, steps=K) -> losses[K]"
-                    e2e["loss_read"] = ("every step's loss is copied D2H behind its kernels into its own pinned row; the host waits "
-                                        "for row i-%d before enqueuing step i and reads all K rows" % args.e2e_depth)
-                    e2e["input_double_buffering"] = True
+        e2e = run_e2e(eng, args, spec, K, num_workers, is_worker, world, pow_, images, labels, barrier, allmax)
 
     # ---- ps traffic implied by the measured step time (BASELINE metric: push/pull GB/s vs 900 GB/s/dir) -----------
     # true-shape bytes: gradients travel as fp32, parameters as fp32 (tf32 engines) / bf16 replicas; every worker moves both every step.
