@@ -263,3 +263,36 @@ def test_train_loop_host_logic_with_a_fake_native_loop():
     n = len(calls)
     out = eng.train_loop(xb, yb, steps=3)
     assert len(calls) == n and list(out) == [7.0] * 3
+
+
+def test_untimed_alignment_step_with_prefetch_hands_the_next_batch_to_the_following_step():
+    """bench.py's alignment steps call ``step(x, y, sync_loss=False, prefetch=next)``: no loss read-back, the next batch's copy is
+    issued into the other buffer set and the following step (or ``train_loop``) skips its own copy."""
+    from types import SimpleNamespace
+    import torch
+    from distributed_tensorflow_b200.parallel.ps_engine import PSTrainEngine
+    log = []
+
+    class Plan:
+        def __init__(self, name):
+            self.name, self.ops = name, [SimpleNamespace(p1=None) for _ in range(3)]
+
+        def run(self):
+            log.append(self.name)
+    eng = PSTrainEngine.__new__(PSTrainEngine)
+    eng.cfg = SimpleNamespace(sync=True, num_workers=1, colocated=True)
+    eng.spec = SimpleNamespace(batch=4, in_dim=8, classes=2)
+    eng.worker_ranks, eng.ps_ranks, eng.head_ctas = [0], [0], 2
+    eng.ranks = {0: SimpleNamespace(step=0)}
+    eng._is_pinned_f32 = lambda t: True
+    eng._native_plans = {"copy": {0: [Plan("copy0"), Plan("copy1")]}, "compute": {0: [Plan("compute0"), Plan("compute1")]},
+                         "ps": {}, "loss": {0: (Plan("loss"), __import__("numpy").array([1.0, 2.0], dtype="float32"), None)},
+                         "pending": {}, "keep": [], "runs": 10, "parity": 0, "prefetched": None, "graphed": True, "loss_async": {}}
+    xs = [torch.zeros(4, 8) + i for i in range(3)]
+    ys = [torch.zeros(4, 2) for _ in range(3)]
+    assert eng.step(xs[0], ys[0], sync_loss=False, prefetch=(xs[1], ys[1])) is None
+    assert log == ["copy0", "compute0", "copy1"]
+    assert eng._native_plans["prefetched"] == (xs[1].data_ptr(), ys[1].data_ptr(), 1)
+    del log[:]
+    assert eng.step(xs[1], ys[1], sync_loss=True, prefetch=(xs[2], ys[2])) == 3.0          # the prefetched batch: no copy1 again
+    assert log == ["compute1", "copy0", "loss"]
