@@ -13,6 +13,16 @@ from distributed_tensorflow_b200.ops import cuda_lib
 from distributed_tensorflow_b200.utils.mnist_data import synthetic_mnist
 
 
+_EMU_DIR = []
+
+
+def _emu_dir():
+    if not _EMU_DIR:
+        import tempfile
+        _EMU_DIR.append(tempfile.mkdtemp(prefix="dtf_emu_fusion_"))
+    return _EMU_DIR[0]
+
+
 def _mnist_graph(hidden=32):
     tf.set_random_seed(3)
     x, y_ = tf.placeholder(tf.float32, [None, 784]), tf.placeholder(tf.float32, [None, 10])
@@ -254,3 +264,79 @@ def test_mean_squared_error_chain_is_one_fused_op(monkeypatch, tmp_path_factory)
         d = a - b
         both = [sess._resolve(tf.reduce_mean(tf.square(d))), sess._resolve(tf.reduce_sum(d))]
         assert sess._plan(both, {a.id, b.id}).fusions is None
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_programs_fused_equals_unfused(seed, monkeypatch):
+    """Randomly assembled programs from the op families the rewrites touch (affine layers in both spellings, scalar / vector biases,
+    optional ReLU, either loss head) with random extra consumers and extra fetches of interior values: whatever the planner decides
+    to fuse or to refuse, fetched values and gradients equal the node-by-node plan's."""
+    rng = np.random.RandomState(100 + seed)
+
+    def build_and_run():
+        r = np.random.RandomState(100 + seed)                    # the same program both times
+        tf.reset_default_graph()
+        tf.set_random_seed(7)
+        B, D = 12, int(r.randint(3, 9))
+        x = tf.placeholder(tf.float32, [None, D])
+        h, width, variables, extras = x, D, [], []
+        for li in range(int(r.randint(1, 4))):
+            out = int(r.randint(2, 7))
+            w = tf.get_variable("w%d" % li, [width, out], initializer=tf.truncated_normal_initializer(0, 0.5))
+            scalar_bias = bool(r.randint(0, 2))
+            b = tf.get_variable("b%d" % li, [] if scalar_bias else [out], initializer=tf.constant_initializer(0.1))
+            spelling = int(r.randint(0, 3))
+            if spelling == 0 and not scalar_bias:
+                pre = tf.nn.xw_plus_b(h, w, b)
+            elif spelling == 1:
+                pre = tf.matmul(h, w) + b
+            else:
+                pre = b + tf.matmul(h, w)                         # bias on the left
+            if r.randint(0, 4) == 0:
+                extras.append(tf.reduce_sum(pre))                 # a second consumer of the pre-activation
+            h = tf.nn.relu(pre) if r.randint(0, 3) else pre
+            if r.randint(0, 5) == 0:
+                extras.append(h)                                  # the activation itself is fetched
+            variables += [w, b]
+            width = out
+        if r.randint(0, 2):
+            t = tf.placeholder(tf.float32, [None, width])
+            diff_first = bool(r.randint(0, 2))
+            loss = tf.reduce_mean(tf.square(h - t if diff_first else t - h))
+        else:
+            t = tf.placeholder(tf.float32, [None, width])
+            y = tf.nn.softmax(h)
+            loss = -tf.reduce_sum(t * tf.log(tf.clip_by_value(y, 1e-10, 1.0)))
+            if r.randint(0, 3) == 0:
+                extras.append(y)
+        grads = tf.gradients(loss, variables)
+        xs = r.rand(B, D).astype(np.float32)
+        ts = r.rand(B, width).astype(np.float32)
+        ts = ts / ts.sum(1, keepdims=True)
+        with tf.Session() as sess:
+            sess.run(tf.global_variables_initializer())
+            fetches = [loss] + list(grads) + extras
+            plan = sess._plan([sess._resolve(f) for f in fetches], {x.id, t.id}).fusions
+            return plan, sess.run(fetches, {x: xs, t: ts})
+    plan, fused = build_and_run()
+    emu = None
+    if seed % 3 == 0 and shutil.which("g++") is not None:        # every third program also on the kernel path (host emulation)
+        cuda_lib.enable_emulation(_emu_dir())
+        try:
+            _, emu = build_and_run()
+        finally:
+            cuda_lib.disable_emulation()
+    monkeypatch.setattr(fusion, "ENABLED", False)
+    plan0, plain = build_and_run()
+    assert plan0 is None and len(fused) == len(plain)
+    for a, b in zip(fused, plain):
+        np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6)
+    if emu is not None:
+        for a, b in zip(emu, plain):
+            np.testing.assert_allclose(a, b, rtol=5e-3, atol=5e-4)
+    test_random_programs_fused_equals_unfused.planned = getattr(test_random_programs_fused_equals_unfused, "planned", 0) + \
+        (0 if plan is None else sum(len(v) for v in plan.values()))
+
+
+def test_random_programs_exercised_the_planner():
+    assert getattr(test_random_programs_fused_equals_unfused, "planned", 0) >= 8
