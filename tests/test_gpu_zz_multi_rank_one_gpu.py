@@ -13,7 +13,7 @@ import sys
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
