@@ -226,3 +226,44 @@ def test_first_use_self_tests_run_clean_under_the_emulation(emulated, monkeypatc
     assert not random_ops._device_fill_checked(torch.device("cpu")) and random_ops.SELF_TEST["state"] == "failed"
     monkeypatch.setitem(native.EW_SELF_TEST, "state", "passed")
     monkeypatch.setitem(random_ops.SELF_TEST, "state", "not run")
+
+
+def test_concat_scatter_and_broadcast_kernels_on_random_shapes(emulated):
+    """Random ranks / axes / part lengths (zero-length parts, non-contiguous inputs) for the gather-scatter kernel, random
+    broadcast patterns for the binary kernel: always what torch computes."""
+    rng = np.random.RandomState(7)
+    g = torch.Generator().manual_seed(7)
+    for _ in range(40):
+        nd = int(rng.randint(1, 5))
+        shape = [int(rng.randint(1, 6)) for _ in range(nd)]
+        ax = int(rng.randint(-nd, nd))
+        parts = []
+        for _ in range(int(rng.randint(2, 7))):
+            s = list(shape)
+            s[ax] = int(rng.randint(0, 5))
+            t = torch.rand(s, generator=g)
+            if nd >= 2 and rng.randint(0, 3) == 0:
+                t = t.transpose(0, nd - 1).contiguous().transpose(0, nd - 1)      # same values, non-contiguous layout
+            parts.append(t)
+        got = cuda_lib.concat(parts, ax)
+        assert got is not None
+        torch.testing.assert_close(got, torch.cat(parts, dim=ax), rtol=0, atol=0)
+    for _ in range(40):
+        nd = int(rng.randint(1, 4))
+        out_shape = [int(rng.randint(1, 6)) for _ in range(nd)]
+        def operand():
+            kind = int(rng.randint(0, 3))
+            if kind == 0:
+                return torch.rand(out_shape, generator=g) + 0.5
+            if kind == 1:
+                return torch.rand([1] * int(rng.randint(0, nd + 1)) or [1], generator=g) + 0.5
+            k = int(rng.randint(1, nd + 1))
+            return torch.rand([1] * int(rng.randint(0, 2)) + out_shape[nd - k:], generator=g) + 0.5
+        a, b = operand(), operand()
+        op = list(native._TORCH_BINARY)[int(rng.randint(0, 5))]
+        try:
+            want = native._TORCH_BINARY[op](a, b)
+        except RuntimeError:
+            continue
+        got = native.binary(op, a, b)
+        torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
