@@ -13,8 +13,10 @@ ps shard s shares worker s's GPU; ``--ps-only-task 1`` gives the ps its own GPU 
   repetitions continue until >= 100 ms of timed region were collected; the MEDIAN repetition is reported (``reps``).
 * inputs: a 55 000 x 784 fp32 synthetic MNIST-shaped training set resident in each worker's HBM
   (172 MB > the 126 MB L2), batches walked in order; the step kernel's TMA reads them in place.
-* ``e2e``: the same metric through ``PSTrainEngine.step(x, y)`` with, every step, the host->device copy
-  of that step's batch from pinned host memory and a device->host read of the loss (same repetition protocol).
+* ``e2e``: the same metric through the public API with, every step, the host->device copy of that step's batch from pinned host
+  memory and a device->host read of the loss (same repetition protocol).  Three arms, the best one reported, all kept:
+  ``synchronous`` (``PSTrainEngine.step(x, y) -> loss``), ``pipelined`` (``step(..., sync_loss="deferred")``: the loss read one
+  step late) and ``native_loop`` (``PSTrainEngine.train_loop(batches, steps=K)``: the K steps enqueued by one native call).
 * ``vs_baseline``: value / the in-repo torch + NCCL + cuBLAS (CUDA-graphed) arm measured in the SAME invocation with the
   same steps, repetitions and precision (``baseline``: its value, e2e and clocks).  The reference itself cannot run.
 * ``--impl reference``: the reference is TensorFlow-1.x example scripts; TF is not installable in this
