@@ -136,5 +136,32 @@ layers = _types.SimpleNamespace(dense=_dense)
 from . import train  # noqa: E402
 from .python_compat import input_data, timeline  # noqa: E402,F401
 
+# -- ops next to the reference's own (framework/ops_extra.py); bound last: some names shadow builtins (range, round) ---------------
+from .framework import ops_extra as _extra  # noqa: E402
+
+for _n in _extra.__all__:
+    globals()[_n] = getattr(_extra, _n)
+for _n in ("relu6", "elu", "leaky_relu", "softplus", "sigmoid_cross_entropy_with_logits", "l2_normalize", "embedding_lookup", "in_top_k",
+           "top_k"):
+    setattr(nn, _n, getattr(_extra, _n))
+
+
+def _mean_squared_error(labels, predictions, scope=None):
+    return _ops.reduce_mean(_ops.square(_ops.subtract(convert_to_tensor(predictions), convert_to_tensor(labels))), name=scope or "mean_squared_error")
+
+
+def _softmax_cross_entropy(onehot_labels, logits, scope=None):
+    return _ops.reduce_mean(_ops.softmax_cross_entropy_with_logits(labels=onehot_labels, logits=logits), name=scope or "softmax_cross_entropy_loss")
+
+
+def _sparse_softmax_cross_entropy(labels, logits, scope=None):
+    return _ops.reduce_mean(_ops.sparse_softmax_cross_entropy_with_logits(labels=labels, logits=logits),
+                            name=scope or "sparse_softmax_cross_entropy_loss")
+
+
+losses = _types.SimpleNamespace(mean_squared_error=_mean_squared_error, softmax_cross_entropy=_softmax_cross_entropy,
+                                sparse_softmax_cross_entropy=_sparse_softmax_cross_entropy)
+del _n
+
 __all__ = [n for n in dir() if not n.startswith("_") and n not in {
     "Any", "Callable", "Dict", "List", "Optional", "Sequence", "Union", "annotations", "np", "torch", "F"}]

@@ -465,7 +465,11 @@ def _to_numpy(v):
         if t.dtype == torch.bfloat16:
             t = t.float()
         a = t.cpu().numpy()
-        return a[()] if a.ndim == 0 else a
+        if a.ndim == 0:
+            return a[()]
+        # a fetched value is the caller's own (TF copies into the result): a host tensor's numpy view would alias the live
+        # variable / an executor value and change under the caller at the next apply
+        return a.copy() if t.device.type == "cpu" else a
     if isinstance(v, list) and v and all(isinstance(x, torch.Tensor) or x is None for x in v):
         return [_to_numpy(x) for x in v]
     return v

@@ -9,8 +9,8 @@ from .hooks import (CheckpointSaverHook, FinalOpsHook, GlobalStepWaiterHook, Log
                     StalenessHook, StepCounterHook, StopAtStepHook, SummarySaverHook)
 from .monitored_session import (ChiefSessionCreator, MonitoredSession, MonitoredTrainingSession, Scaffold,
                                 SessionManager, SingularMonitoredSession, WorkerSessionCreator)
-from .optimizer import (AdamOptimizer, GradientDescentOptimizer, MomentumOptimizer, Optimizer, exponential_decay,
-                        piecewise_constant)
+from .optimizer import (AdagradOptimizer, AdamOptimizer, GradientDescentOptimizer, MomentumOptimizer, Optimizer, RMSPropOptimizer,
+                        exponential_decay, piecewise_constant)
 from .saver import (CheckpointState, NewCheckpointReader, Saver, checkpoint_exists, get_checkpoint_state,
                     latest_checkpoint, list_variables, load_checkpoint, update_checkpoint_state)
 from .sync_replicas import SyncReplicasOptimizer, SyncReplicasOptimizerHook

@@ -109,6 +109,22 @@ class Optimizer:
             named[var.var_name] = s
         return s
 
+    def _const_slot(self, var: Variable, slot_name: str, op_name: str, value: float) -> Variable:
+        """Like :meth:`_zeros_slot` with every element starting at ``value`` (Adagrad's accumulator, RMSProp's mean square)."""
+        named = self._slots.setdefault(slot_name, {})
+        s = named.get(var.var_name)
+        if s is None:
+            g = get_default_graph()
+            name = "%s/%s" % (var.var_name, op_name)
+            if name in g.variables:
+                s = g.variables[name]
+            else:
+                shape, dt = var.shape, var.dtype
+                with _device.device(None), _device.device(var.device or None), g.name_scope(None):
+                    s = Variable(lambda: _ops.constant(float(value), dtype=dt, shape=shape), trainable=False, name=name, _exact_name=True)
+            named[var.var_name] = s
+        return s
+
     def _scalar_slot(self, colocate: Variable, value: float, name: str) -> Variable:
         g = get_default_graph()
         if name in g.variables:
@@ -248,6 +264,81 @@ def _k_apply_momentum(ctx, node, grad, *extra):
                 var.sub_(g * a["lr"] + acc * (a["momentum"] * a["lr"]))
             else:
                 var.sub_(acc, alpha=a["lr"])
+    return None
+
+
+
+class AdagradOptimizer(Optimizer):
+    """TF's Adagrad: ``accum += g^2 ; var -= lr * g / sqrt(accum)`` with ``accum`` starting at ``initial_accumulator_value``
+    (graph tier; the fabric engines fuse SGD / Momentum / Adam only, so ``minimize`` keeps such a program on the control plane /
+    the generic path)."""
+
+    def __init__(self, learning_rate, initial_accumulator_value: float = 0.1, use_locking: bool = False, name: str = "Adagrad"):
+        super().__init__(use_locking, name)
+        if initial_accumulator_value <= 0.0:
+            raise ValueError("initial_accumulator_value must be positive: %s" % initial_accumulator_value)
+        self._lr, self._init_acc = learning_rate, float(initial_accumulator_value)
+
+    def _create_slots(self, var_list):
+        for v in var_list:
+            self._const_slot(v, "accumulator", self._name, self._init_acc)
+
+    def _apply_dense(self, grad, var, prep):
+        slot = self.get_slot(var, "accumulator")
+        extra, lr = _lr_inputs(self._lr)
+        return get_default_graph().create_node(
+            "ApplyAdagrad", [grad] + extra, {"var_name": var.var_name, "accum_name": slot.var_name, "lr": lr},
+            "update_%s/ApplyAdagrad" % var.var_name.replace("/", "_"), device=var.device)
+
+
+@register_kernel("ApplyAdagrad", stateful=True)
+def _k_apply_adagrad(ctx, node, grad, *extra):
+    a = dict(node.attrs, lr=_lr_at_run_time(node, extra))
+    var, acc = ctx.store.read(a["var_name"]), ctx.store.read(a["accum_name"])
+    g = grad.to(device=var.device, dtype=var.dtype)
+    acc.addcmul_(g, g)
+    var.addcdiv_(g, acc.sqrt(), value=-a["lr"])
+    return None
+
+
+class RMSPropOptimizer(Optimizer):
+    """TF's RMSProp: ``ms = decay * ms + (1 - decay) * g^2 ; mom = momentum * mom + lr * g / sqrt(ms + eps) ; var -= mom``
+    (``ms`` starts at one, ``mom`` at zero; ``centered=True`` also tracks the mean gradient and subtracts its square)."""
+
+    def __init__(self, learning_rate, decay: float = 0.9, momentum: float = 0.0, epsilon: float = 1e-10, use_locking: bool = False,
+                 centered: bool = False, name: str = "RMSProp"):
+        super().__init__(use_locking, name)
+        self._lr, self._decay, self._momentum, self._eps, self._centered = learning_rate, float(decay), float(momentum), float(epsilon), bool(centered)
+
+    def _create_slots(self, var_list):
+        for v in var_list:
+            self._const_slot(v, "rms", self._name, 1.0)
+            self._zeros_slot(v, "momentum", self._name + "_1")
+            if self._centered:
+                self._zeros_slot(v, "mg", self._name + "_2")
+
+    def _apply_dense(self, grad, var, prep):
+        extra, lr = _lr_inputs(self._lr)
+        attrs = {"var_name": var.var_name, "ms_name": self.get_slot(var, "rms").var_name,
+                 "mom_name": self.get_slot(var, "momentum").var_name, "lr": lr, "decay": self._decay, "momentum": self._momentum,
+                 "eps": self._eps, "mg_name": self.get_slot(var, "mg").var_name if self._centered else None}
+        return get_default_graph().create_node("ApplyRMSProp", [grad] + extra, attrs,
+                                               "update_%s/ApplyRMSProp" % var.var_name.replace("/", "_"), device=var.device)
+
+
+@register_kernel("ApplyRMSProp", stateful=True)
+def _k_apply_rmsprop(ctx, node, grad, *extra):
+    a = dict(node.attrs, lr=_lr_at_run_time(node, extra))
+    var, ms, mom = ctx.store.read(a["var_name"]), ctx.store.read(a["ms_name"]), ctx.store.read(a["mom_name"])
+    g = grad.to(device=var.device, dtype=var.dtype)
+    ms.mul_(a["decay"]).addcmul_(g, g, value=1.0 - a["decay"])
+    denom = ms
+    if a["mg_name"] is not None:
+        mg = ctx.store.read(a["mg_name"])
+        mg.mul_(a["decay"]).add_(g, alpha=1.0 - a["decay"])
+        denom = ms - mg * mg
+    mom.mul_(a["momentum"]).addcdiv_(g, (denom + a["eps"]).sqrt(), value=a["lr"])
+    var.sub_(mom)
     return None
 
 

@@ -339,3 +339,17 @@ def test_same_shaped_initialisers_on_two_ps_tasks_differ(ports):
     finally:
         for s in servers:
             s.stop()
+
+
+def test_fetched_values_do_not_alias_live_variables():
+    """``sess.run(var)`` hands out a copy (TF semantics): a later apply must not change an array the caller kept."""
+    import numpy as np
+    import distributed_tensorflow_b200 as tf
+    w = tf.get_variable("alias_w", [3, 2], initializer=tf.constant_initializer(1.0))
+    bump = tf.assign_add(w, tf.ones([3, 2]))
+    with tf.Session() as sess:
+        sess.run(tf.global_variables_initializer())
+        before = sess.run(w)
+        sess.run(bump)
+        after = sess.run(w)
+    assert np.array_equal(before, np.ones((3, 2))) and np.array_equal(after, 2 * np.ones((3, 2)))

@@ -1,0 +1,164 @@
+"""framework/ops_extra.py + the Adagrad / RMSProp optimizers: ops a TF-1.x ps/worker program commonly uses next to the ones the
+reference scripts call -- each against numpy / torch, gradients where they exist."""
+import numpy as np
+import pytest
+import torch
+
+import distributed_tensorflow_b200 as tf
+
+
+def _run(fetches, feed=None):
+    with tf.Session() as sess:
+        sess.run(tf.global_variables_initializer())
+        return sess.run(fetches, feed or {})
+
+
+def test_shape_and_selection_ops():
+    a = np.arange(12, dtype=np.float32).reshape(3, 4)
+    x = tf.constant(a)
+    idx = tf.constant(np.array([2, 0], np.int64))
+    cond = tf.greater_equal(x, 5.0)
+    out = _run([tf.tile(x, [2, 1]), tf.gather(x, idx), tf.gather(x, idx, axis=1), tf.where(cond, x, -x), tf.where(cond),
+                tf.size(x), tf.rank(x), tf.range(5), tf.range(2, 11, 3), tf.linspace(0.0, 1.0, 5), tf.cumsum(x, axis=1),
+                tf.cumsum(x, axis=0, exclusive=True, reverse=True), tf.reverse(x, [1]), tf.pad(x, [[1, 0], [0, 2]]),
+                tf.matrix_transpose(x), tf.nn.embedding_lookup(x, idx), tf.eye(3), tf.reduce_prod(x[1:2] if False else tf.constant(a[:, :2] + 1), axis=1)])
+    assert np.array_equal(out[0], np.tile(a, (2, 1))) and np.array_equal(out[1], a[[2, 0]]) and np.array_equal(out[2], a[:, [2, 0]])
+    assert np.array_equal(out[3], np.where(a >= 5, a, -a)) and np.array_equal(out[4], np.argwhere(a >= 5))
+    assert out[5] == 12 and out[6] == 2 and out[7].tolist() == [0, 1, 2, 3, 4] and out[8].tolist() == [2, 5, 8]
+    np.testing.assert_allclose(out[9], np.linspace(0, 1, 5))
+    assert np.array_equal(out[10], np.cumsum(a, 1))
+    assert np.array_equal(out[11], np.flip(np.cumsum(np.flip(a, 0), 0), 0) - a)
+    assert np.array_equal(out[12], a[:, ::-1]) and np.array_equal(out[13], np.pad(a, [[1, 0], [0, 2]]))
+    assert np.array_equal(out[14], a.T) and np.array_equal(out[15], a[[2, 0]]) and np.array_equal(out[16], np.eye(3))
+    assert np.array_equal(out[17], np.prod(a[:, :2] + 1, axis=1))
+    # a vector condition selects whole rows (TF's tf.where)
+    rows = _run(tf.where(tf.constant([True, False, True]), x, tf.zeros([3, 4])))
+    assert np.array_equal(rows, a * np.array([[1], [0], [1]], np.float32))
+
+
+def test_elementwise_logic_and_rounding():
+    v = np.array([-2.5, -0.4, 0.0, 0.5, 1.5, 7.2], np.float32)
+    x = tf.constant(v)
+    t = torch.from_numpy(v)
+    out = _run([tf.floor(x), tf.ceil(x), tf.round(x), tf.sign(x), tf.nn.relu6(x), tf.nn.elu(x), tf.nn.leaky_relu(x, 0.1), tf.nn.softplus(x),
+                tf.erf(x), tf.log1p(tf.abs(x)), tf.expm1(x), tf.logical_and(x > 0.0, x < 2.0), tf.logical_or(x < 0.0, x > 2.0),
+                tf.logical_not(x > 0.0), tf.less_equal(x, 0.5), tf.not_equal(x, 0.0), tf.floordiv(x, 2.0), tf.mod(x, 2.0),
+                tf.reduce_all(x > -3.0), tf.reduce_any(x > 7.0), tf.reduce_any(tf.constant([[True, False], [False, False]]), axis=1)])
+    ref = [torch.floor(t), torch.ceil(t), torch.round(t), torch.sign(t), torch.clamp(t, 0, 6), torch.nn.functional.elu(t),
+           torch.nn.functional.leaky_relu(t, 0.1), torch.nn.functional.softplus(t), torch.erf(t), torch.log1p(t.abs()), torch.expm1(t),
+           (t > 0) & (t < 2), (t < 0) | (t > 2), ~(t > 0), t <= 0.5, t != 0, torch.floor(t / 2), torch.remainder(t, 2.0)]
+    for got, want in zip(out, ref):
+        np.testing.assert_allclose(got, want.numpy(), rtol=1e-6, atol=1e-6)
+    assert out[18] and out[19] and out[20].tolist() == [True, False]
+
+
+def test_norms_and_gradient_clipping_in_a_training_step():
+    tf.set_random_seed(2)
+    w = tf.get_variable("w", [4, 3], initializer=tf.truncated_normal_initializer(stddev=1.0))
+    b = tf.get_variable("b", [3], initializer=tf.constant_initializer(0.5))
+    x = tf.placeholder(tf.float32, [None, 4])
+    loss = tf.reduce_sum(tf.square(tf.matmul(x, w) + b)) * 100.0
+    opt = tf.train.GradientDescentOptimizer(0.1)
+    gv = opt.compute_gradients(loss, [w, b])
+    clipped, gn = tf.clip_by_global_norm([g for g, _ in gv], 1.0)
+    train = opt.apply_gradients(list(zip(clipped, [w, b])))
+    xs = np.random.RandomState(0).rand(8, 4).astype(np.float32)
+    with tf.Session() as sess:
+        sess.run(tf.global_variables_initializer())
+        w0, b0 = sess.run([w, b])
+        g0, g1, gnv, n2, n1, cn = sess.run([gv[0][0], gv[1][0], gn, tf.norm(w), tf.norm(w, ord=1), tf.clip_by_norm(w, 0.5)], {x: xs})
+        sess.run(train, {x: xs})
+        w1, b1 = sess.run([w, b])
+    want_gn = np.sqrt((g0 ** 2).sum() + (g1 ** 2).sum())
+    np.testing.assert_allclose(gnv, want_gn, rtol=1e-5)
+    assert want_gn > 1.0
+    np.testing.assert_allclose(w1, w0 - 0.1 * g0 / want_gn, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(b1, b0 - 0.1 * g1 / want_gn, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(n2, np.sqrt((w0 ** 2).sum()), rtol=1e-5)
+    np.testing.assert_allclose(n1, np.abs(w0).sum(), rtol=1e-5)
+    np.testing.assert_allclose(np.sqrt((cn ** 2).sum()), 0.5, rtol=1e-5)
+
+
+def test_nn_and_loss_helpers():
+    rng = np.random.RandomState(1)
+    z = rng.randn(6, 5).astype(np.float32)
+    y = (rng.rand(6, 5) > 0.5).astype(np.float32)
+    lab = rng.randint(0, 5, 6)
+    zt = torch.from_numpy(z)
+    logits = tf.constant(z)
+    vals, idx = tf.nn.top_k(logits, 2)
+    out = _run([tf.nn.sigmoid_cross_entropy_with_logits(labels=tf.constant(y), logits=logits), tf.nn.l2_normalize(logits, axis=1),
+                tf.nn.in_top_k(logits, tf.constant(lab), 2), vals, idx,
+                tf.losses.mean_squared_error(tf.constant(y), logits), tf.losses.softmax_cross_entropy(tf.constant(np.eye(5, dtype=np.float32)[lab]), logits),
+                tf.losses.sparse_softmax_cross_entropy(tf.constant(lab), logits)])
+    np.testing.assert_allclose(out[0], torch.nn.functional.binary_cross_entropy_with_logits(zt, torch.from_numpy(y), reduction="none").numpy(), rtol=1e-5)
+    np.testing.assert_allclose(out[1], z / np.linalg.norm(z, axis=1, keepdims=True), rtol=1e-5)
+    top2 = np.argsort(-z, axis=1)[:, :2]
+    assert out[2].tolist() == [lab[i] in top2[i] for i in range(6)]
+    np.testing.assert_allclose(out[3], -np.sort(-z, axis=1)[:, :2]) and None
+    assert np.array_equal(out[4], top2)
+    np.testing.assert_allclose(out[5], ((z - y) ** 2).mean(), rtol=1e-5)
+    ce = torch.nn.functional.cross_entropy(zt, torch.from_numpy(lab)).item()
+    np.testing.assert_allclose(out[6], ce, rtol=1e-5)
+    np.testing.assert_allclose(out[7], ce, rtol=1e-5)
+    # differentiable where it should be
+    g = _run(tf.gradients(tf.reduce_sum(tf.nn.l2_normalize(logits, axis=1) * tf.constant(y)), [logits])[0])
+    zt2 = zt.clone().requires_grad_()
+    (torch.nn.functional.normalize(zt2, dim=1) * torch.from_numpy(y)).sum().backward()
+    np.testing.assert_allclose(g, zt2.grad.numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_print_and_py_func(capfd):
+    x = tf.constant(np.array([1.0, 2.0, 3.0, 4.0], np.float32))
+    p = tf.Print(x, [x, tf.reduce_sum(x)], message="x and its sum: ", first_n=2, summarize=3)
+    doubled = tf.py_func(lambda a: a * 2, [x], tf.float32)
+    s, c = tf.py_func(lambda a: (a.sum(), np.int64(a.size)), [x], [tf.float32, tf.int64])
+    with tf.Session() as sess:
+        for _ in range(3):
+            out = sess.run([p, doubled, s, c])
+    assert out[0].tolist() == [1, 2, 3, 4] and out[1].tolist() == [2, 4, 6, 8] and out[2] == 10.0 and out[3] == 4
+    err = capfd.readouterr().err
+    assert err.count("x and its sum: [1 2 3...][10]") == 2                 # first_n
+
+
+@pytest.mark.parametrize("which", ["adagrad", "rmsprop", "rmsprop_momentum_centered"])
+def test_adagrad_and_rmsprop_follow_tensorflows_formulas(which):
+    tf.set_random_seed(3)
+    w = tf.get_variable("w", [5, 2], initializer=tf.truncated_normal_initializer(stddev=0.5))
+    x = tf.placeholder(tf.float32, [None, 5])
+    loss = tf.reduce_mean(tf.square(tf.matmul(x, w) - 1.0))
+    gs = tf.train.get_or_create_global_step()
+    if which == "adagrad":
+        opt = tf.train.AdagradOptimizer(0.1, initial_accumulator_value=0.1)
+    elif which == "rmsprop":
+        opt = tf.train.RMSPropOptimizer(0.01, decay=0.9, epsilon=1e-10)
+    else:
+        opt = tf.train.RMSPropOptimizer(0.01, decay=0.8, momentum=0.5, epsilon=1e-6, centered=True)
+    grad = tf.gradients(loss, [w])[0]
+    train = opt.minimize(loss, global_step=gs)
+    rng = np.random.RandomState(0)
+    with tf.Session() as sess:
+        sess.run(tf.global_variables_initializer())
+        wv = sess.run(w).astype(np.float64)
+        acc = np.full_like(wv, 0.1)
+        ms, mom, mg = np.ones_like(wv), np.zeros_like(wv), np.zeros_like(wv)
+        for _ in range(6):
+            xs = rng.rand(7, 5).astype(np.float32)
+            g = sess.run(grad, {x: xs}).astype(np.float64)
+            sess.run(train, {x: xs})
+            if which == "adagrad":
+                acc += g * g
+                wv -= 0.1 * g / np.sqrt(acc)
+            elif which == "rmsprop":
+                ms = 0.9 * ms + 0.1 * g * g
+                mom = 0.0 * mom + 0.01 * g / np.sqrt(ms + 1e-10)
+                wv -= mom
+            else:
+                ms = 0.8 * ms + 0.2 * g * g
+                mg = 0.8 * mg + 0.2 * g
+                mom = 0.5 * mom + 0.01 * g / np.sqrt(ms - mg * mg + 1e-6)
+                wv -= mom
+            np.testing.assert_allclose(sess.run(w), wv, rtol=2e-5, atol=1e-6)
+        assert sess.run(gs) == 6
+    assert sorted(opt.get_slot_names()) == (["accumulator"] if which == "adagrad" else
+                                            (["momentum", "rms"] if which == "rmsprop" else ["mg", "momentum", "rms"]))
