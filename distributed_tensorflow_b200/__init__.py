@@ -159,6 +159,34 @@ def _sparse_softmax_cross_entropy(labels, logits, scope=None):
                             name=scope or "sparse_softmax_cross_entropy_loss")
 
 
+def _metric_mean(values, weights=None, name="mean"):
+    """``tf.metrics.mean``: ``(value, update_op)`` over two LOCAL variables (``total``, ``count``): run ``update_op`` per batch, read
+    ``value`` at the end; ``tf.local_variables_initializer()`` resets them."""
+    v = cast(convert_to_tensor(values), float32)
+    g = get_default_graph()
+    with g.name_scope(name):
+        total = Variable(lambda: _ops.constant(0.0, dtype=float32), trainable=False, collections=[GraphKeys.LOCAL_VARIABLES], name="total")
+        count = Variable(lambda: _ops.constant(0.0, dtype=float32), trainable=False, collections=[GraphKeys.LOCAL_VARIABLES], name="count")
+        if weights is not None:
+            w = cast(convert_to_tensor(weights), float32)
+            num, den = _ops.reduce_sum(_ops.multiply(v, w)), _ops.reduce_sum(_ops.multiply(_ops.ones_like(v), w))
+        else:
+            num, den = _ops.reduce_sum(v), cast(_extra.size(v), float32)
+        new_total, new_count = assign_add(total, num), assign_add(count, den)
+
+        def safe_div(a, b, nm):
+            return _extra.where(_ops.greater(b, 0.0), _ops.divide(a, _ops.maximum(b, 1e-12)), _ops.zeros_like(a), name=nm)
+        return safe_div(total._node, count._node, "value"), safe_div(new_total, new_count, "update_op")
+
+
+def _metric_accuracy(labels, predictions, weights=None, name="accuracy"):
+    """``tf.metrics.accuracy``: running fraction of ``predictions == labels``."""
+    l, p = convert_to_tensor(labels), convert_to_tensor(predictions)
+    return _metric_mean(cast(_ops.equal(cast(p, int64), cast(l, int64)), float32), weights, name)
+
+
+metrics = _types.SimpleNamespace(mean=_metric_mean, accuracy=_metric_accuracy)
+
 losses = _types.SimpleNamespace(mean_squared_error=_mean_squared_error, softmax_cross_entropy=_softmax_cross_entropy,
                                 sparse_softmax_cross_entropy=_sparse_softmax_cross_entropy)
 del _n

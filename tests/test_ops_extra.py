@@ -162,3 +162,20 @@ def test_adagrad_and_rmsprop_follow_tensorflows_formulas(which):
         assert sess.run(gs) == 6
     assert sorted(opt.get_slot_names()) == (["accumulator"] if which == "adagrad" else
                                             (["momentum", "rms"] if which == "rmsprop" else ["mg", "momentum", "rms"]))
+
+
+def test_streaming_metrics_accumulate_over_batches_and_reset():
+    labels = tf.placeholder(tf.int64, [None])
+    preds = tf.placeholder(tf.int64, [None])
+    acc, acc_update = tf.metrics.accuracy(labels, preds)
+    mean, mean_update = tf.metrics.mean(tf.cast(preds, tf.float32), name="mean_pred")
+    assert len(tf.local_variables()) >= 4 and not any(v in tf.trainable_variables() for v in tf.local_variables())
+    with tf.Session() as sess:
+        sess.run(tf.local_variables_initializer())
+        assert sess.run(acc) == 0.0                                      # nothing seen yet: 0, not NaN
+        u1 = sess.run([acc_update, mean_update], {labels: [1, 2, 3, 4], preds: [1, 2, 0, 0]})
+        u2 = sess.run([acc_update, mean_update], {labels: [5, 6], preds: [5, 6]})
+        assert u1[0] == pytest.approx(0.5) and u2[0] == pytest.approx(4 / 6)
+        assert sess.run(acc) == pytest.approx(4 / 6) and sess.run(mean) == pytest.approx((1 + 2 + 0 + 0 + 5 + 6) / 6)
+        sess.run(tf.local_variables_initializer())
+        assert sess.run(acc) == 0.0
