@@ -187,6 +187,10 @@ def _metric_accuracy(labels, predictions, weights=None, name="accuracy"):
 
 metrics = _types.SimpleNamespace(mean=_metric_mean, accuracy=_metric_accuracy)
 
+from .utils import dataset as _dataset  # noqa: E402
+
+data = _types.SimpleNamespace(Dataset=_dataset.Dataset, Iterator=_dataset.Iterator_)
+
 losses = _types.SimpleNamespace(mean_squared_error=_mean_squared_error, softmax_cross_entropy=_softmax_cross_entropy,
                                 sparse_softmax_cross_entropy=_sparse_softmax_cross_entropy)
 del _n
