@@ -1,8 +1,9 @@
 """Ops a TF-1.x ps/worker program commonly uses NEXT to the ones the reference scripts call (SURVEY section 2.2 lists those):
 shape manipulation, comparisons / selection, rounding, norms and gradient clipping, a few activations and losses, ``tf.Print`` /
 ``tf.py_func``.  Same construction as ``framework/ops.py`` (one node per builder, one kernel per node type over torch tensors, so
-``tf.gradients`` differentiates through them); nothing here is on the benchmarked path.  Graph control flow (``tf.cond`` /
-``tf.while_loop``) is not provided: programs of the reference's kind branch in Python around ``Session.run``."""
+``tf.gradients`` differentiates through them); nothing here is on the benchmarked path.  ``tf.cond`` builds both branches and
+executes the chosen one; graph loops (``tf.while_loop``) are not provided: programs of the reference's kind loop in Python around
+``Session.run``."""
 from __future__ import annotations
 
 from typing import Sequence
@@ -362,3 +363,66 @@ def _k_py_func(ctx, n, *xs):
 
 
 register_kernel("TupleItemRaw")(lambda ctx, n, t: t[n.attrs["index"]])
+
+
+# -- tf.cond --------------------------------------------------------------------------------------------------------------------------
+def cond(pred, true_fn=None, false_fn=None, name="cond", fn1=None, fn2=None):
+    """``tf.cond``: both branches are BUILT (their nodes are created, like TF), only the chosen one is EXECUTED: the branch
+    sub-graphs hang off the ``Cond`` node and run inside its kernel over the values they capture from outside.  Differentiable
+    (the reverse pass follows the branch that ran).  The node must run on the task that built the graph (the usual placement of
+    worker-side compute); graph loops (``tf.while_loop``) are not provided."""
+    from .graph import get_default_graph
+    true_fn, false_fn = true_fn or fn1, false_fn or fn2
+    if true_fn is None or false_fn is None:
+        raise TypeError("cond(): true_fn and false_fn are required")
+    g = get_default_graph()
+    p = convert_to_tensor(pred)
+    start = len(g.nodes)
+    t_res = true_fn()
+    mid = len(g.nodes)
+    f_res = false_fn()
+    end = len(g.nodes)
+
+    def flat(r):
+        return [convert_to_tensor(v) for v in (r if isinstance(r, (list, tuple)) else [r])]
+    single = not isinstance(t_res, (list, tuple))
+    t_out, f_out = flat(t_res), flat(f_res)
+    end = len(g.nodes)                                     # convert_to_tensor may have added constants: they belong to the false side
+    if len(t_out) != len(f_out):
+        raise ValueError("cond(): true_fn and false_fn must return the same number of tensors (%d vs %d)" % (len(t_out), len(f_out)))
+    t_nodes, f_nodes = list(g.nodes[start:mid]), list(g.nodes[mid:end])
+    captured, seen = [], set()
+    for n in t_nodes + f_nodes:
+        for d in list(n.inputs) + list(n.control_inputs):
+            if d.id < start and d.id not in seen:
+                seen.add(d.id)
+                captured.append(d)
+    for o in t_out + f_out:                                   # a branch that returns an outer tensor as it is
+        if o.id < start and o.id not in seen:
+            seen.add(o.id)
+            captured.append(o)
+    node = _node("Cond", [p] + captured, {"t_nodes": t_nodes, "f_nodes": f_nodes, "t_out": [o.id for o in t_out],
+                                          "f_out": [o.id for o in f_out], "captured": [c.id for c in captured]}, name, None, None)
+    outs = [_node("TupleItemRaw", (node,), {"index": i}, "%s_%d" % (name, i), to.dtype or fo.dtype,
+                  to.shape if to.shape == fo.shape else None) for i, (to, fo) in enumerate(zip(t_out, f_out))]
+    return outs[0] if single else outs
+
+
+@register_kernel("Cond")
+def _k_cond(ctx, node, pred, *captured):
+    from .executor import ExecContext, execute
+    a = node.attrs
+    take_true = bool(pred.reshape(-1)[0]) if isinstance(pred, torch.Tensor) else bool(pred)
+    nodes, out_ids = (a["t_nodes"], a["t_out"]) if take_true else (a["f_nodes"], a["f_out"])
+    sub = ExecContext(ctx.store, ctx.task, ctx.gpu_index, ctx.tracer, getattr(ctx, "_seed", None), ctx.allow_soft_placement)
+    sub.force_device, sub.leaves = ctx.force_device, ctx.leaves
+    for attr in ("cancel_event", "server"):
+        if hasattr(ctx, attr):
+            setattr(sub, attr, getattr(ctx, attr))
+    for cid, v in zip(a["captured"], captured):
+        sub.values[cid] = v
+    execute(nodes, sub, torch.is_grad_enabled())
+    return tuple(sub.values[i] for i in out_ids)
+
+
+__all__.append("cond")

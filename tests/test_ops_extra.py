@@ -179,3 +179,33 @@ def test_streaming_metrics_accumulate_over_batches_and_reset():
         assert sess.run(acc) == pytest.approx(4 / 6) and sess.run(mean) == pytest.approx((1 + 2 + 0 + 0 + 5 + 6) / 6)
         sess.run(tf.local_variables_initializer())
         assert sess.run(acc) == 0.0
+
+
+def test_cond_runs_only_the_chosen_branch_and_is_differentiable(capfd):
+    x = tf.placeholder(tf.float32, [None])
+    flag = tf.placeholder(tf.bool, [])
+    w = tf.get_variable("cw", [], initializer=tf.constant_initializer(3.0))
+    calls = []
+
+    def yes():
+        return tf.reduce_sum(tf.Print(x, [x], message="true branch ran ") * w)
+
+    def no():
+        return tf.reduce_sum(tf.py_func(lambda a: (calls.append("f"), a)[1], [x], tf.float32)) - w * w
+    y = tf.cond(flag, yes, no)
+    gw = tf.gradients(y, [w])[0]
+    pair = tf.cond(tf.reduce_sum(x) > 5.0, lambda: (x + 1.0, w), lambda: (x - 1.0, w * 2.0))
+    with tf.Session() as sess:
+        sess.run(tf.global_variables_initializer())
+        xs = np.array([1.0, 2.0, 4.0], np.float32)
+        assert sess.run(y, {x: xs, flag: True}) == pytest.approx(21.0)
+        assert calls == [] and "true branch ran" in capfd.readouterr().err          # the other branch did not execute
+        assert sess.run(y, {x: xs, flag: False}) == pytest.approx(7.0 - 9.0) and calls == ["f"]
+        assert "true branch ran" not in capfd.readouterr().err
+        assert sess.run(gw, {x: xs, flag: True}) == pytest.approx(7.0) and sess.run(gw, {x: xs, flag: False}) == pytest.approx(-6.0)
+        a, b = sess.run(pair, {x: xs})
+        assert a.tolist() == [2.0, 3.0, 5.0] and b == 3.0
+        a, b = sess.run(pair, {x: xs - 1.0})
+        assert a.tolist() == [-1.0, 0.0, 2.0] and b == 6.0
+    with pytest.raises(ValueError):
+        tf.cond(flag, lambda: (x, x), lambda: x)
