@@ -15,6 +15,8 @@ import json
 import os
 import socket
 import struct
+
+import numpy as np
 import threading
 import time
 from typing import Any, Dict, Iterator, List, Optional, Tuple
@@ -272,6 +274,17 @@ def _decode_event(b: bytes) -> Dict[str, Any]:
                             tag = x.decode()
                         elif f3 == 2:
                             simple = struct.unpack("<f", x)[0]
+                        elif f3 == 5:
+                            h: Dict[str, Any] = {}
+                            for f4, _, y in _decode(x):
+                                if f4 in (1, 2, 3, 4, 5):
+                                    h[{1: "min", 2: "max", 3: "num", 4: "sum", 5: "sum_squares"}[f4]] = struct.unpack("<d", y)[0]
+                                elif f4 in (6, 7):
+                                    h["bucket_limit" if f4 == 6 else "bucket"] = list(struct.unpack("<%dd" % (len(y) // 8), y))
+                            rec.setdefault("histograms", []).append({"tag": tag, "histo": h})
+                            simple = "histogram"
+                    if simple == "histogram":
+                        continue
                     rec.setdefault("scalars", []).append({"tag": tag, "value": simple})
                     rec["scalar"] = {"tag": tag, "value": simple}
         elif f == 8:
@@ -317,9 +330,20 @@ class FileWriter:
     def add_scalar(self, tag: str, value: float, global_step: Optional[int] = None) -> None:
         self._write(_event(time.time(), global_step, summary=_f_bytes(1, _f_str(1, tag) + _f_float(2, value))))
 
-    def add_summary(self, summary: Dict[str, float], global_step: Optional[int] = None) -> None:
-        values = b"".join(_f_bytes(1, _f_str(1, k) + _f_float(2, v)) for k, v in summary.items())
+    def add_summary(self, summary: Dict[str, Any], global_step: Optional[int] = None) -> None:
+        """``summary``: what ``sess.run(tf.summary.merge_all())`` returned -- tag -> scalar (``simple_value``) or tag -> array
+        (a ``tf.summary.histogram``: written as a ``HistogramProto`` over TensorFlow's default bucket limits)."""
+        values = b""
+        for k, v in summary.items():
+            arr = np.asarray(v)
+            if arr.ndim == 0:
+                values += _f_bytes(1, _f_str(1, k) + _f_float(2, float(arr)))
+            else:
+                values += _f_bytes(1, _f_str(1, k) + _f_bytes(5, _histogram_proto(arr)))
         self._write(_event(time.time(), global_step, summary=values))
+
+    def add_histogram(self, tag: str, values, global_step: Optional[int] = None) -> None:
+        self.add_summary({tag: np.asarray(values).reshape(-1)}, global_step)
 
     def add_run_metadata(self, run_metadata, tag: str, global_step: Optional[int] = None) -> None:
         """The step trace of one ``Session.run`` (``RunOptions.FULL_TRACE``).  TF stores a serialized ``RunMetadata``
@@ -356,8 +380,53 @@ def scalar(name: str, tensor, collections=None) -> _ScalarSummary:
     return s
 
 
+def histogram(name: str, values, collections=None) -> _ScalarSummary:
+    """``tf.summary.histogram``: the fetched tensor is written as a HistogramProto by ``FileWriter.add_summary``."""
+    from ..framework.ops import reshape
+    s = _ScalarSummary(name, reshape(values, [-1], name=name + "/values"))
+    get_default_graph().add_to_collection(GraphKeys.SUMMARIES, s)
+    return s
+
+
+def merge(inputs, collections=None, name=None) -> Dict[str, Any]:
+    out: Dict[str, Any] = {}
+    for s in inputs:
+        out.update(s if isinstance(s, dict) else {s.tag: s.tensor})
+    return out
+
+
 def merge_all() -> Dict[str, Any]:
     return {s.tag: s.tensor for s in get_default_graph().get_collection(GraphKeys.SUMMARIES)}
+
+
+def _default_bucket_limits() -> List[float]:
+    """TensorFlow's histogram buckets: +-1e-12 * 1.1^k up to 1e20, mirrored around zero, closed by DBL_MAX."""
+    pos, v = [], 1e-12
+    while v < 1e20:
+        pos.append(v)
+        v *= 1.1
+    return [-x for x in reversed(pos)] + [0.0] + pos + [1.7976931348623157e308]
+
+
+_BUCKET_LIMITS: List[float] = []
+
+
+def _histogram_proto(values) -> bytes:
+    global _BUCKET_LIMITS
+    if not _BUCKET_LIMITS:
+        _BUCKET_LIMITS = _default_bucket_limits()
+    v = np.asarray(values, dtype=np.float64).reshape(-1)
+    limits = np.asarray(_BUCKET_LIMITS)
+    counts = np.zeros(len(limits))
+    if v.size:
+        idx = np.searchsorted(limits, v, side="left")            # bucket i holds (limit[i-1], limit[i]]
+        np.add.at(counts, np.minimum(idx, len(limits) - 1), 1.0)
+    nz = np.nonzero(counts)[0]
+    lo, hi = (int(nz[0]), int(nz[-1]) + 1) if nz.size else (0, 1)  # TF drops the empty buckets at both ends
+    out = _f_double(1, float(v.min()) if v.size else 0.0) + _f_double(2, float(v.max()) if v.size else 0.0)
+    out += _f_double(3, float(v.size)) + _f_double(4, float(v.sum())) + _f_double(5, float((v * v).sum()))
+    out += _f_bytes(6, struct.pack("<%dd" % (hi - lo), *limits[lo:hi])) + _f_bytes(7, struct.pack("<%dd" % (hi - lo), *counts[lo:hi]))
+    return out
 
 
 def read_events(path: str) -> List[Dict[str, Any]]:

@@ -120,3 +120,33 @@ def test_event_file_is_tfrecord_of_event_protos(tmp_path):
     assert mine[0]["file_version"] == "brain.Event:2"
     assert any(n["name"] == "y" and n["op"] == "MatMul" for n in mine[1]["graph_def"]["node"])
     assert mine[2]["scalar"] == {"tag": "loss", "value": 0.25} and mine[2]["step"] == 7
+
+
+def test_histogram_summaries_are_real_histogram_protos(tmp_path):
+    import numpy as np
+    import distributed_tensorflow_b200 as tf
+    from distributed_tensorflow_b200.utils import summary as S
+    w = tf.get_variable("hw", [200], initializer=tf.truncated_normal_initializer(stddev=0.5, seed=3))
+    tf.summary.histogram("weights", w)
+    tf.summary.scalar("mean_w", tf.reduce_mean(w))
+    merged = tf.summary.merge_all()
+    with tf.Session() as sess:
+        sess.run(tf.global_variables_initializer())
+        wv, out = sess.run([w, merged])
+        with tf.summary.FileWriter(str(tmp_path)) as fw:
+            fw.add_summary(out, 7)
+            path = fw.path
+    ev = [e for e in S.read_events(path) if "histograms" in e or "scalars" in e][-1]
+    assert ev["step"] == 7 and ev["scalars"][0]["tag"] == "mean_w"
+    h = ev["histograms"][0]["histo"]
+    assert ev["histograms"][0]["tag"] == "weights" and h["num"] == 200.0
+    assert h["min"] == float(wv.min()) and h["max"] == float(wv.max())
+    np.testing.assert_allclose(h["sum"], wv.astype(np.float64).sum(), rtol=1e-12)
+    np.testing.assert_allclose(h["sum_squares"], (wv.astype(np.float64) ** 2).sum(), rtol=1e-12)
+    assert sum(h["bucket"]) == 200.0 and len(h["bucket"]) == len(h["bucket_limit"])
+    lim = np.asarray(h["bucket_limit"])
+    assert np.all(np.diff(lim) > 0) and lim[0] >= wv.min() and lim[-1] >= wv.max()      # trimmed to the occupied range
+    # every value sits in the bucket whose limit is the first one >= the value
+    idx = np.searchsorted(lim, wv.astype(np.float64), side="left")
+    assert np.array_equal(np.bincount(idx, minlength=len(lim)).astype(float), np.asarray(h["bucket"]))
+    assert set(tf.summary.merge([tf.summary.scalar("a", tf.constant(1.0))])) == {"a"}
