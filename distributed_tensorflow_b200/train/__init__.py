@@ -10,7 +10,7 @@ from .hooks import (CheckpointSaverHook, FinalOpsHook, GlobalStepWaiterHook, Log
 from .monitored_session import (ChiefSessionCreator, MonitoredSession, MonitoredTrainingSession, Scaffold,
                                 SessionManager, SingularMonitoredSession, WorkerSessionCreator)
 from .optimizer import (AdagradOptimizer, AdamOptimizer, GradientDescentOptimizer, MomentumOptimizer, Optimizer, RMSPropOptimizer,
-                        exponential_decay, piecewise_constant)
+                        cosine_decay, exponential_decay, inverse_time_decay, natural_exp_decay, piecewise_constant, polynomial_decay)
 from .saver import (CheckpointState, NewCheckpointReader, Saver, checkpoint_exists, get_checkpoint_state,
                     latest_checkpoint, list_variables, load_checkpoint, update_checkpoint_state)
 from .sync_replicas import SyncReplicasOptimizer, SyncReplicasOptimizerHook

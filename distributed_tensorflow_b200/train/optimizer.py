@@ -437,9 +437,57 @@ def piecewise_constant(x, boundaries: Sequence[float], values: Sequence[float], 
             name or "PiecewiseConstant", torch.float32, (), device=xs.device)
 
 
+def _schedule(kind: str, global_step, default_name: str, name=None, **attrs) -> Tensor:
+    gs = convert_to_tensor(global_step)
+    with _device.device(None), _device.device(gs.device or None):
+        return get_default_graph().create_node("LearningRateSchedule", [gs], dict(attrs, kind=kind), name or default_name,
+                                               torch.float32, (), device=gs.device)
+
+
+def inverse_time_decay(learning_rate, global_step, decay_steps, decay_rate, staircase: bool = False, name=None) -> Tensor:
+    """``learning_rate / (1 + decay_rate * global_step / decay_steps)`` (``floor`` of the ratio when ``staircase``)."""
+    return _schedule("inverse_time", global_step, "InverseTimeDecay", name, lr=float(learning_rate), decay_steps=float(decay_steps),
+                     decay_rate=float(decay_rate), staircase=bool(staircase))
+
+
+def natural_exp_decay(learning_rate, global_step, decay_steps, decay_rate, staircase: bool = False, name=None) -> Tensor:
+    """``learning_rate * exp(-decay_rate * global_step / decay_steps)``."""
+    return _schedule("natural_exp", global_step, "NaturalExpDecay", name, lr=float(learning_rate), decay_steps=float(decay_steps),
+                     decay_rate=float(decay_rate), staircase=bool(staircase))
+
+
+def polynomial_decay(learning_rate, global_step, decay_steps, end_learning_rate=0.0001, power=1.0, cycle: bool = False, name=None) -> Tensor:
+    """``(lr - end) * (1 - min(step, decay_steps) / decay_steps) ^ power + end``; ``cycle`` stretches ``decay_steps`` to the next
+    multiple once it has been passed (TF's definition)."""
+    return _schedule("polynomial", global_step, "PolynomialDecay", name, lr=float(learning_rate), decay_steps=float(decay_steps),
+                     end=float(end_learning_rate), power=float(power), cycle=bool(cycle))
+
+
+def cosine_decay(learning_rate, global_step, decay_steps, alpha=0.0, name=None) -> Tensor:
+    """``lr * ((1 - alpha) * 0.5 * (1 + cos(pi * min(step, decay_steps) / decay_steps)) + alpha)``."""
+    return _schedule("cosine", global_step, "CosineDecay", name, lr=float(learning_rate), decay_steps=float(decay_steps), alpha=float(alpha))
+
+
 @register_kernel("LearningRateSchedule")
 def _k_lr_schedule(ctx, node, step):
+    import math
     a, s = node.attrs, float(step)
+    if a["kind"] in ("inverse_time", "natural_exp"):
+        p = s / a["decay_steps"]
+        if a["staircase"]:
+            p = float(int(p))
+        v = a["lr"] / (1.0 + a["decay_rate"] * p) if a["kind"] == "inverse_time" else a["lr"] * math.exp(-a["decay_rate"] * p)
+        return torch.tensor(v, dtype=torch.float32)
+    if a["kind"] == "polynomial":
+        ds = a["decay_steps"]
+        if a["cycle"]:
+            ds = ds * max(1.0, math.ceil(s / ds))
+        else:
+            s = min(s, ds)
+        return torch.tensor((a["lr"] - a["end"]) * (1.0 - s / ds) ** a["power"] + a["end"], dtype=torch.float32)
+    if a["kind"] == "cosine":
+        frac = min(s, a["decay_steps"]) / a["decay_steps"]
+        return torch.tensor(a["lr"] * ((1.0 - a["alpha"]) * 0.5 * (1.0 + math.cos(math.pi * frac)) + a["alpha"]), dtype=torch.float32)
     if a["kind"] == "exponential":
         p = s / a["decay_steps"]
         if a["staircase"]:

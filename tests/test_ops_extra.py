@@ -209,3 +209,31 @@ def test_cond_runs_only_the_chosen_branch_and_is_differentiable(capfd):
         assert a.tolist() == [-1.0, 0.0, 2.0] and b == 6.0
     with pytest.raises(ValueError):
         tf.cond(flag, lambda: (x, x), lambda: x)
+
+
+def test_learning_rate_schedules_follow_tensorflows_definitions():
+    import math
+    gs = tf.train.get_or_create_global_step()
+    bump = tf.assign_add(gs, tf.constant(7, dtype=tf.int64))
+    sch = {"inv": tf.train.inverse_time_decay(0.1, gs, 10, 0.5), "inv_s": tf.train.inverse_time_decay(0.1, gs, 10, 0.5, staircase=True),
+           "nat": tf.train.natural_exp_decay(0.1, gs, 10, 0.5), "poly": tf.train.polynomial_decay(0.1, gs, 20, 0.01, power=2.0),
+           "poly_c": tf.train.polynomial_decay(0.1, gs, 20, 0.01, cycle=True), "cos": tf.train.cosine_decay(0.1, gs, 20, alpha=0.1),
+           "exp": tf.train.exponential_decay(0.1, gs, 10, 0.9)}
+    # a schedule drives an optimizer like a constant would
+    w = tf.get_variable("sw", [], initializer=tf.constant_initializer(1.0))
+    step = tf.train.GradientDescentOptimizer(sch["cos"]).minimize(tf.square(w))
+    with tf.Session() as sess:
+        sess.run(tf.global_variables_initializer())
+        for s in (0, 7, 14, 21, 28):
+            got = sess.run(sch)
+            want = {"inv": 0.1 / (1 + 0.5 * s / 10), "inv_s": 0.1 / (1 + 0.5 * (s // 10)), "nat": 0.1 * math.exp(-0.5 * s / 10),
+                    "poly": (0.1 - 0.01) * (1 - min(s, 20) / 20) ** 2 + 0.01,
+                    "poly_c": (0.1 - 0.01) * (1 - s / (20 * max(1, math.ceil(s / 20)))) + 0.01,
+                    "cos": 0.1 * (0.9 * 0.5 * (1 + math.cos(math.pi * min(s, 20) / 20)) + 0.1), "exp": 0.1 * 0.9 ** (s / 10)}
+            for k in want:
+                assert got[k] == pytest.approx(want[k], rel=1e-5), (k, s)
+            if s == 0:
+                w0 = sess.run(w)
+                sess.run(step)
+                assert sess.run(w) == pytest.approx(w0 - 0.1 * 2 * w0)
+            sess.run(bump)
