@@ -21,6 +21,7 @@ Typical use mirrors the reference scripts::
 """
 from __future__ import annotations
 
+import builtins as _builtins
 import types as _types
 
 import torch as _torch
@@ -130,7 +131,74 @@ def _dense(inputs, units, activation=None, use_bias=True, kernel_initializer=Non
     return activation(y) if activation is not None else y
 
 
-layers = _types.SimpleNamespace(dense=_dense)
+def _pair(v):
+    return (int(v), int(v)) if isinstance(v, int) else (int(v[0]), int(v[1]))
+
+
+def _conv2d_layer(inputs, filters, kernel_size, strides=(1, 1), padding="valid", activation=None, use_bias=True,
+                  kernel_initializer=None, bias_initializer=None, name=None, reuse=None, trainable=True):
+    """``tf.layers.conv2d`` (NHWC): variables ``<name>/kernel`` [kh, kw, in, filters] (glorot uniform) and ``<name>/bias``."""
+    x = convert_to_tensor(inputs)
+    kh, kw = _pair(kernel_size)
+    sh, sw = _pair(strides)
+    cin = int(x.get_shape()[-1])
+    with variable_scope(name or "conv2d", reuse=reuse):
+        kernel = get_variable("kernel", [kh, kw, cin, int(filters)], initializer=kernel_initializer or glorot_uniform_initializer(),
+                              trainable=trainable)
+        y = _ops.conv2d(x, kernel, strides=(1, sh, sw, 1), padding=padding.upper())
+        if use_bias:
+            y = _ops.bias_add(y, get_variable("bias", [int(filters)], initializer=bias_initializer or zeros_initializer(), trainable=trainable))
+    return activation(y) if activation is not None else y
+
+
+def _pool_layer(fn):
+    def layer(inputs, pool_size, strides, padding="valid", name=None):
+        ph, pw = _pair(pool_size)
+        sh, sw = _pair(strides)
+        return fn(inputs, (1, ph, pw, 1), (1, sh, sw, 1), padding=padding.upper(), name=name or fn.__name__)
+    return layer
+
+
+def _flatten_layer(inputs, name=None):
+    x = convert_to_tensor(inputs)
+    dims = x.get_shape()[1:]
+    n = 1
+    for d in dims:
+        n *= int(d)
+    return _ops.reshape(x, [-1, n], name=name or "flatten")
+
+
+def _dropout_layer(inputs, rate=0.5, noise_shape=None, seed=None, training=False, name=None):
+    """``tf.layers.dropout``: active only when ``training`` (a python bool) is true."""
+    return _ops.dropout(inputs, rate=rate, seed=seed, name=name or "dropout") if training else _ops.identity(inputs, name=name or "dropout")
+
+
+def _batch_norm_layer(inputs, axis=-1, momentum=0.99, epsilon=1e-3, center=True, scale=True, training=False, name=None, reuse=None,
+                      trainable=True):
+    """``tf.layers.batch_normalization`` over the last axis: ``gamma`` / ``beta`` / ``moving_mean`` / ``moving_variance``;
+    ``training=True`` normalises with the batch statistics and registers the moving-average updates in
+    ``GraphKeys.UPDATE_OPS`` (run them with the train op, as in TF); otherwise the moving statistics are used."""
+    x = convert_to_tensor(inputs)
+    c = int(x.get_shape()[-1])
+    red = list(_builtins.range(len(x.get_shape()) - 1))          # (the module-level name ``range`` is tf.range)
+    with variable_scope(name or "batch_normalization", reuse=reuse):
+        gamma = get_variable("gamma", [c], initializer=ones_initializer(), trainable=trainable and scale)
+        beta = get_variable("beta", [c], initializer=zeros_initializer(), trainable=trainable and center)
+        mmean = get_variable("moving_mean", [c], initializer=zeros_initializer(), trainable=False)
+        mvar = get_variable("moving_variance", [c], initializer=ones_initializer(), trainable=False)
+        if training:
+            mean, var = _ops.moments(x, red)
+            keep = float(momentum)
+            for mov, cur in ((mmean, mean), (mvar, var)):
+                upd = assign(mov, _ops.add(_ops.multiply(mov._node, keep), _ops.multiply(_ops.stop_gradient(cur), 1.0 - keep)))
+                add_to_collection(GraphKeys.UPDATE_OPS, upd)
+            return _ops.batch_normalization(x, mean, var, beta, gamma, epsilon)
+        return _ops.batch_normalization(x, mmean, mvar, beta, gamma, epsilon)
+
+
+layers = _types.SimpleNamespace(dense=_dense, conv2d=_conv2d_layer, max_pooling2d=_pool_layer(_ops.max_pool),
+                                average_pooling2d=_pool_layer(_ops.avg_pool), flatten=_flatten_layer, dropout=_dropout_layer,
+                                batch_normalization=_batch_norm_layer)
 
 # -- tf.train -----------------------------------------------------------------------------------------
 from . import train  # noqa: E402

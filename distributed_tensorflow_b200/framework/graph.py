@@ -31,6 +31,8 @@ class GraphKeys:
     SUMMARIES = "summaries"
     INIT_OP = "init_op"
     QUEUE_RUNNERS = "queue_runners"
+    UPDATE_OPS = "update_ops"
+    REGULARIZATION_LOSSES = "regularization_losses"
 
 
 class Tensor:

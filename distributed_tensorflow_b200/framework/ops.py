@@ -665,7 +665,26 @@ def conv2d(input, filter, strides=(1, 1, 1, 1), padding="SAME", data_format="NHW
     """K14. ``filter`` is HWIO like TF; data is NHWC (channels-last is also the tensor-core layout)."""
     x, w = convert_to_tensor(input), convert_to_tensor(filter)
     st = tuple(int(s) for s in strides)
-    return _node("Conv2D", (x, w), {"strides": st, "padding": padding, "data_format": data_format}, name, x.dtype, None)
+    shp = None
+    if x.shape is not None and w.shape is not None and len(x.shape) == 4 and len(w.shape) == 4 and data_format == "NHWC":
+        shp = (x.shape[0], _window_out(x.shape[1], w.shape[0], st[1], padding), _window_out(x.shape[2], w.shape[1], st[2], padding),
+               w.shape[3])
+    return _node("Conv2D", (x, w), {"strides": st, "padding": padding, "data_format": data_format}, name, x.dtype, shp)
+
+
+def _window_out(size, k, s, padding):
+    """Static output extent of a sliding window (TF's SAME / VALID arithmetic); ``None`` stays unknown."""
+    if size is None or k is None:
+        return None
+    size, k, s = int(size), int(k), int(s)
+    return -(-size // s) if str(padding).upper() == "SAME" else max(0, (size - k) // s + 1)
+
+
+def _pool_shape(x, ksize, strides, padding):
+    if x.shape is None or len(x.shape) != 4:
+        return None
+    return (x.shape[0], _window_out(x.shape[1], ksize[1], strides[1], padding), _window_out(x.shape[2], ksize[2], strides[2], padding),
+            x.shape[3])
 
 
 @register_kernel("Conv2D")
@@ -681,12 +700,12 @@ def _pool_attrs(ksize, strides, padding):
 
 def max_pool(value, ksize, strides, padding="SAME", name="MaxPool"):
     x = convert_to_tensor(value)
-    return _node("MaxPool", (x,), _pool_attrs(ksize, strides, padding), name, x.dtype, None)
+    return _node("MaxPool", (x,), _pool_attrs(ksize, strides, padding), name, x.dtype, _pool_shape(x, ksize, strides, padding))
 
 
 def avg_pool(value, ksize, strides, padding="SAME", name="AvgPool"):
     x = convert_to_tensor(value)
-    return _node("AvgPool", (x,), _pool_attrs(ksize, strides, padding), name, x.dtype, None)
+    return _node("AvgPool", (x,), _pool_attrs(ksize, strides, padding), name, x.dtype, _pool_shape(x, ksize, strides, padding))
 
 
 def _same_pad(size, k, s):

@@ -237,3 +237,41 @@ def test_learning_rate_schedules_follow_tensorflows_definitions():
                 sess.run(step)
                 assert sess.run(w) == pytest.approx(w0 - 0.1 * 2 * w0)
             sess.run(bump)
+
+
+def test_layers_build_a_small_cnn_that_trains_and_batch_norm_tracks_moving_statistics():
+    rng = np.random.RandomState(0)
+    xs = rng.rand(16, 8, 8, 3).astype(np.float32)
+    ys = np.eye(4, dtype=np.float32)[rng.randint(0, 4, 16)]
+    tf.set_random_seed(5)
+
+    def net(x, training):
+        with tf.variable_scope("cnn", reuse=tf.AUTO_REUSE):
+            h = tf.layers.conv2d(x, 6, 3, padding="same", activation=tf.nn.relu, name="c1")
+            h = tf.layers.batch_normalization(h, training=training, momentum=0.9, name="bn1")
+            h = tf.layers.max_pooling2d(h, 2, 2)
+            h = tf.layers.dropout(h, rate=0.2, training=training, seed=1)
+            h = tf.layers.flatten(h)
+            return tf.layers.dense(h, 4, name="out")
+    x, y_ = tf.placeholder(tf.float32, [None, 8, 8, 3]), tf.placeholder(tf.float32, [None, 4])
+    logits = net(x, True)
+    assert logits.get_shape()[-1] == 4
+    loss = tf.losses.softmax_cross_entropy(y_, logits)
+    updates = tf.get_collection(tf.GraphKeys.UPDATE_OPS)
+    assert len(updates) == 2
+    with tf.control_dependencies(updates):
+        train = tf.train.AdamOptimizer(0.01).minimize(loss)
+    eval_logits = net(x, False)                                    # same variables, moving statistics, no dropout
+    names = sorted(v.var_name for v in tf.global_variables() if v.var_name.startswith("cnn/") and "Adam" not in v.var_name)
+    assert names == ["cnn/bn1/beta", "cnn/bn1/gamma", "cnn/bn1/moving_mean", "cnn/bn1/moving_variance", "cnn/c1/bias", "cnn/c1/kernel",
+                     "cnn/out/bias", "cnn/out/kernel"]
+    assert sorted(v.var_name for v in tf.trainable_variables()) == [n for n in names if "moving" not in n]
+    mm = [v for v in tf.global_variables() if v.var_name == "cnn/bn1/moving_mean"][0]
+    with tf.Session() as sess:
+        sess.run(tf.global_variables_initializer())
+        assert np.array_equal(sess.run(mm), np.zeros(6))
+        losses = [sess.run([train, loss], {x: xs, y_: ys})[1] for _ in range(40)]
+        moved = sess.run(mm)
+        e1, e2 = sess.run(eval_logits, {x: xs}), sess.run(eval_logits, {x: xs})
+    assert losses[-1] < 0.6 * losses[0] and np.abs(moved).max() > 0.01
+    assert np.array_equal(e1, e2) and e1.shape == (16, 4)          # inference is deterministic (no dropout, fixed statistics)
