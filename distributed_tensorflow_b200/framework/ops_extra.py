@@ -426,3 +426,83 @@ def _k_cond(ctx, node, pred, *captured):
 
 
 __all__.append("cond")
+
+
+# -- tf.while_loop ----------------------------------------------------------------------------------------------------------------------
+def while_loop(cond, body, loop_vars, shape_invariants=None, parallel_iterations=10, back_prop=True, swap_memory=False, name="while",
+               maximum_iterations=None):
+    """``tf.while_loop``: ``cond`` and ``body`` are built ONCE over stand-in nodes for the loop variables; the ``While`` node's kernel
+    evaluates the condition sub-graph and, while it holds, the body sub-graph, feeding each iteration's results back in.  The
+    iterations are recorded on the autograd tape as they run, so ``tf.gradients`` differentiates the unrolled loop.  Same
+    placement rule as :func:`cond` (the node runs on the task that built the graph)."""
+    from .graph import get_default_graph
+    g = get_default_graph()
+    single = not isinstance(loop_vars, (list, tuple))
+    init = [convert_to_tensor(v) for v in ([loop_vars] if single else loop_vars)]
+    start = len(g.nodes)
+    stand_ins = [_node("LoopVar", (), {}, "%s/var_%d" % (name, i), v.dtype, v.shape) for i, v in enumerate(init)]
+    c0 = len(g.nodes)
+    c_out = convert_to_tensor(cond(*stand_ins))
+    c1 = len(g.nodes)
+    b_res = body(*stand_ins)
+    b_out = [convert_to_tensor(v) for v in (b_res if isinstance(b_res, (list, tuple)) else [b_res])]
+    end = len(g.nodes)
+    if len(b_out) != len(init):
+        raise ValueError("while_loop(): body must return as many tensors as there are loop variables (%d vs %d)" % (len(b_out), len(init)))
+    c_nodes, b_nodes = list(g.nodes[c0:c1]), list(g.nodes[c1:end])
+    captured, seen = [], set()
+    for n in c_nodes + b_nodes:
+        for d in list(n.inputs) + list(n.control_inputs):
+            if d.id < start and d.id not in seen:
+                seen.add(d.id)
+                captured.append(d)
+    for o in [c_out] + b_out:
+        if o.id < start and o.id not in seen:
+            seen.add(o.id)
+            captured.append(o)
+    node = _node("While", init + captured, {"n": len(init), "vars": [s.id for s in stand_ins], "c_nodes": c_nodes, "b_nodes": b_nodes,
+                                           "c_out": c_out.id, "b_out": [o.id for o in b_out], "captured": [c.id for c in captured],
+                                           "max_iter": maximum_iterations}, name, None, None)
+    outs = [_node("TupleItemRaw", (node,), {"index": i}, "%s_%d" % (name, i), v.dtype, v.shape if b.shape == v.shape else None)
+            for i, (v, b) in enumerate(zip(init, b_out))]
+    return outs[0] if single else outs
+
+
+@register_kernel("LoopVar")
+def _k_loop_var(ctx, node):
+    raise RuntimeError("a while_loop variable (%s) was fetched outside its loop" % node.name)
+
+
+@register_kernel("While")
+def _k_while(ctx, node, *args):
+    from .executor import ExecContext, execute
+    a = node.attrs
+    vals, captured = list(args[:a["n"]]), args[a["n"]:]
+
+    def run(nodes, out_ids):
+        sub = ExecContext(ctx.store, ctx.task, ctx.gpu_index, ctx.tracer, getattr(ctx, "_seed", None), ctx.allow_soft_placement)
+        sub.force_device, sub.leaves = ctx.force_device, ctx.leaves
+        for attr in ("cancel_event", "server"):
+            if hasattr(ctx, attr):
+                setattr(sub, attr, getattr(ctx, attr))
+        for cid, v in zip(a["captured"], captured):
+            sub.values[cid] = v
+        for vid, v in zip(a["vars"], vals):
+            sub.values[vid] = v
+        execute(nodes, sub, torch.is_grad_enabled())
+        return [sub.values[i] for i in out_ids]
+    it = 0
+    while a["max_iter"] is None or it < a["max_iter"]:
+        c = run(a["c_nodes"], [a["c_out"]])[0]
+        if not bool(c.reshape(-1)[0] if isinstance(c, torch.Tensor) else c):
+            break
+        vals = run(a["b_nodes"], a["b_out"])
+        it += 1
+        cancel = getattr(ctx, "cancel_event", None)
+        if cancel is not None and cancel.is_set():
+            from . import errors
+            raise errors.CancelledError("while_loop cancelled")
+    return tuple(vals)
+
+
+__all__.append("while_loop")

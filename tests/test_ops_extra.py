@@ -275,3 +275,24 @@ def test_layers_build_a_small_cnn_that_trains_and_batch_norm_tracks_moving_stati
         e1, e2 = sess.run(eval_logits, {x: xs}), sess.run(eval_logits, {x: xs})
     assert losses[-1] < 0.6 * losses[0] and np.abs(moved).max() > 0.01
     assert np.array_equal(e1, e2) and e1.shape == (16, 4)          # inference is deterministic (no dropout, fixed statistics)
+
+
+def test_while_loop_iterates_captures_outer_values_and_is_differentiable():
+    x = tf.placeholder(tf.float32, [])
+    n = tf.placeholder(tf.int32, [])
+    w = tf.get_variable("lw", [], initializer=tf.constant_initializer(1.5))
+    # y = x * w^n by repeated multiplication; i counts the iterations
+    i0, y0 = tf.constant(0), x
+    i, y = tf.while_loop(lambda i, y: i < n, lambda i, y: (i + 1, y * w), [i0, y0])
+    gw = tf.gradients(y, [w])[0]
+    s = tf.while_loop(lambda v: v < 100.0, lambda v: v * 2.0, tf.constant(3.0))                   # single loop variable
+    capped = tf.while_loop(lambda v: v < 1e9, lambda v: v + 1.0, tf.constant(0.0), maximum_iterations=5)
+    with tf.Session() as sess:
+        sess.run(tf.global_variables_initializer())
+        iv, yv, g = sess.run([i, y, gw], {x: 2.0, n: 4})
+        assert iv == 4 and yv == pytest.approx(2.0 * 1.5 ** 4) and g == pytest.approx(2.0 * 4 * 1.5 ** 3)
+        iv, yv = sess.run([i, y], {x: 2.0, n: 0})
+        assert iv == 0 and yv == 2.0                                   # the body never ran
+        assert sess.run(s) == 192.0 and sess.run(capped) == 5.0
+    with pytest.raises(ValueError):
+        tf.while_loop(lambda a, b: a < 1, lambda a, b: a + 1, [tf.constant(0), tf.constant(0)])
