@@ -69,6 +69,9 @@ def parse_args():
     ap.add_argument("--e2e-native-loop", type=int, default=1,
                     help="1: third e2e arm = PSTrainEngine.train_loop(x_batches_pinned, y_batches_pinned, steps): the same per-step "
                          "H2D copy / kernels / D2H loss read, K steps enqueued by one native call (csrc/step_exec.cu dtf_run_loop)")
+    ap.add_argument("--e2e-native-timeout", type=float, default=120.0,
+                    help="native-loop arm dead-man timer (s): if the arm has not returned by then, the record measured so far is "
+                         "printed (native_loop_error = the timeout, no baseline arm) and the process ends")
     ap.add_argument("--e2e-depth", type=int, default=4, help="native loop: steps the host may run ahead of the landed losses")
     ap.add_argument("--e2e-pipeline", type=int, default=1,
                     help="1 (one-GPU runs and every-rank-a-worker topologies): also time step(..., sync_loss='deferred') -- the loss of step t is read after "
@@ -400,7 +403,33 @@ class CudaStreamTimer:
         return max(e0.elapsed_time(e1) for e0, e1, _ in evs)
 
 
-def run_e2e(eng, args, spec, K, num_workers, is_worker, world, pow_, images, labels, barrier, allmax, timer=None, pin=None):
+class DeadMan:
+    """Dead-man timer around an arm that enqueues work from native code: if the arm neither returns nor raises within
+    ``seconds`` (a hung stream / event wait cannot be cancelled from Python), ``on_fire()`` runs on the timer thread -- it
+    prints the record measured so far -- and the process ends with status 0; the arms measured before it stand."""
+
+    def __init__(self, seconds, on_fire, exit_fn=os._exit):
+        self.fired = False
+        self._t = None
+        if on_fire is not None and seconds and seconds > 0:
+            def fire():
+                self.fired = True
+                try:
+                    on_fire()
+                    sys.stdout.flush()
+                finally:
+                    exit_fn(0)
+            self._t = threading.Timer(seconds, fire)
+            self._t.daemon = True
+            self._t.start()
+
+    def cancel(self):
+        if self._t is not None:
+            self._t.cancel()
+
+
+def run_e2e(eng, args, spec, K, num_workers, is_worker, world, pow_, images, labels, barrier, allmax, timer=None, pin=None,
+            failsafe=None):
     """The end-to-end arms: the same metric through the public API with, every step, the H2D copy of that step's batch from
     pinned host memory and a D2H read of the step's loss -- ``step()`` synchronous, ``step(sync_loss="deferred")`` pipelined,
     ``train_loop()`` (K steps per native call); same repetition protocol as the device-timed number.  ``timer`` / ``pin`` are
@@ -536,12 +565,19 @@ def run_e2e(eng, args, spec, K, num_workers, is_worker, world, pow_, images, lab
         # third arm: the framework's own training loop (one native call per K steps).  A failure on any rank drops the
         # arm on every rank (the flag is agreed on before anything is recorded); the other arms' numbers stand.
         nt, nerr = None, None
+        so_far = json.loads(json.dumps(e2e))
+        so_far["native_loop_error"] = ("dead-man timer: the native-loop arm did not return within %g s; record printed by the "
+                                       "timer, baseline arm not run" % getattr(args, "e2e_native_timeout", 0.0))
+        guard = DeadMan(getattr(args, "e2e_native_timeout", 0.0), (lambda: failsafe(so_far)) if failsafe else None)
         try:
             nt = measure_e2e(e2e_k_steps_native)
         except Exception as e:      # noqa: BLE001
             nerr = repr(e)[:300]
-        nlast = allmax([last[0] if (last[0] is not None and nerr is None) else -1e30])[0]
-        failed = allmax([1.0 if (nerr is not None or not math.isfinite(nlast)) else 0.0])[0] > 0
+        try:                         # the agreement is a collective: a rank that hangs in the arm keeps the others here
+            nlast = allmax([last[0] if (last[0] is not None and nerr is None) else -1e30])[0]
+            failed = allmax([1.0 if (nerr is not None or not math.isfinite(nlast)) else 0.0])[0] > 0
+        finally:
+            guard.cancel()
         if failed:
             e2e["native_loop_error"] = nerr or "non-finite loss %r or a failure on another rank" % (nlast,)
         else:
@@ -742,11 +778,6 @@ def main():
     gstep = eng.read_ctl(0, "global_step") if 0 in eng.ranks else None
     stale = eng.staleness() if (args.mode == "async" and 0 in eng.ranks) else None
 
-    # ---- end-to-end: public API step(x, y) with H2D of the batch and D2H of the loss every step -----------------
-    e2e = None
-    if args.e2e_steps != 0:
-        e2e = run_e2e(eng, args, spec, K, num_workers, is_worker, world, pow_, images, labels, barrier, allmax)
-
     # ---- ps traffic implied by the measured step time (BASELINE metric: push/pull GB/s vs 900 GB/s/dir) -----------
     # true-shape bytes: gradients travel as fp32, parameters as fp32 (tf32 engines) / bf16 replicas; every worker moves both every step.
     n_params = spec.in_dim * spec.hidden + spec.hidden + spec.hidden * spec.classes + spec.classes
@@ -760,22 +791,8 @@ def main():
     traffic["ps_ingest_fraction_of_900"] = traffic["ps_ingest_gbps"] / 900.0
     traffic["ps_egress_fraction_of_900"] = traffic["ps_egress_gbps"] / 900.0
     nvls_on, mc_on = bool(getattr(eng, "nvls", False)), bool(getattr(eng, "nvls_multicast", False))
-    eng.close()
 
-    # ---- the divisor: torch + NCCL + cuBLAS (CUDA-graphed) arm, same invocation / steps / repetitions / precision --------
-    base = None
-    if args.baseline and not args.in_graph:
-        try:
-            from baseline.nccl_ps import run_nccl_baseline
-            bargs = argparse.Namespace(**vars(args))
-            bargs.ps_on_workers, bargs.ps_only_task = int(pow_ or N == 1), int(not pow_ and N > 1)
-            base = run_nccl_baseline(bargs, rank, world, local_rank, sampler_cls=ClockSampler, images=images, labels=labels)
-        except Exception as e:          # noqa: BLE001 - the measured arm must survive a baseline problem
-            if world > 1:
-                raise
-            base = {"error": repr(e)[:300]}
-
-    if rank == 0:
+    def build_out(e2e, base):
         out = {
             "metric": "MNIST MLP samples/sec (whole box, device-timed, max over ranks), sync-replica PS",
             "value": value, "unit": "samples/sec", "n_gpus": N, "steps": K, "warmup": W,
@@ -809,7 +826,35 @@ def main():
                                if base.get(k) is not None}
             if e2e and base.get("e2e") and base["e2e"].get("value"):
                 out["vs_baseline_e2e"] = e2e["value"] / base["e2e"]["value"]
-        print(json.dumps(out))
+        return out
+
+    def failsafe(e2e_so_far):
+        # runs on the dead-man timer's thread when the native-loop arm hangs: the numbers measured so far are the record
+        if rank == 0:
+            print(json.dumps(build_out(e2e_so_far, None)))
+
+    # ---- end-to-end: public API step(x, y) with H2D of the batch and D2H of the loss every step -----------------
+    e2e = None
+    if args.e2e_steps != 0:
+        e2e = run_e2e(eng, args, spec, K, num_workers, is_worker, world, pow_, images, labels, barrier, allmax, failsafe=failsafe)
+
+    eng.close()
+
+    # ---- the divisor: torch + NCCL + cuBLAS (CUDA-graphed) arm, same invocation / steps / repetitions / precision --------
+    base = None
+    if args.baseline and not args.in_graph:
+        try:
+            from baseline.nccl_ps import run_nccl_baseline
+            bargs = argparse.Namespace(**vars(args))
+            bargs.ps_on_workers, bargs.ps_only_task = int(pow_ or N == 1), int(not pow_ and N > 1)
+            base = run_nccl_baseline(bargs, rank, world, local_rank, sampler_cls=ClockSampler, images=images, labels=labels)
+        except Exception as e:          # noqa: BLE001 - the measured arm must survive a baseline problem
+            if world > 1:
+                raise
+            base = {"error": repr(e)[:300]}
+
+    if rank == 0:
+        print(json.dumps(build_out(e2e, base)))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -141,3 +141,44 @@ def test_every_rank_a_worker_topology_runs_all_three_arms_on_a_multi_rank_job():
     assert eng.seen == [(4 * t + 3) % 50 for t in range(len(eng.seen))]
     assert all(c[2] == 4 for c in eng.loop_calls)
     assert e2e["value"] == pytest.approx(4 * 100 * 20 / (e2e["ms_per_step"] * 20 / 1e3))     # whole-job samples/s
+
+
+def test_a_hung_native_loop_trips_the_dead_man_timer_which_emits_the_record_measured_so_far(monkeypatch):
+    """The native arm enqueues from C: a stream / event wait that never returns cannot be cancelled from Python.  The timer's
+    callback receives the e2e record of the arms measured before it (with the reason under native_loop_error) and ends the
+    process; here the exit is replaced by releasing the stand-in loop."""
+    import threading
+    released, emitted, exits = threading.Event(), [], []
+
+    class Hanging(FakeEngine):
+        def train_loop(self, *a, **k):
+            released.wait(20)
+            raise RuntimeError("released by the test")
+
+    def fake_exit(code):
+        exits.append(code)
+        released.set()
+    real = bench.DeadMan
+    monkeypatch.setattr(bench, "DeadMan", lambda s, f, exit_fn=None: real(s, f, exit_fn=fake_exit))
+    nb = 50
+    images = np.repeat(np.arange(nb, dtype=np.float32), 100)[:, None] * np.ones((1, 784), np.float32)
+    labels = np.zeros((nb * 100, 10), np.float32)
+    args = argparse.Namespace(num_train=nb * 100, e2e_prefetch=1, e2e_pipeline=1, e2e_native_loop=1, e2e_depth=4, min_ms=2.0, max_reps=20,
+                              e2e_native_timeout=0.3)
+    spec = SimpleNamespace(batch=100, in_dim=784, classes=10)
+    e2e = bench.run_e2e(Hanging(nb), args, spec, 20, 1, True, 1, False, images, labels, barrier=lambda: None,
+                        allmax=lambda v: [float(x) for x in v], timer=WallTimer(), pin=torch.from_numpy, failsafe=emitted.append)
+    assert exits == [0] and len(emitted) == 1
+    rec = emitted[0]
+    assert "dead-man timer" in rec["native_loop_error"] and "native_loop" not in rec
+    assert rec["value"] == max(rec["synchronous"]["value"], rec["pipelined"]["value"]) and math.isfinite(rec["last_loss"])
+    assert "native_loop" not in e2e                       # (the released loop raised: the arm is dropped on the normal path too)
+
+
+def test_the_timer_is_cancelled_when_the_arm_returns():
+    fired = []
+    g = bench.DeadMan(0.2, lambda: fired.append(1), exit_fn=lambda c: fired.append(("exit", c)))
+    g.cancel()
+    time.sleep(0.4)
+    assert fired == [] and not g.fired
+    assert bench.DeadMan(0.0, lambda: None)._t is None and bench.DeadMan(5.0, None)._t is None      # disabled: no thread
