@@ -231,6 +231,7 @@ class RpcServer:
             Listener((self.host, self.port), backlog=64)
         self._closed = threading.Event()
         self._conns = []
+        self._serving = []               # connection threads (joined by close(): none of them may outlive the interpreter)
         self._thread = threading.Thread(target=self._accept_loop, name="dtf-rpc-accept-%d" % self.port, daemon=True)
         self._thread.start()
 
@@ -246,7 +247,14 @@ class RpcServer:
                 continue
             self._conns = [c for c in self._conns if not getattr(c, "closed", False)]
             self._conns.append(conn)
-            threading.Thread(target=self._serve, args=(conn,), name="dtf-rpc-conn", daemon=True).start()
+            self._serving = [t for t in self._serving if t.is_alive()]
+            try:
+                t = threading.Thread(target=self._serve, args=(conn,), name="dtf-rpc-conn", daemon=True)
+                t.start()
+                self._serving.append(t)
+            except RuntimeError:             # the interpreter is shutting down: no new threads
+                conn.close()
+                return
 
     def _handshake(self, conn: Connection) -> bool:
         """Mutual HMAC challenge in THIS connection's thread (the accept loop never waits on a client), bounded by a
@@ -308,6 +316,14 @@ class RpcServer:
                 c.close()
             except OSError:
                 pass
+        # the connection threads were blocked in a receive: closing their connection wakes them; wait for them (bounded) so
+        # that no thread of this server is inside a native call when the interpreter finalises
+        deadline = time.time() + 2.0
+        me = threading.current_thread()
+        for t in self._serving:
+            if t is not me:
+                t.join(max(0.0, deadline - time.time()))
+        self._serving = [t for t in self._serving if t.is_alive()]
 
 
 class RpcClient:

@@ -15,6 +15,7 @@ task between segments of the same run, so forward and backward of one
 """
 from __future__ import annotations
 
+import atexit
 import os
 import socket
 import sys
@@ -57,6 +58,29 @@ def local_servers() -> List["Server"]:
         if srv is not None and srv.is_running:
             out.append(srv)
     return out
+
+
+def _stop_local_servers_at_exit() -> None:
+    """Registered with ``atexit`` (runs BEFORE the interpreter finalises): a task script that simply returns -- the
+    reference's worker-0 client does, ``example_distributed_server.py:46-70`` -- leaves its in-process Server's accept and
+    connection threads blocked in native socket calls.  CPython ends a daemon thread that comes back from such a call during
+    finalisation with ``pthread_exit``; that forced unwind racing the process's static destructors showed up as a rare
+    ``terminate called without an active exception`` (exit -6) AFTER the script's output was complete.  Closing the
+    listeners / connections here lets every one of those threads return and be joined while the interpreter is whole."""
+    for srv in local_servers():
+        try:
+            rpc = srv._rpc
+            if rpc is not None:
+                rpc.close()
+        except Exception:      # noqa: BLE001 - exit path
+            pass
+    deadline = time.time() + 2.0
+    for t in threading.enumerate():
+        if t.daemon and t is not threading.current_thread() and t.name.startswith("dtf-rpc"):
+            t.join(max(0.0, deadline - time.time()))
+
+
+atexit.register(_stop_local_servers_at_exit)
 
 
 class _GraphStub:

@@ -1,5 +1,6 @@
 """Native control-plane transport (csrc/runtime/transport.cpp + parallel/transport.py): frames of segments, out-of-band
 tensors, deadlines, hang-up detection, close() waking a blocked reader."""
+import os
 import pickle
 import threading
 import time
@@ -112,3 +113,41 @@ def test_hang_up_is_visible_and_close_wakes_a_blocked_reader(pair):
     lst.close()
     with pytest.raises((ConnectionRefusedError, OSError)):
         transport.connect("127.0.0.1", lst.port, timeout=0.5)
+
+
+def test_a_task_script_that_just_returns_leaves_no_server_thread_for_interpreter_finalisation(tmp_path):
+    """The reference's worker-0 client returns from ``main()`` with its in-process Server running
+    (``example_distributed_server.py:46-70``).  Its accept / connection threads sit in native socket calls; a daemon thread that
+    comes back from one while CPython finalises is ended with ``pthread_exit`` -- seen once as ``terminate called without an
+    active exception`` (exit -6) after the script's output was complete.  The package's ``atexit`` hook closes the listeners and
+    connections and joins those threads before finalisation starts."""
+    import subprocess
+    import sys
+    script = tmp_path / "task.py"
+    script.write_text('''
+import atexit, socket, sys, threading
+def _dump():
+    print("ALIVE_AT_EXIT", [t.name for t in threading.enumerate() if t.name.startswith("dtf-") and t.is_alive()])
+atexit.register(_dump)           # registered first -> runs last, after the package's hook
+import distributed_tensorflow_b200 as tf
+from distributed_tensorflow_b200.parallel.rpc import RpcClient
+def port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+cluster = tf.train.ClusterSpec({"ps": ["127.0.0.1:%d" % port()], "worker": ["127.0.0.1:%d" % port()]})
+ps = tf.train.Server(cluster, job_name="ps", task_index=0)
+wk = tf.train.Server(cluster, job_name="worker", task_index=0)
+with tf.device("/job:ps/task:0"):
+    w = tf.Variable(tf.ones([8, 8]), name="w")
+with tf.device("/job:worker/task:0"):
+    y = tf.matmul(w, w)
+print(RpcClient(cluster.task_address("ps", 0)).call("ping")["task"])       # a real connection -> a connection thread on the ps
+with tf.Session(wk.target) as sess:
+    sess.run(tf.global_variables_initializer()); print(float(sess.run(y)[0, 0]))
+print("BEFORE", sorted(t.name for t in threading.enumerate() if t.name.startswith("dtf-rpc")))
+''')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""), CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+    assert "dtf-rpc-conn" in r.stdout.split("BEFORE")[1].splitlines()[0] and "8.0" in r.stdout
+    assert "ALIVE_AT_EXIT []" in r.stdout, r.stdout
