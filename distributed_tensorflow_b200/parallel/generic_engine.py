@@ -243,6 +243,56 @@ class GenericPSEngine:
                     out["global_step"] = torch.tensor(self.read_ctl(0, "global_step"), dtype=torch.int64)
         return out
 
+    def optimizer_state(self) -> Dict[str, torch.Tensor]:
+        """Optimizer slots of the LOCAL ps shards under their TF names + the beta powers (shard 0): what a fabric
+        re-formation carries over next to the graph variables."""
+        out: Dict[str, torch.Tensor] = {}
+        kind = self.opt.get("kind", "sgd")
+        if kind == "sgd":
+            return out
+        for r, rk in self.ranks.items():
+            if r not in self.ps_ranks:
+                continue
+            s = self.ps_ranks.index(r)
+            rk.stream.synchronize()
+            for name in self.names:
+                if self.layout[name][0] != s:
+                    continue
+                out[name + "/" + ("Adam" if kind == "adam" else "Momentum")] = \
+                    self._view(rk.bufs["gslot_m%d" % s], name).detach().cpu().clone()
+                if kind == "adam":
+                    out[name + "/Adam_1"] = self._view(rk.bufs["gslot_v%d" % s], name).detach().cpu().clone()
+            if kind == "adam":
+                b = rk.bufs["gctl%d" % s].tensor(torch.float32, self.off["beta1_power"], 2).cpu()
+                out["beta_powers/%d" % s] = b.clone()
+        return out
+
+    def load_optimizer_state(self, state: Dict[str, torch.Tensor]) -> List[str]:
+        done: List[str] = []
+        suffix = {"Momentum": "gslot_m", "Adam": "gslot_m", "Adam_1": "gslot_v"}
+        for r, rk in self.ranks.items():
+            if r not in self.ps_ranks:
+                continue
+            s = self.ps_ranks.index(r)
+            with torch.cuda.device(rk.device), torch.cuda.stream(rk.stream):
+                for key, val in state.items():
+                    if key == "beta_powers/%d" % s:
+                        rk.bufs["gctl%d" % s].tensor(torch.float32, self.off["beta1_power"], 2).copy_(val.to(rk.device).float())
+                        done.append(key)
+                        continue
+                    if "/" not in key:
+                        continue
+                    name, slot = key.rsplit("/", 1)
+                    if name not in self.layout or self.layout[name][0] != s or slot not in suffix:
+                        continue
+                    view = self._view(rk.bufs["%s%d" % (suffix[slot], s)], name)
+                    if tuple(view.shape) != tuple(val.shape):
+                        continue
+                    view.copy_(val.to(rk.device).float())
+                    done.append(key)
+            rk.stream.synchronize()
+        return done
+
     def read_ctl(self, shard: int, fld: str, count: int = 1):
         rk = self.ranks[self.ps_ranks[shard]]
         t = rk.bufs["gctl%d" % shard].tensor(torch.int64, self.off[fld], count).cpu()

@@ -30,6 +30,7 @@ workers; with a single GPU the ps and the worker share it (and its stream).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import math
 import os
@@ -434,6 +435,40 @@ class PSTrainEngine:
                     b = rk.bufs["ctl0"].tensor(torch.float32, self.off["beta1_power"], 2).cpu()
                     out["beta1_power"], out["beta2_power"] = b[0].clone(), b[1].clone()
         return out
+
+    def optimizer_state(self) -> Dict[str, torch.Tensor]:
+        """The optimizer's own state on the LOCAL ps shards (slots under their TF names, Adam's beta powers): the part of
+        :meth:`state_dict` that is not a graph variable.  Kept across a fabric re-formation by the ps service."""
+        sd = self.state_dict()
+        return {k: v for k, v in sd.items() if "/" in k or k in ("beta1_power", "beta2_power")}
+
+    def load_optimizer_state(self, state: Dict[str, torch.Tensor]) -> List[str]:
+        """Write slots / beta powers saved by :meth:`optimizer_state` back into the local shards (names of other shards and
+        shape mismatches are skipped).  Returns the names restored."""
+        done: List[str] = []
+        suffix = {"Momentum": "slot_m", "Adam": "slot_m", "Adam_1": "slot_v"}
+        for r, rk in self.ranks.items():
+            if r not in self.ps_ranks:
+                continue
+            s = self.ps_ranks.index(r)
+            on_gpu = getattr(rk.device, "type", None) == "cuda"
+            with (torch.cuda.device(rk.device) if on_gpu else contextlib.nullcontext()), \
+                    (torch.cuda.stream(rk.stream) if on_gpu else contextlib.nullcontext()):
+                for key, val in state.items():
+                    if "/" not in key:
+                        continue
+                    name, slot = key.rsplit("/", 1)
+                    lay = self.layout.get(name)
+                    if lay is None or lay.shard != s or slot not in suffix or tuple(val.shape) != tuple(lay.shape):
+                        continue
+                    self._var_view(rk, suffix[slot], lay).reshape(lay.shape).copy_(val.to(rk.device).float())
+                    done.append(key)
+                if s == 0 and self.kind == 2 and "beta1_power" in state and "beta2_power" in state:
+                    b = rk.bufs["ctl0"].tensor(torch.float32, self.off["beta1_power"], 2)
+                    b[0], b[1] = float(state["beta1_power"]), float(state["beta2_power"])
+                    done += ["beta1_power", "beta2_power"]
+            rk.sync()
+        return done
 
     def read_ctl(self, shard: int, fld: str, count: int = 1):
         r = self.ps_ranks[shard]

@@ -175,6 +175,15 @@ class _PsService:
                         bind(name, eng._view(rk.bufs["gmaster%d" % s], name))
                 if s == 0:
                     bind(self.spec["global_step"], rk.bufs["gctl0"].tensor(torch.int64, eng.off["global_step"], 1).view(()))
+            # a re-formed fabric (an earlier generation of this job was torn down on this task): the optimizer's own state
+            # -- slots, Adam's beta powers -- continues where that generation stopped, like the variables do
+            saved = srv.store.resources.pop("fabric_opt_state/" + self.spec.get("base_key", self.spec["key"]), None)
+            if saved and hasattr(eng, "load_optimizer_state"):
+                try:
+                    _dbg("optimizer state carried over: %s" % (eng.load_optimizer_state(saved),))
+                except Exception:      # noqa: BLE001 - the slots restart from zero, as before
+                    import traceback
+                    traceback.print_exc()
             self.ready.set()
             _dbg("ps service loop starts")
             per_round = 1 if eng.cfg.sync else eng.cfg.num_workers
@@ -210,6 +219,14 @@ class _PsService:
         for name in self._bound_names:
             self.server.store.unbind(name)
         self._bound_names = []
+        if eng is not None and hasattr(eng, "optimizer_state"):
+            try:                   # slots / beta powers live only in the engine: keep them for the next generation
+                st = eng.optimizer_state()
+                if st:
+                    self.server.store.resources["fabric_opt_state/" + self.spec.get("base_key", self.spec["key"])] = st
+            except Exception:      # noqa: BLE001 - a GPU in an error state: the next generation's slots start from zero
+                import traceback
+                traceback.print_exc()
         if eng is not None:
             try:
                 eng.close()

@@ -296,3 +296,41 @@ def test_untimed_alignment_step_with_prefetch_hands_the_next_batch_to_the_follow
     del log[:]
     assert eng.step(xs[1], ys[1], sync_loss=True, prefetch=(xs[2], ys[2])) == 3.0          # the prefetched batch: no copy1 again
     assert log == ["compute1", "copy0", "loss"]
+
+
+def test_optimizer_state_round_trip_of_the_mlp_engine_without_a_gpu():
+    """``PSTrainEngine.optimizer_state`` is the non-variable part of ``state_dict`` (slots under TF's names, beta powers);
+    ``load_optimizer_state`` writes it back into the shard that owns each variable and skips foreign / mis-shaped entries."""
+    from types import SimpleNamespace
+    from distributed_tensorflow_b200.parallel.ps_engine import PSTrainEngine
+
+    def make():
+        eng = PSTrainEngine.__new__(PSTrainEngine)
+        store = {("master", "hid_w"): torch.arange(6.0).reshape(2, 3), ("slot_m", "hid_w"): torch.zeros(2, 3),
+                 ("slot_v", "hid_w"): torch.zeros(2, 3), ("master", "sm_b"): torch.ones(3), ("slot_m", "sm_b"): torch.zeros(3),
+                 ("slot_v", "sm_b"): torch.zeros(3)}
+        ctl = torch.zeros(8)
+        ctl[2], ctl[3] = 0.9, 0.999
+        rk = SimpleNamespace(device=None, stream=None, sync=lambda: None,
+                             bufs={"ctl0": SimpleNamespace(tensor=lambda dt, off, n: ctl[off:off + n])})
+        eng.ranks, eng.ps_ranks, eng.kind = {0: rk}, [0], 2
+        eng.off = {"beta1_power": 2, "global_step": 0}
+        eng.layout = {"hid_w": SimpleNamespace(shard=0, shape=(2, 3), name="hid_w"), "sm_b": SimpleNamespace(shard=0, shape=(3,), name="sm_b"),
+                      "other": SimpleNamespace(shard=1, shape=(3,), name="other")}
+        eng._var_view = lambda rk_, base, lay: store[(base, lay.name)]
+        eng.read_ctl = lambda shard, fld, count=1: 41
+        return eng, store, ctl
+    a, sa, ca = make()
+    sa[("slot_m", "hid_w")] += 0.25
+    sa[("slot_v", "sm_b")] += 4.0
+    ca[2] = 0.9 ** 5
+    st = a.optimizer_state()
+    assert sorted(st) == ["beta1_power", "beta2_power", "hid_w/Adam", "hid_w/Adam_1", "sm_b/Adam", "sm_b/Adam_1"]      # no variables, no global_step
+    b, sb, cb = make()
+    st["other/Adam"] = torch.ones(3)                          # owned by another shard
+    st["sm_b/Adam"] = torch.ones(5)                           # wrong shape
+    done = b.load_optimizer_state(st)
+    assert "other/Adam" not in done and "sm_b/Adam" not in done and "beta1_power" in done
+    assert sb[("slot_m", "hid_w")].tolist() == [[0.25] * 3] * 2 and sb[("slot_v", "sm_b")].tolist() == [4.0] * 3
+    assert sb[("slot_m", "sm_b")].tolist() == [0.0] * 3 and float(cb[2]) == pytest.approx(0.9 ** 5) and float(cb[3]) == pytest.approx(0.999)
+    assert sb[("master", "hid_w")].tolist() == torch.arange(6.0).reshape(2, 3).tolist()       # variables untouched

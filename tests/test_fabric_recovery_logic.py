@@ -146,3 +146,65 @@ def test_process_group_follows_the_generation(monkeypatch):
         if dist.is_initialized():
             dist.destroy_process_group()
         S._PG_GEN[0] = None
+
+
+def test_optimizer_slots_live_through_a_fabric_re_formation_on_the_ps_task(monkeypatch):
+    """Slots and Adam's beta powers exist only in the engine's HBM.  When the fabric re-forms (a worker died, the ps task
+    survived) the ps service of the old generation hands them to the next one, as the variable store does for the
+    variables: the optimizer continues instead of restarting its moments from zero."""
+    import time
+    from types import SimpleNamespace
+    from distributed_tensorflow_b200.framework.executor import ResourceStore
+    built = []
+
+    class Eng:
+        def __init__(self):
+            self.ranks = {0: SimpleNamespace(stream=SimpleNamespace(synchronize=lambda: None))}
+            self.ps_ranks, self.cfg = [0], SimpleNamespace(sync=True, num_workers=2)
+            self.layout = {"hid_w": SimpleNamespace(shard=0)}
+            self.w, self.gs = torch.zeros(3), torch.zeros((), dtype=torch.int64)
+            self.slots = {"hid_w/Adam": torch.zeros(3), "hid_w/Adam_1": torch.zeros(3), "beta1_power": torch.tensor(0.9),
+                          "beta2_power": torch.tensor(0.999)}
+            self.loaded, self.closed = None, False
+            built.append(self)
+
+        def var_tensor(self, rank, role):
+            return self.w
+
+        def global_step_tensor(self, rank):
+            return self.gs
+
+        def ps_apply(self, rank, idle_ok=False):
+            time.sleep(0.005)
+
+        def optimizer_state(self):
+            return {k: v.clone() for k, v in self.slots.items()}
+
+        def load_optimizer_state(self, st):
+            self.loaded = {k: v.clone() for k, v in st.items()}
+            return sorted(st)
+
+        def close(self):
+            self.closed = True
+    monkeypatch.setattr(S, "build_engine", lambda *a, **k: Eng())
+    srv = SimpleNamespace(cluster=None, job_name="ps", task_index=0, gpu_index=0, is_running=True, task=("ps", 0),
+                          store=ResourceStore("/job:ps/task:0"))
+    spec0 = {"key": "fjob", "base_key": "fjob", "mlp": {"roles": {"hid_w": "hid_w:0"}}, "global_step": "global_step:0"}
+    assert S.ps_fabric_setup(srv, spec0)
+    e0 = built[0]
+    assert e0.loaded is None                                   # first generation: nothing to carry over
+    srv.store.assign("hid_w:0", torch.zeros(3))                # the chief's init op
+    e0.w += 5.0                                                # training moved the variable and the moments
+    e0.slots["hid_w/Adam"] += 1.5
+    e0.slots["hid_w/Adam_1"] += 2.5
+    e0.slots["beta1_power"] = torch.tensor(0.9 ** 7)
+    spec1 = dict(spec0, key="fjob@1")
+    assert S.ps_fabric_setup(srv, spec1)                       # generation 1 retires generation 0 on this task
+    e1 = built[1]
+    assert e0.closed and "fabric_service/fjob" not in srv.store.resources
+    assert e1.loaded["hid_w/Adam"].tolist() == [1.5] * 3 and e1.loaded["hid_w/Adam_1"].tolist() == [2.5] * 3
+    assert float(e1.loaded["beta1_power"]) == pytest.approx(0.9 ** 7)
+    assert e1.w.tolist() == [5.0] * 3                          # the variable itself came through the store's rebind
+    assert "fabric_opt_state/fjob" not in srv.store.resources  # consumed
+    S.ps_fabric_teardown(srv, "fjob")
+    assert e1.closed and "fabric_opt_state/fjob" in srv.store.resources     # kept for a later generation
