@@ -22,6 +22,22 @@
 #define DTF_CPU_CLONES
 #endif
 
+// Denormals: a weight whose gradient is exactly zero step after step (MNIST's border pixels) has Adam / momentum slots that decay
+// geometrically INTO the denormal range (0.9^t * m0 < 1.2e-38 after ~800 steps) and stay there for a hundred steps and more; x86
+// handles every denormal operand with a micro-code assist -- measured here: 40 us -> 1.2 ms per apply of the 784x100 matrix.
+// TensorFlow's kernels run with flush-to-zero + denormals-are-zero set in its worker threads (ScopedFlushDenormal); so do
+// these loops, for their own duration (the caller's MXCSR is restored).
+#if defined(__x86_64__)
+#include <xmmintrin.h>
+struct ScopedFlushDenormals {
+  unsigned int saved;
+  ScopedFlushDenormals() : saved(_mm_getcsr()) { _mm_setcsr(saved | 0x8040u); }     // FTZ (bit 15) | DAZ (bit 6)
+  ~ScopedFlushDenormals() { _mm_setcsr(saved); }
+};
+#else
+struct ScopedFlushDenormals {};
+#endif
+
 extern "C" {
 
 // kind: 0 sgd, 1 momentum, 2 adam.  All buffers fp32, contiguous, n elements, NOT overlapping.  Returns 0, or -1 on bad
@@ -31,6 +47,7 @@ int dtf_cpu_optimizer_apply(int kind, float* __restrict__ var, float* __restrict
                             const float* __restrict__ g, long long n, float lr, float momentum, int nesterov, float beta1,
                             float beta2, float eps) {
   if (n < 0 || var == nullptr || g == nullptr) return -1;
+  ScopedFlushDenormals no_denormals;
   if (kind == 0) {
     for (long long i = 0; i < n; ++i) var[i] -= lr * g[i];
     return 0;
