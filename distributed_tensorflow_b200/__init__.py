@@ -209,6 +209,11 @@ from .framework import ops_extra as _extra  # noqa: E402
 
 for _n in _extra.__all__:
     globals()[_n] = getattr(_extra, _n)
+from .framework import ops_more as _more  # noqa: E402
+
+for _n in _more.__all__:
+    globals()[_n] = getattr(_more, _n)
+setattr(nn, "softmax_cross_entropy_with_logits_v2", _more.softmax_cross_entropy_with_logits_v2)
 for _n in ("relu6", "elu", "leaky_relu", "softplus", "sigmoid_cross_entropy_with_logits", "l2_normalize", "embedding_lookup", "in_top_k",
            "top_k"):
     setattr(nn, _n, getattr(_extra, _n))

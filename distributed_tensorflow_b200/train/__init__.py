@@ -15,3 +15,5 @@ from .saver import (CheckpointState, NewCheckpointReader, Saver, checkpoint_exis
                     latest_checkpoint, list_variables, load_checkpoint, update_checkpoint_state)
 from .sync_replicas import SyncReplicasOptimizer, SyncReplicasOptimizerHook
 from .supervisor import Supervisor
+from .extras import (AdadeltaOptimizer, ExponentialMovingAverage, add_queue_runner, global_step, init_from_checkpoint, load_variable,
+                     start_queue_runners, write_graph)
