@@ -262,7 +262,19 @@ metrics = _types.SimpleNamespace(mean=_metric_mean, accuracy=_metric_accuracy)
 
 from .utils import dataset as _dataset  # noqa: E402
 
-data = _types.SimpleNamespace(Dataset=_dataset.Dataset, Iterator=_dataset.Iterator_)
+from .utils import tfrecord as _tfrecord  # noqa: E402
+
+data = _types.SimpleNamespace(Dataset=_dataset.Dataset, Iterator=_dataset.Iterator_, TFRecordDataset=_tfrecord.TFRecordDataset)
+python_io = _types.SimpleNamespace(TFRecordWriter=_tfrecord.TFRecordWriter, tf_record_iterator=_tfrecord.tf_record_iterator)
+io = _types.SimpleNamespace(TFRecordWriter=_tfrecord.TFRecordWriter, tf_record_iterator=_tfrecord.tf_record_iterator,
+                            FixedLenFeature=_tfrecord.FixedLenFeature, VarLenFeature=_tfrecord.VarLenFeature,
+                            parse_single_example=_tfrecord.parse_single_example, parse_example=_tfrecord.parse_example,
+                            decode_raw=_tfrecord.decode_raw)
+FixedLenFeature, VarLenFeature = _tfrecord.FixedLenFeature, _tfrecord.VarLenFeature
+string = "string"             # dtype tag of byte-string features (host-side: records, parsed features)
+parse_single_example, parse_example, decode_raw = _tfrecord.parse_single_example, _tfrecord.parse_example, _tfrecord.decode_raw
+for _n in ("Example", "Features", "Feature", "BytesList", "FloatList", "Int64List"):
+    setattr(train, _n, getattr(_tfrecord, _n))
 
 losses = _types.SimpleNamespace(mean_squared_error=_mean_squared_error, softmax_cross_entropy=_softmax_cross_entropy,
                                 sparse_softmax_cross_entropy=_sparse_softmax_cross_entropy)

@@ -5,7 +5,7 @@ AbortedError in case of preempted PS": :class:`AbortedError` and
 :class:`UnavailableError` are the two errors the recoverable session retries on.
 """
 __all__ = ["OpError", "FailedPreconditionError", "AbortedError", "UnavailableError", "OutOfRangeError",
-           "CancelledError", "DeadlineExceededError", "NotFoundError", "InvalidArgumentError"]
+           "CancelledError", "DeadlineExceededError", "NotFoundError", "InvalidArgumentError", "DataLossError"]
 
 
 class OpError(Exception):
@@ -44,3 +44,7 @@ class NotFoundError(OpError):
 
 class InvalidArgumentError(OpError):
     pass
+
+
+class DataLossError(OpError):
+    """Unrecoverable data corruption (a record or checkpoint whose checksum does not match)."""

@@ -1,0 +1,269 @@
+"""TFRecord files and ``tf.train.Example`` records: the on-disk input format of TF-1.x programs that do not feed numpy arrays
+(the reference feeds ``mnist.train.next_batch`` through placeholders, ``/root/reference/distributed_mnist.py:149-152``; this is
+the same role for data sets converted to records).
+
+* ``python_io.TFRecordWriter(path)`` / ``python_io.tf_record_iterator(path)``: TensorFlow's record framing -- ``uint64 length,
+  masked crc32c(length), payload, masked crc32c(payload)`` -- the framing the event files of ``utils/summary.py`` use (files
+  written here are read by TensorFlow and vice versa).
+* ``train.Example`` / ``Features`` / ``Feature`` / ``BytesList`` / ``FloatList`` / ``Int64List``: the ``tensorflow.Example`` message in
+  protobuf wire format (``SerializeToString`` / ``FromString``; packed and unpacked repeated scalars are both read).
+* ``parse_single_example`` / ``parse_example`` with ``FixedLenFeature`` / ``VarLenFeature``: host-side parsing to numpy (the
+  function a ``Dataset.map`` takes), ``decode_raw`` for byte strings holding raw tensors.
+* ``data.TFRecordDataset(filenames)``: a :class:`~.dataset.Dataset` of serialized records (one ``bytes`` object per element).
+"""
+from __future__ import annotations
+
+import struct
+from typing import Any, Dict, Iterator, List, Optional, Sequence, Union
+
+import numpy as np
+
+from .summary import _decode, _f_bytes, _key, _read_tfrecords, _tfrecord, _varint
+
+__all__ = ["TFRecordWriter", "tf_record_iterator", "Example", "Features", "Feature", "BytesList", "FloatList", "Int64List",
+           "FixedLenFeature", "VarLenFeature", "parse_single_example", "parse_example", "decode_raw", "TFRecordDataset"]
+
+
+class TFRecordWriter:
+    def __init__(self, path: str, options=None):
+        if options not in (None, "", 0):
+            raise NotImplementedError("compressed TFRecord files are not provided")
+        self._f = open(path, "wb")
+
+    def write(self, record: Union[bytes, bytearray, memoryview]) -> None:
+        self._f.write(_tfrecord(bytes(record)))
+
+    def flush(self) -> None:
+        self._f.flush()
+
+    def close(self) -> None:
+        if not self._f.closed:
+            self._f.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def tf_record_iterator(path: str, options=None) -> Iterator[bytes]:
+    """Every record of the file, checksums verified (a truncated tail ends the iteration; a corrupt record raises)."""
+    from ..framework import errors
+    try:
+        yield from _read_tfrecords(path)
+    except ValueError as e:
+        raise errors.DataLossError(str(e)) if hasattr(errors, "DataLossError") else errors.OpError(str(e))
+
+
+# ---- tensorflow.Example --------------------------------------------------------------------------------------------------------
+class BytesList:
+    def __init__(self, value: Sequence[bytes] = ()):
+        self.value = [v.encode() if isinstance(v, str) else bytes(v) for v in value]
+
+    def _encode(self) -> bytes:
+        return b"".join(_f_bytes(1, v) for v in self.value)
+
+
+class FloatList:
+    def __init__(self, value: Sequence[float] = ()):
+        self.value = [float(v) for v in np.asarray(value, np.float32).reshape(-1)]
+
+    def _encode(self) -> bytes:          # packed, like every modern writer
+        return _f_bytes(1, np.asarray(self.value, "<f4").tobytes()) if self.value else b""
+
+
+class Int64List:
+    def __init__(self, value: Sequence[int] = ()):
+        self.value = [int(v) for v in np.asarray(value).reshape(-1)]
+
+    def _encode(self) -> bytes:
+        return _f_bytes(1, b"".join(_varint(v) for v in self.value)) if self.value else b""
+
+
+class Feature:
+    def __init__(self, bytes_list: Optional[BytesList] = None, float_list: Optional[FloatList] = None, int64_list: Optional[Int64List] = None):
+        if sum(x is not None for x in (bytes_list, float_list, int64_list)) > 1:
+            raise ValueError("a Feature holds ONE of bytes_list / float_list / int64_list")
+        self.bytes_list, self.float_list, self.int64_list = bytes_list, float_list, int64_list
+
+    @property
+    def kind(self) -> Optional[str]:
+        return "bytes_list" if self.bytes_list is not None else "float_list" if self.float_list is not None else \
+            "int64_list" if self.int64_list is not None else None
+
+    def _encode(self) -> bytes:
+        if self.bytes_list is not None:
+            return _f_bytes(1, self.bytes_list._encode())
+        if self.float_list is not None:
+            return _f_bytes(2, self.float_list._encode())
+        if self.int64_list is not None:
+            return _f_bytes(3, self.int64_list._encode())
+        return b""
+
+    @staticmethod
+    def _parse(buf: bytes) -> "Feature":
+        for f, _, v in _decode(buf):
+            if f == 1:
+                return Feature(bytes_list=BytesList([x for ff, _, x in _decode(v) if ff == 1]))
+            if f == 2:
+                vals: List[float] = []
+                for ff, wire, x in _decode(v):
+                    if ff == 1:
+                        vals += list(np.frombuffer(x, "<f4")) if wire == 2 else [struct.unpack("<f", x)[0]]
+                return Feature(float_list=FloatList(vals))
+            if f == 3:
+                ints: List[int] = []
+                for ff, wire, x in _decode(v):
+                    if ff != 1:
+                        continue
+                    if wire == 2:                # packed varints
+                        ints += [y if y < (1 << 63) else y - (1 << 64) for _, _, y in _decode_varints(x)]
+                    else:
+                        ints.append(x if x < (1 << 63) else x - (1 << 64))
+                return Feature(int64_list=Int64List(ints))
+        return Feature()
+
+
+def _decode_varints(buf: bytes):
+    i, n = 0, len(buf)
+    while i < n:
+        v = shift = 0
+        while True:
+            b = buf[i]
+            i += 1
+            v |= (b & 0x7F) << shift
+            shift += 7
+            if not b & 0x80:
+                break
+        yield (1, 0, v)
+
+
+class Features:
+    def __init__(self, feature: Optional[Dict[str, Feature]] = None):
+        self.feature: Dict[str, Feature] = dict(feature or {})
+
+    def _encode(self) -> bytes:          # map<string, Feature> = repeated entry {1: key, 2: value}; keys sorted: deterministic bytes
+        return b"".join(_f_bytes(1, _f_bytes(1, k.encode()) + _f_bytes(2, self.feature[k]._encode())) for k in sorted(self.feature))
+
+
+class Example:
+    def __init__(self, features: Optional[Features] = None):
+        self.features = features if features is not None else Features()
+
+    def SerializeToString(self) -> bytes:      # noqa: N802 - protobuf's name
+        return _f_bytes(1, self.features._encode())
+
+    @staticmethod
+    def FromString(buf: bytes) -> "Example":   # noqa: N802
+        ex = Example()
+        for f, _, v in _decode(bytes(buf)):
+            if f != 1:
+                continue
+            for ff, _, entry in _decode(v):
+                if ff != 1:
+                    continue
+                key, val = None, Feature()
+                for fff, _, x in _decode(entry):
+                    if fff == 1:
+                        key = x.decode()
+                    elif fff == 2:
+                        val = Feature._parse(x)
+                if key is not None:
+                    ex.features.feature[key] = val
+        return ex
+
+    def ParseFromString(self, buf: bytes) -> None:   # noqa: N802
+        self.features = Example.FromString(buf).features
+
+
+# ---- parsing -------------------------------------------------------------------------------------------------------------------
+class FixedLenFeature:
+    def __init__(self, shape, dtype, default_value=None):
+        self.shape, self.dtype, self.default_value = tuple(int(d) for d in shape), dtype, default_value
+
+
+class VarLenFeature:
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+
+def _np_dtype(dtype):
+    import torch
+    if dtype in (str, bytes, "string") or getattr(dtype, "__name__", "") == "string":
+        return object
+    if isinstance(dtype, torch.dtype):
+        return {torch.float32: np.float32, torch.float64: np.float64, torch.int64: np.int64, torch.int32: np.int32,
+                torch.uint8: np.uint8, torch.bool: np.bool_}[dtype]
+    return np.dtype(dtype)
+
+
+def _values(feat: Feature, want) -> list:
+    if feat.kind is None:
+        return []
+    vals = getattr(feat, feat.kind).value
+    kind_ok = {"bytes_list": want is object, "float_list": want is not object and np.issubdtype(want, np.floating),
+               "int64_list": want is not object and (np.issubdtype(want, np.integer) or want == np.bool_)}[feat.kind]
+    if not kind_ok:
+        raise ValueError("feature holds a %s but %s was asked for" % (feat.kind, want))
+    return vals
+
+
+def parse_single_example(serialized, features: Dict[str, Any], name=None) -> Dict[str, np.ndarray]:
+    """One serialized ``Example`` -> ``{key: numpy array}``: ``FixedLenFeature`` values reshaped to their shape (the default when
+    the key is absent, an error without one), ``VarLenFeature`` values as a 1-D array of whatever length the record holds."""
+    if isinstance(serialized, np.ndarray):
+        serialized = serialized.item() if serialized.shape == () else serialized.tobytes()
+    ex = Example.FromString(serialized)
+    out: Dict[str, np.ndarray] = {}
+    for key, spec in features.items():
+        want = _np_dtype(spec.dtype)
+        feat = ex.features.feature.get(key)
+        if isinstance(spec, VarLenFeature):
+            out[key] = np.asarray(_values(feat, want) if feat is not None else [], dtype=want)
+            continue
+        n = int(np.prod(spec.shape)) if spec.shape else 1
+        if feat is None or feat.kind is None:
+            if spec.default_value is None:
+                raise ValueError("Example has no feature %r and the FixedLenFeature has no default_value" % key)
+            out[key] = np.broadcast_to(np.asarray(spec.default_value, dtype=want), spec.shape).copy()
+            continue
+        vals = _values(feat, want)
+        if len(vals) != n:
+            raise ValueError("feature %r holds %d values, FixedLenFeature%s needs %d" % (key, len(vals), spec.shape, n))
+        out[key] = np.asarray(vals, dtype=want).reshape(spec.shape)
+    return out
+
+
+def parse_example(serialized: Sequence[bytes], features: Dict[str, Any], name=None) -> Dict[str, np.ndarray]:
+    """A batch of serialized Examples -> stacked ``FixedLenFeature`` arrays (``VarLenFeature`` is per-record: use
+    ``parse_single_example`` before batching)."""
+    if any(isinstance(s, VarLenFeature) for s in features.values()):
+        raise NotImplementedError("parse_example with VarLenFeature (sparse batches): parse single examples before batching")
+    rows = [parse_single_example(s, features) for s in (serialized.tolist() if isinstance(serialized, np.ndarray) else serialized)]
+    return {k: np.stack([r[k] for r in rows]) for k in features}
+
+
+def decode_raw(data, out_type, little_endian: bool = True, name=None) -> np.ndarray:
+    """The bytes of a string feature reinterpreted as a 1-D array of ``out_type`` (images stored with ``tobytes()``)."""
+    if isinstance(data, np.ndarray):
+        data = data.item() if data.shape == () else data.tobytes()
+    dt = np.dtype(_np_dtype(out_type))
+    return np.frombuffer(bytes(data), dt.newbyteorder("<" if little_endian else ">")).astype(dt)
+
+
+def TFRecordDataset(filenames, compression_type=None, buffer_size=None, num_parallel_reads=None):      # noqa: N802 - TF's name
+    """``tf.data.TFRecordDataset``: the records of the files, in order, one ``bytes`` object (0-d object array) per element."""
+    from .dataset import Dataset, _Spec
+    if compression_type not in (None, ""):
+        raise NotImplementedError("compressed TFRecord files are not provided")
+    files = [filenames] if isinstance(filenames, (str, bytes)) else [f for f in filenames]
+    files = [f.decode() if isinstance(f, bytes) else str(f) for f in files]
+
+    def make():
+        for path in files:
+            for rec in tf_record_iterator(path):
+                a = np.empty((), dtype=object)
+                a[()] = rec
+                yield a
+    return Dataset(make, _Spec(object, ()))

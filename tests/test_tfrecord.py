@@ -1,0 +1,138 @@
+"""TFRecord files + ``tf.train.Example`` (utils/tfrecord.py): framing and message bytes checked against the protobuf runtime's own
+encoder (a hand-built descriptor of ``tensorflow.Example``), parsing, and a ``TFRecordDataset`` pipeline feeding a training loop."""
+import struct
+
+import numpy as np
+import pytest
+
+import distributed_tensorflow_b200 as tf
+from distributed_tensorflow_b200.utils import tfrecord
+from distributed_tensorflow_b200.utils.summary import masked_crc32c
+
+
+@pytest.fixture(autouse=True)
+def _fresh_graph():
+    tf.reset_default_graph()
+    yield
+    tf.reset_default_graph()
+
+
+def _example(i):
+    img = (np.arange(6, dtype=np.float32) + i).reshape(2, 3)
+    return tf.train.Example(features=tf.train.Features(feature={
+        "image_raw": tf.train.Feature(bytes_list=tf.train.BytesList(value=[img.tobytes()])),
+        "label": tf.train.Feature(int64_list=tf.train.Int64List(value=[i % 3])),
+        "weights": tf.train.Feature(float_list=tf.train.FloatList(value=[0.5 * i, -1.0])),
+        "tags": tf.train.Feature(bytes_list=tf.train.BytesList(value=[b"a"] * (i % 2 + 1))),
+        "big": tf.train.Feature(int64_list=tf.train.Int64List(value=[-1, 2 ** 40 + i])),
+    })), img
+
+
+def test_record_framing_and_checksums(tmp_path):
+    path = str(tmp_path / "d.tfrecord")
+    with tf.python_io.TFRecordWriter(path) as w:
+        for rec in (b"", b"hello", bytes(range(256)) * 5):
+            w.write(rec)
+    raw = open(path, "rb").read()
+    (n,) = struct.unpack("<Q", raw[:8])
+    assert n == 0 and struct.unpack("<I", raw[8:12])[0] == masked_crc32c(raw[:8])          # TensorFlow's layout
+    assert list(tf.python_io.tf_record_iterator(path)) == [b"", b"hello", bytes(range(256)) * 5]
+    bad = bytearray(raw)
+    bad[-10] ^= 0xFF                                                   # inside the last payload
+    open(path, "wb").write(bytes(bad))
+    it = tf.python_io.tf_record_iterator(path)
+    assert next(it) == b"" and next(it) == b"hello"
+    with pytest.raises(tf.errors.DataLossError):
+        next(it)
+
+
+def test_example_bytes_are_what_the_protobuf_runtime_writes_and_reads():
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    fd = descriptor_pb2.FileDescriptorProto(name="ex_test.proto", package="dtftest", syntax="proto3")
+
+    def msg(name, fields):
+        m = fd.message_type.add(name=name)
+        for fname, num, ftype, label, tname in fields:
+            f = m.field.add(name=fname, number=num, type=ftype, label=label)
+            if tname:
+                f.type_name = tname
+        return m
+    T = descriptor_pb2.FieldDescriptorProto
+    msg("BytesList", [("value", 1, T.TYPE_BYTES, T.LABEL_REPEATED, None)])
+    msg("FloatList", [("value", 1, T.TYPE_FLOAT, T.LABEL_REPEATED, None)])
+    msg("Int64List", [("value", 1, T.TYPE_INT64, T.LABEL_REPEATED, None)])
+    feat = msg("Feature", [("bytes_list", 1, T.TYPE_MESSAGE, T.LABEL_OPTIONAL, ".dtftest.BytesList"),
+                           ("float_list", 2, T.TYPE_MESSAGE, T.LABEL_OPTIONAL, ".dtftest.FloatList"),
+                           ("int64_list", 3, T.TYPE_MESSAGE, T.LABEL_OPTIONAL, ".dtftest.Int64List")])
+    feat.oneof_decl.add(name="kind")
+    for f in feat.field:
+        f.oneof_index = 0
+    entry = msg("Entry", [("key", 1, T.TYPE_STRING, T.LABEL_OPTIONAL, None), ("value", 2, T.TYPE_MESSAGE, T.LABEL_OPTIONAL, ".dtftest.Feature")])
+    msg("Features", [("feature", 1, T.TYPE_MESSAGE, T.LABEL_REPEATED, ".dtftest.Entry")])       # a map IS a repeated entry on the wire
+    msg("Example", [("features", 1, T.TYPE_MESSAGE, T.LABEL_OPTIONAL, ".dtftest.Features")])
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    Ex = message_factory.GetMessageClass(pool.FindMessageTypeByName("dtftest.Example"))
+    ours, img = _example(4)
+    theirs = Ex()
+    theirs.ParseFromString(ours.SerializeToString())                       # the runtime reads our bytes
+    got = {e.key: e.value for e in theirs.features.feature}
+    assert got["image_raw"].bytes_list.value[0] == img.tobytes() and list(got["label"].int64_list.value) == [1]
+    assert list(got["weights"].float_list.value) == [2.0, -1.0] and list(got["big"].int64_list.value) == [-1, 2 ** 40 + 4]
+    back = tf.train.Example.FromString(theirs.SerializeToString())         # and we read the runtime's bytes
+    assert back.features.feature["big"].int64_list.value == [-1, 2 ** 40 + 4] and back.features.feature["tags"].bytes_list.value == [b"a"]
+    assert back.features.feature["weights"].float_list.value == [2.0, -1.0]
+    assert back.SerializeToString() == ours.SerializeToString()            # deterministic (sorted keys), round-trips exactly
+
+
+def test_parse_single_example_fixed_var_default_and_errors():
+    ex, img = _example(5)
+    s = ex.SerializeToString()
+    out = tf.parse_single_example(s, {"image_raw": tf.FixedLenFeature([], tf.string), "label": tf.FixedLenFeature([], tf.int64),
+                                      "weights": tf.FixedLenFeature([2], tf.float32), "tags": tf.VarLenFeature(tf.string),
+                                      "missing": tf.FixedLenFeature([2], tf.float32, default_value=7.0),
+                                      "absent_var": tf.VarLenFeature(tf.int64)})
+    assert np.array_equal(tf.decode_raw(out["image_raw"], tf.float32).reshape(2, 3), img) and out["label"] == 2 and out["label"].dtype == np.int64
+    assert out["weights"].tolist() == [2.5, -1.0] and out["tags"].tolist() == [b"a", b"a"] and out["missing"].tolist() == [7.0, 7.0]
+    assert out["absent_var"].shape == (0,)
+    with pytest.raises(ValueError, match="no feature"):
+        tf.parse_single_example(s, {"nope": tf.FixedLenFeature([], tf.int64)})
+    with pytest.raises(ValueError, match="needs 3"):
+        tf.parse_single_example(s, {"weights": tf.FixedLenFeature([3], tf.float32)})
+    with pytest.raises(ValueError, match="float_list"):
+        tf.parse_single_example(s, {"weights": tf.FixedLenFeature([2], tf.int64)})
+    batch = tf.parse_example([_example(i)[0].SerializeToString() for i in range(4)], {"label": tf.FixedLenFeature([], tf.int64),
+                                                                                       "weights": tf.FixedLenFeature([2], tf.float32)})
+    assert batch["label"].tolist() == [0, 1, 2, 0] and batch["weights"].shape == (4, 2)
+
+
+def test_tfrecord_dataset_feeds_a_training_loop(tmp_path):
+    """y = 3x - 2 stored as Example records in two files, read back through TFRecordDataset -> map(parse) -> shuffle / repeat / batch ->
+    get_next, and fitted by gradient descent: the record path end to end."""
+    rng = np.random.default_rng(0)
+    files = []
+    for k in range(2):
+        path = str(tmp_path / ("part-%d.tfrecord" % k))
+        files.append(path)
+        with tf.python_io.TFRecordWriter(path) as w:
+            for _ in range(64):
+                x = float(rng.uniform(-1, 1))
+                w.write(tf.train.Example(features=tf.train.Features(feature={
+                    "x": tf.train.Feature(float_list=tf.train.FloatList(value=[x])),
+                    "y": tf.train.Feature(float_list=tf.train.FloatList(value=[3 * x - 2]))})).SerializeToString())
+    spec = {"x": tf.FixedLenFeature([1], tf.float32), "y": tf.FixedLenFeature([1], tf.float32)}
+
+    def parse(rec):
+        d = tf.parse_single_example(rec, spec)
+        return d["x"], d["y"]
+    ds = tf.data.TFRecordDataset(files).map(parse).shuffle(128, seed=1).repeat().batch(16)
+    assert sum(1 for _ in tf.data.TFRecordDataset(files)._make()) == 128
+    xb, yb = ds.make_one_shot_iterator().get_next()
+    w, b = tf.Variable(0.0, name="w"), tf.Variable(0.0, name="b")
+    loss = tf.reduce_mean(tf.square(w * xb + b - yb))
+    step = tf.train.GradientDescentOptimizer(0.3).minimize(loss)
+    with tf.Session() as sess:
+        sess.run(tf.global_variables_initializer())
+        for _ in range(300):
+            sess.run(step)
+        assert sess.run(w) == pytest.approx(3.0, abs=0.02) and sess.run(b) == pytest.approx(-2.0, abs=0.02)

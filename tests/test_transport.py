@@ -140,7 +140,8 @@ with tf.device("/job:ps/task:0"):
     w = tf.Variable(tf.ones([8, 8]), name="w")
 with tf.device("/job:worker/task:0"):
     y = tf.matmul(w, w)
-print(RpcClient(cluster.task_address("ps", 0)).call("ping")["task"])       # a real connection -> a connection thread on the ps
+client = RpcClient(cluster.task_address("ps", 0))                          # kept alive: its connection stays open until exit
+print(client.call("ping")["task"])                                         # a real connection -> a connection thread on the ps
 with tf.Session(wk.target) as sess:
     sess.run(tf.global_variables_initializer()); print(float(sess.run(y)[0, 0]))
 print("BEFORE", sorted(t.name for t in threading.enumerate() if t.name.startswith("dtf-rpc")))
