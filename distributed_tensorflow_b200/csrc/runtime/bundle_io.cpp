@@ -170,4 +170,37 @@ int dtf_bundle_read(const char* path, int count, void* const* ptrs, const int64_
   return err.load();
 }
 
+// ---- TFRecord files (the record framing of TensorFlow's input files and event logs) ----------------------------------------
+// record = uint64 length | masked crc32c(length) | payload | masked crc32c(payload)        (little endian)
+// Scans a whole file that the caller mapped / read into memory: verifies both checksums of every record (SSE4.2 crc32c, no
+// interpreter involved) and writes the payload offsets / lengths.  Returns the number of complete records found (a truncated
+// tail -- a writer that is still appending -- ends the scan), or -(index + 1) of the first record whose checksum does not match.
+// `max_records` < 0: count only.
+static inline uint32_t dtf_mask_crc(uint32_t c) { return ((c >> 15) | (c << 17)) + 0xA282EAD8u; }
+
+int64_t dtf_tfrecord_scan(const void* data, int64_t nbytes, int64_t* offsets, int64_t* lengths, int64_t max_records, int verify) {
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  int64_t at = 0, n = 0;
+  while (at + 12 <= nbytes) {
+    if (max_records >= 0 && n >= max_records) return n;           // the caller's arrays are full (or it asked for a prefix)
+    uint64_t len;
+    uint32_t hc;
+    memcpy(&len, p + at, 8);
+    memcpy(&hc, p + at + 8, 4);
+    if (verify && dtf_mask_crc(dtf_crc32c(p + at, 8, 0)) != hc) return -(n + 1);
+    if (len > (uint64_t)(nbytes - at - 16) || at + 16 > nbytes) break;                 // truncated tail
+    const int64_t body = at + 12;
+    uint32_t pc;
+    memcpy(&pc, p + body + (int64_t)len, 4);
+    if (verify && dtf_mask_crc(dtf_crc32c(p + body, (int64_t)len, 0)) != pc) return -(n + 1);
+    if (max_records >= 0) {
+      offsets[n] = body;
+      lengths[n] = (int64_t)len;
+    }
+    ++n;
+    at = body + (int64_t)len + 4;
+  }
+  return n;
+}
+
 }  // extern "C"

@@ -136,3 +136,38 @@ def test_tfrecord_dataset_feeds_a_training_loop(tmp_path):
         for _ in range(300):
             sess.run(step)
         assert sess.run(w) == pytest.approx(3.0, abs=0.02) and sess.run(b) == pytest.approx(-2.0, abs=0.02)
+
+
+def test_native_scanner_agrees_with_the_python_reader_on_good_truncated_and_corrupt_files(tmp_path):
+    """``dtf_tfrecord_scan`` (csrc/runtime/bundle_io.cpp) verifies both checksums of every record outside the interpreter; the
+    iterator built on it yields what the record-by-record Python reader yields -- including the records before a corrupt one
+    and the complete records of a file whose writer is still appending."""
+    from distributed_tensorflow_b200.utils.summary import _read_tfrecords
+    if tfrecord._scan_native(b"") is None:
+        pytest.skip("native runtime library not built")
+    rng = np.random.default_rng(3)
+    recs = [bytes(rng.integers(0, 256, int(n), dtype=np.uint8)) for n in (0, 1, 7, 4096, 100_000, 3)]
+    path = str(tmp_path / "r.tfrecord")
+    with tfrecord.TFRecordWriter(path) as w:
+        for r in recs:
+            w.write(r)
+    raw = open(path, "rb").read()
+    off, ln, bad = tfrecord._scan_native(raw)
+    assert bad == -1 and ln.tolist() == [len(r) for r in recs] and [raw[o:o + n] for o, n in zip(off.tolist(), ln.tolist())] == recs
+    assert list(tfrecord.tf_record_iterator(path)) == recs == list(_read_tfrecords(path))
+    # a writer that is still appending: header / payload / trailing checksum cut at every interesting place
+    for cut in (len(raw) - 1, len(raw) - 4, len(raw) - 6, len(raw) - 12, len(raw) - 18):
+        open(path, "wb").write(raw[:cut])
+        assert list(tfrecord.tf_record_iterator(path)) == recs[:-1]
+    # corruption in record 3's payload / in record 1's length field
+    for pos, first_bad in ((int(off[3]) + 100, 3), (int(off[1]) - 12, 1)):
+        dmg = bytearray(raw)
+        dmg[pos] ^= 0x40
+        open(path, "wb").write(bytes(dmg))
+        it, got = tfrecord.tf_record_iterator(path), []
+        with pytest.raises(tf.errors.DataLossError):
+            for r in it:
+                got.append(r)
+        assert got == recs[:first_bad]
+    open(path, "wb").write(b"")
+    assert list(tfrecord.tf_record_iterator(path)) == []
