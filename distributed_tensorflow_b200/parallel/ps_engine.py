@@ -461,7 +461,8 @@ class PSTrainEngine:
                     lay = self.layout.get(name)
                     if lay is None or lay.shard != s or slot not in suffix or tuple(val.shape) != tuple(lay.shape):
                         continue
-                    self._var_view(rk, suffix[slot], lay).reshape(lay.shape).copy_(val.to(rk.device).float())
+                    # (a pitched view: write through it, a reshape would copy)
+                    self._var_view(rk, suffix[slot], lay).copy_(val.to(rk.device).float().reshape(lay.rows, lay.cols))
                     done.append(key)
                 if s == 0 and self.kind == 2 and "beta1_power" in state and "beta2_power" in state:
                     b = rk.bufs["ctl0"].tensor(torch.float32, self.off["beta1_power"], 2)

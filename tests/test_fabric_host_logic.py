@@ -315,8 +315,15 @@ def test_optimizer_state_round_trip_of_the_mlp_engine_without_a_gpu():
                              bufs={"ctl0": SimpleNamespace(tensor=lambda dt, off, n: ctl[off:off + n])})
         eng.ranks, eng.ps_ranks, eng.kind = {0: rk}, [0], 2
         eng.off = {"beta1_power": 2, "global_step": 0}
-        eng.layout = {"hid_w": SimpleNamespace(shard=0, shape=(2, 3), name="hid_w"), "sm_b": SimpleNamespace(shard=0, shape=(3,), name="sm_b"),
-                      "other": SimpleNamespace(shard=1, shape=(3,), name="other")}
+        eng.layout = {"hid_w": SimpleNamespace(shard=0, shape=(2, 3), rows=2, cols=3, name="hid_w"),
+                      "sm_b": SimpleNamespace(shard=0, shape=(3,), rows=1, cols=3, name="sm_b"),
+                      "other": SimpleNamespace(shard=1, shape=(3,), rows=1, cols=3, name="other")}
+        # like the engine's: a [rows, cols] window of a PITCHED buffer (writes must go through the view, a reshape would copy)
+        pitched = {k: torch.zeros(lay_rows, 8) for k, lay_rows in ((("slot_m", "hid_w"), 2), (("slot_v", "hid_w"), 2), (("master", "hid_w"), 2),
+                                                                   (("slot_m", "sm_b"), 1), (("slot_v", "sm_b"), 1), (("master", "sm_b"), 1))}
+        for k, buf in pitched.items():
+            buf[:, :3] = store[k].reshape(buf.shape[0], 3)
+            store[k] = buf[:, :3]
         eng._var_view = lambda rk_, base, lay: store[(base, lay.name)]
         eng.read_ctl = lambda shard, fld, count=1: 41
         return eng, store, ctl
@@ -331,6 +338,6 @@ def test_optimizer_state_round_trip_of_the_mlp_engine_without_a_gpu():
     st["sm_b/Adam"] = torch.ones(5)                           # wrong shape
     done = b.load_optimizer_state(st)
     assert "other/Adam" not in done and "sm_b/Adam" not in done and "beta1_power" in done
-    assert sb[("slot_m", "hid_w")].tolist() == [[0.25] * 3] * 2 and sb[("slot_v", "sm_b")].tolist() == [4.0] * 3
-    assert sb[("slot_m", "sm_b")].tolist() == [0.0] * 3 and float(cb[2]) == pytest.approx(0.9 ** 5) and float(cb[3]) == pytest.approx(0.999)
+    assert sb[("slot_m", "hid_w")].tolist() == [[0.25] * 3] * 2 and sb[("slot_v", "sm_b")].reshape(-1).tolist() == [4.0] * 3
+    assert sb[("slot_m", "sm_b")].reshape(-1).tolist() == [0.0] * 3 and float(cb[2]) == pytest.approx(0.9 ** 5) and float(cb[3]) == pytest.approx(0.999)
     assert sb[("master", "hid_w")].tolist() == torch.arange(6.0).reshape(2, 3).tolist()       # variables untouched
