@@ -181,3 +181,13 @@ def test_supervisor_style_mnist_job(tmp_path, sync):
     vals = [float(v) for v in re.findall(r"validation cross entropy = ([0-9][0-9.eE+-]*)", out)]
     assert len(vals) == 2 and max(vals) < 5000.0                # 5000 validation images, batch-sum loss: ~11500 untrained
     assert (tmp_path / "sv" / "checkpoint").exists()
+
+
+def test_mnist_fed_from_tfrecord_shards(tmp_path):
+    """examples/mnist_tfrecords.py: the training split converted to Example records in four TFRecord shards, read back through
+    TFRecordDataset -> map(parse) -> shuffle / repeat / batch / prefetch -> get_next under a MonitoredTrainingSession."""
+    out = _run([os.path.join(EX, "mnist_tfrecords.py"), "--data_dir", str(tmp_path / "rec"), "--train_steps", "120", "--num_train", "1200"])
+    line = [l for l in out.splitlines() if l.startswith("tfrecords:")][0]
+    assert "120 steps" in line and "(1200 records in 4 shards)" in line
+    assert float(line.split("held-out accuracy ")[1].split()[0]) > 0.9
+    assert len(list((tmp_path / "rec").glob("train-*.tfrecord"))) == 4 and (tmp_path / "rec" / "validation.tfrecord").exists()
