@@ -281,20 +281,108 @@ def parse_single_example(serialized, features: Dict[str, Any], name=None) -> Dic
     return out
 
 
+_KIND = {"bytes": 0, "float": 1, "int64": 2}
+
+
+def _parse_examples_native(records: List[bytes], features: Dict[str, Any]) -> Optional[Dict[str, np.ndarray]]:
+    """The batch through ``csrc/runtime/example_parser.cpp: dtf_parse_examples`` (one call, outside the interpreter): float / int64
+    features land directly in their ``[batch, *shape]`` arrays, a bytes feature comes back as (offset, length) pairs that are
+    sliced here.  None when the native library is missing, a feature is not a float32 / int64 / string ``FixedLenFeature``, or the
+    parser reports a problem -- the Python path then produces the value or the precise error."""
+    import ctypes
+    from . import native_runtime
+    lib = native_runtime.load()
+    if lib is None or not hasattr(lib, "dtf_parse_examples") or not records:
+        return None
+    names = list(features)
+    kinds, counts = [], []
+    for k in names:
+        spec = features[k]
+        if not isinstance(spec, FixedLenFeature):
+            return None
+        want = _np_dtype(spec.dtype)
+        kind = 0 if want is object else 1 if want == np.float32 else 2 if want == np.int64 else None
+        if kind is None:
+            return None
+        kinds.append(kind)
+        counts.append(int(np.prod(spec.shape)) if spec.shape else 1)
+    fn = lib.dtf_parse_examples
+    if not getattr(fn, "_declared", False):
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        fn.restype = ctypes.c_int64
+        fn._declared = True
+    n, nf = len(records), len(names)
+    buf = b"".join(records)
+    lens = np.fromiter((len(r) for r in records), np.int64, n)
+    offs = np.cumsum(lens) - lens
+    outs = [np.zeros((n, c * 2), np.int64) if kd == 0 else np.zeros((n, c), np.float32 if kd == 1 else np.int64) for kd, c in zip(kinds, counts)]
+    keyb = [k.encode() for k in names]
+    keys = (ctypes.c_char_p * nf)(*keyb)
+    klen = (ctypes.c_int * nf)(*[len(k) for k in keyb])
+    kind_a = (ctypes.c_int * nf)(*kinds)
+    cnt_a = (ctypes.c_int64 * nf)(*counts)
+    out_a = (ctypes.c_void_p * nf)(*[o.ctypes.data for o in outs])
+    present = np.zeros((n, nf), np.uint8)
+    ef, ec = ctypes.c_int(0), ctypes.c_int(0)
+    data = np.frombuffer(buf, np.uint8)
+    rc = fn(data.ctypes.data if data.size else None, offs.ctypes.data, lens.ctypes.data, n, nf, keys, klen, kind_a, cnt_a, out_a,
+            present.ctypes.data, ctypes.byref(ef), ctypes.byref(ec))
+    if rc != 0:
+        return None
+    result: Dict[str, np.ndarray] = {}
+    for j, k in enumerate(names):
+        spec, kd, c = features[k], kinds[j], counts[j]
+        missing = present[:, j] == 0
+        if missing.any() and spec.default_value is None:
+            return None                              # the Python path names the record / feature
+        if kd == 0:
+            pairs = outs[j].reshape(n, c, 2)
+            arr = np.empty((n, c), dtype=object)
+            for i in range(n):
+                if missing[i]:
+                    arr[i, :] = spec.default_value if isinstance(spec.default_value, bytes) else str(spec.default_value).encode()
+                else:
+                    for q in range(c):
+                        o, m = int(pairs[i, q, 0]), int(pairs[i, q, 1])
+                        arr[i, q] = buf[o:o + m]
+            result[k] = arr.reshape((n,) + spec.shape)
+        else:
+            arr = outs[j]
+            if missing.any():
+                arr[missing] = np.broadcast_to(np.asarray(spec.default_value, arr.dtype), spec.shape).reshape(-1)
+            result[k] = arr.reshape((n,) + spec.shape)
+    return result
+
+
 def parse_example(serialized: Sequence[bytes], features: Dict[str, Any], name=None) -> Dict[str, np.ndarray]:
-    """A batch of serialized Examples -> stacked ``FixedLenFeature`` arrays (``VarLenFeature`` is per-record: use
-    ``parse_single_example`` before batching)."""
+    """A batch of serialized Examples -> ``[batch, *shape]`` arrays of its ``FixedLenFeature``s (``VarLenFeature`` is per-record: use
+    ``parse_single_example`` before batching).  float32 / int64 / string features take the native batch parser
+    (``dtf_parse_examples``); anything else, and every error report, the per-record Python path."""
     if any(isinstance(s, VarLenFeature) for s in features.values()):
         raise NotImplementedError("parse_example with VarLenFeature (sparse batches): parse single examples before batching")
-    rows = [parse_single_example(s, features) for s in (serialized.tolist() if isinstance(serialized, np.ndarray) else serialized)]
+    recs = serialized.reshape(-1).tolist() if isinstance(serialized, np.ndarray) else list(serialized)
+    recs = [r.item() if isinstance(r, np.ndarray) else bytes(r) for r in recs]
+    got = _parse_examples_native(recs, features)
+    if got is not None:
+        return got
+    rows = [parse_single_example(s, features) for s in recs]
     return {k: np.stack([r[k] for r in rows]) for k in features}
 
 
 def decode_raw(data, out_type, little_endian: bool = True, name=None) -> np.ndarray:
-    """The bytes of a string feature reinterpreted as a 1-D array of ``out_type`` (images stored with ``tobytes()``)."""
+    """The bytes of a string feature reinterpreted as a 1-D array of ``out_type`` (images stored with ``tobytes()``); a batch of
+    equally long strings (a list, or the object array ``parse_example`` returns) gives ``[batch, n]``."""
+    dt = np.dtype(_np_dtype(out_type))
+    if isinstance(data, (list, tuple)) or (isinstance(data, np.ndarray) and data.dtype == object and data.ndim >= 1):
+        rows = [bytes(r) for r in (data.reshape(-1).tolist() if isinstance(data, np.ndarray) else data)]
+        if len({len(r) for r in rows}) > 1:
+            raise ValueError("decode_raw(): the strings of a batch must have the same length")
+        flat = np.frombuffer(b"".join(rows), dt.newbyteorder("<" if little_endian else ">")).astype(dt)
+        lead = data.shape if isinstance(data, np.ndarray) else (len(rows),)
+        return flat.reshape(tuple(lead) + (-1,))
     if isinstance(data, np.ndarray):
         data = data.item() if data.shape == () else data.tobytes()
-    dt = np.dtype(_np_dtype(out_type))
     return np.frombuffer(bytes(data), dt.newbyteorder("<" if little_endian else ">")).astype(dt)
 
 

@@ -4,10 +4,10 @@ to records (the reference feeds ``mnist.train.next_batch`` through placeholders,
     python examples/mnist_tfrecords.py --data_dir /tmp/mnist_records --train_steps 300
 
 Step 1 (once): the training split is written as ``tf.train.Example`` records (``image_raw``: the fp32 pixels as bytes, ``label``:
-int64) into ``--shards`` TFRecord files.  Step 2: ``TFRecordDataset -> map(parse) -> shuffle -> repeat -> batch -> prefetch ->
+int64) into ``--shards`` TFRecord files.  Step 2: ``TFRecordDataset -> shuffle -> repeat -> batch -> map(parse_batch) -> prefetch ->
 get_next`` feeds the same model / clipped batch-sum cross-entropy / Adam as ``distributed_mnist.py`` under a
 ``MonitoredTrainingSession``; prints steps/s and the accuracy on held-out records.  Files are mapped and checksum-verified by the
-native scanner (``csrc/runtime/bundle_io.cpp: dtf_tfrecord_scan``)."""
+native scanner (``csrc/runtime/bundle_io.cpp: dtf_tfrecord_scan``), batches are parsed by ``csrc/runtime/example_parser.cpp``."""
 import os
 import sys
 
@@ -53,14 +53,19 @@ def convert(data_dir: str):
     return train, test
 
 
-def parse(record):
-    d = dtf.parse_single_example(record, {"image_raw": dtf.FixedLenFeature([], dtf.string), "label": dtf.FixedLenFeature([], dtf.int64)})
-    return dtf.decode_raw(d["image_raw"], dtf.float32), np.eye(10, dtype=np.float32)[int(d["label"])]
+SPEC = {"image_raw": dtf.FixedLenFeature([], dtf.string), "label": dtf.FixedLenFeature([], dtf.int64)}
+
+
+def parse_batch(records):
+    """A whole batch of serialized Examples at once (``batch`` BEFORE ``map``, the fast spelling in TensorFlow too): the native batch
+    parser fills the label array and locates the image bytes, ``decode_raw`` views them as ``[batch, 784]`` floats."""
+    d = dtf.parse_example(records, SPEC)
+    return dtf.decode_raw(d["image_raw"], dtf.float32), np.eye(10, dtype=np.float32)[d["label"]]
 
 
 def main():
     train_files, test_file = convert(FLAGS.data_dir)
-    ds = dtf.data.TFRecordDataset(train_files).map(parse).shuffle(2000, seed=0).repeat().batch(FLAGS.batch_size).prefetch(2)
+    ds = dtf.data.TFRecordDataset(train_files).shuffle(2000, seed=0).repeat().batch(FLAGS.batch_size).map(parse_batch).prefetch(2)
     x, y_ = ds.make_one_shot_iterator().get_next()
     global_step = dtf.train.get_or_create_global_step()
     h = FLAGS.hidden_units
@@ -74,8 +79,7 @@ def main():
     loss = -dtf.reduce_sum(y_ * dtf.log(dtf.clip_by_value(dtf.nn.softmax(model(x)), 1e-10, 1.0)))
     train_op = dtf.train.AdamOptimizer(FLAGS.learning_rate).minimize(loss, global_step=global_step)
     # held-out records, parsed eagerly (a python-side use of the same reader)
-    held = [parse(r) for r in dtf.python_io.tf_record_iterator(test_file)]
-    vx, vy = np.stack([a for a, _ in held]), np.stack([b for _, b in held])
+    vx, vy = parse_batch(list(dtf.python_io.tf_record_iterator(test_file)))
     px = dtf.placeholder(dtf.float32, [None, 784])
     pred = dtf.argmax(model(px), 1)
     t0, steps, last = time.time(), 0, float("nan")

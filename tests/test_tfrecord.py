@@ -171,3 +171,63 @@ def test_native_scanner_agrees_with_the_python_reader_on_good_truncated_and_corr
         assert got == recs[:first_bad]
     open(path, "wb").write(b"")
     assert list(tfrecord.tf_record_iterator(path)) == []
+
+
+def test_native_batch_parser_agrees_with_the_per_record_python_path():
+    """``dtf_parse_examples`` (csrc/runtime/example_parser.cpp) against ``parse_single_example`` on the same records: packed and
+    unpacked encodings, negative / 40-bit integers, multi-element features, bytes, unknown keys, defaults for absent keys; its
+    error reports are left to the Python path."""
+    from distributed_tensorflow_b200.utils.summary import _f_bytes, _key, _varint
+    if tfrecord._parse_examples_native([b""], {}) is None and tfrecord._parse_examples_native([_example(0)[0].SerializeToString()],
+                                                                                             {"label": tf.FixedLenFeature([], tf.int64)}) is None:
+        pytest.skip("native runtime library not built")
+    recs = [_example(i)[0].SerializeToString() for i in range(17)]
+    spec = {"image_raw": tf.FixedLenFeature([], tf.string), "label": tf.FixedLenFeature([], tf.int64),
+            "weights": tf.FixedLenFeature([2], tf.float32), "big": tf.FixedLenFeature([2, 1], tf.int64),
+            "absent": tf.FixedLenFeature([3], tf.float32, default_value=[1.0, 2.0, 3.0])}
+    nat = tfrecord._parse_examples_native(recs, spec)
+    assert nat is not None
+    for i, r in enumerate(recs):
+        one = tf.parse_single_example(r, spec)
+        for k in spec:
+            assert np.array_equal(nat[k][i], one[k]) and np.shape(nat[k][i]) == one[k].shape, (i, k)
+    assert nat["big"].shape == (17, 2, 1) and nat["big"][4, :, 0].tolist() == [-1, 2 ** 40 + 4] and nat["label"].dtype == np.int64
+    imgs = tf.decode_raw(nat["image_raw"], tf.float32)                                  # batched: [17, 6]
+    assert imgs.shape == (17, 6) and np.array_equal(imgs[5].reshape(2, 3), _example(5)[1])
+    # unpacked repeated scalars (old writers): FloatList {1: fixed32}{1: fixed32}, Int64List {1: varint}{1: varint}
+    fl = b"".join(_key(1, 5) + struct.pack("<f", v) for v in (0.25, -4.0))
+    il = b"".join(_key(1, 0) + _varint(v) for v in (7, -3))
+    entry = lambda k, feat: _f_bytes(1, _f_bytes(1, k.encode()) + _f_bytes(2, feat))          # noqa: E731
+    rec = _f_bytes(1, entry("weights", _f_bytes(2, fl)) + entry("big", _f_bytes(3, il)) + entry("extra", _f_bytes(1, _f_bytes(1, b"zz"))))
+    got = tfrecord._parse_examples_native([rec], {"weights": tf.FixedLenFeature([2], tf.float32), "big": tf.FixedLenFeature([2], tf.int64)})
+    assert got["weights"].tolist() == [[0.25, -4.0]] and got["big"].tolist() == [[7, -3]]
+    assert tf.parse_single_example(rec, {"big": tf.FixedLenFeature([2], tf.int64)})["big"].tolist() == [7, -3]
+    # problems: the native parser steps aside (None) and parse_example raises what the Python path raises
+    for bad_spec, msg in (({"weights": tf.FixedLenFeature([3], tf.float32)}, "needs 3"), ({"weights": tf.FixedLenFeature([2], tf.int64)}, "float_list"),
+                          ({"nope": tf.FixedLenFeature([], tf.int64)}, "no feature")):
+        assert tfrecord._parse_examples_native(recs, bad_spec) is None
+        with pytest.raises(ValueError, match=msg):
+            tf.parse_example(recs, bad_spec)
+    assert tfrecord._parse_examples_native([recs[0][:-3]], {"label": tf.FixedLenFeature([], tf.int64)}) is None          # truncated record
+    assert tfrecord._parse_examples_native(recs, {"tags": tf.VarLenFeature(tf.string)}) is None                          # not a fixed-length spec
+
+
+def test_batch_then_parse_pipeline_matches_parse_then_batch(tmp_path):
+    path = str(tmp_path / "d.tfrecord")
+    with tf.python_io.TFRecordWriter(path) as w:
+        for i in range(40):
+            w.write(_example(i)[0].SerializeToString())
+    spec = {"image_raw": tf.FixedLenFeature([], tf.string), "label": tf.FixedLenFeature([], tf.int64)}
+
+    def parse_batch(recs):
+        d = tf.parse_example(recs, spec)
+        return tf.decode_raw(d["image_raw"], tf.float32), d["label"]
+
+    def parse_one(rec):
+        d = tf.parse_single_example(rec, spec)
+        return tf.decode_raw(d["image_raw"], tf.float32), d["label"]
+    a = list(tf.data.TFRecordDataset(path).batch(16).map(parse_batch)._make())
+    b = list(tf.data.TFRecordDataset(path).map(parse_one).batch(16)._make())
+    assert len(a) == len(b) == 3 and a[2][0].shape == (8, 6)
+    for (xa, la), (xb, lb) in zip(a, b):
+        assert np.array_equal(xa, xb) and np.array_equal(la, lb)
