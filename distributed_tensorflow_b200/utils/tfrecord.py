@@ -21,7 +21,7 @@ import numpy as np
 from .summary import _decode, _f_bytes, _read_tfrecords, _varint
 
 __all__ = ["TFRecordWriter", "tf_record_iterator", "Example", "Features", "Feature", "BytesList", "FloatList", "Int64List",
-           "FixedLenFeature", "VarLenFeature", "parse_single_example", "parse_example", "decode_raw", "TFRecordDataset"]
+           "FixedLenFeature", "VarLenFeature", "parse_single_example", "parse_example", "decode_raw", "TFRecordDataset", "read_all"]
 
 
 class TFRecordWriter:
@@ -368,6 +368,26 @@ def parse_example(serialized: Sequence[bytes], features: Dict[str, Any], name=No
         return got
     rows = [parse_single_example(s, features) for s in recs]
     return {k: np.stack([r[k] for r in rows]) for k in features}
+
+
+def read_all(filenames, features: Dict[str, Any], chunk: int = 4096) -> Dict[str, np.ndarray]:
+    """Every record of the files parsed into ``{key: [n, *shape]}`` arrays (native scanner + native batch parser, ``chunk`` records
+    per call): the bulk loader in front of ``utils/input_pipeline.EpochBatcher`` -- a data set that lives in record files becomes
+    the in-memory arrays the fabric engine's host-fed loop (``PSTrainEngine.train_loop``) cycles through pinned memory."""
+    files = [filenames] if isinstance(filenames, (str, bytes)) else list(filenames)
+    parts: List[Dict[str, np.ndarray]] = []
+    pending: List[bytes] = []
+    for path in files:
+        for rec in tf_record_iterator(path.decode() if isinstance(path, bytes) else str(path)):
+            pending.append(rec)
+            if len(pending) >= chunk:
+                parts.append(parse_example(pending, features))
+                pending = []
+    if pending:
+        parts.append(parse_example(pending, features))
+    if not parts:
+        return {k: np.zeros((0,) + tuple(getattr(s, "shape", ())), dtype=_np_dtype(s.dtype)) for k, s in features.items()}
+    return {k: np.concatenate([p[k] for p in parts], 0) for k in features}
 
 
 def decode_raw(data, out_type, little_endian: bool = True, name=None) -> np.ndarray:

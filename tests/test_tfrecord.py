@@ -231,3 +231,28 @@ def test_batch_then_parse_pipeline_matches_parse_then_batch(tmp_path):
     assert len(a) == len(b) == 3 and a[2][0].shape == (8, 6)
     for (xa, la), (xb, lb) in zip(a, b):
         assert np.array_equal(xa, xb) and np.array_equal(la, lb)
+
+
+def test_read_all_bulk_loads_record_files_for_the_epoch_batcher(tmp_path):
+    """Record files -> in-memory arrays (``tfrecord.read_all``) -> ``EpochBatcher`` (shuffled epochs in one buffer, native row
+    gather): the bulk path in front of the fabric engine's host-fed loop."""
+    from distributed_tensorflow_b200.utils.input_pipeline import EpochBatcher
+    files = []
+    for k in range(3):
+        path = str(tmp_path / ("p%d.tfrecord" % k))
+        files.append(path)
+        with tf.python_io.TFRecordWriter(path) as w:
+            for i in range(k * 10, k * 10 + 10):
+                w.write(tf.train.Example(features=tf.train.Features(feature={
+                    "x": tf.train.Feature(float_list=tf.train.FloatList(value=[i, i + 0.5, -i])),
+                    "y": tf.train.Feature(int64_list=tf.train.Int64List(value=[i % 4]))})).SerializeToString())
+    spec = {"x": tf.FixedLenFeature([3], tf.float32), "y": tf.FixedLenFeature([], tf.int64)}
+    got = tfrecord.read_all(files, spec, chunk=7)                      # several parser calls per file boundary
+    assert got["x"].shape == (30, 3) and got["x"][:, 0].tolist() == list(map(float, range(30))) and got["y"].tolist() == [i % 4 for i in range(30)]
+    assert tfrecord.read_all([], spec)["x"].shape == (0, 3)
+    onehot = np.eye(4, dtype=np.float32)[got["y"]]
+    eb = EpochBatcher(got["x"], onehot, batch=5, seed=0, pin=False)
+    xb, yb = eb.next_epoch()
+    assert tuple(xb.shape) == (6, 5, 3) and sorted(np.asarray(xb)[:, :, 0].reshape(-1).tolist()) == list(map(float, range(30)))
+    rows = np.asarray(xb).reshape(-1, 3)
+    assert np.array_equal(np.asarray(yb).reshape(-1, 4).argmax(1), rows[:, 0].astype(int) % 4)          # labels travel with their rows
