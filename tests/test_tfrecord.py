@@ -1,5 +1,6 @@
 """TFRecord files + ``tf.train.Example`` (utils/tfrecord.py): framing and message bytes checked against the protobuf runtime's own
 encoder (a hand-built descriptor of ``tensorflow.Example``), parsing, and a ``TFRecordDataset`` pipeline feeding a training loop."""
+import os
 import struct
 
 import numpy as np
@@ -256,3 +257,35 @@ def test_read_all_bulk_loads_record_files_for_the_epoch_batcher(tmp_path):
     assert tuple(xb.shape) == (6, 5, 3) and sorted(np.asarray(xb)[:, :, 0].reshape(-1).tolist()) == list(map(float, range(30)))
     rows = np.asarray(xb).reshape(-1, 3)
     assert np.array_equal(np.asarray(yb).reshape(-1, 4).argmax(1), rows[:, 0].astype(int) % 4)          # labels travel with their rows
+
+
+def test_native_parsers_survive_mutated_records_under_address_and_ub_sanitizers(tmp_path):
+    """Record files are external input: the C++ scanner and Example parser are fuzzed with byte-flipped / truncated / extended
+    records in exact-size heap buffers under ASAN + UBSAN (tests/emu/fuzz_record_parsers.cpp)."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rt = os.path.join(root, "distributed_tensorflow_b200", "csrc", "runtime")
+    exe = str(tmp_path / "fuzz")
+    cc = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer",
+                         "-o", exe, os.path.join(root, "tests", "emu", "fuzz_record_parsers.cpp"), os.path.join(rt, "example_parser.cpp"),
+                         os.path.join(rt, "bundle_io.cpp"), "-pthread"], capture_output=True, text=True)
+    if cc.returncode != 0:
+        pytest.skip("sanitizer build not available here: %s" % cc.stderr[-300:])
+    seeds = str(tmp_path / "seeds.bin")
+    with open(seeds, "wb") as f:
+        recs = []
+        for i in range(8):
+            recs.append(tf.train.Example(features=tf.train.Features(feature={
+                "image_raw": tf.train.Feature(bytes_list=tf.train.BytesList(value=[(np.arange(6, dtype=np.float32) + i).tobytes()])),
+                "label": tf.train.Feature(int64_list=tf.train.Int64List(value=[i % 3, -i])),
+                "weights": tf.train.Feature(float_list=tf.train.FloatList(value=[0.5 * i, -1.0, 2.0]))})).SerializeToString())
+        f.write(struct.pack("<I", len(recs)))
+        for r in recs:
+            f.write(struct.pack("<I", len(r)) + r)
+    r = subprocess.run([exe, seeds, "60000"], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "parsed ok" in r.stdout, (r.returncode, r.stdout[-500:], r.stderr[-2000:])
+    ok, rejected = (int(x) for x in r.stdout.replace(",", "").split() if x.isdigit())
+    assert ok > 1000 and rejected > 1000                       # both outcomes exercised
