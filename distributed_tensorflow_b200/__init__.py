@@ -276,6 +276,87 @@ parse_single_example, parse_example, decode_raw = _tfrecord.parse_single_example
 for _n in ("Example", "Features", "Feature", "BytesList", "FloatList", "Int64List"):
     setattr(train, _n, getattr(_tfrecord, _n))
 
+from .utils import gfile  # noqa: E402,F401
+
+
+def _as_bytes(v, encoding="utf-8"):
+    return v if isinstance(v, bytes) else str(v).encode(encoding)
+
+
+def _as_text(v, encoding="utf-8"):
+    return v.decode(encoding) if isinstance(v, bytes) else str(v)
+
+
+compat = _types.SimpleNamespace(as_bytes=_as_bytes, as_text=_as_text, as_str=_as_text, as_str_any=lambda v: _as_text(v) if isinstance(v, bytes) else str(v))
+VERSION = __version__
+
+
+def _is_gpu_available(cuda_only=False, min_cuda_compute_capability=None):
+    import torch as _t
+    return _t.cuda.is_available() is True
+
+
+test = _types.SimpleNamespace(is_gpu_available=_is_gpu_available, gpu_device_name=lambda: "/device:GPU:0" if _is_gpu_available() else "",
+                              is_built_with_cuda=lambda: True)
+
+
+def is_tensor(x) -> bool:
+    """``tf.contrib.framework.is_tensor`` / ``tf.is_tensor``: a graph tensor or variable (not a numpy array / python value)."""
+    from .framework.graph import Tensor as _T
+    from .framework.variables import Variable as _V
+    return isinstance(x, (_T, _V))
+
+
+def reduce_logsumexp(x, axis=None, keepdims=False, name="ReduceLogSumExp", reduction_indices=None, keep_dims=None):
+    """``log(sum(exp(x)))`` computed stably (the maximum is taken out first; its gradient is blocked, the result's is exact)."""
+    if keep_dims is not None:
+        keepdims = keep_dims
+    ax = axis if axis is not None else reduction_indices
+    x = convert_to_tensor(x)
+    m = _ops.stop_gradient(_ops.reduce_max(x, axis=ax, keepdims=True))
+    out = _ops.add(_ops.log(_ops.reduce_sum(_ops.exp(_ops.subtract(x, m)), axis=ax, keepdims=True)), m)
+    if keepdims:
+        return _ops.identity(out, name=name)
+    return _ops.reduce_sum(out, axis=ax, name=name)          # the kept dimensions have size 1: summing drops them
+
+
+def truncatediv(x, y, name="TruncateDiv"):
+    """Integer division rounding towards zero (``floordiv`` rounds down)."""
+    q = _ops.divide(cast(x, float64), cast(y, float64))
+    return cast(where(_ops.greater_equal(q, 0.0) if hasattr(_ops, "greater_equal") else greater_equal(q, 0.0), floor(q), ceil(q)),
+                convert_to_tensor(x).dtype, name=name)
+
+
+def model_variables():
+    return get_default_graph().get_collection("model_variables")
+
+
+def moving_average_variables():
+    return get_default_graph().get_collection("moving_average_variables")
+
+
+def add_check_numerics_ops():
+    """One op that checks every floating-point tensor of the graph built so far for NaN / Inf (run it next to the train op)."""
+    g = get_default_graph()
+    checks = []
+    for n in list(g.nodes):
+        if n.dtype in (float32, float64, float16, bfloat16) and n.op_type not in ("VariableV2", "Placeholder", "Assign", "CheckNumerics"):
+            with g.control_dependencies(None):
+                checks.append(check_numerics(n, "%s:0" % n.name))
+    return group(*checks, name="check_numerics_all")
+
+
+def timestamp(name="Timestamp"):
+    """Seconds since the epoch at the time the op runs (float64 scalar)."""
+    return py_func(lambda: __import__("numpy").float64(__import__("time").time()), [], float64, name=name)
+
+
+initializers = _types.SimpleNamespace(zeros=zeros_initializer, ones=ones_initializer, constant=constant_initializer,
+                                      random_normal=random_normal_initializer, truncated_normal=truncated_normal_initializer,
+                                      random_uniform=random_uniform_initializer, glorot_uniform=glorot_uniform_initializer,
+                                      variance_scaling=variance_scaling_initializer, global_variables=global_variables_initializer,
+                                      local_variables=local_variables_initializer, variables=variables_initializer)
+
 losses = _types.SimpleNamespace(mean_squared_error=_mean_squared_error, softmax_cross_entropy=_softmax_cross_entropy,
                                 sparse_softmax_cross_entropy=_sparse_softmax_cross_entropy)
 del _n

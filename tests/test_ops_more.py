@@ -176,3 +176,59 @@ def test_init_from_checkpoint_warm_starts_through_the_ordinary_init_op_and_write
     p = tf.train.write_graph(tf.get_default_graph(), str(tmp_path / "g"), "graph.pbtxt")
     text = open(p).read()
     assert "name: 'model/a'" in text and "op: 'VariableV2'" in text
+
+
+def test_gfile_follows_the_checkpoint_path_mapping(tmp_path, monkeypatch):
+    """``tf.gfile`` resolves URL-style paths the way the Saver does (the reference's ``hdfs://`` checkpoint directories,
+    ``distributed_mnist.py:127``): what ``MonitoredTrainingSession(checkpoint_dir=...)`` writes, ``tf.gfile`` sees."""
+    monkeypatch.setenv("DTF_HDFS_ROOT", str(tmp_path / "hdfs"))
+    d = "hdfs://namenode:9000/user/ckpt"
+    assert not tf.gfile.Exists(d)
+    tf.gfile.MakeDirs(d)
+    assert tf.gfile.IsDirectory(d) and (tmp_path / "hdfs" / "user" / "ckpt").is_dir()
+    w = tf.Variable([1.0, 2.0], name="w")
+    with tf.Session() as sess:
+        sess.run(tf.global_variables_initializer())
+        tf.train.Saver().save(sess, d + "/model", global_step=3)
+    assert "checkpoint" in tf.gfile.ListDirectory(d) and tf.gfile.Glob(d + "/model-3.*")
+    with tf.gfile.GFile(d + "/notes.txt", "w") as f:
+        f.write("line1\nline2\n")
+    with tf.gfile.Open(d + "/notes.txt") as f:
+        assert f.readline() == "line1\n" and list(f) == ["line2\n"] and f.size() == 12
+    tf.gfile.Copy(d + "/notes.txt", d + "/copy.txt")
+    with pytest.raises(tf.errors.OpError):
+        tf.gfile.Copy(d + "/notes.txt", d + "/copy.txt")
+    tf.gfile.Rename(d + "/copy.txt", d + "/moved.txt")
+    assert tf.gfile.Stat(d + "/moved.txt").length == 12 and not tf.gfile.Exists(d + "/copy.txt")
+    tf.gfile.Remove(d + "/moved.txt")
+    with pytest.raises(tf.errors.NotFoundError):
+        tf.gfile.Remove(d + "/moved.txt")
+    assert [r for r, _, fs in tf.gfile.Walk(d) if "notes.txt" in fs]
+    tf.gfile.DeleteRecursively(d)
+    assert not tf.gfile.Exists(d)
+
+
+def test_small_helpers_logsumexp_truncatediv_check_all_numerics_and_namespaces():
+    x = tf.Variable(np.array([[1000.0, 1000.5, -5.0], [0.1, 0.2, 0.3]], np.float32))
+    lse = tf.reduce_logsumexp(x, axis=1)
+    lse_all = tf.reduce_logsumexp(x, keepdims=True)
+    g = tf.gradients(tf.reduce_sum(lse), [x])[0]
+    td = tf.truncatediv(tf.constant([7, -7, 9]), tf.constant([2, 2, -4]))
+    y = tf.placeholder(tf.float32, [2])
+    z = tf.log(y) * 2.0
+    guard = tf.add_check_numerics_ops()
+    with tf.Session() as sess:
+        sess.run(tf.global_variables_initializer())
+        a, b, gv, t = sess.run([lse, lse_all, g, td])
+        xt = torch.tensor([[1000.0, 1000.5, -5.0], [0.1, 0.2, 0.3]], requires_grad=True)
+        want = torch.logsumexp(xt, 1)
+        want.sum().backward()
+        assert np.allclose(a, want.detach().numpy(), rtol=1e-6) and np.isfinite(a).all() and b.shape == (1, 1)
+        assert np.allclose(gv, xt.grad.numpy(), atol=2e-5) and t.tolist() == [3, -3, -2]      # (fp32 rounding: ours is the closer one)
+        sess.run([z, guard], {y: [1.0, 2.0]})
+        with pytest.raises(tf.errors.InvalidArgumentError):
+            sess.run([z, guard], {y: [1.0, -2.0]})                     # log of a negative number: NaN somewhere in the graph
+        assert abs(float(sess.run(tf.timestamp())) - __import__("time").time()) < 5.0
+    assert tf.compat.as_bytes("ab") == b"ab" and tf.compat.as_str(b"ab") == "ab" and tf.VERSION == tf.__version__
+    assert tf.is_tensor(x) and tf.is_tensor(lse) and not tf.is_tensor(np.zeros(2))
+    assert tf.test.gpu_device_name() in ("", "/device:GPU:0") and tf.initializers.zeros is tf.zeros_initializer
