@@ -29,7 +29,7 @@ import torch
 from ..framework import errors
 from ..framework.executor import ExecContext, ResourceStore, execute
 from .cluster import ClusterSpec
-from .rpc import PeerAwareCancel, RpcClient, RpcServer, current_connection, parse_address
+from .rpc import PeerAwareCancel, RpcClient, RpcServer, current_connection, parse_address, peer_closed
 
 __all__ = ["Server", "NodeView", "serialize_nodes", "local_server_for", "local_servers"]
 
@@ -67,6 +67,35 @@ def _stop_local_servers_at_exit() -> None:
     finalisation with ``pthread_exit``; that forced unwind racing the process's static destructors showed up as a rare
     ``terminate called without an active exception`` (exit -6) AFTER the script's output was complete.  Closing the
     listeners / connections here lets every one of those threads return and be joined while the interpreter is whole."""
+    # a peer's client session may still be using this task (in-graph replication: the reference's example_distributed_server.py
+    # makes EVERY worker a client of every other one): leave only once those sessions were released or their clients are gone,
+    # within DTF_EXIT_LINGER_S (default 10 s) -- a task that simply drops out fails its peers' in-flight runs with UnavailableError
+    try:
+        linger = float(os.environ.get("DTF_EXIT_LINGER_S", "10"))
+    except ValueError:
+        linger = 10.0
+    # DTF_EXIT_SERVE_S: keep serving for at least this long after the script returned (a task whose peers may not have reached it
+    # yet: every worker of example_distributed_server.py is a client that exits when ITS run is done)
+    try:
+        serve_s = float(os.environ.get("DTF_EXIT_SERVE_S", "0"))
+    except ValueError:
+        serve_s = 0.0
+    if serve_s > 0 and local_servers():
+        t_end = time.time() + serve_s
+        while time.time() < t_end and local_servers():
+            time.sleep(0.1)
+    deadline = time.time() + max(0.0, linger)
+    while time.time() < deadline:
+        busy = False
+        for srv in local_servers():
+            for sid, conn in list(srv._remote_sessions.items()):
+                if getattr(conn, "closed", False) or peer_closed(conn):
+                    srv._remote_sessions.pop(sid, None)
+                else:
+                    busy = True
+        if not busy:
+            break
+        time.sleep(0.05)
     for srv in local_servers():
         try:
             rpc = srv._rpc
@@ -155,6 +184,7 @@ class Server:
         us = float(os.environ.get("DTF_GIL_SWITCH_US", "200"))
         if us > 0 and sys.getswitchinterval() > us * 1e-6:
             sys.setswitchinterval(us * 1e-6)
+        self._remote_sessions: Dict[str, Any] = {}           # open sessions of REMOTE clients that ran something here -> their connection
         self._fabric_gen: Dict[str, Dict[str, Any]] = {}      # fabric incarnations (rpc_fabric_generation); ps task 0 is asked
         self._fabric_gen_lock = threading.Lock()
         if start:
@@ -267,6 +297,8 @@ class Server:
         conn = current_connection()
         if conn is not None:         # remote client: blocking kernels also give up when that client dies
             ctx.cancel_event = PeerAwareCancel(self.cancel_event(opts.get("session_id", "")), conn)
+            if opts.get("session_id"):
+                self._remote_sessions[opts["session_id"]] = conn
         dev_default = None
         for nid, v in inputs.items():
             if isinstance(v, torch.Tensor):
@@ -327,6 +359,7 @@ class Server:
         return True
 
     def rpc_release_session(self, session_id, graph_key=None):
+        self._remote_sessions.pop(session_id, None)
         with self._lock:
             self._cancel.pop(session_id, None)
             if graph_key is not None:

@@ -41,8 +41,10 @@ class _Tasks:
 
     def start(self, script, *args):
         log = open(self.tmp_path / ("task%d.log" % len(self.procs)), "w")
-        self.procs.append(subprocess.Popen(_cmd(script, *args), stdout=log, stderr=subprocess.STDOUT, env=_env(self.tmp_path),
-                                           cwd=str(self.tmp_path)))
+        # a background task that is ALSO a client (every worker of example_distributed_server.py) keeps serving after its own run
+        # is done, until the block ends: the foreground task's success must not depend on which of the two finishes first
+        env = dict(_env(self.tmp_path), DTF_EXIT_SERVE_S="300")
+        self.procs.append(subprocess.Popen(_cmd(script, *args), stdout=log, stderr=subprocess.STDOUT, env=env, cwd=str(self.tmp_path)))
 
     def __enter__(self):
         return self

@@ -152,3 +152,51 @@ print("BEFORE", sorted(t.name for t in threading.enumerate() if t.name.startswit
     assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
     assert "dtf-rpc-conn" in r.stdout.split("BEFORE")[1].splitlines()[0] and "8.0" in r.stdout
     assert "ALIVE_AT_EXIT []" in r.stdout, r.stdout
+
+
+def test_an_exiting_task_lingers_while_a_peer_session_is_still_using_it(tmp_path):
+    """In-graph replication makes tasks clients of each other (the reference's example_distributed_server.py: EVERY worker runs the
+    client code).  A task script that returns while a peer's session still places ops on it used to fail that peer's next run with
+    UnavailableError; now its exit waits (bounded by DTF_EXIT_LINGER_S) until the peer released the session or went away."""
+    import socket
+    import subprocess
+    import sys
+    import distributed_tensorflow_b200 as tf
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "serving_task.py"
+    script.write_text('''
+import sys, time
+import distributed_tensorflow_b200 as tf
+srv = tf.train.Server(tf.train.ClusterSpec({"worker": ["127.0.0.1:%d"]}), job_name="worker", task_index=0)
+print("READY", flush=True)
+sys.stdin.readline()                  # the peer ran its first step: this script is done and returns
+print("RETURNING %%.3f" %% time.time(), flush=True)
+''' % port)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""), CUDA_VISIBLE_DEVICES="", DTF_EXIT_LINGER_S="20")
+    p = subprocess.Popen([sys.executable, str(script)], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, env=env)
+    try:
+        assert p.stdout.readline().startswith("READY")
+        tf.reset_default_graph()
+        with tf.device("/job:worker/task:0"):
+            v = tf.Variable(3.0, name="v")
+            bump = tf.assign_add(v, 1.0)
+        sess = tf.Session("grpc://127.0.0.1:%d" % port)
+        sess.run(tf.global_variables_initializer())
+        assert sess.run(bump) == 4.0
+        p.stdin.write("go\n")
+        p.stdin.flush()
+        t_ret = float(p.stdout.readline().split()[1])
+        time.sleep(1.0)                               # the task has returned from its script; our session is still open
+        assert p.poll() is None                       # ... and it is still there
+        assert sess.run(bump) == 5.0                  # the run that used to hit a dead task
+        sess.close()                                  # released: nothing keeps the task any more
+        p.wait(timeout=15)
+        assert p.returncode == 0 and time.time() - t_ret < 10.0
+    finally:
+        if p.poll() is None:
+            p.kill()
+        tf.reset_default_graph()
