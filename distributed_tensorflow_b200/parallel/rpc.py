@@ -19,6 +19,7 @@ import socket
 import threading
 import time
 import traceback
+import weakref
 from multiprocessing import AuthenticationError
 from multiprocessing.connection import Client, Connection, Listener, answer_challenge, deliver_challenge
 from typing import Any, Callable, Dict, Optional, Tuple
@@ -326,10 +327,24 @@ class RpcServer:
         self._serving = [t for t in self._serving if t.is_alive()]
 
 
+_ALL_CLIENTS: "weakref.WeakSet" = weakref.WeakSet()
+
+
+def close_all_clients() -> None:
+    """Close every live RpcClient of this process (exit path: a session the script never closed must not make its own
+    in-process servers wait for it)."""
+    for c in list(_ALL_CLIENTS):
+        try:
+            c.close()
+        except Exception:      # noqa: BLE001 - exit path
+            pass
+
+
 class RpcClient:
     """Client stub; one connection per calling thread (blocking calls do not serialise threads)."""
 
     def __init__(self, address: str, connect_timeout: float = 30.0):
+        _ALL_CLIENTS.add(self)
         self.address = address
         self.host, self.port = parse_address(address)
         self._tls = threading.local()

@@ -70,6 +70,8 @@ def _stop_local_servers_at_exit() -> None:
     # a peer's client session may still be using this task (in-graph replication: the reference's example_distributed_server.py
     # makes EVERY worker a client of every other one): leave only once those sessions were released or their clients are gone,
     # within DTF_EXIT_LINGER_S (default 10 s) -- a task that simply drops out fails its peers' in-flight runs with UnavailableError
+    from .rpc import close_all_clients
+    close_all_clients()           # this process's own client connections: sessions it never closed are not "peers still using us"
     try:
         linger = float(os.environ.get("DTF_EXIT_LINGER_S", "10"))
     except ValueError:
